@@ -1,0 +1,99 @@
+"""ctypes binding of include/bssm_b200.h (the C ABI).  No torch types here."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libbssm_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_uint32_p = C.POINTER(C.c_uint32)
+
+
+class UngModel(C.Structure):
+    """bssm_ung_model"""
+    _fields_ = [
+        ("n", C.c_int32), ("m", C.c_int32), ("k", C.c_int32),
+        ("distribution", C.c_int32),
+        ("Ztv", C.c_int32), ("Ttv", C.c_int32), ("Rtv", C.c_int32),
+        ("Dtv", C.c_int32), ("Ctv", C.c_int32),
+        ("y", c_double_p), ("Z", c_double_p), ("T", c_double_p), ("R", c_double_p),
+        ("a1", c_double_p), ("P1", c_double_p), ("D", c_double_p), ("C", c_double_p),
+        ("xbeta", c_double_p), ("u", c_double_p),
+        ("phi", C.c_double),
+        ("max_iter", C.c_int32), ("local_approx", C.c_int32),
+        ("conv_tol", C.c_double),
+        ("initial_mode", c_double_p),
+    ]
+
+
+class FilterOut(C.Structure):
+    """bssm_filter_out"""
+    _fields_ = [
+        ("alpha", c_double_p), ("weights", c_double_p), ("indices", c_uint32_p),
+        ("at", c_double_p), ("att", c_double_p), ("Pt", c_double_p), ("Ptt", c_double_p),
+        ("alphahat", c_double_p), ("Vt", c_double_p),
+        ("loglik", C.c_double), ("approx_loglik", C.c_double),
+        ("stopped_at", C.c_int32), ("device_ms", C.c_float),
+    ]
+
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads libbssm_b200.so; raises loudly if the CUDA extension is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(
+            "bssm_b200: %s is missing -- build it with `python -m bssm_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.bssm_b200_last_error.restype = C.c_char_p
+    L.bssm_b200_version.restype = C.c_char_p
+    L.bssm_b200_device_count.restype = C.c_int
+    L.bssm_b200_set_device.argtypes = [C.c_int]
+    L.bssm_b200_shutdown.restype = None
+    L.bssm_b200_stratified_sample.argtypes = [c_double_p, C.c_uint32, c_double_p, C.c_uint32, c_uint32_p]
+    L.bssm_b200_math_probe.argtypes = [C.c_int, c_double_p, c_double_p, C.c_uint32]
+    L.bssm_b200_rng_probe.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, c_double_p, c_double_p]
+    for name in ("bssm_b200_bsf", "bssm_b200_bsf_smoother", "bssm_b200_psi_smoother", "bssm_b200_psi_filter"):
+        getattr(L, name).argtypes = [C.POINTER(UngModel), C.c_uint32, C.c_uint32, C.POINTER(FilterOut)]
+    L.bssm_b200_job_create_ung.argtypes = [
+        C.POINTER(UngModel), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+        C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.bssm_b200_job_run.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.bssm_b200_job_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float * 3)]
+    L.bssm_b200_job_launches.argtypes = [C.c_void_p]
+    L.bssm_b200_job_fetch.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(FilterOut)]
+    L.bssm_b200_job_logliks.argtypes = [C.c_void_p, c_double_p]
+    L.bssm_b200_job_logliks_dev.argtypes = [C.c_void_p, C.c_void_p]
+    L.bssm_b200_job_destroy.argtypes = [C.c_void_p]
+    L.bssm_b200_job_destroy.restype = None
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise EngineError("bssm_b200 error %d: %s" % (rc, lib().bssm_b200_last_error().decode()))
+
+
+def dptr(a):
+    return a.ctypes.data_as(c_double_p) if a is not None else None
+
+
+def uptr(a):
+    return a.ctypes.data_as(c_uint32_p) if a is not None else None
+
+
+def f64(a):
+    """column-major contiguous binary64 copy, the layout R / Armadillo use"""
+    return np.asfortranarray(np.asarray(a, dtype=np.float64))

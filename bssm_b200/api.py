@@ -1,0 +1,167 @@
+"""Host-side mirror of the reference's R surface for the particle-filter path.
+
+  bootstrap_filter   R/bootstrap_filter.R:85-120   -> bssm_b200_bsf
+  particle_smoother  R/particle_smoother.R:140-186 -> bssm_b200_psi_smoother /
+                                                      bssm_b200_bsf_smoother
+  logLik             R/loglik.R (particle part)    -> filter-only jobs
+
+Same argument names and checks as the R functions (particles, seed, method);
+results come back as dicts with the R list's names and array shapes
+(alpha already permuted to (n+1) x m x N as R/bootstrap_filter.R:118 does).
+Everything is computed by the CUDA library; there is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import FilterOut, check, dptr, lib, uptr
+
+METHOD_PSI, METHOD_BSF = 1, 2
+POST_NONE, POST_FILTER_SUMMARY, POST_SMOOTHER = 0, 1, 2
+OUT_ALPHA, OUT_WEIGHTS, OUT_INDICES = 1, 2, 4
+
+
+def _check_particles(model, particles, seed):
+    # R/bootstrap_filter.R:88-105 (check_intmax caps particles at 1e5 in the
+    # reference, R/check_arguments.R:407-418; lifted here: N up to 2^20 is the point)
+    particles = int(particles)
+    if particles < 2:
+        raise ValueError("Argument 'particles' should be an integer >= 2.")
+    seed = int(seed)
+    if not 0 <= seed <= 2 ** 31 - 1:
+        raise ValueError("Argument 'seed' should be an integer in [0, 2^31-1].")
+    return particles, seed
+
+
+class _Buffers:
+    def __init__(self, model, N, alpha=True, weights=True, indices=False, filt=False, smooth=False):
+        n, m = model.n, model.m
+        self.out = FilterOut()
+        self.alpha = np.zeros((m, n + 1, N), order="F") if alpha else None
+        self.weights = np.zeros((N, n + 1), order="F") if weights else None
+        self.indices = np.zeros((N, n), dtype=np.uint32, order="F") if indices else None
+        self.at = np.zeros((m, n + 1), order="F") if filt else None
+        self.att = np.zeros((m, n), order="F") if filt else None
+        self.Pt = np.zeros((m, m, n + 1), order="F") if filt else None
+        self.Ptt = np.zeros((m, m, n), order="F") if filt else None
+        self.alphahat = np.zeros((m, n + 1), order="F") if smooth else None
+        self.Vt = np.zeros((m, m, n + 1), order="F") if smooth else None
+        o = self.out
+        o.alpha, o.weights, o.indices = dptr(self.alpha), dptr(self.weights), uptr(self.indices)
+        o.at, o.att, o.Pt, o.Ptt = dptr(self.at), dptr(self.att), dptr(self.Pt), dptr(self.Ptt)
+        o.alphahat, o.Vt = dptr(self.alphahat), dptr(self.Vt)
+
+
+def _warn_stopped(out):
+    if not np.isfinite(out.loglik):
+        import warnings
+        # src/R_bootstrap_filter.cpp:166-167
+        warnings.warn("Particle filtering stopped prematurely due to nonfinite log-likelihood.")
+
+
+def bootstrap_filter(model, particles, seed=1, return_indices=False):
+    """bootstrap_filter.nongaussian, R/bootstrap_filter.R:85-120."""
+    N, seed = _check_particles(model, particles, seed)
+    b = _Buffers(model, N, indices=return_indices, filt=True)
+    ms = model.c_struct()
+    check(lib().bssm_b200_bsf(C.byref(ms), N, seed, C.byref(b.out)))
+    _warn_stopped(b.out)
+    res = {"at": b.at.T.copy(), "att": b.att.T.copy(), "Pt": b.Pt, "Ptt": b.Ptt,
+           "weights": b.weights, "logLik": b.out.loglik,
+           "alpha": np.transpose(b.alpha, (1, 0, 2)),  # aperm(alpha, c(2, 1, 3))
+           "device_ms": b.out.device_ms, "stopped_at": b.out.stopped_at}
+    if return_indices:
+        res["indices"] = b.indices
+    return res
+
+
+def particle_smoother(model, particles, method="psi", seed=1, return_indices=False):
+    """particle_smoother.nongaussian, R/particle_smoother.R:140-186."""
+    if method not in ("psi", "bsf"):
+        raise ValueError("method must be 'psi' or 'bsf' (EKPF is for ssm_nlg models)")
+    N, seed = _check_particles(model, particles, seed)
+    b = _Buffers(model, N, indices=return_indices, smooth=True)
+    ms = model.c_struct()
+    fn = lib().bssm_b200_psi_smoother if method == "psi" else lib().bssm_b200_bsf_smoother
+    check(fn(C.byref(ms), N, seed, C.byref(b.out)))
+    _warn_stopped(b.out)
+    res = {"alphahat": b.alphahat.T.copy(), "Vt": b.Vt, "weights": b.weights,
+           "logLik": b.out.loglik, "alpha": np.transpose(b.alpha, (1, 0, 2)),
+           "device_ms": b.out.device_ms, "stopped_at": b.out.stopped_at,
+           "approx_logLik": b.out.approx_loglik}
+    if return_indices:
+        res["indices"] = b.indices
+    return res
+
+
+class FilterJob:
+    """Resident batch of replicate filters (bssm_b200_job_*): device-side
+    inputs and outputs, run() launches kernels only."""
+
+    def __init__(self, model, particles, method="psi", seed=1, n_filters=1, first_filter=0,
+                 out_flags=0, post=POST_NONE):
+        N, seed = _check_particles(model, particles, seed)
+        self.model, self.N, self.n_filters = model, N, int(n_filters)
+        self._ms = model.c_struct()
+        self._h = C.c_void_p()
+        meth = METHOD_PSI if method == "psi" else METHOD_BSF
+        check(lib().bssm_b200_job_create_ung(C.byref(self._ms), meth, N, seed, self.n_filters,
+                                             int(first_filter), int(out_flags), int(post),
+                                             C.byref(self._h)))
+
+    def run(self):
+        ms = C.c_float()
+        check(lib().bssm_b200_job_run(self._h, C.byref(ms)))
+        return ms.value
+
+    def kernel_ms(self):
+        a = (C.c_float * 3)()
+        check(lib().bssm_b200_job_kernel_ms(self._h, C.byref(a)))
+        return list(a)
+
+    def launches(self):
+        return lib().bssm_b200_job_launches(self._h)
+
+    def logliks(self):
+        out = np.zeros(self.n_filters)
+        check(lib().bssm_b200_job_logliks(self._h, dptr(out)))
+        return out
+
+    def logliks_to_device(self, dev_ptr):
+        check(lib().bssm_b200_job_logliks_dev(self._h, C.c_void_p(dev_ptr)))
+
+    def fetch(self, f=0, alpha=False, weights=False, indices=False, filt=False, smooth=False):
+        b = _Buffers(self.model, self.N, alpha=alpha, weights=weights, indices=indices, filt=filt, smooth=smooth)
+        check(lib().bssm_b200_job_fetch(self._h, int(f), C.byref(b.out)))
+        return b
+
+    def close(self):
+        if self._h:
+            lib().bssm_b200_job_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def logLik(model, particles, method="psi", seed=1):
+    """logLik.nongaussian (particle part), R/loglik.R:60-120: log-likelihood only."""
+    job = FilterJob(model, particles, method=method, seed=seed)
+    try:
+        job.run()
+        return float(job.logliks()[0])
+    finally:
+        job.close()
+
+
+def stratified_sample(p, r):
+    """Unit hook of src/stratified_sample.cpp:9-28 (fixed-point cumsum)."""
+    p = _lib.f64(np.ravel(p))
+    r = _lib.f64(np.ravel(r))
+    xp = np.zeros(r.size, dtype=np.uint32)
+    check(lib().bssm_b200_stratified_sample(dptr(p), p.size, dptr(r), r.size, uptr(xp)))
+    return xp

@@ -1,0 +1,791 @@
+// api.cu -- C ABI of the engine (include/bssm_b200.h): host-side logic that
+// lays the reference's model list out on the device, picks a launch geometry,
+// runs pre-pass -> filter -> post-processing kernels on one stream and hands
+// results back in the reference's layouts.
+//
+// Host-side model logic restated here (not hot path, O(n) or O(m^3)):
+//   ssm_ung::approximate   /root/reference/src/model_ssm_ung.cpp:87-140
+//   ssm_ulg::fast_smoother src/model_ssm_ulg.cpp:252-305 (scalar case)
+//   chol of P1 sub-block   src/model_ssm_ung.cpp:614-619
+//   distribution constants src/distr_consts.cpp:7-67
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <limits>
+
+#include "bssm_b200.h"
+#include "pf_device.cuh"
+#include "models_ung.cuh"
+#include "prepass_ung.cuh"
+#include "smoother_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      return fail(BSSM_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+int require_device() {
+  int cnt = 0;
+  cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess || cnt == 0) {
+    cudaGetLastError();
+    return fail(BSSM_B200_ERR_NO_DEVICE,
+                "no CUDA device: bssm_b200 has no CPU fallback (cudaGetDeviceCount: " +
+                    std::string(e == cudaSuccess ? "0 devices" : cudaGetErrorString(e)) + ")");
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------- geometry
+struct Geometry {
+  int P, block;
+  uint32_t ranks;
+  int sync_mode;
+};
+
+int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+uint32_t round32(uint32_t a) { return cdiv(a, 32) * 32; }
+
+int choose_geometry(uint32_t N, Geometry* g) {
+  uint32_t ranks;
+  int P;
+  const uint32_t cap4 = 4096, cap8 = 8192;
+  if (N <= 1024) { ranks = 1; P = 2; }
+  else if (N <= cap4) { ranks = 1; P = 4; }
+  else if (N <= 16 * cap4) { ranks = 1; while (ranks * cap4 < N) ranks *= 2; P = 4; }
+  else if (N <= 16 * cap8) { ranks = 16; P = 8; }
+  else { ranks = 0; P = 8; }
+  int forced_ranks = env_int("BSSM_B200_RANKS", 0);
+  int forced_P = env_int("BSSM_B200_P", 0);
+  if (forced_P == 2 || forced_P == 4 || forced_P == 8) P = forced_P;
+  if (forced_ranks > 0) ranks = (uint32_t)forced_ranks;
+  if (ranks == 0) { // grid mode
+    int block = 512;
+    ranks = cdiv(N, (uint32_t)(block * P));
+    g->P = P; g->block = block; g->ranks = ranks; g->sync_mode = pf::SYNC_GRID;
+    return 0;
+  }
+  uint32_t per_rank = cdiv(N, ranks);
+  uint32_t block = round32(cdiv(per_rank, (uint32_t)P));
+  if (block > 1024) return fail(BSSM_B200_ERR_ARG, "geometry: too many particles per CTA");
+  if (block < 32) block = 32;
+  g->P = P; g->block = (int)block; g->ranks = ranks;
+  g->sync_mode = ranks == 1 ? pf::SYNC_BLOCK : (ranks <= 16 ? pf::SYNC_CLUSTER : pf::SYNC_GRID);
+  return 0;
+}
+
+// --------------------------------------------------------------- launching
+template <class Model, int P>
+int launch_filter_P(const pf::FilterParams& fp, const typename Model::Params& mp, const Geometry& g,
+                    uint32_t n_filters, cudaStream_t stream) {
+  auto kern = pf::filter_kernel<Model, P>;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(n_filters * g.ranks, 1, 1);
+  cfg.blockDim = dim3(g.block, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = 0;
+  if (g.sync_mode == pf::SYNC_CLUSTER) {
+    if (g.ranks > 8) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = g.ranks;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.numAttrs = 1;
+  } else if (g.sync_mode == pf::SYNC_GRID) {
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.numAttrs = 1;
+  }
+  CU(cudaLaunchKernelEx(&cfg, kern, fp, mp));
+  return 0;
+}
+
+template <class Model>
+int launch_filter(const pf::FilterParams& fp, const typename Model::Params& mp, const Geometry& g,
+                  uint32_t n_filters, cudaStream_t stream) {
+  switch (g.P) {
+    case 2: return launch_filter_P<Model, 2>(fp, mp, g, n_filters, stream);
+    case 4: return launch_filter_P<Model, 4>(fp, mp, g, n_filters, stream);
+    case 8: return launch_filter_P<Model, 8>(fp, mp, g, n_filters, stream);
+  }
+  return fail(BSSM_B200_ERR_ARG, "bad P");
+}
+
+// ------------------------------------------------------- host model pieces
+bool finite(double x) { return std::isfinite(x); }
+
+// src/distr_consts.cpp:7-67 through the switch at src/model_ssm_ung.cpp:690-710
+double ung_dist_const(const bssm_ung_model* M) {
+  auto lch = [](double n, double k) {
+    return -std::log(n + 1) - std::lgamma(n - k + 1) - std::lgamma(k + 1) + std::lgamma(n + 2);
+  };
+  double res = 0.0;
+  const double phi = M->phi;
+  for (int t = 0; t < M->n; ++t) {
+    const double y = M->y[t];
+    if (!finite(y)) continue;
+    const double u = M->u[t];
+    switch (M->distribution) {
+      case 0: res += -0.5 * std::log(2.0 * M_PI) - std::log(phi); break;
+      case 1: res += y * std::log(u) - std::lgamma(y + 1); break;
+      case 2: res += lch(u, y); break;
+      case 3: res += lch(y + phi - 1, y) + phi * std::log(phi) + y * std::log(u); break;
+      case 4: res += phi * std::log(phi) - std::lgamma(phi) + (phi - 1) * std::log(y) - phi * std::log(u); break;
+    }
+  }
+  return res;
+}
+
+// lower Cholesky factor of the positive-diagonal block of P1 (:614-619)
+void chol_posdiag(const double* P1, int m, std::vector<double>& L) {
+  L.assign((size_t)m * m, 0.0);
+  std::vector<int> idx;
+  for (int d = 0; d < m; ++d)
+    if (P1[d + (size_t)m * d] > 0) idx.push_back(d);
+  const int q = (int)idx.size();
+  for (int c = 0; c < q; ++c)
+    for (int r = c; r < q; ++r) {
+      double s = P1[idx[r] + (size_t)m * idx[c]];
+      for (int l = 0; l < c; ++l) s -= L[idx[r] + (size_t)m * idx[l]] * L[idx[c] + (size_t)m * idx[l]];
+      L[idx[r] + (size_t)m * idx[c]] = (r == c) ? std::sqrt(s) : s / L[idx[c] + (size_t)m * idx[c]];
+    }
+}
+
+// Newton/Laplace iterations for the mode of the Gaussian approximation, m = 1:
+// ssm_ung::approximate (:87-140, local branch) = repeat { laplace_iter (:302-342);
+// fast_smoother (src/model_ssm_ulg.cpp:252-305) } until the mean squared change
+// of the mode is below conv_tol.  Sequential in t, O(n) per sweep: host work.
+void ung_approximate_m1(const bssm_ung_model* M, std::vector<double>& mode) {
+  const int n = M->n;
+  const double zero_tol = 1e-12;
+  const double phi = M->phi;
+  mode.assign(M->initial_mode, M->initial_mode + n);
+  std::vector<double> HH(n), yt(n), at(n + 1), v(n), F(n), K(n), r(n), next(n);
+  auto Z = [&](int t) { return M->Z[t * M->Ztv]; };
+  auto T = [&](int t) { return M->T[t * M->Ttv]; };
+  auto RR = [&](int t) { double x = M->R[t * M->Rtv]; return x * x; };
+  auto C = [&](int t) { return M->C[t * M->Ctv]; };
+  auto D = [&](int t) { return M->D[t * M->Dtv]; };
+  auto xb = [&](int t) { return M->xbeta ? M->xbeta[t] : 0.0; };
+  auto yobs = [&](int t) { return M->xbeta ? yt[t] - M->xbeta[t] : yt[t]; };
+  int it = 0;
+  double diff = M->conv_tol + 1;
+  while (it < M->max_iter && diff > M->conv_tol) {
+    it++;
+    for (int t = 0; t < n; ++t) { // laplace_iter
+      const double y = M->y[t], u = M->u[t], s = mode[t];
+      switch (M->distribution) {
+        case 0: {
+          double tmp = y;
+          if (std::fabs(tmp) < 1e-4) tmp = 1e-4;
+          double q = tmp / phi;
+          HH[t] = 2.0 * pf_exp(s) / (q * q);
+          yt[t] = s + 1.0 - 0.5 * HH[t];
+        } break;
+        case 1: {
+          HH[t] = 1.0 / (pf_exp(s) * u);
+          yt[t] = y * HH[t] + s - 1.0;
+        } break;
+        case 2: {
+          double e = pf_exp(s);
+          HH[t] = (1.0 + e) * (1.0 + e) / (u * e);
+          yt[t] = y * HH[t] + s - 1.0 - e;
+        } break;
+        case 3: {
+          double e = pf_exp(s) * u;
+          HH[t] = (phi + e) * (phi + e) / (phi * e * (y + phi));
+          yt[t] = s + (phi + e) * (y - e) / ((y + phi) * e);
+        } break;
+        default: {
+          double e = pf_exp(s) * u;
+          HH[t] = e / (y * phi);
+          yt[t] = s - e / y + 1;
+        } break;
+      }
+    }
+    // fast_smoother
+    at[0] = M->a1[0];
+    double Pt = M->P1[0];
+    for (int t = 0; t < n; ++t) {
+      F[t] = Z(t) * Pt * Z(t) + HH[t];
+      const double yy = yobs(t);
+      if (finite(yy) && F[t] > zero_tol) {
+        K[t] = Pt * Z(t) / F[t];
+        v[t] = yy - D(t) - Z(t) * at[t];
+        at[t + 1] = C(t) + T(t) * (at[t] + K[t] * v[t]);
+        const double tmp = 1.0 - K[t] * Z(t);
+        Pt = T(t) * (tmp * Pt * tmp + K[t] * HH[t] * K[t]) * T(t) + RR(t);
+      } else {
+        at[t + 1] = C(t) + T(t) * at[t];
+        Pt = T(t) * Pt * T(t) + RR(t);
+      }
+    }
+    r[n - 1] = 0.0;
+    for (int t = n - 1; t > 0; --t) {
+      if (finite(yobs(t)) && F[t] > zero_tol) {
+        const double L = T(t) * (1.0 - K[t] * Z(t));
+        r[t - 1] = Z(t) / F[t] * v[t] + L * r[t];
+      } else {
+        r[t - 1] = T(t) * r[t];
+      }
+    }
+    if (finite(yt[0]) && F[0] > zero_tol) {
+      const double L = T(0) * (1.0 - K[0] * Z(0));
+      at[0] = M->a1[0] + M->P1[0] * (Z(0) / F[0] * v[0] + L * r[0]);
+    } else {
+      at[0] = M->a1[0] + M->P1[0] * T(0) * r[0];
+    }
+    for (int t = 0; t < n - 1; ++t) at[t + 1] = C(t) + T(t) * at[t] + RR(t) * r[t];
+    if (M->distribution == 0) for (int t = 0; t < n; ++t) next[t] = at[t];
+    else for (int t = 0; t < n; ++t) next[t] = xb(t) + D(t) + Z(t) * at[t];
+    // arma::accu(square(new - old)) / n, two accumulators [UNVENDORED]
+    double a1 = 0.0, a2 = 0.0;
+    int j;
+    for (j = 1; j < n; j += 2) {
+      a1 += (next[j - 1] - mode[j - 1]) * (next[j - 1] - mode[j - 1]);
+      a2 += (next[j] - mode[j]) * (next[j] - mode[j]);
+    }
+    if ((j - 1) < n) a1 += (next[j - 1] - mode[j - 1]) * (next[j - 1] - mode[j - 1]);
+    diff = (a1 + a2) / n;
+    mode = next;
+  }
+}
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t count = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t n) {
+    if (p) { cudaFree(p); p = nullptr; }
+    count = n;
+    if (n == 0) return 0;
+    CU(cudaMalloc(&p, n * sizeof(T)));
+    return 0;
+  }
+  int upload(const T* h, size_t n) {
+    int rc = alloc(n);
+    if (rc) return rc;
+    if (n) CU(cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+  }
+};
+
+} // namespace
+
+// ------------------------------------------------------------------- job
+struct bssm_b200_job {
+  int method = 0, post = 0, out_flags = 0;
+  uint32_t N = 0, n_filters = 0, first_filter = 0, seed = 0;
+  int n = 0, m = 0, k = 0;
+  Geometry geo{};
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float ms[3] = {0, 0, 0};
+  int launches = 0;
+  bool has_run = false;
+  // model on device
+  DevBuf<double> y, Z, T, R, a1, P1, LP1, D, C, xbeta, u, mode;
+  // psi pre-pass results
+  DevBuf<double> alphahat, Lt, Ct, ytilde, Htilde, scales, approx_loglik, phi_f, scratch;
+  size_t pstride = 0;
+  // outputs
+  DevBuf<double> alpha_tm, alpha_sm, weights, cube;
+  DevBuf<uint32_t> indices;
+  DevBuf<double> loglik;
+  DevBuf<int32_t> stopped;
+  DevBuf<unsigned long long> xch;
+  DevBuf<unsigned int> barrier;
+  DevBuf<double> s_at, s_att, s_Pt, s_Ptt, s_mean, s_cov;
+  size_t alpha_stride = 0, weights_stride = 0, indices_stride = 0;
+  bool keep_alpha = false, keep_weights = false, keep_indices = false;
+  pf::UngParams up{};
+  pf::PrepassParams pp{};
+  pf::FilterParams fp{};
+  ~bssm_b200_job() {
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace {
+
+template <int M>
+int run_post_M(bssm_b200_job* J) {
+  const uint32_t N = J->N;
+  const int n = J->n;
+  for (uint32_t f = 0; f < J->n_filters; ++f) {
+    const double* a_tm = J->alpha_tm.p + (size_t)f * J->alpha_stride;
+    if (J->post == BSSM_POST_FILTER_SUMMARY) {
+      pf::filter_summary_kernel<M><<<n + 1, 1024, 0, J->stream>>>(
+          a_tm, J->weights.p + (size_t)f * J->weights_stride, N, n,
+          J->s_at.p + (size_t)f * M * (n + 1), J->s_att.p + (size_t)f * M * n,
+          J->s_Pt.p + (size_t)f * M * M * (n + 1), J->s_Ptt.p + (size_t)f * M * M * n);
+      J->launches += 1;
+    } else if (J->post == BSSM_POST_SMOOTHER) {
+      double* a_sm = J->alpha_sm.p + (size_t)f * J->alpha_stride;
+      pf::backtrack_kernel<M><<<cdiv(N, 256), 256, 0, J->stream>>>(
+          a_tm, J->indices.p + (size_t)f * J->indices_stride, a_sm, N, n);
+      pf::summary_kernel<M><<<n + 1, 1024, 0, J->stream>>>(
+          a_sm, N, J->s_mean.p + (size_t)f * M * (n + 1), J->s_cov.p + (size_t)f * M * M * (n + 1));
+      J->launches += 2;
+    }
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int run_post(bssm_b200_job* J) {
+  switch (J->m) {
+    case 1: return run_post_M<1>(J);
+    case 2: return run_post_M<2>(J);
+    case 3: return run_post_M<3>(J);
+    case 4: return run_post_M<4>(J);
+  }
+  return fail(BSSM_B200_ERR_UNSUPPORTED, "post-processing supports m <= 4");
+}
+
+int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
+  pf::FilterParams fp = J->fp;
+  // offset per-filter pointers when launching a sub-range (grid mode: one filter per launch)
+  fp.first_filter = J->first_filter + f0;
+  fp.alpha_tm = J->alpha_tm.p + (size_t)f0 * J->alpha_stride;
+  fp.weights = J->weights.p ? J->weights.p + (size_t)f0 * J->weights_stride : nullptr;
+  fp.indices = J->indices.p + (size_t)f0 * J->indices_stride;
+  fp.loglik = J->loglik.p + f0;
+  fp.stopped_at = J->stopped.p + f0;
+  fp.xch = J->xch.p + (size_t)f0 * 4 * J->geo.ranks;
+  pf::UngParams up = J->up;
+  if (J->method == BSSM_METHOD_PSI) {
+    up.alphahat += (size_t)f0 * J->pstride; up.Lt += (size_t)f0 * J->pstride; up.Ct += (size_t)f0 * J->pstride;
+    up.ytilde += (size_t)f0 * J->pstride; up.Htilde += (size_t)f0 * J->pstride; up.scales += (size_t)f0 * J->pstride;
+    up.approx_loglik += f0;
+    if (up.phi_f) up.phi_f += f0;
+    return launch_filter<pf::UngPsi1>(fp, up, J->geo, nf, J->stream);
+  }
+  const int mk = J->m * 10 + J->k;
+  switch (mk) {
+    case 11: return launch_filter<pf::UngBsf<1, 1>>(fp, up, J->geo, nf, J->stream);
+    case 21: return launch_filter<pf::UngBsf<2, 1>>(fp, up, J->geo, nf, J->stream);
+    case 22: return launch_filter<pf::UngBsf<2, 2>>(fp, up, J->geo, nf, J->stream);
+    case 32: return launch_filter<pf::UngBsf<3, 2>>(fp, up, J->geo, nf, J->stream);
+    case 33: return launch_filter<pf::UngBsf<3, 3>>(fp, up, J->geo, nf, J->stream);
+  }
+  return fail(BSSM_B200_ERR_UNSUPPORTED, "bsf: (m,k) not instantiated in this build");
+}
+
+} // namespace
+
+extern "C" {
+
+const char* bssm_b200_last_error(void) { return g_err.c_str(); }
+const char* bssm_b200_version(void) { return "bssm_b200 0.1 (sm_100a)"; }
+
+int bssm_b200_device_count(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return cnt;
+}
+
+int bssm_b200_set_device(int device) {
+  int rc = require_device();
+  if (rc) return rc;
+  CU(cudaSetDevice(device));
+  return 0;
+}
+
+void bssm_b200_shutdown(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) == cudaSuccess && cnt > 0) cudaDeviceSynchronize();
+  cudaGetLastError();
+}
+
+int bssm_b200_job_create_ung(const bssm_ung_model* M, int method, uint32_t nsim, uint32_t seed,
+                             uint32_t n_filters, uint32_t first_filter_id, int out_flags, int post,
+                             bssm_b200_job** job) {
+  if (!M || !job) return fail(BSSM_B200_ERR_ARG, "null argument");
+  *job = nullptr;
+  if (M->n < 1 || M->m < 1 || M->k < 1 || nsim < 2 || n_filters < 1)
+    return fail(BSSM_B200_ERR_ARG, "need n >= 1, m >= 1, k >= 1, nsim >= 2, n_filters >= 1");
+  if (M->distribution < 0 || M->distribution > 4) return fail(BSSM_B200_ERR_ARG, "distribution must be 0..4");
+  if (method != BSSM_METHOD_PSI && method != BSSM_METHOD_BSF) return fail(BSSM_B200_ERR_ARG, "method must be 1 (psi) or 2 (bsf)");
+  if (method == BSSM_METHOD_PSI && M->m != 1)
+    return fail(BSSM_B200_ERR_UNSUPPORTED, "psi-APF is implemented for m = 1 in this build");
+  if (M->k > M->m) return fail(BSSM_B200_ERR_ARG, "k > m");
+  if (post < 0 || post > 2) return fail(BSSM_B200_ERR_ARG, "post must be 0, 1 or 2");
+  int rc = require_device();
+  if (rc) return rc;
+
+  bssm_b200_job* J = new bssm_b200_job();
+  struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
+  J->method = method; J->post = post; J->out_flags = out_flags;
+  J->N = nsim; J->n_filters = n_filters; J->first_filter = first_filter_id; J->seed = seed;
+  J->n = M->n; J->m = M->m; J->k = M->k;
+  const int n = M->n, m = M->m, k = M->k;
+  rc = choose_geometry(nsim, &J->geo);
+  if (rc) return rc;
+  CU(cudaStreamCreateWithFlags(&J->stream, cudaStreamNonBlocking));
+  for (auto& e : J->ev) CU(cudaEventCreate(&e));
+
+  // ---- model upload (column-major, as R holds it)
+  std::vector<double> xb(n, 0.0);
+  if (M->xbeta) xb.assign(M->xbeta, M->xbeta + n);
+  std::vector<double> LP1;
+  chol_posdiag(M->P1, m, LP1);
+  if ((rc = J->y.upload(M->y, n))) return rc;
+  if ((rc = J->Z.upload(M->Z, (size_t)m * (M->Ztv ? n : 1)))) return rc;
+  if ((rc = J->T.upload(M->T, (size_t)m * m * (M->Ttv ? n : 1)))) return rc;
+  if ((rc = J->R.upload(M->R, (size_t)m * k * (M->Rtv ? n : 1)))) return rc;
+  if ((rc = J->a1.upload(M->a1, m))) return rc;
+  if ((rc = J->P1.upload(M->P1, (size_t)m * m))) return rc;
+  if ((rc = J->LP1.upload(LP1.data(), (size_t)m * m))) return rc;
+  if ((rc = J->D.upload(M->D, M->Dtv ? n : 1))) return rc;
+  if ((rc = J->C.upload(M->C, (size_t)m * (M->Ctv ? n : 1)))) return rc;
+  if ((rc = J->xbeta.upload(xb.data(), n))) return rc;
+  if ((rc = J->u.upload(M->u, n))) return rc;
+
+  pf::UngParams& up = J->up;
+  up.n = n; up.distribution = M->distribution;
+  up.Ztv = M->Ztv; up.Ttv = M->Ttv; up.Rtv = M->Rtv; up.Dtv = M->Dtv; up.Ctv = M->Ctv;
+  up.y = J->y.p; up.Z = J->Z.p; up.T = J->T.p; up.R = J->R.p; up.a1 = J->a1.p; up.LP1 = J->LP1.p;
+  up.D = J->D.p; up.C = J->C.p; up.xbeta = J->xbeta.p; up.u = J->u.p;
+  up.phi = M->phi;
+  const double dconst = ung_dist_const(M);
+  up.loglik_const = dconst;
+
+  if (method == BSSM_METHOD_PSI) {
+    if (!M->initial_mode) return fail(BSSM_B200_ERR_ARG, "psi-APF needs initial_mode");
+    std::vector<double> mode;
+    ung_approximate_m1(M, mode);
+    if ((rc = J->mode.upload(mode.data(), n))) return rc;
+    J->pstride = (size_t)n + 1;
+    const size_t tot = J->pstride * n_filters;
+    if ((rc = J->alphahat.alloc(tot)) || (rc = J->Lt.alloc(tot)) || (rc = J->Ct.alloc(tot)) ||
+        (rc = J->ytilde.alloc(tot)) || (rc = J->Htilde.alloc(tot)) || (rc = J->scales.alloc(tot)) ||
+        (rc = J->scratch.alloc(3 * tot)) || (rc = J->approx_loglik.alloc(n_filters)) ||
+        (rc = J->phi_f.alloc(n_filters)))
+      return rc;
+    pf::PrepassParams& pp = J->pp;
+    pp.n = n; pp.distribution = M->distribution;
+    pp.Ztv = M->Ztv; pp.Ttv = M->Ttv; pp.Rtv = M->Rtv; pp.Dtv = M->Dtv; pp.Ctv = M->Ctv;
+    pp.y = J->y.p; pp.Z = J->Z.p; pp.T = J->T.p; pp.R = J->R.p; pp.a1 = J->a1.p; pp.P1 = J->P1.p;
+    pp.D = J->D.p; pp.C = J->C.p; pp.xbeta = J->xbeta.p; pp.u = J->u.p;
+    pp.has_xbeta = M->xbeta ? 1 : 0;
+    pp.phi = M->phi;
+    pp.theta = nullptr; pp.n_par = 0; pp.svm_type = 0;
+    pp.modes = J->mode.p; pp.mode_stride = 0; // replicates share the mode
+    pp.compute_loglik = 1;
+    pp.dist_const = dconst;
+    pp.log2pi = std::log(2.0 * M_PI);
+    pp.alphahat = J->alphahat.p; pp.Lt = J->Lt.p; pp.Ct = J->Ct.p; pp.ytilde = J->ytilde.p;
+    pp.Htilde = J->Htilde.p; pp.scales = J->scales.p; pp.approx_loglik = J->approx_loglik.p;
+    pp.phi_f = J->phi_f.p; pp.scratch = J->scratch.p; pp.pstride = J->pstride;
+    up.phi_f = J->phi_f.p; up.alphahat = J->alphahat.p; up.Lt = J->Lt.p; up.Ct = J->Ct.p;
+    up.ytilde = J->ytilde.p; up.Htilde = J->Htilde.p; up.scales = J->scales.p;
+    up.approx_loglik = J->approx_loglik.p; up.pstride = J->pstride;
+  }
+
+  // ---- outputs
+  J->keep_alpha = (out_flags & BSSM_OUT_ALPHA) || post != BSSM_POST_NONE;
+  J->keep_weights = (out_flags & BSSM_OUT_WEIGHTS) || post == BSSM_POST_FILTER_SUMMARY;
+  J->keep_indices = (out_flags & BSSM_OUT_INDICES) || post == BSSM_POST_SMOOTHER;
+  J->alpha_stride = (size_t)(J->keep_alpha ? n + 1 : 2) * m * nsim;
+  J->weights_stride = J->keep_weights ? (size_t)nsim * (n + 1) : 0;
+  J->indices_stride = J->keep_indices ? (size_t)nsim * n : (size_t)nsim;
+  if ((rc = J->alpha_tm.alloc(J->alpha_stride * n_filters))) return rc;
+  if (J->keep_weights && (rc = J->weights.alloc(J->weights_stride * n_filters))) return rc;
+  if ((rc = J->indices.alloc(J->indices_stride * n_filters))) return rc;
+  if (post == BSSM_POST_SMOOTHER && (rc = J->alpha_sm.alloc(J->alpha_stride * n_filters))) return rc;
+  if ((rc = J->loglik.alloc(n_filters)) || (rc = J->stopped.alloc(n_filters))) return rc;
+  if ((rc = J->xch.alloc((size_t)4 * J->geo.ranks * n_filters)) || (rc = J->barrier.alloc(1))) return rc;
+  if (post == BSSM_POST_FILTER_SUMMARY) {
+    if ((rc = J->s_at.alloc((size_t)n_filters * m * (n + 1))) || (rc = J->s_att.alloc((size_t)n_filters * m * n)) ||
+        (rc = J->s_Pt.alloc((size_t)n_filters * m * m * (n + 1))) || (rc = J->s_Ptt.alloc((size_t)n_filters * m * m * n)))
+      return rc;
+  } else if (post == BSSM_POST_SMOOTHER) {
+    if ((rc = J->s_mean.alloc((size_t)n_filters * m * (n + 1))) || (rc = J->s_cov.alloc((size_t)n_filters * m * m * (n + 1))))
+      return rc;
+  }
+  pf::FilterParams& fp = J->fp;
+  fp.N = nsim; fp.n = n; fp.seed = seed; fp.first_filter = first_filter_id;
+  fp.ranks = J->geo.ranks; fp.sync_mode = J->geo.sync_mode;
+  fp.keep_alpha = J->keep_alpha ? 1 : 0;
+  fp.alpha_tm = J->alpha_tm.p; fp.alpha_stride = J->alpha_stride;
+  fp.weights = J->weights.p; fp.weights_stride = J->weights_stride;
+  fp.indices = J->indices.p; fp.indices_stride = J->indices_stride;
+  fp.keep_indices = J->keep_indices ? 1 : 0;
+  fp.loglik = J->loglik.p; fp.stopped_at = J->stopped.p;
+  fp.xch = J->xch.p; fp.barrier = J->barrier.p;
+  guard.j = nullptr;
+  *job = J;
+  return 0;
+}
+
+int bssm_b200_job_run(bssm_b200_job* J, float* ms_out) {
+  if (!J) return fail(BSSM_B200_ERR_ARG, "null job");
+  int rc;
+  J->launches = 0;
+  CU(cudaEventRecord(J->ev[0], J->stream));
+  if (J->method == BSSM_METHOD_PSI) {
+    const uint32_t warps_per_block = 4;
+    pf::ung_prepass_m1_kernel<<<cdiv(J->n_filters, warps_per_block), 32 * warps_per_block, 0, J->stream>>>(
+        J->pp, J->n_filters);
+    CU(cudaGetLastError());
+    J->launches += 1;
+  }
+  CU(cudaEventRecord(J->ev[1], J->stream));
+  if (J->geo.sync_mode == pf::SYNC_GRID) {
+    for (uint32_t f = 0; f < J->n_filters; ++f) {
+      CU(cudaMemsetAsync(J->barrier.p, 0, sizeof(unsigned int), J->stream));
+      if ((rc = launch_ung_filter(J, f, 1))) return rc;
+      J->launches += 1;
+    }
+  } else {
+    if ((rc = launch_ung_filter(J, 0, J->n_filters))) return rc;
+    J->launches += 1;
+  }
+  CU(cudaEventRecord(J->ev[2], J->stream));
+  if (J->post != BSSM_POST_NONE && (rc = run_post(J))) return rc;
+  CU(cudaEventRecord(J->ev[3], J->stream));
+  CU(cudaStreamSynchronize(J->stream));
+  CU(cudaEventElapsedTime(&J->ms[0], J->ev[0], J->ev[1]));
+  CU(cudaEventElapsedTime(&J->ms[1], J->ev[1], J->ev[2]));
+  CU(cudaEventElapsedTime(&J->ms[2], J->ev[2], J->ev[3]));
+  float tot = 0;
+  CU(cudaEventElapsedTime(&tot, J->ev[0], J->ev[3]));
+  if (ms_out) *ms_out = tot;
+  J->has_run = true;
+  return 0;
+}
+
+int bssm_b200_job_kernel_ms(const bssm_b200_job* J, float ms[3]) {
+  if (!J || !ms) return fail(BSSM_B200_ERR_ARG, "null argument");
+  ms[0] = J->ms[0]; ms[1] = J->ms[1]; ms[2] = J->ms[2];
+  return 0;
+}
+
+int bssm_b200_job_launches(const bssm_b200_job* J) { return J ? J->launches : 0; }
+
+int bssm_b200_job_logliks(bssm_b200_job* J, double* loglik) {
+  if (!J || !loglik) return fail(BSSM_B200_ERR_ARG, "null argument");
+  if (!J->has_run) return fail(BSSM_B200_ERR_ARG, "job has not run");
+  CU(cudaMemcpy(loglik, J->loglik.p, sizeof(double) * J->n_filters, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bssm_b200_job_logliks_dev(bssm_b200_job* J, double* loglik_dev) {
+  if (!J || !loglik_dev) return fail(BSSM_B200_ERR_ARG, "null argument");
+  if (!J->has_run) return fail(BSSM_B200_ERR_ARG, "job has not run");
+  CU(cudaMemcpy(loglik_dev, J->loglik.p, sizeof(double) * J->n_filters, cudaMemcpyDeviceToDevice));
+  return 0;
+}
+
+int bssm_b200_job_fetch(bssm_b200_job* J, uint32_t f, bssm_filter_out* out) {
+  if (!J || !out) return fail(BSSM_B200_ERR_ARG, "null argument");
+  if (!J->has_run) return fail(BSSM_B200_ERR_ARG, "job has not run");
+  if (f >= J->n_filters) return fail(BSSM_B200_ERR_ARG, "filter index out of range");
+  const int n = J->n, m = J->m;
+  const uint32_t N = J->N;
+  int32_t stopped = -1;
+  CU(cudaMemcpy(&out->loglik, J->loglik.p + f, sizeof(double), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(&stopped, J->stopped.p + f, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  out->stopped_at = stopped;
+  out->approx_loglik = 0.0;
+  if (J->method == BSSM_METHOD_PSI)
+    CU(cudaMemcpy(&out->approx_loglik, J->approx_loglik.p + f, sizeof(double), cudaMemcpyDeviceToHost));
+  out->device_ms = J->ms[0] + J->ms[1] + J->ms[2];
+  // columns the filter never reached stay zero, as in the reference (arma::fill::zeros)
+  const int cols_alpha = stopped >= 0 ? stopped + 1 : n + 1; // state columns 0..stopped exist
+  const int cols_w = stopped >= 0 ? stopped : n + 1;
+  const int cols_i = stopped >= 0 ? stopped : n;
+  if (out->alpha) {
+    if (!J->keep_alpha) return fail(BSSM_B200_ERR_ARG, "job was created without BSSM_OUT_ALPHA");
+    const double* src = (J->post == BSSM_POST_SMOOTHER ? J->alpha_sm.p : J->alpha_tm.p) + (size_t)f * J->alpha_stride;
+    const uint32_t rows = (uint32_t)(n + 1) * m;
+    int rc = J->cube.alloc((size_t)rows * N);
+    if (rc) return rc;
+    if (stopped >= 0) // zero the unreached tail in the time-major source first
+      CU(cudaMemsetAsync((void*)(src + (size_t)cols_alpha * m * N), 0, sizeof(double) * (size_t)(n + 1 - cols_alpha) * m * N, J->stream));
+    dim3 grid(cdiv(N, 32), cdiv(rows, 32));
+    pf::transpose_to_cube_kernel<<<grid, dim3(32, 8), 0, J->stream>>>(src, J->cube.p, rows, N);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out->alpha, J->cube.p, sizeof(double) * (size_t)rows * N, cudaMemcpyDeviceToHost, J->stream));
+    CU(cudaStreamSynchronize(J->stream));
+  }
+  if (out->weights) {
+    if (!J->keep_weights) return fail(BSSM_B200_ERR_ARG, "job was created without BSSM_OUT_WEIGHTS");
+    memset(out->weights, 0, sizeof(double) * (size_t)N * (n + 1));
+    CU(cudaMemcpy(out->weights, J->weights.p + (size_t)f * J->weights_stride, sizeof(double) * (size_t)N * cols_w, cudaMemcpyDeviceToHost));
+  }
+  if (out->indices) {
+    if (!J->keep_indices) return fail(BSSM_B200_ERR_ARG, "job was created without BSSM_OUT_INDICES");
+    memset(out->indices, 0, sizeof(uint32_t) * (size_t)N * n);
+    CU(cudaMemcpy(out->indices, J->indices.p + (size_t)f * J->indices_stride, sizeof(uint32_t) * (size_t)N * cols_i, cudaMemcpyDeviceToHost));
+  }
+  if (J->post == BSSM_POST_FILTER_SUMMARY) {
+    if (out->at) CU(cudaMemcpy(out->at, J->s_at.p + (size_t)f * m * (n + 1), sizeof(double) * m * (n + 1), cudaMemcpyDeviceToHost));
+    if (out->att) CU(cudaMemcpy(out->att, J->s_att.p + (size_t)f * m * n, sizeof(double) * m * n, cudaMemcpyDeviceToHost));
+    if (out->Pt) CU(cudaMemcpy(out->Pt, J->s_Pt.p + (size_t)f * m * m * (n + 1), sizeof(double) * m * m * (n + 1), cudaMemcpyDeviceToHost));
+    if (out->Ptt) CU(cudaMemcpy(out->Ptt, J->s_Ptt.p + (size_t)f * m * m * n, sizeof(double) * m * m * n, cudaMemcpyDeviceToHost));
+  } else if (J->post == BSSM_POST_SMOOTHER) {
+    if (out->alphahat) CU(cudaMemcpy(out->alphahat, J->s_mean.p + (size_t)f * m * (n + 1), sizeof(double) * m * (n + 1), cudaMemcpyDeviceToHost));
+    if (out->Vt) CU(cudaMemcpy(out->Vt, J->s_cov.p + (size_t)f * m * m * (n + 1), sizeof(double) * m * m * (n + 1), cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+void bssm_b200_job_destroy(bssm_b200_job* J) { delete J; }
+
+// ---------------------------------------------------------- one-shot calls
+static int one_shot(const bssm_ung_model* M, int method, uint32_t nsim, uint32_t seed, int post,
+                    bssm_filter_out* out) {
+  if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
+  int flags = 0;
+  if (out->alpha) flags |= BSSM_OUT_ALPHA;
+  if (out->weights) flags |= BSSM_OUT_WEIGHTS;
+  if (out->indices) flags |= BSSM_OUT_INDICES;
+  bssm_b200_job* J = nullptr;
+  int rc = bssm_b200_job_create_ung(M, method, nsim, seed, 1, 0, flags, post, &J);
+  if (rc) return rc;
+  float ms = 0;
+  rc = bssm_b200_job_run(J, &ms);
+  if (!rc) rc = bssm_b200_job_fetch(J, 0, out);
+  bssm_b200_job_destroy(J);
+  return rc;
+}
+
+int bssm_b200_bsf(const bssm_ung_model* M, uint32_t nsim, uint32_t seed, bssm_filter_out* out) {
+  return one_shot(M, BSSM_METHOD_BSF, nsim, seed, BSSM_POST_FILTER_SUMMARY, out);
+}
+int bssm_b200_bsf_smoother(const bssm_ung_model* M, uint32_t nsim, uint32_t seed, bssm_filter_out* out) {
+  return one_shot(M, BSSM_METHOD_BSF, nsim, seed, BSSM_POST_SMOOTHER, out);
+}
+int bssm_b200_psi_smoother(const bssm_ung_model* M, uint32_t nsim, uint32_t seed, bssm_filter_out* out) {
+  return one_shot(M, BSSM_METHOD_PSI, nsim, seed, BSSM_POST_SMOOTHER, out);
+}
+int bssm_b200_psi_filter(const bssm_ung_model* M, uint32_t nsim, uint32_t seed, bssm_filter_out* out) {
+  return one_shot(M, BSSM_METHOD_PSI, nsim, seed, BSSM_POST_NONE, out);
+}
+
+// ------------------------------------------------------------- unit hook
+namespace {
+// single-CTA stratified resampling with caller-supplied uniforms: the same
+// fixed-point cumsum and threshold counting the filter kernel uses, r[] read
+// from memory instead of Philox.
+__global__ void __launch_bounds__(1024)
+stratified_kernel(const double* __restrict__ p, uint32_t n_p, const double* __restrict__ r, uint32_t N,
+                  uint32_t* __restrict__ xp) {
+  __shared__ pf::CollSmem csm;
+  pf::Sync sync; sync.mode = pf::SYNC_BLOCK; sync.counter = nullptr; sync.nblocks = 1; sync.target = 0;
+  pf::Coll coll;
+  coll.sm = &csm; coll.sync = &sync; coll.xch = nullptr; coll.ranks = 1; coll.rank = 0;
+  coll.lane = threadIdx.x & 31; coll.warp = threadIdx.x >> 5; coll.nwarps = (blockDim.x + 31) >> 5;
+  const uint32_t chunk = (n_p + blockDim.x - 1) / blockDim.x;
+  const uint32_t k0 = threadIdx.x * chunk;
+  unsigned long long tot = 0ull;
+  for (uint32_t k = k0; k < k0 + chunk && k < n_p; ++k) tot += pf_cumsum_term(p[k]);
+  unsigned long long run = coll.exscan(tot);
+  const double Nd = (double)N, invN = 1.0 / Nd;
+  auto u = [&](uint32_t j) { return (r[j] + (double)j) * invN; };
+  auto count = [&](double pk) -> uint32_t {
+    // plain binary search here (unit hook, not performance critical)
+    uint32_t lo = 0, hi = N;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (u(mid) <= pk) lo = mid + 1; else hi = mid; }
+    return lo;
+  };
+  uint32_t lo = (k0 == 0) ? 0u : ((k0 - 1 >= n_p - 1) ? N : count(pf_cumsum_value(run)));
+  for (uint32_t k = k0; k < k0 + chunk && k < n_p; ++k) {
+    run += pf_cumsum_term(p[k]);
+    uint32_t c = (k >= n_p - 1) ? N : count(pf_cumsum_value(run));
+    for (uint32_t j = lo; j < c; ++j) xp[j] = k;
+    lo = c > lo ? c : lo;
+  }
+}
+} // namespace
+
+namespace {
+__global__ void math_probe_kernel(int op, const double* __restrict__ x, double* __restrict__ y, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = x[i], s, c;
+  switch (op) {
+    case 0: v = pf_exp(v); break;
+    case 1: v = pf_log(v); break;
+    case 2: v = pf_log1p(v); break;
+    case 3: pf_sincos2pi(v, &s, &c); v = s; break;
+    default: pf_sincos2pi(v, &s, &c); v = c; break;
+  }
+  y[i] = v;
+}
+__global__ void rng_probe_kernel(uint32_t seed, uint32_t filter, uint32_t t, uint32_t count,
+                                 double* __restrict__ z, double* __restrict__ r) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  z[i] = pf_normal(seed, filter, t, 0u, i);
+  r[i] = pf_resample_uniform(seed, filter, t, i);
+}
+} // namespace
+
+int bssm_b200_math_probe(int op, const double* x, double* y, uint32_t n) {
+  if (!x || !y || n == 0 || op < 0 || op > 4) return fail(BSSM_B200_ERR_ARG, "bad argument");
+  int rc = require_device();
+  if (rc) return rc;
+  DevBuf<double> dx, dy;
+  if ((rc = dx.upload(x, n)) || (rc = dy.alloc(n))) return rc;
+  math_probe_kernel<<<cdiv(n, 256), 256>>>(op, dx.p, dy.p, n);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(y, dy.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bssm_b200_rng_probe(uint32_t seed, uint32_t filter, uint32_t t, uint32_t count, double* z, double* r) {
+  if (!z || !r || count == 0) return fail(BSSM_B200_ERR_ARG, "bad argument");
+  int rc = require_device();
+  if (rc) return rc;
+  DevBuf<double> dz, dr;
+  if ((rc = dz.alloc(count)) || (rc = dr.alloc(count))) return rc;
+  rng_probe_kernel<<<cdiv(count, 256), 256>>>(seed, filter, t, count, dz.p, dr.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(z, dz.p, sizeof(double) * count, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(r, dr.p, sizeof(double) * count, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bssm_b200_stratified_sample(const double* p, uint32_t n_p, const double* r, uint32_t N, uint32_t* xp) {
+  if (!p || !r || !xp || n_p == 0 || N == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
+  int rc = require_device();
+  if (rc) return rc;
+  DevBuf<double> dp, dr;
+  DevBuf<uint32_t> dx;
+  if ((rc = dp.upload(p, n_p)) || (rc = dr.upload(r, N)) || (rc = dx.alloc(N))) return rc;
+  stratified_kernel<<<1, 1024>>>(dp.p, n_p, dr.p, N, dx.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(xp, dx.p, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,160 @@
+// models_ung.cuh -- device model policies for the ssm_ung family
+// (ssm_ung / bsm_ng / svm / ar1_ng): linear-Gaussian state, exponential-family
+// observation.  Formulas follow /root/reference/src/model_ssm_ung.cpp:
+//   log_obs_density :447-493, log_weights :385-439,
+//   bsf_filter propagation :663-670, psi_filter propagation :580-587.
+#pragma once
+#include "pf_device.cuh"
+
+namespace pf {
+
+struct UngParams {
+  int n, distribution;
+  int Ztv, Ttv, Rtv, Dtv, Ctv;
+  const double* y;     // n
+  const double* Z;     // m x (1|n)
+  const double* T;     // m x m x (1|n)
+  const double* R;     // m x k x (1|n)
+  const double* a1;    // m
+  const double* LP1;   // m x m lower Cholesky factor of P1 (positive-diagonal block)
+  const double* D;     // (1|n)
+  const double* C;     // m x (1|n)
+  const double* xbeta; // n (zeros when no regressors)
+  const double* u;     // n
+  double phi;
+  double loglik_const; // BSF: state-independent constants, added at the end (:690-710)
+  // psi-APF (m = 1), per filter with stride `pstride`
+  const double* phi_f;     // per-filter phi (post_correct) or null
+  const double* alphahat;  // n+1
+  const double* Lt;        // n+1
+  const double* Ct;        // n+1
+  const double* ytilde;    // n
+  const double* Htilde;    // n
+  const double* scales;    // n
+  const double* approx_loglik; // per filter
+  size_t pstride;
+};
+
+// log g(y_t | signal) up to state-independent constants, :447-493
+__device__ __forceinline__ double ung_log_obs(int dist, double s, double y, double u, double phi,
+                                              double yphi2) {
+  switch (dist) {
+    case 0: return -0.5 * (s + yphi2 * pf_exp(-s));
+    case 1: return y * s - u * pf_exp(s);
+    case 2: return y * s - u * pf_log1p(pf_exp(s));
+    case 3: return y * s - (y + phi) * pf_log(phi + u * pf_exp(s));
+    default: return -phi * (s + (y * pf_exp(-s) / u));
+  }
+}
+
+// ---------------------------------------------------------- bootstrap filter
+template <int M_, int K_>
+struct UngBsf {
+  static constexpr int M = M_, KI = M_, KP = K_;
+  typedef UngParams Params;
+  const UngParams& mp;
+  // per-step constants
+  double y, u, yphi2, Dt, xb;
+  double Z[M_], T[M_ * M_], R[M_ * K_], C[M_];
+
+  __device__ UngBsf(const UngParams& p, uint32_t) : mp(p) {}
+  __device__ double loglik0() const { return 0.0; }
+  __device__ double loglik_end() const { return mp.loglik_const; }
+  __device__ void init(const double* z, double* x) const {
+#pragma unroll
+    for (int d = 0; d < M_; ++d) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < M_; ++j) s += mp.LP1[d + M_ * j] * z[j];
+      x[d] = mp.a1[d] + s;
+    }
+  }
+  __device__ bool observed(int t) const { return pf_isfinite(mp.y[t]); }
+  __device__ void begin_weight(int t) {
+    y = mp.y[t];
+    u = mp.u[t];
+    double q = y / mp.phi;
+    yphi2 = q * q;
+    Dt = mp.D[t * mp.Dtv];
+    xb = mp.xbeta[t];
+#pragma unroll
+    for (int d = 0; d < M_; ++d) Z[d] = mp.Z[d + M_ * (t * mp.Ztv)];
+  }
+  __device__ double logw(const double* x) const {
+    double s;
+    if (mp.distribution == 0) {
+      s = x[0];
+    } else {
+      double zs = 0.0;
+#pragma unroll
+      for (int d = 0; d < M_; ++d) zs += Z[d] * x[d];
+      s = Dt + zs + xb;
+    }
+    return ung_log_obs(mp.distribution, s, y, u, mp.phi, yphi2);
+  }
+  __device__ void begin_step(int t) {
+#pragma unroll
+    for (int e = 0; e < M_ * M_; ++e) T[e] = mp.T[e + M_ * M_ * (t * mp.Ttv)];
+#pragma unroll
+    for (int e = 0; e < M_ * K_; ++e) R[e] = mp.R[e + M_ * K_ * (t * mp.Rtv)];
+#pragma unroll
+    for (int d = 0; d < M_; ++d) C[d] = mp.C[d + M_ * (t * mp.Ctv)];
+  }
+  __device__ void propagate(const double* xa, const double* z, double* x) const {
+#pragma unroll
+    for (int d = 0; d < M_; ++d) {
+      double ta = 0.0, ru = 0.0;
+#pragma unroll
+      for (int j = 0; j < M_; ++j) ta += T[d + M_ * j] * xa[j];
+#pragma unroll
+      for (int j = 0; j < K_; ++j) ru += R[d + M_ * j] * z[j];
+      x[d] = C[d] + ta + ru;
+    }
+  }
+};
+
+// ------------------------------------------------------------ psi-APF, m = 1
+struct UngPsi1 {
+  static constexpr int M = 1, KI = 1, KP = 1;
+  typedef UngParams Params;
+  const UngParams& mp;
+  const double *ah, *Lt, *Ct, *yt, *Ht, *sc;
+  double phi, al0;
+  double y, u, yphi2, Dt, xb, Z0, ytil, Htil, scale;
+  double ah0, ah1, c1, l1;
+
+  __device__ UngPsi1(const UngParams& p, uint32_t f) : mp(p) {
+    const size_t o = (size_t)f * p.pstride;
+    ah = p.alphahat + o; Lt = p.Lt + o; Ct = p.Ct + o;
+    yt = p.ytilde + o; Ht = p.Htilde + o; sc = p.scales + o;
+    phi = p.phi_f ? p.phi_f[f] : p.phi;
+    al0 = p.approx_loglik[f];
+  }
+  __device__ double loglik0() const { return al0; }
+  __device__ double loglik_end() const { return 0.0; }
+  __device__ void init(const double* z, double* x) const { x[0] = ah[0] + Lt[0] * z[0]; }
+  __device__ bool observed(int t) const { return pf_isfinite(mp.y[t]); }
+  __device__ void begin_weight(int t) {
+    y = mp.y[t];
+    u = mp.u[t];
+    double q = y / phi;
+    yphi2 = q * q;
+    Dt = mp.D[t * mp.Dtv];
+    xb = mp.xbeta[t];
+    Z0 = mp.Z[t * mp.Ztv];
+    ytil = yt[t]; Htil = Ht[t]; scale = sc[t];
+  }
+  __device__ double logw(const double* x) const {
+    double s = (mp.distribution == 0) ? x[0] : (Dt + Z0 * x[0] + xb);
+    double q = (ytil - s) / Htil;
+    return (ung_log_obs(mp.distribution, s, y, u, phi, yphi2) + 0.5 * (q * q)) - scale;
+  }
+  __device__ void begin_step(int t) {
+    ah0 = ah[t]; ah1 = ah[t + 1]; c1 = Ct[t + 1]; l1 = Lt[t + 1];
+  }
+  __device__ void propagate(const double* xa, const double* z, double* x) const {
+    x[0] = ah1 + c1 * (xa[0] - ah0) + l1 * z[0];
+  }
+};
+
+} // namespace pf

@@ -1,0 +1,202 @@
+"""Model constructors mirroring the reference's R constructors.
+
+Each returns a plain ``Model`` whose fields are the entries of the R list the
+reference's C++ constructor reads (/root/reference/src/model_ssm_ung.cpp:9-32),
+with the same names, shapes (column-major) and defaults:
+
+  svm      R/models.R:1183-1238
+  bsm_ng   R/models.R:926-1114
+  ar1_ng   R/models.R:1285-1370
+  ssm_ung  general constructor (matrices supplied by the caller)
+
+Priors are MCMC-side and out of scope here: where the R constructors take a
+prior object the Python ones take the initial value.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import UngModel, dptr, f64
+
+DISTRIBUTIONS = {"svm": 0, "poisson": 1, "binomial": 2, "negative binomial": 3, "gamma": 4}
+
+
+def init_mode(y, u, distribution):
+    """R/init_mode.R:3-31"""
+    y = np.array(y, dtype=np.float64)
+    u = np.broadcast_to(np.asarray(u, dtype=np.float64), y.shape)
+    nan = np.isnan(y)
+    if distribution == "poisson":
+        v = y / u
+        v[nan | (v < 0.1)] = 0.1
+        return np.log(v)
+    if distribution == "binomial":
+        p = (np.where(nan, 0.5, y) + 0.5) / (u + 1)
+        return np.log(p / (1 - p))
+    if distribution == "gamma":
+        v = y / u
+        v[nan | (v < 1)] = 1
+        return np.log(v)
+    if distribution == "negative binomial":
+        v = y / u
+        v[nan | (v < 1 / 6)] = 1 / 6
+        return np.log(v)
+    raise ValueError("distribution must be poisson, binomial, gamma or negative binomial")
+
+
+class Model:
+    """An ssm_ung-family model: the R list, as numpy arrays."""
+
+    def __init__(self, cls, y, Z, T, R, a1, P1, D, C_, u, phi, distribution, initial_mode,
+                 xreg=None, beta=None, theta=None, max_iter=100, conv_tol=1e-8, local_approx=True,
+                 extra=None):
+        self.cls = cls
+        self.y = f64(np.ravel(y))
+        self.n = self.y.size
+        self.a1 = f64(np.ravel(a1))
+        self.m = self.a1.size
+        m, n = self.m, self.n
+        self.Z = f64(np.reshape(Z, (m, -1), order="F"))
+        self.T = f64(np.reshape(T, (m, m, -1), order="F"))
+        R = np.asarray(R, dtype=np.float64)
+        self.k = R.shape[1] if R.ndim >= 2 else 1
+        self.R = f64(np.reshape(R, (m, self.k, -1), order="F"))
+        self.P1 = f64(np.reshape(P1, (m, m), order="F"))
+        self.D = f64(np.ravel(D))
+        self.C = f64(np.reshape(C_, (m, -1), order="F"))
+        self.u = f64(np.broadcast_to(np.asarray(u, dtype=np.float64), (n,)))
+        self.phi = float(phi)
+        self.distribution = distribution
+        self.initial_mode = f64(np.ravel(initial_mode))
+        self.xreg = None if xreg is None else f64(xreg)
+        self.beta = None if beta is None else f64(np.ravel(beta))
+        self.theta = np.array([] if theta is None else theta, dtype=np.float64)
+        self.max_iter = int(max_iter)
+        self.conv_tol = float(conv_tol)
+        self.local_approx = bool(local_approx)
+        self.extra = dict(extra or {})
+        for name, arr, last in (("Z", self.Z, 1), ("T", self.T, 2), ("R", self.R, 2), ("C", self.C, 1)):
+            if arr.shape[last] not in (1, n):
+                raise ValueError("%s: last dimension must be 1 or n" % name)
+        if self.D.size not in (1, n):
+            raise ValueError("D must have length 1 or n")
+
+    @property
+    def xbeta(self):
+        if self.xreg is None or self.xreg.size == 0:
+            return None
+        return f64(self.xreg @ self.beta)  # compute_xbeta, src/model_ssm_ung.h:83
+
+    def c_struct(self):
+        """bssm_ung_model view of this model; keeps the arrays alive on the struct."""
+        s = UngModel()
+        s.n, s.m, s.k = self.n, self.m, self.k
+        s.distribution = DISTRIBUTIONS[self.distribution]
+        s.Ztv = int(self.Z.shape[1] > 1)
+        s.Ttv = int(self.T.shape[2] > 1)
+        s.Rtv = int(self.R.shape[2] > 1)
+        s.Dtv = int(self.D.size > 1)
+        s.Ctv = int(self.C.shape[1] > 1)
+        xb = self.xbeta
+        keep = [self.y, self.Z, self.T, self.R, self.a1, self.P1, self.D, self.C, xb, self.u, self.initial_mode]
+        s.y, s.Z, s.T, s.R = dptr(self.y), dptr(self.Z), dptr(self.T), dptr(self.R)
+        s.a1, s.P1, s.D, s.C = dptr(self.a1), dptr(self.P1), dptr(self.D), dptr(self.C)
+        s.xbeta = dptr(xb) if xb is not None else None
+        s.u = dptr(self.u)
+        s.phi = self.phi
+        s.max_iter, s.local_approx, s.conv_tol = self.max_iter, int(self.local_approx), self.conv_tol
+        s.initial_mode = dptr(self.initial_mode)
+        s._keep = keep
+        return s
+
+
+def ssm_ung(y, Z, T, R, a1, P1, distribution, phi=1.0, u=1.0, D=0.0, C=None, initial_mode=None,
+            xreg=None, beta=None, **kw):
+    y = np.ravel(np.asarray(y, dtype=np.float64))
+    a1 = np.ravel(np.asarray(a1, dtype=np.float64))
+    if C is None:
+        C = np.zeros((a1.size, 1))
+    if initial_mode is None:
+        initial_mode = init_mode(y, u, distribution)
+    return Model("ssm_ung", y, Z, T, R, a1, P1, np.ravel(D), C, u, phi, distribution, initial_mode,
+                 xreg=xreg, beta=beta, **kw)
+
+
+def svm(y, rho, sd_ar, sigma=None, mu=None):
+    """Stochastic volatility model, R/models.R:1183-1238."""
+    if (sigma is None) == (mu is None):
+        raise ValueError("Define either sigma or mu, but not both.")
+    y = np.ravel(np.asarray(y, dtype=np.float64))
+    if not -1 < rho < 1:
+        raise ValueError("rho must be in (-1, 1)")
+    if sd_ar <= 0:
+        raise ValueError("sd_ar must be positive")
+    base = np.log(np.maximum(1e-4, y ** 2))
+    if mu is not None:
+        svm_type, initial_mode, a1, phi = 1, base, mu, 1.0
+        Cm = [[mu * (1 - rho)]]
+        theta = [rho, sd_ar, mu]
+    else:
+        svm_type, initial_mode, a1, phi = 0, base - 2 * np.log(sigma), 0.0, sigma
+        Cm = [[0.0]]
+        theta = [rho, sd_ar, sigma]
+    P1 = [[sd_ar ** 2 / (1 - rho ** 2)]]
+    return Model("svm", y, [[1.0]], [[[rho]]], np.reshape([sd_ar], (1, 1, 1)), [a1], P1, [0.0], Cm, 1.0, phi,
+                 "svm", initial_mode, theta=theta, extra={"svm_type": svm_type})
+
+
+def ar1_ng(y, rho, sigma, mu, distribution, phi=1.0, u=1.0, xreg=None, beta=None):
+    """Non-Gaussian model with AR(1) latent process, R/models.R:1285-1370."""
+    y = np.ravel(np.asarray(y, dtype=np.float64))
+    if distribution not in ("poisson", "binomial", "negative binomial", "gamma"):
+        raise ValueError("bad distribution")
+    if distribution in ("poisson", "binomial"):
+        phi = 1.0
+    return Model("ar1_ng", y, [[1.0]], [[[rho]]], np.reshape([sigma], (1, 1, 1)), [mu],
+                 [[sigma ** 2 / (1 - rho ** 2)]], [0.0], [[mu * (1 - rho)]], u, phi, distribution,
+                 init_mode(y, u, distribution), xreg=xreg, beta=beta, theta=[rho, sigma, mu])
+
+
+def bsm_ng(y, sd_level, sd_slope=None, sd_seasonal=None, sd_noise=None, distribution="poisson",
+           phi=1.0, u=1.0, period=1, a1=None, P1=None, xreg=None, beta=None):
+    """Non-Gaussian basic structural model, R/models.R:926-1114."""
+    y = np.ravel(np.asarray(y, dtype=np.float64))
+    if distribution not in ("poisson", "binomial", "negative binomial", "gamma"):
+        raise ValueError("bad distribution")
+    slope = sd_slope is not None
+    seasonal = sd_seasonal is not None
+    noise = sd_noise is not None
+    if not seasonal:
+        period = 1
+    npar_R = 1 + int(slope) + int(seasonal) + int(noise)
+    m = 1 + int(slope) + int(seasonal) * (period - 1) + int(noise)
+    a1 = np.zeros(m) if a1 is None else np.ravel(np.asarray(a1, dtype=np.float64))
+    P1 = np.diag(np.full(m, 100.0)) if P1 is None else np.array(P1, dtype=np.float64)
+    Z = np.zeros((m, 1))
+    Z[0, 0] = 1
+    s0 = 1 + int(slope)  # 0-based row of the first seasonal state
+    if seasonal:
+        Z[s0, 0] = 1
+    T = np.zeros((m, m))
+    T[0, 0] = 1
+    if slope:
+        T[0:2, 1] = 1
+    if seasonal:
+        T[s0, s0:m] = -1  # R: T[(2 + slope), (2 + slope):m] <- -1
+        for j in range(period - 2):
+            T[s0 + 1 + j, s0 + j] = 1
+    R = np.zeros((m, max(1, npar_R)))
+    R[0, 0] = sd_level
+    if slope:
+        R[1, 1] = sd_slope
+    if seasonal:
+        R[s0, s0] = sd_seasonal
+    if noise:
+        P1[m - 1, m - 1] = sd_noise ** 2
+        Z[m - 1, 0] = 1
+        R[m - 1, max(1, R.shape[1] - 1) - 1] = sd_noise
+    if distribution in ("poisson", "binomial"):
+        phi = 1.0
+    return Model("bsm_ng", y, Z, T.reshape(m, m, 1), R.reshape(m, R.shape[1], 1), a1, P1, [0.0],
+                 np.zeros((m, 1)), u, phi, distribution, init_mode(y, u, distribution),
+                 xreg=xreg, beta=beta)

@@ -1,0 +1,182 @@
+/* bssm_b200.h -- C ABI of the B200 particle-filter engine.
+ *
+ * This is the drop-in boundary for the particle-filter hot path of helske/bssm
+ * (SURVEY.md section 8b).  Each entry point replaces one of the reference's
+ * `.Call` targets; the citation after "replaces:" is the reference function
+ * whose argument meaning, output layout and error behaviour it keeps.  All
+ * arrays are column-major binary64 exactly as R / Armadillo hold them, so an R
+ * shim can pass REAL(x) pointers without copying (r/bssm_b200_shim.c).
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in any signature; pointers are HOST
+ *     pointers unless the name ends in _dev;
+ *   - outputs are caller-allocated; a NULL output pointer means "not wanted";
+ *   - return value: 0 = ok, >0 = error (message via bssm_b200_last_error());
+ *     a filter that stops prematurely because all weights vanished is NOT an
+ *     error: status 0, loglik = -inf, stopped_at = the time index, later
+ *     columns left zero (reference: src/model_ssm_ung.cpp:556-560 and the
+ *     warning at src/R_bootstrap_filter.cpp:166-167);
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point returns BSSM_B200_ERR_NO_DEVICE.
+ */
+#ifndef BSSM_B200_H
+#define BSSM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  BSSM_B200_OK = 0,
+  BSSM_B200_ERR_ARG = 1,
+  BSSM_B200_ERR_NO_DEVICE = 2,
+  BSSM_B200_ERR_CUDA = 3,
+  BSSM_B200_ERR_UNSUPPORTED = 4
+};
+
+/* distribution codes, R/bootstrap_filter.R:106-109 */
+enum {
+  BSSM_DIST_SVM = 0, BSSM_DIST_POISSON = 1, BSSM_DIST_BINOMIAL = 2,
+  BSSM_DIST_NEGBIN = 3, BSSM_DIST_GAMMA = 4
+};
+/* sampling_method, R/run_mcmc.R:452-454 */
+enum { BSSM_METHOD_PSI = 1, BSSM_METHOD_BSF = 2 };
+/* post-processing a job runs after the filter */
+enum {
+  BSSM_POST_NONE = 0,           /* filter only */
+  BSSM_POST_FILTER_SUMMARY = 1, /* + filter_summary: at, att, Pt, Ptt (src/summary.cpp:42-79) */
+  BSSM_POST_SMOOTHER = 2        /* + filter_smoother backtrack + summary: alphahat, Vt */
+};
+/* what a job keeps on the device / hands back */
+enum {
+  BSSM_OUT_ALPHA = 1,    /* particle cube m x (n+1) x N            */
+  BSSM_OUT_WEIGHTS = 2,  /* N x (n+1), unnormalised exp(logw - max) */
+  BSSM_OUT_INDICES = 4,  /* N x n uint32 ancestors (parity observable) */
+  BSSM_OUT_ALL = 7
+};
+
+/* Univariate non-Gaussian observation / linear-Gaussian state model:
+ * the fields the reference reads from the R list in
+ * src/model_ssm_ung.cpp:9-32.  xbeta = xreg %*% beta (compute_xbeta,
+ * src/model_ssm_ung.h:83) is formed by the caller; NULL = no regressors. */
+typedef struct {
+  int32_t n, m, k;
+  int32_t distribution;
+  int32_t Ztv, Ttv, Rtv, Dtv, Ctv; /* 1 = last dimension is n, 0 = constant */
+  const double* y;     /* n, non-finite = missing */
+  const double* Z;     /* m x (1|n) */
+  const double* T;     /* m x m x (1|n) */
+  const double* R;     /* m x k x (1|n) */
+  const double* a1;    /* m */
+  const double* P1;    /* m x m */
+  const double* D;     /* (1|n) */
+  const double* C;     /* m x (1|n) */
+  const double* xbeta; /* n or NULL */
+  const double* u;     /* n */
+  double phi;
+  /* Gaussian approximation controls (psi-APF only) */
+  int32_t max_iter;
+  int32_t local_approx;
+  double conv_tol;
+  const double* initial_mode; /* n */
+} bssm_ung_model;
+
+typedef struct {
+  /* particle filter raw outputs */
+  double* alpha;      /* m x (n+1) x N */
+  double* weights;    /* N x (n+1) */
+  uint32_t* indices;  /* N x n */
+  /* filter_summary outputs (src/summary.cpp:42-79), bsf only */
+  double* at;         /* m x (n+1) */
+  double* att;        /* m x n */
+  double* Pt;         /* m x m x (n+1) */
+  double* Ptt;        /* m x m x n */
+  /* smoother outputs (src/summary.cpp:4-17), *_smoother only */
+  double* alphahat;   /* m x (n+1) */
+  double* Vt;         /* m x m x (n+1) */
+  /* scalars written by the callee */
+  double loglik;
+  double approx_loglik; /* psi only: log-likelihood of the Gaussian approximation */
+  int32_t stopped_at;   /* -1, or the time index at which all weights vanished */
+  float device_ms;      /* CUDA-event time of the kernels of this call */
+} bssm_filter_out;
+
+/* ---- library management ------------------------------------------------ */
+const char* bssm_b200_last_error(void);
+int bssm_b200_device_count(void);
+int bssm_b200_set_device(int device);
+/* frees cached device state; hook for .onUnload (reference: R/zzz.R:1-3) */
+void bssm_b200_shutdown(void);
+const char* bssm_b200_version(void);
+
+/* ---- unit hook ---------------------------------------------------------- */
+/* replaces: stratified_sample(p, r, N)  src/stratified_sample.cpp:9-28
+ * (itself .Call-exported, R/RcppExports.R:228).  p (length n_p) is consumed as
+ * the normalised weights; unlike the reference it is NOT mutated.  r: N
+ * uniforms.  xp: N ancestor indices (0-based).  cumsum_mode: 0 = reproducible
+ * fixed-point cumsum (what the filters use), see include/bssm_b200/pf_math.h. */
+int bssm_b200_stratified_sample(const double* p, uint32_t n_p, const double* r,
+                                uint32_t N, uint32_t* xp);
+
+/* Test hooks: evaluate the deterministic math / random stream of
+ * include/bssm_b200/pf_math.h ON THE DEVICE, so tests can check that host and
+ * device agree bit for bit.  op: 0 exp, 1 log, 2 log1p, 3 sin(2 pi x), 4 cos(2 pi x). */
+int bssm_b200_math_probe(int op, const double* x, double* y, uint32_t n);
+/* z: `count` normals of (seed, filter, t) in flat order; r: `count` resampling uniforms */
+int bssm_b200_rng_probe(uint32_t seed, uint32_t filter, uint32_t t, uint32_t count,
+                        double* z, double* r);
+
+/* ---- ssm_ung family (ssm_ung / bsm_ng / svm / ar1_ng) -------------------- */
+/* replaces: bsf(model_, nsim, seed, gaussian=FALSE, model_type)
+ *           src/R_bootstrap_filter.cpp:15-241 -> ssm_ung::bsf_filter
+ *           src/model_ssm_ung.cpp:611-712 + filter_summary src/summary.cpp:42-79 */
+int bssm_b200_bsf(const bssm_ung_model* model, uint32_t nsim, uint32_t seed,
+                  bssm_filter_out* out);
+/* replaces: bsf_smoother(...) src/R_bootstrap_filter.cpp:245-457
+ *           (bsf_filter + filter_smoother src/filter_smoother.cpp:5-18 +
+ *            summary src/summary.cpp:4-17) */
+int bssm_b200_bsf_smoother(const bssm_ung_model* model, uint32_t nsim, uint32_t seed,
+                           bssm_filter_out* out);
+/* replaces: psi_smoother(model_, nsim, seed, model_type) src/R_psi.cpp:52-171
+ *           -> ssm_ung::psi_filter src/model_ssm_ung.cpp:511-609 (including the
+ *           Gaussian approximation, smoother_ccov src/model_ssm_ulg.cpp:419-473
+ *           and conditional_cov src/conditional_dist.cpp:4-32), then
+ *           filter_smoother + summary.  m = 1 in this round. */
+int bssm_b200_psi_smoother(const bssm_ung_model* model, uint32_t nsim, uint32_t seed,
+                           bssm_filter_out* out);
+/* psi-APF filter only (no backtrack/summary): the body of
+ * ssm_ung::log_likelihood(method=1) src/model_ssm_ung.cpp:164-236 */
+int bssm_b200_psi_filter(const bssm_ung_model* model, uint32_t nsim, uint32_t seed,
+                         bssm_filter_out* out);
+
+/* ---- resident jobs: the same filters with inputs kept in HBM ------------- */
+/* A job owns device copies of the model, the pre-pass results and the output
+ * buffers of `n_filters` independent replicate filters (filter f uses random
+ * stream `filter = first_filter_id + f`, see pf_math.h).  run() only launches
+ * kernels; nothing crosses PCIe.  This is what bench.py times for `value`. */
+typedef struct bssm_b200_job bssm_b200_job;
+
+int bssm_b200_job_create_ung(const bssm_ung_model* model, int method, uint32_t nsim,
+                             uint32_t seed, uint32_t n_filters, uint32_t first_filter_id,
+                             int out_flags, int post, bssm_b200_job** job);
+/* launches pre-pass + filter (+ the post-processing kernels) on the
+ * job's stream and waits; ms = CUDA-event time on that stream */
+int bssm_b200_job_run(bssm_b200_job* job, float* ms);
+/* per-kernel CUDA-event times of the last run: [prepass, filter, smoother] */
+int bssm_b200_job_kernel_ms(const bssm_b200_job* job, float ms[3]);
+/* number of kernel launches one run() issues (for gpu_launches accounting) */
+int bssm_b200_job_launches(const bssm_b200_job* job);
+/* copies filter f's outputs to the host buffers in *out */
+int bssm_b200_job_fetch(bssm_b200_job* job, uint32_t f, bssm_filter_out* out);
+/* log-likelihoods of all filters, host copy */
+int bssm_b200_job_logliks(bssm_b200_job* job, double* loglik);
+/* the same into a caller-owned DEVICE buffer (e.g. a torch tensor handed to NCCL) */
+int bssm_b200_job_logliks_dev(bssm_b200_job* job, double* loglik_dev);
+void bssm_b200_job_destroy(bssm_b200_job* job);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSSM_B200_H */

@@ -1,0 +1,745 @@
+/* pf_oracle.cpp -- CPU restatement of the helske/bssm particle-filter hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is linked, imported or
+ * executed by the product (bssm_b200/); only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may use it, and only as
+ * the checker / the CPU baseline.
+ *
+ * PARITY UNPINNED at the Armadillo / sitmo boundary: the reference itself
+ * cannot be built here (no R, Rcpp, RcppArmadillo, sitmo) and its
+ * tests pin no particle-filter output values.  What IS pinned: the helper
+ * KATs in tests/test_oracle.py (stratified_sample hand vectors, Philox
+ * Random123 vectors, Kalman-smoother agreement of the LGSSM particle smoother,
+ * data/poisson_series decoded from the reference's own .rda).
+ *
+ * Every function keeps the reference's loop structure (scalar loops over
+ * particles, sequential two-pointer stratified merge, particle-slowest alpha
+ * cube m x (n+1) x N, column-major everything) and cites the file:line it
+ * follows, relative to /root/reference.
+ *
+ * Two deliberate, documented substitutions:
+ *   RNG   sitmo::prng_engine + std::normal_distribution (src/model_ssm_ung.cpp:
+ *         536-546) -> the counter-based Philox stream of include/bssm_b200/
+ *         pf_math.h, consumed in the reference's order (particle-major).
+ *   libm  std::exp/log/log1p -> pf_exp/pf_log/pf_log1p (<= 4 ulp from glibc).
+ * and one switch, `arith`:
+ *   ORC_ARITH_REFERENCE  sum of weights = Armadillo's two-accumulator
+ *         arrayops::accumulate [UNVENDORED, from memory], cumsum = sequential
+ *         binary64 (arma::cumsum) -- verbatim src/stratified_sample.cpp:12.
+ *   ORC_ARITH_REPRO      the order-independent fixed-point sum / cumsum of
+ *         pf_math.h, which is what the CUDA kernels compute.
+ * tests/test_oracle.py checks that both modes give identical ancestor indices
+ * on the tested configurations and counts near-ties where they could differ.
+ */
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <limits>
+#include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "bssm_b200/pf_math.h"
+#include "bssm_b200.h"
+
+enum { ORC_ARITH_REFERENCE = 0, ORC_ARITH_REPRO = 1 };
+
+static const double ORC_INF = std::numeric_limits<double>::infinity();
+
+/* ---------------------------------------------------------------- helpers */
+
+/* arma::accu on a contiguous vector: arrayops::accumulate, two accumulators
+ * [UNVENDORED: RcppArmadillo, from memory of arrayops_meat.hpp] */
+static double accu_arma(const double* x, size_t n) {
+  double acc1 = 0.0, acc2 = 0.0;
+  size_t j;
+  for (j = 1; j < n; j += 2) {
+    acc1 += x[j - 1];
+    acc2 += x[j];
+  }
+  if ((j - 1) < n) acc1 += x[j - 1];
+  return acc1 + acc2;
+}
+
+static double sum_weights(const double* w, size_t n, int arith) {
+  if (arith == ORC_ARITH_REFERENCE) return accu_arma(w, n);
+  int64_t hi = 0, lo = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (!(w[i] == w[i])) return pf_nan();
+    pf_fixsum t = pf_fixsum_term(w[i]);
+    hi += t.hi;
+    lo += t.lo;
+  }
+  return pf_fixsum_value(hi, lo);
+}
+
+extern "C" {
+
+/* ------------------------------------------------------------ math probes */
+void orc_philox(const uint32_t c[4], const uint32_t k[2], uint32_t out[4]) {
+  pf_u32x4 o = pf_philox4x32_10(c[0], c[1], c[2], c[3], k[0], k[1]);
+  for (int i = 0; i < 4; ++i) out[i] = o.v[i];
+}
+double orc_exp(double x) { return pf_exp(x); }
+double orc_log(double x) { return pf_log(x); }
+double orc_log1p(double x) { return pf_log1p(x); }
+void orc_sincos2pi(double u, double* s, double* c) { pf_sincos2pi(u, s, c); }
+void orc_exp_v(const double* x, double* y, size_t n) { for (size_t i = 0; i < n; ++i) y[i] = pf_exp(x[i]); }
+void orc_log_v(const double* x, double* y, size_t n) { for (size_t i = 0; i < n; ++i) y[i] = pf_log(x[i]); }
+void orc_log1p_v(const double* x, double* y, size_t n) { for (size_t i = 0; i < n; ++i) y[i] = pf_log1p(x[i]); }
+void orc_sincos2pi_v(const double* u, double* s, double* c, size_t n) {
+  for (size_t i = 0; i < n; ++i) pf_sincos2pi(u[i], &s[i], &c[i]);
+}
+void orc_normals(uint32_t seed, uint32_t filter, uint32_t t, uint32_t sub, uint32_t count, double* z) {
+  for (uint32_t f = 0; f < count; ++f) z[f] = pf_normal(seed, filter, t, sub, f);
+}
+void orc_resample_uniforms(uint32_t seed, uint32_t filter, uint32_t t, uint32_t N, double* r) {
+  for (uint32_t j = 0; j < N; ++j) r[j] = pf_resample_uniform(seed, filter, t, j);
+}
+
+/* ------------------------------------------------------------------- a1 */
+/* src/stratified_sample.cpp:9-28, verbatim: in-place cumsum, p[last] = 1,
+ * two-pointer merge with alpha = 1.0/N (reciprocal multiply, :16-18). */
+void orc_stratified_sample(double* p, uint32_t n_p, const double* r, uint32_t N, uint32_t* xp) {
+  for (uint32_t k = 1; k < n_p; ++k) p[k] = p[k - 1] + p[k]; /* arma::cumsum, sequential */
+  p[n_p - 1] = 1;
+  unsigned int j = 0;
+  double alpha = 1.0 / N;
+  for (unsigned int k = 0; k < n_p && j < N; k++) {
+    while (j < N && (r[j] + j) * alpha <= p[k]) {
+      xp[j] = k;
+      j++;
+    }
+  }
+  while (j < N) {
+    xp[j] = n_p - 1;
+    j++;
+  }
+}
+
+/* the same merge, cumsum replaced by the fixed-point scan of pf_math.h */
+void orc_stratified_sample_repro(double* p, uint32_t n_p, const double* r, uint32_t N, uint32_t* xp) {
+  uint64_t q = 0;
+  for (uint32_t k = 0; k < n_p; ++k) {
+    q += pf_cumsum_term(p[k]);
+    p[k] = pf_cumsum_value(q);
+  }
+  p[n_p - 1] = 1;
+  unsigned int j = 0;
+  double alpha = 1.0 / N;
+  for (unsigned int k = 0; k < n_p && j < N; k++) {
+    while (j < N && (r[j] + j) * alpha <= p[k]) {
+      xp[j] = k;
+      j++;
+    }
+  }
+  while (j < N) {
+    xp[j] = n_p - 1;
+    j++;
+  }
+}
+
+} /* extern "C" */
+
+static void resample(std::vector<double>& W, const std::vector<double>& r, uint32_t N,
+                     uint32_t* xp, int arith) {
+  if (arith == ORC_ARITH_REFERENCE) orc_stratified_sample(W.data(), N, r.data(), N, xp);
+  else orc_stratified_sample_repro(W.data(), N, r.data(), N, xp);
+}
+
+/* ------------------------------------------------------ ssm_ung densities */
+
+struct Ung {
+  const bssm_ung_model* M;
+  int n, m, k;
+  std::vector<double> xbeta;
+  /* Gaussian approximation (approx_model of src/model_ssm_ung.h:71) */
+  std::vector<double> ay, aH, aHH, scales, mode;
+  double approx_loglik = 0.0;
+  explicit Ung(const bssm_ung_model* M_) : M(M_), n(M_->n), m(M_->m), k(M_->k) {
+    xbeta.assign(n, 0.0);
+    if (M->xbeta) for (int t = 0; t < n; ++t) xbeta[t] = M->xbeta[t];
+    ay.assign(n, 0.0); aH.assign(n, 0.0); aHH.assign(n, 0.0); scales.assign(n, 0.0);
+    mode.assign(n, 0.0);
+  }
+  const double* Zc(int t) const { return M->Z + (size_t)m * (t * M->Ztv); }
+  const double* Tt(int t) const { return M->T + (size_t)m * m * (t * M->Ttv); }
+  const double* Rt(int t) const { return M->R + (size_t)m * k * (t * M->Rtv); }
+  const double* Cc(int t) const { return M->C + (size_t)m * (t * M->Ctv); }
+  double Dt(int t) const { return M->D[t * M->Dtv]; }
+
+  /* signal of particle state a (length m) at time t:
+   * src/model_ssm_ung.cpp:395 (svm: first state) and :402-403 (others) */
+  double signal(int t, const double* a) const {
+    if (M->distribution == 0) return a[0];
+    double zs = 0.0;
+    const double* Z = Zc(t);
+    for (int d = 0; d < m; ++d) zs += Z[d] * a[d];
+    return Dt(t) + zs + xbeta[t];
+  }
+  /* src/model_ssm_ung.cpp:447-493, one particle */
+  double log_obs_density(int t, double s) const {
+    const double y = M->y[t], phi = M->phi, u = M->u[t];
+    switch (M->distribution) {
+      case 0: return -0.5 * (s + (y / phi) * (y / phi) * pf_exp(-s));
+      case 1: return y * s - u * pf_exp(s);
+      case 2: return y * s - u * pf_log1p(pf_exp(s));
+      case 3: return y * s - (y + phi) * pf_log(phi + u * pf_exp(s));
+      case 4: return -phi * (s + (y * pf_exp(-s) / u));
+    }
+    return 0.0;
+  }
+  /* src/model_ssm_ung.cpp:385-439: log g - log g~ (unnormalised), one particle */
+  double log_weight(int t, double s) const {
+    double q = (ay[t] - s) / aH[t];
+    return log_obs_density(t, s) + 0.5 * (q * q);
+  }
+};
+
+/* state-independent constants: src/distr_consts.cpp:7-67 via the switch at
+ * src/model_ssm_ung.cpp:690-710 (BSF) and :347-370 (psi) */
+static double lchoose_(double n, double k) {
+  return -std::log(n + 1) - std::lgamma(n - k + 1) - std::lgamma(k + 1) + std::lgamma(n + 2);
+}
+static double dist_const(const bssm_ung_model* M) {
+  double res = 0.0;
+  const double phi = M->phi;
+  for (int t = 0; t < M->n; ++t) {
+    const double y = M->y[t];
+    if (!std::isfinite(y)) continue;
+    const double u = M->u[t];
+    switch (M->distribution) {
+      case 0: res += -0.5 * std::log(2.0 * M_PI) - std::log(phi); break;
+      case 1: res += y * std::log(u) - std::lgamma(y + 1); break;
+      case 2: res += lchoose_(u, y); break;
+      case 3: res += lchoose_(y + phi - 1, y) + phi * std::log(phi) + y * std::log(u); break;
+      case 4: res += phi * std::log(phi) - std::lgamma(phi) + (phi - 1) * std::log(y) - phi * std::log(u); break;
+    }
+  }
+  return res;
+}
+
+/* lower Cholesky of the positive-diagonal sub-block of P1,
+ * src/model_ssm_ung.cpp:614-619 */
+static void chol_P1(const double* P1, int m, std::vector<double>& L) {
+  L.assign((size_t)m * m, 0.0);
+  std::vector<int> nz;
+  for (int d = 0; d < m; ++d) if (P1[d + (size_t)m * d] > 0) nz.push_back(d);
+  int q = (int)nz.size();
+  for (int j = 0; j < q; ++j) {
+    for (int i = j; i < q; ++i) {
+      double s = P1[nz[i] + (size_t)m * nz[j]];
+      for (int l = 0; l < j; ++l) s -= L[nz[i] + (size_t)m * nz[l]] * L[nz[j] + (size_t)m * nz[l]];
+      if (i == j) L[nz[i] + (size_t)m * nz[j]] = std::sqrt(s);
+      else L[nz[i] + (size_t)m * nz[j]] = s / L[nz[j] + (size_t)m * nz[j]];
+    }
+  }
+}
+
+/* one normalisation step, src/model_ssm_ung.cpp:633-647 (and :672-683):
+ * logw (length N) -> weights column (unnormalised exp(logw-max)), W normalised.
+ * returns false when the filter must stop (sum_weights > 0 fails). */
+static bool normalise(const double* logw, uint32_t N, double* wcol, std::vector<double>& W,
+                      double* loglik_inc, int arith) {
+  double max_weight = logw[0];
+  bool has_nan = !(logw[0] == logw[0]);
+  for (uint32_t i = 1; i < N; ++i) {
+    if (logw[i] > max_weight) max_weight = logw[i];
+    if (!(logw[i] == logw[i])) has_nan = true;
+  }
+  /* a NaN log-weight gives a NaN sum in the reference (exp(NaN)), a non-finite
+   * max gives exp(-inf - -inf) = NaN: both fail `sum_weights > 0.0` */
+  if (has_nan || !std::isfinite(max_weight)) return false;
+  for (uint32_t i = 0; i < N; ++i) wcol[i] = pf_exp(logw[i] - max_weight);
+  double sum = sum_weights(wcol, N, arith);
+  if (!(sum > 0.0)) return false;
+  for (uint32_t i = 0; i < N; ++i) W[i] = wcol[i] / sum;
+  *loglik_inc = max_weight + pf_log(sum / N);
+  return true;
+}
+
+extern "C" {
+
+/* ------------------------------------------------------------------- a2 */
+/* ssm_ung::bsf_filter, src/model_ssm_ung.cpp:611-712.
+ * alpha m x (n+1) x N, weights N x (n+1), indices N x n; all pre-zeroed by the
+ * caller (reference: arma::fill::zeros, src/R_bootstrap_filter.cpp:162-164). */
+double orc_ung_bsf_filter(const bssm_ung_model* M, uint32_t nsim, uint32_t seed, uint32_t filter,
+                          int arith, double* alpha, double* weights, uint32_t* indices,
+                          int32_t* stopped_at) {
+  Ung g(M);
+  const int n = g.n, m = g.m, k = g.k;
+  const size_t N = nsim;
+  *stopped_at = -1;
+  std::vector<double> L_P1;
+  chol_P1(M->P1, m, L_P1);
+  auto A = [&](int d, int t, size_t i) -> double& { return alpha[d + (size_t)m * (t + (size_t)(n + 1) * i)]; };
+
+  for (size_t i = 0; i < N; ++i) { /* :621-627 */
+    std::vector<double> um(m);
+    for (int j = 0; j < m; ++j) um[j] = pf_normal(seed, filter, 0, 0, (uint32_t)(i * m + j));
+    for (int d = 0; d < m; ++d) {
+      double s = 0.0;
+      for (int j = 0; j < m; ++j) s += L_P1[d + (size_t)m * j] * um[j];
+      A(d, 0, i) = M->a1[d] + s;
+    }
+  }
+  std::vector<double> W(N), logw(N), r(N), atmp((size_t)m * N);
+  double loglik = 0.0;
+  if (std::isfinite(M->y[0])) { /* :633-647 */
+    for (size_t i = 0; i < N; ++i) logw[i] = g.log_obs_density(0, g.signal(0, &A(0, 0, i)));
+    double inc;
+    if (!normalise(logw.data(), nsim, weights, W, &inc, arith)) { *stopped_at = 0; return -ORC_INF; }
+    loglik = inc;
+  } else {
+    for (size_t i = 0; i < N; ++i) { weights[i] = 1.0; W[i] = 1.0 / nsim; }
+  }
+  for (int t = 0; t < n; ++t) { /* :648-688 */
+    for (size_t i = 0; i < N; ++i) r[i] = pf_resample_uniform(seed, filter, t, (uint32_t)i);
+    uint32_t* ind = indices + N * t;
+    resample(W, r, nsim, ind, arith);
+    for (size_t i = 0; i < N; ++i)
+      for (int d = 0; d < m; ++d) atmp[d + (size_t)m * i] = A(d, t, ind[i]);
+    const double* Tm = g.Tt(t); const double* Rm = g.Rt(t); const double* Cv = g.Cc(t);
+    for (size_t i = 0; i < N; ++i) {
+      std::vector<double> uk(k);
+      for (int j = 0; j < k; ++j) uk[j] = pf_normal(seed, filter, t + 1, 0, (uint32_t)(i * k + j));
+      for (int d = 0; d < m; ++d) {
+        double ta = 0.0, ru = 0.0;
+        for (int j = 0; j < m; ++j) ta += Tm[d + (size_t)m * j] * atmp[j + (size_t)m * i];
+        for (int j = 0; j < k; ++j) ru += Rm[d + (size_t)m * j] * uk[j];
+        A(d, t + 1, i) = Cv[d] + ta + ru;
+      }
+    }
+    double* wcol = weights + N * (t + 1);
+    if ((t < (n - 1)) && std::isfinite(M->y[t + 1])) {
+      for (size_t i = 0; i < N; ++i) logw[i] = g.log_obs_density(t + 1, g.signal(t + 1, &A(0, t + 1, i)));
+      double inc;
+      if (!normalise(logw.data(), nsim, wcol, W, &inc, arith)) { *stopped_at = t + 1; return -ORC_INF; }
+      loglik += inc;
+    } else {
+      for (size_t i = 0; i < N; ++i) { wcol[i] = 1.0; W[i] = 1.0 / nsim; }
+    }
+  }
+  loglik += dist_const(M); /* :690-710 */
+  return loglik;
+}
+
+} /* extern "C" */
+
+/* ----------------------------------------- Gaussian approximation, m = 1 */
+/* The scalar (m = 1) specialisation of the approx_model (class ssm_ulg) used by
+ * the psi-APF.  Z, T, R, C, D may be time varying. */
+struct Ulg1 {
+  const Ung& g;
+  explicit Ulg1(const Ung& g_) : g(g_) {}
+  double Z(int t) const { return g.Zc(t)[0]; }
+  double T(int t) const { return g.Tt(t)[0]; }
+  double RR(int t) const { double r = g.Rt(t)[0]; return r * r; }
+  double C(int t) const { return g.Cc(t)[0]; }
+  double D(int t) const { return g.Dt(t); }
+  double HH(int t) const { return g.aHH[t]; }
+  double ytmp(int t) const { return g.M->xbeta ? g.ay[t] - g.xbeta[t] : g.ay[t]; }
+  static constexpr double zero_tol = 1e-12; /* src/model_ssm_ulg.h:19 */
+
+  /* ssm_ulg::log_likelihood, src/model_ssm_ulg.cpp:106-138 */
+  double log_likelihood() const {
+    const int n = g.n;
+    double sumH = 0.0, sumR = 0.0;
+    for (int t = 0; t < n; ++t) sumH += g.aH[t];
+    int nR = g.M->Rtv ? n : 1;
+    for (int t = 0; t < nR; ++t) sumR += g.Rt(t)[0];
+    if (sumH + sumR < zero_tol) return -ORC_INF;
+    double logLik = 0.0;
+    double at = g.M->a1[0], Pt = g.M->P1[0];
+    const double LOG2PI = std::log(2.0 * M_PI);
+    for (int t = 0; t < n; ++t) {
+      double F = Z(t) * Pt * Z(t) + HH(t);
+      double yt = ytmp(t);
+      if (std::isfinite(yt) && F > zero_tol) {
+        double v = yt - D(t) - Z(t) * at;
+        double K = Pt * Z(t) / F;
+        at = C(t) + T(t) * (at + K * v);
+        Pt = T(t) * (Pt - K * K * F) * T(t) + RR(t);
+        logLik -= 0.5 * (LOG2PI + pf_log(F) + v * v / F);
+      } else {
+        at = C(t) + T(t) * at;
+        Pt = T(t) * Pt * T(t) + RR(t);
+      }
+    }
+    return logLik;
+  }
+
+  /* ssm_ulg::fast_smoother, src/model_ssm_ulg.cpp:252-305: returns at (n+1) */
+  void fast_smoother(std::vector<double>& at) const {
+    const int n = g.n;
+    at.assign(n + 1, 0.0);
+    std::vector<double> vt(n), Ft(n), Kt(n), rt(n);
+    at[0] = g.M->a1[0];
+    double Pt = g.M->P1[0];
+    for (int t = 0; t < n; ++t) {
+      Ft[t] = Z(t) * Pt * Z(t) + HH(t);
+      double yt = ytmp(t);
+      if (std::isfinite(yt) && Ft[t] > zero_tol) {
+        Kt[t] = Pt * Z(t) / Ft[t];
+        vt[t] = yt - D(t) - Z(t) * at[t];
+        at[t + 1] = C(t) + T(t) * (at[t] + Kt[t] * vt[t]);
+        double tmp = 1.0 - Kt[t] * Z(t);
+        Pt = T(t) * (tmp * Pt * tmp + Kt[t] * HH(t) * Kt[t]) * T(t) + RR(t);
+      } else {
+        at[t + 1] = C(t) + T(t) * at[t];
+        Pt = T(t) * Pt * T(t) + RR(t);
+      }
+    }
+    rt[n - 1] = 0.0;
+    for (int t = n - 1; t > 0; --t) {
+      if (std::isfinite(ytmp(t)) && Ft[t] > zero_tol) {
+        double L = T(t) * (1.0 - Kt[t] * Z(t));
+        rt[t - 1] = Z(t) / Ft[t] * vt[t] + L * rt[t];
+      } else {
+        rt[t - 1] = T(t) * rt[t];
+      }
+    }
+    if (std::isfinite(g.ay[0]) && Ft[0] > zero_tol) {
+      double L = T(0) * (1.0 - Kt[0] * Z(0));
+      at[0] = g.M->a1[0] + g.M->P1[0] * (Z(0) / Ft[0] * vt[0] + L * rt[0]);
+    } else {
+      at[0] = g.M->a1[0] + g.M->P1[0] * T(0) * rt[0];
+    }
+    for (int t = 0; t < n - 1; ++t) at[t + 1] = C(t) + T(t) * at[t] + RR(t) * rt[t];
+  }
+
+  /* ssm_ulg::smoother_ccov, src/model_ssm_ulg.cpp:419-473 */
+  void smoother_ccov(std::vector<double>& at, std::vector<double>& Pt, std::vector<double>& ccov) const {
+    const int n = g.n;
+    at.assign(n + 1, 0.0); Pt.assign(n + 1, 0.0); ccov.assign(n + 1, 0.0);
+    std::vector<double> vt(n), Ft(n), Kt(n);
+    at[0] = g.M->a1[0];
+    Pt[0] = g.M->P1[0];
+    for (int t = 0; t < n; ++t) {
+      Ft[t] = Z(t) * Pt[t] * Z(t) + HH(t);
+      double yt = ytmp(t);
+      if (std::isfinite(yt) && Ft[t] > zero_tol) {
+        Kt[t] = Pt[t] * Z(t) / Ft[t];
+        vt[t] = yt - D(t) - Z(t) * at[t];
+        at[t + 1] = C(t) + T(t) * (at[t] + Kt[t] * vt[t]);
+        double tmp = 1.0 - Kt[t] * Z(t);
+        Pt[t + 1] = T(t) * (tmp * Pt[t] * tmp + Kt[t] * HH(t) * Kt[t]) * T(t) + RR(t);
+      } else {
+        at[t + 1] = C(t) + T(t) * at[t];
+        Pt[t + 1] = T(t) * Pt[t] * T(t) + RR(t);
+      }
+      ccov[t] = Pt[t + 1];
+    }
+    double rt = 0.0, Nt = 0.0;
+    for (int t = n - 1; t >= 0; --t) {
+      if (std::isfinite(ytmp(t)) && Ft[t] > zero_tol) {
+        double L = T(t) * (1.0 - Kt[t] * Z(t));
+        ccov[t] = Pt[t] * L * (1.0 - Nt * ccov[t]);
+        rt = Z(t) / Ft[t] * vt[t] + L * rt;
+        Nt = Z(t) * Z(t) / Ft[t] + L * Nt * L;
+      } else {
+        ccov[t] = Pt[t] * T(t) * (1.0 - Nt * ccov[t]);
+        rt = T(t) * rt;
+        Nt = T(t) * Nt * T(t);
+      }
+      at[t] += Pt[t] * rt;
+      Pt[t] -= Pt[t] * Nt * Pt[t];
+    }
+    ccov[n] = 0.0;
+  }
+};
+
+/* conditional_cov, SVD branch (default use_svd = true, src/conditional_dist.h:6)
+ * specialised to p = 1: src/conditional_dist.cpp:8-32.  For a 1x1 matrix
+ * svd_econ gives U = 1, s = |V| ; `s > eps*p*s(0)` is false only for s = 0. */
+static void conditional_cov_m1(std::vector<double>& Vt, std::vector<double>& Ct) {
+  const int n1 = (int)Vt.size();
+  const double eps = std::numeric_limits<double>::epsilon();
+  for (int t = n1 - 1; t > 0; --t) {
+    double s = std::fabs(Vt[t - 1]);
+    double tmp = (s > eps * 1 * s) ? Ct[t - 1] * (1.0 / s) : 0.0;
+    Vt[t] -= tmp * Ct[t - 1];
+    Ct[t] = tmp;
+    Vt[t] = std::sqrt(std::fabs(Vt[t]));
+  }
+  Vt[0] = std::sqrt(std::fabs(Vt[0]));
+}
+
+/* ssm_ung::laplace_iter, src/model_ssm_ung.cpp:302-342 */
+static void laplace_iter(Ung& g, const std::vector<double>& signal) {
+  const bssm_ung_model* M = g.M;
+  const double phi = M->phi;
+  for (int t = 0; t < g.n; ++t) {
+    const double y = M->y[t], u = M->u[t], s = signal[t];
+    switch (M->distribution) {
+      case 0: {
+        double tmp = y;
+        if (std::fabs(tmp) < 1e-4) tmp = 1e-4;
+        double q = tmp / phi;
+        g.aHH[t] = 2.0 * pf_exp(s) / (q * q);
+        g.ay[t] = s + 1.0 - 0.5 * g.aHH[t];
+      } break;
+      case 1: {
+        g.aHH[t] = 1.0 / (pf_exp(s) * u);
+        g.ay[t] = y * g.aHH[t] + s - 1.0;
+      } break;
+      case 2: {
+        double e = pf_exp(s);
+        g.aHH[t] = (1.0 + e) * (1.0 + e) / (u * e);
+        g.ay[t] = y * g.aHH[t] + s - 1.0 - e;
+      } break;
+      case 3: {
+        double e = pf_exp(s) * u;
+        g.aHH[t] = (phi + e) * (phi + e) / (phi * e * (y + phi));
+        g.ay[t] = s + (phi + e) * (y - e) / ((y + phi) * e);
+      } break;
+      case 4: {
+        double e = pf_exp(s) * u;
+        g.aHH[t] = e / (y * phi);
+        g.ay[t] = s - e / y + 1;
+      } break;
+    }
+    g.aH[t] = std::sqrt(g.aHH[t]);
+  }
+}
+
+/* ssm_ung::update_scales, src/model_ssm_ung.cpp:241-292 */
+static void update_scales(Ung& g) {
+  for (int t = 0; t < g.n; ++t) {
+    g.scales[t] = 0.0;
+    if (std::isfinite(g.M->y[t])) g.scales[t] = g.log_weight(t, g.mode[t]);
+  }
+}
+
+/* ssm_ung::approximate, src/model_ssm_ung.cpp:87-140 (approx_state < 1, local
+ * approximation branch), m = 1.  mode starts from initial_mode (:174). */
+static void approximate(Ung& g) {
+  const bssm_ung_model* M = g.M;
+  const int n = g.n;
+  for (int t = 0; t < n; ++t) g.mode[t] = M->initial_mode[t];
+  Ulg1 am(g);
+  int i = 0;
+  double diff = M->conv_tol + 1;
+  std::vector<double> at, mode_new(n);
+  while (i < M->max_iter && diff > M->conv_tol) {
+    i++;
+    laplace_iter(g, g.mode);
+    am.fast_smoother(at);
+    if (M->distribution == 0) {
+      for (int t = 0; t < n; ++t) mode_new[t] = at[t];
+    } else {
+      for (int t = 0; t < n; ++t) mode_new[t] = g.xbeta[t] + g.Dt(t) + g.Zc(t)[0] * at[t];
+    }
+    std::vector<double> sq(n);
+    for (int t = 0; t < n; ++t) sq[t] = (mode_new[t] - g.mode[t]) * (mode_new[t] - g.mode[t]);
+    diff = accu_arma(sq.data(), n) / n;
+    g.mode = mode_new;
+  }
+}
+
+/* compute_const_term, src/model_ssm_ung.cpp:347-370 */
+static double const_term(const Ung& g) {
+  double c = dist_const(g.M);
+  int nobs = 0;
+  double sumlog = 0.0;
+  for (int t = 0; t < g.n; ++t)
+    if (std::isfinite(g.M->y[t])) { nobs++; sumlog += pf_log(g.aH[t]); }
+  double norm = -0.5 * nobs * std::log(2 * M_PI) - sumlog;
+  return c - norm;
+}
+
+struct PsiPre {
+  std::vector<double> alphahat, L, Ct;
+};
+
+/* the head of ssm_ung::psi_filter, src/model_ssm_ung.cpp:514-533.
+ * mode_in == NULL: approximate() from initial_mode, approx_loglik computed
+ * (:519-528).  mode_in != NULL: approximate_for_is (:143-161): fixed mode, no
+ * iterations, approx_loglik = 0. */
+static void psi_prepass(Ung& g, const double* mode_in, PsiPre& pre) {
+  Ulg1 am(g);
+  if (mode_in) {
+    for (int t = 0; t < g.n; ++t) g.mode[t] = mode_in[t];
+    laplace_iter(g, g.mode);
+    update_scales(g);
+    g.approx_loglik = 0.0;
+  } else {
+    approximate(g);
+    double gaussian_loglik = am.log_likelihood();
+    update_scales(g);
+    double ct = const_term(g);
+    g.approx_loglik = gaussian_loglik + ct + accu_arma(g.scales.data(), g.n);
+  }
+  std::vector<double> Vt;
+  am.smoother_ccov(pre.alphahat, Vt, pre.Ct);
+  conditional_cov_m1(Vt, pre.Ct);
+  pre.L = Vt;
+}
+
+extern "C" {
+
+/* exposes the pre-pass arrays for parity tests of the device pre-pass kernel */
+int orc_ung_psi_prepass(const bssm_ung_model* M, const double* mode_in, double* mode_out,
+                        double* ytilde, double* Htilde, double* scales, double* alphahat,
+                        double* L, double* Ct, double* approx_loglik) {
+  if (M->m != 1) return 1;
+  Ung g(M);
+  PsiPre pre;
+  psi_prepass(g, mode_in, pre);
+  const int n = g.n;
+  for (int t = 0; t < n; ++t) {
+    if (mode_out) mode_out[t] = g.mode[t];
+    if (ytilde) ytilde[t] = g.ay[t];
+    if (Htilde) Htilde[t] = g.aH[t];
+    if (scales) scales[t] = g.scales[t];
+  }
+  for (int t = 0; t <= n; ++t) {
+    if (alphahat) alphahat[t] = pre.alphahat[t];
+    if (L) L[t] = pre.L[t];
+    if (Ct) Ct[t] = pre.Ct[t];
+  }
+  if (approx_loglik) *approx_loglik = g.approx_loglik;
+  return 0;
+}
+
+/* ------------------------------------------------------------------- a3 */
+/* ssm_ung::psi_filter, src/model_ssm_ung.cpp:511-609, m = 1. */
+double orc_ung_psi_filter(const bssm_ung_model* M, const double* mode_in, uint32_t nsim,
+                          uint32_t seed, uint32_t filter, int arith, double* alpha,
+                          double* weights, uint32_t* indices, double* approx_loglik,
+                          int32_t* stopped_at) {
+  *stopped_at = -1;
+  if (M->m != 1) return pf_nan();
+  Ung g(M);
+  PsiPre pre;
+  psi_prepass(g, mode_in, pre);
+  if (approx_loglik) *approx_loglik = g.approx_loglik;
+  const int n = g.n;
+  const size_t N = nsim;
+  auto A = [&](int t, size_t i) -> double& { return alpha[t + (size_t)(n + 1) * i]; };
+
+  for (size_t i = 0; i < N; ++i) { /* :538-544 */
+    double um = pf_normal(seed, filter, 0, 0, (uint32_t)i);
+    A(0, i) = pre.alphahat[0] + pre.L[0] * um;
+  }
+  std::vector<double> W(N), logw(N), r(N), atmp(N);
+  double loglik = 0.0;
+  if (std::isfinite(M->y[0])) { /* :549-562 */
+    for (size_t i = 0; i < N; ++i) { double a = A(0, i); logw[i] = g.log_weight(0, g.signal(0, &a)) - g.scales[0]; }
+    double inc;
+    if (!normalise(logw.data(), nsim, weights, W, &inc, arith)) { *stopped_at = 0; return -ORC_INF; }
+    loglik = inc + g.approx_loglik;
+  } else {
+    for (size_t i = 0; i < N; ++i) { weights[i] = 1.0; W[i] = 1.0 / nsim; }
+    loglik = g.approx_loglik;
+  }
+  for (int t = 0; t < n; ++t) { /* :568-606 */
+    for (size_t i = 0; i < N; ++i) r[i] = pf_resample_uniform(seed, filter, t, (uint32_t)i);
+    uint32_t* ind = indices + N * t;
+    resample(W, r, nsim, ind, arith);
+    for (size_t i = 0; i < N; ++i) atmp[i] = A(t, ind[i]);
+    for (size_t i = 0; i < N; ++i) {
+      double um = pf_normal(seed, filter, t + 1, 0, (uint32_t)i);
+      A(t + 1, i) = pre.alphahat[t + 1] + pre.Ct[t + 1] * (atmp[i] - pre.alphahat[t]) + pre.L[t + 1] * um;
+    }
+    double* wcol = weights + N * (t + 1);
+    if ((t < (n - 1)) && std::isfinite(M->y[t + 1])) {
+      for (size_t i = 0; i < N; ++i) { double a = A(t + 1, i); logw[i] = g.log_weight(t + 1, g.signal(t + 1, &a)) - g.scales[t + 1]; }
+      double inc;
+      if (!normalise(logw.data(), nsim, wcol, W, &inc, arith)) { *stopped_at = t + 1; return -ORC_INF; }
+      loglik += inc;
+    } else {
+      for (size_t i = 0; i < N; ++i) { wcol[i] = 1.0; W[i] = 1.0 / nsim; }
+    }
+  }
+  return loglik;
+}
+
+/* ------------------------------------------------------------------ a10 */
+/* filter_smoother, src/filter_smoother.cpp:5-18: alpha m x n1 x N in place */
+void orc_filter_smoother(double* alpha, const uint32_t* indices, int m, int n1, uint32_t N) {
+  std::vector<uint32_t> b(N), b2(N);
+  for (uint32_t i = 0; i < N; ++i) b[i] = i;
+  std::vector<double> alphatmp((size_t)m * N);
+  for (int t = n1 - 2; t >= 0; t--) {
+    for (uint32_t i = 0; i < N; ++i)
+      for (int d = 0; d < m; ++d) alphatmp[d + (size_t)m * i] = alpha[d + (size_t)m * (t + (size_t)n1 * i)];
+    const uint32_t* col = indices + (size_t)N * t;
+    for (uint32_t i = 0; i < N; ++i)
+      for (int d = 0; d < m; ++d) alpha[d + (size_t)m * (t + (size_t)n1 * i)] = alphatmp[d + (size_t)m * col[b[i]]];
+    for (uint32_t i = 0; i < N; ++i) b2[i] = col[b[i]];
+    b.swap(b2);
+  }
+}
+
+/* ------------------------------------------------------------------ a11 */
+/* summary, src/summary.cpp:4-17: sequential Welford over particles */
+void orc_summary(const double* x, int m, int n1, uint32_t N, double* mean_x, double* cov_x) {
+  std::fill(mean_x, mean_x + (size_t)m * n1, 0.0);
+  std::fill(cov_x, cov_x + (size_t)m * m * n1, 0.0);
+  std::vector<double> diff((size_t)m * n1);
+  for (uint32_t i = 0; i < N; ++i) {
+    const double* xi = x + (size_t)m * n1 * i;
+    for (size_t e = 0; e < (size_t)m * n1; ++e) {
+      diff[e] = xi[e] - mean_x[e];
+      mean_x[e] += diff[e] / (i + 1);
+    }
+    for (int t = 0; t < n1; ++t)
+      for (int c = 0; c < m; ++c)
+        for (int r = 0; r < m; ++r)
+          cov_x[r + (size_t)m * (c + (size_t)m * t)] +=
+              diff[r + (size_t)m * t] * (xi[c + (size_t)m * t] - mean_x[c + (size_t)m * t]);
+  }
+  for (size_t e = 0; e < (size_t)m * m * n1; ++e) cov_x[e] /= N;
+}
+
+/* filter_summary, src/summary.cpp:42-79.  weights is taken by value in the
+ * reference (normalised copy); here `weights` is read-only. at m x n1,
+ * att m x (n1-1), Pt m x m x n1, Ptt m x m x (n1-1). */
+void orc_filter_summary(const double* alpha, int m, int n1, uint32_t N, const double* weights,
+                        double* at, double* att, double* Pt, double* Ptt) {
+  const int n = n1 - 1;
+  std::fill(at, at + (size_t)m * n1, 0.0);
+  std::fill(att, att + (size_t)m * n, 0.0);
+  std::vector<double> w((size_t)N * n1);
+  for (int t = 0; t < n1; ++t) {
+    double s = accu_arma(weights + (size_t)N * t, N);
+    for (uint32_t i = 0; i < N; ++i) w[i + (size_t)N * t] = weights[i + (size_t)N * t] / s;
+  }
+  auto A = [&](int d, int t, uint32_t i) { return alpha[d + (size_t)m * (t + (size_t)n1 * i)]; };
+  for (int t = 0; t < n; ++t)
+    for (uint32_t i = 0; i < N; ++i)
+      for (int d = 0; d < m; ++d) {
+        att[d + (size_t)m * t] += A(d, t, i) * w[i + (size_t)N * t];
+        at[d + (size_t)m * t] += A(d, t, i);
+      }
+  for (uint32_t i = 0; i < N; ++i)
+    for (int d = 0; d < m; ++d) at[d + (size_t)m * n] += A(d, n, i);
+  for (size_t e = 0; e < (size_t)m * n1; ++e) at[e] /= N;
+  std::fill(Pt, Pt + (size_t)m * m * n1, 0.0);
+  std::fill(Ptt, Ptt + (size_t)m * m * n, 0.0);
+  for (int t = 0; t < n1; ++t)
+    for (uint32_t i = 0; i < N; ++i)
+      for (int c = 0; c < m; ++c)
+        for (int r = 0; r < m; ++r) {
+          Pt[r + (size_t)m * (c + (size_t)m * t)] +=
+              (A(r, t, i) - at[r + (size_t)m * t]) * (A(c, t, i) - at[c + (size_t)m * t]);
+          if (t < n)
+            Ptt[r + (size_t)m * (c + (size_t)m * t)] += w[i + (size_t)N * t] *
+                (A(r, t, i) - att[r + (size_t)m * t]) * (A(c, t, i) - att[c + (size_t)m * t]);
+        }
+  for (size_t e = 0; e < (size_t)m * m * n1; ++e) Pt[e] /= N;
+}
+
+int orc_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+} /* extern "C" */

