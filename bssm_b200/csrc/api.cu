@@ -179,11 +179,12 @@ void chol_posdiag(const double* P1, int m, std::vector<double>& L) {
 // ssm_ung::approximate (:87-140, local branch) = repeat { laplace_iter (:302-342);
 // fast_smoother (src/model_ssm_ulg.cpp:252-305) } until the mean squared change
 // of the mode is below conv_tol.  Sequential in t, O(n) per sweep: host work.
-void ung_approximate_m1(const bssm_ung_model* M, std::vector<double>& mode) {
+void ung_approximate_m1(const bssm_ung_model* M, std::vector<double>& mode, std::vector<double>& mode_lin) {
   const int n = M->n;
   const double zero_tol = 1e-12;
   const double phi = M->phi;
   mode.assign(M->initial_mode, M->initial_mode + n);
+  mode_lin = mode;
   std::vector<double> HH(n), yt(n), at(n + 1), v(n), F(n), K(n), r(n), next(n);
   auto Z = [&](int t) { return M->Z[t * M->Ztv]; };
   auto T = [&](int t) { return M->T[t * M->Ttv]; };
@@ -196,6 +197,7 @@ void ung_approximate_m1(const bssm_ung_model* M, std::vector<double>& mode) {
   double diff = M->conv_tol + 1;
   while (it < M->max_iter && diff > M->conv_tol) {
     it++;
+    mode_lin = mode;
     for (int t = 0; t < n; ++t) { // laplace_iter
       const double y = M->y[t], u = M->u[t], s = mode[t];
       switch (M->distribution) {
@@ -309,7 +311,7 @@ struct bssm_b200_job {
   int launches = 0;
   bool has_run = false;
   // model on device
-  DevBuf<double> y, Z, T, R, a1, P1, LP1, D, C, xbeta, u, mode;
+  DevBuf<double> y, Z, T, R, a1, P1, LP1, D, C, xbeta, u, mode, mode_lin;
   // psi pre-pass results
   DevBuf<double> alphahat, Lt, Ct, ytilde, Htilde, scales, approx_loglik, phi_f, scratch;
   size_t pstride = 0;
@@ -479,9 +481,10 @@ int bssm_b200_job_create_ung(const bssm_ung_model* M, int method, uint32_t nsim,
 
   if (method == BSSM_METHOD_PSI) {
     if (!M->initial_mode) return fail(BSSM_B200_ERR_ARG, "psi-APF needs initial_mode");
-    std::vector<double> mode;
-    ung_approximate_m1(M, mode);
-    if ((rc = J->mode.upload(mode.data(), n))) return rc;
+    if (M->max_iter < 1) return fail(BSSM_B200_ERR_ARG, "max_iter must be >= 1");
+    std::vector<double> mode, mode_lin;
+    ung_approximate_m1(M, mode, mode_lin);
+    if ((rc = J->mode.upload(mode.data(), n)) || (rc = J->mode_lin.upload(mode_lin.data(), n))) return rc;
     J->pstride = (size_t)n + 1;
     const size_t tot = J->pstride * n_filters;
     if ((rc = J->alphahat.alloc(tot)) || (rc = J->Lt.alloc(tot)) || (rc = J->Ct.alloc(tot)) ||
@@ -497,7 +500,7 @@ int bssm_b200_job_create_ung(const bssm_ung_model* M, int method, uint32_t nsim,
     pp.has_xbeta = M->xbeta ? 1 : 0;
     pp.phi = M->phi;
     pp.theta = nullptr; pp.n_par = 0; pp.svm_type = 0;
-    pp.modes = J->mode.p; pp.mode_stride = 0; // replicates share the mode
+    pp.modes = J->mode.p; pp.modes_lin = J->mode_lin.p; pp.mode_stride = 0; // replicates share the mode
     pp.compute_loglik = 1;
     pp.dist_const = dconst;
     pp.log2pi = std::log(2.0 * M_PI);

@@ -28,8 +28,14 @@ struct PrepassParams {
   const double* theta;
   int n_par;
   int svm_type;  // 0: theta[2] = sigma (phi), 1: theta[2] = mu
-  // mode of the Gaussian approximation: n per filter
+  // mode of the Gaussian approximation: n per filter.  `modes_lin` is the point
+  // the pseudo-observations are linearised at: after ssm_ung::approximate() that
+  // is the mode of the LAST BUT ONE Newton sweep (the reference does not
+  // re-linearise after its final smoother pass, src/model_ssm_ung.cpp:115-137),
+  // while update_scales (:241-292) is evaluated at the final mode; for
+  // approximate_for_is (:143-161) both are the stored mode.
   const double* modes;
+  const double* modes_lin;
   size_t mode_stride;
   int compute_loglik;  // 0: approximate_for_is (approx_loglik = 0)
   double dist_const;   // state-independent constants of the observation density
@@ -57,6 +63,7 @@ ung_prepass_m1_kernel(const PrepassParams pp, uint32_t n_filters) {
   double* Ft = vt + pp.pstride;
   double* Kt = Ft + pp.pstride;
   const double* mode = pp.modes + (size_t)f * pp.mode_stride;
+  const double* mode_lin = pp.modes_lin + (size_t)f * pp.mode_stride;
 
   // ---- model of this filter (svm::update_model, src/model_svm.cpp:12-29)
   const bool from_theta = pp.theta != nullptr;
@@ -83,7 +90,8 @@ ung_prepass_m1_kernel(const PrepassParams pp, uint32_t n_filters) {
   // ---- laplace_iter (:302-342) and update_scales (:241-292), lanes over t
   const int dist = pp.distribution;
   for (int t = lane; t < n; t += 32) {
-    const double y = pp.y[t], u = pp.u[t], s = mode[t];
+    const double y = pp.y[t], u = pp.u[t];
+    double s = mode_lin[t];
     double HH, yt;
     switch (dist) {
       case 0: {
@@ -118,6 +126,7 @@ ung_prepass_m1_kernel(const PrepassParams pp, uint32_t n_filters) {
     aH[t] = H;
     Ft[t] = HH; // parked here until the forward pass overwrites it
     double scale = 0.0;
+    s = mode[t];
     if (pf_isfinite(y)) {
       double qy = y / phi;
       double q = (yt - s) / H;
