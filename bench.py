@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the svm psi-APF (BASELINE.json config 2).
+
+Workload ("c2"): stochastic-volatility model, synthetic series T = 1000,
+psi-auxiliary particle filter with N = 65536 particles, fp64.  One STEP = one
+pass of the hot path over a batch of `--filters` independent replicate filters
+of that configuration on each GPU (different random streams, same model) --
+the shape of the reference's only parallel pattern (independent filters,
+src/approx_mcmc.cpp:364-369) and of suggest_N's replications.  A single filter
+cannot fill a B200 (its T = 1000 steps are strictly sequential), so the
+single-filter figure is reported beside the batched one in `config`.
+
+  value      whole-job particle-steps/s, inputs resident in HBM, CUDA events on
+             the launching stream (pre-pass + filter kernels)
+  e2e        the same metric through the C-ABI call bssm_b200_psi_filter with
+             HOST buffers: model upload, kernels, and the device->host copy of
+             the particle cube + weights the reference's .Call returns
+  roofline   filter kernel against the HBM roofline: algorithmic bytes
+             (8m + 12 = 20 B per particle-step: state, weight, ancestor written
+             once) / kernel time
+  cpu_baseline  the CPU oracle (a port of the reference's loops) on host cores
+
+`--impl reference` times the CPU restatement of the reference's path (the
+reference itself cannot be built here: no R/Rcpp/Armadillo) with all host
+threads, one replicate filter per thread, on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOAD = {"N": 65536, "n": 1000, "m": 1, "rho": 0.98, "sd_ar": 0.2, "sigma": 1.0, "gen_seed": 2024}
+BYTES_PER_PS = 20  # 8m (state) + 8 (weight) + 4 (ancestor), m = 1
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for key in ("hbm_gbs", "hbm_gb_s", "hbm_GBs"):
+                if key in d:
+                    return float(d[key]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(int(float(r[0])))
+                mx = max(mx, int(float(r[1])))
+                for nm, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_model():
+    import data
+    w = WORKLOAD
+    return data.svm_model(w["n"], w["rho"], w["sd_ar"], w["sigma"], w["gen_seed"])
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle (a port of the reference's loops) with all host threads."""
+    if rank != 0:
+        return
+    import bssm_b200
+    import data
+    import orc
+    from bssm_b200 import build
+    build.build_oracle()
+    w = WORKLOAD
+    cores = orc.max_threads()
+    n_sample = 50  # first 50 time points of the same series, full N
+    y = data.svm_series(w["n"], w["rho"], w["sd_ar"], w["sigma"], w["gen_seed"])[:n_sample]
+    model = bssm_b200.svm(y, w["rho"], w["sd_ar"], sigma=w["sigma"])
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        orc.filter_batch(model, w["N"], method="psi", seed=1, first_filter=it * cores, n_filters=cores,
+                         arith=orc.ARITH_REFERENCE, threads=cores)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = cores * w["N"] * n_sample * args.steps / total
+    sample = ("%d replicate filters (one per thread, OpenMP static), N=%d, first %d of T=%d time points per step; "
+              "oracle port of the reference loops (reference not buildable here: no R/Rcpp/Armadillo); cpu=%s"
+              % (cores, w["N"], n_sample, w["n"], cpu_model_name()))
+    line = {
+        "impl": "reference", "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "c2: svm psi-APF T=1000 N=65536 (bounded sample, see cpu_baseline.sample)"},
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg():
+    """single-thread oracle on a bounded sample (the reference never threads inside a filter)"""
+    import bssm_b200
+    import data
+    import orc
+    from bssm_b200 import build
+    build.build_oracle()
+    w = WORKLOAD
+    n_sample = 200
+    y = data.svm_series(w["n"], w["rho"], w["sd_ar"], w["sigma"], w["gen_seed"])[:n_sample]
+    model = bssm_b200.svm(y, w["rho"], w["sd_ar"], sigma=w["sigma"])
+    t0 = time.perf_counter()
+    orc.filter_batch(model, w["N"], method="psi", seed=1, n_filters=1, arith=orc.ARITH_REFERENCE, threads=1)
+    dt = time.perf_counter() - t0
+    return {"value": w["N"] * n_sample / dt, "unit": "particle-steps/s", "cores": 1, "kind": "port",
+            "sample": "1 filter, N=%d, first %d of T=%d time points, 1 thread (the reference never threads inside "
+                      "a filter); oracle port, not the reference binary; cpu=%s" % (w["N"], n_sample, w["n"], cpu_model_name())}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--filters", type=int, default=int(os.environ.get("BENCH_FILTERS", "9")),
+                    help="replicate filters per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import bssm_b200
+    from bssm_b200 import build
+    build.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    bssm_b200._lib.check(bssm_b200.lib().bssm_b200_set_device(local_rank))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    w = WORKLOAD
+    N, n, B = w["N"], w["n"], args.filters
+    model = make_model()
+    job = bssm_b200.FilterJob(model, N, method="psi", seed=1, n_filters=B, first_filter=rank * B,
+                              out_flags=7)
+    for _ in range(args.warmup):
+        job.run()
+    barrier()
+    launches, step_ms, filt_ms = 0, [], []
+    with ClockSampler(local_rank) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_ms.append(job.run())
+            filt_ms.append(job.kernel_ms()[1])
+            launches += job.launches()
+        barrier()
+        wall = time.perf_counter() - t0
+    dev_total_ms = float(sum(step_ms))
+    t = torch.tensor([dev_total_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+    # the single NCCL collective of the data path: gather per-filter log-likelihoods
+    ll_local = torch.empty(B, dtype=torch.float64, device="cuda")
+    job.logliks_to_device(ll_local.data_ptr())
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ll_all = [torch.empty_like(ll_local) for _ in range(world)]
+        dist.all_gather(ll_all, ll_local)
+        ll = torch.cat(ll_all).cpu().numpy()
+    else:
+        ll = ll_local.cpu().numpy()
+    dev_total_ms, wall_ms = float(t[0]), float(t[1])
+    total_ps = world * B * N * n * args.steps
+    value = total_ps / (dev_total_ms * 1e-3)
+
+    # single-filter latency (same kernel, one cluster)
+    job.close()
+    single = bssm_b200.FilterJob(model, N, method="psi", seed=1, n_filters=1, out_flags=7)
+    for _ in range(2):
+        single.run()
+    s_ms = min(single.run() for _ in range(3))
+    single.close()
+
+    # end to end through the one-shot C-ABI call with (pinned) host buffers
+    e2e = None
+    if not args.no_e2e:
+        import ctypes as C
+        from bssm_b200._lib import FilterOut, c_double_p
+        alpha_h = torch.empty((n + 1) * N, dtype=torch.float64).pin_memory()
+        w_h = torch.empty((n + 1) * N, dtype=torch.float64).pin_memory()
+        out = FilterOut()
+        out.alpha = C.cast(alpha_h.data_ptr(), c_double_p)
+        out.weights = C.cast(w_h.data_ptr(), c_double_p)
+        ms_struct = model.c_struct()
+        L = bssm_b200.lib()
+        reps = 3
+        L.bssm_b200_psi_filter(C.byref(ms_struct), N, 1, C.byref(out))  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            bssm_b200._lib.check(L.bssm_b200_psi_filter(C.byref(ms_struct), N, 1, C.byref(out)))
+        barrier()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        h2d = 8 * (11 * n + 8)  # model vectors (y, u, xbeta, mode x2, Z, T, R, a1, P1, D, C ...)
+        d2h = 8 * 2 * (n + 1) * N + 32
+        e2e = {"value": world * reps * N * n / float(te[0]), "unit": "particle-steps/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "call": "bssm_b200_psi_filter (1 filter per call, alpha cube + weights to pinned host memory)",
+               "loglik_check": out.loglik}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    filt_ms_avg = float(np.mean(filt_ms))
+    achieved = BYTES_PER_PS * B * N * n / (filt_ms_avg * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("filter_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": "c2: svm psi-APF, T=1000, N=65536 particles, %d replicate filters per GPU per step" % B,
+            "filters_per_gpu": B, "outputs": "state + weights + ancestors kept in HBM (20 B/particle-step)",
+            "l2": "each step writes %.1f GB per GPU (>> 126 MB L2); no explicit flush" % (BYTES_PER_PS * B * N * n / 1e9),
+            "single_filter_ms": s_ms, "single_filter_particle_steps_per_s": N * n / (s_ms * 1e-3),
+            "wall_ms_per_step": wall_ms / args.steps,
+            "loglik_mean": float(np.mean(ll)), "loglik_sd": float(np.std(ll)),
+            "replicas": "replicas only: filters are independent, one NCCL all_gather of log-likelihoods",
+        },
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "pf::filter_kernel<UngPsi1,P>", "kernel_ms": filt_ms_avg,
+                     "algorithmic_bytes_per_launch": BYTES_PER_PS * B * N * n},
+        "clocks": clk.summary(),
+        "gpu_launches": launches,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline_leg()
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -734,6 +734,33 @@ void orc_filter_summary(const double* alpha, int m, int n1, uint32_t N, const do
   for (size_t e = 0; e < (size_t)m * m * n1; ++e) Pt[e] /= N;
 }
 
+/* CPU baseline driver: `n_filters` independent replicate psi-APF / BSF filters,
+ * OpenMP-parallel over filters with schedule(static) -- the reference's only
+ * parallel pattern (over independent filters, src/approx_mcmc.cpp:364-369);
+ * each filter is the single-threaded loop above with per-filter heap
+ * allocation of alpha / weights / indices (src/approx_mcmc.cpp:379-381). */
+void orc_ung_filter_batch(const bssm_ung_model* M, int method, const double* mode_in, uint32_t nsim,
+                          uint32_t seed, uint32_t first_filter, uint32_t n_filters, int arith,
+                          int threads, double* logliks) {
+  const size_t n = M->n, m = M->m, N = nsim;
+#ifdef _OPENMP
+  if (threads < 1) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(threads)
+#endif
+  for (int64_t f = 0; f < (int64_t)n_filters; ++f) {
+    std::vector<double> alpha(m * (n + 1) * N, 0.0), weights(N * (n + 1), 0.0);
+    std::vector<uint32_t> indices(N * n, 0u);
+    int32_t st;
+    double al;
+    if (method == 1)
+      logliks[f] = orc_ung_psi_filter(M, mode_in, nsim, seed, first_filter + (uint32_t)f, arith, alpha.data(),
+                                      weights.data(), indices.data(), &al, &st);
+    else
+      logliks[f] = orc_ung_bsf_filter(M, nsim, seed, first_filter + (uint32_t)f, arith, alpha.data(),
+                                      weights.data(), indices.data(), &st);
+  }
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -34,6 +34,9 @@ def L():
         _L.orc_ung_psi_filter.argtypes = [C.POINTER(UngModel), c_double_p, u32, u32, u32, C.c_int, c_double_p,
                                           c_double_p, c_uint32_p, c_double_p, C.POINTER(i32)]
         _L.orc_ung_psi_prepass.argtypes = [C.POINTER(UngModel), c_double_p] + [c_double_p] * 8
+        _L.orc_ung_filter_batch.argtypes = [C.POINTER(UngModel), C.c_int, c_double_p, u32, u32, u32, u32, C.c_int,
+                                            C.c_int, c_double_p]
+        _L.orc_max_threads.restype = C.c_int
         _L.orc_filter_smoother.argtypes = [c_double_p, c_uint32_p, C.c_int, C.c_int, u32]
         _L.orc_summary.argtypes = [c_double_p, C.c_int, C.c_int, u32, c_double_p, c_double_p]
         _L.orc_filter_summary.argtypes = [c_double_p, C.c_int, C.c_int, u32, c_double_p] + [c_double_p] * 4
@@ -159,3 +162,17 @@ def filter_summary(alpha, weights):
     Pt, Ptt = np.zeros((m, m, n1), order="F"), np.zeros((m, m, n), order="F")
     L().orc_filter_summary(dptr(a), m, n1, N, dptr(w), dptr(at), dptr(att), dptr(Pt), dptr(Ptt))
     return at, att, Pt, Ptt
+
+
+def filter_batch(model, N, method="psi", seed=1, first_filter=0, n_filters=1, arith=ARITH_REFERENCE, threads=0,
+                 mode=None):
+    ms = model.c_struct()
+    ll = np.zeros(n_filters)
+    mode_a = None if mode is None else np.ascontiguousarray(mode, dtype=np.float64)
+    L().orc_ung_filter_batch(C.byref(ms), 1 if method == "psi" else 2, dptr(mode_a), N, seed, first_filter,
+                             n_filters, arith, threads, dptr(ll))
+    return ll
+
+
+def max_threads():
+    return L().orc_max_threads()
