@@ -123,6 +123,14 @@ class FilterJob:
     def launches(self):
         return lib().bssm_b200_job_launches(self._h)
 
+    def phase_cycles(self, cta=0):
+        a = (C.c_uint64 * 6)()
+        check(lib().bssm_b200_job_phase_cycles(self._h, int(cta), C.byref(a)))
+        return list(a)
+
+    def max_concurrent_filters(self):
+        return lib().bssm_b200_job_max_concurrent_filters(self._h)
+
     def logliks(self):
         out = np.zeros(self.n_filters)
         check(lib().bssm_b200_job_logliks(self._h, dptr(out)))

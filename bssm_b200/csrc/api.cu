@@ -87,6 +87,8 @@ int choose_geometry(uint32_t N, Geometry* g) {
   }
   uint32_t per_rank = cdiv(N, ranks);
   uint32_t block = round32(cdiv(per_rank, (uint32_t)P));
+  int forced_block = env_int("BSSM_B200_BLOCK", 0);
+  if (forced_block >= 32 && (uint32_t)forced_block * P * ranks >= N) block = round32((uint32_t)forced_block);
   if (block > 1024) return fail(BSSM_B200_ERR_ARG, "geometry: too many particles per CTA");
   if (block < 32) block = 32;
   g->P = P; g->block = (int)block; g->ranks = ranks;
@@ -95,10 +97,10 @@ int choose_geometry(uint32_t N, Geometry* g) {
 }
 
 // --------------------------------------------------------------- launching
-template <class Model, int P>
-int launch_filter_P(const pf::FilterParams& fp, const typename Model::Params& mp, const Geometry& g,
+template <class Model, int P, int MAXT, int MINB>
+int launch_filter_V(const pf::FilterParams& fp, const typename Model::Params& mp, const Geometry& g,
                     uint32_t n_filters, cudaStream_t stream) {
-  auto kern = pf::filter_kernel<Model, P>;
+  auto kern = pf::filter_kernel<Model, P, MAXT, MINB>;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(n_filters * g.ranks, 1, 1);
@@ -124,13 +126,58 @@ int launch_filter_P(const pf::FilterParams& fp, const typename Model::Params& mp
   return 0;
 }
 
+template <class Model, int P, int MAXT, int MINB>
+int occupancy_V(const Geometry& g, int* out) {
+  auto kern = pf::filter_kernel<Model, P, MAXT, MINB>;
+  int dev = 0, sms = 0;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (g.sync_mode == pf::SYNC_CLUSTER) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(g.ranks * 64, 1, 1);
+    cfg.blockDim = dim3(g.block, 1, 1);
+    cudaLaunchAttribute attr[1];
+    if (g.ranks > 8) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = g.ranks; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int nc = 0;
+    CU(cudaOccupancyMaxActiveClusters(&nc, kern, &cfg));
+    *out = nc;
+    return 0;
+  }
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, g.block, 0));
+  *out = g.sync_mode == pf::SYNC_GRID ? 1 : per_sm * sms;
+  return 0;
+}
+
+template <class Model>
+int occupancy(const Geometry& g, int* out) {
+  const bool small = g.block <= 512;
+  switch (g.P) {
+    case 2: return small ? occupancy_V<Model, 2, 512, 2>(g, out) : occupancy_V<Model, 2, 1024, 1>(g, out);
+    case 4: return small ? occupancy_V<Model, 4, 512, 2>(g, out) : occupancy_V<Model, 4, 1024, 1>(g, out);
+    case 8: return small ? occupancy_V<Model, 8, 512, 2>(g, out) : occupancy_V<Model, 8, 1024, 1>(g, out);
+  }
+  return fail(BSSM_B200_ERR_ARG, "bad P");
+}
+
+// kernel variants: P particles per thread; blocks of <= 512 threads are compiled
+// for 2 resident CTAs per SM (64 registers either way), so that two filters
+// share an SM and one computes while the other waits at a barrier
 template <class Model>
 int launch_filter(const pf::FilterParams& fp, const typename Model::Params& mp, const Geometry& g,
                   uint32_t n_filters, cudaStream_t stream) {
+  const bool small = g.block <= 512;
   switch (g.P) {
-    case 2: return launch_filter_P<Model, 2>(fp, mp, g, n_filters, stream);
-    case 4: return launch_filter_P<Model, 4>(fp, mp, g, n_filters, stream);
-    case 8: return launch_filter_P<Model, 8>(fp, mp, g, n_filters, stream);
+    case 2: return small ? launch_filter_V<Model, 2, 512, 2>(fp, mp, g, n_filters, stream)
+                         : launch_filter_V<Model, 2, 1024, 1>(fp, mp, g, n_filters, stream);
+    case 4: return small ? launch_filter_V<Model, 4, 512, 2>(fp, mp, g, n_filters, stream)
+                         : launch_filter_V<Model, 4, 1024, 1>(fp, mp, g, n_filters, stream);
+    case 8: return small ? launch_filter_V<Model, 8, 512, 2>(fp, mp, g, n_filters, stream)
+                         : launch_filter_V<Model, 8, 1024, 1>(fp, mp, g, n_filters, stream);
   }
   return fail(BSSM_B200_ERR_ARG, "bad P");
 }
@@ -322,6 +369,8 @@ struct bssm_b200_job {
   DevBuf<int32_t> stopped;
   DevBuf<unsigned long long> xch;
   DevBuf<unsigned int> barrier;
+  DevBuf<double> ubuf;
+  DevBuf<unsigned long long> phases;
   DevBuf<double> s_at, s_att, s_Pt, s_Ptt, s_mean, s_cov;
   size_t alpha_stride = 0, weights_stride = 0, indices_stride = 0;
   bool keep_alpha = false, keep_weights = false, keep_indices = false;
@@ -381,6 +430,8 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
   fp.loglik = J->loglik.p + f0;
   fp.stopped_at = J->stopped.p + f0;
   fp.xch = J->xch.p + (size_t)f0 * 4 * J->geo.ranks;
+  fp.ubuf = J->ubuf.p + (size_t)f0 * J->N;
+  if (fp.phase_cycles) fp.phase_cycles = J->phases.p + (size_t)f0 * 6 * J->geo.ranks;
   pf::UngParams up = J->up;
   if (J->method == BSSM_METHOD_PSI) {
     up.alphahat += (size_t)f0 * J->pstride; up.Lt += (size_t)f0 * J->pstride; up.Ct += (size_t)f0 * J->pstride;
@@ -524,7 +575,8 @@ int bssm_b200_job_create_ung(const bssm_ung_model* M, int method, uint32_t nsim,
   if ((rc = J->indices.alloc(J->indices_stride * n_filters))) return rc;
   if (post == BSSM_POST_SMOOTHER && (rc = J->alpha_sm.alloc(J->alpha_stride * n_filters))) return rc;
   if ((rc = J->loglik.alloc(n_filters)) || (rc = J->stopped.alloc(n_filters))) return rc;
-  if ((rc = J->xch.alloc((size_t)4 * J->geo.ranks * n_filters)) || (rc = J->barrier.alloc(1))) return rc;
+  if ((rc = J->xch.alloc((size_t)4 * J->geo.ranks * n_filters)) || (rc = J->barrier.alloc(1)) ||
+      (rc = J->ubuf.alloc((size_t)nsim * n_filters))) return rc;
   if (post == BSSM_POST_FILTER_SUMMARY) {
     if ((rc = J->s_at.alloc((size_t)n_filters * m * (n + 1))) || (rc = J->s_att.alloc((size_t)n_filters * m * n)) ||
         (rc = J->s_Pt.alloc((size_t)n_filters * m * m * (n + 1))) || (rc = J->s_Ptt.alloc((size_t)n_filters * m * m * n)))
@@ -542,7 +594,13 @@ int bssm_b200_job_create_ung(const bssm_ung_model* M, int method, uint32_t nsim,
   fp.indices = J->indices.p; fp.indices_stride = J->indices_stride;
   fp.keep_indices = J->keep_indices ? 1 : 0;
   fp.loglik = J->loglik.p; fp.stopped_at = J->stopped.p;
-  fp.xch = J->xch.p; fp.barrier = J->barrier.p;
+  fp.xch = J->xch.p; fp.barrier = J->barrier.p; fp.ubuf = J->ubuf.p;
+  fp.phase_cycles = nullptr;
+  if (env_int("BSSM_B200_PHASES", 0)) {
+    if ((rc = J->phases.alloc((size_t)6 * J->geo.ranks * n_filters))) return rc;
+    CU(cudaMemset(J->phases.p, 0, sizeof(unsigned long long) * J->phases.count));
+    fp.phase_cycles = J->phases.p;
+  }
   guard.j = nullptr;
   *job = J;
   return 0;
@@ -592,6 +650,23 @@ int bssm_b200_job_kernel_ms(const bssm_b200_job* J, float ms[3]) {
 }
 
 int bssm_b200_job_launches(const bssm_b200_job* J) { return J ? J->launches : 0; }
+
+int bssm_b200_job_phase_cycles(bssm_b200_job* J, uint32_t cta, uint64_t cycles[6]) {
+  if (!J || !cycles) return fail(BSSM_B200_ERR_ARG, "null argument");
+  for (int i = 0; i < 6; ++i) cycles[i] = 0;
+  if (!J->phases.p) return 0;
+  if ((size_t)cta * 6 + 6 > J->phases.count) return fail(BSSM_B200_ERR_ARG, "cta out of range");
+  CU(cudaMemcpy(cycles, J->phases.p + (size_t)cta * 6, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bssm_b200_job_max_concurrent_filters(const bssm_b200_job* J) {
+  if (!J) return 0;
+  int out = 0, rc;
+  if (J->method == BSSM_METHOD_PSI) rc = occupancy<pf::UngPsi1>(J->geo, &out);
+  else rc = occupancy<pf::UngBsf<1, 1>>(J->geo, &out); // same register budget for all (m, k)
+  return rc ? 0 : out;
+}
 
 int bssm_b200_job_logliks(bssm_b200_job* J, double* loglik) {
   if (!J || !loglik) return fail(BSSM_B200_ERR_ARG, "null argument");
@@ -709,9 +784,14 @@ stratified_kernel(const double* __restrict__ p, uint32_t n_p, const double* __re
   coll.lane = threadIdx.x & 31; coll.warp = threadIdx.x >> 5; coll.nwarps = (blockDim.x + 31) >> 5;
   const uint32_t chunk = (n_p + blockDim.x - 1) / blockDim.x;
   const uint32_t k0 = threadIdx.x * chunk;
-  unsigned long long tot = 0ull;
-  for (uint32_t k = k0; k < k0 + chunk && k < n_p; ++k) tot += pf_cumsum_term(p[k]);
-  unsigned long long run = coll.exscan(tot);
+  long long th = 0, tl = 0;
+  for (uint32_t k = k0; k < k0 + chunk && k < n_p; ++k) {
+    pf_fixsum tm = pf_fixsum_term(p[k]);
+    th += tm.hi; tl += tm.lo;
+  }
+  long long rh, rl, Th, Tl;
+  coll.exscan2(th, tl, rh, rl, Th, Tl);
+  const double invS = 1.0 / pf_fixsum_value(Th, Tl);
   const double Nd = (double)N, invN = 1.0 / Nd;
   auto u = [&](uint32_t j) { return (r[j] + (double)j) * invN; };
   auto count = [&](double pk) -> uint32_t {
@@ -720,10 +800,11 @@ stratified_kernel(const double* __restrict__ p, uint32_t n_p, const double* __re
     while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (u(mid) <= pk) lo = mid + 1; else hi = mid; }
     return lo;
   };
-  uint32_t lo = (k0 == 0) ? 0u : ((k0 - 1 >= n_p - 1) ? N : count(pf_cumsum_value(run)));
+  uint32_t lo = (k0 == 0) ? 0u : ((k0 - 1 >= n_p - 1) ? N : count(pf_fixsum_value(rh, rl) * invS));
   for (uint32_t k = k0; k < k0 + chunk && k < n_p; ++k) {
-    run += pf_cumsum_term(p[k]);
-    uint32_t c = (k >= n_p - 1) ? N : count(pf_cumsum_value(run));
+    pf_fixsum tm = pf_fixsum_term(p[k]);
+    rh += tm.hi; rl += tm.lo;
+    uint32_t c = (k >= n_p - 1) ? N : count(pf_fixsum_value(rh, rl) * invS);
     for (uint32_t j = lo; j < c; ++j) xp[j] = k;
     lo = c > lo ? c : lo;
   }

@@ -46,6 +46,13 @@ struct FilterParams {
   // exchange area: per filter 4 * ranks 8-byte words
   unsigned long long* xch;
   unsigned int* barrier; // grid mode only (one counter)
+  // stratum thresholds u_j = (r_j + j) * (1/N) of the current step, N per filter
+  double* ubuf;
+  // diagnostics: when non-null, thread 0 of every CTA accumulates the SM cycles
+  // spent up to each phase boundary: 6 counters per CTA
+  //   [0] log-weights  [1] max collective  [2] exp + thresholds + terms
+  //   [3] scan collective  [4] counts + normals + scatter + barrier  [5] gather + propagate
+  unsigned long long* phase_cycles;
 };
 
 // ---------------------------------------------------------------- barriers
@@ -89,9 +96,6 @@ __device__ __forceinline__ double nanmax(double a, double b) {
 __device__ __forceinline__ double shfl_xor_d(double v, int m) {
   return __shfl_xor_sync(0xffffffffu, v, m);
 }
-__device__ __forceinline__ unsigned long long shfl_up_u64(unsigned long long v, int d) {
-  return __shfl_up_sync(0xffffffffu, v, d);
-}
 __device__ __forceinline__ long long shfl_xor_i64(long long v, int m) {
   return __shfl_xor_sync(0xffffffffu, v, m);
 }
@@ -99,10 +103,8 @@ __device__ __forceinline__ long long shfl_xor_i64(long long v, int m) {
 struct CollSmem {
   double wd[32];
   long long wa[32], wb[32];
-  unsigned long long wu[32];
   double rd;
-  long long ra, rb;
-  unsigned long long ru, ru_total;
+  long long ra, rb, ta, tb;
 };
 
 // Collectives over all threads of a filter.  Exchange between CTAs goes through
@@ -140,98 +142,88 @@ struct Coll {
     return sm->rd;
   }
 
-  __device__ __forceinline__ void allsum2(long long& a, long long& b) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { a += shfl_xor_i64(a, o); b += shfl_xor_i64(b, o); }
-    if (lane == 0) { sm->wa[warp] = a; sm->wb[warp] = b; }
-    __syncthreads();
-    if (warp == 0) {
-      long long x = lane < nwarps ? sm->wa[lane] : 0, y = lane < nwarps ? sm->wb[lane] : 0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { x += shfl_xor_i64(x, o); y += shfl_xor_i64(y, o); }
-      if (ranks == 1) { if (lane == 0) { sm->ra = x; sm->rb = y; } }
-      else if (lane == 0) { ((long long*)xch)[ranks + rank] = x; ((long long*)xch)[2 * ranks + rank] = y; }
-    }
-    sync->all();
-    if (ranks > 1) {
-      if (warp == 0) {
-        long long x = 0, y = 0;
-        for (uint32_t r = lane; r < ranks; r += 32) {
-          x += __ldcg(((const long long*)xch) + ranks + r);
-          y += __ldcg(((const long long*)xch) + 2 * ranks + r);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { x += shfl_xor_i64(x, o); y += shfl_xor_i64(y, o); }
-        if (lane == 0) { sm->ra = x; sm->rb = y; }
-      }
-      __syncthreads();
-    }
-    a = sm->ra; b = sm->rb;
-  }
-
-  // exclusive prefix of per-thread totals in (rank, thread) order
-  __device__ __forceinline__ unsigned long long exscan(unsigned long long tot) {
-    unsigned long long inc = tot;
+  // Exclusive prefix, in (rank, thread) order, of the per-thread totals of the
+  // two fixed-point words, plus the grand totals: one collective serves both the
+  // sum of the weights and their cumulative sum.
+  __device__ __forceinline__ void exscan2(long long th, long long tl, long long& eh, long long& el,
+                                          long long& Th, long long& Tl) {
+    long long ih = th, il = tl;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      unsigned long long o = shfl_up_u64(inc, d);
-      if (lane >= d) inc += o;
+      long long oh = __shfl_up_sync(0xffffffffu, ih, d);
+      long long ol = __shfl_up_sync(0xffffffffu, il, d);
+      if (lane >= d) { ih += oh; il += ol; }
     }
-    if (lane == 31) sm->wu[warp] = inc;
+    if (lane == 31) { sm->wa[warp] = ih; sm->wb[warp] = il; }
     __syncthreads();
     if (warp == 0) {
-      unsigned long long v = lane < nwarps ? sm->wu[lane] : 0ull, w = v;
+      long long vh = lane < nwarps ? sm->wa[lane] : 0, vl = lane < nwarps ? sm->wb[lane] : 0;
+      long long wh = vh, wl = vl;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        unsigned long long o = shfl_up_u64(w, d);
-        if (lane >= d) w += o;
+        long long oh = __shfl_up_sync(0xffffffffu, wh, d);
+        long long ol = __shfl_up_sync(0xffffffffu, wl, d);
+        if (lane >= d) { wh += oh; wl += ol; }
       }
-      sm->wu[lane] = w - v; // exclusive warp prefix
+      sm->wa[lane] = wh - vh; // exclusive warp prefixes
+      sm->wb[lane] = wl - vl;
       if (lane == 31) {
-        if (ranks == 1) sm->ru = 0ull;
-        else xch[3 * ranks + rank] = w;
+        if (ranks == 1) { sm->ra = 0; sm->rb = 0; sm->ta = wh; sm->tb = wl; }
+        else { ((long long*)xch)[ranks + rank] = wh; ((long long*)xch)[2 * ranks + rank] = wl; }
       }
     }
     sync->all();
     if (ranks > 1) {
       if (warp == 0) {
-        unsigned long long x = 0ull;
-        for (uint32_t r = lane; r < rank; r += 32) x += __ldcg(xch + 3 * ranks + r);
+        long long xh = 0, xl = 0, sh = 0, sl = 0;
+        for (uint32_t r = lane; r < ranks; r += 32) {
+          const long long h = __ldcg(((const long long*)xch) + ranks + r);
+          const long long l = __ldcg(((const long long*)xch) + 2 * ranks + r);
+          sh += h; sl += l;
+          if (r < rank) { xh += h; xl += l; }
+        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0) sm->ru = x;
+        for (int o = 16; o > 0; o >>= 1) {
+          xh += shfl_xor_i64(xh, o); xl += shfl_xor_i64(xl, o);
+          sh += shfl_xor_i64(sh, o); sl += shfl_xor_i64(sl, o);
+        }
+        if (lane == 0) { sm->ra = xh; sm->rb = xl; sm->ta = sh; sm->tb = sl; }
       }
       __syncthreads();
     }
-    return sm->ru + sm->wu[warp] + (inc - tot);
+    eh = sm->ra + sm->wa[warp] + (ih - th);
+    el = sm->rb + sm->wb[warp] + (il - tl);
+    Th = sm->ta; Tl = sm->tb;
   }
 };
 
 // --------------------------------------------------- stratified thresholds
-// count(p) = #{ j in [0,N) : (r_j + j) * (1.0/N) <= p }, the position the
-// reference's two-pointer merge (src/stratified_sample.cpp:17-22) reaches when
-// it leaves cumulative weight p.  u_j is non-decreasing in j, so the count is
-// found from the guess floor(p*N) with one or (near an integer) a few Philox
-// evaluations -- no r[] array is ever materialised.
+// count(p) = #{ j in [0,N) : u_j <= p } with u_j = (r_j + j) * (1.0/N): the
+// position the reference's two-pointer merge (src/stratified_sample.cpp:17-22)
+// reaches when it leaves cumulative weight p.  u_j is non-decreasing in j, so
+// the count follows from the guess floor(p*N) with one threshold look-up (a few
+// only when p*N is within 2^-51 of an integer).  The thresholds of the step are
+// generated once by the threads that own the strata (one Philox call per two
+// strata) and parked in `ubuf` (L2-resident, 8 B per particle).
 struct Strata {
-  uint32_t seed, filter, t, N;
-  double Nd, invN;
-  __device__ __forceinline__ double u(uint32_t j) const {
-    return (pf_resample_uniform(seed, filter, t, j) + (double)j) * invN;
+  const double* ubuf;
+  uint32_t N;
+  double Nd;
+  __device__ __forceinline__ double u(uint32_t j) const { return __ldcg(ubuf + j); }
+  __device__ __forceinline__ uint32_t guess(double p) const {
+    uint32_t jj = (uint32_t)(p * Nd);
+    return jj > N - 1 ? N - 1 : jj;
   }
-  __device__ __forceinline__ uint32_t count(double p) const {
+  // resolve the count given the pre-loaded threshold uj = u(guess(p))
+  __device__ __forceinline__ uint32_t resolve(double p, uint32_t jj, double uj) const {
     if (p >= 1.0) return N;
-    double x = p * Nd;
-    uint32_t jj = (uint32_t)x;
-    if (jj > N - 1) jj = N - 1;
+    const double x = p * Nd;
     const double tol = x * 4.440892098500626e-16; // 2^-51 relative guard
-    const bool lo_safe = (x - (double)jj) >= tol;
-    const bool hi_safe = ((double)(jj + 1) - x) >= tol;
-    if (u(jj) <= p) {
+    if (uj <= p) {
       jj++;
-      if (!hi_safe) while (jj < N && u(jj) <= p) jj++;
+      if (((double)jj - x) < tol) while (jj < N && u(jj) <= p) jj++;
     } else {
-      if (!lo_safe) while (jj > 0 && !(u(jj - 1) <= p)) jj--;
+      if ((x - (double)jj) < tol) while (jj > 0 && !(u(jj - 1) <= p)) jj--;
     }
     return jj;
   }
@@ -249,8 +241,8 @@ struct Strata {
 //   double logw(const double* x) const;
 //   void begin_step(int t);           load per-step constants for t -> t+1
 //   void propagate(const double* xa, const double* z, double* x) const;
-template <class Model, int P>
-__global__ void __launch_bounds__(1024, 1)
+template <class Model, int P, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 filter_kernel(const FilterParams fp, const typename Model::Params mp) {
   constexpr int M = Model::M;
   constexpr int KI = Model::KI;
@@ -309,101 +301,136 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
 
   double loglik = model.loglik0();
   int stopped = -1;
-  double W[P];
+  double* ub = fp.ubuf + (size_t)fidx * N;
+  Strata st;
+  st.ubuf = ub; st.N = N; st.Nd = Nd;
+
+  unsigned long long ph[6] = {0, 0, 0, 0, 0, 0};
+  const bool timing = fp.phase_cycles != nullptr && threadIdx.x == 0;
+  long long tc = timing ? clock64() : 0;
+#define PF_PHASE(i) if (timing) { long long now_ = clock64(); ph[i] += (unsigned long long)(now_ - tc); tc = now_; }
 
   for (int t = 0;; ++t) {
     // ---- weights of column t (reference :633-647, :672-687).  Column n is a
     // pure prediction: unit weights (the reference tests t < n-1 before
     // weighting column t+1).
     const bool obs = (t < n) && model.observed(t);
+    double w[P];
+    double mx = 0.0;
     if (obs) {
       model.begin_weight(t);
       double lw[P];
-      double mx = -pf_inf();
+      mx = -pf_inf();
 #pragma unroll
       for (int p = 0; p < P; ++p) {
         lw[p] = (i0 + p < N) ? model.logw(x[p]) : -pf_inf();
         mx = nanmax(mx, lw[p]);
       }
+      PF_PHASE(0)
       mx = coll.allmax(mx);
+      PF_PHASE(1)
       if (!pf_isfinite(mx)) { stopped = t; break; } // uniform over the filter
-      long long hi = 0, lo = 0;
 #pragma unroll
-      for (int p = 0; p < P; ++p) {
-        double w = pf_exp(lw[p] - mx);
-        W[p] = w;
-        pf_fixsum tm = pf_fixsum_term(w);
-        hi += tm.hi;
-        lo += tm.lo;
-      }
-      if (wout) {
-#pragma unroll
-        for (int p = 0; p < P; ++p)
-          if (i0 + p < N) wout[(size_t)t * N + i0 + p] = W[p];
-      }
-      coll.allsum2(hi, lo);
-      const double S = pf_fixsum_value(hi, lo);
-#pragma unroll
-      for (int p = 0; p < P; ++p) W[p] = W[p] / S;
-      loglik += mx + pf_log(S / Nd);
+      for (int p = 0; p < P; ++p) w[p] = pf_exp(lw[p] - mx);
     } else {
 #pragma unroll
-      for (int p = 0; p < P; ++p) W[p] = (i0 + p < N) ? invN : 0.0;
-      if (wout) {
+      for (int p = 0; p < P; ++p) w[p] = (i0 + p < N) ? 1.0 : 0.0;
+    }
+    if (wout) {
 #pragma unroll
-        for (int p = 0; p < P; ++p)
-          if (i0 + p < N) wout[(size_t)t * N + i0 + p] = 1.0;
-      }
+      for (int p = 0; p < P; ++p)
+        if (i0 + p < N) wout[(size_t)t * N + i0 + p] = w[p];
     }
     if (t == n) break;
 
     // ---- stratified resampling -> ancestors of column t+1 (reference :650-655)
     uint32_t* anc = iout + (fp.keep_indices ? (size_t)t * N : 0);
+    double z[P * KP];
     {
-      unsigned long long q[P], tot = 0ull;
+      // thresholds of the strata this thread owns (visible after the scan barrier)
 #pragma unroll
-      for (int p = 0; p < P; ++p) { q[p] = pf_cumsum_term(W[p]); tot += q[p]; }
-      unsigned long long run = coll.exscan(tot);
-      Strata st;
-      st.seed = fp.seed; st.filter = filter; st.t = (uint32_t)t; st.N = N;
-      st.Nd = Nd; st.invN = invN;
-      // offspring range of particle k is [count(p_{k-1}), count(p_k)); p_{N-1} := 1
-      uint32_t lo = (i0 == 0) ? 0u : ((i0 - 1 >= N - 1) ? N : st.count(pf_cumsum_value(run)));
+      for (int h = 0; h < P / 2; ++h) {
+        const uint32_t j = i0 + 2 * h;
+        pf_u32x4 rx = pf_philox4x32_10(j >> 1, 0u, (uint32_t)t, filter, fp.seed, (uint32_t)PF_RNG_RESAMPLE);
+        const double u0 = (pf_u53(rx.v[0], rx.v[1]) + (double)j) * invN;
+        const double u1 = (pf_u53(rx.v[2], rx.v[3]) + (double)(j + 1)) * invN;
+        if (j < N) ub[j] = u0;
+        if (j + 1 < N) ub[j + 1] = u1;
+      }
+      // one scan of the fixed-point weights gives their sum and cumulative sums
+      long long qh[P], ql[P], th = 0, tl = 0;
 #pragma unroll
       for (int p = 0; p < P; ++p) {
-        run += q[p];
-        const uint32_t k = i0 + p;
-        uint32_t c = (k >= N - 1) ? N : st.count(pf_cumsum_value(run));
-        for (uint32_t j = lo; j < c; ++j) anc[j] = k;
-        lo = c > lo ? c : lo;
+        pf_fixsum tm = pf_fixsum_term(w[p]);
+        qh[p] = tm.hi; ql[p] = tm.lo;
+        th += tm.hi; tl += tm.lo;
       }
-    }
-    sync.all();
-
-    // ---- gather ancestors, propagate to column t+1 (reference :657-670)
-    {
-      model.begin_step(t);
-      double z[P * KP];
+      long long rh, rl, Th, Tl;
+      PF_PHASE(2)
+      coll.exscan2(th, tl, rh, rl, Th, Tl);
+      PF_PHASE(3)
+      const double S = pf_fixsum_value(Th, Tl);
+      const double invS = 1.0 / S;
+      if (obs) {
+        if (t == 0) loglik = (mx + loglik) + pf_log_normal(S / Nd); // reference :561
+        else loglik += mx + pf_log_normal(S / Nd);                  // reference :601
+      }
+      // offspring range of particle k is [count(p_{k-1}), count(p_k)); p_{N-1} := 1
+      double pk[P + 1];
+      uint32_t jj[P + 1];
+      double uj[P + 1];
+      pk[0] = (i0 == 0) ? 0.0 : ((i0 - 1 >= N - 1) ? 1.0 : pf_fixsum_value(rh, rl) * invS);
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        rh += qh[p]; rl += ql[p];
+        pk[p + 1] = (i0 + p >= N - 1) ? 1.0 : pf_fixsum_value(rh, rl) * invS;
+      }
+#pragma unroll
+      for (int p = 0; p <= P; ++p) { jj[p] = st.guess(pk[p]); uj[p] = st.u(jj[p]); }
+      // the normals of the next column do not depend on the ancestors: generate
+      // them while the threshold loads are in flight
       const uint32_t pair0 = (i0 * KP) >> 1;
 #pragma unroll
       for (int q = 0; q < (P * KP) / 2; ++q)
         pf_normal_pair(fp.seed, filter, (uint32_t)(t + 1), 0u, pair0 + q, &z[2 * q], &z[2 * q + 1]);
-      const double* src = alpha + (size_t)(fp.keep_alpha ? t : (t & 1)) * M * N;
-      double* dst = alpha + (size_t)(fp.keep_alpha ? t + 1 : ((t + 1) & 1)) * M * N;
+      uint32_t lo = (i0 == 0) ? 0u : st.resolve(pk[0], jj[0], uj[0]);
 #pragma unroll
       for (int p = 0; p < P; ++p) {
-        if (i0 + p < N) {
-          const uint32_t a = __ldcg(anc + i0 + p);
-          double xa[M];
+        const uint32_t c = st.resolve(pk[p + 1], jj[p + 1], uj[p + 1]);
+        for (uint32_t j = lo; j < c; ++j) anc[j] = i0 + p;
+        lo = c > lo ? c : lo;
+      }
+    }
+    sync.all();
+    PF_PHASE(4)
+
+    // ---- gather ancestors, propagate to column t+1 (reference :657-670)
+    {
+      model.begin_step(t);
+      const double* src = alpha + (size_t)(fp.keep_alpha ? t : (t & 1)) * M * N;
+      double* dst = alpha + (size_t)(fp.keep_alpha ? t + 1 : ((t + 1) & 1)) * M * N;
+      uint32_t a[P];
 #pragma unroll
-          for (int d = 0; d < M; ++d) xa[d] = __ldcg(src + (size_t)d * N + a);
-          model.propagate(xa, &z[p * KP], x[p]);
+      for (int p = 0; p < P; ++p) a[p] = (i0 + p < N) ? __ldcg(anc + i0 + p) : 0u;
+      double xa[P][M];
+#pragma unroll
+      for (int p = 0; p < P; ++p)
+#pragma unroll
+        for (int d = 0; d < M; ++d) xa[p][d] = __ldcg(src + (size_t)d * N + a[p]);
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        model.propagate(xa[p], &z[p * KP], x[p]);
+        if (i0 + p < N) {
 #pragma unroll
           for (int d = 0; d < M; ++d) dst[(size_t)d * N + i0 + p] = x[p][d];
         }
       }
     }
+    PF_PHASE(5)
   }
+#undef PF_PHASE
+  if (timing)
+    for (int i = 0; i < 6; ++i) fp.phase_cycles[(size_t)blockIdx.x * 6 + i] = ph[i];
 
   if (stopped >= 0) loglik = -pf_inf();
   else loglik += model.loglik_end();

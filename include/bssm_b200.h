@@ -166,6 +166,16 @@ int bssm_b200_job_create_ung(const bssm_ung_model* model, int method, uint32_t n
 int bssm_b200_job_run(bssm_b200_job* job, float* ms);
 /* per-kernel CUDA-event times of the last run: [prepass, filter, smoother] */
 int bssm_b200_job_kernel_ms(const bssm_b200_job* job, float ms[3]);
+/* how many filters of this job's geometry the device can run concurrently
+ * (cudaOccupancyMaxActiveClusters for cluster launches): batch sizes that are a
+ * multiple of it avoid a nearly empty last wave */
+int bssm_b200_job_max_concurrent_filters(const bssm_b200_job* job);
+/* diagnostics: SM cycles per phase of the filter kernel, accumulated over the
+ * time loop by thread 0 of CTA `cta` during the last run (enabled by the
+ * environment variable BSSM_B200_PHASES=1 at job creation; zeros otherwise):
+ * [log-weights, max collective, exp + thresholds, scan collective,
+ *  counts + normals + scatter + barrier, gather + propagate] */
+int bssm_b200_job_phase_cycles(bssm_b200_job* job, uint32_t cta, uint64_t cycles[6]);
 /* number of kernel launches one run() issues (for gpu_launches accounting) */
 int bssm_b200_job_launches(const bssm_b200_job* job);
 /* copies filter f's outputs to the host buffers in *out */

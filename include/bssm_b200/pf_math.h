@@ -113,6 +113,59 @@ PF_HD double pf_u53_open0(uint32_t hi, uint32_t lo) {
 
 /* ------------------------------------------------------------ exp / log */
 
+/* Polynomial coefficients live in tables: on the device they are __constant__
+ * memory, so a DFMA takes its coefficient as a c[bank][offset] operand instead
+ * of two UMOVs building a 64-bit immediate (that alone was 12% of the executed
+ * instructions of the first filter kernel, profiles/r1_v0_filter_single.md). */
+#define PF_EXP_COEFFS                                                             \
+  1.6059043836821613e-10 /* 1/13! */, 2.08767569878681e-09 /* 1/12! */,           \
+  2.505210838544172e-08 /* 1/11! */, 2.755731922398589e-07 /* 1/10! */,           \
+  2.7557319223985893e-06 /* 1/9! */, 2.48015873015873e-05 /* 1/8! */,             \
+  1.984126984126984e-04 /* 1/7! */, 1.388888888888889e-03 /* 1/6! */,             \
+  8.333333333333333e-03 /* 1/5! */, 4.1666666666666664e-02 /* 1/4! */,            \
+  1.6666666666666666e-01 /* 1/3! */, 0.5,                                         \
+  1.4426950408889634 /* 12: 1/ln2 */, 6755399441055744.0 /* 13: 1.5*2^52 */,      \
+  6.93147180369123816490e-01 /* 14: ln2 hi */, 1.90821492927058770002e-10 /* 15: ln2 lo */
+#define PF_LOG_COEFFS                                                             \
+  9.523809523809523e-02 /* 2/21 */, 1.0526315789473684e-01 /* 2/19 */,            \
+  1.1764705882352941e-01 /* 2/17 */, 1.3333333333333333e-01 /* 2/15 */,           \
+  1.5384615384615385e-01 /* 2/13 */, 1.8181818181818182e-01 /* 2/11 */,           \
+  2.2222222222222222e-01 /* 2/9 */, 2.857142857142857e-01 /* 2/7 */,              \
+  4.0e-01 /* 2/5 */, 6.666666666666666e-01 /* 2/3 */,                             \
+  6.93147180369123816490e-01 /* 10: ln2 hi */, 1.90821492927058770002e-10 /* 11: ln2 lo */, \
+  1.4142135623730951 /* 12: sqrt 2 */
+#define PF_SIN_COEFFS                                                             \
+  -7.647163731819816e-13 /* -1/15! */, 1.6059043836821613e-10 /* 1/13! */,        \
+  -2.505210838544172e-08 /* -1/11! */, 2.7557319223985893e-06 /* 1/9! */,         \
+  -1.984126984126984e-04 /* -1/7! */, 8.333333333333333e-03 /* 1/5! */,           \
+  -1.6666666666666666e-01 /* -1/3! */, 1.5707963267948966 /* 7: pi/2 */
+#define PF_COS_COEFFS                                                             \
+  4.779477332387385e-14 /* 1/16! */, -1.1470745597729725e-11 /* -1/14! */,        \
+  2.08767569878681e-09 /* 1/12! */, -2.755731922398589e-07 /* -1/10! */,          \
+  2.48015873015873e-05 /* 1/8! */, -1.388888888888889e-03 /* -1/6! */,            \
+  4.1666666666666664e-02 /* 1/4! */, -0.5
+static const double pf_hc_exp[] = {PF_EXP_COEFFS};
+static const double pf_hc_log[] = {PF_LOG_COEFFS};
+static const double pf_hc_sin[] = {PF_SIN_COEFFS};
+static const double pf_hc_cos[] = {PF_COS_COEFFS};
+#if defined(__CUDACC__)
+__constant__ double pf_dc_exp[] = {PF_EXP_COEFFS};
+__constant__ double pf_dc_log[] = {PF_LOG_COEFFS};
+__constant__ double pf_dc_sin[] = {PF_SIN_COEFFS};
+__constant__ double pf_dc_cos[] = {PF_COS_COEFFS};
+#endif
+#if defined(__CUDA_ARCH__)
+#define PF_CE pf_dc_exp
+#define PF_CL pf_dc_log
+#define PF_CS pf_dc_sin
+#define PF_CC pf_dc_cos
+#else
+#define PF_CE pf_hc_exp
+#define PF_CL pf_hc_log
+#define PF_CS pf_hc_sin
+#define PF_CC pf_hc_cos
+#endif
+
 /* x * 2^k for |k| <= 2098, one rounding (only when the result is subnormal) */
 PF_HD double pf_scalbn2(double x, int k) {
   int k1 = k >> 1;           /* arithmetic shift: floor(k/2) */
@@ -123,36 +176,64 @@ PF_HD double pf_scalbn2(double x, int k) {
 }
 
 /* exp(x): Cody-Waite reduction by ln2 (hi/lo split), degree-13 Taylor kernel on
- * |r| <= ln2/2 (truncation 4e-18), exact power-of-two scaling. */
+ * |r| <= ln2/2 (truncation 4e-18), exact power-of-two scaling.  Straight-line:
+ * the argument is clamped to [-746, 710], where the scaling already produces
+ * the correctly rounded 0 / +inf; NaN flows through the arithmetic. */
 PF_HD double pf_exp(double x) {
-  if (!(x == x)) return x;
-  if (x > 709.782712893384) return pf_inf();
-  if (x < -745.1332191019412) return 0.0;
-  const double MAGIC = 6755399441055744.0; /* 1.5 * 2^52 */
-  double t = pf_fma(x, 1.4426950408889634, MAGIC);
+  double xc = x < -746.0 ? -746.0 : x;   /* NaN compares false: stays NaN */
+  xc = xc > 710.0 ? 710.0 : xc;
+  const double MAGIC = PF_CE[13];
+  double t = pf_fma(xc, PF_CE[12], MAGIC);
   double kf = t - MAGIC;
   int k = (int)(int32_t)(uint32_t)pf_d2u(t);
-  double r = pf_fma(-kf, 6.93147180369123816490e-01, x);
-  r = pf_fma(-kf, 1.90821492927058770002e-10, r);
-  double q = 1.6059043836821613e-10;            /* 1/13! */
-  q = pf_fma(q, r, 2.08767569878681e-09);       /* 1/12! */
-  q = pf_fma(q, r, 2.505210838544172e-08);      /* 1/11! */
-  q = pf_fma(q, r, 2.755731922398589e-07);      /* 1/10! */
-  q = pf_fma(q, r, 2.7557319223985893e-06);     /* 1/9!  */
-  q = pf_fma(q, r, 2.48015873015873e-05);       /* 1/8!  */
-  q = pf_fma(q, r, 1.984126984126984e-04);      /* 1/7!  */
-  q = pf_fma(q, r, 1.388888888888889e-03);      /* 1/6!  */
-  q = pf_fma(q, r, 8.333333333333333e-03);      /* 1/5!  */
-  q = pf_fma(q, r, 4.1666666666666664e-02);     /* 1/4!  */
-  q = pf_fma(q, r, 1.6666666666666666e-01);     /* 1/3!  */
-  q = pf_fma(q, r, 0.5);
+  double r = pf_fma(-kf, PF_CE[14], xc);
+  r = pf_fma(-kf, PF_CE[15], r);
+  double q = PF_CE[0];
+  q = pf_fma(q, r, PF_CE[1]);
+  q = pf_fma(q, r, PF_CE[2]);
+  q = pf_fma(q, r, PF_CE[3]);
+  q = pf_fma(q, r, PF_CE[4]);
+  q = pf_fma(q, r, PF_CE[5]);
+  q = pf_fma(q, r, PF_CE[6]);
+  q = pf_fma(q, r, PF_CE[7]);
+  q = pf_fma(q, r, PF_CE[8]);
+  q = pf_fma(q, r, PF_CE[9]);
+  q = pf_fma(q, r, PF_CE[10]);
+  q = pf_fma(q, r, PF_CE[11]);
   double e = pf_fma(q, r * r, r);
+  if (!(x == x)) k = 0;                  /* keep the scale finite for NaN input */
   return pf_scalbn2(1.0 + e, k);
 }
 
 /* log(x): x = 2^e * m, m in (sqrt(1/2), sqrt(2)], s = f/(2+f) with f = m-1,
  * log(m) = 2 atanh(s) = f - (f^2/2 - s*(f^2/2 + R(s^2))),
- * R(z) = sum_{j=1..10} 2 z^j/(2j+1) (Taylor; truncation 6e-19 relative). */
+ * R(z) = sum_{j=1..10} 2 z^j/(2j+1) (Taylor; truncation 6e-19 relative).
+ * pf_log_normal is the kernel for positive NORMAL finite x (no special cases):
+ * Box-Muller's u1 in [2^-53, 1] and the log(sum/N) of the filter need no more. */
+PF_HD double pf_log_core(uint64_t ux, int e) {
+  e += (int)(ux >> 52) - 1023;
+  double m = pf_u2d((ux & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
+  if (m > PF_CL[12]) { m = m * 0.5; e += 1; }
+  double f = m - 1.0;
+  double s = f / (2.0 + f);
+  double z = s * s;
+  double R = PF_CL[0];
+  R = pf_fma(R, z, PF_CL[1]);
+  R = pf_fma(R, z, PF_CL[2]);
+  R = pf_fma(R, z, PF_CL[3]);
+  R = pf_fma(R, z, PF_CL[4]);
+  R = pf_fma(R, z, PF_CL[5]);
+  R = pf_fma(R, z, PF_CL[6]);
+  R = pf_fma(R, z, PF_CL[7]);
+  R = pf_fma(R, z, PF_CL[8]);
+  R = pf_fma(R, z, PF_CL[9]);
+  R = R * z;
+  double hfsq = 0.5 * f * f;
+  double dk = (double)e;
+  /* ln2 split: hi has 21 trailing zero bits, so dk*hi is exact */
+  return dk * PF_CL[10] - ((hfsq - (s * (hfsq + R) + dk * PF_CL[11])) - f);
+}
+PF_HD double pf_log_normal(double x) { return pf_log_core(pf_d2u(x), 0); }
 PF_HD double pf_log(double x) {
   if (!(x == x)) return x;
   if (x < 0.0) return pf_nan();
@@ -165,28 +246,7 @@ PF_HD double pf_log(double x) {
     ux = pf_d2u(x);
     e = -54;
   }
-  e += (int)(ux >> 52) - 1023;
-  double m = pf_u2d((ux & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
-  if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
-  double f = m - 1.0;
-  double s = f / (2.0 + f);
-  double z = s * s;
-  double R = 9.523809523809523e-02;            /* 2/21 */
-  R = pf_fma(R, z, 1.0526315789473684e-01);    /* 2/19 */
-  R = pf_fma(R, z, 1.1764705882352941e-01);    /* 2/17 */
-  R = pf_fma(R, z, 1.3333333333333333e-01);    /* 2/15 */
-  R = pf_fma(R, z, 1.5384615384615385e-01);    /* 2/13 */
-  R = pf_fma(R, z, 1.8181818181818182e-01);    /* 2/11 */
-  R = pf_fma(R, z, 2.2222222222222222e-01);    /* 2/9  */
-  R = pf_fma(R, z, 2.857142857142857e-01);     /* 2/7  */
-  R = pf_fma(R, z, 4.0e-01);                   /* 2/5  */
-  R = pf_fma(R, z, 6.666666666666666e-01);     /* 2/3  */
-  R = R * z;
-  double hfsq = 0.5 * f * f;
-  double dk = (double)e;
-  /* ln2 split: hi has 21 trailing zero bits, so dk*hi is exact */
-  return dk * 6.93147180369123816490e-01 -
-         ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+  return pf_log_core(ux, e);
 }
 
 /* log(1+x) for x >= 0 (the only use: binomial log1p(exp(signal))) */
@@ -203,24 +263,24 @@ PF_HD void pf_sincos2pi(double u, double* sn, double* cs) {
   double x4 = u * 4.0;               /* exact */
   double q = floor(x4 + 0.5);        /* nearest quadrant boundary, 0..4 */
   double f = x4 - q;                 /* exact, in [-0.5, 0.5] */
-  double a = f * 1.5707963267948966; /* pi/2 */
+  double a = f * PF_CS[7]; /* pi/2 */
   double a2 = a * a;
-  double ps = -7.647163731819816e-13;          /* -1/15! */
-  ps = pf_fma(ps, a2, 1.6059043836821613e-10); /*  1/13! */
-  ps = pf_fma(ps, a2, -2.505210838544172e-08); /* -1/11! */
-  ps = pf_fma(ps, a2, 2.7557319223985893e-06); /*  1/9!  */
-  ps = pf_fma(ps, a2, -1.984126984126984e-04); /* -1/7!  */
-  ps = pf_fma(ps, a2, 8.333333333333333e-03);  /*  1/5!  */
-  ps = pf_fma(ps, a2, -1.6666666666666666e-01);/* -1/3!  */
+  double ps = PF_CS[0];
+  ps = pf_fma(ps, a2, PF_CS[1]);
+  ps = pf_fma(ps, a2, PF_CS[2]);
+  ps = pf_fma(ps, a2, PF_CS[3]);
+  ps = pf_fma(ps, a2, PF_CS[4]);
+  ps = pf_fma(ps, a2, PF_CS[5]);
+  ps = pf_fma(ps, a2, PF_CS[6]);
   double s = pf_fma(ps * a2, a, a);
-  double pc = 4.779477332387385e-14;           /*  1/16! */
-  pc = pf_fma(pc, a2, -1.1470745597729725e-11);/* -1/14! */
-  pc = pf_fma(pc, a2, 2.08767569878681e-09);   /*  1/12! */
-  pc = pf_fma(pc, a2, -2.755731922398589e-07); /* -1/10! */
-  pc = pf_fma(pc, a2, 2.48015873015873e-05);   /*  1/8!  */
-  pc = pf_fma(pc, a2, -1.388888888888889e-03); /* -1/6!  */
-  pc = pf_fma(pc, a2, 4.1666666666666664e-02); /*  1/4!  */
-  pc = pf_fma(pc, a2, -0.5);
+  double pc = PF_CC[0];
+  pc = pf_fma(pc, a2, PF_CC[1]);
+  pc = pf_fma(pc, a2, PF_CC[2]);
+  pc = pf_fma(pc, a2, PF_CC[3]);
+  pc = pf_fma(pc, a2, PF_CC[4]);
+  pc = pf_fma(pc, a2, PF_CC[5]);
+  pc = pf_fma(pc, a2, PF_CC[6]);
+  pc = pf_fma(pc, a2, PF_CC[7]);
   double c = pf_fma(pc, a2, 1.0);
   int qi = ((int)q) & 3;
   double so = (qi & 1) ? c : s;
@@ -258,7 +318,7 @@ PF_HD void pf_normal_pair(uint32_t seed, uint32_t filter, uint32_t t, uint32_t s
   pf_u32x4 x = pf_philox4x32_10(pair, sub, t, filter, seed, (uint32_t)PF_RNG_NORMAL);
   double u1 = pf_u53_open0(x.v[0], x.v[1]);
   double u2 = pf_u53(x.v[2], x.v[3]);
-  double rad = sqrt(-2.0 * pf_log(u1));
+  double rad = sqrt(-2.0 * pf_log_normal(u1));
   double s, c;
   pf_sincos2pi(u2, &s, &c);
   *z0 = rad * c;
@@ -285,28 +345,28 @@ PF_HD double pf_pick_uniform(uint32_t seed, uint32_t filter) {
 
 /* -------------------------------------------- reproducible sum / cumsum */
 /* Order-independent arithmetic for the two places where the reference's result
- * depends on floating-point summation order:
+ * depends on floating-point summation order: the sum of the
+ * unnormalised weights w_i = exp(logw_i - max) in [0,1] (arma::accu,
+ * src/model_ssm_ung.cpp:555) and the cumulative sum of the normalised weights
+ * (arma::cumsum, src/stratified_sample.cpp:12).
  *
- *  (1) sum of the unnormalised weights w_i = exp(logw_i - max) in [0,1]
- *      (arma::accu, src/model_ssm_ung.cpp:555): each w is split exactly into
- *      hi = floor(w*2^40) and lo = floor((w*2^40 - hi)*2^43); the two integer
- *      sums are associative, and the total is rounded to binary64 once at the
- *      end.  Absolute truncation 2^-83 per term: the result is the correctly
- *      rounded true sum except in astronomically rare double-rounding cases,
- *      and it is the same for ANY reduction tree.
- *  (2) cumulative sum of the normalised weights W_i = w_i / sum
- *      (arma::cumsum, src/stratified_sample.cpp:12): Q_i = floor(W_i*2^62),
- *      integer inclusive scan, p_k = (double)(sum_{i<=k} Q_i) * 2^-62.
- *      Monotone by construction; truncation 2^-62 per term, i.e. closer to
- *      the real-number cumsum than a sequential binary64 cumsum is.
- *
- * The oracle implements both this mode and the reference's verbatim sequential
- * binary64 mode and reports where they differ (oracle/pf_oracle.cpp).
- */
+ * Each w is split exactly into two integers, hi = floor(w*2^40) and
+ * lo = floor((w*2^40 - hi)*2^43) (truncation 2^-83 absolute).  Integer sums are
+ * associative, so ONE inclusive scan of the (hi, lo) pairs gives, for any
+ * reduction tree, block size or number of CTAs,
+ *     C_k = value(sum_{i<=k} hi_i, sum_{i<=k} lo_i),   S = C_{N-1},
+ *     p_k = C_k * (1/S),  p_{N-1} := 1   (the reference forces p[last] = 1 too)
+ * with value(H, L) = fl(H*2^-40 + L*2^-83) rounded once.  p is monotone by
+ * construction.  Against the reference's p_k = sum_{i<=k} fl(w_i/S) (sequential
+ * binary64) the difference is O(2^-53) relative -- the same size as the
+ * reference's own rounding error -- so ancestors differ only when a stratum
+ * threshold falls within ~1e-16 of a cumulative weight.  The oracle implements
+ * both this mode and the verbatim sequential mode and tests compare them
+ * (oracle/pf_oracle.cpp, tests/test_oracle.py). */
 typedef struct { int64_t hi, lo; } pf_fixsum;
 
-PF_HD pf_fixsum pf_fixsum_term(double w) { /* w in [0,1] (NaN -> flagged by caller) */
-  double sc = w * 1099511627776.0;             /* 2^40, exact */
+PF_HD pf_fixsum pf_fixsum_term(double w) { /* w in [0,1] (NaN is caught before) */
+  double sc = w * 1099511627776.0;              /* 2^40, exact */
   double h = floor(sc);
   double l = floor((sc - h) * 8796093022208.0); /* 2^43; sc-h exact */
   pf_fixsum r;
@@ -317,12 +377,6 @@ PF_HD pf_fixsum pf_fixsum_term(double w) { /* w in [0,1] (NaN -> flagged by call
 PF_HD double pf_fixsum_value(int64_t hi, int64_t lo) {
   /* hi*2^-40 + lo*2^-83; conversions round-to-nearest on both sides */
   return pf_fma((double)lo, 1.0339757656912846e-25, (double)hi * 9.094947017729282e-13);
-}
-PF_HD uint64_t pf_cumsum_term(double W) { /* W in [0,1] */
-  return (uint64_t)(W * 4611686018427387904.0); /* 2^62, truncation */
-}
-PF_HD double pf_cumsum_value(uint64_t q) {
-  return (double)q * 2.168404344971009e-19; /* 2^-62 */
 }
 
 #endif /* BSSM_B200_PF_MATH_H */

@@ -119,18 +119,23 @@ void orc_stratified_sample(double* p, uint32_t n_p, const double* r, uint32_t N,
   }
 }
 
-/* the same merge, cumsum replaced by the fixed-point scan of pf_math.h */
-void orc_stratified_sample_repro(double* p, uint32_t n_p, const double* r, uint32_t N, uint32_t* xp) {
-  uint64_t q = 0;
+/* the same merge with the order-independent cumulative weights of pf_math.h:
+ * w are UNNORMALISED weights in [0,1]; p_k = C_k * (1/S) (overwrites w). */
+void orc_stratified_sample_repro(double* w, uint32_t n_p, const double* r, uint32_t N, uint32_t* xp) {
+  int64_t hi = 0, lo = 0;
+  std::vector<int64_t> H(n_p), Lo(n_p);
   for (uint32_t k = 0; k < n_p; ++k) {
-    q += pf_cumsum_term(p[k]);
-    p[k] = pf_cumsum_value(q);
+    pf_fixsum t = pf_fixsum_term(w[k]);
+    hi += t.hi; lo += t.lo;
+    H[k] = hi; Lo[k] = lo;
   }
-  p[n_p - 1] = 1;
+  const double invS = 1.0 / pf_fixsum_value(hi, lo);
+  for (uint32_t k = 0; k < n_p; ++k) w[k] = pf_fixsum_value(H[k], Lo[k]) * invS;
+  w[n_p - 1] = 1;
   unsigned int j = 0;
   double alpha = 1.0 / N;
   for (unsigned int k = 0; k < n_p && j < N; k++) {
-    while (j < N && (r[j] + j) * alpha <= p[k]) {
+    while (j < N && (r[j] + j) * alpha <= w[k]) {
       xp[j] = k;
       j++;
     }
@@ -143,6 +148,9 @@ void orc_stratified_sample_repro(double* p, uint32_t n_p, const double* r, uint3
 
 } /* extern "C" */
 
+/* W holds the reference's normalized_weights in ORC_ARITH_REFERENCE mode and the
+ * unnormalised weights (exp(logw - max), or 1 for an unweighted column) in
+ * ORC_ARITH_REPRO mode, where the normalisation is applied to the cumulative sums */
 static void resample(std::vector<double>& W, const std::vector<double>& r, uint32_t N,
                      uint32_t* xp, int arith) {
   if (arith == ORC_ARITH_REFERENCE) orc_stratified_sample(W.data(), N, r.data(), N, xp);
@@ -242,7 +250,7 @@ static void chol_P1(const double* P1, int m, std::vector<double>& L) {
  * logw (length N) -> weights column (unnormalised exp(logw-max)), W normalised.
  * returns false when the filter must stop (sum_weights > 0 fails). */
 static bool normalise(const double* logw, uint32_t N, double* wcol, std::vector<double>& W,
-                      double* loglik_inc, int arith) {
+                      double* max_out, double* logmean_out, int arith) {
   double max_weight = logw[0];
   bool has_nan = !(logw[0] == logw[0]);
   for (uint32_t i = 1; i < N; ++i) {
@@ -255,8 +263,10 @@ static bool normalise(const double* logw, uint32_t N, double* wcol, std::vector<
   for (uint32_t i = 0; i < N; ++i) wcol[i] = pf_exp(logw[i] - max_weight);
   double sum = sum_weights(wcol, N, arith);
   if (!(sum > 0.0)) return false;
-  for (uint32_t i = 0; i < N; ++i) W[i] = wcol[i] / sum;
-  *loglik_inc = max_weight + pf_log(sum / N);
+  if (arith == ORC_ARITH_REFERENCE) for (uint32_t i = 0; i < N; ++i) W[i] = wcol[i] / sum;
+  else for (uint32_t i = 0; i < N; ++i) W[i] = wcol[i];
+  *max_out = max_weight;
+  *logmean_out = pf_log_normal(sum / N);
   return true;
 }
 
@@ -290,11 +300,11 @@ double orc_ung_bsf_filter(const bssm_ung_model* M, uint32_t nsim, uint32_t seed,
   double loglik = 0.0;
   if (std::isfinite(M->y[0])) { /* :633-647 */
     for (size_t i = 0; i < N; ++i) logw[i] = g.log_obs_density(0, g.signal(0, &A(0, 0, i)));
-    double inc;
-    if (!normalise(logw.data(), nsim, weights, W, &inc, arith)) { *stopped_at = 0; return -ORC_INF; }
-    loglik = inc;
+    double mxw, lmean;
+    if (!normalise(logw.data(), nsim, weights, W, &mxw, &lmean, arith)) { *stopped_at = 0; return -ORC_INF; }
+    loglik = mxw + lmean;
   } else {
-    for (size_t i = 0; i < N; ++i) { weights[i] = 1.0; W[i] = 1.0 / nsim; }
+    for (size_t i = 0; i < N; ++i) { weights[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
   }
   for (int t = 0; t < n; ++t) { /* :648-688 */
     for (size_t i = 0; i < N; ++i) r[i] = pf_resample_uniform(seed, filter, t, (uint32_t)i);
@@ -316,11 +326,11 @@ double orc_ung_bsf_filter(const bssm_ung_model* M, uint32_t nsim, uint32_t seed,
     double* wcol = weights + N * (t + 1);
     if ((t < (n - 1)) && std::isfinite(M->y[t + 1])) {
       for (size_t i = 0; i < N; ++i) logw[i] = g.log_obs_density(t + 1, g.signal(t + 1, &A(0, t + 1, i)));
-      double inc;
-      if (!normalise(logw.data(), nsim, wcol, W, &inc, arith)) { *stopped_at = t + 1; return -ORC_INF; }
-      loglik += inc;
+      double mxw, lmean;
+      if (!normalise(logw.data(), nsim, wcol, W, &mxw, &lmean, arith)) { *stopped_at = t + 1; return -ORC_INF; }
+      loglik += mxw + lmean;
     } else {
-      for (size_t i = 0; i < N; ++i) { wcol[i] = 1.0; W[i] = 1.0 / nsim; }
+      for (size_t i = 0; i < N; ++i) { wcol[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
     }
   }
   loglik += dist_const(M); /* :690-710 */
@@ -629,11 +639,11 @@ double orc_ung_psi_filter(const bssm_ung_model* M, const double* mode_in, uint32
   double loglik = 0.0;
   if (std::isfinite(M->y[0])) { /* :549-562 */
     for (size_t i = 0; i < N; ++i) { double a = A(0, i); logw[i] = g.log_weight(0, g.signal(0, &a)) - g.scales[0]; }
-    double inc;
-    if (!normalise(logw.data(), nsim, weights, W, &inc, arith)) { *stopped_at = 0; return -ORC_INF; }
-    loglik = inc + g.approx_loglik;
+    double mxw, lmean;
+    if (!normalise(logw.data(), nsim, weights, W, &mxw, &lmean, arith)) { *stopped_at = 0; return -ORC_INF; }
+    loglik = mxw + g.approx_loglik + lmean; /* :561, evaluated left to right */
   } else {
-    for (size_t i = 0; i < N; ++i) { weights[i] = 1.0; W[i] = 1.0 / nsim; }
+    for (size_t i = 0; i < N; ++i) { weights[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
     loglik = g.approx_loglik;
   }
   for (int t = 0; t < n; ++t) { /* :568-606 */
@@ -648,11 +658,11 @@ double orc_ung_psi_filter(const bssm_ung_model* M, const double* mode_in, uint32
     double* wcol = weights + N * (t + 1);
     if ((t < (n - 1)) && std::isfinite(M->y[t + 1])) {
       for (size_t i = 0; i < N; ++i) { double a = A(t + 1, i); logw[i] = g.log_weight(t + 1, g.signal(t + 1, &a)) - g.scales[t + 1]; }
-      double inc;
-      if (!normalise(logw.data(), nsim, wcol, W, &inc, arith)) { *stopped_at = t + 1; return -ORC_INF; }
-      loglik += inc;
+      double mxw, lmean;
+      if (!normalise(logw.data(), nsim, wcol, W, &mxw, &lmean, arith)) { *stopped_at = t + 1; return -ORC_INF; }
+      loglik += mxw + lmean;
     } else {
-      for (size_t i = 0; i < N; ++i) { wcol[i] = 1.0; W[i] = 1.0 / nsim; }
+      for (size_t i = 0; i < N; ++i) { wcol[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
     }
   }
   return loglik;
