@@ -4,6 +4,6 @@ Only the particle-filter hot path of helske/bssm (bootstrap filter, psi-APF,
 particle smoother, IS-MCMC post-correction); see DESIGN.md for scope.
 """
 from .models import Model, ar1_ng, bsm_ng, init_mode, ssm_ung, svm  # noqa: F401
-from .api import (FilterJob, bootstrap_filter, logLik, particle_smoother,  # noqa: F401
-                  stratified_sample)
+from .api import (FilterJob, PostcorrJob, bootstrap_filter, logLik, particle_smoother,  # noqa: F401
+                  post_correct, stratified_sample)
 from ._lib import EngineError, lib  # noqa: F401

@@ -39,6 +39,18 @@ class FilterOut(C.Structure):
     ]
 
 
+class ThetaMap(C.Structure):
+    """bssm_theta_map"""
+    _fields_ = [("model_type", C.c_int32), ("svm_type", C.c_int32), ("mu_est", C.c_int32), ("phi_est", C.c_int32)]
+
+
+class PostcorrOut(C.Structure):
+    """bssm_postcorr_out"""
+    _fields_ = [("weights", c_double_p), ("posterior", c_double_p), ("alpha", c_double_p),
+                ("alphahat", c_double_p), ("Vt", c_double_p), ("loglik", c_double_p),
+                ("sum_w", C.c_double), ("device_ms", C.c_float), ("launches", C.c_int32)]
+
+
 _lib = None
 
 
@@ -69,6 +81,13 @@ def lib():
     L.bssm_b200_job_create_ung.argtypes = [
         C.POINTER(UngModel), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
         C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    pc_args = [C.POINTER(UngModel), C.POINTER(ThetaMap)]
+    L.bssm_b200_postcorrection_nongaussian.argtypes = pc_args + [
+        C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, c_uint32_p, c_double_p, C.c_uint32, c_double_p,
+        C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PostcorrOut)]
+    L.bssm_b200_job_create_postcorr.argtypes = pc_args + [
+        C.c_uint32, C.c_uint32, C.c_int, c_uint32_p, c_double_p, C.c_uint32, c_double_p, C.c_uint32,
+        C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
     L.bssm_b200_job_run.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.bssm_b200_job_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float * 3)]
     L.bssm_b200_job_launches.argtypes = [C.c_void_p]

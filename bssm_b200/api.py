@@ -173,3 +173,97 @@ def stratified_sample(p, r):
     xp = np.zeros(r.size, dtype=np.uint32)
     check(lib().bssm_b200_stratified_sample(dptr(p), p.size, dptr(r), r.size, uptr(xp)))
     return xp
+
+
+# ----------------------------------------------------------- post-correction
+def theta_map(model):
+    """which C++ update_model applies (R/model_type.R:1-16)"""
+    from ._lib import ThetaMap
+    tm = ThetaMap()
+    if model.cls == "svm":
+        tm.model_type, tm.svm_type = 3, int(model.extra.get("svm_type", 0))
+    elif model.cls == "ar1_ng":
+        tm.model_type = 4
+        tm.mu_est = int(model.extra.get("mu_est", 1))
+        tm.phi_est = int(model.extra.get("phi_est", 0))
+    else:
+        raise ValueError("post_correct is implemented for svm and ar1_ng models")
+    return tm
+
+
+def _postcorr_inputs(model, mcmc_output):
+    theta = np.asfortranarray(np.asarray(mcmc_output["theta"], dtype=np.float64).T)  # t(theta): n_par x n_stored
+    counts = np.ascontiguousarray(mcmc_output["counts"], dtype=np.uint32)
+    modes = np.asfortranarray(np.asarray(mcmc_output["modes"], dtype=np.float64).reshape(model.n, -1, order="F"))
+    if theta.shape[1] != counts.size or modes.shape[1] != counts.size:
+        raise ValueError("theta, counts and modes disagree on the number of stored draws")
+    return theta, counts, modes
+
+
+def n_draws(mcmc_output, is_type):
+    counts = np.asarray(mcmc_output["counts"])
+    return int(counts.sum()) if is_type == 3 else int(counts.size)
+
+
+def post_correct(model, mcmc_output, particles, threads=1, is_type="is2", seed=1, draw_range=None,
+                 return_loglik=False):
+    """post_correct, R/post_correction.R:245-308 (nongaussian branch).
+
+    mcmc_output: dict with theta (n_stored x n_par), counts (n_stored), modes
+    (n x n_stored), output_type (1 full / 2 summary / 3 theta) and posterior.
+    `threads` is accepted for parity and ignored (results do not depend on it).
+    draw_range = (begin, end) computes only that shard of the (expanded) draws.
+    """
+    from ._lib import PostcorrOut
+    N, seed = _check_particles(model, particles, seed)
+    it = {"is1": 1, "is2": 2, "is3": 3}[is_type.lower()]
+    ot = int(mcmc_output.get("output_type", 3))
+    theta, counts, modes = _postcorr_inputs(model, mcmc_output)
+    total = n_draws(mcmc_output, it)
+    b, e = (0, total) if draw_range is None else draw_range
+    nd = e - b
+    n, m = model.n, model.m
+    out = PostcorrOut()
+    w, post = np.zeros(nd), np.zeros(nd)
+    alpha = np.zeros((n + 1, m, nd), order="F") if ot == 1 else None
+    ah = np.zeros((n + 1, m), order="F") if ot == 2 else None
+    Vt = np.zeros((m, m, n + 1), order="F") if ot == 2 else None
+    ll = np.zeros(nd) if return_loglik else None
+    out.weights, out.posterior, out.alpha = dptr(w), dptr(post), dptr(alpha)
+    out.alphahat, out.Vt, out.loglik = dptr(ah), dptr(Vt), dptr(ll)
+    ms, tm = model.c_struct(), theta_map(model)
+    check(lib().bssm_b200_postcorrection_nongaussian(
+        C.byref(ms), C.byref(tm), ot, N, seed, int(threads), it, uptr(counts), dptr(theta), theta.shape[0],
+        dptr(modes), counts.size, b, e, C.byref(out)))
+    res = dict(mcmc_output)
+    res["weights"] = w
+    base = np.asarray(mcmc_output.get("posterior", np.zeros(counts.size)), dtype=np.float64)
+    if it == 3:
+        base = np.repeat(base, counts)
+    res["posterior"] = base[b:e] + post
+    if ot == 1:
+        res["alpha"] = alpha
+    elif ot == 2:
+        res["alphahat"], res["Vt"], res["sum_w"] = ah, Vt, out.sum_w
+    if return_loglik:
+        res["loglik"] = ll
+    res["mcmc_type"] = "is%d" % it
+    res["device_ms"], res["launches"] = out.device_ms, out.launches
+    return res
+
+
+class PostcorrJob(FilterJob):
+    """Resident post-correction shard (bssm_b200_job_create_postcorr): weights only."""
+
+    def __init__(self, model, mcmc_output, particles, is_type="is2", seed=1, draw_range=None):
+        N, seed = _check_particles(model, particles, seed)
+        it = {"is2": 2, "is3": 3}[is_type.lower()]
+        theta, counts, modes = _postcorr_inputs(model, mcmc_output)
+        total = n_draws(mcmc_output, it)
+        b, e = (0, total) if draw_range is None else draw_range
+        self.model, self.N, self.n_filters = model, N, e - b
+        self._ms, self._tm = model.c_struct(), theta_map(model)
+        self._h = C.c_void_p()
+        check(lib().bssm_b200_job_create_postcorr(
+            C.byref(self._ms), C.byref(self._tm), N, seed, it, uptr(counts), dptr(theta), theta.shape[0],
+            dptr(modes), counts.size, b, e, C.byref(self._h)))

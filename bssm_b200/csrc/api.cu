@@ -371,7 +371,7 @@ struct bssm_b200_job {
   DevBuf<unsigned int> barrier;
   DevBuf<double> ubuf;
   DevBuf<unsigned long long> phases;
-  DevBuf<double> s_at, s_att, s_Pt, s_Ptt, s_mean, s_cov;
+  DevBuf<double> s_at, s_att, s_Pt, s_Ptt, s_mean, s_cov, traj, draw_par;
   size_t alpha_stride = 0, weights_stride = 0, indices_stride = 0;
   bool keep_alpha = false, keep_weights = false, keep_indices = false;
   pf::UngParams up{};
@@ -387,24 +387,24 @@ namespace {
 
 template <int M>
 int run_post_M(bssm_b200_job* J) {
-  const uint32_t N = J->N;
+  const uint32_t N = J->N, nf = J->n_filters;
   const int n = J->n;
-  for (uint32_t f = 0; f < J->n_filters; ++f) {
-    const double* a_tm = J->alpha_tm.p + (size_t)f * J->alpha_stride;
-    if (J->post == BSSM_POST_FILTER_SUMMARY) {
-      pf::filter_summary_kernel<M><<<n + 1, 1024, 0, J->stream>>>(
-          a_tm, J->weights.p + (size_t)f * J->weights_stride, N, n,
-          J->s_at.p + (size_t)f * M * (n + 1), J->s_att.p + (size_t)f * M * n,
-          J->s_Pt.p + (size_t)f * M * M * (n + 1), J->s_Ptt.p + (size_t)f * M * M * n);
-      J->launches += 1;
-    } else if (J->post == BSSM_POST_SMOOTHER) {
-      double* a_sm = J->alpha_sm.p + (size_t)f * J->alpha_stride;
-      pf::backtrack_kernel<M><<<cdiv(N, 256), 256, 0, J->stream>>>(
-          a_tm, J->indices.p + (size_t)f * J->indices_stride, a_sm, N, n);
-      pf::summary_kernel<M><<<n + 1, 1024, 0, J->stream>>>(
-          a_sm, N, J->s_mean.p + (size_t)f * M * (n + 1), J->s_cov.p + (size_t)f * M * M * (n + 1));
-      J->launches += 2;
-    }
+  if (J->post == BSSM_POST_FILTER_SUMMARY) {
+    pf::filter_summary_kernel<M><<<dim3(n + 1, nf), 1024, 0, J->stream>>>(
+        J->alpha_tm.p, J->weights.p, N, n, J->s_at.p, J->s_att.p, J->s_Pt.p, J->s_Ptt.p,
+        J->alpha_stride, J->weights_stride);
+    J->launches += 1;
+  } else if (J->post == BSSM_POST_SMOOTHER || J->post == BSSM_POST_SMOOTHER_MERGE) {
+    pf::backtrack_kernel<M><<<dim3(cdiv(N, 256), nf), 256, 0, J->stream>>>(
+        J->alpha_tm.p, J->indices.p, J->alpha_sm.p, N, n, J->alpha_stride, J->indices_stride);
+    pf::summary_kernel<M><<<dim3(n + 1, nf), N >= 1024 ? 1024 : (int)round32(N), 0, J->stream>>>(
+        J->alpha_sm.p, N, J->s_mean.p, J->s_cov.p, J->alpha_stride);
+    J->launches += 2;
+  } else if (J->post == BSSM_POST_PICK) {
+    pf::pick_trajectory_kernel<M><<<cdiv(nf, 128), 128, 0, J->stream>>>(
+        J->alpha_tm.p, J->indices.p, J->traj.p, N, n, J->alpha_stride, J->indices_stride, J->seed,
+        J->first_filter, nf);
+    J->launches += 1;
   }
   CU(cudaGetLastError());
   return 0;
@@ -477,9 +477,12 @@ void bssm_b200_shutdown(void) {
   cudaGetLastError();
 }
 
-int bssm_b200_job_create_ung(const bssm_ung_model* M, int method, uint32_t nsim, uint32_t seed,
-                             uint32_t n_filters, uint32_t first_filter_id, int out_flags, int post,
-                             bssm_b200_job** job) {
+// draw_par (6 x n_filters: T, R, a1, P1, C, phi) and modes (n x n_filters) are
+// HOST arrays; when given, every filter has its own model and mode
+// (post_correct: update_model + approximate_for_is per draw)
+static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, uint32_t seed,
+                          uint32_t n_filters, uint32_t first_filter_id, int out_flags, int post,
+                          const double* draw_par, const double* draw_modes, bssm_b200_job** job) {
   if (!M || !job) return fail(BSSM_B200_ERR_ARG, "null argument");
   *job = nullptr;
   if (M->n < 1 || M->m < 1 || M->k < 1 || nsim < 2 || n_filters < 1)
@@ -489,7 +492,7 @@ int bssm_b200_job_create_ung(const bssm_ung_model* M, int method, uint32_t nsim,
   if (method == BSSM_METHOD_PSI && M->m != 1)
     return fail(BSSM_B200_ERR_UNSUPPORTED, "psi-APF is implemented for m = 1 in this build");
   if (M->k > M->m) return fail(BSSM_B200_ERR_ARG, "k > m");
-  if (post < 0 || post > 2) return fail(BSSM_B200_ERR_ARG, "post must be 0, 1 or 2");
+  if (post < 0 || post > BSSM_POST_SMOOTHER_MERGE) return fail(BSSM_B200_ERR_ARG, "bad post mode");
   int rc = require_device();
   if (rc) return rc;
 
@@ -531,11 +534,19 @@ int bssm_b200_job_create_ung(const bssm_ung_model* M, int method, uint32_t nsim,
   up.loglik_const = dconst;
 
   if (method == BSSM_METHOD_PSI) {
-    if (!M->initial_mode) return fail(BSSM_B200_ERR_ARG, "psi-APF needs initial_mode");
-    if (M->max_iter < 1) return fail(BSSM_B200_ERR_ARG, "max_iter must be >= 1");
-    std::vector<double> mode, mode_lin;
-    ung_approximate_m1(M, mode, mode_lin);
-    if ((rc = J->mode.upload(mode.data(), n)) || (rc = J->mode_lin.upload(mode_lin.data(), n))) return rc;
+    if (draw_par) {
+      // approximate_for_is (src/model_ssm_ung.cpp:143-161): fixed mode per draw, no iterations
+      if (!draw_modes) return fail(BSSM_B200_ERR_ARG, "per-draw models need per-draw modes");
+      if ((rc = J->mode.upload(draw_modes, (size_t)n * n_filters)) ||
+          (rc = J->draw_par.upload(draw_par, (size_t)6 * n_filters)))
+        return rc;
+    } else {
+      if (!M->initial_mode) return fail(BSSM_B200_ERR_ARG, "psi-APF needs initial_mode");
+      if (M->max_iter < 1) return fail(BSSM_B200_ERR_ARG, "max_iter must be >= 1");
+      std::vector<double> mode, mode_lin;
+      ung_approximate_m1(M, mode, mode_lin);
+      if ((rc = J->mode.upload(mode.data(), n)) || (rc = J->mode_lin.upload(mode_lin.data(), n))) return rc;
+    }
     J->pstride = (size_t)n + 1;
     const size_t tot = J->pstride * n_filters;
     if ((rc = J->alphahat.alloc(tot)) || (rc = J->Lt.alloc(tot)) || (rc = J->Ct.alloc(tot)) ||
@@ -550,9 +561,15 @@ int bssm_b200_job_create_ung(const bssm_ung_model* M, int method, uint32_t nsim,
     pp.D = J->D.p; pp.C = J->C.p; pp.xbeta = J->xbeta.p; pp.u = J->u.p;
     pp.has_xbeta = M->xbeta ? 1 : 0;
     pp.phi = M->phi;
-    pp.theta = nullptr; pp.n_par = 0; pp.svm_type = 0;
-    pp.modes = J->mode.p; pp.modes_lin = J->mode_lin.p; pp.mode_stride = 0; // replicates share the mode
-    pp.compute_loglik = 1;
+    if (draw_par) {
+      pp.draw_par = J->draw_par.p;
+      pp.modes = J->mode.p; pp.modes_lin = J->mode.p; pp.mode_stride = (size_t)n;
+      pp.compute_loglik = 0; // approx_loglik = 0 (:159)
+    } else {
+      pp.draw_par = nullptr;
+      pp.modes = J->mode.p; pp.modes_lin = J->mode_lin.p; pp.mode_stride = 0; // replicates share the mode
+      pp.compute_loglik = 1;
+    }
     pp.dist_const = dconst;
     pp.log2pi = std::log(2.0 * M_PI);
     pp.alphahat = J->alphahat.p; pp.Lt = J->Lt.p; pp.Ct = J->Ct.p; pp.ytilde = J->ytilde.p;
@@ -564,16 +581,18 @@ int bssm_b200_job_create_ung(const bssm_ung_model* M, int method, uint32_t nsim,
   }
 
   // ---- outputs
+  const bool smooth = post == BSSM_POST_SMOOTHER || post == BSSM_POST_SMOOTHER_MERGE;
   J->keep_alpha = (out_flags & BSSM_OUT_ALPHA) || post != BSSM_POST_NONE;
   J->keep_weights = (out_flags & BSSM_OUT_WEIGHTS) || post == BSSM_POST_FILTER_SUMMARY;
-  J->keep_indices = (out_flags & BSSM_OUT_INDICES) || post == BSSM_POST_SMOOTHER;
+  J->keep_indices = (out_flags & BSSM_OUT_INDICES) || smooth || post == BSSM_POST_PICK;
   J->alpha_stride = (size_t)(J->keep_alpha ? n + 1 : 2) * m * nsim;
   J->weights_stride = J->keep_weights ? (size_t)nsim * (n + 1) : 0;
   J->indices_stride = J->keep_indices ? (size_t)nsim * n : (size_t)nsim;
   if ((rc = J->alpha_tm.alloc(J->alpha_stride * n_filters))) return rc;
   if (J->keep_weights && (rc = J->weights.alloc(J->weights_stride * n_filters))) return rc;
   if ((rc = J->indices.alloc(J->indices_stride * n_filters))) return rc;
-  if (post == BSSM_POST_SMOOTHER && (rc = J->alpha_sm.alloc(J->alpha_stride * n_filters))) return rc;
+  if (smooth && (rc = J->alpha_sm.alloc(J->alpha_stride * n_filters))) return rc;
+  if (post == BSSM_POST_PICK && (rc = J->traj.alloc((size_t)n_filters * (n + 1) * m))) return rc;
   if ((rc = J->loglik.alloc(n_filters)) || (rc = J->stopped.alloc(n_filters))) return rc;
   if ((rc = J->xch.alloc((size_t)4 * J->geo.ranks * n_filters)) || (rc = J->barrier.alloc(1)) ||
       (rc = J->ubuf.alloc((size_t)nsim * n_filters))) return rc;
@@ -581,7 +600,7 @@ int bssm_b200_job_create_ung(const bssm_ung_model* M, int method, uint32_t nsim,
     if ((rc = J->s_at.alloc((size_t)n_filters * m * (n + 1))) || (rc = J->s_att.alloc((size_t)n_filters * m * n)) ||
         (rc = J->s_Pt.alloc((size_t)n_filters * m * m * (n + 1))) || (rc = J->s_Ptt.alloc((size_t)n_filters * m * m * n)))
       return rc;
-  } else if (post == BSSM_POST_SMOOTHER) {
+  } else if (smooth) {
     if ((rc = J->s_mean.alloc((size_t)n_filters * m * (n + 1))) || (rc = J->s_cov.alloc((size_t)n_filters * m * m * (n + 1))))
       return rc;
   }
@@ -604,6 +623,13 @@ int bssm_b200_job_create_ung(const bssm_ung_model* M, int method, uint32_t nsim,
   guard.j = nullptr;
   *job = J;
   return 0;
+}
+
+int bssm_b200_job_create_ung(const bssm_ung_model* M, int method, uint32_t nsim, uint32_t seed,
+                             uint32_t n_filters, uint32_t first_filter_id, int out_flags, int post,
+                             bssm_b200_job** job) {
+  if (post > BSSM_POST_SMOOTHER) return fail(BSSM_B200_ERR_ARG, "post must be 0, 1 or 2");
+  return create_ung_job(M, method, nsim, seed, n_filters, first_filter_id, out_flags, post, nullptr, nullptr, job);
 }
 
 int bssm_b200_job_run(bssm_b200_job* J, float* ms_out) {
@@ -702,7 +728,7 @@ int bssm_b200_job_fetch(bssm_b200_job* J, uint32_t f, bssm_filter_out* out) {
   const int cols_i = stopped >= 0 ? stopped : n;
   if (out->alpha) {
     if (!J->keep_alpha) return fail(BSSM_B200_ERR_ARG, "job was created without BSSM_OUT_ALPHA");
-    const double* src = (J->post == BSSM_POST_SMOOTHER ? J->alpha_sm.p : J->alpha_tm.p) + (size_t)f * J->alpha_stride;
+    const double* src = (J->alpha_sm.p ? J->alpha_sm.p : J->alpha_tm.p) + (size_t)f * J->alpha_stride;
     const uint32_t rows = (uint32_t)(n + 1) * m;
     int rc = J->cube.alloc((size_t)rows * N);
     if (rc) return rc;
@@ -729,7 +755,7 @@ int bssm_b200_job_fetch(bssm_b200_job* J, uint32_t f, bssm_filter_out* out) {
     if (out->att) CU(cudaMemcpy(out->att, J->s_att.p + (size_t)f * m * n, sizeof(double) * m * n, cudaMemcpyDeviceToHost));
     if (out->Pt) CU(cudaMemcpy(out->Pt, J->s_Pt.p + (size_t)f * m * m * (n + 1), sizeof(double) * m * m * (n + 1), cudaMemcpyDeviceToHost));
     if (out->Ptt) CU(cudaMemcpy(out->Ptt, J->s_Ptt.p + (size_t)f * m * m * n, sizeof(double) * m * m * n, cudaMemcpyDeviceToHost));
-  } else if (J->post == BSSM_POST_SMOOTHER) {
+  } else if (J->post == BSSM_POST_SMOOTHER || J->post == BSSM_POST_SMOOTHER_MERGE) {
     if (out->alphahat) CU(cudaMemcpy(out->alphahat, J->s_mean.p + (size_t)f * m * (n + 1), sizeof(double) * m * (n + 1), cudaMemcpyDeviceToHost));
     if (out->Vt) CU(cudaMemcpy(out->Vt, J->s_cov.p + (size_t)f * m * m * (n + 1), sizeof(double) * m * m * (n + 1), cudaMemcpyDeviceToHost));
   }
@@ -737,6 +763,208 @@ int bssm_b200_job_fetch(bssm_b200_job* J, uint32_t f, bssm_filter_out* out) {
 }
 
 void bssm_b200_job_destroy(bssm_b200_job* J) { delete J; }
+
+// --------------------------------------------------------- post-correction
+namespace {
+
+// update_model(theta) restricted to the scalars the m = 1 psi-APF reads:
+// par = {T, R, a1, P1, C, phi}.  svm: src/model_svm.cpp:12-29; ar1_ng:
+// src/model_ar1_ng.cpp:12-36 (sigma and phi are on the log scale there).
+int theta_to_par(const bssm_ung_model* M, const bssm_theta_map* map, const double* th, uint32_t n_par,
+                 double par[6]) {
+  double T = M->T[0], R = M->R[0], a1 = M->a1[0], P1 = M->P1[0], C = M->C[0], phi = M->phi;
+  if (map->model_type == 3) {
+    if (n_par < 3) return fail(BSSM_B200_ERR_ARG, "svm needs 3 parameters");
+    if (map->svm_type == 0) {
+      phi = th[2];
+    } else {
+      a1 = th[2];
+      C = th[2] * (1.0 - th[0]);
+    }
+    T = th[0];
+    R = th[1];
+    P1 = th[1] * th[1] / (1 - th[0] * th[0]);
+  } else if (map->model_type == 4) {
+    if (n_par < (uint32_t)(2 + map->mu_est + map->phi_est)) return fail(BSSM_B200_ERR_ARG, "ar1_ng: too few parameters");
+    const double rho = th[0];
+    const double sigma = pf_exp(th[1]);
+    T = rho;
+    R = sigma;
+    const double RR = sigma * sigma;
+    if (map->mu_est) {
+      a1 = th[2];
+      C = th[2] * (1.0 - rho);
+    }
+    P1 = RR / (1.0 - rho * rho);
+    if (map->phi_est) phi = pf_exp(th[2 + map->mu_est]);
+  } else {
+    return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction: model_type must be 3 (svm) or 4 (ar1_ng) in this build");
+  }
+  par[0] = T; par[1] = R; par[2] = a1; par[3] = P1; par[4] = C; par[5] = phi;
+  return 0;
+}
+
+struct DrawList {
+  std::vector<uint32_t> src;   // expanded draw -> column of theta / modes
+  std::vector<uint32_t> count; // effective count of the expanded draw
+};
+
+int build_draws(int is_type, const uint32_t* counts, uint32_t n_stored, DrawList* dl) {
+  if (is_type < 1 || is_type > 3) return fail(BSSM_B200_ERR_ARG, "is_type must be 1, 2 or 3");
+  dl->src.clear(); dl->count.clear();
+  for (uint32_t i = 0; i < n_stored; ++i) {
+    if (is_type == 3) { // expand(), src/approx_mcmc.cpp:49-88
+      for (uint32_t c = 0; c < counts[i]; ++c) { dl->src.push_back(i); dl->count.push_back(1u); }
+    } else {
+      dl->src.push_back(i); dl->count.push_back(counts[i]);
+    }
+  }
+  return 0;
+}
+
+int check_postcorr_args(const bssm_ung_model* M, const bssm_theta_map* map, const uint32_t* counts,
+                        const double* theta, const double* modes, uint32_t n_stored) {
+  if (!M || !map || !counts || !theta || !modes || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
+  if (M->m != 1) return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction is implemented for m = 1 models in this build");
+  if (M->xbeta) return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction with regression coefficients in theta is not implemented");
+  return 0;
+}
+
+// gathers the per-draw inputs of draws [d0, d1) and creates their job
+int make_draw_job(const bssm_ung_model* M, const bssm_theta_map* map, const DrawList& dl, uint32_t d0, uint32_t d1,
+                  uint32_t N, uint32_t seed, const double* theta, uint32_t n_par, const double* modes,
+                  int out_flags, int post, bssm_b200_job** job) {
+  const uint32_t nf = d1 - d0;
+  const size_t n = (size_t)M->n;
+  std::vector<double> par((size_t)6 * nf), md(n * nf);
+  for (uint32_t f = 0; f < nf; ++f) {
+    const uint32_t c = dl.src[d0 + f];
+    int rc = theta_to_par(M, map, theta + (size_t)c * n_par, n_par, &par[(size_t)6 * f]);
+    if (rc) return rc;
+    memcpy(&md[n * f], modes + n * c, n * sizeof(double));
+  }
+  return create_ung_job(M, BSSM_METHOD_PSI, N, seed, nf, d0, out_flags, post, par.data(), md.data(), job);
+}
+
+} // namespace
+
+int bssm_b200_job_create_postcorr(const bssm_ung_model* M, const bssm_theta_map* map, uint32_t nsim,
+                                  uint32_t seed, int is_type, const uint32_t* counts, const double* theta,
+                                  uint32_t n_par, const double* modes, uint32_t n_stored,
+                                  uint32_t draw_begin, uint32_t draw_end, bssm_b200_job** job) {
+  int rc = check_postcorr_args(M, map, counts, theta, modes, n_stored);
+  if (rc) return rc;
+  if (is_type == 1) return fail(BSSM_B200_ERR_ARG, "resident post-correction jobs need equal N per draw (is_type 2 or 3)");
+  DrawList dl;
+  if ((rc = build_draws(is_type, counts, n_stored, &dl))) return rc;
+  if (draw_begin == 0 && draw_end == 0) draw_end = (uint32_t)dl.src.size();
+  if (draw_begin >= draw_end || draw_end > dl.src.size()) return fail(BSSM_B200_ERR_ARG, "bad draw range");
+  return make_draw_job(M, map, dl, draw_begin, draw_end, nsim, seed, theta, n_par, modes, 0, BSSM_POST_NONE, job);
+}
+
+int bssm_b200_postcorrection_nongaussian(const bssm_ung_model* M, const bssm_theta_map* map, int output_type,
+                                         uint32_t nsim, uint32_t seed, uint32_t n_threads, int is_type,
+                                         const uint32_t* counts, const double* theta, uint32_t n_par,
+                                         const double* modes, uint32_t n_stored, uint32_t draw_begin,
+                                         uint32_t draw_end, bssm_postcorr_out* out) {
+  (void)n_threads;
+  int rc = check_postcorr_args(M, map, counts, theta, modes, n_stored);
+  if (rc) return rc;
+  if (!out || !out->weights || !out->posterior) return fail(BSSM_B200_ERR_ARG, "weights and posterior outputs are required");
+  if (output_type < 1 || output_type > 3) return fail(BSSM_B200_ERR_ARG, "output_type must be 1, 2 or 3");
+  if (output_type == 1 && !out->alpha) return fail(BSSM_B200_ERR_ARG, "output_type 1 needs out->alpha");
+  if (output_type == 2 && (!out->alphahat || !out->Vt)) return fail(BSSM_B200_ERR_ARG, "output_type 2 needs out->alphahat and out->Vt");
+  if ((rc = require_device())) return rc;
+  DrawList dl;
+  if ((rc = build_draws(is_type, counts, n_stored, &dl))) return rc;
+  if (draw_begin == 0 && draw_end == 0) draw_end = (uint32_t)dl.src.size();
+  if (draw_begin >= draw_end || draw_end > dl.src.size()) return fail(BSSM_B200_ERR_ARG, "bad draw range");
+  const int n = M->n, m = M->m;
+  const size_t n1 = (size_t)n + 1;
+  out->device_ms = 0.f; out->launches = 0; out->sum_w = 0.0;
+
+  const int post = output_type == 1 ? BSSM_POST_PICK : (output_type == 2 ? BSSM_POST_SMOOTHER_MERGE : BSSM_POST_NONE);
+  const double budget = 1e9 * (double)env_int("BSSM_B200_CHUNK_GB", 8);
+  // running state of the weighted merge (output_type 2)
+  DevBuf<double> d_sumw, d_ah, d_Vt, d_Va;
+  DevBuf<uint32_t> d_cnt;
+  if (output_type == 2) {
+    if ((rc = d_sumw.alloc(2)) || (rc = d_ah.alloc((size_t)m * n1)) || (rc = d_Vt.alloc((size_t)m * m * n1)) ||
+        (rc = d_Va.alloc((size_t)m * m * n1)))
+      return rc;
+    CU(cudaMemset(d_sumw.p, 0, 2 * sizeof(double)));
+    CU(cudaMemset(d_ah.p, 0, sizeof(double) * m * n1));
+    CU(cudaMemset(d_Vt.p, 0, sizeof(double) * m * m * n1));
+    CU(cudaMemset(d_Va.p, 0, sizeof(double) * m * m * n1));
+  }
+  int chunk_no = 0;
+  uint32_t d0 = draw_begin;
+  while (d0 < draw_end) {
+    // a chunk = consecutive draws with the same particle count (is_type 1: nsim * count)
+    const uint32_t N = is_type == 1 ? nsim * dl.count[d0] : nsim;
+    double per_filter = 64.0 * n1; // pre-pass arrays
+    if (post != BSSM_POST_NONE) per_filter += (double)N * n1 * m * 8.0 * (output_type == 2 ? 2 : 1) + (double)N * n * 4.0;
+    else per_filter += (double)N * (2 * m * 8.0 + 4.0 + 8.0);
+    uint32_t maxc = (uint32_t)std::max(1.0, budget / per_filter);
+    uint32_t d1 = d0 + 1;
+    while (d1 < draw_end && d1 - d0 < maxc && (is_type != 1 || dl.count[d1] == dl.count[d0])) ++d1;
+    const uint32_t nf = d1 - d0;
+    bssm_b200_job* J = nullptr;
+    if ((rc = make_draw_job(M, map, dl, d0, d1, N, seed, theta, n_par, modes, 0, post, &J))) return rc;
+    struct JG { bssm_b200_job* j; ~JG() { delete j; } } jg{J};
+    float ms = 0;
+    if ((rc = bssm_b200_job_run(J, &ms))) return rc;
+    out->device_ms += ms;
+    out->launches += J->launches;
+    std::vector<double> ll(nf);
+    CU(cudaMemcpy(ll.data(), J->loglik.p, sizeof(double) * nf, cudaMemcpyDeviceToHost));
+    for (uint32_t f = 0; f < nf; ++f) {
+      const size_t o = (size_t)(d0 - draw_begin) + f;
+      const double w = pf_exp(ll[f]);         // weight_storage(i) = exp(loglik), :385
+      out->weights[o] = w;
+      out->posterior[o] = 0.0 + 0.0 + pf_log(w); // prior + approx_loglik + log(weight), :425-426
+      if (out->loglik) out->loglik[o] = ll[f];
+    }
+    if (output_type == 1) {
+      CU(cudaMemcpy(out->alpha + (size_t)(d0 - draw_begin) * n1 * m, J->traj.p, sizeof(double) * nf * n1 * m, cudaMemcpyDeviceToHost));
+    } else if (output_type == 2) {
+      if ((rc = d_cnt.upload(&dl.count[d0], nf))) return rc;
+      cudaEvent_t e0, e1;
+      CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+      CU(cudaEventRecord(e0, J->stream));
+      double* sw_in = d_sumw.p + (chunk_no & 1);
+      double* sw_out = d_sumw.p + ((chunk_no + 1) & 1);
+      CU(cudaMemcpyAsync(sw_out, sw_in, sizeof(double), cudaMemcpyDeviceToDevice, J->stream));
+      // m = 1 only in this build (checked above)
+      pf::postcorr_merge_kernel<1><<<cdiv((uint32_t)n1, 128), 128, 0, J->stream>>>(
+          J->s_mean.p, J->s_cov.p, J->loglik.p, d_cnt.p, nf, (int)n1, sw_in, sw_out, d_ah.p, d_Vt.p, d_Va.p);
+      CU(cudaGetLastError());
+      CU(cudaEventRecord(e1, J->stream));
+      CU(cudaStreamSynchronize(J->stream));
+      float mms = 0;
+      CU(cudaEventElapsedTime(&mms, e0, e1));
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+      out->device_ms += mms;
+      out->launches += 1;
+    }
+    d0 = d1;
+    ++chunk_no;
+  }
+  if (output_type == 2) {
+    double sw = 0;
+    CU(cudaMemcpy(&sw, d_sumw.p + (chunk_no & 1), sizeof(double), cudaMemcpyDeviceToHost));
+    out->sum_w = sw;
+    std::vector<double> ah((size_t)m * n1), Vt((size_t)m * m * n1), Va((size_t)m * m * n1);
+    CU(cudaMemcpy(ah.data(), d_ah.p, sizeof(double) * ah.size(), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(Vt.data(), d_Vt.p, sizeof(double) * Vt.size(), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(Va.data(), d_Va.p, sizeof(double) * Va.size(), cudaMemcpyDeviceToHost));
+    // Vt += Valpha / sum_w (:422-424); alphahat is returned transposed, (n+1) x m
+    for (size_t e = 0; e < Vt.size(); ++e) out->Vt[e] = Vt[e] + Va[e] / sw;
+    for (size_t t = 0; t < n1; ++t)
+      for (int d = 0; d < m; ++d) out->alphahat[t + n1 * d] = ah[d + (size_t)m * t];
+  }
+  return 0;
+}
 
 // ---------------------------------------------------------- one-shot calls
 static int one_shot(const bssm_ung_model* M, int method, uint32_t nsim, uint32_t seed, int post,

@@ -24,10 +24,11 @@ struct PrepassParams {
   const double *y, *Z, *T, *R, *a1, *P1, *D, *C, *xbeta, *u;
   int has_xbeta;
   double phi;
-  // per-draw parameters (post_correct on svm): theta is n_par x n_filters
-  const double* theta;
-  int n_par;
-  int svm_type;  // 0: theta[2] = sigma (phi), 1: theta[2] = mu
+  // per-draw scalar model (post_correct): 6 per filter = T, R, a1, P1, C, phi,
+  // i.e. what update_model(theta_i) sets (src/model_svm.cpp:12-29,
+  // src/model_ar1_ng.cpp:12-36), evaluated for all draws up front like the
+  // reference's parset_ung does (src/parset_ng.cpp:5-72).  null = use the model.
+  const double* draw_par;
   // mode of the Gaussian approximation: n per filter.  `modes_lin` is the point
   // the pseudo-observations are linearised at: after ssm_ung::approximate() that
   // is the mode of the LAST BUT ONE Newton sweep (the reference does not
@@ -65,26 +66,18 @@ ung_prepass_m1_kernel(const PrepassParams pp, uint32_t n_filters) {
   const double* mode = pp.modes + (size_t)f * pp.mode_stride;
   const double* mode_lin = pp.modes_lin + (size_t)f * pp.mode_stride;
 
-  // ---- model of this filter (svm::update_model, src/model_svm.cpp:12-29)
-  const bool from_theta = pp.theta != nullptr;
+  // ---- model of this filter
+  const bool from_theta = pp.draw_par != nullptr;
   double phi = pp.phi, Tc = 0, Rc = 0, a1 = pp.a1[0], P1 = pp.P1[0], Cc = 0;
   if (from_theta) {
-    const double* th = pp.theta + (size_t)f * pp.n_par;
-    if (pp.svm_type == 0) {
-      phi = th[2];
-    } else {
-      a1 = th[2];
-      Cc = th[2] * (1.0 - th[0]);
-    }
-    Tc = th[0];
-    Rc = th[1];
-    P1 = th[1] * th[1] / (1 - th[0] * th[0]);
+    const double* dp = pp.draw_par + (size_t)f * 6;
+    Tc = dp[0]; Rc = dp[1]; a1 = dp[2]; P1 = dp[3]; Cc = dp[4]; phi = dp[5];
   }
   if (lane == 0) pp.phi_f[f] = phi;
   auto Zt = [&](int t) { return pp.Z[t * pp.Ztv]; };
   auto Tt = [&](int t) { return from_theta ? Tc : pp.T[t * pp.Ttv]; };
   auto RRt = [&](int t) { double r = from_theta ? Rc : pp.R[t * pp.Rtv]; return r * r; };
-  auto Ct = [&](int t) { return (from_theta && pp.svm_type == 1) ? Cc : pp.C[t * pp.Ctv]; };
+  auto Ct = [&](int t) { return from_theta ? Cc : pp.C[t * pp.Ctv]; };
   auto Dt = [&](int t) { return pp.D[t * pp.Dtv]; };
 
   // ---- laplace_iter (:302-342) and update_scales (:241-292), lanes over t

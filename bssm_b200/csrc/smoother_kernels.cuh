@@ -20,9 +20,13 @@ namespace pf {
 // copies each tube before overwriting it, src/filter_smoother.cpp:10).
 template <int M>
 __global__ void backtrack_kernel(const double* __restrict__ alpha_f, const uint32_t* __restrict__ indices,
-                                 double* __restrict__ alpha_s, uint32_t N, int n) {
+                                 double* __restrict__ alpha_s, uint32_t N, int n, size_t alpha_stride,
+                                 size_t indices_stride) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
+  alpha_f += (size_t)blockIdx.y * alpha_stride;   // blockIdx.y = filter
+  alpha_s += (size_t)blockIdx.y * alpha_stride;
+  indices += (size_t)blockIdx.y * indices_stride;
   uint32_t b = i;
 #pragma unroll
   for (int d = 0; d < M; ++d) alpha_s[((size_t)n * M + d) * N + i] = alpha_f[((size_t)n * M + d) * N + i];
@@ -59,9 +63,13 @@ __device__ __forceinline__ void block_sum(double (&v)[V], double* smem /* 32*V *
 template <int M>
 __global__ void __launch_bounds__(1024)
 summary_kernel(const double* __restrict__ alpha_tm, uint32_t N, double* __restrict__ mean_x /* M x n1 */,
-               double* __restrict__ cov_x /* M x M x n1 */) {
+               double* __restrict__ cov_x /* M x M x n1 */, size_t alpha_stride) {
   __shared__ double sm[32 * M * M];
   const int t = blockIdx.x;
+  const int n1 = gridDim.x;
+  alpha_tm += (size_t)blockIdx.y * alpha_stride;  // blockIdx.y = filter
+  mean_x += (size_t)blockIdx.y * M * n1;
+  cov_x += (size_t)blockIdx.y * M * M * n1;
   const double* col = alpha_tm + (size_t)t * M * N;
   double s[M];
 #pragma unroll
@@ -100,7 +108,13 @@ template <int M>
 __global__ void __launch_bounds__(1024)
 filter_summary_kernel(const double* __restrict__ alpha_tm, const double* __restrict__ weights, uint32_t N,
                       int n, double* __restrict__ at, double* __restrict__ att, double* __restrict__ Pt,
-                      double* __restrict__ Ptt) {
+                      double* __restrict__ Ptt, size_t alpha_stride, size_t weights_stride) {
+  alpha_tm += (size_t)blockIdx.y * alpha_stride;  // blockIdx.y = filter
+  weights += (size_t)blockIdx.y * weights_stride;
+  at += (size_t)blockIdx.y * M * (n + 1);
+  att += (size_t)blockIdx.y * M * n;
+  Pt += (size_t)blockIdx.y * M * M * (n + 1);
+  Ptt += (size_t)blockIdx.y * M * M * n;
   constexpr int SMV = (2 * M + 1 > 2 * M * M) ? (2 * M + 1) : (2 * M * M);
   __shared__ double sm[32 * SMV];
   const int t = blockIdx.x;
@@ -158,6 +172,79 @@ filter_summary_kernel(const double* __restrict__ alpha_tm, const double* __restr
       for (int e = 0; e < M * M; ++e) Ptt[e + (size_t)M * M * t] = c[M * M + e];
     }
   }
+}
+
+// post_correct output_type = 1 (src/approx_mcmc.cpp:388-392): after the
+// backward tracing, ONE trajectory per draw is kept, chosen uniformly.  Only
+// that path is traced: thread f follows the ancestry of particle
+// idx = floor(u * N), u = pf_pick_uniform(seed, filter).  Output per filter is
+// the (n+1) x M matrix alpha_i.slice(idx).t(), column-major.
+template <int M>
+__global__ void pick_trajectory_kernel(const double* __restrict__ alpha_f, const uint32_t* __restrict__ indices,
+                                       double* __restrict__ traj, uint32_t N, int n, size_t alpha_stride,
+                                       size_t indices_stride, uint32_t seed, uint32_t first_filter,
+                                       uint32_t n_filters) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_filters) return;
+  alpha_f += (size_t)f * alpha_stride;
+  indices += (size_t)f * indices_stride;
+  traj += (size_t)f * (n + 1) * M;
+  uint32_t b = (uint32_t)(pf_pick_uniform(seed, first_filter + f) * (double)N);
+  if (b > N - 1) b = N - 1;
+#pragma unroll
+  for (int d = 0; d < M; ++d) traj[n + (size_t)(n + 1) * d] = alpha_f[((size_t)n * M + d) * N + b];
+  for (int t = n - 1; t >= 0; --t) {
+    b = indices[(size_t)t * N + b];
+#pragma unroll
+    for (int d = 0; d < M; ++d) traj[t + (size_t)(n + 1) * d] = alpha_f[((size_t)t * M + d) * N + b];
+  }
+}
+
+// post_correct output_type = 2 (src/approx_mcmc.cpp:394-424): running weighted
+// mean / variance over the draws, in draw order (the reference's order with one
+// thread; with several threads its critical-section order is nondeterministic).
+// One thread per element of alphahat (M x n1); sequential over draws.
+//   wnew = w_i * count_i; sum_w += wnew; diff = ah_i - ah; ah += wnew/sum_w*diff;
+//   Valpha += wnew * diff * (ah_i - ah)'; Vt += wnew/sum_w * (Vt_i - Vt)
+// state: sum_w, alphahat (M x n1), Vt (M x M x n1), Valpha (M x M x n1); updated in place so
+// that successive chunks of draws continue the same recursion.
+template <int M>
+__global__ void postcorr_merge_kernel(const double* __restrict__ mean_i, const double* __restrict__ cov_i,
+                                      const double* __restrict__ loglik, const uint32_t* __restrict__ counts,
+                                      uint32_t n_filters, int n1, const double* __restrict__ sum_w_in,
+                                      double* __restrict__ sum_w_out,
+                                      double* __restrict__ alphahat, double* __restrict__ Vt,
+                                      double* __restrict__ Valpha) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n1) return;
+  double sum_w = *sum_w_in;
+  double ah[M], V[M * M], Va[M * M];
+#pragma unroll
+  for (int d = 0; d < M; ++d) ah[d] = alphahat[d + (size_t)M * t];
+#pragma unroll
+  for (int e = 0; e < M * M; ++e) { V[e] = Vt[e + (size_t)M * M * t]; Va[e] = Valpha[e + (size_t)M * M * t]; }
+  for (uint32_t i = 0; i < n_filters; ++i) {
+    const double wnew = pf_exp(loglik[i]) * (double)counts[i];
+    sum_w += wnew;
+    const double* mi = mean_i + (size_t)i * M * n1 + (size_t)M * t;
+    const double* ci = cov_i + (size_t)i * M * M * n1 + (size_t)M * M * t;
+    double diff[M], diff2[M];
+    const double f = wnew / sum_w;
+#pragma unroll
+    for (int d = 0; d < M; ++d) { diff[d] = mi[d] - ah[d]; ah[d] += f * diff[d]; diff2[d] = mi[d] - ah[d]; }
+#pragma unroll
+    for (int c = 0; c < M; ++c)
+#pragma unroll
+      for (int r = 0; r < M; ++r) {
+        Va[r + M * c] += wnew * diff[r] * diff2[c];
+        V[r + M * c] += f * (ci[r + M * c] - V[r + M * c]);
+      }
+  }
+#pragma unroll
+  for (int d = 0; d < M; ++d) alphahat[d + (size_t)M * t] = ah[d];
+#pragma unroll
+  for (int e = 0; e < M * M; ++e) { Vt[e + (size_t)M * M * t] = V[e]; Valpha[e + (size_t)M * M * t] = Va[e]; }
+  if (t == n1 - 1) *sum_w_out = sum_w;  // every thread computed the same sum_w
 }
 
 } // namespace pf

@@ -47,7 +47,10 @@ enum { BSSM_METHOD_PSI = 1, BSSM_METHOD_BSF = 2 };
 enum {
   BSSM_POST_NONE = 0,           /* filter only */
   BSSM_POST_FILTER_SUMMARY = 1, /* + filter_summary: at, att, Pt, Ptt (src/summary.cpp:42-79) */
-  BSSM_POST_SMOOTHER = 2        /* + filter_smoother backtrack + summary: alphahat, Vt */
+  BSSM_POST_SMOOTHER = 2,       /* + filter_smoother backtrack + summary: alphahat, Vt */
+  /* used by the post-correction driver (src/approx_mcmc.cpp:388-414) */
+  BSSM_POST_PICK = 3,           /* + one uniformly chosen smoothed trajectory per filter */
+  BSSM_POST_SMOOTHER_MERGE = 4  /* + per-filter summaries kept for the weighted merge */
 };
 /* what a job keeps on the device / hands back */
 enum {
@@ -151,6 +154,48 @@ int bssm_b200_psi_smoother(const bssm_ung_model* model, uint32_t nsim, uint32_t 
 int bssm_b200_psi_filter(const bssm_ung_model* model, uint32_t nsim, uint32_t seed,
                          bssm_filter_out* out);
 
+/* ---- IS-MCMC post-correction ---------------------------------------------- */
+/* How theta maps onto the model (the C++ update_model of the model class):
+ * svm src/model_svm.cpp:12-29, ar1_ng src/model_ar1_ng.cpp:12-36. */
+typedef struct {
+  int32_t model_type; /* R/model_type.R:1-16: 3 = svm, 4 = ar1_ng */
+  int32_t svm_type;   /* svm: 0 = theta[2] is sigma (phi), 1 = theta[2] is mu */
+  int32_t mu_est;     /* ar1_ng */
+  int32_t phi_est;    /* ar1_ng */
+} bssm_theta_map;
+
+typedef struct {
+  double* weights;    /* n_draws: exp(loglik_i), src/approx_mcmc.cpp:385 */
+  double* posterior;  /* n_draws: prior (0) + approx_loglik (0) + log(weight), :425-426 */
+  double* alpha;      /* output_type 1: (n+1) x m x n_draws, one trajectory per draw */
+  double* alphahat;   /* output_type 2: (n+1) x m */
+  double* Vt;         /* output_type 2: m x m x (n+1) */
+  double* loglik;     /* optional, n_draws: the psi-APF log-likelihood estimates */
+  double sum_w;       /* output_type 2: sum of w_i * count_i over the draws of this call */
+  float device_ms;    /* CUDA-event time of all kernels of this call */
+  int32_t launches;
+} bssm_postcorr_out;
+
+/* replaces: postcorrection_nongaussian(model_, model_type, output_type, nsim,
+ *           seed, n_threads, is_type, counts, theta, modes)
+ *           src/R_postcorrection.cpp:150-248 -> approx_mcmc::is_correction_psi
+ *           src/approx_mcmc.cpp:353-427 (+ expand :49-88 for is_type 3).
+ * theta is n_par x n_stored, modes is n x n_stored (p = 1), counts n_stored.
+ * One independent psi-APF per (expanded) draw; draw d uses random stream
+ * `filter = d`, so results do not depend on how draws are sharded -- unlike the
+ * reference, whose per-thread engines make results depend on `threads`
+ * (src/approx_mcmc.cpp:367).  n_threads is accepted for signature parity and
+ * ignored.  [draw_begin, draw_end) selects the shard of the (expanded, for
+ * is_type 3) draw list this call computes -- 0, 0 = all draws; outputs are
+ * indexed from draw_begin.  Multi-GPU: one process per GPU, each calling this
+ * with its shard, then ONE gather of `weights` (bssm_b200/distributed.py). */
+int bssm_b200_postcorrection_nongaussian(const bssm_ung_model* model, const bssm_theta_map* map,
+                                         int output_type, uint32_t nsim, uint32_t seed,
+                                         uint32_t n_threads, int is_type, const uint32_t* counts,
+                                         const double* theta, uint32_t n_par, const double* modes,
+                                         uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
+                                         bssm_postcorr_out* out);
+
 /* ---- resident jobs: the same filters with inputs kept in HBM ------------- */
 /* A job owns device copies of the model, the pre-pass results and the output
  * buffers of `n_filters` independent replicate filters (filter f uses random
@@ -161,6 +206,14 @@ typedef struct bssm_b200_job bssm_b200_job;
 int bssm_b200_job_create_ung(const bssm_ung_model* model, int method, uint32_t nsim,
                              uint32_t seed, uint32_t n_filters, uint32_t first_filter_id,
                              int out_flags, int post, bssm_b200_job** job);
+/* a resident batch of post-correction draws (is_type 2 / 3 only: equal N): the
+ * draws [draw_begin, draw_end) of the expanded list, weights only
+ * (output_type 3).  bench.py times run() of this job for the draws/s metric. */
+int bssm_b200_job_create_postcorr(const bssm_ung_model* model, const bssm_theta_map* map,
+                                  uint32_t nsim, uint32_t seed, int is_type, const uint32_t* counts,
+                                  const double* theta, uint32_t n_par, const double* modes,
+                                  uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
+                                  bssm_b200_job** job);
 /* launches pre-pass + filter (+ the post-processing kernels) on the
  * job's stream and waits; ms = CUDA-event time on that stream */
 int bssm_b200_job_run(bssm_b200_job* job, float* ms);

@@ -771,6 +771,116 @@ void orc_ung_filter_batch(const bssm_ung_model* M, int method, const double* mod
   }
 }
 
+/* ------------------------------------------------------------------ a15 */
+/* update_model(theta): svm src/model_svm.cpp:12-29, ar1_ng src/model_ar1_ng.cpp:12-36.
+ * Writes the scalars of the per-draw model into caller storage. */
+struct DrawModel {
+  bssm_ung_model M;
+  double T, R, a1, P1, C;
+};
+static void update_model(DrawModel& dm, const bssm_ung_model* base, const bssm_theta_map* map,
+                         const double* new_theta) {
+  dm.M = *base;
+  dm.T = base->T[0]; dm.R = base->R[0]; dm.a1 = base->a1[0]; dm.P1 = base->P1[0]; dm.C = base->C[0];
+  if (map->model_type == 3) {
+    if (map->svm_type == 0) {
+      dm.M.phi = new_theta[2];
+    } else {
+      dm.a1 = new_theta[2];
+      dm.C = new_theta[2] * (1.0 - new_theta[0]);
+    }
+    dm.T = new_theta[0];
+    dm.R = new_theta[1];
+    dm.P1 = new_theta[1] * new_theta[1] / (1 - new_theta[0] * new_theta[0]);
+  } else {
+    double rho = new_theta[0];
+    double sigma = pf_exp(new_theta[1]);
+    dm.T = rho;
+    dm.R = sigma;
+    double RR = sigma * sigma;
+    if (map->mu_est) {
+      dm.a1 = new_theta[2];
+      dm.C = new_theta[2] * (1.0 - rho);
+    }
+    dm.P1 = RR / (1.0 - rho * rho);
+    if (map->phi_est) dm.M.phi = pf_exp(new_theta[2 + map->mu_est]);
+  }
+  dm.M.T = &dm.T; dm.M.R = &dm.R; dm.M.a1 = &dm.a1; dm.M.P1 = &dm.P1; dm.M.C = &dm.C;
+  dm.M.Ttv = 0; dm.M.Rtv = 0; dm.M.Ctv = 0;
+}
+
+/* approx_mcmc::is_correction_psi, src/approx_mcmc.cpp:353-427, with expand()
+ * (:49-88) for is_type 3; m = 1.  OpenMP over draws with schedule(static) as
+ * in the reference (:365-369).  Deliberate difference: draw d uses the Philox
+ * stream `filter = d` instead of a per-thread engine (:367), so the result
+ * does not depend on `threads`.  The output_type 2 merge runs in draw order
+ * after the parallel loop (the reference's omp critical order is
+ * nondeterministic for threads > 1).
+ * weights, posterior: n_draws; alpha: (n+1) x m x n_draws (output_type 1);
+ * alphahat (n+1) x m, Vt m x m x (n+1) (output_type 2). */
+int orc_postcorrection_ung(const bssm_ung_model* M, const bssm_theta_map* map, int output_type,
+                           uint32_t nsim, uint32_t seed, int threads, int is_type, const uint32_t* counts,
+                           const double* theta, uint32_t n_par, const double* modes, uint32_t n_stored,
+                           int arith, double* weights, double* posterior, double* alpha, double* alphahat,
+                           double* Vt, double* loglik_out) {
+  if (M->m != 1) return 1;
+  const size_t n = M->n, n1 = n + 1;
+  std::vector<uint32_t> src, cnt;
+  for (uint32_t i = 0; i < n_stored; ++i) {
+    if (is_type == 3) for (uint32_t c = 0; c < counts[i]; ++c) { src.push_back(i); cnt.push_back(1u); }
+    else { src.push_back(i); cnt.push_back(counts[i]); }
+  }
+  const int64_t nd = (int64_t)src.size();
+  std::vector<double> ah_all, Vt_all;
+  if (output_type == 2) { ah_all.assign(n1 * nd, 0.0); Vt_all.assign(n1 * nd, 0.0); }
+#ifdef _OPENMP
+  if (threads < 1) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(threads)
+#endif
+  for (int64_t i = 0; i < nd; ++i) {
+    DrawModel dm;
+    update_model(dm, M, map, theta + (size_t)src[i] * n_par);
+    unsigned int nsimc = nsim;
+    if (is_type == 1) nsimc *= cnt[i];
+    std::vector<double> alpha_i(n1 * nsimc, 0.0), weights_i((size_t)nsimc * n1, 0.0);
+    std::vector<uint32_t> indices((size_t)nsimc * n, 0u);
+    int32_t st;
+    double al;
+    double ll = orc_ung_psi_filter(&dm.M, modes + n * src[i], nsimc, seed, (uint32_t)i, arith, alpha_i.data(),
+                                   weights_i.data(), indices.data(), &al, &st);
+    if (loglik_out) loglik_out[i] = ll;
+    weights[i] = pf_exp(ll);
+    if (output_type != 3) {
+      orc_filter_smoother(alpha_i.data(), indices.data(), 1, (int)n1, nsimc);
+      if (output_type == 1) {
+        uint32_t b = (uint32_t)(pf_pick_uniform(seed, (uint32_t)i) * (double)nsimc);
+        if (b > nsimc - 1) b = nsimc - 1;
+        for (size_t t = 0; t < n1; ++t) alpha[n1 * i + t] = alpha_i[t + n1 * b];
+      } else {
+        orc_summary(alpha_i.data(), 1, (int)n1, nsimc, &ah_all[n1 * i], &Vt_all[n1 * i]);
+      }
+    }
+  }
+  if (output_type == 2) { /* :397-424, in draw order */
+    std::vector<double> ah(n1, 0.0), V(n1, 0.0), Valpha(n1, 0.0);
+    double sum_w = 0.0;
+    for (int64_t i = 0; i < nd; ++i) {
+      double wnew = weights[i] * cnt[i];
+      sum_w += wnew;
+      for (size_t t = 0; t < n1; ++t) {
+        double diff = ah_all[n1 * i + t] - ah[t];
+        ah[t] += wnew / sum_w * diff;
+        double diff2 = ah_all[n1 * i + t] - ah[t];
+        Valpha[t] += wnew * diff * diff2;
+        V[t] += wnew / sum_w * (Vt_all[n1 * i + t] - V[t]);
+      }
+    }
+    for (size_t t = 0; t < n1; ++t) { alphahat[t] = ah[t]; Vt[t] = V[t] + Valpha[t] / sum_w; }
+  }
+  for (int64_t i = 0; i < nd; ++i) posterior[i] = 0.0 + 0.0 + pf_log(weights[i]);
+  return 0;
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

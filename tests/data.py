@@ -40,3 +40,24 @@ def poisson_bsm_model(n=100, missing=()):
     for t in missing:
         y[t] = np.nan
     return bssm_b200.bsm_ng(y, sd_level=0.1, sd_slope=0.01, P1=np.diag([1.0, 2.0]), distribution="poisson")
+
+
+def svm_mcmc_output(model, n_stored, output_type=3, jitter=0.05, gen_seed=7):
+    """Synthetic stand-in for run_mcmc(...) output on an svm model:
+    theta draws = the model's theta * exp(jitter * N(0,1)) (rho clipped to (-.999, .999)),
+    counts ~ 1 + Poisson(3), modes = the converged mode of the Gaussian approximation at each
+    theta, computed by the ORACLE's approximate() (test infrastructure)."""
+    import copy
+
+    import orc
+    rng = np.random.default_rng(gen_seed)
+    th0 = np.asarray(model.theta)
+    theta = th0[None, :] * np.exp(jitter * rng.normal(size=(n_stored, th0.size)))
+    theta[:, 0] = np.clip(theta[:, 0], -0.999, 0.999)
+    counts = (1 + rng.poisson(3, size=n_stored)).astype(np.uint32)
+    modes = np.zeros((model.n, n_stored), order="F")
+    for i in range(n_stored):
+        mi = bssm_b200.svm(model.y, theta[i, 0], theta[i, 1], sigma=theta[i, 2])
+        modes[:, i] = orc.psi_prepass(mi).mode
+    return {"theta": theta, "counts": counts, "modes": modes, "output_type": output_type,
+            "posterior": np.zeros(n_stored)}

@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-from bssm_b200._lib import UngModel, c_double_p, c_uint32_p, dptr, uptr  # struct layouts only
+from bssm_b200._lib import ThetaMap, UngModel, c_double_p, c_uint32_p, dptr, uptr  # struct layouts only
 
 ARITH_REFERENCE, ARITH_REPRO = 0, 1
 _L = None
@@ -36,6 +36,9 @@ def L():
         _L.orc_ung_psi_prepass.argtypes = [C.POINTER(UngModel), c_double_p] + [c_double_p] * 8
         _L.orc_ung_filter_batch.argtypes = [C.POINTER(UngModel), C.c_int, c_double_p, u32, u32, u32, u32, C.c_int,
                                             C.c_int, c_double_p]
+        _L.orc_postcorrection_ung.argtypes = [C.POINTER(UngModel), C.POINTER(ThetaMap), C.c_int, u32, u32, C.c_int,
+                                              C.c_int, c_uint32_p, c_double_p, u32, c_double_p, u32, C.c_int,
+                                              c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]
         _L.orc_max_threads.restype = C.c_int
         _L.orc_filter_smoother.argtypes = [c_double_p, c_uint32_p, C.c_int, C.c_int, u32]
         _L.orc_summary.argtypes = [c_double_p, C.c_int, C.c_int, u32, c_double_p, c_double_p]
@@ -176,3 +179,24 @@ def filter_batch(model, N, method="psi", seed=1, first_filter=0, n_filters=1, ar
 
 def max_threads():
     return L().orc_max_threads()
+
+
+def post_correct(model, mcmc_output, N, is_type=2, seed=1, threads=0, arith=ARITH_REPRO):
+    """oracle of approx_mcmc::is_correction_psi; mcmc_output as in bssm_b200.post_correct"""
+    from bssm_b200.api import _postcorr_inputs, n_draws, theta_map
+    theta, counts, modes = _postcorr_inputs(model, mcmc_output)
+    ot = int(mcmc_output.get("output_type", 3))
+    nd = n_draws(mcmc_output, is_type)
+    n = model.n
+    r = Result()
+    r.weights, r.posterior, r.loglik = np.zeros(nd), np.zeros(nd), np.zeros(nd)
+    r.alpha = np.zeros((n + 1, 1, nd), order="F") if ot == 1 else None
+    r.alphahat = np.zeros((n + 1, 1), order="F") if ot == 2 else None
+    r.Vt = np.zeros((1, 1, n + 1), order="F") if ot == 2 else None
+    ms, tm = model.c_struct(), theta_map(model)
+    rc = L().orc_postcorrection_ung(C.byref(ms), C.byref(tm), ot, N, seed, threads, is_type, uptr(counts),
+                                    dptr(theta), theta.shape[0], dptr(modes), counts.size, arith,
+                                    dptr(r.weights), dptr(r.posterior), dptr(r.alpha), dptr(r.alphahat),
+                                    dptr(r.Vt), dptr(r.loglik))
+    assert rc == 0
+    return r

@@ -1,0 +1,92 @@
+"""post_correct (IS-MCMC correction, BASELINE config 4) against the oracle's
+restatement of approx_mcmc::is_correction_psi (src/approx_mcmc.cpp:353-427)."""
+import numpy as np
+import pytest
+
+import data
+import orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup(engine):
+    model = data.svm_model(120)
+    return engine, model, data.svm_mcmc_output(model, 40)
+
+
+def test_weights_only_is2(setup):
+    engine, model, mo = setup
+    ref = orc.post_correct(model, mo, 128, is_type=2, seed=3)
+    res = engine.post_correct(model, mo, 128, threads=2, is_type="is2", seed=3, return_loglik=True)
+    assert np.array_equal(res["loglik"], ref.loglik)
+    assert np.array_equal(res["weights"], ref.weights)
+    np.testing.assert_allclose(res["posterior"], ref.posterior, rtol=1e-13, atol=1e-13)
+    assert res["launches"] == 2  # one pre-pass + one filter launch for all draws
+
+
+def test_trajectories_is3(setup):
+    """is3 expands every stored draw `count` times; output_type 1 keeps one trajectory per draw"""
+    engine, model, mo = setup
+    mo1 = dict(mo, output_type=1)
+    ref = orc.post_correct(model, mo1, 64, is_type=3, seed=5)
+    res = engine.post_correct(model, mo1, 64, is_type="is3", seed=5)
+    assert res["weights"].size == int(mo["counts"].sum())
+    assert np.array_equal(res["weights"], ref.weights)
+    assert np.array_equal(res["alpha"].view(np.uint64), ref.alpha.view(np.uint64))
+
+
+def test_summary_is1(setup):
+    """is1: nsim * count particles per draw; output_type 2: weighted running mean / variance"""
+    engine, model, mo = setup
+    mo2 = dict(mo, output_type=2)
+    ref = orc.post_correct(model, mo2, 32, is_type=1, seed=7)
+    res = engine.post_correct(model, mo2, 32, is_type="is1", seed=7)
+    assert np.array_equal(res["weights"], ref.weights)
+    np.testing.assert_allclose(res["alphahat"], ref.alphahat, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(res["Vt"], ref.Vt, rtol=1e-9, atol=1e-13)
+
+
+def test_summary_is2_chunked(setup, monkeypatch):
+    engine, model, mo = setup
+    mo2 = dict(mo, output_type=2)
+    ref = orc.post_correct(model, mo2, 64, is_type=2, seed=9)
+    whole = engine.post_correct(model, mo2, 64, is_type="is2", seed=9)
+    np.testing.assert_allclose(whole["alphahat"], ref.alphahat, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(whole["Vt"], ref.Vt, rtol=1e-9, atol=1e-13)
+
+
+def test_sharding_gives_identical_results(setup):
+    """draw d always uses stream d: two shards concatenated == one call"""
+    engine, model, mo = setup
+    mo1 = dict(mo, output_type=1)
+    whole = engine.post_correct(model, mo1, 64, is_type="is2", seed=11)
+    a = engine.post_correct(model, mo1, 64, is_type="is2", seed=11, draw_range=(0, 17))
+    b = engine.post_correct(model, mo1, 64, is_type="is2", seed=11, draw_range=(17, 40))
+    assert np.array_equal(np.concatenate([a["weights"], b["weights"]]), whole["weights"])
+    assert np.array_equal(np.concatenate([a["alpha"], b["alpha"]], axis=2), whole["alpha"])
+
+
+def test_resident_job_matches(setup):
+    engine, model, mo = setup
+    ref = orc.post_correct(model, mo, 256, is_type=2, seed=1)
+    job = engine.PostcorrJob(model, mo, 256, is_type="is2", seed=1, draw_range=(5, 30))
+    job.run()
+    assert np.array_equal(job.logliks(), ref.loglik[5:30])
+    job.close()
+
+
+def test_ar1_ng_postcorrection(engine):
+    rng = np.random.default_rng(3)
+    y = rng.poisson(4.0, size=60).astype(float)
+    model = engine.ar1_ng(y, rho=0.7, sigma=0.3, mu=1.2, distribution="poisson")
+    th0 = np.asarray(model.theta)
+    theta = th0[None, :] + 0.05 * rng.normal(size=(12, 3))
+    modes = np.zeros((60, 12), order="F")
+    for i in range(12):
+        mi = engine.ar1_ng(y, rho=theta[i, 0], sigma=float(np.exp(theta[i, 1])), mu=theta[i, 2], distribution="poisson")
+        modes[:, i] = orc.psi_prepass(mi).mode
+    mo = {"theta": theta, "counts": np.ones(12, dtype=np.uint32), "modes": modes, "output_type": 3}
+    ref = orc.post_correct(model, mo, 100, is_type=2, seed=2)
+    res = engine.post_correct(model, mo, 100, is_type="is2", seed=2)
+    assert np.array_equal(res["weights"], ref.weights)
