@@ -178,8 +178,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--filters", type=int, default=int(os.environ.get("BENCH_FILTERS", "9")),
-                    help="replicate filters per GPU per step")
+    ap.add_argument("--filters", type=int, default=int(os.environ.get("BENCH_FILTERS", "0")),
+                    help="replicate filters per GPU per step (0 = 2x what the device runs concurrently)")
+    ap.add_argument("--no-c4", action="store_true", help="skip the post_correct (config 4) leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -215,6 +216,10 @@ def main():
     w = WORKLOAD
     N, n, B = w["N"], w["n"], args.filters
     model = make_model()
+    if B <= 0:
+        probe = bssm_b200.FilterJob(model, N, method="psi", seed=1, n_filters=1, out_flags=0)
+        B = 2 * max(1, probe.max_concurrent_filters())
+        probe.close()
     job = bssm_b200.FilterJob(model, N, method="psi", seed=1, n_filters=B, first_filter=rank * B,
                               out_flags=7)
     for _ in range(args.warmup):
@@ -283,6 +288,49 @@ def main():
                "call": "bssm_b200_psi_filter (1 filter per call, alpha cube + weights to pinned host memory)",
                "loglik_check": out.loglik}
 
+    # ---- config 4: post_correct, 15000 draws x psi-APF N=256, sharded over the ranks
+    c4 = None
+    if not args.no_c4:
+        from bssm_b200.distributed import shard_range
+        nd, Np = 15000, 256
+        mo = bssm_b200.synthetic_svm_mcmc_output(model, nd)  # same inputs on every rank (seeded)
+        b, e = shard_range(nd, rank, world)
+        pj = bssm_b200.PostcorrJob(model, mo, Np, is_type="is2", seed=1, draw_range=(b, e))
+        ll_loc = torch.empty(e - b, dtype=torch.float64, device="cuda")
+        maxlen = max(shard_range(nd, r, world)[1] - shard_range(nd, r, world)[0] for r in range(world))
+        pad = torch.zeros(maxlen, dtype=torch.float64, device="cuda")
+        outs = [torch.empty_like(pad) for _ in range(world)]
+
+        def c4_step():
+            ms = pj.run()
+            pj.logliks_to_device(ll_loc.data_ptr())
+            if dist is not None:  # the single NCCL gather of per-draw log-likelihoods
+                pad[:e - b] = ll_loc
+                dist.all_gather(outs, pad)
+            return ms
+        for _ in range(args.warmup):
+            c4_step()
+        barrier()
+        t0 = time.perf_counter()
+        c4_dev = [c4_step() for _ in range(args.steps)]
+        barrier()
+        c4_wall = time.perf_counter() - t0
+        tt = torch.tensor([sum(c4_dev), c4_wall * 1e3], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        c4_launches = pj.launches() * args.steps
+        wsum = float(torch.exp(ll_loc).sum())
+        c4 = {"workload": "c4: post_correct svm, 15000 draws x psi-APF N=256, T=1000, weights only, is2",
+              "draws": nd, "draws_per_s": nd * args.steps / (float(tt[1]) * 1e-3),
+              "particle_steps_per_s": nd * Np * n * args.steps / (float(tt[1]) * 1e-3),
+              "ms_per_pass_wall": float(tt[1]) / args.steps,
+              "ms_per_pass_device_max_rank": float(tt[0]) / args.steps,
+              "timing": "wall clock over K passes incl. the NCCL all_gather, max over ranks",
+              "sharding": "contiguous static blocks of draws per rank, one all_gather of log-likelihoods",
+              "launches": c4_launches, "rank0_weight_sum": wsum}
+        pj.close()
+        launches += c4_launches
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -321,6 +369,8 @@ def main():
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if c4 is not None:
+        line["post_correct"] = c4
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_leg()
     print(json.dumps(line), flush=True)

@@ -5,5 +5,6 @@ particle smoother, IS-MCMC post-correction); see DESIGN.md for scope.
 """
 from .models import Model, ar1_ng, bsm_ng, init_mode, ssm_ung, svm  # noqa: F401
 from .api import (FilterJob, PostcorrJob, bootstrap_filter, logLik, particle_smoother,  # noqa: F401
-                  post_correct, stratified_sample)
+                  post_correct, stratified_sample, gaussian_approx_mode,
+                  synthetic_svm_mcmc_output)
 from ._lib import EngineError, lib  # noqa: F401

@@ -81,6 +81,7 @@ def lib():
     L.bssm_b200_job_create_ung.argtypes = [
         C.POINTER(UngModel), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
         C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.bssm_b200_approximate_mode.argtypes = [C.POINTER(UngModel), c_double_p]
     pc_args = [C.POINTER(UngModel), C.POINTER(ThetaMap)]
     L.bssm_b200_postcorrection_nongaussian.argtypes = pc_args + [
         C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, c_uint32_p, c_double_p, C.c_uint32, c_double_p,

@@ -267,3 +267,32 @@ class PostcorrJob(FilterJob):
         check(lib().bssm_b200_job_create_postcorr(
             C.byref(self._ms), C.byref(self._tm), N, seed, it, uptr(counts), dptr(theta), theta.shape[0],
             dptr(modes), counts.size, b, e, C.byref(self._h)))
+
+
+def gaussian_approx_mode(model):
+    """mode of the Gaussian approximation (ssm_ung::approximate), from model.initial_mode"""
+    ms = model.c_struct()
+    mode = np.zeros(model.n)
+    check(lib().bssm_b200_approximate_mode(C.byref(ms), dptr(mode)))
+    return mode
+
+
+def synthetic_svm_mcmc_output(model, n_stored, output_type=3, jitter=0.05, gen_seed=7):
+    """Synthetic stand-in for run_mcmc output on an svm model (BASELINE config 4):
+    theta_i = theta * exp(jitter * N(0,1)) with rho clipped to (-.999, .999),
+    counts ~ 1 + Poisson(3), modes_i = converged mode at theta_i (Newton sweeps
+    warm-started from the mode at theta)."""
+    from . import models
+    rng = np.random.default_rng(gen_seed)
+    th0 = np.asarray(model.theta)
+    theta = th0[None, :] * np.exp(jitter * rng.normal(size=(n_stored, th0.size)))
+    theta[:, 0] = np.clip(theta[:, 0], -0.999, 0.999)
+    counts = (1 + rng.poisson(3, size=n_stored)).astype(np.uint32)
+    base = gaussian_approx_mode(model)
+    modes = np.zeros((model.n, n_stored), order="F")
+    for i in range(n_stored):
+        mi = models.svm(model.y, theta[i, 0], theta[i, 1], sigma=theta[i, 2])
+        mi.initial_mode = base + 2 * np.log(th0[2] / theta[i, 2])  # the signal shifts with log sigma
+        modes[:, i] = gaussian_approx_mode(mi)
+    return {"theta": theta, "counts": counts, "modes": modes, "output_type": output_type,
+            "posterior": np.zeros(n_stored)}

@@ -848,6 +848,16 @@ int make_draw_job(const bssm_ung_model* M, const bssm_theta_map* map, const Draw
 
 } // namespace
 
+int bssm_b200_approximate_mode(const bssm_ung_model* M, double* mode) {
+  if (!M || !mode || !M->initial_mode) return fail(BSSM_B200_ERR_ARG, "null argument");
+  if (M->m != 1) return fail(BSSM_B200_ERR_UNSUPPORTED, "approximate_mode: m = 1 only in this build");
+  if (M->max_iter < 1) return fail(BSSM_B200_ERR_ARG, "max_iter must be >= 1");
+  std::vector<double> md, lin;
+  ung_approximate_m1(M, md, lin);
+  memcpy(mode, md.data(), sizeof(double) * M->n);
+  return 0;
+}
+
 int bssm_b200_job_create_postcorr(const bssm_ung_model* M, const bssm_theta_map* map, uint32_t nsim,
                                   uint32_t seed, int is_type, const uint32_t* counts, const double* theta,
                                   uint32_t n_par, const double* modes, uint32_t n_stored,

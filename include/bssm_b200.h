@@ -154,6 +154,14 @@ int bssm_b200_psi_smoother(const bssm_ung_model* model, uint32_t nsim, uint32_t 
 int bssm_b200_psi_filter(const bssm_ung_model* model, uint32_t nsim, uint32_t seed,
                          bssm_filter_out* out);
 
+/* Mode of the Gaussian approximation: the Newton / Laplace iterations of
+ * ssm_ung::approximate (src/model_ssm_ung.cpp:87-140) started from
+ * model->initial_mode, m = 1.  This is what run_mcmc stores per draw in
+ * mcmc_output$modes and post_correct consumes.  Host computation (O(n) per
+ * sweep, sequential in t); exported so callers can build post-correction
+ * inputs without R. */
+int bssm_b200_approximate_mode(const bssm_ung_model* model, double* mode);
+
 /* ---- IS-MCMC post-correction ---------------------------------------------- */
 /* How theta maps onto the model (the C++ update_model of the model class):
  * svm src/model_svm.cpp:12-29, ar1_ng src/model_ar1_ng.cpp:12-36. */

@@ -14,11 +14,16 @@ runs = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
 N = int(os.environ.get("PROF_N", "65536"))
 model = data.svm_model(n)
+if filters == 0:  # auto: as many filters as the device runs concurrently
+    probe = bssm_b200.FilterJob(model, N, method="psi", seed=1, n_filters=1, out_flags=0)
+    filters = probe.max_concurrent_filters()
+    probe.close()
 job = bssm_b200.FilterJob(model, N, method="psi", seed=1, n_filters=filters, out_flags=7)
+print("filters", filters)
 print("max concurrent filters", job.max_concurrent_filters())
 for _ in range(runs):
     ms = job.run()
-    print("run ms", ms, job.kernel_ms(), "loglik", job.logliks()[:2])
+    print("run ms", ms, job.kernel_ms(), "p-s/s %.3e" % (filters * N * n / ms * 1e3), "loglik", job.logliks()[:2])
 if os.environ.get('BSSM_B200_PHASES'):
     for cta in (0, 7, 15):
         pc = job.phase_cycles(cta)
