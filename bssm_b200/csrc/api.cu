@@ -16,6 +16,8 @@
 #include <string>
 #include <vector>
 #include <limits>
+#include <mutex>
+#include <algorithm>
 
 #include "bssm_b200.h"
 #include "pf_device.cuh"
@@ -324,16 +326,68 @@ void ung_approximate_m1(const bssm_ung_model* M, std::vector<double>& mode, std:
   }
 }
 
+// Device memory is recycled between calls: a one-shot entry point allocates
+// gigabytes of outputs, and cudaMalloc / cudaFree of that size cost more than
+// the kernels.  Freed blocks are kept (up to BSSM_B200_POOL_GB, default 48) and
+// handed back for requests of the same size class; bssm_b200_shutdown() releases
+// them.
+struct Pool {
+  struct Block { void* p; size_t bytes; };
+  std::vector<Block> free_blocks;
+  size_t cached = 0;
+  std::mutex mu;
+  static size_t size_class(size_t b) { return b <= 4096 ? 4096 : ((b + (1u << 20) - 1) >> 20) << 20; }
+  cudaError_t alloc(void** p, size_t bytes) {
+    const size_t sc = size_class(bytes);
+    {
+      std::lock_guard<std::mutex> g(mu);
+      for (size_t i = 0; i < free_blocks.size(); ++i)
+        if (free_blocks[i].bytes == sc) {
+          *p = free_blocks[i].p;
+          cached -= sc;
+          free_blocks.erase(free_blocks.begin() + i);
+          return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, sc);
+    if (e != cudaSuccess) { // out of memory: drop the cache and retry once
+      cudaGetLastError();
+      release_all();
+      e = cudaMalloc(p, sc);
+    }
+    return e;
+  }
+  void free(void* p, size_t bytes) {
+    const size_t sc = size_class(bytes);
+    const size_t limit = (size_t)env_int("BSSM_B200_POOL_GB", 48) << 30;
+    std::lock_guard<std::mutex> g(mu);
+    if (cached + sc > limit) { cudaFree(p); return; }
+    free_blocks.push_back({p, sc});
+    cached += sc;
+  }
+  void release_all() {
+    std::lock_guard<std::mutex> g(mu);
+    for (auto& b : free_blocks) cudaFree(b.p);
+    free_blocks.clear();
+    cached = 0;
+  }
+};
+Pool g_pool;
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t count = 0;
-  ~DevBuf() { if (p) cudaFree(p); }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) g_pool.free(p, count * sizeof(T));
+    p = nullptr;
+  }
   int alloc(size_t n) {
-    if (p) { cudaFree(p); p = nullptr; }
+    release();
     count = n;
     if (n == 0) return 0;
-    CU(cudaMalloc(&p, n * sizeof(T)));
+    CU(g_pool.alloc((void**)&p, n * sizeof(T)));
     return 0;
   }
   int upload(const T* h, size_t n) {
@@ -472,6 +526,7 @@ int bssm_b200_set_device(int device) {
 }
 
 void bssm_b200_shutdown(void) {
+  g_pool.release_all();
   int cnt = 0;
   if (cudaGetDeviceCount(&cnt) == cudaSuccess && cnt > 0) cudaDeviceSynchronize();
   cudaGetLastError();
@@ -742,12 +797,12 @@ int bssm_b200_job_fetch(bssm_b200_job* J, uint32_t f, bssm_filter_out* out) {
   }
   if (out->weights) {
     if (!J->keep_weights) return fail(BSSM_B200_ERR_ARG, "job was created without BSSM_OUT_WEIGHTS");
-    memset(out->weights, 0, sizeof(double) * (size_t)N * (n + 1));
+    if (stopped >= 0) memset(out->weights + (size_t)N * cols_w, 0, sizeof(double) * (size_t)N * (n + 1 - cols_w));
     CU(cudaMemcpy(out->weights, J->weights.p + (size_t)f * J->weights_stride, sizeof(double) * (size_t)N * cols_w, cudaMemcpyDeviceToHost));
   }
   if (out->indices) {
     if (!J->keep_indices) return fail(BSSM_B200_ERR_ARG, "job was created without BSSM_OUT_INDICES");
-    memset(out->indices, 0, sizeof(uint32_t) * (size_t)N * n);
+    if (stopped >= 0) memset(out->indices + (size_t)N * cols_i, 0, sizeof(uint32_t) * (size_t)N * (n - cols_i));
     CU(cudaMemcpy(out->indices, J->indices.p + (size_t)f * J->indices_stride, sizeof(uint32_t) * (size_t)N * cols_i, cudaMemcpyDeviceToHost));
   }
   if (J->post == BSSM_POST_FILTER_SUMMARY) {
