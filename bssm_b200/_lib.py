@@ -39,6 +39,19 @@ class FilterOut(C.Structure):
     ]
 
 
+class NlgModel(C.Structure):
+    """bssm_nlg_model"""
+    _fields_ = [("model_id", C.c_int32), ("n", C.c_int32), ("p", C.c_int32), ("m", C.c_int32), ("k", C.c_int32),
+                ("y", c_double_p), ("theta", c_double_p), ("n_theta", C.c_int32),
+                ("known_params", c_double_p), ("n_known", C.c_int32)]
+
+
+class SdeModel(C.Structure):
+    """bssm_sde_model"""
+    _fields_ = [("model_id", C.c_int32), ("n", C.c_int32), ("y", c_double_p), ("theta", c_double_p),
+                ("n_theta", C.c_int32), ("x0", C.c_double), ("positive", C.c_int32)]
+
+
 class ThetaMap(C.Structure):
     """bssm_theta_map"""
     _fields_ = [("model_type", C.c_int32), ("svm_type", C.c_int32), ("mu_est", C.c_int32), ("phi_est", C.c_int32)]
@@ -81,6 +94,15 @@ def lib():
     L.bssm_b200_job_create_ung.argtypes = [
         C.POINTER(UngModel), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
         C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    for name in ("bssm_b200_bsf_nlg", "bssm_b200_bsf_smoother_nlg"):
+        getattr(L, name).argtypes = [C.POINTER(NlgModel), C.c_uint32, C.c_uint32, C.POINTER(FilterOut)]
+    for name in ("bssm_b200_bsf_sde", "bssm_b200_bsf_smoother_sde"):
+        getattr(L, name).argtypes = [C.POINTER(SdeModel), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(FilterOut)]
+    L.bssm_b200_loglik_sde.argtypes = [C.POINTER(SdeModel), C.c_uint32, C.c_uint32, C.c_uint32, c_double_p]
+    L.bssm_b200_job_create_nlg.argtypes = [C.POINTER(NlgModel), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                           C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.bssm_b200_job_create_sde.argtypes = [C.POINTER(SdeModel), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                           C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.bssm_b200_approximate_mode.argtypes = [C.POINTER(UngModel), c_double_p]
     pc_args = [C.POINTER(UngModel), C.POINTER(ThetaMap)]
     L.bssm_b200_postcorrection_nongaussian.argtypes = pc_args + [

@@ -60,12 +60,25 @@ def _warn_stopped(out):
         warnings.warn("Particle filtering stopped prematurely due to nonfinite log-likelihood.")
 
 
-def bootstrap_filter(model, particles, seed=1, return_indices=False):
-    """bootstrap_filter.nongaussian, R/bootstrap_filter.R:85-120."""
+def bootstrap_filter(model, particles, seed=1, return_indices=False, L=None):
+    """bootstrap_filter: .nongaussian R/bootstrap_filter.R:85-120, .ssm_nlg :127-159,
+    .ssm_sde :165-202 (L = discretisation level, 2^L Milstein sub-steps)."""
     N, seed = _check_particles(model, particles, seed)
     b = _Buffers(model, N, indices=return_indices, filt=True)
     ms = model.c_struct()
-    check(lib().bssm_b200_bsf(C.byref(ms), N, seed, C.byref(b.out)))
+    if model.cls == "ssm_nlg":
+        check(lib().bssm_b200_bsf_nlg(C.byref(ms), N, seed, C.byref(b.out)))
+    elif model.cls == "ssm_sde":
+        if L is None or int(L) < 1:
+            raise ValueError("Discretization level L must be larger than 0.")  # R/bootstrap_filter.R:169
+        # the reference returns att / Ptt with n+1 columns for SDE models (last one zero)
+        n, m = model.n, model.m
+        b.att = np.zeros((m, n + 1), order="F")
+        b.Ptt = np.zeros((m, m, n + 1), order="F")
+        b.out.att, b.out.Ptt = dptr(b.att), dptr(b.Ptt)
+        check(lib().bssm_b200_bsf_sde(C.byref(ms), N, int(L), seed, C.byref(b.out)))
+    else:
+        check(lib().bssm_b200_bsf(C.byref(ms), N, seed, C.byref(b.out)))
     _warn_stopped(b.out)
     res = {"at": b.at.T.copy(), "att": b.att.T.copy(), "Pt": b.Pt, "Ptt": b.Ptt,
            "weights": b.weights, "logLik": b.out.loglik,
@@ -76,15 +89,25 @@ def bootstrap_filter(model, particles, seed=1, return_indices=False):
     return res
 
 
-def particle_smoother(model, particles, method="psi", seed=1, return_indices=False):
-    """particle_smoother.nongaussian, R/particle_smoother.R:140-186."""
+def particle_smoother(model, particles, method="psi", seed=1, return_indices=False, L=None):
+    """particle_smoother: .nongaussian R/particle_smoother.R:140-186, .ssm_nlg :192-245,
+    .ssm_sde :251-291."""
     if method not in ("psi", "bsf"):
-        raise ValueError("method must be 'psi' or 'bsf' (EKPF is for ssm_nlg models)")
+        raise ValueError("method must be 'psi' or 'bsf' (EKPF is out of scope)")
     N, seed = _check_particles(model, particles, seed)
     b = _Buffers(model, N, indices=return_indices, smooth=True)
     ms = model.c_struct()
-    fn = lib().bssm_b200_psi_smoother if method == "psi" else lib().bssm_b200_bsf_smoother
-    check(fn(C.byref(ms), N, seed, C.byref(b.out)))
+    if model.cls == "ssm_nlg":
+        if method != "bsf":
+            raise ValueError("ssm_nlg: only method='bsf' is implemented in this build")
+        check(lib().bssm_b200_bsf_smoother_nlg(C.byref(ms), N, seed, C.byref(b.out)))
+    elif model.cls == "ssm_sde":
+        if L is None or int(L) < 1:
+            raise ValueError("Discretization level L must be larger than 0.")
+        check(lib().bssm_b200_bsf_smoother_sde(C.byref(ms), N, int(L), seed, C.byref(b.out)))
+    else:
+        fn = lib().bssm_b200_psi_smoother if method == "psi" else lib().bssm_b200_bsf_smoother
+        check(fn(C.byref(ms), N, seed, C.byref(b.out)))
     _warn_stopped(b.out)
     res = {"alphahat": b.alphahat.T.copy(), "Vt": b.Vt, "weights": b.weights,
            "logLik": b.out.loglik, "alpha": np.transpose(b.alpha, (1, 0, 2)),
@@ -100,15 +123,22 @@ class FilterJob:
     inputs and outputs, run() launches kernels only."""
 
     def __init__(self, model, particles, method="psi", seed=1, n_filters=1, first_filter=0,
-                 out_flags=0, post=POST_NONE):
+                 out_flags=0, post=POST_NONE, L=None):
         N, seed = _check_particles(model, particles, seed)
         self.model, self.N, self.n_filters = model, N, int(n_filters)
         self._ms = model.c_struct()
         self._h = C.c_void_p()
         meth = METHOD_PSI if method == "psi" else METHOD_BSF
-        check(lib().bssm_b200_job_create_ung(C.byref(self._ms), meth, N, seed, self.n_filters,
-                                             int(first_filter), int(out_flags), int(post),
-                                             C.byref(self._h)))
+        if model.cls == "ssm_nlg":
+            check(lib().bssm_b200_job_create_nlg(C.byref(self._ms), N, seed, self.n_filters, int(first_filter),
+                                                 int(out_flags), int(post), C.byref(self._h)))
+        elif model.cls == "ssm_sde":
+            check(lib().bssm_b200_job_create_sde(C.byref(self._ms), N, int(L), seed, self.n_filters,
+                                                 int(first_filter), int(out_flags), int(post), C.byref(self._h)))
+        else:
+            check(lib().bssm_b200_job_create_ung(C.byref(self._ms), meth, N, seed, self.n_filters,
+                                                 int(first_filter), int(out_flags), int(post),
+                                                 C.byref(self._h)))
 
     def run(self):
         ms = C.c_float()
@@ -156,9 +186,9 @@ class FilterJob:
             pass
 
 
-def logLik(model, particles, method="psi", seed=1):
-    """logLik.nongaussian (particle part), R/loglik.R:60-120: log-likelihood only."""
-    job = FilterJob(model, particles, method=method, seed=seed)
+def logLik(model, particles, method="psi", seed=1, L=None):
+    """logLik (particle part), R/loglik.R:60-161: log-likelihood only."""
+    job = FilterJob(model, particles, method=method, seed=seed, L=L)
     try:
         job.run()
         return float(job.logliks()[0])

@@ -24,6 +24,7 @@
 #include "models_ung.cuh"
 #include "prepass_ung.cuh"
 #include "smoother_kernels.cuh"
+#include "models_nlg_sde.cuh"
 
 namespace {
 
@@ -401,7 +402,10 @@ struct DevBuf {
 } // namespace
 
 // ------------------------------------------------------------------- job
+enum { KIND_UNG = 0, KIND_NLG = 1, KIND_SDE = 2 };
+
 struct bssm_b200_job {
+  int kind = KIND_UNG;
   int method = 0, post = 0, out_flags = 0;
   uint32_t N = 0, n_filters = 0, first_filter = 0, seed = 0;
   int n = 0, m = 0, k = 0;
@@ -429,6 +433,8 @@ struct bssm_b200_job {
   size_t alpha_stride = 0, weights_stride = 0, indices_stride = 0;
   bool keep_alpha = false, keep_weights = false, keep_indices = false;
   pf::UngParams up{};
+  pf::NlgParams np{};
+  pf::SdeParams sp{};
   pf::PrepassParams pp{};
   pf::FilterParams fp{};
   ~bssm_b200_job() {
@@ -486,6 +492,8 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
   fp.xch = J->xch.p + (size_t)f0 * 4 * J->geo.ranks;
   fp.ubuf = J->ubuf.p + (size_t)f0 * J->N;
   if (fp.phase_cycles) fp.phase_cycles = J->phases.p + (size_t)f0 * 6 * J->geo.ranks;
+  if (J->kind == KIND_NLG) return launch_filter<pf::NlgGrowthBsf>(fp, J->np, J->geo, nf, J->stream);
+  if (J->kind == KIND_SDE) return launch_filter<pf::SdeGbmBsf>(fp, J->sp, J->geo, nf, J->stream);
   pf::UngParams up = J->up;
   if (J->method == BSSM_METHOD_PSI) {
     up.alphahat += (size_t)f0 * J->pstride; up.Lt += (size_t)f0 * J->pstride; up.Ct += (size_t)f0 * J->pstride;
@@ -530,6 +538,54 @@ void bssm_b200_shutdown(void) {
   int cnt = 0;
   if (cudaGetDeviceCount(&cnt) == cudaSuccess && cnt > 0) cudaDeviceSynchronize();
   cudaGetLastError();
+}
+
+// allocates the outputs / exchange buffers common to every model kind and fills FilterParams
+static int finish_job(bssm_b200_job* J, int out_flags, int post) {
+  int rc;
+  const int n = J->n, m = J->m;
+  const uint32_t nsim = J->N, n_filters = J->n_filters;
+  // ---- outputs
+  const bool smooth = post == BSSM_POST_SMOOTHER || post == BSSM_POST_SMOOTHER_MERGE;
+  J->keep_alpha = (out_flags & BSSM_OUT_ALPHA) || post != BSSM_POST_NONE;
+  J->keep_weights = (out_flags & BSSM_OUT_WEIGHTS) || post == BSSM_POST_FILTER_SUMMARY;
+  J->keep_indices = (out_flags & BSSM_OUT_INDICES) || smooth || post == BSSM_POST_PICK;
+  J->alpha_stride = (size_t)(J->keep_alpha ? n + 1 : 2) * m * nsim;
+  J->weights_stride = J->keep_weights ? (size_t)nsim * (n + 1) : 0;
+  J->indices_stride = J->keep_indices ? (size_t)nsim * n : (size_t)nsim;
+  if ((rc = J->alpha_tm.alloc(J->alpha_stride * n_filters))) return rc;
+  if (J->keep_weights && (rc = J->weights.alloc(J->weights_stride * n_filters))) return rc;
+  if ((rc = J->indices.alloc(J->indices_stride * n_filters))) return rc;
+  if (smooth && (rc = J->alpha_sm.alloc(J->alpha_stride * n_filters))) return rc;
+  if (post == BSSM_POST_PICK && (rc = J->traj.alloc((size_t)n_filters * (n + 1) * m))) return rc;
+  if ((rc = J->loglik.alloc(n_filters)) || (rc = J->stopped.alloc(n_filters))) return rc;
+  if ((rc = J->xch.alloc((size_t)4 * J->geo.ranks * n_filters)) || (rc = J->barrier.alloc(1)) ||
+      (rc = J->ubuf.alloc((size_t)nsim * n_filters))) return rc;
+  if (post == BSSM_POST_FILTER_SUMMARY) {
+    if ((rc = J->s_at.alloc((size_t)n_filters * m * (n + 1))) || (rc = J->s_att.alloc((size_t)n_filters * m * n)) ||
+        (rc = J->s_Pt.alloc((size_t)n_filters * m * m * (n + 1))) || (rc = J->s_Ptt.alloc((size_t)n_filters * m * m * n)))
+      return rc;
+  } else if (smooth) {
+    if ((rc = J->s_mean.alloc((size_t)n_filters * m * (n + 1))) || (rc = J->s_cov.alloc((size_t)n_filters * m * m * (n + 1))))
+      return rc;
+  }
+  pf::FilterParams& fp = J->fp;
+  fp.N = nsim; fp.n = n; fp.seed = J->seed; fp.first_filter = J->first_filter;
+  fp.ranks = J->geo.ranks; fp.sync_mode = J->geo.sync_mode;
+  fp.keep_alpha = J->keep_alpha ? 1 : 0;
+  fp.alpha_tm = J->alpha_tm.p; fp.alpha_stride = J->alpha_stride;
+  fp.weights = J->weights.p; fp.weights_stride = J->weights_stride;
+  fp.indices = J->indices.p; fp.indices_stride = J->indices_stride;
+  fp.keep_indices = J->keep_indices ? 1 : 0;
+  fp.loglik = J->loglik.p; fp.stopped_at = J->stopped.p;
+  fp.xch = J->xch.p; fp.barrier = J->barrier.p; fp.ubuf = J->ubuf.p;
+  fp.phase_cycles = nullptr;
+  if (env_int("BSSM_B200_PHASES", 0)) {
+    if ((rc = J->phases.alloc((size_t)6 * J->geo.ranks * n_filters))) return rc;
+    CU(cudaMemset(J->phases.p, 0, sizeof(unsigned long long) * J->phases.count));
+    fp.phase_cycles = J->phases.p;
+  }
+  return 0;
 }
 
 // draw_par (6 x n_filters: T, R, a1, P1, C, phi) and modes (n x n_filters) are
@@ -635,46 +691,7 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
     up.approx_loglik = J->approx_loglik.p; up.pstride = J->pstride;
   }
 
-  // ---- outputs
-  const bool smooth = post == BSSM_POST_SMOOTHER || post == BSSM_POST_SMOOTHER_MERGE;
-  J->keep_alpha = (out_flags & BSSM_OUT_ALPHA) || post != BSSM_POST_NONE;
-  J->keep_weights = (out_flags & BSSM_OUT_WEIGHTS) || post == BSSM_POST_FILTER_SUMMARY;
-  J->keep_indices = (out_flags & BSSM_OUT_INDICES) || smooth || post == BSSM_POST_PICK;
-  J->alpha_stride = (size_t)(J->keep_alpha ? n + 1 : 2) * m * nsim;
-  J->weights_stride = J->keep_weights ? (size_t)nsim * (n + 1) : 0;
-  J->indices_stride = J->keep_indices ? (size_t)nsim * n : (size_t)nsim;
-  if ((rc = J->alpha_tm.alloc(J->alpha_stride * n_filters))) return rc;
-  if (J->keep_weights && (rc = J->weights.alloc(J->weights_stride * n_filters))) return rc;
-  if ((rc = J->indices.alloc(J->indices_stride * n_filters))) return rc;
-  if (smooth && (rc = J->alpha_sm.alloc(J->alpha_stride * n_filters))) return rc;
-  if (post == BSSM_POST_PICK && (rc = J->traj.alloc((size_t)n_filters * (n + 1) * m))) return rc;
-  if ((rc = J->loglik.alloc(n_filters)) || (rc = J->stopped.alloc(n_filters))) return rc;
-  if ((rc = J->xch.alloc((size_t)4 * J->geo.ranks * n_filters)) || (rc = J->barrier.alloc(1)) ||
-      (rc = J->ubuf.alloc((size_t)nsim * n_filters))) return rc;
-  if (post == BSSM_POST_FILTER_SUMMARY) {
-    if ((rc = J->s_at.alloc((size_t)n_filters * m * (n + 1))) || (rc = J->s_att.alloc((size_t)n_filters * m * n)) ||
-        (rc = J->s_Pt.alloc((size_t)n_filters * m * m * (n + 1))) || (rc = J->s_Ptt.alloc((size_t)n_filters * m * m * n)))
-      return rc;
-  } else if (smooth) {
-    if ((rc = J->s_mean.alloc((size_t)n_filters * m * (n + 1))) || (rc = J->s_cov.alloc((size_t)n_filters * m * m * (n + 1))))
-      return rc;
-  }
-  pf::FilterParams& fp = J->fp;
-  fp.N = nsim; fp.n = n; fp.seed = seed; fp.first_filter = first_filter_id;
-  fp.ranks = J->geo.ranks; fp.sync_mode = J->geo.sync_mode;
-  fp.keep_alpha = J->keep_alpha ? 1 : 0;
-  fp.alpha_tm = J->alpha_tm.p; fp.alpha_stride = J->alpha_stride;
-  fp.weights = J->weights.p; fp.weights_stride = J->weights_stride;
-  fp.indices = J->indices.p; fp.indices_stride = J->indices_stride;
-  fp.keep_indices = J->keep_indices ? 1 : 0;
-  fp.loglik = J->loglik.p; fp.stopped_at = J->stopped.p;
-  fp.xch = J->xch.p; fp.barrier = J->barrier.p; fp.ubuf = J->ubuf.p;
-  fp.phase_cycles = nullptr;
-  if (env_int("BSSM_B200_PHASES", 0)) {
-    if ((rc = J->phases.alloc((size_t)6 * J->geo.ranks * n_filters))) return rc;
-    CU(cudaMemset(J->phases.p, 0, sizeof(unsigned long long) * J->phases.count));
-    fp.phase_cycles = J->phases.p;
-  }
+  if ((rc = finish_job(J, out_flags, post))) return rc;
   guard.j = nullptr;
   *job = J;
   return 0;
@@ -692,7 +709,7 @@ int bssm_b200_job_run(bssm_b200_job* J, float* ms_out) {
   int rc;
   J->launches = 0;
   CU(cudaEventRecord(J->ev[0], J->stream));
-  if (J->method == BSSM_METHOD_PSI) {
+  if (J->kind == KIND_UNG && J->method == BSSM_METHOD_PSI) {
     const uint32_t warps_per_block = 4;
     pf::ung_prepass_m1_kernel<<<cdiv(J->n_filters, warps_per_block), 32 * warps_per_block, 0, J->stream>>>(
         J->pp, J->n_filters);
@@ -744,7 +761,9 @@ int bssm_b200_job_phase_cycles(bssm_b200_job* J, uint32_t cta, uint64_t cycles[6
 int bssm_b200_job_max_concurrent_filters(const bssm_b200_job* J) {
   if (!J) return 0;
   int out = 0, rc;
-  if (J->method == BSSM_METHOD_PSI) rc = occupancy<pf::UngPsi1>(J->geo, &out);
+  if (J->kind == KIND_NLG) rc = occupancy<pf::NlgGrowthBsf>(J->geo, &out);
+  else if (J->kind == KIND_SDE) rc = occupancy<pf::SdeGbmBsf>(J->geo, &out);
+  else if (J->method == BSSM_METHOD_PSI) rc = occupancy<pf::UngPsi1>(J->geo, &out);
   else rc = occupancy<pf::UngBsf<1, 1>>(J->geo, &out); // same register budget for all (m, k)
   return rc ? 0 : out;
 }
@@ -774,7 +793,7 @@ int bssm_b200_job_fetch(bssm_b200_job* J, uint32_t f, bssm_filter_out* out) {
   CU(cudaMemcpy(&stopped, J->stopped.p + f, sizeof(int32_t), cudaMemcpyDeviceToHost));
   out->stopped_at = stopped;
   out->approx_loglik = 0.0;
-  if (J->method == BSSM_METHOD_PSI)
+  if (J->kind == KIND_UNG && J->method == BSSM_METHOD_PSI)
     CU(cudaMemcpy(&out->approx_loglik, J->approx_loglik.p + f, sizeof(double), cudaMemcpyDeviceToHost));
   out->device_ms = J->ms[0] + J->ms[1] + J->ms[2];
   // columns the filter never reached stay zero, as in the reference (arma::fill::zeros)
@@ -818,6 +837,150 @@ int bssm_b200_job_fetch(bssm_b200_job* J, uint32_t f, bssm_filter_out* out) {
 }
 
 void bssm_b200_job_destroy(bssm_b200_job* J) { delete J; }
+
+// ------------------------------------------------------------ ssm_nlg / ssm_sde
+namespace {
+
+// psd_chol, src/psd_chol.cpp:5-18
+void psd_chol_host(const double* x, int m, double* L) {
+  const double eps = std::numeric_limits<double>::epsilon();
+  double mx = x[0];
+  for (int d = 1; d < m; ++d) mx = std::max(mx, x[d + (size_t)m * d]);
+  std::vector<double> sub((size_t)m * m, 0.0);
+  for (int c = 0; c < m; ++c)
+    for (int r = 0; r < m; ++r)
+      sub[r + (size_t)m * c] = (x[r + (size_t)m * r] > std::max(eps, eps * m * mx) &&
+                                x[c + (size_t)m * c] > std::max(eps, eps * m * mx)) ? x[r + (size_t)m * c] : 0.0;
+  std::vector<double> Lv;
+  chol_posdiag(sub.data(), m, Lv);
+  for (int e = 0; e < m * m; ++e) L[e] = Lv[e];
+}
+
+int job_common(bssm_b200_job* J, int kind, int n, int m, int k, uint32_t nsim, uint32_t seed,
+               uint32_t n_filters, uint32_t first_filter_id, int out_flags, int post) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (n < 1 || nsim < 2 || n_filters < 1) return fail(BSSM_B200_ERR_ARG, "need n >= 1, nsim >= 2, n_filters >= 1");
+  if (post < 0 || post > BSSM_POST_SMOOTHER) return fail(BSSM_B200_ERR_ARG, "post must be 0, 1 or 2");
+  J->kind = kind; J->method = BSSM_METHOD_BSF; J->post = post; J->out_flags = out_flags;
+  J->N = nsim; J->n_filters = n_filters; J->first_filter = first_filter_id; J->seed = seed;
+  J->n = n; J->m = m; J->k = k;
+  if ((rc = choose_geometry(nsim, &J->geo))) return rc;
+  CU(cudaStreamCreateWithFlags(&J->stream, cudaStreamNonBlocking));
+  for (auto& e : J->ev) CU(cudaEventCreate(&e));
+  return 0;
+}
+
+} // namespace
+
+int bssm_b200_job_create_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t n_filters,
+                             uint32_t first_filter_id, int out_flags, int post, bssm_b200_job** job) {
+  if (!M || !job || !M->y || !M->theta || !M->known_params) return fail(BSSM_B200_ERR_ARG, "null argument");
+  *job = nullptr;
+  if (M->model_id != BSSM_NLG_GROWTH) return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_nlg: unknown model_id (registry: BSSM_NLG_GROWTH)");
+  if (M->p != 1 || M->m != 2 || M->k != 2 || M->n_theta < 3 || M->n_known < 6)
+    return fail(BSSM_B200_ERR_ARG, "growth model: p = 1, m = 2, k = 2, 3 parameters, 6 known parameters");
+  bssm_b200_job* J = new bssm_b200_job();
+  struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
+  int rc = job_common(J, KIND_NLG, M->n, 2, 2, nsim, seed, n_filters, first_filter_id, out_flags, post);
+  if (rc) return rc;
+  if ((rc = J->y.upload(M->y, M->n))) return rc;
+  pf::NlgParams& np = J->np;
+  np.n = M->n; np.y = J->y.p;
+  const double* kp = M->known_params;
+  np.dT = kp[0]; np.K = kp[1];
+  np.a1[0] = kp[2]; np.a1[1] = kp[3];
+  const double P1[4] = {kp[4], 0.0, 0.0, kp[5]};
+  psd_chol_host(P1, 2, np.LP1);
+  np.H = pf_exp(M->theta[0]); np.R0 = pf_exp(M->theta[1]); np.R1 = pf_exp(M->theta[2]);
+  np.wconst = std::log(2.0 * M_PI) + 2.0 * pf_log(np.H);
+  if ((rc = finish_job(J, out_flags, post))) return rc;
+  guard.j = nullptr;
+  *job = J;
+  return 0;
+}
+
+int bssm_b200_job_create_sde(const bssm_sde_model* M, uint32_t nsim, uint32_t L, uint32_t seed,
+                             uint32_t n_filters, uint32_t first_filter_id, int out_flags, int post,
+                             bssm_b200_job** job) {
+  if (!M || !job || !M->y || !M->theta) return fail(BSSM_B200_ERR_ARG, "null argument");
+  *job = nullptr;
+  if (M->model_id != BSSM_SDE_GBM) return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_sde: unknown model_id (registry: BSSM_SDE_GBM)");
+  if (M->n_theta < 3) return fail(BSSM_B200_ERR_ARG, "GBM needs theta = (mu, sigma_x, sigma_y)");
+  if (L < 1 || L > 20) return fail(BSSM_B200_ERR_ARG, "discretisation level L must be in 1..20");
+  bssm_b200_job* J = new bssm_b200_job();
+  struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
+  int rc = job_common(J, KIND_SDE, M->n, 1, 1, nsim, seed, n_filters, first_filter_id, out_flags, post);
+  if (rc) return rc;
+  if ((rc = J->y.upload(M->y, M->n))) return rc;
+  pf::SdeParams& sp = J->sp;
+  sp.n = M->n; sp.y = J->y.p; sp.x0 = M->x0; sp.positive = M->positive ? 1 : 0;
+  sp.nsub = 1 << L;
+  sp.dt = 1.0 / (double)sp.nsub;      // t / n with t = 1, src/milstein.cpp:23-24
+  sp.sqdt = std::sqrt(sp.dt);
+  sp.th0 = M->theta[0]; sp.th1 = M->theta[1]; sp.th2 = M->theta[2];
+  sp.logsd = pf_log(sp.th2);
+  if ((rc = finish_job(J, out_flags, post))) return rc;
+  guard.j = nullptr;
+  *job = J;
+  return 0;
+}
+
+static int run_fetch_destroy(bssm_b200_job* J, bssm_filter_out* out) {
+  float ms = 0;
+  int rc = bssm_b200_job_run(J, &ms);
+  if (!rc) rc = bssm_b200_job_fetch(J, 0, out);
+  bssm_b200_job_destroy(J);
+  return rc;
+}
+
+static int out_flags_of(const bssm_filter_out* out) {
+  return (out->alpha ? BSSM_OUT_ALPHA : 0) | (out->weights ? BSSM_OUT_WEIGHTS : 0) | (out->indices ? BSSM_OUT_INDICES : 0);
+}
+
+int bssm_b200_bsf_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, bssm_filter_out* out) {
+  if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
+  bssm_b200_job* J = nullptr;
+  int rc = bssm_b200_job_create_nlg(M, nsim, seed, 1, 0, out_flags_of(out), BSSM_POST_FILTER_SUMMARY, &J);
+  return rc ? rc : run_fetch_destroy(J, out);
+}
+int bssm_b200_bsf_smoother_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, bssm_filter_out* out) {
+  if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
+  bssm_b200_job* J = nullptr;
+  int rc = bssm_b200_job_create_nlg(M, nsim, seed, 1, 0, out_flags_of(out), BSSM_POST_SMOOTHER, &J);
+  return rc ? rc : run_fetch_destroy(J, out);
+}
+int bssm_b200_bsf_sde(const bssm_sde_model* M, uint32_t nsim, uint32_t L, uint32_t seed, bssm_filter_out* out) {
+  if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
+  bssm_b200_job* J = nullptr;
+  int rc = bssm_b200_job_create_sde(M, nsim, L, seed, 1, 0, out_flags_of(out), BSSM_POST_FILTER_SUMMARY, &J);
+  if (rc) return rc;
+  const int n = M->n;
+  rc = run_fetch_destroy(J, out);
+  // the reference allocates att (1, n+1) and Ptt (1, 1, n+1) here and filter_summary
+  // leaves their last column zero (src/R_sde.cpp:56-60)
+  if (!rc && out->att) out->att[n] = 0.0;
+  if (!rc && out->Ptt) out->Ptt[n] = 0.0;
+  return rc;
+}
+int bssm_b200_bsf_smoother_sde(const bssm_sde_model* M, uint32_t nsim, uint32_t L, uint32_t seed,
+                               bssm_filter_out* out) {
+  if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
+  bssm_b200_job* J = nullptr;
+  int rc = bssm_b200_job_create_sde(M, nsim, L, seed, 1, 0, out_flags_of(out), BSSM_POST_SMOOTHER, &J);
+  return rc ? rc : run_fetch_destroy(J, out);
+}
+int bssm_b200_loglik_sde(const bssm_sde_model* M, uint32_t nsim, uint32_t L, uint32_t seed, double* loglik) {
+  if (!loglik) return fail(BSSM_B200_ERR_ARG, "null loglik");
+  bssm_b200_job* J = nullptr;
+  int rc = bssm_b200_job_create_sde(M, nsim, L, seed, 1, 0, 0, BSSM_POST_NONE, &J);
+  if (rc) return rc;
+  float ms = 0;
+  rc = bssm_b200_job_run(J, &ms);
+  if (!rc) rc = bssm_b200_job_logliks(J, loglik);
+  bssm_b200_job_destroy(J);
+  return rc;
+}
 
 // --------------------------------------------------------- post-correction
 namespace {

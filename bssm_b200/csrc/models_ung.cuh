@@ -49,7 +49,7 @@ __device__ __forceinline__ double ung_log_obs(int dist, double s, double y, doub
 
 // ---------------------------------------------------------- bootstrap filter
 template <int M_, int K_>
-struct UngBsf {
+struct UngBsf : GaussStep<UngBsf<M_, K_>, M_, M_, K_> {
   static constexpr int M = M_, KI = M_, KP = K_;
   typedef UngParams Params;
   const UngParams& mp;
@@ -114,7 +114,7 @@ struct UngBsf {
 };
 
 // ------------------------------------------------------------ psi-APF, m = 1
-struct UngPsi1 {
+struct UngPsi1 : GaussStep<UngPsi1, 1, 1, 1> {
   static constexpr int M = 1, KI = 1, KP = 1;
   typedef UngParams Params;
   const UngParams& mp;

@@ -229,24 +229,59 @@ struct Strata {
   }
 };
 
+// ------------------------------------------------------- per-step context
+struct StepCtx {
+  uint32_t seed, filter, t, i0; // t = time column being produced (0 = initial state)
+};
+
+// Noise handling shared by the models whose step consumes K standard normals per
+// particle (ssm_ung, ssm_nlg): the thread's P*K normals are P*K/2 Box-Muller
+// pairs of the flat index (i*K + d), generated BEFORE the ancestors are known.
+template <class Derived, int M, int KI, int KP>
+struct GaussStep {
+  template <int P> struct Noise { double z[P * KP]; };
+  template <int P>
+  __device__ __forceinline__ void init_all(const StepCtx& c, double (&x)[P][M]) const {
+    double z[P * KI];
+    const uint32_t pair0 = (c.i0 * KI) >> 1;
+#pragma unroll
+    for (int q = 0; q < (P * KI) / 2; ++q)
+      pf_normal_pair(c.seed, c.filter, 0u, 0u, pair0 + q, &z[2 * q], &z[2 * q + 1]);
+#pragma unroll
+    for (int p = 0; p < P; ++p) static_cast<const Derived*>(this)->init(&z[p * KI], x[p]);
+  }
+  template <int P>
+  __device__ __forceinline__ void draw(const StepCtx& c, Noise<P>& nz) const {
+    const uint32_t pair0 = (c.i0 * KP) >> 1;
+#pragma unroll
+    for (int q = 0; q < (P * KP) / 2; ++q)
+      pf_normal_pair(c.seed, c.filter, c.t, 0u, pair0 + q, &nz.z[2 * q], &nz.z[2 * q + 1]);
+  }
+  template <int P>
+  __device__ __forceinline__ void propagate_all(const StepCtx&, const Noise<P>& nz, const double (&xa)[P][M],
+                                                double (&x)[P][M]) const {
+#pragma unroll
+    for (int p = 0; p < P; ++p) static_cast<const Derived*>(this)->propagate(xa[p], &nz.z[p * KP], x[p]);
+  }
+};
+
 // -------------------------------------------------------- the filter kernel
 // Model policy:
-//   static constexpr int M, KI, KP;   state dim, normals at init, normals/step
+//   static constexpr int M;           state dimension
 //   Model(const Params&, uint32_t filter_index_in_launch)
 //   double loglik0() const;           initial log-likelihood (psi: approx_loglik)
 //   double loglik_end() const;        added once at the end (bsf: constants)
-//   void init(const double* z, double* x) const;
 //   bool observed(int t) const;
 //   void begin_weight(int t);         load per-step constants
 //   double logw(const double* x) const;
 //   void begin_step(int t);           load per-step constants for t -> t+1
-//   void propagate(const double* xa, const double* z, double* x) const;
+//   init_all<P>(ctx, x), Noise<P>, draw<P>(ctx, noise), propagate_all<P>(ctx, noise, xa, x):
+//     the random part of the step for the thread's P particles (GaussStep above for
+//     models with K normals per particle; the SDE model runs its Milstein sub-steps)
 template <class Model, int P, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 filter_kernel(const FilterParams fp, const typename Model::Params mp) {
   constexpr int M = Model::M;
-  constexpr int KI = Model::KI;
-  constexpr int KP = Model::KP;
   static_assert(P % 2 == 0, "Box-Muller pairs must be thread-local");
   __shared__ CollSmem csm;
 
@@ -284,13 +319,9 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
 
   // ---- initial state, column 0 (reference :621-627 / :538-544)
   {
-    double z[P * KI];
-    const uint32_t pair0 = (i0 * KI) >> 1;
-#pragma unroll
-    for (int q = 0; q < (P * KI) / 2; ++q)
-      pf_normal_pair(fp.seed, filter, 0u, 0u, pair0 + q, &z[2 * q], &z[2 * q + 1]);
-#pragma unroll
-    for (int p = 0; p < P; ++p) model.init(&z[p * KI], x[p]);
+    StepCtx c0;
+    c0.seed = fp.seed; c0.filter = filter; c0.t = 0u; c0.i0 = i0;
+    model.template init_all<P>(c0, x);
 #pragma unroll
     for (int p = 0; p < P; ++p)
       if (i0 + p < N) {
@@ -345,7 +376,9 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
 
     // ---- stratified resampling -> ancestors of column t+1 (reference :650-655)
     uint32_t* anc = iout + (fp.keep_indices ? (size_t)t * N : 0);
-    double z[P * KP];
+    StepCtx ctx;
+    ctx.seed = fp.seed; ctx.filter = filter; ctx.t = (uint32_t)(t + 1); ctx.i0 = i0;
+    typename Model::template Noise<P> noise;
     {
       // thresholds of the strata this thread owns (visible after the scan barrier)
 #pragma unroll
@@ -389,10 +422,7 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
       for (int p = 0; p <= P; ++p) { jj[p] = st.guess(pk[p]); uj[p] = st.u(jj[p]); }
       // the normals of the next column do not depend on the ancestors: generate
       // them while the threshold loads are in flight
-      const uint32_t pair0 = (i0 * KP) >> 1;
-#pragma unroll
-      for (int q = 0; q < (P * KP) / 2; ++q)
-        pf_normal_pair(fp.seed, filter, (uint32_t)(t + 1), 0u, pair0 + q, &z[2 * q], &z[2 * q + 1]);
+      model.template draw<P>(ctx, noise);
       uint32_t lo = (i0 == 0) ? 0u : st.resolve(pk[0], jj[0], uj[0]);
 #pragma unroll
       for (int p = 0; p < P; ++p) {
@@ -417,9 +447,9 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
       for (int p = 0; p < P; ++p)
 #pragma unroll
         for (int d = 0; d < M; ++d) xa[p][d] = __ldcg(src + (size_t)d * N + a[p]);
+      model.template propagate_all<P>(ctx, noise, xa, x);
 #pragma unroll
       for (int p = 0; p < P; ++p) {
-        model.propagate(xa[p], &z[p * KP], x[p]);
         if (i0 + p < N) {
 #pragma unroll
           for (int d = 0; d < M; ++d) dst[(size_t)d * N + i0 + p] = x[p][d];

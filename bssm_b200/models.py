@@ -201,3 +201,67 @@ def bsm_ng(y, sd_level, sd_slope=None, sd_seasonal=None, sd_noise=None, distribu
     return Model("bsm_ng", y, Z, T.reshape(m, m, 1), R.reshape(m, R.shape[1], 1), a1, P1, [0.0],
                  np.zeros((m, 1)), u, phi, distribution, init_mode(y, u, distribution),
                  xreg=xreg, beta=beta)
+
+
+class NlgModel:
+    """ssm_nlg (R/models.R:1545-1570) with the user functions taken from the device
+    registry instead of compiled function pointers: model="growth" is the
+    nlg_growth example of R/cpp_example_models.R:336-511."""
+    REGISTRY = {"growth": (0, 2, 2, 1, 3, 6)}  # id, m, k, p, n_theta, n_known
+
+    def __init__(self, y, model, theta, known_params):
+        if model not in self.REGISTRY:
+            raise ValueError("ssm_nlg: model must be one of %s" % sorted(self.REGISTRY))
+        self.cls = "ssm_nlg"
+        self.model_id, self.m, self.k, self.p, nth, nkn = self.REGISTRY[model]
+        self.y = f64(np.ravel(y))
+        self.n = self.y.size
+        self.theta = f64(np.ravel(theta))
+        self.known_params = f64(np.ravel(known_params))
+        if self.theta.size < nth or self.known_params.size < nkn:
+            raise ValueError("ssm_nlg %s: needs %d parameters and %d known parameters" % (model, nth, nkn))
+
+    def c_struct(self):
+        from ._lib import NlgModel as S
+        s = S()
+        s.model_id, s.n, s.p, s.m, s.k = self.model_id, self.n, self.p, self.m, self.k
+        s.y, s.theta, s.n_theta = dptr(self.y), dptr(self.theta), self.theta.size
+        s.known_params, s.n_known = dptr(self.known_params), self.known_params.size
+        s._keep = [self.y, self.theta, self.known_params]
+        return s
+
+
+class SdeModel:
+    """ssm_sde (R/models.R:1637-1650); model="gbm" is the sde_gbm example of
+    R/cpp_example_models.R:109-193 (theta = mu, sigma_x, sigma_y)."""
+    REGISTRY = {"gbm": (0, 3)}
+
+    def __init__(self, y, model, theta, x0, positive):
+        if model not in self.REGISTRY:
+            raise ValueError("ssm_sde: model must be one of %s" % sorted(self.REGISTRY))
+        self.cls = "ssm_sde"
+        self.model_id, nth = self.REGISTRY[model]
+        self.m = 1
+        self.y = f64(np.ravel(y))
+        self.n = self.y.size
+        self.theta = f64(np.ravel(theta))
+        self.x0, self.positive = float(x0), bool(positive)
+        if self.theta.size < nth:
+            raise ValueError("ssm_sde %s: needs %d parameters" % (model, nth))
+
+    def c_struct(self):
+        from ._lib import SdeModel as S
+        s = S()
+        s.model_id, s.n = self.model_id, self.n
+        s.y, s.theta, s.n_theta = dptr(self.y), dptr(self.theta), self.theta.size
+        s.x0, s.positive = self.x0, int(self.positive)
+        s._keep = [self.y, self.theta]
+        return s
+
+
+def ssm_nlg(y, model, theta, known_params):
+    return NlgModel(y, model, theta, known_params)
+
+
+def ssm_sde(y, model, theta, x0, positive):
+    return SdeModel(y, model, theta, x0, positive)

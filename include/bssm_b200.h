@@ -154,6 +154,61 @@ int bssm_b200_psi_smoother(const bssm_ung_model* model, uint32_t nsim, uint32_t 
 int bssm_b200_psi_filter(const bssm_ung_model* model, uint32_t nsim, uint32_t seed,
                          bssm_filter_out* out);
 
+/* ---- ssm_nlg and ssm_sde: device functor registry ------------------------- */
+/* The reference defines these model classes through C++ function pointers that
+ * R compiles at run time (externalptr arguments of bsf_nlg / bsf_sde,
+ * src/R_bootstrap_filter.cpp:461-481, src/R_sde.cpp:35-49).  Host function
+ * pointers cannot run in a kernel, so the shipped example models are device
+ * policies selected by id; theta / known_params keep their meaning. */
+enum {
+  BSSM_NLG_GROWTH = 0 /* logistic growth model, R/cpp_example_models.R:336-511 */
+};
+enum {
+  BSSM_SDE_GBM = 0    /* geometric Brownian motion, R/cpp_example_models.R:109-193 */
+};
+
+typedef struct {
+  int32_t model_id;           /* BSSM_NLG_* */
+  int32_t n, p, m, k;         /* time points, series, states, etas */
+  const double* y;            /* p x n (R passes t(model$y), R/bootstrap_filter.R:147) */
+  const double* theta;        int32_t n_theta;
+  const double* known_params; int32_t n_known;
+} bssm_nlg_model;
+
+typedef struct {
+  int32_t model_id;           /* BSSM_SDE_* */
+  int32_t n;
+  const double* y;            /* n */
+  const double* theta;        int32_t n_theta;
+  double x0;
+  int32_t positive;
+} bssm_sde_model;
+
+/* replaces: bsf_nlg(...) src/R_bootstrap_filter.cpp:461-507 -> ssm_nlg::bsf_filter
+ *           src/model_ssm_nlg.cpp:1066-1146 + filter_summary */
+int bssm_b200_bsf_nlg(const bssm_nlg_model* model, uint32_t nsim, uint32_t seed, bssm_filter_out* out);
+/* replaces: bsf_smoother_nlg(...) src/R_bootstrap_filter.cpp:509-551 */
+int bssm_b200_bsf_smoother_nlg(const bssm_nlg_model* model, uint32_t nsim, uint32_t seed,
+                               bssm_filter_out* out);
+/* replaces: bsf_sde(y, x0, positive, ..., theta, nsim, L, seed) src/R_sde.cpp:35-72
+ *           -> ssm_sde::bsf_filter src/model_ssm_sde.cpp:21-82 (Milstein, 2^L sub-steps).
+ * Like the reference, att and Ptt have n+1 columns here with the last one zero. */
+int bssm_b200_bsf_sde(const bssm_sde_model* model, uint32_t nsim, uint32_t L, uint32_t seed,
+                      bssm_filter_out* out);
+/* replaces: bsf_smoother_sde(...) src/R_sde.cpp:75-111 */
+int bssm_b200_bsf_smoother_sde(const bssm_sde_model* model, uint32_t nsim, uint32_t L, uint32_t seed,
+                               bssm_filter_out* out);
+/* replaces: loglik_sde(...) src/R_sde.cpp:10-32 (log-likelihood only) */
+int bssm_b200_loglik_sde(const bssm_sde_model* model, uint32_t nsim, uint32_t L, uint32_t seed,
+                         double* loglik);
+/* resident jobs of replicate filters, as bssm_b200_job_create_ung */
+int bssm_b200_job_create_nlg(const bssm_nlg_model* model, uint32_t nsim, uint32_t seed,
+                             uint32_t n_filters, uint32_t first_filter_id, int out_flags, int post,
+                             struct bssm_b200_job** job);
+int bssm_b200_job_create_sde(const bssm_sde_model* model, uint32_t nsim, uint32_t L, uint32_t seed,
+                             uint32_t n_filters, uint32_t first_filter_id, int out_flags, int post,
+                             struct bssm_b200_job** job);
+
 /* Mode of the Gaussian approximation: the Newton / Laplace iterations of
  * ssm_ung::approximate (src/model_ssm_ung.cpp:87-140) started from
  * model->initial_mode, m = 1.  This is what run_mcmc stores per draw in

@@ -771,6 +771,182 @@ void orc_ung_filter_batch(const bssm_ung_model* M, int method, const double* mod
   }
 }
 
+/* ------------------------------------------------------------------ a13 */
+/* psd_chol, src/psd_chol.cpp:5-18 */
+static void psd_chol(const double* x, int m, std::vector<double>& cholx) {
+  const double eps = std::numeric_limits<double>::epsilon();
+  double mx = x[0];
+  for (int d = 1; d < m; ++d) mx = std::max(mx, x[d + (size_t)m * d]);
+  const double thr = std::max(eps, eps * m * mx);
+  std::vector<int> nz;
+  for (int d = 0; d < m; ++d) if (x[d + (size_t)m * d] > thr) nz.push_back(d);
+  cholx.assign((size_t)m * m, 0.0);
+  int q = (int)nz.size();
+  for (int j = 0; j < q; ++j)
+    for (int i = j; i < q; ++i) {
+      double s = x[nz[i] + (size_t)m * nz[j]];
+      for (int l = 0; l < j; ++l) s -= cholx[nz[i] + (size_t)m * nz[l]] * cholx[nz[j] + (size_t)m * nz[l]];
+      if (i == j) cholx[nz[i] + (size_t)m * nz[j]] = std::sqrt(s);
+      else cholx[nz[i] + (size_t)m * nz[j]] = s / cholx[nz[j] + (size_t)m * nz[j]];
+    }
+}
+
+/* the growth model's user functions, R/cpp_example_models.R:350-428 */
+struct Growth {
+  const double* theta; const double* known;
+  void a1_fn(double* a1) const { a1[0] = known[2]; a1[1] = known[3]; }
+  void P1_fn(double* P1) const { P1[0] = known[4]; P1[1] = 0; P1[2] = 0; P1[3] = known[5]; }
+  double H_fn() const { return pf_exp(theta[0]); }
+  void R_fn(double* R) const { R[0] = pf_exp(theta[1]); R[1] = 0; R[2] = 0; R[3] = pf_exp(theta[2]); }
+  double Z_fn(const double* alpha) const { return alpha[1]; }
+  void T_fn(const double* alpha, double* an) const {
+    double dT = known[0], K = known[1];
+    an[0] = alpha[0];
+    double r = pf_exp(alpha[0]) / (1.0 + pf_exp(alpha[0]));
+    an[1] = K * alpha[1] * pf_exp(r * dT) / (K + alpha[1] * (pf_exp(r * dT) - 1));
+  }
+};
+
+/* dmvnorm(x, mean, sigma, lwr = true, logd = true) for one series, src/dmvnorm.cpp:9-12 */
+static double dmvnorm1(double x, double mean, double sigma) {
+  double q = (x - mean) / sigma;
+  return -0.5 * (std::log(2.0 * M_PI) + 2.0 * pf_log(sigma) + q * q);
+}
+
+/* ssm_nlg::bsf_filter, src/model_ssm_nlg.cpp:1066-1146 (growth model, p = 1, m = k = 2) */
+double orc_nlg_bsf_filter(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t filter, int arith,
+                          double* alpha, double* weights, uint32_t* indices, int32_t* stopped_at) {
+  *stopped_at = -1;
+  if (M->model_id != BSSM_NLG_GROWTH || M->p != 1) return pf_nan();
+  Growth fn{M->theta, M->known_params};
+  const int n = M->n, m = 2, k = 2;
+  const size_t N = nsim;
+  double a1[2], P1[4];
+  fn.a1_fn(a1); fn.P1_fn(P1);
+  std::vector<double> L_P1;
+  psd_chol(P1, m, L_P1);
+  auto A = [&](int d, int t, size_t i) -> double& { return alpha[d + (size_t)m * (t + (size_t)(n + 1) * i)]; };
+  for (size_t i = 0; i < N; ++i) {
+    double um[2];
+    for (int j = 0; j < m; ++j) um[j] = pf_normal(seed, filter, 0, 0, (uint32_t)(i * m + j));
+    for (int d = 0; d < m; ++d) {
+      double s = 0.0;
+      for (int j = 0; j < m; ++j) s += L_P1[d + (size_t)m * j] * um[j];
+      A(d, 0, i) = a1[d] + s;
+    }
+  }
+  std::vector<double> W(N), logw(N), r(N), atmp((size_t)m * N);
+  double loglik = 0.0;
+  auto weigh = [&](int t) {
+    const double H = fn.H_fn();
+    for (size_t i = 0; i < N; ++i) logw[i] = dmvnorm1(M->y[t], fn.Z_fn(&A(0, t, i)), H);
+  };
+  if (std::isfinite(M->y[0])) {
+    weigh(0);
+    double mxw, lmean;
+    if (!normalise(logw.data(), nsim, weights, W, &mxw, &lmean, arith)) { *stopped_at = 0; return -ORC_INF; }
+    loglik = mxw + lmean;
+  } else {
+    for (size_t i = 0; i < N; ++i) { weights[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
+  }
+  for (int t = 0; t < n; ++t) {
+    for (size_t i = 0; i < N; ++i) r[i] = pf_resample_uniform(seed, filter, t, (uint32_t)i);
+    uint32_t* ind = indices + N * t;
+    resample(W, r, nsim, ind, arith);
+    for (size_t i = 0; i < N; ++i)
+      for (int d = 0; d < m; ++d) atmp[d + (size_t)m * i] = A(d, t, ind[i]);
+    double R[4];
+    fn.R_fn(R);
+    for (size_t i = 0; i < N; ++i) {
+      double uk[2], Tv[2];
+      for (int j = 0; j < k; ++j) uk[j] = pf_normal(seed, filter, t + 1, 0, (uint32_t)(i * k + j));
+      fn.T_fn(&atmp[(size_t)m * i], Tv);
+      /* R is diagonal: the off-diagonal zeros contribute +-0 */
+      A(0, t + 1, i) = Tv[0] + R[0] * uk[0];
+      A(1, t + 1, i) = Tv[1] + R[3] * uk[1];
+    }
+    double* wcol = weights + N * (t + 1);
+    if (t < (n - 1) && std::isfinite(M->y[t + 1])) {
+      weigh(t + 1);
+      double mxw, lmean;
+      if (!normalise(logw.data(), nsim, wcol, W, &mxw, &lmean, arith)) { *stopped_at = t + 1; return -ORC_INF; }
+      loglik += mxw + lmean;
+    } else {
+      for (size_t i = 0; i < N; ++i) { wcol[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
+    }
+  }
+  return loglik;
+}
+
+/* ------------------------------------------------------------------ a14 */
+/* GBM user functions, R/cpp_example_models.R:129-171 */
+struct Gbm {
+  const double* theta;
+  double drift(double x) const { return theta[0] * x; }
+  double diffusion(double x) const { return std::max(0.0, theta[1] * x); }
+  double ddiffusion(double x) const { return theta[1] * (x > 0.0); }
+  /* R::dnorm(y, log(alpha), theta(2), 1)  [UNVENDORED: R nmath dnorm.c:
+   * -(M_LN_SQRT_2PI + 0.5 * x * x + log(sigma)) with x = (y - mu) / sigma] */
+  double log_obs(double y, double alpha) const {
+    double x = (y - pf_log(alpha)) / theta[2];
+    return -(0.918938533204672741780329736406 + 0.5 * x * x + pf_log(theta[2]));
+  }
+};
+
+/* milstein + milstein_worker, src/milstein.cpp:18-48; dB(k) = N(0, sqrt(dt)) drawn
+ * as sqrt(dt) * z with z the (particle i, sub-step k) normal of the Philox stream */
+static double milstein(double x, unsigned int L, const Gbm& fn, bool positive, uint32_t seed, uint32_t filter,
+                       uint32_t t, uint32_t i) {
+  unsigned int n = 1u << L;
+  double dt = 1.0 / n;
+  double sd = std::sqrt(dt);
+  for (unsigned int k = 0; k < n; k++) {
+    double dB = pf_normal(seed, filter, t, k, i) * sd;
+    x += fn.drift(x) * dt + fn.diffusion(x) * dB + 0.5 * fn.diffusion(x) * fn.ddiffusion(x) * (dB * dB - dt);
+    if (positive) x = std::abs(x);
+  }
+  return x;
+}
+
+/* ssm_sde::bsf_filter, src/model_ssm_sde.cpp:21-82 (alpha is 1 x (n+1) x N) */
+double orc_sde_bsf_filter(const bssm_sde_model* M, uint32_t nsim, uint32_t L, uint32_t seed, uint32_t filter,
+                          int arith, double* alpha, double* weights, uint32_t* indices, int32_t* stopped_at) {
+  *stopped_at = -1;
+  if (M->model_id != BSSM_SDE_GBM) return pf_nan();
+  Gbm fn{M->theta};
+  const int n = M->n;
+  const size_t N = nsim;
+  auto A = [&](int t, size_t i) -> double& { return alpha[t + (size_t)(n + 1) * i]; };
+  for (size_t i = 0; i < N; ++i) A(0, i) = milstein(M->x0, L, fn, M->positive, seed, filter, 0, (uint32_t)i);
+  std::vector<double> W(N), logw(N), r(N);
+  double loglik = 0.0;
+  if (std::isfinite(M->y[0])) {
+    for (size_t i = 0; i < N; ++i) logw[i] = fn.log_obs(M->y[0], A(0, i));
+    double mxw, lmean;
+    if (!normalise(logw.data(), nsim, weights, W, &mxw, &lmean, arith)) { *stopped_at = 0; return -ORC_INF; }
+    loglik = mxw + lmean;
+  } else {
+    for (size_t i = 0; i < N; ++i) { weights[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
+  }
+  for (int t = 0; t < n; ++t) {
+    for (size_t i = 0; i < N; ++i) r[i] = pf_resample_uniform(seed, filter, t, (uint32_t)i);
+    uint32_t* ind = indices + N * t;
+    resample(W, r, nsim, ind, arith);
+    for (size_t i = 0; i < N; ++i)
+      A(t + 1, i) = milstein(A(t, ind[i]), L, fn, M->positive, seed, filter, t + 1, (uint32_t)i);
+    double* wcol = weights + N * (t + 1);
+    if ((t < (n - 1)) && std::isfinite(M->y[t + 1])) {
+      for (size_t i = 0; i < N; ++i) logw[i] = fn.log_obs(M->y[t + 1], A(t + 1, i));
+      double mxw, lmean;
+      if (!normalise(logw.data(), nsim, wcol, W, &mxw, &lmean, arith)) { *stopped_at = t + 1; return -ORC_INF; }
+      loglik += mxw + lmean;
+    } else {
+      for (size_t i = 0; i < N; ++i) { wcol[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
+    }
+  }
+  return loglik;
+}
+
 /* ------------------------------------------------------------------ a15 */
 /* update_model(theta): svm src/model_svm.cpp:12-29, ar1_ng src/model_ar1_ng.cpp:12-36.
  * Writes the scalars of the per-draw model into caller storage. */

@@ -61,3 +61,39 @@ def svm_mcmc_output(model, n_stored, output_type=3, jitter=0.05, gen_seed=7):
         modes[:, i] = orc.psi_prepass(mi).mode
     return {"theta": theta, "counts": counts, "modes": modes, "output_type": output_type,
             "posterior": np.zeros(n_stored)}
+
+
+def growth_model(n=200, gen_seed=11, missing=()):
+    """BASELINE config 3: the logistic growth model of vignettes/psi_pf.Rmd:133-158 (dT=.1, K=500,
+    p1=50, r'1=-1.5, H=1, R1=.05, R2=1, a1=(-1.5, 50), P1=diag(1, 100)) in the packaged
+    (log-theta) parameterisation of R/cpp_example_models.R:336-511."""
+    rng = np.random.default_rng(gen_seed)
+    dT, K, H, R1, R2 = 0.1, 500.0, 1.0, 0.05, 1.0
+    r_, p_ = np.empty(n), np.empty(n)
+    r_[0], p_[0] = -1.5, 50.0
+    for t in range(1, n):
+        r = np.exp(r_[t - 1]) / (1 + np.exp(r_[t - 1]))
+        p_[t] = K * p_[t - 1] * np.exp(r * dT) / (K + p_[t - 1] * (np.exp(r * dT) - 1)) + R2 * rng.normal()
+        r_[t] = r_[t - 1] + R1 * rng.normal()
+    y = p_ + H * rng.normal(size=n)
+    for t in missing:
+        y[t] = np.nan
+    return bssm_b200.ssm_nlg(y, "growth", theta=np.log([H, R1, R2]),
+                             known_params=[dT, K, -1.5, 50.0, 1.0, 100.0])
+
+
+def gbm_model(n=50, gen_seed=42, missing=()):
+    """BASELINE config 5: GBM as tests/testthat/test_sde.R:7-25 (mu=.05, sigma_x=.3, sigma_y=1, x0=1),
+    filter theta = (.08, .4, 1.5), positive = TRUE."""
+    rng = np.random.default_rng(gen_seed)
+    mu, sx, sy, x = 0.05, 0.3, 1.0, 1.0
+    dt = 1.0 / 64
+    xs = np.empty(n)
+    for k in range(n):
+        for _ in range(64):
+            x = x * np.exp((mu - 0.5 * sx ** 2) * dt + sx * np.sqrt(dt) * rng.normal())
+        xs[k] = x
+    y = np.log(xs) + sy * rng.normal(size=n)
+    for t in missing:
+        y[t] = np.nan
+    return bssm_b200.ssm_sde(y, "gbm", theta=[0.08, 0.4, 1.5], x0=1.0, positive=True)

@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-from bssm_b200._lib import ThetaMap, UngModel, c_double_p, c_uint32_p, dptr, uptr  # struct layouts only
+from bssm_b200._lib import NlgModel, SdeModel, ThetaMap, UngModel, c_double_p, c_uint32_p, dptr, uptr  # struct layouts only
 
 ARITH_REFERENCE, ARITH_REPRO = 0, 1
 _L = None
@@ -39,6 +39,12 @@ def L():
         _L.orc_postcorrection_ung.argtypes = [C.POINTER(UngModel), C.POINTER(ThetaMap), C.c_int, u32, u32, C.c_int,
                                               C.c_int, c_uint32_p, c_double_p, u32, c_double_p, u32, C.c_int,
                                               c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]
+        _L.orc_nlg_bsf_filter.restype = d
+        _L.orc_nlg_bsf_filter.argtypes = [C.POINTER(NlgModel), u32, u32, u32, C.c_int, c_double_p, c_double_p,
+                                          c_uint32_p, C.POINTER(i32)]
+        _L.orc_sde_bsf_filter.restype = d
+        _L.orc_sde_bsf_filter.argtypes = [C.POINTER(SdeModel), u32, u32, u32, u32, C.c_int, c_double_p, c_double_p,
+                                          c_uint32_p, C.POINTER(i32)]
         _L.orc_max_threads.restype = C.c_int
         _L.orc_filter_smoother.argtypes = [c_double_p, c_uint32_p, C.c_int, C.c_int, u32]
         _L.orc_summary.argtypes = [c_double_p, C.c_int, C.c_int, u32, c_double_p, c_double_p]
@@ -199,4 +205,24 @@ def post_correct(model, mcmc_output, N, is_type=2, seed=1, threads=0, arith=ARIT
                                     dptr(r.weights), dptr(r.posterior), dptr(r.alpha), dptr(r.alphahat),
                                     dptr(r.Vt), dptr(r.loglik))
     assert rc == 0
+    return r
+
+
+def nlg_bsf_filter(model, N, seed, filt=0, arith=ARITH_REPRO):
+    r = _alloc(model, N)
+    ms = model.c_struct()
+    st = C.c_int32(-1)
+    r.loglik = L().orc_nlg_bsf_filter(C.byref(ms), N, seed, filt, arith, dptr(r.alpha), dptr(r.weights),
+                                      uptr(r.indices), C.byref(st))
+    r.stopped_at = st.value
+    return r
+
+
+def sde_bsf_filter(model, N, Lvl, seed, filt=0, arith=ARITH_REPRO):
+    r = _alloc(model, N)
+    ms = model.c_struct()
+    st = C.c_int32(-1)
+    r.loglik = L().orc_sde_bsf_filter(C.byref(ms), N, Lvl, seed, filt, arith, dptr(r.alpha), dptr(r.weights),
+                                      uptr(r.indices), C.byref(st))
+    r.stopped_at = st.value
     return r
