@@ -69,33 +69,43 @@ int env_int(const char* name, int dflt) {
 uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 uint32_t round32(uint32_t a) { return cdiv(a, 32) * 32; }
 
-int choose_geometry(uint32_t N, Geometry* g) {
-  uint32_t ranks;
+// Launch geometry.  One CTA while the filter fits (N <= 4096); otherwise a group
+// of `ranks` CTAs of 256 threads synchronised through L2 (SYNC_GROUP).  Few
+// filters: many ranks with few particles per thread (latency); many filters:
+// fewer ranks with P = 8, several CTAs of different filters per SM (throughput).
+// Results never depend on the geometry (fixed-point sums), so this is free to tune.
+// Environment overrides (experiments): BSSM_B200_RANKS / _P / _BLOCK / _SYNC=cluster.
+int choose_geometry(uint32_t N, uint32_t n_filters, Geometry* g) {
+  uint32_t ranks = 1, block;
   int P;
-  const uint32_t cap4 = 4096, cap8 = 8192;
-  if (N <= 1024) { ranks = 1; P = 2; }
-  else if (N <= cap4) { ranks = 1; P = 4; }
-  else if (N <= 16 * cap4) { ranks = 1; while (ranks * cap4 < N) ranks *= 2; P = 4; }
-  else if (N <= 16 * cap8) { ranks = 16; P = 8; }
-  else { ranks = 0; P = 8; }
-  int forced_ranks = env_int("BSSM_B200_RANKS", 0);
-  int forced_P = env_int("BSSM_B200_P", 0);
-  if (forced_P == 2 || forced_P == 4 || forced_P == 8) P = forced_P;
-  if (forced_ranks > 0) ranks = (uint32_t)forced_ranks;
-  if (ranks == 0) { // grid mode
-    int block = 512;
-    ranks = cdiv(N, (uint32_t)(block * P));
-    g->P = P; g->block = block; g->ranks = ranks; g->sync_mode = pf::SYNC_GRID;
-    return 0;
+  int mode = pf::SYNC_BLOCK;
+  if (N <= 1024) { P = 2; }
+  else if (N <= 4096) { P = 4; }
+  else {
+    mode = pf::SYNC_GROUP;
+    const uint32_t tb = 256;
+    const uint32_t capacity = 148u * 4u;                   // co-resident CTAs of 256 threads at 64 registers
+    const uint32_t rmin = cdiv(N, tb * 8), rmax = cdiv(N, tb * 2);
+    uint32_t want = capacity / (n_filters ? n_filters : 1);
+    if (want > 148u && n_filters == 1) want = 148u;        // one CTA per SM is enough for a single filter
+    ranks = want < rmin ? rmin : (want > rmax ? rmax : want);
+    const uint32_t per_thread = cdiv(N, ranks * tb);
+    P = per_thread <= 2 ? 2 : (per_thread <= 4 ? 4 : 8);
+    ranks = cdiv(N, tb * (uint32_t)P);
+    if (ranks > capacity) return fail(BSSM_B200_ERR_UNSUPPORTED, "too many particles for one resident group (N <= 1.2M)");
   }
-  uint32_t per_rank = cdiv(N, ranks);
-  uint32_t block = round32(cdiv(per_rank, (uint32_t)P));
-  int forced_block = env_int("BSSM_B200_BLOCK", 0);
+  const int forced_ranks = env_int("BSSM_B200_RANKS", 0);
+  const int forced_P = env_int("BSSM_B200_P", 0);
+  if (forced_P == 2 || forced_P == 4 || forced_P == 8) P = forced_P;
+  if (forced_ranks > 0) { ranks = (uint32_t)forced_ranks; mode = ranks == 1 ? pf::SYNC_BLOCK : pf::SYNC_GROUP; }
+  const char* sm = getenv("BSSM_B200_SYNC");
+  if (sm && !strcmp(sm, "cluster") && ranks > 1 && ranks <= 16) mode = pf::SYNC_CLUSTER;
+  block = round32(cdiv(cdiv(N, ranks), (uint32_t)P));
+  const int forced_block = env_int("BSSM_B200_BLOCK", 0);
   if (forced_block >= 32 && (uint32_t)forced_block * P * ranks >= N) block = round32((uint32_t)forced_block);
   if (block > 1024) return fail(BSSM_B200_ERR_ARG, "geometry: too many particles per CTA");
   if (block < 32) block = 32;
-  g->P = P; g->block = (int)block; g->ranks = ranks;
-  g->sync_mode = ranks == 1 ? pf::SYNC_BLOCK : (ranks <= 16 ? pf::SYNC_CLUSTER : pf::SYNC_GRID);
+  g->P = P; g->block = (int)block; g->ranks = ranks; g->sync_mode = mode;
   return 0;
 }
 
@@ -120,7 +130,7 @@ int launch_filter_V(const pf::FilterParams& fp, const typename Model::Params& mp
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.numAttrs = 1;
-  } else if (g.sync_mode == pf::SYNC_GRID) {
+  } else if (g.sync_mode == pf::SYNC_GROUP) {
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
     cfg.numAttrs = 1;
@@ -152,7 +162,7 @@ int occupancy_V(const Geometry& g, int* out) {
   }
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, g.block, 0));
-  *out = g.sync_mode == pf::SYNC_GRID ? 1 : per_sm * sms;
+  *out = g.sync_mode == pf::SYNC_GROUP ? (per_sm * sms) / (int)g.ranks : per_sm * sms;
   return 0;
 }
 
@@ -426,7 +436,8 @@ struct bssm_b200_job {
   DevBuf<double> loglik;
   DevBuf<int32_t> stopped;
   DevBuf<unsigned long long> xch;
-  DevBuf<unsigned int> barrier;
+  DevBuf<unsigned long long> slots;
+  int wave = 0; // filters per launch in SYNC_GROUP mode (all CTAs of a launch must be co-resident)
   DevBuf<double> ubuf;
   DevBuf<unsigned long long> phases;
   DevBuf<double> s_at, s_att, s_Pt, s_Ptt, s_mean, s_cov, traj, draw_par;
@@ -490,6 +501,7 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
   fp.loglik = J->loglik.p + f0;
   fp.stopped_at = J->stopped.p + f0;
   fp.xch = J->xch.p + (size_t)f0 * 4 * J->geo.ranks;
+  fp.slots = J->slots.p + (size_t)f0 * 8 * J->geo.ranks;
   fp.ubuf = J->ubuf.p + (size_t)f0 * J->N;
   if (fp.phase_cycles) fp.phase_cycles = J->phases.p + (size_t)f0 * 6 * J->geo.ranks;
   if (J->kind == KIND_NLG) return launch_filter<pf::NlgGrowthBsf>(fp, J->np, J->geo, nf, J->stream);
@@ -559,7 +571,7 @@ static int finish_job(bssm_b200_job* J, int out_flags, int post) {
   if (smooth && (rc = J->alpha_sm.alloc(J->alpha_stride * n_filters))) return rc;
   if (post == BSSM_POST_PICK && (rc = J->traj.alloc((size_t)n_filters * (n + 1) * m))) return rc;
   if ((rc = J->loglik.alloc(n_filters)) || (rc = J->stopped.alloc(n_filters))) return rc;
-  if ((rc = J->xch.alloc((size_t)4 * J->geo.ranks * n_filters)) || (rc = J->barrier.alloc(1)) ||
+  if ((rc = J->xch.alloc((size_t)4 * J->geo.ranks * n_filters)) || (rc = J->slots.alloc((size_t)8 * J->geo.ranks * n_filters)) ||
       (rc = J->ubuf.alloc((size_t)nsim * n_filters))) return rc;
   if (post == BSSM_POST_FILTER_SUMMARY) {
     if ((rc = J->s_at.alloc((size_t)n_filters * m * (n + 1))) || (rc = J->s_att.alloc((size_t)n_filters * m * n)) ||
@@ -578,7 +590,7 @@ static int finish_job(bssm_b200_job* J, int out_flags, int post) {
   fp.indices = J->indices.p; fp.indices_stride = J->indices_stride;
   fp.keep_indices = J->keep_indices ? 1 : 0;
   fp.loglik = J->loglik.p; fp.stopped_at = J->stopped.p;
-  fp.xch = J->xch.p; fp.barrier = J->barrier.p; fp.ubuf = J->ubuf.p;
+  fp.xch = J->xch.p; fp.slots = J->slots.p; fp.ubuf = J->ubuf.p;
   fp.phase_cycles = nullptr;
   if (env_int("BSSM_B200_PHASES", 0)) {
     if ((rc = J->phases.alloc((size_t)6 * J->geo.ranks * n_filters))) return rc;
@@ -613,7 +625,7 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
   J->N = nsim; J->n_filters = n_filters; J->first_filter = first_filter_id; J->seed = seed;
   J->n = M->n; J->m = M->m; J->k = M->k;
   const int n = M->n, m = M->m, k = M->k;
-  rc = choose_geometry(nsim, &J->geo);
+  rc = choose_geometry(nsim, n_filters, &J->geo);
   if (rc) return rc;
   CU(cudaStreamCreateWithFlags(&J->stream, cudaStreamNonBlocking));
   for (auto& e : J->ev) CU(cudaEventCreate(&e));
@@ -717,10 +729,15 @@ int bssm_b200_job_run(bssm_b200_job* J, float* ms_out) {
     J->launches += 1;
   }
   CU(cudaEventRecord(J->ev[1], J->stream));
-  if (J->geo.sync_mode == pf::SYNC_GRID) {
-    for (uint32_t f = 0; f < J->n_filters; ++f) {
-      CU(cudaMemsetAsync(J->barrier.p, 0, sizeof(unsigned int), J->stream));
-      if ((rc = launch_ung_filter(J, f, 1))) return rc;
+  if (J->geo.sync_mode == pf::SYNC_GROUP) {
+    if (J->wave == 0) {
+      J->wave = bssm_b200_job_max_concurrent_filters(J);
+      if (J->wave < 1) return fail(BSSM_B200_ERR_UNSUPPORTED, "filter group does not fit on the device");
+    }
+    CU(cudaMemsetAsync(J->slots.p, 0, sizeof(unsigned long long) * J->slots.count, J->stream));
+    for (uint32_t f = 0; f < J->n_filters; f += (uint32_t)J->wave) {
+      const uint32_t nf = std::min<uint32_t>((uint32_t)J->wave, J->n_filters - f);
+      if ((rc = launch_ung_filter(J, f, nf))) return rc;
       J->launches += 1;
     }
   } else {
@@ -865,7 +882,7 @@ int job_common(bssm_b200_job* J, int kind, int n, int m, int k, uint32_t nsim, u
   J->kind = kind; J->method = BSSM_METHOD_BSF; J->post = post; J->out_flags = out_flags;
   J->N = nsim; J->n_filters = n_filters; J->first_filter = first_filter_id; J->seed = seed;
   J->n = n; J->m = m; J->k = k;
-  if ((rc = choose_geometry(nsim, &J->geo))) return rc;
+  if ((rc = choose_geometry(nsim, n_filters, &J->geo))) return rc;
   CU(cudaStreamCreateWithFlags(&J->stream, cudaStreamNonBlocking));
   for (auto& e : J->ev) CU(cudaEventCreate(&e));
   return 0;
@@ -1234,7 +1251,7 @@ __global__ void __launch_bounds__(1024)
 stratified_kernel(const double* __restrict__ p, uint32_t n_p, const double* __restrict__ r, uint32_t N,
                   uint32_t* __restrict__ xp) {
   __shared__ pf::CollSmem csm;
-  pf::Sync sync; sync.mode = pf::SYNC_BLOCK; sync.counter = nullptr; sync.nblocks = 1; sync.target = 0;
+  pf::Sync sync; sync.mode = pf::SYNC_BLOCK; sync.slots = nullptr; sync.epoch = 0ull;
   pf::Coll coll;
   coll.sm = &csm; coll.sync = &sync; coll.xch = nullptr; coll.ranks = 1; coll.rank = 0;
   coll.lane = threadIdx.x & 31; coll.warp = threadIdx.x >> 5; coll.nwarps = (blockDim.x + 31) >> 5;

@@ -183,15 +183,18 @@ def test_particle_smoother_m2_parity(engine):
     np.testing.assert_allclose(res["Vt"], cov, rtol=1e-9, atol=1e-13)
 
 
-@pytest.mark.parametrize("ranks,P", [(1, 8), (2, 4), (4, 2), (8, 2), (16, 2)])
-def test_results_do_not_depend_on_launch_geometry(engine, ranks, P, monkeypatch):
-    """cluster sizes 1..16 and P = 2/4/8 give the same bits as the oracle: the
-    fixed-point sum / cumsum make the filter independent of the reduction tree"""
+@pytest.mark.parametrize("ranks,P,sync", [(1, 8, "group"), (2, 4, "group"), (4, 2, "group"), (8, 2, "cluster"),
+                                           (16, 2, "cluster"), (16, 2, "group"), (32, 2, "group"), (7, 8, "group")])
+def test_results_do_not_depend_on_launch_geometry(engine, ranks, P, sync, monkeypatch):
+    """1..32 CTAs per filter, P = 2/4/8, L2 group synchronisation or hardware cluster
+    barrier: all give the same bits as the oracle -- the fixed-point sum / cumsum make
+    the filter independent of the reduction tree"""
     model = data.svm_model(40)
     N = 8192
     ref = orc.psi_filter(model, N, seed=1)
     monkeypatch.setenv("BSSM_B200_RANKS", str(ranks))
     monkeypatch.setenv("BSSM_B200_P", str(P))
+    monkeypatch.setenv("BSSM_B200_SYNC", sync)
     job = engine.FilterJob(model, N, method="psi", seed=1, out_flags=7)
     job.run()
     b = job.fetch(0, alpha=True, weights=True, indices=True)
@@ -201,8 +204,8 @@ def test_results_do_not_depend_on_launch_geometry(engine, ranks, P, monkeypatch)
     job.close()
 
 
-def test_grid_mode_parity(engine, monkeypatch):
-    """more ranks than a cluster holds -> cooperative grid with the software barrier"""
+def test_many_rank_group_parity(engine, monkeypatch):
+    """more ranks than a cluster holds: cooperative launch, synchronisation through L2"""
     model = data.svm_model(30)
     N = 40000
     ref = orc.psi_filter(model, N, seed=1)
@@ -213,6 +216,21 @@ def test_grid_mode_parity(engine, monkeypatch):
     b = job.fetch(0, alpha=False, weights=True, indices=True)
     assert np.array_equal(b.indices, ref.indices)
     assert b.out.loglik == ref.loglik
+    job.close()
+
+
+def test_batch_of_group_filters_in_waves(engine, monkeypatch):
+    """more multi-CTA filters than fit on the device at once -> several cooperative launches"""
+    model = data.svm_model(20)
+    monkeypatch.setenv("BSSM_B200_RANKS", "64")
+    monkeypatch.setenv("BSSM_B200_P", "2")
+    monkeypatch.setenv("BSSM_B200_BLOCK", "256")
+    job = engine.FilterJob(model, 30000, method="psi", seed=2, n_filters=12, out_flags=0)
+    job.run()
+    assert job.launches() >= 2 + 1  # pre-pass + at least two waves
+    ll = job.logliks()
+    for f in (0, 7, 11):
+        assert ll[f] == orc.psi_filter(model, 30000, seed=2, filt=f).loglik
     job.close()
 
 
