@@ -436,7 +436,7 @@ struct bssm_b200_job {
   DevBuf<double> loglik;
   DevBuf<int32_t> stopped;
   DevBuf<unsigned long long> xch;
-  DevBuf<unsigned long long> slots;
+  DevBuf<unsigned int> counters;
   int wave = 0; // filters per launch in SYNC_GROUP mode (all CTAs of a launch must be co-resident)
   DevBuf<double> ubuf;
   DevBuf<unsigned long long> phases;
@@ -501,7 +501,7 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
   fp.loglik = J->loglik.p + f0;
   fp.stopped_at = J->stopped.p + f0;
   fp.xch = J->xch.p + (size_t)f0 * 4 * J->geo.ranks;
-  fp.slots = J->slots.p + (size_t)f0 * 8 * J->geo.ranks;
+  fp.counters = J->counters.p + f0;
   fp.ubuf = J->ubuf.p + (size_t)f0 * J->N;
   if (fp.phase_cycles) fp.phase_cycles = J->phases.p + (size_t)f0 * 6 * J->geo.ranks;
   if (J->kind == KIND_NLG) return launch_filter<pf::NlgGrowthBsf>(fp, J->np, J->geo, nf, J->stream);
@@ -571,7 +571,7 @@ static int finish_job(bssm_b200_job* J, int out_flags, int post) {
   if (smooth && (rc = J->alpha_sm.alloc(J->alpha_stride * n_filters))) return rc;
   if (post == BSSM_POST_PICK && (rc = J->traj.alloc((size_t)n_filters * (n + 1) * m))) return rc;
   if ((rc = J->loglik.alloc(n_filters)) || (rc = J->stopped.alloc(n_filters))) return rc;
-  if ((rc = J->xch.alloc((size_t)4 * J->geo.ranks * n_filters)) || (rc = J->slots.alloc((size_t)8 * J->geo.ranks * n_filters)) ||
+  if ((rc = J->xch.alloc((size_t)4 * J->geo.ranks * n_filters)) || (rc = J->counters.alloc(n_filters)) ||
       (rc = J->ubuf.alloc((size_t)nsim * n_filters))) return rc;
   if (post == BSSM_POST_FILTER_SUMMARY) {
     if ((rc = J->s_at.alloc((size_t)n_filters * m * (n + 1))) || (rc = J->s_att.alloc((size_t)n_filters * m * n)) ||
@@ -590,7 +590,7 @@ static int finish_job(bssm_b200_job* J, int out_flags, int post) {
   fp.indices = J->indices.p; fp.indices_stride = J->indices_stride;
   fp.keep_indices = J->keep_indices ? 1 : 0;
   fp.loglik = J->loglik.p; fp.stopped_at = J->stopped.p;
-  fp.xch = J->xch.p; fp.slots = J->slots.p; fp.ubuf = J->ubuf.p;
+  fp.xch = J->xch.p; fp.counters = J->counters.p; fp.ubuf = J->ubuf.p;
   fp.phase_cycles = nullptr;
   if (env_int("BSSM_B200_PHASES", 0)) {
     if ((rc = J->phases.alloc((size_t)6 * J->geo.ranks * n_filters))) return rc;
@@ -734,7 +734,7 @@ int bssm_b200_job_run(bssm_b200_job* J, float* ms_out) {
       J->wave = bssm_b200_job_max_concurrent_filters(J);
       if (J->wave < 1) return fail(BSSM_B200_ERR_UNSUPPORTED, "filter group does not fit on the device");
     }
-    CU(cudaMemsetAsync(J->slots.p, 0, sizeof(unsigned long long) * J->slots.count, J->stream));
+    CU(cudaMemsetAsync(J->counters.p, 0, sizeof(unsigned int) * J->counters.count, J->stream));
     for (uint32_t f = 0; f < J->n_filters; f += (uint32_t)J->wave) {
       const uint32_t nf = std::min<uint32_t>((uint32_t)J->wave, J->n_filters - f);
       if ((rc = launch_ung_filter(J, f, nf))) return rc;
@@ -1251,7 +1251,7 @@ __global__ void __launch_bounds__(1024)
 stratified_kernel(const double* __restrict__ p, uint32_t n_p, const double* __restrict__ r, uint32_t N,
                   uint32_t* __restrict__ xp) {
   __shared__ pf::CollSmem csm;
-  pf::Sync sync; sync.mode = pf::SYNC_BLOCK; sync.slots = nullptr; sync.epoch = 0ull;
+  pf::Sync sync; sync.mode = pf::SYNC_BLOCK; sync.counter = nullptr; sync.nranks = 1; sync.target = 0;
   pf::Coll coll;
   coll.sm = &csm; coll.sync = &sync; coll.xch = nullptr; coll.ranks = 1; coll.rank = 0;
   coll.lane = threadIdx.x & 31; coll.warp = threadIdx.x >> 5; coll.nwarps = (blockDim.x + 31) >> 5;

@@ -43,10 +43,10 @@ struct FilterParams {
   int keep_indices;
   double* loglik;        // [n_filters]
   int32_t* stopped_at;   // [n_filters]
-  // SYNC_CLUSTER exchange area: per filter 4 * ranks 8-byte words
+  // exchange area for the partials: per filter 4 * ranks 8-byte words
   unsigned long long* xch;
-  // SYNC_GROUP descriptor slots: per filter 2 * ranks Slots, zeroed before the launch
-  void* slots;
+  // SYNC_GROUP: one barrier counter per filter, zeroed before the launch
+  unsigned int* counters;
   // stratum thresholds u_j = (r_j + j) * (1/N) of the current step, N per filter
   double* ubuf;
   // diagnostics: when non-null, thread 0 of every CTA accumulates the SM cycles
@@ -57,42 +57,49 @@ struct FilterParams {
 };
 
 // ---------------------------------------------------------- synchronisation
-// A filter that spans several CTAs synchronises three times per time step.
-// Two mechanisms:
+// A filter that spans several CTAs synchronises three times per time step
+// (max, scan, scatter).  Partials are exchanged through L2 (`xch`), separated by
+// a barrier over the CTAs of the filter:
 //
-//  SYNC_GROUP (default): every collective is ONE round trip through L2.  Each
-//    rank publishes its partial together with an epoch tag as a single 16-byte
-//    store ({value, epoch}); warp 0 of every rank polls the slots of all ranks
-//    until the tags match the epoch and combines the values.  Data and "I have
-//    arrived" travel in the same transaction, so there is no separate barrier
-//    followed by a read of the partials.  Slots are double-buffered by epoch
-//    parity (a rank can be at most one collective ahead of the slowest).  All
-//    CTAs of a launch must be co-resident: cooperative launch.
-//  SYNC_CLUSTER: hardware barrier.cluster (release/acquire) around an exchange
-//    of the partials through L2; kept for comparison (needs a cluster launch,
-//    <= 16 CTAs per filter, and a GPC with that many free SMs).
+//  SYNC_GROUP (default): software barrier -- one monotonically increasing
+//    counter per filter, one atomicAdd and one polling thread per CTA, fences on
+//    both sides.  Works for any number of CTAs per filter and any number of
+//    filters per launch; all CTAs of a launch must be co-resident (cooperative
+//    launch; the host splits a batch into waves).  Measured 1.2 us (8 CTAs) to
+//    2.6 us (148 CTAs) per collective including the read of the partials
+//    (tools/bench_sync.cu); publishing {value, epoch} descriptors polled by a
+//    whole warp was tried and is slower (1.6 - 4.2 us: L2 contention).
+//  SYNC_CLUSTER: hardware barrier.cluster (release/acquire); needs a cluster
+//    launch, <= 16 CTAs per filter and a GPC with that many free SMs, which
+//    limits how many filters run concurrently.  Kept for comparison.
 //
-// In both, the release by the publishing thread (after the CTA barrier) and the
-// acquire by the polling lanes (before the CTA barrier) also order the bulk
-// exchange through global memory (state rows, thresholds, ancestors), which the
-// consumers read with ld.cg.
-struct Desc { unsigned long long val, tag; };  // 16 bytes, written/read as one transaction
-struct Slot { Desc d0, d1; };                  // 32 bytes per rank and parity
-
-__device__ __forceinline__ void desc_store(Desc* p, unsigned long long val, unsigned long long tag) {
-  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(val), "l"(tag) : "memory");
-}
-__device__ __forceinline__ void desc_load(const Desc* p, unsigned long long& val, unsigned long long& tag) {
-  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(val), "=l"(tag) : "l"(p) : "memory");
-}
-
+// The release / acquire of the barrier also orders the bulk exchange through
+// global memory (state rows, thresholds, ancestors); consumers read with ld.cg.
 struct Sync {
   int mode;
-  Slot* slots;              // SYNC_GROUP: [2][ranks] for this filter
-  unsigned long long epoch; // number of collectives so far (same in every thread of the filter)
-  __device__ __forceinline__ void cluster_barrier() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n"
-                 "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+  unsigned int* counter; // SYNC_GROUP: this filter's counter (zeroed before the launch)
+  unsigned int nranks;
+  unsigned int target;
+  __device__ __forceinline__ void all() {
+    if (mode == SYNC_BLOCK) {
+      __syncthreads();
+    } else if (mode == SYNC_CLUSTER) {
+      asm volatile("barrier.cluster.arrive.release.aligned;\n"
+                   "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    } else {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        target += nranks;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned int v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while ((int)(v - target) < 0);
+        __threadfence();
+      }
+      __syncthreads();
+    }
   }
 };
 
@@ -122,44 +129,11 @@ struct CollSmem {
 struct Coll {
   CollSmem* sm;
   Sync* sync;
-  unsigned long long* xch; // SYNC_CLUSTER: this filter's exchange area
+  unsigned long long* xch; // this filter's exchange area, 3 * ranks words
   uint32_t ranks, rank;
   int lane, warp, nwarps;
 
-  // ---- SYNC_GROUP primitives (warp 0 only)
-  __device__ __forceinline__ Slot* slot(uint32_t r) const {
-    return sync->slots + (sync->epoch & 1ull) * ranks + r;
-  }
-  __device__ __forceinline__ void publish(unsigned long long v0, unsigned long long v1, bool two) {
-    // lane 0 of warp 0, after the CTA barrier: release everything this CTA wrote
-    __threadfence();
-    Slot* me = slot(rank);
-    desc_store(&me->d0, v0, sync->epoch + 1);
-    if (two) desc_store(&me->d1, v1, sync->epoch + 1);
-  }
-  __device__ __forceinline__ void wait0(uint32_t r, unsigned long long& v0) const {
-    unsigned long long tag;
-    do { desc_load(&slot(r)->d0, v0, tag); } while ((long long)(tag - (sync->epoch + 1)) < 0);
-  }
-  __device__ __forceinline__ void wait1(uint32_t r, unsigned long long& v1) const {
-    unsigned long long tag;
-    do { desc_load(&slot(r)->d1, v1, tag); } while ((long long)(tag - (sync->epoch + 1)) < 0);
-  }
-
-  // pure barrier over the filter (plus release/acquire of global memory)
-  __device__ __forceinline__ void barrier() {
-    if (ranks == 1) { __syncthreads(); return; }
-    if (sync->mode == SYNC_CLUSTER) { sync->cluster_barrier(); return; }
-    __syncthreads();
-    if (warp == 0) {
-      if (lane == 0) publish(0ull, 0ull, false);
-      unsigned long long v;
-      for (uint32_t r = lane; r < ranks; r += 32) wait0(r, v);
-      __threadfence();
-    }
-    sync->epoch++;
-    __syncthreads();
-  }
+  __device__ __forceinline__ void barrier() { sync->all(); }
 
   __device__ __forceinline__ double allmax(double v) {
 #pragma unroll
@@ -170,26 +144,11 @@ struct Coll {
       double x = lane < nwarps ? sm->wd[lane] : -pf_inf();
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) x = nanmax(x, shfl_xor_d(x, o));
-      if (ranks == 1) {
-        if (lane == 0) sm->rd = x;
-      } else if (sync->mode == SYNC_GROUP) {
-        if (lane == 0) publish((unsigned long long)__double_as_longlong(x), 0ull, false);
-        double y = -pf_inf();
-        for (uint32_t r = lane; r < ranks; r += 32) {
-          unsigned long long bits;
-          wait0(r, bits);
-          y = nanmax(y, __longlong_as_double((long long)bits));
-        }
-        __threadfence();
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) y = nanmax(y, shfl_xor_d(y, o));
-        if (lane == 0) sm->rd = y;
-      } else if (lane == 0) {
-        ((double*)xch)[rank] = x;
-      }
+      if (ranks == 1) { if (lane == 0) sm->rd = x; }
+      else if (lane == 0) ((double*)xch)[rank] = x;
     }
-    if (ranks > 1 && sync->mode == SYNC_CLUSTER) {
-      sync->cluster_barrier();
+    sync->all();
+    if (ranks > 1) {
       if (warp == 0) {
         double x = -pf_inf();
         for (uint32_t r = lane; r < ranks; r += 32) x = nanmax(x, __ldcg(((const double*)xch) + r));
@@ -197,9 +156,8 @@ struct Coll {
         for (int o = 16; o > 0; o >>= 1) x = nanmax(x, shfl_xor_d(x, o));
         if (lane == 0) sm->rd = x;
       }
+      __syncthreads();
     }
-    if (ranks > 1) sync->epoch++;
-    __syncthreads();
     return sm->rd;
   }
 
@@ -228,33 +186,13 @@ struct Coll {
       }
       sm->wa[lane] = wh - vh; // exclusive warp prefixes
       sm->wb[lane] = wl - vl;
-      const long long toth = __shfl_sync(0xffffffffu, wh, 31), totl = __shfl_sync(0xffffffffu, wl, 31);
-      if (ranks == 1) {
-        if (lane == 0) { sm->ra = 0; sm->rb = 0; sm->ta = toth; sm->tb = totl; }
-      } else if (sync->mode == SYNC_GROUP) {
-        if (lane == 0) publish((unsigned long long)toth, (unsigned long long)totl, true);
-        long long xh = 0, xl = 0, sh = 0, sl = 0;
-        for (uint32_t r = lane; r < ranks; r += 32) {
-          unsigned long long h, l;
-          wait0(r, h);
-          wait1(r, l);
-          sh += (long long)h; sl += (long long)l;
-          if (r < rank) { xh += (long long)h; xl += (long long)l; }
-        }
-        __threadfence();
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          xh += shfl_xor_i64(xh, o); xl += shfl_xor_i64(xl, o);
-          sh += shfl_xor_i64(sh, o); sl += shfl_xor_i64(sl, o);
-        }
-        if (lane == 0) { sm->ra = xh; sm->rb = xl; sm->ta = sh; sm->tb = sl; }
-      } else if (lane == 0) {
-        ((long long*)xch)[ranks + rank] = toth;
-        ((long long*)xch)[2 * ranks + rank] = totl;
+      if (lane == 31) {
+        if (ranks == 1) { sm->ra = 0; sm->rb = 0; sm->ta = wh; sm->tb = wl; }
+        else { ((long long*)xch)[ranks + rank] = wh; ((long long*)xch)[2 * ranks + rank] = wl; }
       }
     }
-    if (ranks > 1 && sync->mode == SYNC_CLUSTER) {
-      sync->cluster_barrier();
+    sync->all();
+    if (ranks > 1) {
       if (warp == 0) {
         long long xh = 0, xl = 0, sh = 0, sl = 0;
         for (uint32_t r = lane; r < ranks; r += 32) {
@@ -270,9 +208,8 @@ struct Coll {
         }
         if (lane == 0) { sm->ra = xh; sm->rb = xl; sm->ta = sh; sm->tb = sl; }
       }
+      __syncthreads();
     }
-    if (ranks > 1) sync->epoch++;
-    __syncthreads();
     eh = sm->ra + sm->wa[warp] + (ih - th);
     el = sm->rb + sm->wb[warp] + (il - tl);
     Th = sm->ta; Tl = sm->tb;
@@ -378,8 +315,9 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
 
   Sync sync;
   sync.mode = fp.sync_mode;
-  sync.slots = (Slot*)fp.slots + (size_t)fidx * 2 * ranks;
-  sync.epoch = 0ull;
+  sync.counter = fp.counters + fidx;
+  sync.nranks = ranks;
+  sync.target = 0;
   Coll coll;
   coll.sm = &csm;
   coll.sync = &sync;
