@@ -177,9 +177,10 @@ int occupancy(const Geometry& g, int* out) {
   return fail(BSSM_B200_ERR_ARG, "bad P");
 }
 
-// kernel variants: P particles per thread; blocks of <= 512 threads are compiled
-// for 2 resident CTAs per SM (64 registers either way), so that two filters
-// share an SM and one computes while the other waits at a barrier
+// kernel variants: P particles per thread, 64 registers per thread in all of them.
+// A 128-register variant (no spills, half the warps) was measured and is 15-40%
+// slower on every workload: latency hiding by resident warps matters more than
+// the ~50-300 bytes of spills.
 template <class Model>
 int launch_filter(const pf::FilterParams& fp, const typename Model::Params& mp, const Geometry& g,
                   uint32_t n_filters, cudaStream_t stream) {

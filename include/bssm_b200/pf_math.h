@@ -67,14 +67,10 @@ PF_HD int pf_isfinite(double x) {
 typedef struct { uint32_t v[4]; } pf_u32x4;
 
 PF_HD void pf_mulhilo(uint32_t a, uint32_t b, uint32_t* hi, uint32_t* lo) {
-#if defined(__CUDA_ARCH__)
-  *lo = a * b;
-  *hi = __umulhi(a, b);
-#else
+  /* one 32x32->64 multiply (IMAD.WIDE.U32 on the device), not mul.lo + mul.hi */
   uint64_t p = (uint64_t)a * (uint64_t)b;
   *lo = (uint32_t)p;
   *hi = (uint32_t)(p >> 32);
-#endif
 }
 
 PF_HD pf_u32x4 pf_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
