@@ -179,7 +179,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--filters", type=int, default=int(os.environ.get("BENCH_FILTERS", "0")),
-                    help="replicate filters per GPU per step (0 = 2x what the device runs concurrently)")
+                    help="replicate filters per GPU per step (0 = one full wave of the device: 18)")
     ap.add_argument("--no-c4", action="store_true", help="skip the post_correct (config 4) leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
@@ -217,9 +217,9 @@ def main():
     N, n, B = w["N"], w["n"], args.filters
     model = make_model()
     if B <= 0:
-        probe = bssm_b200.FilterJob(model, N, method="psi", seed=1, n_filters=1, out_flags=0)
-        B = 2 * max(1, probe.max_concurrent_filters())
-        probe.close()
+        # one wave of the engine's throughput geometry: 148 SMs x 4 resident CTAs of 256 threads
+        # = 592 CTAs, 32 CTAs (x 256 threads x 8 particles) per 65536-particle filter -> 18 filters
+        B = 18
     job = bssm_b200.FilterJob(model, N, method="psi", seed=1, n_filters=B, first_filter=rank * B,
                               out_flags=7)
     for _ in range(args.warmup):
