@@ -123,7 +123,8 @@ def run_reference(args, rank, world):
     from bssm_b200 import build
     build.build_oracle()
     w = WORKLOAD
-    cores = orc.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1: ask the OS, not OpenMP, how many cores this process may use
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     n_sample = 50  # first 50 time points of the same series, full N
     y = data.svm_series(w["n"], w["rho"], w["sd_ar"], w["sigma"], w["gen_seed"])[:n_sample]
     model = bssm_b200.svm(y, w["rho"], w["sd_ar"], sigma=w["sigma"])
