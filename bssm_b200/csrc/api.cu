@@ -25,6 +25,7 @@
 #include "prepass_ung.cuh"
 #include "smoother_kernels.cuh"
 #include "models_nlg_sde.cuh"
+#include "bssm_b200/ung_gauss_approx.h"
 
 namespace {
 
@@ -508,6 +509,11 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
   if (J->kind == KIND_NLG) return launch_filter<pf::NlgGrowthBsf>(fp, J->np, J->geo, nf, J->stream);
   if (J->kind == KIND_SDE) return launch_filter<pf::SdeGbmBsf>(fp, J->sp, J->geo, nf, J->stream);
   pf::UngParams up = J->up;
+  if (J->method == BSSM_METHOD_PSI && J->m > 1) {
+    up.approx_loglik += f0;
+    if (J->m == 2) return launch_filter<pf::UngPsiM<2>>(fp, up, J->geo, nf, J->stream);
+    return launch_filter<pf::UngPsiM<3>>(fp, up, J->geo, nf, J->stream);
+  }
   if (J->method == BSSM_METHOD_PSI) {
     up.alphahat += (size_t)f0 * J->pstride; up.Lt += (size_t)f0 * J->pstride; up.Ct += (size_t)f0 * J->pstride;
     up.ytilde += (size_t)f0 * J->pstride; up.Htilde += (size_t)f0 * J->pstride; up.scales += (size_t)f0 * J->pstride;
@@ -613,8 +619,8 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
     return fail(BSSM_B200_ERR_ARG, "need n >= 1, m >= 1, k >= 1, nsim >= 2, n_filters >= 1");
   if (M->distribution < 0 || M->distribution > 4) return fail(BSSM_B200_ERR_ARG, "distribution must be 0..4");
   if (method != BSSM_METHOD_PSI && method != BSSM_METHOD_BSF) return fail(BSSM_B200_ERR_ARG, "method must be 1 (psi) or 2 (bsf)");
-  if (method == BSSM_METHOD_PSI && M->m != 1)
-    return fail(BSSM_B200_ERR_UNSUPPORTED, "psi-APF is implemented for m = 1 in this build");
+  if (method == BSSM_METHOD_PSI && (M->m > 3 || (M->m != 1 && draw_par)))
+    return fail(BSSM_B200_ERR_UNSUPPORTED, "psi-APF: m <= 3 (and m = 1 for per-draw models) in this build");
   if (M->k > M->m) return fail(BSSM_B200_ERR_ARG, "k > m");
   if (post < 0 || post > BSSM_POST_SMOOTHER_MERGE) return fail(BSSM_B200_ERR_ARG, "bad post mode");
   int rc = require_device();
@@ -657,7 +663,23 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
   const double dconst = ung_dist_const(M);
   up.loglik_const = dconst;
 
-  if (method == BSSM_METHOD_PSI) {
+  if (method == BSSM_METHOD_PSI && m > 1) {
+    // Gaussian approximation on the host (O(n m^3), sequential in t), shared by all replicates
+    if (!M->initial_mode) return fail(BSSM_B200_ERR_ARG, "psi-APF needs initial_mode");
+    if (M->max_iter < 1) return fail(BSSM_B200_ERR_ARG, "max_iter must be >= 1");
+    pfga::UngApprox ga(M);
+    ga.run(nullptr);
+    std::vector<double> al(n_filters, ga.approx_loglik);
+    if ((rc = J->alphahat.upload(ga.alphahat.data(), ga.alphahat.size())) || (rc = J->Lt.upload(ga.L.data(), ga.L.size())) ||
+        (rc = J->Ct.upload(ga.Ct.data(), ga.Ct.size())) || (rc = J->ytilde.upload(ga.ay.data(), n)) ||
+        (rc = J->Htilde.upload(ga.aH.data(), n)) || (rc = J->scales.upload(ga.scales.data(), n)) ||
+        (rc = J->approx_loglik.upload(al.data(), n_filters)))
+      return rc;
+    J->pstride = 0;
+    up.phi_f = nullptr; up.alphahat = J->alphahat.p; up.Lt = J->Lt.p; up.Ct = J->Ct.p;
+    up.ytilde = J->ytilde.p; up.Htilde = J->Htilde.p; up.scales = J->scales.p;
+    up.approx_loglik = J->approx_loglik.p; up.pstride = 0;
+  } else if (method == BSSM_METHOD_PSI) {
     if (draw_par) {
       // approximate_for_is (src/model_ssm_ung.cpp:143-161): fixed mode per draw, no iterations
       if (!draw_modes) return fail(BSSM_B200_ERR_ARG, "per-draw models need per-draw modes");
@@ -722,7 +744,7 @@ int bssm_b200_job_run(bssm_b200_job* J, float* ms_out) {
   int rc;
   J->launches = 0;
   CU(cudaEventRecord(J->ev[0], J->stream));
-  if (J->kind == KIND_UNG && J->method == BSSM_METHOD_PSI) {
+  if (J->kind == KIND_UNG && J->method == BSSM_METHOD_PSI && J->m == 1) {
     const uint32_t warps_per_block = 4;
     pf::ung_prepass_m1_kernel<<<cdiv(J->n_filters, warps_per_block), 32 * warps_per_block, 0, J->stream>>>(
         J->pp, J->n_filters);

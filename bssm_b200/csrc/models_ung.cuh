@@ -157,4 +157,80 @@ struct UngPsi1 : GaussStep<UngPsi1, 1, 1, 1> {
   }
 };
 
+// ------------------------------------------------------------ psi-APF, m > 1
+// alpha_{t+1} = ahat_{t+1} + Ct_{t+1} (alpha_anc - ahat_t) + L_{t+1} u, u ~ N(0, I_m)
+// (src/model_ssm_ung.cpp:580-587); the Gaussian approximation (ahat, Ct, L, pseudo
+// observations, scales) comes from the host (include/bssm_b200/ung_gauss_approx.h) and
+// is shared by all replicate filters of a job (pstride = 0).
+template <int M_>
+struct UngPsiM : GaussStep<UngPsiM<M_>, M_, M_, M_> {
+  static constexpr int M = M_, KI = M_, KP = M_;
+  typedef UngParams Params;
+  const UngParams& mp;
+  double al0;
+  double y, u, yphi2, Dt, xb, ytil, Htil, scale;
+  double Z[M_], ah0[M_], ah1[M_], Cm[M_ * M_], Lm[M_ * M_];
+
+  __device__ UngPsiM(const UngParams& p, uint32_t f) : mp(p) { al0 = p.approx_loglik[f]; }
+  __device__ double loglik0() const { return al0; }
+  __device__ double loglik_end() const { return 0.0; }
+  __device__ void init(const double* z, double* x) const {
+#pragma unroll
+    for (int d = 0; d < M_; ++d) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < M_; ++j) s += mp.Lt[d + M_ * j] * z[j];
+      x[d] = mp.alphahat[d] + s;
+    }
+  }
+  __device__ bool observed(int t) const { return pf_isfinite(mp.y[t]); }
+  __device__ void begin_weight(int t) {
+    y = mp.y[t];
+    u = mp.u[t];
+    double q = y / mp.phi;
+    yphi2 = q * q;
+    Dt = mp.D[t * mp.Dtv];
+    xb = mp.xbeta[t];
+#pragma unroll
+    for (int d = 0; d < M_; ++d) Z[d] = mp.Z[d + M_ * (t * mp.Ztv)];
+    ytil = mp.ytilde[t]; Htil = mp.Htilde[t]; scale = mp.scales[t];
+  }
+  __device__ double logw(const double* x) const {
+    double s;
+    if (mp.distribution == 0) {
+      s = x[0];
+    } else {
+      double zs = 0.0;
+#pragma unroll
+      for (int d = 0; d < M_; ++d) zs += Z[d] * x[d];
+      s = Dt + zs + xb;
+    }
+    double q = (ytil - s) / Htil;
+    return (ung_log_obs(mp.distribution, s, y, u, mp.phi, yphi2) + 0.5 * (q * q)) - scale;
+  }
+  __device__ void begin_step(int t) {
+#pragma unroll
+    for (int d = 0; d < M_; ++d) { ah0[d] = mp.alphahat[d + M_ * t]; ah1[d] = mp.alphahat[d + M_ * (t + 1)]; }
+#pragma unroll
+    for (int e = 0; e < M_ * M_; ++e) {
+      Cm[e] = mp.Ct[e + M_ * M_ * (t + 1)];
+      Lm[e] = mp.Lt[e + M_ * M_ * (t + 1)];
+    }
+  }
+  __device__ void propagate(const double* xa, const double* z, double* x) const {
+    double diff[M_];
+#pragma unroll
+    for (int j = 0; j < M_; ++j) diff[j] = xa[j] - ah0[j];
+#pragma unroll
+    for (int d = 0; d < M_; ++d) {
+      double cd = 0.0, lu = 0.0;
+#pragma unroll
+      for (int j = 0; j < M_; ++j) cd += Cm[d + M_ * j] * diff[j];
+#pragma unroll
+      for (int j = 0; j < M_; ++j) lu += Lm[d + M_ * j] * z[j];
+      x[d] = ah1[d] + cd + lu;
+    }
+  }
+};
+
 } // namespace pf

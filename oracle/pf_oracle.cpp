@@ -43,6 +43,7 @@
 
 #include "bssm_b200/pf_math.h"
 #include "bssm_b200.h"
+#include "bssm_b200/ung_gauss_approx.h"
 
 enum { ORC_ARITH_REFERENCE = 0, ORC_ARITH_REPRO = 1 };
 
@@ -658,6 +659,80 @@ double orc_ung_psi_filter(const bssm_ung_model* M, const double* mode_in, uint32
     double* wcol = weights + N * (t + 1);
     if ((t < (n - 1)) && std::isfinite(M->y[t + 1])) {
       for (size_t i = 0; i < N; ++i) { double a = A(t + 1, i); logw[i] = g.log_weight(t + 1, g.signal(t + 1, &a)) - g.scales[t + 1]; }
+      double mxw, lmean;
+      if (!normalise(logw.data(), nsim, wcol, W, &mxw, &lmean, arith)) { *stopped_at = t + 1; return -ORC_INF; }
+      loglik += mxw + lmean;
+    } else {
+      for (size_t i = 0; i < N; ++i) { wcol[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
+    }
+  }
+  return loglik;
+}
+
+/* ssm_ung::psi_filter for any state dimension m (src/model_ssm_ung.cpp:511-609).  The
+ * Gaussian approximation is the shared host implementation of
+ * include/bssm_b200/ung_gauss_approx.h (for m = 1 it reproduces Ulg1 above bit for bit,
+ * tests/test_oracle.py); the particle loop is restated here. */
+double orc_ung_psi_filter_m(const bssm_ung_model* M, const double* mode_in, uint32_t nsim, uint32_t seed,
+                            uint32_t filter, int arith, double* alpha, double* weights, uint32_t* indices,
+                            double* approx_loglik, int32_t* stopped_at, double* alphahat_out, double* L_out,
+                            double* Ct_out) {
+  *stopped_at = -1;
+  pfga::UngApprox ga(M);
+  ga.run(mode_in);
+  if (approx_loglik) *approx_loglik = ga.approx_loglik;
+  const int n = M->n, m = M->m;
+  const size_t N = nsim, mm = (size_t)m * m;
+  if (alphahat_out) std::copy(ga.alphahat.begin(), ga.alphahat.end(), alphahat_out);
+  if (L_out) std::copy(ga.L.begin(), ga.L.end(), L_out);
+  if (Ct_out) std::copy(ga.Ct.begin(), ga.Ct.end(), Ct_out);
+  Ung g(M);
+  g.ay = ga.ay; g.aH = ga.aH; g.scales = ga.scales;
+  auto A = [&](int d, int t, size_t i) -> double& { return alpha[d + (size_t)m * (t + (size_t)(n + 1) * i)]; };
+  for (size_t i = 0; i < N; ++i) { /* :538-544 */
+    std::vector<double> um(m);
+    for (int j = 0; j < m; ++j) um[j] = pf_normal(seed, filter, 0, 0, (uint32_t)(i * m + j));
+    for (int d = 0; d < m; ++d) {
+      double s = 0.0;
+      for (int j = 0; j < m; ++j) s += ga.L[d + (size_t)m * j] * um[j];
+      A(d, 0, i) = ga.alphahat[d] + s;
+    }
+  }
+  std::vector<double> W(N), logw(N), r(N), atmp((size_t)m * N);
+  double loglik = 0.0;
+  if (std::isfinite(M->y[0])) {
+    for (size_t i = 0; i < N; ++i) logw[i] = g.log_weight(0, g.signal(0, &A(0, 0, i))) - g.scales[0];
+    double mxw, lmean;
+    if (!normalise(logw.data(), nsim, weights, W, &mxw, &lmean, arith)) { *stopped_at = 0; return -ORC_INF; }
+    loglik = mxw + ga.approx_loglik + lmean;
+  } else {
+    for (size_t i = 0; i < N; ++i) { weights[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
+    loglik = ga.approx_loglik;
+  }
+  for (int t = 0; t < n; ++t) { /* :568-606 */
+    for (size_t i = 0; i < N; ++i) r[i] = pf_resample_uniform(seed, filter, t, (uint32_t)i);
+    uint32_t* ind = indices + N * t;
+    resample(W, r, nsim, ind, arith);
+    for (size_t i = 0; i < N; ++i)
+      for (int d = 0; d < m; ++d) atmp[d + (size_t)m * i] = A(d, t, ind[i]);
+    const double* ah0 = &ga.alphahat[(size_t)m * t];
+    const double* ah1 = &ga.alphahat[(size_t)m * (t + 1)];
+    const double* Ctm = &ga.Ct[mm * (t + 1)];
+    const double* Lm = &ga.L[mm * (t + 1)];
+    for (size_t i = 0; i < N; ++i) {
+      std::vector<double> um(m), diff(m);
+      for (int j = 0; j < m; ++j) um[j] = pf_normal(seed, filter, t + 1, 0, (uint32_t)(i * m + j));
+      for (int j = 0; j < m; ++j) diff[j] = atmp[j + (size_t)m * i] - ah0[j];
+      for (int d = 0; d < m; ++d) {
+        double cd = 0.0, lu = 0.0;
+        for (int j = 0; j < m; ++j) cd += Ctm[d + (size_t)m * j] * diff[j];
+        for (int j = 0; j < m; ++j) lu += Lm[d + (size_t)m * j] * um[j];
+        A(d, t + 1, i) = ah1[d] + cd + lu;
+      }
+    }
+    double* wcol = weights + N * (t + 1);
+    if ((t < (n - 1)) && std::isfinite(M->y[t + 1])) {
+      for (size_t i = 0; i < N; ++i) logw[i] = g.log_weight(t + 1, g.signal(t + 1, &A(0, t + 1, i))) - g.scales[t + 1];
       double mxw, lmean;
       if (!normalise(logw.data(), nsim, wcol, W, &mxw, &lmean, arith)) { *stopped_at = t + 1; return -ORC_INF; }
       loglik += mxw + lmean;

@@ -33,6 +33,10 @@ def L():
         _L.orc_ung_psi_filter.restype = d
         _L.orc_ung_psi_filter.argtypes = [C.POINTER(UngModel), c_double_p, u32, u32, u32, C.c_int, c_double_p,
                                           c_double_p, c_uint32_p, c_double_p, C.POINTER(i32)]
+        _L.orc_ung_psi_filter_m.restype = d
+        _L.orc_ung_psi_filter_m.argtypes = [C.POINTER(UngModel), c_double_p, u32, u32, u32, C.c_int, c_double_p,
+                                            c_double_p, c_uint32_p, c_double_p, C.POINTER(i32), c_double_p,
+                                            c_double_p, c_double_p]
         _L.orc_ung_psi_prepass.argtypes = [C.POINTER(UngModel), c_double_p] + [c_double_p] * 8
         _L.orc_ung_filter_batch.argtypes = [C.POINTER(UngModel), C.c_int, c_double_p, u32, u32, u32, u32, C.c_int,
                                             C.c_int, c_double_p]
@@ -224,5 +228,24 @@ def sde_bsf_filter(model, N, Lvl, seed, filt=0, arith=ARITH_REPRO):
     st = C.c_int32(-1)
     r.loglik = L().orc_sde_bsf_filter(C.byref(ms), N, Lvl, seed, filt, arith, dptr(r.alpha), dptr(r.weights),
                                       uptr(r.indices), C.byref(st))
+    r.stopped_at = st.value
+    return r
+
+
+def psi_filter_m(model, N, seed, filt=0, arith=ARITH_REPRO, mode=None):
+    """general-m psi-APF (Gaussian approximation from include/bssm_b200/ung_gauss_approx.h)"""
+    r = _alloc(model, N)
+    n, m = model.n, model.m
+    ms = model.c_struct()
+    st = C.c_int32(-1)
+    al = C.c_double(0)
+    r.alphahat = np.zeros((m, n + 1), order="F")
+    r.L = np.zeros((m, m, n + 1), order="F")
+    r.Ct = np.zeros((m, m, n + 1), order="F")
+    mode_a = None if mode is None else np.ascontiguousarray(mode, dtype=np.float64)
+    r.loglik = L().orc_ung_psi_filter_m(C.byref(ms), dptr(mode_a), N, seed, filt, arith, dptr(r.alpha),
+                                        dptr(r.weights), uptr(r.indices), C.byref(al), C.byref(st),
+                                        dptr(r.alphahat), dptr(r.L), dptr(r.Ct))
+    r.approx_loglik = al.value
     r.stopped_at = st.value
     return r

@@ -298,3 +298,40 @@ def test_full_size_properties_c2(engine):
     job.run()
     assert job.logliks()[0] == ll, "same seed, same bits"
     job.close()
+
+
+@pytest.mark.parametrize("N", [100, 2000])
+def test_psi_apf_bsm_ng_m2_parity(engine, N):
+    """psi-APF with a 2-dimensional state (bsm_ng level + slope, Poisson): host Gaussian
+    approximation + device particle loop against the oracle's general-m restatement"""
+    model = data.poisson_bsm_model()
+    ref = orc.psi_filter_m(model, N, seed=1)
+    res = engine.particle_smoother(model, N, method="psi", seed=1, return_indices=True)
+    assert np.array_equal(res["indices"], ref.indices)
+    assert res["logLik"] == ref.loglik
+    assert res["approx_logLik"] == ref.approx_loglik
+    sm = orc.filter_smoother(ref.alpha, ref.indices)
+    assert np.array_equal(_alpha_cube(res).view(np.uint64), sm.view(np.uint64))
+    mean, cov = orc.summary(sm)
+    np.testing.assert_allclose(res["alphahat"].T, mean, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(res["Vt"], cov, rtol=1e-8, atol=1e-12)
+
+
+def test_psi_apf_m3_and_missing_parity(engine):
+    rng = np.random.default_rng(8)
+    y = rng.poisson(5.0, size=50).astype(float)
+    y[[4, 20]] = np.nan
+    model = engine.bsm_ng(y, sd_level=0.1, sd_slope=0.02, sd_noise=0.1, distribution="poisson",
+                          P1=np.diag([1.0, 0.5, 1.0]))
+    assert (model.m, model.k) == (3, 3)
+    ref = orc.psi_filter_m(model, 300, seed=6)
+    job = engine.FilterJob(model, 300, method="psi", seed=6, out_flags=7)
+    job.run()
+    b = job.fetch(0, alpha=True, weights=True, indices=True)
+    assert np.array_equal(b.indices, ref.indices)
+    assert np.array_equal(b.alpha.view(np.uint64), ref.alpha.view(np.uint64))
+    assert b.out.loglik == ref.loglik
+    job.close()
+    refb = orc.bsf_filter(model, 300, seed=6)
+    resb = engine.bootstrap_filter(model, 300, seed=6, return_indices=True)
+    assert np.array_equal(resb["indices"], refb.indices) and resb["logLik"] == refb.loglik
