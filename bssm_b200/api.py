@@ -68,6 +68,8 @@ def bootstrap_filter(model, particles, seed=1, return_indices=False, L=None):
     ms = model.c_struct()
     if model.cls == "ssm_nlg":
         check(lib().bssm_b200_bsf_nlg(C.byref(ms), N, seed, C.byref(b.out)))
+    elif model.cls == "ssm_mng":
+        check(lib().bssm_b200_bsf_mng(C.byref(ms), N, seed, C.byref(b.out)))
     elif model.cls == "ssm_sde":
         if L is None or int(L) < 1:
             raise ValueError("Discretization level L must be larger than 0.")  # R/bootstrap_filter.R:169
@@ -97,10 +99,11 @@ def particle_smoother(model, particles, method="psi", seed=1, return_indices=Fal
     N, seed = _check_particles(model, particles, seed)
     b = _Buffers(model, N, indices=return_indices, smooth=True)
     ms = model.c_struct()
-    if model.cls == "ssm_nlg":
+    if model.cls in ("ssm_nlg", "ssm_mng"):
         if method != "bsf":
-            raise ValueError("ssm_nlg: only method='bsf' is implemented in this build")
-        check(lib().bssm_b200_bsf_smoother_nlg(C.byref(ms), N, seed, C.byref(b.out)))
+            raise ValueError("%s: only method='bsf' is implemented in this build" % model.cls)
+        fn = lib().bssm_b200_bsf_smoother_nlg if model.cls == "ssm_nlg" else lib().bssm_b200_bsf_smoother_mng
+        check(fn(C.byref(ms), N, seed, C.byref(b.out)))
     elif model.cls == "ssm_sde":
         if L is None or int(L) < 1:
             raise ValueError("Discretization level L must be larger than 0.")
@@ -129,7 +132,10 @@ class FilterJob:
         self._ms = model.c_struct()
         self._h = C.c_void_p()
         meth = METHOD_PSI if method == "psi" else METHOD_BSF
-        if model.cls == "ssm_nlg":
+        if model.cls == "ssm_mng":
+            check(lib().bssm_b200_job_create_mng(C.byref(self._ms), N, seed, self.n_filters, int(first_filter),
+                                                 int(out_flags), int(post), C.byref(self._h)))
+        elif model.cls == "ssm_nlg":
             check(lib().bssm_b200_job_create_nlg(C.byref(self._ms), N, seed, self.n_filters, int(first_filter),
                                                  int(out_flags), int(post), C.byref(self._h)))
         elif model.cls == "ssm_sde":

@@ -414,7 +414,7 @@ struct DevBuf {
 } // namespace
 
 // ------------------------------------------------------------------- job
-enum { KIND_UNG = 0, KIND_NLG = 1, KIND_SDE = 2 };
+enum { KIND_UNG = 0, KIND_NLG = 1, KIND_SDE = 2, KIND_MNG = 3 };
 
 struct bssm_b200_job {
   int kind = KIND_UNG;
@@ -448,6 +448,9 @@ struct bssm_b200_job {
   pf::UngParams up{};
   pf::NlgParams np{};
   pf::SdeParams sp{};
+  pf::MngParams gp{};
+  DevBuf<double> phi_v;
+  DevBuf<int> dist_v;
   pf::PrepassParams pp{};
   pf::FilterParams fp{};
   ~bssm_b200_job() {
@@ -508,6 +511,15 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
   if (fp.phase_cycles) fp.phase_cycles = J->phases.p + (size_t)f0 * 6 * J->geo.ranks;
   if (J->kind == KIND_NLG) return launch_filter<pf::NlgGrowthBsf>(fp, J->np, J->geo, nf, J->stream);
   if (J->kind == KIND_SDE) return launch_filter<pf::SdeGbmBsf>(fp, J->sp, J->geo, nf, J->stream);
+  if (J->kind == KIND_MNG) {
+    switch (J->m * 10 + J->k) {
+      case 11: return launch_filter<pf::MngBsf<1, 1>>(fp, J->gp, J->geo, nf, J->stream);
+      case 21: return launch_filter<pf::MngBsf<2, 1>>(fp, J->gp, J->geo, nf, J->stream);
+      case 22: return launch_filter<pf::MngBsf<2, 2>>(fp, J->gp, J->geo, nf, J->stream);
+      case 33: return launch_filter<pf::MngBsf<3, 3>>(fp, J->gp, J->geo, nf, J->stream);
+    }
+    return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_mng bsf: (m,k) not instantiated in this build");
+  }
   pf::UngParams up = J->up;
   if (J->method == BSSM_METHOD_PSI && J->m > 1) {
     up.approx_loglik += f0;
@@ -803,6 +815,7 @@ int bssm_b200_job_max_concurrent_filters(const bssm_b200_job* J) {
   int out = 0, rc;
   if (J->kind == KIND_NLG) rc = occupancy<pf::NlgGrowthBsf>(J->geo, &out);
   else if (J->kind == KIND_SDE) rc = occupancy<pf::SdeGbmBsf>(J->geo, &out);
+  else if (J->kind == KIND_MNG) rc = occupancy<pf::MngBsf<1, 1>>(J->geo, &out);
   else if (J->method == BSSM_METHOD_PSI) rc = occupancy<pf::UngPsi1>(J->geo, &out);
   else rc = occupancy<pf::UngBsf<1, 1>>(J->geo, &out); // same register budget for all (m, k)
   return rc ? 0 : out;
@@ -966,6 +979,62 @@ int bssm_b200_job_create_sde(const bssm_sde_model* M, uint32_t nsim, uint32_t L,
   return 0;
 }
 
+int bssm_b200_job_create_mng(const bssm_mng_model* M, uint32_t nsim, uint32_t seed, uint32_t n_filters,
+                             uint32_t first_filter_id, int out_flags, int post, bssm_b200_job** job) {
+  if (!M || !job || !M->y || !M->u || !M->Z || !M->T || !M->R || !M->a1 || !M->P1 || !M->D || !M->C ||
+      !M->phi || !M->distribution)
+    return fail(BSSM_B200_ERR_ARG, "null argument");
+  *job = nullptr;
+  if (M->p < 1 || M->p > 8 || M->m < 1 || M->k < 1 || M->k > M->m) return fail(BSSM_B200_ERR_ARG, "ssm_mng: 1 <= p <= 8, 1 <= k <= m");
+  for (int j = 0; j < M->p; ++j)
+    if (M->distribution[j] < 1 || M->distribution[j] > 5) return fail(BSSM_B200_ERR_ARG, "ssm_mng: distribution codes 1..5");
+  bssm_b200_job* J = new bssm_b200_job();
+  struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
+  const int n = M->n, m = M->m, k = M->k, p = M->p;
+  int rc = job_common(J, KIND_MNG, n, m, k, nsim, seed, n_filters, first_filter_id, out_flags, post);
+  if (rc) return rc;
+  std::vector<double> LP1;
+  chol_posdiag(M->P1, m, LP1);
+  std::vector<int> dist(M->distribution, M->distribution + p);
+  if ((rc = J->y.upload(M->y, (size_t)n * p)) || (rc = J->u.upload(M->u, (size_t)n * p)) ||
+      (rc = J->Z.upload(M->Z, (size_t)p * m * (M->Ztv ? n : 1))) ||
+      (rc = J->T.upload(M->T, (size_t)m * m * (M->Ttv ? n : 1))) ||
+      (rc = J->R.upload(M->R, (size_t)m * k * (M->Rtv ? n : 1))) || (rc = J->a1.upload(M->a1, m)) ||
+      (rc = J->LP1.upload(LP1.data(), (size_t)m * m)) || (rc = J->D.upload(M->D, (size_t)p * (M->Dtv ? n : 1))) ||
+      (rc = J->C.upload(M->C, (size_t)m * (M->Ctv ? n : 1))) || (rc = J->phi_v.upload(M->phi, p)) ||
+      (rc = J->dist_v.upload(dist.data(), p)))
+    return rc;
+  pf::MngParams& gp = J->gp;
+  gp.n = n; gp.p = p;
+  gp.Ztv = M->Ztv; gp.Ttv = M->Ttv; gp.Rtv = M->Rtv; gp.Dtv = M->Dtv; gp.Ctv = M->Ctv;
+  gp.y = J->y.p; gp.u = J->u.p; gp.Z = J->Z.p; gp.T = J->T.p; gp.R = J->R.p; gp.a1 = J->a1.p; gp.LP1 = J->LP1.p;
+  gp.D = J->D.p; gp.C = J->C.p; gp.phi = J->phi_v.p; gp.distribution = J->dist_v.p;
+  // state-independent constants, src/model_ssm_mng.cpp:636-666 (pre-summed here)
+  auto lch = [](double nn, double kk) {
+    return -std::log(nn + 1) - std::lgamma(nn - kk + 1) - std::lgamma(kk + 1) + std::lgamma(nn + 2);
+  };
+  double cst = 0.0;
+  for (int i = 0; i < p; ++i) {
+    const double phi = M->phi[i];
+    for (int t = 0; t < n; ++t) {
+      const double y = M->y[t + (size_t)n * i], u = M->u[t + (size_t)n * i];
+      if (!std::isfinite(y)) continue;
+      switch (M->distribution[i]) {
+        case 1: cst += -std::lgamma(y + 1) + y * std::log(u); break;
+        case 2: cst += lch(u, y); break;
+        case 3: cst += lch(y + phi - 1, y) + phi * std::log(phi) + y * std::log(u); break;
+        case 4: cst += phi * std::log(phi) - std::lgamma(phi) + (phi - 1) * std::log(y) - phi * std::log(u); break;
+        case 5: cst += -0.5 * std::log(2.0 * M_PI) - std::log(phi); break;
+      }
+    }
+  }
+  gp.loglik_const = cst;
+  if ((rc = finish_job(J, out_flags, post))) return rc;
+  guard.j = nullptr;
+  *job = J;
+  return 0;
+}
+
 static int run_fetch_destroy(bssm_b200_job* J, bssm_filter_out* out) {
   float ms = 0;
   int rc = bssm_b200_job_run(J, &ms);
@@ -988,6 +1057,18 @@ int bssm_b200_bsf_smoother_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t 
   if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
   bssm_b200_job* J = nullptr;
   int rc = bssm_b200_job_create_nlg(M, nsim, seed, 1, 0, out_flags_of(out), BSSM_POST_SMOOTHER, &J);
+  return rc ? rc : run_fetch_destroy(J, out);
+}
+int bssm_b200_bsf_mng(const bssm_mng_model* M, uint32_t nsim, uint32_t seed, bssm_filter_out* out) {
+  if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
+  bssm_b200_job* J = nullptr;
+  int rc = bssm_b200_job_create_mng(M, nsim, seed, 1, 0, out_flags_of(out), BSSM_POST_FILTER_SUMMARY, &J);
+  return rc ? rc : run_fetch_destroy(J, out);
+}
+int bssm_b200_bsf_smoother_mng(const bssm_mng_model* M, uint32_t nsim, uint32_t seed, bssm_filter_out* out) {
+  if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
+  bssm_b200_job* J = nullptr;
+  int rc = bssm_b200_job_create_mng(M, nsim, seed, 1, 0, out_flags_of(out), BSSM_POST_SMOOTHER, &J);
   return rc ? rc : run_fetch_destroy(J, out);
 }
 int bssm_b200_bsf_sde(const bssm_sde_model* M, uint32_t nsim, uint32_t L, uint32_t seed, bssm_filter_out* out) {

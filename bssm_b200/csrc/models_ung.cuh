@@ -233,4 +233,97 @@ struct UngPsiM : GaussStep<UngPsiM<M_>, M_, M_, M_> {
   }
 };
 
+// ------------------------------------------------- ssm_mng: bootstrap filter
+// p observation series with their own exponential-family (or Gaussian) densities, one
+// m-dimensional linear-Gaussian state: ssm_mng::bsf_filter src/model_ssm_mng.cpp:562-668,
+// log_obs_density :407-442.  simsignal = D_t + Z_t alpha is a (p x m)(m x 1) product per
+// particle; with m, p <= 8 this is a handful of fused loops per particle and stays on the
+// FP64 pipe: there is no tile here that a tcgen05 MMA could usefully take (fp64, K = m <= 8).
+struct MngParams {
+  int n, p;
+  int Ztv, Ttv, Rtv, Dtv, Ctv;
+  const double* y;     // n x p as R holds it (the reference transposes to p x n)
+  const double* u;     // n x p
+  const double* Z;     // p x m x (1|n)
+  const double* T;     // m x m x (1|n)
+  const double* R;     // m x k x (1|n)
+  const double* a1;
+  const double* LP1;
+  const double* D;     // p x (1|n)
+  const double* C;     // m x (1|n)
+  const double* phi;   // p
+  const int* distribution; // p (1 poisson, 2 binomial, 3 negbin, 4 gamma, 5 gaussian)
+  double loglik_const;
+};
+
+template <int M_, int K_>
+struct MngBsf : GaussStep<MngBsf<M_, K_>, M_, M_, K_> {
+  static constexpr int M = M_, KI = M_, KP = K_;
+  typedef MngParams Params;
+  const MngParams& mp;
+  int tw;
+  double T[M_ * M_], R[M_ * K_], C[M_];
+
+  __device__ MngBsf(const MngParams& p, uint32_t) : mp(p), tw(0) {}
+  __device__ double loglik0() const { return 0.0; }
+  __device__ double loglik_end() const { return mp.loglik_const; }
+  __device__ void init(const double* z, double* x) const {
+#pragma unroll
+    for (int d = 0; d < M_; ++d) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < M_; ++j) s += mp.LP1[d + M_ * j] * z[j];
+      x[d] = mp.a1[d] + s;
+    }
+  }
+  // weighted when at least one series is observed (:586, :620)
+  __device__ bool observed(int t) const {
+    for (int j = 0; j < mp.p; ++j)
+      if (pf_isfinite(mp.y[t + (size_t)mp.n * j])) return true;
+    return false;
+  }
+  __device__ void begin_weight(int t) { tw = t; }
+  __device__ double logw(const double* x) const {
+    double w = 0.0;
+    const double* Zt = mp.Z + (size_t)mp.p * M_ * (tw * mp.Ztv);
+    const double* Dt = mp.D + (size_t)mp.p * (tw * mp.Dtv);
+    for (int j = 0; j < mp.p; ++j) {
+      const double y = mp.y[tw + (size_t)mp.n * j];
+      if (!pf_isfinite(y)) continue;
+      double zs = 0.0;
+#pragma unroll
+      for (int d = 0; d < M_; ++d) zs += Zt[j + mp.p * d] * x[d];
+      const double s = Dt[j] + zs;
+      const double u = mp.u[tw + (size_t)mp.n * j], phi = mp.phi[j];
+      switch (mp.distribution[j]) {
+        case 1: w += y * s - u * pf_exp(s); break;
+        case 2: w += y * s - u * pf_log1p(pf_exp(s)); break;
+        case 3: w += y * s - (y + phi) * pf_log(phi + u * pf_exp(s)); break;
+        case 4: w += -phi * (s + (y * pf_exp(-s) / u)); break;
+        default: { double q = (y - s) / phi; w += -0.5 * (q * q); } break;
+      }
+    }
+    return w;
+  }
+  __device__ void begin_step(int t) {
+#pragma unroll
+    for (int e = 0; e < M_ * M_; ++e) T[e] = mp.T[e + M_ * M_ * (t * mp.Ttv)];
+#pragma unroll
+    for (int e = 0; e < M_ * K_; ++e) R[e] = mp.R[e + M_ * K_ * (t * mp.Rtv)];
+#pragma unroll
+    for (int d = 0; d < M_; ++d) C[d] = mp.C[d + M_ * (t * mp.Ctv)];
+  }
+  __device__ void propagate(const double* xa, const double* z, double* x) const {
+#pragma unroll
+    for (int d = 0; d < M_; ++d) {
+      double ta = 0.0, ru = 0.0;
+#pragma unroll
+      for (int j = 0; j < M_; ++j) ta += T[d + M_ * j] * xa[j];
+#pragma unroll
+      for (int j = 0; j < K_; ++j) ru += R[d + M_ * j] * z[j];
+      x[d] = C[d] + ta + ru;
+    }
+  }
+};
+
 } // namespace pf

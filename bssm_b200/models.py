@@ -265,3 +265,46 @@ def ssm_nlg(y, model, theta, known_params):
 
 def ssm_sde(y, model, theta, x0, positive):
     return SdeModel(y, model, theta, x0, positive)
+
+
+class MngModel:
+    """ssm_mng (R/models.R:538-600): p observation series with their own distributions,
+    one linear-Gaussian state.  y, u: n x p; Z: p x m x (1|n); D: p x (1|n)."""
+    CODES = {"poisson": 1, "binomial": 2, "negative binomial": 3, "gamma": 4, "gaussian": 5}
+
+    def __init__(self, y, Z, T, R, a1, P1, distribution, phi=1.0, u=None, D=None, C=None):
+        self.cls = "ssm_mng"
+        self.y = f64(np.atleast_2d(np.asarray(y, dtype=np.float64)))
+        self.n, self.p = self.y.shape
+        self.a1 = f64(np.ravel(a1))
+        self.m = self.a1.size
+        n, p, m = self.n, self.p, self.m
+        self.Z = f64(np.reshape(Z, (p, m, -1), order="F"))
+        self.T = f64(np.reshape(T, (m, m, -1), order="F"))
+        R = np.asarray(R, dtype=np.float64)
+        self.k = R.shape[1]
+        self.R = f64(np.reshape(R, (m, self.k, -1), order="F"))
+        self.P1 = f64(np.reshape(P1, (m, m), order="F"))
+        self.D = f64(np.zeros((p, 1)) if D is None else np.reshape(D, (p, -1), order="F"))
+        self.C = f64(np.zeros((m, 1)) if C is None else np.reshape(C, (m, -1), order="F"))
+        self.u = f64(np.ones((n, p)) if u is None else np.broadcast_to(np.asarray(u, dtype=np.float64), (n, p)))
+        if isinstance(distribution, str):
+            distribution = [distribution] * p
+        self.distribution = np.array([self.CODES[d] for d in distribution], dtype=np.int32)
+        self.phi = f64(np.broadcast_to(np.asarray(phi, dtype=np.float64), (p,)))
+
+    def c_struct(self):
+        from ._lib import MngModel as S
+        s = S()
+        s.n, s.m, s.k, s.p = self.n, self.m, self.k, self.p
+        s.Ztv, s.Ttv, s.Rtv = int(self.Z.shape[2] > 1), int(self.T.shape[2] > 1), int(self.R.shape[2] > 1)
+        s.Dtv, s.Ctv = int(self.D.shape[1] > 1), int(self.C.shape[1] > 1)
+        s.distribution = self.distribution.ctypes.data_as(C.POINTER(C.c_int32))
+        s.y, s.u, s.Z, s.T, s.R = dptr(self.y), dptr(self.u), dptr(self.Z), dptr(self.T), dptr(self.R)
+        s.a1, s.P1, s.D, s.C, s.phi = dptr(self.a1), dptr(self.P1), dptr(self.D), dptr(self.C), dptr(self.phi)
+        s._keep = [self.y, self.u, self.Z, self.T, self.R, self.a1, self.P1, self.D, self.C, self.phi, self.distribution]
+        return s
+
+
+def ssm_mng(y, Z, T, R, a1, P1, distribution, phi=1.0, u=None, D=None, C=None):
+    return MngModel(y, Z, T, R, a1, P1, distribution, phi=phi, u=u, D=D, C=C)

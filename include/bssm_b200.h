@@ -154,6 +154,36 @@ int bssm_b200_psi_smoother(const bssm_ung_model* model, uint32_t nsim, uint32_t 
 int bssm_b200_psi_filter(const bssm_ung_model* model, uint32_t nsim, uint32_t seed,
                          bssm_filter_out* out);
 
+/* ---- ssm_mng: multivariate observations ------------------------------------ */
+/* The fields the reference reads in src/model_ssm_mng.cpp:7-30.  y and u are n x p
+ * column-major exactly as R holds them (the reference transposes them on entry). */
+typedef struct {
+  int32_t n, m, k, p;
+  int32_t Ztv, Ttv, Rtv, Dtv, Ctv;
+  const int32_t* distribution; /* p: 1 poisson, 2 binomial, 3 negative binomial, 4 gamma, 5 gaussian */
+  const double* y;     /* n x p */
+  const double* u;     /* n x p */
+  const double* Z;     /* p x m x (1|n) */
+  const double* T;     /* m x m x (1|n) */
+  const double* R;     /* m x k x (1|n) */
+  const double* a1;    /* m */
+  const double* P1;    /* m x m */
+  const double* D;     /* p x (1|n) */
+  const double* C;     /* m x (1|n) */
+  const double* phi;   /* p */
+} bssm_mng_model;
+
+/* replaces: bsf(model_, nsim, seed, gaussian = FALSE, model_type = 0)
+ *           src/R_bootstrap_filter.cpp:130-155 -> ssm_mng::bsf_filter
+ *           src/model_ssm_mng.cpp:562-668 + filter_summary.  p <= 8. */
+int bssm_b200_bsf_mng(const bssm_mng_model* model, uint32_t nsim, uint32_t seed, bssm_filter_out* out);
+/* replaces: bsf_smoother(..., model_type = 0) src/R_bootstrap_filter.cpp:360-385 */
+int bssm_b200_bsf_smoother_mng(const bssm_mng_model* model, uint32_t nsim, uint32_t seed,
+                               bssm_filter_out* out);
+int bssm_b200_job_create_mng(const bssm_mng_model* model, uint32_t nsim, uint32_t seed,
+                             uint32_t n_filters, uint32_t first_filter_id, int out_flags, int post,
+                             struct bssm_b200_job** job);
+
 /* ---- ssm_nlg and ssm_sde: device functor registry ------------------------- */
 /* The reference defines these model classes through C++ function pointers that
  * R compiles at run time (externalptr arguments of bsf_nlg / bsf_sde,

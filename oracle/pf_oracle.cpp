@@ -846,6 +846,116 @@ void orc_ung_filter_batch(const bssm_ung_model* M, int method, const double* mod
   }
 }
 
+/* ------------------------------------------------------------------ a12 */
+/* ssm_mng::log_obs_density, src/model_ssm_mng.cpp:407-442, one particle.  y, u are n x p. */
+static double mng_log_obs(const bssm_mng_model* M, int t, const double* alpha) {
+  const int n = M->n, m = M->m, p = M->p;
+  const double* Z = M->Z + (size_t)p * m * (t * M->Ztv);
+  const double* D = M->D + (size_t)p * (t * M->Dtv);
+  double w = 0.0;
+  for (int j = 0; j < p; ++j) {
+    const double y = M->y[t + (size_t)n * j];
+    if (!std::isfinite(y)) continue;
+    double zs = 0.0;
+    for (int d = 0; d < m; ++d) zs += Z[j + (size_t)p * d] * alpha[d];
+    const double s = D[j] + zs; /* simsignal = D + Z alpha */
+    const double u = M->u[t + (size_t)n * j], phi = M->phi[j];
+    switch (M->distribution[j]) {
+      case 1: w += y * s - u * pf_exp(s); break;
+      case 2: w += y * s - u * pf_log1p(pf_exp(s)); break;
+      case 3: w += y * s - (y + phi) * pf_log(phi + u * pf_exp(s)); break;
+      case 4: w += -phi * (s + (y * pf_exp(-s) / u)); break;
+      case 5: { double q = (y - s) / phi; w += -0.5 * (q * q); } break;
+    }
+  }
+  return w;
+}
+
+/* ssm_mng::bsf_filter, src/model_ssm_mng.cpp:562-668 */
+double orc_mng_bsf_filter(const bssm_mng_model* M, uint32_t nsim, uint32_t seed, uint32_t filter, int arith,
+                          double* alpha, double* weights, uint32_t* indices, int32_t* stopped_at) {
+  *stopped_at = -1;
+  const int n = M->n, m = M->m, k = M->k, p = M->p;
+  const size_t N = nsim;
+  std::vector<double> L_P1;
+  chol_P1(M->P1, m, L_P1);
+  auto A = [&](int d, int t, size_t i) -> double& { return alpha[d + (size_t)m * (t + (size_t)(n + 1) * i)]; };
+  auto any_obs = [&](int t) {
+    int na = 0;
+    for (int j = 0; j < p; ++j) if (!std::isfinite(M->y[t + (size_t)n * j])) na++;
+    return na < p;
+  };
+  for (size_t i = 0; i < N; ++i) {
+    std::vector<double> um(m);
+    for (int j = 0; j < m; ++j) um[j] = pf_normal(seed, filter, 0, 0, (uint32_t)(i * m + j));
+    for (int d = 0; d < m; ++d) {
+      double s = 0.0;
+      for (int j = 0; j < m; ++j) s += L_P1[d + (size_t)m * j] * um[j];
+      A(d, 0, i) = M->a1[d] + s;
+    }
+  }
+  std::vector<double> W(N), logw(N), r(N), atmp((size_t)m * N);
+  double loglik = 0.0;
+  if (any_obs(0)) {
+    for (size_t i = 0; i < N; ++i) logw[i] = mng_log_obs(M, 0, &A(0, 0, i));
+    double mxw, lmean;
+    if (!normalise(logw.data(), nsim, weights, W, &mxw, &lmean, arith)) { *stopped_at = 0; return -ORC_INF; }
+    loglik = mxw + lmean;
+  } else {
+    for (size_t i = 0; i < N; ++i) { weights[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
+  }
+  for (int t = 0; t < n; ++t) {
+    for (size_t i = 0; i < N; ++i) r[i] = pf_resample_uniform(seed, filter, t, (uint32_t)i);
+    uint32_t* ind = indices + N * t;
+    resample(W, r, nsim, ind, arith);
+    for (size_t i = 0; i < N; ++i)
+      for (int d = 0; d < m; ++d) atmp[d + (size_t)m * i] = A(d, t, ind[i]);
+    const double* Tm = M->T + (size_t)m * m * (t * M->Ttv);
+    const double* Rm = M->R + (size_t)m * k * (t * M->Rtv);
+    const double* Cv = M->C + (size_t)m * (t * M->Ctv);
+    for (size_t i = 0; i < N; ++i) {
+      std::vector<double> uk(k);
+      for (int j = 0; j < k; ++j) uk[j] = pf_normal(seed, filter, t + 1, 0, (uint32_t)(i * k + j));
+      for (int d = 0; d < m; ++d) {
+        double ta = 0.0, ru = 0.0;
+        for (int j = 0; j < m; ++j) ta += Tm[d + (size_t)m * j] * atmp[j + (size_t)m * i];
+        for (int j = 0; j < k; ++j) ru += Rm[d + (size_t)m * j] * uk[j];
+        A(d, t + 1, i) = Cv[d] + ta + ru;
+      }
+    }
+    double* wcol = weights + N * (t + 1);
+    if ((t < (n - 1)) && any_obs(t + 1)) {
+      for (size_t i = 0; i < N; ++i) logw[i] = mng_log_obs(M, t + 1, &A(0, t + 1, i));
+      double mxw, lmean;
+      if (!normalise(logw.data(), nsim, wcol, W, &mxw, &lmean, arith)) { *stopped_at = t + 1; return -ORC_INF; }
+      loglik += mxw + lmean;
+    } else {
+      for (size_t i = 0; i < N; ++i) { wcol[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
+    }
+  }
+  /* constants added term by term, :636-666 */
+  for (int i = 0; i < p; ++i) {
+    const double phi = M->phi[i];
+    for (int t = 0; t < n; ++t) {
+      const double y = M->y[t + (size_t)n * i], u = M->u[t + (size_t)n * i];
+      if (!std::isfinite(y)) continue;
+      switch (M->distribution[i]) {
+        case 1: loglik += -std::lgamma(y + 1) + y * std::log(u); break;
+        case 2: loglik += lchoose_(u, y); break;
+        case 3: loglik += lchoose_(y + phi - 1, y) + phi * std::log(phi) + y * std::log(u); break;
+        case 4: loglik += phi * std::log(phi) - std::lgamma(phi) + (phi - 1) * std::log(y) - phi * std::log(u); break;
+        case 5: break; /* added below as count * norm_log_const(phi) */
+      }
+    }
+    if (M->distribution[i] == 5) {
+      int cnt = 0;
+      for (int t = 0; t < n; ++t) if (std::isfinite(M->y[t + (size_t)n * i])) cnt++;
+      loglik += cnt * (-0.5 * std::log(2.0 * M_PI) - std::log(phi));
+    }
+  }
+  return loglik;
+}
+
 /* ------------------------------------------------------------------ a13 */
 /* psd_chol, src/psd_chol.cpp:5-18 */
 static void psd_chol(const double* x, int m, std::vector<double>& cholx) {

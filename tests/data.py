@@ -97,3 +97,25 @@ def gbm_model(n=50, gen_seed=42, missing=()):
     for t in missing:
         y[t] = np.nan
     return bssm_b200.ssm_sde(y, "gbm", theta=[0.08, 0.4, 1.5], x0=1.0, positive=True)
+
+
+def mng_model(n=60, gen_seed=5, missing=True):
+    """a 3-variate ssm_mng (Poisson, negative binomial, Gaussian) driven by a 2-dimensional state,
+    in the spirit of the 4-variate model of tests/testthat/test_basics.R:100-160"""
+    rng = np.random.default_rng(gen_seed)
+    a = np.zeros((n, 2))
+    for t in range(1, n):
+        a[t] = [a[t - 1, 0] + a[t - 1, 1] + 0.1 * rng.normal(), 0.95 * a[t - 1, 1] + 0.02 * rng.normal()]
+    Z = np.array([[1.0, 0.0], [0.8, 0.5], [1.0, 1.0]])
+    sig = a @ Z.T + np.array([1.0, 0.5, 0.0])
+    y = np.column_stack([rng.poisson(np.exp(sig[:, 0])), rng.negative_binomial(3, 3 / (3 + np.exp(sig[:, 1]))),
+                         sig[:, 2] + 0.5 * rng.normal(size=n)]).astype(float)
+    if missing:
+        y[3, 0] = np.nan
+        y[7, :] = np.nan
+        y[n - 1, 2] = np.nan
+    T = np.array([[1.0, 1.0], [0.0, 0.95]])
+    R = np.diag([0.1, 0.02])
+    return bssm_b200.ssm_mng(y, Z, T, R, a1=[0.0, 0.0], P1=np.diag([1.0, 0.1]),
+                             distribution=["poisson", "negative binomial", "gaussian"], phi=[1.0, 3.0, 0.5],
+                             D=[1.0, 0.5, 0.0])

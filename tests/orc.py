@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-from bssm_b200._lib import NlgModel, SdeModel, ThetaMap, UngModel, c_double_p, c_uint32_p, dptr, uptr  # struct layouts only
+from bssm_b200._lib import MngModel, NlgModel, SdeModel, ThetaMap, UngModel, c_double_p, c_uint32_p, dptr, uptr  # struct layouts only
 
 ARITH_REFERENCE, ARITH_REPRO = 0, 1
 _L = None
@@ -43,6 +43,9 @@ def L():
         _L.orc_postcorrection_ung.argtypes = [C.POINTER(UngModel), C.POINTER(ThetaMap), C.c_int, u32, u32, C.c_int,
                                               C.c_int, c_uint32_p, c_double_p, u32, c_double_p, u32, C.c_int,
                                               c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]
+        _L.orc_mng_bsf_filter.restype = d
+        _L.orc_mng_bsf_filter.argtypes = [C.POINTER(MngModel), u32, u32, u32, C.c_int, c_double_p, c_double_p,
+                                          c_uint32_p, C.POINTER(i32)]
         _L.orc_nlg_bsf_filter.restype = d
         _L.orc_nlg_bsf_filter.argtypes = [C.POINTER(NlgModel), u32, u32, u32, C.c_int, c_double_p, c_double_p,
                                           c_uint32_p, C.POINTER(i32)]
@@ -247,5 +250,15 @@ def psi_filter_m(model, N, seed, filt=0, arith=ARITH_REPRO, mode=None):
                                         dptr(r.weights), uptr(r.indices), C.byref(al), C.byref(st),
                                         dptr(r.alphahat), dptr(r.L), dptr(r.Ct))
     r.approx_loglik = al.value
+    r.stopped_at = st.value
+    return r
+
+
+def mng_bsf_filter(model, N, seed, filt=0, arith=ARITH_REPRO):
+    r = _alloc(model, N)
+    ms = model.c_struct()
+    st = C.c_int32(-1)
+    r.loglik = L().orc_mng_bsf_filter(C.byref(ms), N, seed, filt, arith, dptr(r.alpha), dptr(r.weights),
+                                      uptr(r.indices), C.byref(st))
     r.stopped_at = st.value
     return r

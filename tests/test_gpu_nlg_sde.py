@@ -75,3 +75,20 @@ def test_growth_loglik_close_to_large_n_reference(engine):
     ll_big = engine.logLik(model, 131072, method="bsf", seed=1)
     ll_ref = np.mean([orc.nlg_bsf_filter(model, 4000, seed=s).loglik for s in (1, 2, 3)])
     assert abs(ll_big - ll_ref) < 0.5
+
+
+@pytest.mark.parametrize("N", [100, 3000])
+def test_mng_bsf_parity(engine, N):
+    """ssm_mng: three series (Poisson, negative binomial, Gaussian), 2-dim state, missing values"""
+    model = data.mng_model()
+    ref = orc.mng_bsf_filter(model, N, seed=1)
+    res = engine.bootstrap_filter(model, N, seed=1, return_indices=True)
+    assert np.array_equal(res["indices"], ref.indices)
+    assert np.array_equal(_cube(res).view(np.uint64), ref.alpha.view(np.uint64))
+    assert np.array_equal(res["weights"].view(np.uint64), ref.weights.view(np.uint64))
+    # the reference adds the constants term by term, the kernel adds their sum: few-ulp difference
+    assert res["logLik"] == pytest.approx(ref.loglik, rel=1e-13)
+    assert np.all(res["weights"][:, 7] == 1.0)  # all series missing at t = 7
+    sm = orc.filter_smoother(ref.alpha, ref.indices)
+    res2 = engine.particle_smoother(model, N, method="bsf", seed=1)
+    assert np.array_equal(_cube(res2).view(np.uint64), sm.view(np.uint64))
