@@ -99,7 +99,11 @@ def particle_smoother(model, particles, method="psi", seed=1, return_indices=Fal
     N, seed = _check_particles(model, particles, seed)
     b = _Buffers(model, N, indices=return_indices, smooth=True)
     ms = model.c_struct()
-    if model.cls in ("ssm_nlg", "ssm_mng"):
+    if model.cls == "ssm_nlg" and method == "psi":
+        # particle_smoother.ssm_nlg -> psi_smoother_nlg(..., max_iter, conv_tol, iekf_iter), R/particle_smoother.R:221-228
+        check(lib().bssm_b200_psi_smoother_nlg(C.byref(ms), N, seed, int(getattr(model, "max_iter", 100)),
+                                               float(getattr(model, "conv_tol", 1e-8)), 0, C.byref(b.out)))
+    elif model.cls in ("ssm_nlg", "ssm_mng"):
         if method != "bsf":
             raise ValueError("%s: only method='bsf' is implemented in this build" % model.cls)
         fn = lib().bssm_b200_bsf_smoother_nlg if model.cls == "ssm_nlg" else lib().bssm_b200_bsf_smoother_mng
@@ -135,6 +139,10 @@ class FilterJob:
         if model.cls == "ssm_mng":
             check(lib().bssm_b200_job_create_mng(C.byref(self._ms), N, seed, self.n_filters, int(first_filter),
                                                  int(out_flags), int(post), C.byref(self._h)))
+        elif model.cls == "ssm_nlg" and method == "psi":
+            check(lib().bssm_b200_job_create_nlg_psi(C.byref(self._ms), N, seed, int(getattr(model, "max_iter", 100)),
+                                                     float(getattr(model, "conv_tol", 1e-8)), self.n_filters,
+                                                     int(first_filter), int(out_flags), int(post), C.byref(self._h)))
         elif model.cls == "ssm_nlg":
             check(lib().bssm_b200_job_create_nlg(C.byref(self._ms), N, seed, self.n_filters, int(first_filter),
                                                  int(out_flags), int(post), C.byref(self._h)))

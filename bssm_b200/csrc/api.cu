@@ -26,6 +26,7 @@
 #include "smoother_kernels.cuh"
 #include "models_nlg_sde.cuh"
 #include "bssm_b200/ung_gauss_approx.h"
+#include "bssm_b200/nlg_gauss_approx.h"
 
 namespace {
 
@@ -449,6 +450,8 @@ struct bssm_b200_job {
   pf::NlgParams np{};
   pf::SdeParams sp{};
   pf::MngParams gp{};
+  pf::NlgPsiParams npp{};
+  DevBuf<double> stepc;
   DevBuf<double> phi_v;
   DevBuf<int> dist_v;
   pf::PrepassParams pp{};
@@ -509,6 +512,11 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
   fp.counters = J->counters.p + f0;
   fp.ubuf = J->ubuf.p + (size_t)f0 * J->N;
   if (fp.phase_cycles) fp.phase_cycles = J->phases.p + (size_t)f0 * 6 * J->geo.ranks;
+  if (J->kind == KIND_NLG && J->method == BSSM_METHOD_PSI) {
+    pf::NlgPsiParams npp = J->npp;
+    npp.approx_loglik += f0;
+    return launch_filter<pf::NlgGrowthPsi>(fp, npp, J->geo, nf, J->stream);
+  }
   if (J->kind == KIND_NLG) return launch_filter<pf::NlgGrowthBsf>(fp, J->np, J->geo, nf, J->stream);
   if (J->kind == KIND_SDE) return launch_filter<pf::SdeGbmBsf>(fp, J->sp, J->geo, nf, J->stream);
   if (J->kind == KIND_MNG) {
@@ -813,7 +821,8 @@ int bssm_b200_job_phase_cycles(bssm_b200_job* J, uint32_t cta, uint64_t cycles[6
 int bssm_b200_job_max_concurrent_filters(const bssm_b200_job* J) {
   if (!J) return 0;
   int out = 0, rc;
-  if (J->kind == KIND_NLG) rc = occupancy<pf::NlgGrowthBsf>(J->geo, &out);
+  if (J->kind == KIND_NLG && J->method == BSSM_METHOD_PSI) rc = occupancy<pf::NlgGrowthPsi>(J->geo, &out);
+  else if (J->kind == KIND_NLG) rc = occupancy<pf::NlgGrowthBsf>(J->geo, &out);
   else if (J->kind == KIND_SDE) rc = occupancy<pf::SdeGbmBsf>(J->geo, &out);
   else if (J->kind == KIND_MNG) rc = occupancy<pf::MngBsf<1, 1>>(J->geo, &out);
   else if (J->method == BSSM_METHOD_PSI) rc = occupancy<pf::UngPsi1>(J->geo, &out);
@@ -846,7 +855,7 @@ int bssm_b200_job_fetch(bssm_b200_job* J, uint32_t f, bssm_filter_out* out) {
   CU(cudaMemcpy(&stopped, J->stopped.p + f, sizeof(int32_t), cudaMemcpyDeviceToHost));
   out->stopped_at = stopped;
   out->approx_loglik = 0.0;
-  if (J->kind == KIND_UNG && J->method == BSSM_METHOD_PSI)
+  if (J->method == BSSM_METHOD_PSI && J->approx_loglik.p)
     CU(cudaMemcpy(&out->approx_loglik, J->approx_loglik.p + f, sizeof(double), cudaMemcpyDeviceToHost));
   out->device_ms = J->ms[0] + J->ms[1] + J->ms[2];
   // columns the filter never reached stay zero, as in the reference (arma::fill::zeros)
@@ -947,6 +956,59 @@ int bssm_b200_job_create_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t se
   psd_chol_host(P1, 2, np.LP1);
   np.H = pf_exp(M->theta[0]); np.R0 = pf_exp(M->theta[1]); np.R1 = pf_exp(M->theta[2]);
   np.wconst = std::log(2.0 * M_PI) + 2.0 * pf_log(np.H);
+  if ((rc = finish_job(J, out_flags, post))) return rc;
+  guard.j = nullptr;
+  *job = J;
+  return 0;
+}
+
+int bssm_b200_job_create_nlg_psi(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t max_iter,
+                                 double conv_tol, uint32_t n_filters, uint32_t first_filter_id,
+                                 int out_flags, int post, bssm_b200_job** job) {
+  if (!M || !job || !M->y || !M->theta || !M->known_params) return fail(BSSM_B200_ERR_ARG, "null argument");
+  *job = nullptr;
+  if (M->model_id != BSSM_NLG_GROWTH) return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_nlg: unknown model_id (registry: BSSM_NLG_GROWTH)");
+  if (M->p != 1 || M->m != 2 || M->k != 2 || M->n_theta < 3 || M->n_known < 6)
+    return fail(BSSM_B200_ERR_ARG, "growth model: p = 1, m = 2, k = 2, 3 parameters, 6 known parameters");
+  bssm_b200_job* J = new bssm_b200_job();
+  struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
+  int rc = job_common(J, KIND_NLG, M->n, 2, 2, nsim, seed, n_filters, first_filter_id, out_flags, post);
+  if (rc) return rc;
+  J->method = BSSM_METHOD_PSI;
+  const int n = M->n, m = 2;
+  // Gaussian approximation on the host: EKF start, relinearisation sweeps, Kalman smoother
+  pfga::NlgApprox ga(M);
+  ga.max_iter = (int)max_iter;
+  ga.conv_tol = conv_tol;
+  ga.run(nullptr);
+  if (!ga.finite_mode) return fail(BSSM_B200_ERR_ARG, "Approximation did not converge.");
+  std::vector<double> sc((size_t)32 * n, 0.0);
+  const double LOG2PI = std::log(2.0 * M_PI);
+  for (int t = 0; t < n; ++t) {
+    double* c = &sc[(size_t)32 * t];
+    const double Ht = ga.H[t], HHt = Ht * Ht;
+    c[0] = M->y[t]; c[1] = LOG2PI + 2.0 * pf_log(Ht); c[2] = Ht; c[3] = LOG2PI + pf_log(HHt); c[4] = HHt;
+    c[5] = ga.D[t]; c[6] = ga.Z[(size_t)m * t]; c[7] = ga.Z[(size_t)m * t + 1]; c[8] = ga.scales[t];
+    if (t >= 1) {
+      c[10] = ga.C[(size_t)m * (t - 1)]; c[11] = ga.C[(size_t)m * (t - 1) + 1];
+      for (int e = 0; e < 4; ++e) {
+        c[12 + e] = ga.T[(size_t)4 * (t - 1) + e];
+        c[16 + e] = ga.f_approx[t - 1].rooti[e];
+        c[21 + e] = ga.f_true[t - 1].rooti[e];
+      }
+      c[20] = ga.f_approx[t - 1].cst;
+      c[25] = ga.f_true[t - 1].cst;
+    }
+  }
+  std::vector<double> al(n_filters, ga.approx_loglik);
+  if ((rc = J->stepc.upload(sc.data(), sc.size())) || (rc = J->alphahat.upload(ga.alphahat.data(), ga.alphahat.size())) ||
+      (rc = J->Lt.upload(ga.L.data(), ga.L.size())) || (rc = J->Ct.upload(ga.Ct.data(), ga.Ct.size())) ||
+      (rc = J->approx_loglik.upload(al.data(), n_filters)))
+    return rc;
+  pf::NlgPsiParams& pp = J->npp;
+  pp.n = n; pp.stepc = J->stepc.p; pp.alphahat = J->alphahat.p; pp.Lt = J->Lt.p; pp.Ct = J->Ct.p;
+  pp.approx_loglik = J->approx_loglik.p;
+  pp.dT = M->known_params[0]; pp.K = M->known_params[1];
   if ((rc = finish_job(J, out_flags, post))) return rc;
   guard.j = nullptr;
   *job = J;
@@ -1057,6 +1119,22 @@ int bssm_b200_bsf_smoother_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t 
   if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
   bssm_b200_job* J = nullptr;
   int rc = bssm_b200_job_create_nlg(M, nsim, seed, 1, 0, out_flags_of(out), BSSM_POST_SMOOTHER, &J);
+  return rc ? rc : run_fetch_destroy(J, out);
+}
+int bssm_b200_psi_smoother_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t max_iter,
+                               double conv_tol, uint32_t iekf_iter, bssm_filter_out* out) {
+  if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
+  if (iekf_iter != 0) return fail(BSSM_B200_ERR_UNSUPPORTED, "iekf_iter > 0 is not implemented");
+  bssm_b200_job* J = nullptr;
+  int rc = bssm_b200_job_create_nlg_psi(M, nsim, seed, max_iter, conv_tol, 1, 0, out_flags_of(out), BSSM_POST_SMOOTHER, &J);
+  return rc ? rc : run_fetch_destroy(J, out);
+}
+int bssm_b200_psi_filter_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t max_iter,
+                             double conv_tol, uint32_t iekf_iter, bssm_filter_out* out) {
+  if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
+  if (iekf_iter != 0) return fail(BSSM_B200_ERR_UNSUPPORTED, "iekf_iter > 0 is not implemented");
+  bssm_b200_job* J = nullptr;
+  int rc = bssm_b200_job_create_nlg_psi(M, nsim, seed, max_iter, conv_tol, 1, 0, out_flags_of(out), BSSM_POST_NONE, &J);
   return rc ? rc : run_fetch_destroy(J, out);
 }
 int bssm_b200_bsf_mng(const bssm_mng_model* M, uint32_t nsim, uint32_t seed, bssm_filter_out* out) {

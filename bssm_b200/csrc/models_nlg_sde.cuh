@@ -63,6 +63,122 @@ struct NlgGrowthBsf : GaussStep<NlgGrowthBsf, 2, 2, 2> {
   }
 };
 
+// ------------------------------------------------- ssm_nlg: growth, psi-APF
+// ssm_nlg::psi_filter src/model_ssm_nlg.cpp:971-1063 with log_weights :880-935.  The
+// Gaussian approximation (EKF start, relinearisation sweeps, Kalman smoother, conditional
+// covariances, scales) is host work (include/bssm_b200/nlg_gauss_approx.h); per time point
+// the host packs the 32 doubles the weights need into `stepc`:
+//   [0] y_t  [1] c_sd = log 2pi + 2 log H_t  [2] H_t  [3] c_var = log 2pi + log HH_t  [4] HH_t
+//   [5] D_t  [6..7] Z_t  [8] scales_t
+//   transition from t-1 (t >= 1): [10..11] C_{t-1}  [12..15] T_{t-1}
+//   [16..19] rooti of RR_{t-1} (approximate)  [20] its constant
+//   [21..24] rooti of R R' (true)  [25] its constant
+struct NlgPsiParams {
+  int n;
+  const double* stepc;     // n x 32
+  const double* alphahat;  // 2 x (n+1)
+  const double* Lt;        // 2 x 2 x (n+1)
+  const double* Ct;        // 2 x 2 x (n+1)
+  const double* approx_loglik; // per filter
+  double dT, K;
+};
+
+struct NlgGrowthPsi : GaussStep<NlgGrowthPsi, 2, 2, 2> {
+  static constexpr int M = 2, KI = 2, KP = 2;
+  typedef NlgPsiParams Params;
+  const NlgPsiParams& mp;
+  double al0;
+  double y, c_sd, H, c_var, HH, D, Z0, Z1, scale;
+  double ah0[2], ah1[2], Cm[4], Lm[4];
+  double Ca[2], Ta[4], ra[4], ca, rt[4], ct;
+  bool has_prev;
+
+  __device__ NlgGrowthPsi(const NlgPsiParams& p, uint32_t f) : mp(p), has_prev(false) { al0 = p.approx_loglik[f]; }
+  __device__ double loglik0() const { return al0; }
+  __device__ double loglik_end() const { return 0.0; }
+  __device__ void init(const double* z, double* x) const {
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) s += mp.Lt[d + 2 * j] * z[j];
+      x[d] = mp.alphahat[d] + s;
+    }
+  }
+  __device__ bool observed(int t) const { return pf_isfinite(mp.stepc[(size_t)32 * t]); }
+  __device__ void begin_weight(int t) {
+    const double* c = mp.stepc + (size_t)32 * t;
+    y = c[0]; c_sd = c[1]; H = c[2]; c_var = c[3]; HH = c[4]; D = c[5]; Z0 = c[6]; Z1 = c[7]; scale = c[8];
+  }
+  // observation part of log_weights (:888-896): dmvnorm(y; Z_fn, H, lwr) - dmvnorm(y; D + Z a, HH)
+  __device__ double logw(const double* x) const {
+    const double q = (y - x[1]) / H;
+    const double tru = -0.5 * (c_sd + q * q);
+    const double zs = Z0 * x[0] + Z1 * x[1];
+    const double mean = D + zs;
+    const double app = -0.5 * (c_var + (y - mean) * (y - mean) / HH);
+    return tru - app;
+  }
+  __device__ double finish_logw(double w, double carry) const { return (w - carry) - scale; }
+  __device__ void begin_step(int t) {
+#pragma unroll
+    for (int d = 0; d < 2; ++d) { ah0[d] = mp.alphahat[d + 2 * t]; ah1[d] = mp.alphahat[d + 2 * (t + 1)]; }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { Cm[e] = mp.Ct[e + 4 * (t + 1)]; Lm[e] = mp.Lt[e + 4 * (t + 1)]; }
+    // factors of the transition t -> t+1, used by the weights of column t+1 (if it is weighted)
+    has_prev = (t + 1 < mp.n);
+    if (has_prev) {
+      const double* c = mp.stepc + (size_t)32 * (t + 1);
+      Ca[0] = c[10]; Ca[1] = c[11];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { Ta[e] = c[12 + e]; ra[e] = c[16 + e]; rt[e] = c[21 + e]; }
+      ca = c[20]; ct = c[25];
+    }
+  }
+  __device__ void propagate(const double* xa, const double* z, double* x) const {
+    double diff[2];
+    diff[0] = xa[0] - ah0[0]; diff[1] = xa[1] - ah0[1];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      double cd = 0.0, lu = 0.0;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) cd += Cm[d + 2 * j] * diff[j];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) lu += Lm[d + 2 * j] * z[j];
+      x[d] = ah1[d] + cd + lu;
+    }
+  }
+  __device__ __forceinline__ double mvn(const double* r, double cst, const double* x, const double* mean) const {
+    double dot = 0.0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      double z2 = 0.0;
+#pragma unroll
+      for (int l = 0; l < 2; ++l) z2 += r[i + 2 * l] * (x[l] - mean[l]);
+      dot += z2 * z2;
+    }
+    return cst - 0.5 * dot;
+  }
+  // dmvnorm(a_t; C + T a_prev, RR) - dmvnorm(a_t; T_fn(a_prev), R R')   (:915-931)
+  __device__ double trans_term(const double* xa, const double* x) const {
+    if (!has_prev) return 0.0;
+    double am[2], tm[2];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) s += Ta[d + 2 * j] * xa[j];
+      am[d] = Ca[d] + s;
+    }
+    const double e0 = pf_exp(xa[0]);
+    const double r = e0 / (1.0 + e0);
+    const double erdt = pf_exp(r * mp.dT);
+    tm[0] = xa[0];
+    tm[1] = mp.K * xa[1] * erdt / (mp.K + xa[1] * (erdt - 1));
+    return mvn(ra, ca, x, am) - mvn(rt, ct, x, tm);
+  }
+};
+
 // --------------------------------------------------------------- ssm_sde: GBM
 // dx = mu x dt + sigma_x x dB, y_k ~ N(log x_k, sigma_y^2).  Bootstrap filter:
 // ssm_sde::bsf_filter src/model_ssm_sde.cpp:21-82; every particle step is 2^L
@@ -129,11 +245,12 @@ struct SdeGbmBsf {
   __device__ __forceinline__ void draw(const StepCtx&, Noise<P>&) const {}
   template <int P>
   __device__ __forceinline__ void propagate_all(const StepCtx& c, const Noise<P>&, const double (&xa)[P][1],
-                                                double (&x)[P][1]) const {
+                                                double (&x)[P][1], double (&)[P]) const {
 #pragma unroll
     for (int p = 0; p < P; ++p) x[p][0] = xa[p][0];
     run<P>(c, x);
   }
+  __device__ __forceinline__ double finish_logw(double w, double) const { return w; }
 };
 
 } // namespace pf

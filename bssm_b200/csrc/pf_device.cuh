@@ -276,12 +276,20 @@ struct GaussStep {
     for (int q = 0; q < (P * KP) / 2; ++q)
       pf_normal_pair(c.seed, c.filter, c.t, 0u, pair0 + q, &nz.z[2 * q], &nz.z[2 * q + 1]);
   }
+  // `carry` is one double per particle that survives from the propagation into the next
+  // weighting: the psi-APF of ssm_nlg needs the ancestor's state in its weights (ratio of
+  // true and approximate transition densities, src/model_ssm_nlg.cpp:915-931).
   template <int P>
   __device__ __forceinline__ void propagate_all(const StepCtx&, const Noise<P>& nz, const double (&xa)[P][M],
-                                                double (&x)[P][M]) const {
+                                                double (&x)[P][M], double (&carry)[P]) const {
 #pragma unroll
-    for (int p = 0; p < P; ++p) static_cast<const Derived*>(this)->propagate(xa[p], &nz.z[p * KP], x[p]);
+    for (int p = 0; p < P; ++p) {
+      static_cast<const Derived*>(this)->propagate(xa[p], &nz.z[p * KP], x[p]);
+      carry[p] = static_cast<const Derived*>(this)->trans_term(xa[p], x[p]);
+    }
   }
+  __device__ __forceinline__ double trans_term(const double*, const double*) const { return 0.0; }
+  __device__ __forceinline__ double finish_logw(double w, double) const { return w; }
 };
 
 // -------------------------------------------------------- the filter kernel
@@ -351,6 +359,9 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
 
   double loglik = model.loglik0();
   int stopped = -1;
+  double carry[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) carry[p] = 0.0;
   double* ub = fp.ubuf + (size_t)fidx * N;
   Strata st;
   st.ubuf = ub; st.N = N; st.Nd = Nd;
@@ -373,7 +384,7 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
       mx = -pf_inf();
 #pragma unroll
       for (int p = 0; p < P; ++p) {
-        lw[p] = (i0 + p < N) ? model.logw(x[p]) : -pf_inf();
+        lw[p] = (i0 + p < N) ? model.finish_logw(model.logw(x[p]), carry[p]) : -pf_inf();
         mx = nanmax(mx, lw[p]);
       }
       PF_PHASE(0)
@@ -466,7 +477,7 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
       for (int p = 0; p < P; ++p)
 #pragma unroll
         for (int d = 0; d < M; ++d) xa[p][d] = __ldcg(src + (size_t)d * N + a[p]);
-      model.template propagate_all<P>(ctx, noise, xa, x);
+      model.template propagate_all<P>(ctx, noise, xa, x, carry);
 #pragma unroll
       for (int p = 0; p < P; ++p) {
         if (i0 + p < N) {

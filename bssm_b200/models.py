@@ -220,6 +220,7 @@ class NlgModel:
         self.known_params = f64(np.ravel(known_params))
         if self.theta.size < nth or self.known_params.size < nkn:
             raise ValueError("ssm_nlg %s: needs %d parameters and %d known parameters" % (model, nth, nkn))
+        self.max_iter, self.conv_tol = 100, 1e-8  # R/models.R:1567
 
     def c_struct(self):
         from ._lib import NlgModel as S

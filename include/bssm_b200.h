@@ -220,6 +220,20 @@ int bssm_b200_bsf_nlg(const bssm_nlg_model* model, uint32_t nsim, uint32_t seed,
 /* replaces: bsf_smoother_nlg(...) src/R_bootstrap_filter.cpp:509-551 */
 int bssm_b200_bsf_smoother_nlg(const bssm_nlg_model* model, uint32_t nsim, uint32_t seed,
                                bssm_filter_out* out);
+/* replaces: psi_smoother_nlg(..., nsim, seed, max_iter, conv_tol, iekf_iter) src/R_psi.cpp:173-221
+ *           -> ssm_nlg::approximate + psi_filter (src/model_ssm_nlg.cpp:62-150, :971-1063),
+ *           filter_smoother, summary.  p = 1 models of the registry; iekf_iter must be 0.
+ * bssm_b200_psi_filter_nlg is the same without backtrack / summary. */
+int bssm_b200_psi_smoother_nlg(const bssm_nlg_model* model, uint32_t nsim, uint32_t seed,
+                               uint32_t max_iter, double conv_tol, uint32_t iekf_iter,
+                               bssm_filter_out* out);
+int bssm_b200_psi_filter_nlg(const bssm_nlg_model* model, uint32_t nsim, uint32_t seed,
+                             uint32_t max_iter, double conv_tol, uint32_t iekf_iter,
+                             bssm_filter_out* out);
+int bssm_b200_job_create_nlg_psi(const bssm_nlg_model* model, uint32_t nsim, uint32_t seed,
+                                 uint32_t max_iter, double conv_tol, uint32_t n_filters,
+                                 uint32_t first_filter_id, int out_flags, int post,
+                                 struct bssm_b200_job** job);
 /* replaces: bsf_sde(y, x0, positive, ..., theta, nsim, L, seed) src/R_sde.cpp:35-72
  *           -> ssm_sde::bsf_filter src/model_ssm_sde.cpp:21-82 (Milstein, 2^L sub-steps).
  * Like the reference, att and Ptt have n+1 columns here with the last one zero. */

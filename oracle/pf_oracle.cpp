@@ -44,6 +44,7 @@
 #include "bssm_b200/pf_math.h"
 #include "bssm_b200.h"
 #include "bssm_b200/ung_gauss_approx.h"
+#include "bssm_b200/nlg_gauss_approx.h"
 
 enum { ORC_ARITH_REFERENCE = 0, ORC_ARITH_REPRO = 1 };
 
@@ -1053,6 +1054,99 @@ double orc_nlg_bsf_filter(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed,
     double* wcol = weights + N * (t + 1);
     if (t < (n - 1) && std::isfinite(M->y[t + 1])) {
       weigh(t + 1);
+      double mxw, lmean;
+      if (!normalise(logw.data(), nsim, wcol, W, &mxw, &lmean, arith)) { *stopped_at = t + 1; return -ORC_INF; }
+      loglik += mxw + lmean;
+    } else {
+      for (size_t i = 0; i < N; ++i) { wcol[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
+    }
+  }
+  return loglik;
+}
+
+/* ssm_nlg::psi_filter, src/model_ssm_nlg.cpp:971-1063, with log_weights :880-935 (the
+ * per-particle dmvnorm branch: time_varying = TRUE is the R default, R/models.R:1547).
+ * The Gaussian approximation is include/bssm_b200/nlg_gauss_approx.h. */
+double orc_nlg_psi_filter(const bssm_nlg_model* M, const double* mode_in, uint32_t max_iter, double conv_tol,
+                          uint32_t nsim, uint32_t seed, uint32_t filter, int arith, double* alpha,
+                          double* weights, uint32_t* indices, double* approx_loglik, int32_t* stopped_at,
+                          double* mode_out) {
+  *stopped_at = -1;
+  if (M->model_id != BSSM_NLG_GROWTH || M->p != 1) return pf_nan();
+  pfga::NlgApprox ga(M);
+  ga.max_iter = (int)max_iter;
+  ga.conv_tol = conv_tol;
+  ga.run(mode_in);
+  if (!ga.finite_mode) return -ORC_INF;
+  if (approx_loglik) *approx_loglik = ga.approx_loglik;
+  if (mode_out) std::copy(ga.mode.begin(), ga.mode.end(), mode_out);
+  const pfga::NlgFns& fn = ga.fn;
+  const int n = M->n, m = 2;
+  const size_t N = nsim, mm = 4;
+  auto A = [&](int d, int t, size_t i) -> double& { return alpha[d + (size_t)m * (t + (size_t)(n + 1) * i)]; };
+  for (size_t i = 0; i < N; ++i) {
+    double um[2];
+    for (int j = 0; j < m; ++j) um[j] = pf_normal(seed, filter, 0, 0, (uint32_t)(i * m + j));
+    for (int d = 0; d < m; ++d) {
+      double s = 0.0;
+      for (int j = 0; j < m; ++j) s += ga.L[d + (size_t)m * j] * um[j];
+      A(d, 0, i) = ga.alphahat[d] + s;
+    }
+  }
+  std::vector<double> W(N), logw(N), r(N), atmp((size_t)m * N, 0.0);
+  /* log_weights(t, alpha, alpha_prev) for one particle */
+  auto log_weight = [&](int t, const double* a, const double* aprev) {
+    double w = 0.0;
+    if (std::isfinite(M->y[t])) {
+      double za = 0.0;
+      for (int d = 0; d < m; ++d) za += ga.Z[d + (size_t)m * t] * a[d];
+      w = pfga::dnorm1_sd(M->y[t], fn.Z_fn(t, a), fn.H_fn(t, a)) -
+          pfga::dnorm1_var(M->y[t], ga.D[t] + za, ga.H[t] * ga.H[t]);
+    }
+    if (t > 0) {
+      double mean[2], amean[2], tmpv[2];
+      fn.T_fn(t - 1, aprev, mean);
+      pf_mm(&ga.T[mm * (t - 1)], aprev, tmpv, m, m, 1);
+      for (int d = 0; d < m; ++d) amean[d] = ga.C[d + (size_t)m * (t - 1)] + tmpv[d];
+      w -= ga.f_approx[t - 1].logpdf(a, amean) - ga.f_true[t - 1].logpdf(a, mean);
+    }
+    return w;
+  };
+  double loglik = 0.0;
+  if (std::isfinite(M->y[0])) {
+    for (size_t i = 0; i < N; ++i) logw[i] = log_weight(0, &A(0, 0, i), &atmp[(size_t)m * i]) - ga.scales[0];
+    double mxw, lmean;
+    if (!normalise(logw.data(), nsim, weights, W, &mxw, &lmean, arith)) { *stopped_at = 0; return -ORC_INF; }
+    loglik = mxw + ga.approx_loglik + lmean;
+  } else {
+    for (size_t i = 0; i < N; ++i) { weights[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
+    loglik = ga.approx_loglik;
+  }
+  for (int t = 0; t < n; ++t) {
+    for (size_t i = 0; i < N; ++i) r[i] = pf_resample_uniform(seed, filter, t, (uint32_t)i);
+    uint32_t* ind = indices + N * t;
+    resample(W, r, nsim, ind, arith);
+    for (size_t i = 0; i < N; ++i)
+      for (int d = 0; d < m; ++d) atmp[d + (size_t)m * i] = A(d, t, ind[i]);
+    const double* ah0 = &ga.alphahat[(size_t)m * t];
+    const double* ah1 = &ga.alphahat[(size_t)m * (t + 1)];
+    const double* Ctm = &ga.Ct[mm * (t + 1)];
+    const double* Lm = &ga.L[mm * (t + 1)];
+    for (size_t i = 0; i < N; ++i) {
+      double um[2], diff[2];
+      for (int j = 0; j < m; ++j) um[j] = pf_normal(seed, filter, t + 1, 0, (uint32_t)(i * m + j));
+      for (int j = 0; j < m; ++j) diff[j] = atmp[j + (size_t)m * i] - ah0[j];
+      for (int d = 0; d < m; ++d) {
+        double cd = 0.0, lu = 0.0;
+        for (int j = 0; j < m; ++j) cd += Ctm[d + (size_t)m * j] * diff[j];
+        for (int j = 0; j < m; ++j) lu += Lm[d + (size_t)m * j] * um[j];
+        A(d, t + 1, i) = ah1[d] + cd + lu;
+      }
+    }
+    double* wcol = weights + N * (t + 1);
+    if (t < (n - 1) && std::isfinite(M->y[t + 1])) {
+      for (size_t i = 0; i < N; ++i)
+        logw[i] = log_weight(t + 1, &A(0, t + 1, i), &atmp[(size_t)m * i]) - ga.scales[t + 1];
       double mxw, lmean;
       if (!normalise(logw.data(), nsim, wcol, W, &mxw, &lmean, arith)) { *stopped_at = t + 1; return -ORC_INF; }
       loglik += mxw + lmean;

@@ -49,6 +49,9 @@ def L():
         _L.orc_nlg_bsf_filter.restype = d
         _L.orc_nlg_bsf_filter.argtypes = [C.POINTER(NlgModel), u32, u32, u32, C.c_int, c_double_p, c_double_p,
                                           c_uint32_p, C.POINTER(i32)]
+        _L.orc_nlg_psi_filter.restype = d
+        _L.orc_nlg_psi_filter.argtypes = [C.POINTER(NlgModel), c_double_p, u32, d, u32, u32, u32, C.c_int, c_double_p,
+                                          c_double_p, c_uint32_p, c_double_p, C.POINTER(i32), c_double_p]
         _L.orc_sde_bsf_filter.restype = d
         _L.orc_sde_bsf_filter.argtypes = [C.POINTER(SdeModel), u32, u32, u32, u32, C.c_int, c_double_p, c_double_p,
                                           c_uint32_p, C.POINTER(i32)]
@@ -260,5 +263,20 @@ def mng_bsf_filter(model, N, seed, filt=0, arith=ARITH_REPRO):
     st = C.c_int32(-1)
     r.loglik = L().orc_mng_bsf_filter(C.byref(ms), N, seed, filt, arith, dptr(r.alpha), dptr(r.weights),
                                       uptr(r.indices), C.byref(st))
+    r.stopped_at = st.value
+    return r
+
+
+def nlg_psi_filter(model, N, seed, filt=0, arith=ARITH_REPRO, mode=None, max_iter=100, conv_tol=1e-8):
+    r = _alloc(model, N)
+    ms = model.c_struct()
+    st = C.c_int32(-1)
+    al = C.c_double(0)
+    r.mode = np.zeros((model.m, model.n), order="F")
+    mode_a = None if mode is None else np.asfortranarray(mode, dtype=np.float64)
+    r.loglik = L().orc_nlg_psi_filter(C.byref(ms), dptr(mode_a), max_iter, conv_tol, N, seed, filt, arith,
+                                      dptr(r.alpha), dptr(r.weights), uptr(r.indices), C.byref(al), C.byref(st),
+                                      dptr(r.mode))
+    r.approx_loglik = al.value
     r.stopped_at = st.value
     return r

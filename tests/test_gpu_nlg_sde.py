@@ -92,3 +92,34 @@ def test_mng_bsf_parity(engine, N):
     sm = orc.filter_smoother(ref.alpha, ref.indices)
     res2 = engine.particle_smoother(model, N, method="bsf", seed=1)
     assert np.array_equal(_cube(res2).view(np.uint64), sm.view(np.uint64))
+
+
+@pytest.mark.parametrize("N", [100, 2000])
+def test_growth_psi_apf_parity(engine, N):
+    """psi-APF for ssm_nlg (growth model): EKF-started Gaussian approximation on the host,
+    particle loop with the transition-density ratio in the weights on the device"""
+    model = data.growth_model(80)
+    ref = orc.nlg_psi_filter(model, N, seed=1)
+    res = engine.particle_smoother(model, N, method="psi", seed=1, return_indices=True)
+    assert res["approx_logLik"] == ref.approx_loglik
+    assert np.array_equal(res["indices"], ref.indices)
+    assert res["logLik"] == ref.loglik
+    sm = orc.filter_smoother(ref.alpha, ref.indices)
+    assert np.array_equal(_cube(res).view(np.uint64), sm.view(np.uint64))
+    job = engine.FilterJob(model, N, method="psi", seed=1, out_flags=2)
+    job.run()
+    b = job.fetch(0, weights=True)
+    assert np.array_equal(b.weights.view(np.uint64), ref.weights.view(np.uint64))
+    job.close()
+
+
+def test_growth_psi_missing_and_statistics(engine):
+    model = data.growth_model(60, missing=(0, 7, 8, 59))
+    ref = orc.nlg_psi_filter(model, 500, seed=4)
+    res = engine.particle_smoother(model, 500, method="psi", seed=4, return_indices=True)
+    assert np.array_equal(res["indices"], ref.indices) and res["logLik"] == ref.loglik
+    # psi-APF and BSF estimate the same likelihood (vignettes/psi_pf.Rmd table 1: psi has far lower variance)
+    full = data.growth_model(60)
+    lp = np.array([engine.logLik(full, 200, method="psi", seed=s) for s in range(1, 7)])
+    lb = np.array([engine.logLik(full, 20000, method="bsf", seed=s) for s in range(1, 4)])
+    assert lp.std() < 0.1 and abs(lp.mean() - lb.mean()) < 0.3
