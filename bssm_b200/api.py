@@ -238,7 +238,8 @@ def theta_map(model):
 def _postcorr_inputs(model, mcmc_output):
     theta = np.asfortranarray(np.asarray(mcmc_output["theta"], dtype=np.float64).T)  # t(theta): n_par x n_stored
     counts = np.ascontiguousarray(mcmc_output["counts"], dtype=np.uint32)
-    modes = np.asfortranarray(np.asarray(mcmc_output["modes"], dtype=np.float64).reshape(model.n, -1, order="F"))
+    rows = model.n * (model.m if model.cls == "ssm_nlg" else 1)  # nlg stores m x n modes per draw
+    modes = np.asfortranarray(np.asarray(mcmc_output["modes"], dtype=np.float64).reshape(rows, -1, order="F"))
     if theta.shape[1] != counts.size or modes.shape[1] != counts.size:
         raise ValueError("theta, counts and modes disagree on the number of stored draws")
     return theta, counts, modes
@@ -275,10 +276,16 @@ def post_correct(model, mcmc_output, particles, threads=1, is_type="is2", seed=1
     ll = np.zeros(nd) if return_loglik else None
     out.weights, out.posterior, out.alpha = dptr(w), dptr(post), dptr(alpha)
     out.alphahat, out.Vt, out.loglik = dptr(ah), dptr(Vt), dptr(ll)
-    ms, tm = model.c_struct(), theta_map(model)
-    check(lib().bssm_b200_postcorrection_nongaussian(
-        C.byref(ms), C.byref(tm), ot, N, seed, int(threads), it, uptr(counts), dptr(theta), theta.shape[0],
-        dptr(modes), counts.size, b, e, C.byref(out)))
+    ms = model.c_struct()
+    if model.cls == "ssm_nlg":  # post_correct -> postcorrection_nonlinear, R/post_correction.R:272-283
+        check(lib().bssm_b200_postcorrection_nonlinear(
+            C.byref(ms), ot, N, seed, int(threads), it, uptr(counts), dptr(theta), theta.shape[0],
+            dptr(modes), counts.size, b, e, C.byref(out)))
+    else:
+        tm = theta_map(model)
+        check(lib().bssm_b200_postcorrection_nongaussian(
+            C.byref(ms), C.byref(tm), ot, N, seed, int(threads), it, uptr(counts), dptr(theta), theta.shape[0],
+            dptr(modes), counts.size, b, e, C.byref(out)))
     res = dict(mcmc_output)
     res["weights"] = w
     base = np.asarray(mcmc_output.get("posterior", np.zeros(counts.size)), dtype=np.float64)

@@ -21,9 +21,9 @@ def nvcc_cmd(verbose=False):
     cmd = [
         "nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
         "-fmad=false", "-std=c++17",
-        "-Xcompiler", "-fPIC,-ffp-contract=off,-mfma",
+        "-Xcompiler", "-fPIC,-ffp-contract=off,-mfma,-fopenmp",
         "-shared", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
-        "-o", LIB,
+        "-lgomp", "-o", LIB,
     ] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd += ["-Xptxas", "-v"]

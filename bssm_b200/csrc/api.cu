@@ -515,6 +515,8 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
   if (J->kind == KIND_NLG && J->method == BSSM_METHOD_PSI) {
     pf::NlgPsiParams npp = J->npp;
     npp.approx_loglik += f0;
+    npp.stepc += (size_t)f0 * npp.fstride_stepc; npp.alphahat += (size_t)f0 * npp.fstride_a;
+    npp.Lt += (size_t)f0 * npp.fstride_m; npp.Ct += (size_t)f0 * npp.fstride_m;
     return launch_filter<pf::NlgGrowthPsi>(fp, npp, J->geo, nf, J->stream);
   }
   if (J->kind == KIND_NLG) return launch_filter<pf::NlgGrowthBsf>(fp, J->np, J->geo, nf, J->stream);
@@ -1009,6 +1011,7 @@ int bssm_b200_job_create_nlg_psi(const bssm_nlg_model* M, uint32_t nsim, uint32_
   pp.n = n; pp.stepc = J->stepc.p; pp.alphahat = J->alphahat.p; pp.Lt = J->Lt.p; pp.Ct = J->Ct.p;
   pp.approx_loglik = J->approx_loglik.p;
   pp.dT = M->known_params[0]; pp.K = M->known_params[1];
+  pp.fstride_stepc = 0; pp.fstride_a = 0; pp.fstride_m = 0; // replicates share the approximation
   if ((rc = finish_job(J, out_flags, post))) return rc;
   guard.j = nullptr;
   *job = J;
@@ -1289,14 +1292,15 @@ int bssm_b200_job_create_postcorr(const bssm_ung_model* M, const bssm_theta_map*
   return make_draw_job(M, map, dl, draw_begin, draw_end, nsim, seed, theta, n_par, modes, 0, BSSM_POST_NONE, job);
 }
 
-int bssm_b200_postcorrection_nongaussian(const bssm_ung_model* M, const bssm_theta_map* map, int output_type,
-                                         uint32_t nsim, uint32_t seed, uint32_t n_threads, int is_type,
-                                         const uint32_t* counts, const double* theta, uint32_t n_par,
-                                         const double* modes, uint32_t n_stored, uint32_t draw_begin,
-                                         uint32_t draw_end, bssm_postcorr_out* out) {
-  (void)n_threads;
-  int rc = check_postcorr_args(M, map, counts, theta, modes, n_stored);
-  if (rc) return rc;
+} // extern "C"
+
+// The draw loop of approx_mcmc::is_correction_psi (src/approx_mcmc.cpp:353-427) for any model
+// kind: `make_job(d0, d1, N, post, &job)` builds the resident batch of draws [d0, d1).
+template <class MakeJob>
+static int postcorr_driver(int n, int m, int output_type, uint32_t nsim, int is_type, const uint32_t* counts,
+                           uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end, bssm_postcorr_out* out,
+                           MakeJob&& make_job) {
+  int rc;
   if (!out || !out->weights || !out->posterior) return fail(BSSM_B200_ERR_ARG, "weights and posterior outputs are required");
   if (output_type < 1 || output_type > 3) return fail(BSSM_B200_ERR_ARG, "output_type must be 1, 2 or 3");
   if (output_type == 1 && !out->alpha) return fail(BSSM_B200_ERR_ARG, "output_type 1 needs out->alpha");
@@ -1306,7 +1310,6 @@ int bssm_b200_postcorrection_nongaussian(const bssm_ung_model* M, const bssm_the
   if ((rc = build_draws(is_type, counts, n_stored, &dl))) return rc;
   if (draw_begin == 0 && draw_end == 0) draw_end = (uint32_t)dl.src.size();
   if (draw_begin >= draw_end || draw_end > dl.src.size()) return fail(BSSM_B200_ERR_ARG, "bad draw range");
-  const int n = M->n, m = M->m;
   const size_t n1 = (size_t)n + 1;
   out->device_ms = 0.f; out->launches = 0; out->sum_w = 0.0;
 
@@ -1337,7 +1340,7 @@ int bssm_b200_postcorrection_nongaussian(const bssm_ung_model* M, const bssm_the
     while (d1 < draw_end && d1 - d0 < maxc && (is_type != 1 || dl.count[d1] == dl.count[d0])) ++d1;
     const uint32_t nf = d1 - d0;
     bssm_b200_job* J = nullptr;
-    if ((rc = make_draw_job(M, map, dl, d0, d1, N, seed, theta, n_par, modes, 0, post, &J))) return rc;
+    if ((rc = make_job(dl, d0, d1, N, post, &J))) return rc;
     struct JG { bssm_b200_job* j; ~JG() { delete j; } } jg{J};
     float ms = 0;
     if ((rc = bssm_b200_job_run(J, &ms))) return rc;
@@ -1362,9 +1365,14 @@ int bssm_b200_postcorrection_nongaussian(const bssm_ung_model* M, const bssm_the
       double* sw_in = d_sumw.p + (chunk_no & 1);
       double* sw_out = d_sumw.p + ((chunk_no + 1) & 1);
       CU(cudaMemcpyAsync(sw_out, sw_in, sizeof(double), cudaMemcpyDeviceToDevice, J->stream));
-      // m = 1 only in this build (checked above)
-      pf::postcorr_merge_kernel<1><<<cdiv((uint32_t)n1, 128), 128, 0, J->stream>>>(
-          J->s_mean.p, J->s_cov.p, J->loglik.p, d_cnt.p, nf, (int)n1, sw_in, sw_out, d_ah.p, d_Vt.p, d_Va.p);
+      if (m == 1)
+        pf::postcorr_merge_kernel<1><<<cdiv((uint32_t)n1, 128), 128, 0, J->stream>>>(
+            J->s_mean.p, J->s_cov.p, J->loglik.p, d_cnt.p, nf, (int)n1, sw_in, sw_out, d_ah.p, d_Vt.p, d_Va.p);
+      else if (m == 2)
+        pf::postcorr_merge_kernel<2><<<cdiv((uint32_t)n1, 128), 128, 0, J->stream>>>(
+            J->s_mean.p, J->s_cov.p, J->loglik.p, d_cnt.p, nf, (int)n1, sw_in, sw_out, d_ah.p, d_Vt.p, d_Va.p);
+      else
+        return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction summaries: m <= 2");
       CU(cudaGetLastError());
       CU(cudaEventRecord(e1, J->stream));
       CU(cudaStreamSynchronize(J->stream));
@@ -1391,6 +1399,105 @@ int bssm_b200_postcorrection_nongaussian(const bssm_ung_model* M, const bssm_the
       for (int d = 0; d < m; ++d) out->alphahat[t + n1 * d] = ah[d + (size_t)m * t];
   }
   return 0;
+}
+
+
+extern "C" {
+
+int bssm_b200_postcorrection_nongaussian(const bssm_ung_model* M, const bssm_theta_map* map, int output_type,
+                                         uint32_t nsim, uint32_t seed, uint32_t n_threads, int is_type,
+                                         const uint32_t* counts, const double* theta, uint32_t n_par,
+                                         const double* modes, uint32_t n_stored, uint32_t draw_begin,
+                                         uint32_t draw_end, bssm_postcorr_out* out) {
+  (void)n_threads;
+  int rc = check_postcorr_args(M, map, counts, theta, modes, n_stored);
+  if (rc) return rc;
+  return postcorr_driver(M->n, M->m, output_type, nsim, is_type, counts, n_stored, draw_begin, draw_end, out,
+                         [&](const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N, int post, bssm_b200_job** J) {
+                           return make_draw_job(M, map, dl, d0, d1, N, seed, theta, n_par, modes, 0, post, J);
+                         });
+}
+
+// per-draw Gaussian approximation of an ssm_nlg model: approximate_for_is at the stored mode
+// (src/model_ssm_nlg.cpp:153-186) + smoother, for the draws [d0, d1).  Host work, OpenMP over
+// draws (the reference does this inside its OpenMP region too, src/approx_mcmc.cpp:372-373).
+static int make_nlg_draw_job(const bssm_nlg_model* M, const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N,
+                             uint32_t seed, const double* theta, uint32_t n_par, const double* modes, int post,
+                             bssm_b200_job** job) {
+  *job = nullptr;
+  const uint32_t nf = d1 - d0;
+  const int n = M->n, m = 2;
+  const size_t n1 = (size_t)n + 1;
+  bssm_b200_job* J = new bssm_b200_job();
+  struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
+  int rc = job_common(J, KIND_NLG, n, 2, 2, N, seed, nf, d0, 0, BSSM_POST_NONE);
+  if (rc) return rc;
+  J->method = BSSM_METHOD_PSI;
+  J->post = post;
+  std::vector<double> sc((size_t)32 * n * nf, 0.0), ah((size_t)m * n1 * nf), Lt((size_t)4 * n1 * nf), Ct((size_t)4 * n1 * nf),
+      al(nf, 0.0);
+  const double LOG2PI = std::log(2.0 * M_PI);
+  int bad = 0;
+#pragma omp parallel for schedule(static)
+  for (int64_t f = 0; f < (int64_t)nf; ++f) {
+    const uint32_t c = dl.src[d0 + f];
+    bssm_nlg_model Mi = *M;
+    Mi.theta = theta + (size_t)c * n_par;
+    Mi.n_theta = (int32_t)n_par;
+    pfga::NlgApprox ga(&Mi);
+    ga.run(modes + (size_t)m * n * c);
+    if (!ga.finite_mode) { bad = 1; continue; }
+    al[f] = 0.0; // approximate_for_is: the correction weight only (src/approx_mcmc.cpp:385)
+    double* scf = &sc[(size_t)32 * n * f];
+    for (int t = 0; t < n; ++t) {
+      double* cc = scf + (size_t)32 * t;
+      const double Ht = ga.H[t], HHt = Ht * Ht;
+      cc[0] = M->y[t]; cc[1] = LOG2PI + 2.0 * pf_log(Ht); cc[2] = Ht; cc[3] = LOG2PI + pf_log(HHt); cc[4] = HHt;
+      cc[5] = ga.D[t]; cc[6] = ga.Z[(size_t)m * t]; cc[7] = ga.Z[(size_t)m * t + 1]; cc[8] = ga.scales[t];
+      if (t >= 1) {
+        cc[10] = ga.C[(size_t)m * (t - 1)]; cc[11] = ga.C[(size_t)m * (t - 1) + 1];
+        for (int e = 0; e < 4; ++e) {
+          cc[12 + e] = ga.T[(size_t)4 * (t - 1) + e];
+          cc[16 + e] = ga.f_approx[t - 1].rooti[e];
+          cc[21 + e] = ga.f_true[t - 1].rooti[e];
+        }
+        cc[20] = ga.f_approx[t - 1].cst;
+        cc[25] = ga.f_true[t - 1].cst;
+      }
+    }
+    std::copy(ga.alphahat.begin(), ga.alphahat.end(), &ah[(size_t)m * n1 * f]);
+    std::copy(ga.L.begin(), ga.L.end(), &Lt[(size_t)4 * n1 * f]);
+    std::copy(ga.Ct.begin(), ga.Ct.end(), &Ct[(size_t)4 * n1 * f]);
+  }
+  if (bad) return fail(BSSM_B200_ERR_ARG, "post-correction: non-finite Gaussian approximation for a draw");
+  if ((rc = J->stepc.upload(sc.data(), sc.size())) || (rc = J->alphahat.upload(ah.data(), ah.size())) ||
+      (rc = J->Lt.upload(Lt.data(), Lt.size())) || (rc = J->Ct.upload(Ct.data(), Ct.size())) ||
+      (rc = J->approx_loglik.upload(al.data(), nf)))
+    return rc;
+  pf::NlgPsiParams& pp = J->npp;
+  pp.n = n; pp.stepc = J->stepc.p; pp.alphahat = J->alphahat.p; pp.Lt = J->Lt.p; pp.Ct = J->Ct.p;
+  pp.approx_loglik = J->approx_loglik.p;
+  pp.dT = M->known_params[0]; pp.K = M->known_params[1];
+  pp.fstride_stepc = (size_t)32 * n; pp.fstride_a = (size_t)m * n1; pp.fstride_m = (size_t)4 * n1;
+  if ((rc = finish_job(J, 0, post))) return rc;
+  guard.j = nullptr;
+  *job = J;
+  return 0;
+}
+
+int bssm_b200_postcorrection_nonlinear(const bssm_nlg_model* M, int output_type, uint32_t nsim, uint32_t seed,
+                                       uint32_t n_threads, int is_type, const uint32_t* counts,
+                                       const double* theta, uint32_t n_par, const double* modes,
+                                       uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
+                                       bssm_postcorr_out* out) {
+  (void)n_threads;
+  if (!M || !counts || !theta || !modes || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
+  if (M->model_id != BSSM_NLG_GROWTH || M->p != 1 || M->m != 2 || M->k != 2 || n_par < 3)
+    return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction (nonlinear): growth model of the registry only");
+  return postcorr_driver(M->n, 2, output_type, nsim, is_type, counts, n_stored, draw_begin, draw_end, out,
+                         [&](const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N, int post, bssm_b200_job** J) {
+                           return make_nlg_draw_job(M, dl, d0, d1, N, seed, theta, n_par, modes, post, J);
+                         });
 }
 
 // ---------------------------------------------------------- one-shot calls

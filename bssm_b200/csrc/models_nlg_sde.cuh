@@ -81,19 +81,29 @@ struct NlgPsiParams {
   const double* Ct;        // 2 x 2 x (n+1)
   const double* approx_loglik; // per filter
   double dT, K;
+  // per-filter strides of stepc / alphahat / (Lt, Ct): 0 when replicates share one
+  // approximation, non-zero for post_correct (one approximation per draw)
+  size_t fstride_stepc, fstride_a, fstride_m;
 };
 
 struct NlgGrowthPsi : GaussStep<NlgGrowthPsi, 2, 2, 2> {
   static constexpr int M = 2, KI = 2, KP = 2;
   typedef NlgPsiParams Params;
   const NlgPsiParams& mp;
+  const double *stepc, *alphahat, *Ltp, *Ctp;
   double al0;
   double y, c_sd, H, c_var, HH, D, Z0, Z1, scale;
   double ah0[2], ah1[2], Cm[4], Lm[4];
   double Ca[2], Ta[4], ra[4], ca, rt[4], ct;
   bool has_prev;
 
-  __device__ NlgGrowthPsi(const NlgPsiParams& p, uint32_t f) : mp(p), has_prev(false) { al0 = p.approx_loglik[f]; }
+  __device__ NlgGrowthPsi(const NlgPsiParams& p, uint32_t f) : mp(p), has_prev(false) {
+    al0 = p.approx_loglik[f];
+    stepc = p.stepc + (size_t)f * p.fstride_stepc;
+    alphahat = p.alphahat + (size_t)f * p.fstride_a;
+    Ltp = p.Lt + (size_t)f * p.fstride_m;
+    Ctp = p.Ct + (size_t)f * p.fstride_m;
+  }
   __device__ double loglik0() const { return al0; }
   __device__ double loglik_end() const { return 0.0; }
   __device__ void init(const double* z, double* x) const {
@@ -101,13 +111,13 @@ struct NlgGrowthPsi : GaussStep<NlgGrowthPsi, 2, 2, 2> {
     for (int d = 0; d < 2; ++d) {
       double s = 0.0;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) s += mp.Lt[d + 2 * j] * z[j];
-      x[d] = mp.alphahat[d] + s;
+      for (int j = 0; j < 2; ++j) s += Ltp[d + 2 * j] * z[j];
+      x[d] = alphahat[d] + s;
     }
   }
-  __device__ bool observed(int t) const { return pf_isfinite(mp.stepc[(size_t)32 * t]); }
+  __device__ bool observed(int t) const { return pf_isfinite(stepc[(size_t)32 * t]); }
   __device__ void begin_weight(int t) {
-    const double* c = mp.stepc + (size_t)32 * t;
+    const double* c = stepc + (size_t)32 * t;
     y = c[0]; c_sd = c[1]; H = c[2]; c_var = c[3]; HH = c[4]; D = c[5]; Z0 = c[6]; Z1 = c[7]; scale = c[8];
   }
   // observation part of log_weights (:888-896): dmvnorm(y; Z_fn, H, lwr) - dmvnorm(y; D + Z a, HH)
@@ -122,13 +132,13 @@ struct NlgGrowthPsi : GaussStep<NlgGrowthPsi, 2, 2, 2> {
   __device__ double finish_logw(double w, double carry) const { return (w - carry) - scale; }
   __device__ void begin_step(int t) {
 #pragma unroll
-    for (int d = 0; d < 2; ++d) { ah0[d] = mp.alphahat[d + 2 * t]; ah1[d] = mp.alphahat[d + 2 * (t + 1)]; }
+    for (int d = 0; d < 2; ++d) { ah0[d] = alphahat[d + 2 * t]; ah1[d] = alphahat[d + 2 * (t + 1)]; }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { Cm[e] = mp.Ct[e + 4 * (t + 1)]; Lm[e] = mp.Lt[e + 4 * (t + 1)]; }
+    for (int e = 0; e < 4; ++e) { Cm[e] = Ctp[e + 4 * (t + 1)]; Lm[e] = Ltp[e + 4 * (t + 1)]; }
     // factors of the transition t -> t+1, used by the weights of column t+1 (if it is weighted)
     has_prev = (t + 1 < mp.n);
     if (has_prev) {
-      const double* c = mp.stepc + (size_t)32 * (t + 1);
+      const double* c = stepc + (size_t)32 * (t + 1);
       Ca[0] = c[10]; Ca[1] = c[11];
 #pragma unroll
       for (int e = 0; e < 4; ++e) { Ta[e] = c[12 + e]; ra[e] = c[16 + e]; rt[e] = c[21 + e]; }

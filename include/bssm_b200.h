@@ -303,6 +303,18 @@ int bssm_b200_postcorrection_nongaussian(const bssm_ung_model* model, const bssm
                                          uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
                                          bssm_postcorr_out* out);
 
+/* replaces: postcorrection_nonlinear(y, Z, H, T, R, Zg, Tg, a1, P1, theta, ..., output_type, nsim,
+ *           seed, n_threads, is_type, counts, theta, modes) src/R_postcorrection.cpp:252-317 ->
+ *           is_correction_psi<ssm_nlg> (src/approx_mcmc.cpp:353-427); modes is m x n x n_stored.
+ * Registry models with p = 1 (growth).  The per-draw Gaussian approximation
+ * (approximate_for_is + Kalman smoother, O(n m^3) per draw) runs on the host with OpenMP
+ * in this build; the particle filters of all draws run as one device batch. */
+int bssm_b200_postcorrection_nonlinear(const bssm_nlg_model* model, int output_type, uint32_t nsim,
+                                       uint32_t seed, uint32_t n_threads, int is_type,
+                                       const uint32_t* counts, const double* theta, uint32_t n_par,
+                                       const double* modes, uint32_t n_stored, uint32_t draw_begin,
+                                       uint32_t draw_end, bssm_postcorr_out* out);
+
 /* ---- resident jobs: the same filters with inputs kept in HBM ------------- */
 /* A job owns device copies of the model, the pre-pass results and the output
  * buffers of `n_filters` independent replicate filters (filter f uses random

@@ -324,7 +324,11 @@ struct NlgApprox {
     }
   }
 
-  /* mode_in == nullptr: approximate() + approx_loglik (:973-981); else approximate_for_is */
+  /* mode_in == nullptr: approximate() + approx_loglik (:973-981).
+   * mode_in != nullptr: approximate_for_is (:153-186) -- relinearise at the stored mode and
+   * nothing else: unlike its ssm_ung namesake it neither recomputes the scales nor touches
+   * approx_loglik, so inside the IS-correction (fresh model object, src/R_postcorrection.cpp:
+   * 290-300) both stay at their initial value zero.  Mirrored here. */
   void run(const double* mode_in) {
     fn.a1_fn(a1.data());
     fn.P1_fn(P1.data());
@@ -336,13 +340,18 @@ struct NlgApprox {
       if (!finite_mode) return;
     }
     View v(*this);
-    const double gl = v.ga.log_likelihood();
-    update_scales();
-    double acc1 = 0.0, acc2 = 0.0; /* arma::accu(scales) */
-    int j;
-    for (j = 1; j < n; j += 2) { acc1 += scales[j - 1]; acc2 += scales[j]; }
-    if ((j - 1) < n) acc1 += scales[j - 1];
-    approx_loglik = gl + (acc1 + acc2);
+    if (mode_in) {
+      scales.assign(n, 0.0);
+      approx_loglik = 0.0;
+    } else {
+      const double gl = v.ga.log_likelihood();
+      update_scales();
+      double acc1 = 0.0, acc2 = 0.0; /* arma::accu(scales) */
+      int j;
+      for (j = 1; j < n; j += 2) { acc1 += scales[j - 1]; acc2 += scales[j]; }
+      if ((j - 1) < n) acc1 += scales[j - 1];
+      approx_loglik = gl + (acc1 + acc2);
+    }
     v.ga.smoother_and_conditional();
     alphahat = v.ga.alphahat; L = v.ga.L; Ct = v.ga.Ct;
     /* transition-density factors for the particle weights (log_weights :915-931) */

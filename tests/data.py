@@ -119,3 +119,19 @@ def mng_model(n=60, gen_seed=5, missing=True):
     return bssm_b200.ssm_mng(y, Z, T, R, a1=[0.0, 0.0], P1=np.diag([1.0, 0.1]),
                              distribution=["poisson", "negative binomial", "gaussian"], phi=[1.0, 3.0, 0.5],
                              D=[1.0, 0.5, 0.0])
+
+
+def growth_mcmc_output(model, n_stored, output_type=3, jitter=0.03, gen_seed=9):
+    """synthetic run_mcmc stand-in for the growth model: theta_i = theta + jitter * N(0,1) (theta is on
+    the log scale), counts ~ 1 + Poisson(2), modes_i = the oracle's converged mode at theta_i (m x n)"""
+    import orc
+    rng = np.random.default_rng(gen_seed)
+    th0 = np.asarray(model.theta)
+    theta = th0[None, :] + jitter * rng.normal(size=(n_stored, th0.size))
+    counts = (1 + rng.poisson(2, size=n_stored)).astype(np.uint32)
+    modes = np.zeros((model.m * model.n, n_stored), order="F")
+    for i in range(n_stored):
+        mi = bssm_b200.ssm_nlg(model.y, "growth", theta=theta[i], known_params=model.known_params)
+        modes[:, i] = orc.nlg_psi_filter(mi, 4, seed=1).mode.ravel(order="F")
+    return {"theta": theta, "counts": counts, "modes": modes, "output_type": output_type,
+            "posterior": np.zeros(n_stored)}

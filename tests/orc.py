@@ -55,6 +55,9 @@ def L():
         _L.orc_sde_bsf_filter.restype = d
         _L.orc_sde_bsf_filter.argtypes = [C.POINTER(SdeModel), u32, u32, u32, u32, C.c_int, c_double_p, c_double_p,
                                           c_uint32_p, C.POINTER(i32)]
+        _L.orc_postcorrection_nlg.argtypes = [C.POINTER(NlgModel), C.c_int, u32, u32, C.c_int, C.c_int, c_uint32_p,
+                                              c_double_p, u32, c_double_p, u32, C.c_int, c_double_p, c_double_p,
+                                              c_double_p, c_double_p, c_double_p, c_double_p]
         _L.orc_max_threads.restype = C.c_int
         _L.orc_filter_smoother.argtypes = [c_double_p, c_uint32_p, C.c_int, C.c_int, u32]
         _L.orc_summary.argtypes = [c_double_p, C.c_int, C.c_int, u32, c_double_p, c_double_p]
@@ -203,12 +206,20 @@ def post_correct(model, mcmc_output, N, is_type=2, seed=1, threads=0, arith=ARIT
     theta, counts, modes = _postcorr_inputs(model, mcmc_output)
     ot = int(mcmc_output.get("output_type", 3))
     nd = n_draws(mcmc_output, is_type)
-    n = model.n
+    n, m = model.n, model.m
     r = Result()
     r.weights, r.posterior, r.loglik = np.zeros(nd), np.zeros(nd), np.zeros(nd)
-    r.alpha = np.zeros((n + 1, 1, nd), order="F") if ot == 1 else None
-    r.alphahat = np.zeros((n + 1, 1), order="F") if ot == 2 else None
-    r.Vt = np.zeros((1, 1, n + 1), order="F") if ot == 2 else None
+    r.alpha = np.zeros((n + 1, m, nd), order="F") if ot == 1 else None
+    r.alphahat = np.zeros((n + 1, m), order="F") if ot == 2 else None
+    r.Vt = np.zeros((m, m, n + 1), order="F") if ot == 2 else None
+    if model.cls == "ssm_nlg":
+        ms = model.c_struct()
+        rc = L().orc_postcorrection_nlg(C.byref(ms), ot, N, seed, threads, is_type, uptr(counts), dptr(theta),
+                                        theta.shape[0], dptr(modes), counts.size, arith, dptr(r.weights),
+                                        dptr(r.posterior), dptr(r.alpha), dptr(r.alphahat), dptr(r.Vt),
+                                        dptr(r.loglik))
+        assert rc == 0
+        return r
     ms, tm = model.c_struct(), theta_map(model)
     rc = L().orc_postcorrection_ung(C.byref(ms), C.byref(tm), ot, N, seed, threads, is_type, uptr(counts),
                                     dptr(theta), theta.shape[0], dptr(modes), counts.size, arith,

@@ -90,3 +90,24 @@ def test_ar1_ng_postcorrection(engine):
     ref = orc.post_correct(model, mo, 100, is_type=2, seed=2)
     res = engine.post_correct(model, mo, 100, is_type="is2", seed=2)
     assert np.array_equal(res["weights"], ref.weights)
+
+
+def test_nonlinear_postcorrection_growth(engine):
+    """postcorrection_nonlinear (src/R_postcorrection.cpp:252-317) on the growth model: weights,
+    one trajectory per draw, and the weighted summary, against the oracle"""
+    model = data.growth_model(40)
+    mo = data.growth_mcmc_output(model, 12)
+    ref = orc.post_correct(model, mo, 64, is_type=2, seed=3)
+    res = engine.post_correct(model, mo, 64, is_type="is2", seed=3, return_loglik=True)
+    assert np.array_equal(res["loglik"], ref.loglik)
+    assert np.array_equal(res["weights"], ref.weights)
+    mo1 = dict(mo, output_type=1)
+    ref1 = orc.post_correct(model, mo1, 32, is_type=3, seed=4)
+    res1 = engine.post_correct(model, mo1, 32, is_type="is3", seed=4)
+    assert np.array_equal(res1["weights"], ref1.weights)
+    assert np.array_equal(res1["alpha"].view(np.uint64), ref1.alpha.view(np.uint64))
+    mo2 = dict(mo, output_type=2)
+    ref2 = orc.post_correct(model, mo2, 32, is_type=1, seed=5)
+    res2 = engine.post_correct(model, mo2, 32, is_type="is1", seed=5)
+    np.testing.assert_allclose(res2["alphahat"], ref2.alphahat, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(res2["Vt"], ref2.Vt, rtol=1e-8, atol=1e-12)
