@@ -306,15 +306,21 @@ def post_correct(model, mcmc_output, particles, threads=1, is_type="is2", seed=1
 class PostcorrJob(FilterJob):
     """Resident post-correction shard (bssm_b200_job_create_postcorr): weights only."""
 
-    def __init__(self, model, mcmc_output, particles, is_type="is2", seed=1, draw_range=None):
+    def __init__(self, model, mcmc_output, particles, is_type="is2", seed=1, draw_range=None, out_flags=0):
         N, seed = _check_particles(model, particles, seed)
         it = {"is2": 2, "is3": 3}[is_type.lower()]
         theta, counts, modes = _postcorr_inputs(model, mcmc_output)
         total = n_draws(mcmc_output, it)
         b, e = (0, total) if draw_range is None else draw_range
         self.model, self.N, self.n_filters = model, N, e - b
-        self._ms, self._tm = model.c_struct(), theta_map(model)
         self._h = C.c_void_p()
+        self._ms = model.c_struct()
+        if model.cls == "ssm_nlg":
+            check(lib().bssm_b200_job_create_postcorr_nlg(
+                C.byref(self._ms), N, seed, it, uptr(counts), dptr(theta), theta.shape[0], dptr(modes),
+                counts.size, b, e, int(out_flags), C.byref(self._h)))
+            return
+        self._tm = theta_map(model)
         check(lib().bssm_b200_job_create_postcorr(
             C.byref(self._ms), C.byref(self._tm), N, seed, it, uptr(counts), dptr(theta), theta.shape[0],
             dptr(modes), counts.size, b, e, C.byref(self._h)))

@@ -14,7 +14,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "bssm_b200", "csrc")
 LIB = os.path.join(CSRC, "libbssm_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["pf_device.cuh", "models_ung.cuh", "prepass_ung.cuh", "smoother_kernels.cuh"]
 
 
 def nvcc_cmd(verbose=False):
@@ -34,9 +33,9 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
-    deps += [os.path.join(ROOT, "include", "bssm_b200.h"),
-             os.path.join(ROOT, "include", "bssm_b200", "pf_math.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    for base, _, files in os.walk(os.path.join(ROOT, "include")):
+        deps += [os.path.join(base, f) for f in files if f.endswith(".h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -1423,7 +1423,7 @@ int bssm_b200_postcorrection_nongaussian(const bssm_ung_model* M, const bssm_the
 // draws (the reference does this inside its OpenMP region too, src/approx_mcmc.cpp:372-373).
 static int make_nlg_draw_job(const bssm_nlg_model* M, const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N,
                              uint32_t seed, const double* theta, uint32_t n_par, const double* modes, int post,
-                             bssm_b200_job** job) {
+                             bssm_b200_job** job, int out_flags = 0) {
   *job = nullptr;
   const uint32_t nf = d1 - d0;
   const int n = M->n, m = 2;
@@ -1479,10 +1479,27 @@ static int make_nlg_draw_job(const bssm_nlg_model* M, const DrawList& dl, uint32
   pp.approx_loglik = J->approx_loglik.p;
   pp.dT = M->known_params[0]; pp.K = M->known_params[1];
   pp.fstride_stepc = (size_t)32 * n; pp.fstride_a = (size_t)m * n1; pp.fstride_m = (size_t)4 * n1;
-  if ((rc = finish_job(J, 0, post))) return rc;
+  if ((rc = finish_job(J, out_flags, post))) return rc;
   guard.j = nullptr;
   *job = J;
   return 0;
+}
+
+int bssm_b200_job_create_postcorr_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, int is_type,
+                                      const uint32_t* counts, const double* theta, uint32_t n_par,
+                                      const double* modes, uint32_t n_stored, uint32_t draw_begin,
+                                      uint32_t draw_end, int out_flags, bssm_b200_job** job) {
+  if (!M || !counts || !theta || !modes || !job || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
+  if (M->model_id != BSSM_NLG_GROWTH || M->p != 1 || M->m != 2 || M->k != 2 || n_par < 3)
+    return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction (nonlinear): growth model of the registry only");
+  if (is_type == 1) return fail(BSSM_B200_ERR_ARG, "resident post-correction jobs need equal N per draw (is_type 2 or 3)");
+  int rc = require_device();
+  if (rc) return rc;
+  DrawList dl;
+  if ((rc = build_draws(is_type, counts, n_stored, &dl))) return rc;
+  if (draw_begin == 0 && draw_end == 0) draw_end = (uint32_t)dl.src.size();
+  if (draw_begin >= draw_end || draw_end > dl.src.size()) return fail(BSSM_B200_ERR_ARG, "bad draw range");
+  return make_nlg_draw_job(M, dl, draw_begin, draw_end, nsim, seed, theta, n_par, modes, BSSM_POST_NONE, job, out_flags);
 }
 
 int bssm_b200_postcorrection_nonlinear(const bssm_nlg_model* M, int output_type, uint32_t nsim, uint32_t seed,

@@ -333,6 +333,12 @@ int bssm_b200_job_create_postcorr(const bssm_ung_model* model, const bssm_theta_
                                   const double* theta, uint32_t n_par, const double* modes,
                                   uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
                                   bssm_b200_job** job);
+/* the same for ssm_nlg (growth): draws [draw_begin, draw_end), out_flags as in job_create_ung */
+int bssm_b200_job_create_postcorr_nlg(const bssm_nlg_model* model, uint32_t nsim, uint32_t seed,
+                                      int is_type, const uint32_t* counts, const double* theta,
+                                      uint32_t n_par, const double* modes, uint32_t n_stored,
+                                      uint32_t draw_begin, uint32_t draw_end, int out_flags,
+                                      bssm_b200_job** job);
 /* launches pre-pass + filter (+ the post-processing kernels) on the
  * job's stream and waits; ms = CUDA-event time on that stream */
 int bssm_b200_job_run(bssm_b200_job* job, float* ms);
