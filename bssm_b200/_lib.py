@@ -25,6 +25,7 @@ class UngModel(C.Structure):
         ("max_iter", C.c_int32), ("local_approx", C.c_int32),
         ("conv_tol", C.c_double),
         ("initial_mode", c_double_p),
+        ("H", c_double_p), ("Htv", C.c_int32),
     ]
 
 
@@ -96,6 +97,7 @@ def lib():
     L.bssm_b200_set_device.argtypes = [C.c_int]
     L.bssm_b200_shutdown.restype = None
     L.bssm_b200_stratified_sample.argtypes = [c_double_p, C.c_uint32, c_double_p, C.c_uint32, c_uint32_p]
+    L.bssm_b200_gaussian_psi_smoother.argtypes = [C.POINTER(UngModel), C.c_uint32, C.c_uint32, c_double_p]
     L.bssm_b200_math_probe.argtypes = [C.c_int, c_double_p, c_double_p, C.c_uint32]
     L.bssm_b200_rng_probe.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, c_double_p, c_double_p]
     for name in ("bssm_b200_bsf", "bssm_b200_bsf_smoother", "bssm_b200_psi_smoother", "bssm_b200_psi_filter"):

@@ -353,3 +353,14 @@ def synthetic_svm_mcmc_output(model, n_stored, output_type=3, jitter=0.05, gen_s
         modes[:, i] = gaussian_approx_mode(mi)
     return {"theta": theta, "counts": counts, "modes": modes, "output_type": output_type,
             "posterior": np.zeros(n_stored)}
+
+
+def gaussian_psi_smoother(model, particles, seed=1):
+    """particle_smoother.lineargaussian(method = "psi") -> gaussian_psi_smoother, R/particle_smoother.R:90-110:
+    `particles` independent draws from the smoothing distribution; returns (n+1) x m x N plus their summary."""
+    N, seed = _check_particles(model, particles, seed)
+    alpha = np.zeros((model.m, model.n + 1, N), order="F")
+    ms = model.c_struct()
+    check(lib().bssm_b200_gaussian_psi_smoother(C.byref(ms), N, seed, dptr(alpha)))
+    return {"alpha": np.transpose(alpha, (1, 0, 2)), "alphahat": alpha.mean(axis=2).T,
+            "Vt": np.stack([np.atleast_2d(np.cov(alpha[:, t, :], bias=True)) for t in range(model.n + 1)], axis=2)}

@@ -238,6 +238,21 @@ void chol_posdiag(const double* P1, int m, std::vector<double>& L) {
     }
 }
 
+// psd_chol, src/psd_chol.cpp:5-18
+void psd_chol_host(const double* x, int m, double* L) {
+  const double eps = std::numeric_limits<double>::epsilon();
+  double mx = x[0];
+  for (int d = 1; d < m; ++d) mx = std::max(mx, x[d + (size_t)m * d]);
+  std::vector<double> sub((size_t)m * m, 0.0);
+  for (int c = 0; c < m; ++c)
+    for (int r = 0; r < m; ++r)
+      sub[r + (size_t)m * c] = (x[r + (size_t)m * r] > std::max(eps, eps * m * mx) &&
+                                x[c + (size_t)m * c] > std::max(eps, eps * m * mx)) ? x[r + (size_t)m * c] : 0.0;
+  std::vector<double> Lv;
+  chol_posdiag(sub.data(), m, Lv);
+  for (int e = 0; e < m * m; ++e) L[e] = Lv[e];
+}
+
 // Newton/Laplace iterations for the mode of the Gaussian approximation, m = 1:
 // ssm_ung::approximate (:87-140, local branch) = repeat { laplace_iter (:302-342);
 // fast_smoother (src/model_ssm_ulg.cpp:252-305) } until the mean squared change
@@ -452,7 +467,7 @@ struct bssm_b200_job {
   pf::MngParams gp{};
   pf::NlgPsiParams npp{};
   DevBuf<double> stepc;
-  DevBuf<double> phi_v;
+  DevBuf<double> phi_v, HH_v, hconst_v;
   DevBuf<int> dist_v;
   pf::PrepassParams pp{};
   pf::FilterParams fp{};
@@ -639,7 +654,11 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
   *job = nullptr;
   if (M->n < 1 || M->m < 1 || M->k < 1 || nsim < 2 || n_filters < 1)
     return fail(BSSM_B200_ERR_ARG, "need n >= 1, m >= 1, k >= 1, nsim >= 2, n_filters >= 1");
-  if (M->distribution < 0 || M->distribution > 4) return fail(BSSM_B200_ERR_ARG, "distribution must be 0..4");
+  if (M->distribution < 0 || M->distribution > 5) return fail(BSSM_B200_ERR_ARG, "distribution must be 0..5");
+  const bool gaussian = M->distribution == BSSM_DIST_GAUSSIAN;
+  if (gaussian && (!M->H || method != BSSM_METHOD_BSF))
+    return fail(BSSM_B200_ERR_ARG, "linear-Gaussian models: bootstrap filter only, H required "
+                                   "(their psi 'filter' is bssm_b200_gaussian_psi_smoother)");
   if (method != BSSM_METHOD_PSI && method != BSSM_METHOD_BSF) return fail(BSSM_B200_ERR_ARG, "method must be 1 (psi) or 2 (bsf)");
   if (method == BSSM_METHOD_PSI && (M->m > 3 || (M->m != 1 && draw_par)))
     return fail(BSSM_B200_ERR_UNSUPPORTED, "psi-APF: m <= 3 (and m = 1 for per-draw models) in this build");
@@ -663,7 +682,9 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
   std::vector<double> xb(n, 0.0);
   if (M->xbeta) xb.assign(M->xbeta, M->xbeta + n);
   std::vector<double> LP1;
-  chol_posdiag(M->P1, m, LP1);
+  if (gaussian) { LP1.resize((size_t)m * m); psd_chol_host(M->P1, m, LP1.data()); } // psd_chol, src/model_ssm_ulg.cpp:560
+  else chol_posdiag(M->P1, m, LP1);
+  std::vector<double> ones(n, 1.0);
   if ((rc = J->y.upload(M->y, n))) return rc;
   if ((rc = J->Z.upload(M->Z, (size_t)m * (M->Ztv ? n : 1)))) return rc;
   if ((rc = J->T.upload(M->T, (size_t)m * m * (M->Ttv ? n : 1)))) return rc;
@@ -674,7 +695,7 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
   if ((rc = J->D.upload(M->D, M->Dtv ? n : 1))) return rc;
   if ((rc = J->C.upload(M->C, (size_t)m * (M->Ctv ? n : 1)))) return rc;
   if ((rc = J->xbeta.upload(xb.data(), n))) return rc;
-  if ((rc = J->u.upload(M->u, n))) return rc;
+  if ((rc = J->u.upload(M->u ? M->u : ones.data(), n))) return rc;
 
   pf::UngParams& up = J->up;
   up.n = n; up.distribution = M->distribution;
@@ -682,8 +703,19 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
   up.y = J->y.p; up.Z = J->Z.p; up.T = J->T.p; up.R = J->R.p; up.a1 = J->a1.p; up.LP1 = J->LP1.p;
   up.D = J->D.p; up.C = J->C.p; up.xbeta = J->xbeta.p; up.u = J->u.p;
   up.phi = M->phi;
-  const double dconst = ung_dist_const(M);
+  const double dconst = gaussian ? 0.0 : ung_dist_const(M);
   up.loglik_const = dconst;
+  up.HH = nullptr; up.hconst = nullptr;
+  if (gaussian) { // HH = H^2 (compute_HH) and norm_log_const(H_t) per time point (src/distr_consts.cpp:12-14)
+    std::vector<double> HH(n), hc(n);
+    for (int t = 0; t < n; ++t) {
+      const double h = M->H[t * M->Htv];
+      HH[t] = h * h;
+      hc[t] = -0.5 * std::log(2.0 * M_PI) - std::log(h);
+    }
+    if ((rc = J->HH_v.upload(HH.data(), n)) || (rc = J->hconst_v.upload(hc.data(), n))) return rc;
+    up.HH = J->HH_v.p; up.hconst = J->hconst_v.p;
+  }
 
   if (method == BSSM_METHOD_PSI && m > 1) {
     // Gaussian approximation on the host (O(n m^3), sequential in t), shared by all replicates
@@ -905,21 +937,6 @@ void bssm_b200_job_destroy(bssm_b200_job* J) { delete J; }
 // ------------------------------------------------------------ ssm_nlg / ssm_sde
 namespace {
 
-// psd_chol, src/psd_chol.cpp:5-18
-void psd_chol_host(const double* x, int m, double* L) {
-  const double eps = std::numeric_limits<double>::epsilon();
-  double mx = x[0];
-  for (int d = 1; d < m; ++d) mx = std::max(mx, x[d + (size_t)m * d]);
-  std::vector<double> sub((size_t)m * m, 0.0);
-  for (int c = 0; c < m; ++c)
-    for (int r = 0; r < m; ++r)
-      sub[r + (size_t)m * c] = (x[r + (size_t)m * r] > std::max(eps, eps * m * mx) &&
-                                x[c + (size_t)m * c] > std::max(eps, eps * m * mx)) ? x[r + (size_t)m * c] : 0.0;
-  std::vector<double> Lv;
-  chol_posdiag(sub.data(), m, Lv);
-  for (int e = 0; e < m * m; ++e) L[e] = Lv[e];
-}
-
 int job_common(bssm_b200_job* J, int kind, int n, int m, int k, uint32_t nsim, uint32_t seed,
                uint32_t n_filters, uint32_t first_filter_id, int out_flags, int post) {
   int rc = require_device();
@@ -1140,6 +1157,37 @@ int bssm_b200_psi_filter_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t se
   int rc = bssm_b200_job_create_nlg_psi(M, nsim, seed, max_iter, conv_tol, 1, 0, out_flags_of(out), BSSM_POST_NONE, &J);
   return rc ? rc : run_fetch_destroy(J, out);
 }
+int bssm_b200_gaussian_psi_smoother(const bssm_ung_model* M, uint32_t nsim, uint32_t seed, double* alpha) {
+  if (!M || !alpha) return fail(BSSM_B200_ERR_ARG, "null argument");
+  if (M->distribution != BSSM_DIST_GAUSSIAN || !M->H) return fail(BSSM_B200_ERR_ARG, "gaussian_psi_smoother: linear-Gaussian model with H required");
+  if (M->m > 3) return fail(BSSM_B200_ERR_UNSUPPORTED, "gaussian_psi_smoother: m <= 3 in this build");
+  int rc = require_device();
+  if (rc) return rc;
+  const int n = M->n, m = M->m;
+  // smoother_ccov + conditional_cov of the model itself (src/model_ssm_ulg.cpp:646-652): host, O(n m^3)
+  pfga::UngApprox ga(M);
+  for (int t = 0; t < n; ++t) {
+    const double h = M->H[t * M->Htv];
+    ga.ay[t] = M->y[t]; ga.aH[t] = h; ga.aHH[t] = h * h;
+  }
+  ga.smoother_and_conditional();
+  DevBuf<double> ah, Lt, Ct, tm, cube;
+  const uint32_t rows = (uint32_t)(n + 1) * m;
+  if ((rc = ah.upload(ga.alphahat.data(), ga.alphahat.size())) || (rc = Lt.upload(ga.L.data(), ga.L.size())) ||
+      (rc = Ct.upload(ga.Ct.data(), ga.Ct.size())) || (rc = tm.alloc((size_t)rows * nsim)) ||
+      (rc = cube.alloc((size_t)rows * nsim)))
+    return rc;
+  const dim3 g1(cdiv(nsim, 128));
+  if (m == 1) pf::gaussian_psi_kernel<1><<<g1, 128>>>(ah.p, Lt.p, Ct.p, tm.p, nsim, n, seed);
+  else if (m == 2) pf::gaussian_psi_kernel<2><<<g1, 128>>>(ah.p, Lt.p, Ct.p, tm.p, nsim, n, seed);
+  else pf::gaussian_psi_kernel<3><<<g1, 128>>>(ah.p, Lt.p, Ct.p, tm.p, nsim, n, seed);
+  CU(cudaGetLastError());
+  pf::transpose_to_cube_kernel<<<dim3(cdiv(nsim, 32), cdiv(rows, 32)), dim3(32, 8)>>>(tm.p, cube.p, rows, nsim);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(alpha, cube.p, sizeof(double) * (size_t)rows * nsim, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int bssm_b200_bsf_mng(const bssm_mng_model* M, uint32_t nsim, uint32_t seed, bssm_filter_out* out) {
   if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
   bssm_b200_job* J = nullptr;

@@ -261,6 +261,7 @@ struct SdeGbmBsf {
     run<P>(c, x);
   }
   __device__ __forceinline__ double finish_logw(double w, double) const { return w; }
+  __device__ __forceinline__ double step_const() const { return 0.0; }
 };
 
 } // namespace pf

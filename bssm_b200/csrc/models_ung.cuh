@@ -23,6 +23,9 @@ struct UngParams {
   const double* u;     // n
   double phi;
   double loglik_const; // BSF: state-independent constants, added at the end (:690-710)
+  // distribution 5 (ssm_ulg): HH_t = H_t^2 and norm_log_const(H_t), n each
+  const double* HH;
+  const double* hconst;
   // psi-APF (m = 1), per filter with stride `pstride`
   const double* phi_f;     // per-filter phi (post_correct) or null
   const double* alphahat;  // n+1
@@ -54,10 +57,11 @@ struct UngBsf : GaussStep<UngBsf<M_, K_>, M_, M_, K_> {
   typedef UngParams Params;
   const UngParams& mp;
   // per-step constants
-  double y, u, yphi2, Dt, xb;
+  double y, u, yphi2, Dt, xb, HHt, hc;
   double Z[M_], T[M_ * M_], R[M_ * K_], C[M_];
 
-  __device__ UngBsf(const UngParams& p, uint32_t) : mp(p) {}
+  __device__ UngBsf(const UngParams& p, uint32_t) : mp(p), hc(0.0) {}
+  __device__ double step_const() const { return hc; }
   __device__ double loglik0() const { return 0.0; }
   __device__ double loglik_end() const { return mp.loglik_const; }
   __device__ void init(const double* z, double* x) const {
@@ -79,6 +83,7 @@ struct UngBsf : GaussStep<UngBsf<M_, K_>, M_, M_, K_> {
     xb = mp.xbeta[t];
 #pragma unroll
     for (int d = 0; d < M_; ++d) Z[d] = mp.Z[d + M_ * (t * mp.Ztv)];
+    if (mp.distribution == 5) { HHt = mp.HH[t]; hc = mp.hconst[t]; }
   }
   __device__ double logw(const double* x) const {
     double s;
@@ -88,6 +93,10 @@ struct UngBsf : GaussStep<UngBsf<M_, K_>, M_, M_, K_> {
       double zs = 0.0;
 #pragma unroll
       for (int d = 0; d < M_; ++d) zs += Z[d] * x[d];
+      if (mp.distribution == 5) { // ssm_ulg::bsf_filter, src/model_ssm_ulg.cpp:577-580: mu = D + Z'a
+        const double mu = Dt + zs;
+        return -0.5 * ((y - mu) * (y - mu)) / HHt;
+      }
       s = Dt + zs + xb;
     }
     return ung_log_obs(mp.distribution, s, y, u, mp.phi, yphi2);

@@ -289,6 +289,7 @@ struct GaussStep {
     }
   }
   __device__ __forceinline__ double trans_term(const double*, const double*) const { return 0.0; }
+  __device__ __forceinline__ double step_const() const { return 0.0; }
   __device__ __forceinline__ double finish_logw(double w, double) const { return w; }
 };
 
@@ -435,8 +436,10 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
       const double S = pf_fixsum_value(Th, Tl);
       const double invS = 1.0 / S;
       if (obs) {
-        if (t == 0) loglik = (mx + loglik) + pf_log_normal(S / Nd); // reference :561
-        else loglik += mx + pf_log_normal(S / Nd);                  // reference :601
+        // step_const: per-step normalising constant (ssm_ulg adds norm_log_const(H_t) every
+        // step, src/model_ssm_ulg.cpp:588, :631); zero for the other models
+        if (t == 0) loglik = ((mx + loglik) + pf_log_normal(S / Nd)) + model.step_const(); // reference :561
+        else loglik += (mx + pf_log_normal(S / Nd)) + model.step_const();                  // reference :601
       }
       // offspring range of particle k is [count(p_{k-1}), count(p_k)); p_{N-1} := 1
       double pk[P + 1];

@@ -174,6 +174,36 @@ filter_summary_kernel(const double* __restrict__ alpha_tm, const double* __restr
   }
 }
 
+// ssm_ulg::psi_filter (src/model_ssm_ulg.cpp:646-672): N independent draws from the smoothing
+// distribution, alpha_{t+1} = ahat_{t+1} + Ct_{t+1} (alpha_t - ahat_t) + L_{t+1} u.  No weights,
+// no resampling: one thread per trajectory, written in the time-major layout.
+template <int M>
+__global__ void gaussian_psi_kernel(const double* __restrict__ alphahat, const double* __restrict__ Lt,
+                                    const double* __restrict__ Ct, double* __restrict__ alpha_tm, uint32_t N,
+                                    int n, uint32_t seed) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double x[M], z[M];
+  for (int t = 0; t <= n; ++t) {
+#pragma unroll
+    for (int d = 0; d < M; ++d) z[d] = pf_normal(seed, 0u, (uint32_t)t, 0u, i * M + d);
+    double nx[M];
+#pragma unroll
+    for (int d = 0; d < M; ++d) {
+      double cd = 0.0, lu = 0.0;
+      if (t > 0) {
+#pragma unroll
+        for (int j = 0; j < M; ++j) cd += Ct[d + M * j + (size_t)M * M * t] * (x[j] - alphahat[j + (size_t)M * (t - 1)]);
+      }
+#pragma unroll
+      for (int j = 0; j < M; ++j) lu += Lt[d + M * j + (size_t)M * M * t] * z[j];
+      nx[d] = t > 0 ? alphahat[d + (size_t)M * t] + cd + lu : alphahat[d] + lu;
+    }
+#pragma unroll
+    for (int d = 0; d < M; ++d) { x[d] = nx[d]; alpha_tm[((size_t)t * M + d) * N + i] = nx[d]; }
+  }
+}
+
 // post_correct output_type = 1 (src/approx_mcmc.cpp:388-392): after the
 // backward tracing, ONE trajectory per draw is kept, chosen uniformly.  Only
 // that path is traced: thread f follows the ancestry of particle

@@ -18,7 +18,7 @@ import numpy as np
 
 from ._lib import UngModel, dptr, f64
 
-DISTRIBUTIONS = {"svm": 0, "poisson": 1, "binomial": 2, "negative binomial": 3, "gamma": 4}
+DISTRIBUTIONS = {"svm": 0, "poisson": 1, "binomial": 2, "negative binomial": 3, "gamma": 4, "gaussian": 5}
 
 
 def init_mode(y, u, distribution):
@@ -49,7 +49,7 @@ class Model:
 
     def __init__(self, cls, y, Z, T, R, a1, P1, D, C_, u, phi, distribution, initial_mode,
                  xreg=None, beta=None, theta=None, max_iter=100, conv_tol=1e-8, local_approx=True,
-                 extra=None):
+                 extra=None, H=None):
         self.cls = cls
         self.y = f64(np.ravel(y))
         self.n = self.y.size
@@ -75,6 +75,9 @@ class Model:
         self.conv_tol = float(conv_tol)
         self.local_approx = bool(local_approx)
         self.extra = dict(extra or {})
+        self.H = None if H is None else f64(np.ravel(H))  # linear-Gaussian models only
+        if self.H is not None and self.H.size not in (1, n):
+            raise ValueError("H must have length 1 or n")
         for name, arr, last in (("Z", self.Z, 1), ("T", self.T, 2), ("R", self.R, 2), ("C", self.C, 1)):
             if arr.shape[last] not in (1, n):
                 raise ValueError("%s: last dimension must be 1 or n" % name)
@@ -106,6 +109,9 @@ class Model:
         s.phi = self.phi
         s.max_iter, s.local_approx, s.conv_tol = self.max_iter, int(self.local_approx), self.conv_tol
         s.initial_mode = dptr(self.initial_mode)
+        s.H = dptr(self.H) if self.H is not None else None
+        s.Htv = int(self.H is not None and self.H.size > 1)
+        keep.append(self.H)
         s._keep = keep
         return s
 
@@ -309,3 +315,30 @@ class MngModel:
 
 def ssm_mng(y, Z, T, R, a1, P1, distribution, phi=1.0, u=None, D=None, C=None):
     return MngModel(y, Z, T, R, a1, P1, distribution, phi=phi, u=u, D=D, C=C)
+
+
+def ssm_ulg(y, Z, H, T, R, a1, P1, D=0.0, C=None):
+    """General univariate linear-Gaussian model, R/models.R ssm_ulg (src/model_ssm_ulg.cpp:9-37)."""
+    y = np.ravel(np.asarray(y, dtype=np.float64))
+    a1 = np.ravel(np.asarray(a1, dtype=np.float64))
+    if C is None:
+        C = np.zeros((a1.size, 1))
+    return Model("ssm_ulg", y, Z, T, R, a1, P1, np.ravel(D), C, 1.0, 1.0, "gaussian", np.zeros(y.size), H=H)
+
+
+def bsm_lg(y, sd_y, sd_level, sd_slope=None, a1=None, P1=None):
+    """Basic structural Gaussian model (level + optional slope), R/models.R bsm_lg."""
+    y = np.ravel(np.asarray(y, dtype=np.float64))
+    slope = sd_slope is not None
+    m = 1 + int(slope)
+    a1 = np.zeros(m) if a1 is None else np.ravel(np.asarray(a1, dtype=np.float64))
+    P1 = np.diag(np.full(m, 100.0)) if P1 is None else np.array(P1, dtype=np.float64)
+    Z = np.zeros((m, 1)); Z[0, 0] = 1
+    T = np.zeros((m, m)); T[0, 0] = 1
+    R = np.zeros((m, m)); R[0, 0] = sd_level
+    if slope:
+        T[0:2, 1] = 1
+        R[1, 1] = sd_slope
+    mdl = ssm_ulg(y, Z, [sd_y], T.reshape(m, m, 1), R.reshape(m, m, 1), a1, P1)
+    mdl.cls = "bsm_lg"
+    return mdl

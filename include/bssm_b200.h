@@ -39,7 +39,10 @@ enum {
 /* distribution codes, R/bootstrap_filter.R:106-109 */
 enum {
   BSSM_DIST_SVM = 0, BSSM_DIST_POISSON = 1, BSSM_DIST_BINOMIAL = 2,
-  BSSM_DIST_NEGBIN = 3, BSSM_DIST_GAMMA = 4
+  BSSM_DIST_NEGBIN = 3, BSSM_DIST_GAMMA = 4,
+  /* univariate linear-Gaussian model (ssm_ulg / bsm_lg / ar1_lg): the `gaussian = TRUE`
+   * branch of bsf / bsf_smoother (src/R_bootstrap_filter.cpp:24-105) */
+  BSSM_DIST_GAUSSIAN = 5
 };
 /* sampling_method, R/run_mcmc.R:452-454 */
 enum { BSSM_METHOD_PSI = 1, BSSM_METHOD_BSF = 2 };
@@ -84,6 +87,9 @@ typedef struct {
   int32_t local_approx;
   double conv_tol;
   const double* initial_mode; /* n */
+  /* BSSM_DIST_GAUSSIAN only: observation standard deviation H (1|n), src/model_ssm_ulg.cpp:9-37 */
+  const double* H;
+  int32_t Htv;
 } bssm_ung_model;
 
 typedef struct {
@@ -149,6 +155,12 @@ int bssm_b200_bsf_smoother(const bssm_ung_model* model, uint32_t nsim, uint32_t 
  *           filter_smoother + summary.  m = 1 in this round. */
 int bssm_b200_psi_smoother(const bssm_ung_model* model, uint32_t nsim, uint32_t seed,
                            bssm_filter_out* out);
+/* replaces: gaussian_psi_smoother(model_, nsim, seed, model_type) src/R_psi.cpp:16-49 ->
+ *           ssm_ulg::psi_filter src/model_ssm_ulg.cpp:646-672: nsim independent draws from the
+ *           smoothing distribution of a linear-Gaussian model (no weights, no resampling).
+ *           model->distribution must be BSSM_DIST_GAUSSIAN; alpha is m x (n+1) x nsim. */
+int bssm_b200_gaussian_psi_smoother(const bssm_ung_model* model, uint32_t nsim, uint32_t seed,
+                                    double* alpha);
 /* psi-APF filter only (no backtrack/summary): the body of
  * ssm_ung::log_likelihood(method=1) src/model_ssm_ung.cpp:164-236 */
 int bssm_b200_psi_filter(const bssm_ung_model* model, uint32_t nsim, uint32_t seed,

@@ -341,6 +341,120 @@ double orc_ung_bsf_filter(const bssm_ung_model* M, uint32_t nsim, uint32_t seed,
 
 } /* extern "C" */
 
+/* ----------------------------------------------------- ssm_ulg filters */
+extern "C" {
+/* ssm_ulg::bsf_filter, src/model_ssm_ulg.cpp:557-643.  The model arrives as a bssm_ung_model
+ * with distribution 5 and H (standard deviation, 1|n).  Like the reference, mu = D + Z'alpha
+ * ignores xbeta and the normalising constant of every weighted step is added on the spot. */
+double orc_ulg_bsf_filter(const bssm_ung_model* M, uint32_t nsim, uint32_t seed, uint32_t filter, int arith,
+                          double* alpha, double* weights, uint32_t* indices, int32_t* stopped_at) {
+  *stopped_at = -1;
+  const int n = M->n, m = M->m, k = M->k;
+  const size_t N = nsim;
+  std::vector<double> L_P1;
+  {
+    /* psd_chol, src/psd_chol.cpp:5-18 */
+    const double eps = std::numeric_limits<double>::epsilon();
+    double mx = M->P1[0];
+    for (int d = 1; d < m; ++d) mx = std::max(mx, M->P1[d + (size_t)m * d]);
+    const double thr = std::max(eps, eps * m * mx);
+    std::vector<double> sub((size_t)m * m, 0.0);
+    for (int c = 0; c < m; ++c)
+      for (int r = 0; r < m; ++r)
+        if (M->P1[r + (size_t)m * r] > thr && M->P1[c + (size_t)m * c] > thr) sub[r + (size_t)m * c] = M->P1[r + (size_t)m * c];
+    chol_P1(sub.data(), m, L_P1);
+  }
+  auto A = [&](int d, int t, size_t i) -> double& { return alpha[d + (size_t)m * (t + (size_t)(n + 1) * i)]; };
+  auto H = [&](int t) { return M->H[t * M->Htv]; };
+  auto norm_log_const = [](double sd) { return -0.5 * std::log(2.0 * M_PI) - std::log(sd); };
+  for (size_t i = 0; i < N; ++i) {
+    std::vector<double> um(m);
+    for (int j = 0; j < m; ++j) um[j] = pf_normal(seed, filter, 0, 0, (uint32_t)(i * m + j));
+    for (int d = 0; d < m; ++d) {
+      double s = 0.0;
+      for (int j = 0; j < m; ++j) s += L_P1[d + (size_t)m * j] * um[j];
+      A(d, 0, i) = M->a1[d] + s;
+    }
+  }
+  std::vector<double> W(N), logw(N), r(N), atmp((size_t)m * N);
+  auto weigh = [&](int t) {
+    const double* Z = M->Z + (size_t)m * (t * M->Ztv);
+    const double HH = H(t) * H(t);
+    for (size_t i = 0; i < N; ++i) {
+      double zs = 0.0;
+      for (int d = 0; d < m; ++d) zs += Z[d] * A(d, t, i);
+      double mu = M->D[t * M->Dtv] + zs;
+      logw[i] = -0.5 * ((M->y[t] - mu) * (M->y[t] - mu)) / HH;
+    }
+  };
+  double loglik = 0.0;
+  if (std::isfinite(M->y[0])) {
+    weigh(0);
+    double mxw, lmean;
+    if (!normalise(logw.data(), nsim, weights, W, &mxw, &lmean, arith)) { *stopped_at = 0; return -ORC_INF; }
+    loglik = mxw + lmean + norm_log_const(H(0));
+  } else {
+    for (size_t i = 0; i < N; ++i) { weights[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
+  }
+  for (int t = 0; t < n; ++t) {
+    for (size_t i = 0; i < N; ++i) r[i] = pf_resample_uniform(seed, filter, t, (uint32_t)i);
+    uint32_t* ind = indices + N * t;
+    resample(W, r, nsim, ind, arith);
+    for (size_t i = 0; i < N; ++i)
+      for (int d = 0; d < m; ++d) atmp[d + (size_t)m * i] = A(d, t, ind[i]);
+    const double* Tm = M->T + (size_t)m * m * (t * M->Ttv);
+    const double* Rm = M->R + (size_t)m * k * (t * M->Rtv);
+    const double* Cv = M->C + (size_t)m * (t * M->Ctv);
+    for (size_t i = 0; i < N; ++i) {
+      std::vector<double> uk(k);
+      for (int j = 0; j < k; ++j) uk[j] = pf_normal(seed, filter, t + 1, 0, (uint32_t)(i * k + j));
+      for (int d = 0; d < m; ++d) {
+        double ta = 0.0, ru = 0.0;
+        for (int j = 0; j < m; ++j) ta += Tm[d + (size_t)m * j] * atmp[j + (size_t)m * i];
+        for (int j = 0; j < k; ++j) ru += Rm[d + (size_t)m * j] * uk[j];
+        A(d, t + 1, i) = Cv[d] + ta + ru;
+      }
+    }
+    double* wcol = weights + N * (t + 1);
+    if ((t < (n - 1)) && std::isfinite(M->y[t + 1])) {
+      weigh(t + 1);
+      double mxw, lmean;
+      if (!normalise(logw.data(), nsim, wcol, W, &mxw, &lmean, arith)) { *stopped_at = t + 1; return -ORC_INF; }
+      loglik += mxw + lmean + norm_log_const(H(t + 1));
+    } else {
+      for (size_t i = 0; i < N; ++i) { wcol[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
+    }
+  }
+  return loglik;
+}
+
+/* ssm_ulg::psi_filter, src/model_ssm_ulg.cpp:646-672: alpha m x (n+1) x N */
+void orc_ulg_psi_filter(const bssm_ung_model* M, uint32_t nsim, uint32_t seed, double* alpha) {
+  const int n = M->n, m = M->m;
+  const size_t mm = (size_t)m * m;
+  pfga::UngApprox ga(M); /* smoother_ccov + conditional_cov of the model itself */
+  for (int t = 0; t < n; ++t) {
+    const double h = M->H[t * M->Htv];
+    ga.ay[t] = M->y[t]; ga.aH[t] = h; ga.aHH[t] = h * h;
+  }
+  ga.smoother_and_conditional();
+  auto A = [&](int d, int t, size_t i) -> double& { return alpha[d + (size_t)m * (t + (size_t)(n + 1) * i)]; };
+  for (size_t i = 0; i < nsim; ++i) {
+    for (int t = 0; t <= n; ++t) {
+      std::vector<double> um(m);
+      for (int j = 0; j < m; ++j) um[j] = pf_normal(seed, 0, t, 0, (uint32_t)(i * m + j));
+      for (int d = 0; d < m; ++d) {
+        double cd = 0.0, lu = 0.0;
+        if (t > 0)
+          for (int j = 0; j < m; ++j) cd += ga.Ct[d + (size_t)m * j + mm * t] * (A(j, t - 1, i) - ga.alphahat[j + (size_t)m * (t - 1)]);
+        for (int j = 0; j < m; ++j) lu += ga.L[d + (size_t)m * j + mm * t] * um[j];
+        A(d, t, i) = t > 0 ? ga.alphahat[d + (size_t)m * t] + cd + lu : ga.alphahat[d] + lu;
+      }
+    }
+  }
+}
+} /* extern "C" */
+
 /* ----------------------------------------- Gaussian approximation, m = 1 */
 /* The scalar (m = 1) specialisation of the approx_model (class ssm_ulg) used by
  * the psi-APF.  Z, T, R, C, D may be time varying. */

@@ -135,3 +135,16 @@ def growth_mcmc_output(model, n_stored, output_type=3, jitter=0.03, gen_seed=9):
         modes[:, i] = orc.nlg_psi_filter(mi, 4, seed=1).mode.ravel(order="F")
     return {"theta": theta, "counts": counts, "modes": modes, "output_type": output_type,
             "posterior": np.zeros(n_stored)}
+
+
+def lg_model(n=80, gen_seed=21, missing=()):
+    """local linear trend Gaussian model (bsm_lg: level + slope), as in
+    tests/testthat/test_particle_smoother.R:17-31"""
+    rng = np.random.default_rng(gen_seed)
+    lvl, slp, y = 0.0, 0.1, np.empty(n)
+    for t in range(n):
+        y[t] = lvl + rng.normal()
+        lvl, slp = lvl + slp + 0.3 * rng.normal(), slp + 0.05 * rng.normal()
+    for t in missing:
+        y[t] = np.nan
+    return bssm_b200.bsm_lg(y, sd_y=1.0, sd_level=0.3, sd_slope=0.05, P1=np.diag([4.0, 1.0]))

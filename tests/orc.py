@@ -43,6 +43,10 @@ def L():
         _L.orc_postcorrection_ung.argtypes = [C.POINTER(UngModel), C.POINTER(ThetaMap), C.c_int, u32, u32, C.c_int,
                                               C.c_int, c_uint32_p, c_double_p, u32, c_double_p, u32, C.c_int,
                                               c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]
+        _L.orc_ulg_bsf_filter.restype = d
+        _L.orc_ulg_bsf_filter.argtypes = [C.POINTER(UngModel), u32, u32, u32, C.c_int, c_double_p, c_double_p,
+                                          c_uint32_p, C.POINTER(i32)]
+        _L.orc_ulg_psi_filter.argtypes = [C.POINTER(UngModel), u32, u32, c_double_p]
         _L.orc_mng_bsf_filter.restype = d
         _L.orc_mng_bsf_filter.argtypes = [C.POINTER(MngModel), u32, u32, u32, C.c_int, c_double_p, c_double_p,
                                           c_uint32_p, C.POINTER(i32)]
@@ -291,3 +295,20 @@ def nlg_psi_filter(model, N, seed, filt=0, arith=ARITH_REPRO, mode=None, max_ite
     r.approx_loglik = al.value
     r.stopped_at = st.value
     return r
+
+
+def ulg_bsf_filter(model, N, seed, filt=0, arith=ARITH_REPRO):
+    r = _alloc(model, N)
+    ms = model.c_struct()
+    st = C.c_int32(-1)
+    r.loglik = L().orc_ulg_bsf_filter(C.byref(ms), N, seed, filt, arith, dptr(r.alpha), dptr(r.weights),
+                                      uptr(r.indices), C.byref(st))
+    r.stopped_at = st.value
+    return r
+
+
+def ulg_psi_filter(model, N, seed):
+    alpha = np.zeros((model.m, model.n + 1, N), order="F")
+    ms = model.c_struct()
+    L().orc_ulg_psi_filter(C.byref(ms), N, seed, dptr(alpha))
+    return alpha
