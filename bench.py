@@ -206,6 +206,8 @@ def main():
     bssm_b200._lib.check(bssm_b200.lib().bssm_b200_set_device(local_rank))
     dist = None
     if world > 1:
+        # keep stdout to the one JSON line: NCCL_DEBUG=VERSION/INFO prints to stdout
+        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
