@@ -135,15 +135,16 @@ struct Coll {
 
   __device__ __forceinline__ void barrier() { sync->all(); }
 
+  // max over the filter; the caller maps NaN to +inf beforehand, so a plain max suffices
   __device__ __forceinline__ double allmax(double v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = nanmax(v, shfl_xor_d(v, o));
+    for (int o = 16; o > 0; o >>= 1) { const double y = shfl_xor_d(v, o); v = y > v ? y : v; }
     if (lane == 0) sm->wd[warp] = v;
     __syncthreads();
     if (warp == 0) {
       double x = lane < nwarps ? sm->wd[lane] : -pf_inf();
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) x = nanmax(x, shfl_xor_d(x, o));
+      for (int o = 16; o > 0; o >>= 1) { const double y = shfl_xor_d(x, o); x = y > x ? y : x; }
       if (ranks == 1) { if (lane == 0) sm->rd = x; }
       else if (lane == 0) ((double*)xch)[rank] = x;
     }
@@ -151,9 +152,9 @@ struct Coll {
     if (ranks > 1) {
       if (warp == 0) {
         double x = -pf_inf();
-        for (uint32_t r = lane; r < ranks; r += 32) x = nanmax(x, __ldcg(((const double*)xch) + r));
+        for (uint32_t r = lane; r < ranks; r += 32) { const double y = __ldcg(((const double*)xch) + r); x = y > x ? y : x; }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x = nanmax(x, shfl_xor_d(x, o));
+        for (int o = 16; o > 0; o >>= 1) { const double y = shfl_xor_d(x, o); x = y > x ? y : x; }
         if (lane == 0) sm->rd = x;
       }
       __syncthreads();
@@ -293,6 +294,42 @@ struct GaussStep {
   __device__ __forceinline__ double finish_logw(double w, double) const { return w; }
 };
 
+// ------------------------------------------------ per-thread row accesses
+// A thread's P particles are contiguous in every per-time row (weights column,
+// state row, threshold row, ancestor column): when the row base is 16-byte
+// aligned (`vec`: N even, resp. N % 4 == 0 for the 32-bit ancestors) and the
+// thread is not the ragged last one, P doubles go out as P/2 128-bit stores.
+template <int P>
+__device__ __forceinline__ void store_row(double* row, uint32_t i0, uint32_t N, bool vec, const double (&v)[P]) {
+  if (vec && i0 + P <= N) {
+    double2* q = reinterpret_cast<double2*>(row + i0);
+#pragma unroll
+    for (int h = 0; h < P / 2; ++h) q[h] = make_double2(v[2 * h], v[2 * h + 1]);
+  } else {
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+      if (i0 + p < N) row[i0 + p] = v[p];
+  }
+}
+template <int P>
+__device__ __forceinline__ void load_anc(const uint32_t* anc, uint32_t i0, uint32_t N, bool vec4, uint32_t (&a)[P]) {
+  if (vec4 && i0 + P <= N) {
+    if (P == 2) {
+      const uint2 v = __ldcg(reinterpret_cast<const uint2*>(anc + i0));
+      a[0] = v.x; a[1] = v.y;
+    } else {
+#pragma unroll
+      for (int h = 0; h < P / 4; ++h) {
+        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(anc + i0) + h);
+        a[4 * h] = v.x; a[4 * h + 1] = v.y; a[4 * h + 2] = v.z; a[4 * h + 3] = v.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int p = 0; p < P; ++p) a[p] = (i0 + p < N) ? __ldcg(anc + i0 + p) : 0u;
+  }
+}
+
 // -------------------------------------------------------- the filter kernel
 // Model policy:
 //   static constexpr int M;           state dimension
@@ -342,6 +379,9 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
   double* wout = fp.weights ? fp.weights + (size_t)fidx * fp.weights_stride : nullptr;
   uint32_t* iout = fp.indices + (size_t)fidx * fp.indices_stride;
 
+  // row bases are multiples of N elements from 256-byte aligned allocations
+  const bool vec2 = (N & 1u) == 0;  // 16-byte alignment of fp64 rows
+  const bool vec4 = (N & 3u) == 0;  // 16-byte alignment of the uint32 ancestor column (8-byte for P = 2 needs N even)
   Model model(mp, fidx);
   double x[P][M];
 
@@ -351,11 +391,12 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
     c0.seed = fp.seed; c0.filter = filter; c0.t = 0u; c0.i0 = i0;
     model.template init_all<P>(c0, x);
 #pragma unroll
-    for (int p = 0; p < P; ++p)
-      if (i0 + p < N) {
+    for (int d = 0; d < M; ++d) {
+      double col[P];
 #pragma unroll
-        for (int d = 0; d < M; ++d) alpha[(size_t)d * N + i0 + p] = x[p][d];
-      }
+      for (int p = 0; p < P; ++p) col[p] = x[p][d];
+      store_row<P>(alpha + (size_t)d * N, i0, N, vec2, col);
+    }
   }
 
   double loglik = model.loglik0();
@@ -383,11 +424,16 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
       model.begin_weight(t);
       double lw[P];
       mx = -pf_inf();
+      bool bad = false;
 #pragma unroll
       for (int p = 0; p < P; ++p) {
         lw[p] = (i0 + p < N) ? model.finish_logw(model.logw(x[p]), carry[p]) : -pf_inf();
-        mx = nanmax(mx, lw[p]);
+        bad = bad || (lw[p] != lw[p]);
+        mx = lw[p] > mx ? lw[p] : mx;
       }
+      // a NaN log-weight must stop the filter (the reference's sum of weights becomes NaN):
+      // +inf survives the plain max of the collective and fails the finiteness test below
+      if (bad) mx = pf_inf();
       PF_PHASE(0)
       mx = coll.allmax(mx);
       PF_PHASE(1)
@@ -398,11 +444,7 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
 #pragma unroll
       for (int p = 0; p < P; ++p) w[p] = (i0 + p < N) ? 1.0 : 0.0;
     }
-    if (wout) {
-#pragma unroll
-      for (int p = 0; p < P; ++p)
-        if (i0 + p < N) wout[(size_t)t * N + i0 + p] = w[p];
-    }
+    if (wout) store_row<P>(wout + (size_t)t * N, i0, N, vec2, w);
     if (t == n) break;
 
     // ---- stratified resampling -> ancestors of column t+1 (reference :650-655)
@@ -412,15 +454,15 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
     typename Model::template Noise<P> noise;
     {
       // thresholds of the strata this thread owns (visible after the scan barrier)
+      double uth[P];
 #pragma unroll
       for (int h = 0; h < P / 2; ++h) {
         const uint32_t j = i0 + 2 * h;
         pf_u32x4 rx = pf_philox4x32_10(j >> 1, 0u, (uint32_t)t, filter, fp.seed, (uint32_t)PF_RNG_RESAMPLE);
-        const double u0 = (pf_u53(rx.v[0], rx.v[1]) + (double)j) * invN;
-        const double u1 = (pf_u53(rx.v[2], rx.v[3]) + (double)(j + 1)) * invN;
-        if (j < N) ub[j] = u0;
-        if (j + 1 < N) ub[j + 1] = u1;
+        uth[2 * h] = (pf_u53(rx.v[0], rx.v[1]) + (double)j) * invN;
+        uth[2 * h + 1] = (pf_u53(rx.v[2], rx.v[3]) + (double)(j + 1)) * invN;
       }
+      store_row<P>(ub, i0, N, vec2, uth);
       // one scan of the fixed-point weights gives their sum and cumulative sums
       long long qh[P], ql[P], th = 0, tl = 0;
 #pragma unroll
@@ -473,8 +515,7 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
       const double* src = alpha + (size_t)(fp.keep_alpha ? t : (t & 1)) * M * N;
       double* dst = alpha + (size_t)(fp.keep_alpha ? t + 1 : ((t + 1) & 1)) * M * N;
       uint32_t a[P];
-#pragma unroll
-      for (int p = 0; p < P; ++p) a[p] = (i0 + p < N) ? __ldcg(anc + i0 + p) : 0u;
+      load_anc<P>(anc, i0, N, P == 2 ? vec2 : vec4, a);
       double xa[P][M];
 #pragma unroll
       for (int p = 0; p < P; ++p)
@@ -482,11 +523,11 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
         for (int d = 0; d < M; ++d) xa[p][d] = __ldcg(src + (size_t)d * N + a[p]);
       model.template propagate_all<P>(ctx, noise, xa, x, carry);
 #pragma unroll
-      for (int p = 0; p < P; ++p) {
-        if (i0 + p < N) {
+      for (int d = 0; d < M; ++d) {
+        double col[P];
 #pragma unroll
-          for (int d = 0; d < M; ++d) dst[(size_t)d * N + i0 + p] = x[p][d];
-        }
+        for (int p = 0; p < P; ++p) col[p] = x[p][d];
+        store_row<P>(dst + (size_t)d * N, i0, N, vec2, col);
       }
     }
     PF_PHASE(5)
