@@ -5,7 +5,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libbssm_b200.so")
+# BSSM_B200_LIB: developer override used to A/B kernel build variants (tools/build_variants.sh)
+LIB_PATH = os.environ.get("BSSM_B200_LIB") or os.path.join(_HERE, "csrc", "libbssm_b200.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_uint32_p = C.POINTER(C.c_uint32)

@@ -25,6 +25,7 @@
 #include "prepass_ung.cuh"
 #include "smoother_kernels.cuh"
 #include "models_nlg_sde.cuh"
+#include "filters.h"
 #include "bssm_b200/ung_gauss_approx.h"
 #include "bssm_b200/nlg_gauss_approx.h"
 
@@ -57,11 +58,7 @@ int require_device() {
 }
 
 // ---------------------------------------------------------------- geometry
-struct Geometry {
-  int P, block;
-  uint32_t ranks;
-  int sync_mode;
-};
+using pfl::Geometry;
 
 int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
@@ -112,90 +109,11 @@ int choose_geometry(uint32_t N, uint32_t n_filters, Geometry* g) {
 }
 
 // --------------------------------------------------------------- launching
-template <class Model, int P, int MAXT, int MINB>
-int launch_filter_V(const pf::FilterParams& fp, const typename Model::Params& mp, const Geometry& g,
-                    uint32_t n_filters, cudaStream_t stream) {
-  auto kern = pf::filter_kernel<Model, P, MAXT, MINB>;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(n_filters * g.ranks, 1, 1);
-  cfg.blockDim = dim3(g.block, 1, 1);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  cfg.attrs = attr;
-  cfg.numAttrs = 0;
-  if (g.sync_mode == pf::SYNC_CLUSTER) {
-    if (g.ranks > 8) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = g.ranks;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.numAttrs = 1;
-  } else if (g.sync_mode == pf::SYNC_GROUP) {
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
-    cfg.numAttrs = 1;
-  }
-  CU(cudaLaunchKernelEx(&cfg, kern, fp, mp));
-  return 0;
-}
-
-template <class Model, int P, int MAXT, int MINB>
-int occupancy_V(const Geometry& g, int* out) {
-  auto kern = pf::filter_kernel<Model, P, MAXT, MINB>;
-  int dev = 0, sms = 0;
-  CU(cudaGetDevice(&dev));
-  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  if (g.sync_mode == pf::SYNC_CLUSTER) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(g.ranks * 64, 1, 1);
-    cfg.blockDim = dim3(g.block, 1, 1);
-    cudaLaunchAttribute attr[1];
-    if (g.ranks > 8) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = g.ranks; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    int nc = 0;
-    CU(cudaOccupancyMaxActiveClusters(&nc, kern, &cfg));
-    *out = nc;
-    return 0;
-  }
-  int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, g.block, 0));
-  *out = g.sync_mode == pf::SYNC_GROUP ? (per_sm * sms) / (int)g.ranks : per_sm * sms;
-  return 0;
-}
-
-template <class Model>
-int occupancy(const Geometry& g, int* out) {
-  const bool small = g.block <= 512;
-  switch (g.P) {
-    case 2: return small ? occupancy_V<Model, 2, 512, 2>(g, out) : occupancy_V<Model, 2, 1024, 1>(g, out);
-    case 4: return small ? occupancy_V<Model, 4, 512, 2>(g, out) : occupancy_V<Model, 4, 1024, 1>(g, out);
-    case 8: return small ? occupancy_V<Model, 8, 512, 2>(g, out) : occupancy_V<Model, 8, 1024, 1>(g, out);
-  }
-  return fail(BSSM_B200_ERR_ARG, "bad P");
-}
-
-// kernel variants: P particles per thread, 64 registers per thread in all of them.
-// A 128-register variant (no spills, half the warps) was measured and is 15-40%
-// slower on every workload: latency hiding by resident warps matters more than
-// the ~50-300 bytes of spills.
-template <class Model>
-int launch_filter(const pf::FilterParams& fp, const typename Model::Params& mp, const Geometry& g,
-                  uint32_t n_filters, cudaStream_t stream) {
-  const bool small = g.block <= 512;
-  switch (g.P) {
-    case 2: return small ? launch_filter_V<Model, 2, 512, 2>(fp, mp, g, n_filters, stream)
-                         : launch_filter_V<Model, 2, 1024, 1>(fp, mp, g, n_filters, stream);
-    case 4: return small ? launch_filter_V<Model, 4, 512, 2>(fp, mp, g, n_filters, stream)
-                         : launch_filter_V<Model, 4, 1024, 1>(fp, mp, g, n_filters, stream);
-    case 8: return small ? launch_filter_V<Model, 8, 512, 2>(fp, mp, g, n_filters, stream)
-                         : launch_filter_V<Model, 8, 1024, 1>(fp, mp, g, n_filters, stream);
-  }
-  return fail(BSSM_B200_ERR_ARG, "bad P");
+// status of the pfl:: layer (launch.cuh) -> C ABI status + message
+int launch_status(int rc, const char* what) {
+  if (rc == 0) return 0;
+  if (rc < 0) return fail(BSSM_B200_ERR_UNSUPPORTED, std::string(what) + ": variant not instantiated in this build");
+  return fail(BSSM_B200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString((cudaError_t)rc));
 }
 
 // ------------------------------------------------------- host model pieces
@@ -532,41 +450,27 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
     npp.approx_loglik += f0;
     npp.stepc += (size_t)f0 * npp.fstride_stepc; npp.alphahat += (size_t)f0 * npp.fstride_a;
     npp.Lt += (size_t)f0 * npp.fstride_m; npp.Ct += (size_t)f0 * npp.fstride_m;
-    return launch_filter<pf::NlgGrowthPsi>(fp, npp, J->geo, nf, J->stream);
+    return launch_status(pfl::launch_nlg_psi(fp, npp, J->geo, nf, J->stream), "nlg psi filter");
   }
-  if (J->kind == KIND_NLG) return launch_filter<pf::NlgGrowthBsf>(fp, J->np, J->geo, nf, J->stream);
-  if (J->kind == KIND_SDE) return launch_filter<pf::SdeGbmBsf>(fp, J->sp, J->geo, nf, J->stream);
+  if (J->kind == KIND_NLG) return launch_status(pfl::launch_nlg_bsf(fp, J->np, J->geo, nf, J->stream), "nlg bsf");
+  if (J->kind == KIND_SDE) return launch_status(pfl::launch_sde_bsf(fp, J->sp, J->geo, nf, J->stream), "sde bsf");
   if (J->kind == KIND_MNG) {
-    switch (J->m * 10 + J->k) {
-      case 11: return launch_filter<pf::MngBsf<1, 1>>(fp, J->gp, J->geo, nf, J->stream);
-      case 21: return launch_filter<pf::MngBsf<2, 1>>(fp, J->gp, J->geo, nf, J->stream);
-      case 22: return launch_filter<pf::MngBsf<2, 2>>(fp, J->gp, J->geo, nf, J->stream);
-      case 33: return launch_filter<pf::MngBsf<3, 3>>(fp, J->gp, J->geo, nf, J->stream);
-    }
-    return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_mng bsf: (m,k) not instantiated in this build");
+    return launch_status(pfl::launch_mng_bsf(J->m, J->k, fp, J->gp, J->geo, nf, J->stream), "ssm_mng bsf (m,k)");
   }
   pf::UngParams up = J->up;
   if (J->method == BSSM_METHOD_PSI && J->m > 1) {
     up.approx_loglik += f0;
-    if (J->m == 2) return launch_filter<pf::UngPsiM<2>>(fp, up, J->geo, nf, J->stream);
-    return launch_filter<pf::UngPsiM<3>>(fp, up, J->geo, nf, J->stream);
+    return launch_status(pfl::launch_ung_psim(J->m, fp, up, J->geo, nf, J->stream), "psi filter (m)");
   }
   if (J->method == BSSM_METHOD_PSI) {
     up.alphahat += (size_t)f0 * J->pstride; up.Lt += (size_t)f0 * J->pstride; up.Ct += (size_t)f0 * J->pstride;
     up.ytilde += (size_t)f0 * J->pstride; up.Htilde += (size_t)f0 * J->pstride; up.scales += (size_t)f0 * J->pstride;
     up.approx_loglik += f0;
     if (up.phi_f) up.phi_f += f0;
-    return launch_filter<pf::UngPsi1>(fp, up, J->geo, nf, J->stream);
+    return launch_status(pfl::launch_ung_psi1(fp, up, J->geo, nf, J->stream), "psi filter");
   }
-  const int mk = J->m * 10 + J->k;
-  switch (mk) {
-    case 11: return launch_filter<pf::UngBsf<1, 1>>(fp, up, J->geo, nf, J->stream);
-    case 21: return launch_filter<pf::UngBsf<2, 1>>(fp, up, J->geo, nf, J->stream);
-    case 22: return launch_filter<pf::UngBsf<2, 2>>(fp, up, J->geo, nf, J->stream);
-    case 32: return launch_filter<pf::UngBsf<3, 2>>(fp, up, J->geo, nf, J->stream);
-    case 33: return launch_filter<pf::UngBsf<3, 3>>(fp, up, J->geo, nf, J->stream);
-  }
-  return fail(BSSM_B200_ERR_UNSUPPORTED, "bsf: (m,k) not instantiated in this build");
+  if (J->m <= 2) return launch_status(pfl::launch_ung_bsf_a(J->m, J->k, fp, up, J->geo, nf, J->stream), "bsf (m,k)");
+  return launch_status(pfl::launch_ung_bsf_b(J->m, J->k, fp, up, J->geo, nf, J->stream), "bsf (m,k)");
 }
 
 } // namespace
@@ -855,12 +759,12 @@ int bssm_b200_job_phase_cycles(bssm_b200_job* J, uint32_t cta, uint64_t cycles[6
 int bssm_b200_job_max_concurrent_filters(const bssm_b200_job* J) {
   if (!J) return 0;
   int out = 0, rc;
-  if (J->kind == KIND_NLG && J->method == BSSM_METHOD_PSI) rc = occupancy<pf::NlgGrowthPsi>(J->geo, &out);
-  else if (J->kind == KIND_NLG) rc = occupancy<pf::NlgGrowthBsf>(J->geo, &out);
-  else if (J->kind == KIND_SDE) rc = occupancy<pf::SdeGbmBsf>(J->geo, &out);
-  else if (J->kind == KIND_MNG) rc = occupancy<pf::MngBsf<1, 1>>(J->geo, &out);
-  else if (J->method == BSSM_METHOD_PSI) rc = occupancy<pf::UngPsi1>(J->geo, &out);
-  else rc = occupancy<pf::UngBsf<1, 1>>(J->geo, &out); // same register budget for all (m, k)
+  if (J->kind == KIND_NLG && J->method == BSSM_METHOD_PSI) rc = pfl::occupancy_nlg_psi(J->geo, &out);
+  else if (J->kind == KIND_NLG) rc = pfl::occupancy_nlg_bsf(J->geo, &out);
+  else if (J->kind == KIND_SDE) rc = pfl::occupancy_sde_bsf(J->geo, &out);
+  else if (J->kind == KIND_MNG) rc = pfl::occupancy_mng_bsf(J->geo, &out);
+  else if (J->method == BSSM_METHOD_PSI) rc = pfl::occupancy_ung_psi1(J->geo, &out);
+  else rc = pfl::occupancy_ung_bsf(J->geo, &out);
   return rc ? 0 : out;
 }
 

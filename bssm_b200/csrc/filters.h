@@ -1,0 +1,30 @@
+// filters.h -- the filter-kernel launchers, one translation unit per model family
+// (see launch.cuh for the status convention).
+#pragma once
+#include "launch.cuh"
+#include "models_ung.cuh"
+#include "models_nlg_sde.cuh"
+
+namespace pfl {
+using Stream = cudaStream_t;
+// k_ung_psi1.cu: psi-APF, m = 1 (svm, ar1_ng, univariate ssm_ung / ssm_ulg)
+int launch_ung_psi1(const pf::FilterParams&, const pf::UngParams&, const Geometry&, uint32_t nf, Stream);
+int occupancy_ung_psi1(const Geometry&, int* out);
+// k_ung_psim.cu: psi-APF, m in {2, 3}
+int launch_ung_psim(int m, const pf::FilterParams&, const pf::UngParams&, const Geometry&, uint32_t nf, Stream);
+// k_ung_bsf_a.cu / k_ung_bsf_b.cu: bootstrap filter, (m, k) in {(1,1),(2,1),(2,2)} / {(3,2),(3,3)}
+int launch_ung_bsf_a(int m, int k, const pf::FilterParams&, const pf::UngParams&, const Geometry&, uint32_t nf, Stream);
+int launch_ung_bsf_b(int m, int k, const pf::FilterParams&, const pf::UngParams&, const Geometry&, uint32_t nf, Stream);
+int occupancy_ung_bsf(const Geometry&, int* out);
+// k_mng.cu: multivariate-observation bootstrap filter
+int launch_mng_bsf(int m, int k, const pf::FilterParams&, const pf::MngParams&, const Geometry&, uint32_t nf, Stream);
+int occupancy_mng_bsf(const Geometry&, int* out);
+// k_nlg.cu: growth functor, bootstrap and psi-APF
+int launch_nlg_bsf(const pf::FilterParams&, const pf::NlgParams&, const Geometry&, uint32_t nf, Stream);
+int launch_nlg_psi(const pf::FilterParams&, const pf::NlgPsiParams&, const Geometry&, uint32_t nf, Stream);
+int occupancy_nlg_bsf(const Geometry&, int* out);
+int occupancy_nlg_psi(const Geometry&, int* out);
+// k_sde.cu: GBM functor, Milstein bootstrap filter
+int launch_sde_bsf(const pf::FilterParams&, const pf::SdeParams&, const Geometry&, uint32_t nf, Stream);
+int occupancy_sde_bsf(const Geometry&, int* out);
+} // namespace pfl

@@ -22,6 +22,21 @@
 #include <stdint.h>
 #include "bssm_b200/pf_math.h"
 
+#ifndef PF_RECOMP_TERMS
+#define PF_RECOMP_TERMS 0
+#endif
+#ifndef PF_COUNT_CHUNK
+#define PF_COUNT_CHUNK 4
+#endif
+// where the normals of the next column are generated: 0 = with the threshold
+// loads, 2 = inside the scan collective, 3 = inside the scatter barrier, 4 = after it
+#ifndef PF_DRAW_AT
+#define PF_DRAW_AT 3
+#endif
+#ifndef PF_SCATTER_UNROLL1
+#define PF_SCATTER_UNROLL1 1
+#endif
+
 namespace pf {
 
 enum SyncMode { SYNC_BLOCK = 0, SYNC_CLUSTER = 1, SYNC_GROUP = 2 };
@@ -80,18 +95,33 @@ struct Sync {
   unsigned int* counter; // SYNC_GROUP: this filter's counter (zeroed before the launch)
   unsigned int nranks;
   unsigned int target;
-  __device__ __forceinline__ void all() {
+  // Split-phase barrier.  arrive(): every write of this CTA so far is released;
+  // wait(): the writes of all CTAs of the filter released by their arrive() are
+  // visible.  Work placed between the two overlaps the barrier latency; it must
+  // not depend on what the barrier orders.
+  // `cta_synced`: the caller has just passed a __syncthreads() that every thread
+  // reaches after its last write the barrier has to publish, and thread 0 wrote
+  // (or is ordered after) the exchange partials.
+  __device__ __forceinline__ void arrive(bool cta_synced = false) {
     if (mode == SYNC_BLOCK) {
-      __syncthreads();
     } else if (mode == SYNC_CLUSTER) {
-      asm volatile("barrier.cluster.arrive.release.aligned;\n"
-                   "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+      asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     } else {
-      __syncthreads();
+      if (!cta_synced) __syncthreads();
       if (threadIdx.x == 0) {
         target += nranks;
         __threadfence();
         atomicAdd(counter, 1u);
+      }
+    }
+  }
+  __device__ __forceinline__ void wait() {
+    if (mode == SYNC_BLOCK) {
+      __syncthreads();
+    } else if (mode == SYNC_CLUSTER) {
+      asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    } else {
+      if (threadIdx.x == 0) {
         unsigned int v;
         do {
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
@@ -101,6 +131,7 @@ struct Sync {
       __syncthreads();
     }
   }
+  __device__ __forceinline__ void all() { arrive(); wait(); }
 };
 
 // NaN-propagating max (a NaN log-weight must stop the filter, see oracle normalise())
@@ -134,9 +165,13 @@ struct Coll {
   int lane, warp, nwarps;
 
   __device__ __forceinline__ void barrier() { sync->all(); }
+  __device__ __forceinline__ void barrier_arrive() { sync->arrive(); }
+  __device__ __forceinline__ void barrier_wait() { sync->wait(); }
 
-  // max over the filter; the caller maps NaN to +inf beforehand, so a plain max suffices
-  __device__ __forceinline__ double allmax(double v) {
+  // max over the filter; the caller maps NaN to +inf beforehand, so a plain max
+  // suffices.  Split in two: independent work between _begin and _end hides the
+  // latency of the exchange between CTAs.
+  __device__ __forceinline__ void allmax_begin(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { const double y = shfl_xor_d(v, o); v = y > v ? y : v; }
     if (lane == 0) sm->wd[warp] = v;
@@ -148,7 +183,11 @@ struct Coll {
       if (ranks == 1) { if (lane == 0) sm->rd = x; }
       else if (lane == 0) ((double*)xch)[rank] = x;
     }
-    sync->all();
+    // thread 0 wrote the partial itself; nothing else has to be published here
+    sync->arrive(true);
+  }
+  __device__ __forceinline__ double allmax_end() {
+    sync->wait();
     if (ranks > 1) {
       if (warp == 0) {
         double x = -pf_inf();
@@ -161,13 +200,14 @@ struct Coll {
     }
     return sm->rd;
   }
+  __device__ __forceinline__ double allmax(double v) { allmax_begin(v); return allmax_end(); }
 
   // Exclusive prefix, in (rank, thread) order, of the per-thread totals of the
   // two fixed-point words, plus the grand totals: one collective serves both the
-  // sum of the weights and their cumulative sum.
-  __device__ __forceinline__ void exscan2(long long th, long long tl, long long& eh, long long& el,
-                                          long long& Th, long long& Tl) {
-    long long ih = th, il = tl;
+  // sum of the weights and their cumulative sum.  _begin returns the thread's
+  // inclusive prefix within its warp (needed by _end).
+  __device__ __forceinline__ void exscan2_begin(long long th, long long tl, long long& ih, long long& il) {
+    ih = th; il = tl;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       long long oh = __shfl_up_sync(0xffffffffu, ih, d);
@@ -191,9 +231,18 @@ struct Coll {
         if (ranks == 1) { sm->ra = 0; sm->rb = 0; sm->ta = wh; sm->tb = wl; }
         else { ((long long*)xch)[ranks + rank] = wh; ((long long*)xch)[2 * ranks + rank] = wl; }
       }
+      __syncwarp(); // lane 31's partials before thread 0 releases them
     }
-    sync->all();
+    // every thread passed the __syncthreads above after its stores of this step
+    // (weights row, thresholds): thread 0's release publishes them too
+    sync->arrive(true);
+  }
+  __device__ __forceinline__ void exscan2_end(long long th, long long tl, long long ih, long long il,
+                                              long long& eh, long long& el, long long& Th, long long& Tl) {
+    sync->wait();
     if (ranks > 1) {
+      // rank partials are combined by warp 0 only: letting every warp read them
+      // (saving the CTA barrier) was measured 1-8% slower
       if (warp == 0) {
         long long xh = 0, xl = 0, sh = 0, sl = 0;
         for (uint32_t r = lane; r < ranks; r += 32) {
@@ -214,6 +263,12 @@ struct Coll {
     eh = sm->ra + sm->wa[warp] + (ih - th);
     el = sm->rb + sm->wb[warp] + (il - tl);
     Th = sm->ta; Tl = sm->tb;
+  }
+  __device__ __forceinline__ void exscan2(long long th, long long tl, long long& eh, long long& el,
+                                          long long& Th, long long& Tl) {
+    long long ih, il;
+    exscan2_begin(th, tl, ih, il);
+    exscan2_end(th, tl, ih, il, eh, el, Th, Tl);
   }
 };
 
@@ -418,11 +473,10 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
     // pure prediction: unit weights (the reference tests t < n-1 before
     // weighting column t+1).
     const bool obs = (t < n) && model.observed(t);
-    double w[P];
+    double w[P], lw[P];
     double mx = 0.0;
     if (obs) {
       model.begin_weight(t);
-      double lw[P];
       mx = -pf_inf();
       bool bad = false;
 #pragma unroll
@@ -435,7 +489,25 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
       // +inf survives the plain max of the collective and fails the finiteness test below
       if (bad) mx = pf_inf();
       PF_PHASE(0)
-      mx = coll.allmax(mx);
+      coll.allmax_begin(mx);
+    }
+    // ---- stratified resampling -> ancestors of column t+1 (reference :650-655)
+    uint32_t* anc = iout + (fp.keep_indices ? (size_t)t * N : 0);
+    if (t < n) {
+      // thresholds of the strata this thread owns, generated while the maxima
+      // travel between the CTAs (visible to the filter after the scan barrier)
+      double uth[P];
+#pragma unroll
+      for (int h = 0; h < P / 2; ++h) {
+        const uint32_t j = i0 + 2 * h;
+        pf_u32x4 rx = pf_philox4x32_10(j >> 1, 0u, (uint32_t)t, filter, fp.seed, (uint32_t)PF_RNG_RESAMPLE);
+        uth[2 * h] = (pf_u53(rx.v[0], rx.v[1]) + (double)j) * invN;
+        uth[2 * h + 1] = (pf_u53(rx.v[2], rx.v[3]) + (double)(j + 1)) * invN;
+      }
+      store_row<P>(ub, i0, N, vec2, uth);
+    }
+    if (obs) {
+      mx = coll.allmax_end();
       PF_PHASE(1)
       if (!pf_isfinite(mx)) { stopped = t; break; } // uniform over the filter
 #pragma unroll
@@ -447,23 +519,19 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
     if (wout) store_row<P>(wout + (size_t)t * N, i0, N, vec2, w);
     if (t == n) break;
 
-    // ---- stratified resampling -> ancestors of column t+1 (reference :650-655)
-    uint32_t* anc = iout + (fp.keep_indices ? (size_t)t * N : 0);
     StepCtx ctx;
     ctx.seed = fp.seed; ctx.filter = filter; ctx.t = (uint32_t)(t + 1); ctx.i0 = i0;
     typename Model::template Noise<P> noise;
     {
-      // thresholds of the strata this thread owns (visible after the scan barrier)
-      double uth[P];
-#pragma unroll
-      for (int h = 0; h < P / 2; ++h) {
-        const uint32_t j = i0 + 2 * h;
-        pf_u32x4 rx = pf_philox4x32_10(j >> 1, 0u, (uint32_t)t, filter, fp.seed, (uint32_t)PF_RNG_RESAMPLE);
-        uth[2 * h] = (pf_u53(rx.v[0], rx.v[1]) + (double)j) * invN;
-        uth[2 * h + 1] = (pf_u53(rx.v[2], rx.v[3]) + (double)(j + 1)) * invN;
-      }
-      store_row<P>(ub, i0, N, vec2, uth);
       // one scan of the fixed-point weights gives their sum and cumulative sums
+#if PF_RECOMP_TERMS
+      long long th = 0, tl = 0;
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        pf_fixsum tm = pf_fixsum_term(w[p]);
+        th += tm.hi; tl += tm.lo;
+      }
+#else
       long long qh[P], ql[P], th = 0, tl = 0;
 #pragma unroll
       for (int p = 0; p < P; ++p) {
@@ -471,9 +539,15 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
         qh[p] = tm.hi; ql[p] = tm.lo;
         th += tm.hi; tl += tm.lo;
       }
-      long long rh, rl, Th, Tl;
+#endif
+      long long rh, rl, Th, Tl, ih, il;
       PF_PHASE(2)
-      coll.exscan2(th, tl, rh, rl, Th, Tl);
+      coll.exscan2_begin(th, tl, ih, il);
+#if PF_DRAW_AT == 2
+      // the normals of the next column depend on nothing the collectives order
+      model.template draw<P>(ctx, noise);
+#endif
+      coll.exscan2_end(th, tl, ih, il, rh, rl, Th, Tl);
       PF_PHASE(3)
       const double S = pf_fixsum_value(Th, Tl);
       const double invS = 1.0 / S;
@@ -483,35 +557,62 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
         if (t == 0) loglik = ((mx + loglik) + pf_log_normal(S / Nd)) + model.step_const(); // reference :561
         else loglik += (mx + pf_log_normal(S / Nd)) + model.step_const();                  // reference :601
       }
-      // offspring range of particle k is [count(p_{k-1}), count(p_k)); p_{N-1} := 1
-      double pk[P + 1];
-      uint32_t jj[P + 1];
-      double uj[P + 1];
-      pk[0] = (i0 == 0) ? 0.0 : ((i0 - 1 >= N - 1) ? 1.0 : pf_fixsum_value(rh, rl) * invS);
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        rh += qh[p]; rl += ql[p];
-        pk[p + 1] = (i0 + p >= N - 1) ? 1.0 : pf_fixsum_value(rh, rl) * invS;
-      }
-#pragma unroll
-      for (int p = 0; p <= P; ++p) { jj[p] = st.guess(pk[p]); uj[p] = st.u(jj[p]); }
+      // offspring range of particle k is [count(p_{k-1}), count(p_k)); p_{N-1} := 1.
+      // Particles are resolved in chunks of CH so that only CH+1 cumulative
+      // probabilities / threshold loads are live at a time.
+      constexpr int CH = (P > PF_COUNT_CHUNK) ? PF_COUNT_CHUNK : P;
+      double pk0 = (i0 == 0) ? 0.0 : ((i0 - 1 >= N - 1) ? 1.0 : pf_fixsum_value(rh, rl) * invS);
+      uint32_t j0 = st.guess(pk0);
+      double u0 = st.u(j0);
+#if PF_DRAW_AT == 0
       // the normals of the next column do not depend on the ancestors: generate
       // them while the threshold loads are in flight
       model.template draw<P>(ctx, noise);
-      uint32_t lo = (i0 == 0) ? 0u : st.resolve(pk[0], jj[0], uj[0]);
+#endif
+      uint32_t lo = (i0 == 0) ? 0u : st.resolve(pk0, j0, u0);
 #pragma unroll
-      for (int p = 0; p < P; ++p) {
-        const uint32_t c = st.resolve(pk[p + 1], jj[p + 1], uj[p + 1]);
-        for (uint32_t j = lo; j < c; ++j) anc[j] = i0 + p;
-        lo = c > lo ? c : lo;
+      for (int c0 = 0; c0 < P; c0 += CH) {
+        double pk[CH];
+        uint32_t jj[CH];
+        double uj[CH];
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+          const int p = c0 + q;
+#if PF_RECOMP_TERMS
+          pf_fixsum tm = pf_fixsum_term(w[p]);
+          rh += tm.hi; rl += tm.lo;
+#else
+          rh += qh[p]; rl += ql[p];
+#endif
+          pk[q] = (i0 + p >= N - 1) ? 1.0 : pf_fixsum_value(rh, rl) * invS;
+          jj[q] = st.guess(pk[q]);
+          uj[q] = st.u(jj[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+          const uint32_t c = st.resolve(pk[q], jj[q], uj[q]);
+#if PF_SCATTER_UNROLL1
+#pragma unroll 1
+#endif
+          for (uint32_t j = lo; j < c; ++j) anc[j] = i0 + c0 + q;
+          lo = c > lo ? c : lo;
+        }
       }
     }
-    coll.barrier();
+    coll.barrier_arrive();
+#if PF_DRAW_AT == 3
+    // normals of the next column, generated while the scatter barrier completes
+    model.template draw<P>(ctx, noise);
+#endif
+    coll.barrier_wait();
     PF_PHASE(4)
 
     // ---- gather ancestors, propagate to column t+1 (reference :657-670)
     {
       model.begin_step(t);
+#if PF_DRAW_AT == 4
+      model.template draw<P>(ctx, noise);
+#endif
       const double* src = alpha + (size_t)(fp.keep_alpha ? t : (t & 1)) * M * N;
       double* dst = alpha + (size_t)(fp.keep_alpha ? t + 1 : ((t + 1) & 1)) * M * N;
       uint32_t a[P];
@@ -541,25 +642,6 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
   if (rank == 0 && threadIdx.x == 0) {
     fp.loglik[fidx] = loglik;
     fp.stopped_at[fidx] = stopped;
-  }
-}
-
-// ------------------------------------------------ layout change for output
-// alpha_tm [(t*M+d)*N + i]  ->  cube [d + M*(t + n1*i)]  (Armadillo cube
-// m x (n+1) x N, src/R_bootstrap_filter.cpp:162).  A plain tiled transpose of
-// the (n1*M) x N matrix; both sides coalesced.
-__global__ void transpose_to_cube_kernel(const double* __restrict__ tm, double* __restrict__ cube,
-                                         uint32_t rows /* n1*M */, uint32_t N) {
-  __shared__ double tile[32][33];
-  const uint32_t r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  for (int k = threadIdx.y; k < 32; k += blockDim.y) {
-    uint32_t r = r0 + k, c = c0 + threadIdx.x;
-    if (r < rows && c < N) tile[k][threadIdx.x] = tm[(size_t)r * N + c];
-  }
-  __syncthreads();
-  for (int k = threadIdx.y; k < 32; k += blockDim.y) {
-    uint32_t c = c0 + k, r = r0 + threadIdx.x;
-    if (r < rows && c < N) cube[(size_t)c * rows + r] = tile[threadIdx.x][k];
   }
 }
 

@@ -145,10 +145,10 @@ static const double pf_hc_log[] = {PF_LOG_COEFFS};
 static const double pf_hc_sin[] = {PF_SIN_COEFFS};
 static const double pf_hc_cos[] = {PF_COS_COEFFS};
 #if defined(__CUDACC__)
-__constant__ double pf_dc_exp[] = {PF_EXP_COEFFS};
-__constant__ double pf_dc_log[] = {PF_LOG_COEFFS};
-__constant__ double pf_dc_sin[] = {PF_SIN_COEFFS};
-__constant__ double pf_dc_cos[] = {PF_COS_COEFFS};
+static __constant__ double pf_dc_exp[] = {PF_EXP_COEFFS};
+static __constant__ double pf_dc_log[] = {PF_LOG_COEFFS};
+static __constant__ double pf_dc_sin[] = {PF_SIN_COEFFS};
+static __constant__ double pf_dc_cos[] = {PF_COS_COEFFS};
 #endif
 #if defined(__CUDA_ARCH__)
 #define PF_CE pf_dc_exp
