@@ -47,7 +47,9 @@ class MngModel(C.Structure):
                 ("Ztv", C.c_int32), ("Ttv", C.c_int32), ("Rtv", C.c_int32), ("Dtv", C.c_int32), ("Ctv", C.c_int32),
                 ("distribution", C.POINTER(C.c_int32)),
                 ("y", c_double_p), ("u", c_double_p), ("Z", c_double_p), ("T", c_double_p), ("R", c_double_p),
-                ("a1", c_double_p), ("P1", c_double_p), ("D", c_double_p), ("C", c_double_p), ("phi", c_double_p)]
+                ("a1", c_double_p), ("P1", c_double_p), ("D", c_double_p), ("C", c_double_p), ("phi", c_double_p),
+                ("max_iter", C.c_int32), ("local_approx", C.c_int32), ("conv_tol", C.c_double),
+                ("initial_mode", c_double_p)]
 
 
 class NlgModel(C.Structure):
@@ -106,10 +108,12 @@ def lib():
     L.bssm_b200_job_create_ung.argtypes = [
         C.POINTER(UngModel), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
         C.c_int, C.c_int, C.POINTER(C.c_void_p)]
-    for name in ("bssm_b200_bsf_mng", "bssm_b200_bsf_smoother_mng"):
+    for name in ("bssm_b200_bsf_mng", "bssm_b200_bsf_smoother_mng", "bssm_b200_psi_smoother_mng",
+                 "bssm_b200_psi_filter_mng"):
         getattr(L, name).argtypes = [C.POINTER(MngModel), C.c_uint32, C.c_uint32, C.POINTER(FilterOut)]
-    L.bssm_b200_job_create_mng.argtypes = [C.POINTER(MngModel), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
-                                           C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    for name in ("bssm_b200_job_create_mng", "bssm_b200_job_create_mng_psi"):
+        getattr(L, name).argtypes = [C.POINTER(MngModel), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                     C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     for name in ("bssm_b200_bsf_nlg", "bssm_b200_bsf_smoother_nlg"):
         getattr(L, name).argtypes = [C.POINTER(NlgModel), C.c_uint32, C.c_uint32, C.POINTER(FilterOut)]
     for name in ("bssm_b200_psi_smoother_nlg", "bssm_b200_psi_filter_nlg"):

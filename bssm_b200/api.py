@@ -103,11 +103,12 @@ def particle_smoother(model, particles, method="psi", seed=1, return_indices=Fal
         # particle_smoother.ssm_nlg -> psi_smoother_nlg(..., max_iter, conv_tol, iekf_iter), R/particle_smoother.R:221-228
         check(lib().bssm_b200_psi_smoother_nlg(C.byref(ms), N, seed, int(getattr(model, "max_iter", 100)),
                                                float(getattr(model, "conv_tol", 1e-8)), 0, C.byref(b.out)))
-    elif model.cls in ("ssm_nlg", "ssm_mng"):
-        if method != "bsf":
-            raise ValueError("%s: only method='bsf' is implemented in this build" % model.cls)
-        fn = lib().bssm_b200_bsf_smoother_nlg if model.cls == "ssm_nlg" else lib().bssm_b200_bsf_smoother_mng
+    elif model.cls == "ssm_mng":
+        # psi_smoother(model_type = 0) src/R_psi.cpp:57-78 / bsf_smoother src/R_bootstrap_filter.cpp:360-385
+        fn = lib().bssm_b200_psi_smoother_mng if method == "psi" else lib().bssm_b200_bsf_smoother_mng
         check(fn(C.byref(ms), N, seed, C.byref(b.out)))
+    elif model.cls == "ssm_nlg":
+        check(lib().bssm_b200_bsf_smoother_nlg(C.byref(ms), N, seed, C.byref(b.out)))
     elif model.cls == "ssm_sde":
         if L is None or int(L) < 1:
             raise ValueError("Discretization level L must be larger than 0.")
@@ -137,7 +138,8 @@ class FilterJob:
         self._h = C.c_void_p()
         meth = METHOD_PSI if method == "psi" else METHOD_BSF
         if model.cls == "ssm_mng":
-            check(lib().bssm_b200_job_create_mng(C.byref(self._ms), N, seed, self.n_filters, int(first_filter),
+            create = lib().bssm_b200_job_create_mng_psi if method == "psi" else lib().bssm_b200_job_create_mng
+            check(create(C.byref(self._ms), N, seed, self.n_filters, int(first_filter),
                                                  int(out_flags), int(post), C.byref(self._h)))
         elif model.cls == "ssm_nlg" and method == "psi":
             check(lib().bssm_b200_job_create_nlg_psi(C.byref(self._ms), N, seed, int(getattr(model, "max_iter", 100)),

@@ -28,6 +28,7 @@
 #include "filters.h"
 #include "bssm_b200/ung_gauss_approx.h"
 #include "bssm_b200/nlg_gauss_approx.h"
+#include "bssm_b200/mng_gauss_approx.h"
 
 namespace {
 
@@ -455,6 +456,11 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
   if (J->kind == KIND_NLG) return launch_status(pfl::launch_nlg_bsf(fp, J->np, J->geo, nf, J->stream), "nlg bsf");
   if (J->kind == KIND_SDE) return launch_status(pfl::launch_sde_bsf(fp, J->sp, J->geo, nf, J->stream), "sde bsf");
   if (J->kind == KIND_MNG) {
+    if (J->method == BSSM_METHOD_PSI) {
+      pf::MngParams gp = J->gp;
+      gp.approx_loglik += f0;
+      return launch_status(pfl::launch_mng_psi(J->m, fp, gp, J->geo, nf, J->stream), "ssm_mng psi filter (m)");
+    }
     return launch_status(pfl::launch_mng_bsf(J->m, J->k, fp, J->gp, J->geo, nf, J->stream), "ssm_mng bsf (m,k)");
   }
   pf::UngParams up = J->up;
@@ -965,8 +971,8 @@ int bssm_b200_job_create_sde(const bssm_sde_model* M, uint32_t nsim, uint32_t L,
   return 0;
 }
 
-int bssm_b200_job_create_mng(const bssm_mng_model* M, uint32_t nsim, uint32_t seed, uint32_t n_filters,
-                             uint32_t first_filter_id, int out_flags, int post, bssm_b200_job** job) {
+static int create_mng_job(const bssm_mng_model* M, int method, uint32_t nsim, uint32_t seed, uint32_t n_filters,
+                          uint32_t first_filter_id, int out_flags, int post, bssm_b200_job** job) {
   if (!M || !job || !M->y || !M->u || !M->Z || !M->T || !M->R || !M->a1 || !M->P1 || !M->D || !M->C ||
       !M->phi || !M->distribution)
     return fail(BSSM_B200_ERR_ARG, "null argument");
@@ -1015,10 +1021,43 @@ int bssm_b200_job_create_mng(const bssm_mng_model* M, uint32_t nsim, uint32_t se
     }
   }
   gp.loglik_const = cst;
+  if (method == BSSM_METHOD_PSI) {
+    // Gaussian approximation on the host (O(n (m^3 + p^3)), sequential in t), shared by all replicates
+    if (m > 3) return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_mng psi-APF: m <= 3 in this build");
+    if (!M->initial_mode) return fail(BSSM_B200_ERR_ARG, "psi-APF needs initial_mode");
+    if (M->max_iter < 1) return fail(BSSM_B200_ERR_ARG, "max_iter must be >= 1");
+    J->method = BSSM_METHOD_PSI;
+    pfga::MngApprox ga(M);
+    ga.run(nullptr);
+    // pseudo-observations in the layout of y (n x p)
+    std::vector<double> yt((size_t)n * p), Ht((size_t)n * p);
+    for (int t = 0; t < n; ++t)
+      for (int j = 0; j < p; ++j) {
+        yt[t + (size_t)n * j] = ga.ay[j + (size_t)p * t];
+        Ht[t + (size_t)n * j] = ga.aH[j + (size_t)p * t];
+      }
+    std::vector<double> al(n_filters, ga.approx_loglik);
+    if ((rc = J->alphahat.upload(ga.alphahat.data(), ga.alphahat.size())) || (rc = J->Lt.upload(ga.L.data(), ga.L.size())) ||
+        (rc = J->Ct.upload(ga.Ct.data(), ga.Ct.size())) || (rc = J->ytilde.upload(yt.data(), yt.size())) ||
+        (rc = J->Htilde.upload(Ht.data(), Ht.size())) || (rc = J->scales.upload(ga.scales.data(), n)) ||
+        (rc = J->approx_loglik.upload(al.data(), n_filters)))
+      return rc;
+    gp.alphahat = J->alphahat.p; gp.Lt = J->Lt.p; gp.Ct = J->Ct.p; gp.ytilde = J->ytilde.p;
+    gp.Htilde = J->Htilde.p; gp.scales = J->scales.p; gp.approx_loglik = J->approx_loglik.p;
+  }
   if ((rc = finish_job(J, out_flags, post))) return rc;
   guard.j = nullptr;
   *job = J;
   return 0;
+}
+
+int bssm_b200_job_create_mng(const bssm_mng_model* M, uint32_t nsim, uint32_t seed, uint32_t n_filters,
+                             uint32_t first_filter_id, int out_flags, int post, bssm_b200_job** job) {
+  return create_mng_job(M, BSSM_METHOD_BSF, nsim, seed, n_filters, first_filter_id, out_flags, post, job);
+}
+int bssm_b200_job_create_mng_psi(const bssm_mng_model* M, uint32_t nsim, uint32_t seed, uint32_t n_filters,
+                                 uint32_t first_filter_id, int out_flags, int post, bssm_b200_job** job) {
+  return create_mng_job(M, BSSM_METHOD_PSI, nsim, seed, n_filters, first_filter_id, out_flags, post, job);
 }
 
 static int run_fetch_destroy(bssm_b200_job* J, bssm_filter_out* out) {
@@ -1102,6 +1141,18 @@ int bssm_b200_bsf_smoother_mng(const bssm_mng_model* M, uint32_t nsim, uint32_t 
   if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
   bssm_b200_job* J = nullptr;
   int rc = bssm_b200_job_create_mng(M, nsim, seed, 1, 0, out_flags_of(out), BSSM_POST_SMOOTHER, &J);
+  return rc ? rc : run_fetch_destroy(J, out);
+}
+int bssm_b200_psi_smoother_mng(const bssm_mng_model* M, uint32_t nsim, uint32_t seed, bssm_filter_out* out) {
+  if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
+  bssm_b200_job* J = nullptr;
+  int rc = bssm_b200_job_create_mng_psi(M, nsim, seed, 1, 0, out_flags_of(out), BSSM_POST_SMOOTHER, &J);
+  return rc ? rc : run_fetch_destroy(J, out);
+}
+int bssm_b200_psi_filter_mng(const bssm_mng_model* M, uint32_t nsim, uint32_t seed, bssm_filter_out* out) {
+  if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
+  bssm_b200_job* J = nullptr;
+  int rc = bssm_b200_job_create_mng_psi(M, nsim, seed, 1, 0, out_flags_of(out), BSSM_POST_NONE, &J);
   return rc ? rc : run_fetch_destroy(J, out);
 }
 int bssm_b200_bsf_sde(const bssm_sde_model* M, uint32_t nsim, uint32_t L, uint32_t seed, bssm_filter_out* out) {

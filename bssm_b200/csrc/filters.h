@@ -16,8 +16,9 @@ int launch_ung_psim(int m, const pf::FilterParams&, const pf::UngParams&, const 
 int launch_ung_bsf_a(int m, int k, const pf::FilterParams&, const pf::UngParams&, const Geometry&, uint32_t nf, Stream);
 int launch_ung_bsf_b(int m, int k, const pf::FilterParams&, const pf::UngParams&, const Geometry&, uint32_t nf, Stream);
 int occupancy_ung_bsf(const Geometry&, int* out);
-// k_mng.cu: multivariate-observation bootstrap filter
+// k_mng.cu: multivariate-observation bootstrap filter and psi-APF (m <= 3)
 int launch_mng_bsf(int m, int k, const pf::FilterParams&, const pf::MngParams&, const Geometry&, uint32_t nf, Stream);
+int launch_mng_psi(int m, const pf::FilterParams&, const pf::MngParams&, const Geometry&, uint32_t nf, Stream);
 int occupancy_mng_bsf(const Geometry&, int* out);
 // k_nlg.cu: growth functor, bootstrap and psi-APF
 int launch_nlg_bsf(const pf::FilterParams&, const pf::NlgParams&, const Geometry&, uint32_t nf, Stream);

@@ -263,7 +263,26 @@ struct MngParams {
   const double* phi;   // p
   const int* distribution; // p (1 poisson, 2 binomial, 3 negbin, 4 gamma, 5 gaussian)
   double loglik_const;
+  // psi-APF only: Gaussian approximation from the host (include/bssm_b200/mng_gauss_approx.h)
+  const double* alphahat;      // m x (n+1)
+  const double* Ct;            // m x m x (n+1)
+  const double* Lt;            // m x m x (n+1)
+  const double* ytilde;        // n x p pseudo-observations (same layout as y)
+  const double* Htilde;        // n x p their standard deviations
+  const double* scales;        // n
+  const double* approx_loglik; // per filter
 };
+
+// log g(y_j | s) up to constants, src/model_ssm_mng.cpp:364-386 (shared by log_obs_density :407-442)
+__device__ __forceinline__ double mng_log_obs(int dist, double s, double y, double u, double phi) {
+  switch (dist) {
+    case 1: return y * s - u * pf_exp(s);
+    case 2: return y * s - u * pf_log1p(pf_exp(s));
+    case 3: return y * s - (y + phi) * pf_log(phi + u * pf_exp(s));
+    case 4: return -phi * (s + (y * pf_exp(-s) / u));
+    default: { double q = (y - s) / phi; return -0.5 * (q * q); }
+  }
+}
 
 template <int M_, int K_>
 struct MngBsf : GaussStep<MngBsf<M_, K_>, M_, M_, K_> {
@@ -304,13 +323,7 @@ struct MngBsf : GaussStep<MngBsf<M_, K_>, M_, M_, K_> {
       for (int d = 0; d < M_; ++d) zs += Zt[j + mp.p * d] * x[d];
       const double s = Dt[j] + zs;
       const double u = mp.u[tw + (size_t)mp.n * j], phi = mp.phi[j];
-      switch (mp.distribution[j]) {
-        case 1: w += y * s - u * pf_exp(s); break;
-        case 2: w += y * s - u * pf_log1p(pf_exp(s)); break;
-        case 3: w += y * s - (y + phi) * pf_log(phi + u * pf_exp(s)); break;
-        case 4: w += -phi * (s + (y * pf_exp(-s) / u)); break;
-        default: { double q = (y - s) / phi; w += -0.5 * (q * q); } break;
-      }
+      w += mng_log_obs(mp.distribution[j], s, y, u, phi);
     }
     return w;
   }
@@ -331,6 +344,80 @@ struct MngBsf : GaussStep<MngBsf<M_, K_>, M_, M_, K_> {
 #pragma unroll
       for (int j = 0; j < K_; ++j) ru += R[d + M_ * j] * z[j];
       x[d] = C[d] + ta + ru;
+    }
+  }
+};
+
+// ---------------------------------------------------- ssm_mng: psi-APF
+// ssm_mng::psi_filter src/model_ssm_mng.cpp:461-559: the proposal of UngPsiM with the
+// multivariate weights of log_weights (:357-393): per observed series
+// log g(y_j | s_j) + 0.5 ((ytilde_j - s_j) / Htilde_j)^2, minus scales_t.
+template <int M_>
+struct MngPsi : GaussStep<MngPsi<M_>, M_, M_, M_> {
+  static constexpr int M = M_, KI = M_, KP = M_;
+  typedef MngParams Params;
+  const MngParams& mp;
+  double al0, scale;
+  int tw;
+  double ah0[M_], ah1[M_], Cm[M_ * M_], Lm[M_ * M_];
+
+  __device__ MngPsi(const MngParams& p, uint32_t f) : mp(p), tw(0) { al0 = p.approx_loglik[f]; scale = 0.0; }
+  __device__ double loglik0() const { return al0; }
+  __device__ double loglik_end() const { return 0.0; }
+  __device__ void init(const double* z, double* x) const {
+#pragma unroll
+    for (int d = 0; d < M_; ++d) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < M_; ++j) s += mp.Lt[d + M_ * j] * z[j];
+      x[d] = mp.alphahat[d] + s;
+    }
+  }
+  __device__ bool observed(int t) const {
+    for (int j = 0; j < mp.p; ++j)
+      if (pf_isfinite(mp.y[t + (size_t)mp.n * j])) return true;
+    return false;
+  }
+  __device__ void begin_weight(int t) { tw = t; scale = mp.scales[t]; }
+  __device__ double logw(const double* x) const {
+    double w = 0.0;
+    const double* Zt = mp.Z + (size_t)mp.p * M_ * (tw * mp.Ztv);
+    const double* Dt = mp.D + (size_t)mp.p * (tw * mp.Dtv);
+    for (int j = 0; j < mp.p; ++j) {
+      const size_t e = tw + (size_t)mp.n * j;
+      const double y = mp.y[e];
+      if (!pf_isfinite(y)) continue;
+      double zs = 0.0;
+#pragma unroll
+      for (int d = 0; d < M_; ++d) zs += Zt[j + mp.p * d] * x[d];
+      const double s = Dt[j] + zs;
+      w += mng_log_obs(mp.distribution[j], s, y, mp.u[e], mp.phi[j]);
+      const double q = (mp.ytilde[e] - s) / mp.Htilde[e];
+      w += 0.5 * (q * q);
+    }
+    return w - scale;
+  }
+  __device__ void begin_step(int t) {
+#pragma unroll
+    for (int d = 0; d < M_; ++d) { ah0[d] = mp.alphahat[d + M_ * t]; ah1[d] = mp.alphahat[d + M_ * (t + 1)]; }
+#pragma unroll
+    for (int e = 0; e < M_ * M_; ++e) {
+      Cm[e] = mp.Ct[e + M_ * M_ * (t + 1)];
+      Lm[e] = mp.Lt[e + M_ * M_ * (t + 1)];
+    }
+  }
+  __device__ void propagate(const double* xa, const double* z, double* x) const {
+    double diff[M_];
+#pragma unroll
+    for (int j = 0; j < M_; ++j) diff[j] = xa[j] - ah0[j];
+#pragma unroll
+    for (int d = 0; d < M_; ++d) {
+      double cd = 0.0, lu = 0.0;
+#pragma unroll
+      for (int j = 0; j < M_; ++j) cd += Cm[d + M_ * j] * diff[j];
+#pragma unroll
+      for (int j = 0; j < M_; ++j) lu += Lm[d + M_ * j] * z[j];
+      x[d] = ah1[d] + cd + lu;
     }
   }
 };

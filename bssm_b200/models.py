@@ -41,7 +41,9 @@ def init_mode(y, u, distribution):
         v = y / u
         v[nan | (v < 1 / 6)] = 1 / 6
         return np.log(v)
-    raise ValueError("distribution must be poisson, binomial, gamma or negative binomial")
+    if distribution == "gaussian":
+        return y
+    raise ValueError("distribution must be poisson, binomial, gamma, gaussian or negative binomial")
 
 
 class Model:
@@ -279,8 +281,10 @@ class MngModel:
     one linear-Gaussian state.  y, u: n x p; Z: p x m x (1|n); D: p x (1|n)."""
     CODES = {"poisson": 1, "binomial": 2, "negative binomial": 3, "gamma": 4, "gaussian": 5}
 
-    def __init__(self, y, Z, T, R, a1, P1, distribution, phi=1.0, u=None, D=None, C=None):
+    def __init__(self, y, Z, T, R, a1, P1, distribution, phi=1.0, u=None, D=None, C=None,
+                 max_iter=100, conv_tol=1e-8, local_approx=True):
         self.cls = "ssm_mng"
+        self.max_iter, self.conv_tol, self.local_approx = int(max_iter), float(conv_tol), bool(local_approx)
         self.y = f64(np.atleast_2d(np.asarray(y, dtype=np.float64)))
         self.n, self.p = self.y.shape
         self.a1 = f64(np.ravel(a1))
@@ -299,6 +303,10 @@ class MngModel:
             distribution = [distribution] * p
         self.distribution = np.array([self.CODES[d] for d in distribution], dtype=np.int32)
         self.phi = f64(np.broadcast_to(np.asarray(phi, dtype=np.float64), (p,)))
+        # R/models.R:576-579: column-wise init_mode
+        names = {v: k for k, v in self.CODES.items()}
+        self.initial_mode = f64(np.column_stack(
+            [init_mode(self.y[:, j], self.u[:, j], names[int(self.distribution[j])]) for j in range(p)]))
 
     def c_struct(self):
         from ._lib import MngModel as S
@@ -309,12 +317,15 @@ class MngModel:
         s.distribution = self.distribution.ctypes.data_as(C.POINTER(C.c_int32))
         s.y, s.u, s.Z, s.T, s.R = dptr(self.y), dptr(self.u), dptr(self.Z), dptr(self.T), dptr(self.R)
         s.a1, s.P1, s.D, s.C, s.phi = dptr(self.a1), dptr(self.P1), dptr(self.D), dptr(self.C), dptr(self.phi)
-        s._keep = [self.y, self.u, self.Z, self.T, self.R, self.a1, self.P1, self.D, self.C, self.phi, self.distribution]
+        s.max_iter, s.local_approx, s.conv_tol = self.max_iter, int(self.local_approx), self.conv_tol
+        s.initial_mode = dptr(self.initial_mode)
+        s._keep = [self.y, self.u, self.Z, self.T, self.R, self.a1, self.P1, self.D, self.C, self.phi, self.distribution,
+                   self.initial_mode]
         return s
 
 
-def ssm_mng(y, Z, T, R, a1, P1, distribution, phi=1.0, u=None, D=None, C=None):
-    return MngModel(y, Z, T, R, a1, P1, distribution, phi=phi, u=u, D=D, C=C)
+def ssm_mng(y, Z, T, R, a1, P1, distribution, phi=1.0, u=None, D=None, C=None, **kw):
+    return MngModel(y, Z, T, R, a1, P1, distribution, phi=phi, u=u, D=D, C=C, **kw)
 
 
 def ssm_ulg(y, Z, H, T, R, a1, P1, D=0.0, C=None):

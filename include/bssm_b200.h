@@ -183,6 +183,10 @@ typedef struct {
   const double* D;     /* p x (1|n) */
   const double* C;     /* m x (1|n) */
   const double* phi;   /* p */
+  /* psi-APF only (src/model_ssm_mng.cpp:19-22): Laplace iteration control and start */
+  int32_t max_iter, local_approx;
+  double conv_tol;
+  const double* initial_mode; /* n x p as R holds it, or NULL for the bootstrap filter */
 } bssm_mng_model;
 
 /* replaces: bsf(model_, nsim, seed, gaussian = FALSE, model_type = 0)
@@ -195,6 +199,18 @@ int bssm_b200_bsf_smoother_mng(const bssm_mng_model* model, uint32_t nsim, uint3
 int bssm_b200_job_create_mng(const bssm_mng_model* model, uint32_t nsim, uint32_t seed,
                              uint32_t n_filters, uint32_t first_filter_id, int out_flags, int post,
                              struct bssm_b200_job** job);
+/* replaces: psi_smoother(model_, nsim, seed, model_type = 0) src/R_psi.cpp:57-78 ->
+ *           ssm_mng::psi_filter src/model_ssm_mng.cpp:461-559 + filter_smoother + summary.
+ *           m <= 3, p <= 8; needs initial_mode / max_iter / conv_tol. */
+int bssm_b200_psi_smoother_mng(const bssm_mng_model* model, uint32_t nsim, uint32_t seed,
+                               bssm_filter_out* out);
+/* psi-APF filter only: ssm_mng::log_likelihood(method = 1) src/model_ssm_mng.cpp:138-172
+ * (nongaussian_loglik, src/R_loglik.cpp:49-55) */
+int bssm_b200_psi_filter_mng(const bssm_mng_model* model, uint32_t nsim, uint32_t seed,
+                             bssm_filter_out* out);
+int bssm_b200_job_create_mng_psi(const bssm_mng_model* model, uint32_t nsim, uint32_t seed,
+                                 uint32_t n_filters, uint32_t first_filter_id, int out_flags, int post,
+                                 struct bssm_b200_job** job);
 
 /* ---- ssm_nlg and ssm_sde: device functor registry ------------------------- */
 /* The reference defines these model classes through C++ function pointers that

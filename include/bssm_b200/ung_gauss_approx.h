@@ -45,6 +45,37 @@ inline double ung_log_obs(int dist, double s, double y, double u, double phi) {
   }
 }
 
+/* conditional_cov, SVD branch (src/conditional_dist.cpp:8-32), in place:
+ * Pt (m x m x (n+1) smoothed covariances) becomes the factors L_t = U sqrt(s),
+ * ccov (lag-one covariances) becomes C_t = Cov_{t-1}' V_{t-1}^+ */
+inline void conditional_cov_svd(int m, int n, std::vector<double>& Pt, std::vector<double>& ccov) {
+  const size_t mm = (size_t)m * m;
+  const double eps = std::numeric_limits<double>::epsilon();
+  std::vector<double> vals(m), U(mm), tmp(mm), W(mm), A(mm);
+  auto factor = [&](double* V) { /* V <- U diag(sqrt(s)) */
+    pf_jacobi_eig_sym(V, m, vals.data(), U.data());
+    for (int j = 0; j < m; ++j)
+      for (int i = 0; i < m; ++i) V[i + (size_t)m * j] = U[i + (size_t)m * j] * std::sqrt(std::fabs(vals[j]));
+  };
+  for (int t = n; t > 0; --t) {
+    pf_jacobi_eig_sym(&Pt[mm * (t - 1)], m, vals.data(), U.data());
+    const double s0 = std::fabs(vals[0]);
+    /* tmp = Ct(t-1)' * U_nz * diag(1/s_nz) * U_nz' */
+    pf_mtm(&ccov[mm * (t - 1)], U.data(), W.data(), m, m, m);
+    for (int j = 0; j < m; ++j) {
+      const double s = std::fabs(vals[j]);
+      const double inv = (s > eps * m * s0) ? 1.0 / s : 0.0;
+      for (int i = 0; i < m; ++i) W[i + (size_t)m * j] = W[i + (size_t)m * j] * inv;
+    }
+    pf_mmt(W.data(), U.data(), tmp.data(), m, m, m);
+    pf_mm(tmp.data(), &ccov[mm * (t - 1)], A.data(), m, m, m);
+    for (size_t e = 0; e < mm; ++e) Pt[mm * t + e] -= A[e];
+    for (size_t e = 0; e < mm; ++e) ccov[mm * t + e] = tmp[e];
+    factor(&Pt[mm * t]);
+  }
+  factor(&Pt[0]);
+}
+
 struct UngApprox {
   const bssm_ung_model* M;
   int n, m;
@@ -333,31 +364,7 @@ struct UngApprox {
     }
     for (size_t e = 0; e < mm; ++e) ccov[mm * n + e] = 0.0;
 
-    /* conditional_cov, SVD branch: src/conditional_dist.cpp:8-32 */
-    const double eps = std::numeric_limits<double>::epsilon();
-    std::vector<double> vals(m), U(mm), tmp(mm), W(mm);
-    auto factor = [&](double* V) { /* V <- U diag(sqrt(s)) */
-      pf_jacobi_eig_sym(V, m, vals.data(), U.data());
-      for (int j = 0; j < m; ++j)
-        for (int i = 0; i < m; ++i) V[i + (size_t)m * j] = U[i + (size_t)m * j] * std::sqrt(std::fabs(vals[j]));
-    };
-    for (int t = n; t > 0; --t) {
-      pf_jacobi_eig_sym(&Pt[mm * (t - 1)], m, vals.data(), U.data());
-      const double s0 = std::fabs(vals[0]);
-      /* tmp = Ct(t-1)' * U_nz * diag(1/s_nz) * U_nz' */
-      pf_mtm(&ccov[mm * (t - 1)], U.data(), W.data(), m, m, m);
-      for (int j = 0; j < m; ++j) {
-        const double s = std::fabs(vals[j]);
-        const double inv = (s > eps * m * s0) ? 1.0 / s : 0.0;
-        for (int i = 0; i < m; ++i) W[i + (size_t)m * j] = W[i + (size_t)m * j] * inv;
-      }
-      pf_mmt(W.data(), U.data(), tmp.data(), m, m, m);
-      pf_mm(tmp.data(), &ccov[mm * (t - 1)], A.data(), m, m, m);
-      for (size_t e = 0; e < mm; ++e) Pt[mm * t + e] -= A[e];
-      for (size_t e = 0; e < mm; ++e) ccov[mm * t + e] = tmp[e];
-      factor(&Pt[mm * t]);
-    }
-    factor(&Pt[0]);
+    conditional_cov_svd(m, n, Pt, ccov);
     L = Pt;
     Ct = ccov;
   }

@@ -45,6 +45,7 @@
 #include "bssm_b200.h"
 #include "bssm_b200/ung_gauss_approx.h"
 #include "bssm_b200/nlg_gauss_approx.h"
+#include "bssm_b200/mng_gauss_approx.h"
 
 enum { ORC_ARITH_REFERENCE = 0, ORC_ARITH_REPRO = 1 };
 
@@ -1069,6 +1070,115 @@ double orc_mng_bsf_filter(const bssm_mng_model* M, uint32_t nsim, uint32_t seed,
     }
   }
   return loglik;
+}
+
+/* ssm_mng::log_weights, src/model_ssm_mng.cpp:357-393, one particle: per observed
+ * series log g(y_j | s_j) + 0.5 ((ytilde_j - s_j) / Htilde_j)^2 */
+static double mng_log_weight(const bssm_mng_model* M, const pfga::MngApprox& ga, int t, const double* alpha) {
+  const int n = M->n, m = M->m, p = M->p;
+  const double* Z = M->Z + (size_t)p * m * (t * M->Ztv);
+  const double* D = M->D + (size_t)p * (t * M->Dtv);
+  double w = 0.0;
+  for (int j = 0; j < p; ++j) {
+    const double y = M->y[t + (size_t)n * j];
+    if (!std::isfinite(y)) continue;
+    double zs = 0.0;
+    for (int d = 0; d < m; ++d) zs += Z[j + (size_t)p * d] * alpha[d];
+    const double s = D[j] + zs;
+    const double u = M->u[t + (size_t)n * j], phi = M->phi[j];
+    switch (M->distribution[j]) {
+      case 1: w += y * s - u * pf_exp(s); break;
+      case 2: w += y * s - u * pf_log1p(pf_exp(s)); break;
+      case 3: w += y * s - (y + phi) * pf_log(phi + u * pf_exp(s)); break;
+      case 4: w -= phi * (s + (y * pf_exp(-s) / u)); break;
+      case 5: { double q = (y - s) / phi; w -= 0.5 * (q * q); } break;
+    }
+    const double q = (ga.ay[j + (size_t)p * t] - s) / ga.aH[j + (size_t)p * t];
+    w += 0.5 * (q * q);
+  }
+  return w;
+}
+
+/* ssm_mng::psi_filter, src/model_ssm_mng.cpp:461-559.  mode_in (p x n) selects
+ * approximate_for_is (:121-137); NULL runs approximate() from initial_mode. */
+double orc_mng_psi_filter(const bssm_mng_model* M, const double* mode_in, uint32_t nsim, uint32_t seed,
+                          uint32_t filter, int arith, double* alpha, double* weights, uint32_t* indices,
+                          double* approx_loglik, int32_t* stopped_at) {
+  *stopped_at = -1;
+  pfga::MngApprox ga(M);
+  ga.run(mode_in);
+  if (approx_loglik) *approx_loglik = ga.approx_loglik;
+  const int n = M->n, m = M->m, p = M->p;
+  const size_t N = nsim, mm = (size_t)m * m;
+  auto A = [&](int d, int t, size_t i) -> double& { return alpha[d + (size_t)m * (t + (size_t)(n + 1) * i)]; };
+  auto any_obs = [&](int t) {
+    int na = 0;
+    for (int j = 0; j < p; ++j) if (!std::isfinite(M->y[t + (size_t)n * j])) na++;
+    return na < p;
+  };
+  for (size_t i = 0; i < N; ++i) { /* :490-496 */
+    std::vector<double> um(m);
+    for (int j = 0; j < m; ++j) um[j] = pf_normal(seed, filter, 0, 0, (uint32_t)(i * m + j));
+    for (int d = 0; d < m; ++d) {
+      double s = 0.0;
+      for (int j = 0; j < m; ++j) s += ga.L[d + (size_t)m * j] * um[j];
+      A(d, 0, i) = ga.alphahat[d] + s;
+    }
+  }
+  std::vector<double> W(N), logw(N), r(N), atmp((size_t)m * N);
+  double loglik = 0.0;
+  if (any_obs(0)) { /* :502-514 */
+    for (size_t i = 0; i < N; ++i) logw[i] = mng_log_weight(M, ga, 0, &A(0, 0, i)) - ga.scales[0];
+    double mxw, lmean;
+    if (!normalise(logw.data(), nsim, weights, W, &mxw, &lmean, arith)) { *stopped_at = 0; return -ORC_INF; }
+    loglik = mxw + ga.approx_loglik + lmean;
+  } else {
+    for (size_t i = 0; i < N; ++i) { weights[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
+    loglik = ga.approx_loglik;
+  }
+  for (int t = 0; t < n; ++t) { /* :521-556 */
+    for (size_t i = 0; i < N; ++i) r[i] = pf_resample_uniform(seed, filter, t, (uint32_t)i);
+    uint32_t* ind = indices + N * t;
+    resample(W, r, nsim, ind, arith);
+    for (size_t i = 0; i < N; ++i)
+      for (int d = 0; d < m; ++d) atmp[d + (size_t)m * i] = A(d, t, ind[i]);
+    const double* ah0 = &ga.alphahat[(size_t)m * t];
+    const double* ah1 = &ga.alphahat[(size_t)m * (t + 1)];
+    const double* Ctm = &ga.Ct[mm * (t + 1)];
+    const double* Lm = &ga.L[mm * (t + 1)];
+    for (size_t i = 0; i < N; ++i) {
+      std::vector<double> um(m), diff(m);
+      for (int j = 0; j < m; ++j) um[j] = pf_normal(seed, filter, t + 1, 0, (uint32_t)(i * m + j));
+      for (int j = 0; j < m; ++j) diff[j] = atmp[j + (size_t)m * i] - ah0[j];
+      for (int d = 0; d < m; ++d) {
+        double cd = 0.0, lu = 0.0;
+        for (int j = 0; j < m; ++j) cd += Ctm[d + (size_t)m * j] * diff[j];
+        for (int j = 0; j < m; ++j) lu += Lm[d + (size_t)m * j] * um[j];
+        A(d, t + 1, i) = ah1[d] + cd + lu;
+      }
+    }
+    double* wcol = weights + N * (t + 1);
+    if ((t < (n - 1)) && any_obs(t + 1)) {
+      for (size_t i = 0; i < N; ++i) logw[i] = mng_log_weight(M, ga, t + 1, &A(0, t + 1, i)) - ga.scales[t + 1];
+      double mxw, lmean;
+      if (!normalise(logw.data(), nsim, wcol, W, &mxw, &lmean, arith)) { *stopped_at = t + 1; return -ORC_INF; }
+      loglik += mxw + lmean;
+    } else {
+      for (size_t i = 0; i < N; ++i) { wcol[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
+    }
+  }
+  return loglik;
+}
+
+/* the Gaussian approximation alone (checked against an independent numpy Kalman
+ * smoother in tests/test_oracle.py): alphahat m x (n+1), mode p x n */
+double orc_mng_approx(const bssm_mng_model* M, double* alphahat, double* mode, double* scales) {
+  pfga::MngApprox ga(M);
+  ga.run(nullptr);
+  std::copy(ga.alphahat.begin(), ga.alphahat.end(), alphahat);
+  std::copy(ga.mode.begin(), ga.mode.end(), mode);
+  std::copy(ga.scales.begin(), ga.scales.end(), scales);
+  return ga.approx_loglik;
 }
 
 /* ------------------------------------------------------------------ a13 */

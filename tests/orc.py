@@ -282,6 +282,36 @@ def mng_bsf_filter(model, N, seed, filt=0, arith=ARITH_REPRO):
     return r
 
 
+def mng_psi_filter(model, N, seed, filt=0, arith=ARITH_REPRO, mode=None):
+    r = _alloc(model, N)
+    ms = model.c_struct()
+    st = C.c_int32(-1)
+    al = C.c_double(0)
+    f = L().orc_mng_psi_filter
+    f.restype = C.c_double
+    f.argtypes = [C.POINTER(MngModel), c_double_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, c_double_p,
+                  c_double_p, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+    mode_a = None if mode is None else np.asfortranarray(mode, dtype=np.float64)
+    r.loglik = f(C.byref(ms), dptr(mode_a), N, seed, filt, arith, dptr(r.alpha), dptr(r.weights),
+                 uptr(r.indices), C.byref(al), C.byref(st))
+    r.approx_loglik = al.value
+    r.stopped_at = st.value
+    return r
+
+
+def mng_approx(model):
+    """Gaussian approximation alone: (approx_loglik, alphahat m x (n+1), mode p x n, scales n)"""
+    ms = model.c_struct()
+    f = L().orc_mng_approx
+    f.restype = C.c_double
+    f.argtypes = [C.POINTER(MngModel), c_double_p, c_double_p, c_double_p]
+    ah = np.zeros((model.m, model.n + 1), order="F")
+    mode = np.zeros((model.p, model.n), order="F")
+    sc = np.zeros(model.n)
+    al = f(C.byref(ms), dptr(ah), dptr(mode), dptr(sc))
+    return al, ah, mode, sc
+
+
 def nlg_psi_filter(model, N, seed, filt=0, arith=ARITH_REPRO, mode=None, max_iter=100, conv_tol=1e-8):
     r = _alloc(model, N)
     ms = model.c_struct()

@@ -6,6 +6,7 @@ import pytest
 
 import data
 import orc
+import bssm_b200 as engine_mod
 
 pytestmark = pytest.mark.gpu
 
@@ -92,6 +93,60 @@ def test_mng_bsf_parity(engine, N):
     sm = orc.filter_smoother(ref.alpha, ref.indices)
     res2 = engine.particle_smoother(model, N, method="bsf", seed=1)
     assert np.array_equal(_cube(res2).view(np.uint64), sm.view(np.uint64))
+
+
+def _mng_variant(kind):
+    if kind == "mixed_missing":      # Gaussian series with NAs: the reference stops its sweeps after one
+        return data.mng_model(60)
+    if kind == "mixed":
+        m = data.mng_model(60, missing=False)
+        m.y[3, 0] = np.nan
+        m.y[11, :2] = np.nan
+        return m
+    rng = np.random.default_rng(11)
+    if kind == "m1p2":               # one state, Poisson + binomial
+        n = 50
+        a = np.cumsum(0.15 * rng.normal(size=n))
+        y = np.column_stack([rng.poisson(np.exp(a + 1.0)), rng.binomial(10, 1 / (1 + np.exp(-a)))]).astype(float)
+        y[6, 1] = np.nan
+        u = np.column_stack([np.ones(n), np.full(n, 10.0)])
+        return engine_mod.ssm_mng(y, np.array([[1.0], [1.0]]), [[1.0]], [[0.15]], a1=[0.0], P1=[[1.0]],
+                                  distribution=["poisson", "binomial"], u=u, D=[1.0, 0.0])
+    # m = 3, p = 3 with a gamma series and time-varying D
+    n = 40
+    a = np.zeros((n, 3))
+    for t in range(1, n):
+        a[t] = [0.9 * a[t - 1, 0] + 0.2 * rng.normal(), a[t - 1, 1] + a[t - 1, 2] + 0.05 * rng.normal(),
+                0.8 * a[t - 1, 2] + 0.02 * rng.normal()]
+    Z = np.array([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.5, 0.5, 1.0]])
+    D = np.vstack([np.full(n, 0.5), np.linspace(0, 0.3, n), np.zeros(n)])
+    sig = a @ Z.T + D.T
+    y = np.column_stack([rng.poisson(np.exp(sig[:, 0])), rng.gamma(2.0, np.exp(sig[:, 1]) / 2.0),
+                         rng.poisson(3 * np.exp(sig[:, 2]))]).astype(float)
+    y[0, 0] = np.nan
+    u = np.column_stack([np.ones(n), np.ones(n), np.full(n, 3.0)])
+    T = np.array([[0.9, 0, 0], [0, 1, 1], [0, 0, 0.8]])
+    return engine_mod.ssm_mng(y, Z, T, np.diag([0.2, 0.05, 0.02]), a1=[0, 0, 0], P1=np.diag([0.3, 1.0, 0.1]),
+                              distribution=["poisson", "gamma", "poisson"], phi=[1.0, 2.0, 1.0], u=u, D=D)
+
+
+@pytest.mark.parametrize("kind,N", [("mixed", 100), ("mixed", 3000), ("mixed_missing", 500), ("m1p2", 1000),
+                                    ("m3p3", 700)])
+def test_mng_psi_apf_parity(engine, kind, N):
+    """psi-APF for ssm_mng (src/model_ssm_mng.cpp:461-559): multivariate Gaussian approximation on
+    the host, particle loop on the device; bit-exact against the oracle"""
+    model = _mng_variant(kind)
+    ref = orc.mng_psi_filter(model, N, seed=3)
+    res = engine.particle_smoother(model, N, method="psi", seed=3, return_indices=True)
+    assert res["approx_logLik"] == ref.approx_loglik
+    assert np.array_equal(res["indices"], ref.indices)
+    assert np.array_equal(res["weights"].view(np.uint64), ref.weights.view(np.uint64))
+    assert res["logLik"] == ref.loglik
+    sm = orc.filter_smoother(ref.alpha, ref.indices)
+    assert np.array_equal(_cube(res).view(np.uint64), sm.view(np.uint64))
+    ah, Vt = orc.summary(sm)
+    np.testing.assert_allclose(res["alphahat"], ah.T, rtol=1e-12, atol=1e-14)
+    assert engine.logLik(model, N, method="psi", seed=3) == ref.loglik
 
 
 @pytest.mark.parametrize("N", [100, 2000])
