@@ -67,7 +67,10 @@ class SdeModel(C.Structure):
 
 class ThetaMap(C.Structure):
     """bssm_theta_map"""
-    _fields_ = [("model_type", C.c_int32), ("svm_type", C.c_int32), ("mu_est", C.c_int32), ("phi_est", C.c_int32)]
+    _fields_ = [("model_type", C.c_int32), ("svm_type", C.c_int32), ("mu_est", C.c_int32), ("phi_est", C.c_int32),
+                ("slope", C.c_int32), ("seasonal", C.c_int32), ("noise", C.c_int32),
+                ("level_est", C.c_int32), ("slope_est", C.c_int32), ("seasonal_est", C.c_int32),
+                ("n_xreg", C.c_int32), ("xreg", c_double_p)]
 
 
 class PostcorrOut(C.Structure):

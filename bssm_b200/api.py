@@ -232,8 +232,16 @@ def theta_map(model):
         tm.model_type = 4
         tm.mu_est = int(model.extra.get("mu_est", 1))
         tm.phi_est = int(model.extra.get("phi_est", 0))
+    elif model.cls == "bsm_ng":
+        tm.model_type = 2
+        for key in ("slope", "seasonal", "noise", "level_est", "slope_est", "seasonal_est", "phi_est"):
+            setattr(tm, key, int(bool(model.extra.get(key, False))))
+        if model.xreg is not None and model.xreg.size:
+            xr = _lib.f64(np.asfortranarray(model.xreg.reshape(model.n, -1)))
+            tm.n_xreg, tm.xreg = xr.shape[1], dptr(xr)
+            tm._keep = xr
     else:
-        raise ValueError("post_correct is implemented for svm and ar1_ng models")
+        raise ValueError("post_correct is implemented for svm, ar1_ng, bsm_ng and ssm_nlg models")
     return tm
 
 

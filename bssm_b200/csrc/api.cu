@@ -351,6 +351,12 @@ struct DevBuf {
 // ------------------------------------------------------------------- job
 enum { KIND_UNG = 0, KIND_NLG = 1, KIND_SDE = 2, KIND_MNG = 3 };
 
+// per-draw pieces of an m > 1 ssm_ung-family model (what bsm_ng::update_model changes,
+// src/model_bsm_ng.cpp:17-51) plus the stored mode of each draw: host arrays, one block per filter
+struct DrawModels {
+  std::vector<double> R, P1, phi, xbeta, modes; // nf x (m*k), nf x (m*m), nf, nf x n (or empty), nf x n
+};
+
 struct bssm_b200_job {
   int kind = KIND_UNG;
   int method = 0, post = 0, out_flags = 0;
@@ -466,6 +472,10 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
   pf::UngParams up = J->up;
   if (J->method == BSSM_METHOD_PSI && J->m > 1) {
     up.approx_loglik += f0;
+    up.alphahat += (size_t)f0 * up.fs_a; up.Lt += (size_t)f0 * up.fs_m; up.Ct += (size_t)f0 * up.fs_m;
+    up.ytilde += (size_t)f0 * up.fs_n; up.Htilde += (size_t)f0 * up.fs_n; up.scales += (size_t)f0 * up.fs_n;
+    up.xbeta += (size_t)f0 * up.fs_x;
+    if (up.phi_f) up.phi_f += f0;
     return launch_status(pfl::launch_ung_psim(J->m, fp, up, J->geo, nf, J->stream), "psi filter (m)");
   }
   if (J->method == BSSM_METHOD_PSI) {
@@ -559,7 +569,8 @@ static int finish_job(bssm_b200_job* J, int out_flags, int post) {
 // (post_correct: update_model + approximate_for_is per draw)
 static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, uint32_t seed,
                           uint32_t n_filters, uint32_t first_filter_id, int out_flags, int post,
-                          const double* draw_par, const double* draw_modes, bssm_b200_job** job) {
+                          const double* draw_par, const double* draw_modes, bssm_b200_job** job,
+                          const DrawModels* dm = nullptr) {
   if (!M || !job) return fail(BSSM_B200_ERR_ARG, "null argument");
   *job = nullptr;
   if (M->n < 1 || M->m < 1 || M->k < 1 || nsim < 2 || n_filters < 1)
@@ -570,7 +581,7 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
     return fail(BSSM_B200_ERR_ARG, "linear-Gaussian models: bootstrap filter only, H required "
                                    "(their psi 'filter' is bssm_b200_gaussian_psi_smoother)");
   if (method != BSSM_METHOD_PSI && method != BSSM_METHOD_BSF) return fail(BSSM_B200_ERR_ARG, "method must be 1 (psi) or 2 (bsf)");
-  if (method == BSSM_METHOD_PSI && (M->m > 3 || (M->m != 1 && draw_par)))
+  if (method == BSSM_METHOD_PSI && (M->m > 3 || (M->m != 1 && draw_par) || (M->m == 1 && dm)))
     return fail(BSSM_B200_ERR_UNSUPPORTED, "psi-APF: m <= 3 (and m = 1 for per-draw models) in this build");
   if (M->k > M->m) return fail(BSSM_B200_ERR_ARG, "k > m");
   if (post < 0 || post > BSSM_POST_SMOOTHER_MERGE) return fail(BSSM_B200_ERR_ARG, "bad post mode");
@@ -627,7 +638,45 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
     up.HH = J->HH_v.p; up.hconst = J->hconst_v.p;
   }
 
-  if (method == BSSM_METHOD_PSI && m > 1) {
+  if (method == BSSM_METHOD_PSI && m > 1 && dm) {
+    // approximate_for_is (src/model_ssm_ung.cpp:143-161) per draw on the host, OpenMP over draws:
+    // laplace_iter at the stored mode, scales, Kalman smoother + conditional covariances
+    if (M->Rtv) return fail(BSSM_B200_ERR_UNSUPPORTED, "per-draw models: time-invariant R only");
+    const size_t n1 = (size_t)n + 1, mm = (size_t)m * m, nf = n_filters;
+    const bool has_xb = !dm->xbeta.empty();
+    std::vector<double> ah((size_t)m * n1 * nf), Lt(mm * n1 * nf), Ct(mm * n1 * nf), yt((size_t)n * nf),
+        Ht((size_t)n * nf), sc((size_t)n * nf), al(nf, 0.0);
+#pragma omp parallel for schedule(static)
+    for (int64_t f = 0; f < (int64_t)nf; ++f) {
+      bssm_ung_model Mi = *M;
+      Mi.R = &dm->R[(size_t)m * k * f]; Mi.Rtv = 0;
+      Mi.P1 = &dm->P1[mm * f];
+      Mi.phi = dm->phi[f];
+      if (has_xb) Mi.xbeta = &dm->xbeta[(size_t)n * f];
+      pfga::UngApprox ga(&Mi);
+      ga.run(&dm->modes[(size_t)n * f]);
+      std::copy(ga.alphahat.begin(), ga.alphahat.end(), &ah[(size_t)m * n1 * f]);
+      std::copy(ga.L.begin(), ga.L.end(), &Lt[mm * n1 * f]);
+      std::copy(ga.Ct.begin(), ga.Ct.end(), &Ct[mm * n1 * f]);
+      std::copy(ga.ay.begin(), ga.ay.end(), &yt[(size_t)n * f]);
+      std::copy(ga.aH.begin(), ga.aH.end(), &Ht[(size_t)n * f]);
+      std::copy(ga.scales.begin(), ga.scales.end(), &sc[(size_t)n * f]);
+    }
+    if ((rc = J->alphahat.upload(ah.data(), ah.size())) || (rc = J->Lt.upload(Lt.data(), Lt.size())) ||
+        (rc = J->Ct.upload(Ct.data(), Ct.size())) || (rc = J->ytilde.upload(yt.data(), yt.size())) ||
+        (rc = J->Htilde.upload(Ht.data(), Ht.size())) || (rc = J->scales.upload(sc.data(), sc.size())) ||
+        (rc = J->approx_loglik.upload(al.data(), nf)) || (rc = J->phi_f.upload(dm->phi.data(), nf)))
+      return rc;
+    if (has_xb) {
+      if ((rc = J->xbeta.upload(dm->xbeta.data(), dm->xbeta.size()))) return rc;
+      up.xbeta = J->xbeta.p;
+    }
+    J->pstride = 0;
+    up.phi_f = J->phi_f.p; up.alphahat = J->alphahat.p; up.Lt = J->Lt.p; up.Ct = J->Ct.p;
+    up.ytilde = J->ytilde.p; up.Htilde = J->Htilde.p; up.scales = J->scales.p;
+    up.approx_loglik = J->approx_loglik.p; up.pstride = 0;
+    up.fs_a = (size_t)m * n1; up.fs_m = mm * n1; up.fs_n = (size_t)n; up.fs_x = has_xb ? (size_t)n : 0;
+  } else if (method == BSSM_METHOD_PSI && m > 1) {
     // Gaussian approximation on the host (O(n m^3), sequential in t), shared by all replicates
     if (!M->initial_mode) return fail(BSSM_B200_ERR_ARG, "psi-APF needs initial_mode");
     if (M->max_iter < 1) return fail(BSSM_B200_ERR_ARG, "max_iter must be >= 1");
@@ -1220,10 +1269,50 @@ int theta_to_par(const bssm_ung_model* M, const bssm_theta_map* map, const doubl
     }
     P1 = RR / (1.0 - rho * rho);
     if (map->phi_est) phi = pf_exp(th[2 + map->mu_est]);
+  } else if (map->model_type == 2) {
+    // bsm_ng with a level only (m = 1), src/model_bsm_ng.cpp:17-45
+    if (n_par < (uint32_t)(map->level_est + map->phi_est)) return fail(BSSM_B200_ERR_ARG, "bsm_ng: too few parameters");
+    if (map->level_est) R = pf_exp(th[0]);
+    if (map->phi_est) phi = pf_exp(th[map->level_est]);
   } else {
-    return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction: model_type must be 3 (svm) or 4 (ar1_ng) in this build");
+    return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction: model_type must be 2 (bsm_ng), 3 (svm) or 4 (ar1_ng) in this build");
   }
   par[0] = T; par[1] = R; par[2] = a1; par[3] = P1; par[4] = C; par[5] = phi;
+  return 0;
+}
+
+// bsm_ng::update_model (src/model_bsm_ng.cpp:17-51) for any m: R, P1 (m x k, m x m copies of the
+// model's), phi and xbeta (n, when the model has regressors) of one draw
+int theta_to_bsm(const bssm_ung_model* M, const bssm_theta_map* map, const double* th, uint32_t n_par,
+                 double* R, double* P1, double* phi, double* xbeta) {
+  const int m = M->m, k = M->k, n = M->n;
+  const int need = map->level_est + map->slope_est + map->seasonal_est + map->noise + map->phi_est + map->n_xreg;
+  if ((int)n_par < need) return fail(BSSM_B200_ERR_ARG, "bsm_ng: too few parameters");
+  if (1 + map->slope + map->seasonal + map->noise > k || 1 + map->slope > m)
+    return fail(BSSM_B200_ERR_ARG, "bsm_ng: component flags do not fit the model's R");
+  std::copy(M->R, M->R + (size_t)m * k, R);
+  std::copy(M->P1, M->P1 + (size_t)m * m, P1);
+  if (map->level_est) R[0] = pf_exp(th[0]);
+  if (map->slope_est) R[1 + (size_t)m * 1] = pf_exp(th[map->level_est]);
+  if (map->seasonal_est) {
+    const int r = 1 + map->slope;
+    R[r + (size_t)m * r] = pf_exp(th[map->level_est + map->slope_est]);
+  }
+  if (map->noise) {
+    const int c = 1 + map->slope + map->seasonal;
+    const double sd = pf_exp(th[map->level_est + map->slope_est + map->seasonal_est]);
+    R[(m - 1) + (size_t)m * c] = sd;
+    P1[(m - 1) + (size_t)m * (m - 1)] = sd * sd;
+  }
+  *phi = map->phi_est ? pf_exp(th[map->level_est + map->slope_est + map->seasonal_est + map->noise]) : M->phi;
+  if (map->n_xreg > 0) { // compute_xbeta, src/model_ssm_ung.h:83
+    const double* beta = th + (n_par - map->n_xreg);
+    for (int t = 0; t < n; ++t) {
+      double sum = 0.0;
+      for (int j = 0; j < map->n_xreg; ++j) sum += map->xreg[t + (size_t)n * j] * beta[j];
+      xbeta[t] = sum;
+    }
+  }
   return 0;
 }
 
@@ -1248,8 +1337,13 @@ int build_draws(int is_type, const uint32_t* counts, uint32_t n_stored, DrawList
 int check_postcorr_args(const bssm_ung_model* M, const bssm_theta_map* map, const uint32_t* counts,
                         const double* theta, const double* modes, uint32_t n_stored) {
   if (!M || !map || !counts || !theta || !modes || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
-  if (M->m != 1) return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction is implemented for m = 1 models in this build");
-  if (M->xbeta) return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction with regression coefficients in theta is not implemented");
+  const bool general = map->model_type == 2 && (M->m > 1 || map->n_xreg > 0);
+  if (M->m != 1 && !general)
+    return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction with m > 1 is implemented for bsm_ng (model_type 2) in this build");
+  if (general && (M->m < 2 || M->m > 3))
+    return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction for bsm_ng: 2 <= m <= 3 (or m = 1 without regressors) in this build");
+  if (map->n_xreg > 0 && !map->xreg) return fail(BSSM_B200_ERR_ARG, "n_xreg > 0 needs xreg");
+  if (M->xbeta && !general) return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction with regression coefficients in theta: bsm_ng only");
   return 0;
 }
 
@@ -1259,6 +1353,20 @@ int make_draw_job(const bssm_ung_model* M, const bssm_theta_map* map, const Draw
                   int out_flags, int post, bssm_b200_job** job) {
   const uint32_t nf = d1 - d0;
   const size_t n = (size_t)M->n;
+  if (map->model_type == 2 && (M->m > 1 || map->n_xreg > 0)) {
+    const size_t mk = (size_t)M->m * M->k, mm = (size_t)M->m * M->m;
+    DrawModels dm;
+    dm.R.resize(mk * nf); dm.P1.resize(mm * nf); dm.phi.resize(nf); dm.modes.resize(n * nf);
+    if (map->n_xreg > 0) dm.xbeta.resize(n * nf);
+    for (uint32_t f = 0; f < nf; ++f) {
+      const uint32_t c = dl.src[d0 + f];
+      int rc = theta_to_bsm(M, map, theta + (size_t)c * n_par, n_par, &dm.R[mk * f], &dm.P1[mm * f], &dm.phi[f],
+                            map->n_xreg > 0 ? &dm.xbeta[n * f] : nullptr);
+      if (rc) return rc;
+      memcpy(&dm.modes[n * f], modes + n * c, n * sizeof(double));
+    }
+    return create_ung_job(M, BSSM_METHOD_PSI, N, seed, nf, d0, out_flags, post, nullptr, nullptr, job, &dm);
+  }
   std::vector<double> par((size_t)6 * nf), md(n * nf);
   for (uint32_t f = 0; f < nf; ++f) {
     const uint32_t c = dl.src[d0 + f];
@@ -1374,8 +1482,11 @@ static int postcorr_driver(int n, int m, int output_type, uint32_t nsim, int is_
       else if (m == 2)
         pf::postcorr_merge_kernel<2><<<cdiv((uint32_t)n1, 128), 128, 0, J->stream>>>(
             J->s_mean.p, J->s_cov.p, J->loglik.p, d_cnt.p, nf, (int)n1, sw_in, sw_out, d_ah.p, d_Vt.p, d_Va.p);
+      else if (m == 3)
+        pf::postcorr_merge_kernel<3><<<cdiv((uint32_t)n1, 128), 128, 0, J->stream>>>(
+            J->s_mean.p, J->s_cov.p, J->loglik.p, d_cnt.p, nf, (int)n1, sw_in, sw_out, d_ah.p, d_Vt.p, d_Va.p);
       else
-        return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction summaries: m <= 2");
+        return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction summaries: m <= 3");
       CU(cudaGetLastError());
       CU(cudaEventRecord(e1, J->stream));
       CU(cudaStreamSynchronize(J->stream));

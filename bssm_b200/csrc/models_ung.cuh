@@ -36,6 +36,9 @@ struct UngParams {
   const double* scales;    // n
   const double* approx_loglik; // per filter
   size_t pstride;
+  // psi-APF (m > 1): per-filter strides of alphahat / (Lt, Ct) / (ytilde, Htilde, scales) / xbeta;
+  // all zero when the replicates of a job share one approximation
+  size_t fs_a, fs_m, fs_n, fs_x;
 };
 
 // log g(y_t | signal) up to state-independent constants, :447-493
@@ -176,11 +179,19 @@ struct UngPsiM : GaussStep<UngPsiM<M_>, M_, M_, M_> {
   static constexpr int M = M_, KI = M_, KP = M_;
   typedef UngParams Params;
   const UngParams& mp;
-  double al0;
+  double al0, phi;
+  const double *p_ah, *p_Lt, *p_Ct, *p_yt, *p_Ht, *p_sc, *p_xb;
   double y, u, yphi2, Dt, xb, ytil, Htil, scale;
   double Z[M_], ah0[M_], ah1[M_], Cm[M_ * M_], Lm[M_ * M_];
 
-  __device__ UngPsiM(const UngParams& p, uint32_t f) : mp(p) { al0 = p.approx_loglik[f]; }
+  __device__ UngPsiM(const UngParams& p, uint32_t f) : mp(p) {
+    al0 = p.approx_loglik[f];
+    phi = p.phi_f ? p.phi_f[f] : p.phi;
+    p_ah = p.alphahat + (size_t)f * p.fs_a;
+    p_Lt = p.Lt + (size_t)f * p.fs_m; p_Ct = p.Ct + (size_t)f * p.fs_m;
+    p_yt = p.ytilde + (size_t)f * p.fs_n; p_Ht = p.Htilde + (size_t)f * p.fs_n; p_sc = p.scales + (size_t)f * p.fs_n;
+    p_xb = p.xbeta + (size_t)f * p.fs_x;
+  }
   __device__ double loglik0() const { return al0; }
   __device__ double loglik_end() const { return 0.0; }
   __device__ void init(const double* z, double* x) const {
@@ -188,21 +199,21 @@ struct UngPsiM : GaussStep<UngPsiM<M_>, M_, M_, M_> {
     for (int d = 0; d < M_; ++d) {
       double s = 0.0;
 #pragma unroll
-      for (int j = 0; j < M_; ++j) s += mp.Lt[d + M_ * j] * z[j];
-      x[d] = mp.alphahat[d] + s;
+      for (int j = 0; j < M_; ++j) s += p_Lt[d + M_ * j] * z[j];
+      x[d] = p_ah[d] + s;
     }
   }
   __device__ bool observed(int t) const { return pf_isfinite(mp.y[t]); }
   __device__ void begin_weight(int t) {
     y = mp.y[t];
     u = mp.u[t];
-    double q = y / mp.phi;
+    double q = y / phi;
     yphi2 = q * q;
     Dt = mp.D[t * mp.Dtv];
-    xb = mp.xbeta[t];
+    xb = p_xb[t];
 #pragma unroll
     for (int d = 0; d < M_; ++d) Z[d] = mp.Z[d + M_ * (t * mp.Ztv)];
-    ytil = mp.ytilde[t]; Htil = mp.Htilde[t]; scale = mp.scales[t];
+    ytil = p_yt[t]; Htil = p_Ht[t]; scale = p_sc[t];
   }
   __device__ double logw(const double* x) const {
     double s;
@@ -215,15 +226,15 @@ struct UngPsiM : GaussStep<UngPsiM<M_>, M_, M_, M_> {
       s = Dt + zs + xb;
     }
     double q = (ytil - s) / Htil;
-    return (ung_log_obs(mp.distribution, s, y, u, mp.phi, yphi2) + 0.5 * (q * q)) - scale;
+    return (ung_log_obs(mp.distribution, s, y, u, phi, yphi2) + 0.5 * (q * q)) - scale;
   }
   __device__ void begin_step(int t) {
 #pragma unroll
-    for (int d = 0; d < M_; ++d) { ah0[d] = mp.alphahat[d + M_ * t]; ah1[d] = mp.alphahat[d + M_ * (t + 1)]; }
+    for (int d = 0; d < M_; ++d) { ah0[d] = p_ah[d + M_ * t]; ah1[d] = p_ah[d + M_ * (t + 1)]; }
 #pragma unroll
     for (int e = 0; e < M_ * M_; ++e) {
-      Cm[e] = mp.Ct[e + M_ * M_ * (t + 1)];
-      Lm[e] = mp.Lt[e + M_ * M_ * (t + 1)];
+      Cm[e] = p_Ct[e + M_ * M_ * (t + 1)];
+      Lm[e] = p_Lt[e + M_ * M_ * (t + 1)];
     }
   }
   __device__ void propagate(const double* xa, const double* z, double* x) const {

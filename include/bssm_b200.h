@@ -291,12 +291,20 @@ int bssm_b200_approximate_mode(const bssm_ung_model* model, double* mode);
 
 /* ---- IS-MCMC post-correction ---------------------------------------------- */
 /* How theta maps onto the model (the C++ update_model of the model class):
- * svm src/model_svm.cpp:12-29, ar1_ng src/model_ar1_ng.cpp:12-36. */
+ * svm src/model_svm.cpp:12-29, ar1_ng src/model_ar1_ng.cpp:12-36,
+ * bsm_ng src/model_bsm_ng.cpp:17-51 (any m <= 3). */
 typedef struct {
-  int32_t model_type; /* R/model_type.R:1-16: 3 = svm, 4 = ar1_ng */
+  int32_t model_type; /* R/model_type.R:1-16: 2 = bsm_ng, 3 = svm, 4 = ar1_ng */
   int32_t svm_type;   /* svm: 0 = theta[2] is sigma (phi), 1 = theta[2] is mu */
   int32_t mu_est;     /* ar1_ng */
-  int32_t phi_est;    /* ar1_ng */
+  int32_t phi_est;    /* ar1_ng, bsm_ng */
+  /* bsm_ng (src/model_bsm_ng.cpp:4-51): which components exist and which
+   * standard deviations are in theta (fixed(i) == 0), then the regression
+   * coefficients as the last n_xreg entries of theta */
+  int32_t slope, seasonal, noise;
+  int32_t level_est, slope_est, seasonal_est;
+  int32_t n_xreg;
+  const double* xreg; /* n x n_xreg column-major, or NULL */
 } bssm_theta_map;
 
 typedef struct {

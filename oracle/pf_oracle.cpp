@@ -1560,6 +1560,111 @@ int orc_postcorrection_ung(const bssm_ung_model* M, const bssm_theta_map* map, i
   return 0;
 }
 
+/* converged mode of ssm_ung::approximate() (src/model_ssm_ung.cpp:87-140) for any m: what
+ * run_mcmc stores per draw in mcmc_output$modes */
+void orc_ung_approx_mode_m(const bssm_ung_model* M, double* mode) {
+  pfga::UngApprox ga(M);
+  ga.approximate();
+  std::copy(ga.mode.begin(), ga.mode.end(), mode);
+}
+
+/* is_correction_psi<bsm_ng> (src/approx_mcmc.cpp:353-427) for any state dimension m:
+ * bsm_ng::update_model (src/model_bsm_ng.cpp:17-51) per draw, then the general-m
+ * psi-APF with approximate_for_is at the stored mode.  Same conventions as
+ * orc_postcorrection_ung; alpha (n+1) x m x n_draws, alphahat (n+1) x m, Vt m x m x (n+1). */
+int orc_postcorrection_bsm(const bssm_ung_model* M, const bssm_theta_map* map, int output_type, uint32_t nsim,
+                           uint32_t seed, int threads, int is_type, const uint32_t* counts, const double* theta,
+                           uint32_t n_par, const double* modes, uint32_t n_stored, int arith, double* weights,
+                           double* posterior, double* alpha, double* alphahat, double* Vt, double* loglik_out) {
+  if (map->model_type != 2) return 1;
+  const size_t n = M->n, n1 = n + 1, m = M->m, k = M->k;
+  std::vector<uint32_t> src, cnt;
+  for (uint32_t i = 0; i < n_stored; ++i) {
+    if (is_type == 3) for (uint32_t c = 0; c < counts[i]; ++c) { src.push_back(i); cnt.push_back(1u); }
+    else { src.push_back(i); cnt.push_back(counts[i]); }
+  }
+  const int64_t nd = (int64_t)src.size();
+  std::vector<double> ah_all, Vt_all;
+  if (output_type == 2) { ah_all.assign(m * n1 * nd, 0.0); Vt_all.assign(m * m * n1 * nd, 0.0); }
+#ifdef _OPENMP
+  if (threads < 1) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(threads)
+#endif
+  for (int64_t i = 0; i < nd; ++i) {
+    const double* new_theta = theta + (size_t)src[i] * n_par;
+    /* model.update_model(theta_i), src/model_bsm_ng.cpp:17-45 */
+    bssm_ung_model Mi = *M;
+    std::vector<double> R(M->R, M->R + m * k), P1(M->P1, M->P1 + m * m), xb;
+    const int slope = map->slope, seasonal = map->seasonal, noise = map->noise;
+    const int level_est = map->level_est, slope_est = map->slope_est, seasonal_est = map->seasonal_est;
+    if (level_est) R[0 + m * 0] = pf_exp(new_theta[0]);
+    if (slope_est) R[1 + m * 1] = pf_exp(new_theta[level_est]);
+    if (seasonal_est) R[(1 + slope) + m * (1 + slope)] = pf_exp(new_theta[level_est + slope_est]);
+    if (noise) {
+      R[(m - 1) + m * (1 + slope + seasonal)] = pf_exp(new_theta[level_est + slope_est + seasonal_est]);
+      const double r = R[(m - 1) + m * (1 + slope + seasonal)];
+      P1[(m - 1) + m * (m - 1)] = r * r;
+    }
+    if (map->phi_est) Mi.phi = pf_exp(new_theta[level_est + slope_est + seasonal_est + noise]);
+    if (map->n_xreg > 0) {
+      xb.assign(n, 0.0);
+      for (size_t t = 0; t < n; ++t) {
+        double sum = 0.0;
+        for (int j = 0; j < map->n_xreg; ++j) sum += map->xreg[t + n * j] * new_theta[n_par - map->n_xreg + j];
+        xb[t] = sum;
+      }
+      Mi.xbeta = xb.data();
+    }
+    Mi.R = R.data(); Mi.Rtv = 0; Mi.P1 = P1.data();
+    unsigned int nsimc = nsim;
+    if (is_type == 1) nsimc *= cnt[i];
+    std::vector<double> alpha_i(m * n1 * nsimc, 0.0), weights_i((size_t)nsimc * n1, 0.0);
+    std::vector<uint32_t> indices((size_t)nsimc * n, 0u);
+    int32_t st;
+    double al;
+    double ll = orc_ung_psi_filter_m(&Mi, modes + n * src[i], nsimc, seed, (uint32_t)i, arith, alpha_i.data(),
+                                     weights_i.data(), indices.data(), &al, &st, nullptr, nullptr, nullptr);
+    if (loglik_out) loglik_out[i] = ll;
+    weights[i] = pf_exp(ll);
+    if (output_type != 3) {
+      orc_filter_smoother(alpha_i.data(), indices.data(), (int)m, (int)n1, nsimc);
+      if (output_type == 1) {
+        uint32_t b = (uint32_t)(pf_pick_uniform(seed, (uint32_t)i) * (double)nsimc);
+        if (b > nsimc - 1) b = nsimc - 1;
+        for (size_t t = 0; t < n1; ++t)
+          for (size_t d = 0; d < m; ++d) alpha[m * n1 * i + t + n1 * d] = alpha_i[d + m * (t + n1 * b)];
+      } else {
+        orc_summary(alpha_i.data(), (int)m, (int)n1, nsimc, &ah_all[m * n1 * i], &Vt_all[m * m * n1 * i]);
+      }
+    }
+  }
+  if (output_type == 2) { /* :397-424, in draw order */
+    std::vector<double> ah(m * n1, 0.0), V(m * m * n1, 0.0), Valpha(m * m * n1, 0.0), diff(m), diff2(m);
+    double sum_w = 0.0;
+    for (int64_t i = 0; i < nd; ++i) {
+      double wnew = weights[i] * cnt[i];
+      sum_w += wnew;
+      for (size_t t = 0; t < n1; ++t) {
+        for (size_t d = 0; d < m; ++d) {
+          diff[d] = ah_all[m * n1 * i + d + m * t] - ah[d + m * t];
+          ah[d + m * t] += wnew / sum_w * diff[d];
+          diff2[d] = ah_all[m * n1 * i + d + m * t] - ah[d + m * t];
+        }
+        for (size_t c = 0; c < m; ++c)
+          for (size_t r = 0; r < m; ++r) {
+            Valpha[r + m * (c + m * t)] += wnew * diff[r] * diff2[c];
+            V[r + m * (c + m * t)] += wnew / sum_w * (Vt_all[m * m * n1 * i + r + m * (c + m * t)] - V[r + m * (c + m * t)]);
+          }
+      }
+    }
+    for (size_t t = 0; t < n1; ++t)
+      for (size_t d = 0; d < m; ++d) alphahat[t + n1 * d] = ah[d + m * t]; /* alphahat.t() */
+    for (size_t e = 0; e < m * m * n1; ++e) Vt[e] = V[e] + Valpha[e] / sum_w;
+  }
+  for (int64_t i = 0; i < nd; ++i) posterior[i] = 0.0 + 0.0 + pf_log(weights[i]);
+  return 0;
+}
+
 /* is_correction_psi<ssm_nlg> (src/approx_mcmc.cpp:353-427), growth model: theta is
  * n_par x n_stored, modes m x n x n_stored.  Same conventions as orc_postcorrection_ung. */
 int orc_postcorrection_nlg(const bssm_nlg_model* M, int output_type, uint32_t nsim, uint32_t seed, int threads,

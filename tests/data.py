@@ -63,6 +63,40 @@ def svm_mcmc_output(model, n_stored, output_type=3, jitter=0.05, gen_seed=7):
             "posterior": np.zeros(n_stored)}
 
 
+def bsm_mcmc_output(model, n_stored, output_type=3, jitter=0.1, gen_seed=13):
+    """synthetic run_mcmc stand-in for a bsm_ng model: theta_i = theta + jitter * N(0,1) on the log
+    scale (regression coefficients: additive), modes = converged mode at each theta (oracle)."""
+    import copy
+
+    import orc
+    rng = np.random.default_rng(gen_seed)
+    th0 = np.asarray(model.theta)
+    theta = th0[None, :] + jitter * rng.normal(size=(n_stored, th0.size))
+    counts = (1 + rng.poisson(3, size=n_stored)).astype(np.uint32)
+    modes = np.zeros((model.n, n_stored), order="F")
+    ex = model.extra
+    for i in range(n_stored):
+        mi = copy.copy(model)
+        mi.R = model.R.copy(); mi.P1 = model.P1.copy()
+        j = 0
+        mi.R[0, 0, 0] = np.exp(theta[i, j]); j += 1
+        if ex["slope"]:
+            mi.R[1, 1, 0] = np.exp(theta[i, j]); j += 1
+        if ex["seasonal"]:
+            r = 1 + int(ex["slope"])
+            mi.R[r, r, 0] = np.exp(theta[i, j]); j += 1
+        if ex["noise"]:
+            c = 1 + int(ex["slope"]) + int(ex["seasonal"])
+            mi.R[model.m - 1, c, 0] = np.exp(theta[i, j]); mi.P1[-1, -1] = mi.R[model.m - 1, c, 0] ** 2; j += 1
+        if ex["phi_est"]:
+            mi.phi = float(np.exp(theta[i, j])); j += 1
+        if model.xreg is not None:
+            mi.beta = theta[i, j:].copy()
+        modes[:, i] = orc.approx_mode_m(mi)
+    return {"theta": theta, "counts": counts, "modes": modes, "output_type": output_type,
+            "posterior": np.zeros(n_stored)}
+
+
 def growth_model(n=200, gen_seed=11, missing=()):
     """BASELINE config 3: the logistic growth model of vignettes/psi_pf.Rmd:133-158 (dT=.1, K=500,
     p1=50, r'1=-1.5, H=1, R1=.05, R2=1, a1=(-1.5, 50), P1=diag(1, 100)) in the packaged

@@ -225,6 +225,14 @@ def post_correct(model, mcmc_output, N, is_type=2, seed=1, threads=0, arith=ARIT
         assert rc == 0
         return r
     ms, tm = model.c_struct(), theta_map(model)
+    if model.cls == "bsm_ng":
+        f = L().orc_postcorrection_bsm
+        f.argtypes = L().orc_postcorrection_ung.argtypes
+        rc = f(C.byref(ms), C.byref(tm), ot, N, seed, threads, is_type, uptr(counts), dptr(theta), theta.shape[0],
+               dptr(modes), counts.size, arith, dptr(r.weights), dptr(r.posterior), dptr(r.alpha),
+               dptr(r.alphahat), dptr(r.Vt), dptr(r.loglik))
+        assert rc == 0
+        return r
     rc = L().orc_postcorrection_ung(C.byref(ms), C.byref(tm), ot, N, seed, threads, is_type, uptr(counts),
                                     dptr(theta), theta.shape[0], dptr(modes), counts.size, arith,
                                     dptr(r.weights), dptr(r.posterior), dptr(r.alpha), dptr(r.alphahat),
@@ -251,6 +259,17 @@ def sde_bsf_filter(model, N, Lvl, seed, filt=0, arith=ARITH_REPRO):
                                       uptr(r.indices), C.byref(st))
     r.stopped_at = st.value
     return r
+
+
+def approx_mode_m(model):
+    """converged mode of approximate() for any m (n values)"""
+    ms = model.c_struct()
+    f = L().orc_ung_approx_mode_m
+    f.restype = None
+    f.argtypes = [C.POINTER(UngModel), c_double_p]
+    mode = np.zeros(model.n)
+    f(C.byref(ms), dptr(mode))
+    return mode
 
 
 def psi_filter_m(model, N, seed, filt=0, arith=ARITH_REPRO, mode=None):

@@ -111,3 +111,47 @@ def test_nonlinear_postcorrection_growth(engine):
     res2 = engine.post_correct(model, mo2, 32, is_type="is1", seed=5)
     np.testing.assert_allclose(res2["alphahat"], ref2.alphahat, rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(res2["Vt"], ref2.Vt, rtol=1e-8, atol=1e-12)
+
+
+def _bsm_case(kind):
+    import bssm_b200
+    y = data.poisson_series()
+    if kind == "level_slope":      # m = 2, the documented bsm_ng example
+        return data.poisson_bsm_model(80)
+    if kind == "level":            # m = 1: goes through the m = 1 device pre-pass
+        return bssm_b200.bsm_ng(y[:70], sd_level=0.1, P1=[[1.0]], distribution="poisson")
+    if kind == "negbin_xreg":      # m = 2, negative binomial with phi and one regression coefficient in theta
+        n = 60
+        rng = np.random.default_rng(4)
+        xreg = rng.normal(size=(n, 1))
+        return bssm_b200.bsm_ng(y[:n], sd_level=0.1, sd_slope=0.02, P1=np.diag([1.0, 0.5]),
+                                distribution="negative binomial", phi=4.0, xreg=xreg, beta=[0.2])
+    # m = 3: level + slope + extra noise state
+    return bssm_b200.bsm_ng(y[:50], sd_level=0.1, sd_slope=0.02, sd_noise=0.1, P1=np.diag([1.0, 0.5, 1.0]),
+                            distribution="poisson")
+
+
+@pytest.mark.parametrize("kind", ["level_slope", "level", "negbin_xreg", "noise"])
+def test_bsm_ng_post_correction(engine, kind):
+    """is_correction_psi for bsm_ng (src/approx_mcmc.cpp:685-804): bsm_ng::update_model per draw
+    (src/model_bsm_ng.cpp:17-51), Gaussian approximation at the stored mode (host, OpenMP for m > 1)"""
+    model = _bsm_case(kind)
+    mo = data.bsm_mcmc_output(model, 24)
+    ref = orc.post_correct(model, mo, 96, is_type=2, seed=3)
+    res = engine.post_correct(model, mo, 96, is_type="is2", seed=3, return_loglik=True)
+    if kind == "level":
+        # m = 1 runs the device pre-pass; the general-m host approximation of the oracle reduces to it
+        np.testing.assert_allclose(res["loglik"], ref.loglik, rtol=1e-12)
+    else:
+        assert np.array_equal(res["loglik"], ref.loglik)
+        assert np.array_equal(res["weights"], ref.weights)
+    mo1 = dict(mo, output_type=1)
+    ref1 = orc.post_correct(model, mo1, 64, is_type=3, seed=5)
+    res1 = engine.post_correct(model, mo1, 64, is_type="is3", seed=5)
+    if kind != "level":
+        assert np.array_equal(res1["alpha"].view(np.uint64), ref1.alpha.view(np.uint64))
+    mo2 = dict(mo, output_type=2)
+    ref2 = orc.post_correct(model, mo2, 32, is_type=1, seed=7)
+    res2 = engine.post_correct(model, mo2, 32, is_type="is1", seed=7)
+    np.testing.assert_allclose(res2["alphahat"], ref2.alphahat, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(res2["Vt"], ref2.Vt, rtol=1e-8, atol=1e-12)
