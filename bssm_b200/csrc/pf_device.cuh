@@ -90,6 +90,11 @@ struct FilterParams {
 //
 // The release / acquire of the barrier also orders the bulk exchange through
 // global memory (state rows, thresholds, ancestors); consumers read with ld.cg.
+// Tried and rejected (measured on the C2 workloads, tools/build_variants.py):
+//  * named barriers (bar.arrive for the producer warps, bar.sync for warp 0) so that
+//    producers run on into the overlap window: no gain;
+//  * warp 0 polling AND combining the rank partials before a single CTA barrier
+//    (one __syncthreads less per collective): 13% slower on both workloads.
 struct Sync {
   int mode;
   unsigned int* counter; // SYNC_GROUP: this filter's counter (zeroed before the launch)
@@ -99,15 +104,15 @@ struct Sync {
   // wait(): the writes of all CTAs of the filter released by their arrive() are
   // visible.  Work placed between the two overlaps the barrier latency; it must
   // not depend on what the barrier orders.
-  // `cta_synced`: the caller has just passed a __syncthreads() that every thread
+  // `joined`: the caller has just passed a __syncthreads() that every thread
   // reaches after its last write the barrier has to publish, and thread 0 wrote
   // (or is ordered after) the exchange partials.
-  __device__ __forceinline__ void arrive(bool cta_synced = false) {
+  __device__ __forceinline__ void arrive(bool joined = false) {
     if (mode == SYNC_BLOCK) {
     } else if (mode == SYNC_CLUSTER) {
       asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     } else {
-      if (!cta_synced) __syncthreads();
+      if (!joined) __syncthreads();
       if (threadIdx.x == 0) {
         target += nranks;
         __threadfence();
@@ -115,19 +120,27 @@ struct Sync {
       }
     }
   }
+  // SYNC_GROUP, warp 0 only: returns when every CTA of the filter has arrived
+  __device__ __forceinline__ void poll_warp0() {
+    if (threadIdx.x == 0) {
+      // relaxed polling, ONE acquire fence at the end: an acquire load invalidates
+      // the SM's L1 (CCTL.IVALL) on every iteration, which evicts the spill lines of
+      // all resident CTAs while this thread spins
+      unsigned int v;
+      do {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      } while ((int)(v - target) < 0);
+      __threadfence();
+    }
+    __syncwarp();
+  }
   __device__ __forceinline__ void wait() {
     if (mode == SYNC_BLOCK) {
       __syncthreads();
     } else if (mode == SYNC_CLUSTER) {
       asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     } else {
-      if (threadIdx.x == 0) {
-        unsigned int v;
-        do {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-        } while ((int)(v - target) < 0);
-        __threadfence();
-      }
+      if (threadIdx.x < 32) poll_warp0();
       __syncthreads();
     }
   }
@@ -233,8 +246,8 @@ struct Coll {
       }
       __syncwarp(); // lane 31's partials before thread 0 releases them
     }
-    // every thread passed the __syncthreads above after its stores of this step
-    // (weights row, thresholds): thread 0's release publishes them too
+    // every thread joined warp 0 above after its stores of this step (weights
+    // row, thresholds): thread 0's release publishes them too
     sync->arrive(true);
   }
   __device__ __forceinline__ void exscan2_end(long long th, long long tl, long long ih, long long il,

@@ -18,7 +18,8 @@ if filters == 0:  # auto: as many filters as the device runs concurrently
     probe = bssm_b200.FilterJob(model, N, method="psi", seed=1, n_filters=1, out_flags=0)
     filters = probe.max_concurrent_filters()
     probe.close()
-job = bssm_b200.FilterJob(model, N, method="psi", seed=1, n_filters=filters, out_flags=7)
+job = bssm_b200.FilterJob(model, N, method="psi", seed=1, n_filters=filters,
+                         out_flags=int(os.environ.get("PROF_FLAGS", "7")))
 print("filters", filters)
 print("max concurrent filters", job.max_concurrent_filters())
 for _ in range(runs):

@@ -2,7 +2,7 @@
 # times each build variant on the C2 batch and single-filter workloads
 for so in build_variants/*.so; do
   echo "== $so"
-  for nf in ${FILTERS:-18 13 1}; do
+  for nf in ${FILTERS:-18 1}; do
     echo -n "filters=$nf: "; BSSM_B200_LIB=$PWD/$so python tools/profile_run.py $nf 3 1000 2>&1 | grep -E "run ms" | tail -1
   done
 done
