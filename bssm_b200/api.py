@@ -245,6 +245,34 @@ def theta_map(model):
     return tm
 
 
+def suggest_N(model, theta, candidates=tuple(range(10, 101, 10)), replications=100, seed=1):
+    """suggest_N, R/post_correction.R:85-134: sd of the psi-APF log-likelihood estimate for each
+    candidate particle count; N = the first candidate with sd < 1."""
+    replications = int(replications)
+    if not 2 <= replications <= 1000:
+        raise ValueError("replications must be in 2..1000")  # check_intmax(..., max = 1000)
+    cand = np.ascontiguousarray(candidates, dtype=np.int64)
+    if cand.size < 1 or np.any(cand < 1):
+        raise ValueError("Argument 'candidates' should be vector of positive integers. ")
+    theta = _lib.f64(np.ravel(theta))
+    if theta.size != np.size(model.theta):
+        raise ValueError("Length of 'theta' does not match length of 'model$theta'.")
+    cand32 = np.ascontiguousarray(cand, dtype=np.uint32)
+    sds = np.zeros(cand.size)
+    ms = model.c_struct()
+    if model.cls == "ssm_nlg":
+        check(lib().bssm_b200_suggest_n_nonlinear(C.byref(ms), dptr(theta), theta.size, uptr(cand32), cand32.size,
+                                                  replications, int(seed), int(getattr(model, "max_iter", 100)),
+                                                  float(getattr(model, "conv_tol", 1e-8)), dptr(sds)))
+    else:
+        tm = theta_map(model)
+        check(lib().bssm_b200_suggest_n_nongaussian(C.byref(ms), C.byref(tm), dptr(theta), theta.size, uptr(cand32),
+                                                    cand32.size, replications, int(seed), dptr(sds)))
+    below = np.nonzero(sds < 1)[0]
+    return {"N": int(cand[below[0]]) if below.size else None,
+            "results": {"N": cand.copy(), "sd": sds}}
+
+
 def _postcorr_inputs(model, mcmc_output):
     theta = np.asfortranarray(np.asarray(mcmc_output["theta"], dtype=np.float64).T)  # t(theta): n_par x n_stored
     counts = np.ascontiguousarray(mcmc_output["counts"], dtype=np.uint32)

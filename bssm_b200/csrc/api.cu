@@ -389,6 +389,8 @@ struct bssm_b200_job {
   pf::UngParams up{};
   pf::NlgParams np{};
   pf::SdeParams sp{};
+  int sde_model_id = 0;
+  DevBuf<double> lgy;
   pf::MngParams gp{};
   pf::NlgPsiParams npp{};
   DevBuf<double> stepc;
@@ -460,7 +462,7 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
     return launch_status(pfl::launch_nlg_psi(fp, npp, J->geo, nf, J->stream), "nlg psi filter");
   }
   if (J->kind == KIND_NLG) return launch_status(pfl::launch_nlg_bsf(fp, J->np, J->geo, nf, J->stream), "nlg bsf");
-  if (J->kind == KIND_SDE) return launch_status(pfl::launch_sde_bsf(fp, J->sp, J->geo, nf, J->stream), "sde bsf");
+  if (J->kind == KIND_SDE) return launch_status(pfl::launch_sde_bsf(J->sde_model_id, fp, J->sp, J->geo, nf, J->stream), "sde bsf");
   if (J->kind == KIND_MNG) {
     if (J->method == BSSM_METHOD_PSI) {
       pf::MngParams gp = J->gp;
@@ -999,8 +1001,9 @@ int bssm_b200_job_create_sde(const bssm_sde_model* M, uint32_t nsim, uint32_t L,
                              bssm_b200_job** job) {
   if (!M || !job || !M->y || !M->theta) return fail(BSSM_B200_ERR_ARG, "null argument");
   *job = nullptr;
-  if (M->model_id != BSSM_SDE_GBM) return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_sde: unknown model_id (registry: BSSM_SDE_GBM)");
-  if (M->n_theta < 3) return fail(BSSM_B200_ERR_ARG, "GBM needs theta = (mu, sigma_x, sigma_y)");
+  if (M->model_id != BSSM_SDE_GBM && M->model_id != BSSM_SDE_POISSON_OU)
+    return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_sde: unknown model_id (registry: BSSM_SDE_GBM, BSSM_SDE_POISSON_OU)");
+  if (M->n_theta < 3) return fail(BSSM_B200_ERR_ARG, "ssm_sde registry models need 3 parameters");
   if (L < 1 || L > 20) return fail(BSSM_B200_ERR_ARG, "discretisation level L must be in 1..20");
   bssm_b200_job* J = new bssm_b200_job();
   struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
@@ -1013,7 +1016,17 @@ int bssm_b200_job_create_sde(const bssm_sde_model* M, uint32_t nsim, uint32_t L,
   sp.dt = 1.0 / (double)sp.nsub;      // t / n with t = 1, src/milstein.cpp:23-24
   sp.sqdt = std::sqrt(sp.dt);
   sp.th0 = M->theta[0]; sp.th1 = M->theta[1]; sp.th2 = M->theta[2];
-  sp.logsd = pf_log(sp.th2);
+  J->sde_model_id = M->model_id;
+  sp.lgy = nullptr; sp.logsd = 0.0; sp.e0 = 0.0; sp.e2 = 0.0;
+  if (M->model_id == BSSM_SDE_GBM) {
+    sp.logsd = pf_log(sp.th2);
+  } else { // Poisson-OU: theta = (log rho, nu, log sigma), R/cpp_example_models.R:37-39
+    sp.e0 = pf_exp(sp.th0); sp.e2 = pf_exp(sp.th2);
+    std::vector<double> lg(M->n, 0.0);
+    for (int t = 0; t < M->n; ++t) if (std::isfinite(M->y[t])) lg[t] = std::lgamma(M->y[t] + 1.0);
+    if ((rc = J->lgy.upload(lg.data(), M->n))) return rc;
+    sp.lgy = J->lgy.p;
+  }
   if ((rc = finish_job(J, out_flags, post))) return rc;
   guard.j = nullptr;
   *job = J;
@@ -1629,6 +1642,80 @@ int bssm_b200_postcorrection_nonlinear(const bssm_nlg_model* M, int output_type,
                          [&](const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N, int post, bssm_b200_job** J) {
                            return make_nlg_draw_job(M, dl, d0, d1, N, seed, theta, n_par, modes, post, J);
                          });
+}
+
+// ------------------------------------------------------------- suggest_N
+// sd of `replications` psi-APF log-likelihood estimates for one particle count: a batch of
+// replicate filters at fixed theta; the streams of candidate c are c*replications ... so that
+// candidates do not share random numbers (the reference continues one engine, src/R_postcorrection.cpp:27-35)
+static int loglik_sd(bssm_b200_job* J, uint32_t replications, double* sd) {
+  struct JG { bssm_b200_job* j; ~JG() { delete j; } } jg{J};
+  float ms = 0;
+  int rc = bssm_b200_job_run(J, &ms);
+  if (rc) return rc;
+  std::vector<double> ll(replications);
+  if ((rc = bssm_b200_job_logliks(J, ll.data()))) return rc;
+  // arma::stddev: two-pass, N - 1 normalisation
+  double mean = 0.0;
+  for (double v : ll) mean += v;
+  mean /= (double)replications;
+  double acc = 0.0;
+  for (double v : ll) acc += (v - mean) * (v - mean);
+  *sd = std::sqrt(acc / (double)(replications - 1));
+  return 0;
+}
+
+int bssm_b200_suggest_n_nongaussian(const bssm_ung_model* M, const bssm_theta_map* map, const double* theta,
+                                    uint32_t n_par, const uint32_t* candidates, uint32_t n_candidates,
+                                    uint32_t replications, uint32_t seed, double* sds) {
+  if (!M || !map || !theta || !candidates || !sds || n_candidates == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
+  if (replications < 2) return fail(BSSM_B200_ERR_ARG, "replications must be >= 2");
+  // model.update_model(theta)
+  bssm_ung_model Mi = *M;
+  double par[6];
+  std::vector<double> R, P1, xb;
+  if (M->m == 1 && !(map->model_type == 2 && map->n_xreg > 0)) {
+    if (M->xbeta) return fail(BSSM_B200_ERR_UNSUPPORTED, "suggest_N with regression coefficients in theta: bsm_ng only");
+    int rc = theta_to_par(M, map, theta, n_par, par);
+    if (rc) return rc;
+    Mi.T = &par[0]; Mi.R = &par[1]; Mi.a1 = &par[2]; Mi.P1 = &par[3]; Mi.C = &par[4]; Mi.phi = par[5];
+    Mi.Ttv = 0; Mi.Rtv = 0; Mi.Ctv = 0;
+  } else {
+    if (map->model_type != 2) return fail(BSSM_B200_ERR_UNSUPPORTED, "suggest_N with m > 1: bsm_ng (model_type 2) in this build");
+    if (M->Rtv) return fail(BSSM_B200_ERR_UNSUPPORTED, "time-invariant R only");
+    R.resize((size_t)M->m * M->k); P1.resize((size_t)M->m * M->m);
+    if (map->n_xreg > 0) xb.resize(M->n);
+    int rc = theta_to_bsm(M, map, theta, n_par, R.data(), P1.data(), &Mi.phi, xb.empty() ? nullptr : xb.data());
+    if (rc) return rc;
+    Mi.R = R.data(); Mi.P1 = P1.data();
+    if (!xb.empty()) Mi.xbeta = xb.data();
+  }
+  for (uint32_t c = 0; c < n_candidates; ++c) {
+    bssm_b200_job* J = nullptr;
+    int rc = create_ung_job(&Mi, BSSM_METHOD_PSI, candidates[c], seed, replications, c * replications, 0,
+                            BSSM_POST_NONE, nullptr, nullptr, &J);
+    if (rc) return rc;
+    if ((rc = loglik_sd(J, replications, &sds[c]))) return rc;
+  }
+  return 0;
+}
+
+int bssm_b200_suggest_n_nonlinear(const bssm_nlg_model* M, const double* theta, uint32_t n_par,
+                                  const uint32_t* candidates, uint32_t n_candidates, uint32_t replications,
+                                  uint32_t seed, uint32_t max_iter, double conv_tol, double* sds) {
+  if (!M || !theta || !candidates || !sds || n_candidates == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
+  if (replications < 2) return fail(BSSM_B200_ERR_ARG, "replications must be >= 2");
+  bssm_nlg_model Mi = *M;
+  Mi.theta = theta;
+  Mi.n_theta = (int32_t)n_par;
+  for (uint32_t c = 0; c < n_candidates; ++c) {
+    bssm_b200_job* J = nullptr;
+    int rc = bssm_b200_job_create_nlg_psi(&Mi, candidates[c], seed, max_iter, conv_tol, replications,
+                                          c * replications, 0, BSSM_POST_NONE, &J);
+    if (rc) return rc;
+    if ((rc = loglik_sd(J, replications, &sds[c]))) return rc;
+  }
+  return 0;
 }
 
 // ---------------------------------------------------------- one-shot calls

@@ -25,7 +25,7 @@ int launch_nlg_bsf(const pf::FilterParams&, const pf::NlgParams&, const Geometry
 int launch_nlg_psi(const pf::FilterParams&, const pf::NlgPsiParams&, const Geometry&, uint32_t nf, Stream);
 int occupancy_nlg_bsf(const Geometry&, int* out);
 int occupancy_nlg_psi(const Geometry&, int* out);
-// k_sde.cu: GBM functor, Milstein bootstrap filter
-int launch_sde_bsf(const pf::FilterParams&, const pf::SdeParams&, const Geometry&, uint32_t nf, Stream);
+// k_sde.cu: Milstein bootstrap filter; model_id 0 = GBM, 1 = Poisson-OU (device functor registry)
+int launch_sde_bsf(int model_id, const pf::FilterParams&, const pf::SdeParams&, const Geometry&, uint32_t nf, Stream);
 int occupancy_sde_bsf(const Geometry&, int* out);
 } // namespace pfl

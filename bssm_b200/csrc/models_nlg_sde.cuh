@@ -189,44 +189,74 @@ struct NlgGrowthPsi : GaussStep<NlgGrowthPsi, 2, 2, 2> {
   }
 };
 
-// --------------------------------------------------------------- ssm_sde: GBM
-// dx = mu x dt + sigma_x x dB, y_k ~ N(log x_k, sigma_y^2).  Bootstrap filter:
-// ssm_sde::bsf_filter src/model_ssm_sde.cpp:21-82; every particle step is 2^L
-// Milstein sub-steps (src/milstein.cpp:18-48) with fresh N(0, sqrt(dt))
+// ------------------------------------------------------------------- ssm_sde
+// Bootstrap filter ssm_sde::bsf_filter src/model_ssm_sde.cpp:21-82; every particle
+// step is 2^L Milstein sub-steps (src/milstein.cpp:18-48) with fresh N(0, sqrt(dt))
 // increments: sub-step s of particle i at column t uses normal (flat index i,
-// sub = s) of the stream contract in pf_math.h.
+// sub = s) of the stream contract in pf_math.h.  The reference takes drift,
+// diffusion, its derivative and the observation log-density as compiled function
+// pointers (src/model_ssm_sde.h:9-16); here they are functors of a device registry:
+//   SdeGbm        dx = mu x dt + sigma_x x dB, y_k ~ N(log x_k, sigma_y^2)
+//                 (R/cpp_example_models.R:109-193)
+//   SdePoissonOu  dx = rho (nu - x) dt + sigma dB, y_k ~ Poisson(exp(x_k))
+//                 (R/cpp_example_models.R:24-108)
 struct SdeParams {
   int n;
   const double* y;
+  const double* lgy; // lgamma(y_t + 1) per time point (Poisson-OU), host-computed
   double x0;
   int positive;
   int nsub;         // 2^L
   double dt, sqdt;  // 1/2^L, sqrt(dt)
   double th0, th1, th2;
-  double logsd;     // log(theta2)
+  double logsd;     // GBM: log(theta2)
+  double e0, e2;    // Poisson-OU: exp(theta0), exp(theta2)
 };
 
-struct SdeGbmBsf {
+struct SdeGbm {
+  static __device__ __forceinline__ double drift(const SdeParams& mp, double x) { return mp.th0 * x; }
+  static __device__ __forceinline__ double diffusion(const SdeParams& mp, double x) {
+    const double tx = mp.th1 * x;
+    return tx > 0.0 ? tx : 0.0;                       // std::max(0.0, theta1 * x)
+  }
+  static __device__ __forceinline__ double ddiffusion(const SdeParams& mp, double x) {
+    return mp.th1 * (x > 0.0 ? 1.0 : 0.0);
+  }
+  // R::dnorm(y, log(x), theta2, log = TRUE): -(M_LN_SQRT_2PI + 0.5 q^2 + log(sd)) [UNVENDORED: R nmath]
+  static __device__ __forceinline__ double log_obs(const SdeParams& mp, double y, double, double x) {
+    const double q = (y - pf_log(x)) / mp.th2;
+    return -(0.918938533204672741780329736406 + 0.5 * q * q + mp.logsd);
+  }
+};
+
+struct SdePoissonOu {
+  static __device__ __forceinline__ double drift(const SdeParams& mp, double x) { return mp.e0 * (mp.th1 - x); }
+  static __device__ __forceinline__ double diffusion(const SdeParams& mp, double) { return mp.e2; }
+  static __device__ __forceinline__ double ddiffusion(const SdeParams&, double) { return 0.0; }
+  // R::dpois(y, exp(x), log = TRUE) = y x - exp(x) - lgamma(y + 1) [UNVENDORED: R nmath dpois.c
+  // evaluates the same quantity through stirlerr / bd0]
+  static __device__ __forceinline__ double log_obs(const SdeParams&, double y, double lgy, double x) {
+    return (y * x - pf_exp(x)) - lgy;
+  }
+};
+
+template <class Fn>
+struct SdeBsf {
   static constexpr int M = 1;
   typedef SdeParams Params;
   const SdeParams& mp;
-  double y;
-  __device__ SdeGbmBsf(const SdeParams& p, uint32_t) : mp(p) {}
+  double y, lgy;
+  __device__ SdeBsf(const SdeParams& p, uint32_t) : mp(p), y(0.0), lgy(0.0) {}
   __device__ double loglik0() const { return 0.0; }
   __device__ double loglik_end() const { return 0.0; }
   __device__ bool observed(int t) const { return pf_isfinite(mp.y[t]); }
-  __device__ void begin_weight(int t) { y = mp.y[t]; }
-  // R::dnorm(y, log(x), theta2, log = TRUE): -(M_LN_SQRT_2PI + 0.5 q^2 + log(sd)) [UNVENDORED: R nmath]
-  __device__ double logw(const double* x) const {
-    const double q = (y - pf_log(x[0])) / mp.th2;
-    return -(0.918938533204672741780329736406 + 0.5 * q * q + mp.logsd);
-  }
+  __device__ void begin_weight(int t) { y = mp.y[t]; lgy = mp.lgy ? mp.lgy[t] : 0.0; }
+  __device__ double logw(const double* x) const { return Fn::log_obs(mp, y, lgy, x[0]); }
   __device__ void begin_step(int) {}
   __device__ __forceinline__ double milstein_step(double x, double dB) const {
-    const double drift = mp.th0 * x;
-    const double tx = mp.th1 * x;
-    const double diff = tx > 0.0 ? tx : 0.0;           // std::max(0.0, theta1 * x)
-    const double ddiff = mp.th1 * (x > 0.0 ? 1.0 : 0.0);
+    const double drift = Fn::drift(mp, x);
+    const double diff = Fn::diffusion(mp, x);
+    const double ddiff = Fn::ddiffusion(mp, x);
     x += drift * mp.dt + diff * dB + 0.5 * diff * ddiff * (dB * dB - mp.dt);
     if (mp.positive) x = fabs(x);
     return x;
@@ -263,5 +293,7 @@ struct SdeGbmBsf {
   __device__ __forceinline__ double finish_logw(double w, double) const { return w; }
   __device__ __forceinline__ double step_const() const { return 0.0; }
 };
+typedef SdeBsf<SdeGbm> SdeGbmBsf;
+typedef SdeBsf<SdePoissonOu> SdePoissonOuBsf;
 
 } // namespace pf

@@ -249,8 +249,9 @@ class NlgModel:
 
 class SdeModel:
     """ssm_sde (R/models.R:1637-1650); model="gbm" is the sde_gbm example of
-    R/cpp_example_models.R:109-193 (theta = mu, sigma_x, sigma_y)."""
-    REGISTRY = {"gbm": (0, 3)}
+    R/cpp_example_models.R:109-193 (theta = mu, sigma_x, sigma_y), model="poisson_ou" the
+    sde_poisson_ou example of :24-108 (theta = log rho, nu, log sigma)."""
+    REGISTRY = {"gbm": (0, 3), "poisson_ou": (1, 3)}
 
     def __init__(self, y, model, theta, x0, positive):
         if model not in self.REGISTRY:

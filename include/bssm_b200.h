@@ -222,7 +222,9 @@ enum {
   BSSM_NLG_GROWTH = 0 /* logistic growth model, R/cpp_example_models.R:336-511 */
 };
 enum {
-  BSSM_SDE_GBM = 0    /* geometric Brownian motion, R/cpp_example_models.R:109-193 */
+  BSSM_SDE_GBM = 0,       /* geometric Brownian motion, R/cpp_example_models.R:109-193 */
+  BSSM_SDE_POISSON_OU = 1 /* Ornstein-Uhlenbeck state, Poisson observations, R/cpp_example_models.R:24-108:
+                           * theta = (log rho, nu, log sigma) */
 };
 
 typedef struct {
@@ -338,6 +340,21 @@ int bssm_b200_postcorrection_nongaussian(const bssm_ung_model* model, const bssm
                                          const double* theta, uint32_t n_par, const double* modes,
                                          uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
                                          bssm_postcorr_out* out);
+
+/* replaces: suggest_n_nongaussian(model_, theta, candidates, replications, seed, model_type)
+ *           src/R_postcorrection.cpp:14-104: for every candidate particle count, the standard
+ *           deviation (arma::stddev, N - 1) of `replications` psi-APF log-likelihood estimates at
+ *           theta.  One device batch of replicate filters per candidate; replicate j of candidate
+ *           c uses stream c * replications + j.  Models: as bssm_b200_postcorrection_nongaussian. */
+int bssm_b200_suggest_n_nongaussian(const bssm_ung_model* model, const bssm_theta_map* map,
+                                    const double* theta, uint32_t n_par, const uint32_t* candidates,
+                                    uint32_t n_candidates, uint32_t replications, uint32_t seed,
+                                    double* sds);
+/* replaces: suggest_n_nonlinear(...) src/R_postcorrection.cpp:107-147 (registry models) */
+int bssm_b200_suggest_n_nonlinear(const bssm_nlg_model* model, const double* theta, uint32_t n_par,
+                                  const uint32_t* candidates, uint32_t n_candidates,
+                                  uint32_t replications, uint32_t seed, uint32_t max_iter,
+                                  double conv_tol, double* sds);
 
 /* replaces: postcorrection_nonlinear(y, Z, H, T, R, Zg, Tg, a1, P1, theta, ..., output_type, nsim,
  *           seed, n_threads, is_type, counts, theta, modes) src/R_postcorrection.cpp:252-317 ->

@@ -1396,9 +1396,22 @@ struct Gbm {
   }
 };
 
+/* Poisson-OU user functions, R/cpp_example_models.R:41-86: theta = (log rho, nu, log sigma) */
+struct PoissonOu {
+  const double* theta;
+  double drift(double x) const { return pf_exp(theta[0]) * (theta[1] - x); }
+  double diffusion(double) const { return pf_exp(theta[2]); }
+  double ddiffusion(double) const { return 0.0; }
+  /* R::dpois(y, exp(alpha), 1) [UNVENDORED: R nmath dpois.c, via stirlerr / bd0] = y alpha - exp(alpha) - lgamma(y + 1) */
+  double log_obs(double y, double alpha) const { return (y * alpha - pf_exp(alpha)) - std::lgamma(y + 1.0); }
+};
+
 /* milstein + milstein_worker, src/milstein.cpp:18-48; dB(k) = N(0, sqrt(dt)) drawn
  * as sqrt(dt) * z with z the (particle i, sub-step k) normal of the Philox stream */
-static double milstein(double x, unsigned int L, const Gbm& fn, bool positive, uint32_t seed, uint32_t filter,
+} /* extern "C": the two templates below need C++ linkage */
+
+template <class Fn>
+static double milstein(double x, unsigned int L, const Fn& fn, bool positive, uint32_t seed, uint32_t filter,
                        uint32_t t, uint32_t i) {
   unsigned int n = 1u << L;
   double dt = 1.0 / n;
@@ -1412,11 +1425,11 @@ static double milstein(double x, unsigned int L, const Gbm& fn, bool positive, u
 }
 
 /* ssm_sde::bsf_filter, src/model_ssm_sde.cpp:21-82 (alpha is 1 x (n+1) x N) */
-double orc_sde_bsf_filter(const bssm_sde_model* M, uint32_t nsim, uint32_t L, uint32_t seed, uint32_t filter,
-                          int arith, double* alpha, double* weights, uint32_t* indices, int32_t* stopped_at) {
+template <class Fn>
+static double sde_bsf_filter(const Fn& fn, const bssm_sde_model* M, uint32_t nsim, uint32_t L, uint32_t seed,
+                             uint32_t filter, int arith, double* alpha, double* weights, uint32_t* indices,
+                             int32_t* stopped_at) {
   *stopped_at = -1;
-  if (M->model_id != BSSM_SDE_GBM) return pf_nan();
-  Gbm fn{M->theta};
   const int n = M->n;
   const size_t N = nsim;
   auto A = [&](int t, size_t i) -> double& { return alpha[t + (size_t)(n + 1) * i]; };
@@ -1448,6 +1461,18 @@ double orc_sde_bsf_filter(const bssm_sde_model* M, uint32_t nsim, uint32_t L, ui
     }
   }
   return loglik;
+}
+
+extern "C" {
+
+double orc_sde_bsf_filter(const bssm_sde_model* M, uint32_t nsim, uint32_t L, uint32_t seed, uint32_t filter,
+                          int arith, double* alpha, double* weights, uint32_t* indices, int32_t* stopped_at) {
+  if (M->model_id == BSSM_SDE_GBM)
+    return sde_bsf_filter(Gbm{M->theta}, M, nsim, L, seed, filter, arith, alpha, weights, indices, stopped_at);
+  if (M->model_id == BSSM_SDE_POISSON_OU)
+    return sde_bsf_filter(PoissonOu{M->theta}, M, nsim, L, seed, filter, arith, alpha, weights, indices, stopped_at);
+  *stopped_at = -1;
+  return pf_nan();
 }
 
 /* ------------------------------------------------------------------ a15 */

@@ -133,6 +133,22 @@ def gbm_model(n=50, gen_seed=42, missing=()):
     return bssm_b200.ssm_sde(y, "gbm", theta=[0.08, 0.4, 1.5], x0=1.0, positive=True)
 
 
+def poisson_ou_model(n=50, gen_seed=8, missing=()):
+    """Ornstein-Uhlenbeck state with Poisson observations, as vignettes/sde_model.Rmd simulates it
+    (rho = 0.5, nu = 2, sigma = 0.3, x0 = nu, unit spacing, Euler on a fine mesh)."""
+    rng = np.random.default_rng(gen_seed)
+    rho, nu, sigma = 0.5, 2.0, 0.3
+    x, dt = nu, 1.0 / 64
+    y = np.empty(n)
+    for k in range(n):
+        for _ in range(64):
+            x += rho * (nu - x) * dt + sigma * np.sqrt(dt) * rng.normal()
+        y[k] = rng.poisson(np.exp(x))
+    for t in missing:
+        y[t] = np.nan
+    return bssm_b200.ssm_sde(y, "poisson_ou", theta=[np.log(0.45), 1.9, np.log(0.35)], x0=2.0, positive=False)
+
+
 def mng_model(n=60, gen_seed=5, missing=True):
     """a 3-variate ssm_mng (Poisson, negative binomial, Gaussian) driven by a 2-dimensional state,
     in the spirit of the 4-variate model of tests/testthat/test_basics.R:100-160"""

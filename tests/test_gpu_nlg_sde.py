@@ -62,6 +62,22 @@ def test_gbm_smoother_and_missing(engine):
     assert res["logLik"] == ref.loglik
 
 
+@pytest.mark.parametrize("N,L", [(200, 2), (3000, 3)])
+def test_poisson_ou_bsf_parity(engine, N, L):
+    """second functor of the ssm_sde registry: OU state, Poisson observations (sde_poisson_ou)"""
+    model = data.poisson_ou_model(40, missing=(6,))
+    ref = orc.sde_bsf_filter(model, N, L, seed=4)
+    res = engine.bootstrap_filter(model, N, seed=4, return_indices=True, L=L)
+    assert np.array_equal(res["indices"], ref.indices)
+    assert np.array_equal(_cube(res).view(np.uint64), ref.alpha.view(np.uint64))
+    assert np.array_equal(res["weights"].view(np.uint64), ref.weights.view(np.uint64))
+    assert res["logLik"] == ref.loglik
+    assert np.all(res["weights"][:, 6] == 1.0)
+    sm = orc.filter_smoother(ref.alpha, ref.indices)
+    res2 = engine.particle_smoother(model, N, method="bsf", seed=4, L=L)
+    assert np.array_equal(_cube(res2).view(np.uint64), sm.view(np.uint64))
+
+
 def test_sde_argument_checks(engine):
     model = data.gbm_model(10)
     with pytest.raises(ValueError, match="Discretization level"):

@@ -155,3 +155,32 @@ def test_bsm_ng_post_correction(engine, kind):
     res2 = engine.post_correct(model, mo2, 32, is_type="is1", seed=7)
     np.testing.assert_allclose(res2["alphahat"], ref2.alphahat, rtol=1e-9, atol=1e-11)
     np.testing.assert_allclose(res2["Vt"], ref2.Vt, rtol=1e-8, atol=1e-12)
+
+
+def test_suggest_N(engine):
+    """suggest_N (R/post_correction.R:85-134, src/R_postcorrection.cpp:14-104): sd of replicate psi-APF
+    log-likelihoods per candidate N, at theta applied through svm::update_model"""
+    import bssm_b200
+    model = data.svm_model(100)
+    theta = np.array([0.97, 0.25, 1.1])
+    cands, reps = [16, 64, 256], 20
+    res = engine.suggest_N(model, theta, candidates=cands, replications=reps, seed=11)
+    mi = bssm_b200.svm(model.y, theta[0], theta[1], sigma=theta[2])
+    mi.initial_mode = model.initial_mode  # update_model does not touch initial_mode (src/model_svm.cpp:12-29)
+    for c, N in enumerate(cands):
+        ll = orc.filter_batch(mi, N, "psi", seed=11, first_filter=c * reps, n_filters=reps, arith=orc.ARITH_REPRO)
+        assert res["results"]["sd"][c] == pytest.approx(np.std(ll, ddof=1), rel=1e-10)
+    sd = res["results"]["sd"]
+    assert sd[0] > sd[2]
+    assert res["N"] == next((N for N, s in zip(cands, sd) if s < 1), None)
+    with pytest.raises(ValueError, match="Length of 'theta'"):
+        engine.suggest_N(model, theta[:2])
+
+
+def test_suggest_N_bsm_and_growth(engine):
+    model = data.poisson_bsm_model(60)
+    res = engine.suggest_N(model, np.asarray(model.theta) + 0.1, candidates=[20, 200], replications=12, seed=2)
+    assert np.all(np.isfinite(res["results"]["sd"])) and res["results"]["sd"][1] < res["results"]["sd"][0]
+    g = data.growth_model(40)
+    res = engine.suggest_N(g, np.asarray(g.theta), candidates=[50, 500], replications=12, seed=2)
+    assert np.all(np.isfinite(res["results"]["sd"])) and res["results"]["sd"][1] < res["results"]["sd"][0]
