@@ -288,7 +288,7 @@ def main():
         d2h = 8 * 2 * (n + 1) * N + 32
         e2e = {"value": world * reps * N * n / float(te[0]), "unit": "particle-steps/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "call": "bssm_b200_psi_filter (1 filter per call, alpha cube + weights to pinned host memory)",
+               "call": "bssm_b200_psi_filter (1 filter per call, alpha cube + weights to pinned host memory; finished blocks of columns are copied while the filter kernel runs)",
                "loglik_check": out.loglik}
 
     # ---- config 4: post_correct, 15000 draws x psi-APF N=256, sharded over the ranks

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 #include <limits>
@@ -322,6 +323,37 @@ struct Pool {
 };
 Pool g_pool;
 
+// Resources of the streaming fetch (run_fetch_streaming), created once per process:
+// cudaHostAlloc / cudaFreeHost synchronise the device and cost milliseconds per call.
+struct StreamCtx {
+  std::mutex mu;          // one streaming call at a time
+  int* flag = nullptr;    // host-mapped progress word
+  int* dflag = nullptr;   // its device address
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t done = nullptr;
+  int device = -1;
+  cudaError_t ensure() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (flag && dev == device) return cudaSuccess;
+    release();
+    if ((e = cudaHostAlloc((void**)&flag, sizeof(int), cudaHostAllocMapped)) != cudaSuccess) return e;
+    if ((e = cudaHostGetDevicePointer((void**)&dflag, flag, 0)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming)) != cudaSuccess) return e;
+    device = dev;
+    return cudaSuccess;
+  }
+  void release() {
+    if (done) cudaEventDestroy(done);
+    if (s2) cudaStreamDestroy(s2);
+    if (flag) cudaFreeHost(flag);
+    done = nullptr; s2 = nullptr; flag = nullptr; dflag = nullptr; device = -1;
+  }
+};
+StreamCtx g_sctx;
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
@@ -513,6 +545,10 @@ int bssm_b200_set_device(int device) {
 
 void bssm_b200_shutdown(void) {
   g_pool.release_all();
+  {
+    std::lock_guard<std::mutex> g(g_sctx.mu);
+    g_sctx.release();
+  }
   int cnt = 0;
   if (cudaGetDeviceCount(&cnt) == cudaSuccess && cnt > 0) cudaDeviceSynchronize();
   cudaGetLastError();
@@ -754,8 +790,8 @@ int bssm_b200_job_create_ung(const bssm_ung_model* M, int method, uint32_t nsim,
   return create_ung_job(M, method, nsim, seed, n_filters, first_filter_id, out_flags, post, nullptr, nullptr, job);
 }
 
-int bssm_b200_job_run(bssm_b200_job* J, float* ms_out) {
-  if (!J) return fail(BSSM_B200_ERR_ARG, "null job");
+// enqueues the pre-pass and the filter kernel(s) on the job's stream (events 0..2)
+static int job_launch_filters(bssm_b200_job* J) {
   int rc;
   J->launches = 0;
   CU(cudaEventRecord(J->ev[0], J->stream));
@@ -783,6 +819,12 @@ int bssm_b200_job_run(bssm_b200_job* J, float* ms_out) {
     J->launches += 1;
   }
   CU(cudaEventRecord(J->ev[2], J->stream));
+  return 0;
+}
+
+// post-processing kernels, synchronisation, timings
+static int job_finish(bssm_b200_job* J, float* ms_out) {
+  int rc;
   if (J->post != BSSM_POST_NONE && (rc = run_post(J))) return rc;
   CU(cudaEventRecord(J->ev[3], J->stream));
   CU(cudaStreamSynchronize(J->stream));
@@ -794,6 +836,12 @@ int bssm_b200_job_run(bssm_b200_job* J, float* ms_out) {
   if (ms_out) *ms_out = tot;
   J->has_run = true;
   return 0;
+}
+
+int bssm_b200_job_run(bssm_b200_job* J, float* ms_out) {
+  if (!J) return fail(BSSM_B200_ERR_ARG, "null job");
+  int rc = job_launch_filters(J);
+  return rc ? rc : job_finish(J, ms_out);
 }
 
 int bssm_b200_job_kernel_ms(const bssm_b200_job* J, float ms[3]) {
@@ -866,7 +914,7 @@ int bssm_b200_job_fetch(bssm_b200_job* J, uint32_t f, bssm_filter_out* out) {
     if (stopped >= 0) // zero the unreached tail in the time-major source first
       CU(cudaMemsetAsync((void*)(src + (size_t)cols_alpha * m * N), 0, sizeof(double) * (size_t)(n + 1 - cols_alpha) * m * N, J->stream));
     dim3 grid(cdiv(N, 32), cdiv(rows, 32));
-    pf::transpose_to_cube_kernel<<<grid, dim3(32, 8), 0, J->stream>>>(src, J->cube.p, rows, N);
+    pf::transpose_to_cube_kernel<<<grid, dim3(32, 8), 0, J->stream>>>(src, J->cube.p, rows, N, 0u, rows);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out->alpha, J->cube.p, sizeof(double) * (size_t)rows * N, cudaMemcpyDeviceToHost, J->stream));
     CU(cudaStreamSynchronize(J->stream));
@@ -1122,10 +1170,102 @@ int bssm_b200_job_create_mng_psi(const bssm_mng_model* M, uint32_t nsim, uint32_
   return create_mng_job(M, BSSM_METHOD_PSI, nsim, seed, n_filters, first_filter_id, out_flags, post, job);
 }
 
-static int run_fetch_destroy(bssm_b200_job* J, bssm_filter_out* out) {
+// One-shot calls with large host outputs: ship finished blocks of time points to the host
+// WHILE the persistent filter kernel is still running.  The kernel publishes its progress
+// (complete columns) through host-mapped memory every `every` steps; this thread polls it and
+// enqueues, on a second stream, the transpose of the block into the cube layout and the strided
+// device-to-host copies.  For C2 (1.05 GB of outputs, PCIe-bound) the call then takes about
+// max(kernel, copy) instead of kernel + copy.  Falls back to the plain path when there is nothing
+// to stream; a filter that stopped early is re-fetched the plain way (zero-filled tail).
+static int run_fetch_streaming(bssm_b200_job* J, bssm_filter_out* out) {
+  const bool smoothed = J->post == BSSM_POST_SMOOTHER || J->post == BSSM_POST_SMOOTHER_MERGE;
+  const bool s_alpha = out->alpha && J->keep_alpha && !smoothed; // the smoother rewrites alpha afterwards
+  const bool s_w = out->weights && J->keep_weights;
+  const bool s_i = out->indices && J->keep_indices;
+  const int n = J->n, m = J->m;
+  const uint32_t N = J->N;
+  const size_t bytes = (size_t)N * (n + 1) * 8 * ((s_alpha ? m : 0) + (s_w ? 1 : 0));
+  const size_t min_bytes = (size_t)env_int("BSSM_B200_STREAM_MIN_MB", 32) << 20; // tests force 0
+  if (J->n_filters != 1 || bytes == 0 || bytes < min_bytes || env_int("BSSM_B200_NO_STREAMING", 0)) {
+    float ms = 0;
+    int rc = bssm_b200_job_run(J, &ms);
+    return rc ? rc : bssm_b200_job_fetch(J, 0, out);
+  }
+  int rc;
+  std::lock_guard<std::mutex> sguard(g_sctx.mu);
+  CU(g_sctx.ensure());
+  StreamCtx& R = g_sctx;
+  *R.flag = 0;
+  int* dflag = R.dflag;
+  const int every = std::max(8, (n + 1) / std::max(1, env_int("BSSM_B200_STREAM_CHUNKS", 6)));
+  const bool dbg = env_int("BSSM_B200_STREAM_DEBUG", 0) != 0;
+  auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+  const double t_start = now_ms();
+  J->fp.progress = dflag; J->fp.progress_every = every;
+  const uint32_t rows = (uint32_t)(n + 1) * m;
+  if (s_alpha && (rc = J->cube.alloc((size_t)rows * N))) return rc;
+  if ((rc = job_launch_filters(J))) return rc;
+  CU(cudaEventRecord(R.done, J->stream));
+  J->fp.progress = nullptr;
+
+  int shipped = 0; // columns [0, shipped) are on their way to the host
+  auto ship = [&](int c1) -> int { // columns [shipped, c1)
+    const int c0 = shipped;
+    if (c1 <= c0) return 0;
+    if (s_alpha) {
+      const uint32_t rb = (uint32_t)c0 * m, re = (uint32_t)c1 * m;
+      dim3 grid(cdiv(N, 32), cdiv(re - rb, 32));
+      pf::transpose_to_cube_kernel<<<grid, dim3(32, 8), 0, R.s2>>>(J->alpha_tm.p, J->cube.p, rows, N, rb, re);
+      CU(cudaGetLastError());
+      CU(cudaMemcpy2DAsync(out->alpha + rb, (size_t)rows * 8, J->cube.p + rb, (size_t)rows * 8, (size_t)(re - rb) * 8, N,
+                           cudaMemcpyDeviceToHost, R.s2));
+    }
+    if (s_w)
+      CU(cudaMemcpyAsync(out->weights + (size_t)N * c0, J->weights.p + (size_t)N * c0, sizeof(double) * (size_t)N * (c1 - c0),
+                         cudaMemcpyDeviceToHost, R.s2));
+    if (s_i) {
+      const int i1 = std::min(c1, n);
+      if (i1 > c0)
+        CU(cudaMemcpyAsync(out->indices + (size_t)N * c0, J->indices.p + (size_t)N * c0,
+                           sizeof(uint32_t) * (size_t)N * (i1 - c0), cudaMemcpyDeviceToHost, R.s2));
+    }
+    if (dbg) fprintf(stderr, "[stream] %.2f ms: shipped columns [%d, %d)\n", now_ms() - t_start, c0, c1);
+    shipped = c1;
+    return 0;
+  };
+  for (;;) {
+    const int p = *(volatile int*)R.flag;
+    if (p > shipped) { if ((rc = ship(p))) return rc; continue; }
+    const cudaError_t q = cudaEventQuery(R.done);
+    if (q == cudaSuccess) break;
+    if (q != cudaErrorNotReady) return fail(BSSM_B200_ERR_CUDA, std::string("filter kernel: ") + cudaGetErrorString(q));
+  }
+  if (dbg) fprintf(stderr, "[stream] %.2f ms: filter kernel done\n", now_ms() - t_start);
+  int32_t stopped = -1;
+  CU(cudaMemcpyAsync(&stopped, J->stopped.p, sizeof(int32_t), cudaMemcpyDeviceToHost, J->stream));
+  CU(cudaStreamSynchronize(J->stream));
   float ms = 0;
-  int rc = bssm_b200_job_run(J, &ms);
-  if (!rc) rc = bssm_b200_job_fetch(J, 0, out);
+  if (stopped >= 0) { // rare: let the plain path zero-fill what the filter never reached
+    CU(cudaStreamSynchronize(R.s2));
+    if ((rc = job_finish(J, &ms))) return rc;
+    return bssm_b200_job_fetch(J, 0, out);
+  }
+  if ((rc = ship(n + 1))) return rc;
+  if ((rc = job_finish(J, &ms))) return rc; // filter summary / smoother on the job's stream, overlapping the last copies
+  bssm_filter_out rest = *out;
+  if (s_alpha) rest.alpha = nullptr;
+  if (s_w) rest.weights = nullptr;
+  if (s_i) rest.indices = nullptr;
+  rc = bssm_b200_job_fetch(J, 0, &rest);
+  out->loglik = rest.loglik; out->stopped_at = rest.stopped_at; out->approx_loglik = rest.approx_loglik;
+  out->device_ms = rest.device_ms;
+  CU(cudaStreamSynchronize(R.s2));
+  if (dbg) fprintf(stderr, "[stream] %.2f ms: all copies done\n", now_ms() - t_start);
+  return rc;
+}
+
+static int run_fetch_destroy(bssm_b200_job* J, bssm_filter_out* out) {
+  int rc = run_fetch_streaming(J, out);
   bssm_b200_job_destroy(J);
   return rc;
 }
@@ -1187,7 +1327,7 @@ int bssm_b200_gaussian_psi_smoother(const bssm_ung_model* M, uint32_t nsim, uint
   else if (m == 2) pf::gaussian_psi_kernel<2><<<g1, 128>>>(ah.p, Lt.p, Ct.p, tm.p, nsim, n, seed);
   else pf::gaussian_psi_kernel<3><<<g1, 128>>>(ah.p, Lt.p, Ct.p, tm.p, nsim, n, seed);
   CU(cudaGetLastError());
-  pf::transpose_to_cube_kernel<<<dim3(cdiv(nsim, 32), cdiv(rows, 32)), dim3(32, 8)>>>(tm.p, cube.p, rows, nsim);
+  pf::transpose_to_cube_kernel<<<dim3(cdiv(nsim, 32), cdiv(rows, 32)), dim3(32, 8)>>>(tm.p, cube.p, rows, nsim, 0u, rows);
   CU(cudaGetLastError());
   CU(cudaMemcpy(alpha, cube.p, sizeof(double) * (size_t)rows * nsim, cudaMemcpyDeviceToHost));
   return 0;
@@ -1729,11 +1869,7 @@ static int one_shot(const bssm_ung_model* M, int method, uint32_t nsim, uint32_t
   bssm_b200_job* J = nullptr;
   int rc = bssm_b200_job_create_ung(M, method, nsim, seed, 1, 0, flags, post, &J);
   if (rc) return rc;
-  float ms = 0;
-  rc = bssm_b200_job_run(J, &ms);
-  if (!rc) rc = bssm_b200_job_fetch(J, 0, out);
-  bssm_b200_job_destroy(J);
-  return rc;
+  return run_fetch_destroy(J, out);
 }
 
 int bssm_b200_bsf(const bssm_ung_model* M, uint32_t nsim, uint32_t seed, bssm_filter_out* out) {

@@ -69,6 +69,10 @@ struct FilterParams {
   //   [0] log-weights  [1] max collective  [2] exp + thresholds + terms
   //   [3] scan collective  [4] counts + normals + scatter + barrier  [5] gather + propagate
   unsigned long long* phase_cycles;
+  // streaming fetch: when non-null (host-mapped memory, one int per filter), rank 0 publishes
+  // the number of complete columns every `progress_every` steps with a system-scope fence
+  int* progress;
+  int progress_every;
 };
 
 // ---------------------------------------------------------- synchronisation
@@ -619,6 +623,11 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
 #endif
     coll.barrier_wait();
     PF_PHASE(4)
+    // columns 0..t of state, weights and ancestors are complete and visible to this thread
+    if (fp.progress && rank == 0 && threadIdx.x == 0 && ((t + 1) % fp.progress_every) == 0) {
+      __threadfence_system();
+      *((volatile int*)fp.progress + fidx) = t + 1;
+    }
 
     // ---- gather ancestors, propagate to column t+1 (reference :657-670)
     {

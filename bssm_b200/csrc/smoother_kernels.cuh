@@ -281,18 +281,20 @@ __global__ void postcorr_merge_kernel(const double* __restrict__ mean_i, const d
 // alpha_tm [(t*M+d)*N + i]  ->  cube [d + M*(t + n1*i)]  (Armadillo cube
 // m x (n+1) x N, src/R_bootstrap_filter.cpp:162).  A plain tiled transpose of
 // the (n1*M) x N matrix; both sides coalesced.
+// Rows [rbeg, rend) only: the streaming fetch transposes a block of finished
+// time points while the filter kernel is still running.
 __global__ void transpose_to_cube_kernel(const double* __restrict__ tm, double* __restrict__ cube,
-                                         uint32_t rows /* n1*M */, uint32_t N) {
+                                         uint32_t rows /* n1*M */, uint32_t N, uint32_t rbeg, uint32_t rend) {
   __shared__ double tile[32][33];
-  const uint32_t r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const uint32_t r0 = rbeg + blockIdx.y * 32, c0 = blockIdx.x * 32;
   for (int k = threadIdx.y; k < 32; k += blockDim.y) {
     uint32_t r = r0 + k, c = c0 + threadIdx.x;
-    if (r < rows && c < N) tile[k][threadIdx.x] = tm[(size_t)r * N + c];
+    if (r < rend && c < N) tile[k][threadIdx.x] = tm[(size_t)r * N + c];
   }
   __syncthreads();
   for (int k = threadIdx.y; k < 32; k += blockDim.y) {
     uint32_t c = c0 + k, r = r0 + threadIdx.x;
-    if (r < rows && c < N) cube[(size_t)c * rows + r] = tile[threadIdx.x][k];
+    if (r < rend && c < N) cube[(size_t)c * rows + r] = tile[threadIdx.x][k];
   }
 }
 

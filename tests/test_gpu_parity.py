@@ -335,3 +335,23 @@ def test_psi_apf_m3_and_missing_parity(engine):
     refb = orc.bsf_filter(model, 300, seed=6)
     resb = engine.bootstrap_filter(model, 300, seed=6, return_indices=True)
     assert np.array_equal(resb["indices"], refb.indices) and resb["logLik"] == refb.loglik
+
+
+@pytest.mark.parametrize("method", ["psi", "bsf"])
+def test_streaming_fetch_matches_plain_fetch(engine, method, monkeypatch):
+    """one-shot calls ship finished blocks of columns to the host while the filter kernel runs
+    (run_fetch_streaming in api.cu); forced on here, the outputs must equal the plain path's"""
+    model = data.svm_model(150, missing=(20,))
+    monkeypatch.setenv("BSSM_B200_NO_STREAMING", "1")
+    plain = engine.bootstrap_filter(model, 3000, seed=5, return_indices=True) if method == "bsf" else \
+        engine.particle_smoother(model, 3000, method="psi", seed=5, return_indices=True)
+    monkeypatch.delenv("BSSM_B200_NO_STREAMING")
+    monkeypatch.setenv("BSSM_B200_STREAM_MIN_MB", "0")
+    stream = engine.bootstrap_filter(model, 3000, seed=5, return_indices=True) if method == "bsf" else \
+        engine.particle_smoother(model, 3000, method="psi", seed=5, return_indices=True)
+    for key in ("alpha", "weights", "indices"):
+        assert np.array_equal(plain[key], stream[key]), key
+    assert plain["logLik"] == stream["logLik"]
+    for key in ("at", "att", "Pt", "Ptt", "alphahat", "Vt"):
+        if key in plain:
+            assert np.array_equal(plain[key], stream[key]), key
