@@ -289,19 +289,32 @@ def n_draws(mcmc_output, is_type):
 
 
 def post_correct(model, mcmc_output, particles, threads=1, is_type="is2", seed=1, draw_range=None,
-                 return_loglik=False):
+                 return_loglik=False, L=None):
     """post_correct, R/post_correction.R:245-308 (nongaussian branch).
 
     mcmc_output: dict with theta (n_stored x n_par), counts (n_stored), modes
     (n x n_stored), output_type (1 full / 2 summary / 3 theta) and posterior.
     `threads` is accepted for parity and ignored (results do not depend on it).
     draw_range = (begin, end) computes only that shard of the (expanded) draws.
+
+    ssm_sde models: the correction phase of run_mcmc.ssm_sde (is_correction_bsf on the fine mesh
+    L, src/approx_mcmc.cpp:522-591); mcmc_output then carries approx_loglik (n_stored) instead of modes.
     """
     from ._lib import PostcorrOut
     N, seed = _check_particles(model, particles, seed)
     it = {"is1": 1, "is2": 2, "is3": 3}[is_type.lower()]
     ot = int(mcmc_output.get("output_type", 3))
-    theta, counts, modes = _postcorr_inputs(model, mcmc_output)
+    if model.cls == "ssm_sde":
+        if L is None or int(L) < 1:
+            raise ValueError("Discretization level L must be larger than 0.")
+        theta = np.asfortranarray(np.asarray(mcmc_output["theta"], dtype=np.float64).T)
+        counts = np.ascontiguousarray(mcmc_output["counts"], dtype=np.uint32)
+        approx = _lib.f64(np.ravel(mcmc_output["approx_loglik"]))
+        if theta.shape[1] != counts.size or approx.size != counts.size:
+            raise ValueError("theta, counts and approx_loglik disagree on the number of stored draws")
+        modes = None
+    else:
+        theta, counts, modes = _postcorr_inputs(model, mcmc_output)
     total = n_draws(mcmc_output, it)
     b, e = (0, total) if draw_range is None else draw_range
     nd = e - b
@@ -315,7 +328,11 @@ def post_correct(model, mcmc_output, particles, threads=1, is_type="is2", seed=1
     out.weights, out.posterior, out.alpha = dptr(w), dptr(post), dptr(alpha)
     out.alphahat, out.Vt, out.loglik = dptr(ah), dptr(Vt), dptr(ll)
     ms = model.c_struct()
-    if model.cls == "ssm_nlg":  # post_correct -> postcorrection_nonlinear, R/post_correction.R:272-283
+    if model.cls == "ssm_sde":
+        check(lib().bssm_b200_is_correction_bsf_sde(
+            C.byref(ms), int(L), ot, N, seed, int(threads), it, uptr(counts), dptr(theta), theta.shape[0],
+            dptr(approx), counts.size, b, e, C.byref(out)))
+    elif model.cls == "ssm_nlg":  # post_correct -> postcorrection_nonlinear, R/post_correction.R:272-283
         check(lib().bssm_b200_postcorrection_nonlinear(
             C.byref(ms), ot, N, seed, int(threads), it, uptr(counts), dptr(theta), theta.shape[0],
             dptr(modes), counts.size, b, e, C.byref(out)))

@@ -422,7 +422,7 @@ struct bssm_b200_job {
   pf::NlgParams np{};
   pf::SdeParams sp{};
   int sde_model_id = 0;
-  DevBuf<double> lgy;
+  DevBuf<double> lgy, theta_f;
   pf::MngParams gp{};
   pf::NlgPsiParams npp{};
   DevBuf<double> stepc;
@@ -494,7 +494,11 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
     return launch_status(pfl::launch_nlg_psi(fp, npp, J->geo, nf, J->stream), "nlg psi filter");
   }
   if (J->kind == KIND_NLG) return launch_status(pfl::launch_nlg_bsf(fp, J->np, J->geo, nf, J->stream), "nlg bsf");
-  if (J->kind == KIND_SDE) return launch_status(pfl::launch_sde_bsf(J->sde_model_id, fp, J->sp, J->geo, nf, J->stream), "sde bsf");
+  if (J->kind == KIND_SDE) {
+    pf::SdeParams sp = J->sp;
+    if (sp.theta_f) sp.theta_f += (size_t)6 * f0;
+    return launch_status(pfl::launch_sde_bsf(J->sde_model_id, fp, sp, J->geo, nf, J->stream), "sde bsf");
+  }
   if (J->kind == KIND_MNG) {
     if (J->method == BSSM_METHOD_PSI) {
       pf::MngParams gp = J->gp;
@@ -1044,9 +1048,17 @@ int bssm_b200_job_create_nlg_psi(const bssm_nlg_model* M, uint32_t nsim, uint32_
   return 0;
 }
 
-int bssm_b200_job_create_sde(const bssm_sde_model* M, uint32_t nsim, uint32_t L, uint32_t seed,
-                             uint32_t n_filters, uint32_t first_filter_id, int out_flags, int post,
-                             bssm_b200_job** job) {
+// the derived parameters the device functors read, for one theta: {th0, th1, th2, logsd, e0, e2}
+static void sde_theta_block(int model_id, const double* th, double* b) {
+  b[0] = th[0]; b[1] = th[1]; b[2] = th[2]; b[3] = 0.0; b[4] = 0.0; b[5] = 0.0;
+  if (model_id == BSSM_SDE_GBM) b[3] = pf_log(th[2]);
+  else { b[4] = pf_exp(th[0]); b[5] = pf_exp(th[2]); } // Poisson-OU: theta = (log rho, nu, log sigma)
+}
+
+// draw_theta: null (all filters share model->theta) or n_par x n_filters, one theta per filter
+static int create_sde_job(const bssm_sde_model* M, uint32_t nsim, uint32_t L, uint32_t seed,
+                          uint32_t n_filters, uint32_t first_filter_id, int out_flags, int post,
+                          const double* draw_theta, uint32_t n_par, bssm_b200_job** job) {
   if (!M || !job || !M->y || !M->theta) return fail(BSSM_B200_ERR_ARG, "null argument");
   *job = nullptr;
   if (M->model_id != BSSM_SDE_GBM && M->model_id != BSSM_SDE_POISSON_OU)
@@ -1055,8 +1067,10 @@ int bssm_b200_job_create_sde(const bssm_sde_model* M, uint32_t nsim, uint32_t L,
   if (L < 1 || L > 20) return fail(BSSM_B200_ERR_ARG, "discretisation level L must be in 1..20");
   bssm_b200_job* J = new bssm_b200_job();
   struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
-  int rc = job_common(J, KIND_SDE, M->n, 1, 1, nsim, seed, n_filters, first_filter_id, out_flags, post);
+  int rc = job_common(J, KIND_SDE, M->n, 1, 1, nsim, seed, n_filters, first_filter_id, out_flags,
+                      post > BSSM_POST_SMOOTHER ? BSSM_POST_NONE : post);
   if (rc) return rc;
+  J->post = post; // PICK / SMOOTHER_MERGE: the IS-correction drivers
   if ((rc = J->y.upload(M->y, M->n))) return rc;
   pf::SdeParams& sp = J->sp;
   sp.n = M->n; sp.y = J->y.p; sp.x0 = M->x0; sp.positive = M->positive ? 1 : 0;
@@ -1065,11 +1079,20 @@ int bssm_b200_job_create_sde(const bssm_sde_model* M, uint32_t nsim, uint32_t L,
   sp.sqdt = std::sqrt(sp.dt);
   sp.th0 = M->theta[0]; sp.th1 = M->theta[1]; sp.th2 = M->theta[2];
   J->sde_model_id = M->model_id;
-  sp.lgy = nullptr; sp.logsd = 0.0; sp.e0 = 0.0; sp.e2 = 0.0;
-  if (M->model_id == BSSM_SDE_GBM) {
-    sp.logsd = pf_log(sp.th2);
-  } else { // Poisson-OU: theta = (log rho, nu, log sigma), R/cpp_example_models.R:37-39
-    sp.e0 = pf_exp(sp.th0); sp.e2 = pf_exp(sp.th2);
+  sp.lgy = nullptr; sp.theta_f = nullptr;
+  {
+    double b[6];
+    sde_theta_block(M->model_id, M->theta, b);
+    sp.logsd = b[3]; sp.e0 = b[4]; sp.e2 = b[5];
+  }
+  if (draw_theta) {
+    if (n_par < 3) return fail(BSSM_B200_ERR_ARG, "ssm_sde registry models need 3 parameters");
+    std::vector<double> blk((size_t)6 * n_filters);
+    for (uint32_t f = 0; f < n_filters; ++f) sde_theta_block(M->model_id, draw_theta + (size_t)f * n_par, &blk[(size_t)6 * f]);
+    if ((rc = J->theta_f.upload(blk.data(), blk.size()))) return rc;
+    sp.theta_f = J->theta_f.p;
+  }
+  if (M->model_id == BSSM_SDE_POISSON_OU) { // log y! per time point, R/cpp_example_models.R:37-39
     std::vector<double> lg(M->n, 0.0);
     for (int t = 0; t < M->n; ++t) if (std::isfinite(M->y[t])) lg[t] = std::lgamma(M->y[t] + 1.0);
     if ((rc = J->lgy.upload(lg.data(), M->n))) return rc;
@@ -1079,6 +1102,12 @@ int bssm_b200_job_create_sde(const bssm_sde_model* M, uint32_t nsim, uint32_t L,
   guard.j = nullptr;
   *job = J;
   return 0;
+}
+
+int bssm_b200_job_create_sde(const bssm_sde_model* M, uint32_t nsim, uint32_t L, uint32_t seed,
+                             uint32_t n_filters, uint32_t first_filter_id, int out_flags, int post,
+                             bssm_b200_job** job) {
+  return create_sde_job(M, nsim, L, seed, n_filters, first_filter_id, out_flags, post, nullptr, 0, job);
 }
 
 static int create_mng_job(const bssm_mng_model* M, int method, uint32_t nsim, uint32_t seed, uint32_t n_filters,
@@ -1563,7 +1592,8 @@ int bssm_b200_job_create_postcorr(const bssm_ung_model* M, const bssm_theta_map*
 template <class MakeJob>
 static int postcorr_driver(int n, int m, int output_type, uint32_t nsim, int is_type, const uint32_t* counts,
                            uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end, bssm_postcorr_out* out,
-                           MakeJob&& make_job) {
+                           MakeJob&& make_job, const double* approx_ll = nullptr, bool posterior_adds_approx = false) {
+  // approx_ll (per stored draw): is_correction_bsf weights exp(loglik - approx_loglik), src/approx_mcmc.cpp:478
   int rc;
   if (!out || !out->weights || !out->posterior) return fail(BSSM_B200_ERR_ARG, "weights and posterior outputs are required");
   if (output_type < 1 || output_type > 3) return fail(BSSM_B200_ERR_ARG, "output_type must be 1, 2 or 3");
@@ -1614,11 +1644,16 @@ static int postcorr_driver(int n, int m, int output_type, uint32_t nsim, int is_
     CU(cudaMemcpy(ll.data(), J->loglik.p, sizeof(double) * nf, cudaMemcpyDeviceToHost));
     for (uint32_t f = 0; f < nf; ++f) {
       const size_t o = (size_t)(d0 - draw_begin) + f;
-      const double w = pf_exp(ll[f]);         // weight_storage(i) = exp(loglik), :385
-      out->weights[o] = w;
-      out->posterior[o] = 0.0 + 0.0 + pf_log(w); // prior + approx_loglik + log(weight), :425-426
+      const double off = approx_ll ? approx_ll[dl.src[d0 + f]] : 0.0;
       if (out->loglik) out->loglik[o] = ll[f];
+      ll[f] = ll[f] - off;
+      const double w = pf_exp(ll[f]);         // weight_storage(i) = exp(loglik [- approx_loglik]), :385, :478
+      out->weights[o] = w;
+      // prior (0: the caller adds it) + approx_loglik + log(weight), :425-426, :520, :590
+      out->posterior[o] = 0.0 + (posterior_adds_approx ? off : 0.0) + pf_log(w);
     }
+    if (approx_ll && output_type == 2) // the merge below weights the draws by exp(J->loglik)
+      CU(cudaMemcpyAsync(J->loglik.p, ll.data(), sizeof(double) * nf, cudaMemcpyHostToDevice, J->stream));
     if (output_type == 1) {
       CU(cudaMemcpy(out->alpha + (size_t)(d0 - draw_begin) * n1 * m, J->traj.p, sizeof(double) * nf * n1 * m, cudaMemcpyDeviceToHost));
     } else if (output_type == 2) {
@@ -1782,6 +1817,27 @@ int bssm_b200_postcorrection_nonlinear(const bssm_nlg_model* M, int output_type,
                          [&](const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N, int post, bssm_b200_job** J) {
                            return make_nlg_draw_job(M, dl, d0, d1, N, seed, theta, n_par, modes, post, J);
                          });
+}
+
+// ------------------------------------------------- is_correction_bsf (ssm_sde)
+int bssm_b200_is_correction_bsf_sde(const bssm_sde_model* M, uint32_t L_f, int output_type, uint32_t nsim,
+                                    uint32_t seed, uint32_t n_threads, int is_type, const uint32_t* counts,
+                                    const double* theta, uint32_t n_par, const double* approx_loglik,
+                                    uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
+                                    bssm_postcorr_out* out) {
+  (void)n_threads;
+  if (!M || !counts || !theta || !approx_loglik || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
+  return postcorr_driver(
+      M->n, 1, output_type, nsim, is_type, counts, n_stored, draw_begin, draw_end, out,
+      [&](const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N, int post, bssm_b200_job** J) {
+        const uint32_t nf = d1 - d0;
+        std::vector<double> th((size_t)n_par * nf);
+        for (uint32_t f = 0; f < nf; ++f)
+          memcpy(&th[(size_t)n_par * f], theta + (size_t)dl.src[d0 + f] * n_par, sizeof(double) * n_par);
+        int flags = post == BSSM_POST_NONE ? 0 : (BSSM_OUT_ALPHA | BSSM_OUT_INDICES);
+        return create_sde_job(M, N, L_f, seed, nf, d0, flags, post, th.data(), n_par, J);
+      },
+      approx_loglik, /*posterior_adds_approx=*/true);
 }
 
 // ------------------------------------------------------------- suggest_N

@@ -211,6 +211,8 @@ struct SdeParams {
   double th0, th1, th2;
   double logsd;     // GBM: log(theta2)
   double e0, e2;    // Poisson-OU: exp(theta0), exp(theta2)
+  // IS-correction (one theta per filter): 6 doubles per filter {th0, th1, th2, logsd, e0, e2}, or null
+  const double* theta_f;
 };
 
 struct SdeGbm {
@@ -240,13 +242,22 @@ struct SdePoissonOu {
   }
 };
 
-template <class Fn>
+// PerFilter: every filter of the launch has its own theta (is_correction_bsf for ssm_sde,
+// src/approx_mcmc.cpp:522-591); otherwise the parameters stay in the constant bank.
+template <class Fn, bool PerFilter = false>
 struct SdeBsf {
   static constexpr int M = 1;
   typedef SdeParams Params;
+  SdeParams loc;
   const SdeParams& mp;
   double y, lgy;
-  __device__ SdeBsf(const SdeParams& p, uint32_t) : mp(p), y(0.0), lgy(0.0) {}
+  __device__ SdeBsf(const SdeParams& p, uint32_t f) : mp(PerFilter ? loc : p), y(0.0), lgy(0.0) {
+    if (PerFilter) {
+      loc = p;
+      const double* th = p.theta_f + (size_t)6 * f;
+      loc.th0 = th[0]; loc.th1 = th[1]; loc.th2 = th[2]; loc.logsd = th[3]; loc.e0 = th[4]; loc.e2 = th[5];
+    }
+  }
   __device__ double loglik0() const { return 0.0; }
   __device__ double loglik_end() const { return 0.0; }
   __device__ bool observed(int t) const { return pf_isfinite(mp.y[t]); }
@@ -295,5 +306,7 @@ struct SdeBsf {
 };
 typedef SdeBsf<SdeGbm> SdeGbmBsf;
 typedef SdeBsf<SdePoissonOu> SdePoissonOuBsf;
+typedef SdeBsf<SdeGbm, true> SdeGbmBsfDraws;
+typedef SdeBsf<SdePoissonOu, true> SdePoissonOuBsfDraws;
 
 } // namespace pf

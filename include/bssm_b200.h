@@ -341,6 +341,19 @@ int bssm_b200_postcorrection_nongaussian(const bssm_ung_model* model, const bssm
                                          uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
                                          bssm_postcorr_out* out);
 
+/* replaces: the draw loop of approx_mcmc::is_correction_bsf<ssm_sde> (src/approx_mcmc.cpp:522-591),
+ *           the correction phase of sde_is_mcmc (src/R_sde.cpp:221-282): one bootstrap filter per
+ *           stored draw on the FINE mesh L_f at that draw's theta;
+ *           weight_i = exp(loglik_i - approx_loglik_i), posterior_i = approx_loglik_i + log weight_i
+ *           (the caller adds the prior).  theta is n_par x n_stored, approx_loglik has n_stored
+ *           entries (the coarse-mesh estimates stored by the MCMC phase).  Other arguments and
+ *           outputs as bssm_b200_postcorrection_nongaussian; draws shard the same way. */
+int bssm_b200_is_correction_bsf_sde(const bssm_sde_model* model, uint32_t L_f, int output_type,
+                                    uint32_t nsim, uint32_t seed, uint32_t n_threads, int is_type,
+                                    const uint32_t* counts, const double* theta, uint32_t n_par,
+                                    const double* approx_loglik, uint32_t n_stored,
+                                    uint32_t draw_begin, uint32_t draw_end, bssm_postcorr_out* out);
+
 /* replaces: suggest_n_nongaussian(model_, theta, candidates, replications, seed, model_type)
  *           src/R_postcorrection.cpp:14-104: for every candidate particle count, the standard
  *           deviation (arma::stddev, N - 1) of `replications` psi-APF log-likelihood estimates at

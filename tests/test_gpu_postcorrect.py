@@ -184,3 +184,36 @@ def test_suggest_N_bsm_and_growth(engine):
     g = data.growth_model(40)
     res = engine.suggest_N(g, np.asarray(g.theta), candidates=[50, 500], replications=12, seed=2)
     assert np.all(np.isfinite(res["results"]["sd"])) and res["results"]["sd"][1] < res["results"]["sd"][0]
+
+
+@pytest.mark.parametrize("kind", ["gbm", "poisson_ou"])
+def test_sde_is_correction(engine, kind):
+    """correction phase of run_mcmc.ssm_sde: fine-mesh bootstrap filter per stored draw
+    (is_correction_bsf<ssm_sde>, src/approx_mcmc.cpp:522-591), weight = exp(loglik_f - approx_loglik)"""
+    model = data.gbm_model(30) if kind == "gbm" else data.poisson_ou_model(30)
+    rng = np.random.default_rng(3)
+    ns = 20
+    th0 = np.asarray(model.theta)
+    theta = th0[None, :] + 0.05 * rng.normal(size=(ns, 3))
+    if kind == "gbm":
+        theta[:, 1:] = np.abs(theta[:, 1:])
+    counts = (1 + rng.poisson(2, size=ns)).astype(np.uint32)
+    # coarse-mesh estimates as the MCMC phase would have stored them (any numbers do for parity)
+    approx = np.array([orc.sde_bsf_filter(engine.ssm_sde(model.y, kind, theta[i], model.x0, model.positive),
+                                          64, 1, seed=100 + i).loglik for i in range(ns)])
+    mo = {"theta": theta, "counts": counts, "approx_loglik": approx, "output_type": 3, "posterior": np.zeros(ns)}
+    ref = orc.is_correction_bsf_sde(model, mo, 128, 3, is_type=2, seed=4)
+    res = engine.post_correct(model, mo, 128, is_type="is2", seed=4, return_loglik=True, L=3)
+    assert np.array_equal(res["loglik"], ref.loglik)
+    assert np.array_equal(res["weights"], ref.weights)
+    np.testing.assert_allclose(res["posterior"], ref.posterior, rtol=1e-13, atol=1e-13)
+    assert np.all(np.abs(np.log(res["weights"])) < 5)  # fine vs coarse mesh estimates of the same likelihood
+    mo1 = dict(mo, output_type=1)
+    ref1 = orc.is_correction_bsf_sde(model, mo1, 64, 2, is_type=3, seed=6)
+    res1 = engine.post_correct(model, mo1, 64, is_type="is3", seed=6, L=2)
+    assert np.array_equal(res1["alpha"].view(np.uint64), ref1.alpha.view(np.uint64))
+    mo2 = dict(mo, output_type=2)
+    ref2 = orc.is_correction_bsf_sde(model, mo2, 32, 2, is_type=1, seed=8)
+    res2 = engine.post_correct(model, mo2, 32, is_type="is1", seed=8, L=2)
+    np.testing.assert_allclose(res2["alphahat"], ref2.alphahat, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(res2["Vt"], ref2.Vt, rtol=1e-9, atol=1e-13)
