@@ -355,3 +355,25 @@ def test_streaming_fetch_matches_plain_fetch(engine, method, monkeypatch):
     for key in ("at", "att", "Pt", "Ptt", "alphahat", "Vt"):
         if key in plain:
             assert np.array_equal(plain[key], stream[key]), key
+
+
+@pytest.mark.parametrize("N,n", [(2, 5), (3, 1), (33, 7), (101, 40), (1025, 12), (4097, 9), (6001, 6), (70001, 3)])
+def test_ragged_and_tiny_sizes_parity(engine, N, n):
+    """particle counts that are odd, below a warp, one past a geometry boundary (1024 / 4096) or not a
+    multiple of the per-thread tile: the unvectorised row stores and the padded lanes must not change
+    any output; n = 1 has a single resampling step"""
+    model = data.svm_model(max(n, 2))
+    if n == 1:
+        import bssm_b200
+        model = bssm_b200.svm(model.y[:1], 0.98, 0.2, sigma=1.0)
+    ref = orc.psi_filter(model, N, seed=9)
+    res = engine.particle_smoother(model, N, method="psi", seed=9, return_indices=True)
+    assert np.array_equal(res["indices"], ref.indices)
+    assert np.array_equal(res["weights"].view(np.uint64), ref.weights.view(np.uint64))
+    assert res["logLik"] == ref.loglik
+    sm = orc.filter_smoother(ref.alpha, ref.indices)
+    assert np.array_equal(np.transpose(res["alpha"], (1, 0, 2)).view(np.uint64), sm.view(np.uint64))
+    refb = orc.bsf_filter(model, N, seed=9)
+    resb = engine.bootstrap_filter(model, N, seed=9, return_indices=True)
+    assert np.array_equal(resb["indices"], refb.indices)
+    assert resb["logLik"] == pytest.approx(refb.loglik, rel=1e-13)
