@@ -289,13 +289,17 @@ def n_draws(mcmc_output, is_type):
 
 
 def post_correct(model, mcmc_output, particles, threads=1, is_type="is2", seed=1, draw_range=None,
-                 return_loglik=False, L=None):
+                 return_loglik=False, L=None, sampling_method="psi"):
     """post_correct, R/post_correction.R:245-308 (nongaussian branch).
 
     mcmc_output: dict with theta (n_stored x n_par), counts (n_stored), modes
     (n x n_stored), output_type (1 full / 2 summary / 3 theta) and posterior.
     `threads` is accepted for parity and ignored (results do not depend on it).
     draw_range = (begin, end) computes only that shard of the (expanded) draws.
+
+    sampling_method = "bsf": the correction phase of run_mcmc(..., sampling_method = "bsf")
+    (is_correction_bsf, src/approx_mcmc.cpp:447-518) for m = 1 ung-family models; mcmc_output carries
+    approx_loglik (n_stored) and the weights are exp(loglik_bsf - approx_loglik).
 
     ssm_sde models: the correction phase of run_mcmc.ssm_sde (is_correction_bsf on the fine mesh
     L, src/approx_mcmc.cpp:522-591); mcmc_output then carries approx_loglik (n_stored) instead of modes.
@@ -304,8 +308,11 @@ def post_correct(model, mcmc_output, particles, threads=1, is_type="is2", seed=1
     N, seed = _check_particles(model, particles, seed)
     it = {"is1": 1, "is2": 2, "is3": 3}[is_type.lower()]
     ot = int(mcmc_output.get("output_type", 3))
-    if model.cls == "ssm_sde":
-        if L is None or int(L) < 1:
+    if sampling_method not in ("psi", "bsf"):
+        raise ValueError("sampling_method must be 'psi' or 'bsf'")
+    bsf = sampling_method == "bsf" and model.cls != "ssm_sde"
+    if model.cls == "ssm_sde" or bsf:
+        if model.cls == "ssm_sde" and (L is None or int(L) < 1):
             raise ValueError("Discretization level L must be larger than 0.")
         theta = np.asfortranarray(np.asarray(mcmc_output["theta"], dtype=np.float64).T)
         counts = np.ascontiguousarray(mcmc_output["counts"], dtype=np.uint32)
@@ -328,7 +335,12 @@ def post_correct(model, mcmc_output, particles, threads=1, is_type="is2", seed=1
     out.weights, out.posterior, out.alpha = dptr(w), dptr(post), dptr(alpha)
     out.alphahat, out.Vt, out.loglik = dptr(ah), dptr(Vt), dptr(ll)
     ms = model.c_struct()
-    if model.cls == "ssm_sde":
+    if bsf:
+        tm = theta_map(model)
+        check(lib().bssm_b200_is_correction_bsf(
+            C.byref(ms), C.byref(tm), ot, N, seed, int(threads), it, uptr(counts), dptr(theta), theta.shape[0],
+            dptr(approx), counts.size, b, e, C.byref(out)))
+    elif model.cls == "ssm_sde":
         check(lib().bssm_b200_is_correction_bsf_sde(
             C.byref(ms), int(L), ot, N, seed, int(threads), it, uptr(counts), dptr(theta), theta.shape[0],
             dptr(approx), counts.size, b, e, C.byref(out)))

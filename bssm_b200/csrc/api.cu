@@ -525,6 +525,10 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
     if (up.phi_f) up.phi_f += f0;
     return launch_status(pfl::launch_ung_psi1(fp, up, J->geo, nf, J->stream), "psi filter");
   }
+  if (up.bsf_par) {
+    up.bsf_par += (size_t)7 * f0;
+    return launch_status(pfl::launch_ung_bsf_draws(fp, up, J->geo, nf, J->stream), "bsf (per-draw models)");
+  }
   if (J->m <= 2) return launch_status(pfl::launch_ung_bsf_a(J->m, J->k, fp, up, J->geo, nf, J->stream), "bsf (m,k)");
   return launch_status(pfl::launch_ung_bsf_b(J->m, J->k, fp, up, J->geo, nf, J->stream), "bsf (m,k)");
 }
@@ -625,6 +629,8 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
     return fail(BSSM_B200_ERR_ARG, "linear-Gaussian models: bootstrap filter only, H required "
                                    "(their psi 'filter' is bssm_b200_gaussian_psi_smoother)");
   if (method != BSSM_METHOD_PSI && method != BSSM_METHOD_BSF) return fail(BSSM_B200_ERR_ARG, "method must be 1 (psi) or 2 (bsf)");
+  if (method == BSSM_METHOD_BSF && draw_par && M->m != 1)
+    return fail(BSSM_B200_ERR_UNSUPPORTED, "per-draw bootstrap filters: m = 1 in this build");
   if (method == BSSM_METHOD_PSI && (M->m > 3 || (M->m != 1 && draw_par) || (M->m == 1 && dm)))
     return fail(BSSM_B200_ERR_UNSUPPORTED, "psi-APF: m <= 3 (and m = 1 for per-draw models) in this build");
   if (M->k > M->m) return fail(BSSM_B200_ERR_ARG, "k > m");
@@ -680,6 +686,24 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
     }
     if ((rc = J->HH_v.upload(HH.data(), n)) || (rc = J->hconst_v.upload(hc.data(), n))) return rc;
     up.HH = J->HH_v.p; up.hconst = J->hconst_v.p;
+  }
+
+  if (method == BSSM_METHOD_BSF && draw_par) {
+    // is_correction_bsf: one (T, R, a1, P1, C, phi) per filter; sqrt(P1) and the state-independent
+    // constants of the log-likelihood (they depend on phi) per filter on the host
+    if (m != 1 || gaussian) return fail(BSSM_B200_ERR_UNSUPPORTED, "per-draw bootstrap filters: m = 1, non-Gaussian observations");
+    std::vector<double> bp((size_t)7 * n_filters);
+    for (uint32_t f = 0; f < n_filters; ++f) {
+      const double* q = draw_par + (size_t)6 * f;
+      bssm_ung_model Mi = *M;
+      Mi.phi = q[5];
+      double* b = &bp[(size_t)7 * f];
+      b[0] = q[0]; b[1] = q[1]; b[2] = q[2];
+      b[3] = q[3] > 0.0 ? std::sqrt(q[3]) : 0.0; // chol of the positive-diagonal block, src/model_ssm_ung.cpp:616-618
+      b[4] = q[4]; b[5] = q[5]; b[6] = ung_dist_const(&Mi);
+    }
+    if ((rc = J->draw_par.upload(bp.data(), bp.size()))) return rc;
+    up.bsf_par = J->draw_par.p;
   }
 
   if (method == BSSM_METHOD_PSI && m > 1 && dm) {
@@ -1819,6 +1843,29 @@ int bssm_b200_postcorrection_nonlinear(const bssm_nlg_model* M, int output_type,
                          [&](const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N, int post, bssm_b200_job** J) {
                            return make_nlg_draw_job(M, dl, d0, d1, N, seed, theta, n_par, modes, post, J);
                          });
+}
+
+// ---------------------------------------------- is_correction_bsf (ung family)
+int bssm_b200_is_correction_bsf(const bssm_ung_model* M, const bssm_theta_map* map, int output_type,
+                                uint32_t nsim, uint32_t seed, uint32_t n_threads, int is_type,
+                                const uint32_t* counts, const double* theta, uint32_t n_par,
+                                const double* approx_loglik, uint32_t n_stored, uint32_t draw_begin,
+                                uint32_t draw_end, bssm_postcorr_out* out) {
+  (void)n_threads;
+  if (!M || !map || !counts || !theta || !approx_loglik || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
+  if (M->m != 1 || M->xbeta) return fail(BSSM_B200_ERR_UNSUPPORTED, "is_correction_bsf: m = 1 models without regressors in this build");
+  return postcorr_driver(
+      M->n, 1, output_type, nsim, is_type, counts, n_stored, draw_begin, draw_end, out,
+      [&](const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N, int post, bssm_b200_job** J) {
+        const uint32_t nf = d1 - d0;
+        std::vector<double> par((size_t)6 * nf);
+        for (uint32_t f = 0; f < nf; ++f) {
+          int rc = theta_to_par(M, map, theta + (size_t)dl.src[d0 + f] * n_par, n_par, &par[(size_t)6 * f]);
+          if (rc) return rc;
+        }
+        return create_ung_job(M, BSSM_METHOD_BSF, N, seed, nf, d0, 0, post, par.data(), nullptr, J);
+      },
+      approx_loglik, /*posterior_adds_approx=*/false);
 }
 
 // ------------------------------------------------- is_correction_bsf (ssm_sde)

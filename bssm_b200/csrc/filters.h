@@ -15,6 +15,7 @@ int launch_ung_psim(int m, const pf::FilterParams&, const pf::UngParams&, const 
 // k_ung_bsf_a.cu / k_ung_bsf_b.cu: bootstrap filter, (m, k) in {(1,1),(2,1),(2,2)} / {(3,2),(3,3)}
 int launch_ung_bsf_a(int m, int k, const pf::FilterParams&, const pf::UngParams&, const Geometry&, uint32_t nf, Stream);
 int launch_ung_bsf_b(int m, int k, const pf::FilterParams&, const pf::UngParams&, const Geometry&, uint32_t nf, Stream);
+int launch_ung_bsf_draws(const pf::FilterParams&, const pf::UngParams&, const Geometry&, uint32_t nf, Stream); // m = 1, one model per filter
 int occupancy_ung_bsf(const Geometry&, int* out);
 // k_mng.cu: multivariate-observation bootstrap filter and psi-APF (m <= 3)
 int launch_mng_bsf(int m, int k, const pf::FilterParams&, const pf::MngParams&, const Geometry&, uint32_t nf, Stream);

@@ -7,4 +7,7 @@ int launch_ung_bsf_b(int m, int k, const pf::FilterParams& fp, const pf::UngPara
   }
   return -1;
 }
+int launch_ung_bsf_draws(const pf::FilterParams& fp, const pf::UngParams& mp, const Geometry& g, uint32_t nf, Stream s) {
+  return launch<pf::UngBsfDraw>(fp, mp, g, nf, s);
+}
 } // namespace pfl

@@ -39,6 +39,9 @@ struct UngParams {
   // psi-APF (m > 1): per-filter strides of alphahat / (Lt, Ct) / (ytilde, Htilde, scales) / xbeta;
   // all zero when the replicates of a job share one approximation
   size_t fs_a, fs_m, fs_n, fs_x;
+  // bootstrap filter with one model per filter (is_correction_bsf, m = 1): 7 doubles per filter
+  // {T, R, a1, sqrt(P1), C, phi, loglik_const}, or null
+  const double* bsf_par;
 };
 
 // log g(y_t | signal) up to state-independent constants, :447-493
@@ -122,6 +125,44 @@ struct UngBsf : GaussStep<UngBsf<M_, K_>, M_, M_, K_> {
       for (int j = 0; j < K_; ++j) ru += R[d + M_ * j] * z[j];
       x[d] = C[d] + ta + ru;
     }
+  }
+};
+
+// ------------------------------------- bootstrap filter, m = 1, one model per filter
+// is_correction_bsf (src/approx_mcmc.cpp:447-518) runs ssm_ung::bsf_filter once per stored MCMC
+// draw after update_model(theta_i): T, R, a1, P1, C and phi differ between the filters of a batch.
+struct UngBsfDraw : GaussStep<UngBsfDraw, 1, 1, 1> {
+  static constexpr int M = 1, KI = 1, KP = 1;
+  typedef UngParams Params;
+  const UngParams& mp;
+  double T, R, a1, L, C, phi, lconst;
+  double y, u, yphi2, Dt, xb, Z0;
+
+  __device__ UngBsfDraw(const UngParams& p, uint32_t f) : mp(p) {
+    const double* q = p.bsf_par + (size_t)7 * f;
+    T = q[0]; R = q[1]; a1 = q[2]; L = q[3]; C = q[4]; phi = q[5]; lconst = q[6];
+  }
+  __device__ double step_const() const { return 0.0; }
+  __device__ double loglik0() const { return 0.0; }
+  __device__ double loglik_end() const { return lconst; }
+  __device__ void init(const double* z, double* x) const { x[0] = a1 + L * z[0]; }
+  __device__ bool observed(int t) const { return pf_isfinite(mp.y[t]); }
+  __device__ void begin_weight(int t) {
+    y = mp.y[t];
+    u = mp.u[t];
+    double q = y / phi;
+    yphi2 = q * q;
+    Dt = mp.D[t * mp.Dtv];
+    xb = mp.xbeta[t];
+    Z0 = mp.Z[t * mp.Ztv];
+  }
+  __device__ double logw(const double* x) const {
+    const double s = (mp.distribution == 0) ? x[0] : (Dt + Z0 * x[0] + xb);
+    return ung_log_obs(mp.distribution, s, y, u, phi, yphi2);
+  }
+  __device__ void begin_step(int) {}
+  __device__ void propagate(const double* xa, const double* z, double* x) const {
+    x[0] = C + T * xa[0] + R * z[0];
   }
 };
 

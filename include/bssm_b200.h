@@ -341,6 +341,18 @@ int bssm_b200_postcorrection_nongaussian(const bssm_ung_model* model, const bssm
                                          uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
                                          bssm_postcorr_out* out);
 
+/* replaces: the draw loop of approx_mcmc::is_correction_bsf (src/approx_mcmc.cpp:447-518), the
+ *           correction phase of run_mcmc(..., sampling_method = "bsf") for svm / ar1_ng / bsm_ng
+ *           (level only): one bootstrap filter per stored draw at that draw's theta;
+ *           weight_i = exp(loglik_i - approx_loglik_i), posterior_i = log weight_i (caller adds the
+ *           prior).  m = 1.  Arguments as bssm_b200_postcorrection_nongaussian, with
+ *           approx_loglik (n_stored) in place of the modes. */
+int bssm_b200_is_correction_bsf(const bssm_ung_model* model, const bssm_theta_map* map, int output_type,
+                                uint32_t nsim, uint32_t seed, uint32_t n_threads, int is_type,
+                                const uint32_t* counts, const double* theta, uint32_t n_par,
+                                const double* approx_loglik, uint32_t n_stored, uint32_t draw_begin,
+                                uint32_t draw_end, bssm_postcorr_out* out);
+
 /* replaces: the draw loop of approx_mcmc::is_correction_bsf<ssm_sde> (src/approx_mcmc.cpp:522-591),
  *           the correction phase of sde_is_mcmc (src/R_sde.cpp:221-282): one bootstrap filter per
  *           stored draw on the FINE mesh L_f at that draw's theta;

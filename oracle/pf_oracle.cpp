@@ -1764,6 +1764,70 @@ int orc_postcorrection_nlg(const bssm_nlg_model* M, int output_type, uint32_t ns
   return 0;
 }
 
+/* is_correction_bsf, src/approx_mcmc.cpp:447-518 (svm / ar1_ng, m = 1): bootstrap filter per stored
+ * draw after update_model(theta_i); weight = exp(loglik - approx_loglik), posterior = log(weight). */
+int orc_is_correction_bsf_ung(const bssm_ung_model* M, const bssm_theta_map* map, int output_type, uint32_t nsim,
+                              uint32_t seed, int threads, int is_type, const uint32_t* counts, const double* theta,
+                              uint32_t n_par, const double* approx_loglik, uint32_t n_stored, int arith,
+                              double* weights, double* posterior, double* alpha, double* alphahat, double* Vt,
+                              double* loglik_out) {
+  if (M->m != 1) return 1;
+  const size_t n = M->n, n1 = n + 1;
+  std::vector<uint32_t> src, cnt;
+  for (uint32_t i = 0; i < n_stored; ++i) {
+    if (is_type == 3) for (uint32_t c = 0; c < counts[i]; ++c) { src.push_back(i); cnt.push_back(1u); }
+    else { src.push_back(i); cnt.push_back(counts[i]); }
+  }
+  const int64_t nd = (int64_t)src.size();
+  std::vector<double> ah_all, Vt_all;
+  if (output_type == 2) { ah_all.assign(n1 * nd, 0.0); Vt_all.assign(n1 * nd, 0.0); }
+#ifdef _OPENMP
+  if (threads < 1) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(threads)
+#endif
+  for (int64_t i = 0; i < nd; ++i) {
+    DrawModel dm;
+    update_model(dm, M, map, theta + (size_t)src[i] * n_par);
+    unsigned int nsimc = nsim;
+    if (is_type == 1) nsimc *= cnt[i];
+    std::vector<double> alpha_i(n1 * nsimc, 0.0), weights_i((size_t)nsimc * n1, 0.0);
+    std::vector<uint32_t> indices((size_t)nsimc * n, 0u);
+    int32_t st;
+    double ll = orc_ung_bsf_filter(&dm.M, nsimc, seed, (uint32_t)i, arith, alpha_i.data(), weights_i.data(),
+                                   indices.data(), &st);
+    if (loglik_out) loglik_out[i] = ll;
+    weights[i] = pf_exp(ll - approx_loglik[src[i]]);
+    if (output_type != 3) {
+      orc_filter_smoother(alpha_i.data(), indices.data(), 1, (int)n1, nsimc);
+      if (output_type == 1) {
+        uint32_t b = (uint32_t)(pf_pick_uniform(seed, (uint32_t)i) * (double)nsimc);
+        if (b > nsimc - 1) b = nsimc - 1;
+        for (size_t t = 0; t < n1; ++t) alpha[n1 * i + t] = alpha_i[t + n1 * b];
+      } else {
+        orc_summary(alpha_i.data(), 1, (int)n1, nsimc, &ah_all[n1 * i], &Vt_all[n1 * i]);
+      }
+    }
+  }
+  if (output_type == 2) {
+    std::vector<double> ah(n1, 0.0), V(n1, 0.0), Valpha(n1, 0.0);
+    double sum_w = 0.0;
+    for (int64_t i = 0; i < nd; ++i) {
+      double wnew = weights[i] * cnt[i];
+      sum_w += wnew;
+      for (size_t t = 0; t < n1; ++t) {
+        double diff = ah_all[n1 * i + t] - ah[t];
+        ah[t] += wnew / sum_w * diff;
+        double diff2 = ah_all[n1 * i + t] - ah[t];
+        Valpha[t] += wnew * diff * diff2;
+        V[t] += wnew / sum_w * (Vt_all[n1 * i + t] - V[t]);
+      }
+    }
+    for (size_t t = 0; t < n1; ++t) { alphahat[t] = ah[t]; Vt[t] = V[t] + Valpha[t] / sum_w; }
+  }
+  for (int64_t i = 0; i < nd; ++i) posterior[i] = 0.0 + pf_log(weights[i]);
+  return 0;
+}
+
 /* is_correction_bsf<ssm_sde>, src/approx_mcmc.cpp:522-591: bootstrap filter on the fine mesh L_f per
  * stored draw, weight = exp(loglik - approx_loglik), posterior = approx_loglik + log(weight) (prior 0).
  * Draw d uses Philox stream d (the reference re-seeds two engines per thread, :537-538). */

@@ -241,6 +241,31 @@ def post_correct(model, mcmc_output, N, is_type=2, seed=1, threads=0, arith=ARIT
     return r
 
 
+def is_correction_bsf(model, mcmc_output, N, is_type=2, seed=1, threads=0, arith=ARITH_REPRO):
+    """oracle of approx_mcmc::is_correction_bsf (src/approx_mcmc.cpp:447-518), m = 1 ung-family models"""
+    from bssm_b200.api import n_draws, theta_map
+    theta = np.asfortranarray(np.asarray(mcmc_output["theta"], dtype=np.float64).T)
+    counts = np.ascontiguousarray(mcmc_output["counts"], dtype=np.uint32)
+    approx = np.ascontiguousarray(mcmc_output["approx_loglik"], dtype=np.float64)
+    ot = int(mcmc_output.get("output_type", 3))
+    nd = n_draws(mcmc_output, is_type)
+    n = model.n
+    r = Result()
+    r.weights, r.posterior, r.loglik = np.zeros(nd), np.zeros(nd), np.zeros(nd)
+    r.alpha = np.zeros((n + 1, 1, nd), order="F") if ot == 1 else None
+    r.alphahat = np.zeros((n + 1, 1), order="F") if ot == 2 else None
+    r.Vt = np.zeros((1, 1, n + 1), order="F") if ot == 2 else None
+    ms, tm = model.c_struct(), theta_map(model)
+    f = L().orc_is_correction_bsf_ung
+    f.argtypes = [C.POINTER(UngModel), C.POINTER(ThetaMap), C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                  c_uint32_p, c_double_p, C.c_uint32, c_double_p, C.c_uint32, C.c_int] + [c_double_p] * 6
+    rc = f(C.byref(ms), C.byref(tm), ot, N, seed, threads, is_type, uptr(counts), dptr(theta), theta.shape[0],
+           dptr(approx), counts.size, arith, dptr(r.weights), dptr(r.posterior), dptr(r.alpha), dptr(r.alphahat),
+           dptr(r.Vt), dptr(r.loglik))
+    assert rc == 0
+    return r
+
+
 def is_correction_bsf_sde(model, mcmc_output, N, Lf, is_type=2, seed=1, threads=0, arith=ARITH_REPRO):
     """oracle of approx_mcmc::is_correction_bsf<ssm_sde> (src/approx_mcmc.cpp:522-591)"""
     from bssm_b200.api import n_draws

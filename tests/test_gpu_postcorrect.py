@@ -217,3 +217,24 @@ def test_sde_is_correction(engine, kind):
     res2 = engine.post_correct(model, mo2, 32, is_type="is1", seed=8, L=2)
     np.testing.assert_allclose(res2["alphahat"], ref2.alphahat, rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(res2["Vt"], ref2.Vt, rtol=1e-9, atol=1e-13)
+
+
+def test_bsf_is_correction(setup):
+    """correction phase of run_mcmc(sampling_method = "bsf"): bootstrap filter per stored draw,
+    weight = exp(loglik_bsf - approx_loglik) (is_correction_bsf, src/approx_mcmc.cpp:447-518)"""
+    engine, model, mo = setup
+    rng = np.random.default_rng(5)
+    mo = dict(mo, approx_loglik=-221.0 + rng.normal(size=mo["counts"].size))
+    ref = orc.is_correction_bsf(model, mo, 128, is_type=2, seed=3)
+    res = engine.post_correct(model, mo, 128, is_type="is2", seed=3, return_loglik=True, sampling_method="bsf")
+    np.testing.assert_allclose(res["loglik"], ref.loglik, rtol=1e-13)  # constants pre-summed per draw
+    np.testing.assert_allclose(res["weights"], ref.weights, rtol=1e-10)
+    mo1 = dict(mo, output_type=1)
+    ref1 = orc.is_correction_bsf(model, mo1, 64, is_type=3, seed=5)
+    res1 = engine.post_correct(model, mo1, 64, is_type="is3", seed=5, sampling_method="bsf")
+    assert np.array_equal(res1["alpha"].view(np.uint64), ref1.alpha.view(np.uint64))
+    mo2 = dict(mo, output_type=2)
+    ref2 = orc.is_correction_bsf(model, mo2, 32, is_type=1, seed=7)
+    res2 = engine.post_correct(model, mo2, 32, is_type="is1", seed=7, sampling_method="bsf")
+    np.testing.assert_allclose(res2["alphahat"], ref2.alphahat, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(res2["Vt"], ref2.Vt, rtol=1e-8, atol=1e-12)
