@@ -206,8 +206,14 @@ def main():
     bssm_b200._lib.check(bssm_b200.lib().bssm_b200_set_device(local_rank))
     dist = None
     if world > 1:
-        # keep stdout to the one JSON line: NCCL_DEBUG=VERSION/INFO prints to stdout
-        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")
+        # keep stdout to the one JSON line: any NCCL_DEBUG level (even WARN) prints "NCCL version ..."
+        # to stdout; BENCH_NCCL_DEBUG=INFO re-enables it, routed to stderr
+        dbg = os.environ.get("BENCH_NCCL_DEBUG")
+        if dbg:
+            os.environ["NCCL_DEBUG"] = dbg
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
