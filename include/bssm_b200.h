@@ -28,6 +28,9 @@
 extern "C" {
 #endif
 
+/* a resident batch of filters (device-side inputs and outputs), see bssm_b200_job_* below */
+typedef struct bssm_b200_job bssm_b200_job;
+
 enum {
   BSSM_B200_OK = 0,
   BSSM_B200_ERR_ARG = 1,
@@ -398,7 +401,6 @@ int bssm_b200_postcorrection_nonlinear(const bssm_nlg_model* model, int output_t
  * buffers of `n_filters` independent replicate filters (filter f uses random
  * stream `filter = first_filter_id + f`, see pf_math.h).  run() only launches
  * kernels; nothing crosses PCIe.  This is what bench.py times for `value`. */
-typedef struct bssm_b200_job bssm_b200_job;
 
 int bssm_b200_job_create_ung(const bssm_ung_model* model, int method, uint32_t nsim,
                              uint32_t seed, uint32_t n_filters, uint32_t first_filter_id,

@@ -27,8 +27,30 @@ postcorrection_nongaussian <- function(model_, model_type, output_type, nsim, se
         n_threads, is_type, as.integer(counts), theta, modes)
 }
 
+bsf_smoother <- function(model_, nsim, seed, gaussian, model_type) {
+  if (gaussian) return(bssm:::bsf_smoother(model_, nsim, seed, gaussian, model_type))
+  model_$u <- rep_len(model_$u, length(model_$y))
+  out <- .Call("_bssmb200_bsf_smoother", model_, nsim, seed, gaussian, model_type)
+  out$alphahat <- t(out$alphahat)
+  out
+}
+
+nongaussian_loglik <- function(model_, nsim, sampling_method, seed, model_type) {
+  if (sampling_method > 2 || nsim == 0)   # SPDK / pure approximation stay on the CPU path
+    return(bssm:::nongaussian_loglik(model_, nsim, sampling_method, seed, model_type))
+  model_$u <- rep_len(model_$u, length(model_$y))
+  .Call("_bssmb200_nongaussian_loglik", model_, nsim, sampling_method, seed, model_type)
+}
+
+suggest_n_nongaussian <- function(model_, theta, candidates, replications, seed, model_type) {
+  model_$u <- rep_len(model_$u, length(model_$y))
+  .Call("_bssmb200_suggest_n_nongaussian", model_, theta, as.numeric(candidates), replications, seed, model_type)
+}
+
 # check_intmax caps particles at 1e5 (R/check_arguments.R:407-418); the GPU path lifts it
-environment(bsf) <- environment(psi_smoother) <- environment(postcorrection_nongaussian) <- asNamespace("bssm")
-utils::assignInNamespace("bsf", bsf, "bssm")
-utils::assignInNamespace("psi_smoother", psi_smoother, "bssm")
-utils::assignInNamespace("postcorrection_nongaussian", postcorrection_nongaussian, "bssm")
+for (f in c("bsf", "bsf_smoother", "psi_smoother", "nongaussian_loglik", "suggest_n_nongaussian",
+            "postcorrection_nongaussian")) {
+  fn <- get(f)
+  environment(fn) <- asNamespace("bssm")
+  utils::assignInNamespace(f, fn, "bssm")
+}

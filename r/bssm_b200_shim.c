@@ -1,8 +1,11 @@
 /* bssm_b200_shim.c -- the `.Call` side of the drop-in boundary.
  *
- * NOT COMPILED IN THIS REPOSITORY'S CI: it needs R's headers (Rinternals.h),
- * which the build image does not have.  It is the ~150-line glue a bssm
- * maintainer adds to reach libbssm_b200.so from R; everything it calls is the
+ * NOT BUILT IN THIS REPOSITORY: it needs R's headers (Rinternals.h), which the
+ * build image does not have; tests/test_abi.py only type-checks it with gcc
+ * against declaration-only stand-ins (tests/mock_R/).  It is the glue a bssm
+ * maintainer adds to reach libbssm_b200.so from R for the ssm_ung family (the
+ * ssm_mng / ssm_nlg / ssm_sde entry points follow the same pattern with their
+ * own fill_* function); everything it calls is the
  * plain C ABI of include/bssm_b200.h, which IS built and tested here (through
  * ctypes, tests/test_gpu_*.py).  Build inside an R installation with
  *   R CMD SHLIB bssm_b200_shim.c -I../include -L../bssm_b200/csrc -lbssm_b200
@@ -114,42 +117,126 @@ SEXP _bssmb200_psi_smoother(SEXP model_, SEXP nsim_, SEXP seed_, SEXP model_type
   return res;
 }
 
-/* postcorrection_nongaussian(model_, model_type, output_type, nsim, seed, n_threads, is_type,
- *                            counts, theta, modes): src/R_postcorrection.cpp:150-248 (output_type 3 shown) */
-SEXP _bssmb200_postcorrection_nongaussian(SEXP model_, SEXP model_type_, SEXP output_type_, SEXP nsim_,
-                                          SEXP seed_, SEXP n_threads_, SEXP is_type_, SEXP counts_,
-                                          SEXP theta_, SEXP modes_) {
+/* theta -> model mapping of the model classes whose update_model is C++ (R/model_type.R:1-16) */
+static void fill_map(SEXP model, int model_type, bssm_theta_map* map) {
+  memset(map, 0, sizeof(*map));
+  map->model_type = model_type;
+  if (model_type == 3) map->svm_type = asInteger(list_get(model, "svm_type"));
+  if (model_type == 4) { map->mu_est = asLogical(list_get(model, "mu_est")); map->phi_est = asLogical(list_get(model, "phi_est")); }
+  if (model_type == 2) { /* bsm_ng, src/model_bsm_ng.cpp:4-14 */
+    SEXP fixed = list_get(model, "fixed"), xreg = list_get(model, "xreg");
+    map->slope = asLogical(list_get(model, "slope")); map->seasonal = asLogical(list_get(model, "seasonal"));
+    map->noise = asLogical(list_get(model, "noise")); map->phi_est = asLogical(list_get(model, "phi_est"));
+    map->level_est = INTEGER(fixed)[0] == 0;
+    map->slope_est = map->slope && INTEGER(fixed)[1] == 0;
+    map->seasonal_est = map->seasonal && INTEGER(fixed)[2] == 0;
+    map->n_xreg = XLENGTH(xreg) > 0 ? INTEGER(getAttrib(xreg, R_DimSymbol))[1] : 0;
+    map->xreg = map->n_xreg > 0 ? REAL(xreg) : NULL;
+  }
+}
+
+/* bsf_smoother(model_, nsim, seed, gaussian, model_type): src/R_bootstrap_filter.cpp:245-457 */
+SEXP _bssmb200_bsf_smoother(SEXP model_, SEXP nsim_, SEXP seed_, SEXP gaussian_, SEXP model_type_) {
+  if (asLogical(gaussian_)) error("bssm_b200: Gaussian models use bssm's own Kalman/BSF code path");
+  bssm_ung_model M;
+  int n = (int)XLENGTH(list_get(model_, "y")), m = (int)XLENGTH(list_get(model_, "a1"));
+  unsigned N = (unsigned)asInteger(nsim_);
+  double* xb = (double*)R_alloc(n, sizeof(double));
+  fill_ung(model_, &M, xb);
+  SEXP ah = PROTECT(allocMatrix(REALSXP, m, n + 1)), Vt = PROTECT(alloc3DArray(REALSXP, m, m, n + 1));
+  SEXP w = PROTECT(allocMatrix(REALSXP, N, n + 1)), alpha = PROTECT(alloc3DArray(REALSXP, m, n + 1, N));
+  bssm_filter_out out;
+  memset(&out, 0, sizeof(out));
+  out.alphahat = REAL(ah); out.Vt = REAL(Vt); out.weights = REAL(w); out.alpha = REAL(alpha);
+  check_rc(bssm_b200_bsf_smoother(&M, N, (unsigned)asInteger(seed_), &out));
+  if (!R_FINITE(out.loglik))
+    warning("Particle filtering stopped prematurely due to nonfinite log-likelihood.");
+  const char* nm[] = {"alphahat", "Vt", "weights", "logLik", "alpha", ""};
+  SEXP res = PROTECT(mkNamed(VECSXP, nm));
+  SET_VECTOR_ELT(res, 0, ah); SET_VECTOR_ELT(res, 1, Vt); SET_VECTOR_ELT(res, 2, w);
+  SET_VECTOR_ELT(res, 3, ScalarReal(out.loglik)); SET_VECTOR_ELT(res, 4, alpha);
+  UNPROTECT(5);
+  return res;
+}
+
+/* nongaussian_loglik(model_, nsim, sampling_method, seed, model_type): src/R_loglik.cpp:41-87.
+ * sampling_method 1 = psi-APF, 2 = bootstrap filter; nothing but the scalar crosses PCIe. */
+SEXP _bssmb200_nongaussian_loglik(SEXP model_, SEXP nsim_, SEXP sampling_method_, SEXP seed_, SEXP model_type_) {
   bssm_ung_model M;
   int n = (int)XLENGTH(list_get(model_, "y"));
   double* xb = (double*)R_alloc(n, sizeof(double));
   fill_ung(model_, &M, xb);
+  bssm_filter_out out;
+  memset(&out, 0, sizeof(out));
+  int method = asInteger(sampling_method_);
+  if (method == 1) check_rc(bssm_b200_psi_filter(&M, (unsigned)asInteger(nsim_), (unsigned)asInteger(seed_), &out));
+  else if (method == 2) check_rc(bssm_b200_bsf(&M, (unsigned)asInteger(nsim_), (unsigned)asInteger(seed_), &out));
+  else error("bssm_b200: sampling_method must be 1 (psi) or 2 (bsf); SPDK stays on bssm's CPU path");
+  return ScalarReal(out.loglik);
+}
+
+/* suggest_n_nongaussian(model_, theta, candidates, replications, seed, model_type): src/R_postcorrection.cpp:14-104 */
+SEXP _bssmb200_suggest_n_nongaussian(SEXP model_, SEXP theta_, SEXP candidates_, SEXP replications_, SEXP seed_,
+                                     SEXP model_type_) {
+  bssm_ung_model M;
+  int n = (int)XLENGTH(list_get(model_, "y")), nc = (int)XLENGTH(candidates_);
+  double* xb = (double*)R_alloc(n, sizeof(double));
+  fill_ung(model_, &M, xb);
   bssm_theta_map map;
-  memset(&map, 0, sizeof(map));
-  map.model_type = asInteger(model_type_);
-  if (map.model_type == 3) map.svm_type = asInteger(list_get(model_, "svm_type"));
-  if (map.model_type == 4) { map.mu_est = asLogical(list_get(model_, "mu_est")); map.phi_est = asLogical(list_get(model_, "phi_est")); }
+  fill_map(model_, asInteger(model_type_), &map);
+  uint32_t* cand = (uint32_t*)R_alloc(nc, sizeof(uint32_t));
+  for (int i = 0; i < nc; i++) cand[i] = (uint32_t)REAL(candidates_)[i]; /* arma::vec candidates */
+  SEXP sds = PROTECT(allocVector(REALSXP, nc));
+  check_rc(bssm_b200_suggest_n_nongaussian(&M, &map, REAL(theta_), (unsigned)XLENGTH(theta_), cand, (unsigned)nc,
+                                           (unsigned)asInteger(replications_), (unsigned)asInteger(seed_), REAL(sds)));
+  UNPROTECT(1);
+  return sds;
+}
+
+/* postcorrection_nongaussian(model_, model_type, output_type, nsim, seed, n_threads, is_type,
+ *                            counts, theta, modes): src/R_postcorrection.cpp:150-248.
+ * Returns what the reference returns per output_type (:226-245): alpha (n+1) x m x n_draws for 1,
+ * alphahat / Vt for 2, weights and posterior always. */
+SEXP _bssmb200_postcorrection_nongaussian(SEXP model_, SEXP model_type_, SEXP output_type_, SEXP nsim_,
+                                          SEXP seed_, SEXP n_threads_, SEXP is_type_, SEXP counts_,
+                                          SEXP theta_, SEXP modes_) {
+  bssm_ung_model M;
+  int n = (int)XLENGTH(list_get(model_, "y")), m = (int)XLENGTH(list_get(model_, "a1"));
+  double* xb = (double*)R_alloc(n, sizeof(double));
+  fill_ung(model_, &M, xb);
+  bssm_theta_map map;
+  fill_map(model_, asInteger(model_type_), &map);
   int n_stored = (int)XLENGTH(counts_), n_par = INTEGER(getAttrib(theta_, R_DimSymbol))[0];
-  int is_type = asInteger(is_type_);
+  int is_type = asInteger(is_type_), output_type = asInteger(output_type_);
   R_xlen_t nd = 0;
   for (int i = 0; i < n_stored; i++) nd += is_type == 3 ? INTEGER(counts_)[i] : 1;
   SEXP w = PROTECT(allocVector(REALSXP, nd)), post = PROTECT(allocVector(REALSXP, nd));
+  SEXP alpha = PROTECT(output_type == 1 ? alloc3DArray(REALSXP, n + 1, m, (int)nd) : allocVector(REALSXP, 0));
+  SEXP ah = PROTECT(output_type == 2 ? allocMatrix(REALSXP, n + 1, m) : allocVector(REALSXP, 0));
+  SEXP Vt = PROTECT(output_type == 2 ? alloc3DArray(REALSXP, m, m, n + 1) : allocVector(REALSXP, 0));
   bssm_postcorr_out out;
   memset(&out, 0, sizeof(out));
   out.weights = REAL(w); out.posterior = REAL(post);
-  check_rc(bssm_b200_postcorrection_nongaussian(&M, &map, 3, (unsigned)asInteger(nsim_), (unsigned)asInteger(seed_),
-                                                (unsigned)asInteger(n_threads_), is_type,
+  if (output_type == 1) out.alpha = REAL(alpha);
+  if (output_type == 2) { out.alphahat = REAL(ah); out.Vt = REAL(Vt); }
+  check_rc(bssm_b200_postcorrection_nongaussian(&M, &map, output_type, (unsigned)asInteger(nsim_),
+                                                (unsigned)asInteger(seed_), (unsigned)asInteger(n_threads_), is_type,
                                                 (const uint32_t*)INTEGER(counts_), REAL(theta_), (unsigned)n_par,
                                                 REAL(modes_), (unsigned)n_stored, 0, 0, &out));
-  const char* nm[] = {"weights", "posterior", ""};
+  const char* nm[] = {"alpha", "alphahat", "Vt", "weights", "posterior", ""};
   SEXP res = PROTECT(mkNamed(VECSXP, nm));
-  SET_VECTOR_ELT(res, 0, w); SET_VECTOR_ELT(res, 1, post);
-  UNPROTECT(3);
+  SET_VECTOR_ELT(res, 0, alpha); SET_VECTOR_ELT(res, 1, ah); SET_VECTOR_ELT(res, 2, Vt);
+  SET_VECTOR_ELT(res, 3, w); SET_VECTOR_ELT(res, 4, post);
+  UNPROTECT(6);
   return res;
 }
 
 static const R_CallMethodDef CallEntries[] = {
   {"_bssmb200_bsf", (DL_FUNC)&_bssmb200_bsf, 5},
   {"_bssmb200_psi_smoother", (DL_FUNC)&_bssmb200_psi_smoother, 4},
+  {"_bssmb200_bsf_smoother", (DL_FUNC)&_bssmb200_bsf_smoother, 5},
+  {"_bssmb200_nongaussian_loglik", (DL_FUNC)&_bssmb200_nongaussian_loglik, 5},
+  {"_bssmb200_suggest_n_nongaussian", (DL_FUNC)&_bssmb200_suggest_n_nongaussian, 6},
   {"_bssmb200_postcorrection_nongaussian", (DL_FUNC)&_bssmb200_postcorrection_nongaussian, 10},
   {NULL, NULL, 0}
 };

@@ -73,3 +73,19 @@ def test_model_constructors_match_reference_layout(engine):
     assert seas.m == 5 and seas.k == 3
     assert np.array_equal(seas.T[2, 2:, 0], [-1, -1, -1])
     assert seas.T[3, 2, 0] == 1 and seas.T[4, 3, 0] == 1
+
+
+def test_header_is_plain_c_and_r_shim_type_checks():
+    """include/bssm_b200.h must compile as C99 (it is the FFI boundary), and the R `.Call` shim a
+    maintainer would build (r/bssm_b200_shim.c) must at least type-check against it: R's headers are
+    not in this image, so declaration-only stand-ins (tests/mock_R/) take their place -- a syntax /
+    signature check, not a build."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-Wpedantic", "-Werror", "-x", "c",
+                          os.path.join(root, "include", "bssm_b200.h")], capture_output=True, text=True)
+    assert hdr.returncode == 0, hdr.stderr
+    shim = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I" + os.path.join(root, "tests", "mock_R"),
+                           "-I" + os.path.join(root, "include"), os.path.join(root, "r", "bssm_b200_shim.c")],
+                          capture_output=True, text=True)
+    assert shim.returncode == 0, shim.stderr
