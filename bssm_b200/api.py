@@ -161,6 +161,13 @@ class FilterJob:
         check(lib().bssm_b200_job_run(self._h, C.byref(ms)))
         return ms.value
 
+    def set_theta(self, theta):
+        """Re-parameterise the resident job (the filter inside an MCMC loop, src/mcmc.cpp:338-491):
+        update_model(theta) + approximate() on the host, then run() again."""
+        theta = _lib.f64(np.ravel(theta))
+        tm = theta_map(self.model)
+        check(lib().bssm_b200_job_set_theta(self._h, C.byref(self._ms), C.byref(tm), dptr(theta), theta.size))
+
     def kernel_ms(self):
         a = (C.c_float * 3)()
         check(lib().bssm_b200_job_kernel_ms(self._h, C.byref(a)))

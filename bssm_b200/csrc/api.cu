@@ -1597,6 +1597,51 @@ int bssm_b200_approximate_mode(const bssm_ung_model* M, double* mode) {
   return 0;
 }
 
+// A resident job inside an MCMC loop: new theta, same data and buffers (pm_mcmc / da_mcmc call the
+// particle filter once per iteration at a new theta, src/mcmc.cpp:338-491).  update_model(theta) +
+// approximate() on the host (O(n) per Newton sweep), then only the mode (n doubles) and the model
+// scalars cross PCIe; the next run() redoes the device pre-pass and the filters.
+int bssm_b200_job_set_theta(bssm_b200_job* J, const bssm_ung_model* M, const bssm_theta_map* map,
+                            const double* theta, uint32_t n_par) {
+  if (!J || !M || !map || !theta) return fail(BSSM_B200_ERR_ARG, "null argument");
+  if (J->kind != KIND_UNG || J->m != 1 || M->m != 1 || M->n != J->n)
+    return fail(BSSM_B200_ERR_UNSUPPORTED, "job_set_theta: m = 1 ssm_ung-family jobs created from the same data");
+  if (M->xbeta) return fail(BSSM_B200_ERR_UNSUPPORTED, "job_set_theta: models without regressors in this build");
+  double par[6];
+  int rc = theta_to_par(M, map, theta, n_par, par);
+  if (rc) return rc;
+  bssm_ung_model Mi = *M;
+  Mi.T = &par[0]; Mi.R = &par[1]; Mi.a1 = &par[2]; Mi.P1 = &par[3]; Mi.C = &par[4]; Mi.phi = par[5];
+  Mi.Ttv = 0; Mi.Rtv = 0; Mi.Ctv = 0;
+  const uint32_t nf = J->n_filters;
+  if (J->method == BSSM_METHOD_PSI) {
+    if (J->pp.draw_par && J->pp.mode_stride != 0)
+      return fail(BSSM_B200_ERR_ARG, "job_set_theta: post-correction jobs carry one theta per filter already");
+    if (!M->initial_mode || M->max_iter < 1) return fail(BSSM_B200_ERR_ARG, "psi-APF needs initial_mode and max_iter >= 1");
+    std::vector<double> mode, mode_lin, dp((size_t)6 * nf);
+    ung_approximate_m1(&Mi, mode, mode_lin);
+    for (uint32_t f = 0; f < nf; ++f) memcpy(&dp[(size_t)6 * f], par, sizeof(par));
+    if ((rc = J->mode.upload(mode.data(), J->n)) || (rc = J->mode_lin.upload(mode_lin.data(), J->n)) ||
+        (rc = J->draw_par.upload(dp.data(), dp.size())))
+      return rc;
+    pf::PrepassParams& pp = J->pp;
+    pp.draw_par = J->draw_par.p;
+    pp.modes = J->mode.p; pp.modes_lin = J->mode_lin.p; pp.mode_stride = 0;
+    pp.compute_loglik = 1;
+    pp.dist_const = ung_dist_const(&Mi);
+  } else {
+    std::vector<double> bp((size_t)7 * nf);
+    for (uint32_t f = 0; f < nf; ++f) {
+      double* b = &bp[(size_t)7 * f];
+      b[0] = par[0]; b[1] = par[1]; b[2] = par[2]; b[3] = par[3] > 0.0 ? std::sqrt(par[3]) : 0.0;
+      b[4] = par[4]; b[5] = par[5]; b[6] = ung_dist_const(&Mi);
+    }
+    if ((rc = J->draw_par.upload(bp.data(), bp.size()))) return rc;
+    J->up.bsf_par = J->draw_par.p;
+  }
+  return 0;
+}
+
 int bssm_b200_job_create_postcorr(const bssm_ung_model* M, const bssm_theta_map* map, uint32_t nsim,
                                   uint32_t seed, int is_type, const uint32_t* counts, const double* theta,
                                   uint32_t n_par, const double* modes, uint32_t n_stored,

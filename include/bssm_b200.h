@@ -421,6 +421,13 @@ int bssm_b200_job_create_postcorr_nlg(const bssm_nlg_model* model, uint32_t nsim
                                       bssm_b200_job** job);
 /* launches pre-pass + filter (+ the post-processing kernels) on the
  * job's stream and waits; ms = CUDA-event time on that stream */
+/* The particle filter inside an MCMC loop (pm_mcmc / da_mcmc, src/mcmc.cpp:338-491: one filter
+ * per iteration at a new theta): re-parameterise a resident job in place.  update_model(theta)
+ * and the Newton sweeps of approximate() run on the host, only the mode (n doubles) and six
+ * scalars are uploaded, the next job_run redoes the device pre-pass and all replicate filters.
+ * `model` is the model the job was created from; m = 1 models (svm, ar1_ng, bsm_ng level). */
+int bssm_b200_job_set_theta(bssm_b200_job* job, const bssm_ung_model* model, const bssm_theta_map* map,
+                            const double* theta, uint32_t n_par);
 int bssm_b200_job_run(bssm_b200_job* job, float* ms);
 /* per-kernel CUDA-event times of the last run: [prepass, filter, smoother] */
 int bssm_b200_job_kernel_ms(const bssm_b200_job* job, float ms[3]);

@@ -41,3 +41,17 @@ for N in (100, 1000):
     res = (time.perf_counter() - t0) / 20 * 1e3
     print("svm psi n=1000 N=%5d: resident job run %.3f ms (device %s)" % (N, res, ["%.3f" % v for v in job.kernel_ms()]))
     job.close()
+# the filter inside an MCMC loop: set_theta + run per iteration on a resident job
+mdl = data.svm_model(1000)
+for N in (100, 1000):
+    job = bssm_b200.FilterJob(mdl, N, method="psi", seed=1, out_flags=0)
+    rng = np.random.default_rng(1)
+    th0 = np.asarray(mdl.theta)
+    for _ in range(3):
+        job.set_theta(th0); job.run()
+    t0 = time.perf_counter()
+    for i in range(20):
+        job.set_theta(th0 * np.exp(0.02 * rng.normal(size=3)) * [1, 1, 1]); job.run()
+    it = (time.perf_counter() - t0) / 20 * 1e3
+    print("svm psi n=1000 N=%5d: MCMC-style iteration (set_theta + run) %.3f ms" % (N, it))
+    job.close()
