@@ -5,12 +5,24 @@
  * and bench.py's cpu_baseline / --impl reference legs may use it, and only as
  * the checker / the CPU baseline.
  *
- * PARITY UNPINNED at the Armadillo / sitmo boundary: the reference itself
- * cannot be built here (no R, Rcpp, RcppArmadillo, sitmo) and its
- * tests pin no particle-filter output values.  What IS pinned: the helper
- * KATs in tests/test_oracle.py (stratified_sample hand vectors, Philox
- * Random123 vectors, Kalman-smoother agreement of the LGSSM particle smoother,
- * data/poisson_series decoded from the reference's own .rda).
+ * PARITY: PARTLY PINNED.  The reference itself cannot be built here (no R,
+ * Rcpp, RcppArmadillo, sitmo).  Pinned against the reference's
+ * OWN golden vectors (tests/test_reference_golden.py, inputs regenerated with a
+ * restatement of R's set.seed / rnorm stream, tests/r_rng.py):
+ *   - the Gaussian approximation of an svm model -- model construction,
+ *     laplace_iter, Kalman fast smoother, Newton-sweep semantics -- to the 15
+ *     digits of tests/testthat/test_approx.R:38-53;
+ *   - dmvnorm (the density of the ssm_nlg weights), test_basics.R:176-201;
+ *   - the GBM data set of test_sde.R with its log-likelihood assertion, plus
+ *     the closed-form likelihood of that model.
+ * Also pinned: stratified_sample hand vectors, Philox Random123 vectors,
+ * exact Kalman smoothers (numpy) for the general-m / multivariate
+ * approximations and the LGSSM particle smoothers, data/poisson_series and
+ * data/exchange decoded from the reference's own .rda (tests/test_oracle.py).
+ * STILL UNPINNED: the particle loop's random numbers (sitmo + libstdc++
+ * <random>) and Armadillo's summation order -- the reference's tests pin no
+ * particle-filter output value, so indices / weights / log-likelihoods are
+ * defined by this restatement.
  *
  * Every function keeps the reference's loop structure (scalar loops over
  * particles, sequential two-pointer stratified merge, particle-slowest alpha
@@ -1891,6 +1903,18 @@ int orc_is_correction_bsf_sde(const bssm_sde_model* M, uint32_t L_f, int output_
   }
   for (int64_t i = 0; i < nd; ++i) posterior[i] = 0.0 + approx_loglik[src[i]] + pf_log(weights[i]);
   return 0;
+}
+
+/* dmvnorm(x, mean, sigma, lwr = false, logd = true) for a full-rank m x m covariance
+ * (src/dmvnorm.cpp:4-60), the density the ssm_nlg weights are built from: test hook for the
+ * reference's own known-answer test (tests/testthat/test_basics.R:176-201) */
+double orc_dmvnorm_logpdf(const double* x, const double* mean, const double* sigma, int m) {
+  pfga::MvnFactor f;
+  f.set(sigma, m);
+  return f.logpdf(x, mean);
+}
+double orc_dnorm1(double x, double mean, double s, int lwr) {
+  return lwr ? pfga::dnorm1_sd(x, mean, s) : pfga::dnorm1_var(x, mean, s);
 }
 
 int orc_max_threads(void) {

@@ -1,0 +1,123 @@
+"""The reference's OWN known-answer tests for pieces of the hot path, reproduced without R.
+
+helske/bssm's testthat files pin a few numerical results whose inputs come from R's random number
+stream (`set.seed()` + `rnorm`).  tests/r_rng.py restates that stream (Mersenne-Twister with R's
+seeding, normals by inversion), so these golden vectors can be regenerated here and held against the
+oracle (CPU, this file) and the product (tests/test_gpu_golden.py):
+
+  * tests/testthat/test_approx.R:38-53   Gaussian approximation of an svm model: pseudo-observations,
+    their standard deviations and the smoothed mode after two Newton sweeps, 15 digits
+  * tests/testthat/test_basics.R:176-201 dmvnorm log-density (the density behind the ssm_nlg weights)
+  * tests/testthat/test_sde.R:7-25,55-58 the GBM data set and its log-likelihood "about -17"
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import bssm_b200
+import orc
+from r_rng import RStream
+
+# ---- golden values copied from the reference's test files (cited above)
+SVM_APPROX_Y = [-1.47548927809174, -11.2190916117862, 0.263154138901814, -121.519769682058, -36.0386937004332]
+SVM_APPROX_H = [2.01061310553144, 4.84658294043645, 0.712674409714633, 15.6217737012134, 8.54936618861792]
+SVM_SMOOTHED = [-0.0999179077423753, -0.101594935319188, -0.0985572218431492, -0.103275329248674,
+                -0.103028083292436]
+DMVNORM_LOGP = -14.0607446337904
+
+
+def svm_kat_model():
+    """test_approx.R:39-44: svm(rnorm(5), sigma = uniform(1, 0, 10), rho = uniform(0.95, 0, 1),
+    sd_ar = uniform(0.1, 0, 1)); gaussian_approx(model, max_iter = 2, conv_tol = 1e-8)"""
+    y = RStream(123).rnorm(5)
+    m = bssm_b200.svm(y, rho=0.95, sd_ar=0.1, sigma=1.0)
+    m.max_iter, m.conv_tol = 2, 1e-8
+    return m
+
+
+def gbm_kat_model():
+    """test_sde.R:7-25"""
+    rs = RStream(42)
+    n, dt, mu, sigma_x, sigma_y, x = 50, 1.0, 0.05, 0.3, 1.0, 1.0
+    y = np.empty(n)
+    for k in range(n):
+        x = x * np.exp((mu - 0.5 * sigma_x ** 2) * dt + np.sqrt(dt) * rs.rnorm(1, sd=sigma_x)[0])
+        y[k] = rs.rnorm(1, np.log(x), sigma_y)[0]
+    return bssm_b200.ssm_sde(y, "gbm", theta=[0.08, 0.4, 1.5], x0=1.0, positive=True)
+
+
+def test_r_stream_restatement():
+    """values every R user has seen: set.seed(123); rnorm(5) etc."""
+    np.testing.assert_allclose(RStream(123).rnorm(5), [-0.560475646552213, -0.23017748948328, 1.55870831414912,
+                                                       0.070508391424576, 0.129287735160946], rtol=1e-13)
+    np.testing.assert_allclose(RStream(1).rnorm(3), [-0.626453810742332, 0.183643324222082, -0.835628612410047],
+                               rtol=1e-13)
+    np.testing.assert_allclose(RStream(42).runif(3), [0.914806043496355, 0.937075413297862, 0.286139534786344],
+                               rtol=1e-13)
+
+
+def test_svm_gaussian_approximation_matches_reference_golden_vector():
+    """pins svm model construction (initial mode, P1), laplace_iter, the Kalman fast smoother and the
+    fact that approximate() leaves the pseudo-observations linearised at the last-but-one mode"""
+    m = svm_kat_model()
+    r = orc.psi_prepass(m)
+    np.testing.assert_allclose(r.ytilde, SVM_APPROX_Y, rtol=2e-14)
+    np.testing.assert_allclose(r.Htilde, SVM_APPROX_H, rtol=2e-14)
+    np.testing.assert_allclose(r.mode, SVM_SMOOTHED, rtol=2e-14)
+    # the general-m restatement (the product's host path for m > 1) gives the same numbers at m = 1
+    r2 = orc.psi_filter_m(m, 8, seed=1)
+    np.testing.assert_allclose(orc.approx_mode_m(m), SVM_SMOOTHED, rtol=2e-14)
+    assert r2.approx_loglik == pytest.approx(r.approx_loglik, rel=1e-13)
+
+
+def test_dmvnorm_matches_reference_golden_value():
+    f = orc.L().orc_dmvnorm_logpdf
+    f.restype = C.c_double
+    f.argtypes = [orc.c_double_p, orc.c_double_p, orc.c_double_p, C.c_int]
+    g = orc.L().orc_dnorm1
+    g.restype = C.c_double
+    g.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int]
+    # test_basics.R:178-181: dmvnorm(1, 3, 2, lwr = TRUE) == dnorm(1, 3, 2, log = TRUE)
+    for sd in (2.0, 4.0):
+        ref = -0.5 * np.log(2 * np.pi) - np.log(sd) - 0.5 * ((1 - 3) / sd) ** 2
+        assert g(1.0, 3.0, sd, 1) == pytest.approx(ref, rel=1e-14)
+        assert g(1.0, 3.0, sd * sd, 0) == pytest.approx(ref, rel=1e-14)
+    # test_basics.R:183-186: set.seed(1); a <- crossprod(matrix(rnorm(9), 3, 3))
+    A = RStream(1).rnorm(9).reshape(3, 3, order="F")
+    a = np.asfortranarray(A.T @ A)
+    x = np.array([1.0, 2.0, 3.0])
+    mean = -0.1 * np.array([3.0, 2.0, 1.0])
+    assert f(orc.dptr(x), orc.dptr(mean), orc.dptr(a), 3) == pytest.approx(DMVNORM_LOGP, abs=1e-12)
+
+
+def gbm_exact_loglik(m):
+    """log x of a geometric Brownian motion is a Gaussian random walk with drift, and the observations
+    are N(log x, sigma_y^2): the exact log-likelihood is a scalar Kalman filter on z = log x."""
+    mu, sx, sy = m.theta
+    drift, q, h = mu - 0.5 * sx * sx, sx * sx, sy * sy
+    a, p, ll = np.log(m.x0), 0.0, 0.0
+    for yk in m.y:
+        a, p = a + drift, p + q
+        if np.isfinite(yk):
+            f = p + h
+            v = yk - a
+            ll += -0.5 * (np.log(2 * np.pi * f) + v * v / f)
+            k = p / f
+            a, p = a + k * v, p * (1 - k)
+    return ll
+
+
+def test_gbm_loglik_reference_assertion_and_exact_value():
+    """test_sde.R:55-58 asserts `expect_equal(ll, -17, tol = 1)` for logLik(model, 10000, L = 3): with
+    all.equal's relative difference |ll + 17| / |ll| < 1 that only says ll < -8.5.  The same assertion is
+    made here on the regenerated data set, and the estimate is ALSO held against the exact value: the
+    log of a GBM is a Gaussian random walk, so a Kalman filter gives the likelihood in closed form
+    (the Milstein filter approaches it as L grows)."""
+    m = gbm_kat_model()
+    exact = gbm_exact_loglik(m)
+    ll3 = np.mean([orc.sde_bsf_filter(m, 10000, 3, seed=s).loglik for s in (1, 2)])
+    assert abs(ll3 + 17.0) / abs(ll3) < 1.0          # the reference's own assertion
+    ll6 = np.mean([orc.sde_bsf_filter(m, 10000, 6, seed=s).loglik for s in (1, 2)])
+    assert abs(ll6 - exact) < 0.15                   # discretisation + Monte Carlo error
+    assert abs(ll3 - exact) < 0.5
