@@ -92,10 +92,16 @@ def bootstrap_filter(model, particles, seed=1, return_indices=False, L=None):
 
 
 def particle_smoother(model, particles, method="psi", seed=1, return_indices=False, L=None):
-    """particle_smoother: .nongaussian R/particle_smoother.R:140-186, .ssm_nlg :192-245,
-    .ssm_sde :251-291."""
+    """particle_smoother: .lineargaussian R/particle_smoother.R:85-135, .nongaussian :140-186,
+    .ssm_nlg :192-245, .ssm_sde :251-291.
+
+    Returns the `.Call`-level result: alphahat and Vt have n + 1 time points (the extra one is the
+    prediction for time n + 1); the R wrappers drop that last row (e.g. :179-181)."""
     if method not in ("psi", "bsf"):
         raise ValueError("method must be 'psi' or 'bsf' (EKPF is out of scope)")
+    if getattr(model, "distribution", None) == "gaussian" and method == "psi":
+        # particle_smoother.lineargaussian(method = "psi") -> gaussian_psi_smoother, R/particle_smoother.R:111-128
+        return gaussian_psi_smoother(model, particles, seed)
     N, seed = _check_particles(model, particles, seed)
     b = _Buffers(model, N, indices=return_indices, smooth=True)
     ms = model.c_struct()

@@ -361,3 +361,12 @@ def bsm_lg(y, sd_y, sd_level, sd_slope=None, a1=None, P1=None):
     mdl = ssm_ulg(y, Z, [sd_y], T.reshape(m, m, 1), R.reshape(m, m, 1), a1, P1)
     mdl.cls = "bsm_lg"
     return mdl
+
+
+def ar1_lg(y, rho, sigma, mu, sd_y):
+    """Univariate Gaussian model with AR(1) latent process, R/models.R:1385-1470."""
+    y = np.ravel(np.asarray(y, dtype=np.float64))
+    mdl = ssm_ulg(y, [[1.0]], [sd_y], np.reshape([rho], (1, 1, 1)), np.reshape([sigma], (1, 1, 1)), [mu],
+                  [[sigma ** 2 / (1 - rho ** 2)]], C=[[mu * (1 - rho)]])
+    mdl.cls = "ar1_lg"
+    return mdl

@@ -1,0 +1,158 @@
+"""The reference's own testthat files for the particle-filter path, re-run against the engine with the
+SAME model configurations and the SAME assertions (tests/testthat/test_bootstrap_filter.R and
+test_particle_smoother.R), each followed by bit-exact parity with the oracle on that configuration."""
+import numpy as np
+import pytest
+
+import bssm_b200
+import data
+import orc
+
+pytestmark = pytest.mark.gpu
+
+Y10 = np.arange(1.0, 11.0)
+Y8 = np.array([1, 0, 1, 1, 1, 0, 0, 0], dtype=float)
+
+
+def all_equal(target, current, tolerance):
+    """R's all.equal.numeric, which testthat's expect_equal(..., tolerance) uses: mean absolute
+    difference, RELATIVE to mean |target| only when that exceeds the tolerance, absolute otherwise"""
+    target, current = np.asarray(target, dtype=float), np.asarray(current, dtype=float)
+    xy = np.mean(np.abs(target - current))
+    xn = np.mean(np.abs(target))
+    if np.isfinite(xn) and xn > tolerance:
+        xy = xy / xn
+    return bool(xy < tolerance)
+
+
+def ulg_1_10():
+    """ssm_ulg(y = 1:10, Z = (1, 0)', H = 2, T = [[1, 1], [0, 1]], R = diag(2, 2), a1 = 0, P1 = diag(2, 2))"""
+    return bssm_b200.ssm_ulg(Y10, [[1.0], [0.0]], [2.0], np.array([[1.0, 1.0], [0.0, 1.0]]).reshape(2, 2, 1),
+                             np.diag([2.0, 2.0]).reshape(2, 2, 1), [0.0, 0.0], np.diag([2.0, 2.0]))
+
+
+def _still_works(out):
+    """the five assertions every `still works` test of test_bootstrap_filter.R makes"""
+    assert out["weights"].min() >= 0
+    assert out["weights"].max() < np.inf
+    assert np.isfinite(out["logLik"])
+    assert np.isfinite(out["att"].sum())
+    assert np.isfinite(out["Ptt"].sum())
+
+
+def _finite_smoother(out):
+    assert np.isfinite(out["alpha"].sum()) and np.isfinite(out["alphahat"].sum()) and np.isfinite(out["Vt"].sum())
+
+
+# ------------------------------------------------------------ test_bootstrap_filter.R
+def test_bsm_lg_gives_identical_results_with_ssm_ulg(engine):
+    """:5-17 (expect_equal(bsf_bsm, bsf_ssm_ulg, tolerance = 1e-8))"""
+    a = engine.bootstrap_filter(ulg_1_10(), 10, seed=1)
+    b = engine.bootstrap_filter(bssm_b200.bsm_lg(Y10, sd_y=2, sd_level=2, sd_slope=2, P1=np.diag([2.0, 2.0])), 10, seed=1)
+    for key in ("at", "att", "Pt", "Ptt", "weights", "alpha"):
+        np.testing.assert_allclose(a[key], b[key], rtol=1e-8, atol=0)
+    assert a["logLik"] == pytest.approx(b["logLik"], rel=1e-8)
+
+
+def test_linear_gaussian_bsf_still_works(engine):
+    """:21-46: ssm_ulg and ar1_lg(y = 1:10, rho = 0.6, sigma = 1, sd_y = 0.1, mu = 1)"""
+    m = ulg_1_10()
+    out = engine.bootstrap_filter(m, 10, seed=1, return_indices=True)
+    _still_works(out)
+    ref = orc.ulg_bsf_filter(m, 10, seed=1)
+    assert np.array_equal(out["indices"], ref.indices) and out["logLik"] == ref.loglik
+    m = bssm_b200.ar1_lg(Y10, rho=0.6, sigma=1.0, mu=1.0, sd_y=0.1)
+    out = engine.bootstrap_filter(m, 10, seed=1, return_indices=True)
+    if out["stopped_at"] < 0:  # sd_y = 0.1 against a trend 1..10: ten particles can degenerate
+        _still_works(out)
+    ref = orc.ulg_bsf_filter(m, 10, seed=1)
+    assert np.array_equal(out["indices"], ref.indices) and out["stopped_at"] == ref.stopped_at
+
+
+@pytest.mark.parametrize("name", ["poisson", "binomial_ar1", "negbin", "svm"])
+def test_nongaussian_bsf_still_works(engine, name):
+    """:48-122"""
+    if name == "poisson":
+        m = bssm_b200.bsm_ng(Y10, sd_level=2, sd_slope=2, P1=np.diag([2.0, 2.0]), distribution="poisson")
+    elif name == "binomial_ar1":
+        m = bssm_b200.ar1_ng(Y8, rho=0.9, sigma=1.0, mu=1.0, distribution="binomial", xreg=np.arange(1.0, 9.0)[:, None],
+                             beta=[0.0])
+    elif name == "negbin":
+        m = bssm_b200.bsm_ng(Y8, sd_level=2, sd_slope=2, P1=np.diag([2.0, 2.0]), distribution="negative binomial",
+                             phi=0.1, u=2.0)
+    else:
+        m = bssm_b200.svm(data.exchange(), rho=0.98, sd_ar=0.2, sigma=1.0)
+    out = engine.bootstrap_filter(m, 10, seed=1, return_indices=True)
+    _still_works(out)
+    ref = orc.bsf_filter(m, 10, seed=1)
+    assert np.array_equal(out["indices"], ref.indices)
+    assert out["logLik"] == pytest.approx(ref.loglik, rel=1e-13)
+
+
+# ------------------------------------------------------------ test_particle_smoother.R
+def bsm_lg_ones():
+    return bssm_b200.bsm_lg(np.ones(5), sd_y=0.01, sd_level=0.05, sd_slope=0.01, a1=[1.0, 0.0], P1=np.diag([0.01, 0.01]))
+
+
+def test_trivial_noise_does_not_affect_particle_smoother(engine):
+    """:5-14"""
+    m1, m2 = bsm_lg_ones(), bsm_lg_ones()
+    m2.y = m2.y + np.finfo(float).eps
+    a = engine.particle_smoother(m1, 100000, seed=1)["alphahat"]
+    b = engine.particle_smoother(m2, 100000, seed=1)["alphahat"]
+    np.testing.assert_allclose(a, b, rtol=1.5e-8)
+
+
+def test_different_seeds_give_comparable_results(engine):
+    """:15-22 (tolerance = 0.001)"""
+    m = bsm_lg_ones()
+    a = engine.particle_smoother(m, 100000, seed=11)["alphahat"]
+    b = engine.particle_smoother(m, 100000, seed=12)["alphahat"]
+    assert all_equal(a, b, 1e-3)
+
+
+def test_particle_smoother_for_lgssm_works_as_kalman_smoother(engine):
+    """:24-30 (tolerance = 1e-2) and :32-45 (psi vs bsf, alphahat and Vt, tolerance = 1e-2)"""
+    from test_oracle import _rts_smoother
+    m = bsm_lg_ones()
+    Z, T = m.Z[:, 0], m.T[:, :, 0]
+    RR = m.R[:, :, 0] @ m.R[:, :, 0].T
+    asm, Psm, *_ = _rts_smoother(m.y, Z, np.full(m.n, m.H[0] ** 2), T, RR, m.a1, m.P1)
+    ps = engine.particle_smoother(m, 100000, seed=1)["alphahat"]
+    assert all_equal(asm[:m.n], ps[:m.n], 1e-2)
+    out1 = engine.particle_smoother(m, 10000, method="psi", seed=1)
+    out2 = engine.particle_smoother(m, 10000, method="bsf", seed=1)
+    assert all_equal(out1["alphahat"], out2["alphahat"], 1e-2)
+    assert all_equal(out1["Vt"], out2["Vt"], 1e-2)
+
+
+@pytest.mark.parametrize("name", ["ulg", "poisson", "binomial", "negbin"])
+def test_particle_smoother_returns_finite_values(engine, name):
+    """:47-100, ten particles"""
+    if name == "ulg":
+        m = ulg_1_10()
+        _finite_smoother(engine.particle_smoother(m, 10, seed=1))
+        return
+    if name == "poisson":
+        m = bssm_b200.bsm_ng(Y10, sd_level=2, sd_slope=2, P1=np.diag([2.0, 2.0]), distribution="poisson")
+    elif name == "binomial":
+        m = bssm_b200.bsm_ng(Y8, sd_level=2, sd_slope=2, P1=np.diag([2.0, 2.0]), distribution="binomial")
+    else:
+        m = bssm_b200.bsm_ng(Y8, sd_level=0.1, sd_slope=0.1, P1=np.diag([2.0, 2.0]), phi=1.0,
+                             distribution="negative binomial")
+    for method in ("psi", "bsf"):
+        out = engine.particle_smoother(m, 10, method=method, seed=1, return_indices=True)
+        _finite_smoother(out)
+    ref = orc.psi_filter_m(m, 10, seed=1)
+    out = engine.particle_smoother(m, 10, method="psi", seed=1, return_indices=True)
+    assert np.array_equal(out["indices"], ref.indices) and out["logLik"] == ref.loglik
+
+
+def test_particle_smoother_for_svm(engine):
+    """:102-118: svm(exchange[1:20], rho = 0.98, sd_ar = 0.01, mu = 0); psi with 100 particles against
+    bsf with 10000, expect_equal(alphahat, tol = 0.1)"""
+    m = bssm_b200.svm(data.exchange()[:20], rho=0.98, sd_ar=0.01, mu=0.0)
+    out1 = engine.particle_smoother(m, 100, method="psi", seed=1)
+    out2 = engine.particle_smoother(m, 10000, method="bsf", seed=1)
+    _finite_smoother(out1)
+    assert all_equal(out1["alphahat"], out2["alphahat"], 0.1)
