@@ -156,3 +156,40 @@ def test_particle_smoother_for_svm(engine):
     out2 = engine.particle_smoother(m, 10000, method="bsf", seed=1)
     _finite_smoother(out1)
     assert all_equal(out1["alphahat"], out2["alphahat"], 0.1)
+
+
+# ------------------------------------------------------------ test_post_correct.R (data set only)
+def growth_reference_model():
+    """test_post_correct.R:58-95: the logistic growth data set (set.seed(1)), observations 2..15
+    missing, initial_theta = (0, log 0.05, 0), known_params = (dT = .1, K = 500, -1, 50, 1, 100).
+    (The test itself needs run_mcmc, which is out of scope; its model and data are reused here.)"""
+    from r_rng import RStream
+    rs = RStream(1)
+    p1, K, H, R_1, R_2, dT = 50.0, 500.0, 1.0, 0.05, 1.0, 0.1
+    t = np.arange(0.1, 10.0 + 1e-9, dT)
+    n = t.size
+    z = np.cumsum(np.concatenate([[-1.5], rs.rnorm(n - 1, sd=R_1)]))
+    r = 1.0 / (1.0 + np.exp(-z))
+    p = np.empty(n)
+    p[0] = p1
+    for i in range(1, n):
+        p[i] = rs.rnorm(1, K * p[i - 1] * np.exp(r[i - 1] * dT) / (K + p[i - 1] * (np.exp(r[i - 1] * dT) - 1)), R_2)[0]
+    y = p + rs.rnorm(n, 0.0, H)
+    y[1:15] = np.nan
+    return bssm_b200.ssm_nlg(y, "growth", theta=[0.0, np.log(0.05), 0.0], known_params=[dT, K, -1.0, 50.0, 1.0, 100.0])
+
+
+@pytest.mark.parametrize("method", ["bsf", "psi"])
+def test_growth_model_of_the_reference_post_correct_test(engine, method):
+    m = growth_reference_model()
+    assert m.n == 100 and np.isnan(m.y[1:15]).all() and np.isfinite(m.y[0])
+    if method == "bsf":
+        ref = orc.nlg_bsf_filter(m, 1000, seed=1)
+        out = engine.bootstrap_filter(m, 1000, seed=1, return_indices=True)
+    else:
+        ref = orc.nlg_psi_filter(m, 1000, seed=1)
+        out = engine.particle_smoother(m, 1000, method="psi", seed=1, return_indices=True)
+    assert np.array_equal(out["indices"], ref.indices)
+    assert out["logLik"] == ref.loglik
+    assert np.all(out["weights"][:, 1:15] == 1.0)  # missing observations: unit weights
+    assert np.isfinite(out["logLik"])
