@@ -30,6 +30,14 @@
 #else
 #define PF_HD static inline
 #endif
+/* The heavy kernels (exp, log, sincos, Philox, the Box-Muller pair) can be compiled as real
+ * functions on the device (-DPF_NOINLINE_MATH=1): the unrolled per-particle copies then share one
+ * body, which shrinks the instruction footprint of the filter kernel (experiment switch). */
+#if defined(__CUDACC__) && defined(PF_NOINLINE_MATH) && PF_NOINLINE_MATH
+#define PF_HDX static __host__ __device__ __noinline__
+#else
+#define PF_HDX PF_HD
+#endif
 
 /* ------------------------------------------------------------------ bits */
 
@@ -73,7 +81,7 @@ PF_HD void pf_mulhilo(uint32_t a, uint32_t b, uint32_t* hi, uint32_t* lo) {
   *hi = (uint32_t)(p >> 32);
 }
 
-PF_HD pf_u32x4 pf_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+PF_HDX pf_u32x4 pf_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                 uint32_t k0, uint32_t k1) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -175,7 +183,7 @@ PF_HD double pf_scalbn2(double x, int k) {
  * |r| <= ln2/2 (truncation 4e-18), exact power-of-two scaling.  Straight-line:
  * the argument is clamped to [-746, 710], where the scaling already produces
  * the correctly rounded 0 / +inf; NaN flows through the arithmetic. */
-PF_HD double pf_exp(double x) {
+PF_HDX double pf_exp(double x) {
   double xc = x < -746.0 ? -746.0 : x;   /* NaN compares false: stays NaN */
   xc = xc > 710.0 ? 710.0 : xc;
   const double MAGIC = PF_CE[13];
@@ -206,7 +214,7 @@ PF_HD double pf_exp(double x) {
  * R(z) = sum_{j=1..10} 2 z^j/(2j+1) (Taylor; truncation 6e-19 relative).
  * pf_log_normal is the kernel for positive NORMAL finite x (no special cases):
  * Box-Muller's u1 in [2^-53, 1] and the log(sum/N) of the filter need no more. */
-PF_HD double pf_log_core(uint64_t ux, int e) {
+PF_HDX double pf_log_core(uint64_t ux, int e) {
   e += (int)(ux >> 52) - 1023;
   double m = pf_u2d((ux & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
   if (m > PF_CL[12]) { m = m * 0.5; e += 1; }
@@ -255,7 +263,7 @@ PF_HD double pf_log1p(double x) {
 
 /* sin(2*pi*u), cos(2*pi*u) for u in [0,1): exact quadrant reduction, Taylor
  * kernels on |a| <= pi/4. */
-PF_HD void pf_sincos2pi(double u, double* sn, double* cs) {
+PF_HDX void pf_sincos2pi(double u, double* sn, double* cs) {
   double x4 = u * 4.0;               /* exact */
   double q = floor(x4 + 0.5);        /* nearest quadrant boundary, 0..4 */
   double f = x4 - q;                 /* exact, in [-0.5, 0.5] */
