@@ -99,7 +99,8 @@ def particle_smoother(model, particles, method="psi", seed=1, return_indices=Fal
     prediction for time n + 1); the R wrappers drop that last row (e.g. :179-181)."""
     if method not in ("psi", "bsf"):
         raise ValueError("method must be 'psi' or 'bsf' (EKPF is out of scope)")
-    if getattr(model, "distribution", None) == "gaussian" and method == "psi":
+    dist = getattr(model, "distribution", None)
+    if isinstance(dist, str) and dist == "gaussian" and method == "psi":
         # particle_smoother.lineargaussian(method = "psi") -> gaussian_psi_smoother, R/particle_smoother.R:111-128
         return gaussian_psi_smoother(model, particles, seed)
     N, seed = _check_particles(model, particles, seed)
@@ -108,7 +109,8 @@ def particle_smoother(model, particles, method="psi", seed=1, return_indices=Fal
     if model.cls == "ssm_nlg" and method == "psi":
         # particle_smoother.ssm_nlg -> psi_smoother_nlg(..., max_iter, conv_tol, iekf_iter), R/particle_smoother.R:221-228
         check(lib().bssm_b200_psi_smoother_nlg(C.byref(ms), N, seed, int(getattr(model, "max_iter", 100)),
-                                               float(getattr(model, "conv_tol", 1e-8)), 0, C.byref(b.out)))
+                                               float(getattr(model, "conv_tol", 1e-8)),
+                                               int(getattr(model, "iekf_iter", 0)), C.byref(b.out)))
     elif model.cls == "ssm_mng":
         # psi_smoother(model_type = 0) src/R_psi.cpp:57-78 / bsf_smoother src/R_bootstrap_filter.cpp:360-385
         fn = lib().bssm_b200_psi_smoother_mng if method == "psi" else lib().bssm_b200_bsf_smoother_mng

@@ -423,7 +423,7 @@ struct bssm_b200_job {
   pf::UngParams up{};
   pf::NlgParams np{};
   pf::SdeParams sp{};
-  int sde_model_id = 0;
+  int sde_model_id = 0, nlg_model_id = 0;
   DevBuf<double> lgy, theta_f;
   pf::MngParams gp{};
   pf::NlgPsiParams npp{};
@@ -493,9 +493,9 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
     npp.approx_loglik += f0;
     npp.stepc += (size_t)f0 * npp.fstride_stepc; npp.alphahat += (size_t)f0 * npp.fstride_a;
     npp.Lt += (size_t)f0 * npp.fstride_m; npp.Ct += (size_t)f0 * npp.fstride_m;
-    return launch_status(pfl::launch_nlg_psi(fp, npp, J->geo, nf, J->stream), "nlg psi filter");
+    return launch_status(pfl::launch_nlg_psi(J->nlg_model_id, fp, npp, J->geo, nf, J->stream), "nlg psi filter");
   }
-  if (J->kind == KIND_NLG) return launch_status(pfl::launch_nlg_bsf(fp, J->np, J->geo, nf, J->stream), "nlg bsf");
+  if (J->kind == KIND_NLG) return launch_status(pfl::launch_nlg_bsf(J->nlg_model_id, fp, J->np, J->geo, nf, J->stream), "nlg bsf");
   if (J->kind == KIND_SDE) {
     pf::SdeParams sp = J->sp;
     if (sp.theta_f) sp.theta_f += (size_t)6 * f0;
@@ -993,27 +993,121 @@ int job_common(bssm_b200_job* J, int kind, int n, int m, int k, uint32_t nsim, u
 
 } // namespace
 
+// registry models of ssm_nlg: shapes and parameter counts
+static int check_nlg_model(const bssm_nlg_model* M) {
+  if (M->model_id == BSSM_NLG_GROWTH) {
+    if (M->p != 1 || M->m != 2 || M->k != 2 || M->n_theta < 3 || M->n_known < 6)
+      return fail(BSSM_B200_ERR_ARG, "growth model: p = 1, m = 2, k = 2, 3 parameters, 6 known parameters");
+    return 0;
+  }
+  if (M->model_id == BSSM_NLG_AR_EXP) {
+    if (M->p != 1 || M->m != 1 || M->k != 1 || M->n_theta < 4)
+      return fail(BSSM_B200_ERR_ARG, "ar_exp model: p = 1, m = 1, k = 1, 4 parameters (mu, rho, log sigma, log H)");
+    return 0;
+  }
+  return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_nlg: unknown model_id (registry: BSSM_NLG_GROWTH, BSSM_NLG_AR_EXP)");
+}
+
 int bssm_b200_job_create_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t n_filters,
                              uint32_t first_filter_id, int out_flags, int post, bssm_b200_job** job) {
-  if (!M || !job || !M->y || !M->theta || !M->known_params) return fail(BSSM_B200_ERR_ARG, "null argument");
+  if (!M || !job || !M->y || !M->theta) return fail(BSSM_B200_ERR_ARG, "null argument");
   *job = nullptr;
-  if (M->model_id != BSSM_NLG_GROWTH) return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_nlg: unknown model_id (registry: BSSM_NLG_GROWTH)");
-  if (M->p != 1 || M->m != 2 || M->k != 2 || M->n_theta < 3 || M->n_known < 6)
-    return fail(BSSM_B200_ERR_ARG, "growth model: p = 1, m = 2, k = 2, 3 parameters, 6 known parameters");
+  int rc = check_nlg_model(M);
+  if (rc) return rc;
+  if (M->model_id == BSSM_NLG_GROWTH && !M->known_params) return fail(BSSM_B200_ERR_ARG, "null argument");
+  const int m = M->model_id == BSSM_NLG_AR_EXP ? 1 : 2;
   bssm_b200_job* J = new bssm_b200_job();
   struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
-  int rc = job_common(J, KIND_NLG, M->n, 2, 2, nsim, seed, n_filters, first_filter_id, out_flags, post);
+  rc = job_common(J, KIND_NLG, M->n, m, m, nsim, seed, n_filters, first_filter_id, out_flags, post);
   if (rc) return rc;
+  J->nlg_model_id = M->model_id;
   if ((rc = J->y.upload(M->y, M->n))) return rc;
   pf::NlgParams& np = J->np;
+  memset(&np, 0, sizeof(np));
   np.n = M->n; np.y = J->y.p;
-  const double* kp = M->known_params;
-  np.dT = kp[0]; np.K = kp[1];
-  np.a1[0] = kp[2]; np.a1[1] = kp[3];
-  const double P1[4] = {kp[4], 0.0, 0.0, kp[5]};
-  psd_chol_host(P1, 2, np.LP1);
-  np.H = pf_exp(M->theta[0]); np.R0 = pf_exp(M->theta[1]); np.R1 = pf_exp(M->theta[2]);
+  if (M->model_id == BSSM_NLG_AR_EXP) { // theta = (mu, rho, log sigma, log H), R/cpp_example_models.R:200-236
+    const double e = pf_exp(M->theta[2]);
+    const double P1 = e * e / (1 - M->theta[1] * M->theta[1]);
+    np.a1[0] = M->theta[0];
+    psd_chol_host(&P1, 1, np.LP1);
+    np.mu = M->theta[0]; np.rho = M->theta[1];
+    np.H = pf_exp(M->theta[3]); np.R0 = e;
+  } else {
+    const double* kp = M->known_params;
+    np.dT = kp[0]; np.K = kp[1];
+    np.a1[0] = kp[2]; np.a1[1] = kp[3];
+    const double P1[4] = {kp[4], 0.0, 0.0, kp[5]};
+    psd_chol_host(P1, 2, np.LP1);
+    np.H = pf_exp(M->theta[0]); np.R0 = pf_exp(M->theta[1]); np.R1 = pf_exp(M->theta[2]);
+  }
   np.wconst = std::log(2.0 * M_PI) + 2.0 * pf_log(np.H);
+  if ((rc = finish_job(J, out_flags, post))) return rc;
+  guard.j = nullptr;
+  *job = J;
+  return 0;
+}
+
+// the 32 doubles per time point that the psi-APF weights of an ssm_nlg registry model read
+// (layout: NlgPsiParams in models_nlg_sde.cuh), m = 1 or 2
+static void pack_nlg_step(const pfga::NlgApprox& ga, const double* y, int m, int t, double* c) {
+  const double LOG2PI = std::log(2.0 * M_PI);
+  const size_t mm = (size_t)m * m;
+  const double Ht = ga.H[t], HHt = Ht * Ht;
+  c[0] = y[t]; c[1] = LOG2PI + 2.0 * pf_log(Ht); c[2] = Ht; c[3] = LOG2PI + pf_log(HHt); c[4] = HHt;
+  c[5] = ga.D[t]; c[8] = ga.scales[t];
+  for (int d = 0; d < m; ++d) c[6 + d] = ga.Z[(size_t)m * t + d];
+  if (t >= 1) {
+    for (int d = 0; d < m; ++d) c[10 + d] = ga.C[(size_t)m * (t - 1) + d];
+    for (size_t e = 0; e < mm; ++e) c[12 + e] = ga.T[mm * (t - 1) + e];
+    if (m == 1) { // scalar dmvnorm branch: variances instead of inverse Cholesky factors
+      c[16] = ga.f_approx[t - 1].var1;
+      c[21] = ga.f_true[t - 1].var1;
+    } else {
+      for (size_t e = 0; e < mm; ++e) {
+        c[16 + e] = ga.f_approx[t - 1].rooti[e];
+        c[21 + e] = ga.f_true[t - 1].rooti[e];
+      }
+    }
+    c[20] = ga.f_approx[t - 1].cst;
+    c[25] = ga.f_true[t - 1].cst;
+  }
+}
+
+static int create_nlg_psi_job(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t max_iter,
+                              double conv_tol, uint32_t iekf_iter, uint32_t n_filters, uint32_t first_filter_id,
+                              int out_flags, int post, bssm_b200_job** job) {
+  if (!M || !job || !M->y || !M->theta) return fail(BSSM_B200_ERR_ARG, "null argument");
+  *job = nullptr;
+  int rc = check_nlg_model(M);
+  if (rc) return rc;
+  if (M->model_id == BSSM_NLG_GROWTH && !M->known_params) return fail(BSSM_B200_ERR_ARG, "null argument");
+  const int n = M->n, m = M->model_id == BSSM_NLG_AR_EXP ? 1 : 2;
+  bssm_b200_job* J = new bssm_b200_job();
+  struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
+  rc = job_common(J, KIND_NLG, n, m, m, nsim, seed, n_filters, first_filter_id, out_flags, post);
+  if (rc) return rc;
+  J->method = BSSM_METHOD_PSI;
+  J->nlg_model_id = M->model_id;
+  // Gaussian approximation on the host: (iterated) EKF start, relinearisation sweeps, Kalman smoother
+  pfga::NlgApprox ga(M);
+  ga.max_iter = (int)max_iter;
+  ga.conv_tol = conv_tol;
+  ga.iekf_iter = (int)iekf_iter;
+  ga.run(nullptr);
+  if (!ga.finite_mode) return fail(BSSM_B200_ERR_ARG, "Approximation did not converge.");
+  std::vector<double> sc((size_t)32 * n, 0.0);
+  for (int t = 0; t < n; ++t) pack_nlg_step(ga, M->y, m, t, &sc[(size_t)32 * t]);
+  std::vector<double> al(n_filters, ga.approx_loglik);
+  if ((rc = J->stepc.upload(sc.data(), sc.size())) || (rc = J->alphahat.upload(ga.alphahat.data(), ga.alphahat.size())) ||
+      (rc = J->Lt.upload(ga.L.data(), ga.L.size())) || (rc = J->Ct.upload(ga.Ct.data(), ga.Ct.size())) ||
+      (rc = J->approx_loglik.upload(al.data(), n_filters)))
+    return rc;
+  pf::NlgPsiParams& pp = J->npp;
+  pp.n = n; pp.stepc = J->stepc.p; pp.alphahat = J->alphahat.p; pp.Lt = J->Lt.p; pp.Ct = J->Ct.p;
+  pp.approx_loglik = J->approx_loglik.p;
+  if (M->model_id == BSSM_NLG_AR_EXP) { pp.dT = M->theta[0]; pp.K = M->theta[1]; } // (mu, rho) for T_fn
+  else { pp.dT = M->known_params[0]; pp.K = M->known_params[1]; }
+  pp.fstride_stepc = 0; pp.fstride_a = 0; pp.fstride_m = 0; // replicates share the approximation
   if ((rc = finish_job(J, out_flags, post))) return rc;
   guard.j = nullptr;
   *job = J;
@@ -1023,55 +1117,7 @@ int bssm_b200_job_create_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t se
 int bssm_b200_job_create_nlg_psi(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t max_iter,
                                  double conv_tol, uint32_t n_filters, uint32_t first_filter_id,
                                  int out_flags, int post, bssm_b200_job** job) {
-  if (!M || !job || !M->y || !M->theta || !M->known_params) return fail(BSSM_B200_ERR_ARG, "null argument");
-  *job = nullptr;
-  if (M->model_id != BSSM_NLG_GROWTH) return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_nlg: unknown model_id (registry: BSSM_NLG_GROWTH)");
-  if (M->p != 1 || M->m != 2 || M->k != 2 || M->n_theta < 3 || M->n_known < 6)
-    return fail(BSSM_B200_ERR_ARG, "growth model: p = 1, m = 2, k = 2, 3 parameters, 6 known parameters");
-  bssm_b200_job* J = new bssm_b200_job();
-  struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
-  int rc = job_common(J, KIND_NLG, M->n, 2, 2, nsim, seed, n_filters, first_filter_id, out_flags, post);
-  if (rc) return rc;
-  J->method = BSSM_METHOD_PSI;
-  const int n = M->n, m = 2;
-  // Gaussian approximation on the host: EKF start, relinearisation sweeps, Kalman smoother
-  pfga::NlgApprox ga(M);
-  ga.max_iter = (int)max_iter;
-  ga.conv_tol = conv_tol;
-  ga.run(nullptr);
-  if (!ga.finite_mode) return fail(BSSM_B200_ERR_ARG, "Approximation did not converge.");
-  std::vector<double> sc((size_t)32 * n, 0.0);
-  const double LOG2PI = std::log(2.0 * M_PI);
-  for (int t = 0; t < n; ++t) {
-    double* c = &sc[(size_t)32 * t];
-    const double Ht = ga.H[t], HHt = Ht * Ht;
-    c[0] = M->y[t]; c[1] = LOG2PI + 2.0 * pf_log(Ht); c[2] = Ht; c[3] = LOG2PI + pf_log(HHt); c[4] = HHt;
-    c[5] = ga.D[t]; c[6] = ga.Z[(size_t)m * t]; c[7] = ga.Z[(size_t)m * t + 1]; c[8] = ga.scales[t];
-    if (t >= 1) {
-      c[10] = ga.C[(size_t)m * (t - 1)]; c[11] = ga.C[(size_t)m * (t - 1) + 1];
-      for (int e = 0; e < 4; ++e) {
-        c[12 + e] = ga.T[(size_t)4 * (t - 1) + e];
-        c[16 + e] = ga.f_approx[t - 1].rooti[e];
-        c[21 + e] = ga.f_true[t - 1].rooti[e];
-      }
-      c[20] = ga.f_approx[t - 1].cst;
-      c[25] = ga.f_true[t - 1].cst;
-    }
-  }
-  std::vector<double> al(n_filters, ga.approx_loglik);
-  if ((rc = J->stepc.upload(sc.data(), sc.size())) || (rc = J->alphahat.upload(ga.alphahat.data(), ga.alphahat.size())) ||
-      (rc = J->Lt.upload(ga.L.data(), ga.L.size())) || (rc = J->Ct.upload(ga.Ct.data(), ga.Ct.size())) ||
-      (rc = J->approx_loglik.upload(al.data(), n_filters)))
-    return rc;
-  pf::NlgPsiParams& pp = J->npp;
-  pp.n = n; pp.stepc = J->stepc.p; pp.alphahat = J->alphahat.p; pp.Lt = J->Lt.p; pp.Ct = J->Ct.p;
-  pp.approx_loglik = J->approx_loglik.p;
-  pp.dT = M->known_params[0]; pp.K = M->known_params[1];
-  pp.fstride_stepc = 0; pp.fstride_a = 0; pp.fstride_m = 0; // replicates share the approximation
-  if ((rc = finish_job(J, out_flags, post))) return rc;
-  guard.j = nullptr;
-  *job = J;
-  return 0;
+  return create_nlg_psi_job(M, nsim, seed, max_iter, conv_tol, 0, n_filters, first_filter_id, out_flags, post, job);
 }
 
 // the derived parameters the device functors read, for one theta: {th0, th1, th2, logsd, e0, e2}
@@ -1344,17 +1390,15 @@ int bssm_b200_bsf_smoother_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t 
 int bssm_b200_psi_smoother_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t max_iter,
                                double conv_tol, uint32_t iekf_iter, bssm_filter_out* out) {
   if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
-  if (iekf_iter != 0) return fail(BSSM_B200_ERR_UNSUPPORTED, "iekf_iter > 0 is not implemented");
   bssm_b200_job* J = nullptr;
-  int rc = bssm_b200_job_create_nlg_psi(M, nsim, seed, max_iter, conv_tol, 1, 0, out_flags_of(out), BSSM_POST_SMOOTHER, &J);
+  int rc = create_nlg_psi_job(M, nsim, seed, max_iter, conv_tol, iekf_iter, 1, 0, out_flags_of(out), BSSM_POST_SMOOTHER, &J);
   return rc ? rc : run_fetch_destroy(J, out);
 }
 int bssm_b200_psi_filter_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t max_iter,
                              double conv_tol, uint32_t iekf_iter, bssm_filter_out* out) {
   if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
-  if (iekf_iter != 0) return fail(BSSM_B200_ERR_UNSUPPORTED, "iekf_iter > 0 is not implemented");
   bssm_b200_job* J = nullptr;
-  int rc = bssm_b200_job_create_nlg_psi(M, nsim, seed, max_iter, conv_tol, 1, 0, out_flags_of(out), BSSM_POST_NONE, &J);
+  int rc = create_nlg_psi_job(M, nsim, seed, max_iter, conv_tol, iekf_iter, 1, 0, out_flags_of(out), BSSM_POST_NONE, &J);
   return rc ? rc : run_fetch_destroy(J, out);
 }
 int bssm_b200_gaussian_psi_smoother(const bssm_ung_model* M, uint32_t nsim, uint32_t seed, double* alpha) {

@@ -21,9 +21,9 @@ int occupancy_ung_bsf(const Geometry&, int* out);
 int launch_mng_bsf(int m, int k, const pf::FilterParams&, const pf::MngParams&, const Geometry&, uint32_t nf, Stream);
 int launch_mng_psi(int m, const pf::FilterParams&, const pf::MngParams&, const Geometry&, uint32_t nf, Stream);
 int occupancy_mng_bsf(const Geometry&, int* out);
-// k_nlg.cu: growth functor, bootstrap and psi-APF
-int launch_nlg_bsf(const pf::FilterParams&, const pf::NlgParams&, const Geometry&, uint32_t nf, Stream);
-int launch_nlg_psi(const pf::FilterParams&, const pf::NlgPsiParams&, const Geometry&, uint32_t nf, Stream);
+// k_nlg.cu: ssm_nlg functor registry (growth, ar_exp), bootstrap and psi-APF
+int launch_nlg_bsf(int model_id, const pf::FilterParams&, const pf::NlgParams&, const Geometry&, uint32_t nf, Stream);
+int launch_nlg_psi(int model_id, const pf::FilterParams&, const pf::NlgPsiParams&, const Geometry&, uint32_t nf, Stream);
 int occupancy_nlg_bsf(const Geometry&, int* out);
 int occupancy_nlg_psi(const Geometry&, int* out);
 // k_sde.cu: Milstein bootstrap filter; model_id 0 = GBM, 1 = Poisson-OU (device functor registry)

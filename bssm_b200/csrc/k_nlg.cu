@@ -1,10 +1,19 @@
 #include "filters.h"
 namespace pfl {
-int launch_nlg_bsf(const pf::FilterParams& fp, const pf::NlgParams& mp, const Geometry& g, uint32_t nf, Stream s) {
-  return launch<pf::NlgGrowthBsf>(fp, mp, g, nf, s);
+// model_id: 0 = growth, 1 = ar_exp (device functor registry, include/bssm_b200.h)
+int launch_nlg_bsf(int model_id, const pf::FilterParams& fp, const pf::NlgParams& mp, const Geometry& g, uint32_t nf, Stream s) {
+  switch (model_id) {
+    case 0: return launch<pf::NlgGrowthBsf>(fp, mp, g, nf, s);
+    case 1: return launch<pf::NlgArExpBsf>(fp, mp, g, nf, s);
+  }
+  return -1;
 }
-int launch_nlg_psi(const pf::FilterParams& fp, const pf::NlgPsiParams& mp, const Geometry& g, uint32_t nf, Stream s) {
-  return launch<pf::NlgGrowthPsi>(fp, mp, g, nf, s);
+int launch_nlg_psi(int model_id, const pf::FilterParams& fp, const pf::NlgPsiParams& mp, const Geometry& g, uint32_t nf, Stream s) {
+  switch (model_id) {
+    case 0: return launch<pf::NlgGrowthPsi>(fp, mp, g, nf, s);
+    case 1: return launch<pf::NlgArExpPsi>(fp, mp, g, nf, s);
+  }
+  return -1;
 }
 int occupancy_nlg_bsf(const Geometry& g, int* out) { return occupancy<pf::NlgGrowthBsf>(g, out); }
 int occupancy_nlg_psi(const Geometry& g, int* out) { return occupancy<pf::NlgGrowthPsi>(g, out); }

@@ -26,6 +26,7 @@ struct NlgParams {
   double H;           // exp(theta0)
   double R0, R1;      // exp(theta1), exp(theta2)
   double wconst;      // log(2 pi) + 2 log(H)
+  double mu, rho;     // ar_exp: theta(0), theta(1); its R is R0, its a1 / sqrt(P1) are a1[0] / LP1[0]
 };
 
 struct NlgGrowthBsf : GaussStep<NlgGrowthBsf, 2, 2, 2> {
@@ -60,6 +61,30 @@ struct NlgGrowthBsf : GaussStep<NlgGrowthBsf, 2, 2, 2> {
     // T_fn(...) + R_fn(...) * uk with R = diag(R0, R1) (the zero entries of R add +-0)
     x[0] = xa[0] + mp.R0 * z[0];
     x[1] = t1 + mp.R1 * z[1];
+  }
+};
+
+// ------------------------------------------------------------ ssm_nlg: ar_exp
+// AR(1) state observed through its exponential (nlg_ar_exp, R/cpp_example_models.R:194-335):
+// alpha_{t+1} = mu (1 - rho) + rho alpha_t + e^{theta2} eta, y_t ~ N(e^{alpha_t}, e^{2 theta3}).
+struct NlgArExpBsf : GaussStep<NlgArExpBsf, 1, 1, 1> {
+  static constexpr int M = 1, KI = 1, KP = 1;
+  typedef NlgParams Params;
+  const NlgParams& mp;
+  double y;
+  __device__ NlgArExpBsf(const NlgParams& p, uint32_t) : mp(p) {}
+  __device__ double loglik0() const { return 0.0; }
+  __device__ double loglik_end() const { return 0.0; }
+  __device__ void init(const double* z, double* x) const { x[0] = mp.a1[0] + mp.LP1[0] * z[0]; }
+  __device__ bool observed(int t) const { return pf_isfinite(mp.y[t]); }
+  __device__ void begin_weight(int t) { y = mp.y[t]; }
+  __device__ double logw(const double* x) const {
+    const double q = (y - pf_exp(x[0])) / mp.H;
+    return -0.5 * (mp.wconst + q * q);
+  }
+  __device__ void begin_step(int) {}
+  __device__ void propagate(const double* xa, const double* z, double* x) const {
+    x[0] = (mp.mu * (1 - mp.rho) + mp.rho * xa[0]) + mp.R0 * z[0]; // T_fn(...) + R_fn(...) * uk
   }
 };
 
@@ -186,6 +211,68 @@ struct NlgGrowthPsi : GaussStep<NlgGrowthPsi, 2, 2, 2> {
     tm[0] = xa[0];
     tm[1] = mp.K * xa[1] * erdt / (mp.K + xa[1] * (erdt - 1));
     return mvn(ra, ca, x, am) - mvn(rt, ct, x, tm);
+  }
+};
+
+// ------------------------------------------------- ssm_nlg: ar_exp, psi-APF
+// psi-APF for ar_exp: same stepc packing as the growth model with the m = 1 entries
+//   [6] Z_t  [10] C_{t-1}  [12] T_{t-1}  [16] RR_{t-1} (approximate variance)  [20] log 2pi + log RR
+//   [21] R R' (true variance)  [25] log 2pi + log(R R')
+// (for one state dmvnorm takes its scalar branch, src/dmvnorm.cpp:9-16)
+struct NlgArExpPsi : GaussStep<NlgArExpPsi, 1, 1, 1> {
+  static constexpr int M = 1, KI = 1, KP = 1;
+  typedef NlgPsiParams Params;
+  const NlgPsiParams& mp;
+  const double *stepc, *alphahat, *Ltp, *Ctp;
+  double al0;
+  double y, c_sd, H, c_var, HH, D, Z0, scale;
+  double ah0, ah1, Cm, Lm;
+  double Ca, Ta, va, ca, vt, ct;
+  bool has_prev;
+
+  __device__ NlgArExpPsi(const NlgPsiParams& p, uint32_t f) : mp(p), has_prev(false) {
+    al0 = p.approx_loglik[f];
+    stepc = p.stepc + (size_t)f * p.fstride_stepc;
+    alphahat = p.alphahat + (size_t)f * p.fstride_a;
+    Ltp = p.Lt + (size_t)f * p.fstride_m;
+    Ctp = p.Ct + (size_t)f * p.fstride_m;
+  }
+  __device__ double loglik0() const { return al0; }
+  __device__ double loglik_end() const { return 0.0; }
+  __device__ void init(const double* z, double* x) const { x[0] = alphahat[0] + Ltp[0] * z[0]; }
+  __device__ bool observed(int t) const { return pf_isfinite(stepc[(size_t)32 * t]); }
+  __device__ void begin_weight(int t) {
+    const double* c = stepc + (size_t)32 * t;
+    y = c[0]; c_sd = c[1]; H = c[2]; c_var = c[3]; HH = c[4]; D = c[5]; Z0 = c[6]; scale = c[8];
+  }
+  __device__ double logw(const double* x) const {
+    const double q = (y - pf_exp(x[0])) / H;
+    const double tru = -0.5 * (c_sd + q * q);
+    const double mean = D + Z0 * x[0];
+    const double app = -0.5 * (c_var + (y - mean) * (y - mean) / HH);
+    return tru - app;
+  }
+  __device__ double finish_logw(double w, double carry) const { return (w - carry) - scale; }
+  __device__ void begin_step(int t) {
+    ah0 = alphahat[t]; ah1 = alphahat[t + 1];
+    Cm = Ctp[t + 1]; Lm = Ltp[t + 1];
+    has_prev = (t + 1 < mp.n);
+    if (has_prev) {
+      const double* c = stepc + (size_t)32 * (t + 1);
+      Ca = c[10]; Ta = c[12]; va = c[16]; ca = c[20]; vt = c[21]; ct = c[25];
+    }
+  }
+  __device__ void propagate(const double* xa, const double* z, double* x) const {
+    x[0] = ah1 + Cm * (xa[0] - ah0) + Lm * z[0];
+  }
+  // dmvnorm(a_t; C + T a_prev, RR) - dmvnorm(a_t; T_fn(a_prev), R R'), scalar branch (:915-931)
+  __device__ double trans_term(const double* xa, const double* x) const {
+    if (!has_prev) return 0.0;
+    const double am = Ca + Ta * xa[0];
+    const double tm = mp.dT * (1 - mp.K) + mp.K * xa[0]; // (mu, rho) travel in the (dT, K) slots
+    const double app = -0.5 * (ca + (x[0] - am) * (x[0] - am) / va);
+    const double tru = -0.5 * (ct + (x[0] - tm) * (x[0] - tm) / vt);
+    return app - tru;
   }
 };
 

@@ -221,10 +221,11 @@ def bsm_ng(y, sd_level, sd_slope=None, sd_seasonal=None, sd_noise=None, distribu
 class NlgModel:
     """ssm_nlg (R/models.R:1545-1570) with the user functions taken from the device
     registry instead of compiled function pointers: model="growth" is the
-    nlg_growth example of R/cpp_example_models.R:336-511."""
-    REGISTRY = {"growth": (0, 2, 2, 1, 3, 6)}  # id, m, k, p, n_theta, n_known
+    nlg_growth example of R/cpp_example_models.R:336-511, model="ar_exp" the nlg_ar_exp
+    example of :194-335 (theta = mu, rho, log sigma, log H; no known parameters)."""
+    REGISTRY = {"growth": (0, 2, 2, 1, 3, 6), "ar_exp": (1, 1, 1, 1, 4, 0)}  # id, m, k, p, n_theta, n_known
 
-    def __init__(self, y, model, theta, known_params):
+    def __init__(self, y, model, theta, known_params=(), iekf_iter=0):
         if model not in self.REGISTRY:
             raise ValueError("ssm_nlg: model must be one of %s" % sorted(self.REGISTRY))
         self.cls = "ssm_nlg"
@@ -236,6 +237,9 @@ class NlgModel:
         if self.theta.size < nth or self.known_params.size < nkn:
             raise ValueError("ssm_nlg %s: needs %d parameters and %d known parameters" % (model, nth, nkn))
         self.max_iter, self.conv_tol = 100, 1e-8  # R/models.R:1567
+        self.iekf_iter = int(iekf_iter)            # particle_smoother(..., iekf_iter), R/particle_smoother.R:192-228
+        if self.known_params.size == 0:
+            self.known_params = f64(np.zeros(1))   # never read; keeps the pointer valid
 
     def c_struct(self):
         from ._lib import NlgModel as S
@@ -276,8 +280,8 @@ class SdeModel:
         return s
 
 
-def ssm_nlg(y, model, theta, known_params):
-    return NlgModel(y, model, theta, known_params)
+def ssm_nlg(y, model, theta, known_params=(), iekf_iter=0):
+    return NlgModel(y, model, theta, known_params, iekf_iter=iekf_iter)
 
 
 def ssm_sde(y, model, theta, x0, positive):

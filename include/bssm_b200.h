@@ -222,7 +222,10 @@ int bssm_b200_job_create_mng_psi(const bssm_mng_model* model, uint32_t nsim, uin
  * pointers cannot run in a kernel, so the shipped example models are device
  * policies selected by id; theta / known_params keep their meaning. */
 enum {
-  BSSM_NLG_GROWTH = 0 /* logistic growth model, R/cpp_example_models.R:336-511 */
+  BSSM_NLG_GROWTH = 0, /* logistic growth model, R/cpp_example_models.R:336-511: m = k = 2, p = 1,
+                        * theta = (log H, log R1, log R2), known_params = (dT, K, a11, a12, P11, P12) */
+  BSSM_NLG_AR_EXP = 1  /* AR(1) state observed through exp(alpha), R/cpp_example_models.R:194-335:
+                        * m = k = p = 1, theta = (mu, rho, log sigma, log H), no known_params */
 };
 enum {
   BSSM_SDE_GBM = 0,       /* geometric Brownian motion, R/cpp_example_models.R:109-193 */
@@ -255,7 +258,7 @@ int bssm_b200_bsf_smoother_nlg(const bssm_nlg_model* model, uint32_t nsim, uint3
                                bssm_filter_out* out);
 /* replaces: psi_smoother_nlg(..., nsim, seed, max_iter, conv_tol, iekf_iter) src/R_psi.cpp:173-221
  *           -> ssm_nlg::approximate + psi_filter (src/model_ssm_nlg.cpp:62-150, :971-1063),
- *           filter_smoother, summary.  p = 1 models of the registry; iekf_iter must be 0.
+ *           filter_smoother, summary.  p = 1 models of the registry; iekf_iter > 0 iterates the EKF start (src/model_ssm_nlg.cpp:325-356).
  * bssm_b200_psi_filter_nlg is the same without backtrack / summary. */
 int bssm_b200_psi_smoother_nlg(const bssm_nlg_model* model, uint32_t nsim, uint32_t seed,
                                uint32_t max_iter, double conv_tol, uint32_t iekf_iter,

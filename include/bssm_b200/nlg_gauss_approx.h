@@ -2,7 +2,7 @@
  * one observation series (p = 1), for the psi-APF: what ssm_nlg::psi_filter needs
  * before its particle loop (/root/reference/src/model_ssm_nlg.cpp:971-993).
  *
- *   ekf (iekf_iter = 0)     src/model_ssm_nlg.cpp:284-378
+ *   ekf / iterated ekf      src/model_ssm_nlg.cpp:284-378
  *   approximate_by_ekf      src/model_ssm_nlg.cpp:188-222
  *   approximate             src/model_ssm_nlg.cpp:62-150  (relinearisation sweeps with
  *                                                          log_signal_pdf convergence and
@@ -41,20 +41,38 @@ struct NlgFns {
   int model_id;
   const double* theta;
   const double* known;
-  int m = 2, k = 2;
-  void a1_fn(double* a1) const { a1[0] = known[2]; a1[1] = known[3]; }
-  void P1_fn(double* P1) const { P1[0] = known[4]; P1[1] = 0; P1[2] = 0; P1[3] = known[5]; }
-  double H_fn(int, const double*) const { return pf_exp(theta[0]); }
-  void R_fn(int, const double*, double* R) const { R[0] = pf_exp(theta[1]); R[1] = 0; R[2] = 0; R[3] = pf_exp(theta[2]); }
-  double Z_fn(int, const double* alpha) const { return alpha[1]; }
-  void Z_gn(int, const double*, double* Zg) const { Zg[0] = 0.0; Zg[1] = 1.0; }
+  /* registry (include/bssm_b200.h): 0 = logistic growth (m = k = 2), R/cpp_example_models.R:336-511;
+   * 1 = AR(1) state observed through exp(alpha) (m = k = 1), R/cpp_example_models.R:194-335,
+   *     theta = (mu, rho, log sigma, log H) */
+  int m() const { return model_id == 1 ? 1 : 2; }
+  int k() const { return model_id == 1 ? 1 : 2; }
+  void a1_fn(double* a1) const {
+    if (model_id == 1) { a1[0] = theta[0]; return; }
+    a1[0] = known[2]; a1[1] = known[3];
+  }
+  void P1_fn(double* P1) const {
+    if (model_id == 1) { const double e = pf_exp(theta[2]); P1[0] = e * e / (1 - theta[1] * theta[1]); return; }
+    P1[0] = known[4]; P1[1] = 0; P1[2] = 0; P1[3] = known[5];
+  }
+  double H_fn(int, const double*) const { return model_id == 1 ? pf_exp(theta[3]) : pf_exp(theta[0]); }
+  void R_fn(int, const double*, double* R) const {
+    if (model_id == 1) { R[0] = pf_exp(theta[2]); return; }
+    R[0] = pf_exp(theta[1]); R[1] = 0; R[2] = 0; R[3] = pf_exp(theta[2]);
+  }
+  double Z_fn(int, const double* alpha) const { return model_id == 1 ? pf_exp(alpha[0]) : alpha[1]; }
+  void Z_gn(int, const double* alpha, double* Zg) const {
+    if (model_id == 1) { Zg[0] = pf_exp(alpha[0]); return; }
+    Zg[0] = 0.0; Zg[1] = 1.0;
+  }
   void T_fn(int, const double* alpha, double* an) const {
+    if (model_id == 1) { an[0] = theta[0] * (1 - theta[1]) + theta[1] * alpha[0]; return; }
     const double dT = known[0], K = known[1];
     an[0] = alpha[0];
     const double r = pf_exp(alpha[0]) / (1.0 + pf_exp(alpha[0]));
     an[1] = K * alpha[1] * pf_exp(r * dT) / (K + alpha[1] * (pf_exp(r * dT) - 1));
   }
-  void T_gn(int, const double* alpha, double* Tg) const { /* column-major 2 x 2 */
+  void T_gn(int, const double* alpha, double* Tg) const { /* column-major m x m */
+    if (model_id == 1) { Tg[0] = theta[1]; return; }
     const double dT = known[0], K = known[1];
     const double r = pf_exp(alpha[0]) / (1 + pf_exp(alpha[0]));
     const double den = K + alpha[1] * (pf_exp(r * dT) - 1);
@@ -72,8 +90,10 @@ struct MvnFactor {
   int m;
   std::vector<double> rooti;
   double cst;
+  double var1 = 0.0; /* m == 1: dmvnorm takes its scalar branch (src/dmvnorm.cpp:9-16, lwr = false) */
   void set(const double* S, int m_) { /* S symmetric positive definite (diag > eps assumed) */
     m = m_;
+    if (m == 1) { var1 = S[0]; rooti.assign(1, 0.0); cst = std::log(2.0 * M_PI) + pf_log(var1); return; }
     std::vector<double> Lc((size_t)m * m, 0.0);
     for (int j = 0; j < m; ++j)
       for (int i = j; i < m; ++i) {
@@ -95,6 +115,7 @@ struct MvnFactor {
     cst = sl - 0.5 * m * std::log(2.0 * M_PI);
   }
   double logpdf(const double* x, const double* mean) const {
+    if (m == 1) return -0.5 * (cst + (x[0] - mean[0]) * (x[0] - mean[0]) / var1);
     double dot = 0.0;
     for (int i = 0; i < m; ++i) {
       double z2 = 0.0;
@@ -120,6 +141,7 @@ struct NlgApprox {
   NlgFns fn;
   int n, m, k;
   int max_iter = 100;
+  int iekf_iter = 0;
   double conv_tol = 1e-8;
   /* approximating linear-Gaussian model, everything time varying */
   std::vector<double> Z, T, R, C, D, H, a1, P1;
@@ -133,7 +155,7 @@ struct NlgApprox {
   std::vector<MvnFactor> f_approx, f_true;
 
   explicit NlgApprox(const bssm_nlg_model* M_)
-      : M(M_), fn{M_->model_id, M_->theta, M_->known_params}, n(M_->n), m(M_->m), k(M_->k) {
+      : M(M_), fn{M_->model_id, M_->theta, M_->known_params}, n(M_->n), m(fn.m()), k(fn.k()) {
     const size_t mm = (size_t)m * m;
     Z.assign((size_t)m * n, 0.0); T.assign(mm * n, 0.0); R.assign((size_t)m * k * n, 0.0);
     C.assign((size_t)m * n, 0.0); D.assign(n, 0.0); H.assign(n, 0.0);
@@ -179,7 +201,7 @@ struct NlgApprox {
     return U;
   }
 
-  /* ekf with iekf_iter = 0 (:284-378): at m x (n+1), att m x n */
+  /* ekf, iterated when iekf_iter > 0 (:284-378): at m x (n+1), att m x n */
   bool ekf(std::vector<double>& at, std::vector<double>& att) const {
     const size_t mm = (size_t)m * m;
     at.assign((size_t)m * (n + 1), 0.0); att.assign((size_t)m * n, 0.0);
@@ -203,12 +225,46 @@ struct NlgApprox {
         pf_mm(Pt.data(), Zg.data(), K.data(), m, m, 1); /* Pt Zg' inv_cholF inv_cholF' */
         for (int i = 0; i < m; ++i) K[i] = K[i] * inv * inv;
         for (int i = 0; i < m; ++i) af[i] = a[i] + K[i] * v;
+        /* iterated EKF (:325-356): relinearise the observation equation at the updated state */
+        double HHi = HHt;
+        {
+          double diff = 1.0;
+          int it = 0;
+          std::vector<double> anew(m);
+          while (diff > 1e-4 && it < iekf_iter) {
+            it++;
+            fn.Z_gn(t, af, Zg.data());
+            const double Hi = fn.H_fn(t, af);
+            HHi = Hi * Hi;
+            pf_mtm(Zg.data(), Pt.data(), zp.data(), 1, m, m);
+            double Fi = 0.0;
+            for (int i = 0; i < m; ++i) Fi += zp[i] * Zg[i];
+            Fi = Fi + HHi;
+            if (!(std::isfinite(Fi) && Fi > 0)) return false;
+            const double invi = 1.0 / std::sqrt(Fi);
+            double zd = 0.0;
+            for (int i = 0; i < m; ++i) zd += Zg[i] * (a[i] - af[i]);
+            const double vi = M->y[t] - fn.Z_fn(t, af) - zd;
+            pf_mm(Pt.data(), Zg.data(), K.data(), m, m, 1);
+            for (int i = 0; i < m; ++i) K[i] = K[i] * invi * invi;
+            for (int i = 0; i < m; ++i) anew[i] = a[i] + K[i] * vi;
+            double a1s = 0.0, a2s = 0.0; /* arma::mean(arma::square(.)): two accumulators, then / m */
+            int j;
+            for (j = 1; j < m; j += 2) {
+              a1s += (af[j - 1] - anew[j - 1]) * (af[j - 1] - anew[j - 1]);
+              a2s += (af[j] - anew[j]) * (af[j] - anew[j]);
+            }
+            if ((j - 1) < m) a1s += (af[j - 1] - anew[j - 1]) * (af[j - 1] - anew[j - 1]);
+            diff = (a1s + a2s) / (double)m;
+            for (int i = 0; i < m; ++i) af[i] = anew[i];
+          }
+        }
         for (int j = 0; j < m; ++j)
           for (int i = 0; i < m; ++i) tmp[i + (size_t)m * j] = (i == j ? 1.0 : 0.0) - K[i] * Zg[j];
         pf_mm(tmp.data(), Pt.data(), A.data(), m, m, m);
         pf_mmt(A.data(), tmp.data(), B.data(), m, m, m);
         for (int j = 0; j < m; ++j)
-          for (int i = 0; i < m; ++i) Ptt[i + (size_t)m * j] = B[i + (size_t)m * j] + K[i] * HHt * K[j];
+          for (int i = 0; i < m; ++i) Ptt[i + (size_t)m * j] = B[i + (size_t)m * j] + K[i] * HHi * K[j];
       } else {
         for (int i = 0; i < m; ++i) af[i] = a[i];
         Ptt = Pt;

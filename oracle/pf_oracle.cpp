@@ -1235,10 +1235,69 @@ static double dmvnorm1(double x, double mean, double sigma) {
   return -0.5 * (std::log(2.0 * M_PI) + 2.0 * pf_log(sigma) + q * q);
 }
 
+/* nlg_ar_exp user functions, R/cpp_example_models.R:200-262: theta = (mu, rho, log sigma, log H) */
+struct ArExp {
+  const double* theta;
+  double a1_fn() const { return theta[0]; }
+  double P1_fn() const { double e = pf_exp(theta[2]); return e * e / (1 - theta[1] * theta[1]); } /* pow(exp(.), 2) */
+  double H_fn() const { return pf_exp(theta[3]); }
+  double R_fn() const { return pf_exp(theta[2]); }
+  double Z_fn(double alpha) const { return pf_exp(alpha); }
+  double T_fn(double alpha) const { return theta[0] * (1 - theta[1]) + theta[1] * alpha; }
+};
+
+/* ssm_nlg::bsf_filter, src/model_ssm_nlg.cpp:1066-1146 for the one-state ar_exp model */
+static double nlg_ar_exp_bsf_filter(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t filter, int arith,
+                                    double* alpha, double* weights, uint32_t* indices, int32_t* stopped_at) {
+  ArExp fn{M->theta};
+  const int n = M->n;
+  const size_t N = nsim;
+  const double a1 = fn.a1_fn(), P1 = fn.P1_fn();
+  std::vector<double> L_P1;
+  psd_chol(&P1, 1, L_P1);
+  auto A = [&](int t, size_t i) -> double& { return alpha[t + (size_t)(n + 1) * i]; };
+  for (size_t i = 0; i < N; ++i) A(0, i) = a1 + L_P1[0] * pf_normal(seed, filter, 0, 0, (uint32_t)i);
+  std::vector<double> W(N), logw(N), r(N), atmp(N);
+  double loglik = 0.0;
+  auto weigh = [&](int t) {
+    const double H = fn.H_fn();
+    for (size_t i = 0; i < N; ++i) logw[i] = dmvnorm1(M->y[t], fn.Z_fn(A(t, i)), H);
+  };
+  if (std::isfinite(M->y[0])) {
+    weigh(0);
+    double mxw, lmean;
+    if (!normalise(logw.data(), nsim, weights, W, &mxw, &lmean, arith)) { *stopped_at = 0; return -ORC_INF; }
+    loglik = mxw + lmean;
+  } else {
+    for (size_t i = 0; i < N; ++i) { weights[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
+  }
+  for (int t = 0; t < n; ++t) {
+    for (size_t i = 0; i < N; ++i) r[i] = pf_resample_uniform(seed, filter, t, (uint32_t)i);
+    uint32_t* ind = indices + N * t;
+    resample(W, r, nsim, ind, arith);
+    for (size_t i = 0; i < N; ++i) atmp[i] = A(t, ind[i]);
+    const double R = fn.R_fn();
+    for (size_t i = 0; i < N; ++i)
+      A(t + 1, i) = fn.T_fn(atmp[i]) + R * pf_normal(seed, filter, t + 1, 0, (uint32_t)i);
+    double* wcol = weights + N * (t + 1);
+    if (t < (n - 1) && std::isfinite(M->y[t + 1])) {
+      weigh(t + 1);
+      double mxw, lmean;
+      if (!normalise(logw.data(), nsim, wcol, W, &mxw, &lmean, arith)) { *stopped_at = t + 1; return -ORC_INF; }
+      loglik += mxw + lmean;
+    } else {
+      for (size_t i = 0; i < N; ++i) { wcol[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
+    }
+  }
+  return loglik;
+}
+
 /* ssm_nlg::bsf_filter, src/model_ssm_nlg.cpp:1066-1146 (growth model, p = 1, m = k = 2) */
 double orc_nlg_bsf_filter(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t filter, int arith,
                           double* alpha, double* weights, uint32_t* indices, int32_t* stopped_at) {
   *stopped_at = -1;
+  if (M->model_id == BSSM_NLG_AR_EXP && M->p == 1)
+    return nlg_ar_exp_bsf_filter(M, nsim, seed, filter, arith, alpha, weights, indices, stopped_at);
   if (M->model_id != BSSM_NLG_GROWTH || M->p != 1) return pf_nan();
   Growth fn{M->theta, M->known_params};
   const int n = M->n, m = 2, k = 2;
@@ -1303,22 +1362,23 @@ double orc_nlg_bsf_filter(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed,
 /* ssm_nlg::psi_filter, src/model_ssm_nlg.cpp:971-1063, with log_weights :880-935 (the
  * per-particle dmvnorm branch: time_varying = TRUE is the R default, R/models.R:1547).
  * The Gaussian approximation is include/bssm_b200/nlg_gauss_approx.h. */
-double orc_nlg_psi_filter(const bssm_nlg_model* M, const double* mode_in, uint32_t max_iter, double conv_tol,
-                          uint32_t nsim, uint32_t seed, uint32_t filter, int arith, double* alpha,
-                          double* weights, uint32_t* indices, double* approx_loglik, int32_t* stopped_at,
-                          double* mode_out) {
+static double nlg_psi_filter_impl(const bssm_nlg_model* M, const double* mode_in, uint32_t max_iter, double conv_tol,
+                                  uint32_t iekf_iter, uint32_t nsim, uint32_t seed, uint32_t filter, int arith,
+                                  double* alpha, double* weights, uint32_t* indices, double* approx_loglik,
+                                  int32_t* stopped_at, double* mode_out) {
   *stopped_at = -1;
-  if (M->model_id != BSSM_NLG_GROWTH || M->p != 1) return pf_nan();
+  if ((M->model_id != BSSM_NLG_GROWTH && M->model_id != BSSM_NLG_AR_EXP) || M->p != 1) return pf_nan();
   pfga::NlgApprox ga(M);
   ga.max_iter = (int)max_iter;
   ga.conv_tol = conv_tol;
+  ga.iekf_iter = (int)iekf_iter;
   ga.run(mode_in);
   if (!ga.finite_mode) return -ORC_INF;
   if (approx_loglik) *approx_loglik = ga.approx_loglik;
   if (mode_out) std::copy(ga.mode.begin(), ga.mode.end(), mode_out);
   const pfga::NlgFns& fn = ga.fn;
-  const int n = M->n, m = 2;
-  const size_t N = nsim, mm = 4;
+  const int n = M->n, m = ga.m; /* 1 or 2 */
+  const size_t N = nsim, mm = (size_t)m * m;
   auto A = [&](int d, int t, size_t i) -> double& { return alpha[d + (size_t)m * (t + (size_t)(n + 1) * i)]; };
   for (size_t i = 0; i < N; ++i) {
     double um[2];
@@ -1391,6 +1451,22 @@ double orc_nlg_psi_filter(const bssm_nlg_model* M, const double* mode_in, uint32
     }
   }
   return loglik;
+}
+
+double orc_nlg_psi_filter(const bssm_nlg_model* M, const double* mode_in, uint32_t max_iter, double conv_tol,
+                          uint32_t nsim, uint32_t seed, uint32_t filter, int arith, double* alpha,
+                          double* weights, uint32_t* indices, double* approx_loglik, int32_t* stopped_at,
+                          double* mode_out) {
+  return nlg_psi_filter_impl(M, mode_in, max_iter, conv_tol, 0, nsim, seed, filter, arith, alpha, weights, indices,
+                             approx_loglik, stopped_at, mode_out);
+}
+/* the same with an iterated-EKF start (iekf_iter > 0, src/model_ssm_nlg.cpp:325-356) */
+double orc_nlg_psi_filter_iekf(const bssm_nlg_model* M, uint32_t max_iter, double conv_tol, uint32_t iekf_iter,
+                               uint32_t nsim, uint32_t seed, uint32_t filter, int arith, double* alpha,
+                               double* weights, uint32_t* indices, double* approx_loglik, int32_t* stopped_at,
+                               double* mode_out) {
+  return nlg_psi_filter_impl(M, nullptr, max_iter, conv_tol, iekf_iter, nsim, seed, filter, arith, alpha, weights,
+                             indices, approx_loglik, stopped_at, mode_out);
 }
 
 /* ------------------------------------------------------------------ a14 */

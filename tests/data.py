@@ -116,6 +116,20 @@ def growth_model(n=200, gen_seed=11, missing=()):
                              known_params=[dT, K, -1.5, 50.0, 1.0, 100.0])
 
 
+def ar_exp_model(n=80, gen_seed=21, missing=(), iekf_iter=0):
+    """nlg_ar_exp (R/cpp_example_models.R:194-335): AR(1) state observed through its exponential"""
+    rng = np.random.default_rng(gen_seed)
+    mu, rho, sigma, H = 0.5, 0.9, 0.25, 0.4
+    a = np.empty(n)
+    a[0] = mu + sigma / np.sqrt(1 - rho ** 2) * rng.normal()
+    for t in range(1, n):
+        a[t] = mu * (1 - rho) + rho * a[t - 1] + sigma * rng.normal()
+    y = np.exp(a) + H * rng.normal(size=n)
+    for t in missing:
+        y[t] = np.nan
+    return bssm_b200.ssm_nlg(y, "ar_exp", theta=[0.4, 0.85, np.log(0.3), np.log(0.5)], iekf_iter=iekf_iter)
+
+
 def gbm_model(n=50, gen_seed=42, missing=()):
     """BASELINE config 5: GBM as tests/testthat/test_sde.R:7-25 (mu=.05, sigma_x=.3, sigma_y=1, x0=1),
     filter theta = (.08, .4, 1.5), positive = TRUE."""

@@ -381,13 +381,24 @@ def mng_approx(model):
     return al, ah, mode, sc
 
 
-def nlg_psi_filter(model, N, seed, filt=0, arith=ARITH_REPRO, mode=None, max_iter=100, conv_tol=1e-8):
+def nlg_psi_filter(model, N, seed, filt=0, arith=ARITH_REPRO, mode=None, max_iter=100, conv_tol=1e-8, iekf_iter=0):
     r = _alloc(model, N)
     ms = model.c_struct()
     st = C.c_int32(-1)
     al = C.c_double(0)
     r.mode = np.zeros((model.m, model.n), order="F")
     mode_a = None if mode is None else np.asfortranarray(mode, dtype=np.float64)
+    if iekf_iter:
+        f = L().orc_nlg_psi_filter_iekf
+        f.restype = C.c_double
+        f.argtypes = [C.POINTER(NlgModel), C.c_uint32, C.c_double, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                      C.c_int, c_double_p, c_double_p, c_uint32_p, C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                      c_double_p]
+        r.loglik = f(C.byref(ms), max_iter, conv_tol, iekf_iter, N, seed, filt, arith, dptr(r.alpha), dptr(r.weights),
+                     uptr(r.indices), C.byref(al), C.byref(st), dptr(r.mode))
+        r.approx_loglik = al.value
+        r.stopped_at = st.value
+        return r
     r.loglik = L().orc_nlg_psi_filter(C.byref(ms), dptr(mode_a), max_iter, conv_tol, N, seed, filt, arith,
                                       dptr(r.alpha), dptr(r.weights), uptr(r.indices), C.byref(al), C.byref(st),
                                       dptr(r.mode))

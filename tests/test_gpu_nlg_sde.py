@@ -78,6 +78,41 @@ def test_poisson_ou_bsf_parity(engine, N, L):
     assert np.array_equal(_cube(res2).view(np.uint64), sm.view(np.uint64))
 
 
+@pytest.mark.parametrize("N", [100, 3000])
+def test_ar_exp_bsf_parity(engine, N):
+    """second functor of the ssm_nlg registry: AR(1) state observed through exp(alpha) (nlg_ar_exp), m = 1"""
+    model = data.ar_exp_model(70, missing=(4, 5))
+    ref = orc.nlg_bsf_filter(model, N, seed=2)
+    res = engine.bootstrap_filter(model, N, seed=2, return_indices=True)
+    assert np.array_equal(res["indices"], ref.indices)
+    assert np.array_equal(_cube(res).view(np.uint64), ref.alpha.view(np.uint64))
+    assert np.array_equal(res["weights"].view(np.uint64), ref.weights.view(np.uint64))
+    assert res["logLik"] == ref.loglik
+    sm = orc.filter_smoother(ref.alpha, ref.indices)
+    res2 = engine.particle_smoother(model, N, method="bsf", seed=2)
+    assert np.array_equal(_cube(res2).view(np.uint64), sm.view(np.uint64))
+
+
+@pytest.mark.parametrize("N,iekf", [(100, 0), (2000, 0), (500, 5)])
+def test_ar_exp_psi_apf_parity(engine, N, iekf):
+    """psi-APF for the one-state registry model: dmvnorm takes its scalar branch for the transition
+    densities (src/dmvnorm.cpp:9-16); iekf_iter > 0 iterates the EKF start (src/model_ssm_nlg.cpp:325-356)"""
+    model = data.ar_exp_model(70, missing=(4, 5), iekf_iter=iekf)
+    ref = orc.nlg_psi_filter(model, N, seed=3, iekf_iter=iekf)
+    res = engine.particle_smoother(model, N, method="psi", seed=3, return_indices=True)
+    assert res["approx_logLik"] == ref.approx_loglik
+    assert np.array_equal(res["indices"], ref.indices)
+    assert np.array_equal(res["weights"].view(np.uint64), ref.weights.view(np.uint64))
+    assert res["logLik"] == ref.loglik
+    sm = orc.filter_smoother(ref.alpha, ref.indices)
+    assert np.array_equal(_cube(res).view(np.uint64), sm.view(np.uint64))
+    if iekf == 0:
+        assert engine.logLik(model, N, method="psi", seed=3) == ref.loglik
+        # psi-APF and bootstrap filter estimate the same likelihood
+        lb = engine.logLik(model, 50000, method="bsf", seed=1)
+        assert abs(res["logLik"] - lb) < 1.0
+
+
 def test_sde_argument_checks(engine):
     model = data.gbm_model(10)
     with pytest.raises(ValueError, match="Discretization level"):
