@@ -1062,6 +1062,7 @@ static void pack_nlg_step(const pfga::NlgApprox& ga, const double* y, int m, int
     if (m == 1) { // scalar dmvnorm branch: variances instead of inverse Cholesky factors
       c[16] = ga.f_approx[t - 1].var1;
       c[21] = ga.f_true[t - 1].var1;
+      c[26] = ga.fn.theta[0]; c[27] = ga.fn.theta[1]; // ar_exp: T_fn = mu (1 - rho) + rho alpha
     } else {
       for (size_t e = 0; e < mm; ++e) {
         c[16 + e] = ga.f_approx[t - 1].rooti[e];
@@ -1105,8 +1106,8 @@ static int create_nlg_psi_job(const bssm_nlg_model* M, uint32_t nsim, uint32_t s
   pf::NlgPsiParams& pp = J->npp;
   pp.n = n; pp.stepc = J->stepc.p; pp.alphahat = J->alphahat.p; pp.Lt = J->Lt.p; pp.Ct = J->Ct.p;
   pp.approx_loglik = J->approx_loglik.p;
-  if (M->model_id == BSSM_NLG_AR_EXP) { pp.dT = M->theta[0]; pp.K = M->theta[1]; } // (mu, rho) for T_fn
-  else { pp.dT = M->known_params[0]; pp.K = M->known_params[1]; }
+  pp.dT = 0.0; pp.K = 0.0;
+  if (M->model_id == BSSM_NLG_GROWTH) { pp.dT = M->known_params[0]; pp.K = M->known_params[1]; }
   pp.fstride_stepc = 0; pp.fstride_a = 0; pp.fstride_m = 0; // replicates share the approximation
   if ((rc = finish_job(J, out_flags, post))) return rc;
   guard.j = nullptr;
@@ -1843,17 +1844,17 @@ static int make_nlg_draw_job(const bssm_nlg_model* M, const DrawList& dl, uint32
                              bssm_b200_job** job, int out_flags = 0) {
   *job = nullptr;
   const uint32_t nf = d1 - d0;
-  const int n = M->n, m = 2;
-  const size_t n1 = (size_t)n + 1;
+  const int n = M->n, m = M->model_id == BSSM_NLG_AR_EXP ? 1 : 2;
+  const size_t n1 = (size_t)n + 1, mm = (size_t)m * m;
   bssm_b200_job* J = new bssm_b200_job();
   struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
-  int rc = job_common(J, KIND_NLG, n, 2, 2, N, seed, nf, d0, 0, BSSM_POST_NONE);
+  int rc = job_common(J, KIND_NLG, n, m, m, N, seed, nf, d0, 0, BSSM_POST_NONE);
   if (rc) return rc;
   J->method = BSSM_METHOD_PSI;
   J->post = post;
-  std::vector<double> sc((size_t)32 * n * nf, 0.0), ah((size_t)m * n1 * nf), Lt((size_t)4 * n1 * nf), Ct((size_t)4 * n1 * nf),
+  J->nlg_model_id = M->model_id;
+  std::vector<double> sc((size_t)32 * n * nf, 0.0), ah((size_t)m * n1 * nf), Lt(mm * n1 * nf), Ct(mm * n1 * nf),
       al(nf, 0.0);
-  const double LOG2PI = std::log(2.0 * M_PI);
   int bad = 0;
 #pragma omp parallel for schedule(static)
   for (int64_t f = 0; f < (int64_t)nf; ++f) {
@@ -1866,25 +1867,10 @@ static int make_nlg_draw_job(const bssm_nlg_model* M, const DrawList& dl, uint32
     if (!ga.finite_mode) { bad = 1; continue; }
     al[f] = 0.0; // approximate_for_is: the correction weight only (src/approx_mcmc.cpp:385)
     double* scf = &sc[(size_t)32 * n * f];
-    for (int t = 0; t < n; ++t) {
-      double* cc = scf + (size_t)32 * t;
-      const double Ht = ga.H[t], HHt = Ht * Ht;
-      cc[0] = M->y[t]; cc[1] = LOG2PI + 2.0 * pf_log(Ht); cc[2] = Ht; cc[3] = LOG2PI + pf_log(HHt); cc[4] = HHt;
-      cc[5] = ga.D[t]; cc[6] = ga.Z[(size_t)m * t]; cc[7] = ga.Z[(size_t)m * t + 1]; cc[8] = ga.scales[t];
-      if (t >= 1) {
-        cc[10] = ga.C[(size_t)m * (t - 1)]; cc[11] = ga.C[(size_t)m * (t - 1) + 1];
-        for (int e = 0; e < 4; ++e) {
-          cc[12 + e] = ga.T[(size_t)4 * (t - 1) + e];
-          cc[16 + e] = ga.f_approx[t - 1].rooti[e];
-          cc[21 + e] = ga.f_true[t - 1].rooti[e];
-        }
-        cc[20] = ga.f_approx[t - 1].cst;
-        cc[25] = ga.f_true[t - 1].cst;
-      }
-    }
+    for (int t = 0; t < n; ++t) pack_nlg_step(ga, M->y, m, t, scf + (size_t)32 * t);
     std::copy(ga.alphahat.begin(), ga.alphahat.end(), &ah[(size_t)m * n1 * f]);
-    std::copy(ga.L.begin(), ga.L.end(), &Lt[(size_t)4 * n1 * f]);
-    std::copy(ga.Ct.begin(), ga.Ct.end(), &Ct[(size_t)4 * n1 * f]);
+    std::copy(ga.L.begin(), ga.L.end(), &Lt[mm * n1 * f]);
+    std::copy(ga.Ct.begin(), ga.Ct.end(), &Ct[mm * n1 * f]);
   }
   if (bad) return fail(BSSM_B200_ERR_ARG, "post-correction: non-finite Gaussian approximation for a draw");
   if ((rc = J->stepc.upload(sc.data(), sc.size())) || (rc = J->alphahat.upload(ah.data(), ah.size())) ||
@@ -1894,8 +1880,8 @@ static int make_nlg_draw_job(const bssm_nlg_model* M, const DrawList& dl, uint32
   pf::NlgPsiParams& pp = J->npp;
   pp.n = n; pp.stepc = J->stepc.p; pp.alphahat = J->alphahat.p; pp.Lt = J->Lt.p; pp.Ct = J->Ct.p;
   pp.approx_loglik = J->approx_loglik.p;
-  pp.dT = M->known_params[0]; pp.K = M->known_params[1];
-  pp.fstride_stepc = (size_t)32 * n; pp.fstride_a = (size_t)m * n1; pp.fstride_m = (size_t)4 * n1;
+  if (M->model_id == BSSM_NLG_GROWTH) { pp.dT = M->known_params[0]; pp.K = M->known_params[1]; }
+  pp.fstride_stepc = (size_t)32 * n; pp.fstride_a = (size_t)m * n1; pp.fstride_m = mm * n1;
   if ((rc = finish_job(J, out_flags, post))) return rc;
   guard.j = nullptr;
   *job = J;
@@ -1907,8 +1893,11 @@ int bssm_b200_job_create_postcorr_nlg(const bssm_nlg_model* M, uint32_t nsim, ui
                                       const double* modes, uint32_t n_stored, uint32_t draw_begin,
                                       uint32_t draw_end, int out_flags, bssm_b200_job** job) {
   if (!M || !counts || !theta || !modes || !job || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
-  if (M->model_id != BSSM_NLG_GROWTH || M->p != 1 || M->m != 2 || M->k != 2 || n_par < 3)
-    return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction (nonlinear): growth model of the registry only");
+  {
+    int rcm = check_nlg_model(M);
+    if (rcm) return rcm;
+    if (n_par < (uint32_t)(M->model_id == BSSM_NLG_AR_EXP ? 4 : 3)) return fail(BSSM_B200_ERR_ARG, "post-correction (nonlinear): too few parameters");
+  }
   if (is_type == 1) return fail(BSSM_B200_ERR_ARG, "resident post-correction jobs need equal N per draw (is_type 2 or 3)");
   int rc = require_device();
   if (rc) return rc;
@@ -1926,9 +1915,13 @@ int bssm_b200_postcorrection_nonlinear(const bssm_nlg_model* M, int output_type,
                                        bssm_postcorr_out* out) {
   (void)n_threads;
   if (!M || !counts || !theta || !modes || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
-  if (M->model_id != BSSM_NLG_GROWTH || M->p != 1 || M->m != 2 || M->k != 2 || n_par < 3)
-    return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction (nonlinear): growth model of the registry only");
-  return postcorr_driver(M->n, 2, output_type, nsim, is_type, counts, n_stored, draw_begin, draw_end, out,
+  {
+    int rcm = check_nlg_model(M);
+    if (rcm) return rcm;
+    if (n_par < (uint32_t)(M->model_id == BSSM_NLG_AR_EXP ? 4 : 3)) return fail(BSSM_B200_ERR_ARG, "post-correction (nonlinear): too few parameters");
+  }
+  return postcorr_driver(M->n, M->model_id == BSSM_NLG_AR_EXP ? 1 : 2, output_type, nsim, is_type, counts, n_stored,
+                         draw_begin, draw_end, out,
                          [&](const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N, int post, bssm_b200_job** J) {
                            return make_nlg_draw_job(M, dl, d0, d1, N, seed, theta, n_par, modes, post, J);
                          });

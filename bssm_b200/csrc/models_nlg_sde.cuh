@@ -217,7 +217,7 @@ struct NlgGrowthPsi : GaussStep<NlgGrowthPsi, 2, 2, 2> {
 // ------------------------------------------------- ssm_nlg: ar_exp, psi-APF
 // psi-APF for ar_exp: same stepc packing as the growth model with the m = 1 entries
 //   [6] Z_t  [10] C_{t-1}  [12] T_{t-1}  [16] RR_{t-1} (approximate variance)  [20] log 2pi + log RR
-//   [21] R R' (true variance)  [25] log 2pi + log(R R')
+//   [21] R R' (true variance)  [25] log 2pi + log(R R')  [26..27] (mu, rho) of the true transition
 // (for one state dmvnorm takes its scalar branch, src/dmvnorm.cpp:9-16)
 struct NlgArExpPsi : GaussStep<NlgArExpPsi, 1, 1, 1> {
   static constexpr int M = 1, KI = 1, KP = 1;
@@ -227,7 +227,7 @@ struct NlgArExpPsi : GaussStep<NlgArExpPsi, 1, 1, 1> {
   double al0;
   double y, c_sd, H, c_var, HH, D, Z0, scale;
   double ah0, ah1, Cm, Lm;
-  double Ca, Ta, va, ca, vt, ct;
+  double Ca, Ta, va, ca, vt, ct, mu, rho;
   bool has_prev;
 
   __device__ NlgArExpPsi(const NlgPsiParams& p, uint32_t f) : mp(p), has_prev(false) {
@@ -259,7 +259,7 @@ struct NlgArExpPsi : GaussStep<NlgArExpPsi, 1, 1, 1> {
     has_prev = (t + 1 < mp.n);
     if (has_prev) {
       const double* c = stepc + (size_t)32 * (t + 1);
-      Ca = c[10]; Ta = c[12]; va = c[16]; ca = c[20]; vt = c[21]; ct = c[25];
+      Ca = c[10]; Ta = c[12]; va = c[16]; ca = c[20]; vt = c[21]; ct = c[25]; mu = c[26]; rho = c[27];
     }
   }
   __device__ void propagate(const double* xa, const double* z, double* x) const {
@@ -269,7 +269,7 @@ struct NlgArExpPsi : GaussStep<NlgArExpPsi, 1, 1, 1> {
   __device__ double trans_term(const double* xa, const double* x) const {
     if (!has_prev) return 0.0;
     const double am = Ca + Ta * xa[0];
-    const double tm = mp.dT * (1 - mp.K) + mp.K * xa[0]; // (mu, rho) travel in the (dT, K) slots
+    const double tm = mu * (1 - rho) + rho * xa[0]; // T_fn of the true model
     const double app = -0.5 * (ca + (x[0] - am) * (x[0] - am) / va);
     const double tru = -0.5 * (ct + (x[0] - tm) * (x[0] - tm) / vt);
     return app - tru;

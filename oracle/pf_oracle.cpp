@@ -1784,8 +1784,8 @@ int orc_postcorrection_nlg(const bssm_nlg_model* M, int output_type, uint32_t ns
                            int is_type, const uint32_t* counts, const double* theta, uint32_t n_par,
                            const double* modes, uint32_t n_stored, int arith, double* weights, double* posterior,
                            double* alpha, double* alphahat, double* Vt, double* loglik_out) {
-  if (M->m != 2 || M->p != 1) return 1;
-  const size_t n = M->n, n1 = n + 1, m = 2;
+  if ((M->model_id != BSSM_NLG_GROWTH && M->model_id != BSSM_NLG_AR_EXP) || M->p != 1) return 1;
+  const size_t n = M->n, n1 = n + 1, m = M->model_id == BSSM_NLG_AR_EXP ? 1 : 2;
   std::vector<uint32_t> src, cnt;
   for (uint32_t i = 0; i < n_stored; ++i) {
     if (is_type == 3) for (uint32_t c = 0; c < counts[i]; ++c) { src.push_back(i); cnt.push_back(1u); }

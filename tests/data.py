@@ -195,7 +195,10 @@ def growth_mcmc_output(model, n_stored, output_type=3, jitter=0.03, gen_seed=9):
     counts = (1 + rng.poisson(2, size=n_stored)).astype(np.uint32)
     modes = np.zeros((model.m * model.n, n_stored), order="F")
     for i in range(n_stored):
-        mi = bssm_b200.ssm_nlg(model.y, "growth", theta=theta[i], known_params=model.known_params)
+        name = {0: "growth", 1: "ar_exp"}[model.model_id]
+        if name == "ar_exp":
+            theta[i, 1] = np.clip(theta[i, 1], -0.98, 0.98)
+        mi = bssm_b200.ssm_nlg(model.y, name, theta=theta[i], known_params=model.known_params)
         modes[:, i] = orc.nlg_psi_filter(mi, 4, seed=1).mode.ravel(order="F")
     return {"theta": theta, "counts": counts, "modes": modes, "output_type": output_type,
             "posterior": np.zeros(n_stored)}

@@ -238,3 +238,25 @@ def test_bsf_is_correction(setup):
     res2 = engine.post_correct(model, mo2, 32, is_type="is1", seed=7, sampling_method="bsf")
     np.testing.assert_allclose(res2["alphahat"], ref2.alphahat, rtol=1e-9, atol=1e-11)
     np.testing.assert_allclose(res2["Vt"], ref2.Vt, rtol=1e-8, atol=1e-12)
+
+
+def test_ar_exp_post_correction_and_suggest_N(engine):
+    """postcorrection_nonlinear / suggest_n_nonlinear for the one-state registry model: (mu, rho) of the
+    true transition differ per draw, so they travel with the per-draw approximation"""
+    model = data.ar_exp_model(50, missing=(3,))
+    mo = data.growth_mcmc_output(model, 16, jitter=0.04)
+    ref = orc.post_correct(model, mo, 96, is_type=2, seed=3)
+    res = engine.post_correct(model, mo, 96, is_type="is2", seed=3, return_loglik=True)
+    assert np.array_equal(res["loglik"], ref.loglik)
+    assert np.array_equal(res["weights"], ref.weights)
+    mo1 = dict(mo, output_type=1)
+    ref1 = orc.post_correct(model, mo1, 64, is_type=3, seed=5)
+    res1 = engine.post_correct(model, mo1, 64, is_type="is3", seed=5)
+    assert np.array_equal(res1["alpha"].view(np.uint64), ref1.alpha.view(np.uint64))
+    mo2 = dict(mo, output_type=2)
+    ref2 = orc.post_correct(model, mo2, 32, is_type=1, seed=7)
+    res2 = engine.post_correct(model, mo2, 32, is_type="is1", seed=7)
+    np.testing.assert_allclose(res2["alphahat"], ref2.alphahat, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(res2["Vt"], ref2.Vt, rtol=1e-8, atol=1e-12)
+    sn = engine.suggest_N(model, np.asarray(model.theta), candidates=[20, 400], replications=12, seed=2)
+    assert np.all(np.isfinite(sn["results"]["sd"])) and sn["results"]["sd"][1] < sn["results"]["sd"][0]
