@@ -994,6 +994,10 @@ int job_common(bssm_b200_job* J, int kind, int n, int m, int k, uint32_t nsim, u
 } // namespace
 
 // registry models of ssm_nlg: shapes and parameter counts
+static int nlg_state_dim(const bssm_nlg_model* M) { return M->model_id == BSSM_NLG_GROWTH ? 2 : 1; }
+static int nlg_n_theta(const bssm_nlg_model* M) {
+  return M->model_id == BSSM_NLG_AR_EXP ? 4 : (M->model_id == BSSM_NLG_SIN_EXP ? 2 : 3);
+}
 static int check_nlg_model(const bssm_nlg_model* M) {
   if (M->model_id == BSSM_NLG_GROWTH) {
     if (M->p != 1 || M->m != 2 || M->k != 2 || M->n_theta < 3 || M->n_known < 6)
@@ -1005,7 +1009,12 @@ static int check_nlg_model(const bssm_nlg_model* M) {
       return fail(BSSM_B200_ERR_ARG, "ar_exp model: p = 1, m = 1, k = 1, 4 parameters (mu, rho, log sigma, log H)");
     return 0;
   }
-  return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_nlg: unknown model_id (registry: BSSM_NLG_GROWTH, BSSM_NLG_AR_EXP)");
+  if (M->model_id == BSSM_NLG_SIN_EXP) {
+    if (M->p != 1 || M->m != 1 || M->k != 1 || M->n_theta < 2)
+      return fail(BSSM_B200_ERR_ARG, "sin_exp model: p = 1, m = 1, k = 1, 2 parameters (log H, log R)");
+    return 0;
+  }
+  return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_nlg: unknown model_id (registry: BSSM_NLG_GROWTH, BSSM_NLG_AR_EXP, BSSM_NLG_SIN_EXP)");
 }
 
 int bssm_b200_job_create_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t n_filters,
@@ -1015,7 +1024,7 @@ int bssm_b200_job_create_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t se
   int rc = check_nlg_model(M);
   if (rc) return rc;
   if (M->model_id == BSSM_NLG_GROWTH && !M->known_params) return fail(BSSM_B200_ERR_ARG, "null argument");
-  const int m = M->model_id == BSSM_NLG_AR_EXP ? 1 : 2;
+  const int m = nlg_state_dim(M);
   bssm_b200_job* J = new bssm_b200_job();
   struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
   rc = job_common(J, KIND_NLG, M->n, m, m, nsim, seed, n_filters, first_filter_id, out_flags, post);
@@ -1032,6 +1041,11 @@ int bssm_b200_job_create_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t se
     psd_chol_host(&P1, 1, np.LP1);
     np.mu = M->theta[0]; np.rho = M->theta[1];
     np.H = pf_exp(M->theta[3]); np.R0 = e;
+  } else if (M->model_id == BSSM_NLG_SIN_EXP) { // a1 = 0, P1 = 1, theta = (log H, log R), R/cpp_example_models.R:640-662
+    const double P1 = 1.0;
+    np.a1[0] = 0.0;
+    psd_chol_host(&P1, 1, np.LP1);
+    np.H = pf_exp(M->theta[0]); np.R0 = pf_exp(M->theta[1]);
   } else {
     const double* kp = M->known_params;
     np.dT = kp[0]; np.K = kp[1];
@@ -1082,7 +1096,7 @@ static int create_nlg_psi_job(const bssm_nlg_model* M, uint32_t nsim, uint32_t s
   int rc = check_nlg_model(M);
   if (rc) return rc;
   if (M->model_id == BSSM_NLG_GROWTH && !M->known_params) return fail(BSSM_B200_ERR_ARG, "null argument");
-  const int n = M->n, m = M->model_id == BSSM_NLG_AR_EXP ? 1 : 2;
+  const int n = M->n, m = nlg_state_dim(M);
   bssm_b200_job* J = new bssm_b200_job();
   struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
   rc = job_common(J, KIND_NLG, n, m, m, nsim, seed, n_filters, first_filter_id, out_flags, post);
@@ -1844,7 +1858,7 @@ static int make_nlg_draw_job(const bssm_nlg_model* M, const DrawList& dl, uint32
                              bssm_b200_job** job, int out_flags = 0) {
   *job = nullptr;
   const uint32_t nf = d1 - d0;
-  const int n = M->n, m = M->model_id == BSSM_NLG_AR_EXP ? 1 : 2;
+  const int n = M->n, m = nlg_state_dim(M);
   const size_t n1 = (size_t)n + 1, mm = (size_t)m * m;
   bssm_b200_job* J = new bssm_b200_job();
   struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
@@ -1896,7 +1910,7 @@ int bssm_b200_job_create_postcorr_nlg(const bssm_nlg_model* M, uint32_t nsim, ui
   {
     int rcm = check_nlg_model(M);
     if (rcm) return rcm;
-    if (n_par < (uint32_t)(M->model_id == BSSM_NLG_AR_EXP ? 4 : 3)) return fail(BSSM_B200_ERR_ARG, "post-correction (nonlinear): too few parameters");
+    if (n_par < (uint32_t)nlg_n_theta(M)) return fail(BSSM_B200_ERR_ARG, "post-correction (nonlinear): too few parameters");
   }
   if (is_type == 1) return fail(BSSM_B200_ERR_ARG, "resident post-correction jobs need equal N per draw (is_type 2 or 3)");
   int rc = require_device();
@@ -1918,9 +1932,9 @@ int bssm_b200_postcorrection_nonlinear(const bssm_nlg_model* M, int output_type,
   {
     int rcm = check_nlg_model(M);
     if (rcm) return rcm;
-    if (n_par < (uint32_t)(M->model_id == BSSM_NLG_AR_EXP ? 4 : 3)) return fail(BSSM_B200_ERR_ARG, "post-correction (nonlinear): too few parameters");
+    if (n_par < (uint32_t)nlg_n_theta(M)) return fail(BSSM_B200_ERR_ARG, "post-correction (nonlinear): too few parameters");
   }
-  return postcorr_driver(M->n, M->model_id == BSSM_NLG_AR_EXP ? 1 : 2, output_type, nsim, is_type, counts, n_stored,
+  return postcorr_driver(M->n, nlg_state_dim(M), output_type, nsim, is_type, counts, n_stored,
                          draw_begin, draw_end, out,
                          [&](const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N, int post, bssm_b200_job** J) {
                            return make_nlg_draw_job(M, dl, d0, d1, N, seed, theta, n_par, modes, post, J);
@@ -2124,7 +2138,9 @@ __global__ void math_probe_kernel(int op, const double* __restrict__ x, double* 
     case 1: v = pf_log(v); break;
     case 2: v = pf_log1p(v); break;
     case 3: pf_sincos2pi(v, &s, &c); v = s; break;
-    default: pf_sincos2pi(v, &s, &c); v = c; break;
+    case 4: pf_sincos2pi(v, &s, &c); v = c; break;
+    case 5: v = pf_sin(v); break;
+    default: v = pf_cos(v); break;
   }
   y[i] = v;
 }
@@ -2138,7 +2154,7 @@ __global__ void rng_probe_kernel(uint32_t seed, uint32_t filter, uint32_t t, uin
 } // namespace
 
 int bssm_b200_math_probe(int op, const double* x, double* y, uint32_t n) {
-  if (!x || !y || n == 0 || op < 0 || op > 4) return fail(BSSM_B200_ERR_ARG, "bad argument");
+  if (!x || !y || n == 0 || op < 0 || op > 6) return fail(BSSM_B200_ERR_ARG, "bad argument");
   int rc = require_device();
   if (rc) return rc;
   DevBuf<double> dx, dy;

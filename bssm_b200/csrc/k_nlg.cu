@@ -1,10 +1,11 @@
 #include "filters.h"
 namespace pfl {
-// model_id: 0 = growth, 1 = ar_exp (device functor registry, include/bssm_b200.h)
+// model_id: 0 = growth, 1 = ar_exp, 2 = sin_exp (device functor registry, include/bssm_b200.h)
 int launch_nlg_bsf(int model_id, const pf::FilterParams& fp, const pf::NlgParams& mp, const Geometry& g, uint32_t nf, Stream s) {
   switch (model_id) {
     case 0: return launch<pf::NlgGrowthBsf>(fp, mp, g, nf, s);
     case 1: return launch<pf::NlgArExpBsf>(fp, mp, g, nf, s);
+    case 2: return launch<pf::NlgSinExpBsf>(fp, mp, g, nf, s);
   }
   return -1;
 }
@@ -12,6 +13,7 @@ int launch_nlg_psi(int model_id, const pf::FilterParams& fp, const pf::NlgPsiPar
   switch (model_id) {
     case 0: return launch<pf::NlgGrowthPsi>(fp, mp, g, nf, s);
     case 1: return launch<pf::NlgArExpPsi>(fp, mp, g, nf, s);
+    case 2: return launch<pf::NlgSinExpPsi>(fp, mp, g, nf, s);
   }
   return -1;
 }

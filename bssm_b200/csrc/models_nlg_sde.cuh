@@ -67,12 +67,15 @@ struct NlgGrowthBsf : GaussStep<NlgGrowthBsf, 2, 2, 2> {
 // ------------------------------------------------------------ ssm_nlg: ar_exp
 // AR(1) state observed through its exponential (nlg_ar_exp, R/cpp_example_models.R:194-335):
 // alpha_{t+1} = mu (1 - rho) + rho alpha_t + e^{theta2} eta, y_t ~ N(e^{alpha_t}, e^{2 theta3}).
-struct NlgArExpBsf : GaussStep<NlgArExpBsf, 1, 1, 1> {
+// SINE = true: the nlg_sin_exp model (R/cpp_example_models.R:635-757), alpha_{t+1} = sin(alpha_t) + e^{theta1} eta
+// with the same observation equation, a1 = 0, P1 = 1.
+template <bool SINE>
+struct Nlg1Bsf : GaussStep<Nlg1Bsf<SINE>, 1, 1, 1> {
   static constexpr int M = 1, KI = 1, KP = 1;
   typedef NlgParams Params;
   const NlgParams& mp;
   double y;
-  __device__ NlgArExpBsf(const NlgParams& p, uint32_t) : mp(p) {}
+  __device__ Nlg1Bsf(const NlgParams& p, uint32_t) : mp(p) {}
   __device__ double loglik0() const { return 0.0; }
   __device__ double loglik_end() const { return 0.0; }
   __device__ void init(const double* z, double* x) const { x[0] = mp.a1[0] + mp.LP1[0] * z[0]; }
@@ -84,9 +87,12 @@ struct NlgArExpBsf : GaussStep<NlgArExpBsf, 1, 1, 1> {
   }
   __device__ void begin_step(int) {}
   __device__ void propagate(const double* xa, const double* z, double* x) const {
-    x[0] = (mp.mu * (1 - mp.rho) + mp.rho * xa[0]) + mp.R0 * z[0]; // T_fn(...) + R_fn(...) * uk
+    const double tf = SINE ? pf_sin(xa[0]) : (mp.mu * (1 - mp.rho) + mp.rho * xa[0]);
+    x[0] = tf + mp.R0 * z[0]; // T_fn(...) + R_fn(...) * uk
   }
 };
+typedef Nlg1Bsf<false> NlgArExpBsf;
+typedef Nlg1Bsf<true> NlgSinExpBsf;
 
 // ------------------------------------------------- ssm_nlg: growth, psi-APF
 // ssm_nlg::psi_filter src/model_ssm_nlg.cpp:971-1063 with log_weights :880-935.  The
@@ -219,7 +225,8 @@ struct NlgGrowthPsi : GaussStep<NlgGrowthPsi, 2, 2, 2> {
 //   [6] Z_t  [10] C_{t-1}  [12] T_{t-1}  [16] RR_{t-1} (approximate variance)  [20] log 2pi + log RR
 //   [21] R R' (true variance)  [25] log 2pi + log(R R')  [26..27] (mu, rho) of the true transition
 // (for one state dmvnorm takes its scalar branch, src/dmvnorm.cpp:9-16)
-struct NlgArExpPsi : GaussStep<NlgArExpPsi, 1, 1, 1> {
+template <bool SINE>
+struct Nlg1Psi : GaussStep<Nlg1Psi<SINE>, 1, 1, 1> {
   static constexpr int M = 1, KI = 1, KP = 1;
   typedef NlgPsiParams Params;
   const NlgPsiParams& mp;
@@ -230,7 +237,7 @@ struct NlgArExpPsi : GaussStep<NlgArExpPsi, 1, 1, 1> {
   double Ca, Ta, va, ca, vt, ct, mu, rho;
   bool has_prev;
 
-  __device__ NlgArExpPsi(const NlgPsiParams& p, uint32_t f) : mp(p), has_prev(false) {
+  __device__ Nlg1Psi(const NlgPsiParams& p, uint32_t f) : mp(p), has_prev(false) {
     al0 = p.approx_loglik[f];
     stepc = p.stepc + (size_t)f * p.fstride_stepc;
     alphahat = p.alphahat + (size_t)f * p.fstride_a;
@@ -269,12 +276,14 @@ struct NlgArExpPsi : GaussStep<NlgArExpPsi, 1, 1, 1> {
   __device__ double trans_term(const double* xa, const double* x) const {
     if (!has_prev) return 0.0;
     const double am = Ca + Ta * xa[0];
-    const double tm = mu * (1 - rho) + rho * xa[0]; // T_fn of the true model
+    const double tm = SINE ? pf_sin(xa[0]) : (mu * (1 - rho) + rho * xa[0]); // T_fn of the true model
     const double app = -0.5 * (ca + (x[0] - am) * (x[0] - am) / va);
     const double tru = -0.5 * (ct + (x[0] - tm) * (x[0] - tm) / vt);
     return app - tru;
   }
 };
+typedef Nlg1Psi<false> NlgArExpPsi;
+typedef Nlg1Psi<true> NlgSinExpPsi;
 
 // ------------------------------------------------------------------- ssm_sde
 // Bootstrap filter ssm_sde::bsf_filter src/model_ssm_sde.cpp:21-82; every particle

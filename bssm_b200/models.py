@@ -222,8 +222,10 @@ class NlgModel:
     """ssm_nlg (R/models.R:1545-1570) with the user functions taken from the device
     registry instead of compiled function pointers: model="growth" is the
     nlg_growth example of R/cpp_example_models.R:336-511, model="ar_exp" the nlg_ar_exp
-    example of :194-335 (theta = mu, rho, log sigma, log H; no known parameters)."""
-    REGISTRY = {"growth": (0, 2, 2, 1, 3, 6), "ar_exp": (1, 1, 1, 1, 4, 0)}  # id, m, k, p, n_theta, n_known
+    example of :194-335 (theta = mu, rho, log sigma, log H; no known parameters), model="sin_exp"
+    the nlg_sin_exp example of :635-757 (theta = log H, log R)."""
+    REGISTRY = {"growth": (0, 2, 2, 1, 3, 6), "ar_exp": (1, 1, 1, 1, 4, 0),
+                "sin_exp": (2, 1, 1, 1, 2, 0)}  # id, m, k, p, n_theta, n_known
 
     def __init__(self, y, model, theta, known_params=(), iekf_iter=0):
         if model not in self.REGISTRY:

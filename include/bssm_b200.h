@@ -134,7 +134,8 @@ int bssm_b200_stratified_sample(const double* p, uint32_t n_p, const double* r,
 
 /* Test hooks: evaluate the deterministic math / random stream of
  * include/bssm_b200/pf_math.h ON THE DEVICE, so tests can check that host and
- * device agree bit for bit.  op: 0 exp, 1 log, 2 log1p, 3 sin(2 pi x), 4 cos(2 pi x). */
+ * device agree bit for bit.  op: 0 exp, 1 log, 2 log1p, 3 sin(2 pi x), 4 cos(2 pi x),
+ * 5 sin(x), 6 cos(x). */
 int bssm_b200_math_probe(int op, const double* x, double* y, uint32_t n);
 /* z: `count` normals of (seed, filter, t) in flat order; r: `count` resampling uniforms */
 int bssm_b200_rng_probe(uint32_t seed, uint32_t filter, uint32_t t, uint32_t count,
@@ -226,6 +227,9 @@ enum {
                         * theta = (log H, log R1, log R2), known_params = (dT, K, a11, a12, P11, P12) */
   BSSM_NLG_AR_EXP = 1  /* AR(1) state observed through exp(alpha), R/cpp_example_models.R:194-335:
                         * m = k = p = 1, theta = (mu, rho, log sigma, log H), no known_params */
+  ,
+  BSSM_NLG_SIN_EXP = 2 /* sine transition observed through exp(alpha), R/cpp_example_models.R:635-757:
+                        * m = k = p = 1, theta = (log H, log R), a1 = 0, P1 = 1 */
 };
 enum {
   BSSM_SDE_GBM = 0,       /* geometric Brownian motion, R/cpp_example_models.R:109-193 */

@@ -294,6 +294,16 @@ PF_HDX void pf_sincos2pi(double u, double* sn, double* cs) {
   *sn = so; *cs = co;
 }
 
+/* sin(x), cos(x) for moderate |x| (state values): one multiplication by 1/(2 pi), the exact
+ * fractional part, then the kernel above.  The reduction error is |x| * 2^-53 in the angle. */
+PF_HD void pf_sincos(double x, double* sn, double* cs) {
+  double t = x * 0.15915494309189535; /* 1 / (2 pi) */
+  double u = t - floor(t);            /* [0, 1]; 1 only by rounding, which the kernel maps onto 0 */
+  pf_sincos2pi(u, sn, cs);
+}
+PF_HD double pf_sin(double x) { double s, c; pf_sincos(x, &s, &c); return s; }
+PF_HD double pf_cos(double x) { double s, c; pf_sincos(x, &s, &c); return c; }
+
 /* ----------------------------------------------------- the random stream */
 /* Stream contract (key = (seed, purpose); counter = (index, sub, t, filter)):
  *

@@ -130,6 +130,20 @@ def ar_exp_model(n=80, gen_seed=21, missing=(), iekf_iter=0):
     return bssm_b200.ssm_nlg(y, "ar_exp", theta=[0.4, 0.85, np.log(0.3), np.log(0.5)], iekf_iter=iekf_iter)
 
 
+def sin_exp_model(n=60, gen_seed=33, missing=()):
+    """nlg_sin_exp (R/cpp_example_models.R:635-757): alpha_{t+1} = sin(alpha_t) + R eta, y = exp(alpha) + H eps"""
+    rng = np.random.default_rng(gen_seed)
+    H, R = 0.3, 0.5
+    a = np.empty(n)
+    a[0] = rng.normal()
+    for t in range(1, n):
+        a[t] = np.sin(a[t - 1]) + R * rng.normal()
+    y = np.exp(a) + H * rng.normal(size=n)
+    for t in missing:
+        y[t] = np.nan
+    return bssm_b200.ssm_nlg(y, "sin_exp", theta=[np.log(0.35), np.log(0.45)])
+
+
 def gbm_model(n=50, gen_seed=42, missing=()):
     """BASELINE config 5: GBM as tests/testthat/test_sde.R:7-25 (mu=.05, sigma_x=.3, sigma_y=1, x0=1),
     filter theta = (.08, .4, 1.5), positive = TRUE."""
@@ -195,7 +209,7 @@ def growth_mcmc_output(model, n_stored, output_type=3, jitter=0.03, gen_seed=9):
     counts = (1 + rng.poisson(2, size=n_stored)).astype(np.uint32)
     modes = np.zeros((model.m * model.n, n_stored), order="F")
     for i in range(n_stored):
-        name = {0: "growth", 1: "ar_exp"}[model.model_id]
+        name = {0: "growth", 1: "ar_exp", 2: "sin_exp"}[model.model_id]
         if name == "ar_exp":
             theta[i, 1] = np.clip(theta[i, 1], -0.98, 0.98)
         mi = bssm_b200.ssm_nlg(model.y, name, theta=theta[i], known_params=model.known_params)

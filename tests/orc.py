@@ -19,7 +19,7 @@ def L():
         for fn in ("orc_exp", "orc_log", "orc_log1p"):
             getattr(_L, fn).restype = d
             getattr(_L, fn).argtypes = [d]
-        for fn in ("orc_exp_v", "orc_log_v", "orc_log1p_v"):
+        for fn in ("orc_exp_v", "orc_log_v", "orc_log1p_v", "orc_sin_v", "orc_cos_v"):
             getattr(_L, fn).argtypes = [c_double_p, c_double_p, sz]
         _L.orc_sincos2pi_v.argtypes = [c_double_p, c_double_p, c_double_p, sz]
         _L.orc_philox.argtypes = [c_uint32_p, c_uint32_p, c_uint32_p]

@@ -113,6 +113,29 @@ def test_ar_exp_psi_apf_parity(engine, N, iekf):
         assert abs(res["logLik"] - lb) < 1.0
 
 
+@pytest.mark.parametrize("N", [100, 2500])
+def test_sin_exp_parity(engine, N):
+    """third functor of the ssm_nlg registry (nlg_sin_exp): a genuinely nonlinear transition, so the
+    psi-APF weights carry a non-trivial ratio of true and linearised transition densities"""
+    model = data.sin_exp_model(60, missing=(7,))
+    ref = orc.nlg_bsf_filter(model, N, seed=2)
+    res = engine.bootstrap_filter(model, N, seed=2, return_indices=True)
+    assert np.array_equal(res["indices"], ref.indices)
+    assert np.array_equal(_cube(res).view(np.uint64), ref.alpha.view(np.uint64))
+    assert res["logLik"] == ref.loglik
+    refp = orc.nlg_psi_filter(model, N, seed=3)
+    resp = engine.particle_smoother(model, N, method="psi", seed=3, return_indices=True)
+    assert resp["approx_logLik"] == refp.approx_loglik
+    assert np.array_equal(resp["indices"], refp.indices)
+    assert np.array_equal(resp["weights"].view(np.uint64), refp.weights.view(np.uint64))
+    assert resp["logLik"] == refp.loglik
+    sm = orc.filter_smoother(refp.alpha, refp.indices)
+    assert np.array_equal(_cube(resp).view(np.uint64), sm.view(np.uint64))
+    lb = engine.logLik(model, 50000, method="bsf", seed=1)
+    lp = np.mean([engine.logLik(model, 2000, method="psi", seed=s) for s in range(1, 6)])
+    assert abs(lp - lb) < 0.5
+
+
 def test_sde_argument_checks(engine):
     model = data.gbm_model(10)
     with pytest.raises(ValueError, match="Discretization level"):

@@ -33,6 +33,8 @@ def test_device_math_is_bit_identical_to_host(engine):
         0: ("orc_exp_v", np.concatenate([rng.uniform(-750, 710, 100000), rng.normal(0, 2, 100000), [0.0, -np.inf, np.inf]])),
         1: ("orc_log_v", np.concatenate([np.exp(rng.uniform(-740, 700, 100000)), rng.uniform(0.5, 2, 100000), [5e-324, 1.0, np.inf, 0.0]])),
         2: ("orc_log1p_v", np.exp(rng.uniform(-40, 40, 100000))),
+        5: ("orc_sin_v", np.concatenate([rng.uniform(-50, 50, 100000), [0.0, -0.0, 1e-300, -1e-20]])),
+        6: ("orc_cos_v", np.concatenate([rng.uniform(-50, 50, 100000), [0.0, -0.0, 1e-300, -1e-20]])),
     }
     for op, (fn, x) in cases.items():
         x = np.ascontiguousarray(x)

@@ -90,3 +90,15 @@ def test_normals_moments_and_stream_layout():
     assert not np.array_equal(orc.normals(8, 3, 5, 100), z[:100])
     r = orc.resample_uniforms(7, 3, 5, 100000)
     assert r.min() >= 0 and r.max() < 1 and abs(r.mean() - 0.5) < 5e-3
+
+
+def test_sin_cos_accuracy():
+    """pf_sin / pf_cos (the T_fn / T_gn of the nlg_sin_exp model): one multiplication by 1/(2 pi) as
+    argument reduction, so the error grows like |x| * 2^-53 in the angle; state values are O(1)"""
+    rng = np.random.default_rng(4)
+    x = np.concatenate([rng.uniform(-20, 20, 200000), [0.0, -0.0, 1e-300, -1e-20, np.pi, -np.pi / 2]])
+    s, c = orc.vec("orc_sin_v", x), orc.vec("orc_cos_v", x)
+    assert np.max(np.abs(s - np.sin(x))) < 4e-15
+    assert np.max(np.abs(c - np.cos(x))) < 4e-15
+    small = np.abs(x) < 1
+    assert np.max(np.abs(s[small] - np.sin(x[small]))) < 5e-16  # absolute: tiny |x| lose their sign to the reduction
