@@ -348,11 +348,13 @@ def main():
     peak, peak_src = peaks()
     filt_ms_avg = float(np.mean(filt_ms))
     achieved = BYTES_PER_PS * B * N * n / (filt_ms_avg * 1e-3) / 1e9
-    traffic = None
+    traffic, ncu_note = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("filter_kernel_dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("filter_kernel_dram_bytes_per_launch")
+            ncu_note = tj.get("ncu")  # static: what the committed ncu capture says bounds the kernel
         except Exception:
             traffic = None
     line = {
@@ -372,7 +374,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "kernel": "pf::filter_kernel<UngPsi1,P>", "kernel_ms": filt_ms_avg,
-                     "algorithmic_bytes_per_launch": BYTES_PER_PS * B * N * n},
+                     "algorithmic_bytes_per_launch": BYTES_PER_PS * B * N * n, "ncu": ncu_note},
         "clocks": clk.summary(),
         "gpu_launches": launches,
     }
