@@ -117,7 +117,8 @@ def lib():
     for name in ("bssm_b200_job_create_mng", "bssm_b200_job_create_mng_psi"):
         getattr(L, name).argtypes = [C.POINTER(MngModel), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_int, C.c_int, C.POINTER(C.c_void_p)]
-    for name in ("bssm_b200_bsf_nlg", "bssm_b200_bsf_smoother_nlg"):
+    for name in ("bssm_b200_bsf_nlg", "bssm_b200_bsf_smoother_nlg", "bssm_b200_ekpf_nlg",
+                 "bssm_b200_ekpf_smoother_nlg"):
         getattr(L, name).argtypes = [C.POINTER(NlgModel), C.c_uint32, C.c_uint32, C.POINTER(FilterOut)]
     for name in ("bssm_b200_psi_smoother_nlg", "bssm_b200_psi_filter_nlg"):
         getattr(L, name).argtypes = [C.POINTER(NlgModel), C.c_uint32, C.c_uint32, C.c_uint32, C.c_double,
@@ -127,8 +128,9 @@ def lib():
     for name in ("bssm_b200_bsf_sde", "bssm_b200_bsf_smoother_sde"):
         getattr(L, name).argtypes = [C.POINTER(SdeModel), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(FilterOut)]
     L.bssm_b200_loglik_sde.argtypes = [C.POINTER(SdeModel), C.c_uint32, C.c_uint32, C.c_uint32, c_double_p]
-    L.bssm_b200_job_create_nlg.argtypes = [C.POINTER(NlgModel), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
-                                           C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    for name in ("bssm_b200_job_create_nlg", "bssm_b200_job_create_nlg_ekpf"):
+        getattr(L, name).argtypes = [C.POINTER(NlgModel), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                     C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.bssm_b200_job_create_sde.argtypes = [C.POINTER(SdeModel), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                            C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.bssm_b200_approximate_mode.argtypes = [C.POINTER(UngModel), c_double_p]

@@ -91,14 +91,34 @@ def bootstrap_filter(model, particles, seed=1, return_indices=False, L=None):
     return res
 
 
+def ekpf_filter(model, particles, seed=1, return_indices=False):
+    """ekpf_filter, R/ekpf_filter.R (-> ekpf, src/R_ekpf.cpp:7-53): EKF-based particle filter of an
+    ssm_nlg model; same outputs as bootstrap_filter."""
+    if model.cls != "ssm_nlg":
+        raise ValueError("ekpf_filter is defined for ssm_nlg models")
+    N, seed = _check_particles(model, particles, seed)
+    b = _Buffers(model, N, indices=return_indices, filt=True)
+    ms = model.c_struct()
+    check(lib().bssm_b200_ekpf_nlg(C.byref(ms), N, seed, C.byref(b.out)))
+    _warn_stopped(b.out)
+    res = {"at": b.at.T.copy(), "att": b.att.T.copy(), "Pt": b.Pt, "Ptt": b.Ptt,
+           "weights": b.weights, "logLik": b.out.loglik, "alpha": np.transpose(b.alpha, (1, 0, 2)),
+           "device_ms": b.out.device_ms, "stopped_at": b.out.stopped_at}
+    if return_indices:
+        res["indices"] = b.indices
+    return res
+
+
 def particle_smoother(model, particles, method="psi", seed=1, return_indices=False, L=None):
     """particle_smoother: .lineargaussian R/particle_smoother.R:85-135, .nongaussian :140-186,
     .ssm_nlg :192-245, .ssm_sde :251-291.
 
     Returns the `.Call`-level result: alphahat and Vt have n + 1 time points (the extra one is the
     prediction for time n + 1); the R wrappers drop that last row (e.g. :179-181)."""
-    if method not in ("psi", "bsf"):
-        raise ValueError("method must be 'psi' or 'bsf' (EKPF is out of scope)")
+    if method not in ("psi", "bsf", "ekf"):
+        raise ValueError("method must be 'psi', 'bsf' or 'ekf'")
+    if method == "ekf" and model.cls != "ssm_nlg":
+        raise ValueError("method = 'ekf' is defined for ssm_nlg models")  # R/particle_smoother.R:192-245
     dist = getattr(model, "distribution", None)
     if isinstance(dist, str) and dist == "gaussian" and method == "psi":
         # particle_smoother.lineargaussian(method = "psi") -> gaussian_psi_smoother, R/particle_smoother.R:111-128
@@ -115,6 +135,8 @@ def particle_smoother(model, particles, method="psi", seed=1, return_indices=Fal
         # psi_smoother(model_type = 0) src/R_psi.cpp:57-78 / bsf_smoother src/R_bootstrap_filter.cpp:360-385
         fn = lib().bssm_b200_psi_smoother_mng if method == "psi" else lib().bssm_b200_bsf_smoother_mng
         check(fn(C.byref(ms), N, seed, C.byref(b.out)))
+    elif model.cls == "ssm_nlg" and method == "ekf":
+        check(lib().bssm_b200_ekpf_smoother_nlg(C.byref(ms), N, seed, C.byref(b.out)))
     elif model.cls == "ssm_nlg":
         check(lib().bssm_b200_bsf_smoother_nlg(C.byref(ms), N, seed, C.byref(b.out)))
     elif model.cls == "ssm_sde":
@@ -154,7 +176,8 @@ class FilterJob:
                                                      float(getattr(model, "conv_tol", 1e-8)), self.n_filters,
                                                      int(first_filter), int(out_flags), int(post), C.byref(self._h)))
         elif model.cls == "ssm_nlg":
-            check(lib().bssm_b200_job_create_nlg(C.byref(self._ms), N, seed, self.n_filters, int(first_filter),
+            create = lib().bssm_b200_job_create_nlg_ekpf if method == "ekf" else lib().bssm_b200_job_create_nlg
+            check(create(C.byref(self._ms), N, seed, self.n_filters, int(first_filter),
                                                  int(out_flags), int(post), C.byref(self._h)))
         elif model.cls == "ssm_sde":
             check(lib().bssm_b200_job_create_sde(C.byref(self._ms), N, int(L), seed, self.n_filters,

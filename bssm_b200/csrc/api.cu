@@ -30,6 +30,7 @@
 #include "bssm_b200/ung_gauss_approx.h"
 #include "bssm_b200/nlg_gauss_approx.h"
 #include "bssm_b200/mng_gauss_approx.h"
+#include "bssm_b200/pf_ekpf.h"
 
 namespace {
 
@@ -382,6 +383,27 @@ struct DevBuf {
 
 } // namespace
 
+// the EKF update of (a1, P1) with y_0 and its factor: the proposal of the first column of the
+// EKF particle filter (src/model_ssm_nlg.cpp:1153-1160)
+template <int MM>
+static void ekpf_first_column(const bssm_nlg_model* M, pf::NlgParams& np) {
+  pfga::NlgFns fn{M->model_id, M->theta, M->known_params};
+  double a1[MM], P1[MM * MM], att[MM], Ptt[MM * MM], Zg[MM];
+  fn.a1_fn(a1);
+  fn.P1_fn(P1);
+  if (std::isfinite(M->y[0])) {
+    fn.Z_gn(0, a1, Zg);
+    const double H = fn.H_fn(0, a1);
+    pf_ekf_update<MM>(M->y[0], a1, P1, Zg, fn.Z_fn(0, a1), H * H, att, Ptt);
+  } else {
+    for (int d = 0; d < MM; ++d) att[d] = a1[d];
+    for (int e = 0; e < MM * MM; ++e) Ptt[e] = P1[e];
+  }
+  pf_psd_chol<MM>(Ptt, np.L1);
+  for (int d = 0; d < MM; ++d) np.att1[d] = att[d];
+  for (int e = 0; e < MM * MM; ++e) np.P1[e] = P1[e];
+}
+
 // ------------------------------------------------------------------- job
 enum { KIND_UNG = 0, KIND_NLG = 1, KIND_SDE = 2, KIND_MNG = 3 };
 
@@ -495,6 +517,8 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
     npp.Lt += (size_t)f0 * npp.fstride_m; npp.Ct += (size_t)f0 * npp.fstride_m;
     return launch_status(pfl::launch_nlg_psi(J->nlg_model_id, fp, npp, J->geo, nf, J->stream), "nlg psi filter");
   }
+  if (J->kind == KIND_NLG && J->method == BSSM_METHOD_EKPF)
+    return launch_status(pfl::launch_nlg_ekpf(J->nlg_model_id, fp, J->np, J->geo, nf, J->stream), "nlg ekpf");
   if (J->kind == KIND_NLG) return launch_status(pfl::launch_nlg_bsf(J->nlg_model_id, fp, J->np, J->geo, nf, J->stream), "nlg bsf");
   if (J->kind == KIND_SDE) {
     pf::SdeParams sp = J->sp;
@@ -1017,8 +1041,8 @@ static int check_nlg_model(const bssm_nlg_model* M) {
   return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_nlg: unknown model_id (registry: BSSM_NLG_GROWTH, BSSM_NLG_AR_EXP, BSSM_NLG_SIN_EXP)");
 }
 
-int bssm_b200_job_create_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t n_filters,
-                             uint32_t first_filter_id, int out_flags, int post, bssm_b200_job** job) {
+static int create_nlg_job(const bssm_nlg_model* M, int method, uint32_t nsim, uint32_t seed, uint32_t n_filters,
+                          uint32_t first_filter_id, int out_flags, int post, bssm_b200_job** job) {
   if (!M || !job || !M->y || !M->theta) return fail(BSSM_B200_ERR_ARG, "null argument");
   *job = nullptr;
   int rc = check_nlg_model(M);
@@ -1055,10 +1079,23 @@ int bssm_b200_job_create_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t se
     np.H = pf_exp(M->theta[0]); np.R0 = pf_exp(M->theta[1]); np.R1 = pf_exp(M->theta[2]);
   }
   np.wconst = std::log(2.0 * M_PI) + 2.0 * pf_log(np.H);
+  if (method == BSSM_METHOD_EKPF) {
+    J->method = BSSM_METHOD_EKPF;
+    if (m == 1) ekpf_first_column<1>(M, np); else ekpf_first_column<2>(M, np);
+  }
   if ((rc = finish_job(J, out_flags, post))) return rc;
   guard.j = nullptr;
   *job = J;
   return 0;
+}
+
+int bssm_b200_job_create_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t n_filters,
+                             uint32_t first_filter_id, int out_flags, int post, bssm_b200_job** job) {
+  return create_nlg_job(M, BSSM_METHOD_BSF, nsim, seed, n_filters, first_filter_id, out_flags, post, job);
+}
+int bssm_b200_job_create_nlg_ekpf(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t n_filters,
+                                  uint32_t first_filter_id, int out_flags, int post, bssm_b200_job** job) {
+  return create_nlg_job(M, BSSM_METHOD_EKPF, nsim, seed, n_filters, first_filter_id, out_flags, post, job);
 }
 
 // the 32 doubles per time point that the psi-APF weights of an ssm_nlg registry model read
@@ -1400,6 +1437,18 @@ int bssm_b200_bsf_smoother_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t 
   if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
   bssm_b200_job* J = nullptr;
   int rc = bssm_b200_job_create_nlg(M, nsim, seed, 1, 0, out_flags_of(out), BSSM_POST_SMOOTHER, &J);
+  return rc ? rc : run_fetch_destroy(J, out);
+}
+int bssm_b200_ekpf_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, bssm_filter_out* out) {
+  if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
+  bssm_b200_job* J = nullptr;
+  int rc = bssm_b200_job_create_nlg_ekpf(M, nsim, seed, 1, 0, out_flags_of(out), BSSM_POST_FILTER_SUMMARY, &J);
+  return rc ? rc : run_fetch_destroy(J, out);
+}
+int bssm_b200_ekpf_smoother_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, bssm_filter_out* out) {
+  if (!out) return fail(BSSM_B200_ERR_ARG, "null out");
+  bssm_b200_job* J = nullptr;
+  int rc = bssm_b200_job_create_nlg_ekpf(M, nsim, seed, 1, 0, out_flags_of(out), BSSM_POST_SMOOTHER, &J);
   return rc ? rc : run_fetch_destroy(J, out);
 }
 int bssm_b200_psi_smoother_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t max_iter,

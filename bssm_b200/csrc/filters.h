@@ -24,6 +24,7 @@ int occupancy_mng_bsf(const Geometry&, int* out);
 // k_nlg.cu: ssm_nlg functor registry (growth, ar_exp), bootstrap and psi-APF
 int launch_nlg_bsf(int model_id, const pf::FilterParams&, const pf::NlgParams&, const Geometry&, uint32_t nf, Stream);
 int launch_nlg_psi(int model_id, const pf::FilterParams&, const pf::NlgPsiParams&, const Geometry&, uint32_t nf, Stream);
+int launch_nlg_ekpf(int model_id, const pf::FilterParams&, const pf::NlgParams&, const Geometry&, uint32_t nf, Stream); // EKF particle filter
 int occupancy_nlg_bsf(const Geometry&, int* out);
 int occupancy_nlg_psi(const Geometry&, int* out);
 // k_sde.cu: Milstein bootstrap filter; model_id 0 = GBM, 1 = Poisson-OU (device functor registry)

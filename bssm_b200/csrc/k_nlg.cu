@@ -17,6 +17,14 @@ int launch_nlg_psi(int model_id, const pf::FilterParams& fp, const pf::NlgPsiPar
   }
   return -1;
 }
+int launch_nlg_ekpf(int model_id, const pf::FilterParams& fp, const pf::NlgParams& mp, const Geometry& g, uint32_t nf, Stream s) {
+  switch (model_id) {
+    case 0: return launch<pf::NlgEkpf<0>>(fp, mp, g, nf, s);
+    case 1: return launch<pf::NlgEkpf<1>>(fp, mp, g, nf, s);
+    case 2: return launch<pf::NlgEkpf<2>>(fp, mp, g, nf, s);
+  }
+  return -1;
+}
 int occupancy_nlg_bsf(const Geometry& g, int* out) { return occupancy<pf::NlgGrowthBsf>(g, out); }
 int occupancy_nlg_psi(const Geometry& g, int* out) { return occupancy<pf::NlgGrowthPsi>(g, out); }
 } // namespace pfl

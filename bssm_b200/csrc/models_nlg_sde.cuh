@@ -9,6 +9,7 @@
 //   BSSM_SDE_GBM     geometric Brownian motion, R/cpp_example_models.R:109-193
 #pragma once
 #include "pf_device.cuh"
+#include "bssm_b200/pf_ekpf.h"
 
 namespace pf {
 
@@ -27,6 +28,8 @@ struct NlgParams {
   double R0, R1;      // exp(theta1), exp(theta2)
   double wconst;      // log(2 pi) + 2 log(H)
   double mu, rho;     // ar_exp: theta(0), theta(1); its R is R0, its a1 / sqrt(P1) are a1[0] / LP1[0]
+  // EKF particle filter only: prior covariance and the EKF update of (a1, P1) with y_0 (host)
+  double P1[4], att1[2], L1[4];
 };
 
 struct NlgGrowthBsf : GaussStep<NlgGrowthBsf, 2, 2, 2> {
@@ -284,6 +287,120 @@ struct Nlg1Psi : GaussStep<Nlg1Psi<SINE>, 1, 1, 1> {
 };
 typedef Nlg1Psi<false> NlgArExpPsi;
 typedef Nlg1Psi<true> NlgSinExpPsi;
+
+// ---------------------------------------------- ssm_nlg: EKF particle filter
+// ssm_nlg::ekf_filter src/model_ssm_nlg.cpp:1150-1260 (van der Merwe et al.): every particle runs
+// its own EKF update from its resampled ancestor -- at = T_fn(a), Pt = R R', (att, Ptt) =
+// ekf_update_step(y_{t+1}; at, Pt) -- and draws alpha_{t+1} ~ N(att, Ptt); the weights are
+// log g(y | alpha) + log N(alpha; at, Pt) - log N(alpha; att, Ptt).  The per-particle linear algebra
+// (include/bssm_b200/pf_ekpf.h, M <= 2) stays in registers.  Model functions per registry id:
+template <int MODEL> struct NlgDev;
+template <> struct NlgDev<0> { // growth
+  static constexpr int M = 2;
+  static __device__ __forceinline__ void T_fn(const NlgParams& p, const double* x, double* an) {
+    const double e0 = pf_exp(x[0]);
+    const double r = e0 / (1.0 + e0);
+    const double erdt = pf_exp(r * p.dT);
+    an[0] = x[0];
+    an[1] = p.K * x[1] * erdt / (p.K + x[1] * (erdt - 1));
+  }
+  static __device__ __forceinline__ void RR(const NlgParams& p, double* rr) {
+    rr[0] = p.R0 * p.R0; rr[1] = 0.0; rr[2] = 0.0; rr[3] = p.R1 * p.R1;
+  }
+  static __device__ __forceinline__ double Z_fn(const double* x) { return x[1]; }
+  static __device__ __forceinline__ void Z_gn(const double*, double* Zg) { Zg[0] = 0.0; Zg[1] = 1.0; }
+};
+template <> struct NlgDev<1> { // ar_exp
+  static constexpr int M = 1;
+  static __device__ __forceinline__ void T_fn(const NlgParams& p, const double* x, double* an) {
+    an[0] = p.mu * (1 - p.rho) + p.rho * x[0];
+  }
+  static __device__ __forceinline__ void RR(const NlgParams& p, double* rr) { rr[0] = p.R0 * p.R0; }
+  static __device__ __forceinline__ double Z_fn(const double* x) { return pf_exp(x[0]); }
+  static __device__ __forceinline__ void Z_gn(const double* x, double* Zg) { Zg[0] = pf_exp(x[0]); }
+};
+template <> struct NlgDev<2> { // sin_exp
+  static constexpr int M = 1;
+  static __device__ __forceinline__ void T_fn(const NlgParams&, const double* x, double* an) { an[0] = pf_sin(x[0]); }
+  static __device__ __forceinline__ void RR(const NlgParams& p, double* rr) { rr[0] = p.R0 * p.R0; }
+  static __device__ __forceinline__ double Z_fn(const double* x) { return pf_exp(x[0]); }
+  static __device__ __forceinline__ void Z_gn(const double* x, double* Zg) { Zg[0] = pf_exp(x[0]); }
+};
+
+template <int MODEL>
+struct NlgEkpf : GaussStep<NlgEkpf<MODEL>, NlgDev<MODEL>::M, NlgDev<MODEL>::M, NlgDev<MODEL>::M> {
+  typedef NlgDev<MODEL> Dev;
+  static constexpr int M = Dev::M, KI = Dev::M, KP = Dev::M;
+  typedef NlgParams Params;
+  const NlgParams& mp;
+  double y, ynext, HH;
+  bool first, last, upd;
+  __device__ NlgEkpf(const NlgParams& p, uint32_t) : mp(p), y(0.0), ynext(0.0), first(false), last(false), upd(false) {
+    HH = p.H * p.H;
+  }
+  __device__ double loglik0() const { return 0.0; }
+  __device__ double loglik_end() const { return 0.0; }
+  __device__ void init(const double* z, double* x) const { // alpha_0 = att1 + L um (:1160-1172)
+#pragma unroll
+    for (int d = 0; d < M; ++d) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < M; ++j) s += mp.L1[d + M * j] * z[j];
+      x[d] = mp.att1[d] + s;
+    }
+  }
+  __device__ bool observed(int t) const { return pf_isfinite(mp.y[t]); }
+  __device__ void begin_weight(int t) { y = mp.y[t]; first = (t == 0); }
+  __device__ double logw(const double* x) const {
+    const double q = (y - Dev::Z_fn(x)) / mp.H;
+    double w = -0.5 * (mp.wconst + q * q);                       // log_obs_density
+    if (first) w += pf_dmvnorm_var<M>(x, mp.a1, mp.P1) - pf_dmvnorm_lwr<M>(x, mp.att1, mp.L1); // :1180-1183
+    return w;
+  }
+  __device__ double finish_logw(double w, double carry) const { return w + carry; }
+  __device__ void begin_step(int t) {
+    last = !(t < mp.n - 1);
+    ynext = last ? 0.0 : mp.y[t + 1];
+    upd = !last && pf_isfinite(ynext);
+  }
+  template <int P>
+  __device__ __forceinline__ void propagate_all(const StepCtx&, const typename NlgEkpf::template Noise<P>& nz,
+                                                const double (&xa)[P][M], double (&x)[P][M], double (&carry)[P]) const {
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      double at[M], Pt[M * M], att[M], Lc[M * M];
+      Dev::T_fn(mp, xa[p], at);
+      Dev::RR(mp, Pt);
+      if (!last) {
+        double Ptt[M * M];
+        if (upd) {
+          double Zg[M];
+          Dev::Z_gn(at, Zg);
+          pf_ekf_update<M>(ynext, at, Pt, Zg, Dev::Z_fn(at), HH, att, Ptt);
+        } else {
+#pragma unroll
+          for (int d = 0; d < M; ++d) att[d] = at[d];
+#pragma unroll
+          for (int e = 0; e < M * M; ++e) Ptt[e] = Pt[e];
+        }
+        pf_psd_chol<M>(Ptt, Lc);
+      } else { // the last column uses the covariance itself as the factor (:1222-1225)
+#pragma unroll
+        for (int d = 0; d < M; ++d) att[d] = at[d];
+#pragma unroll
+        for (int e = 0; e < M * M; ++e) Lc[e] = Pt[e];
+      }
+#pragma unroll
+      for (int d = 0; d < M; ++d) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; ++j) s += Lc[d + M * j] * nz.z[p * M + j];
+        x[p][d] = att[d] + s;
+      }
+      carry[p] = upd ? pf_dmvnorm_var<M>(x[p], at, Pt) - pf_dmvnorm_lwr<M>(x[p], att, Lc) : 0.0; // :1238-1240
+    }
+  }
+};
 
 // ------------------------------------------------------------------- ssm_sde
 // Bootstrap filter ssm_sde::bsf_filter src/model_ssm_sde.cpp:21-82; every particle

@@ -48,7 +48,7 @@ enum {
   BSSM_DIST_GAUSSIAN = 5
 };
 /* sampling_method, R/run_mcmc.R:452-454 */
-enum { BSSM_METHOD_PSI = 1, BSSM_METHOD_BSF = 2 };
+enum { BSSM_METHOD_PSI = 1, BSSM_METHOD_BSF = 2, BSSM_METHOD_EKPF = 4 }; /* sampling_method codes of R/run_mcmc.R */
 /* post-processing a job runs after the filter */
 enum {
   BSSM_POST_NONE = 0,           /* filter only */
@@ -260,6 +260,16 @@ int bssm_b200_bsf_nlg(const bssm_nlg_model* model, uint32_t nsim, uint32_t seed,
 /* replaces: bsf_smoother_nlg(...) src/R_bootstrap_filter.cpp:509-551 */
 int bssm_b200_bsf_smoother_nlg(const bssm_nlg_model* model, uint32_t nsim, uint32_t seed,
                                bssm_filter_out* out);
+/* replaces: ekpf(...) and ekpf_smoother(...) src/R_ekpf.cpp:7-100 -> ssm_nlg::ekf_filter
+ *           src/model_ssm_nlg.cpp:1150-1260 (EKF-based particle filter: every particle proposes from
+ *           its own EKF update) + filter_summary / filter_smoother + summary.  Registry models. */
+int bssm_b200_ekpf_nlg(const bssm_nlg_model* model, uint32_t nsim, uint32_t seed, bssm_filter_out* out);
+int bssm_b200_ekpf_smoother_nlg(const bssm_nlg_model* model, uint32_t nsim, uint32_t seed,
+                                bssm_filter_out* out);
+int bssm_b200_job_create_nlg_ekpf(const bssm_nlg_model* model, uint32_t nsim, uint32_t seed,
+                                  uint32_t n_filters, uint32_t first_filter_id, int out_flags, int post,
+                                  bssm_b200_job** job);
+
 /* replaces: psi_smoother_nlg(..., nsim, seed, max_iter, conv_tol, iekf_iter) src/R_psi.cpp:173-221
  *           -> ssm_nlg::approximate + psi_filter (src/model_ssm_nlg.cpp:62-150, :971-1063),
  *           filter_smoother, summary.  p = 1 models of the registry; iekf_iter > 0 iterates the EKF start (src/model_ssm_nlg.cpp:325-356).

@@ -58,6 +58,7 @@
 #include "bssm_b200/ung_gauss_approx.h"
 #include "bssm_b200/nlg_gauss_approx.h"
 #include "bssm_b200/mng_gauss_approx.h"
+#include "bssm_b200/pf_ekpf.h"
 
 enum { ORC_ARITH_REFERENCE = 0, ORC_ARITH_REPRO = 1 };
 
@@ -1503,7 +1504,107 @@ struct PoissonOu {
 
 /* milstein + milstein_worker, src/milstein.cpp:18-48; dB(k) = N(0, sqrt(dt)) drawn
  * as sqrt(dt) * z with z the (particle i, sub-step k) normal of the Philox stream */
-} /* extern "C": the two templates below need C++ linkage */
+} /* extern "C": the templates below need C++ linkage */
+
+/* ssm_nlg::ekf_filter, src/model_ssm_nlg.cpp:1150-1260 (EKF-based particle filter), p = 1, M states.
+ * The per-particle linear algebra is include/bssm_b200/pf_ekpf.h (shared with the device policy,
+ * like pf_math.h); the loop structure and the model functions (pfga::NlgFns) are restated here. */
+template <int M>
+static double nlg_ekf_filter(const bssm_nlg_model* Mo, uint32_t nsim, uint32_t seed, uint32_t filter, int arith,
+                             double* alpha, double* weights, uint32_t* indices, int32_t* stopped_at) {
+  *stopped_at = -1;
+  pfga::NlgFns fn{Mo->model_id, Mo->theta, Mo->known_params};
+  const int n = Mo->n, m = M;
+  const size_t N = nsim;
+  double a1[2] = {0, 0}, P1[4] = {0, 0, 0, 0}, att1[2], Ptt1[4], L1[4]; /* sized for the largest registry model */
+  fn.a1_fn(a1);
+  fn.P1_fn(P1);
+  auto update = [&](int t, const double* at, const double* Pt, double* att, double* Ptt) { /* ekf_update_step */
+    if (std::isfinite(Mo->y[t])) {
+      double Zg[2];
+      fn.Z_gn(t, at, Zg);
+      const double H = fn.H_fn(t, at);
+      pf_ekf_update<M>(Mo->y[t], at, Pt, Zg, fn.Z_fn(t, at), H * H, att, Ptt);
+    } else {
+      for (int d = 0; d < M; ++d) att[d] = at[d];
+      for (int e = 0; e < M * M; ++e) Ptt[e] = Pt[e];
+    }
+  };
+  update(0, a1, P1, att1, Ptt1);
+  pf_psd_chol<M>(Ptt1, L1);
+  auto A = [&](int d, int t, size_t i) -> double& { return alpha[d + (size_t)m * (t + (size_t)(n + 1) * i)]; };
+  for (size_t i = 0; i < N; ++i) {
+    double um[2];
+    for (int j = 0; j < M; ++j) um[j] = pf_normal(seed, filter, 0, 0, (uint32_t)(i * m + j));
+    for (int d = 0; d < M; ++d) {
+      double sacc = 0.0;
+      for (int j = 0; j < M; ++j) sacc += L1[d + M * j] * um[j];
+      A(d, 0, i) = att1[d] + sacc;
+    }
+  }
+  auto log_obs = [&](int t, const double* a) { return pfga::dnorm1_sd(Mo->y[t], fn.Z_fn(t, a), fn.H_fn(t, a)); };
+  std::vector<double> W(N), logw(N), r(N), atmp((size_t)m * N), attv((size_t)m * N), Lv((size_t)m * m * N);
+  double loglik = 0.0;
+  if (std::isfinite(Mo->y[0])) {
+    for (size_t i = 0; i < N; ++i) {
+      double w = log_obs(0, &A(0, 0, i));
+      w += pf_dmvnorm_var<M>(&A(0, 0, i), a1, P1) - pf_dmvnorm_lwr<M>(&A(0, 0, i), att1, L1);
+      logw[i] = w;
+    }
+    double mxw, lmean;
+    if (!normalise(logw.data(), nsim, weights, W, &mxw, &lmean, arith)) { *stopped_at = 0; return -ORC_INF; }
+    loglik = mxw + lmean;
+  } else {
+    for (size_t i = 0; i < N; ++i) { weights[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
+  }
+  for (int t = 0; t < n; ++t) {
+    for (size_t i = 0; i < N; ++i) r[i] = pf_resample_uniform(seed, filter, t, (uint32_t)i);
+    uint32_t* ind = indices + N * t;
+    resample(W, r, nsim, ind, arith);
+    for (size_t i = 0; i < N; ++i) {
+      for (int d = 0; d < M; ++d) atmp[d + (size_t)m * i] = A(d, t, ind[i]);
+      double Rt[4] = {0, 0, 0, 0}, Pt[4], at[2] = {0, 0}, Ptt[4];
+      fn.R_fn(t, &atmp[(size_t)m * i], Rt);
+      pf_mmt(Rt, Rt, Pt, M, M, M);
+      fn.T_fn(t, &atmp[(size_t)m * i], at);
+      if (t < (n - 1)) {
+        update(t + 1, at, Pt, &attv[(size_t)m * i], Ptt);
+        pf_psd_chol<M>(Ptt, &Lv[(size_t)m * m * i]);
+      } else { /* :1222-1225: the covariance itself takes the place of its factor */
+        for (int d = 0; d < M; ++d) attv[d + (size_t)m * i] = at[d];
+        for (int e = 0; e < M * M; ++e) Lv[e + (size_t)m * m * i] = Pt[e];
+      }
+    }
+    for (size_t i = 0; i < N; ++i) {
+      double um[2];
+      for (int j = 0; j < M; ++j) um[j] = pf_normal(seed, filter, t + 1, 0, (uint32_t)(i * m + j));
+      for (int d = 0; d < M; ++d) {
+        double sacc = 0.0;
+        for (int j = 0; j < M; ++j) sacc += Lv[d + M * j + (size_t)m * m * i] * um[j];
+        A(d, t + 1, i) = attv[d + (size_t)m * i] + sacc;
+      }
+    }
+    double* wcol = weights + N * (t + 1);
+    if (t < (n - 1) && std::isfinite(Mo->y[t + 1])) {
+      for (size_t i = 0; i < N; ++i) {
+        double Rt[4] = {0, 0, 0, 0}, RR[4], mean[2] = {0, 0};
+        fn.R_fn(t, &atmp[(size_t)m * i], Rt);
+        pf_mmt(Rt, Rt, RR, M, M, M);
+        fn.T_fn(t, &atmp[(size_t)m * i], mean);
+        double w = log_obs(t + 1, &A(0, t + 1, i));
+        w += pf_dmvnorm_var<M>(&A(0, t + 1, i), mean, RR) -
+             pf_dmvnorm_lwr<M>(&A(0, t + 1, i), &attv[(size_t)m * i], &Lv[(size_t)m * m * i]);
+        logw[i] = w;
+      }
+      double mxw, lmean;
+      if (!normalise(logw.data(), nsim, wcol, W, &mxw, &lmean, arith)) { *stopped_at = t + 1; return -ORC_INF; }
+      loglik += mxw + lmean;
+    } else {
+      for (size_t i = 0; i < N; ++i) { wcol[i] = 1.0; W[i] = (arith == ORC_ARITH_REFERENCE) ? 1.0 / nsim : 1.0; }
+    }
+  }
+  return loglik;
+}
 
 template <class Fn>
 static double milstein(double x, unsigned int L, const Fn& fn, bool positive, uint32_t seed, uint32_t filter,
@@ -1559,6 +1660,17 @@ static double sde_bsf_filter(const Fn& fn, const bssm_sde_model* M, uint32_t nsi
 }
 
 extern "C" {
+
+double orc_nlg_ekf_filter(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t filter, int arith,
+                          double* alpha, double* weights, uint32_t* indices, int32_t* stopped_at) {
+  if (M->p != 1) { *stopped_at = -1; return pf_nan(); }
+  if (M->model_id == BSSM_NLG_GROWTH)
+    return nlg_ekf_filter<2>(M, nsim, seed, filter, arith, alpha, weights, indices, stopped_at);
+  if (M->model_id == BSSM_NLG_AR_EXP || M->model_id == BSSM_NLG_SIN_EXP)
+    return nlg_ekf_filter<1>(M, nsim, seed, filter, arith, alpha, weights, indices, stopped_at);
+  *stopped_at = -1;
+  return pf_nan();
+}
 
 double orc_sde_bsf_filter(const bssm_sde_model* M, uint32_t nsim, uint32_t L, uint32_t seed, uint32_t filter,
                           int arith, double* alpha, double* weights, uint32_t* indices, int32_t* stopped_at) {

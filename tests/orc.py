@@ -407,6 +407,20 @@ def nlg_psi_filter(model, N, seed, filt=0, arith=ARITH_REPRO, mode=None, max_ite
     return r
 
 
+def nlg_ekf_filter(model, N, seed, filt=0, arith=ARITH_REPRO):
+    """oracle of ssm_nlg::ekf_filter (EKF-based particle filter)"""
+    r = _alloc(model, N)
+    ms = model.c_struct()
+    st = C.c_int32(-1)
+    f = L().orc_nlg_ekf_filter
+    f.restype = C.c_double
+    f.argtypes = [C.POINTER(NlgModel), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, c_double_p, c_double_p,
+                  c_uint32_p, C.POINTER(C.c_int32)]
+    r.loglik = f(C.byref(ms), N, seed, filt, arith, dptr(r.alpha), dptr(r.weights), uptr(r.indices), C.byref(st))
+    r.stopped_at = st.value
+    return r
+
+
 def ulg_bsf_filter(model, N, seed, filt=0, arith=ARITH_REPRO):
     r = _alloc(model, N)
     ms = model.c_struct()

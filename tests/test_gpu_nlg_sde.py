@@ -136,6 +136,28 @@ def test_sin_exp_parity(engine, N):
     assert abs(lp - lb) < 0.5
 
 
+@pytest.mark.parametrize("name,N", [("growth", 100), ("growth", 3000), ("ar_exp", 1000), ("sin_exp", 1000)])
+def test_ekpf_parity(engine, name, N):
+    """EKF-based particle filter (ssm_nlg::ekf_filter, src/model_ssm_nlg.cpp:1150-1260): every particle
+    proposes from its own EKF update; 2 x 2 linear algebra per particle for the growth model"""
+    model = {"growth": lambda: data.growth_model(60, missing=(4,)),
+             "ar_exp": lambda: data.ar_exp_model(70, missing=(4, 5)),
+             "sin_exp": lambda: data.sin_exp_model(60, missing=(7,))}[name]()
+    ref = orc.nlg_ekf_filter(model, N, seed=5)
+    res = engine.ekpf_filter(model, N, seed=5, return_indices=True)
+    assert np.array_equal(res["indices"], ref.indices)
+    assert np.array_equal(res["weights"].view(np.uint64), ref.weights.view(np.uint64))
+    assert np.array_equal(_cube(res).view(np.uint64), ref.alpha.view(np.uint64))
+    assert res["logLik"] == ref.loglik
+    sm = orc.filter_smoother(ref.alpha, ref.indices)
+    res2 = engine.particle_smoother(model, N, method="ekf", seed=5)
+    assert np.array_equal(_cube(res2).view(np.uint64), sm.view(np.uint64))
+    # the three filters estimate the same likelihood
+    lb = engine.logLik(model, 50000, method="bsf", seed=1)
+    le = np.mean([engine.logLik(model, 5000, method="ekf", seed=s) for s in range(1, 5)])
+    assert abs(le - lb) < 0.5
+
+
 def test_sde_argument_checks(engine):
     model = data.gbm_model(10)
     with pytest.raises(ValueError, match="Discretization level"):
