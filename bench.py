@@ -154,6 +154,31 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def other_configs_leg(bssm_b200):
+    """BASELINE configs 3 and 5 at full size, device-timed (CUDA events inside the job): reported next to
+    the headline so that every configuration of BASELINE.json has a measured number."""
+    import data
+    out = {}
+    N3, n3 = 1 << 20, 200
+    job = bssm_b200.FilterJob(data.growth_model(n3), N3, method="bsf", seed=1, n_filters=1, out_flags=0, post=2)
+    for _ in range(3):
+        ms = job.run()
+    k = job.kernel_ms()
+    out["c3"] = {"workload": "ssm_nlg growth model, bootstrap filter + particle smoother (backtrack + summary), "
+                             "N=2^20, T=200, m=2", "filter_ms": k[1], "smoother_ms": k[2], "total_ms": ms,
+                 "particle_steps_per_s": N3 * n3 / (ms * 1e-3)}
+    job.close()
+    N5, n5, L5 = 1 << 18, 500, 4
+    job = bssm_b200.FilterJob(data.gbm_model(n5), N5, method="bsf", seed=1, n_filters=1, out_flags=7, post=0, L=L5)
+    for _ in range(3):
+        ms = job.run()
+    out["c5"] = {"workload": "ssm_sde GBM, Milstein bootstrap filter, L=4 (16 sub-steps), N=2^18, T=500",
+                 "total_ms": ms, "particle_steps_per_s": N5 * n5 / (ms * 1e-3),
+                 "milstein_substeps_per_s": N5 * n5 * (1 << L5) / (ms * 1e-3)}
+    job.close()
+    return out
+
+
 def cpu_baseline_leg():
     """single-thread oracle on a bounded sample (the reference never threads inside a filter)"""
     import bssm_b200
@@ -382,6 +407,8 @@ def main():
         line["e2e"] = e2e
     if c4 is not None:
         line["post_correct"] = c4
+    if world == 1 and not args.no_c4:
+        line["other_configs"] = other_configs_leg(bssm_b200)
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_leg()
     print(json.dumps(line), flush=True)
