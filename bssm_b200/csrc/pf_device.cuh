@@ -22,20 +22,11 @@
 #include <stdint.h>
 #include "bssm_b200/pf_math.h"
 
-#ifndef PF_RECOMP_TERMS
-#define PF_RECOMP_TERMS 0
-#endif
-#ifndef PF_COUNT_CHUNK
-#define PF_COUNT_CHUNK 4
-#endif
-// where the normals of the next column are generated: 0 = with the threshold
-// loads, 2 = inside the scan collective, 3 = inside the scatter barrier, 4 = after it
-#ifndef PF_DRAW_AT
-#define PF_DRAW_AT 3
-#endif
-#ifndef PF_SCATTER_UNROLL1
-#define PF_SCATTER_UNROLL1 1
-#endif
+// Measured alternatives that were dropped (tools/build_variants.py, C2 batch of 18 filters):
+// recomputing the fixed-point terms after the scan instead of keeping them in registers (no
+// change), resolving all P + 1 counts at once instead of in chunks of 4 (-5%), drawing the
+// normals with the threshold loads or inside the scan collective instead of inside the scatter
+// barrier (-4% / -1%), letting the compiler unroll the scatter loop (-3%).
 
 namespace pf {
 
@@ -541,14 +532,6 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
     typename Model::template Noise<P> noise;
     {
       // one scan of the fixed-point weights gives their sum and cumulative sums
-#if PF_RECOMP_TERMS
-      long long th = 0, tl = 0;
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        pf_fixsum tm = pf_fixsum_term(w[p]);
-        th += tm.hi; tl += tm.lo;
-      }
-#else
       long long qh[P], ql[P], th = 0, tl = 0;
 #pragma unroll
       for (int p = 0; p < P; ++p) {
@@ -556,15 +539,9 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
         qh[p] = tm.hi; ql[p] = tm.lo;
         th += tm.hi; tl += tm.lo;
       }
-#endif
-      long long rh, rl, Th, Tl, ih, il;
+      long long rh, rl, Th, Tl;
       PF_PHASE(2)
-      coll.exscan2_begin(th, tl, ih, il);
-#if PF_DRAW_AT == 2
-      // the normals of the next column depend on nothing the collectives order
-      model.template draw<P>(ctx, noise);
-#endif
-      coll.exscan2_end(th, tl, ih, il, rh, rl, Th, Tl);
+      coll.exscan2(th, tl, rh, rl, Th, Tl);
       PF_PHASE(3)
       const double S = pf_fixsum_value(Th, Tl);
       const double invS = 1.0 / S;
@@ -577,15 +554,10 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
       // offspring range of particle k is [count(p_{k-1}), count(p_k)); p_{N-1} := 1.
       // Particles are resolved in chunks of CH so that only CH+1 cumulative
       // probabilities / threshold loads are live at a time.
-      constexpr int CH = (P > PF_COUNT_CHUNK) ? PF_COUNT_CHUNK : P;
+      constexpr int CH = P > 4 ? 4 : P;
       double pk0 = (i0 == 0) ? 0.0 : ((i0 - 1 >= N - 1) ? 1.0 : pf_fixsum_value(rh, rl) * invS);
       uint32_t j0 = st.guess(pk0);
       double u0 = st.u(j0);
-#if PF_DRAW_AT == 0
-      // the normals of the next column do not depend on the ancestors: generate
-      // them while the threshold loads are in flight
-      model.template draw<P>(ctx, noise);
-#endif
       uint32_t lo = (i0 == 0) ? 0u : st.resolve(pk0, j0, u0);
 #pragma unroll
       for (int c0 = 0; c0 < P; c0 += CH) {
@@ -595,12 +567,7 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
 #pragma unroll
         for (int q = 0; q < CH; ++q) {
           const int p = c0 + q;
-#if PF_RECOMP_TERMS
-          pf_fixsum tm = pf_fixsum_term(w[p]);
-          rh += tm.hi; rl += tm.lo;
-#else
           rh += qh[p]; rl += ql[p];
-#endif
           pk[q] = (i0 + p >= N - 1) ? 1.0 : pf_fixsum_value(rh, rl) * invS;
           jj[q] = st.guess(pk[q]);
           uj[q] = st.u(jj[q]);
@@ -608,19 +575,15 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
 #pragma unroll
         for (int q = 0; q < CH; ++q) {
           const uint32_t c = st.resolve(pk[q], jj[q], uj[q]);
-#if PF_SCATTER_UNROLL1
 #pragma unroll 1
-#endif
           for (uint32_t j = lo; j < c; ++j) anc[j] = i0 + c0 + q;
           lo = c > lo ? c : lo;
         }
       }
     }
     coll.barrier_arrive();
-#if PF_DRAW_AT == 3
     // normals of the next column, generated while the scatter barrier completes
     model.template draw<P>(ctx, noise);
-#endif
     coll.barrier_wait();
     PF_PHASE(4)
     // columns 0..t of state, weights and ancestors are complete and visible to this thread
@@ -632,9 +595,6 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
     // ---- gather ancestors, propagate to column t+1 (reference :657-670)
     {
       model.begin_step(t);
-#if PF_DRAW_AT == 4
-      model.template draw<P>(ctx, noise);
-#endif
       const double* src = alpha + (size_t)(fp.keep_alpha ? t : (t & 1)) * M * N;
       double* dst = alpha + (size_t)(fp.keep_alpha ? t + 1 : ((t + 1) & 1)) * M * N;
       uint32_t a[P];
