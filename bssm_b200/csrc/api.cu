@@ -284,17 +284,19 @@ void ung_approximate_m1(const bssm_ung_model* M, std::vector<double>& mode, std:
 // handed back for requests of the same size class; bssm_b200_shutdown() releases
 // them.
 struct Pool {
-  struct Block { void* p; size_t bytes; };
+  struct Block { void* p; size_t bytes; int device; }; // blocks are only reused on the device that owns them
   std::vector<Block> free_blocks;
   size_t cached = 0;
   std::mutex mu;
   static size_t size_class(size_t b) { return b <= 4096 ? 4096 : ((b + (1u << 20) - 1) >> 20) << 20; }
   cudaError_t alloc(void** p, size_t bytes) {
     const size_t sc = size_class(bytes);
+    int dev = 0;
+    cudaGetDevice(&dev);
     {
       std::lock_guard<std::mutex> g(mu);
       for (size_t i = 0; i < free_blocks.size(); ++i)
-        if (free_blocks[i].bytes == sc) {
+        if (free_blocks[i].bytes == sc && free_blocks[i].device == dev) {
           *p = free_blocks[i].p;
           cached -= sc;
           free_blocks.erase(free_blocks.begin() + i);
@@ -312,9 +314,12 @@ struct Pool {
   void free(void* p, size_t bytes) {
     const size_t sc = size_class(bytes);
     const size_t limit = (size_t)env_int("BSSM_B200_POOL_GB", 48) << 30;
+    cudaPointerAttributes at;
+    int dev = 0;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess) dev = at.device; else { cudaGetLastError(); cudaGetDevice(&dev); }
     std::lock_guard<std::mutex> g(mu);
     if (cached + sc > limit) { cudaFree(p); return; }
-    free_blocks.push_back({p, sc});
+    free_blocks.push_back({p, sc, dev});
     cached += sc;
   }
   void release_all() {
