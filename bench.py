@@ -59,9 +59,43 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.stop, self.th = index, [], False, None
+        self.index, self.rows, self.stop, self.th, self.source = index, [], False, None, "nvidia-smi"
+
+    def _nvml_handle(self):
+        """NVML handle of CUDA device `index` (by PCI bus id: NVML and CUDA may enumerate differently)"""
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(self.index)
+        bus = "%08x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+
+    def _run_nvml(self, nv, h):
+        # NVML is cheap enough to sample every few milliseconds, i.e. many times inside the timed region
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self.stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(sm), str(mx)] + ["Active" if r & bits[k] else "Not Active"
+                                                         for k in ("hw_slowdown", "hw_thermal_slowdown",
+                                                                   "sw_thermal_slowdown", "sw_power_cap")])
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def _run(self):
+        try:
+            nv, h = self._nvml_handle()
+        except Exception:
+            nv = None
+        if nv is not None:
+            self.source = "nvml"
+            return self._run_nvml(nv, h)
         while not self.stop:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -94,7 +128,7 @@ class ClockSampler:
                 continue
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def make_model():
