@@ -404,3 +404,24 @@ def test_job_set_theta_matches_fresh_job(engine, method):
         assert not np.array_equal(job.logliks(), ll0)
         fresh.close()
     job.close()
+
+
+def test_streaming_fetch_with_a_filter_that_stops_midway(engine, monkeypatch):
+    """a filter whose weights all vanish at t = 40 (an absurd observation): blocks of columns were already
+    shipped when it stops; the call must still return the plain path's zero-filled tail"""
+    model = data.svm_model(120)
+    model.y[40] = 1e200  # exp(-s) * (y / sigma)^2 overflows: every log-weight is -inf at t = 40
+    monkeypatch.setenv("BSSM_B200_NO_STREAMING", "1")
+    with pytest.warns(UserWarning, match="stopped prematurely"):
+        plain = engine.bootstrap_filter(model, 2000, seed=3, return_indices=True)
+    monkeypatch.delenv("BSSM_B200_NO_STREAMING")
+    monkeypatch.setenv("BSSM_B200_STREAM_MIN_MB", "0")
+    monkeypatch.setenv("BSSM_B200_STREAM_CHUNKS", "12")
+    with pytest.warns(UserWarning, match="stopped prematurely"):
+        stream = engine.bootstrap_filter(model, 2000, seed=3, return_indices=True)
+    assert plain["stopped_at"] == stream["stopped_at"] == 40
+    for key in ("alpha", "weights", "indices"):
+        assert np.array_equal(plain[key], stream[key]), key
+    assert np.all(stream["weights"][:, 40:] == 0) and np.any(stream["weights"][:, 39] > 0)
+    ref = orc.bsf_filter(model, 2000, seed=3)
+    assert ref.stopped_at == 40 and np.array_equal(stream["indices"], ref.indices)
