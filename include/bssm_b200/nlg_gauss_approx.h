@@ -208,8 +208,11 @@ struct NlgApprox {
     return U;
   }
 
-  /* ekf, iterated when iekf_iter > 0 (:284-378): at m x (n+1), att m x n */
-  bool ekf(std::vector<double>& at, std::vector<double>& att) const {
+  /* ekf, iterated when iekf_iter > 0 (:284-378): at m x (n+1), att m x n; *loglik (optional) receives the
+   * EKF log-likelihood (:369-371), -inf when an innovation variance is not positive */
+  bool ekf(std::vector<double>& at, std::vector<double>& att, double* loglik = nullptr) const {
+    double ll = 0.0;
+    if (loglik) *loglik = -std::numeric_limits<double>::infinity();
     const size_t mm = (size_t)m * m;
     at.assign((size_t)m * (n + 1), 0.0); att.assign((size_t)m * n, 0.0);
     std::vector<double> Pt(mm), Ptt(mm), Zg(m), K(m), Tg(mm), Rt((size_t)m * k), A(mm), B(mm), rr(mm), tmp(mm), zp(m);
@@ -234,6 +237,7 @@ struct NlgApprox {
         for (int i = 0; i < m; ++i) af[i] = a[i] + K[i] * v;
         /* iterated EKF (:325-356): relinearise the observation equation at the updated state */
         double HHi = HHt;
+        double v_last = v, cholF_last = cholF; /* what the log-likelihood term sees after the iterations */
         {
           double diff = 1.0;
           int it = 0;
@@ -249,9 +253,11 @@ struct NlgApprox {
             Fi = Fi + HHi;
             if (!(std::isfinite(Fi) && Fi > 0)) return false;
             const double invi = 1.0 / std::sqrt(Fi);
+            cholF_last = std::sqrt(Fi);
             double zd = 0.0;
             for (int i = 0; i < m; ++i) zd += Zg[i] * (a[i] - af[i]);
             const double vi = M->y[t] - fn.Z_fn(t, af) - zd;
+            v_last = vi;
             pf_mm(Pt.data(), Zg.data(), K.data(), m, m, 1);
             for (int i = 0; i < m; ++i) K[i] = K[i] * invi * invi;
             for (int i = 0; i < m; ++i) anew[i] = a[i] + K[i] * vi;
@@ -272,6 +278,8 @@ struct NlgApprox {
         pf_mmt(A.data(), tmp.data(), B.data(), m, m, m);
         for (int j = 0; j < m; ++j)
           for (int i = 0; i < m; ++i) Ptt[i + (size_t)m * j] = B[i + (size_t)m * j] + K[i] * HHi * K[j];
+        const double Fv = v_last / cholF_last;
+        ll -= 0.5 * (std::log(2.0 * M_PI) + 2.0 * std::log(cholF_last) + Fv * Fv);
       } else {
         for (int i = 0; i < m; ++i) af[i] = a[i];
         Ptt = Pt;
@@ -284,6 +292,7 @@ struct NlgApprox {
       pf_mmt(Rt.data(), Rt.data(), rr.data(), m, k, m);
       for (size_t e = 0; e < mm; ++e) Pt[e] = B[e] + rr[e];
     }
+    if (loglik) *loglik = ll;
     return true;
   }
 

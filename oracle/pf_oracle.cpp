@@ -1477,6 +1477,19 @@ double orc_nlg_psi_filter_iekf(const bssm_nlg_model* M, uint32_t max_iter, doubl
                              indices, approx_loglik, stopped_at, mode_out);
 }
 
+/* ssm_nlg::ekf log-likelihood (src/model_ssm_nlg.cpp:284-378), p = 1: the known answers of
+ * tests/testthat/test_ekpf.R:64-69 pin the (iterated) EKF that starts the psi-APF approximation;
+ * att_out (m x n, optional) receives the filtered means */
+double orc_nlg_ekf_loglik(const bssm_nlg_model* M, uint32_t iekf_iter, double* att_out) {
+  pfga::NlgApprox A(M);
+  A.iekf_iter = (int)iekf_iter;
+  std::vector<double> at, att;
+  double ll;
+  A.ekf(at, att, &ll);
+  if (att_out) std::memcpy(att_out, att.data(), att.size() * sizeof(double));
+  return ll;
+}
+
 /* ------------------------------------------------------------------ a14 */
 /* GBM user functions, R/cpp_example_models.R:129-171 */
 struct Gbm {

@@ -144,6 +144,22 @@ def sin_exp_model(n=60, gen_seed=33, missing=()):
     return bssm_b200.ssm_nlg(y, "sin_exp", theta=[np.log(0.35), np.log(0.45)])
 
 
+def r_sin_exp_data(n=10, na=()):
+    """test_ekpf.R:7-14 / :47-55: set.seed(1); y[1] <- rnorm(1, exp(x[1]), 0.1); then alternately
+    x[i+1] <- rnorm(1, sin(x[i]), 0.1), y[i+1] <- rnorm(1, exp(x[i+1]), 0.1)"""
+    from r_rng import RStream
+    rs = RStream(1)
+    x = np.zeros(n)
+    y = np.zeros(n)
+    y[0] = rs.rnorm(1, np.exp(x[0]), 0.1)[0]
+    for i in range(n - 1):
+        x[i + 1] = rs.rnorm(1, np.sin(x[i]), 0.1)[0]
+        y[i + 1] = rs.rnorm(1, np.exp(x[i + 1]), 0.1)[0]
+    for t in na:
+        y[t] = np.nan
+    return y
+
+
 def gbm_model(n=50, gen_seed=42, missing=()):
     """BASELINE config 5: GBM as tests/testthat/test_sde.R:7-25 (mu=.05, sigma_x=.3, sigma_y=1, x0=1),
     filter theta = (.08, .4, 1.5), positive = TRUE."""

@@ -421,6 +421,17 @@ def nlg_ekf_filter(model, N, seed, filt=0, arith=ARITH_REPRO):
     return r
 
 
+def nlg_ekf_loglik(model, iekf_iter=0):
+    """oracle of ssm_nlg::ekf: (log-likelihood, filtered means m x n)"""
+    ms = model.c_struct()
+    att = np.zeros((model.m, model.n), order="F")
+    f = L().orc_nlg_ekf_loglik
+    f.restype = C.c_double
+    f.argtypes = [C.POINTER(NlgModel), C.c_uint32, c_double_p]
+    ll = f(C.byref(ms), int(iekf_iter), dptr(att))
+    return ll, att
+
+
 def ulg_bsf_filter(model, N, seed, filt=0, arith=ARITH_REPRO):
     r = _alloc(model, N)
     ms = model.c_struct()

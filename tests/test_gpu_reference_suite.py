@@ -193,3 +193,22 @@ def test_growth_model_of_the_reference_post_correct_test(engine, method):
     assert out["logLik"] == ref.loglik
     assert np.all(out["weights"][:, 1:15] == 1.0)  # missing observations: unit weights
     assert np.isfinite(out["logLik"])
+
+
+# ------------------------------------------------------------ test_ekpf.R
+def test_particle_filtering_based_on_ekf_works(engine):
+    """:3-43: nlg_sin_exp, the reference's data (set.seed(1), regenerated through tests/r_rng.py),
+    theta = (log .1, log .1); the same assertions, then parity with the oracle"""
+    y = data.r_sin_exp_data(10)
+    model = bssm_b200.ssm_nlg(y, "sin_exp", theta=[np.log(0.1), np.log(0.1)])
+    out = engine.ekpf_filter(model, 100, seed=1, return_indices=True)
+    assert 1 < out["logLik"] < 6
+    assert out["weights"].min() >= 0 and out["weights"].max() <= 1
+    ref = orc.nlg_ekf_filter(model, 100, 1)
+    assert np.array_equal(out["indices"], ref.indices)
+    assert np.array_equal(out["weights"], ref.weights)
+    assert out["logLik"] == ref.loglik
+    target = [0.0263875638744833, 0.0734903567971838]
+    for method in ("ekf", "psi", "bsf"):
+        sm = engine.particle_smoother(model, 1000, method=method, seed=1)
+        assert all_equal(target, np.ravel(sm["alphahat"])[8:10], 0.1), method

@@ -16,6 +16,7 @@ import numpy as np
 import pytest
 
 import bssm_b200
+import data
 import orc
 from r_rng import RStream
 
@@ -121,3 +122,19 @@ def test_gbm_loglik_reference_assertion_and_exact_value():
     ll6 = np.mean([orc.sde_bsf_filter(m, 10000, 6, seed=s).loglik for s in (1, 2)])
     assert abs(ll6 - exact) < 0.15                   # discretisation + Monte Carlo error
     assert abs(ll3 - exact) < 0.5
+
+
+def test_sin_exp_ekf_loglik_matches_reference_known_answers():
+    """test_ekpf.R:64-69: for the nlg_sin_exp model with y[2:3] <- NA and theta = (log .1, log .1),
+    `ekf(model)$logLik` is 2.65163101109689, with iekf_iter = 1 it is 2.61650080342709, and one
+    iteration of the iterated EKF already equals two.  The EKF is the start of the psi-APF
+    approximation and the proposal of the EKF particle filter (include/bssm_b200/nlg_gauss_approx.h)."""
+    y = data.r_sin_exp_data(10, na=(1, 2))
+    model = bssm_b200.ssm_nlg(y, "sin_exp", theta=[np.log(0.1), np.log(0.1)])
+    ll0, _ = orc.nlg_ekf_loglik(model, 0)
+    ll1, att1 = orc.nlg_ekf_loglik(model, 1)
+    ll2, att2 = orc.nlg_ekf_loglik(model, 2)
+    assert ll0 == pytest.approx(2.65163101109689, rel=1.5e-8)   # expect_equal's default tolerance
+    assert ll1 == pytest.approx(2.61650080342709, rel=1.5e-8)
+    assert ll2 == pytest.approx(ll1, rel=1.5e-8)
+    np.testing.assert_allclose(att2, att1, rtol=1.5e-8)
