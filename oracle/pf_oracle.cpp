@@ -13,6 +13,9 @@
  *     laplace_iter, Kalman fast smoother, Newton-sweep semantics -- to the 15
  *     digits of tests/testthat/test_approx.R:38-53;
  *   - dmvnorm (the density of the ssm_nlg weights), test_basics.R:176-201;
+ *   - the EKF and iterated-EKF log-likelihoods of the nlg_sin_exp model (the
+ *     start of the ssm_nlg approximation and the EKPF proposal), to
+ *     expect_equal's 1.5e-8, test_ekpf.R:64-69;
  *   - the GBM data set of test_sde.R with its log-likelihood assertion, plus
  *     the closed-form likelihood of that model.
  * Also pinned: stratified_sample hand vectors, Philox Random123 vectors,
