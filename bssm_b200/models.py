@@ -208,9 +208,10 @@ def bsm_ng(y, sd_level, sd_slope=None, sd_seasonal=None, sd_noise=None, distribu
         phi = 1.0
     # theta as R/models.R:1092-1100 orders it: log sds of the estimated components, log phi, beta
     phi_est = distribution in ("negative binomial", "gamma")
-    theta = [np.log(sd_level)] + ([np.log(sd_slope)] if slope else []) + ([np.log(sd_seasonal)] if seasonal else []) \
-        + ([np.log(sd_noise)] if noise else []) + ([np.log(phi)] if phi_est else []) \
-        + ([] if beta is None else list(np.ravel(beta)))
+    with np.errstate(divide="ignore"):  # a fixed sd of 0 (constant component) has log sd = -inf
+        theta = [np.log(sd_level)] + ([np.log(sd_slope)] if slope else []) + ([np.log(sd_seasonal)] if seasonal else []) \
+            + ([np.log(sd_noise)] if noise else []) + ([np.log(phi)] if phi_est else []) \
+            + ([] if beta is None else list(np.ravel(beta)))
     extra = {"slope": slope, "seasonal": seasonal, "noise": noise, "level_est": True, "slope_est": slope,
              "seasonal_est": seasonal, "phi_est": phi_est}
     return Model("bsm_ng", y, Z, T.reshape(m, m, 1), R.reshape(m, R.shape[1], 1), a1, P1, [0.0],

@@ -16,6 +16,8 @@
  *   - the EKF and iterated-EKF log-likelihoods of the nlg_sin_exp model (the
  *     start of the ssm_nlg approximation and the EKPF proposal), to
  *     expect_equal's 1.5e-8, test_ekpf.R:64-69;
+ *   - the GLM fixed points (Poisson, binomial, negative binomial), the
+ *     ssm_mng = 2 x ssm_ung and the two-sweep nlg tests of test_approx.R:60-199;
  *   - the GBM data set of test_sde.R with its log-likelihood assertion, plus
  *     the closed-form likelihood of that model.
  * Also pinned: stratified_sample hand vectors, Philox Random123 vectors,
