@@ -28,6 +28,8 @@ def _check_particles(model, particles, seed):
     particles = int(particles)
     if particles < 2:
         raise ValueError("Argument 'particles' should be an integer >= 2.")
+    if particles > 2 ** 21:  # one filter must fit one resident group of CTAs (about 1.2M particles on a B200)
+        raise ValueError("Argument 'particles' is too large for one filter (at most 2^21).")
     seed = int(seed)
     if not 0 <= seed <= 2 ** 31 - 1:
         raise ValueError("Argument 'seed' should be an integer in [0, 2^31-1].")
@@ -274,12 +276,13 @@ def theta_map(model):
         tm.model_type = 2
         for key in ("slope", "seasonal", "noise", "level_est", "slope_est", "seasonal_est", "phi_est"):
             setattr(tm, key, int(bool(model.extra.get(key, False))))
-        if model.xreg is not None and model.xreg.size:
-            xr = _lib.f64(np.asfortranarray(model.xreg.reshape(model.n, -1)))
-            tm.n_xreg, tm.xreg = xr.shape[1], dptr(xr)
-            tm._keep = xr
     else:
         raise ValueError("post_correct is implemented for svm, ar1_ng, bsm_ng and ssm_nlg models")
+    if model.cls in ("ar1_ng", "bsm_ng") and model.xreg is not None and model.xreg.size:
+        # beta is the tail of theta: update_model recomputes xbeta (src/model_ar1_ng.cpp:28-31, model_bsm_ng.cpp:46-49)
+        xr = _lib.f64(np.asfortranarray(model.xreg.reshape(model.n, -1)))
+        tm.n_xreg, tm.xreg = xr.shape[1], dptr(xr)
+        tm._keep = xr
     return tm
 
 

@@ -429,6 +429,7 @@ struct bssm_b200_job {
   float ms[3] = {0, 0, 0};
   int launches = 0;
   bool has_run = false;
+  bool xbeta_per_filter = false; // m = 1 psi-APF whose filters carry their own regression part (beta in theta)
   // model on device
   DevBuf<double> y, Z, T, R, a1, P1, LP1, D, C, xbeta, u, mode, mode_lin;
   // psi pre-pass results
@@ -539,7 +540,7 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
     return launch_status(pfl::launch_mng_bsf(J->m, J->k, fp, J->gp, J->geo, nf, J->stream), "ssm_mng bsf (m,k)");
   }
   pf::UngParams up = J->up;
-  if (J->method == BSSM_METHOD_PSI && J->m > 1) {
+  if (J->method == BSSM_METHOD_PSI && (J->m > 1 || J->xbeta_per_filter)) {
     up.approx_loglik += f0;
     up.alphahat += (size_t)f0 * up.fs_a; up.Lt += (size_t)f0 * up.fs_m; up.Ct += (size_t)f0 * up.fs_m;
     up.ytilde += (size_t)f0 * up.fs_n; up.Htilde += (size_t)f0 * up.fs_n; up.scales += (size_t)f0 * up.fs_n;
@@ -660,7 +661,7 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
   if (method != BSSM_METHOD_PSI && method != BSSM_METHOD_BSF) return fail(BSSM_B200_ERR_ARG, "method must be 1 (psi) or 2 (bsf)");
   if (method == BSSM_METHOD_BSF && draw_par && M->m != 1)
     return fail(BSSM_B200_ERR_UNSUPPORTED, "per-draw bootstrap filters: m = 1 in this build");
-  if (method == BSSM_METHOD_PSI && (M->m > 3 || (M->m != 1 && draw_par) || (M->m == 1 && dm)))
+  if (method == BSSM_METHOD_PSI && (M->m > 3 || (M->m != 1 && draw_par) || (M->m == 1 && dm && !draw_par)))
     return fail(BSSM_B200_ERR_UNSUPPORTED, "psi-APF: m <= 3 (and m = 1 for per-draw models) in this build");
   if (M->k > M->m) return fail(BSSM_B200_ERR_ARG, "k > m");
   if (post < 0 || post > BSSM_POST_SMOOTHER_MERGE) return fail(BSSM_B200_ERR_ARG, "bad post mode");
@@ -834,6 +835,16 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
     up.phi_f = J->phi_f.p; up.alphahat = J->alphahat.p; up.Lt = J->Lt.p; up.Ct = J->Ct.p;
     up.ytilde = J->ytilde.p; up.Htilde = J->Htilde.p; up.scales = J->scales.p;
     up.approx_loglik = J->approx_loglik.p; up.pstride = J->pstride;
+    if (draw_par && dm && !dm->xbeta.empty()) {
+      // beta is part of theta (ar1_ng / bsm_ng update_model -> compute_xbeta): one regression part per
+      // filter; the pre-pass reads its own column, the filter runs the per-filter-pointer policy at m = 1
+      if (dm->xbeta.size() != (size_t)n * n_filters) return fail(BSSM_B200_ERR_ARG, "per-draw xbeta: n x n_filters");
+      if ((rc = J->xbeta.upload(dm->xbeta.data(), dm->xbeta.size()))) return rc;
+      pp.xbeta = J->xbeta.p; pp.xbeta_stride = (size_t)n; pp.has_xbeta = 1;
+      up.xbeta = J->xbeta.p; up.fs_x = (size_t)n;
+      up.fs_a = up.fs_m = up.fs_n = J->pstride;
+      J->xbeta_per_filter = true;
+    }
   }
 
   if ((rc = finish_job(J, out_flags, post))) return rc;
@@ -1637,6 +1648,16 @@ int theta_to_bsm(const bssm_ung_model* M, const bssm_theta_map* map, const doubl
   return 0;
 }
 
+// compute_xbeta (src/model_ssm_ung.h:83) of one draw: beta = the last n_xreg entries of theta
+void theta_to_xbeta(const bssm_theta_map* map, int n, const double* th, uint32_t n_par, double* xbeta) {
+  const double* beta = th + (n_par - map->n_xreg);
+  for (int t = 0; t < n; ++t) {
+    double sum = 0.0;
+    for (int j = 0; j < map->n_xreg; ++j) sum += map->xreg[t + (size_t)n * j] * beta[j];
+    xbeta[t] = sum;
+  }
+}
+
 struct DrawList {
   std::vector<uint32_t> src;   // expanded draw -> column of theta / modes
   std::vector<uint32_t> count; // effective count of the expanded draw
@@ -1658,13 +1679,14 @@ int build_draws(int is_type, const uint32_t* counts, uint32_t n_stored, DrawList
 int check_postcorr_args(const bssm_ung_model* M, const bssm_theta_map* map, const uint32_t* counts,
                         const double* theta, const double* modes, uint32_t n_stored) {
   if (!M || !map || !counts || !theta || !modes || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
-  const bool general = map->model_type == 2 && (M->m > 1 || map->n_xreg > 0);
+  const bool general = map->model_type == 2 && M->m > 1;
   if (M->m != 1 && !general)
     return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction with m > 1 is implemented for bsm_ng (model_type 2) in this build");
   if (general && (M->m < 2 || M->m > 3))
-    return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction for bsm_ng: 2 <= m <= 3 (or m = 1 without regressors) in this build");
+    return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction for bsm_ng: m <= 3 in this build");
   if (map->n_xreg > 0 && !map->xreg) return fail(BSSM_B200_ERR_ARG, "n_xreg > 0 needs xreg");
-  if (M->xbeta && !general) return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction with regression coefficients in theta: bsm_ng only");
+  if (M->xbeta && map->n_xreg <= 0) return fail(BSSM_B200_ERR_ARG, "the model has regressors: theta_map needs n_xreg and xreg");
+  if (map->n_xreg > 0 && map->model_type == 3) return fail(BSSM_B200_ERR_ARG, "svm has no regression part");
   return 0;
 }
 
@@ -1674,7 +1696,7 @@ int make_draw_job(const bssm_ung_model* M, const bssm_theta_map* map, const Draw
                   int out_flags, int post, bssm_b200_job** job) {
   const uint32_t nf = d1 - d0;
   const size_t n = (size_t)M->n;
-  if (map->model_type == 2 && (M->m > 1 || map->n_xreg > 0)) {
+  if (map->model_type == 2 && M->m > 1) {
     const size_t mk = (size_t)M->m * M->k, mm = (size_t)M->m * M->m;
     DrawModels dm;
     dm.R.resize(mk * nf); dm.P1.resize(mm * nf); dm.phi.resize(nf); dm.modes.resize(n * nf);
@@ -1689,13 +1711,20 @@ int make_draw_job(const bssm_ung_model* M, const bssm_theta_map* map, const Draw
     return create_ung_job(M, BSSM_METHOD_PSI, N, seed, nf, d0, out_flags, post, nullptr, nullptr, job, &dm);
   }
   std::vector<double> par((size_t)6 * nf), md(n * nf);
+  DrawModels dm; // m = 1: only the regression part of each draw
+  if (map->n_xreg > 0) {
+    if ((int)n_par < map->n_xreg) return fail(BSSM_B200_ERR_ARG, "too few parameters for n_xreg");
+    dm.xbeta.resize(n * nf);
+  }
   for (uint32_t f = 0; f < nf; ++f) {
     const uint32_t c = dl.src[d0 + f];
     int rc = theta_to_par(M, map, theta + (size_t)c * n_par, n_par, &par[(size_t)6 * f]);
     if (rc) return rc;
+    if (map->n_xreg > 0) theta_to_xbeta(map, (int)n, theta + (size_t)c * n_par, n_par, &dm.xbeta[n * f]);
     memcpy(&md[n * f], modes + n * c, n * sizeof(double));
   }
-  return create_ung_job(M, BSSM_METHOD_PSI, N, seed, nf, d0, out_flags, post, par.data(), md.data(), job);
+  return create_ung_job(M, BSSM_METHOD_PSI, N, seed, nf, d0, out_flags, post, par.data(), md.data(), job,
+                        map->n_xreg > 0 ? &dm : nullptr);
 }
 
 } // namespace
@@ -2070,9 +2099,15 @@ int bssm_b200_suggest_n_nongaussian(const bssm_ung_model* M, const bssm_theta_ma
   double par[6];
   std::vector<double> R, P1, xb;
   if (M->m == 1 && !(map->model_type == 2 && map->n_xreg > 0)) {
-    if (M->xbeta) return fail(BSSM_B200_ERR_UNSUPPORTED, "suggest_N with regression coefficients in theta: bsm_ng only");
+    if (M->xbeta && map->n_xreg <= 0) return fail(BSSM_B200_ERR_ARG, "the model has regressors: theta_map needs n_xreg and xreg");
     int rc = theta_to_par(M, map, theta, n_par, par);
     if (rc) return rc;
+    if (map->n_xreg > 0) { // ar1_ng with regressors: beta = the tail of theta
+      if (!map->xreg || (int)n_par < map->n_xreg) return fail(BSSM_B200_ERR_ARG, "n_xreg > 0 needs xreg and beta in theta");
+      xb.resize(M->n);
+      theta_to_xbeta(map, M->n, theta, n_par, xb.data());
+      Mi.xbeta = xb.data();
+    }
     Mi.T = &par[0]; Mi.R = &par[1]; Mi.a1 = &par[2]; Mi.P1 = &par[3]; Mi.C = &par[4]; Mi.phi = par[5];
     Mi.Ttv = 0; Mi.Rtv = 0; Mi.Ctv = 0;
   } else {

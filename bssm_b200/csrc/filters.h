@@ -10,7 +10,7 @@ using Stream = cudaStream_t;
 // k_ung_psi1.cu: psi-APF, m = 1 (svm, ar1_ng, univariate ssm_ung / ssm_ulg)
 int launch_ung_psi1(const pf::FilterParams&, const pf::UngParams&, const Geometry&, uint32_t nf, Stream);
 int occupancy_ung_psi1(const Geometry&, int* out);
-// k_ung_psim.cu: psi-APF, m in {2, 3}
+// k_ung_psim.cu: psi-APF with per-filter approximations: m in {2, 3}, and m = 1 when each filter has its own xbeta
 int launch_ung_psim(int m, const pf::FilterParams&, const pf::UngParams&, const Geometry&, uint32_t nf, Stream);
 // k_ung_bsf_a.cu / k_ung_bsf_b.cu: bootstrap filter, (m, k) in {(1,1),(2,1),(2,2)} / {(3,2),(3,3)}
 int launch_ung_bsf_a(int m, int k, const pf::FilterParams&, const pf::UngParams&, const Geometry&, uint32_t nf, Stream);

@@ -24,6 +24,7 @@ struct PrepassParams {
   int Ztv, Ttv, Rtv, Dtv, Ctv;
   const double *y, *Z, *T, *R, *a1, *P1, *D, *C, *xbeta, *u;
   int has_xbeta;
+  size_t xbeta_stride; // 0: one regression part for all filters; n: one per filter (beta is part of theta)
   double phi;
   // per-draw scalar model (post_correct): 6 per filter = T, R, a1, P1, C, phi,
   // i.e. what update_model(theta_i) sets (src/model_svm.cpp:12-29,
@@ -138,7 +139,8 @@ ung_prepass_m1_kernel(const PrepassParams pp, uint32_t n_filters) {
   // Every expression is evaluated exactly as in the one-lane formulation (same operands, same order).
   auto bc = [](double v, int k) { return __shfl_sync(0xffffffffu, v, k); };
   const double zero_tol = 1e-12; // src/model_ssm_ulg.h:19
-  auto ytmp = [&](int t) { return pp.has_xbeta ? ay[t] - pp.xbeta[t] : ay[t]; };
+  const double* xbeta = pp.xbeta + (size_t)f * pp.xbeta_stride;
+  auto ytmp = [&](int t) { return pp.has_xbeta ? ay[t] - xbeta[t] : ay[t]; };
 
   // coefficients that do not vary in time are read once instead of being broadcast every step
   const bool tvZ = pp.Ztv != 0, tvT = !from_theta && pp.Ttv != 0, tvR = !from_theta && pp.Rtv != 0;

@@ -162,7 +162,8 @@ def ar1_ng(y, rho, sigma, mu, distribution, phi=1.0, u=1.0, xreg=None, beta=None
         phi = 1.0
     return Model("ar1_ng", y, [[1.0]], [[[rho]]], np.reshape([sigma], (1, 1, 1)), [mu],
                  [[sigma ** 2 / (1 - rho ** 2)]], [0.0], [[mu * (1 - rho)]], u, phi, distribution,
-                 init_mode(y, u, distribution), xreg=xreg, beta=beta, theta=[rho, np.log(sigma), mu],
+                 init_mode(y, u, distribution), xreg=xreg, beta=beta,
+                 theta=[rho, np.log(sigma), mu] + ([] if beta is None else list(np.ravel(beta))),
                  extra={"mu_est": 1, "phi_est": 0})
 
 

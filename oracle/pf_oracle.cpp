@@ -1706,9 +1706,10 @@ double orc_sde_bsf_filter(const bssm_sde_model* M, uint32_t nsim, uint32_t L, ui
 struct DrawModel {
   bssm_ung_model M;
   double T, R, a1, P1, C;
+  std::vector<double> xb; /* xbeta of this draw when beta is part of theta */
 };
 static void update_model(DrawModel& dm, const bssm_ung_model* base, const bssm_theta_map* map,
-                         const double* new_theta) {
+                         const double* new_theta, uint32_t n_par) {
   dm.M = *base;
   dm.T = base->T[0]; dm.R = base->R[0]; dm.a1 = base->a1[0]; dm.P1 = base->P1[0]; dm.C = base->C[0];
   if (map->model_type == 3) {
@@ -1736,6 +1737,18 @@ static void update_model(DrawModel& dm, const bssm_ung_model* base, const bssm_t
   }
   dm.M.T = &dm.T; dm.M.R = &dm.R; dm.M.a1 = &dm.a1; dm.M.P1 = &dm.P1; dm.M.C = &dm.C;
   dm.M.Ttv = 0; dm.M.Rtv = 0; dm.M.Ctv = 0;
+  if (map->n_xreg > 0) {
+    /* beta = new_theta.subvec(n_elem - xreg.n_cols, n_elem - 1); compute_xbeta()
+     * (src/model_ar1_ng.cpp:28-31, src/model_ssm_ung.h:83: xbeta = xreg * beta) */
+    const size_t n = (size_t)base->n;
+    dm.xb.assign(n, 0.0);
+    for (size_t t = 0; t < n; ++t) {
+      double sum = 0.0;
+      for (int j = 0; j < map->n_xreg; ++j) sum += map->xreg[t + n * j] * new_theta[n_par - map->n_xreg + j];
+      dm.xb[t] = sum;
+    }
+    dm.M.xbeta = dm.xb.data();
+  }
 }
 
 /* approx_mcmc::is_correction_psi, src/approx_mcmc.cpp:353-427, with expand()
@@ -1768,7 +1781,7 @@ int orc_postcorrection_ung(const bssm_ung_model* M, const bssm_theta_map* map, i
 #endif
   for (int64_t i = 0; i < nd; ++i) {
     DrawModel dm;
-    update_model(dm, M, map, theta + (size_t)src[i] * n_par);
+    update_model(dm, M, map, theta + (size_t)src[i] * n_par, n_par);
     unsigned int nsimc = nsim;
     if (is_type == 1) nsimc *= cnt[i];
     std::vector<double> alpha_i(n1 * nsimc, 0.0), weights_i((size_t)nsimc * n1, 0.0);
@@ -2012,7 +2025,7 @@ int orc_is_correction_bsf_ung(const bssm_ung_model* M, const bssm_theta_map* map
 #endif
   for (int64_t i = 0; i < nd; ++i) {
     DrawModel dm;
-    update_model(dm, M, map, theta + (size_t)src[i] * n_par);
+    update_model(dm, M, map, theta + (size_t)src[i] * n_par, n_par);
     unsigned int nsimc = nsim;
     if (is_type == 1) nsimc *= cnt[i];
     std::vector<double> alpha_i(n1 * nsimc, 0.0), weights_i((size_t)nsimc * n1, 0.0);

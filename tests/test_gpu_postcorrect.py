@@ -120,6 +120,11 @@ def _bsm_case(kind):
         return data.poisson_bsm_model(80)
     if kind == "level":            # m = 1: goes through the m = 1 device pre-pass
         return bssm_b200.bsm_ng(y[:70], sd_level=0.1, P1=[[1.0]], distribution="poisson")
+    if kind == "level_xreg":       # m = 1 with two regression coefficients in theta: device pre-pass, one xbeta per draw
+        n = 64
+        rng = np.random.default_rng(5)
+        return bssm_b200.bsm_ng(y[:n], sd_level=0.1, P1=[[1.0]], distribution="poisson",
+                                xreg=rng.normal(size=(n, 2)), beta=[0.15, -0.1])
     if kind == "negbin_xreg":      # m = 2, negative binomial with phi and one regression coefficient in theta
         n = 60
         rng = np.random.default_rng(4)
@@ -131,7 +136,7 @@ def _bsm_case(kind):
                             distribution="poisson")
 
 
-@pytest.mark.parametrize("kind", ["level_slope", "level", "negbin_xreg", "noise"])
+@pytest.mark.parametrize("kind", ["level_slope", "level", "level_xreg", "negbin_xreg", "noise"])
 def test_bsm_ng_post_correction(engine, kind):
     """is_correction_psi for bsm_ng (src/approx_mcmc.cpp:685-804): bsm_ng::update_model per draw
     (src/model_bsm_ng.cpp:17-51), Gaussian approximation at the stored mode (host, OpenMP for m > 1)"""
@@ -139,7 +144,7 @@ def test_bsm_ng_post_correction(engine, kind):
     mo = data.bsm_mcmc_output(model, 24)
     ref = orc.post_correct(model, mo, 96, is_type=2, seed=3)
     res = engine.post_correct(model, mo, 96, is_type="is2", seed=3, return_loglik=True)
-    if kind == "level":
+    if kind in ("level", "level_xreg"):
         # m = 1 runs the device pre-pass; the general-m host approximation of the oracle reduces to it
         np.testing.assert_allclose(res["loglik"], ref.loglik, rtol=1e-12)
     else:
@@ -148,7 +153,7 @@ def test_bsm_ng_post_correction(engine, kind):
     mo1 = dict(mo, output_type=1)
     ref1 = orc.post_correct(model, mo1, 64, is_type=3, seed=5)
     res1 = engine.post_correct(model, mo1, 64, is_type="is3", seed=5)
-    if kind != "level":
+    if kind not in ("level", "level_xreg"):
         assert np.array_equal(res1["alpha"].view(np.uint64), ref1.alpha.view(np.uint64))
     mo2 = dict(mo, output_type=2)
     ref2 = orc.post_correct(model, mo2, 32, is_type=1, seed=7)

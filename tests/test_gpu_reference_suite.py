@@ -212,3 +212,81 @@ def test_particle_filtering_based_on_ekf_works(engine):
     for method in ("ekf", "psi", "bsf"):
         sm = engine.particle_smoother(model, 1000, method=method, seed=1)
         assert all_equal(target, np.ravel(sm["alphahat"])[8:10], 0.1), method
+
+
+# ------------------------------------------------------------ test_post_correct.R
+def _ar1_binomial_xreg(theta=None):
+    """the model of test_post_correct.R:4-24: binomial ar1_ng, n = 14, two harmonic regressors, exposure u;
+    theta = (rho, log sigma, mu, beta1, beta2).  R's rpois / rbinom streams are not restated: a seeded numpy
+    sample with the same structure stands in (the assertions of that test do not depend on the data)."""
+    n = 14
+    tt = np.arange(1.0, n + 1)
+    x1, x2 = np.sin(2 * np.pi / 12 * tt), np.cos(2 * np.pi / 12 * tt)
+    rng = np.random.default_rng(1)
+    alpha = np.zeros(n)
+    for i in range(1, n):
+        alpha[i] = rng.normal(1.0 * (1 - 0.7) + 0.7 * alpha[i - 1], 2.0)
+    u = rng.poisson(50, size=n).astype(float)
+    y = rng.binomial(u.astype(int), 1.0 / (1.0 + np.exp(-(0.5 * x1 + x2 + alpha)))).astype(float)
+    th = np.array([0.5, 0.0, 0.0, 0.0, 0.0]) if theta is None else np.asarray(theta, dtype=float)
+    return bssm_b200.ar1_ng(y, rho=th[0], sigma=float(np.exp(th[1])), mu=th[2], distribution="binomial", u=u,
+                            xreg=np.column_stack([x1, x2]), beta=th[3:5])
+
+
+def test_post_correction_for_ar1_model_with_regressors(engine):
+    """:4-56: suggest_N and post_correct on the approx-MCMC output of a binomial ar1_ng model whose theta
+    holds (rho, log sigma, mu) AND the regression coefficients, so every stored draw has its own xbeta
+    (ar1_ng::update_model -> compute_xbeta, src/model_ar1_ng.cpp:12-36)"""
+    model = _ar1_binomial_xreg()
+    assert model.theta.size == 5
+    rng = np.random.default_rng(7)
+    ns = 24
+    center = np.array([0.6, np.log(1.5), 0.8, 0.4, 0.9])
+    theta = center[None, :] + rng.normal(size=(ns, 5)) * np.array([0.05, 0.1, 0.3, 0.2, 0.2])
+    counts = (1 + rng.poisson(1.5, size=ns)).astype(np.uint32)
+    modes = np.zeros((model.n, ns), order="F")
+    for i in range(ns):   # what run_mcmc(mcmc_type = "approx") stores per draw: the mode at theta_i
+        modes[:, i] = orc.psi_prepass(_ar1_binomial_xreg(theta[i])).mode
+    mo = {"theta": theta, "counts": counts, "modes": modes, "output_type": 3}
+
+    # suggest_N(model, out_approx, replications = 10, candidates = c(5, 10)) at the posterior mean
+    th_hat = np.average(theta, axis=0, weights=counts)
+    est = engine.suggest_N(model, th_hat, candidates=[5, 10], replications=10, seed=1)
+    mi = _ar1_binomial_xreg(th_hat)
+    mi.initial_mode = model.initial_mode
+    for c, N in enumerate([5, 10]):
+        ll = orc.filter_batch(mi, N, "psi", seed=1, first_filter=c * 10, n_filters=10, arith=orc.ARITH_REPRO)
+        assert est["results"]["sd"][c] == pytest.approx(np.std(ll, ddof=1), rel=1e-10)
+    assert est["N"] in (5, 10, None)
+
+    # post_correct(model, out_approx, particles = estN$N): finite theta / alphahat / Vt / weights (:47-56) ...
+    N = est["N"] or 10
+    for ot, ist in ((3, 2), (2, 1), (1, 3)):
+        mo_t = dict(mo, output_type=ot)
+        res = engine.post_correct(model, mo_t, N, is_type="is%d" % ist, seed=3, return_loglik=True)
+        ref = orc.post_correct(model, mo_t, N, is_type=ist, seed=3)
+        assert 0 < res["weights"].max() < np.inf
+        # ... and parity with the oracle, draw by draw
+        assert np.array_equal(res["loglik"], ref.loglik)
+        assert np.array_equal(res["weights"], ref.weights)
+        if ot == 2:
+            assert np.isfinite(res["alphahat"].sum()) and np.isfinite(res["Vt"].sum())
+            np.testing.assert_allclose(res["alphahat"], ref.alphahat, rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(res["Vt"], ref.Vt, rtol=1e-8, atol=1e-12)
+        if ot == 1:
+            assert np.array_equal(res["alpha"].view(np.uint64), ref.alpha.view(np.uint64))
+    # the regression part matters: the same draws with beta zeroed give different weights
+    theta0 = theta.copy()
+    theta0[:, 3:] = 0.0
+    res0 = engine.post_correct(model, dict(mo, theta=theta0), N, is_type="is2", seed=3)
+    ref0 = orc.post_correct(model, dict(mo, theta=theta0), N, is_type=2, seed=3)
+    assert np.array_equal(res0["weights"], ref0.weights)
+    assert not np.allclose(res0["weights"], engine.post_correct(model, mo, N, is_type="is2", seed=3)["weights"])
+
+    # the argument checks of :35-45
+    with pytest.raises((ValueError, AttributeError, TypeError)):
+        engine.post_correct(object(), mo, N)
+    with pytest.raises(ValueError):
+        engine.post_correct(model, mo, int(1e12))
+    with pytest.raises((ValueError, RuntimeError)):
+        engine.post_correct(model, dict(mo, theta=np.eye(2)), 10)
