@@ -124,12 +124,15 @@ static void fill_map(SEXP model, int model_type, bssm_theta_map* map) {
   if (model_type == 3) map->svm_type = asInteger(list_get(model, "svm_type"));
   if (model_type == 4) { map->mu_est = asLogical(list_get(model, "mu_est")); map->phi_est = asLogical(list_get(model, "phi_est")); }
   if (model_type == 2) { /* bsm_ng, src/model_bsm_ng.cpp:4-14 */
-    SEXP fixed = list_get(model, "fixed"), xreg = list_get(model, "xreg");
+    SEXP fixed = list_get(model, "fixed");
     map->slope = asLogical(list_get(model, "slope")); map->seasonal = asLogical(list_get(model, "seasonal"));
     map->noise = asLogical(list_get(model, "noise")); map->phi_est = asLogical(list_get(model, "phi_est"));
     map->level_est = INTEGER(fixed)[0] == 0;
     map->slope_est = map->slope && INTEGER(fixed)[1] == 0;
     map->seasonal_est = map->seasonal && INTEGER(fixed)[2] == 0;
+  }
+  if (model_type == 2 || model_type == 4) { /* beta is the tail of theta: update_model -> compute_xbeta */
+    SEXP xreg = list_get(model, "xreg");
     map->n_xreg = XLENGTH(xreg) > 0 ? INTEGER(getAttrib(xreg, R_DimSymbol))[1] : 0;
     map->xreg = map->n_xreg > 0 ? REAL(xreg) : NULL;
   }
