@@ -557,6 +557,7 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
   }
   if (up.bsf_par) {
     up.bsf_par += (size_t)7 * f0;
+    up.xbeta += (size_t)f0 * up.fs_x;
     return launch_status(pfl::launch_ung_bsf_draws(fp, up, J->geo, nf, J->stream), "bsf (per-draw models)");
   }
   if (J->m <= 2) return launch_status(pfl::launch_ung_bsf_a(J->m, J->k, fp, up, J->geo, nf, J->stream), "bsf (m,k)");
@@ -734,6 +735,11 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
     }
     if ((rc = J->draw_par.upload(bp.data(), bp.size()))) return rc;
     up.bsf_par = J->draw_par.p;
+    if (dm && !dm->xbeta.empty()) { // beta is part of theta: one regression part per filter
+      if (dm->xbeta.size() != (size_t)n * n_filters) return fail(BSSM_B200_ERR_ARG, "per-draw xbeta: n x n_filters");
+      if ((rc = J->xbeta.upload(dm->xbeta.data(), dm->xbeta.size()))) return rc;
+      up.xbeta = J->xbeta.p; up.fs_x = (size_t)n;
+    }
   }
 
   if (method == BSSM_METHOD_PSI && m > 1 && dm) {
@@ -1748,13 +1754,24 @@ int bssm_b200_job_set_theta(bssm_b200_job* J, const bssm_ung_model* M, const bss
   if (!J || !M || !map || !theta) return fail(BSSM_B200_ERR_ARG, "null argument");
   if (J->kind != KIND_UNG || J->m != 1 || M->m != 1 || M->n != J->n)
     return fail(BSSM_B200_ERR_UNSUPPORTED, "job_set_theta: m = 1 ssm_ung-family jobs created from the same data");
-  if (M->xbeta) return fail(BSSM_B200_ERR_UNSUPPORTED, "job_set_theta: models without regressors in this build");
+  if (M->xbeta && map->n_xreg <= 0) return fail(BSSM_B200_ERR_ARG, "the model has regressors: theta_map needs n_xreg and xreg");
+  if (J->xbeta_per_filter) return fail(BSSM_B200_ERR_ARG, "job_set_theta: post-correction jobs carry one theta per filter already");
   double par[6];
   int rc = theta_to_par(M, map, theta, n_par, par);
   if (rc) return rc;
   bssm_ung_model Mi = *M;
   Mi.T = &par[0]; Mi.R = &par[1]; Mi.a1 = &par[2]; Mi.P1 = &par[3]; Mi.C = &par[4]; Mi.phi = par[5];
   Mi.Ttv = 0; Mi.Rtv = 0; Mi.Ctv = 0;
+  std::vector<double> xb;
+  if (map->n_xreg > 0) { // beta = the tail of theta: new regression part, shared by the job's replicates
+    if (!map->xreg || (int)n_par < map->n_xreg || map->model_type == 3)
+      return fail(BSSM_B200_ERR_ARG, "n_xreg > 0 needs xreg, beta in theta and a model with a regression part");
+    xb.resize(J->n);
+    theta_to_xbeta(map, J->n, theta, n_par, xb.data());
+    Mi.xbeta = xb.data();
+    if ((rc = J->xbeta.upload(xb.data(), xb.size()))) return rc;
+    J->up.xbeta = J->xbeta.p; J->pp.xbeta = J->xbeta.p; J->pp.has_xbeta = 1;
+  }
   const uint32_t nf = J->n_filters;
   if (J->method == BSSM_METHOD_PSI) {
     if (J->pp.draw_par && J->pp.mode_stride != 0)
@@ -2032,17 +2049,25 @@ int bssm_b200_is_correction_bsf(const bssm_ung_model* M, const bssm_theta_map* m
                                 uint32_t draw_end, bssm_postcorr_out* out) {
   (void)n_threads;
   if (!M || !map || !counts || !theta || !approx_loglik || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
-  if (M->m != 1 || M->xbeta) return fail(BSSM_B200_ERR_UNSUPPORTED, "is_correction_bsf: m = 1 models without regressors in this build");
+  if (M->m != 1) return fail(BSSM_B200_ERR_UNSUPPORTED, "is_correction_bsf: m = 1 models in this build");
+  if (M->xbeta && map->n_xreg <= 0) return fail(BSSM_B200_ERR_ARG, "the model has regressors: theta_map needs n_xreg and xreg");
+  if (map->n_xreg > 0 && (!map->xreg || (int)n_par < map->n_xreg || map->model_type == 3))
+    return fail(BSSM_B200_ERR_ARG, "n_xreg > 0 needs xreg, beta in theta and a model with a regression part");
   return postcorr_driver(
       M->n, 1, output_type, nsim, is_type, counts, n_stored, draw_begin, draw_end, out,
       [&](const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N, int post, bssm_b200_job** J) {
         const uint32_t nf = d1 - d0;
         std::vector<double> par((size_t)6 * nf);
+        DrawModels dm;
+        if (map->n_xreg > 0) dm.xbeta.resize((size_t)M->n * nf);
         for (uint32_t f = 0; f < nf; ++f) {
-          int rc = theta_to_par(M, map, theta + (size_t)dl.src[d0 + f] * n_par, n_par, &par[(size_t)6 * f]);
+          const double* th = theta + (size_t)dl.src[d0 + f] * n_par;
+          int rc = theta_to_par(M, map, th, n_par, &par[(size_t)6 * f]);
           if (rc) return rc;
+          if (map->n_xreg > 0) theta_to_xbeta(map, M->n, th, n_par, &dm.xbeta[(size_t)M->n * f]);
         }
-        return create_ung_job(M, BSSM_METHOD_BSF, N, seed, nf, d0, 0, post, par.data(), nullptr, J);
+        return create_ung_job(M, BSSM_METHOD_BSF, N, seed, nf, d0, 0, post, par.data(), nullptr, J,
+                              map->n_xreg > 0 ? &dm : nullptr);
       },
       approx_loglik, /*posterior_adds_approx=*/false);
 }

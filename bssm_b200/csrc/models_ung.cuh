@@ -135,10 +135,12 @@ struct UngBsfDraw : GaussStep<UngBsfDraw, 1, 1, 1> {
   static constexpr int M = 1, KI = 1, KP = 1;
   typedef UngParams Params;
   const UngParams& mp;
+  const double* xbp;
   double T, R, a1, L, C, phi, lconst;
   double y, u, yphi2, Dt, xb, Z0;
 
   __device__ UngBsfDraw(const UngParams& p, uint32_t f) : mp(p) {
+    xbp = p.xbeta + (size_t)f * p.fs_x; // fs_x = n when beta is part of theta, else 0
     const double* q = p.bsf_par + (size_t)7 * f;
     T = q[0]; R = q[1]; a1 = q[2]; L = q[3]; C = q[4]; phi = q[5]; lconst = q[6];
   }
@@ -153,7 +155,7 @@ struct UngBsfDraw : GaussStep<UngBsfDraw, 1, 1, 1> {
     double q = y / phi;
     yphi2 = q * q;
     Dt = mp.D[t * mp.Dtv];
-    xb = mp.xbeta[t];
+    xb = xbp[t];
     Z0 = mp.Z[t * mp.Ztv];
   }
   __device__ double logw(const double* x) const {

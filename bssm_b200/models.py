@@ -90,7 +90,13 @@ class Model:
     def xbeta(self):
         if self.xreg is None or self.xreg.size == 0:
             return None
-        return f64(self.xreg @ self.beta)  # compute_xbeta, src/model_ssm_ung.h:83
+        # compute_xbeta, src/model_ssm_ung.h:83 -- column by column in a fixed order (no BLAS, no FMA), the
+        # same sums update_model(theta) forms inside the library when beta is part of theta
+        xr = self.xreg.reshape(self.n, -1)
+        xb = np.zeros(self.n)
+        for j in range(xr.shape[1]):
+            xb = xb + xr[:, j] * self.beta[j]
+        return f64(xb)
 
     def c_struct(self):
         """bssm_ung_model view of this model; keeps the arrays alive on the struct."""

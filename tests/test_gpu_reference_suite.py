@@ -290,3 +290,44 @@ def test_post_correction_for_ar1_model_with_regressors(engine):
         engine.post_correct(model, mo, int(1e12))
     with pytest.raises((ValueError, RuntimeError)):
         engine.post_correct(model, dict(mo, theta=np.eye(2)), 10)
+
+
+def test_ar1_with_regressors_bsf_correction_and_mcmc_loop(engine):
+    """the same model through the two other callers of update_model: the bootstrap-filter correction
+    (is_correction_bsf, src/approx_mcmc.cpp:447-518) and a resident job re-parameterised per MCMC
+    iteration (the log_likelihood call of src/mcmc.cpp:338-491)"""
+    model = _ar1_binomial_xreg()
+    rng = np.random.default_rng(9)
+    ns = 16
+    center = np.array([0.6, np.log(1.5), 0.8, 0.4, 0.9])
+    theta = center[None, :] + rng.normal(size=(ns, 5)) * np.array([0.05, 0.1, 0.3, 0.2, 0.2])
+    counts = (1 + rng.poisson(1.5, size=ns)).astype(np.uint32)
+    mo = {"theta": theta, "counts": counts, "approx_loglik": -45.0 + rng.normal(size=ns), "output_type": 3,
+          "modes": np.zeros((model.n, ns), order="F")}
+    ref = orc.is_correction_bsf(model, mo, 64, is_type=2, seed=3)
+    res = engine.post_correct(model, mo, 64, is_type="is2", seed=3, return_loglik=True, sampling_method="bsf")
+    np.testing.assert_allclose(res["loglik"], ref.loglik, rtol=1e-13)  # constants pre-summed per draw
+    np.testing.assert_allclose(res["weights"], ref.weights, rtol=1e-10)
+    mo1 = dict(mo, output_type=1)
+    ref1 = orc.is_correction_bsf(model, mo1, 32, is_type=3, seed=5)
+    res1 = engine.post_correct(model, mo1, 32, is_type="is3", seed=5, sampling_method="bsf")
+    assert np.array_equal(res1["alpha"].view(np.uint64), ref1.alpha.view(np.uint64))
+
+    for method in ("psi", "bsf"):
+        job = engine.FilterJob(model, 200, method=method, seed=4, n_filters=3)
+        job.run()
+        ll0 = job.logliks().copy()
+        for th in theta[:2]:
+            job.set_theta(th)
+            job.run()
+            m2 = _ar1_binomial_xreg(th)
+            m2.initial_mode = model.initial_mode
+            fresh = engine.FilterJob(m2, 200, method=method, seed=4, n_filters=3)
+            fresh.run()
+            if method == "psi":
+                assert np.array_equal(job.logliks(), fresh.logliks())
+            else:
+                np.testing.assert_allclose(job.logliks(), fresh.logliks(), rtol=1e-13)
+            assert not np.array_equal(job.logliks(), ll0)
+            fresh.close()
+        job.close()
