@@ -3,6 +3,7 @@ they come from and how their inputs are regenerated without R)."""
 import numpy as np
 import pytest
 
+import bssm_b200
 import orc
 from test_reference_golden import SVM_SMOOTHED, gbm_exact_loglik, gbm_kat_model, svm_kat_model
 
@@ -33,3 +34,17 @@ def test_gbm_loglik_against_exact_value(engine):
     assert abs(ll6 - exact) < 0.1
     out = engine.bootstrap_filter(m, 1000, seed=3, L=3)
     assert abs(out["logLik"] - ll3) / abs(ll3) < 1.0  # test_sde.R:57-58
+
+
+def test_gbm_smoothed_states_against_the_published_posterior_means(engine):
+    """test_sde.R:30-34 holds the IS-MCMC posterior means against the values of the paper the example
+    comes from: theta = (0.053, 0.253, 1.058), states x_1 = 1.254 and x_50 = 2.960, tolerance 0.1
+    (relative).  Plugging the published theta into the particle smoother on the regenerated data set
+    reproduces the two state means within that tolerance (the MCMC itself stays in R)."""
+    m = gbm_kat_model()
+    mm = bssm_b200.ssm_sde(m.y, "gbm", theta=[0.053, 0.253, 1.058], x0=1.0, positive=True)
+    target = np.array([1.254, 2.960])
+    got = np.mean([np.ravel(engine.particle_smoother(mm, 50000, method="bsf", seed=s, L=5)["alphahat"])[[0, 49]]
+                   for s in (1, 2)], axis=0)
+    assert np.mean(np.abs(got - target)) / np.mean(np.abs(target)) < 0.1   # all.equal's measure
+    assert np.all(np.abs(got / target - 1.0) < 0.1)

@@ -233,3 +233,21 @@ def test_sin_exp_approximation_converges_in_two_sweeps():
     two = orc.nlg_psi_filter(model, 8, 1, max_iter=2)
     np.testing.assert_allclose(two.mode, full.mode, rtol=1.5e-8, atol=1e-12)
     assert two.approx_loglik == pytest.approx(full.approx_loglik, rel=1.5e-8)
+
+
+def test_gbm_smoothed_states_match_the_published_posterior_means():
+    """test_sde.R:30-34: posterior means theta = (0.053, 0.253, 1.058), x_1 = 1.254, x_50 = 2.960 (from the
+    paper of the example), tolerance 0.1: the bootstrap particle smoother at the published theta, on the
+    regenerated data set, gives those two state means within the reference's tolerance"""
+    m = gbm_kat_model()
+    mm = bssm_b200.ssm_sde(m.y, "gbm", theta=[0.053, 0.253, 1.058], x0=1.0, positive=True)
+    got = []
+    for s in (1, 2, 3):
+        r = orc.sde_bsf_filter(mm, 5000, 4, seed=s)
+        a = r.alpha.copy()
+        out = orc.filter_smoother(a, r.indices)
+        a = a if out is None else out
+        got.append(np.ravel(a.mean(axis=-1))[[0, 49]])
+    got = np.mean(got, axis=0)
+    target = np.array([1.254, 2.960])
+    assert np.mean(np.abs(got - target)) / np.mean(np.abs(target)) < 0.1
