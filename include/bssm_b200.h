@@ -321,10 +321,12 @@ typedef struct {
   int32_t mu_est;     /* ar1_ng */
   int32_t phi_est;    /* ar1_ng, bsm_ng */
   /* bsm_ng (src/model_bsm_ng.cpp:4-51): which components exist and which
-   * standard deviations are in theta (fixed(i) == 0), then the regression
-   * coefficients as the last n_xreg entries of theta */
+   * standard deviations are in theta (fixed(i) == 0) */
   int32_t slope, seasonal, noise;
   int32_t level_est, slope_est, seasonal_est;
+  /* bsm_ng and ar1_ng: the regression coefficients are the last n_xreg entries
+   * of theta; update_model recomputes xbeta = xreg * beta for every theta
+   * (src/model_bsm_ng.cpp:46-49, src/model_ar1_ng.cpp:28-31) */
   int32_t n_xreg;
   const double* xreg; /* n x n_xreg column-major, or NULL */
 } bssm_theta_map;
