@@ -139,6 +139,8 @@ def lib():
         C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, c_uint32_p, c_double_p, C.c_uint32, c_double_p,
         C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PostcorrOut)]
     L.bssm_b200_job_set_theta.argtypes = [C.c_void_p] + pc_args + [c_double_p, C.c_uint32]
+    L.bssm_b200_job_set_theta_nlg.argtypes = [C.c_void_p, C.POINTER(NlgModel), c_double_p, C.c_uint32]
+    L.bssm_b200_job_set_theta_sde.argtypes = [C.c_void_p, c_double_p, C.c_uint32]
     L.bssm_b200_is_correction_bsf.argtypes = pc_args + [
         C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, c_uint32_p, c_double_p, C.c_uint32, c_double_p,
         C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PostcorrOut)]

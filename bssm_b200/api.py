@@ -198,6 +198,12 @@ class FilterJob:
         """Re-parameterise the resident job (the filter inside an MCMC loop, src/mcmc.cpp:338-491):
         update_model(theta) + approximate() on the host, then run() again."""
         theta = _lib.f64(np.ravel(theta))
+        if self.model.cls == "ssm_nlg":    # bootstrap / EKF particle filter jobs: theta travels by value
+            check(lib().bssm_b200_job_set_theta_nlg(self._h, C.byref(self._ms), dptr(theta), theta.size))
+            return
+        if self.model.cls == "ssm_sde":
+            check(lib().bssm_b200_job_set_theta_sde(self._h, dptr(theta), theta.size))
+            return
         tm = theta_map(self.model)
         check(lib().bssm_b200_job_set_theta(self._h, C.byref(self._ms), C.byref(tm), dptr(theta), theta.size))
 

@@ -1063,23 +1063,9 @@ static int check_nlg_model(const bssm_nlg_model* M) {
   return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_nlg: unknown model_id (registry: BSSM_NLG_GROWTH, BSSM_NLG_AR_EXP, BSSM_NLG_SIN_EXP)");
 }
 
-static int create_nlg_job(const bssm_nlg_model* M, int method, uint32_t nsim, uint32_t seed, uint32_t n_filters,
-                          uint32_t first_filter_id, int out_flags, int post, bssm_b200_job** job) {
-  if (!M || !job || !M->y || !M->theta) return fail(BSSM_B200_ERR_ARG, "null argument");
-  *job = nullptr;
-  int rc = check_nlg_model(M);
-  if (rc) return rc;
-  if (M->model_id == BSSM_NLG_GROWTH && !M->known_params) return fail(BSSM_B200_ERR_ARG, "null argument");
-  const int m = nlg_state_dim(M);
-  bssm_b200_job* J = new bssm_b200_job();
-  struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
-  rc = job_common(J, KIND_NLG, M->n, m, m, nsim, seed, n_filters, first_filter_id, out_flags, post);
-  if (rc) return rc;
-  J->nlg_model_id = M->model_id;
-  if ((rc = J->y.upload(M->y, M->n))) return rc;
-  pf::NlgParams& np = J->np;
-  memset(&np, 0, sizeof(np));
-  np.n = M->n; np.y = J->y.p;
+// everything of NlgParams that depends on theta / known_params (np.n and np.y stay): the registry
+// models' a1_fn, P1_fn, H_fn, R_fn constants and, for the EKF particle filter, the first EKF update
+static void fill_nlg_params(const bssm_nlg_model* M, int method, pf::NlgParams& np) {
   if (M->model_id == BSSM_NLG_AR_EXP) { // theta = (mu, rho, log sigma, log H), R/cpp_example_models.R:200-236
     const double e = pf_exp(M->theta[2]);
     const double P1 = e * e / (1 - M->theta[1] * M->theta[1]);
@@ -1102,9 +1088,29 @@ static int create_nlg_job(const bssm_nlg_model* M, int method, uint32_t nsim, ui
   }
   np.wconst = std::log(2.0 * M_PI) + 2.0 * pf_log(np.H);
   if (method == BSSM_METHOD_EKPF) {
-    J->method = BSSM_METHOD_EKPF;
-    if (m == 1) ekpf_first_column<1>(M, np); else ekpf_first_column<2>(M, np);
+    if (nlg_state_dim(M) == 1) ekpf_first_column<1>(M, np); else ekpf_first_column<2>(M, np);
   }
+}
+
+static int create_nlg_job(const bssm_nlg_model* M, int method, uint32_t nsim, uint32_t seed, uint32_t n_filters,
+                          uint32_t first_filter_id, int out_flags, int post, bssm_b200_job** job) {
+  if (!M || !job || !M->y || !M->theta) return fail(BSSM_B200_ERR_ARG, "null argument");
+  *job = nullptr;
+  int rc = check_nlg_model(M);
+  if (rc) return rc;
+  if (M->model_id == BSSM_NLG_GROWTH && !M->known_params) return fail(BSSM_B200_ERR_ARG, "null argument");
+  const int m = nlg_state_dim(M);
+  bssm_b200_job* J = new bssm_b200_job();
+  struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
+  rc = job_common(J, KIND_NLG, M->n, m, m, nsim, seed, n_filters, first_filter_id, out_flags, post);
+  if (rc) return rc;
+  J->nlg_model_id = M->model_id;
+  if ((rc = J->y.upload(M->y, M->n))) return rc;
+  pf::NlgParams& np = J->np;
+  memset(&np, 0, sizeof(np));
+  np.n = M->n; np.y = J->y.p;
+  if (method == BSSM_METHOD_EKPF) J->method = BSSM_METHOD_EKPF;
+  fill_nlg_params(M, method, np);
   if ((rc = finish_job(J, out_flags, post))) return rc;
   guard.j = nullptr;
   *job = J;
@@ -1118,6 +1124,38 @@ int bssm_b200_job_create_nlg(const bssm_nlg_model* M, uint32_t nsim, uint32_t se
 int bssm_b200_job_create_nlg_ekpf(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t n_filters,
                                   uint32_t first_filter_id, int out_flags, int post, bssm_b200_job** job) {
   return create_nlg_job(M, BSSM_METHOD_EKPF, nsim, seed, n_filters, first_filter_id, out_flags, post, job);
+}
+
+// The filter inside an MCMC loop for ssm_nlg (bootstrap / EKF particle filter) and ssm_sde models:
+// nonlinear_pm_mcmc / sde_pm_mcmc run the filter once per iteration at a new theta (src/R_mcmc.cpp:551-609 ->
+// src/mcmc.cpp:338-491; src/R_sde.cpp:114-166 -> src/mcmc.cpp:694-820, model.bsf_filter at :710, :759).  theta reaches the kernels by value, so a resident job only needs its parameter block rewritten.
+int bssm_b200_job_set_theta_nlg(bssm_b200_job* J, const bssm_nlg_model* M, const double* theta, uint32_t n_par) {
+  if (!J || !M || !theta) return fail(BSSM_B200_ERR_ARG, "null argument");
+  if (J->kind != KIND_NLG || M->model_id != J->nlg_model_id || M->n != J->n)
+    return fail(BSSM_B200_ERR_ARG, "job_set_theta_nlg: an ssm_nlg job created from the same model and data");
+  if (J->method != BSSM_METHOD_BSF && J->method != BSSM_METHOD_EKPF)
+    return fail(BSSM_B200_ERR_UNSUPPORTED, "job_set_theta_nlg: bootstrap and EKF particle filter jobs (psi-APF jobs are rebuilt per theta)");
+  bssm_nlg_model Mi = *M;
+  Mi.theta = theta;
+  Mi.n_theta = (int32_t)n_par;
+  int rc = check_nlg_model(&Mi);
+  if (rc) return rc;
+  fill_nlg_params(&Mi, J->method, J->np);
+  return 0;
+}
+
+static void sde_theta_block(int model_id, const double* th, double* b);
+int bssm_b200_job_set_theta_sde(bssm_b200_job* J, const double* theta, uint32_t n_par) {
+  if (!J || !theta) return fail(BSSM_B200_ERR_ARG, "null argument");
+  if (J->kind != KIND_SDE) return fail(BSSM_B200_ERR_ARG, "job_set_theta_sde: an ssm_sde job");
+  if (J->sp.theta_f) return fail(BSSM_B200_ERR_ARG, "job_set_theta_sde: IS-correction jobs carry one theta per filter already");
+  if (n_par < 3) return fail(BSSM_B200_ERR_ARG, "ssm_sde registry models need 3 parameters");
+  double b[6];
+  sde_theta_block(J->sde_model_id, theta, b);
+  pf::SdeParams& sp = J->sp;
+  sp.th0 = theta[0]; sp.th1 = theta[1]; sp.th2 = theta[2];
+  sp.logsd = b[3]; sp.e0 = b[4]; sp.e2 = b[5];
+  return 0;
 }
 
 // the 32 doubles per time point that the psi-APF weights of an ssm_nlg registry model read

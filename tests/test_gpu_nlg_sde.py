@@ -274,3 +274,42 @@ def test_growth_psi_missing_and_statistics(engine):
     lp = np.array([engine.logLik(full, 200, method="psi", seed=s) for s in range(1, 7)])
     lb = np.array([engine.logLik(full, 20000, method="bsf", seed=s) for s in range(1, 4)])
     assert lp.std() < 0.1 and abs(lp.mean() - lb.mean()) < 0.3
+
+
+@pytest.mark.parametrize("case", ["growth_bsf", "growth_ekf", "ar_exp_ekf", "sin_exp_bsf", "gbm", "poisson_ou"])
+def test_job_set_theta_nlg_sde_matches_fresh_job(engine, case):
+    """the filter inside nonlinear_pm_mcmc / sde_pm_mcmc (one bootstrap or EKF particle filter per iteration
+    at a new theta): re-parameterising a resident job equals building the job at that theta, bit for bit"""
+    import bssm_b200
+    method = "bsf"
+    if case in ("gbm", "poisson_ou"):
+        model = data.gbm_model(30) if case == "gbm" else data.poisson_ou_model(30)
+        make = lambda th: bssm_b200.ssm_sde(model.y, case, th, model.x0, model.positive)
+        kw = {"L": 3}
+        thetas = [np.abs(np.asarray(model.theta) * s) for s in (1.1, 0.85)]
+    else:
+        kind, method = case.rsplit("_", 1)
+        model = {"growth": data.growth_model, "ar_exp": data.ar_exp_model, "sin_exp": data.sin_exp_model}[kind](40)
+        known = getattr(model, "known_params", ())
+        make = lambda th: bssm_b200.ssm_nlg(model.y, kind, theta=th, known_params=known)
+        kw = {}
+        thetas = [np.asarray(model.theta) + d for d in (0.07, -0.05)]
+        if kind == "ar_exp":
+            thetas = [np.asarray(model.theta) + np.array([d, -d / 4, d, d]) for d in (0.07, -0.05)]
+    job = engine.FilterJob(model, 300, method=method, seed=4, n_filters=3, **kw)
+    job.run()
+    ll0 = job.logliks().copy()
+    for th in thetas:
+        job.set_theta(th)
+        job.run()
+        fresh = engine.FilterJob(make(th), 300, method=method, seed=4, n_filters=3, **kw)
+        fresh.run()
+        assert np.array_equal(job.logliks(), fresh.logliks())
+        assert not np.array_equal(job.logliks(), ll0)
+        fresh.close()
+    job.close()
+    if case == "growth_bsf":  # psi-APF jobs hold a per-theta approximation: refused, not silently wrong
+        pj = engine.FilterJob(model, 300, method="psi", seed=4)
+        with pytest.raises(Exception, match="psi"):
+            pj.set_theta(thetas[0])
+        pj.close()
