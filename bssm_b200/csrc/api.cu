@@ -429,6 +429,8 @@ struct bssm_b200_job {
   float ms[3] = {0, 0, 0};
   int launches = 0;
   bool has_run = false;
+  uint32_t nlg_max_iter = 100, nlg_iekf_iter = 0; // psi-APF jobs of ssm_nlg: settings of approximate(), kept for set_theta
+  double nlg_conv_tol = 1e-8;
   bool xbeta_per_filter = false; // m = 1 psi-APF whose filters carry their own regression part (beta in theta)
   // model on device
   DevBuf<double> y, Z, T, R, a1, P1, LP1, D, C, xbeta, u, mode, mode_lin;
@@ -1128,18 +1130,21 @@ int bssm_b200_job_create_nlg_ekpf(const bssm_nlg_model* M, uint32_t nsim, uint32
 
 // The filter inside an MCMC loop for ssm_nlg (bootstrap / EKF particle filter) and ssm_sde models:
 // nonlinear_pm_mcmc / sde_pm_mcmc run the filter once per iteration at a new theta (src/R_mcmc.cpp:551-609 ->
-// src/mcmc.cpp:338-491; src/R_sde.cpp:114-166 -> src/mcmc.cpp:694-820, model.bsf_filter at :710, :759).  theta reaches the kernels by value, so a resident job only needs its parameter block rewritten.
+// src/mcmc.cpp:338-491; src/R_sde.cpp:114-166 -> src/mcmc.cpp:694-820, model.bsf_filter at :710, :759).
+static int nlg_psi_approximation(bssm_b200_job* J, const bssm_nlg_model* M);
 int bssm_b200_job_set_theta_nlg(bssm_b200_job* J, const bssm_nlg_model* M, const double* theta, uint32_t n_par) {
   if (!J || !M || !theta) return fail(BSSM_B200_ERR_ARG, "null argument");
   if (J->kind != KIND_NLG || M->model_id != J->nlg_model_id || M->n != J->n)
     return fail(BSSM_B200_ERR_ARG, "job_set_theta_nlg: an ssm_nlg job created from the same model and data");
-  if (J->method != BSSM_METHOD_BSF && J->method != BSSM_METHOD_EKPF)
-    return fail(BSSM_B200_ERR_UNSUPPORTED, "job_set_theta_nlg: bootstrap and EKF particle filter jobs (psi-APF jobs are rebuilt per theta)");
   bssm_nlg_model Mi = *M;
   Mi.theta = theta;
   Mi.n_theta = (int32_t)n_par;
   int rc = check_nlg_model(&Mi);
   if (rc) return rc;
+  if (J->method == BSSM_METHOD_PSI) {
+    if (J->npp.fstride_stepc != 0) return fail(BSSM_B200_ERR_ARG, "job_set_theta_nlg: post-correction jobs carry one theta per filter already");
+    return nlg_psi_approximation(J, &Mi); // approximate() at the new theta on the host, same buffers
+  }
   fill_nlg_params(&Mi, J->method, J->np);
   return 0;
 }
@@ -1185,26 +1190,16 @@ static void pack_nlg_step(const pfga::NlgApprox& ga, const double* y, int m, int
   }
 }
 
-static int create_nlg_psi_job(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t max_iter,
-                              double conv_tol, uint32_t iekf_iter, uint32_t n_filters, uint32_t first_filter_id,
-                              int out_flags, int post, bssm_b200_job** job) {
-  if (!M || !job || !M->y || !M->theta) return fail(BSSM_B200_ERR_ARG, "null argument");
-  *job = nullptr;
-  int rc = check_nlg_model(M);
-  if (rc) return rc;
-  if (M->model_id == BSSM_NLG_GROWTH && !M->known_params) return fail(BSSM_B200_ERR_ARG, "null argument");
+// Gaussian approximation of an ssm_nlg model at M->theta on the host ((iterated) EKF start, relinearisation
+// sweeps, Kalman smoother), packed and uploaded for the job's replicate filters (which share it)
+static int nlg_psi_approximation(bssm_b200_job* J, const bssm_nlg_model* M) {
   const int n = M->n, m = nlg_state_dim(M);
-  bssm_b200_job* J = new bssm_b200_job();
-  struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
-  rc = job_common(J, KIND_NLG, n, m, m, nsim, seed, n_filters, first_filter_id, out_flags, post);
-  if (rc) return rc;
-  J->method = BSSM_METHOD_PSI;
-  J->nlg_model_id = M->model_id;
-  // Gaussian approximation on the host: (iterated) EKF start, relinearisation sweeps, Kalman smoother
+  const uint32_t n_filters = J->n_filters;
+  int rc;
   pfga::NlgApprox ga(M);
-  ga.max_iter = (int)max_iter;
-  ga.conv_tol = conv_tol;
-  ga.iekf_iter = (int)iekf_iter;
+  ga.max_iter = (int)J->nlg_max_iter;
+  ga.conv_tol = J->nlg_conv_tol;
+  ga.iekf_iter = (int)J->nlg_iekf_iter;
   ga.run(nullptr);
   if (!ga.finite_mode) return fail(BSSM_B200_ERR_ARG, "Approximation did not converge.");
   std::vector<double> sc((size_t)32 * n, 0.0);
@@ -1220,6 +1215,26 @@ static int create_nlg_psi_job(const bssm_nlg_model* M, uint32_t nsim, uint32_t s
   pp.dT = 0.0; pp.K = 0.0;
   if (M->model_id == BSSM_NLG_GROWTH) { pp.dT = M->known_params[0]; pp.K = M->known_params[1]; }
   pp.fstride_stepc = 0; pp.fstride_a = 0; pp.fstride_m = 0; // replicates share the approximation
+  return 0;
+}
+
+static int create_nlg_psi_job(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t max_iter,
+                              double conv_tol, uint32_t iekf_iter, uint32_t n_filters, uint32_t first_filter_id,
+                              int out_flags, int post, bssm_b200_job** job) {
+  if (!M || !job || !M->y || !M->theta) return fail(BSSM_B200_ERR_ARG, "null argument");
+  *job = nullptr;
+  int rc = check_nlg_model(M);
+  if (rc) return rc;
+  if (M->model_id == BSSM_NLG_GROWTH && !M->known_params) return fail(BSSM_B200_ERR_ARG, "null argument");
+  const int n = M->n, m = nlg_state_dim(M);
+  bssm_b200_job* J = new bssm_b200_job();
+  struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
+  rc = job_common(J, KIND_NLG, n, m, m, nsim, seed, n_filters, first_filter_id, out_flags, post);
+  if (rc) return rc;
+  J->method = BSSM_METHOD_PSI;
+  J->nlg_model_id = M->model_id;
+  J->nlg_max_iter = max_iter; J->nlg_conv_tol = conv_tol; J->nlg_iekf_iter = iekf_iter;
+  if ((rc = nlg_psi_approximation(J, M))) return rc;
   if ((rc = finish_job(J, out_flags, post))) return rc;
   guard.j = nullptr;
   *job = J;

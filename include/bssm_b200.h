@@ -448,10 +448,11 @@ int bssm_b200_job_create_postcorr_nlg(const bssm_nlg_model* model, uint32_t nsim
 int bssm_b200_job_set_theta(bssm_b200_job* job, const bssm_ung_model* model, const bssm_theta_map* map,
                             const double* theta, uint32_t n_par);
 
-/* The same for ssm_nlg (bootstrap / EKF particle filter jobs) and ssm_sde jobs: the filter that
+/* The same for ssm_nlg (bootstrap / EKF particle filter / psi-APF jobs) and ssm_sde jobs: the filter that
  * nonlinear_pm_mcmc / sde_pm_mcmc call once per iteration at a new theta (src/R_mcmc.cpp:551-609 ->
  * mcmc::pm_mcmc src/mcmc.cpp:338-491; src/R_sde.cpp:114-166 -> the ssm_sde pm_mcmc src/mcmc.cpp:694-820,
- * `model.bsf_filter(nsim, L_f, ...)` at :710 and :759).  theta reaches the kernels by value: no transfer. */
+ * `model.bsf_filter(nsim, L_f, ...)` at :710 and :759).  Bootstrap / EKF jobs take theta by value (no
+ * transfer); psi-APF jobs redo approximate() on the host and refill the job's device buffers. */
 int bssm_b200_job_set_theta_nlg(bssm_b200_job* job, const bssm_nlg_model* model, const double* theta,
                                 uint32_t n_par);
 int bssm_b200_job_set_theta_sde(bssm_b200_job* job, const double* theta, uint32_t n_par);

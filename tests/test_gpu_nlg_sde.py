@@ -276,10 +276,12 @@ def test_growth_psi_missing_and_statistics(engine):
     assert lp.std() < 0.1 and abs(lp.mean() - lb.mean()) < 0.3
 
 
-@pytest.mark.parametrize("case", ["growth_bsf", "growth_ekf", "ar_exp_ekf", "sin_exp_bsf", "gbm", "poisson_ou"])
+@pytest.mark.parametrize("case", ["growth_bsf", "growth_ekf", "growth_psi", "ar_exp_ekf", "ar_exp_psi", "sin_exp_bsf",
+                                  "sin_exp_psi", "gbm", "poisson_ou"])
 def test_job_set_theta_nlg_sde_matches_fresh_job(engine, case):
-    """the filter inside nonlinear_pm_mcmc / sde_pm_mcmc (one bootstrap or EKF particle filter per iteration
-    at a new theta): re-parameterising a resident job equals building the job at that theta, bit for bit"""
+    """the filter inside nonlinear_pm_mcmc / sde_pm_mcmc (one bootstrap, EKF or psi particle filter per
+    iteration at a new theta): re-parameterising a resident job equals building the job at that theta, bit
+    for bit (psi-APF jobs redo approximate() on the host and refill the same device buffers)"""
     import bssm_b200
     method = "bsf"
     if case in ("gbm", "poisson_ou"):
@@ -308,8 +310,3 @@ def test_job_set_theta_nlg_sde_matches_fresh_job(engine, case):
         assert not np.array_equal(job.logliks(), ll0)
         fresh.close()
     job.close()
-    if case == "growth_bsf":  # psi-APF jobs hold a per-theta approximation: refused, not silently wrong
-        pj = engine.FilterJob(model, 300, method="psi", seed=4)
-        with pytest.raises(Exception, match="psi"):
-            pj.set_theta(thetas[0])
-        pj.close()
