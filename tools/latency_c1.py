@@ -55,3 +55,20 @@ for N in (100, 1000):
     it = (time.perf_counter() - t0) / 20 * 1e3
     print("svm psi n=1000 N=%5d: MCMC-style iteration (set_theta + run) %.3f ms" % (N, it))
     job.close()
+# the same loop for the ssm_nlg / ssm_sde registry models (nonlinear_pm_mcmc / sde_pm_mcmc)
+for name, mdl, method, kw in (("growth bsf n=200", data.growth_model(200), "bsf", {}),
+                              ("growth ekf n=200", data.growth_model(200), "ekf", {}),
+                              ("growth psi n=200", data.growth_model(200), "psi", {}),
+                              ("gbm bsf n=50 L=4", data.gbm_model(50), "bsf", {"L": 4})):
+    for N in (100, 1000):
+        job = bssm_b200.FilterJob(mdl, N, method=method, seed=1, out_flags=0, **kw)
+        rng = np.random.default_rng(1)
+        th0 = np.asarray(mdl.theta)
+        for _ in range(3):
+            job.set_theta(th0); job.run()
+        t0 = time.perf_counter()
+        for i in range(20):
+            job.set_theta(th0 + 0.01 * rng.normal(size=th0.size) * (mdl.cls != "ssm_sde")); job.run()
+        it = (time.perf_counter() - t0) / 20 * 1e3
+        print("%s N=%5d: MCMC-style iteration (set_theta + run) %.3f ms" % (name, N, it))
+        job.close()
