@@ -175,7 +175,7 @@ struct UngPsi1 : GaussStep<UngPsi1, 1, 1, 1> {
   const UngParams& mp;
   const double *ah, *Lt, *Ct, *yt, *Ht, *sc;
   double phi, al0;
-  double y, u, yphi2, Dt, xb, Z0, ytil, Htil, scale;
+  double y, u, yphi2, Dt, xb, Z0, ytil, rH, scale;
   double ah0, ah1, c1, l1;
 
   __device__ UngPsi1(const UngParams& p, uint32_t f) : mp(p) {
@@ -197,11 +197,11 @@ struct UngPsi1 : GaussStep<UngPsi1, 1, 1, 1> {
     Dt = mp.D[t * mp.Dtv];
     xb = mp.xbeta[t];
     Z0 = mp.Z[t * mp.Ztv];
-    ytil = yt[t]; Htil = Ht[t]; scale = sc[t];
+    ytil = yt[t]; rH = 1.0 / Ht[t]; scale = sc[t];
   }
   __device__ double logw(const double* x) const {
     double s = (mp.distribution == 0) ? x[0] : (Dt + Z0 * x[0] + xb);
-    double q = (ytil - s) / Htil;
+    double q = (ytil - s) * rH; // reciprocal once per time point, as in the oracle's log_weight_pf
     return (ung_log_obs(mp.distribution, s, y, u, phi, yphi2) + 0.5 * (q * q)) - scale;
   }
   __device__ void begin_step(int t) {
@@ -224,7 +224,7 @@ struct UngPsiM : GaussStep<UngPsiM<M_>, M_, M_, M_> {
   const UngParams& mp;
   double al0, phi;
   const double *p_ah, *p_Lt, *p_Ct, *p_yt, *p_Ht, *p_sc, *p_xb;
-  double y, u, yphi2, Dt, xb, ytil, Htil, scale;
+  double y, u, yphi2, Dt, xb, ytil, rH, scale;
   double Z[M_], ah0[M_], ah1[M_], Cm[M_ * M_], Lm[M_ * M_];
 
   __device__ UngPsiM(const UngParams& p, uint32_t f) : mp(p) {
@@ -256,7 +256,7 @@ struct UngPsiM : GaussStep<UngPsiM<M_>, M_, M_, M_> {
     xb = p_xb[t];
 #pragma unroll
     for (int d = 0; d < M_; ++d) Z[d] = mp.Z[d + M_ * (t * mp.Ztv)];
-    ytil = p_yt[t]; Htil = p_Ht[t]; scale = p_sc[t];
+    ytil = p_yt[t]; rH = 1.0 / p_Ht[t]; scale = p_sc[t];
   }
   __device__ double logw(const double* x) const {
     double s;
@@ -268,7 +268,7 @@ struct UngPsiM : GaussStep<UngPsiM<M_>, M_, M_, M_> {
       for (int d = 0; d < M_; ++d) zs += Z[d] * x[d];
       s = Dt + zs + xb;
     }
-    double q = (ytil - s) / Htil;
+    double q = (ytil - s) * rH; // as UngPsi1
     return (ung_log_obs(mp.distribution, s, y, u, phi, yphi2) + 0.5 * (q * q)) - scale;
   }
   __device__ void begin_step(int t) {

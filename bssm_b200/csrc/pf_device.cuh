@@ -28,6 +28,13 @@
 // normals with the threshold loads or inside the scan collective instead of inside the scatter
 // barrier (-4% / -1%), letting the compiler unroll the scatter loop (-3%).
 
+#ifndef PF_PHASE_TIMING
+#define PF_PHASE_TIMING 0 // 1: per-phase cycle counters (cost 14 registers per thread; diagnostics builds only)
+#endif
+#ifndef PF_SCATTER_CAP
+#define PF_SCATTER_CAP 4 // offspring written by the owner lane itself; longer runs are written by the whole warp
+#endif
+
 namespace pf {
 
 enum SyncMode { SYNC_BLOCK = 0, SYNC_CLUSTER = 1, SYNC_GROUP = 2 };
@@ -110,7 +117,9 @@ struct Sync {
       if (!joined) __syncthreads();
       if (threadIdx.x == 0) {
         target += nranks;
-        __threadfence();
+        // release only (MEMBAR.ALL.GPU): __threadfence() is fence.sc + CCTL.IVALL, and the L1
+        // invalidation evicts the spill lines of every CTA resident on the SM (round 2)
+        asm volatile("fence.release.gpu;" ::: "memory");
         atomicAdd(counter, 1u);
       }
     }
@@ -118,14 +127,14 @@ struct Sync {
   // SYNC_GROUP, warp 0 only: returns when every CTA of the filter has arrived
   __device__ __forceinline__ void poll_warp0() {
     if (threadIdx.x == 0) {
-      // relaxed polling, ONE acquire fence at the end: an acquire load invalidates
-      // the SM's L1 (CCTL.IVALL) on every iteration, which evicts the spill lines of
-      // all resident CTAs while this thread spins
+      // relaxed polling and NO acquire fence: a gpu-scope acquire is a CCTL.IVALL, which evicts
+      // the spill lines of all resident CTAs; it is not needed because everything another CTA
+      // wrote (partials, state row, thresholds, ancestors) is read with L2 loads (ld.cg) issued
+      // behind the CTA barrier that follows, never through a possibly stale L1 line
       unsigned int v;
       do {
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
       } while ((int)(v - target) < 0);
-      __threadfence();
     }
     __syncwarp();
   }
@@ -156,6 +165,19 @@ __device__ __forceinline__ long long shfl_xor_i64(long long v, int m) {
   return __shfl_xor_sync(0xffffffffu, v, m);
 }
 
+// warp maximum of a double (no NaN) with two 32-bit REDUX instead of five shuffle / compare /
+// select rounds: the bit pattern is mapped to an unsigned key with the same order
+__device__ __forceinline__ double warp_max_d(double v) {
+  unsigned long long b = pf_d2u(v);
+  b = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+  const uint32_t hi = (uint32_t)(b >> 32), lo = (uint32_t)b;
+  const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+  const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  b = ((unsigned long long)mh << 32) | ml;
+  b = (b >> 63) ? (b & 0x7fffffffffffffffull) : ~b;
+  return pf_u2d(b);
+}
+
 struct CollSmem {
   double wd[32];
   long long wa[32], wb[32];
@@ -180,14 +202,11 @@ struct Coll {
   // suffices.  Split in two: independent work between _begin and _end hides the
   // latency of the exchange between CTAs.
   __device__ __forceinline__ void allmax_begin(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const double y = shfl_xor_d(v, o); v = y > v ? y : v; }
+    v = warp_max_d(v);
     if (lane == 0) sm->wd[warp] = v;
     __syncthreads();
     if (warp == 0) {
-      double x = lane < nwarps ? sm->wd[lane] : -pf_inf();
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { const double y = shfl_xor_d(x, o); x = y > x ? y : x; }
+      const double x = warp_max_d(lane < nwarps ? sm->wd[lane] : -pf_inf());
       if (ranks == 1) { if (lane == 0) sm->rd = x; }
       else if (lane == 0) ((double*)xch)[rank] = x;
     }
@@ -200,8 +219,7 @@ struct Coll {
       if (warp == 0) {
         double x = -pf_inf();
         for (uint32_t r = lane; r < ranks; r += 32) { const double y = __ldcg(((const double*)xch) + r); x = y > x ? y : x; }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const double y = shfl_xor_d(x, o); x = y > x ? y : x; }
+        x = warp_max_d(x);
         if (lane == 0) sm->rd = x;
       }
       __syncthreads();
@@ -288,6 +306,12 @@ struct Coll {
 // only when p*N is within 2^-51 of an integer).  The thresholds of the step are
 // generated once by the threads that own the strata (one Philox call per two
 // strata) and parked in `ubuf` (L2-resident, 8 B per particle).
+// p * N within 2^-51 (relative) of an integer: walk the thresholds (out of line, rare)
+static __device__ __noinline__ uint32_t strata_walk(const double* ubuf, uint32_t N, double p, uint32_t c, bool up) {
+  if (up) { while (c < N && __ldcg(ubuf + c) <= p) c++; }
+  else { while (c > 0 && !(__ldcg(ubuf + c - 1) <= p)) c--; }
+  return c;
+}
 struct Strata {
   const double* ubuf;
   uint32_t N;
@@ -299,18 +323,29 @@ struct Strata {
   }
   // resolve the count given the pre-loaded threshold uj = u(guess(p))
   __device__ __forceinline__ uint32_t resolve(double p, uint32_t jj, double uj) const {
-    if (p >= 1.0) return N;
     const double x = p * Nd;
-    const double tol = x * 4.440892098500626e-16; // 2^-51 relative guard
-    if (uj <= p) {
-      jj++;
-      if (((double)jj - x) < tol) while (jj < N && u(jj) <= p) jj++;
-    } else {
-      if ((x - (double)jj) < tol) while (jj > 0 && !(u(jj - 1) <= p)) jj--;
-    }
-    return jj;
+    const bool le = uj <= p;
+    uint32_t c = jj + (le ? 1u : 0u);
+    const double dc = (double)c;
+    const double d = le ? dc - x : x - dc;  // distance of p * N to the integer that would change the count
+    if (d < x * 4.440892098500626e-16) c = strata_walk(ubuf, N, p, c, le);
+    return p >= 1.0 ? N : c;
   }
 };
+
+// offspring runs longer than PF_SCATTER_CAP: every lane of the warp calls this with the same
+// `heavy` mask; the lanes in it broadcast their run [s, e) and value, the whole warp writes it
+static __device__ __noinline__ void scatter_heavy(uint32_t* anc, unsigned heavy, uint32_t s, uint32_t e, uint32_t val) {
+  const uint32_t lane = threadIdx.x & 31u;
+  while (heavy) {
+    const int src = __ffs(heavy) - 1;
+    heavy &= heavy - 1;
+    const uint32_t s0 = __shfl_sync(0xffffffffu, s, src), e0 = __shfl_sync(0xffffffffu, e, src);
+    const uint32_t v0 = __shfl_sync(0xffffffffu, val, src);
+#pragma unroll 1
+    for (uint32_t j = s0 + lane; j < e0; j += 32) anc[j] = v0;
+  }
+}
 
 // ------------------------------------------------------- per-step context
 struct StepCtx {
@@ -471,10 +506,14 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
   Strata st;
   st.ubuf = ub; st.N = N; st.Nd = Nd;
 
+#if PF_PHASE_TIMING
   unsigned long long ph[6] = {0, 0, 0, 0, 0, 0};
   const bool timing = fp.phase_cycles != nullptr && threadIdx.x == 0;
   long long tc = timing ? clock64() : 0;
 #define PF_PHASE(i) if (timing) { long long now_ = clock64(); ph[i] += (unsigned long long)(now_ - tc); tc = now_; }
+#else
+#define PF_PHASE(i)
+#endif
 
   for (int t = 0;; ++t) {
     // ---- weights of column t (reference :633-647, :672-687).  Column n is a
@@ -545,7 +584,7 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
       PF_PHASE(3)
       const double S = pf_fixsum_value(Th, Tl);
       const double invS = 1.0 / S;
-      if (obs) {
+      if (obs && rank == 0 && threadIdx.x == 0) { // the log-likelihood is thread 0's business (a log and a division)
         // step_const: per-step normalising constant (ssm_ulg adds norm_log_const(H_t) every
         // step, src/model_ssm_ulg.cpp:588, :631); zero for the other models
         if (t == 0) loglik = ((mx + loglik) + pf_log_normal(S / Nd)) + model.step_const(); // reference :561
@@ -575,8 +614,15 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
 #pragma unroll
         for (int q = 0; q < CH; ++q) {
           const uint32_t c = st.resolve(pk[q], jj[q], uj[q]);
-#pragma unroll 1
-          for (uint32_t j = lo; j < c; ++j) anc[j] = i0 + c0 + q;
+          const uint32_t val = i0 + c0 + q;
+          // the owner writes the first PF_SCATTER_CAP offspring itself (predicated stores, no loop),
+          // a longer run (a heavy particle) is written by the whole warp, coalesced
+#pragma unroll
+          for (int o = 0; o < PF_SCATTER_CAP; ++o)
+            if (lo + o < c) anc[lo + o] = val;
+          const uint32_t ce = lo + PF_SCATTER_CAP;
+          const unsigned heavy = __ballot_sync(0xffffffffu, c > ce);
+          if (heavy) scatter_heavy(anc, heavy, ce, c, val);
           lo = c > lo ? c : lo;
         }
       }
@@ -616,12 +662,14 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
     PF_PHASE(5)
   }
 #undef PF_PHASE
+#if PF_PHASE_TIMING
   if (timing)
     for (int i = 0; i < 6; ++i) fp.phase_cycles[(size_t)blockIdx.x * 6 + i] = ph[i];
+#endif
 
-  if (stopped >= 0) loglik = -pf_inf();
-  else loglik += model.loglik_end();
   if (rank == 0 && threadIdx.x == 0) {
+    if (stopped >= 0) loglik = -pf_inf();
+    else loglik += model.loglik_end();
     fp.loglik[fidx] = loglik;
     fp.stopped_at[fidx] = stopped;
   }

@@ -170,26 +170,20 @@ static __constant__ double pf_dc_cos[] = {PF_COS_COEFFS};
 #define PF_CC pf_hc_cos
 #endif
 
-/* x * 2^k for |k| <= 2098, one rounding (only when the result is subnormal) */
-PF_HD double pf_scalbn2(double x, int k) {
-  int k1 = k >> 1;           /* arithmetic shift: floor(k/2) */
-  int k2 = k - k1;
-  double s1 = pf_u2d((uint64_t)(k1 + 1023) << 52);
-  double s2 = pf_u2d((uint64_t)(k2 + 1023) << 52);
-  return (x * s1) * s2;
-}
-
 /* exp(x): Cody-Waite reduction by ln2 (hi/lo split), degree-13 Taylor kernel on
- * |r| <= ln2/2 (truncation 4e-18), exact power-of-two scaling.  Straight-line:
- * the argument is clamped to [-746, 710], where the scaling already produces
- * the correctly rounded 0 / +inf; NaN flows through the arithmetic. */
+ * |r| <= ln2/2 (truncation 4e-18), power-of-two scaling.  Straight-line code:
+ * y * 2^k is evaluated as 2 * (y * 2^(k-1)); the inner scaling is an integer add
+ * on the exponent field (y in [0.70, 1.42] and k - 1 in [-1020, 1023] keep the
+ * field inside [2, 2046]), the final doubling is exact and overflows to +inf where
+ * exp does.  Results below 2^-1020 (x < -706.5) FLUSH TO ZERO: the reference's
+ * std::exp returns subnormals there (< 1e-307; as a weight relative to the largest
+ * weight of a column that is nothing).  NaN flows through. */
 PF_HDX double pf_exp(double x) {
-  double xc = x < -746.0 ? -746.0 : x;   /* NaN compares false: stays NaN */
-  xc = xc > 710.0 ? 710.0 : xc;
+  double xc = x > 710.0 ? 710.0 : x;     /* NaN compares false: stays NaN */
   const double MAGIC = PF_CE[13];
   double t = pf_fma(xc, PF_CE[12], MAGIC);
   double kf = t - MAGIC;
-  int k = (int)(int32_t)(uint32_t)pf_d2u(t);
+  uint32_t k = (uint32_t)pf_d2u(t);      /* two's complement of round(x / ln2) */
   double r = pf_fma(-kf, PF_CE[14], xc);
   r = pf_fma(-kf, PF_CE[15], r);
   double q = PF_CE[0];
@@ -205,8 +199,13 @@ PF_HDX double pf_exp(double x) {
   q = pf_fma(q, r, PF_CE[10]);
   q = pf_fma(q, r, PF_CE[11]);
   double e = pf_fma(q, r * r, r);
-  if (!(x == x)) k = 0;                  /* keep the scale finite for NaN input */
-  return pf_scalbn2(1.0 + e, k);
+  uint64_t yb = pf_d2u(1.0 + e);
+  /* add (k - 1) to the exponent field: only the high word changes */
+  uint32_t hi = (uint32_t)(yb >> 32) + ((k - 1u) << 20);
+  double res = pf_u2d(((uint64_t)hi << 32) | (yb & 0xffffffffULL)) * 2.0;
+  if (x < -706.5) res = 0.0;
+  if (!(x == x)) res = x;
+  return res;
 }
 
 /* log(x): x = 2^e * m, m in (sqrt(1/2), sqrt(2)], s = f/(2+f) with f = m-1,

@@ -227,6 +227,14 @@ struct Ung {
     double q = (ay[t] - s) / aH[t];
     return log_obs_density(t, s) + 0.5 * (q * q);
   }
+  /* the same inside the particle loop, where the kernels multiply by the reciprocal 1/H~_t
+   * (one division per time point instead of one per particle): a declared 1-ulp deviation
+   * from the reference's (approx_y - signal) / H of src/model_ssm_ung.cpp:398 */
+  double log_weight_pf(int t, double s) const {
+    const double rH = 1.0 / aH[t];
+    double q = (ay[t] - s) * rH;
+    return log_obs_density(t, s) + 0.5 * (q * q);
+  }
 };
 
 /* state-independent constants: src/distr_consts.cpp:7-67 via the switch at
@@ -775,7 +783,7 @@ double orc_ung_psi_filter(const bssm_ung_model* M, const double* mode_in, uint32
   std::vector<double> W(N), logw(N), r(N), atmp(N);
   double loglik = 0.0;
   if (std::isfinite(M->y[0])) { /* :549-562 */
-    for (size_t i = 0; i < N; ++i) { double a = A(0, i); logw[i] = g.log_weight(0, g.signal(0, &a)) - g.scales[0]; }
+    for (size_t i = 0; i < N; ++i) { double a = A(0, i); logw[i] = g.log_weight_pf(0, g.signal(0, &a)) - g.scales[0]; }
     double mxw, lmean;
     if (!normalise(logw.data(), nsim, weights, W, &mxw, &lmean, arith)) { *stopped_at = 0; return -ORC_INF; }
     loglik = mxw + g.approx_loglik + lmean; /* :561, evaluated left to right */
@@ -794,7 +802,7 @@ double orc_ung_psi_filter(const bssm_ung_model* M, const double* mode_in, uint32
     }
     double* wcol = weights + N * (t + 1);
     if ((t < (n - 1)) && std::isfinite(M->y[t + 1])) {
-      for (size_t i = 0; i < N; ++i) { double a = A(t + 1, i); logw[i] = g.log_weight(t + 1, g.signal(t + 1, &a)) - g.scales[t + 1]; }
+      for (size_t i = 0; i < N; ++i) { double a = A(t + 1, i); logw[i] = g.log_weight_pf(t + 1, g.signal(t + 1, &a)) - g.scales[t + 1]; }
       double mxw, lmean;
       if (!normalise(logw.data(), nsim, wcol, W, &mxw, &lmean, arith)) { *stopped_at = t + 1; return -ORC_INF; }
       loglik += mxw + lmean;
@@ -837,7 +845,7 @@ double orc_ung_psi_filter_m(const bssm_ung_model* M, const double* mode_in, uint
   std::vector<double> W(N), logw(N), r(N), atmp((size_t)m * N);
   double loglik = 0.0;
   if (std::isfinite(M->y[0])) {
-    for (size_t i = 0; i < N; ++i) logw[i] = g.log_weight(0, g.signal(0, &A(0, 0, i))) - g.scales[0];
+    for (size_t i = 0; i < N; ++i) logw[i] = g.log_weight_pf(0, g.signal(0, &A(0, 0, i))) - g.scales[0];
     double mxw, lmean;
     if (!normalise(logw.data(), nsim, weights, W, &mxw, &lmean, arith)) { *stopped_at = 0; return -ORC_INF; }
     loglik = mxw + ga.approx_loglik + lmean;
@@ -868,7 +876,7 @@ double orc_ung_psi_filter_m(const bssm_ung_model* M, const double* mode_in, uint
     }
     double* wcol = weights + N * (t + 1);
     if ((t < (n - 1)) && std::isfinite(M->y[t + 1])) {
-      for (size_t i = 0; i < N; ++i) logw[i] = g.log_weight(t + 1, g.signal(t + 1, &A(0, t + 1, i))) - g.scales[t + 1];
+      for (size_t i = 0; i < N; ++i) logw[i] = g.log_weight_pf(t + 1, g.signal(t + 1, &A(0, t + 1, i))) - g.scales[t + 1];
       double mxw, lmean;
       if (!normalise(logw.data(), nsim, wcol, W, &mxw, &lmean, arith)) { *stopped_at = t + 1; return -ORC_INF; }
       loglik += mxw + lmean;

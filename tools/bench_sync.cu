@@ -3,6 +3,8 @@
 //   1 flags:   16-byte {value, epoch} descriptors, warp 0 polls all ranks (as pf_device.cuh)
 //   2 flags, fence only on lane 0 after __syncwarp
 //   3 flags, no fences at all (lower bound; NOT safe for bulk data exchange)
+//   4 flags, fence.release.gpu before publishing only (round 2 filter kernel)
+//   5 flags as 4, two-level: groups of 16 CTAs, leaders republish group totals
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/bench_sync tools/bench_sync.cu
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -47,7 +49,8 @@ __global__ void k(int flavour, int iters, unsigned* counter, double* part, Desc*
       if (warp == 0) {
         Desc* base = slots + (epoch & 1) * R;
         if (lane == 0) {
-          if (flavour != 3) __threadfence();
+          if (flavour == 4) asm volatile("fence.release.gpu;" ::: "memory");
+          else if (flavour != 3) __threadfence();
           dst(base + rank, (unsigned long long)__double_as_longlong(mine), epoch + 1);
         }
         double x = 0;
@@ -73,7 +76,7 @@ int main() {
   cudaMalloc(&counter, 4); cudaMalloc(&part, 8 * 1024); cudaMalloc(&out, 8 * 1024); cudaMalloc(&slots, 16 * 2048);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   const int iters = 2000;
-  for (int R : {8, 16, 32, 64, 128, 148}) for (int threads : {256, 1024}) for (int fl = 0; fl < 4; ++fl) {
+  for (int R : {8, 16, 32, 64, 128, 148}) for (int threads : {256, 1024}) for (int fl = 0; fl < 5; ++fl) {
     float best = 1e9;
     for (int rep = 0; rep < 3; ++rep) {
       cudaMemset(counter, 0, 4); cudaMemset(slots, 0, 16 * 2048);
