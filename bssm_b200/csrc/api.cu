@@ -435,7 +435,7 @@ struct bssm_b200_job {
   // model on device
   DevBuf<double> y, Z, T, R, a1, P1, LP1, D, C, xbeta, u, mode, mode_lin;
   // psi pre-pass results
-  DevBuf<double> alphahat, Lt, Ct, ytilde, Htilde, scales, approx_loglik, phi_f, scratch;
+  DevBuf<double> alphahat, Lt, Ct, ytilde, Htilde, scales, approx_loglik, phi_f, scratch, rHt, yphi2;
   size_t pstride = 0;
   // outputs
   DevBuf<double> alpha_tm, alpha_sm, weights, cube;
@@ -515,7 +515,7 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
   fp.loglik = J->loglik.p + f0;
   fp.stopped_at = J->stopped.p + f0;
   fp.xch = J->xch.p + (size_t)f0 * 4 * J->geo.ranks;
-  fp.counters = J->counters.p + f0;
+  fp.counters = J->counters.p + (size_t)f0 * pf::COUNTER_STRIDE;
   fp.ubuf = J->ubuf.p + (size_t)f0 * J->N;
   if (fp.phase_cycles) fp.phase_cycles = J->phases.p + (size_t)f0 * 6 * J->geo.ranks;
   if (J->kind == KIND_NLG && J->method == BSSM_METHOD_PSI) {
@@ -553,6 +553,7 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
   if (J->method == BSSM_METHOD_PSI) {
     up.alphahat += (size_t)f0 * J->pstride; up.Lt += (size_t)f0 * J->pstride; up.Ct += (size_t)f0 * J->pstride;
     up.ytilde += (size_t)f0 * J->pstride; up.Htilde += (size_t)f0 * J->pstride; up.scales += (size_t)f0 * J->pstride;
+    up.rHt += (size_t)f0 * J->pstride; up.yphi2 += (size_t)f0 * J->pstride;
     up.approx_loglik += f0;
     if (up.phi_f) up.phi_f += f0;
     return launch_status(pfl::launch_ung_psi1(fp, up, J->geo, nf, J->stream), "psi filter");
@@ -616,7 +617,7 @@ static int finish_job(bssm_b200_job* J, int out_flags, int post) {
   if (smooth && (rc = J->alpha_sm.alloc(J->alpha_stride * n_filters))) return rc;
   if (post == BSSM_POST_PICK && (rc = J->traj.alloc((size_t)n_filters * (n + 1) * m))) return rc;
   if ((rc = J->loglik.alloc(n_filters)) || (rc = J->stopped.alloc(n_filters))) return rc;
-  if ((rc = J->xch.alloc((size_t)4 * J->geo.ranks * n_filters)) || (rc = J->counters.alloc(n_filters)) ||
+  if ((rc = J->xch.alloc((size_t)4 * J->geo.ranks * n_filters)) || (rc = J->counters.alloc((size_t)n_filters * pf::COUNTER_STRIDE)) ||
       (rc = J->ubuf.alloc((size_t)nsim * n_filters))) return rc;
   if (post == BSSM_POST_FILTER_SUMMARY) {
     if ((rc = J->s_at.alloc((size_t)n_filters * m * (n + 1))) || (rc = J->s_att.alloc((size_t)n_filters * m * n)) ||
@@ -817,7 +818,7 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
     if ((rc = J->alphahat.alloc(tot)) || (rc = J->Lt.alloc(tot)) || (rc = J->Ct.alloc(tot)) ||
         (rc = J->ytilde.alloc(tot)) || (rc = J->Htilde.alloc(tot)) || (rc = J->scales.alloc(tot)) ||
         (rc = J->scratch.alloc(3 * tot)) || (rc = J->approx_loglik.alloc(n_filters)) ||
-        (rc = J->phi_f.alloc(n_filters)))
+        (rc = J->phi_f.alloc(n_filters)) || (rc = J->rHt.alloc(tot)) || (rc = J->yphi2.alloc(tot)))
       return rc;
     pf::PrepassParams& pp = J->pp;
     pp.n = n; pp.distribution = M->distribution;
@@ -840,6 +841,8 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
     pp.alphahat = J->alphahat.p; pp.Lt = J->Lt.p; pp.Ct = J->Ct.p; pp.ytilde = J->ytilde.p;
     pp.Htilde = J->Htilde.p; pp.scales = J->scales.p; pp.approx_loglik = J->approx_loglik.p;
     pp.phi_f = J->phi_f.p; pp.scratch = J->scratch.p; pp.pstride = J->pstride;
+    pp.rHt = J->rHt.p; pp.yphi2 = J->yphi2.p;
+    up.rHt = J->rHt.p; up.yphi2 = J->yphi2.p;
     up.phi_f = J->phi_f.p; up.alphahat = J->alphahat.p; up.Lt = J->Lt.p; up.Ct = J->Ct.p;
     up.ytilde = J->ytilde.p; up.Htilde = J->Htilde.p; up.scales = J->scales.p;
     up.approx_loglik = J->approx_loglik.p; up.pstride = J->pstride;

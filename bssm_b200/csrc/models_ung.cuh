@@ -36,6 +36,8 @@ struct UngParams {
   const double* scales;    // n
   const double* approx_loglik; // per filter
   size_t pstride;
+  const double* rHt;       // n: 1 / Htilde_t   (m = 1 pre-pass)
+  const double* yphi2;     // n: (y_t / phi)^2  (m = 1 pre-pass)
   // psi-APF (m > 1): per-filter strides of alphahat / (Lt, Ct) / (ytilde, Htilde, scales) / xbeta;
   // all zero when the replicates of a job share one approximation
   size_t fs_a, fs_m, fs_n, fs_x;
@@ -173,7 +175,7 @@ struct UngPsi1 : GaussStep<UngPsi1, 1, 1, 1> {
   static constexpr int M = 1, KI = 1, KP = 1;
   typedef UngParams Params;
   const UngParams& mp;
-  const double *ah, *Lt, *Ct, *yt, *Ht, *sc;
+  const double *ah, *Lt, *Ct, *yt, *rHp, *yp2, *sc;
   double phi, al0;
   double y, u, yphi2, Dt, xb, Z0, ytil, rH, scale;
   double ah0, ah1, c1, l1;
@@ -181,23 +183,25 @@ struct UngPsi1 : GaussStep<UngPsi1, 1, 1, 1> {
   __device__ UngPsi1(const UngParams& p, uint32_t f) : mp(p) {
     const size_t o = (size_t)f * p.pstride;
     ah = p.alphahat + o; Lt = p.Lt + o; Ct = p.Ct + o;
-    yt = p.ytilde + o; Ht = p.Htilde + o; sc = p.scales + o;
+    yt = p.ytilde + o; rHp = p.rHt + o; yp2 = p.yphi2 + o; sc = p.scales + o;
     phi = p.phi_f ? p.phi_f[f] : p.phi;
     al0 = p.approx_loglik[f];
+    y = u = Dt = xb = Z0 = 0.0;
   }
   __device__ double loglik0() const { return al0; }
   __device__ double loglik_end() const { return 0.0; }
   __device__ void init(const double* z, double* x) const { x[0] = ah[0] + Lt[0] * z[0]; }
   __device__ bool observed(int t) const { return pf_isfinite(mp.y[t]); }
   __device__ void begin_weight(int t) {
-    y = mp.y[t];
-    u = mp.u[t];
-    double q = y / phi;
-    yphi2 = q * q;
-    Dt = mp.D[t * mp.Dtv];
-    xb = mp.xbeta[t];
-    Z0 = mp.Z[t * mp.Ztv];
-    ytil = yt[t]; rH = 1.0 / Ht[t]; scale = sc[t];
+    // 1 / Htilde_t and (y_t / phi)^2 come from the pre-pass: no division per thread and step
+    ytil = yt[t]; rH = rHp[t]; scale = sc[t]; yphi2 = yp2[t];
+    if (mp.distribution != 0) {
+      y = mp.y[t];
+      u = mp.u[t];
+      Dt = mp.D[t * mp.Dtv];
+      xb = mp.xbeta[t];
+      Z0 = mp.Z[t * mp.Ztv];
+    }
   }
   __device__ double logw(const double* x) const {
     double s = (mp.distribution == 0) ? x[0] : (Dt + Z0 * x[0] + xb);

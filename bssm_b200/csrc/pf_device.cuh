@@ -31,11 +31,18 @@
 #ifndef PF_PHASE_TIMING
 #define PF_PHASE_TIMING 0 // 1: per-phase cycle counters (cost 14 registers per thread; diagnostics builds only)
 #endif
+#ifndef PF_POLL_NS
+#define PF_POLL_NS 32
+#endif
 #ifndef PF_SCATTER_CAP
 #define PF_SCATTER_CAP 4 // offspring written by the owner lane itself; longer runs are written by the whole warp
 #endif
 
 namespace pf {
+
+// the barrier counter of every filter sits in its own 128-byte line: the counters of a batch used to
+// share one line, and every arrival and every poll of every CTA of the launch went to one L2 slice
+constexpr int COUNTER_STRIDE = 32;
 
 enum SyncMode { SYNC_BLOCK = 0, SYNC_CLUSTER = 1, SYNC_GROUP = 2 };
 
@@ -132,9 +139,16 @@ struct Sync {
       // wrote (partials, state row, thresholds, ancestors) is read with L2 loads (ld.cg) issued
       // behind the CTA barrier that follows, never through a possibly stale L1 line
       unsigned int v;
-      do {
+      for (;;) {
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-      } while ((int)(v - target) < 0);
+#ifdef PF_ABL_NOWAIT
+        break;
+#endif
+        if ((int)(v - target) >= 0) break;
+        // the polling warps of all CTAs of an SM share one scheduler (warp 0 of every CTA): back off
+        // so that the spin does not eat its issue slots
+        if (PF_POLL_NS > 0) __nanosleep(PF_POLL_NS);
+      }
     }
     __syncwarp();
   }
@@ -318,7 +332,7 @@ struct Strata {
   double Nd;
   __device__ __forceinline__ double u(uint32_t j) const { return __ldcg(ubuf + j); }
   __device__ __forceinline__ uint32_t guess(double p) const {
-    uint32_t jj = (uint32_t)(p * Nd);
+    const uint32_t jj = (uint32_t)(p * Nd);
     return jj > N - 1 ? N - 1 : jj;
   }
   // resolve the count given the pre-loaded threshold uj = u(guess(p))
@@ -326,7 +340,7 @@ struct Strata {
     const double x = p * Nd;
     const bool le = uj <= p;
     uint32_t c = jj + (le ? 1u : 0u);
-    const double dc = (double)c;
+    const double dc = pf_u32_to_f64(c);
     const double d = le ? dc - x : x - dc;  // distance of p * N to the integer that would change the count
     if (d < x * 4.440892098500626e-16) c = strata_walk(ubuf, N, p, c, le);
     return p >= 1.0 ? N : c;
@@ -371,9 +385,14 @@ struct GaussStep {
   template <int P>
   __device__ __forceinline__ void draw(const StepCtx& c, Noise<P>& nz) const {
     const uint32_t pair0 = (c.i0 * KP) >> 1;
+#ifdef PF_ABL_NONORMAL
+#pragma unroll
+    for (int q = 0; q < P * KP; ++q) nz.z[q] = 0.3 + 1e-9 * (double)(pair0 + q + c.t);
+#else
 #pragma unroll
     for (int q = 0; q < (P * KP) / 2; ++q)
       pf_normal_pair(c.seed, c.filter, c.t, 0u, pair0 + q, &nz.z[2 * q], &nz.z[2 * q + 1]);
+#endif
   }
   // `carry` is one double per particle that survives from the propagation into the next
   // weighting: the psi-APF of ssm_nlg needs the ancestor's state in its weights (ratio of
@@ -459,7 +478,7 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
 
   Sync sync;
   sync.mode = fp.sync_mode;
-  sync.counter = fp.counters + fidx;
+  sync.counter = fp.counters + (size_t)fidx * COUNTER_STRIDE;
   sync.nranks = ranks;
   sync.target = 0;
   Coll coll;
@@ -548,8 +567,8 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
       for (int h = 0; h < P / 2; ++h) {
         const uint32_t j = i0 + 2 * h;
         pf_u32x4 rx = pf_philox4x32_10(j >> 1, 0u, (uint32_t)t, filter, fp.seed, (uint32_t)PF_RNG_RESAMPLE);
-        uth[2 * h] = (pf_u53(rx.v[0], rx.v[1]) + (double)j) * invN;
-        uth[2 * h + 1] = (pf_u53(rx.v[2], rx.v[3]) + (double)(j + 1)) * invN;
+        uth[2 * h] = pf_u53_plus(rx.v[0], rx.v[1], pf_u32_to_f64(j)) * invN;
+        uth[2 * h + 1] = pf_u53_plus(rx.v[2], rx.v[3], pf_u32_to_f64(j + 1)) * invN;
       }
       store_row<P>(ub, i0, N, vec2, uth);
     }
@@ -558,7 +577,7 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
       PF_PHASE(1)
       if (!pf_isfinite(mx)) { stopped = t; break; } // uniform over the filter
 #pragma unroll
-      for (int p = 0; p < P; ++p) w[p] = pf_exp(lw[p] - mx);
+      for (int p = 0; p < P; ++p) w[p] = pf_exp_nonpos(lw[p] - mx);
     } else {
 #pragma unroll
       for (int p = 0; p < P; ++p) w[p] = (i0 + p < N) ? 1.0 : 0.0;
@@ -617,11 +636,20 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
           const uint32_t val = i0 + c0 + q;
           // the owner writes the first PF_SCATTER_CAP offspring itself (predicated stores, no loop),
           // a longer run (a heavy particle) is written by the whole warp, coalesced
-#pragma unroll
-          for (int o = 0; o < PF_SCATTER_CAP; ++o)
-            if (lo + o < c) anc[lo + o] = val;
+          const uint32_t cnt = c > lo ? c - lo : 0u;
+          if (cnt) {
+            uint32_t* q = anc + lo;
+            q[0] = val;
+            if (cnt > 1) {
+              q[1] = val;
+              if (cnt > 2) {
+                q[2] = val;
+                if (cnt > 3) q[3] = val;
+              }
+            }
+          }
           const uint32_t ce = lo + PF_SCATTER_CAP;
-          const unsigned heavy = __ballot_sync(0xffffffffu, c > ce);
+          const unsigned heavy = __ballot_sync(0xffffffffu, cnt > PF_SCATTER_CAP);
           if (heavy) scatter_heavy(anc, heavy, ce, c, val);
           lo = c > lo ? c : lo;
         }

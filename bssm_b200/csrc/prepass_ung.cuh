@@ -47,6 +47,8 @@ struct PrepassParams {
   double *alphahat, *Lt, *Ct, *ytilde, *Htilde, *scales, *approx_loglik, *phi_f;
   double* scratch;  // 3 * pstride per filter: vt, Ft, Kt
   size_t pstride;
+  // per-step scalars every thread of the filter kernel would otherwise divide for: 1 / Htilde_t and (y_t / phi)^2
+  double *rHt, *yphi2;
 };
 
 __global__ void __launch_bounds__(128)
@@ -119,6 +121,8 @@ ung_prepass_m1_kernel(const PrepassParams pp, uint32_t n_filters) {
     const double H = sqrt(HH);
     ay[t] = yt;
     aH[t] = H;
+    pp.rHt[o + t] = 1.0 / H;
+    { const double qy = y / phi; pp.yphi2[o + t] = qy * qy; }
     Ft[t] = HH; // parked here until the forward pass overwrites it
     double scale = 0.0;
     s = mode[t];

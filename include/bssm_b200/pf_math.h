@@ -101,18 +101,53 @@ PF_HDX pf_u32x4 pf_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t
   return o;
 }
 
+/* (double)v for a 32-bit unsigned v.  On the device the conversion instructions (I2F / F2I /
+ * FRND) run at 16 lanes per clock and SM, a quarter of the DFMA rate (measured, tools/bench_lat.cu);
+ * the exponent trick -- v placed in the low mantissa bits of 2^52, minus 2^52 -- is one DADD and
+ * gives the same value exactly.  Measured on the C2 batch it is a LOSS (32.3 -> 34.4 ms together
+ * with the rounding-trick variants of floor / F2I below): the conversion pipe overlaps with the
+ * FP64 pipe, which is the one that binds, so the trick stays behind -DPF_CONVERT_BY_DADD. */
+PF_HD double pf_u32_to_f64(uint32_t v) {
+#if defined(__CUDA_ARCH__) && defined(PF_CONVERT_BY_DADD)
+  return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+#else
+  return (double)v;
+#endif
+}
+
+/* (double)v for a signed 32-bit v, same trick with the sign bit flipped (bias 2^52 + 2^31) */
+PF_HD double pf_i32_to_f64(int32_t v) {
+#if defined(__CUDA_ARCH__) && defined(PF_CONVERT_BY_DADD)
+  return __hiloint2double(0x43300000, v ^ (int)0x80000000) - 4503601774854144.0;
+#else
+  return (double)v;
+#endif
+}
+/* round-to-nearest-even integer of x (|x| < 2^51) as a double and as a two's-complement integer,
+ * by adding 1.5 * 2^52: one DADD each instead of FRND / F2I */
+#define PF_RN_MAGIC 6755399441055744.0
+PF_HD double pf_rn_magic(double x) { return x + PF_RN_MAGIC; }
+PF_HD int64_t pf_rn_int64(double t) { return (int64_t)(pf_d2u(t) - 0x4338000000000000ULL); }
+PF_HD int32_t pf_rn_int32(double t) { return (int32_t)(uint32_t)pf_d2u(t); }
+
 /* 53-bit uniform in [0,1) from two 32-bit words: k = (hi>>5)*2^26 + (lo>>6).
  * Every step is exact in binary64, so host and device agree trivially. */
 PF_HD double pf_u53(uint32_t hi, uint32_t lo) {
-  double a = (double)(hi >> 5);
-  double b = (double)(lo >> 6);
-  return (a * 67108864.0 + b) * 1.1102230246251565e-16; /* 2^26, 2^-53 */
+  double a = pf_u32_to_f64(hi >> 5);
+  double b = pf_u32_to_f64(lo >> 6);
+  return pf_fma(a, 67108864.0, b) * 1.1102230246251565e-16; /* 2^26, 2^-53; the fma is exact (k < 2^53) */
+}
+/* (u + j) for the stratum thresholds, u the 53-bit uniform of (hi, lo): one rounding, as pf_u53() + j */
+PF_HD double pf_u53_plus(uint32_t hi, uint32_t lo, double j) {
+  double a = pf_u32_to_f64(hi >> 5);
+  double b = pf_u32_to_f64(lo >> 6);
+  return pf_fma(pf_fma(a, 67108864.0, b), 1.1102230246251565e-16, j);
 }
 /* 53-bit uniform in (0,1]: (k+1) * 2^-53 (argument of the Box-Muller log) */
 PF_HD double pf_u53_open0(uint32_t hi, uint32_t lo) {
-  double a = (double)(hi >> 5);
-  double b = (double)(lo >> 6);
-  return (a * 67108864.0 + (b + 1.0)) * 1.1102230246251565e-16;
+  double a = pf_u32_to_f64(hi >> 5);
+  double b = pf_u32_to_f64(lo >> 6);
+  return pf_fma(a, 67108864.0, b + 1.0) * 1.1102230246251565e-16;
 }
 
 /* ------------------------------------------------------------ exp / log */
@@ -170,6 +205,18 @@ static __constant__ double pf_dc_cos[] = {PF_COS_COEFFS};
 #define PF_CC pf_hc_cos
 #endif
 
+/* y * 2^k as 2 * (y * 2^(k-1)), k in two's complement: add (k - 1) to the exponent field (only
+ * the high word changes), then double */
+PF_HD double pf_exp_scale(double y, uint32_t k) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(y) + (int)((k - 1u) << 20), __double2loint(y)) * 2.0;
+#else
+  uint64_t yb = pf_d2u(y);
+  uint32_t hi = (uint32_t)(yb >> 32) + ((k - 1u) << 20);
+  return pf_u2d(((uint64_t)hi << 32) | (yb & 0xffffffffULL)) * 2.0;
+#endif
+}
+
 /* exp(x): Cody-Waite reduction by ln2 (hi/lo split), degree-13 Taylor kernel on
  * |r| <= ln2/2 (truncation 4e-18), power-of-two scaling.  Straight-line code:
  * y * 2^k is evaluated as 2 * (y * 2^(k-1)); the inner scaling is an integer add
@@ -199,13 +246,36 @@ PF_HDX double pf_exp(double x) {
   q = pf_fma(q, r, PF_CE[10]);
   q = pf_fma(q, r, PF_CE[11]);
   double e = pf_fma(q, r * r, r);
-  uint64_t yb = pf_d2u(1.0 + e);
-  /* add (k - 1) to the exponent field: only the high word changes */
-  uint32_t hi = (uint32_t)(yb >> 32) + ((k - 1u) << 20);
-  double res = pf_u2d(((uint64_t)hi << 32) | (yb & 0xffffffffULL)) * 2.0;
+  double res = pf_exp_scale(1.0 + e, k);
   if (x < -706.5) res = 0.0;
   if (!(x == x)) res = x;
   return res;
+}
+
+/* The same for an argument that is known to be <= 0 and not NaN (the weights exp(logw - max)):
+ * no upper clamp, no NaN guard; -inf gives 0 through the flush. */
+PF_HDX double pf_exp_nonpos(double x) {
+  const double MAGIC = PF_CE[13];
+  double t = pf_fma(x, PF_CE[12], MAGIC);
+  double kf = t - MAGIC;
+  uint32_t k = (uint32_t)pf_d2u(t);
+  double r = pf_fma(-kf, PF_CE[14], x);
+  r = pf_fma(-kf, PF_CE[15], r);
+  double q = PF_CE[0];
+  q = pf_fma(q, r, PF_CE[1]);
+  q = pf_fma(q, r, PF_CE[2]);
+  q = pf_fma(q, r, PF_CE[3]);
+  q = pf_fma(q, r, PF_CE[4]);
+  q = pf_fma(q, r, PF_CE[5]);
+  q = pf_fma(q, r, PF_CE[6]);
+  q = pf_fma(q, r, PF_CE[7]);
+  q = pf_fma(q, r, PF_CE[8]);
+  q = pf_fma(q, r, PF_CE[9]);
+  q = pf_fma(q, r, PF_CE[10]);
+  q = pf_fma(q, r, PF_CE[11]);
+  double e = pf_fma(q, r * r, r);
+  double res = pf_exp_scale(1.0 + e, k);
+  return x < -706.5 ? 0.0 : res;
 }
 
 /* log(x): x = 2^e * m, m in (sqrt(1/2), sqrt(2)], s = f/(2+f) with f = m-1,
@@ -232,7 +302,7 @@ PF_HDX double pf_log_core(uint64_t ux, int e) {
   R = pf_fma(R, z, PF_CL[9]);
   R = R * z;
   double hfsq = 0.5 * f * f;
-  double dk = (double)e;
+  double dk = pf_i32_to_f64(e);
   /* ln2 split: hi has 21 trailing zero bits, so dk*hi is exact */
   return dk * PF_CL[10] - ((hfsq - (s * (hfsq + R) + dk * PF_CL[11])) - f);
 }
@@ -378,6 +448,9 @@ PF_HD double pf_pick_uniform(uint32_t seed, uint32_t filter) {
  * (oracle/pf_oracle.cpp, tests/test_oracle.py). */
 typedef struct { int64_t hi, lo; } pf_fixsum;
 
+/* floor() and the conversions run on the conversion pipe (16 lanes per clock and SM), which overlaps
+ * with the FP64 pipe; a variant that rounds by adding 1.5 * 2^52 (no conversion instruction, three
+ * more DADD) was measured slower on the C2 batch because the FP64 pipe is the one that binds. */
 PF_HD pf_fixsum pf_fixsum_term(double w) { /* w in [0,1] (NaN is caught before) */
   double sc = w * 1099511627776.0;              /* 2^40, exact */
   double h = floor(sc);

@@ -291,7 +291,7 @@ static bool normalise(const double* logw, uint32_t N, double* wcol, std::vector<
   /* a NaN log-weight gives a NaN sum in the reference (exp(NaN)), a non-finite
    * max gives exp(-inf - -inf) = NaN: both fail `sum_weights > 0.0` */
   if (has_nan || !std::isfinite(max_weight)) return false;
-  for (uint32_t i = 0; i < N; ++i) wcol[i] = pf_exp(logw[i] - max_weight);
+  for (uint32_t i = 0; i < N; ++i) wcol[i] = pf_exp_nonpos(logw[i] - max_weight);
   double sum = sum_weights(wcol, N, arith);
   if (!(sum > 0.0)) return false;
   if (arith == ORC_ARITH_REFERENCE) for (uint32_t i = 0; i < N; ++i) W[i] = wcol[i] / sum;
