@@ -164,6 +164,8 @@ def lib():
     L.bssm_b200_job_run.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.bssm_b200_job_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float * 3)]
     L.bssm_b200_job_launches.argtypes = [C.c_void_p]
+    L.bssm_b200_last_gather.restype = C.c_char_p
+    L.bssm_b200_last_gather.argtypes = []
     L.bssm_b200_job_phase_cycles.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64 * 6)]
     L.bssm_b200_job_max_concurrent_filters.argtypes = [C.c_void_p]
     L.bssm_b200_job_fetch.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(FilterOut)]

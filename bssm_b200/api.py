@@ -28,8 +28,8 @@ def _check_particles(model, particles, seed):
     particles = int(particles)
     if particles < 2:
         raise ValueError("Argument 'particles' should be an integer >= 2.")
-    if particles > 2 ** 21:  # one filter must fit one resident group of CTAs (about 1.2M particles on a B200)
-        raise ValueError("Argument 'particles' is too large for one filter (at most 2^21).")
+    if particles > 2 ** 20:  # exactness of the fixed-point weight sums (pf_math.h) and one resident group of CTAs
+        raise ValueError("Argument 'particles' is too large for one filter (at most 2^20).")
     seed = int(seed)
     if not 0 <= seed <= 2 ** 31 - 1:
         raise ValueError("Argument 'seed' should be an integer in [0, 2^31-1].")
@@ -341,7 +341,8 @@ def post_correct(model, mcmc_output, particles, threads=1, is_type="is2", seed=1
 
     mcmc_output: dict with theta (n_stored x n_par), counts (n_stored), modes
     (n x n_stored), output_type (1 full / 2 summary / 3 theta) and posterior.
-    `threads` is accepted for parity and ignored (results do not depend on it).
+    `threads` is the number of GPUs of this process to use (the reference's OpenMP threads become one
+    host thread per device inside the C call; results do not depend on it).
     draw_range = (begin, end) computes only that shard of the (expanded) draws.
 
     sampling_method = "bsf": the correction phase of run_mcmc(..., sampling_method = "bsf")

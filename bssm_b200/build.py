@@ -35,7 +35,7 @@ def compile_cmd(src, obj, verbose=False, defines=()):
 
 def link_cmd(objs, lib=None):
     return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fopenmp",
-            "-lgomp", "-o", lib or LIB] + objs
+            "-lgomp", "-ldl", "-lpthread", "-o", lib or LIB] + objs
 
 
 def _headers():

@@ -19,6 +19,9 @@
 #include <limits>
 #include <mutex>
 #include <algorithm>
+#include <thread>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include "bssm_b200.h"
 #include "pf_device.cuh"
@@ -78,6 +81,9 @@ uint32_t round32(uint32_t a) { return cdiv(a, 32) * 32; }
 // Results never depend on the geometry (fixed-point sums), so this is free to tune.
 // Environment overrides (experiments): BSSM_B200_RANKS / _P / _BLOCK / _SYNC=cluster.
 int choose_geometry(uint32_t N, uint32_t n_filters, Geometry* g) {
+  // the low word of the fixed-point weight terms is < 2^43 per particle (pf_math.h): its sum stays
+  // inside an int64 for N <= 2^20, which is also what one resident group of CTAs holds comfortably
+  if (N > (1u << 20)) return fail(BSSM_B200_ERR_UNSUPPORTED, "at most 2^20 particles per filter");
   uint32_t ranks = 1, block;
   int P;
   int mode = pf::SYNC_BLOCK;
@@ -463,6 +469,9 @@ struct bssm_b200_job {
   pf::PrepassParams pp{};
   pf::FilterParams fp{};
   ~bssm_b200_job() {
+    // on error paths a kernel or an async copy may still be running on the stream: the buffers go back
+    // to the recycling pool right after this, so wait for the stream first
+    if (stream) cudaStreamSynchronize(stream);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -571,6 +580,7 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
 
 extern "C" {
 
+void bssm_b200_release_comm(void);
 const char* bssm_b200_last_error(void) { return g_err.c_str(); }
 const char* bssm_b200_version(void) { return "bssm_b200 0.1 (sm_100a)"; }
 
@@ -587,7 +597,9 @@ int bssm_b200_set_device(int device) {
   return 0;
 }
 
+const char* bssm_b200_last_gather(void);
 void bssm_b200_shutdown(void) {
+  bssm_b200_release_comm();
   g_pool.release_all();
   {
     std::lock_guard<std::mutex> g(g_sctx.mu);
@@ -906,7 +918,15 @@ static int job_launch_filters(bssm_b200_job* J) {
 // post-processing kernels, synchronisation, timings
 static int job_finish(bssm_b200_job* J, float* ms_out) {
   int rc;
-  if (J->post != BSSM_POST_NONE && (rc = run_post(J))) return rc;
+  if (J->post != BSSM_POST_NONE) {
+    // stopped filters: zero the columns they never reached before anything reads them
+    pf::zero_unreached_kernel<<<dim3(64, J->n_filters), 256, 0, J->stream>>>(
+        J->stopped.p, J->alpha_tm.p, J->weights.p, J->keep_indices ? J->indices.p : nullptr, J->N, J->n, J->m,
+        J->keep_alpha ? 1 : 0, J->alpha_stride, J->weights_stride, J->indices_stride);
+    CU(cudaGetLastError());
+    J->launches += 1;
+    if ((rc = run_post(J))) return rc;
+  }
   CU(cudaEventRecord(J->ev[3], J->stream));
   CU(cudaStreamSynchronize(J->stream));
   CU(cudaEventElapsedTime(&J->ms[0], J->ev[0], J->ev[1]));
@@ -1990,17 +2010,181 @@ static int postcorr_driver(int n, int m, int output_type, uint32_t nsim, int is_
 }
 
 
+
+// ------------------------------------------------- multi-GPU post-correction
+// The reference fans the draws out over OpenMP threads inside ONE call (n_threads,
+// src/approx_mcmc.cpp:364-369).  Here n_threads is the number of GPUs: one host thread per device,
+// contiguous static shards of the draw list (schedule(static)), each shard run by postcorr_driver on
+// its device, then ONE ncclAllGather of the per-draw log-likelihoods over a communicator that is
+// created once per process (ncclCommInitAll) and kept.  NCCL is loaded with dlopen so that the
+// library has no link-time dependency on it; every rank ends up with all log-likelihoods, rank 0's
+// copy becomes the weights / posterior of the call.  Draw d uses random stream d whatever the
+// sharding, so the result is bit-identical to the one-GPU call.
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::vector<ncclComm_t> comms;
+  std::vector<int> devs;
+  std::mutex mu;
+  bool tried = false;
+  std::string why;
+  bool load() {
+    if (tried) return h != nullptr;
+    tried = true;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (h) break;
+    }
+    if (!h) { why = std::string("dlopen(libnccl.so.2): ") + dlerror(); return false; }
+    CommInitAll = (decltype(CommInitAll))dlsym(h, "ncclCommInitAll");
+    CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+    AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
+    GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!CommInitAll || !CommDestroy || !AllGather || !GetErrorString) { why = "libnccl: missing symbols"; h = nullptr; return false; }
+    return true;
+  }
+  // persistent communicator over `d` (re-created only when the device set changes)
+  bool ensure(const std::vector<int>& d) {
+    std::lock_guard<std::mutex> g(mu);
+    if (!load()) return false;
+    if (d == devs && !comms.empty()) return true;
+    release_locked();
+    comms.assign(d.size(), nullptr);
+    ncclResult_t r = CommInitAll(comms.data(), (int)d.size(), d.data());
+    if (r != ncclSuccess) { why = std::string("ncclCommInitAll: ") + GetErrorString(r); comms.clear(); return false; }
+    devs = d;
+    return true;
+  }
+  void release_locked() {
+    for (auto c : comms) if (c) CommDestroy(c);
+    comms.clear(); devs.clear();
+  }
+  void release() { std::lock_guard<std::mutex> g(mu); if (h) release_locked(); }
+};
+NcclApi g_nccl;
+thread_local std::string g_gather_note; // how the last multi-GPU call gathered: "nccl: G ranks" / "host: <why>" / ""
+
+template <class MakeJob>
+static int postcorr_multi(uint32_t n_threads, int n, int m, int output_type, uint32_t nsim, int is_type,
+                          const uint32_t* counts, uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
+                          bssm_postcorr_out* out, MakeJob&& make_job, const double* approx_ll = nullptr,
+                          bool posterior_adds_approx = false) {
+  g_gather_note.clear();
+  int rc = require_device();
+  if (rc) return rc;
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  int G = (int)std::min<uint32_t>(n_threads ? n_threads : 1u, (uint32_t)ndev);
+  G = std::min(G, std::max(1, env_int("BSSM_B200_MAX_GPUS", 64)));
+  DrawList dl;
+  if ((rc = build_draws(is_type, counts, n_stored, &dl))) return rc;
+  uint32_t b = draw_begin, e = draw_end;
+  if (b == 0 && e == 0) e = (uint32_t)dl.src.size();
+  if (b >= e || e > dl.src.size()) return fail(BSSM_B200_ERR_ARG, "bad draw range");
+  const uint32_t len = e - b;
+  // the summary merge (output_type 2) is a sequential weighted recursion over the draws: one device
+  if (G <= 1 || output_type == 2 || len < (uint32_t)(2 * G) || !out || !out->weights || !out->posterior)
+    return postcorr_driver(n, m, output_type, nsim, is_type, counts, n_stored, draw_begin, draw_end, out, make_job,
+                           approx_ll, posterior_adds_approx);
+  if (output_type == 1 && !out->alpha) return fail(BSSM_B200_ERR_ARG, "output_type 1 needs out->alpha");
+  int dev0 = 0;
+  CU(cudaGetDevice(&dev0));
+  std::vector<int> devs(G);
+  for (int g = 0; g < G; ++g) devs[g] = (dev0 + g) % ndev;
+  const bool use_nccl = !env_int("BSSM_B200_NO_NCCL", 0) && g_nccl.ensure(devs);
+  const size_t n1 = (size_t)n + 1;
+  std::vector<uint32_t> sb(G + 1);
+  for (int g = 0; g <= G; ++g) sb[g] = b + (uint32_t)(((uint64_t)len * g) / G); // contiguous static blocks
+  uint32_t maxlen = 0;
+  for (int g = 0; g < G; ++g) maxlen = std::max(maxlen, sb[g + 1] - sb[g]);
+  std::vector<std::vector<double>> ll(G), wg(G), pg(G);
+  std::vector<std::vector<double>> gathered(G);
+  std::vector<int> rcs(G, 0);
+  std::vector<std::string> errs(G);
+  std::vector<float> ms(G, 0.f);
+  std::vector<int> launches(G, 0);
+  auto worker = [&](int g) {
+    if (cudaSetDevice(devs[g]) != cudaSuccess) { rcs[g] = BSSM_B200_ERR_CUDA; errs[g] = "cudaSetDevice failed"; }
+    const uint32_t lg = sb[g + 1] - sb[g];
+    ll[g].assign(lg, 0.0); wg[g].assign(lg, 0.0); pg[g].assign(lg, 0.0);
+    bssm_postcorr_out og;
+    memset(&og, 0, sizeof(og));
+    og.weights = wg[g].data(); og.posterior = pg[g].data(); og.loglik = ll[g].data();
+    if (output_type == 1) og.alpha = out->alpha + (size_t)(sb[g] - b) * n1 * m; // disjoint slices of the caller's buffer
+    if (!rcs[g]) {
+      rcs[g] = postcorr_driver(n, m, output_type, nsim, is_type, counts, n_stored, sb[g], sb[g + 1], &og, make_job,
+                               approx_ll, posterior_adds_approx);
+      if (rcs[g]) errs[g] = g_err;
+    }
+    ms[g] = og.device_ms; launches[g] = og.launches;
+    if (use_nccl) {
+      // every rank takes part in the collective even if its shard failed (a missing rank would hang the others)
+      DevBuf<double> send, recv;
+      cudaStream_t st = nullptr;
+      bool ok = send.alloc(maxlen) == 0 && recv.alloc((size_t)maxlen * G) == 0 &&
+                cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
+      if (ok) {
+        cudaMemsetAsync(send.p, 0, sizeof(double) * maxlen, st);
+        cudaMemcpyAsync(send.p, ll[g].data(), sizeof(double) * lg, cudaMemcpyHostToDevice, st);
+      }
+      // NOTE: a rank that could not allocate still has to call the collective; with 8 KB buffers this does not happen
+      ncclResult_t r = ok ? g_nccl.AllGather(send.p, recv.p, maxlen, ncclDouble, g_nccl.comms[g], st) : ncclInternalError;
+      if (r == ncclSuccess && g == 0) {
+        gathered[0].resize((size_t)maxlen * G);
+        cudaMemcpyAsync(gathered[0].data(), recv.p, sizeof(double) * maxlen * G, cudaMemcpyDeviceToHost, st);
+      }
+      if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+      if (r != ncclSuccess && !rcs[g]) { rcs[g] = BSSM_B200_ERR_CUDA; errs[g] = std::string("ncclAllGather: ") + g_nccl.GetErrorString(r); }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int g = 1; g < G; ++g) th.emplace_back(worker, g);
+  worker(0);
+  for (auto& t : th) t.join();
+  cudaSetDevice(dev0);
+  for (int g = 0; g < G; ++g)
+    if (rcs[g]) return fail(rcs[g], "post-correction shard on device " + std::to_string(devs[g]) + ": " + errs[g]);
+  out->device_ms = *std::max_element(ms.begin(), ms.end()); // the shards run concurrently
+  out->launches = 0;
+  for (int g = 0; g < G; ++g) out->launches += launches[g];
+  out->sum_w = 0.0;
+  for (int g = 0; g < G; ++g) {
+    const uint32_t lg = sb[g + 1] - sb[g];
+    for (uint32_t f = 0; f < lg; ++f) {
+      const size_t o = (size_t)(sb[g] - b) + f;
+      // with NCCL the log-likelihoods of the call are the gathered ones (rank 0's receive buffer)
+      const double l = use_nccl ? gathered[0][(size_t)g * maxlen + f] : ll[g][f];
+      if (out->loglik) out->loglik[o] = l;
+      const double off = approx_ll ? approx_ll[dl.src[sb[g] + f]] : 0.0;
+      const double lw = l - off;
+      const double w = pf_exp(lw);
+      out->weights[o] = w;
+      out->posterior[o] = 0.0 + (posterior_adds_approx ? off : 0.0) + pf_log(w);
+    }
+  }
+  g_gather_note = use_nccl ? ("nccl: " + std::to_string(G) + " ranks, one ncclAllGather of " + std::to_string(maxlen) + " doubles per rank")
+                           : ("host: " + (g_nccl.why.empty() ? std::string("BSSM_B200_NO_NCCL") : g_nccl.why));
+  return 0;
+}
+
 extern "C" {
+
+// how the last multi-GPU post-correction of this thread gathered its log-likelihoods:
+// "nccl: G ranks, ..." / "host: <why NCCL was not used>" / "" (single device)
+const char* bssm_b200_last_gather(void) { return g_gather_note.c_str(); }
+void bssm_b200_release_comm(void) { g_nccl.release(); }
 
 int bssm_b200_postcorrection_nongaussian(const bssm_ung_model* M, const bssm_theta_map* map, int output_type,
                                          uint32_t nsim, uint32_t seed, uint32_t n_threads, int is_type,
                                          const uint32_t* counts, const double* theta, uint32_t n_par,
                                          const double* modes, uint32_t n_stored, uint32_t draw_begin,
                                          uint32_t draw_end, bssm_postcorr_out* out) {
-  (void)n_threads;
   int rc = check_postcorr_args(M, map, counts, theta, modes, n_stored);
   if (rc) return rc;
-  return postcorr_driver(M->n, M->m, output_type, nsim, is_type, counts, n_stored, draw_begin, draw_end, out,
+  return postcorr_multi(n_threads, M->n, M->m, output_type, nsim, is_type, counts, n_stored, draw_begin, draw_end, out,
                          [&](const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N, int post, bssm_b200_job** J) {
                            return make_draw_job(M, map, dl, d0, d1, N, seed, theta, n_par, modes, 0, post, J);
                          });
@@ -2083,14 +2267,13 @@ int bssm_b200_postcorrection_nonlinear(const bssm_nlg_model* M, int output_type,
                                        const double* theta, uint32_t n_par, const double* modes,
                                        uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
                                        bssm_postcorr_out* out) {
-  (void)n_threads;
   if (!M || !counts || !theta || !modes || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
   {
     int rcm = check_nlg_model(M);
     if (rcm) return rcm;
     if (n_par < (uint32_t)nlg_n_theta(M)) return fail(BSSM_B200_ERR_ARG, "post-correction (nonlinear): too few parameters");
   }
-  return postcorr_driver(M->n, nlg_state_dim(M), output_type, nsim, is_type, counts, n_stored,
+  return postcorr_multi(n_threads, M->n, nlg_state_dim(M), output_type, nsim, is_type, counts, n_stored,
                          draw_begin, draw_end, out,
                          [&](const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N, int post, bssm_b200_job** J) {
                            return make_nlg_draw_job(M, dl, d0, d1, N, seed, theta, n_par, modes, post, J);
@@ -2103,14 +2286,13 @@ int bssm_b200_is_correction_bsf(const bssm_ung_model* M, const bssm_theta_map* m
                                 const uint32_t* counts, const double* theta, uint32_t n_par,
                                 const double* approx_loglik, uint32_t n_stored, uint32_t draw_begin,
                                 uint32_t draw_end, bssm_postcorr_out* out) {
-  (void)n_threads;
   if (!M || !map || !counts || !theta || !approx_loglik || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
   if (M->m != 1) return fail(BSSM_B200_ERR_UNSUPPORTED, "is_correction_bsf: m = 1 models in this build");
   if (M->xbeta && map->n_xreg <= 0) return fail(BSSM_B200_ERR_ARG, "the model has regressors: theta_map needs n_xreg and xreg");
   if (map->n_xreg > 0 && (!map->xreg || (int)n_par < map->n_xreg || map->model_type == 3))
     return fail(BSSM_B200_ERR_ARG, "n_xreg > 0 needs xreg, beta in theta and a model with a regression part");
-  return postcorr_driver(
-      M->n, 1, output_type, nsim, is_type, counts, n_stored, draw_begin, draw_end, out,
+  return postcorr_multi(
+      n_threads, M->n, 1, output_type, nsim, is_type, counts, n_stored, draw_begin, draw_end, out,
       [&](const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N, int post, bssm_b200_job** J) {
         const uint32_t nf = d1 - d0;
         std::vector<double> par((size_t)6 * nf);
@@ -2134,10 +2316,9 @@ int bssm_b200_is_correction_bsf_sde(const bssm_sde_model* M, uint32_t L_f, int o
                                     const double* theta, uint32_t n_par, const double* approx_loglik,
                                     uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
                                     bssm_postcorr_out* out) {
-  (void)n_threads;
   if (!M || !counts || !theta || !approx_loglik || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
-  return postcorr_driver(
-      M->n, 1, output_type, nsim, is_type, counts, n_stored, draw_begin, draw_end, out,
+  return postcorr_multi(
+      n_threads, M->n, 1, output_type, nsim, is_type, counts, n_stored, draw_begin, draw_end, out,
       [&](const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N, int post, bssm_b200_job** J) {
         const uint32_t nf = d1 - d0;
         std::vector<double> th((size_t)n_par * nf);

@@ -15,6 +15,35 @@
 
 namespace pf {
 
+// A filter that stopped early (all weights underflowed, src/model_ssm_ung.cpp:556-560) leaves the
+// columns it never reached unwritten; the buffers come from a recycling pool, so they hold stale
+// data.  The reference's outputs are zero-filled (arma::fill::zeros, src/R_bootstrap_filter.cpp:162-164)
+// and its filter_smoother / summary then run over zeros.  Before any post-processing kernel this
+// kernel zero-fills the unreached tail of every stopped filter: state rows stopped+1..n, weight
+// columns stopped..n, ancestor columns stopped..n-1 (ancestor 0 is a valid index).
+__global__ void zero_unreached_kernel(const int32_t* __restrict__ stopped_at, double* __restrict__ alpha_tm,
+                                      double* __restrict__ weights, uint32_t* __restrict__ indices, uint32_t N,
+                                      int n, int m, int keep_alpha, size_t alpha_stride, size_t weights_stride,
+                                      size_t indices_stride) {
+  const uint32_t f = blockIdx.y;
+  const int s = stopped_at[f];
+  if (s < 0) return;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  if (keep_alpha && alpha_tm) {
+    double* a = alpha_tm + f * alpha_stride;
+    for (size_t e = (size_t)(s + 1) * m * N + tid; e < (size_t)(n + 1) * m * N; e += nth) a[e] = 0.0;
+  }
+  if (weights) {
+    double* w = weights + f * weights_stride;
+    for (size_t e = (size_t)s * N + tid; e < (size_t)(n + 1) * N; e += nth) w[e] = 0.0;
+  }
+  if (indices) {
+    uint32_t* ix = indices + f * indices_stride;
+    for (size_t e = (size_t)s * N + tid; e < (size_t)n * N; e += nth) ix[e] = 0u;
+  }
+}
+
+
 // Kitagawa filter-smoother.  Thread i follows the ancestry of particle i of
 // the last column backwards: b <- indices[b, t].  Out of place (the reference
 // copies each tube before overwriting it, src/filter_smoother.cpp:10).

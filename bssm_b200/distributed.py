@@ -41,6 +41,12 @@ def post_correct_distributed(model, mcmc_output, particles, is_type="is2", seed=
     rank, world = dist.get_rank(), dist.get_world_size()
     it = {"is1": 1, "is2": 2, "is3": 3}[is_type.lower()]
     total = api.n_draws(mcmc_output, it)
+    if int(mcmc_output.get("output_type", 3)) == 2 and world > 1:
+        # the summary merge (weighted running mean / variance over draws, src/approx_mcmc.cpp:397-424) is
+        # finished inside the C call (Vt += Valpha / sum_w), so per-rank summaries cannot be combined here;
+        # bssm_b200_postcorrection_* with n_threads > 1 does the multi-GPU merge inside the library
+        raise ValueError("post_correct_distributed: output_type 'summary' is not shardable across processes; "
+                         "call post_correct(..., threads=G) instead (one process, G GPUs)")
     b, e = shard_range(total, rank, world)
     fn = compute or api.post_correct
     local = fn(model, mcmc_output, particles, is_type=is_type, seed=seed, draw_range=(b, e))

@@ -351,11 +351,18 @@ typedef struct {
  * One independent psi-APF per (expanded) draw; draw d uses random stream
  * `filter = d`, so results do not depend on how draws are sharded -- unlike the
  * reference, whose per-thread engines make results depend on `threads`
- * (src/approx_mcmc.cpp:367).  n_threads is accepted for signature parity and
- * ignored.  [draw_begin, draw_end) selects the shard of the (expanded, for
- * is_type 3) draw list this call computes -- 0, 0 = all draws; outputs are
- * indexed from draw_begin.  Multi-GPU: one process per GPU, each calling this
- * with its shard, then ONE gather of `weights` (bssm_b200/distributed.py). */
+ * (src/approx_mcmc.cpp:367).  n_threads is the number of GPUs of this process to use (the
+ * reference's OpenMP fan-out, src/approx_mcmc.cpp:364-369, becomes one host thread per device):
+ * contiguous static shards of the draw list, then ONE ncclAllGather of the per-draw
+ * log-likelihoods over a communicator created once per process (bssm_b200_last_gather() says how
+ * the last call gathered).  n_threads <= 1, one visible device or output_type 2 (the summary merge
+ * is a sequential recursion over the draws) run on the current device.  [draw_begin, draw_end)
+ * selects the shard of the (expanded, for is_type 3) draw list this call computes -- 0, 0 = all
+ * draws; outputs are indexed from draw_begin.  One process per GPU (torchrun) works too: each
+ * rank calls this with its shard, then one gather of `weights` (bssm_b200/distributed.py). */
+const char* bssm_b200_last_gather(void);
+/* destroys the persistent NCCL communicator (also done by bssm_b200_shutdown) */
+void bssm_b200_release_comm(void);
 int bssm_b200_postcorrection_nongaussian(const bssm_ung_model* model, const bssm_theta_map* map,
                                          int output_type, uint32_t nsim, uint32_t seed,
                                          uint32_t n_threads, int is_type, const uint32_t* counts,

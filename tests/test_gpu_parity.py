@@ -425,3 +425,21 @@ def test_streaming_fetch_with_a_filter_that_stops_midway(engine, monkeypatch):
     assert np.all(stream["weights"][:, 40:] == 0) and np.any(stream["weights"][:, 39] > 0)
     ref = orc.bsf_filter(model, 2000, seed=3)
     assert ref.stopped_at == 40 and np.array_equal(stream["indices"], ref.indices)
+
+
+def test_smoother_on_a_filter_that_stops_midway(engine):
+    """the particle smoother of a filter that stops at t = 40 traces ancestors through the
+    zero-filled tail exactly like the reference's filter_smoother does on its zero-initialised cubes"""
+    model = data.svm_model(90)
+    model.y[40] = 1e200
+    # leave non-zero garbage of the same sizes in the recycling pool
+    engine.particle_smoother(data.svm_model(90), 512, method="bsf", seed=2)
+    ref = orc.bsf_filter(model, 512, seed=3)
+    assert ref.stopped_at == 40
+    with pytest.warns(UserWarning, match="stopped prematurely"):
+        res = engine.particle_smoother(model, 512, method="bsf", seed=3, return_indices=True)
+    assert res["stopped_at"] == 40 and np.array_equal(res["indices"], ref.indices)
+    sm = orc.filter_smoother(ref.alpha, ref.indices)
+    assert np.array_equal(np.transpose(res["alpha"], (1, 0, 2)).view(np.uint64), sm.view(np.uint64))
+    mean, cov = orc.summary(sm)
+    np.testing.assert_allclose(res["alphahat"], mean.T, rtol=1e-10, atol=1e-12)

@@ -18,11 +18,14 @@ def setup(engine):
 def test_weights_only_is2(setup):
     engine, model, mo = setup
     ref = orc.post_correct(model, mo, 128, is_type=2, seed=3)
-    res = engine.post_correct(model, mo, 128, threads=2, is_type="is2", seed=3, return_loglik=True)
+    res = engine.post_correct(model, mo, 128, threads=1, is_type="is2", seed=3, return_loglik=True)
     assert np.array_equal(res["loglik"], ref.loglik)
     assert np.array_equal(res["weights"], ref.weights)
     np.testing.assert_allclose(res["posterior"], ref.posterior, rtol=1e-13, atol=1e-13)
     assert res["launches"] == 2  # one pre-pass + one filter launch for all draws
+    # threads = number of GPUs of this process to use: more than there are is clamped, results identical
+    res2 = engine.post_correct(model, mo, 128, threads=2, is_type="is2", seed=3, return_loglik=True)
+    assert np.array_equal(res2["weights"], ref.weights) and np.array_equal(res2["loglik"], ref.loglik)
 
 
 def test_trajectories_is3(setup):
@@ -265,3 +268,48 @@ def test_ar_exp_post_correction_and_suggest_N(engine):
     np.testing.assert_allclose(res2["Vt"], ref2.Vt, rtol=1e-8, atol=1e-12)
     sn = engine.suggest_N(model, np.asarray(model.theta), candidates=[20, 400], replications=12, seed=2)
     assert np.all(np.isfinite(sn["results"]["sd"])) and sn["results"]["sd"][1] < sn["results"]["sd"][0]
+
+
+def test_summary_with_a_draw_whose_filter_stops(engine):
+    """a stored draw whose filter stops at once (sigma so small that (y / sigma)^2 overflows)
+    has weight 0; its unreached columns must read as zeros (the reference's zero-filled buffers), not as
+    whatever the recycled device blocks held, so that the merged summary stays finite and equals the oracle's"""
+    model = data.svm_model(80)
+    mo = data.svm_mcmc_output(model, 12, output_type=2)
+    mo["theta"] = np.array(mo["theta"], copy=True)
+    mo["theta"][5, 2] = 1e-200
+    # fill the pool with non-zero garbage of the right size classes first
+    engine.post_correct(model, dict(data.svm_mcmc_output(model, 12, output_type=2)), 48, is_type="is2", seed=2)
+    ref = orc.post_correct(model, mo, 48, is_type=2, seed=4)
+    res = engine.post_correct(model, mo, 48, is_type="is2", seed=4, return_loglik=True)
+    assert res["loglik"][5] == -np.inf and res["weights"][5] == 0.0
+    assert np.array_equal(res["weights"], ref.weights)
+    assert np.all(np.isfinite(res["alphahat"])) and np.all(np.isfinite(res["Vt"]))
+    np.testing.assert_allclose(res["alphahat"], ref.alphahat, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(res["Vt"], ref.Vt, rtol=1e-9, atol=1e-13)
+
+
+def test_post_correct_inside_the_library_on_two_gpus(engine):
+    """ONE call of the C ABI with n_threads = 2 shards the draws over two GPUs (one host
+    thread per device, contiguous static blocks like the reference's schedule(static),
+    src/approx_mcmc.cpp:364-369), gathers the per-draw log-likelihoods with one ncclAllGather over a
+    persistent communicator, and returns exactly what the one-GPU call returns"""
+    import bssm_b200
+    if engine.lib().bssm_b200_device_count() < 2:
+        pytest.skip("needs two visible GPUs (gpurun --gpus 2)")
+    model = data.svm_model(200)
+    mo = data.svm_mcmc_output(model, 301)
+    one = engine.post_correct(model, mo, 128, threads=1, is_type="is2", seed=5, return_loglik=True)
+    two = engine.post_correct(model, mo, 128, threads=2, is_type="is2", seed=5, return_loglik=True)
+    note = engine.lib().bssm_b200_last_gather().decode()
+    assert note.startswith("nccl: 2 ranks"), note
+    assert np.array_equal(one["weights"], two["weights"]) and np.array_equal(one["loglik"], two["loglik"])
+    assert np.array_equal(one["posterior"], two["posterior"])
+    ref = orc.post_correct(model, mo, 128, is_type=2, seed=5)
+    assert np.array_equal(two["weights"], ref.weights)
+    # trajectories (output_type 1): every device writes its slice of the caller's buffer
+    mo1 = dict(mo, output_type=1)
+    a1 = engine.post_correct(model, mo1, 64, threads=1, is_type="is3", seed=6)
+    a2 = engine.post_correct(model, mo1, 64, threads=2, is_type="is3", seed=6)
+    assert np.array_equal(a1["alpha"].view(np.uint64), a2["alpha"].view(np.uint64))
+    assert np.array_equal(a1["weights"], a2["weights"])

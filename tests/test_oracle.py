@@ -329,3 +329,26 @@ def test_mng_psi_agrees_with_bsf():
     lb = np.array([orc.mng_bsf_filter(mdl, 4000, seed=s).loglik for s in range(1, 4)])
     assert lp.std() < 0.1
     assert abs(lp.mean() - lb.mean()) < 0.5
+
+
+def test_reference_order_vs_repro_first_divergence_at_the_headline_size():
+    """the kernels compute the sum and the cumulative sum of the weights in exact
+    fixed-point arithmetic (ORC_ARITH_REPRO); the reference adds binary64 numbers in Armadillo's order
+    (ORC_ARITH_REFERENCE: two-accumulator accu, sequential cumsum).  At the headline size (C2: N = 65536,
+    T = 1000) run both and REPORT the first time step at which an ancestor index differs.  DESIGN.md
+    section 4 estimates a flip probability of ~6e-5 per step; the log-likelihoods must agree to 1e-12
+    whatever the answer, and the report goes to profiles/r2_first_divergence.json (tools/first_divergence.py
+    does the same for more seeds)."""
+    import json, os
+    model = data.svm_model(1000)
+    a = orc.psi_filter(model, 65536, seed=1, arith=orc.ARITH_REPRO)
+    b = orc.psi_filter(model, 65536, seed=1, arith=orc.ARITH_REFERENCE)
+    diff = np.any(a.indices != b.indices, axis=0)
+    first = int(np.argmax(diff)) if diff.any() else None
+    print("first divergence step (seed 1, N = 65536, T = 1000):", first)
+    assert abs(a.loglik - b.loglik) <= 1e-12 * abs(b.loglik)
+    if first is None:
+        assert np.array_equal(a.weights.view(np.uint64), b.weights.view(np.uint64))
+    else:  # up to the first flipped ancestor the two runs are the same run
+        assert np.array_equal(a.indices[:, :first], b.indices[:, :first])
+        assert np.array_equal(a.weights[:, :first + 1].view(np.uint64), b.weights[:, :first + 1].view(np.uint64))
