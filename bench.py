@@ -154,33 +154,35 @@ def run_reference(args, rank, world):
     import bssm_b200
     import data
     import orc
-    from bssm_b200 import build
-    build.build_oracle()
+    orc.build()
     w = WORKLOAD
     # torchrun exports OMP_NUM_THREADS=1: ask the OS, not OpenMP, how many cores this process may use
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    n_sample = 50  # first 50 time points of the same series, full N
+    # the SAME workload as the GPU arm: the full T = 1000 series, N = 65536, one replicate filter per host
+    # thread and step (~6 s per step); one warm-up step is enough for a CPU loop
+    n_sample = w["n"]
     y = data.svm_series(w["n"], w["rho"], w["sd_ar"], w["sigma"], w["gen_seed"])[:n_sample]
     model = bssm_b200.svm(y, w["rho"], w["sd_ar"], sigma=w["sigma"])
     times = []
-    for it in range(args.warmup + args.steps):
+    cpu_warmup = min(args.warmup, 1)
+    for it in range(cpu_warmup + args.steps):
         t0 = time.perf_counter()
         orc.filter_batch(model, w["N"], method="psi", seed=1, first_filter=it * cores, n_filters=cores,
                          arith=orc.ARITH_REFERENCE, threads=cores)
         dt = time.perf_counter() - t0
-        if it >= args.warmup:
+        if it >= cpu_warmup:
             times.append(dt)
     total = sum(times)
     value = cores * w["N"] * n_sample * args.steps / total
-    sample = ("%d replicate filters (one per thread, OpenMP static), N=%d, first %d of T=%d time points per step; "
-              "oracle port of the reference loops (reference not buildable here: no R/Rcpp/Armadillo); cpu=%s"
-              % (cores, w["N"], n_sample, w["n"], cpu_model_name()))
+    sample = ("%d replicate filters (one per thread, OpenMP static), N=%d, the full series of T=%d time points per step "
+              "(%d warm-up step); oracle port of the reference loops (reference not buildable here: no R/Rcpp/Armadillo); cpu=%s"
+              % (cores, w["N"], w["n"], cpu_warmup, cpu_model_name()))
     line = {
         "impl": "reference", "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": cpu_warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "c2: svm psi-APF T=1000 N=65536 (bounded sample, see cpu_baseline.sample)"},
+        "config": {"workload": "c2: svm psi-APF, T=1000, N=65536 particles, %d replicate filters per step (one per host thread)" % cores},
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -218,8 +220,7 @@ def cpu_baseline_leg():
     import bssm_b200
     import data
     import orc
-    from bssm_b200 import build
-    build.build_oracle()
+    orc.build()
     w = WORKLOAD
     n_sample = 200
     y = data.svm_series(w["n"], w["rho"], w["sd_ar"], w["sigma"], w["gen_seed"])[:n_sample]
@@ -241,6 +242,9 @@ def main():
     ap.add_argument("--filters", type=int, default=int(os.environ.get("BENCH_FILTERS", "0")),
                     help="replicate filters per GPU per step (0 = one full wave of the device: 18)")
     ap.add_argument("--no-c4", action="store_true", help="skip the post_correct (config 4) leg")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+                    help="c2 (default): the headline metric; c4: ONLY the post_correct leg, printed as its own "
+                         "strong-scaling line (15000 draws in total whatever the number of GPUs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -265,14 +269,15 @@ def main():
     bssm_b200._lib.check(bssm_b200.lib().bssm_b200_set_device(local_rank))
     dist = None
     if world > 1:
-        # keep stdout to the one JSON line: any NCCL_DEBUG level (even WARN) prints "NCCL version ..."
-        # to stdout; BENCH_NCCL_DEBUG=INFO re-enables it, routed to stderr
-        dbg = os.environ.get("BENCH_NCCL_DEBUG")
-        if dbg:
-            os.environ["NCCL_DEBUG"] = dbg
-            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        else:
+        # NCCL's INFO lines (communicator, ranks, NVLS / ring choice) go to STDERR so that stdout stays the
+        # one JSON line; BENCH_NCCL_DEBUG=off silences them
+        dbg = os.environ.get("BENCH_NCCL_DEBUG", os.environ.get("NCCL_DEBUG", "INFO"))
+        if dbg.lower() in ("off", "0", "none"):
             os.environ.pop("NCCL_DEBUG", None)
+        else:
+            os.environ["NCCL_DEBUG"] = dbg
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,COLL")
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -284,6 +289,67 @@ def main():
     w = WORKLOAD
     N, n, B = w["N"], w["n"], args.filters
     model = make_model()
+    launches = 0
+
+    def c4_leg():
+        """config 4: post_correct, 15000 draws x psi-APF N=256, sharded over the ranks"""
+        nonlocal launches
+        from bssm_b200.distributed import shard_range
+        nd, Np = 15000, 256
+        mo = bssm_b200.synthetic_svm_mcmc_output(model, nd)  # same inputs on every rank (seeded)
+        b, e = shard_range(nd, rank, world)
+        pj = bssm_b200.PostcorrJob(model, mo, Np, is_type="is2", seed=1, draw_range=(b, e))
+        ll_loc = torch.empty(e - b, dtype=torch.float64, device="cuda")
+        maxlen = max(shard_range(nd, r, world)[1] - shard_range(nd, r, world)[0] for r in range(world))
+        pad = torch.zeros(maxlen, dtype=torch.float64, device="cuda")
+        outs = [torch.empty_like(pad) for _ in range(world)]
+
+        def c4_step():
+            ms = pj.run()
+            pj.logliks_to_device(ll_loc.data_ptr())
+            if dist is not None:  # the single NCCL gather of per-draw log-likelihoods
+                pad[:e - b] = ll_loc
+                dist.all_gather(outs, pad)
+            return ms
+        for _ in range(args.warmup):
+            c4_step()
+        barrier()
+        t0 = time.perf_counter()
+        c4_dev = [c4_step() for _ in range(args.steps)]
+        barrier()
+        c4_wall = time.perf_counter() - t0
+        tt = torch.tensor([sum(c4_dev), c4_wall * 1e3], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        c4_launches = pj.launches() * args.steps
+        wsum = float(torch.exp(ll_loc).sum())
+        c4 = {"workload": "c4: post_correct svm, 15000 draws x psi-APF N=256, T=1000, weights only, is2",
+              "draws": nd, "draws_per_s": nd * args.steps / (float(tt[1]) * 1e-3),
+              "particle_steps_per_s": nd * Np * n * args.steps / (float(tt[1]) * 1e-3),
+              "ms_per_pass_wall": float(tt[1]) / args.steps,
+              "ms_per_pass_device_max_rank": float(tt[0]) / args.steps,
+              "timing": "wall clock over K passes incl. the NCCL all_gather, max over ranks",
+              "sharding": "contiguous static blocks of draws per rank, one all_gather of log-likelihoods",
+              "launches": c4_launches, "rank0_weight_sum": wsum}
+        pj.close()
+        launches += c4_launches
+        return c4
+
+
+
+    if args.workload == "c4":
+        with ClockSampler(local_rank) as clk:
+            c4 = c4_leg()
+        if rank == 0:
+            print(json.dumps({
+                "metric": "post_correct draws/s", "value": c4["draws_per_s"], "unit": "draws/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": c4["ms_per_pass_wall"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": c4["workload"], "timing": c4["timing"], "sharding": c4["sharding"]},
+                "post_correct": c4, "clocks": clk.summary(), "gpu_launches": launches}), flush=True)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     if B <= 0:
         # one wave of the engine's throughput geometry: 148 SMs x 4 resident CTAs of 256 threads
         # = 592 CTAs, 32 CTAs (x 256 threads x 8 particles) per 65536-particle filter -> 18 filters
@@ -293,7 +359,7 @@ def main():
     for _ in range(args.warmup):
         job.run()
     barrier()
-    launches, step_ms, filt_ms = 0, [], []
+    step_ms, filt_ms = [], []
     with ClockSampler(local_rank) as clk:
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -356,48 +422,9 @@ def main():
                "call": "bssm_b200_psi_filter (1 filter per call, alpha cube + weights to pinned host memory; finished blocks of columns are copied while the filter kernel runs)",
                "loglik_check": out.loglik}
 
-    # ---- config 4: post_correct, 15000 draws x psi-APF N=256, sharded over the ranks
     c4 = None
     if not args.no_c4:
-        from bssm_b200.distributed import shard_range
-        nd, Np = 15000, 256
-        mo = bssm_b200.synthetic_svm_mcmc_output(model, nd)  # same inputs on every rank (seeded)
-        b, e = shard_range(nd, rank, world)
-        pj = bssm_b200.PostcorrJob(model, mo, Np, is_type="is2", seed=1, draw_range=(b, e))
-        ll_loc = torch.empty(e - b, dtype=torch.float64, device="cuda")
-        maxlen = max(shard_range(nd, r, world)[1] - shard_range(nd, r, world)[0] for r in range(world))
-        pad = torch.zeros(maxlen, dtype=torch.float64, device="cuda")
-        outs = [torch.empty_like(pad) for _ in range(world)]
-
-        def c4_step():
-            ms = pj.run()
-            pj.logliks_to_device(ll_loc.data_ptr())
-            if dist is not None:  # the single NCCL gather of per-draw log-likelihoods
-                pad[:e - b] = ll_loc
-                dist.all_gather(outs, pad)
-            return ms
-        for _ in range(args.warmup):
-            c4_step()
-        barrier()
-        t0 = time.perf_counter()
-        c4_dev = [c4_step() for _ in range(args.steps)]
-        barrier()
-        c4_wall = time.perf_counter() - t0
-        tt = torch.tensor([sum(c4_dev), c4_wall * 1e3], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        c4_launches = pj.launches() * args.steps
-        wsum = float(torch.exp(ll_loc).sum())
-        c4 = {"workload": "c4: post_correct svm, 15000 draws x psi-APF N=256, T=1000, weights only, is2",
-              "draws": nd, "draws_per_s": nd * args.steps / (float(tt[1]) * 1e-3),
-              "particle_steps_per_s": nd * Np * n * args.steps / (float(tt[1]) * 1e-3),
-              "ms_per_pass_wall": float(tt[1]) / args.steps,
-              "ms_per_pass_device_max_rank": float(tt[0]) / args.steps,
-              "timing": "wall clock over K passes incl. the NCCL all_gather, max over ranks",
-              "sharding": "contiguous static blocks of draws per rank, one all_gather of log-likelihoods",
-              "launches": c4_launches, "rank0_weight_sum": wsum}
-        pj.close()
-        launches += c4_launches
+        c4 = c4_leg()
 
     if rank != 0:
         if dist is not None:
@@ -413,7 +440,8 @@ def main():
         try:
             tj = json.load(open(tp))
             traffic = tj.get("filter_kernel_dram_bytes_per_launch")
-            ncu_note = tj.get("ncu")  # static: what the committed ncu capture says bounds the kernel
+            ncu_note = dict(tj.get("ncu") or {})  # static: what the committed ncu capture says bounds the kernel
+            ncu_note["traffic_measured"] = tj.get("measured")
         except Exception:
             traffic = None
     line = {

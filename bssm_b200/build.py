@@ -108,13 +108,6 @@ def build(force=False, verbose=False, defines=(), lib=None, objdir=None):
     return lib or LIB
 
 
-def build_oracle():
-    """Compile the CPU oracle (test infrastructure) with its own Makefile."""
-    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True,
-                   capture_output=True, text=True)
-    return os.path.join(ROOT, "oracle", "_build", "liborc.so")
-
-
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(LIB)

@@ -11,6 +11,13 @@ ARITH_REFERENCE, ARITH_REPRO = 0, 1
 _L = None
 
 
+def build():
+    """compile the oracle with its own Makefile (g++, no dependencies): building the checker is not using it"""
+    import subprocess
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True, text=True)
+    return os.path.join(ROOT, "oracle", "_build", "liborc.so")
+
+
 def L():
     global _L
     if _L is None:
