@@ -15,7 +15,7 @@ CSRC = os.path.join(ROOT, "bssm_b200", "csrc")
 LIB = os.path.join(CSRC, "libbssm_b200.so")
 OBJ = os.path.join(CSRC, "_obj")
 # one translation unit per model family: the kernel instantiations dominate build time
-SOURCES = ["api.cu", "k_ung_psi1.cu", "k_ung_psim.cu", "k_ung_bsf_a.cu", "k_ung_bsf_b.cu",
+SOURCES = ["api.cu", "k_ung_psi1.cu", "k_ung_psim.cu", "k_ung_bsf_a.cu", "k_ung_bsf_b.cu", "k_ung_dyn.cu",
            "k_mng.cu", "k_nlg.cu", "k_sde.cu"]
 
 NVCC_FLAGS = [

@@ -80,7 +80,7 @@ uint32_t round32(uint32_t a) { return cdiv(a, 32) * 32; }
 // fewer ranks with P = 8, several CTAs of different filters per SM (throughput).
 // Results never depend on the geometry (fixed-point sums), so this is free to tune.
 // Environment overrides (experiments): BSSM_B200_RANKS / _P / _BLOCK / _SYNC=cluster.
-int choose_geometry(uint32_t N, uint32_t n_filters, Geometry* g) {
+int choose_geometry(uint32_t N, uint32_t n_filters, Geometry* g, bool p2_only = false) {
   // the low word of the fixed-point weight terms is < 2^43 per particle (pf_math.h): its sum stays
   // inside an int64 for N <= 2^20, which is also what one resident group of CTAs holds comfortably
   if (N > (1u << 20)) return fail(BSSM_B200_ERR_UNSUPPORTED, "at most 2^20 particles per filter");
@@ -104,9 +104,14 @@ int choose_geometry(uint32_t N, uint32_t n_filters, Geometry* g) {
     ranks = cdiv(N, tb * (uint32_t)P);
     if (ranks > capacity) return fail(BSSM_B200_ERR_UNSUPPORTED, "too many particles for one resident group (N <= 1.2M)");
   }
+  if (p2_only) { // run-time-m policies: two particles per thread, whatever the size
+    P = 2;
+    if (N <= 2048) { ranks = 1; mode = pf::SYNC_BLOCK; }
+    else { mode = pf::SYNC_GROUP; ranks = cdiv(N, 256u * 2u); if (ranks > 148u * 4u) return fail(BSSM_B200_ERR_UNSUPPORTED, "too many particles for the general-m kernels"); }
+  }
   const int forced_ranks = env_int("BSSM_B200_RANKS", 0);
   const int forced_P = env_int("BSSM_B200_P", 0);
-  if (forced_P == 2 || forced_P == 4 || forced_P == 8) P = forced_P;
+  if (!p2_only && (forced_P == 2 || forced_P == 4 || forced_P == 8)) P = forced_P;
   if (forced_ranks > 0) { ranks = (uint32_t)forced_ranks; mode = ranks == 1 ? pf::SYNC_BLOCK : pf::SYNC_GROUP; }
   const char* sm = getenv("BSSM_B200_SYNC");
   if (sm && !strcmp(sm, "cluster") && ranks > 1 && ranks <= 16) mode = pf::SYNC_CLUSTER;
@@ -437,6 +442,7 @@ struct bssm_b200_job {
   bool has_run = false;
   uint32_t nlg_max_iter = 100, nlg_iekf_iter = 0; // psi-APF jobs of ssm_nlg: settings of approximate(), kept for set_theta
   double nlg_conv_tol = 1e-8;
+  bool dyn = false; // run-time state dimension (models_ung_dyn.cuh): (m, k) without a specialised instantiation
   bool xbeta_per_filter = false; // m = 1 psi-APF whose filters carry their own regression part (beta in theta)
   // model on device
   DevBuf<double> y, Z, T, R, a1, P1, LP1, D, C, xbeta, u, mode, mode_lin;
@@ -504,7 +510,29 @@ int run_post_M(bssm_b200_job* J) {
   return 0;
 }
 
+int run_post_dyn(bssm_b200_job* J) {
+  const uint32_t N = J->N, nf = J->n_filters;
+  const int n = J->n, m = J->m;
+  const int bs = N >= 1024 ? 1024 : (int)round32(N);
+  if (J->post == BSSM_POST_FILTER_SUMMARY) {
+    pf::summary_dyn_kernel<<<dim3(n + 1, nf), bs, 0, J->stream>>>(J->alpha_tm.p, J->weights.p, N, n, m, J->s_at.p, J->s_Pt.p,
+                                                              J->s_att.p, J->s_Ptt.p, J->alpha_stride, J->weights_stride);
+    J->launches += 1;
+  } else if (J->post == BSSM_POST_SMOOTHER) {
+    pf::backtrack_dyn_kernel<<<dim3(cdiv(N, 256), nf), 256, 0, J->stream>>>(J->alpha_tm.p, J->indices.p, J->alpha_sm.p, N, n, m,
+                                                                         J->alpha_stride, J->indices_stride);
+    pf::summary_dyn_kernel<<<dim3(n + 1, nf), bs, 0, J->stream>>>(J->alpha_sm.p, nullptr, N, n, m, J->s_mean.p, J->s_cov.p,
+                                                              nullptr, nullptr, J->alpha_stride, 0);
+    J->launches += 2;
+  } else {
+    return fail(BSSM_B200_ERR_UNSUPPORTED, "this post-processing mode supports m <= 4");
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
 int run_post(bssm_b200_job* J) {
+  if (J->m > 4) return run_post_dyn(J);
   switch (J->m) {
     case 1: return run_post_M<1>(J);
     case 2: return run_post_M<2>(J);
@@ -557,6 +585,7 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
     up.ytilde += (size_t)f0 * up.fs_n; up.Htilde += (size_t)f0 * up.fs_n; up.scales += (size_t)f0 * up.fs_n;
     up.xbeta += (size_t)f0 * up.fs_x;
     if (up.phi_f) up.phi_f += f0;
+    if (J->dyn) return launch_status(pfl::launch_ung_psi_dyn(fp, up, J->geo, nf, J->stream), "psi filter (run-time m)");
     return launch_status(pfl::launch_ung_psim(J->m, fp, up, J->geo, nf, J->stream), "psi filter (m)");
   }
   if (J->method == BSSM_METHOD_PSI) {
@@ -572,6 +601,7 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
     up.xbeta += (size_t)f0 * up.fs_x;
     return launch_status(pfl::launch_ung_bsf_draws(fp, up, J->geo, nf, J->stream), "bsf (per-draw models)");
   }
+  if (J->dyn) return launch_status(pfl::launch_ung_bsf_dyn(fp, up, J->geo, nf, J->stream), "bsf (run-time m)");
   if (J->m <= 2) return launch_status(pfl::launch_ung_bsf_a(J->m, J->k, fp, up, J->geo, nf, J->stream), "bsf (m,k)");
   return launch_status(pfl::launch_ung_bsf_b(J->m, J->k, fp, up, J->geo, nf, J->stream), "bsf (m,k)");
 }
@@ -677,8 +707,10 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
   if (method != BSSM_METHOD_PSI && method != BSSM_METHOD_BSF) return fail(BSSM_B200_ERR_ARG, "method must be 1 (psi) or 2 (bsf)");
   if (method == BSSM_METHOD_BSF && draw_par && M->m != 1)
     return fail(BSSM_B200_ERR_UNSUPPORTED, "per-draw bootstrap filters: m = 1 in this build");
-  if (method == BSSM_METHOD_PSI && (M->m > 3 || (M->m != 1 && draw_par) || (M->m == 1 && dm && !draw_par)))
-    return fail(BSSM_B200_ERR_UNSUPPORTED, "psi-APF: m <= 3 (and m = 1 for per-draw models) in this build");
+  if (M->m > 16) return fail(BSSM_B200_ERR_UNSUPPORTED, "state dimension m <= 16 in this build");
+  if (method == BSSM_METHOD_PSI && ((M->m != 1 && draw_par) || (M->m == 1 && dm && !draw_par)))
+    return fail(BSSM_B200_ERR_UNSUPPORTED, "psi-APF with per-draw models: m = 1 (or bsm_ng through the DrawModels path)");
+  if (dm && M->m > 3) return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction with per-draw models: m <= 3 in this build");
   if (M->k > M->m) return fail(BSSM_B200_ERR_ARG, "k > m");
   if (post < 0 || post > BSSM_POST_SMOOTHER_MERGE) return fail(BSSM_B200_ERR_ARG, "bad post mode");
   int rc = require_device();
@@ -690,7 +722,12 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
   J->N = nsim; J->n_filters = n_filters; J->first_filter = first_filter_id; J->seed = seed;
   J->n = M->n; J->m = M->m; J->k = M->k;
   const int n = M->n, m = M->m, k = M->k;
-  rc = choose_geometry(nsim, n_filters, &J->geo);
+  {
+    const int mk = M->m * 10 + M->k;
+    const bool bsf_inst = mk == 11 || mk == 21 || mk == 22 || mk == 32 || mk == 33;
+    J->dyn = M->m > 3 || (method == BSSM_METHOD_BSF && !bsf_inst);
+  }
+  rc = choose_geometry(nsim, n_filters, &J->geo, J->dyn);
   if (rc) return rc;
   CU(cudaStreamCreateWithFlags(&J->stream, cudaStreamNonBlocking));
   for (auto& e : J->ev) CU(cudaEventCreate(&e));
@@ -716,6 +753,7 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
 
   pf::UngParams& up = J->up;
   up.n = n; up.distribution = M->distribution;
+  up.m_dyn = m; up.k_dyn = k;
   up.Ztv = M->Ztv; up.Ttv = M->Ttv; up.Rtv = M->Rtv; up.Dtv = M->Dtv; up.Ctv = M->Ctv;
   up.y = J->y.p; up.Z = J->Z.p; up.T = J->T.p; up.R = J->R.p; up.a1 = J->a1.p; up.LP1 = J->LP1.p;
   up.D = J->D.p; up.C = J->C.p; up.xbeta = J->xbeta.p; up.u = J->u.p;
@@ -969,6 +1007,7 @@ int bssm_b200_job_max_concurrent_filters(const bssm_b200_job* J) {
   else if (J->kind == KIND_NLG) rc = pfl::occupancy_nlg_bsf(J->geo, &out);
   else if (J->kind == KIND_SDE) rc = pfl::occupancy_sde_bsf(J->geo, &out);
   else if (J->kind == KIND_MNG) rc = pfl::occupancy_mng_bsf(J->geo, &out);
+  else if (J->dyn) rc = pfl::occupancy_ung_dyn(J->geo, &out);
   else if (J->method == BSSM_METHOD_PSI) rc = pfl::occupancy_ung_psi1(J->geo, &out);
   else rc = pfl::occupancy_ung_bsf(J->geo, &out);
   return rc ? 0 : out;

@@ -17,6 +17,10 @@ int launch_ung_bsf_a(int m, int k, const pf::FilterParams&, const pf::UngParams&
 int launch_ung_bsf_b(int m, int k, const pf::FilterParams&, const pf::UngParams&, const Geometry&, uint32_t nf, Stream);
 int launch_ung_bsf_draws(const pf::FilterParams&, const pf::UngParams&, const Geometry&, uint32_t nf, Stream); // m = 1, one model per filter
 int occupancy_ung_bsf(const Geometry&, int* out);
+// k_ung_dyn.cu: bootstrap filter and psi-APF with a run-time state dimension (m <= 16, k <= m), P = 2 only
+int launch_ung_bsf_dyn(const pf::FilterParams&, const pf::UngParams&, const Geometry&, uint32_t nf, Stream);
+int launch_ung_psi_dyn(const pf::FilterParams&, const pf::UngParams&, const Geometry&, uint32_t nf, Stream);
+int occupancy_ung_dyn(const Geometry&, int* out);
 // k_mng.cu: multivariate-observation bootstrap filter and psi-APF (m <= 3)
 int launch_mng_bsf(int m, int k, const pf::FilterParams&, const pf::MngParams&, const Geometry&, uint32_t nf, Stream);
 int launch_mng_psi(int m, const pf::FilterParams&, const pf::MngParams&, const Geometry&, uint32_t nf, Stream);

@@ -10,6 +10,7 @@ namespace pf {
 
 struct UngParams {
   int n, distribution;
+  int m_dyn, k_dyn;    // state / noise dimension of the run-time-m policies (models_ung_dyn.cuh)
   int Ztv, Ttv, Rtv, Dtv, Ctv;
   const double* y;     // n
   const double* Z;     // m x (1|n)

@@ -1,0 +1,182 @@
+// models_ung_dyn.cuh -- ssm_ung family with a state dimension chosen at run time (m <= MAXM,
+// k <= m): the bootstrap filter and the psi-APF of models whose (m, k) has no specialised
+// instantiation in models_ung.cuh -- bsm_ng with a seasonal component has m = 2 + period - 1
+// (src/model_bsm_ng.cpp:17-51: 5 for quarterly, 13 for monthly data).  Same formulas, same random
+// stream layout (flat normal index i * K + d, K = m for the initial draw and the psi-APF, k for
+// bootstrap steps) and therefore the same bits as the static policies and the oracle; loops run to
+// the run-time m, so the per-particle arrays live in local memory -- this is the general path, not
+// the fast one (the batched (N x m)(m x m) products are measured in tools/bench_mma.cu).
+#pragma once
+#include "models_ung.cuh"
+
+namespace pf {
+
+template <int MAXM>
+struct UngDynBase {
+  static constexpr int M = MAXM;
+  static constexpr bool DYN = true;
+  typedef UngParams Params;
+  const UngParams& mp;
+  int m, k;
+  template <int P> struct Noise { double z[P * MAXM]; };
+  __device__ UngDynBase(const UngParams& p) : mp(p), m(p.m_dyn), k(p.k_dyn) {}
+  __device__ bool observed(int t) const { return pf_isfinite(mp.y[t]); }
+  __device__ __forceinline__ double finish_logw(double w, double) const { return w; }
+  // `cnt` standard normals with flat indices f0, f0 + 1, ... (f0 even) of column t
+  __device__ void normals(const StepCtx& c, uint32_t f0, int cnt, double* z) const {
+    for (int q = 0; q < (cnt + 1) / 2; ++q) {
+      double z0, z1;
+      pf_normal_pair(c.seed, c.filter, c.t, 0u, (f0 >> 1) + q, &z0, &z1);
+      z[2 * q] = z0;
+      if (2 * q + 1 < cnt) z[2 * q + 1] = z1;
+    }
+  }
+  __device__ double signal(const double* x, double Dt, double xb, int t) const {
+    if (mp.distribution == 0) return x[0];
+    const double* Z = mp.Z + (size_t)m * (t * mp.Ztv);
+    double zs = 0.0;
+    for (int d = 0; d < m; ++d) zs += Z[d] * x[d];
+    return Dt + zs + xb;
+  }
+};
+
+// ---------------------------------------------------------------- bootstrap filter
+template <int MAXM>
+struct UngBsfDyn : UngDynBase<MAXM> {
+  typedef UngDynBase<MAXM> B;
+  using B::mp; using B::m; using B::k;
+  double y, u, yphi2, Dt, xb, HHt, hc;
+  int tw, ts;
+  __device__ UngBsfDyn(const UngParams& p, uint32_t) : B(p), hc(0.0), tw(0), ts(0) {}
+  __device__ double step_const() const { return hc; }
+  __device__ double loglik0() const { return 0.0; }
+  __device__ double loglik_end() const { return mp.loglik_const; }
+  template <int P>
+  __device__ void init_all(const StepCtx& c, double (&x)[P][MAXM]) const {
+    double z[P * MAXM];
+    B::normals(c, c.i0 * (uint32_t)m, P * m, z); // i0 * m is even: P is
+    for (int p = 0; p < P; ++p)
+      for (int d = 0; d < m; ++d) {
+        double s = 0.0;
+        for (int j = 0; j < m; ++j) s += mp.LP1[d + m * j] * z[p * m + j];
+        x[p][d] = mp.a1[d] + s;
+      }
+  }
+  __device__ void begin_weight(int t) {
+    tw = t;
+    y = mp.y[t];
+    u = mp.u[t];
+    double q = y / mp.phi;
+    yphi2 = q * q;
+    Dt = mp.D[t * mp.Dtv];
+    xb = mp.xbeta[t];
+    if (mp.distribution == 5) { HHt = mp.HH[t]; hc = mp.hconst[t]; }
+  }
+  __device__ double logw(const double* x) const {
+    if (mp.distribution == 5) { // ssm_ulg::bsf_filter, src/model_ssm_ulg.cpp:577-580: mu = D + Z'a
+      const double* Z = mp.Z + (size_t)m * (tw * mp.Ztv);
+      double zs = 0.0;
+      for (int d = 0; d < m; ++d) zs += Z[d] * x[d];
+      const double mu = Dt + zs;
+      return -0.5 * ((y - mu) * (y - mu)) / HHt;
+    }
+    return ung_log_obs(mp.distribution, B::signal(x, Dt, xb, tw), y, u, mp.phi, yphi2);
+  }
+  __device__ void begin_step(int t) { ts = t; }
+  template <int P>
+  __device__ void draw(const StepCtx& c, typename B::template Noise<P>& nz) const {
+    B::normals(c, c.i0 * (uint32_t)k, P * k, nz.z);
+  }
+  template <int P>
+  __device__ void propagate_all(const StepCtx&, const typename B::template Noise<P>& nz, const double (&xa)[P][MAXM],
+                                double (&x)[P][MAXM], double (&carry)[P]) const {
+    const double* T = mp.T + (size_t)m * m * (ts * mp.Ttv);
+    const double* R = mp.R + (size_t)m * k * (ts * mp.Rtv);
+    const double* C = mp.C + (size_t)m * (ts * mp.Ctv);
+    for (int p = 0; p < P; ++p) {
+      for (int d = 0; d < m; ++d) {
+        double ta = 0.0, ru = 0.0;
+        for (int j = 0; j < m; ++j) ta += T[d + m * j] * xa[p][j];
+        for (int j = 0; j < k; ++j) ru += R[d + m * j] * nz.z[p * k + j];
+        x[p][d] = C[d] + ta + ru;
+      }
+      carry[p] = 0.0;
+    }
+  }
+};
+
+// ------------------------------------------------------------------------ psi-APF
+// alpha_{t+1} = ahat_{t+1} + Ct_{t+1} (alpha_anc - ahat_t) + L_{t+1} u, u ~ N(0, I_m)
+// (src/model_ssm_ung.cpp:580-587), Gaussian approximation from the host (ung_gauss_approx.h)
+template <int MAXM>
+struct UngPsiDyn : UngDynBase<MAXM> {
+  typedef UngDynBase<MAXM> B;
+  using B::mp; using B::m;
+  double al0, phi;
+  const double *p_ah, *p_Lt, *p_Ct, *p_yt, *p_Ht, *p_sc, *p_xb;
+  double y, u, yphi2, Dt, xb, ytil, rH, scale;
+  int tw, ts;
+  __device__ UngPsiDyn(const UngParams& p, uint32_t f) : B(p), tw(0), ts(0) {
+    al0 = p.approx_loglik[f];
+    phi = p.phi_f ? p.phi_f[f] : p.phi;
+    p_ah = p.alphahat + (size_t)f * p.fs_a;
+    p_Lt = p.Lt + (size_t)f * p.fs_m; p_Ct = p.Ct + (size_t)f * p.fs_m;
+    p_yt = p.ytilde + (size_t)f * p.fs_n; p_Ht = p.Htilde + (size_t)f * p.fs_n; p_sc = p.scales + (size_t)f * p.fs_n;
+    p_xb = p.xbeta + (size_t)f * p.fs_x;
+  }
+  __device__ double step_const() const { return 0.0; }
+  __device__ double loglik0() const { return al0; }
+  __device__ double loglik_end() const { return 0.0; }
+  template <int P>
+  __device__ void init_all(const StepCtx& c, double (&x)[P][MAXM]) const {
+    double z[P * MAXM];
+    B::normals(c, c.i0 * (uint32_t)m, P * m, z);
+    for (int p = 0; p < P; ++p)
+      for (int d = 0; d < m; ++d) {
+        double s = 0.0;
+        for (int j = 0; j < m; ++j) s += p_Lt[d + m * j] * z[p * m + j];
+        x[p][d] = p_ah[d] + s;
+      }
+  }
+  __device__ void begin_weight(int t) {
+    tw = t;
+    y = mp.y[t];
+    u = mp.u[t];
+    double q = y / phi;
+    yphi2 = q * q;
+    Dt = mp.D[t * mp.Dtv];
+    xb = p_xb[t];
+    ytil = p_yt[t]; rH = 1.0 / p_Ht[t]; scale = p_sc[t];
+  }
+  __device__ double logw(const double* x) const {
+    const double s = B::signal(x, Dt, xb, tw);
+    const double q = (ytil - s) * rH;
+    return (ung_log_obs(mp.distribution, s, y, u, phi, yphi2) + 0.5 * (q * q)) - scale;
+  }
+  __device__ void begin_step(int t) { ts = t; }
+  template <int P>
+  __device__ void draw(const StepCtx& c, typename B::template Noise<P>& nz) const {
+    B::normals(c, c.i0 * (uint32_t)m, P * m, nz.z);
+  }
+  template <int P>
+  __device__ void propagate_all(const StepCtx&, const typename B::template Noise<P>& nz, const double (&xa)[P][MAXM],
+                                double (&x)[P][MAXM], double (&carry)[P]) const {
+    const double* ah0 = p_ah + (size_t)m * ts;
+    const double* ah1 = p_ah + (size_t)m * (ts + 1);
+    const double* Cm = p_Ct + (size_t)m * m * (ts + 1);
+    const double* Lm = p_Lt + (size_t)m * m * (ts + 1);
+    for (int p = 0; p < P; ++p) {
+      double diff[MAXM];
+      for (int j = 0; j < m; ++j) diff[j] = xa[p][j] - ah0[j];
+      for (int d = 0; d < m; ++d) {
+        double cd = 0.0, lu = 0.0;
+        for (int j = 0; j < m; ++j) cd += Cm[d + m * j] * diff[j];
+        for (int j = 0; j < m; ++j) lu += Lm[d + m * j] * nz.z[p * m + j];
+        x[p][d] = ah1[d] + cd + lu;
+      }
+      carry[p] = 0.0;
+    }
+  }
+};
+
+} // namespace pf

@@ -469,6 +469,14 @@ __device__ __forceinline__ void load_anc(const uint32_t* anc, uint32_t i0, uint3
 //   init_all<P>(ctx, x), Noise<P>, draw<P>(ctx, noise), propagate_all<P>(ctx, noise, xa, x):
 //     the random part of the step for the thread's P particles (GaussStep above for
 //     models with K normals per particle; the SDE model runs its Milstein sub-steps)
+// Model::DYN (models_ung_dyn.cuh): the state dimension is model.m <= Model::M, chosen at run time
+template <class T, class = void> struct ModelDyn { static constexpr bool value = false; };
+template <class T> struct ModelDyn<T, decltype((void)T::DYN)> { static constexpr bool value = T::DYN; };
+template <class Model> __device__ __forceinline__ int model_dim(const Model& model) {
+  if constexpr (ModelDyn<Model>::value) return model.m;
+  else return Model::M;
+}
+
 template <class Model, int P, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 filter_kernel(const FilterParams fp, const typename Model::Params mp) {
@@ -509,6 +517,7 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
   const bool vec2 = (N & 1u) == 0;  // 16-byte alignment of fp64 rows
   const bool vec4 = (N & 3u) == 0;  // 16-byte alignment of the uint32 ancestor column (8-byte for P = 2 needs N even)
   Model model(mp, fidx);
+  const int Md = model_dim(model); // rows of the state per time point (== M unless Model::DYN)
   double x[P][M];
 
   // ---- initial state, column 0 (reference :621-627 / :538-544)
@@ -518,6 +527,7 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
     model.template init_all<P>(c0, x);
 #pragma unroll
     for (int d = 0; d < M; ++d) {
+      if (d >= Md) break;
       double col[P];
 #pragma unroll
       for (int p = 0; p < P; ++p) col[p] = x[p][d];
@@ -678,18 +688,19 @@ filter_kernel(const FilterParams fp, const typename Model::Params mp) {
     // ---- gather ancestors, propagate to column t+1 (reference :657-670)
     {
       model.begin_step(t);
-      const double* src = alpha + (size_t)(fp.keep_alpha ? t : (t & 1)) * M * N;
-      double* dst = alpha + (size_t)(fp.keep_alpha ? t + 1 : ((t + 1) & 1)) * M * N;
+      const double* src = alpha + (size_t)(fp.keep_alpha ? t : (t & 1)) * Md * N;
+      double* dst = alpha + (size_t)(fp.keep_alpha ? t + 1 : ((t + 1) & 1)) * Md * N;
       uint32_t a[P];
       load_anc<P>(anc, i0, N, P == 2 ? vec2 : vec4, a);
       double xa[P][M];
 #pragma unroll
       for (int p = 0; p < P; ++p)
 #pragma unroll
-        for (int d = 0; d < M; ++d) xa[p][d] = __ldcg(src + (size_t)d * N + a[p]);
+        for (int d = 0; d < M; ++d) xa[p][d] = d < Md ? __ldcg(src + (size_t)d * N + a[p]) : 0.0;
       model.template propagate_all<P>(ctx, noise, xa, x, carry);
 #pragma unroll
       for (int d = 0; d < M; ++d) {
+        if (d >= Md) break;
         double col[P];
 #pragma unroll
         for (int p = 0; p < P; ++p) col[p] = x[p][d];

@@ -203,6 +203,83 @@ filter_summary_kernel(const double* __restrict__ alpha_tm, const double* __restr
   }
 }
 
+
+// ---- the same three kernels for a state dimension given at run time (m > 4: bsm_ng with a
+// seasonal component).  The means and the covariance entries are reduced one (or a few) at a time
+// with the same fixed-tree block sum, so the results equal the templated kernels' for m <= 4.
+__global__ void backtrack_dyn_kernel(const double* __restrict__ alpha_f, const uint32_t* __restrict__ indices,
+                                     double* __restrict__ alpha_s, uint32_t N, int n, int m, size_t alpha_stride,
+                                     size_t indices_stride) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  alpha_f += (size_t)blockIdx.y * alpha_stride;
+  alpha_s += (size_t)blockIdx.y * alpha_stride;
+  indices += (size_t)blockIdx.y * indices_stride;
+  uint32_t b = i;
+  for (int d = 0; d < m; ++d) alpha_s[((size_t)n * m + d) * N + i] = alpha_f[((size_t)n * m + d) * N + i];
+  for (int t = n - 1; t >= 0; --t) {
+    b = indices[(size_t)t * N + b];
+    for (int d = 0; d < m; ++d) alpha_s[((size_t)t * m + d) * N + i] = alpha_f[((size_t)t * m + d) * N + b];
+  }
+}
+
+// one block per time column; `weights` null: plain summary (mean, cov / N) into (o_mean, o_cov);
+// otherwise filter_summary: unweighted (at, Pt) into (o_mean, o_cov) and weighted (att, Ptt) into
+// (o_meanw, o_covw) for t < n
+__global__ void __launch_bounds__(1024)
+summary_dyn_kernel(const double* __restrict__ alpha_tm, const double* __restrict__ weights, uint32_t N, int n, int m,
+                   double* __restrict__ o_mean, double* __restrict__ o_cov, double* __restrict__ o_meanw,
+                   double* __restrict__ o_covw, size_t alpha_stride, size_t weights_stride) {
+  __shared__ double sm[32 * 3];
+  __shared__ double mu[16], muw[16];
+  const int t = blockIdx.x, n1 = n + 1;
+  alpha_tm += (size_t)blockIdx.y * alpha_stride;
+  o_mean += (size_t)blockIdx.y * m * n1;
+  o_cov += (size_t)blockIdx.y * m * m * n1;
+  const bool wtd = weights != nullptr;
+  const bool filt = wtd && t < n;
+  const double* w = wtd ? weights + (size_t)blockIdx.y * weights_stride + (size_t)t * N : nullptr;
+  if (wtd) { o_meanw += (size_t)blockIdx.y * m * n; o_covw += (size_t)blockIdx.y * m * m * n; }
+  const double* col = alpha_tm + (size_t)t * m * N;
+  double sw = 1.0;
+  if (wtd) {
+    double a[1] = {0.0};
+    for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) a[0] += w[i];
+    block_sum<1>(a, sm);
+    sw = a[0];
+  }
+  for (int d = 0; d < m; ++d) {
+    double a[2] = {0.0, 0.0};
+    for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
+      const double x = col[(size_t)d * N + i];
+      a[0] += x;
+      if (wtd) a[1] += x * w[i];
+    }
+    block_sum<2>(a, sm);
+    if (threadIdx.x == 0) { mu[d] = a[0] / (double)N; muw[d] = wtd ? a[1] / sw : 0.0; }
+  }
+  __syncthreads();
+  for (int cc = 0; cc < m; ++cc)
+    for (int r = 0; r < m; ++r) {
+      double a[2] = {0.0, 0.0};
+      for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) {
+        const double xr = col[(size_t)r * N + i], xc = col[(size_t)cc * N + i];
+        a[0] += (xr - mu[r]) * (xc - mu[cc]);
+        if (wtd) a[1] += (w[i] / sw) * (xr - muw[r]) * (xc - muw[cc]);
+      }
+      block_sum<2>(a, sm);
+      if (threadIdx.x == 0) {
+        o_cov[r + (size_t)m * cc + (size_t)m * m * t] = a[0] / (double)N;
+        if (filt) o_covw[r + (size_t)m * cc + (size_t)m * m * t] = a[1];
+      }
+    }
+  if (threadIdx.x == 0)
+    for (int d = 0; d < m; ++d) {
+      o_mean[d + (size_t)m * t] = mu[d];
+      if (filt) o_meanw[d + (size_t)m * t] = muw[d];
+    }
+}
+
 // ssm_ulg::psi_filter (src/model_ssm_ulg.cpp:646-672): N independent draws from the smoothing
 // distribution, alpha_{t+1} = ahat_{t+1} + Ct_{t+1} (alpha_t - ahat_t) + L_{t+1} u.  No weights,
 // no resampling: one thread per trajectory, written in the time-major layout.

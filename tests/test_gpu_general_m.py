@@ -1,0 +1,69 @@
+"""General state dimension: bsm_ng with a seasonal component has m = 2 + period - 1
+states (src/model_bsm_ng.cpp:17-51, R/models.R:926-1114) -- 5 for quarterly, 13 for monthly data.  The
+run-time-m policies (bssm_b200/csrc/models_ung_dyn.cuh, m <= 16, k <= m) must give the oracle's bits:
+bootstrap filter, psi-APF, and the particle smoother built on either."""
+import numpy as np
+import pytest
+
+import bssm_b200
+import data
+import orc
+
+pytestmark = pytest.mark.gpu
+
+
+def seasonal_model(period, n=72, dist="poisson", seed=3):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n)
+    season = 0.6 * np.sin(2 * np.pi * t / period)
+    level = 1.0 + np.cumsum(rng.normal(0, 0.05, n))
+    lam = np.exp(level + season)
+    y = rng.poisson(lam).astype(float) if dist == "poisson" else rng.negative_binomial(5, 5 / (5 + lam)).astype(float)
+    y[7] = np.nan  # a missing observation
+    return bssm_b200.bsm_ng(y, sd_level=0.1, sd_slope=0.01, sd_seasonal=0.05, distribution=dist, phi=5.0,
+                            period=period, P1=np.diag(np.full(2 + period - 1, 1.0)))
+
+
+@pytest.mark.parametrize("period,N", [(4, 100), (4, 3000), (12, 100), (12, 1000)])
+def test_bootstrap_filter_general_m(engine, period, N):
+    model = seasonal_model(period)
+    assert model.m == 2 + period - 1 and model.k == 3
+    ref = orc.bsf_filter(model, N, seed=2)
+    res = engine.bootstrap_filter(model, N, seed=2, return_indices=True)
+    assert np.array_equal(res["indices"], ref.indices)
+    assert np.array_equal(res["weights"].view(np.uint64), ref.weights.view(np.uint64))
+    assert res["logLik"] == ref.loglik
+    assert np.array_equal(np.transpose(res["alpha"], (1, 0, 2)).view(np.uint64), ref.alpha.view(np.uint64))
+    at, att, Pt, Ptt = orc.filter_summary(ref.alpha, ref.weights)
+    np.testing.assert_allclose(res["att"], att.T, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(res["Ptt"], Ptt, rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(res["at"], at.T, rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize("period,N,dist", [(4, 200, "poisson"), (12, 200, "poisson"), (12, 2500, "negative binomial")])
+def test_psi_apf_and_smoother_general_m(engine, period, N, dist):
+    model = seasonal_model(period, dist=dist)
+    ref = orc.psi_filter_m(model, N, seed=4)
+    res = engine.particle_smoother(model, N, method="psi", seed=4, return_indices=True)
+    assert np.array_equal(res["indices"], ref.indices)
+    assert np.array_equal(res["weights"].view(np.uint64), ref.weights.view(np.uint64))
+    assert res["logLik"] == ref.loglik
+    sm = orc.filter_smoother(ref.alpha, ref.indices)
+    assert np.array_equal(np.transpose(res["alpha"], (1, 0, 2)).view(np.uint64), sm.view(np.uint64))
+    mean, cov = orc.summary(sm)
+    np.testing.assert_allclose(res["alphahat"], mean.T, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(res["Vt"], cov, rtol=1e-8, atol=1e-11)
+
+
+def test_bsf_smoother_general_m_and_unusual_k(engine):
+    """m = 4 with k = 2 (no specialised instantiation of (m, k)): the run-time policy takes over"""
+    rng = np.random.default_rng(9)
+    y = rng.poisson(3.0, 50).astype(float)
+    model = bssm_b200.bsm_ng(y, sd_level=0.1, sd_seasonal=0.05, distribution="poisson", period=4,
+                             P1=np.diag(np.full(4, 1.0)))
+    assert (model.m, model.k) == (4, 2)
+    ref = orc.bsf_filter(model, 500, seed=6)
+    res = engine.particle_smoother(model, 500, method="bsf", seed=6, return_indices=True)
+    assert np.array_equal(res["indices"], ref.indices) and res["logLik"] == ref.loglik
+    sm = orc.filter_smoother(ref.alpha, ref.indices)
+    assert np.array_equal(np.transpose(res["alpha"], (1, 0, 2)).view(np.uint64), sm.view(np.uint64))
