@@ -47,9 +47,73 @@ suggest_n_nongaussian <- function(model_, theta, candidates, replications, seed,
   .Call("_bssmb200_suggest_n_nongaussian", model_, theta, as.numeric(candidates), replications, seed, model_type)
 }
 
+
+# ---- ssm_nlg / ssm_sde: the shipped example models are device policies selected by id
+# (include/bssm_b200.h BSSM_NLG_* / BSSM_SDE_*).  A model built with bssm's cpp_example_model("nlg_growth")
+# etc. carries compiled function pointers that cannot run in a kernel; tag it once with
+#   model$b200_id <- b200_model_id("nlg_growth")
+# and the masked stubs below put the id in place of the first pointer argument.
+b200_model_id <- function(name) {
+  switch(name, nlg_growth = 0L, nlg_ar_exp = 1L, nlg_sin_exp = 2L, nlg_linear_gaussian = 3L,
+         sde_gbm = 0L, sde_poisson_OU = 1L, stop("no device policy for this example model"))
+}
+.b200_id <- function(ptr) {
+  id <- attr(ptr, "b200_id")
+  if (is.null(id)) stop("bssm_b200: tag the model's Z_fn / drift pointer with attr(., 'b200_id') <- b200_model_id(name)")
+  as.integer(id)
+}
+
+bsf_nlg <- function(y, Z, H, T, R, Zg, Tg, a1, P1, theta, log_prior_pdf, known_params, known_tv_params,
+                    n_states, n_etas, time_varying, nsim, seed) {
+  out <- .Call("_bssmb200_bsf_nlg", y, .b200_id(Z), H, T, R, Zg, Tg, a1, P1, theta, log_prior_pdf, known_params,
+               known_tv_params, n_states, n_etas, time_varying, nsim, seed)
+  out$at <- t(out$at); out$att <- t(out$att)
+  out
+}
+bsf_smoother_nlg <- function(y, Z, H, T, R, Zg, Tg, a1, P1, theta, log_prior_pdf, known_params, known_tv_params,
+                             n_states, n_etas, time_varying, nsim, seed) {
+  out <- .Call("_bssmb200_bsf_smoother_nlg", y, .b200_id(Z), H, T, R, Zg, Tg, a1, P1, theta, log_prior_pdf,
+               known_params, known_tv_params, n_states, n_etas, time_varying, nsim, seed)
+  out$alphahat <- t(out$alphahat)
+  out
+}
+psi_smoother_nlg <- function(y, Z, H, T, R, Zg, Tg, a1, P1, theta, log_prior_pdf, known_params, known_tv_params,
+                             n_states, n_etas, time_varying, nsim, seed, max_iter, conv_tol, iekf_iter) {
+  out <- .Call("_bssmb200_psi_smoother_nlg", y, .b200_id(Z), H, T, R, Zg, Tg, a1, P1, theta, log_prior_pdf,
+               known_params, known_tv_params, n_states, n_etas, time_varying, nsim, seed, max_iter, conv_tol, iekf_iter)
+  out$alphahat <- t(out$alphahat)
+  out
+}
+postcorrection_nonlinear <- function(y, Z, H, T, R, Zg, Tg, a1, P1, theta_init, log_prior_pdf, known_params,
+                                     known_tv_params, n_states, n_etas, time_varying, output_type, nsim, seed,
+                                     n_threads, is_type, counts, theta, modes) {
+  .Call("_bssmb200_postcorrection_nonlinear", y, .b200_id(Z), H, T, R, Zg, Tg, a1, P1, theta_init, log_prior_pdf,
+        known_params, known_tv_params, n_states, n_etas, time_varying, output_type, nsim, seed, n_threads, is_type,
+        as.integer(counts), theta, modes)
+}
+bsf_sde <- function(y, x0, positive, drift, diffusion, ddiffusion, log_prior_pdf, log_obs_density, theta, nsim, L, seed) {
+  out <- .Call("_bssmb200_bsf_sde", y, x0, positive, .b200_id(drift), diffusion, ddiffusion, log_prior_pdf,
+               log_obs_density, theta, nsim, L, seed)
+  out$at <- t(out$at); out$att <- t(out$att)
+  out
+}
+bsf_smoother_sde <- function(y, x0, positive, drift, diffusion, ddiffusion, log_prior_pdf, log_obs_density, theta,
+                             nsim, L, seed) {
+  out <- .Call("_bssmb200_bsf_smoother_sde", y, x0, positive, .b200_id(drift), diffusion, ddiffusion, log_prior_pdf,
+               log_obs_density, theta, nsim, L, seed)
+  out$alphahat <- t(out$alphahat)
+  out
+}
+loglik_sde <- function(y, x0, positive, drift, diffusion, ddiffusion, log_prior_pdf, log_obs_density, theta, nsim, L, seed) {
+  .Call("_bssmb200_loglik_sde", y, x0, positive, .b200_id(drift), diffusion, ddiffusion, log_prior_pdf,
+        log_obs_density, theta, nsim, L, seed)
+}
+stratified_sample <- function(p, r, N) .Call("_bssmb200_stratified_sample", as.numeric(p), as.numeric(r), as.integer(N))
+
 # check_intmax caps particles at 1e5 (R/check_arguments.R:407-418); the GPU path lifts it
 for (f in c("bsf", "bsf_smoother", "psi_smoother", "nongaussian_loglik", "suggest_n_nongaussian",
-            "postcorrection_nongaussian")) {
+            "postcorrection_nongaussian", "bsf_nlg", "bsf_smoother_nlg", "psi_smoother_nlg",
+            "postcorrection_nonlinear", "bsf_sde", "bsf_smoother_sde", "loglik_sde", "stratified_sample")) {
   fn <- get(f)
   environment(fn) <- asNamespace("bssm")
   utils::assignInNamespace(f, fn, "bssm")

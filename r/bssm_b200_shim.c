@@ -3,9 +3,9 @@
  * NOT BUILT IN THIS REPOSITORY: it needs R's headers (Rinternals.h), which the
  * build image does not have; tests/test_abi.py only type-checks it with gcc
  * against declaration-only stand-ins (tests/mock_R/).  It is the glue a bssm
- * maintainer adds to reach libbssm_b200.so from R for the ssm_ung family (the
- * ssm_mng / ssm_nlg / ssm_sde entry points follow the same pattern with their
- * own fill_* function); everything it calls is the
+ * maintainer adds to reach libbssm_b200.so from R: the ssm_ung family, the
+ * ssm_nlg / ssm_sde registry models (13 of the 13 entry points of SURVEY.md 8b;
+ * gaussian_psi_smoother stays on bssm's Kalman path); everything it calls is the
  * plain C ABI of include/bssm_b200.h, which IS built and tested here (through
  * ctypes, tests/test_gpu_*.py).  Build inside an R installation with
  *   R CMD SHLIB bssm_b200_shim.c -I../include -L../bssm_b200/csrc -lbssm_b200
@@ -234,6 +234,212 @@ SEXP _bssmb200_postcorrection_nongaussian(SEXP model_, SEXP model_type_, SEXP ou
   return res;
 }
 
+
+/* ---------------------------------------------------------------- ssm_nlg / ssm_sde
+ * The reference passes these model classes as compiled function pointers (externalptr arguments Z, H,
+ * T, R, Zg, Tg, a1, P1, log_prior_pdf; drift / diffusion / ddiffusion / log_obs_density for ssm_sde).
+ * Host function pointers cannot run in a kernel: the sibling R file (r/bssm_b200.R) puts the REGISTRY
+ * ID of the shipped example model (BSSM_NLG_* / BSSM_SDE_*, include/bssm_b200.h) into the first
+ * pointer argument and passes the others through untouched, so that the argument lists stay those of
+ * R/RcppExports.R. */
+static void fill_nlg(SEXP y, SEXP id_, SEXP theta, SEXP known_params, SEXP n_states, SEXP n_etas, bssm_nlg_model* M) {
+  memset(M, 0, sizeof(*M));
+  if (TYPEOF(id_) != INTSXP && TYPEOF(id_) != REALSXP) error("bssm_b200: ssm_nlg needs a registry model id in place of the Z pointer");
+  M->model_id = asInteger(id_);
+  M->p = INTEGER(getAttrib(y, R_DimSymbol))[0]; /* R passes t(model$y): p x n */
+  M->n = INTEGER(getAttrib(y, R_DimSymbol))[1];
+  M->m = asInteger(n_states); M->k = asInteger(n_etas);
+  M->y = REAL(y);
+  M->theta = REAL(theta); M->n_theta = (int)XLENGTH(theta);
+  M->known_params = REAL(known_params); M->n_known = (int)XLENGTH(known_params);
+}
+static SEXP filter_result(SEXP at, SEXP att, SEXP Pt, SEXP Ptt, SEXP w, double loglik, SEXP alpha) {
+  const char* nm[] = {"at", "att", "Pt", "Ptt", "weights", "logLik", "alpha", ""};
+  SEXP res = PROTECT(mkNamed(VECSXP, nm));
+  SET_VECTOR_ELT(res, 0, at); SET_VECTOR_ELT(res, 1, att); SET_VECTOR_ELT(res, 2, Pt); SET_VECTOR_ELT(res, 3, Ptt);
+  SET_VECTOR_ELT(res, 4, w); SET_VECTOR_ELT(res, 5, ScalarReal(loglik)); SET_VECTOR_ELT(res, 6, alpha);
+  UNPROTECT(1);
+  return res;
+}
+static SEXP smoother_result(SEXP ah, SEXP Vt, SEXP w, double loglik, SEXP alpha) {
+  const char* nm[] = {"alphahat", "Vt", "weights", "logLik", "alpha", ""};
+  SEXP res = PROTECT(mkNamed(VECSXP, nm));
+  SET_VECTOR_ELT(res, 0, ah); SET_VECTOR_ELT(res, 1, Vt); SET_VECTOR_ELT(res, 2, w);
+  SET_VECTOR_ELT(res, 3, ScalarReal(loglik)); SET_VECTOR_ELT(res, 4, alpha);
+  UNPROTECT(1);
+  return res;
+}
+static void warn_stop(double loglik) {
+  if (!R_FINITE(loglik)) warning("Particle filtering stopped prematurely due to nonfinite log-likelihood.");
+}
+
+/* bsf_nlg(y, Z, H, T, R, Zg, Tg, a1, P1, theta, log_prior_pdf, known_params, known_tv_params, n_states,
+ *         n_etas, time_varying, nsim, seed): src/R_bootstrap_filter.cpp:461-507 */
+SEXP _bssmb200_bsf_nlg(SEXP y, SEXP Z, SEXP H, SEXP T, SEXP R, SEXP Zg, SEXP Tg, SEXP a1, SEXP P1, SEXP theta,
+                       SEXP log_prior_pdf, SEXP known_params, SEXP known_tv_params, SEXP n_states, SEXP n_etas,
+                       SEXP time_varying, SEXP nsim_, SEXP seed_) {
+  bssm_nlg_model M;
+  fill_nlg(y, Z, theta, known_params, n_states, n_etas, &M);
+  const int n = M.n, m = M.m;
+  unsigned N = (unsigned)asInteger(nsim_);
+  SEXP at = PROTECT(allocMatrix(REALSXP, m, n + 1)), att = PROTECT(allocMatrix(REALSXP, m, n));
+  SEXP Pt = PROTECT(alloc3DArray(REALSXP, m, m, n + 1)), Ptt = PROTECT(alloc3DArray(REALSXP, m, m, n));
+  SEXP w = PROTECT(allocMatrix(REALSXP, N, n + 1)), alpha = PROTECT(alloc3DArray(REALSXP, m, n + 1, N));
+  bssm_filter_out out;
+  memset(&out, 0, sizeof(out));
+  out.at = REAL(at); out.att = REAL(att); out.Pt = REAL(Pt); out.Ptt = REAL(Ptt); out.weights = REAL(w); out.alpha = REAL(alpha);
+  check_rc(bssm_b200_bsf_nlg(&M, N, (unsigned)asInteger(seed_), &out));
+  warn_stop(out.loglik);
+  SEXP res = filter_result(at, att, Pt, Ptt, w, out.loglik, alpha);
+  UNPROTECT(6);
+  return res;
+}
+
+/* bsf_smoother_nlg(same 18 arguments): src/R_bootstrap_filter.cpp:509-551 */
+SEXP _bssmb200_bsf_smoother_nlg(SEXP y, SEXP Z, SEXP H, SEXP T, SEXP R, SEXP Zg, SEXP Tg, SEXP a1, SEXP P1, SEXP theta,
+                                SEXP log_prior_pdf, SEXP known_params, SEXP known_tv_params, SEXP n_states,
+                                SEXP n_etas, SEXP time_varying, SEXP nsim_, SEXP seed_) {
+  bssm_nlg_model M;
+  fill_nlg(y, Z, theta, known_params, n_states, n_etas, &M);
+  const int n = M.n, m = M.m;
+  unsigned N = (unsigned)asInteger(nsim_);
+  SEXP ah = PROTECT(allocMatrix(REALSXP, m, n + 1)), Vt = PROTECT(alloc3DArray(REALSXP, m, m, n + 1));
+  SEXP w = PROTECT(allocMatrix(REALSXP, N, n + 1)), alpha = PROTECT(alloc3DArray(REALSXP, m, n + 1, N));
+  bssm_filter_out out;
+  memset(&out, 0, sizeof(out));
+  out.alphahat = REAL(ah); out.Vt = REAL(Vt); out.weights = REAL(w); out.alpha = REAL(alpha);
+  check_rc(bssm_b200_bsf_smoother_nlg(&M, N, (unsigned)asInteger(seed_), &out));
+  warn_stop(out.loglik);
+  SEXP res = smoother_result(ah, Vt, w, out.loglik, alpha);
+  UNPROTECT(4);
+  return res;
+}
+
+/* psi_smoother_nlg(the 16 model arguments, nsim, seed, max_iter, conv_tol, iekf_iter): src/R_psi.cpp:173-221 */
+SEXP _bssmb200_psi_smoother_nlg(SEXP y, SEXP Z, SEXP H, SEXP T, SEXP R, SEXP Zg, SEXP Tg, SEXP a1, SEXP P1, SEXP theta,
+                                SEXP log_prior_pdf, SEXP known_params, SEXP known_tv_params, SEXP n_states,
+                                SEXP n_etas, SEXP time_varying, SEXP nsim_, SEXP seed_, SEXP max_iter_,
+                                SEXP conv_tol_, SEXP iekf_iter_) {
+  bssm_nlg_model M;
+  fill_nlg(y, Z, theta, known_params, n_states, n_etas, &M);
+  const int n = M.n, m = M.m;
+  unsigned N = (unsigned)asInteger(nsim_);
+  SEXP ah = PROTECT(allocMatrix(REALSXP, m, n + 1)), Vt = PROTECT(alloc3DArray(REALSXP, m, m, n + 1));
+  SEXP w = PROTECT(allocMatrix(REALSXP, N, n + 1)), alpha = PROTECT(alloc3DArray(REALSXP, m, n + 1, N));
+  bssm_filter_out out;
+  memset(&out, 0, sizeof(out));
+  out.alphahat = REAL(ah); out.Vt = REAL(Vt); out.weights = REAL(w); out.alpha = REAL(alpha);
+  check_rc(bssm_b200_psi_smoother_nlg(&M, N, (unsigned)asInteger(seed_), (unsigned)asInteger(max_iter_),
+                                      asReal(conv_tol_), (unsigned)asInteger(iekf_iter_), &out));
+  warn_stop(out.loglik);
+  SEXP res = smoother_result(ah, Vt, w, out.loglik, alpha);
+  UNPROTECT(4);
+  return res;
+}
+
+/* postcorrection_nonlinear(the 16 model arguments, output_type, nsim, seed, n_threads, is_type, counts,
+ *                          theta, modes): src/R_postcorrection.cpp:252-317 */
+SEXP _bssmb200_postcorrection_nonlinear(SEXP y, SEXP Z, SEXP H, SEXP T, SEXP R, SEXP Zg, SEXP Tg, SEXP a1, SEXP P1,
+                                        SEXP theta_init, SEXP log_prior_pdf, SEXP known_params, SEXP known_tv_params,
+                                        SEXP n_states, SEXP n_etas, SEXP time_varying, SEXP output_type_, SEXP nsim_,
+                                        SEXP seed_, SEXP n_threads_, SEXP is_type_, SEXP counts_, SEXP theta_,
+                                        SEXP modes_) {
+  bssm_nlg_model M;
+  fill_nlg(y, Z, theta_init, known_params, n_states, n_etas, &M);
+  const int n = M.n, m = M.m;
+  int n_stored = (int)XLENGTH(counts_), n_par = INTEGER(getAttrib(theta_, R_DimSymbol))[0];
+  int is_type = asInteger(is_type_), output_type = asInteger(output_type_);
+  R_xlen_t nd = 0;
+  for (int i = 0; i < n_stored; i++) nd += is_type == 3 ? INTEGER(counts_)[i] : 1;
+  SEXP w = PROTECT(allocVector(REALSXP, nd)), post = PROTECT(allocVector(REALSXP, nd));
+  SEXP alpha = PROTECT(output_type == 1 ? alloc3DArray(REALSXP, n + 1, m, (int)nd) : allocVector(REALSXP, 0));
+  SEXP ah = PROTECT(output_type == 2 ? allocMatrix(REALSXP, n + 1, m) : allocVector(REALSXP, 0));
+  SEXP Vt = PROTECT(output_type == 2 ? alloc3DArray(REALSXP, m, m, n + 1) : allocVector(REALSXP, 0));
+  bssm_postcorr_out out;
+  memset(&out, 0, sizeof(out));
+  out.weights = REAL(w); out.posterior = REAL(post);
+  if (output_type == 1) out.alpha = REAL(alpha);
+  if (output_type == 2) { out.alphahat = REAL(ah); out.Vt = REAL(Vt); }
+  check_rc(bssm_b200_postcorrection_nonlinear(&M, output_type, (unsigned)asInteger(nsim_), (unsigned)asInteger(seed_),
+                                              (unsigned)asInteger(n_threads_), is_type, (const uint32_t*)INTEGER(counts_),
+                                              REAL(theta_), (unsigned)n_par, REAL(modes_), (unsigned)n_stored, 0, 0, &out));
+  const char* nm[] = {"alpha", "alphahat", "Vt", "weights", "posterior", ""};
+  SEXP res = PROTECT(mkNamed(VECSXP, nm));
+  SET_VECTOR_ELT(res, 0, alpha); SET_VECTOR_ELT(res, 1, ah); SET_VECTOR_ELT(res, 2, Vt);
+  SET_VECTOR_ELT(res, 3, w); SET_VECTOR_ELT(res, 4, post);
+  UNPROTECT(6);
+  return res;
+}
+
+static void fill_sde(SEXP y, SEXP x0, SEXP positive, SEXP id_, SEXP theta, bssm_sde_model* M) {
+  memset(M, 0, sizeof(*M));
+  if (TYPEOF(id_) != INTSXP && TYPEOF(id_) != REALSXP) error("bssm_b200: ssm_sde needs a registry model id in place of the drift pointer");
+  M->model_id = asInteger(id_);
+  M->n = (int)XLENGTH(y); M->y = REAL(y);
+  M->theta = REAL(theta); M->n_theta = (int)XLENGTH(theta);
+  M->x0 = asReal(x0); M->positive = asLogical(positive);
+}
+
+/* bsf_sde(y, x0, positive, drift, diffusion, ddiffusion, log_prior_pdf, log_obs_density, theta, nsim, L, seed):
+ * src/R_sde.cpp:35-72.  att / Ptt have n + 1 columns for SDE models (the last one zero), as in the reference. */
+SEXP _bssmb200_bsf_sde(SEXP y, SEXP x0, SEXP positive, SEXP drift, SEXP diffusion, SEXP ddiffusion, SEXP log_prior_pdf,
+                       SEXP log_obs_density, SEXP theta, SEXP nsim_, SEXP L_, SEXP seed_) {
+  bssm_sde_model M;
+  fill_sde(y, x0, positive, drift, theta, &M);
+  const int n = M.n;
+  unsigned N = (unsigned)asInteger(nsim_);
+  SEXP at = PROTECT(allocMatrix(REALSXP, 1, n + 1)), att = PROTECT(allocMatrix(REALSXP, 1, n + 1));
+  SEXP Pt = PROTECT(alloc3DArray(REALSXP, 1, 1, n + 1)), Ptt = PROTECT(alloc3DArray(REALSXP, 1, 1, n + 1));
+  SEXP w = PROTECT(allocMatrix(REALSXP, N, n + 1)), alpha = PROTECT(alloc3DArray(REALSXP, 1, n + 1, N));
+  memset(REAL(att), 0, sizeof(double) * (n + 1)); memset(REAL(Ptt), 0, sizeof(double) * (n + 1));
+  bssm_filter_out out;
+  memset(&out, 0, sizeof(out));
+  out.at = REAL(at); out.att = REAL(att); out.Pt = REAL(Pt); out.Ptt = REAL(Ptt); out.weights = REAL(w); out.alpha = REAL(alpha);
+  check_rc(bssm_b200_bsf_sde(&M, N, (unsigned)asInteger(L_), (unsigned)asInteger(seed_), &out));
+  warn_stop(out.loglik);
+  SEXP res = filter_result(at, att, Pt, Ptt, w, out.loglik, alpha);
+  UNPROTECT(6);
+  return res;
+}
+
+/* bsf_smoother_sde(same 12 arguments): src/R_sde.cpp:75-111 */
+SEXP _bssmb200_bsf_smoother_sde(SEXP y, SEXP x0, SEXP positive, SEXP drift, SEXP diffusion, SEXP ddiffusion,
+                                SEXP log_prior_pdf, SEXP log_obs_density, SEXP theta, SEXP nsim_, SEXP L_, SEXP seed_) {
+  bssm_sde_model M;
+  fill_sde(y, x0, positive, drift, theta, &M);
+  const int n = M.n;
+  unsigned N = (unsigned)asInteger(nsim_);
+  SEXP ah = PROTECT(allocMatrix(REALSXP, 1, n + 1)), Vt = PROTECT(alloc3DArray(REALSXP, 1, 1, n + 1));
+  SEXP w = PROTECT(allocMatrix(REALSXP, N, n + 1)), alpha = PROTECT(alloc3DArray(REALSXP, 1, n + 1, N));
+  bssm_filter_out out;
+  memset(&out, 0, sizeof(out));
+  out.alphahat = REAL(ah); out.Vt = REAL(Vt); out.weights = REAL(w); out.alpha = REAL(alpha);
+  check_rc(bssm_b200_bsf_smoother_sde(&M, N, (unsigned)asInteger(L_), (unsigned)asInteger(seed_), &out));
+  warn_stop(out.loglik);
+  SEXP res = smoother_result(ah, Vt, w, out.loglik, alpha);
+  UNPROTECT(4);
+  return res;
+}
+
+/* loglik_sde(same 12 arguments): src/R_sde.cpp:10-32 -- nothing but the scalar crosses PCIe */
+SEXP _bssmb200_loglik_sde(SEXP y, SEXP x0, SEXP positive, SEXP drift, SEXP diffusion, SEXP ddiffusion, SEXP log_prior_pdf,
+                          SEXP log_obs_density, SEXP theta, SEXP nsim_, SEXP L_, SEXP seed_) {
+  bssm_sde_model M;
+  fill_sde(y, x0, positive, drift, theta, &M);
+  double loglik = 0.0;
+  check_rc(bssm_b200_loglik_sde(&M, (unsigned)asInteger(nsim_), (unsigned)asInteger(L_), (unsigned)asInteger(seed_), &loglik));
+  return ScalarReal(loglik);
+}
+
+/* stratified_sample(p, r, N): src/stratified_sample.cpp:9-28 (unit hook, R/RcppExports.R:228) */
+SEXP _bssmb200_stratified_sample(SEXP p, SEXP r, SEXP N_) {
+  unsigned N = (unsigned)asInteger(N_);
+  SEXP xp = PROTECT(allocVector(INTSXP, N));
+  check_rc(bssm_b200_stratified_sample(REAL(p), (unsigned)XLENGTH(p), REAL(r), N, (uint32_t*)INTEGER(xp)));
+  UNPROTECT(1);
+  return xp;
+}
+
 static const R_CallMethodDef CallEntries[] = {
   {"_bssmb200_bsf", (DL_FUNC)&_bssmb200_bsf, 5},
   {"_bssmb200_psi_smoother", (DL_FUNC)&_bssmb200_psi_smoother, 4},
@@ -241,6 +447,14 @@ static const R_CallMethodDef CallEntries[] = {
   {"_bssmb200_nongaussian_loglik", (DL_FUNC)&_bssmb200_nongaussian_loglik, 5},
   {"_bssmb200_suggest_n_nongaussian", (DL_FUNC)&_bssmb200_suggest_n_nongaussian, 6},
   {"_bssmb200_postcorrection_nongaussian", (DL_FUNC)&_bssmb200_postcorrection_nongaussian, 10},
+  {"_bssmb200_bsf_nlg", (DL_FUNC)&_bssmb200_bsf_nlg, 18},
+  {"_bssmb200_bsf_smoother_nlg", (DL_FUNC)&_bssmb200_bsf_smoother_nlg, 18},
+  {"_bssmb200_psi_smoother_nlg", (DL_FUNC)&_bssmb200_psi_smoother_nlg, 21},
+  {"_bssmb200_postcorrection_nonlinear", (DL_FUNC)&_bssmb200_postcorrection_nonlinear, 24},
+  {"_bssmb200_bsf_sde", (DL_FUNC)&_bssmb200_bsf_sde, 12},
+  {"_bssmb200_bsf_smoother_sde", (DL_FUNC)&_bssmb200_bsf_smoother_sde, 12},
+  {"_bssmb200_loglik_sde", (DL_FUNC)&_bssmb200_loglik_sde, 12},
+  {"_bssmb200_stratified_sample", (DL_FUNC)&_bssmb200_stratified_sample, 3},
   {NULL, NULL, 0}
 };
 

@@ -11,6 +11,7 @@ extern SEXP R_NilValue, R_NamesSymbol, R_DimSymbol;
 SEXP Rf_getAttrib(SEXP, SEXP);
 #define getAttrib Rf_getAttrib
 R_xlen_t XLENGTH(SEXP);
+int TYPEOF(SEXP);
 SEXP STRING_ELT(SEXP, R_xlen_t);
 SEXP VECTOR_ELT(SEXP, R_xlen_t);
 SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP);
