@@ -1106,7 +1106,7 @@ int job_common(bssm_b200_job* J, int kind, int n, int m, int k, uint32_t nsim, u
 // registry models of ssm_nlg: shapes and parameter counts
 static int nlg_state_dim(const bssm_nlg_model* M) { return M->model_id == BSSM_NLG_GROWTH ? 2 : 1; }
 static int nlg_n_theta(const bssm_nlg_model* M) {
-  return M->model_id == BSSM_NLG_AR_EXP ? 4 : (M->model_id == BSSM_NLG_SIN_EXP ? 2 : 3);
+  return M->model_id == BSSM_NLG_AR_EXP ? 4 : (M->model_id == BSSM_NLG_SIN_EXP ? 2 : (M->model_id == BSSM_NLG_LINEAR_GAUSSIAN ? 1 : 3));
 }
 static int check_nlg_model(const bssm_nlg_model* M) {
   if (M->model_id == BSSM_NLG_GROWTH) {
@@ -1124,7 +1124,13 @@ static int check_nlg_model(const bssm_nlg_model* M) {
       return fail(BSSM_B200_ERR_ARG, "sin_exp model: p = 1, m = 1, k = 1, 2 parameters (log H, log R)");
     return 0;
   }
-  return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_nlg: unknown model_id (registry: BSSM_NLG_GROWTH, BSSM_NLG_AR_EXP, BSSM_NLG_SIN_EXP)");
+  if (M->model_id == BSSM_NLG_LINEAR_GAUSSIAN) {
+    if (M->p != 1 || M->m != 1 || M->k != 1 || M->n_theta < 1)
+      return fail(BSSM_B200_ERR_ARG, "linear_gaussian model: p = 1, m = 1, k = 1, 1 parameter (log H)");
+    return 0;
+  }
+  return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_nlg: unknown model_id (registry: BSSM_NLG_GROWTH, BSSM_NLG_AR_EXP, BSSM_NLG_SIN_EXP, "
+                                         "BSSM_NLG_LINEAR_GAUSSIAN)");
 }
 
 // everything of NlgParams that depends on theta / known_params (np.n and np.y stay): the registry
@@ -1137,6 +1143,12 @@ static void fill_nlg_params(const bssm_nlg_model* M, int method, pf::NlgParams& 
     psd_chol_host(&P1, 1, np.LP1);
     np.mu = M->theta[0]; np.rho = M->theta[1];
     np.H = pf_exp(M->theta[3]); np.R0 = e;
+  } else if (M->model_id == BSSM_NLG_LINEAR_GAUSSIAN) { // a1 = 0, P1 = 1, R = 1, theta = (log H), R/cpp_example_models.R:519-553
+    const double P1 = 1.0;
+    np.a1[0] = 0.0;
+    psd_chol_host(&P1, 1, np.LP1);
+    np.mu = 0.0; np.rho = 1.0; // T_fn(alpha) = alpha = mu (1 - rho) + rho alpha exactly
+    np.H = pf_exp(M->theta[0]); np.R0 = 1.0;
   } else if (M->model_id == BSSM_NLG_SIN_EXP) { // a1 = 0, P1 = 1, theta = (log H, log R), R/cpp_example_models.R:640-662
     const double P1 = 1.0;
     np.a1[0] = 0.0;
@@ -1241,6 +1253,7 @@ static void pack_nlg_step(const pfga::NlgApprox& ga, const double* y, int m, int
       c[16] = ga.f_approx[t - 1].var1;
       c[21] = ga.f_true[t - 1].var1;
       c[26] = ga.fn.theta[0]; c[27] = ga.fn.theta[1]; // ar_exp: T_fn = mu (1 - rho) + rho alpha
+      if (ga.fn.model_id == BSSM_NLG_LINEAR_GAUSSIAN) { c[26] = 0.0; c[27] = 1.0; } // T_fn(alpha) = alpha
     } else {
       for (size_t e = 0; e < mm; ++e) {
         c[16 + e] = ga.f_approx[t - 1].rooti[e];

@@ -70,10 +70,16 @@ struct NlgGrowthBsf : GaussStep<NlgGrowthBsf, 2, 2, 2> {
 // ------------------------------------------------------------ ssm_nlg: ar_exp
 // AR(1) state observed through its exponential (nlg_ar_exp, R/cpp_example_models.R:194-335):
 // alpha_{t+1} = mu (1 - rho) + rho alpha_t + e^{theta2} eta, y_t ~ N(e^{alpha_t}, e^{2 theta3}).
-// SINE = true: the nlg_sin_exp model (R/cpp_example_models.R:635-757), alpha_{t+1} = sin(alpha_t) + e^{theta1} eta
-// with the same observation equation, a1 = 0, P1 = 1.
-template <bool SINE>
-struct Nlg1Bsf : GaussStep<Nlg1Bsf<SINE>, 1, 1, 1> {
+// KIND 1: the nlg_sin_exp model (R/cpp_example_models.R:635-757), alpha_{t+1} = sin(alpha_t) + e^{theta1} eta
+// with the same observation equation, a1 = 0, P1 = 1.  KIND 2: nlg_linear_gaussian (:512-634), the random walk
+// alpha_{t+1} = alpha_t + eta observed directly, y_t ~ N(alpha_t, e^{2 theta0}) (mu = 0, rho = 1, R = 1 in NlgParams).
+enum { NLG1_AR_EXP = 0, NLG1_SIN_EXP = 1, NLG1_LINEAR = 2 };
+template <int KIND> __device__ __forceinline__ double nlg1_Z(double a) { return KIND == NLG1_LINEAR ? a : pf_exp(a); }
+template <int KIND> __device__ __forceinline__ double nlg1_T(double a, double mu, double rho) {
+  return KIND == NLG1_SIN_EXP ? pf_sin(a) : (mu * (1 - rho) + rho * a);
+}
+template <int KIND>
+struct Nlg1Bsf : GaussStep<Nlg1Bsf<KIND>, 1, 1, 1> {
   static constexpr int M = 1, KI = 1, KP = 1;
   typedef NlgParams Params;
   const NlgParams& mp;
@@ -85,17 +91,18 @@ struct Nlg1Bsf : GaussStep<Nlg1Bsf<SINE>, 1, 1, 1> {
   __device__ bool observed(int t) const { return pf_isfinite(mp.y[t]); }
   __device__ void begin_weight(int t) { y = mp.y[t]; }
   __device__ double logw(const double* x) const {
-    const double q = (y - pf_exp(x[0])) / mp.H;
+    const double q = (y - nlg1_Z<KIND>(x[0])) / mp.H;
     return -0.5 * (mp.wconst + q * q);
   }
   __device__ void begin_step(int) {}
   __device__ void propagate(const double* xa, const double* z, double* x) const {
-    const double tf = SINE ? pf_sin(xa[0]) : (mp.mu * (1 - mp.rho) + mp.rho * xa[0]);
+    const double tf = nlg1_T<KIND>(xa[0], mp.mu, mp.rho);
     x[0] = tf + mp.R0 * z[0]; // T_fn(...) + R_fn(...) * uk
   }
 };
-typedef Nlg1Bsf<false> NlgArExpBsf;
-typedef Nlg1Bsf<true> NlgSinExpBsf;
+typedef Nlg1Bsf<NLG1_AR_EXP> NlgArExpBsf;
+typedef Nlg1Bsf<NLG1_SIN_EXP> NlgSinExpBsf;
+typedef Nlg1Bsf<NLG1_LINEAR> NlgLinearBsf;
 
 // ------------------------------------------------- ssm_nlg: growth, psi-APF
 // ssm_nlg::psi_filter src/model_ssm_nlg.cpp:971-1063 with log_weights :880-935.  The
@@ -228,8 +235,8 @@ struct NlgGrowthPsi : GaussStep<NlgGrowthPsi, 2, 2, 2> {
 //   [6] Z_t  [10] C_{t-1}  [12] T_{t-1}  [16] RR_{t-1} (approximate variance)  [20] log 2pi + log RR
 //   [21] R R' (true variance)  [25] log 2pi + log(R R')  [26..27] (mu, rho) of the true transition
 // (for one state dmvnorm takes its scalar branch, src/dmvnorm.cpp:9-16)
-template <bool SINE>
-struct Nlg1Psi : GaussStep<Nlg1Psi<SINE>, 1, 1, 1> {
+template <int KIND>
+struct Nlg1Psi : GaussStep<Nlg1Psi<KIND>, 1, 1, 1> {
   static constexpr int M = 1, KI = 1, KP = 1;
   typedef NlgPsiParams Params;
   const NlgPsiParams& mp;
@@ -256,7 +263,7 @@ struct Nlg1Psi : GaussStep<Nlg1Psi<SINE>, 1, 1, 1> {
     y = c[0]; c_sd = c[1]; H = c[2]; c_var = c[3]; HH = c[4]; D = c[5]; Z0 = c[6]; scale = c[8];
   }
   __device__ double logw(const double* x) const {
-    const double q = (y - pf_exp(x[0])) / H;
+    const double q = (y - nlg1_Z<KIND>(x[0])) / H;
     const double tru = -0.5 * (c_sd + q * q);
     const double mean = D + Z0 * x[0];
     const double app = -0.5 * (c_var + (y - mean) * (y - mean) / HH);
@@ -279,14 +286,15 @@ struct Nlg1Psi : GaussStep<Nlg1Psi<SINE>, 1, 1, 1> {
   __device__ double trans_term(const double* xa, const double* x) const {
     if (!has_prev) return 0.0;
     const double am = Ca + Ta * xa[0];
-    const double tm = SINE ? pf_sin(xa[0]) : (mu * (1 - rho) + rho * xa[0]); // T_fn of the true model
+    const double tm = nlg1_T<KIND>(xa[0], mu, rho); // T_fn of the true model
     const double app = -0.5 * (ca + (x[0] - am) * (x[0] - am) / va);
     const double tru = -0.5 * (ct + (x[0] - tm) * (x[0] - tm) / vt);
     return app - tru;
   }
 };
-typedef Nlg1Psi<false> NlgArExpPsi;
-typedef Nlg1Psi<true> NlgSinExpPsi;
+typedef Nlg1Psi<NLG1_AR_EXP> NlgArExpPsi;
+typedef Nlg1Psi<NLG1_SIN_EXP> NlgSinExpPsi;
+typedef Nlg1Psi<NLG1_LINEAR> NlgLinearPsi;
 
 // ---------------------------------------------- ssm_nlg: EKF particle filter
 // ssm_nlg::ekf_filter src/model_ssm_nlg.cpp:1150-1260 (van der Merwe et al.): every particle runs
@@ -325,6 +333,14 @@ template <> struct NlgDev<2> { // sin_exp
   static __device__ __forceinline__ void RR(const NlgParams& p, double* rr) { rr[0] = p.R0 * p.R0; }
   static __device__ __forceinline__ double Z_fn(const double* x) { return pf_exp(x[0]); }
   static __device__ __forceinline__ void Z_gn(const double* x, double* Zg) { Zg[0] = pf_exp(x[0]); }
+};
+
+template <> struct NlgDev<3> { // linear_gaussian
+  static constexpr int M = 1;
+  static __device__ __forceinline__ void T_fn(const NlgParams&, const double* x, double* an) { an[0] = x[0]; }
+  static __device__ __forceinline__ void RR(const NlgParams& p, double* rr) { rr[0] = p.R0 * p.R0; }
+  static __device__ __forceinline__ double Z_fn(const double* x) { return x[0]; }
+  static __device__ __forceinline__ void Z_gn(const double*, double* Zg) { Zg[0] = 1.0; }
 };
 
 template <int MODEL>

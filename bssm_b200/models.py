@@ -231,9 +231,11 @@ class NlgModel:
     registry instead of compiled function pointers: model="growth" is the
     nlg_growth example of R/cpp_example_models.R:336-511, model="ar_exp" the nlg_ar_exp
     example of :194-335 (theta = mu, rho, log sigma, log H; no known parameters), model="sin_exp"
-    the nlg_sin_exp example of :635-757 (theta = log H, log R)."""
+    the nlg_sin_exp example of :635-757 (theta = log H, log R), model="linear_gaussian" the
+    nlg_linear_gaussian example of :512-634 (theta = log H; a random walk observed with noise)."""
     REGISTRY = {"growth": (0, 2, 2, 1, 3, 6), "ar_exp": (1, 1, 1, 1, 4, 0),
-                "sin_exp": (2, 1, 1, 1, 2, 0)}  # id, m, k, p, n_theta, n_known
+                "sin_exp": (2, 1, 1, 1, 2, 0),
+                "linear_gaussian": (3, 1, 1, 1, 1, 0)}  # id, m, k, p, n_theta, n_known
 
     def __init__(self, y, model, theta, known_params=(), iekf_iter=0):
         if model not in self.REGISTRY:

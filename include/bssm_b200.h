@@ -230,6 +230,9 @@ enum {
   ,
   BSSM_NLG_SIN_EXP = 2 /* sine transition observed through exp(alpha), R/cpp_example_models.R:635-757:
                         * m = k = p = 1, theta = (log H, log R), a1 = 0, P1 = 1 */
+  ,
+  BSSM_NLG_LINEAR_GAUSSIAN = 3 /* random walk observed with noise, R/cpp_example_models.R:512-634:
+                        * m = k = p = 1, theta = (log H), a1 = 0, P1 = 1, R = 1, Z(alpha) = T(alpha) = alpha */
 };
 enum {
   BSSM_SDE_GBM = 0,       /* geometric Brownian motion, R/cpp_example_models.R:109-193 */

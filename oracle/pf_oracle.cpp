@@ -1254,23 +1254,27 @@ static double dmvnorm1(double x, double mean, double sigma) {
 /* nlg_ar_exp user functions, R/cpp_example_models.R:200-262: theta = (mu, rho, log sigma, log H) */
 struct ArExp {
   const double* theta;
-  bool sine; /* nlg_sin_exp, R/cpp_example_models.R:640-690: a1 = 0, P1 = 1, theta = (log H, log R), T_fn = sin */
-  double a1_fn() const { return sine ? 0.0 : theta[0]; }
+  int kind; /* model_id: 1 = nlg_ar_exp;
+             * 2 = nlg_sin_exp, R/cpp_example_models.R:640-690: a1 = 0, P1 = 1, theta = (log H, log R), T_fn = sin;
+             * 3 = nlg_linear_gaussian, :519-580: a1 = 0, P1 = 1, theta = (log H), R = 1, Z_fn = T_fn = identity */
+  double a1_fn() const { return kind != 1 ? 0.0 : theta[0]; }
   double P1_fn() const {
-    if (sine) return 1.0;
+    if (kind != 1) return 1.0;
     double e = pf_exp(theta[2]);
     return e * e / (1 - theta[1] * theta[1]); /* pow(exp(.), 2) */
   }
-  double H_fn() const { return sine ? pf_exp(theta[0]) : pf_exp(theta[3]); }
-  double R_fn() const { return sine ? pf_exp(theta[1]) : pf_exp(theta[2]); }
-  double Z_fn(double alpha) const { return pf_exp(alpha); }
-  double T_fn(double alpha) const { return sine ? pf_sin(alpha) : theta[0] * (1 - theta[1]) + theta[1] * alpha; }
+  double H_fn() const { return kind != 1 ? pf_exp(theta[0]) : pf_exp(theta[3]); }
+  double R_fn() const { return kind == 3 ? 1.0 : (kind == 2 ? pf_exp(theta[1]) : pf_exp(theta[2])); }
+  double Z_fn(double alpha) const { return kind == 3 ? alpha : pf_exp(alpha); }
+  double T_fn(double alpha) const {
+    return kind == 3 ? alpha : (kind == 2 ? pf_sin(alpha) : theta[0] * (1 - theta[1]) + theta[1] * alpha);
+  }
 };
 
 /* ssm_nlg::bsf_filter, src/model_ssm_nlg.cpp:1066-1146 for the one-state ar_exp model */
 static double nlg_ar_exp_bsf_filter(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t filter, int arith,
                                     double* alpha, double* weights, uint32_t* indices, int32_t* stopped_at) {
-  ArExp fn{M->theta, M->model_id == BSSM_NLG_SIN_EXP};
+  ArExp fn{M->theta, M->model_id};
   const int n = M->n;
   const size_t N = nsim;
   const double a1 = fn.a1_fn(), P1 = fn.P1_fn();
@@ -1317,7 +1321,7 @@ static double nlg_ar_exp_bsf_filter(const bssm_nlg_model* M, uint32_t nsim, uint
 double orc_nlg_bsf_filter(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed, uint32_t filter, int arith,
                           double* alpha, double* weights, uint32_t* indices, int32_t* stopped_at) {
   *stopped_at = -1;
-  if ((M->model_id == BSSM_NLG_AR_EXP || M->model_id == BSSM_NLG_SIN_EXP) && M->p == 1)
+  if ((M->model_id == BSSM_NLG_AR_EXP || M->model_id == BSSM_NLG_SIN_EXP || M->model_id == BSSM_NLG_LINEAR_GAUSSIAN) && M->p == 1)
     return nlg_ar_exp_bsf_filter(M, nsim, seed, filter, arith, alpha, weights, indices, stopped_at);
   if (M->model_id != BSSM_NLG_GROWTH || M->p != 1) return pf_nan();
   Growth fn{M->theta, M->known_params};
@@ -1388,7 +1392,7 @@ static double nlg_psi_filter_impl(const bssm_nlg_model* M, const double* mode_in
                                   double* alpha, double* weights, uint32_t* indices, double* approx_loglik,
                                   int32_t* stopped_at, double* mode_out) {
   *stopped_at = -1;
-  if (M->model_id < BSSM_NLG_GROWTH || M->model_id > BSSM_NLG_SIN_EXP || M->p != 1) return pf_nan();
+  if (M->model_id < BSSM_NLG_GROWTH || M->model_id > BSSM_NLG_LINEAR_GAUSSIAN || M->p != 1) return pf_nan();
   pfga::NlgApprox ga(M);
   ga.max_iter = (int)max_iter;
   ga.conv_tol = conv_tol;
@@ -1692,7 +1696,7 @@ double orc_nlg_ekf_filter(const bssm_nlg_model* M, uint32_t nsim, uint32_t seed,
   if (M->p != 1) { *stopped_at = -1; return pf_nan(); }
   if (M->model_id == BSSM_NLG_GROWTH)
     return nlg_ekf_filter<2>(M, nsim, seed, filter, arith, alpha, weights, indices, stopped_at);
-  if (M->model_id == BSSM_NLG_AR_EXP || M->model_id == BSSM_NLG_SIN_EXP)
+  if (M->model_id == BSSM_NLG_AR_EXP || M->model_id == BSSM_NLG_SIN_EXP || M->model_id == BSSM_NLG_LINEAR_GAUSSIAN)
     return nlg_ekf_filter<1>(M, nsim, seed, filter, arith, alpha, weights, indices, stopped_at);
   *stopped_at = -1;
   return pf_nan();
@@ -1942,7 +1946,7 @@ int orc_postcorrection_nlg(const bssm_nlg_model* M, int output_type, uint32_t ns
                            int is_type, const uint32_t* counts, const double* theta, uint32_t n_par,
                            const double* modes, uint32_t n_stored, int arith, double* weights, double* posterior,
                            double* alpha, double* alphahat, double* Vt, double* loglik_out) {
-  if (M->model_id < BSSM_NLG_GROWTH || M->model_id > BSSM_NLG_SIN_EXP || M->p != 1) return 1;
+  if (M->model_id < BSSM_NLG_GROWTH || M->model_id > BSSM_NLG_LINEAR_GAUSSIAN || M->p != 1) return 1;
   const size_t n = M->n, n1 = n + 1, m = M->model_id == BSSM_NLG_GROWTH ? 2 : 1;
   std::vector<uint32_t> src, cnt;
   for (uint32_t i = 0; i < n_stored; ++i) {

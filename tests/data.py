@@ -245,3 +245,14 @@ def lg_model(n=80, gen_seed=21, missing=()):
     for t in missing:
         y[t] = np.nan
     return bssm_b200.bsm_lg(y, sd_y=1.0, sd_level=0.3, sd_slope=0.05, P1=np.diag([4.0, 1.0]))
+
+
+def linear_gaussian_model(n=60, gen_seed=17, missing=(), log_H=-0.3):
+    """nlg_linear_gaussian (R/cpp_example_models.R:512-634): alpha_{t+1} = alpha_t + eta, y_t = alpha_t + e^{theta0} eps,
+    a1 = 0, P1 = 1"""
+    rng = np.random.default_rng(gen_seed)
+    a = np.cumsum(np.concatenate([[rng.normal()], rng.normal(size=n - 1)]))
+    y = a + np.exp(log_H) * rng.normal(size=n)
+    for t in missing:
+        y[t] = np.nan
+    return bssm_b200.ssm_nlg(y, "linear_gaussian", theta=[log_H])

@@ -310,3 +310,44 @@ def test_job_set_theta_nlg_sde_matches_fresh_job(engine, case):
         assert not np.array_equal(job.logliks(), ll0)
         fresh.close()
     job.close()
+
+
+def _kalman_loglik_random_walk(y, H):
+    """exact log-likelihood of alpha_{t+1} = alpha_t + eta, y_t = alpha_t + H eps, a1 = 0, P1 = 1 (numpy, independent)"""
+    a, P, ll = 0.0, 1.0, 0.0
+    for yt in y:
+        if np.isfinite(yt):
+            F = P + H * H
+            v = yt - a
+            ll += -0.5 * (np.log(2 * np.pi) + np.log(F) + v * v / F)
+            K = P / F
+            a, P = a + K * v, P - K * P
+        P = P + 1.0
+    return ll
+
+
+def test_linear_gaussian_functor(engine):
+    """the sixth shipped example model, nlg_linear_gaussian (R/cpp_example_models.R:512-634): bootstrap filter,
+    psi-APF and EKF particle filter bit-exact against the oracle; and pinned INDEPENDENTLY of the oracle: for a
+    linear-Gaussian model the psi-APF proposes from the exact smoothing distribution, so its log-likelihood
+    estimate IS the Kalman log-likelihood (up to rounding) whatever the number of particles"""
+    model = data.linear_gaussian_model(70, missing=(11, 12))
+    N = 600
+    ref = orc.nlg_bsf_filter(model, N, seed=3)
+    res = engine.bootstrap_filter(model, N, seed=3, return_indices=True)
+    assert np.array_equal(res["indices"], ref.indices) and res["logLik"] == ref.loglik
+    assert np.array_equal(res["weights"].view(np.uint64), ref.weights.view(np.uint64))
+    refp = orc.nlg_psi_filter(model, N, seed=4)
+    resp = engine.particle_smoother(model, N, method="psi", seed=4, return_indices=True)
+    assert np.array_equal(resp["indices"], refp.indices) and resp["logLik"] == refp.loglik
+    exact = _kalman_loglik_random_walk(model.y, np.exp(model.theta[0]))
+    assert abs(resp["logLik"] - exact) < 1e-8 * abs(exact)
+    assert abs(res["logLik"] - exact) < 1.0  # bootstrap filter: Monte Carlo error only
+    refe = orc.nlg_ekf_filter(model, N, seed=5)
+    rese = engine.FilterJob(model, N, method="ekf", seed=5, out_flags=engine_mod.api.OUT_INDICES)
+    rese.run()
+    be = rese.fetch(0, indices=True)
+    assert np.array_equal(be.indices, refe.indices) and rese.logliks()[0] == refe.loglik
+    rese.close()
+    # for a linear model the EKF proposal is the optimal proposal: its estimate is close to exact as well
+    assert abs(refe.loglik - exact) < 0.5
