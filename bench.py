@@ -271,7 +271,8 @@ def main():
     if world > 1:
         # NCCL's INFO lines (communicator, ranks, NVLS / ring choice) go to STDERR so that stdout stays the
         # one JSON line; BENCH_NCCL_DEBUG=off silences them
-        dbg = os.environ.get("BENCH_NCCL_DEBUG", os.environ.get("NCCL_DEBUG", "INFO"))
+        # (the image exports NCCL_DEBUG=VERSION: it is overridden, not inherited)
+        dbg = os.environ.get("BENCH_NCCL_DEBUG", "INFO")
         if dbg.lower() in ("off", "0", "none"):
             os.environ.pop("NCCL_DEBUG", None)
         else:
