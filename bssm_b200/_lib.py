@@ -155,6 +155,7 @@ def lib():
     L.bssm_b200_postcorrection_nonlinear.argtypes = [
         C.POINTER(NlgModel), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, c_uint32_p, c_double_p,
         C.c_uint32, c_double_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PostcorrOut)]
+    L.bssm_b200_is_correction_bsf_nlg.argtypes = L.bssm_b200_postcorrection_nonlinear.argtypes
     L.bssm_b200_job_create_postcorr_nlg.argtypes = [
         C.POINTER(NlgModel), C.c_uint32, C.c_uint32, C.c_int, c_uint32_p, c_double_p, C.c_uint32, c_double_p,
         C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]

@@ -346,8 +346,9 @@ def post_correct(model, mcmc_output, particles, threads=1, is_type="is2", seed=1
     draw_range = (begin, end) computes only that shard of the (expanded) draws.
 
     sampling_method = "bsf": the correction phase of run_mcmc(..., sampling_method = "bsf")
-    (is_correction_bsf, src/approx_mcmc.cpp:447-518) for m = 1 ung-family models; mcmc_output carries
-    approx_loglik (n_stored) and the weights are exp(loglik_bsf - approx_loglik).
+    (is_correction_bsf, src/approx_mcmc.cpp:447-518) for m = 1 ung-family models and the ssm_nlg
+    registry models; mcmc_output carries approx_loglik (n_stored) and the weights are
+    exp(loglik_bsf - approx_loglik).
 
     ssm_sde models: the correction phase of run_mcmc.ssm_sde (is_correction_bsf on the fine mesh
     L, src/approx_mcmc.cpp:522-591); mcmc_output then carries approx_loglik (n_stored) instead of modes.
@@ -383,7 +384,11 @@ def post_correct(model, mcmc_output, particles, threads=1, is_type="is2", seed=1
     out.weights, out.posterior, out.alpha = dptr(w), dptr(post), dptr(alpha)
     out.alphahat, out.Vt, out.loglik = dptr(ah), dptr(Vt), dptr(ll)
     ms = model.c_struct()
-    if bsf:
+    if bsf and model.cls == "ssm_nlg":
+        check(lib().bssm_b200_is_correction_bsf_nlg(
+            C.byref(ms), ot, N, seed, int(threads), it, uptr(counts), dptr(theta), theta.shape[0],
+            dptr(approx), counts.size, b, e, C.byref(out)))
+    elif bsf:
         tm = theta_map(model)
         check(lib().bssm_b200_is_correction_bsf(
             C.byref(ms), C.byref(tm), ot, N, seed, int(threads), it, uptr(counts), dptr(theta), theta.shape[0],

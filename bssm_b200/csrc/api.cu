@@ -564,6 +564,11 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
   }
   if (J->kind == KIND_NLG && J->method == BSSM_METHOD_EKPF)
     return launch_status(pfl::launch_nlg_ekpf(J->nlg_model_id, fp, J->np, J->geo, nf, J->stream), "nlg ekpf");
+  if (J->kind == KIND_NLG && J->np.draw_blk) {
+    pf::NlgParams np = J->np;
+    np.draw_blk += (size_t)pf::NLG_DRAW_BLOCK * f0;
+    return launch_status(pfl::launch_nlg_bsf_draws(J->nlg_model_id, fp, np, J->geo, nf, J->stream), "nlg bsf (draws)");
+  }
   if (J->kind == KIND_NLG) return launch_status(pfl::launch_nlg_bsf(J->nlg_model_id, fp, J->np, J->geo, nf, J->stream), "nlg bsf");
   if (J->kind == KIND_SDE) {
     pf::SdeParams sp = J->sp;
@@ -1168,8 +1173,10 @@ static void fill_nlg_params(const bssm_nlg_model* M, int method, pf::NlgParams& 
   }
 }
 
+// draw_theta: n_filters columns of n_par parameters, one bootstrap filter each (is_correction_bsf)
 static int create_nlg_job(const bssm_nlg_model* M, int method, uint32_t nsim, uint32_t seed, uint32_t n_filters,
-                          uint32_t first_filter_id, int out_flags, int post, bssm_b200_job** job) {
+                          uint32_t first_filter_id, int out_flags, int post, bssm_b200_job** job,
+                          const double* draw_theta = nullptr, uint32_t n_par = 0) {
   if (!M || !job || !M->y || !M->theta) return fail(BSSM_B200_ERR_ARG, "null argument");
   *job = nullptr;
   int rc = check_nlg_model(M);
@@ -1178,8 +1185,10 @@ static int create_nlg_job(const bssm_nlg_model* M, int method, uint32_t nsim, ui
   const int m = nlg_state_dim(M);
   bssm_b200_job* J = new bssm_b200_job();
   struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
-  rc = job_common(J, KIND_NLG, M->n, m, m, nsim, seed, n_filters, first_filter_id, out_flags, post);
+  rc = job_common(J, KIND_NLG, M->n, m, m, nsim, seed, n_filters, first_filter_id, out_flags,
+                  post > BSSM_POST_SMOOTHER ? BSSM_POST_NONE : post);
   if (rc) return rc;
+  J->post = post; // PICK / SMOOTHER_MERGE: the IS-correction drivers
   J->nlg_model_id = M->model_id;
   if ((rc = J->y.upload(M->y, M->n))) return rc;
   pf::NlgParams& np = J->np;
@@ -1187,6 +1196,23 @@ static int create_nlg_job(const bssm_nlg_model* M, int method, uint32_t nsim, ui
   np.n = M->n; np.y = J->y.p;
   if (method == BSSM_METHOD_EKPF) J->method = BSSM_METHOD_EKPF;
   fill_nlg_params(M, method, np);
+  if (draw_theta) {
+    if (method != BSSM_METHOD_BSF) return fail(BSSM_B200_ERR_UNSUPPORTED, "per-filter theta: bootstrap filter only");
+    std::vector<double> blk((size_t)pf::NLG_DRAW_BLOCK * n_filters);
+    for (uint32_t f = 0; f < n_filters; ++f) {
+      bssm_nlg_model Mi = *M;
+      Mi.theta = draw_theta + (size_t)f * n_par;
+      Mi.n_theta = (int32_t)n_par;
+      pf::NlgParams di = np;
+      fill_nlg_params(&Mi, method, di);
+      double* b = &blk[(size_t)pf::NLG_DRAW_BLOCK * f];
+      b[0] = di.a1[0]; b[1] = di.a1[1];
+      for (int e = 0; e < 4; ++e) b[2 + e] = di.LP1[e];
+      b[6] = di.H; b[7] = di.R0; b[8] = di.R1; b[9] = di.wconst; b[10] = di.mu; b[11] = di.rho;
+    }
+    if ((rc = J->theta_f.upload(blk.data(), blk.size()))) return rc;
+    np.draw_blk = J->theta_f.p;
+  }
   if ((rc = finish_job(J, out_flags, post))) return rc;
   guard.j = nullptr;
   *job = J;
@@ -2358,6 +2384,32 @@ int bssm_b200_is_correction_bsf(const bssm_ung_model* M, const bssm_theta_map* m
         }
         return create_ung_job(M, BSSM_METHOD_BSF, N, seed, nf, d0, 0, post, par.data(), nullptr, J,
                               map->n_xreg > 0 ? &dm : nullptr);
+      },
+      approx_loglik, /*posterior_adds_approx=*/false);
+}
+
+// ------------------------------------------------- is_correction_bsf (ssm_nlg)
+// approx_mcmc::is_correction_bsf<ssm_nlg>, src/approx_mcmc.cpp:442-518: update_model(theta_i), bsf_filter,
+// weight = exp(loglik - approx_loglik_i), posterior = prior + log(weight)
+int bssm_b200_is_correction_bsf_nlg(const bssm_nlg_model* M, int output_type, uint32_t nsim, uint32_t seed,
+                                    uint32_t n_threads, int is_type, const uint32_t* counts, const double* theta,
+                                    uint32_t n_par, const double* approx_loglik, uint32_t n_stored,
+                                    uint32_t draw_begin, uint32_t draw_end, bssm_postcorr_out* out) {
+  if (!M || !counts || !theta || !approx_loglik || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
+  {
+    int rcm = check_nlg_model(M);
+    if (rcm) return rcm;
+    if (n_par < (uint32_t)nlg_n_theta(M)) return fail(BSSM_B200_ERR_ARG, "is_correction_bsf (nonlinear): too few parameters");
+  }
+  return postcorr_multi(
+      n_threads, M->n, nlg_state_dim(M), output_type, nsim, is_type, counts, n_stored, draw_begin, draw_end, out,
+      [&](const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N, int post, bssm_b200_job** J) {
+        const uint32_t nf = d1 - d0;
+        std::vector<double> th((size_t)n_par * nf);
+        for (uint32_t f = 0; f < nf; ++f)
+          memcpy(&th[(size_t)n_par * f], theta + (size_t)dl.src[d0 + f] * n_par, sizeof(double) * n_par);
+        int flags = post == BSSM_POST_NONE ? 0 : (BSSM_OUT_ALPHA | BSSM_OUT_INDICES);
+        return create_nlg_job(M, BSSM_METHOD_BSF, N, seed, nf, d0, flags, post, J, th.data(), n_par);
       },
       approx_loglik, /*posterior_adds_approx=*/false);
 }

@@ -27,6 +27,7 @@ int launch_mng_psi(int m, const pf::FilterParams&, const pf::MngParams&, const G
 int occupancy_mng_bsf(const Geometry&, int* out);
 // k_nlg.cu: ssm_nlg functor registry (growth, ar_exp), bootstrap and psi-APF
 int launch_nlg_bsf(int model_id, const pf::FilterParams&, const pf::NlgParams&, const Geometry&, uint32_t nf, Stream);
+int launch_nlg_bsf_draws(int model_id, const pf::FilterParams&, const pf::NlgParams&, const Geometry&, uint32_t nf, Stream); // k_nlg_draws.cu: one theta per filter
 int launch_nlg_psi(int model_id, const pf::FilterParams&, const pf::NlgPsiParams&, const Geometry&, uint32_t nf, Stream);
 int launch_nlg_ekpf(int model_id, const pf::FilterParams&, const pf::NlgParams&, const Geometry&, uint32_t nf, Stream); // EKF particle filter
 int occupancy_nlg_bsf(const Geometry&, int* out);

@@ -30,14 +30,30 @@ struct NlgParams {
   double mu, rho;     // ar_exp: theta(0), theta(1); its R is R0, its a1 / sqrt(P1) are a1[0] / LP1[0]
   // EKF particle filter only: prior covariance and the EKF update of (a1, P1) with y_0 (host)
   double P1[4], att1[2], L1[4];
+  // is_correction_bsf (src/approx_mcmc.cpp:447-518): one theta per filter.  NLG_DRAW_BLOCK doubles per
+  // filter, (a1[2], LP1[4], H, R0, R1, wconst, mu, rho) = what update_model(theta_i) changes; else null
+  const double* draw_blk;
 };
+constexpr int NLG_DRAW_BLOCK = 12;
+// PerFilter policies copy the launch parameters and overwrite the theta-dependent part with their draw's
+__device__ __forceinline__ void nlg_load_draw(NlgParams& loc, const NlgParams& p, uint32_t f) {
+  loc = p;
+  const double* b = p.draw_blk + (size_t)NLG_DRAW_BLOCK * f;
+  loc.a1[0] = b[0]; loc.a1[1] = b[1];
+  loc.LP1[0] = b[2]; loc.LP1[1] = b[3]; loc.LP1[2] = b[4]; loc.LP1[3] = b[5];
+  loc.H = b[6]; loc.R0 = b[7]; loc.R1 = b[8]; loc.wconst = b[9]; loc.mu = b[10]; loc.rho = b[11];
+}
 
-struct NlgGrowthBsf : GaussStep<NlgGrowthBsf, 2, 2, 2> {
+template <bool PerFilter>
+struct NlgGrowthBsfT : GaussStep<NlgGrowthBsfT<PerFilter>, 2, 2, 2> {
   static constexpr int M = 2, KI = 2, KP = 2;
   typedef NlgParams Params;
+  NlgParams loc;
   const NlgParams& mp;
   double y;
-  __device__ NlgGrowthBsf(const NlgParams& p, uint32_t) : mp(p) {}
+  __device__ NlgGrowthBsfT(const NlgParams& p, uint32_t f) : mp(PerFilter ? loc : p) {
+    if (PerFilter) nlg_load_draw(loc, p, f);
+  }
   __device__ double loglik0() const { return 0.0; }
   __device__ double loglik_end() const { return 0.0; } // normalised densities: no constant afterwards
   __device__ void init(const double* z, double* x) const {
@@ -66,6 +82,8 @@ struct NlgGrowthBsf : GaussStep<NlgGrowthBsf, 2, 2, 2> {
     x[1] = t1 + mp.R1 * z[1];
   }
 };
+typedef NlgGrowthBsfT<false> NlgGrowthBsf;
+typedef NlgGrowthBsfT<true> NlgGrowthBsfDraws;
 
 // ------------------------------------------------------------ ssm_nlg: ar_exp
 // AR(1) state observed through its exponential (nlg_ar_exp, R/cpp_example_models.R:194-335):
@@ -78,13 +96,16 @@ template <int KIND> __device__ __forceinline__ double nlg1_Z(double a) { return 
 template <int KIND> __device__ __forceinline__ double nlg1_T(double a, double mu, double rho) {
   return KIND == NLG1_SIN_EXP ? pf_sin(a) : (mu * (1 - rho) + rho * a);
 }
-template <int KIND>
-struct Nlg1Bsf : GaussStep<Nlg1Bsf<KIND>, 1, 1, 1> {
+template <int KIND, bool PerFilter = false>
+struct Nlg1Bsf : GaussStep<Nlg1Bsf<KIND, PerFilter>, 1, 1, 1> {
   static constexpr int M = 1, KI = 1, KP = 1;
   typedef NlgParams Params;
+  NlgParams loc;
   const NlgParams& mp;
   double y;
-  __device__ Nlg1Bsf(const NlgParams& p, uint32_t) : mp(p) {}
+  __device__ Nlg1Bsf(const NlgParams& p, uint32_t f) : mp(PerFilter ? loc : p) {
+    if (PerFilter) nlg_load_draw(loc, p, f);
+  }
   __device__ double loglik0() const { return 0.0; }
   __device__ double loglik_end() const { return 0.0; }
   __device__ void init(const double* z, double* x) const { x[0] = mp.a1[0] + mp.LP1[0] * z[0]; }
@@ -103,6 +124,9 @@ struct Nlg1Bsf : GaussStep<Nlg1Bsf<KIND>, 1, 1, 1> {
 typedef Nlg1Bsf<NLG1_AR_EXP> NlgArExpBsf;
 typedef Nlg1Bsf<NLG1_SIN_EXP> NlgSinExpBsf;
 typedef Nlg1Bsf<NLG1_LINEAR> NlgLinearBsf;
+typedef Nlg1Bsf<NLG1_AR_EXP, true> NlgArExpBsfDraws;
+typedef Nlg1Bsf<NLG1_SIN_EXP, true> NlgSinExpBsfDraws;
+typedef Nlg1Bsf<NLG1_LINEAR, true> NlgLinearBsfDraws;
 
 // ------------------------------------------------- ssm_nlg: growth, psi-APF
 // ssm_nlg::psi_filter src/model_ssm_nlg.cpp:971-1063 with log_weights :880-935.  The

@@ -385,6 +385,18 @@ int bssm_b200_is_correction_bsf(const bssm_ung_model* model, const bssm_theta_ma
                                 const double* approx_loglik, uint32_t n_stored, uint32_t draw_begin,
                                 uint32_t draw_end, bssm_postcorr_out* out);
 
+/* replaces: the draw loop of approx_mcmc::is_correction_bsf<ssm_nlg> (src/approx_mcmc.cpp:442-518), the
+ *           correction phase of run_mcmc(..., sampling_method = "bsf") for ssm_nlg models
+ *           (src/R_mcmc.cpp:790): one bootstrap filter per stored draw after update_model(theta_i);
+ *           weight_i = exp(loglik_i - approx_loglik_i), posterior_i = log weight_i (the caller adds
+ *           the prior).  Registry models (model->model_id), m = 1 or 2.  theta is n_par x n_stored;
+ *           other arguments and outputs as bssm_b200_is_correction_bsf; draws shard the same way. */
+int bssm_b200_is_correction_bsf_nlg(const bssm_nlg_model* model, int output_type, uint32_t nsim,
+                                    uint32_t seed, uint32_t n_threads, int is_type, const uint32_t* counts,
+                                    const double* theta, uint32_t n_par, const double* approx_loglik,
+                                    uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
+                                    bssm_postcorr_out* out);
+
 /* replaces: the draw loop of approx_mcmc::is_correction_bsf<ssm_sde> (src/approx_mcmc.cpp:522-591),
  *           the correction phase of sde_is_mcmc (src/R_sde.cpp:221-282): one bootstrap filter per
  *           stored draw on the FINE mesh L_f at that draw's theta;

@@ -1942,10 +1942,14 @@ int orc_postcorrection_bsm(const bssm_ung_model* M, const bssm_theta_map* map, i
 
 /* is_correction_psi<ssm_nlg> (src/approx_mcmc.cpp:353-427), growth model: theta is
  * n_par x n_stored, modes m x n x n_stored.  Same conventions as orc_postcorrection_ung. */
-int orc_postcorrection_nlg(const bssm_nlg_model* M, int output_type, uint32_t nsim, uint32_t seed, int threads,
-                           int is_type, const uint32_t* counts, const double* theta, uint32_t n_par,
-                           const double* modes, uint32_t n_stored, int arith, double* weights, double* posterior,
-                           double* alpha, double* alphahat, double* Vt, double* loglik_out) {
+/* shared draw loop of the two ssm_nlg correction phases: modes != null is is_correction_psi (psi-APF around the
+ * stored mode, weight = exp(loglik)), approx_loglik != null is is_correction_bsf (bootstrap filter,
+ * weight = exp(loglik - approx_loglik_i)), src/approx_mcmc.cpp:345-425 and :447-518 */
+static int nlg_correction(const bssm_nlg_model* M, int output_type, uint32_t nsim, uint32_t seed, int threads,
+                          int is_type, const uint32_t* counts, const double* theta, uint32_t n_par,
+                          const double* modes, const double* approx_loglik, uint32_t n_stored, int arith,
+                          double* weights, double* posterior, double* alpha, double* alphahat, double* Vt,
+                          double* loglik_out) {
   if (M->model_id < BSSM_NLG_GROWTH || M->model_id > BSSM_NLG_LINEAR_GAUSSIAN || M->p != 1) return 1;
   const size_t n = M->n, n1 = n + 1, m = M->model_id == BSSM_NLG_GROWTH ? 2 : 1;
   std::vector<uint32_t> src, cnt;
@@ -1970,10 +1974,12 @@ int orc_postcorrection_nlg(const bssm_nlg_model* M, int output_type, uint32_t ns
     std::vector<uint32_t> indices((size_t)nsimc * n, 0u);
     int32_t st;
     double al;
-    double ll = orc_nlg_psi_filter(&Mi, modes + m * n * src[i], 100, 1e-8, nsimc, seed, (uint32_t)i, arith,
-                                   alpha_i.data(), weights_i.data(), indices.data(), &al, &st, nullptr);
+    double ll = modes ? orc_nlg_psi_filter(&Mi, modes + m * n * src[i], 100, 1e-8, nsimc, seed, (uint32_t)i, arith,
+                                           alpha_i.data(), weights_i.data(), indices.data(), &al, &st, nullptr)
+                      : orc_nlg_bsf_filter(&Mi, nsimc, seed, (uint32_t)i, arith, alpha_i.data(), weights_i.data(),
+                                           indices.data(), &st);
     if (loglik_out) loglik_out[i] = ll;
-    weights[i] = pf_exp(ll);
+    weights[i] = modes ? pf_exp(ll) : pf_exp(ll - approx_loglik[src[i]]);
     if (output_type != 3) {
       orc_filter_smoother(alpha_i.data(), indices.data(), (int)m, (int)n1, nsimc);
       if (output_type == 1) {
@@ -2012,6 +2018,24 @@ int orc_postcorrection_nlg(const bssm_nlg_model* M, int output_type, uint32_t ns
   }
   for (int64_t i = 0; i < nd; ++i) posterior[i] = 0.0 + 0.0 + pf_log(weights[i]);
   return 0;
+}
+int orc_postcorrection_nlg(const bssm_nlg_model* M, int output_type, uint32_t nsim, uint32_t seed, int threads,
+                           int is_type, const uint32_t* counts, const double* theta, uint32_t n_par,
+                           const double* modes, uint32_t n_stored, int arith, double* weights, double* posterior,
+                           double* alpha, double* alphahat, double* Vt, double* loglik_out) {
+  if (!modes) return 1;
+  return nlg_correction(M, output_type, nsim, seed, threads, is_type, counts, theta, n_par, modes, nullptr, n_stored,
+                        arith, weights, posterior, alpha, alphahat, Vt, loglik_out);
+}
+/* is_correction_bsf<ssm_nlg>, src/approx_mcmc.cpp:442-518: update_model(theta_i), bsf_filter,
+ * weight = exp(loglik - approx_loglik_i), posterior = prior (0 here) + log(weight); draw d uses Philox stream d */
+int orc_is_correction_bsf_nlg(const bssm_nlg_model* M, int output_type, uint32_t nsim, uint32_t seed, int threads,
+                              int is_type, const uint32_t* counts, const double* theta, uint32_t n_par,
+                              const double* approx_loglik, uint32_t n_stored, int arith, double* weights,
+                              double* posterior, double* alpha, double* alphahat, double* Vt, double* loglik_out) {
+  if (!approx_loglik) return 1;
+  return nlg_correction(M, output_type, nsim, seed, threads, is_type, counts, theta, n_par, nullptr, approx_loglik,
+                        n_stored, arith, weights, posterior, alpha, alphahat, Vt, loglik_out);
 }
 
 /* is_correction_bsf, src/approx_mcmc.cpp:447-518 (svm / ar1_ng, m = 1): bootstrap filter per stored

@@ -298,6 +298,30 @@ def is_correction_bsf_sde(model, mcmc_output, N, Lf, is_type=2, seed=1, threads=
     return r
 
 
+def is_correction_bsf_nlg(model, mcmc_output, N, is_type=2, seed=1, threads=0, arith=ARITH_REPRO):
+    """oracle of approx_mcmc::is_correction_bsf<ssm_nlg>; mcmc_output carries theta, counts, approx_loglik"""
+    from bssm_b200.api import n_draws
+    theta = np.asfortranarray(np.asarray(mcmc_output["theta"], dtype=np.float64).T)
+    counts = np.ascontiguousarray(mcmc_output["counts"], dtype=np.uint32)
+    approx = np.ascontiguousarray(mcmc_output["approx_loglik"], dtype=np.float64)
+    ot = int(mcmc_output.get("output_type", 3))
+    nd = n_draws(mcmc_output, is_type)
+    n, m = model.n, model.m
+    r = Result()
+    r.weights, r.posterior, r.loglik = np.zeros(nd), np.zeros(nd), np.zeros(nd)
+    r.alpha = np.zeros((n + 1, m, nd), order="F") if ot == 1 else None
+    r.alphahat = np.zeros((n + 1, m), order="F") if ot == 2 else None
+    r.Vt = np.zeros((m, m, n + 1), order="F") if ot == 2 else None
+    ms = model.c_struct()
+    f = L().orc_is_correction_bsf_nlg
+    f.argtypes = L().orc_postcorrection_nlg.argtypes
+    rc = f(C.byref(ms), ot, N, seed, threads, is_type, uptr(counts), dptr(theta), theta.shape[0], dptr(approx),
+           counts.size, arith, dptr(r.weights), dptr(r.posterior), dptr(r.alpha), dptr(r.alphahat), dptr(r.Vt),
+           dptr(r.loglik))
+    assert rc == 0
+    return r
+
+
 def nlg_bsf_filter(model, N, seed, filt=0, arith=ARITH_REPRO):
     r = _alloc(model, N)
     ms = model.c_struct()

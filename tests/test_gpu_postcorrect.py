@@ -313,3 +313,36 @@ def test_post_correct_inside_the_library_on_two_gpus(engine):
     a2 = engine.post_correct(model, mo1, 64, threads=2, is_type="is3", seed=6)
     assert np.array_equal(a1["alpha"].view(np.uint64), a2["alpha"].view(np.uint64))
     assert np.array_equal(a1["weights"], a2["weights"])
+
+
+@pytest.mark.parametrize("kind", ["growth", "ar_exp", "sin_exp", "linear_gaussian"])
+def test_bsf_is_correction_nlg(engine, kind):
+    """correction phase of run_mcmc(sampling_method = "bsf") for ssm_nlg: update_model(theta_i), bootstrap
+    filter, weight = exp(loglik_bsf - approx_loglik_i) (is_correction_bsf<ssm_nlg>, src/approx_mcmc.cpp:442-518)"""
+    model = {"growth": lambda: data.growth_model(40, missing=(5,)), "ar_exp": lambda: data.ar_exp_model(50),
+             "sin_exp": lambda: data.sin_exp_model(40), "linear_gaussian": lambda: data.linear_gaussian_model(40)}[kind]()
+    rng = np.random.default_rng(13)
+    ns = 14
+    th0 = np.asarray(model.theta, dtype=np.float64)
+    theta = th0[None, :] + 0.04 * rng.normal(size=(ns, th0.size))
+    if kind == "ar_exp":
+        theta[:, 1] = np.clip(theta[:, 1], -0.98, 0.98)
+    counts = (1 + rng.poisson(2, size=ns)).astype(np.uint32)
+    base = orc.nlg_bsf_filter(model, 256, seed=77).loglik
+    approx = base + 0.5 * rng.normal(size=ns)
+    mo = {"theta": theta, "counts": counts, "approx_loglik": approx, "output_type": 3, "posterior": np.zeros(ns)}
+    ref = orc.is_correction_bsf_nlg(model, mo, 128, is_type=2, seed=3)
+    res = engine.post_correct(model, mo, 128, is_type="is2", seed=3, return_loglik=True, sampling_method="bsf")
+    assert np.array_equal(res["loglik"], ref.loglik)
+    assert np.array_equal(res["weights"], ref.weights)
+    np.testing.assert_allclose(res["posterior"], ref.posterior, rtol=1e-13, atol=1e-13)
+    assert len(set(res["loglik"])) == ns  # every draw ran at its own theta
+    mo1 = dict(mo, output_type=1)
+    ref1 = orc.is_correction_bsf_nlg(model, mo1, 64, is_type=3, seed=5)
+    res1 = engine.post_correct(model, mo1, 64, is_type="is3", seed=5, sampling_method="bsf")
+    assert np.array_equal(res1["alpha"].view(np.uint64), ref1.alpha.view(np.uint64))
+    mo2 = dict(mo, output_type=2)
+    ref2 = orc.is_correction_bsf_nlg(model, mo2, 32, is_type=1, seed=7)
+    res2 = engine.post_correct(model, mo2, 32, is_type="is1", seed=7, sampling_method="bsf")
+    np.testing.assert_allclose(res2["alphahat"], ref2.alphahat, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(res2["Vt"], ref2.Vt, rtol=1e-8, atol=1e-12)
