@@ -80,6 +80,13 @@ class PostcorrOut(C.Structure):
                 ("sum_w", C.c_double), ("device_ms", C.c_float), ("launches", C.c_int32)]
 
 
+class Parset(C.Structure):
+    """bssm_parset (parset_ung / parset_mng, src/parset_ng.h:11-62)"""
+    _fields_ = [("phi", c_double_p), ("Z", c_double_p), ("T", c_double_p), ("R", c_double_p), ("a1", c_double_p),
+                ("P1", c_double_p), ("D", c_double_p), ("C", c_double_p), ("beta", c_double_p),
+                ("xreg", c_double_p), ("n_xreg", C.c_int32)]
+
+
 _lib = None
 
 
@@ -156,6 +163,11 @@ def lib():
         C.POINTER(NlgModel), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, c_uint32_p, c_double_p,
         C.c_uint32, c_double_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PostcorrOut)]
     L.bssm_b200_is_correction_bsf_nlg.argtypes = L.bssm_b200_postcorrection_nonlinear.argtypes
+    for name, mt in (("ung", UngModel), ("mng", MngModel)):
+        for fn in ("bssm_b200_postcorrection_%s_parset", "bssm_b200_is_correction_bsf_%s_parset"):
+            getattr(L, fn % name).argtypes = [
+                C.POINTER(mt), C.POINTER(Parset), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, c_uint32_p,
+                c_double_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PostcorrOut)]
     L.bssm_b200_job_create_postcorr_nlg.argtypes = [
         C.POINTER(NlgModel), C.c_uint32, C.c_uint32, C.c_int, c_uint32_p, c_double_p, C.c_uint32, c_double_p,
         C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]

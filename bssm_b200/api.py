@@ -330,6 +330,44 @@ def _postcorr_inputs(model, mcmc_output):
     return theta, counts, modes
 
 
+PARSET_FIELDS = ("phi", "Z", "T", "R", "a1", "P1", "D", "C", "beta")
+
+
+def build_parset(model, theta):
+    """parset_ung / parset_mng constructors (src/parset_ng.cpp:5-82, :127-183): evaluates
+    model.update_fn(theta_i) for every stored draw and stacks the components it returns.
+
+    theta: n_stored x n_par.  update_fn returns a dict with any of phi, Z, T, R, a1, P1, D, C (and beta
+    for ssm_ung), each shaped like the model's own array.  Returns (Parset struct, arrays kept alive)."""
+    from ._lib import Parset
+    theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+    first = model.update_fn(theta[0])
+    unknown = set(first) - set(PARSET_FIELDS)
+    if unknown:
+        raise ValueError("update_fn returned unknown components: %s" % sorted(unknown))
+    if "beta" in first and model.cls != "ssm_ung":
+        raise ValueError("only ssm_ung models have a regression part")
+    ps, keep = Parset(), {}
+    for name in first:
+        own = {"a1": model.a1, "P1": model.P1, "phi": np.atleast_1d(model.phi), "Z": model.Z, "T": model.T,
+               "R": model.R, "D": model.D, "C": model.C, "beta": getattr(model, "beta", None)}[name]
+        size = int(np.size(own))
+        stack = np.empty((theta.shape[0], size))
+        for i in range(theta.shape[0]):
+            comp = first if i == 0 else model.update_fn(theta[i])
+            v = np.ravel(np.asarray(comp[name], dtype=np.float64), order="F")
+            if v.size != size:
+                raise ValueError("update_fn: %s has %d elements, the model's has %d" % (name, v.size, size))
+            stack[i] = v
+        keep[name] = _lib.f64(np.ravel(stack))
+        setattr(ps, name, dptr(keep[name]))
+    if "beta" in first:
+        keep["xreg"] = _lib.f64(np.ravel(np.asarray(model.xreg, dtype=np.float64).reshape(model.n, -1), order="F"))
+        ps.xreg, ps.n_xreg = dptr(keep["xreg"]), keep["xreg"].size // model.n
+    ps._keep = keep
+    return ps
+
+
 def n_draws(mcmc_output, is_type):
     counts = np.asarray(mcmc_output["counts"])
     return int(counts.sum()) if is_type == 3 else int(counts.size)
@@ -360,7 +398,17 @@ def post_correct(model, mcmc_output, particles, threads=1, is_type="is2", seed=1
     if sampling_method not in ("psi", "bsf"):
         raise ValueError("sampling_method must be 'psi' or 'bsf'")
     bsf = sampling_method == "bsf" and model.cls != "ssm_sde"
-    if model.cls == "ssm_sde" or bsf:
+    use_parset = getattr(model, "update_fn", None) is not None and model.cls in ("ssm_ung", "ssm_mng")
+    if model.cls == "ssm_mng" and not use_parset:
+        raise ValueError("post_correct for ssm_mng needs model.update_fn (theta -> dict of model components)")
+    if use_parset and not bsf:
+        theta = np.asfortranarray(np.asarray(mcmc_output["theta"], dtype=np.float64).T)
+        counts = np.ascontiguousarray(mcmc_output["counts"], dtype=np.uint32)
+        rows = model.n * (model.p if model.cls == "ssm_mng" else 1)  # mode_storage: p x n per draw
+        modes = np.asfortranarray(np.asarray(mcmc_output["modes"], dtype=np.float64).reshape(rows, -1, order="F"))
+        if theta.shape[1] != counts.size or modes.shape[1] != counts.size:
+            raise ValueError("theta, counts and modes disagree on the number of stored draws")
+    elif model.cls == "ssm_sde" or bsf:
         if model.cls == "ssm_sde" and (L is None or int(L) < 1):
             raise ValueError("Discretization level L must be larger than 0.")
         theta = np.asfortranarray(np.asarray(mcmc_output["theta"], dtype=np.float64).T)
@@ -384,7 +432,15 @@ def post_correct(model, mcmc_output, particles, threads=1, is_type="is2", seed=1
     out.weights, out.posterior, out.alpha = dptr(w), dptr(post), dptr(alpha)
     out.alphahat, out.Vt, out.loglik = dptr(ah), dptr(Vt), dptr(ll)
     ms = model.c_struct()
-    if bsf and model.cls == "ssm_nlg":
+    if use_parset:
+        # postcorrection_nongaussian(model_type = 0 | 1): update_fn is evaluated here for every stored draw,
+        # as the parset constructors do before the reference's OpenMP region (src/approx_mcmc.cpp:698, :1051)
+        ps = build_parset(model, np.asarray(mcmc_output["theta"], dtype=np.float64))
+        kind = "mng" if model.cls == "ssm_mng" else "ung"
+        fn = getattr(lib(), ("bssm_b200_is_correction_bsf_%s_parset" if bsf else "bssm_b200_postcorrection_%s_parset") % kind)
+        check(fn(C.byref(ms), C.byref(ps), ot, N, seed, int(threads), it, uptr(counts),
+                 dptr(approx) if bsf else dptr(modes), counts.size, b, e, C.byref(out)))
+    elif bsf and model.cls == "ssm_nlg":
         check(lib().bssm_b200_is_correction_bsf_nlg(
             C.byref(ms), ot, N, seed, int(threads), it, uptr(counts), dptr(theta), theta.shape[0],
             dptr(approx), counts.size, b, e, C.byref(out)))

@@ -427,7 +427,26 @@ enum { KIND_UNG = 0, KIND_NLG = 1, KIND_SDE = 2, KIND_MNG = 3 };
 // src/model_bsm_ng.cpp:17-51) plus the stored mode of each draw: host arrays, one block per filter
 struct DrawModels {
   std::vector<double> R, P1, phi, xbeta, modes; // nf x (m*k), nf x (m*m), nf, nf x n (or empty), nf x n
+  // parameter sets (parset_ung, src/parset_ng.h:11-40): any of the model's arrays per filter, each slice
+  // shaped like the model's own array; empty = shared.  R, P1, phi, xbeta above may be empty too then.
+  std::vector<double> Z, T, a1, D, C;
+  bool parset = false;
 };
+
+// parset_ung::update(model, i), src/parset_ng.cpp:84-124: the model with filter f's components swapped in
+static void draw_model(const bssm_ung_model* M, const DrawModels& dm, size_t f, bssm_ung_model& Mi) {
+  Mi = *M;
+  const size_t n = (size_t)M->n, m = (size_t)M->m, k = (size_t)M->k;
+  if (!dm.Z.empty()) Mi.Z = &dm.Z[m * (M->Ztv ? n : 1) * f];
+  if (!dm.T.empty()) Mi.T = &dm.T[m * m * (M->Ttv ? n : 1) * f];
+  if (!dm.R.empty()) Mi.R = &dm.R[m * k * (M->Rtv ? n : 1) * f];
+  if (!dm.a1.empty()) Mi.a1 = &dm.a1[m * f];
+  if (!dm.P1.empty()) Mi.P1 = &dm.P1[m * m * f];
+  if (!dm.D.empty()) Mi.D = &dm.D[(M->Dtv ? n : 1) * f];
+  if (!dm.C.empty()) Mi.C = &dm.C[m * (M->Ctv ? n : 1) * f];
+  if (!dm.phi.empty()) Mi.phi = dm.phi[f];
+  if (!dm.xbeta.empty()) Mi.xbeta = &dm.xbeta[n * f];
+}
 
 struct bssm_b200_job {
   int kind = KIND_UNG;
@@ -444,10 +463,12 @@ struct bssm_b200_job {
   double nlg_conv_tol = 1e-8;
   bool dyn = false; // run-time state dimension (models_ung_dyn.cuh): (m, k) without a specialised instantiation
   bool xbeta_per_filter = false; // m = 1 psi-APF whose filters carry their own regression part (beta in theta)
+  bool host_approx_per_filter = false; // psi-APF whose filters each carry a host-side approximation (any m)
+  bool mng_draws = false; // ssm_mng with one model per filter (parameter sets)
   // model on device
   DevBuf<double> y, Z, T, R, a1, P1, LP1, D, C, xbeta, u, mode, mode_lin;
   // psi pre-pass results
-  DevBuf<double> alphahat, Lt, Ct, ytilde, Htilde, scales, approx_loglik, phi_f, scratch, rHt, yphi2;
+  DevBuf<double> alphahat, Lt, Ct, ytilde, Htilde, scales, approx_loglik, phi_f, lconst_f, scratch, rHt, yphi2;
   size_t pstride = 0;
   // outputs
   DevBuf<double> alpha_tm, alpha_sm, weights, cube;
@@ -575,6 +596,20 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
     if (sp.theta_f) sp.theta_f += (size_t)6 * f0;
     return launch_status(pfl::launch_sde_bsf(J->sde_model_id, fp, sp, J->geo, nf, J->stream), "sde bsf");
   }
+  if (J->kind == KIND_MNG && J->mng_draws) {
+    pf::MngParams gp = J->gp;
+    gp.Z += (size_t)f0 * gp.fs_Z; gp.T += (size_t)f0 * gp.fs_T; gp.R += (size_t)f0 * gp.fs_R; gp.C += (size_t)f0 * gp.fs_C;
+    gp.D += (size_t)f0 * gp.fs_D; gp.a1 += (size_t)f0 * gp.fs_a1; gp.LP1 += (size_t)f0 * gp.fs_LP1;
+    gp.phi += (size_t)f0 * gp.fs_phi;
+    if (gp.lconst_f) gp.lconst_f += f0;
+    if (J->method == BSSM_METHOD_PSI) {
+      gp.approx_loglik += f0;
+      gp.alphahat += (size_t)f0 * gp.fs_a; gp.Lt += (size_t)f0 * gp.fs_m; gp.Ct += (size_t)f0 * gp.fs_m;
+      gp.ytilde += (size_t)f0 * gp.fs_np; gp.Htilde += (size_t)f0 * gp.fs_np; gp.scales += (size_t)f0 * gp.fs_n;
+      return launch_status(pfl::launch_mng_psi_draws(J->m, fp, gp, J->geo, nf, J->stream), "ssm_mng psi filter (draws)");
+    }
+    return launch_status(pfl::launch_mng_bsf_draws(J->m, J->k, fp, gp, J->geo, nf, J->stream), "ssm_mng bsf (draws)");
+  }
   if (J->kind == KIND_MNG) {
     if (J->method == BSSM_METHOD_PSI) {
       pf::MngParams gp = J->gp;
@@ -584,7 +619,11 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
     return launch_status(pfl::launch_mng_bsf(J->m, J->k, fp, J->gp, J->geo, nf, J->stream), "ssm_mng bsf (m,k)");
   }
   pf::UngParams up = J->up;
-  if (J->method == BSSM_METHOD_PSI && (J->m > 1 || J->xbeta_per_filter)) {
+  up.Z += (size_t)f0 * up.fs_Z; up.D += (size_t)f0 * up.fs_D; // parameter sets: one model per filter
+  up.T += (size_t)f0 * up.fs_T; up.R += (size_t)f0 * up.fs_R; up.C += (size_t)f0 * up.fs_C;
+  up.a1 += (size_t)f0 * up.fs_a1; up.LP1 += (size_t)f0 * up.fs_LP1;
+  if (up.lconst_f) up.lconst_f += f0;
+  if (J->method == BSSM_METHOD_PSI && (J->m > 1 || J->xbeta_per_filter || J->host_approx_per_filter)) {
     up.approx_loglik += f0;
     up.alphahat += (size_t)f0 * up.fs_a; up.Lt += (size_t)f0 * up.fs_m; up.Ct += (size_t)f0 * up.fs_m;
     up.ytilde += (size_t)f0 * up.fs_n; up.Htilde += (size_t)f0 * up.fs_n; up.scales += (size_t)f0 * up.fs_n;
@@ -606,7 +645,11 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
     up.xbeta += (size_t)f0 * up.fs_x;
     return launch_status(pfl::launch_ung_bsf_draws(fp, up, J->geo, nf, J->stream), "bsf (per-draw models)");
   }
-  if (J->dyn) return launch_status(pfl::launch_ung_bsf_dyn(fp, up, J->geo, nf, J->stream), "bsf (run-time m)");
+  if (J->dyn) {
+    up.xbeta += (size_t)f0 * up.fs_x;
+    if (up.phi_f) up.phi_f += f0;
+    return launch_status(pfl::launch_ung_bsf_dyn(fp, up, J->geo, nf, J->stream), "bsf (run-time m)");
+  }
   if (J->m <= 2) return launch_status(pfl::launch_ung_bsf_a(J->m, J->k, fp, up, J->geo, nf, J->stream), "bsf (m,k)");
   return launch_status(pfl::launch_ung_bsf_b(J->m, J->k, fp, up, J->geo, nf, J->stream), "bsf (m,k)");
 }
@@ -713,9 +756,13 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
   if (method == BSSM_METHOD_BSF && draw_par && M->m != 1)
     return fail(BSSM_B200_ERR_UNSUPPORTED, "per-draw bootstrap filters: m = 1 in this build");
   if (M->m > 16) return fail(BSSM_B200_ERR_UNSUPPORTED, "state dimension m <= 16 in this build");
-  if (method == BSSM_METHOD_PSI && ((M->m != 1 && draw_par) || (M->m == 1 && dm && !draw_par)))
+  const bool parset = dm && dm->parset;
+  if (method == BSSM_METHOD_PSI && !parset && ((M->m != 1 && draw_par) || (M->m == 1 && dm && !draw_par)))
     return fail(BSSM_B200_ERR_UNSUPPORTED, "psi-APF with per-draw models: m = 1 (or bsm_ng through the DrawModels path)");
-  if (dm && M->m > 3) return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction with per-draw models: m <= 3 in this build");
+  if (dm && !parset && M->m > 3) return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction with per-draw models: m <= 3 in this build");
+  if (parset && (draw_par || gaussian)) return fail(BSSM_B200_ERR_ARG, "parameter sets: non-Gaussian ssm_ung models, no draw_par");
+  if (parset && post != BSSM_POST_NONE && M->m > 3)
+    return fail(BSSM_B200_ERR_UNSUPPORTED, "parameter sets: trajectories and summaries (output_type 1, 2) for m <= 3 in this build");
   if (M->k > M->m) return fail(BSSM_B200_ERR_ARG, "k > m");
   if (post < 0 || post > BSSM_POST_SMOOTHER_MERGE) return fail(BSSM_B200_ERR_ARG, "bad post mode");
   int rc = require_device();
@@ -730,7 +777,8 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
   {
     const int mk = M->m * 10 + M->k;
     const bool bsf_inst = mk == 11 || mk == 21 || mk == 22 || mk == 32 || mk == 33;
-    J->dyn = M->m > 3 || (method == BSSM_METHOD_BSF && !bsf_inst);
+    // per-filter models of the bootstrap filter are read by the run-time-m policy only
+    J->dyn = M->m > 3 || (method == BSSM_METHOD_BSF && (!bsf_inst || parset));
   }
   rc = choose_geometry(nsim, n_filters, &J->geo, J->dyn);
   if (rc) return rc;
@@ -800,21 +848,62 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
     }
   }
 
-  if (method == BSSM_METHOD_PSI && m > 1 && dm) {
+  // parameter sets: the per-filter model arrays the kernels read (Z, D for the psi-APF; all for the bootstrap filter)
+  auto upload_slices = [&](const std::vector<double>& v, DevBuf<double>& buf, size_t slice, const double** ptr,
+                           size_t* stride) -> int {
+    if (v.empty()) return 0;
+    if (v.size() != slice * n_filters) return fail(BSSM_B200_ERR_ARG, "parameter set: slice size x n_filters expected");
+    int r = buf.upload(v.data(), v.size());
+    if (r) return r;
+    *ptr = buf.p; *stride = slice;
+    return 0;
+  };
+  if (parset) {
+    if ((rc = upload_slices(dm->Z, J->Z, (size_t)m * (M->Ztv ? n : 1), &up.Z, &up.fs_Z)) ||
+        (rc = upload_slices(dm->D, J->D, (size_t)(M->Dtv ? n : 1), &up.D, &up.fs_D)))
+      return rc;
+  }
+  if (method == BSSM_METHOD_BSF && parset) {
+    // is_correction_bsf<ssm_ung> (src/approx_mcmc.cpp:806-921): every filter runs its own model
+    if ((rc = upload_slices(dm->T, J->T, (size_t)m * m * (M->Ttv ? n : 1), &up.T, &up.fs_T)) ||
+        (rc = upload_slices(dm->R, J->R, (size_t)m * k * (M->Rtv ? n : 1), &up.R, &up.fs_R)) ||
+        (rc = upload_slices(dm->C, J->C, (size_t)m * (M->Ctv ? n : 1), &up.C, &up.fs_C)) ||
+        (rc = upload_slices(dm->a1, J->a1, (size_t)m, &up.a1, &up.fs_a1)) ||
+        (rc = upload_slices(dm->xbeta, J->xbeta, (size_t)n, &up.xbeta, &up.fs_x)))
+      return rc;
+    if (!dm->P1.empty()) { // chol of each draw's P1 (positive-diagonal block), src/model_ssm_ung.cpp:616-618
+      std::vector<double> L((size_t)m * m * n_filters), Lf;
+      for (uint32_t f = 0; f < n_filters; ++f) {
+        chol_posdiag(&dm->P1[(size_t)m * m * f], m, Lf);
+        std::copy(Lf.begin(), Lf.end(), &L[(size_t)m * m * f]);
+      }
+      if ((rc = upload_slices(L, J->LP1, (size_t)m * m, &up.LP1, &up.fs_LP1))) return rc;
+    }
+    if (!dm->phi.empty()) { // phi enters the state-independent constants of the log-likelihood
+      std::vector<double> lc(n_filters);
+      for (uint32_t f = 0; f < n_filters; ++f) {
+        bssm_ung_model Mi = *M;
+        Mi.phi = dm->phi[f];
+        lc[f] = ung_dist_const(&Mi);
+      }
+      if ((rc = J->phi_f.upload(dm->phi.data(), n_filters)) || (rc = J->lconst_f.upload(lc.data(), n_filters))) return rc;
+      up.phi_f = J->phi_f.p; up.lconst_f = J->lconst_f.p;
+    }
+  }
+
+  if (method == BSSM_METHOD_PSI && dm && (m > 1 || parset)) {
     // approximate_for_is (src/model_ssm_ung.cpp:143-161) per draw on the host, OpenMP over draws:
     // laplace_iter at the stored mode, scales, Kalman smoother + conditional covariances
-    if (M->Rtv) return fail(BSSM_B200_ERR_UNSUPPORTED, "per-draw models: time-invariant R only");
+    if (M->Rtv && !parset) return fail(BSSM_B200_ERR_UNSUPPORTED, "per-draw models: time-invariant R only");
+    if (dm->modes.size() != (size_t)n * n_filters) return fail(BSSM_B200_ERR_ARG, "per-draw models need per-draw modes");
     const size_t n1 = (size_t)n + 1, mm = (size_t)m * m, nf = n_filters;
     const bool has_xb = !dm->xbeta.empty();
     std::vector<double> ah((size_t)m * n1 * nf), Lt(mm * n1 * nf), Ct(mm * n1 * nf), yt((size_t)n * nf),
         Ht((size_t)n * nf), sc((size_t)n * nf), al(nf, 0.0);
 #pragma omp parallel for schedule(static)
     for (int64_t f = 0; f < (int64_t)nf; ++f) {
-      bssm_ung_model Mi = *M;
-      Mi.R = &dm->R[(size_t)m * k * f]; Mi.Rtv = 0;
-      Mi.P1 = &dm->P1[mm * f];
-      Mi.phi = dm->phi[f];
-      if (has_xb) Mi.xbeta = &dm->xbeta[(size_t)n * f];
+      bssm_ung_model Mi;
+      draw_model(M, *dm, (size_t)f, Mi);
       pfga::UngApprox ga(&Mi);
       ga.run(&dm->modes[(size_t)n * f]);
       std::copy(ga.alphahat.begin(), ga.alphahat.end(), &ah[(size_t)m * n1 * f]);
@@ -827,14 +916,16 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
     if ((rc = J->alphahat.upload(ah.data(), ah.size())) || (rc = J->Lt.upload(Lt.data(), Lt.size())) ||
         (rc = J->Ct.upload(Ct.data(), Ct.size())) || (rc = J->ytilde.upload(yt.data(), yt.size())) ||
         (rc = J->Htilde.upload(Ht.data(), Ht.size())) || (rc = J->scales.upload(sc.data(), sc.size())) ||
-        (rc = J->approx_loglik.upload(al.data(), nf)) || (rc = J->phi_f.upload(dm->phi.data(), nf)))
+        (rc = J->approx_loglik.upload(al.data(), nf)))
       return rc;
+    if (!dm->phi.empty() && (rc = J->phi_f.upload(dm->phi.data(), nf))) return rc;
     if (has_xb) {
       if ((rc = J->xbeta.upload(dm->xbeta.data(), dm->xbeta.size()))) return rc;
       up.xbeta = J->xbeta.p;
     }
     J->pstride = 0;
-    up.phi_f = J->phi_f.p; up.alphahat = J->alphahat.p; up.Lt = J->Lt.p; up.Ct = J->Ct.p;
+    J->host_approx_per_filter = true;
+    up.phi_f = dm->phi.empty() ? nullptr : J->phi_f.p; up.alphahat = J->alphahat.p; up.Lt = J->Lt.p; up.Ct = J->Ct.p;
     up.ytilde = J->ytilde.p; up.Htilde = J->Htilde.p; up.scales = J->scales.p;
     up.approx_loglik = J->approx_loglik.p; up.pstride = 0;
     up.fs_a = (size_t)m * n1; up.fs_m = mm * n1; up.fs_n = (size_t)n; up.fs_x = has_xb ? (size_t)n : 0;
@@ -931,7 +1022,7 @@ static int job_launch_filters(bssm_b200_job* J) {
   int rc;
   J->launches = 0;
   CU(cudaEventRecord(J->ev[0], J->stream));
-  if (J->kind == KIND_UNG && J->method == BSSM_METHOD_PSI && J->m == 1) {
+  if (J->kind == KIND_UNG && J->method == BSSM_METHOD_PSI && J->m == 1 && !J->host_approx_per_filter) {
     const uint32_t warps_per_block = 4;
     pf::ung_prepass_m1_kernel<<<cdiv(J->n_filters, warps_per_block), 32 * warps_per_block, 0, J->stream>>>(
         J->pp, J->n_filters);
@@ -1410,37 +1501,9 @@ int bssm_b200_job_create_sde(const bssm_sde_model* M, uint32_t nsim, uint32_t L,
   return create_sde_job(M, nsim, L, seed, n_filters, first_filter_id, out_flags, post, nullptr, 0, job);
 }
 
-static int create_mng_job(const bssm_mng_model* M, int method, uint32_t nsim, uint32_t seed, uint32_t n_filters,
-                          uint32_t first_filter_id, int out_flags, int post, bssm_b200_job** job) {
-  if (!M || !job || !M->y || !M->u || !M->Z || !M->T || !M->R || !M->a1 || !M->P1 || !M->D || !M->C ||
-      !M->phi || !M->distribution)
-    return fail(BSSM_B200_ERR_ARG, "null argument");
-  *job = nullptr;
-  if (M->p < 1 || M->p > 8 || M->m < 1 || M->k < 1 || M->k > M->m) return fail(BSSM_B200_ERR_ARG, "ssm_mng: 1 <= p <= 8, 1 <= k <= m");
-  for (int j = 0; j < M->p; ++j)
-    if (M->distribution[j] < 1 || M->distribution[j] > 5) return fail(BSSM_B200_ERR_ARG, "ssm_mng: distribution codes 1..5");
-  bssm_b200_job* J = new bssm_b200_job();
-  struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
-  const int n = M->n, m = M->m, k = M->k, p = M->p;
-  int rc = job_common(J, KIND_MNG, n, m, k, nsim, seed, n_filters, first_filter_id, out_flags, post);
-  if (rc) return rc;
-  std::vector<double> LP1;
-  chol_posdiag(M->P1, m, LP1);
-  std::vector<int> dist(M->distribution, M->distribution + p);
-  if ((rc = J->y.upload(M->y, (size_t)n * p)) || (rc = J->u.upload(M->u, (size_t)n * p)) ||
-      (rc = J->Z.upload(M->Z, (size_t)p * m * (M->Ztv ? n : 1))) ||
-      (rc = J->T.upload(M->T, (size_t)m * m * (M->Ttv ? n : 1))) ||
-      (rc = J->R.upload(M->R, (size_t)m * k * (M->Rtv ? n : 1))) || (rc = J->a1.upload(M->a1, m)) ||
-      (rc = J->LP1.upload(LP1.data(), (size_t)m * m)) || (rc = J->D.upload(M->D, (size_t)p * (M->Dtv ? n : 1))) ||
-      (rc = J->C.upload(M->C, (size_t)m * (M->Ctv ? n : 1))) || (rc = J->phi_v.upload(M->phi, p)) ||
-      (rc = J->dist_v.upload(dist.data(), p)))
-    return rc;
-  pf::MngParams& gp = J->gp;
-  gp.n = n; gp.p = p;
-  gp.Ztv = M->Ztv; gp.Ttv = M->Ttv; gp.Rtv = M->Rtv; gp.Dtv = M->Dtv; gp.Ctv = M->Ctv;
-  gp.y = J->y.p; gp.u = J->u.p; gp.Z = J->Z.p; gp.T = J->T.p; gp.R = J->R.p; gp.a1 = J->a1.p; gp.LP1 = J->LP1.p;
-  gp.D = J->D.p; gp.C = J->C.p; gp.phi = J->phi_v.p; gp.distribution = J->dist_v.p;
-  // state-independent constants, src/model_ssm_mng.cpp:636-666 (pre-summed here)
+// state-independent constants of the ssm_mng log-likelihood, src/model_ssm_mng.cpp:636-666 (pre-summed)
+static double mng_dist_const(const bssm_mng_model* M) {
+  const int n = M->n, p = M->p;
   auto lch = [](double nn, double kk) {
     return -std::log(nn + 1) - std::lgamma(nn - kk + 1) - std::lgamma(kk + 1) + std::lgamma(nn + 2);
   };
@@ -1459,8 +1522,135 @@ static int create_mng_job(const bssm_mng_model* M, int method, uint32_t nsim, ui
       }
     }
   }
-  gp.loglik_const = cst;
-  if (method == BSSM_METHOD_PSI) {
+  return cst;
+}
+
+// parameter sets of ssm_mng (parset_mng, src/parset_ng.h:42-62) for the filters of one job: slices shaped like
+// the model's own arrays, empty = shared; modes p x n per filter (psi-APF)
+struct MngDraws {
+  std::vector<double> phi, Z, T, R, a1, P1, D, C, modes;
+};
+// parset_mng::update(model, i), src/parset_ng.cpp:185-215
+static void draw_model_mng(const bssm_mng_model* M, const MngDraws& dm, size_t f, bssm_mng_model& Mi) {
+  Mi = *M;
+  const size_t n = (size_t)M->n, m = (size_t)M->m, k = (size_t)M->k, p = (size_t)M->p;
+  if (!dm.phi.empty()) Mi.phi = &dm.phi[p * f];
+  if (!dm.Z.empty()) Mi.Z = &dm.Z[p * m * (M->Ztv ? n : 1) * f];
+  if (!dm.T.empty()) Mi.T = &dm.T[m * m * (M->Ttv ? n : 1) * f];
+  if (!dm.R.empty()) Mi.R = &dm.R[m * k * (M->Rtv ? n : 1) * f];
+  if (!dm.a1.empty()) Mi.a1 = &dm.a1[m * f];
+  if (!dm.P1.empty()) Mi.P1 = &dm.P1[m * m * f];
+  if (!dm.D.empty()) Mi.D = &dm.D[p * (M->Dtv ? n : 1) * f];
+  if (!dm.C.empty()) Mi.C = &dm.C[m * (M->Ctv ? n : 1) * f];
+}
+
+static int create_mng_job(const bssm_mng_model* M, int method, uint32_t nsim, uint32_t seed, uint32_t n_filters,
+                          uint32_t first_filter_id, int out_flags, int post, bssm_b200_job** job,
+                          const MngDraws* dm = nullptr) {
+  if (!M || !job || !M->y || !M->u || !M->Z || !M->T || !M->R || !M->a1 || !M->P1 || !M->D || !M->C ||
+      !M->phi || !M->distribution)
+    return fail(BSSM_B200_ERR_ARG, "null argument");
+  *job = nullptr;
+  if (M->p < 1 || M->p > 8 || M->m < 1 || M->k < 1 || M->k > M->m) return fail(BSSM_B200_ERR_ARG, "ssm_mng: 1 <= p <= 8, 1 <= k <= m");
+  for (int j = 0; j < M->p; ++j)
+    if (M->distribution[j] < 1 || M->distribution[j] > 5) return fail(BSSM_B200_ERR_ARG, "ssm_mng: distribution codes 1..5");
+  bssm_b200_job* J = new bssm_b200_job();
+  struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
+  const int n = M->n, m = M->m, k = M->k, p = M->p;
+  int rc = job_common(J, KIND_MNG, n, m, k, nsim, seed, n_filters, first_filter_id, out_flags,
+                      post > BSSM_POST_SMOOTHER ? BSSM_POST_NONE : post);
+  if (rc) return rc;
+  J->post = post; // PICK / SMOOTHER_MERGE: the IS-correction drivers
+  std::vector<double> LP1;
+  chol_posdiag(M->P1, m, LP1);
+  std::vector<int> dist(M->distribution, M->distribution + p);
+  if ((rc = J->y.upload(M->y, (size_t)n * p)) || (rc = J->u.upload(M->u, (size_t)n * p)) ||
+      (rc = J->Z.upload(M->Z, (size_t)p * m * (M->Ztv ? n : 1))) ||
+      (rc = J->T.upload(M->T, (size_t)m * m * (M->Ttv ? n : 1))) ||
+      (rc = J->R.upload(M->R, (size_t)m * k * (M->Rtv ? n : 1))) || (rc = J->a1.upload(M->a1, m)) ||
+      (rc = J->LP1.upload(LP1.data(), (size_t)m * m)) || (rc = J->D.upload(M->D, (size_t)p * (M->Dtv ? n : 1))) ||
+      (rc = J->C.upload(M->C, (size_t)m * (M->Ctv ? n : 1))) || (rc = J->phi_v.upload(M->phi, p)) ||
+      (rc = J->dist_v.upload(dist.data(), p)))
+    return rc;
+  pf::MngParams& gp = J->gp;
+  gp.n = n; gp.p = p;
+  gp.Ztv = M->Ztv; gp.Ttv = M->Ttv; gp.Rtv = M->Rtv; gp.Dtv = M->Dtv; gp.Ctv = M->Ctv;
+  gp.y = J->y.p; gp.u = J->u.p; gp.Z = J->Z.p; gp.T = J->T.p; gp.R = J->R.p; gp.a1 = J->a1.p; gp.LP1 = J->LP1.p;
+  gp.D = J->D.p; gp.C = J->C.p; gp.phi = J->phi_v.p; gp.distribution = J->dist_v.p;
+  gp.loglik_const = mng_dist_const(M);
+  if (dm) {
+    // one model per filter: upload the per-filter slices of what the parameter set carries
+    J->mng_draws = true;
+    auto slices = [&](const std::vector<double>& v, DevBuf<double>& buf, size_t slice, const double** ptr,
+                      size_t* stride) -> int {
+      if (v.empty()) return 0;
+      if (v.size() != slice * n_filters) return fail(BSSM_B200_ERR_ARG, "parameter set: slice size x n_filters expected");
+      int r = buf.upload(v.data(), v.size());
+      if (r) return r;
+      *ptr = buf.p; *stride = slice;
+      return 0;
+    };
+    if ((rc = slices(dm->Z, J->Z, (size_t)p * m * (M->Ztv ? n : 1), &gp.Z, &gp.fs_Z)) ||
+        (rc = slices(dm->T, J->T, (size_t)m * m * (M->Ttv ? n : 1), &gp.T, &gp.fs_T)) ||
+        (rc = slices(dm->R, J->R, (size_t)m * k * (M->Rtv ? n : 1), &gp.R, &gp.fs_R)) ||
+        (rc = slices(dm->C, J->C, (size_t)m * (M->Ctv ? n : 1), &gp.C, &gp.fs_C)) ||
+        (rc = slices(dm->D, J->D, (size_t)p * (M->Dtv ? n : 1), &gp.D, &gp.fs_D)) ||
+        (rc = slices(dm->a1, J->a1, (size_t)m, &gp.a1, &gp.fs_a1)) ||
+        (rc = slices(dm->phi, J->phi_v, (size_t)p, &gp.phi, &gp.fs_phi)))
+      return rc;
+    if (!dm->P1.empty()) {
+      std::vector<double> L((size_t)m * m * n_filters), Lf;
+      for (uint32_t f = 0; f < n_filters; ++f) {
+        chol_posdiag(&dm->P1[(size_t)m * m * f], m, Lf);
+        std::copy(Lf.begin(), Lf.end(), &L[(size_t)m * m * f]);
+      }
+      if ((rc = slices(L, J->LP1, (size_t)m * m, &gp.LP1, &gp.fs_LP1))) return rc;
+    }
+    if (!dm->phi.empty() && method == BSSM_METHOD_BSF) {
+      std::vector<double> lc(n_filters);
+      for (uint32_t f = 0; f < n_filters; ++f) {
+        bssm_mng_model Mi = *M;
+        Mi.phi = &dm->phi[(size_t)p * f];
+        lc[f] = mng_dist_const(&Mi);
+      }
+      if ((rc = J->lconst_f.upload(lc.data(), n_filters))) return rc;
+      gp.lconst_f = J->lconst_f.p;
+    }
+  }
+  if (method == BSSM_METHOD_PSI && dm) {
+    // approximate_for_is (src/model_ssm_mng.cpp:119-135) per draw on the host, OpenMP over draws
+    if (m > 3) return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_mng psi-APF: m <= 3 in this build");
+    if (dm->modes.size() != (size_t)p * n * n_filters) return fail(BSSM_B200_ERR_ARG, "parameter set: p x n modes per filter");
+    J->method = BSSM_METHOD_PSI;
+    const size_t n1 = (size_t)n + 1, mm = (size_t)m * m, np = (size_t)n * p, nf = n_filters;
+    std::vector<double> ah((size_t)m * n1 * nf), Lt(mm * n1 * nf), Ct(mm * n1 * nf), yt(np * nf), Ht(np * nf),
+        sc((size_t)n * nf), al(nf, 0.0);
+#pragma omp parallel for schedule(static)
+    for (int64_t f = 0; f < (int64_t)nf; ++f) {
+      bssm_mng_model Mi;
+      draw_model_mng(M, *dm, (size_t)f, Mi);
+      pfga::MngApprox ga(&Mi);
+      ga.run(&dm->modes[np * f]);
+      al[f] = ga.approx_loglik;
+      std::copy(ga.alphahat.begin(), ga.alphahat.end(), &ah[(size_t)m * n1 * f]);
+      std::copy(ga.L.begin(), ga.L.end(), &Lt[mm * n1 * f]);
+      std::copy(ga.Ct.begin(), ga.Ct.end(), &Ct[mm * n1 * f]);
+      std::copy(ga.scales.begin(), ga.scales.end(), &sc[(size_t)n * f]);
+      for (int t = 0; t < n; ++t)
+        for (int j = 0; j < p; ++j) { // pseudo-observations in the layout of y (n x p)
+          yt[np * f + t + (size_t)n * j] = ga.ay[j + (size_t)p * t];
+          Ht[np * f + t + (size_t)n * j] = ga.aH[j + (size_t)p * t];
+        }
+    }
+    if ((rc = J->alphahat.upload(ah.data(), ah.size())) || (rc = J->Lt.upload(Lt.data(), Lt.size())) ||
+        (rc = J->Ct.upload(Ct.data(), Ct.size())) || (rc = J->ytilde.upload(yt.data(), yt.size())) ||
+        (rc = J->Htilde.upload(Ht.data(), Ht.size())) || (rc = J->scales.upload(sc.data(), sc.size())) ||
+        (rc = J->approx_loglik.upload(al.data(), nf)))
+      return rc;
+    gp.alphahat = J->alphahat.p; gp.Lt = J->Lt.p; gp.Ct = J->Ct.p; gp.ytilde = J->ytilde.p;
+    gp.Htilde = J->Htilde.p; gp.scales = J->scales.p; gp.approx_loglik = J->approx_loglik.p;
+    gp.fs_a = (size_t)m * n1; gp.fs_m = mm * n1; gp.fs_np = np; gp.fs_n = (size_t)n;
+  } else if (method == BSSM_METHOD_PSI) {
     // Gaussian approximation on the host (O(n (m^3 + p^3)), sequential in t), shared by all replicates
     if (m > 3) return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_mng psi-APF: m <= 3 in this build");
     if (!M->initial_mode) return fail(BSSM_B200_ERR_ARG, "psi-APF needs initial_mode");
@@ -2384,6 +2574,129 @@ int bssm_b200_is_correction_bsf(const bssm_ung_model* M, const bssm_theta_map* m
         }
         return create_ung_job(M, BSSM_METHOD_BSF, N, seed, nf, d0, 0, post, par.data(), nullptr, J,
                               map->n_xreg > 0 ? &dm : nullptr);
+      },
+      approx_loglik, /*posterior_adds_approx=*/false);
+}
+
+// ------------------------------------------ parameter sets (ssm_ung with an R update_fn)
+// slices of the stored draws [d0, d1) of one parset component (nullptr -> empty = shared)
+static void gather_slices(const double* src, size_t slice, const DrawList& dl, uint32_t d0, uint32_t d1,
+                          std::vector<double>& dst) {
+  dst.clear();
+  if (!src) return;
+  dst.resize(slice * (d1 - d0));
+  for (uint32_t f = 0; f < d1 - d0; ++f)
+    memcpy(&dst[slice * f], src + slice * dl.src[d0 + f], sizeof(double) * slice);
+}
+
+static int check_ung_parset(const bssm_ung_model* M, const bssm_parset* ps) {
+  if (M->distribution == BSSM_DIST_GAUSSIAN) return fail(BSSM_B200_ERR_ARG, "parameter sets: non-Gaussian ssm_ung models");
+  if (ps->beta && (!ps->xreg || ps->n_xreg < 1)) return fail(BSSM_B200_ERR_ARG, "parset: beta needs xreg and n_xreg");
+  return 0;
+}
+
+// parset_ung::update for the draws [d0, d1): gathers the components update_fn returned
+static void ung_parset_draws(const bssm_ung_model* M, const bssm_parset* ps, const DrawList& dl, uint32_t d0,
+                             uint32_t d1, DrawModels& dm) {
+  const size_t n = (size_t)M->n, m = (size_t)M->m, k = (size_t)M->k;
+  dm.parset = true;
+  gather_slices(ps->phi, 1, dl, d0, d1, dm.phi);
+  gather_slices(ps->Z, m * (M->Ztv ? n : 1), dl, d0, d1, dm.Z);
+  gather_slices(ps->T, m * m * (M->Ttv ? n : 1), dl, d0, d1, dm.T);
+  gather_slices(ps->R, m * k * (M->Rtv ? n : 1), dl, d0, d1, dm.R);
+  gather_slices(ps->a1, m, dl, d0, d1, dm.a1);
+  gather_slices(ps->P1, m * m, dl, d0, d1, dm.P1);
+  gather_slices(ps->D, M->Dtv ? n : 1, dl, d0, d1, dm.D);
+  gather_slices(ps->C, m * (M->Ctv ? n : 1), dl, d0, d1, dm.C);
+  if (ps->beta) { // compute_xbeta, src/model_ssm_ung.h:83
+    dm.xbeta.resize(n * (d1 - d0));
+    for (uint32_t f = 0; f < d1 - d0; ++f) {
+      const double* beta = ps->beta + (size_t)ps->n_xreg * dl.src[d0 + f];
+      for (size_t t = 0; t < n; ++t) {
+        double sum = 0.0;
+        for (int j = 0; j < ps->n_xreg; ++j) sum += ps->xreg[t + n * j] * beta[j];
+        dm.xbeta[n * f + t] = sum;
+      }
+    }
+  }
+}
+
+int bssm_b200_postcorrection_ung_parset(const bssm_ung_model* M, const bssm_parset* ps, int output_type,
+                                        uint32_t nsim, uint32_t seed, uint32_t n_threads, int is_type,
+                                        const uint32_t* counts, const double* modes, uint32_t n_stored,
+                                        uint32_t draw_begin, uint32_t draw_end, bssm_postcorr_out* out) {
+  if (!M || !ps || !counts || !modes || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
+  int rc = check_ung_parset(M, ps);
+  if (rc) return rc;
+  return postcorr_multi(
+      n_threads, M->n, M->m, output_type, nsim, is_type, counts, n_stored, draw_begin, draw_end, out,
+      [&](const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N, int post, bssm_b200_job** J) {
+        DrawModels dm;
+        ung_parset_draws(M, ps, dl, d0, d1, dm);
+        gather_slices(modes, (size_t)M->n, dl, d0, d1, dm.modes);
+        return create_ung_job(M, BSSM_METHOD_PSI, N, seed, d1 - d0, d0, 0, post, nullptr, nullptr, J, &dm);
+      });
+}
+
+int bssm_b200_is_correction_bsf_ung_parset(const bssm_ung_model* M, const bssm_parset* ps, int output_type,
+                                           uint32_t nsim, uint32_t seed, uint32_t n_threads, int is_type,
+                                           const uint32_t* counts, const double* approx_loglik, uint32_t n_stored,
+                                           uint32_t draw_begin, uint32_t draw_end, bssm_postcorr_out* out) {
+  if (!M || !ps || !counts || !approx_loglik || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
+  int rc = check_ung_parset(M, ps);
+  if (rc) return rc;
+  return postcorr_multi(
+      n_threads, M->n, M->m, output_type, nsim, is_type, counts, n_stored, draw_begin, draw_end, out,
+      [&](const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N, int post, bssm_b200_job** J) {
+        DrawModels dm;
+        ung_parset_draws(M, ps, dl, d0, d1, dm);
+        return create_ung_job(M, BSSM_METHOD_BSF, N, seed, d1 - d0, d0, 0, post, nullptr, nullptr, J, &dm);
+      },
+      approx_loglik, /*posterior_adds_approx=*/false);
+}
+
+// ------------------------------------------ parameter sets (ssm_mng with an R update_fn)
+static void mng_parset_draws(const bssm_mng_model* M, const bssm_parset* ps, const DrawList& dl, uint32_t d0,
+                             uint32_t d1, MngDraws& dm) {
+  const size_t n = (size_t)M->n, m = (size_t)M->m, k = (size_t)M->k, p = (size_t)M->p;
+  gather_slices(ps->phi, p, dl, d0, d1, dm.phi);
+  gather_slices(ps->Z, p * m * (M->Ztv ? n : 1), dl, d0, d1, dm.Z);
+  gather_slices(ps->T, m * m * (M->Ttv ? n : 1), dl, d0, d1, dm.T);
+  gather_slices(ps->R, m * k * (M->Rtv ? n : 1), dl, d0, d1, dm.R);
+  gather_slices(ps->a1, m, dl, d0, d1, dm.a1);
+  gather_slices(ps->P1, m * m, dl, d0, d1, dm.P1);
+  gather_slices(ps->D, p * (M->Dtv ? n : 1), dl, d0, d1, dm.D);
+  gather_slices(ps->C, m * (M->Ctv ? n : 1), dl, d0, d1, dm.C);
+}
+
+int bssm_b200_postcorrection_mng_parset(const bssm_mng_model* M, const bssm_parset* ps, int output_type,
+                                        uint32_t nsim, uint32_t seed, uint32_t n_threads, int is_type,
+                                        const uint32_t* counts, const double* modes, uint32_t n_stored,
+                                        uint32_t draw_begin, uint32_t draw_end, bssm_postcorr_out* out) {
+  if (!M || !ps || !counts || !modes || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
+  if (ps->beta) return fail(BSSM_B200_ERR_ARG, "ssm_mng has no regression part");
+  return postcorr_multi(
+      n_threads, M->n, M->m, output_type, nsim, is_type, counts, n_stored, draw_begin, draw_end, out,
+      [&](const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N, int post, bssm_b200_job** J) {
+        MngDraws dm;
+        mng_parset_draws(M, ps, dl, d0, d1, dm);
+        gather_slices(modes, (size_t)M->p * M->n, dl, d0, d1, dm.modes);
+        return create_mng_job(M, BSSM_METHOD_PSI, N, seed, d1 - d0, d0, 0, post, J, &dm);
+      });
+}
+
+int bssm_b200_is_correction_bsf_mng_parset(const bssm_mng_model* M, const bssm_parset* ps, int output_type,
+                                           uint32_t nsim, uint32_t seed, uint32_t n_threads, int is_type,
+                                           const uint32_t* counts, const double* approx_loglik, uint32_t n_stored,
+                                           uint32_t draw_begin, uint32_t draw_end, bssm_postcorr_out* out) {
+  if (!M || !ps || !counts || !approx_loglik || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
+  if (ps->beta) return fail(BSSM_B200_ERR_ARG, "ssm_mng has no regression part");
+  return postcorr_multi(
+      n_threads, M->n, M->m, output_type, nsim, is_type, counts, n_stored, draw_begin, draw_end, out,
+      [&](const DrawList& dl, uint32_t d0, uint32_t d1, uint32_t N, int post, bssm_b200_job** J) {
+        MngDraws dm;
+        mng_parset_draws(M, ps, dl, d0, d1, dm);
+        return create_mng_job(M, BSSM_METHOD_BSF, N, seed, d1 - d0, d0, 0, post, J, &dm);
       },
       approx_loglik, /*posterior_adds_approx=*/false);
 }

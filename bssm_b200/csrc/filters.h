@@ -25,6 +25,9 @@ int occupancy_ung_dyn(const Geometry&, int* out);
 int launch_mng_bsf(int m, int k, const pf::FilterParams&, const pf::MngParams&, const Geometry&, uint32_t nf, Stream);
 int launch_mng_psi(int m, const pf::FilterParams&, const pf::MngParams&, const Geometry&, uint32_t nf, Stream);
 int occupancy_mng_bsf(const Geometry&, int* out);
+// k_mng_draws.cu: the same with one model (and one approximation) per filter -- parameter sets
+int launch_mng_bsf_draws(int m, int k, const pf::FilterParams&, const pf::MngParams&, const Geometry&, uint32_t nf, Stream);
+int launch_mng_psi_draws(int m, const pf::FilterParams&, const pf::MngParams&, const Geometry&, uint32_t nf, Stream);
 // k_nlg.cu: ssm_nlg functor registry (growth, ar_exp), bootstrap and psi-APF
 int launch_nlg_bsf(int model_id, const pf::FilterParams&, const pf::NlgParams&, const Geometry&, uint32_t nf, Stream);
 int launch_nlg_bsf_draws(int model_id, const pf::FilterParams&, const pf::NlgParams&, const Geometry&, uint32_t nf, Stream); // k_nlg_draws.cu: one theta per filter

@@ -45,6 +45,11 @@ struct UngParams {
   // bootstrap filter with one model per filter (is_correction_bsf, m = 1): 7 doubles per filter
   // {T, R, a1, sqrt(P1), C, phi, loglik_const}, or null
   const double* bsf_par;
+  // parameter sets (parset_ung, src/parset_ng.h:11-40): per-filter strides of the model arrays, 0 = shared.
+  // The psi-APF reads Z and D only (the rest enters through the approximation); the run-time-m
+  // bootstrap filter reads all of them, with phi from phi_f and the constants from lconst_f.
+  size_t fs_Z, fs_D, fs_T, fs_R, fs_C, fs_a1, fs_LP1;
+  const double* lconst_f;
 };
 
 // log g(y_t | signal) up to state-independent constants, :447-493
@@ -228,7 +233,7 @@ struct UngPsiM : GaussStep<UngPsiM<M_>, M_, M_, M_> {
   typedef UngParams Params;
   const UngParams& mp;
   double al0, phi;
-  const double *p_ah, *p_Lt, *p_Ct, *p_yt, *p_Ht, *p_sc, *p_xb;
+  const double *p_ah, *p_Lt, *p_Ct, *p_yt, *p_Ht, *p_sc, *p_xb, *p_Z, *p_D;
   double y, u, yphi2, Dt, xb, ytil, rH, scale;
   double Z[M_], ah0[M_], ah1[M_], Cm[M_ * M_], Lm[M_ * M_];
 
@@ -239,6 +244,7 @@ struct UngPsiM : GaussStep<UngPsiM<M_>, M_, M_, M_> {
     p_Lt = p.Lt + (size_t)f * p.fs_m; p_Ct = p.Ct + (size_t)f * p.fs_m;
     p_yt = p.ytilde + (size_t)f * p.fs_n; p_Ht = p.Htilde + (size_t)f * p.fs_n; p_sc = p.scales + (size_t)f * p.fs_n;
     p_xb = p.xbeta + (size_t)f * p.fs_x;
+    p_Z = p.Z + (size_t)f * p.fs_Z; p_D = p.D + (size_t)f * p.fs_D;
   }
   __device__ double loglik0() const { return al0; }
   __device__ double loglik_end() const { return 0.0; }
@@ -257,10 +263,10 @@ struct UngPsiM : GaussStep<UngPsiM<M_>, M_, M_, M_> {
     u = mp.u[t];
     double q = y / phi;
     yphi2 = q * q;
-    Dt = mp.D[t * mp.Dtv];
+    Dt = p_D[t * mp.Dtv];
     xb = p_xb[t];
 #pragma unroll
-    for (int d = 0; d < M_; ++d) Z[d] = mp.Z[d + M_ * (t * mp.Ztv)];
+    for (int d = 0; d < M_; ++d) Z[d] = p_Z[d + M_ * (t * mp.Ztv)];
     ytil = p_yt[t]; rH = 1.0 / p_Ht[t]; scale = p_sc[t];
   }
   __device__ double logw(const double* x) const {
@@ -330,7 +336,24 @@ struct MngParams {
   const double* Htilde;        // n x p their standard deviations
   const double* scales;        // n
   const double* approx_loglik; // per filter
+  // parameter sets (parset_mng, src/parset_ng.h:42-62; the *Draws policies): per-filter strides of the model
+  // arrays and of the approximation, 0 = shared; lconst_f = per-filter loglik_const (phi enters it) or null
+  size_t fs_Z, fs_T, fs_R, fs_C, fs_D, fs_a1, fs_LP1, fs_phi;
+  size_t fs_a, fs_m, fs_np, fs_n; // alphahat / (Lt, Ct) / (ytilde, Htilde) / scales
+  const double* lconst_f;
 };
+// the launch parameters with every per-filter array advanced to filter f
+__device__ __forceinline__ void mng_load_draw(MngParams& loc, const MngParams& p, uint32_t f) {
+  loc = p;
+  loc.Z += (size_t)f * p.fs_Z; loc.T += (size_t)f * p.fs_T; loc.R += (size_t)f * p.fs_R; loc.C += (size_t)f * p.fs_C;
+  loc.D += (size_t)f * p.fs_D; loc.a1 += (size_t)f * p.fs_a1; loc.LP1 += (size_t)f * p.fs_LP1;
+  loc.phi += (size_t)f * p.fs_phi;
+  if (p.lconst_f) loc.loglik_const = p.lconst_f[f];
+  if (p.alphahat) {
+    loc.alphahat += (size_t)f * p.fs_a; loc.Lt += (size_t)f * p.fs_m; loc.Ct += (size_t)f * p.fs_m;
+    loc.ytilde += (size_t)f * p.fs_np; loc.Htilde += (size_t)f * p.fs_np; loc.scales += (size_t)f * p.fs_n;
+  }
+}
 
 // log g(y_j | s) up to constants, src/model_ssm_mng.cpp:364-386 (shared by log_obs_density :407-442)
 __device__ __forceinline__ double mng_log_obs(int dist, double s, double y, double u, double phi) {
@@ -343,15 +366,18 @@ __device__ __forceinline__ double mng_log_obs(int dist, double s, double y, doub
   }
 }
 
-template <int M_, int K_>
-struct MngBsf : GaussStep<MngBsf<M_, K_>, M_, M_, K_> {
+template <int M_, int K_, bool PerFilter = false>
+struct MngBsf : GaussStep<MngBsf<M_, K_, PerFilter>, M_, M_, K_> {
   static constexpr int M = M_, KI = M_, KP = K_;
   typedef MngParams Params;
+  MngParams loc;
   const MngParams& mp;
   int tw;
   double T[M_ * M_], R[M_ * K_], C[M_];
 
-  __device__ MngBsf(const MngParams& p, uint32_t) : mp(p), tw(0) {}
+  __device__ MngBsf(const MngParams& p, uint32_t f) : mp(PerFilter ? loc : p), tw(0) {
+    if (PerFilter) mng_load_draw(loc, p, f);
+  }
   __device__ double loglik0() const { return 0.0; }
   __device__ double loglik_end() const { return mp.loglik_const; }
   __device__ void init(const double* z, double* x) const {
@@ -411,16 +437,20 @@ struct MngBsf : GaussStep<MngBsf<M_, K_>, M_, M_, K_> {
 // ssm_mng::psi_filter src/model_ssm_mng.cpp:461-559: the proposal of UngPsiM with the
 // multivariate weights of log_weights (:357-393): per observed series
 // log g(y_j | s_j) + 0.5 ((ytilde_j - s_j) / Htilde_j)^2, minus scales_t.
-template <int M_>
-struct MngPsi : GaussStep<MngPsi<M_>, M_, M_, M_> {
+template <int M_, bool PerFilter = false>
+struct MngPsi : GaussStep<MngPsi<M_, PerFilter>, M_, M_, M_> {
   static constexpr int M = M_, KI = M_, KP = M_;
   typedef MngParams Params;
+  MngParams loc;
   const MngParams& mp;
   double al0, scale;
   int tw;
   double ah0[M_], ah1[M_], Cm[M_ * M_], Lm[M_ * M_];
 
-  __device__ MngPsi(const MngParams& p, uint32_t f) : mp(p), tw(0) { al0 = p.approx_loglik[f]; scale = 0.0; }
+  __device__ MngPsi(const MngParams& p, uint32_t f) : mp(PerFilter ? loc : p), tw(0) {
+    if (PerFilter) mng_load_draw(loc, p, f);
+    al0 = p.approx_loglik[f]; scale = 0.0;
+  }
   __device__ double loglik0() const { return al0; }
   __device__ double loglik_end() const { return 0.0; }
   __device__ void init(const double* z, double* x) const {

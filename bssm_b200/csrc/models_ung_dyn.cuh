@@ -18,8 +18,12 @@ struct UngDynBase {
   typedef UngParams Params;
   const UngParams& mp;
   int m, k;
+  const double *pZ, *pD; // this filter's Z and D (parameter sets: one model per filter, else the shared arrays)
   template <int P> struct Noise { double z[P * MAXM]; };
-  __device__ UngDynBase(const UngParams& p) : mp(p), m(p.m_dyn), k(p.k_dyn) {}
+  __device__ UngDynBase(const UngParams& p, uint32_t f) : mp(p), m(p.m_dyn), k(p.k_dyn) {
+    pZ = p.Z + (size_t)f * p.fs_Z;
+    pD = p.D + (size_t)f * p.fs_D;
+  }
   __device__ bool observed(int t) const { return pf_isfinite(mp.y[t]); }
   __device__ __forceinline__ double finish_logw(double w, double) const { return w; }
   // `cnt` standard normals with flat indices f0, f0 + 1, ... (f0 even) of column t
@@ -33,7 +37,7 @@ struct UngDynBase {
   }
   __device__ double signal(const double* x, double Dt, double xb, int t) const {
     if (mp.distribution == 0) return x[0];
-    const double* Z = mp.Z + (size_t)m * (t * mp.Ztv);
+    const double* Z = pZ + (size_t)m * (t * mp.Ztv);
     double zs = 0.0;
     for (int d = 0; d < m; ++d) zs += Z[d] * x[d];
     return Dt + zs + xb;
@@ -44,13 +48,20 @@ struct UngDynBase {
 template <int MAXM>
 struct UngBsfDyn : UngDynBase<MAXM> {
   typedef UngDynBase<MAXM> B;
-  using B::mp; using B::m; using B::k;
-  double y, u, yphi2, Dt, xb, HHt, hc;
+  using B::mp; using B::m; using B::k; using B::pZ; using B::pD;
+  double y, u, yphi2, Dt, xb, HHt, hc, phi, lconst;
+  const double *pT, *pR, *pC, *pa1, *pLP1, *p_xb;
   int tw, ts;
-  __device__ UngBsfDyn(const UngParams& p, uint32_t) : B(p), hc(0.0), tw(0), ts(0) {}
+  __device__ UngBsfDyn(const UngParams& p, uint32_t f) : B(p, f), hc(0.0), tw(0), ts(0) {
+    phi = p.phi_f ? p.phi_f[f] : p.phi;
+    lconst = p.lconst_f ? p.lconst_f[f] : p.loglik_const;
+    pT = p.T + (size_t)f * p.fs_T; pR = p.R + (size_t)f * p.fs_R; pC = p.C + (size_t)f * p.fs_C;
+    pa1 = p.a1 + (size_t)f * p.fs_a1; pLP1 = p.LP1 + (size_t)f * p.fs_LP1;
+    p_xb = p.xbeta + (size_t)f * p.fs_x;
+  }
   __device__ double step_const() const { return hc; }
   __device__ double loglik0() const { return 0.0; }
-  __device__ double loglik_end() const { return mp.loglik_const; }
+  __device__ double loglik_end() const { return lconst; }
   template <int P>
   __device__ void init_all(const StepCtx& c, double (&x)[P][MAXM]) const {
     double z[P * MAXM];
@@ -58,29 +69,29 @@ struct UngBsfDyn : UngDynBase<MAXM> {
     for (int p = 0; p < P; ++p)
       for (int d = 0; d < m; ++d) {
         double s = 0.0;
-        for (int j = 0; j < m; ++j) s += mp.LP1[d + m * j] * z[p * m + j];
-        x[p][d] = mp.a1[d] + s;
+        for (int j = 0; j < m; ++j) s += pLP1[d + m * j] * z[p * m + j];
+        x[p][d] = pa1[d] + s;
       }
   }
   __device__ void begin_weight(int t) {
     tw = t;
     y = mp.y[t];
     u = mp.u[t];
-    double q = y / mp.phi;
+    double q = y / phi;
     yphi2 = q * q;
-    Dt = mp.D[t * mp.Dtv];
-    xb = mp.xbeta[t];
+    Dt = pD[t * mp.Dtv];
+    xb = p_xb[t];
     if (mp.distribution == 5) { HHt = mp.HH[t]; hc = mp.hconst[t]; }
   }
   __device__ double logw(const double* x) const {
     if (mp.distribution == 5) { // ssm_ulg::bsf_filter, src/model_ssm_ulg.cpp:577-580: mu = D + Z'a
-      const double* Z = mp.Z + (size_t)m * (tw * mp.Ztv);
+      const double* Z = pZ + (size_t)m * (tw * mp.Ztv);
       double zs = 0.0;
       for (int d = 0; d < m; ++d) zs += Z[d] * x[d];
       const double mu = Dt + zs;
       return -0.5 * ((y - mu) * (y - mu)) / HHt;
     }
-    return ung_log_obs(mp.distribution, B::signal(x, Dt, xb, tw), y, u, mp.phi, yphi2);
+    return ung_log_obs(mp.distribution, B::signal(x, Dt, xb, tw), y, u, phi, yphi2);
   }
   __device__ void begin_step(int t) { ts = t; }
   template <int P>
@@ -90,9 +101,9 @@ struct UngBsfDyn : UngDynBase<MAXM> {
   template <int P>
   __device__ void propagate_all(const StepCtx&, const typename B::template Noise<P>& nz, const double (&xa)[P][MAXM],
                                 double (&x)[P][MAXM], double (&carry)[P]) const {
-    const double* T = mp.T + (size_t)m * m * (ts * mp.Ttv);
-    const double* R = mp.R + (size_t)m * k * (ts * mp.Rtv);
-    const double* C = mp.C + (size_t)m * (ts * mp.Ctv);
+    const double* T = pT + (size_t)m * m * (ts * mp.Ttv);
+    const double* R = pR + (size_t)m * k * (ts * mp.Rtv);
+    const double* C = pC + (size_t)m * (ts * mp.Ctv);
     for (int p = 0; p < P; ++p) {
       for (int d = 0; d < m; ++d) {
         double ta = 0.0, ru = 0.0;
@@ -111,12 +122,12 @@ struct UngBsfDyn : UngDynBase<MAXM> {
 template <int MAXM>
 struct UngPsiDyn : UngDynBase<MAXM> {
   typedef UngDynBase<MAXM> B;
-  using B::mp; using B::m;
+  using B::mp; using B::m; using B::pD;
   double al0, phi;
   const double *p_ah, *p_Lt, *p_Ct, *p_yt, *p_Ht, *p_sc, *p_xb;
   double y, u, yphi2, Dt, xb, ytil, rH, scale;
   int tw, ts;
-  __device__ UngPsiDyn(const UngParams& p, uint32_t f) : B(p), tw(0), ts(0) {
+  __device__ UngPsiDyn(const UngParams& p, uint32_t f) : B(p, f), tw(0), ts(0) {
     al0 = p.approx_loglik[f];
     phi = p.phi_f ? p.phi_f[f] : p.phi;
     p_ah = p.alphahat + (size_t)f * p.fs_a;
@@ -144,7 +155,7 @@ struct UngPsiDyn : UngDynBase<MAXM> {
     u = mp.u[t];
     double q = y / phi;
     yphi2 = q * q;
-    Dt = mp.D[t * mp.Dtv];
+    Dt = pD[t * mp.Dtv];
     xb = p_xb[t];
     ytil = p_yt[t]; rH = 1.0 / p_Ht[t]; scale = p_sc[t];
   }

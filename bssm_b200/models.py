@@ -132,8 +132,12 @@ def ssm_ung(y, Z, T, R, a1, P1, distribution, phi=1.0, u=1.0, D=0.0, C=None, ini
         C = np.zeros((a1.size, 1))
     if initial_mode is None:
         initial_mode = init_mode(y, u, distribution)
-    return Model("ssm_ung", y, Z, T, R, a1, P1, np.ravel(D), C, u, phi, distribution, initial_mode,
-                 xreg=xreg, beta=beta, **kw)
+    update_fn = kw.pop("update_fn", None)
+    model = Model("ssm_ung", y, Z, T, R, a1, P1, np.ravel(D), C, u, phi, distribution, initial_mode,
+                  xreg=xreg, beta=beta, **kw)
+    # R/models.R ssm_ung(update_fn = ...): theta -> list of the model components that depend on it
+    model.update_fn = update_fn
+    return model
 
 
 def svm(y, rho, sd_ar, sigma=None, mu=None):
@@ -349,7 +353,10 @@ class MngModel:
 
 
 def ssm_mng(y, Z, T, R, a1, P1, distribution, phi=1.0, u=None, D=None, C=None, **kw):
-    return MngModel(y, Z, T, R, a1, P1, distribution, phi=phi, u=u, D=D, C=C, **kw)
+    update_fn = kw.pop("update_fn", None)
+    model = MngModel(y, Z, T, R, a1, P1, distribution, phi=phi, u=u, D=D, C=C, **kw)
+    model.update_fn = update_fn  # R/models.R ssm_mng(update_fn = ...)
+    return model
 
 
 def ssm_ulg(y, Z, H, T, R, a1, P1, D=0.0, C=None):

@@ -373,6 +373,60 @@ int bssm_b200_postcorrection_nongaussian(const bssm_ung_model* model, const bssm
                                          uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
                                          bssm_postcorr_out* out);
 
+/* ---- models whose update_fn lives in R: pre-evaluated parameter sets ---------- */
+/* parset_ung / parset_mng (src/parset_ng.h:11-62, src/parset_ng.cpp:5-215).  ssm_ung and ssm_mng
+ * models map theta onto the model through an R closure (update_fn); the reference evaluates it
+ * for every stored draw BEFORE its OpenMP region and keeps the results in a parset, and
+ * parset::update(model, i) swaps them in per draw.  This struct is that parset: for each
+ * component that update_fn returns, n_stored consecutive slices, each with the shape of the
+ * model's own array (time-varying or not as the model says); NULL = not returned by update_fn
+ * (the model's own array is used for every draw).
+ *   ssm_ung: phi n_stored; Z m x (1|n); T m x m x (1|n); R m x k x (1|n); a1 m; P1 m x m;
+ *            D (1|n); C m x (1|n); beta n_xreg (then xreg n x n_xreg is needed: compute_xbeta)
+ *   ssm_mng: phi p; Z p x m x (1|n); T, R, a1, P1, C as above; D p x (1|n); no beta */
+typedef struct {
+  const double* phi;
+  const double* Z;
+  const double* T;
+  const double* R;
+  const double* a1;
+  const double* P1;
+  const double* D;
+  const double* C;
+  const double* beta;
+  const double* xreg; /* n x n_xreg column-major, with beta */
+  int32_t n_xreg;
+} bssm_parset;
+
+/* replaces: postcorrection_nongaussian(..., model_type = 1) -> approx_mcmc::is_correction_psi<ssm_ung>
+ *           (src/approx_mcmc.cpp:685-804) and, with approx_loglik instead of modes, the ssm_ung
+ *           specialisation of is_correction_bsf (:806-921).  Any m <= 16 for output_type 3
+ *           (weights); output_type 1 / 2 for m <= 3.  modes is n x n_stored.  Other arguments
+ *           and outputs as bssm_b200_postcorrection_nongaussian. */
+int bssm_b200_postcorrection_ung_parset(const bssm_ung_model* model, const bssm_parset* parset,
+                                        int output_type, uint32_t nsim, uint32_t seed, uint32_t n_threads,
+                                        int is_type, const uint32_t* counts, const double* modes,
+                                        uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
+                                        bssm_postcorr_out* out);
+int bssm_b200_is_correction_bsf_ung_parset(const bssm_ung_model* model, const bssm_parset* parset,
+                                           int output_type, uint32_t nsim, uint32_t seed, uint32_t n_threads,
+                                           int is_type, const uint32_t* counts, const double* approx_loglik,
+                                           uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
+                                           bssm_postcorr_out* out);
+/* replaces: postcorrection_nongaussian(..., model_type = 0) -> approx_mcmc::is_correction_psi<ssm_mng>
+ *           (src/approx_mcmc.cpp:1038-1157) and is_correction_bsf<ssm_mng> (:1159-1273).
+ *           modes is p x n x n_stored (mode_storage, src/approx_mcmc.cpp:29).  m <= 3, p <= 8. */
+int bssm_b200_postcorrection_mng_parset(const bssm_mng_model* model, const bssm_parset* parset,
+                                        int output_type, uint32_t nsim, uint32_t seed, uint32_t n_threads,
+                                        int is_type, const uint32_t* counts, const double* modes,
+                                        uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
+                                        bssm_postcorr_out* out);
+int bssm_b200_is_correction_bsf_mng_parset(const bssm_mng_model* model, const bssm_parset* parset,
+                                           int output_type, uint32_t nsim, uint32_t seed, uint32_t n_threads,
+                                           int is_type, const uint32_t* counts, const double* approx_loglik,
+                                           uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
+                                           bssm_postcorr_out* out);
+
 /* replaces: the draw loop of approx_mcmc::is_correction_bsf (src/approx_mcmc.cpp:447-518), the
  *           correction phase of run_mcmc(..., sampling_method = "bsf") for svm / ar1_ng / bsm_ng
  *           (level only): one bootstrap filter per stored draw at that draw's theta;

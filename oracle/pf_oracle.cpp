@@ -2167,6 +2167,161 @@ int orc_is_correction_bsf_sde(const bssm_sde_model* M, uint32_t L_f, int output_
   return 0;
 }
 
+/* ------------------------------------------------ parameter sets (parset_ng) */
+} /* extern "C" */
+/* the draw loop shared by is_correction_psi / is_correction_bsf of the ssm_ung and ssm_mng specialisations
+ * (src/approx_mcmc.cpp:685-804, :806-921, :1038-1157, :1159-1273): filter(c, i, nsimc, alpha_i, weights_i,
+ * indices) runs draw i (stored column c) and returns its log-likelihood; weight = exp(loglik [- approx_loglik_c]),
+ * posterior = prior (0) + log(weight) */
+template <class Filter>
+static int parset_correction(size_t n, size_t m, int output_type, uint32_t nsim, uint32_t seed, int threads,
+                             int is_type, const uint32_t* counts, uint32_t n_stored, const double* approx_loglik,
+                             double* weights, double* posterior, double* alpha, double* alphahat, double* Vt,
+                             double* loglik_out, Filter&& filter) {
+  const size_t n1 = n + 1;
+  std::vector<uint32_t> src, cnt;
+  for (uint32_t i = 0; i < n_stored; ++i) {
+    if (is_type == 3) for (uint32_t c = 0; c < counts[i]; ++c) { src.push_back(i); cnt.push_back(1u); }
+    else { src.push_back(i); cnt.push_back(counts[i]); }
+  }
+  const int64_t nd = (int64_t)src.size();
+  std::vector<double> ah_all, Vt_all;
+  if (output_type == 2) { ah_all.assign(m * n1 * nd, 0.0); Vt_all.assign(m * m * n1 * nd, 0.0); }
+#ifdef _OPENMP
+  if (threads < 1) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(threads)
+#endif
+  for (int64_t i = 0; i < nd; ++i) {
+    unsigned int nsimc = nsim;
+    if (is_type == 1) nsimc *= cnt[i];
+    std::vector<double> alpha_i(m * n1 * nsimc, 0.0), weights_i((size_t)nsimc * n1, 0.0);
+    std::vector<uint32_t> indices((size_t)nsimc * n, 0u);
+    const double ll = filter(src[i], (uint32_t)i, nsimc, alpha_i.data(), weights_i.data(), indices.data());
+    if (loglik_out) loglik_out[i] = ll;
+    weights[i] = pf_exp(approx_loglik ? ll - approx_loglik[src[i]] : ll);
+    if (output_type != 3) {
+      orc_filter_smoother(alpha_i.data(), indices.data(), (int)m, (int)n1, nsimc);
+      if (output_type == 1) {
+        uint32_t b = (uint32_t)(pf_pick_uniform(seed, (uint32_t)i) * (double)nsimc);
+        if (b > nsimc - 1) b = nsimc - 1;
+        for (size_t t = 0; t < n1; ++t)
+          for (size_t d = 0; d < m; ++d) alpha[m * n1 * i + t + n1 * d] = alpha_i[d + m * (t + n1 * b)];
+      } else {
+        orc_summary(alpha_i.data(), (int)m, (int)n1, nsimc, &ah_all[m * n1 * i], &Vt_all[m * m * n1 * i]);
+      }
+    }
+  }
+  if (output_type == 2) {
+    std::vector<double> ah(m * n1, 0.0), V(m * m * n1, 0.0), Valpha(m * m * n1, 0.0), diff(m), diff2(m);
+    double sum_w = 0.0;
+    for (int64_t i = 0; i < nd; ++i) {
+      double wnew = weights[i] * cnt[i];
+      sum_w += wnew;
+      for (size_t t = 0; t < n1; ++t) {
+        for (size_t d = 0; d < m; ++d) {
+          diff[d] = ah_all[m * n1 * i + d + m * t] - ah[d + m * t];
+          ah[d + m * t] += wnew / sum_w * diff[d];
+          diff2[d] = ah_all[m * n1 * i + d + m * t] - ah[d + m * t];
+        }
+        for (size_t c = 0; c < m; ++c)
+          for (size_t r = 0; r < m; ++r) {
+            Valpha[r + m * (c + m * t)] += wnew * diff[r] * diff2[c];
+            V[r + m * (c + m * t)] += wnew / sum_w * (Vt_all[m * m * n1 * i + r + m * (c + m * t)] - V[r + m * (c + m * t)]);
+          }
+      }
+    }
+    for (size_t t = 0; t < n1; ++t)
+      for (size_t d = 0; d < m; ++d) alphahat[t + n1 * d] = ah[d + m * t]; /* alphahat.t() */
+    for (size_t e = 0; e < m * m * n1; ++e) Vt[e] = V[e] + Valpha[e] / sum_w;
+  }
+  for (int64_t i = 0; i < nd; ++i) posterior[i] = 0.0 + 0.0 + pf_log(weights[i]);
+  return 0;
+}
+
+/* parset_ung::update(model, i), src/parset_ng.cpp:84-124 (xb: storage for compute_xbeta) */
+static void parset_update_ung(const bssm_ung_model* M, const bssm_parset* ps, uint32_t c, bssm_ung_model& Mi,
+                              std::vector<double>& xb) {
+  Mi = *M;
+  const size_t n = M->n, m = M->m, k = M->k;
+  if (ps->phi) Mi.phi = ps->phi[c];
+  if (ps->Z) Mi.Z = ps->Z + m * (M->Ztv ? n : 1) * c;
+  if (ps->T) Mi.T = ps->T + m * m * (M->Ttv ? n : 1) * c;
+  if (ps->R) Mi.R = ps->R + m * k * (M->Rtv ? n : 1) * c;
+  if (ps->a1) Mi.a1 = ps->a1 + m * c;
+  if (ps->P1) Mi.P1 = ps->P1 + m * m * c;
+  if (ps->D) Mi.D = ps->D + (M->Dtv ? n : 1) * c;
+  if (ps->C) Mi.C = ps->C + m * (M->Ctv ? n : 1) * c;
+  if (ps->beta) {
+    xb.assign(n, 0.0);
+    for (size_t t = 0; t < n; ++t) {
+      double sum = 0.0;
+      for (int j = 0; j < ps->n_xreg; ++j) sum += ps->xreg[t + n * j] * ps->beta[(size_t)ps->n_xreg * c + j];
+      xb[t] = sum;
+    }
+    Mi.xbeta = xb.data();
+  }
+}
+/* parset_mng::update(model, i), src/parset_ng.cpp:185-215 */
+static void parset_update_mng(const bssm_mng_model* M, const bssm_parset* ps, uint32_t c, bssm_mng_model& Mi) {
+  Mi = *M;
+  const size_t n = M->n, m = M->m, k = M->k, p = M->p;
+  if (ps->phi) Mi.phi = ps->phi + p * c;
+  if (ps->Z) Mi.Z = ps->Z + p * m * (M->Ztv ? n : 1) * c;
+  if (ps->T) Mi.T = ps->T + m * m * (M->Ttv ? n : 1) * c;
+  if (ps->R) Mi.R = ps->R + m * k * (M->Rtv ? n : 1) * c;
+  if (ps->a1) Mi.a1 = ps->a1 + m * c;
+  if (ps->P1) Mi.P1 = ps->P1 + m * m * c;
+  if (ps->D) Mi.D = ps->D + p * (M->Dtv ? n : 1) * c;
+  if (ps->C) Mi.C = ps->C + m * (M->Ctv ? n : 1) * c;
+}
+extern "C" {
+
+/* is_correction_psi<ssm_ung> (src/approx_mcmc.cpp:685-804; modes != null) and is_correction_bsf<ssm_ung>
+ * (:806-921; approx_loglik != null) with the parameter sets of src/parset_ng.cpp */
+int orc_correction_ung_parset(const bssm_ung_model* M, const bssm_parset* ps, int output_type, uint32_t nsim,
+                              uint32_t seed, int threads, int is_type, const uint32_t* counts, const double* modes,
+                              const double* approx_loglik, uint32_t n_stored, int arith, double* weights,
+                              double* posterior, double* alpha, double* alphahat, double* Vt, double* loglik_out) {
+  if ((modes != nullptr) == (approx_loglik != nullptr)) return 1;
+  const size_t n = M->n;
+  return parset_correction(
+      n, M->m, output_type, nsim, seed, threads, is_type, counts, n_stored, approx_loglik, weights, posterior, alpha,
+      alphahat, Vt, loglik_out,
+      [&](uint32_t c, uint32_t i, uint32_t nsimc, double* alpha_i, double* weights_i, uint32_t* indices) {
+        bssm_ung_model Mi;
+        std::vector<double> xb;
+        parset_update_ung(M, ps, c, Mi, xb);
+        int32_t st;
+        double al;
+        if (modes)
+          return orc_ung_psi_filter_m(&Mi, modes + n * c, nsimc, seed, i, arith, alpha_i, weights_i, indices, &al, &st,
+                                      nullptr, nullptr, nullptr);
+        return orc_ung_bsf_filter(&Mi, nsimc, seed, i, arith, alpha_i, weights_i, indices, &st);
+      });
+}
+
+/* is_correction_psi<ssm_mng> (src/approx_mcmc.cpp:1038-1157) and is_correction_bsf<ssm_mng> (:1159-1273);
+ * modes is p x n x n_stored (mode_storage, :29) */
+int orc_correction_mng_parset(const bssm_mng_model* M, const bssm_parset* ps, int output_type, uint32_t nsim,
+                              uint32_t seed, int threads, int is_type, const uint32_t* counts, const double* modes,
+                              const double* approx_loglik, uint32_t n_stored, int arith, double* weights,
+                              double* posterior, double* alpha, double* alphahat, double* Vt, double* loglik_out) {
+  if ((modes != nullptr) == (approx_loglik != nullptr)) return 1;
+  const size_t n = M->n, p = M->p;
+  return parset_correction(
+      n, M->m, output_type, nsim, seed, threads, is_type, counts, n_stored, approx_loglik, weights, posterior, alpha,
+      alphahat, Vt, loglik_out,
+      [&](uint32_t c, uint32_t i, uint32_t nsimc, double* alpha_i, double* weights_i, uint32_t* indices) {
+        bssm_mng_model Mi;
+        parset_update_mng(M, ps, c, Mi);
+        int32_t st;
+        double al;
+        if (modes)
+          return orc_mng_psi_filter(&Mi, modes + p * n * c, nsimc, seed, i, arith, alpha_i, weights_i, indices, &al, &st);
+        return orc_mng_bsf_filter(&Mi, nsimc, seed, i, arith, alpha_i, weights_i, indices, &st);
+      });
+}
+
 /* dmvnorm(x, mean, sigma, lwr = false, logd = true) for a full-rank m x m covariance
  * (src/dmvnorm.cpp:4-60), the density the ssm_nlg weights are built from: test hook for the
  * reference's own known-answer test (tests/testthat/test_basics.R:176-201) */

@@ -322,6 +322,39 @@ def is_correction_bsf_nlg(model, mcmc_output, N, is_type=2, seed=1, threads=0, a
     return r
 
 
+def correction_parset(model, mcmc_output, N, is_type=2, seed=1, threads=0, arith=ARITH_REPRO, bsf=False):
+    """oracle of is_correction_psi / is_correction_bsf for ssm_ung and ssm_mng models with an update_fn
+    (src/approx_mcmc.cpp:685-921, :1038-1273); the parset is built like bssm_b200.post_correct builds it"""
+    from bssm_b200.api import build_parset, n_draws
+    from bssm_b200._lib import Parset
+    mng = model.cls == "ssm_mng"
+    counts = np.ascontiguousarray(mcmc_output["counts"], dtype=np.uint32)
+    ps = build_parset(model, np.asarray(mcmc_output["theta"], dtype=np.float64))
+    modes = approx = None
+    if bsf:
+        approx = np.ascontiguousarray(mcmc_output["approx_loglik"], dtype=np.float64)
+    else:
+        rows = model.n * (model.p if mng else 1)
+        modes = np.asfortranarray(np.asarray(mcmc_output["modes"], dtype=np.float64).reshape(rows, -1, order="F"))
+    ot = int(mcmc_output.get("output_type", 3))
+    nd = n_draws(mcmc_output, is_type)
+    n, m = model.n, model.m
+    r = Result()
+    r.weights, r.posterior, r.loglik = np.zeros(nd), np.zeros(nd), np.zeros(nd)
+    r.alpha = np.zeros((n + 1, m, nd), order="F") if ot == 1 else None
+    r.alphahat = np.zeros((n + 1, m), order="F") if ot == 2 else None
+    r.Vt = np.zeros((m, m, n + 1), order="F") if ot == 2 else None
+    ms = model.c_struct()
+    f = L().orc_correction_mng_parset if mng else L().orc_correction_ung_parset
+    f.argtypes = [C.POINTER(MngModel if mng else UngModel), C.POINTER(Parset), C.c_int, C.c_uint32, C.c_uint32,
+                  C.c_int, C.c_int, c_uint32_p, c_double_p, c_double_p, C.c_uint32, C.c_int] + [c_double_p] * 6
+    rc = f(C.byref(ms), C.byref(ps), ot, N, seed, threads, is_type, uptr(counts), dptr(modes), dptr(approx),
+           counts.size, arith, dptr(r.weights), dptr(r.posterior), dptr(r.alpha), dptr(r.alphahat), dptr(r.Vt),
+           dptr(r.loglik))
+    assert rc == 0
+    return r
+
+
 def nlg_bsf_filter(model, N, seed, filt=0, arith=ARITH_REPRO):
     r = _alloc(model, N)
     ms = model.c_struct()
