@@ -66,9 +66,119 @@ static void check_rc(int rc) {
   if (rc != 0) error("bssm_b200: %s", bssm_b200_last_error()); /* C++ exception -> R error, as BEGIN_RCPP does */
 }
 
+/* Rcpp::List::containsElementNamed + operator[] */
+static SEXP list_find(SEXP list, const char* name) {
+  SEXP names = getAttrib(list, R_NamesSymbol);
+  if (names == R_NilValue) return R_NilValue;
+  for (R_xlen_t i = 0; i < XLENGTH(list); i++)
+    if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) return VECTOR_ELT(list, i);
+  return R_NilValue;
+}
+
+/* R list -> bssm_mng_model (model_type 0), the fields of src/model_ssm_mng.cpp:7-30.  y, u and initial_mode are
+ * n x p as R holds them (the reference transposes on entry; the library reads them as they are). */
+static void fill_mng(SEXP model, bssm_mng_model* M) {
+  SEXP y = list_get(model, "y"), Z = list_get(model, "Z"), T = list_get(model, "T"), R = list_get(model, "R");
+  SEXP a1 = list_get(model, "a1"), D = list_get(model, "D"), C = list_get(model, "C");
+  memset(M, 0, sizeof(*M));
+  M->n = INTEGER(getAttrib(y, R_DimSymbol))[0]; M->p = INTEGER(getAttrib(y, R_DimSymbol))[1];
+  M->m = (int)XLENGTH(a1); M->k = INTEGER(getAttrib(R, R_DimSymbol))[1];
+  M->Ztv = XLENGTH(Z) > (R_xlen_t)M->p * M->m; M->Ttv = XLENGTH(T) > (R_xlen_t)M->m * M->m;
+  M->Rtv = XLENGTH(R) > (R_xlen_t)M->m * M->k; M->Dtv = XLENGTH(D) > M->p; M->Ctv = XLENGTH(C) > M->m;
+  /* R/post_correction.R:262-264 leaves doubles after pmatch(...) - 1: 1 poisson .. 5 gaussian */
+  SEXP dist = PROTECT(coerceVector(list_get(model, "distribution"), INTSXP));
+  int32_t* dcode = (int32_t*)R_alloc(M->p, sizeof(int32_t));
+  for (int j = 0; j < M->p; j++) dcode[j] = INTEGER(dist)[j];
+  UNPROTECT(1);
+  M->distribution = dcode;
+  M->y = REAL(y); M->u = REAL(list_get(model, "u")); M->Z = REAL(Z); M->T = REAL(T); M->R = REAL(R);
+  M->a1 = REAL(a1); M->P1 = REAL(list_get(model, "P1")); M->D = REAL(D); M->C = REAL(C);
+  M->phi = REAL(list_get(model, "phi"));
+  M->max_iter = asInteger(list_get(model, "max_iter"));
+  M->conv_tol = asReal(list_get(model, "conv_tol"));
+  M->local_approx = asLogical(list_get(model, "local_approx"));
+  M->initial_mode = REAL(list_get(model, "initial_mode"));
+}
+
+/* parset_ung / parset_mng constructors (src/parset_ng.cpp:5-82, :127-183): update_fn(theta_i) for every stored
+ * draw, on R's main thread and before any device work, exactly where the reference evaluates it (before its
+ * OpenMP region, src/approx_mcmc.cpp:698, :1051).  Components update_fn does not return stay NULL. */
+static void build_parset(SEXP model, SEXP theta_, int n_par, int n_stored, int p_phi, bssm_parset* ps) {
+  static const char* names[9] = {"phi", "Z", "T", "R", "a1", "P1", "D", "C", "beta"};
+  const double** slots[9] = {&ps->phi, &ps->Z, &ps->T, &ps->R, &ps->a1, &ps->P1, &ps->D, &ps->C, &ps->beta};
+  double* bufs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  R_xlen_t sizes[9];
+  SEXP update_fn = list_get(model, "update_fn");
+  memset(ps, 0, sizeof(*ps));
+  for (int c = 0; c < 9; c++) sizes[c] = c == 0 ? p_phi : (list_find(model, names[c]) == R_NilValue ? 0 : XLENGTH(list_get(model, names[c])));
+  for (int i = 0; i < n_stored; i++) {
+    SEXP th = PROTECT(allocVector(REALSXP, n_par));
+    memcpy(REAL(th), REAL(theta_) + (R_xlen_t)n_par * i, sizeof(double) * n_par);
+    SEXP call = PROTECT(lang2(update_fn, th));
+    SEXP res = PROTECT(eval(call, R_GlobalEnv));
+    for (int c = 0; c < 9; c++) {
+      SEXP e = list_find(res, names[c]);
+      if (e == R_NilValue) continue;
+      if (XLENGTH(e) != sizes[c]) error("bssm_b200: update_fn returned '%s' with a different size than the model's", names[c]);
+      if (!bufs[c]) bufs[c] = (double*)R_alloc((size_t)sizes[c] * n_stored, sizeof(double));
+      SEXP d = PROTECT(coerceVector(e, REALSXP));
+      memcpy(bufs[c] + sizes[c] * i, REAL(d), sizeof(double) * sizes[c]);
+      UNPROTECT(1);
+    }
+    UNPROTECT(3);
+  }
+  for (int c = 0; c < 9; c++) *slots[c] = bufs[c];
+  if (ps->beta) {
+    SEXP xreg = list_get(model, "xreg");
+    ps->xreg = REAL(xreg);
+    ps->n_xreg = (int)sizes[8];
+  }
+}
+
+/* model_type 0 (ssm_mng) of bsf / bsf_smoother / psi_smoother / nongaussian_loglik
+ * (src/R_bootstrap_filter.cpp:130-155, :366-386, src/R_psi.cpp:60-77, src/R_loglik.cpp:49-55).
+ * which: 0 bsf (filter summaries), 1 bsf_smoother, 2 psi_smoother, 3 psi log-likelihood, 4 bsf log-likelihood */
+static SEXP mng_call(SEXP model_, unsigned N, unsigned seed, int which) {
+  bssm_mng_model G;
+  fill_mng(model_, &G);
+  const int n = G.n, m = G.m;
+  bssm_filter_out out;
+  memset(&out, 0, sizeof(out));
+  if (which >= 3) {
+    check_rc(which == 3 ? bssm_b200_psi_filter_mng(&G, N, seed, &out) : bssm_b200_bsf_mng(&G, N, seed, &out));
+    return ScalarReal(out.loglik);
+  }
+  SEXP w = PROTECT(allocMatrix(REALSXP, N, n + 1)), alpha = PROTECT(alloc3DArray(REALSXP, m, n + 1, N));
+  out.weights = REAL(w); out.alpha = REAL(alpha);
+  SEXP res;
+  if (which == 0) {
+    SEXP at = PROTECT(allocMatrix(REALSXP, m, n + 1)), att = PROTECT(allocMatrix(REALSXP, m, n));
+    SEXP Pt = PROTECT(alloc3DArray(REALSXP, m, m, n + 1)), Ptt = PROTECT(alloc3DArray(REALSXP, m, m, n));
+    out.at = REAL(at); out.att = REAL(att); out.Pt = REAL(Pt); out.Ptt = REAL(Ptt);
+    check_rc(bssm_b200_bsf_mng(&G, N, seed, &out));
+    const char* nm[] = {"at", "att", "Pt", "Ptt", "weights", "logLik", "alpha", ""};
+    res = PROTECT(mkNamed(VECSXP, nm));
+    SET_VECTOR_ELT(res, 0, at); SET_VECTOR_ELT(res, 1, att); SET_VECTOR_ELT(res, 2, Pt); SET_VECTOR_ELT(res, 3, Ptt);
+    SET_VECTOR_ELT(res, 4, w); SET_VECTOR_ELT(res, 5, ScalarReal(out.loglik)); SET_VECTOR_ELT(res, 6, alpha);
+    UNPROTECT(7);
+  } else {
+    SEXP ah = PROTECT(allocMatrix(REALSXP, m, n + 1)), Vt = PROTECT(alloc3DArray(REALSXP, m, m, n + 1));
+    out.alphahat = REAL(ah); out.Vt = REAL(Vt);
+    check_rc(which == 1 ? bssm_b200_bsf_smoother_mng(&G, N, seed, &out) : bssm_b200_psi_smoother_mng(&G, N, seed, &out));
+    const char* nm[] = {"alphahat", "Vt", "weights", "logLik", "alpha", ""};
+    res = PROTECT(mkNamed(VECSXP, nm));
+    SET_VECTOR_ELT(res, 0, ah); SET_VECTOR_ELT(res, 1, Vt); SET_VECTOR_ELT(res, 2, w);
+    SET_VECTOR_ELT(res, 3, ScalarReal(out.loglik)); SET_VECTOR_ELT(res, 4, alpha);
+    UNPROTECT(5);
+  }
+  if (!R_FINITE(out.loglik)) warning("Particle filtering stopped prematurely due to nonfinite log-likelihood.");
+  return res;
+}
+
 /* bsf(model_, nsim, seed, gaussian, model_type): src/R_bootstrap_filter.cpp:15-241 */
 SEXP _bssmb200_bsf(SEXP model_, SEXP nsim_, SEXP seed_, SEXP gaussian_, SEXP model_type_) {
   if (asLogical(gaussian_)) error("bssm_b200: Gaussian models use bssm's own Kalman/BSF code path");
+  if (asInteger(model_type_) == 0) return mng_call(model_, (unsigned)asInteger(nsim_), (unsigned)asInteger(seed_), 0);
   bssm_ung_model M;
   int n = (int)XLENGTH(list_get(model_, "y")), m = (int)XLENGTH(list_get(model_, "a1"));
   unsigned N = (unsigned)asInteger(nsim_);
@@ -96,6 +206,7 @@ SEXP _bssmb200_bsf(SEXP model_, SEXP nsim_, SEXP seed_, SEXP gaussian_, SEXP mod
 
 /* psi_smoother(model_, nsim, seed, model_type): src/R_psi.cpp:52-171 */
 SEXP _bssmb200_psi_smoother(SEXP model_, SEXP nsim_, SEXP seed_, SEXP model_type_) {
+  if (asInteger(model_type_) == 0) return mng_call(model_, (unsigned)asInteger(nsim_), (unsigned)asInteger(seed_), 2);
   bssm_ung_model M;
   int n = (int)XLENGTH(list_get(model_, "y")), m = (int)XLENGTH(list_get(model_, "a1"));
   unsigned N = (unsigned)asInteger(nsim_);
@@ -141,6 +252,7 @@ static void fill_map(SEXP model, int model_type, bssm_theta_map* map) {
 /* bsf_smoother(model_, nsim, seed, gaussian, model_type): src/R_bootstrap_filter.cpp:245-457 */
 SEXP _bssmb200_bsf_smoother(SEXP model_, SEXP nsim_, SEXP seed_, SEXP gaussian_, SEXP model_type_) {
   if (asLogical(gaussian_)) error("bssm_b200: Gaussian models use bssm's own Kalman/BSF code path");
+  if (asInteger(model_type_) == 0) return mng_call(model_, (unsigned)asInteger(nsim_), (unsigned)asInteger(seed_), 1);
   bssm_ung_model M;
   int n = (int)XLENGTH(list_get(model_, "y")), m = (int)XLENGTH(list_get(model_, "a1"));
   unsigned N = (unsigned)asInteger(nsim_);
@@ -165,6 +277,11 @@ SEXP _bssmb200_bsf_smoother(SEXP model_, SEXP nsim_, SEXP seed_, SEXP gaussian_,
 /* nongaussian_loglik(model_, nsim, sampling_method, seed, model_type): src/R_loglik.cpp:41-87.
  * sampling_method 1 = psi-APF, 2 = bootstrap filter; nothing but the scalar crosses PCIe. */
 SEXP _bssmb200_nongaussian_loglik(SEXP model_, SEXP nsim_, SEXP sampling_method_, SEXP seed_, SEXP model_type_) {
+  if (asInteger(model_type_) == 0) {
+    int sm = asInteger(sampling_method_);
+    if (sm != 1 && sm != 2) error("bssm_b200: sampling_method must be 1 (psi) or 2 (bsf); SPDK stays on bssm's CPU path");
+    return mng_call(model_, (unsigned)asInteger(nsim_), (unsigned)asInteger(seed_), sm == 1 ? 3 : 4);
+  }
   bssm_ung_model M;
   int n = (int)XLENGTH(list_get(model_, "y"));
   double* xb = (double*)R_alloc(n, sizeof(double));
@@ -203,13 +320,24 @@ SEXP _bssmb200_suggest_n_nongaussian(SEXP model_, SEXP theta_, SEXP candidates_,
 SEXP _bssmb200_postcorrection_nongaussian(SEXP model_, SEXP model_type_, SEXP output_type_, SEXP nsim_,
                                           SEXP seed_, SEXP n_threads_, SEXP is_type_, SEXP counts_,
                                           SEXP theta_, SEXP modes_) {
+  const int model_type = asInteger(model_type_);
   bssm_ung_model M;
-  int n = (int)XLENGTH(list_get(model_, "y")), m = (int)XLENGTH(list_get(model_, "a1"));
-  double* xb = (double*)R_alloc(n, sizeof(double));
-  fill_ung(model_, &M, xb);
+  bssm_mng_model G;
   bssm_theta_map map;
-  fill_map(model_, asInteger(model_type_), &map);
+  bssm_parset ps;
+  int n, m = (int)XLENGTH(list_get(model_, "a1"));
   int n_stored = (int)XLENGTH(counts_), n_par = INTEGER(getAttrib(theta_, R_DimSymbol))[0];
+  if (model_type == 0) { /* ssm_mng: y is n x p, update_fn in R (src/R_postcorrection.cpp:186-194) */
+    fill_mng(model_, &G);
+    n = G.n;
+    build_parset(model_, theta_, n_par, n_stored, G.p, &ps);
+  } else {
+    n = (int)XLENGTH(list_get(model_, "y"));
+    double* xb = (double*)R_alloc(n, sizeof(double));
+    fill_ung(model_, &M, xb);
+    if (model_type == 1) build_parset(model_, theta_, n_par, n_stored, 1, &ps); /* ssm_ung, :195-202 */
+    else fill_map(model_, model_type, &map);
+  }
   int is_type = asInteger(is_type_), output_type = asInteger(output_type_);
   R_xlen_t nd = 0;
   for (int i = 0; i < n_stored; i++) nd += is_type == 3 ? INTEGER(counts_)[i] : 1;
@@ -222,10 +350,17 @@ SEXP _bssmb200_postcorrection_nongaussian(SEXP model_, SEXP model_type_, SEXP ou
   out.weights = REAL(w); out.posterior = REAL(post);
   if (output_type == 1) out.alpha = REAL(alpha);
   if (output_type == 2) { out.alphahat = REAL(ah); out.Vt = REAL(Vt); }
-  check_rc(bssm_b200_postcorrection_nongaussian(&M, &map, output_type, (unsigned)asInteger(nsim_),
-                                                (unsigned)asInteger(seed_), (unsigned)asInteger(n_threads_), is_type,
-                                                (const uint32_t*)INTEGER(counts_), REAL(theta_), (unsigned)n_par,
-                                                REAL(modes_), (unsigned)n_stored, 0, 0, &out));
+  const unsigned nsim = (unsigned)asInteger(nsim_), seed = (unsigned)asInteger(seed_), thr = (unsigned)asInteger(n_threads_);
+  const uint32_t* counts = (const uint32_t*)INTEGER(counts_);
+  if (model_type == 0)
+    check_rc(bssm_b200_postcorrection_mng_parset(&G, &ps, output_type, nsim, seed, thr, is_type, counts, REAL(modes_),
+                                                 (unsigned)n_stored, 0, 0, &out));
+  else if (model_type == 1)
+    check_rc(bssm_b200_postcorrection_ung_parset(&M, &ps, output_type, nsim, seed, thr, is_type, counts, REAL(modes_),
+                                                 (unsigned)n_stored, 0, 0, &out));
+  else
+    check_rc(bssm_b200_postcorrection_nongaussian(&M, &map, output_type, nsim, seed, thr, is_type, counts, REAL(theta_),
+                                                  (unsigned)n_par, REAL(modes_), (unsigned)n_stored, 0, 0, &out));
   const char* nm[] = {"alpha", "alphahat", "Vt", "weights", "posterior", ""};
   SEXP res = PROTECT(mkNamed(VECSXP, nm));
   SET_VECTOR_ELT(res, 0, alpha); SET_VECTOR_ELT(res, 1, ah); SET_VECTOR_ELT(res, 2, Vt);

@@ -38,4 +38,11 @@ SEXP Rf_ScalarReal(double);
 #define alloc3DArray Rf_alloc3DArray
 #define mkNamed Rf_mkNamed
 #define ScalarReal Rf_ScalarReal
+extern SEXP R_GlobalEnv;
+SEXP Rf_lang2(SEXP, SEXP);
+SEXP Rf_eval(SEXP, SEXP);
+SEXP Rf_coerceVector(SEXP, SEXPTYPE);
+#define lang2 Rf_lang2
+#define eval Rf_eval
+#define coerceVector Rf_coerceVector
 #endif
