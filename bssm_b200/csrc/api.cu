@@ -104,6 +104,10 @@ int choose_geometry(uint32_t N, uint32_t n_filters, Geometry* g, bool p2_only = 
     ranks = cdiv(N, tb * (uint32_t)P);
     if (ranks > capacity) return fail(BSSM_B200_ERR_UNSUPPORTED, "too many particles for one resident group (N <= 1.2M)");
   }
+  // the latency path (pf_small.cuh): few small filters cannot fill the device, what counts is the length of
+  // one step's dependency chain.  Many small filters (post_correct) are a throughput problem: general kernel.
+  const uint32_t small_max = (uint32_t)env_int("BSSM_B200_SMALL_MAX_FILTERS", 148);
+  const bool small_path = !p2_only && N <= 1024 && n_filters <= small_max && !env_int("BSSM_B200_NO_SMALL", 0);
   if (p2_only) { // run-time-m policies: two particles per thread, whatever the size
     P = 2;
     if (N <= 2048) { ranks = 1; mode = pf::SYNC_BLOCK; }
@@ -120,6 +124,10 @@ int choose_geometry(uint32_t N, uint32_t n_filters, Geometry* g, bool p2_only = 
   if (forced_block >= 32 && (uint32_t)forced_block * P * ranks >= N) block = round32((uint32_t)forced_block);
   if (block > 1024) return fail(BSSM_B200_ERR_ARG, "geometry: too many particles per CTA");
   if (block < 32) block = 32;
+  if (small_path && forced_ranks <= 0 && forced_P == 0 && forced_block == 0) {
+    P = 2; ranks = 1; mode = pf::SYNC_SMALL;
+    block = 2 * round32(cdiv(N, 2u)); // consumers + producers
+  }
   g->P = P; g->block = (int)block; g->ranks = ranks; g->sync_mode = mode;
   return 0;
 }
@@ -1705,7 +1713,8 @@ static int run_fetch_streaming(bssm_b200_job* J, bssm_filter_out* out) {
   const uint32_t N = J->N;
   const size_t bytes = (size_t)N * (n + 1) * 8 * ((s_alpha ? m : 0) + (s_w ? 1 : 0));
   const size_t min_bytes = (size_t)env_int("BSSM_B200_STREAM_MIN_MB", 32) << 20; // tests force 0
-  if (J->n_filters != 1 || bytes == 0 || bytes < min_bytes || env_int("BSSM_B200_NO_STREAMING", 0)) {
+  if (J->n_filters != 1 || bytes == 0 || bytes < min_bytes || env_int("BSSM_B200_NO_STREAMING", 0) ||
+      J->geo.sync_mode == pf::SYNC_SMALL) { // the latency kernel does not publish its progress
     float ms = 0;
     int rc = bssm_b200_job_run(J, &ms);
     return rc ? rc : bssm_b200_job_fetch(J, 0, out);

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <cstring>
 #include "pf_device.cuh"
+#include "pf_small.cuh"
 
 #ifndef PF_SMALL_MAXT
 #define PF_SMALL_MAXT 512
@@ -86,6 +87,22 @@ int occupancy_V(const Geometry& g, int* out) {
   return 0;
 }
 
+// the latency path (pf_small.cuh): one CTA per filter, N <= 1024, half the CTA produces the random numbers
+template <class Model>
+int launch_small(const pf::FilterParams& fp, const typename Model::Params& mp, const Geometry& g,
+                 uint32_t n_filters, cudaStream_t stream) {
+  if constexpr (pf::ModelDyn<Model>::value) {
+    return -1;
+  } else {
+    auto kern = pf::small_filter_kernel<Model>;
+    const size_t smem = pf::small_smem_bytes<Model>(fp.N);
+    if (smem > 48 * 1024) PFL_CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<n_filters, g.block, smem, stream>>>(fp, mp);
+    PFL_CU(cudaGetLastError());
+    return 0;
+  }
+}
+
 // kernel variants: P particles per thread, 64 registers per thread in all of them.
 // A 128-register variant (no spills, half the warps) was measured and is 15-40%
 // slower on every workload: latency hiding by resident warps matters more than
@@ -93,6 +110,7 @@ int occupancy_V(const Geometry& g, int* out) {
 template <class Model>
 int launch(const pf::FilterParams& fp, const typename Model::Params& mp, const Geometry& g,
            uint32_t n_filters, cudaStream_t stream) {
+  if (g.sync_mode == pf::SYNC_SMALL) return launch_small<Model>(fp, mp, g, n_filters, stream);
   const bool small = g.block <= 512;
   switch (g.P) {
     case 2: return small ? launch_V<Model, 2, PF_SMALL_MAXT, PF_SMALL_MINB>(fp, mp, g, n_filters, stream)

@@ -443,3 +443,42 @@ def test_smoother_on_a_filter_that_stops_midway(engine):
     assert np.array_equal(np.transpose(res["alpha"], (1, 0, 2)).view(np.uint64), sm.view(np.uint64))
     mean, cov = orc.summary(sm)
     np.testing.assert_allclose(res["alphahat"], mean.T, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("kind", ["svm_psi", "bsm_bsf", "growth_bsf", "growth_psi", "gbm", "mng_psi", "stopped"])
+@pytest.mark.parametrize("N", [2, 100, 257, 1024])
+def test_latency_kernel_equals_general_kernel(engine, kind, N, monkeypatch):
+    """few small filters run on the one-CTA latency kernel (pf_small.cuh: half the CTA produces the random
+    numbers and the log-likelihood, the state column lives in shared memory); BSSM_B200_NO_SMALL=1 sends the
+    same call through the general kernel.  Same bits, and both equal the oracle (checked for one kind)."""
+    if kind == "svm_psi":
+        model, call = data.svm_model(60, missing=(7,)), lambda: engine.particle_smoother(model, N, method="psi", seed=3, return_indices=True)
+    elif kind == "bsm_bsf":
+        model, call = data.poisson_bsm_model(50), lambda: engine.bootstrap_filter(model, N, seed=3, return_indices=True)
+    elif kind == "growth_bsf":
+        model, call = data.growth_model(40, missing=(5,)), lambda: engine.bootstrap_filter(model, N, seed=3, return_indices=True)
+    elif kind == "growth_psi":
+        model, call = data.growth_model(40), lambda: engine.particle_smoother(model, N, method="psi", seed=3, return_indices=True)
+    elif kind == "gbm":
+        model, call = data.gbm_model(30), lambda: engine.bootstrap_filter(model, N, seed=3, L=3, return_indices=True)
+    elif kind == "mng_psi":
+        model, call = data.mng_model(40), lambda: engine.particle_smoother(model, N, method="psi", seed=3, return_indices=True)
+    else:
+        model = data.svm_model(30)
+        model.phi = 0.0
+
+        def call():
+            with pytest.warns(UserWarning, match="stopped prematurely"):
+                return engine.bootstrap_filter(model, N, seed=3, return_indices=True)
+    small = call()
+    monkeypatch.setenv("BSSM_B200_NO_SMALL", "1")
+    general = call()
+    for key in small:
+        a, b = small[key], general[key]
+        if isinstance(a, np.ndarray):
+            assert np.array_equal(a, b, equal_nan=True), key
+        elif isinstance(a, float):
+            assert a == b or (np.isnan(a) and np.isnan(b)), key
+    if kind == "svm_psi":
+        ref = orc.psi_filter(model, N, seed=3)
+        assert np.array_equal(small["indices"], ref.indices) and small["logLik"] == ref.loglik
