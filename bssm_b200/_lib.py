@@ -163,6 +163,7 @@ def lib():
         C.POINTER(NlgModel), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, c_uint32_p, c_double_p,
         C.c_uint32, c_double_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PostcorrOut)]
     L.bssm_b200_is_correction_bsf_nlg.argtypes = L.bssm_b200_postcorrection_nonlinear.argtypes
+    L.bssm_b200_sde_register.argtypes = [C.c_char_p, C.POINTER(C.c_int32)]
     for name, mt in (("ung", UngModel), ("mng", MngModel)):
         for fn in ("bssm_b200_postcorrection_%s_parset", "bssm_b200_is_correction_bsf_%s_parset"):
             getattr(L, fn % name).argtypes = [

@@ -16,7 +16,7 @@ LIB = os.path.join(CSRC, "libbssm_b200.so")
 OBJ = os.path.join(CSRC, "_obj")
 # one translation unit per model family: the kernel instantiations dominate build time
 SOURCES = ["api.cu", "k_ung_psi1.cu", "k_ung_psim.cu", "k_ung_bsf_a.cu", "k_ung_bsf_b.cu", "k_ung_dyn.cu",
-           "k_mng.cu", "k_mng_draws.cu", "k_nlg.cu", "k_nlg_lin.cu", "k_nlg_draws.cu", "k_sde.cu"]
+           "k_mng.cu", "k_mng_draws.cu", "k_nlg.cu", "k_nlg_lin.cu", "k_nlg_draws.cu", "k_sde.cu", "user_models.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",

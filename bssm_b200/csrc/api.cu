@@ -136,6 +136,7 @@ int choose_geometry(uint32_t N, uint32_t n_filters, Geometry* g, bool p2_only = 
 // status of the pfl:: layer (launch.cuh) -> C ABI status + message
 int launch_status(int rc, const char* what) {
   if (rc == 0) return 0;
+  if (rc == -2) return fail(BSSM_B200_ERR_ARG, std::string(what) + ": " + pfl::user_model_error());
   if (rc < 0) return fail(BSSM_B200_ERR_UNSUPPORTED, std::string(what) + ": variant not instantiated in this build");
   return fail(BSSM_B200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString((cudaError_t)rc));
 }
@@ -495,7 +496,7 @@ struct bssm_b200_job {
   pf::NlgParams np{};
   pf::SdeParams sp{};
   int sde_model_id = 0, nlg_model_id = 0;
-  DevBuf<double> lgy, theta_f;
+  DevBuf<double> lgy, theta_f, theta_u;
   pf::MngParams gp{};
   pf::NlgPsiParams npp{};
   DevBuf<double> stepc;
@@ -602,6 +603,10 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
   if (J->kind == KIND_SDE) {
     pf::SdeParams sp = J->sp;
     if (sp.theta_f) sp.theta_f += (size_t)6 * f0;
+    if (sp.theta_u) sp.theta_u += (size_t)f0 * sp.theta_u_stride;
+    if (J->sde_model_id >= BSSM_USER_MODEL_BASE)
+      return launch_status(pfl::launch_user_sde(J->sde_model_id, fp, sp, J->geo, nf, sp.theta_u_stride != 0, J->stream),
+                           "sde bsf (user model)");
     return launch_status(pfl::launch_sde_bsf(J->sde_model_id, fp, sp, J->geo, nf, J->stream), "sde bsf");
   }
   if (J->kind == KIND_MNG && J->mng_draws) {
@@ -1109,6 +1114,8 @@ int bssm_b200_job_max_concurrent_filters(const bssm_b200_job* J) {
   int out = 0, rc;
   if (J->kind == KIND_NLG && J->method == BSSM_METHOD_PSI) rc = pfl::occupancy_nlg_psi(J->geo, &out);
   else if (J->kind == KIND_NLG) rc = pfl::occupancy_nlg_bsf(J->geo, &out);
+  else if (J->kind == KIND_SDE && J->sde_model_id >= BSSM_USER_MODEL_BASE)
+    rc = pfl::occupancy_user_sde(J->sde_model_id, J->geo, J->sp.theta_u_stride != 0, &out);
   else if (J->kind == KIND_SDE) rc = pfl::occupancy_sde_bsf(J->geo, &out);
   else if (J->kind == KIND_MNG) rc = pfl::occupancy_mng_bsf(J->geo, &out);
   else if (J->dyn) rc = pfl::occupancy_ung_dyn(J->geo, &out);
@@ -1352,7 +1359,13 @@ static void sde_theta_block(int model_id, const double* th, double* b);
 int bssm_b200_job_set_theta_sde(bssm_b200_job* J, const double* theta, uint32_t n_par) {
   if (!J || !theta) return fail(BSSM_B200_ERR_ARG, "null argument");
   if (J->kind != KIND_SDE) return fail(BSSM_B200_ERR_ARG, "job_set_theta_sde: an ssm_sde job");
-  if (J->sp.theta_f) return fail(BSSM_B200_ERR_ARG, "job_set_theta_sde: IS-correction jobs carry one theta per filter already");
+  if (J->sp.theta_f || J->sp.theta_u_stride) return fail(BSSM_B200_ERR_ARG, "job_set_theta_sde: IS-correction jobs carry one theta per filter already");
+  if (J->sde_model_id >= BSSM_USER_MODEL_BASE) { // user functors read theta from the device
+    if (n_par != J->theta_u.count) return fail(BSSM_B200_ERR_ARG, "job_set_theta_sde: theta has another length than the model's");
+    CU(cudaMemcpyAsync(J->theta_u.p, theta, sizeof(double) * n_par, cudaMemcpyHostToDevice, J->stream));
+    CU(cudaStreamSynchronize(J->stream)); // theta is the caller's buffer
+    return 0;
+  }
   if (n_par < 3) return fail(BSSM_B200_ERR_ARG, "ssm_sde registry models need 3 parameters");
   double b[6];
   sde_theta_block(J->sde_model_id, theta, b);
@@ -1460,9 +1473,13 @@ static int create_sde_job(const bssm_sde_model* M, uint32_t nsim, uint32_t L, ui
                           const double* draw_theta, uint32_t n_par, bssm_b200_job** job) {
   if (!M || !job || !M->y || !M->theta) return fail(BSSM_B200_ERR_ARG, "null argument");
   *job = nullptr;
-  if (M->model_id != BSSM_SDE_GBM && M->model_id != BSSM_SDE_POISSON_OU)
-    return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_sde: unknown model_id (registry: BSSM_SDE_GBM, BSSM_SDE_POISSON_OU)");
-  if (M->n_theta < 3) return fail(BSSM_B200_ERR_ARG, "ssm_sde registry models need 3 parameters");
+  const bool user = M->model_id >= BSSM_USER_MODEL_BASE;
+  if (user && !pfl::user_sde_exists(M->model_id)) return fail(BSSM_B200_ERR_ARG, "ssm_sde: model_id was not returned by bssm_b200_sde_register");
+  if (!user && M->model_id != BSSM_SDE_GBM && M->model_id != BSSM_SDE_POISSON_OU)
+    return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_sde: unknown model_id (registry: BSSM_SDE_GBM, BSSM_SDE_POISSON_OU; "
+                                           "or a model registered with bssm_b200_sde_register)");
+  if (!user && M->n_theta < 3) return fail(BSSM_B200_ERR_ARG, "ssm_sde registry models need 3 parameters");
+  if (user && M->n_theta < 1) return fail(BSSM_B200_ERR_ARG, "ssm_sde: empty theta");
   if (L < 1 || L > 20) return fail(BSSM_B200_ERR_ARG, "discretisation level L must be in 1..20");
   bssm_b200_job* J = new bssm_b200_job();
   struct Guard { bssm_b200_job* j; ~Guard() { delete j; } } guard{J};
@@ -1476,15 +1493,24 @@ static int create_sde_job(const bssm_sde_model* M, uint32_t nsim, uint32_t L, ui
   sp.nsub = 1 << L;
   sp.dt = 1.0 / (double)sp.nsub;      // t / n with t = 1, src/milstein.cpp:23-24
   sp.sqdt = std::sqrt(sp.dt);
-  sp.th0 = M->theta[0]; sp.th1 = M->theta[1]; sp.th2 = M->theta[2];
   J->sde_model_id = M->model_id;
-  sp.lgy = nullptr; sp.theta_f = nullptr;
-  {
+  sp.lgy = nullptr; sp.theta_f = nullptr; sp.theta_u = nullptr; sp.theta_u_stride = 0;
+  if (user) {
+    // the functors read the theta vector itself (src/model_ssm_sde.h:8-11), from device memory
+    if (draw_theta) {
+      if ((rc = J->theta_u.upload(draw_theta, (size_t)n_par * n_filters))) return rc;
+      sp.theta_u_stride = n_par;
+    } else if ((rc = J->theta_u.upload(M->theta, (size_t)M->n_theta))) {
+      return rc;
+    }
+    sp.theta_u = J->theta_u.p;
+  } else {
+    sp.th0 = M->theta[0]; sp.th1 = M->theta[1]; sp.th2 = M->theta[2];
     double b[6];
     sde_theta_block(M->model_id, M->theta, b);
     sp.logsd = b[3]; sp.e0 = b[4]; sp.e2 = b[5];
   }
-  if (draw_theta) {
+  if (draw_theta && !user) {
     if (n_par < 3) return fail(BSSM_B200_ERR_ARG, "ssm_sde registry models need 3 parameters");
     std::vector<double> blk((size_t)6 * n_filters);
     for (uint32_t f = 0; f < n_filters; ++f) sde_theta_block(M->model_id, draw_theta + (size_t)f * n_par, &blk[(size_t)6 * f]);
@@ -1500,6 +1526,17 @@ static int create_sde_job(const bssm_sde_model* M, uint32_t nsim, uint32_t L, ui
   if ((rc = finish_job(J, out_flags, post))) return rc;
   guard.j = nullptr;
   *job = J;
+  return 0;
+}
+
+int bssm_b200_sde_register(const char* cuda_source, int32_t* model_id) {
+  if (!cuda_source || !model_id) return fail(BSSM_B200_ERR_ARG, "null argument");
+  int rc = require_device();
+  if (rc) return rc;
+  int id = -1;
+  rc = pfl::user_sde_register(cuda_source, &id);
+  if (rc) return launch_status(rc, "ssm_sde user model");
+  *model_id = id;
   return 0;
 }
 

@@ -38,4 +38,11 @@ int occupancy_nlg_psi(const Geometry&, int* out);
 // k_sde.cu: Milstein bootstrap filter; model_id 0 = GBM, 1 = Poisson-OU (device functor registry)
 int launch_sde_bsf(int model_id, const pf::FilterParams&, const pf::SdeParams&, const Geometry&, uint32_t nf, Stream);
 int occupancy_sde_bsf(const Geometry&, int* out);
+// user_models.cu: ssm_sde functors given as CUDA source, compiled at run time (NVRTC) into the same kernels.
+// Status: as above, and -2 = registration / compilation failed (text in user_model_error()).
+int user_sde_register(const char* source, int* model_id);
+bool user_sde_exists(int model_id);
+const char* user_model_error();
+int launch_user_sde(int model_id, const pf::FilterParams&, const pf::SdeParams&, const Geometry&, uint32_t nf, bool per_filter, Stream);
+int occupancy_user_sde(int model_id, const Geometry&, bool per_filter, int* out);
 } // namespace pfl

@@ -466,6 +466,11 @@ struct SdeParams {
   double e0, e2;    // Poisson-OU: exp(theta0), exp(theta2)
   // IS-correction (one theta per filter): 6 doubles per filter {th0, th1, th2, logsd, e0, e2}, or null
   const double* theta_f;
+  // user functors compiled at run time (user_models.cu): the model's theta vector on the device, as the
+  // reference hands `theta` to drift / diffusion / ddiffusion / log_obs_density (src/model_ssm_sde.h:8-11);
+  // theta_u_stride = 0: one theta for the launch, else one per filter (PerFilter policies)
+  const double* theta_u;
+  size_t theta_u_stride;
 };
 
 struct SdeGbm {
@@ -507,8 +512,11 @@ struct SdeBsf {
   __device__ SdeBsf(const SdeParams& p, uint32_t f) : mp(PerFilter ? loc : p), y(0.0), lgy(0.0) {
     if (PerFilter) {
       loc = p;
-      const double* th = p.theta_f + (size_t)6 * f;
-      loc.th0 = th[0]; loc.th1 = th[1]; loc.th2 = th[2]; loc.logsd = th[3]; loc.e0 = th[4]; loc.e2 = th[5];
+      if (p.theta_f) {
+        const double* th = p.theta_f + (size_t)6 * f;
+        loc.th0 = th[0]; loc.th1 = th[1]; loc.th2 = th[2]; loc.logsd = th[3]; loc.e0 = th[4]; loc.e2 = th[5];
+      }
+      loc.theta_u = p.theta_u + (size_t)f * p.theta_u_stride;
     }
   }
   __device__ double loglik0() const { return 0.0; }

@@ -18,8 +18,10 @@
 // fixed-point form of include/bssm_b200/pf_math.h, so results do not depend on
 // P, block size, number of ranks or number of GPUs.
 #pragma once
+#if !defined(__CUDACC_RTC__)
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 #include "bssm_b200/pf_math.h"
 
 // Measured alternatives that were dropped (tools/build_variants.py, C2 batch of 18 filters):

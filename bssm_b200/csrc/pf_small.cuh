@@ -62,7 +62,7 @@ __host__ __device__ constexpr size_t small_noise_bytes() {
   return (sizeof(typename Model::template Noise<2>) + 7) / 8 * 8;
 }
 template <class Model>
-inline size_t small_smem_bytes(uint32_t N) {
+__host__ __device__ inline size_t small_smem_bytes(uint32_t N) {
   const size_t CT = (size_t)((((N + 1) / 2) + 31) / 32) * 32, Np = 2 * CT;
   return 2 * Model::M * Np * 8 + 2 * Np * 8 + 2 * CT * small_noise_bytes<Model>() + Np * 4;
 }

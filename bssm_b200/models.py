@@ -274,10 +274,13 @@ class SdeModel:
     REGISTRY = {"gbm": (0, 3), "poisson_ou": (1, 3)}
 
     def __init__(self, y, model, theta, x0, positive):
-        if model not in self.REGISTRY:
-            raise ValueError("ssm_sde: model must be one of %s" % sorted(self.REGISTRY))
         self.cls = "ssm_sde"
-        self.model_id, nth = self.REGISTRY[model]
+        if isinstance(model, (int, np.integer)) and int(model) >= 1000:
+            self.model_id, nth = int(model), 1  # an id from sde_register: user functors, any theta
+        elif model in self.REGISTRY:
+            self.model_id, nth = self.REGISTRY[model]
+        else:
+            raise ValueError("ssm_sde: model must be one of %s or an id returned by sde_register" % sorted(self.REGISTRY))
         self.m = 1
         self.y = f64(np.ravel(y))
         self.n = self.y.size
@@ -298,6 +301,19 @@ class SdeModel:
 
 def ssm_nlg(y, model, theta, known_params=(), iekf_iter=0):
     return NlgModel(y, model, theta, known_params, iekf_iter=iekf_iter)
+
+
+def sde_register(source):
+    """Registers an ssm_sde model given by its four functions as CUDA C++ source (the counterpart of the
+    drift / diffusion / ddiffusion / obs_density pointers of R/models.R ssm_sde, compiled there with
+    Rcpp::sourceCpp): `__device__ double drift(double x, const double* theta)`, `diffusion`, `ddiffusion`
+    with the same signature and `__device__ double log_obs_density(double y, double x, const double* theta)`.
+    Compiled at run time into the engine's filter kernels; returns the id to pass as ssm_sde(model=...)."""
+    import ctypes as C
+    from ._lib import check, lib
+    mid = C.c_int32(-1)
+    check(lib().bssm_b200_sde_register(source.encode(), C.byref(mid)))
+    return int(mid.value)
 
 
 def ssm_sde(y, model, theta, x0, positive):

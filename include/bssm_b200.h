@@ -287,6 +287,22 @@ int bssm_b200_job_create_nlg_psi(const bssm_nlg_model* model, uint32_t nsim, uin
                                  uint32_t max_iter, double conv_tol, uint32_t n_filters,
                                  uint32_t first_filter_id, int out_flags, int post,
                                  struct bssm_b200_job** job);
+/* replaces: the compiled function pointers of an ssm_sde model -- drift, diffusion, ddiffusion,
+ *           log_obs_density (src/model_ssm_sde.h:8-11; written by the user and compiled with
+ *           Rcpp::sourceCpp, vignettes/sde_model.Rmd).  A host pointer cannot be called from a
+ *           kernel: the four functions are given as CUDA C++ SOURCE with the scalar signatures
+ *             __device__ double drift(double x, const double* theta);
+ *             __device__ double diffusion(double x, const double* theta);
+ *             __device__ double ddiffusion(double x, const double* theta);
+ *             __device__ double log_obs_density(double y, double x, const double* theta);
+ *           and compiled at run time (NVRTC) into the filter kernels the registry models use.
+ *           The returned id (>= BSSM_USER_MODEL_BASE) goes into bssm_sde_model.model_id; theta
+ *           then has any length >= 1.  The source may call the deterministic math of
+ *           include/bssm_b200/pf_math.h (pf_exp, pf_log, pf_log1p, pf_sin, pf_cos).  A source that
+ *           does not compile returns BSSM_B200_ERR_ARG with the compiler log in last_error. */
+#define BSSM_USER_MODEL_BASE 1000
+int bssm_b200_sde_register(const char* cuda_source, int32_t* model_id);
+
 /* replaces: bsf_sde(y, x0, positive, ..., theta, nsim, L, seed) src/R_sde.cpp:35-72
  *           -> ssm_sde::bsf_filter src/model_ssm_sde.cpp:21-82 (Milstein, 2^L sub-steps).
  * Like the reference, att and Ptt have n+1 columns here with the last one zero. */

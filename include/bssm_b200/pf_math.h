@@ -21,9 +21,18 @@
 #ifndef BSSM_B200_PF_MATH_H
 #define BSSM_B200_PF_MATH_H
 
+#if defined(__CUDACC_RTC__)
+/* run-time compilation of user model functors (NVRTC, bssm_b200/csrc/user_models.cu): no host headers */
+typedef unsigned char uint8_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#else
 #include <stdint.h>
 #include <string.h>
 #include <math.h>
+#endif
 
 #if defined(__CUDACC__)
 #define PF_HD __host__ __device__ __forceinline__

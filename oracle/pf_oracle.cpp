@@ -1522,6 +1522,20 @@ struct Gbm {
   }
 };
 
+/* a model given by its four function pointers, as the reference takes them (src/model_ssm_sde.h:8-11):
+ * the tests compile the SAME source text the engine hands to NVRTC with g++ and pass the addresses */
+typedef double (*orc_sde_fn)(double x, const double* theta);
+typedef double (*orc_sde_obs_fn)(double y, double x, const double* theta);
+static orc_sde_fn g_user_drift = nullptr, g_user_diffusion = nullptr, g_user_ddiffusion = nullptr;
+static orc_sde_obs_fn g_user_log_obs = nullptr;
+struct UserSde {
+  const double* theta;
+  double drift(double x) const { return g_user_drift(x, theta); }
+  double diffusion(double x) const { return g_user_diffusion(x, theta); }
+  double ddiffusion(double x) const { return g_user_ddiffusion(x, theta); }
+  double log_obs(double y, double alpha) const { return g_user_log_obs(y, alpha, theta); }
+};
+
 /* Poisson-OU user functions, R/cpp_example_models.R:41-86: theta = (log rho, nu, log sigma) */
 struct PoissonOu {
   const double* theta;
@@ -1708,8 +1722,15 @@ double orc_sde_bsf_filter(const bssm_sde_model* M, uint32_t nsim, uint32_t L, ui
     return sde_bsf_filter(Gbm{M->theta}, M, nsim, L, seed, filter, arith, alpha, weights, indices, stopped_at);
   if (M->model_id == BSSM_SDE_POISSON_OU)
     return sde_bsf_filter(PoissonOu{M->theta}, M, nsim, L, seed, filter, arith, alpha, weights, indices, stopped_at);
+  if (M->model_id >= BSSM_USER_MODEL_BASE && g_user_drift && g_user_diffusion && g_user_ddiffusion && g_user_log_obs)
+    return sde_bsf_filter(UserSde{M->theta}, M, nsim, L, seed, filter, arith, alpha, weights, indices, stopped_at);
   *stopped_at = -1;
   return pf_nan();
+}
+/* the function pointers every model_id >= BSSM_USER_MODEL_BASE runs with */
+void orc_sde_set_user(void* drift, void* diffusion, void* ddiffusion, void* log_obs) {
+  g_user_drift = (orc_sde_fn)drift; g_user_diffusion = (orc_sde_fn)diffusion;
+  g_user_ddiffusion = (orc_sde_fn)ddiffusion; g_user_log_obs = (orc_sde_obs_fn)log_obs;
 }
 
 /* ------------------------------------------------------------------ a15 */

@@ -57,7 +57,13 @@ b200_model_id <- function(name) {
   switch(name, nlg_growth = 0L, nlg_ar_exp = 1L, nlg_sin_exp = 2L, nlg_linear_gaussian = 3L,
          sde_gbm = 0L, sde_poisson_OU = 1L, stop("no device policy for this example model"))
 }
+# An ssm_sde model of the user's own: the drift pointer carries the CUDA source of the four functions
+#   attr(model$drift, "b200_source") <- "__device__ double drift(double x, const double* theta) {...} ..."
+# (same bodies as the Rcpp::sourceCpp file of vignettes/sde_model.Rmd, scalar signatures of
+# include/bssm_b200.h bssm_b200_sde_register); the shim compiles it on first use.
 .b200_id <- function(ptr) {
+  src <- attr(ptr, "b200_source")
+  if (!is.null(src)) return(as.character(src))
   id <- attr(ptr, "b200_id")
   if (is.null(id)) stop("bssm_b200: tag the model's Z_fn / drift pointer with attr(., 'b200_id') <- b200_model_id(name)")
   as.integer(id)

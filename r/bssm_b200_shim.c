@@ -508,8 +508,17 @@ SEXP _bssmb200_postcorrection_nonlinear(SEXP y, SEXP Z, SEXP H, SEXP T, SEXP R, 
 
 static void fill_sde(SEXP y, SEXP x0, SEXP positive, SEXP id_, SEXP theta, bssm_sde_model* M) {
   memset(M, 0, sizeof(*M));
-  if (TYPEOF(id_) != INTSXP && TYPEOF(id_) != REALSXP) error("bssm_b200: ssm_sde needs a registry model id in place of the drift pointer");
-  M->model_id = asInteger(id_);
+  if (TYPEOF(id_) == STRSXP) {
+    /* the four model functions as CUDA source (one string) in place of the drift pointer: compiled at run
+     * time into the filter kernels (bssm_b200_sde_register caches by source text) */
+    int32_t id = -1;
+    check_rc(bssm_b200_sde_register(CHAR(STRING_ELT(id_, 0)), &id));
+    M->model_id = id;
+  } else if (TYPEOF(id_) == INTSXP || TYPEOF(id_) == REALSXP) {
+    M->model_id = asInteger(id_);
+  } else {
+    error("bssm_b200: ssm_sde needs a registry model id or the model's CUDA source in place of the drift pointer");
+  }
   M->n = (int)XLENGTH(y); M->y = REAL(y);
   M->theta = REAL(theta); M->n_theta = (int)XLENGTH(theta);
   M->x0 = asReal(x0); M->positive = asLogical(positive);

@@ -7,6 +7,7 @@ typedef unsigned int SEXPTYPE;
 #define REALSXP 14
 #define INTSXP 13
 #define VECSXP 19
+#define STRSXP 16
 extern SEXP R_NilValue, R_NamesSymbol, R_DimSymbol;
 SEXP Rf_getAttrib(SEXP, SEXP);
 #define getAttrib Rf_getAttrib
