@@ -164,6 +164,7 @@ def lib():
         C.c_uint32, c_double_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PostcorrOut)]
     L.bssm_b200_is_correction_bsf_nlg.argtypes = L.bssm_b200_postcorrection_nonlinear.argtypes
     L.bssm_b200_sde_register.argtypes = [C.c_char_p, C.POINTER(C.c_int32)]
+    L.bssm_b200_nlg_register.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
     for name, mt in (("ung", UngModel), ("mng", MngModel)):
         for fn in ("bssm_b200_postcorrection_%s_parset", "bssm_b200_is_correction_bsf_%s_parset"):
             getattr(L, fn % name).argtypes = [

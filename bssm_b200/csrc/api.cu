@@ -496,7 +496,7 @@ struct bssm_b200_job {
   pf::NlgParams np{};
   pf::SdeParams sp{};
   int sde_model_id = 0, nlg_model_id = 0;
-  DevBuf<double> lgy, theta_f, theta_u;
+  DevBuf<double> lgy, theta_f, theta_u, known_u, init_u;
   pf::MngParams gp{};
   pf::NlgPsiParams npp{};
   DevBuf<double> stepc;
@@ -594,6 +594,13 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
   }
   if (J->kind == KIND_NLG && J->method == BSSM_METHOD_EKPF)
     return launch_status(pfl::launch_nlg_ekpf(J->nlg_model_id, fp, J->np, J->geo, nf, J->stream), "nlg ekpf");
+  if (J->kind == KIND_NLG && J->nlg_model_id >= BSSM_USER_MODEL_BASE) {
+    pf::NlgParams np = J->np;
+    np.theta_u += (size_t)f0 * np.theta_u_stride;
+    np.init_u += (size_t)f0 * np.init_u_stride;
+    return launch_status(pfl::launch_user_nlg(J->nlg_model_id, J->m, J->k, fp, np, J->geo, nf, np.theta_u_stride != 0, J->stream),
+                         "nlg bsf (user model)");
+  }
   if (J->kind == KIND_NLG && J->np.draw_blk) {
     pf::NlgParams np = J->np;
     np.draw_blk += (size_t)pf::NLG_DRAW_BLOCK * f0;
@@ -1112,7 +1119,9 @@ int bssm_b200_job_phase_cycles(bssm_b200_job* J, uint32_t cta, uint64_t cycles[6
 int bssm_b200_job_max_concurrent_filters(const bssm_b200_job* J) {
   if (!J) return 0;
   int out = 0, rc;
-  if (J->kind == KIND_NLG && J->method == BSSM_METHOD_PSI) rc = pfl::occupancy_nlg_psi(J->geo, &out);
+  if (J->kind == KIND_NLG && J->nlg_model_id >= BSSM_USER_MODEL_BASE)
+    rc = pfl::occupancy_user_nlg(J->nlg_model_id, J->m, J->k, J->geo, J->np.theta_u_stride != 0, &out);
+  else if (J->kind == KIND_NLG && J->method == BSSM_METHOD_PSI) rc = pfl::occupancy_nlg_psi(J->geo, &out);
   else if (J->kind == KIND_NLG) rc = pfl::occupancy_nlg_bsf(J->geo, &out);
   else if (J->kind == KIND_SDE && J->sde_model_id >= BSSM_USER_MODEL_BASE)
     rc = pfl::occupancy_user_sde(J->sde_model_id, J->geo, J->sp.theta_u_stride != 0, &out);
@@ -1215,11 +1224,23 @@ int job_common(bssm_b200_job* J, int kind, int n, int m, int k, uint32_t nsim, u
 } // namespace
 
 // registry models of ssm_nlg: shapes and parameter counts
-static int nlg_state_dim(const bssm_nlg_model* M) { return M->model_id == BSSM_NLG_GROWTH ? 2 : 1; }
+static bool nlg_user(const bssm_nlg_model* M) { return M->model_id >= BSSM_USER_MODEL_BASE; }
+static int nlg_state_dim(const bssm_nlg_model* M) { return nlg_user(M) ? M->m : (M->model_id == BSSM_NLG_GROWTH ? 2 : 1); }
 static int nlg_n_theta(const bssm_nlg_model* M) {
+  if (nlg_user(M)) return 1;
   return M->model_id == BSSM_NLG_AR_EXP ? 4 : (M->model_id == BSSM_NLG_SIN_EXP ? 2 : (M->model_id == BSSM_NLG_LINEAR_GAUSSIAN ? 1 : 3));
 }
-static int check_nlg_model(const bssm_nlg_model* M) {
+// allow_user: the bootstrap-filter paths also take models registered with bssm_b200_nlg_register
+static int check_nlg_model(const bssm_nlg_model* M, bool allow_user = false) {
+  if (nlg_user(M)) {
+    if (!allow_user)
+      return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_nlg models from user source run the bootstrap filter; the psi-APF and the EKF "
+                                             "particle filter need the host-side approximation (registry models)");
+    if (!pfl::user_nlg_exists(M->model_id)) return fail(BSSM_B200_ERR_ARG, "ssm_nlg: model_id was not returned by bssm_b200_nlg_register");
+    if (M->p != 1 || M->m < 1 || M->m > 4 || M->k < 1 || M->k > M->m || M->n_theta < 1)
+      return fail(BSSM_B200_ERR_ARG, "ssm_nlg user model: p = 1, 1 <= k <= m <= 4, at least one parameter");
+    return 0;
+  }
   if (M->model_id == BSSM_NLG_GROWTH) {
     if (M->p != 1 || M->m != 2 || M->k != 2 || M->n_theta < 3 || M->n_known < 6)
       return fail(BSSM_B200_ERR_ARG, "growth model: p = 1, m = 2, k = 2, 3 parameters, 6 known parameters");
@@ -1279,13 +1300,38 @@ static void fill_nlg_params(const bssm_nlg_model* M, int method, pf::NlgParams& 
   }
 }
 
+// a1_fn / P1_fn of a user model for `nt` parameter vectors (J->theta_u): evaluated on the device, P1 factored
+// with psd_chol (src/psd_chol.cpp:5-18) on the host, (a1, L) uploaded as the filters' initial distribution
+static int nlg_user_initial(bssm_b200_job* J, uint32_t nt) {
+  const int m = J->m;
+  const size_t blk = (size_t)m + (size_t)m * m;
+  int rc;
+  if ((rc = J->init_u.alloc(blk * nt))) return rc;
+  if ((rc = launch_status(pfl::user_nlg_init(J->nlg_model_id, m, J->np.theta_u, J->np.theta_u_stride, J->np.known_u, nt,
+                                             J->init_u.p, J->stream), "ssm_nlg user model (a1_fn, P1_fn)")))
+    return rc;
+  std::vector<double> h(blk * nt);
+  CU(cudaMemcpyAsync(h.data(), J->init_u.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, J->stream));
+  CU(cudaStreamSynchronize(J->stream));
+  for (uint32_t f = 0; f < nt; ++f) {
+    double L[16];
+    psd_chol_host(&h[blk * f + m], m, L);
+    std::copy(L, L + (size_t)m * m, &h[blk * f + m]);
+  }
+  CU(cudaMemcpyAsync(J->init_u.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, J->stream));
+  CU(cudaStreamSynchronize(J->stream)); // h goes out of scope
+  J->np.init_u = J->init_u.p;
+  J->np.init_u_stride = nt > 1 ? blk : 0;
+  return 0;
+}
+
 // draw_theta: n_filters columns of n_par parameters, one bootstrap filter each (is_correction_bsf)
 static int create_nlg_job(const bssm_nlg_model* M, int method, uint32_t nsim, uint32_t seed, uint32_t n_filters,
                           uint32_t first_filter_id, int out_flags, int post, bssm_b200_job** job,
                           const double* draw_theta = nullptr, uint32_t n_par = 0) {
   if (!M || !job || !M->y || !M->theta) return fail(BSSM_B200_ERR_ARG, "null argument");
   *job = nullptr;
-  int rc = check_nlg_model(M);
+  int rc = check_nlg_model(M, method == BSSM_METHOD_BSF);
   if (rc) return rc;
   if (M->model_id == BSSM_NLG_GROWTH && !M->known_params) return fail(BSSM_B200_ERR_ARG, "null argument");
   const int m = nlg_state_dim(M);
@@ -1301,8 +1347,21 @@ static int create_nlg_job(const bssm_nlg_model* M, int method, uint32_t nsim, ui
   memset(&np, 0, sizeof(np));
   np.n = M->n; np.y = J->y.p;
   if (method == BSSM_METHOD_EKPF) J->method = BSSM_METHOD_EKPF;
-  fill_nlg_params(M, method, np);
-  if (draw_theta) {
+  if (nlg_user(M)) {
+    // functors from user source: theta (one per filter for the correction phase) and known_params on the
+    // device; a1_fn / P1_fn evaluated there, psd_chol(P1) on the host
+    J->k = M->k;
+    const double one = 0.0;
+    if ((rc = J->theta_u.upload(draw_theta ? draw_theta : M->theta, draw_theta ? (size_t)n_par * n_filters : (size_t)M->n_theta)) ||
+        (rc = J->known_u.upload(M->n_known > 0 ? M->known_params : &one, M->n_known > 0 ? (size_t)M->n_known : 1)))
+      return rc;
+    np.theta_u = J->theta_u.p; np.theta_u_stride = draw_theta ? n_par : 0;
+    np.known_u = J->known_u.p;
+    if ((rc = nlg_user_initial(J, draw_theta ? n_filters : 1u))) return rc;
+  } else {
+    fill_nlg_params(M, method, np);
+  }
+  if (draw_theta && !nlg_user(M)) {
     if (method != BSSM_METHOD_BSF) return fail(BSSM_B200_ERR_UNSUPPORTED, "per-filter theta: bootstrap filter only");
     std::vector<double> blk((size_t)pf::NLG_DRAW_BLOCK * n_filters);
     for (uint32_t f = 0; f < n_filters; ++f) {
@@ -1345,8 +1404,15 @@ int bssm_b200_job_set_theta_nlg(bssm_b200_job* J, const bssm_nlg_model* M, const
   bssm_nlg_model Mi = *M;
   Mi.theta = theta;
   Mi.n_theta = (int32_t)n_par;
-  int rc = check_nlg_model(&Mi);
+  int rc = check_nlg_model(&Mi, J->method == BSSM_METHOD_BSF);
   if (rc) return rc;
+  if (nlg_user(M)) { // new theta on the device, a1_fn / P1_fn again
+    if (J->np.theta_u_stride) return fail(BSSM_B200_ERR_ARG, "job_set_theta_nlg: IS-correction jobs carry one theta per filter already");
+    if (n_par != J->theta_u.count) return fail(BSSM_B200_ERR_ARG, "job_set_theta_nlg: theta has another length than the model's");
+    CU(cudaMemcpyAsync(J->theta_u.p, theta, sizeof(double) * n_par, cudaMemcpyHostToDevice, J->stream));
+    CU(cudaStreamSynchronize(J->stream));
+    return nlg_user_initial(J, 1u);
+  }
   if (J->method == BSSM_METHOD_PSI) {
     if (J->npp.fstride_stepc != 0) return fail(BSSM_B200_ERR_ARG, "job_set_theta_nlg: post-correction jobs carry one theta per filter already");
     return nlg_psi_approximation(J, &Mi); // approximate() at the new theta on the host, same buffers
@@ -1526,6 +1592,18 @@ static int create_sde_job(const bssm_sde_model* M, uint32_t nsim, uint32_t L, ui
   if ((rc = finish_job(J, out_flags, post))) return rc;
   guard.j = nullptr;
   *job = J;
+  return 0;
+}
+
+int bssm_b200_nlg_register(const char* cuda_source, int32_t m, int32_t k, int32_t* model_id) {
+  if (!cuda_source || !model_id) return fail(BSSM_B200_ERR_ARG, "null argument");
+  if (m < 1 || m > 4 || k < 1 || k > m) return fail(BSSM_B200_ERR_ARG, "ssm_nlg user model: 1 <= k <= m <= 4");
+  int rc = require_device();
+  if (rc) return rc;
+  int id = -1;
+  rc = pfl::user_nlg_register(cuda_source, m, k, &id);
+  if (rc) return launch_status(rc, "ssm_nlg user model");
+  *model_id = id;
   return 0;
 }
 
@@ -2756,7 +2834,7 @@ int bssm_b200_is_correction_bsf_nlg(const bssm_nlg_model* M, int output_type, ui
                                     uint32_t draw_begin, uint32_t draw_end, bssm_postcorr_out* out) {
   if (!M || !counts || !theta || !approx_loglik || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
   {
-    int rcm = check_nlg_model(M);
+    int rcm = check_nlg_model(M, true);
     if (rcm) return rcm;
     if (n_par < (uint32_t)nlg_n_theta(M)) return fail(BSSM_B200_ERR_ARG, "is_correction_bsf (nonlinear): too few parameters");
   }

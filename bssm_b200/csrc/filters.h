@@ -45,4 +45,11 @@ bool user_sde_exists(int model_id);
 const char* user_model_error();
 int launch_user_sde(int model_id, const pf::FilterParams&, const pf::SdeParams&, const Geometry&, uint32_t nf, bool per_filter, Stream);
 int occupancy_user_sde(int model_id, const Geometry&, bool per_filter, int* out);
+// ssm_nlg bootstrap filter from user source (Z_fn, H_fn, T_fn, R_fn, a1_fn, P1_fn; p = 1, state dimension m, k etas)
+int user_nlg_register(const char* source, int m, int k, int* model_id);
+bool user_nlg_exists(int model_id);
+int launch_user_nlg(int model_id, int m, int k, const pf::FilterParams&, const pf::NlgParams&, const Geometry&, uint32_t nf,
+                    bool per_filter, Stream);
+int user_nlg_init(int model_id, int m, const double* theta, size_t stride, const double* known, uint32_t nf, double* out, Stream);
+int occupancy_user_nlg(int model_id, int m, int k, const Geometry&, bool per_filter, int* out);
 } // namespace pfl

@@ -33,6 +33,14 @@ struct NlgParams {
   // is_correction_bsf (src/approx_mcmc.cpp:447-518): one theta per filter.  NLG_DRAW_BLOCK doubles per
   // filter, (a1[2], LP1[4], H, R0, R1, wconst, mu, rho) = what update_model(theta_i) changes; else null
   const double* draw_blk;
+  // user functors compiled at run time (user_models.cu, NlgFnBsf below): theta and known_params on the
+  // device as the reference hands them to Z_fn / H_fn / T_fn / R_fn (src/model_ssm_nlg.h:10-21), and per
+  // filter (or shared: stride 0) the initial distribution (a1 (m), psd_chol(P1) (m x m)) from a1_fn / P1_fn
+  const double* theta_u;
+  size_t theta_u_stride;
+  const double* known_u;
+  const double* init_u;
+  size_t init_u_stride;
 };
 constexpr int NLG_DRAW_BLOCK = 12;
 // PerFilter policies copy the launch parameters and overwrite the theta-dependent part with their draw's
@@ -127,6 +135,65 @@ typedef Nlg1Bsf<NLG1_LINEAR> NlgLinearBsf;
 typedef Nlg1Bsf<NLG1_AR_EXP, true> NlgArExpBsfDraws;
 typedef Nlg1Bsf<NLG1_SIN_EXP, true> NlgSinExpBsfDraws;
 typedef Nlg1Bsf<NLG1_LINEAR, true> NlgLinearBsfDraws;
+
+// ------------------------------------------- ssm_nlg: functors from the caller
+// Bootstrap filter of an ssm_nlg model whose Z_fn, H_fn, T_fn, R_fn come as device functions (p = 1):
+// ssm_nlg::bsf_filter src/model_ssm_nlg.cpp:1066-1146 -- alpha_1 = a1 + psd_chol(P1) u, weights
+// dmvnorm(y_t, Z_fn(t, alpha), H_fn(t, alpha), lwr = true, logd = true) (src/dmvnorm.cpp:9-12),
+// alpha_{t+1} = T_fn(t, alpha) + R_fn(t, alpha) eta.  Fn is the adapter user_models.cu generates.
+template <class Fn, int M_, int K_, bool PerFilter>
+struct NlgFnBsf : GaussStep<NlgFnBsf<Fn, M_, K_, PerFilter>, M_, M_, K_> {
+  static constexpr int M = M_, KI = M_, KP = K_;
+  typedef NlgParams Params;
+  const NlgParams& mp;
+  const double *th, *ini;
+  double y;
+  int tw, ts;
+  __device__ NlgFnBsf(const NlgParams& p, uint32_t f) : mp(p), y(0.0), tw(0), ts(0) {
+    th = p.theta_u + (PerFilter ? (size_t)f * p.theta_u_stride : 0);
+    ini = p.init_u + (PerFilter ? (size_t)f * p.init_u_stride : 0);
+  }
+  __device__ double loglik0() const { return 0.0; }
+  __device__ double loglik_end() const { return 0.0; }
+  __device__ void init(const double* z, double* x) const {
+#pragma unroll
+    for (int d = 0; d < M_; ++d) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < M_; ++j) s += ini[M_ + d + M_ * j] * z[j];
+      x[d] = ini[d] + s;
+    }
+  }
+  __device__ bool observed(int t) const { return pf_isfinite(mp.y[t]); }
+  __device__ void begin_weight(int t) { y = mp.y[t]; tw = t; }
+  __device__ double logw(const double* x) const {
+    const double H = Fn::H(tw, x, th, mp.known_u);
+    const double q = (y - Fn::Z(tw, x, th, mp.known_u)) / H;
+    return -0.5 * ((1.8378770664093453 + 2.0 * pf_log(H)) + q * q); // log(2 pi) + 2 log(H) + q^2
+  }
+  __device__ void begin_step(int t) { ts = t; }
+  __device__ void propagate(const double* xa, const double* z, double* x) const {
+    double Tx[M_], Rm[M_ * K_];
+    Fn::T(ts, xa, th, mp.known_u, Tx);
+    Fn::R(ts, xa, th, mp.known_u, Rm);
+#pragma unroll
+    for (int d = 0; d < M_; ++d) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < K_; ++j) s += Rm[d + M_ * j] * z[j];
+      x[d] = Tx[d] + s; // T_fn(...) + R_fn(...) * uk
+    }
+  }
+};
+// a1_fn / P1_fn of every filter's theta: out = nf x (m + m m), a1 then P1 (column-major)
+template <class Fn, int M_>
+__global__ void nlg_user_init_kernel(const double* theta, size_t stride, const double* known, uint32_t nf, double* out) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  double* o = out + (size_t)f * (M_ + M_ * M_);
+  Fn::a1(theta + (size_t)f * stride, known, o);
+  Fn::P1(theta + (size_t)f * stride, known, o + M_);
+}
 
 // ------------------------------------------------- ssm_nlg: growth, psi-APF
 // ssm_nlg::psi_filter src/model_ssm_nlg.cpp:971-1063 with log_weights :880-935.  The

@@ -14,6 +14,18 @@
 // NVRTC for the kernel variant a launch needs (lazily, one variant per compilation, cached), loads the
 // cubin with cudaLibraryLoadData and launches the cudaKernel_t like any other kernel.  The user code
 // can call the deterministic math of include/bssm_b200/pf_math.h (pf_exp, pf_log, pf_log1p, ...).
+//
+// ssm_nlg (bootstrap filter, p = 1; src/model_ssm_nlg.h:10-21: Z_fn, H_fn, T_fn, R_fn, a1_fn, P1_fn with
+// arma::vec / arma::mat returns) the same way, with the outputs written through a pointer:
+//   __device__ double Z_fn(int t, const double* alpha, const double* theta, const double* known_params);
+//   __device__ double H_fn(int t, const double* alpha, const double* theta, const double* known_params);   // sd
+//   __device__ void   T_fn(int t, const double* alpha, const double* theta, const double* known_params, double* out); // m
+//   __device__ void   R_fn(int t, const double* alpha, const double* theta, const double* known_params, double* out); // m x k
+//   __device__ void   a1_fn(const double* theta, const double* known_params, double* out);                // m
+//   __device__ void   P1_fn(const double* theta, const double* known_params, double* out);                // m x m
+// (matrices column-major; the reference's known_tv_params go to the tail of known_params, indexed with t).
+// The Jacobians Z_gn / T_gn are not needed by the bootstrap filter; the psi-APF and the EKF particle
+// filter of user models need the host-side approximation and stay with the registry models.
 // libnvrtc is dlopen'ed on first use: the library does not depend on it otherwise.
 #include "filters.h"
 #include <dlfcn.h>
@@ -54,7 +66,9 @@ struct NvrtcApi {
   }
 };
 
+enum { USER_SDE = 0, USER_NLG = 1 };
 struct UserModel {
+  int kind = USER_SDE;
   std::string source;
   std::map<std::string, cudaKernel_t> kernels; // kernel name expression -> loaded kernel (this device context)
   std::vector<cudaLibrary_t> libs;
@@ -88,12 +102,28 @@ std::string sde_program(const std::string& user) {
          "};\n}\n";
 }
 
+std::string nlg_program(const std::string& user) {
+  return std::string(
+             "#include \"models_nlg_sde.cuh\"\n#include \"pf_small.cuh\"\n"
+             "namespace bssm_user {\n#line 1 \"user_model\"\n") +
+         user +
+         "\n}\nnamespace pf {\n"
+         "struct UserNlg {\n"
+         "  static __device__ __forceinline__ double Z(int t, const double* a, const double* th, const double* kp) { return bssm_user::Z_fn(t, a, th, kp); }\n"
+         "  static __device__ __forceinline__ double H(int t, const double* a, const double* th, const double* kp) { return bssm_user::H_fn(t, a, th, kp); }\n"
+         "  static __device__ __forceinline__ void T(int t, const double* a, const double* th, const double* kp, double* o) { bssm_user::T_fn(t, a, th, kp, o); }\n"
+         "  static __device__ __forceinline__ void R(int t, const double* a, const double* th, const double* kp, double* o) { bssm_user::R_fn(t, a, th, kp, o); }\n"
+         "  static __device__ __forceinline__ void a1(const double* th, const double* kp, double* o) { bssm_user::a1_fn(th, kp, o); }\n"
+         "  static __device__ __forceinline__ void P1(const double* th, const double* kp, double* o) { bssm_user::P1_fn(th, kp, o); }\n"
+         "};\n}\n";
+}
+
 // compiles `expr` (a __global__ template instantiation) of the model's program and loads it
 int get_kernel(UserModel& um, const std::string& expr, cudaKernel_t* out) {
   auto it = um.kernels.find(expr);
   if (it != um.kernels.end()) { *out = it->second; return 0; }
   if (!g_rtc.load(g_uerr)) return -2;
-  const std::string prog_src = sde_program(um.source);
+  const std::string prog_src = um.kind == USER_NLG ? nlg_program(um.source) : sde_program(um.source);
   nvrtcProgram prog = nullptr;
   nvrtcResult r = g_rtc.CreateProgram(&prog, prog_src.c_str(), "bssm_b200_user_model.cu", 0, nullptr, nullptr);
   if (r != NVRTC_SUCCESS) { g_uerr = std::string("nvrtcCreateProgram: ") + g_rtc.GetErrorString(r); return -2; }
@@ -132,8 +162,14 @@ int get_kernel(UserModel& um, const std::string& expr, cudaKernel_t* out) {
   return 0;
 }
 
+std::string filter_kernel_expr(const std::string& model, const Geometry& g);
 std::string sde_kernel_expr(const Geometry& g, bool per_filter) {
-  const std::string model = std::string("pf::SdeBsf<pf::UserSde, ") + (per_filter ? "true" : "false") + ">";
+  return filter_kernel_expr(std::string("pf::SdeBsf<pf::UserSde, ") + (per_filter ? "true" : "false") + ">", g);
+}
+std::string nlg_model_expr(int m, int k, bool per_filter) {
+  return "pf::NlgFnBsf<pf::UserNlg, " + std::to_string(m) + ", " + std::to_string(k) + ", " + (per_filter ? "true" : "false") + ">";
+}
+std::string filter_kernel_expr(const std::string& model, const Geometry& g) {
   if (g.sync_mode == pf::SYNC_SMALL) return "pf::small_filter_kernel<" + model + ">";
   const bool small = g.block <= 512;
   return "pf::filter_kernel<" + model + ", " + std::to_string(g.P) + ", " +
@@ -151,7 +187,8 @@ UserModel* find(int model_id) {
 const char* user_model_error() { return g_uerr.c_str(); }
 bool user_sde_exists(int model_id) {
   std::lock_guard<std::mutex> lk(g_mu);
-  return find(model_id) != nullptr;
+  UserModel* um = find(model_id);
+  return um && um->kind == USER_SDE;
 }
 
 // registers the source and compiles the latency-kernel variant at once, so that errors in the user's
@@ -160,7 +197,7 @@ int user_sde_register(const char* source, int* model_id) {
   std::lock_guard<std::mutex> lk(g_mu);
   g_uerr.clear();
   for (size_t i = 0; i < g_models.size(); ++i)
-    if (g_models[i]->source == source) { *model_id = 1000 + (int)i; return 0; }
+    if (g_models[i]->kind == USER_SDE && g_models[i]->source == source) { *model_id = 1000 + (int)i; return 0; }
   std::unique_ptr<UserModel> um(new UserModel());
   um->source = source;
   Geometry g;
@@ -173,16 +210,98 @@ int user_sde_register(const char* source, int* model_id) {
   return 0;
 }
 
+static int launch_kernel(cudaKernel_t k, void** args, const Geometry& g, uint32_t nf, size_t small_smem, Stream stream);
 int launch_user_sde(int model_id, const pf::FilterParams& fp, const pf::SdeParams& mp, const Geometry& g, uint32_t nf,
                     bool per_filter, Stream stream) {
   std::lock_guard<std::mutex> lk(g_mu);
   g_uerr.clear();
   UserModel* um = find(model_id);
-  if (!um) { g_uerr = "unknown user model id"; return -2; }
+  if (!um || um->kind != USER_SDE) { g_uerr = "unknown ssm_sde user model id"; return -2; }
   cudaKernel_t k;
   int rc = get_kernel(*um, sde_kernel_expr(g, per_filter), &k);
   if (rc) return rc;
   void* args[2] = {const_cast<pf::FilterParams*>(&fp), const_cast<pf::SdeParams*>(&mp)};
+  return launch_kernel(k, args, g, nf, pf::small_smem_bytes<pf::SdeGbmBsf>(fp.N), stream); // same state dimension and noise record
+}
+
+// shared-memory bytes of the latency kernel for an (m, k) Gaussian-step policy (pf_small.cuh)
+static size_t small_smem_mk(uint32_t N, int m, int k) {
+  const size_t CT = (size_t)((((N + 1) / 2) + 31) / 32) * 32, Np = 2 * CT;
+  return 2 * (size_t)m * Np * 8 + 2 * Np * 8 + 2 * CT * ((size_t)2 * k * 8) + Np * 4;
+}
+
+int user_nlg_register(const char* source, int m, int k, int* model_id) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_uerr.clear();
+  for (size_t i = 0; i < g_models.size(); ++i)
+    if (g_models[i]->kind == USER_NLG && g_models[i]->source == source) { *model_id = 1000 + (int)i; return 0; }
+  std::unique_ptr<UserModel> um(new UserModel());
+  um->kind = USER_NLG;
+  um->source = source;
+  Geometry g;
+  g.P = 2; g.block = 64; g.ranks = 1; g.sync_mode = pf::SYNC_SMALL;
+  cudaKernel_t kk;
+  int rc = get_kernel(*um, filter_kernel_expr(nlg_model_expr(m, k, false), g), &kk); // compile errors surface here
+  if (rc) return rc;
+  g_models.push_back(std::move(um));
+  *model_id = 1000 + (int)g_models.size() - 1;
+  return 0;
+}
+bool user_nlg_exists(int model_id) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  UserModel* um = find(model_id);
+  return um && um->kind == USER_NLG;
+}
+
+int launch_user_nlg(int model_id, int m, int k, const pf::FilterParams& fp, const pf::NlgParams& mp, const Geometry& g,
+                    uint32_t nf, bool per_filter, Stream stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_uerr.clear();
+  UserModel* um = find(model_id);
+  if (!um || um->kind != USER_NLG) { g_uerr = "unknown ssm_nlg user model id"; return -2; }
+  cudaKernel_t kk;
+  int rc = get_kernel(*um, filter_kernel_expr(nlg_model_expr(m, k, per_filter), g), &kk);
+  if (rc) return rc;
+  void* args[2] = {const_cast<pf::FilterParams*>(&fp), const_cast<pf::NlgParams*>(&mp)};
+  return launch_kernel(kk, args, g, nf, small_smem_mk(fp.N, m, k), stream);
+}
+
+// a1_fn / P1_fn on the device for nf parameter vectors: out (device) = nf x (m + m m)
+int user_nlg_init(int model_id, int m, const double* theta, size_t stride, const double* known, uint32_t nf, double* out,
+                  Stream stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_uerr.clear();
+  UserModel* um = find(model_id);
+  if (!um || um->kind != USER_NLG) { g_uerr = "unknown ssm_nlg user model id"; return -2; }
+  cudaKernel_t kk;
+  int rc = get_kernel(*um, "pf::nlg_user_init_kernel<pf::UserNlg, " + std::to_string(m) + ">", &kk);
+  if (rc) return rc;
+  void* args[5] = {&theta, &stride, &known, &nf, &out};
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((nf + 127) / 128, 1, 1);
+  cfg.blockDim = dim3(128, 1, 1);
+  cfg.stream = stream;
+  PFL_CU(cudaLaunchKernelExC(&cfg, (const void*)kk, args));
+  return 0;
+}
+
+int occupancy_user_nlg(int model_id, int m, int k, const Geometry& g, bool per_filter, int* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  UserModel* um = find(model_id);
+  if (!um || um->kind != USER_NLG) { g_uerr = "unknown ssm_nlg user model id"; return -2; }
+  cudaKernel_t kk;
+  int rc = get_kernel(*um, filter_kernel_expr(nlg_model_expr(m, k, per_filter), g), &kk);
+  if (rc) return rc;
+  int dev = 0, sms = 0, per_sm = 0;
+  PFL_CU(cudaGetDevice(&dev));
+  PFL_CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  PFL_CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kk, g.block, 0));
+  *out = g.sync_mode == pf::SYNC_GROUP ? (per_sm * sms) / (int)g.ranks : per_sm * sms;
+  return 0;
+}
+
+static int launch_kernel(cudaKernel_t k, void** args, const Geometry& g, uint32_t nf, size_t small_smem, Stream stream) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(nf * g.ranks, 1, 1);
@@ -192,7 +311,8 @@ int launch_user_sde(int model_id, const pf::FilterParams& fp, const pf::SdeParam
   cfg.attrs = attr;
   cfg.numAttrs = 0;
   if (g.sync_mode == pf::SYNC_SMALL) {
-    cfg.dynamicSmemBytes = pf::small_smem_bytes<pf::SdeGbmBsf>(fp.N); // same state dimension and noise record
+    cfg.dynamicSmemBytes = small_smem;
+    if (small_smem > 48 * 1024) PFL_CU(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
   } else if (g.sync_mode == pf::SYNC_CLUSTER) {
     if (g.ranks > 8) PFL_CU(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -211,7 +331,7 @@ int launch_user_sde(int model_id, const pf::FilterParams& fp, const pf::SdeParam
 int occupancy_user_sde(int model_id, const Geometry& g, bool per_filter, int* out) {
   std::lock_guard<std::mutex> lk(g_mu);
   UserModel* um = find(model_id);
-  if (!um) { g_uerr = "unknown user model id"; return -2; }
+  if (!um || um->kind != USER_SDE) { g_uerr = "unknown ssm_sde user model id"; return -2; }
   cudaKernel_t k;
   int rc = get_kernel(*um, sde_kernel_expr(g, per_filter), &k);
   if (rc) return rc;

@@ -241,11 +241,15 @@ class NlgModel:
                 "sin_exp": (2, 1, 1, 1, 2, 0),
                 "linear_gaussian": (3, 1, 1, 1, 1, 0)}  # id, m, k, p, n_theta, n_known
 
-    def __init__(self, y, model, theta, known_params=(), iekf_iter=0):
-        if model not in self.REGISTRY:
-            raise ValueError("ssm_nlg: model must be one of %s" % sorted(self.REGISTRY))
+    def __init__(self, y, model, theta, known_params=(), iekf_iter=0, n_states=None, n_etas=None):
         self.cls = "ssm_nlg"
-        self.model_id, self.m, self.k, self.p, nth, nkn = self.REGISTRY[model]
+        if isinstance(model, (int, np.integer)) and int(model) >= 1000:
+            # an id from nlg_register: user functors (bootstrap filter), dimensions as given there
+            self.model_id, self.m, self.k, self.p, nth, nkn = int(model), int(n_states), int(n_etas), 1, 1, 0
+        elif model in self.REGISTRY:
+            self.model_id, self.m, self.k, self.p, nth, nkn = self.REGISTRY[model]
+        else:
+            raise ValueError("ssm_nlg: model must be one of %s or an id returned by nlg_register" % sorted(self.REGISTRY))
         self.y = f64(np.ravel(y))
         self.n = self.y.size
         self.theta = f64(np.ravel(theta))
@@ -299,8 +303,20 @@ class SdeModel:
         return s
 
 
-def ssm_nlg(y, model, theta, known_params=(), iekf_iter=0):
-    return NlgModel(y, model, theta, known_params, iekf_iter=iekf_iter)
+def nlg_register(source, n_states, n_etas):
+    """Registers an ssm_nlg model given by Z_fn, H_fn, T_fn, R_fn, a1_fn, P1_fn as CUDA C++ source (the
+    counterpart of the function pointers of R/models.R ssm_nlg; signatures in include/bssm_b200.h
+    bssm_b200_nlg_register).  Bootstrap filter / smoother, the filter inside an MCMC loop and the
+    bootstrap correction phase run on it; returns the id to pass as ssm_nlg(model=..., n_states, n_etas)."""
+    import ctypes as C
+    from ._lib import check, lib
+    mid = C.c_int32(-1)
+    check(lib().bssm_b200_nlg_register(source.encode(), int(n_states), int(n_etas), C.byref(mid)))
+    return int(mid.value)
+
+
+def ssm_nlg(y, model, theta, known_params=(), iekf_iter=0, n_states=None, n_etas=None):
+    return NlgModel(y, model, theta, known_params, iekf_iter=iekf_iter, n_states=n_states, n_etas=n_etas)
 
 
 def sde_register(source):

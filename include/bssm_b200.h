@@ -302,6 +302,20 @@ int bssm_b200_job_create_nlg_psi(const bssm_nlg_model* model, uint32_t nsim, uin
  *           does not compile returns BSSM_B200_ERR_ARG with the compiler log in last_error. */
 #define BSSM_USER_MODEL_BASE 1000
 int bssm_b200_sde_register(const char* cuda_source, int32_t* model_id);
+/* replaces: the function pointers of an ssm_nlg model that the bootstrap filter calls -- Z_fn, H_fn,
+ *           T_fn, R_fn, a1_fn, P1_fn (src/model_ssm_nlg.h:10-21; arma::vec / arma::mat returns),
+ *           as CUDA C++ source with the outputs written through a pointer (p = 1, 1 <= k <= m <= 4):
+ *             __device__ double Z_fn(int t, const double* alpha, const double* theta, const double* known_params);
+ *             __device__ double H_fn(int t, const double* alpha, const double* theta, const double* known_params); // sd
+ *             __device__ void T_fn(int t, const double* alpha, const double* theta, const double* known_params, double* out);
+ *             __device__ void R_fn(int t, const double* alpha, const double* theta, const double* known_params, double* out);
+ *             __device__ void a1_fn(const double* theta, const double* known_params, double* out);
+ *             __device__ void P1_fn(const double* theta, const double* known_params, double* out);
+ *           (matrices column-major; known_tv_params go to the tail of known_params, indexed with t).
+ *           The id is valid for bssm_b200_bsf_nlg, bssm_b200_bsf_smoother_nlg, bssm_b200_job_create_nlg
+ *           (+ job_set_theta_nlg) and bssm_b200_is_correction_bsf_nlg; the psi-APF and the EKF particle
+ *           filter need the host-side Gaussian approximation and stay with the registry models. */
+int bssm_b200_nlg_register(const char* cuda_source, int32_t m, int32_t k, int32_t* model_id);
 
 /* replaces: bsf_sde(y, x0, positive, ..., theta, nsim, L, seed) src/R_sde.cpp:35-72
  *           -> ssm_sde::bsf_filter src/model_ssm_sde.cpp:21-82 (Milstein, 2^L sub-steps).

@@ -379,8 +379,17 @@ SEXP _bssmb200_postcorrection_nongaussian(SEXP model_, SEXP model_type_, SEXP ou
  * R/RcppExports.R. */
 static void fill_nlg(SEXP y, SEXP id_, SEXP theta, SEXP known_params, SEXP n_states, SEXP n_etas, bssm_nlg_model* M) {
   memset(M, 0, sizeof(*M));
-  if (TYPEOF(id_) != INTSXP && TYPEOF(id_) != REALSXP) error("bssm_b200: ssm_nlg needs a registry model id in place of the Z pointer");
-  M->model_id = asInteger(id_);
+  if (TYPEOF(id_) == STRSXP) {
+    /* Z_fn, H_fn, T_fn, R_fn, a1_fn, P1_fn as CUDA source (one string) in place of the Z pointer: bootstrap
+     * filter only, compiled at run time (bssm_b200_nlg_register caches by source text) */
+    int32_t id = -1;
+    check_rc(bssm_b200_nlg_register(CHAR(STRING_ELT(id_, 0)), asInteger(n_states), asInteger(n_etas), &id));
+    M->model_id = id;
+  } else if (TYPEOF(id_) == INTSXP || TYPEOF(id_) == REALSXP) {
+    M->model_id = asInteger(id_);
+  } else {
+    error("bssm_b200: ssm_nlg needs a registry model id or the model's CUDA source in place of the Z pointer");
+  }
   M->p = INTEGER(getAttrib(y, R_DimSymbol))[0]; /* R passes t(model$y): p x n */
   M->n = INTEGER(getAttrib(y, R_DimSymbol))[1];
   M->m = asInteger(n_states); M->k = asInteger(n_etas);

@@ -121,3 +121,72 @@ def test_user_model_against_the_oracle_running_the_same_source(engine):
 def test_user_source_that_does_not_compile(engine):
     with pytest.raises(Exception, match="does not compile"):
         engine.sde_register("__device__ double drift(double x, const double* theta) { return undefined_symbol; }")
+
+
+GROWTH_SRC = r"""
+// nlg_growth of R/cpp_example_models.R:336-511: state (logit r, p), theta = (log H, log R1, log R2),
+// known_params = (dT, K, a11, a12, P11, P12)
+__device__ double Z_fn(int t, const double* a, const double* th, const double* kp) { return a[1]; }
+__device__ double H_fn(int t, const double* a, const double* th, const double* kp) { return pf_exp(th[0]); }
+__device__ void T_fn(int t, const double* a, const double* th, const double* kp, double* o) {
+  const double e0 = pf_exp(a[0]);
+  const double r = e0 / (1.0 + e0);
+  const double erdt = pf_exp(r * kp[0]);
+  o[0] = a[0];
+  o[1] = kp[1] * a[1] * erdt / (kp[1] + a[1] * (erdt - 1));
+}
+__device__ void R_fn(int t, const double* a, const double* th, const double* kp, double* o) {
+  o[0] = pf_exp(th[1]); o[1] = 0.0; o[2] = 0.0; o[3] = pf_exp(th[2]);
+}
+__device__ void a1_fn(const double* th, const double* kp, double* o) { o[0] = kp[2]; o[1] = kp[3]; }
+__device__ void P1_fn(const double* th, const double* kp, double* o) { o[0] = kp[4]; o[1] = 0.0; o[2] = 0.0; o[3] = kp[5]; }
+"""
+
+SIN_EXP_SRC = r"""
+// nlg_sin_exp of R/cpp_example_models.R:635-757: theta = (log H, log R), a1 = 0, P1 = 1
+__device__ double Z_fn(int t, const double* a, const double* th, const double* kp) { return pf_exp(a[0]); }
+__device__ double H_fn(int t, const double* a, const double* th, const double* kp) { return pf_exp(th[0]); }
+__device__ void T_fn(int t, const double* a, const double* th, const double* kp, double* o) { o[0] = pf_sin(a[0]); }
+__device__ void R_fn(int t, const double* a, const double* th, const double* kp, double* o) { o[0] = pf_exp(th[1]); }
+__device__ void a1_fn(const double* th, const double* kp, double* o) { o[0] = 0.0; }
+__device__ void P1_fn(const double* th, const double* kp, double* o) { o[0] = 1.0; }
+"""
+
+
+@pytest.mark.parametrize("kind", ["growth", "sin_exp"])
+def test_user_nlg_equals_registry_model(engine, kind):
+    """the shipped ssm_nlg examples written as user source: bootstrap filter, smoother, MCMC-style set_theta and the
+    bootstrap correction phase give the registry policies' bits (which the other tests pin to the oracle)"""
+    if kind == "growth":
+        reg, src, m, k = data.growth_model(50, missing=(4,)), GROWTH_SRC, 2, 2
+    else:
+        reg, src, m, k = data.sin_exp_model(50), SIN_EXP_SRC, 1, 1
+    mid = engine.nlg_register(src, m, k)
+    user = engine.ssm_nlg(reg.y, mid, reg.theta, reg.known_params, n_states=m, n_etas=k)
+    for N in (100, 3000, 9000):  # latency kernel, one-CTA kernel, group of CTAs
+        a = engine.bootstrap_filter(reg, N, seed=2, return_indices=True)
+        b = engine.bootstrap_filter(user, N, seed=2, return_indices=True)
+        for key in ("alpha", "weights", "indices", "at", "att", "Pt", "Ptt"):
+            assert np.array_equal(a[key], b[key]), (N, key)
+        assert a["logLik"] == b["logLik"]
+    sa = engine.particle_smoother(reg, 500, method="bsf", seed=4)
+    sb = engine.particle_smoother(user, 500, method="bsf", seed=4)
+    assert np.array_equal(sa["alphahat"], sb["alphahat"]) and np.array_equal(sa["Vt"], sb["Vt"])
+    th2 = np.asarray(reg.theta) + 0.05
+    ja = engine.FilterJob(reg, 128, method="bsf", seed=3, out_flags=0)
+    jb = engine.FilterJob(user, 128, method="bsf", seed=3, out_flags=0)
+    for job in (ja, jb):
+        job.set_theta(th2)
+        job.run()
+    assert ja.logliks()[0] == jb.logliks()[0]
+    ja.close(); jb.close()
+    rng = np.random.default_rng(3)
+    ns = 10
+    theta = np.asarray(reg.theta)[None, :] + 0.04 * rng.normal(size=(ns, np.size(reg.theta)))
+    mo = {"theta": theta, "counts": (1 + rng.poisson(2, size=ns)).astype(np.uint32),
+          "approx_loglik": a["logLik"] + rng.normal(size=ns), "output_type": 1, "posterior": np.zeros(ns)}
+    ra = engine.post_correct(reg, mo, 64, is_type="is2", seed=5, return_loglik=True, sampling_method="bsf")
+    rb = engine.post_correct(user, mo, 64, is_type="is2", seed=5, return_loglik=True, sampling_method="bsf")
+    assert np.array_equal(ra["loglik"], rb["loglik"]) and np.array_equal(ra["alpha"], rb["alpha"])
+    with pytest.raises(Exception, match="bootstrap filter"):
+        engine.particle_smoother(user, 100, method="psi", seed=1)
