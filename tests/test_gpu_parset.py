@@ -160,3 +160,23 @@ def test_mng_parset_psi_and_bsf(engine):
     refb1 = orc.correction_parset(model, mo1, 64, is_type=3, seed=6, bsf=True)
     resb1 = engine.post_correct(model, mo1, 64, is_type="is3", seed=6, sampling_method="bsf")
     assert np.array_equal(resb1["alpha"].view(np.uint64), refb1.alpha.view(np.uint64))
+
+
+def test_parset_path_meets_the_svm_path(engine):
+    """the same draws through both routes of postcorrection_nongaussian: model_type 3 (svm::update_model in the
+    library, approximation per draw on the device) and model_type 1 (parameter set built from an update_fn that does
+    what svm::update_model does, approximation per draw on the host)"""
+    import bssm_b200
+    model = data.svm_model(80, missing=(9,))
+    mo = data.svm_mcmc_output(model, 12)
+
+    def update_fn(theta):
+        return {"T": [[theta[0]]], "R": [[theta[1]]], "P1": [[theta[1] ** 2 / (1 - theta[0] ** 2)]], "phi": theta[2]}
+
+    ung = bssm_b200.ssm_ung(model.y, model.Z, model.T, model.R, model.a1, model.P1, "svm", phi=model.phi, u=model.u,
+                            D=model.D, C=model.C, initial_mode=model.initial_mode, update_fn=update_fn)
+    a = engine.post_correct(model, mo, 96, is_type="is2", seed=3, return_loglik=True)
+    b = engine.post_correct(ung, mo, 96, is_type="is2", seed=3, return_loglik=True)
+    ref = orc.correction_parset(ung, mo, 96, is_type=2, seed=3)
+    assert np.array_equal(b["loglik"], ref.loglik)
+    np.testing.assert_allclose(a["loglik"], b["loglik"], rtol=1e-12)

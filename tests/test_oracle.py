@@ -352,3 +352,22 @@ def test_reference_order_vs_repro_first_divergence_at_the_headline_size():
     else:  # up to the first flipped ancestor the two runs are the same run
         assert np.array_equal(a.indices[:, :first], b.indices[:, :first])
         assert np.array_equal(a.weights[:, :first + 1].view(np.uint64), b.weights[:, :first + 1].view(np.uint64))
+
+
+def test_parset_correction_reproduces_the_svm_update_model_path():
+    """two restatements of is_correction_psi meet: the svm specialisation (update_model in C++,
+    src/model_svm.cpp:12-29, scalar m = 1 approximation) and the ssm_ung specialisation with a parameter set
+    (src/approx_mcmc.cpp:685-804, src/parset_ng.cpp) whose update_fn does what svm::update_model does"""
+    import bssm_b200
+    model = data.svm_model(60, missing=(9,))
+    mo = data.svm_mcmc_output(model, 10)
+    ref = orc.post_correct(model, mo, 48, is_type=2, seed=3)
+
+    def update_fn(theta):  # svm_type 0: theta = (rho, sd_ar, sigma)
+        return {"T": [[theta[0]]], "R": [[theta[1]]], "P1": [[theta[1] ** 2 / (1 - theta[0] ** 2)]], "phi": theta[2]}
+
+    ung = bssm_b200.ssm_ung(model.y, model.Z, model.T, model.R, model.a1, model.P1, "svm", phi=model.phi, u=model.u,
+                            D=model.D, C=model.C, initial_mode=model.initial_mode, update_fn=update_fn)
+    res = orc.correction_parset(ung, mo, 48, is_type=2, seed=3)
+    assert np.array_equal(res.loglik, ref.loglik)
+    assert np.array_equal(res.weights, ref.weights)
