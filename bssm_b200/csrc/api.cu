@@ -548,14 +548,16 @@ int run_post_dyn(bssm_b200_job* J) {
     pf::summary_dyn_kernel<<<dim3(n + 1, nf), bs, 0, J->stream>>>(J->alpha_tm.p, J->weights.p, N, n, m, J->s_at.p, J->s_Pt.p,
                                                               J->s_att.p, J->s_Ptt.p, J->alpha_stride, J->weights_stride);
     J->launches += 1;
-  } else if (J->post == BSSM_POST_SMOOTHER) {
+  } else if (J->post == BSSM_POST_SMOOTHER || J->post == BSSM_POST_SMOOTHER_MERGE) {
     pf::backtrack_dyn_kernel<<<dim3(cdiv(N, 256), nf), 256, 0, J->stream>>>(J->alpha_tm.p, J->indices.p, J->alpha_sm.p, N, n, m,
                                                                          J->alpha_stride, J->indices_stride);
     pf::summary_dyn_kernel<<<dim3(n + 1, nf), bs, 0, J->stream>>>(J->alpha_sm.p, nullptr, N, n, m, J->s_mean.p, J->s_cov.p,
                                                               nullptr, nullptr, J->alpha_stride, 0);
     J->launches += 2;
-  } else {
-    return fail(BSSM_B200_ERR_UNSUPPORTED, "this post-processing mode supports m <= 4");
+  } else if (J->post == BSSM_POST_PICK) {
+    pf::pick_trajectory_dyn_kernel<<<cdiv(nf, 128), 128, 0, J->stream>>>(
+        J->alpha_tm.p, J->indices.p, J->traj.p, N, n, m, J->alpha_stride, J->indices_stride, J->seed, J->first_filter, nf);
+    J->launches += 1;
   }
   CU(cudaGetLastError());
   return 0;
@@ -779,10 +781,7 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
   const bool parset = dm && dm->parset;
   if (method == BSSM_METHOD_PSI && !parset && ((M->m != 1 && draw_par) || (M->m == 1 && dm && !draw_par)))
     return fail(BSSM_B200_ERR_UNSUPPORTED, "psi-APF with per-draw models: m = 1 (or bsm_ng through the DrawModels path)");
-  if (dm && !parset && M->m > 3) return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction with per-draw models: m <= 3 in this build");
   if (parset && (draw_par || gaussian)) return fail(BSSM_B200_ERR_ARG, "parameter sets: non-Gaussian ssm_ung models, no draw_par");
-  if (parset && post != BSSM_POST_NONE && M->m > 3)
-    return fail(BSSM_B200_ERR_UNSUPPORTED, "parameter sets: trajectories and summaries (output_type 1, 2) for m <= 3 in this build");
   if (M->k > M->m) return fail(BSSM_B200_ERR_ARG, "k > m");
   if (post < 0 || post > BSSM_POST_SMOOTHER_MERGE) return fail(BSSM_B200_ERR_ARG, "bad post mode");
   int rc = require_device();
@@ -2156,8 +2155,8 @@ int check_postcorr_args(const bssm_ung_model* M, const bssm_theta_map* map, cons
   const bool general = map->model_type == 2 && M->m > 1;
   if (M->m != 1 && !general)
     return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction with m > 1 is implemented for bsm_ng (model_type 2) in this build");
-  if (general && (M->m < 2 || M->m > 3))
-    return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction for bsm_ng: m <= 3 in this build");
+  if (general && (M->m < 2 || M->m > 16))
+    return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction for bsm_ng: m <= 16 in this build");
   if (map->n_xreg > 0 && !map->xreg) return fail(BSSM_B200_ERR_ARG, "n_xreg > 0 needs xreg");
   if (M->xbeta && map->n_xreg <= 0) return fail(BSSM_B200_ERR_ARG, "the model has regressors: theta_map needs n_xreg and xreg");
   if (map->n_xreg > 0 && map->model_type == 3) return fail(BSSM_B200_ERR_ARG, "svm has no regression part");
@@ -2311,11 +2310,12 @@ static int postcorr_driver(int n, int m, int output_type, uint32_t nsim, int is_
   DevBuf<double> d_sumw, d_ah, d_Vt, d_Va;
   DevBuf<uint32_t> d_cnt;
   if (output_type == 2) {
-    if ((rc = d_sumw.alloc(2)) || (rc = d_ah.alloc((size_t)m * n1)) || (rc = d_Vt.alloc((size_t)m * m * n1)) ||
+    // d_ah: two copies for the run-time-m merge (m > 3), which reads one and writes the other
+    if ((rc = d_sumw.alloc(2)) || (rc = d_ah.alloc((size_t)2 * m * n1)) || (rc = d_Vt.alloc((size_t)m * m * n1)) ||
         (rc = d_Va.alloc((size_t)m * m * n1)))
       return rc;
     CU(cudaMemset(d_sumw.p, 0, 2 * sizeof(double)));
-    CU(cudaMemset(d_ah.p, 0, sizeof(double) * m * n1));
+    CU(cudaMemset(d_ah.p, 0, sizeof(double) * 2 * m * n1));
     CU(cudaMemset(d_Vt.p, 0, sizeof(double) * m * m * n1));
     CU(cudaMemset(d_Va.p, 0, sizeof(double) * m * m * n1));
   }
@@ -2371,8 +2371,12 @@ static int postcorr_driver(int n, int m, int output_type, uint32_t nsim, int is_
       else if (m == 3)
         pf::postcorr_merge_kernel<3><<<cdiv((uint32_t)n1, 128), 128, 0, J->stream>>>(
             J->s_mean.p, J->s_cov.p, J->loglik.p, d_cnt.p, nf, (int)n1, sw_in, sw_out, d_ah.p, d_Vt.p, d_Va.p);
-      else
-        return fail(BSSM_B200_ERR_UNSUPPORTED, "post-correction summaries: m <= 3");
+      else { // ping-pong over the chunks: chunk c reads copy c & 1, writes the other
+        const size_t total = (size_t)m * m * n1;
+        pf::postcorr_merge_dyn_kernel<<<(unsigned)((total + 127) / 128), 128, 0, J->stream>>>(
+            J->s_mean.p, J->s_cov.p, J->loglik.p, d_cnt.p, nf, (int)n1, m, sw_in, sw_out,
+            d_ah.p + (size_t)(chunk_no & 1) * m * n1, d_ah.p + (size_t)((chunk_no + 1) & 1) * m * n1, d_Vt.p, d_Va.p);
+      }
       CU(cudaGetLastError());
       CU(cudaEventRecord(e1, J->stream));
       CU(cudaStreamSynchronize(J->stream));
@@ -2390,7 +2394,8 @@ static int postcorr_driver(int n, int m, int output_type, uint32_t nsim, int is_
     CU(cudaMemcpy(&sw, d_sumw.p + (chunk_no & 1), sizeof(double), cudaMemcpyDeviceToHost));
     out->sum_w = sw;
     std::vector<double> ah((size_t)m * n1), Vt((size_t)m * m * n1), Va((size_t)m * m * n1);
-    CU(cudaMemcpy(ah.data(), d_ah.p, sizeof(double) * ah.size(), cudaMemcpyDeviceToHost));
+    // m <= 3 updates copy 0 in place; the run-time-m merge left its result in copy (number of chunks) & 1
+    CU(cudaMemcpy(ah.data(), d_ah.p + (m > 3 ? (size_t)(chunk_no & 1) * m * n1 : 0), sizeof(double) * ah.size(), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(Vt.data(), d_Vt.p, sizeof(double) * Vt.size(), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(Va.data(), d_Va.p, sizeof(double) * Va.size(), cudaMemcpyDeviceToHost));
     // Vt += Valpha / sum_w (:422-424); alphahat is returned transposed, (n+1) x m

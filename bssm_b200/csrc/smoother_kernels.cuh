@@ -383,6 +383,56 @@ __global__ void postcorr_merge_kernel(const double* __restrict__ mean_i, const d
   if (t == n1 - 1) *sum_w_out = sum_w;  // every thread computed the same sum_w
 }
 
+// The same two for a run-time state dimension (m > 3).  The merge runs one thread per element (r, c, t) of the
+// covariance; each thread carries the recursions of alphahat_r and alphahat_c itself (same operations, same
+// order as above), reads the state from *_in and writes *_out so that no thread reads what another has updated.
+__global__ void pick_trajectory_dyn_kernel(const double* __restrict__ alpha_f, const uint32_t* __restrict__ indices,
+                                           double* __restrict__ traj, uint32_t N, int n, int m, size_t alpha_stride,
+                                           size_t indices_stride, uint32_t seed, uint32_t first_filter,
+                                           uint32_t n_filters) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_filters) return;
+  alpha_f += (size_t)f * alpha_stride;
+  indices += (size_t)f * indices_stride;
+  traj += (size_t)f * (n + 1) * m;
+  uint32_t b = (uint32_t)(pf_pick_uniform(seed, first_filter + f) * (double)N);
+  if (b > N - 1) b = N - 1;
+  for (int d = 0; d < m; ++d) traj[n + (size_t)(n + 1) * d] = alpha_f[((size_t)n * m + d) * N + b];
+  for (int t = n - 1; t >= 0; --t) {
+    b = indices[(size_t)t * N + b];
+    for (int d = 0; d < m; ++d) traj[t + (size_t)(n + 1) * d] = alpha_f[((size_t)t * m + d) * N + b];
+  }
+}
+__global__ void postcorr_merge_dyn_kernel(const double* __restrict__ mean_i, const double* __restrict__ cov_i,
+                                          const double* __restrict__ loglik, const uint32_t* __restrict__ counts,
+                                          uint32_t n_filters, int n1, int m, const double* __restrict__ sum_w_in,
+                                          double* __restrict__ sum_w_out, const double* __restrict__ ah_in,
+                                          double* __restrict__ ah_out, double* __restrict__ Vt,
+                                          double* __restrict__ Valpha) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x, total = (size_t)m * m * n1;
+  if (idx >= total) return;
+  const int r = (int)(idx % m), c = (int)((idx / m) % m);
+  const size_t t = idx / ((size_t)m * m);
+  double sum_w = *sum_w_in, ar = ah_in[r + (size_t)m * t], ac = ah_in[c + (size_t)m * t], V = Vt[idx], Va = Valpha[idx];
+  for (uint32_t i = 0; i < n_filters; ++i) {
+    const double wnew = pf_exp(loglik[i]) * (double)counts[i];
+    sum_w += wnew;
+    const double* mi = mean_i + (size_t)i * m * n1 + (size_t)m * t;
+    const double ci = cov_i[(size_t)i * m * m * n1 + idx];
+    const double f = wnew / sum_w;
+    const double dr = mi[r] - ar;
+    ar += f * dr;
+    const double dc = mi[c] - ac;
+    ac += f * dc;
+    const double d2c = mi[c] - ac;
+    Va += wnew * dr * d2c;
+    V += f * (ci - V);
+  }
+  Vt[idx] = V; Valpha[idx] = Va;
+  if (c == 0) ah_out[r + (size_t)m * t] = ar;
+  if (idx == total - 1) *sum_w_out = sum_w;
+}
+
 // ------------------------------------------------ layout change for output
 // alpha_tm [(t*M+d)*N + i]  ->  cube [d + M*(t + n1*i)]  (Armadillo cube
 // m x (n+1) x N, src/R_bootstrap_filter.cpp:162).  A plain tiled transpose of

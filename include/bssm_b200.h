@@ -347,7 +347,7 @@ int bssm_b200_approximate_mode(const bssm_ung_model* model, double* mode);
 /* ---- IS-MCMC post-correction ---------------------------------------------- */
 /* How theta maps onto the model (the C++ update_model of the model class):
  * svm src/model_svm.cpp:12-29, ar1_ng src/model_ar1_ng.cpp:12-36,
- * bsm_ng src/model_bsm_ng.cpp:17-51 (any m <= 3). */
+ * bsm_ng src/model_bsm_ng.cpp:17-51 (any m <= 16: seasonal components included). */
 typedef struct {
   int32_t model_type; /* R/model_type.R:1-16: 2 = bsm_ng, 3 = svm, 4 = ar1_ng */
   int32_t svm_type;   /* svm: 0 = theta[2] is sigma (phi), 1 = theta[2] is mu */
@@ -430,8 +430,7 @@ typedef struct {
 
 /* replaces: postcorrection_nongaussian(..., model_type = 1) -> approx_mcmc::is_correction_psi<ssm_ung>
  *           (src/approx_mcmc.cpp:685-804) and, with approx_loglik instead of modes, the ssm_ung
- *           specialisation of is_correction_bsf (:806-921).  Any m <= 16 for output_type 3
- *           (weights); output_type 1 / 2 for m <= 3.  modes is n x n_stored.  Other arguments
+ *           specialisation of is_correction_bsf (:806-921).  Any m <= 16.  modes is n x n_stored.  Other arguments
  *           and outputs as bssm_b200_postcorrection_nongaussian. */
 int bssm_b200_postcorrection_ung_parset(const bssm_ung_model* model, const bssm_parset* parset,
                                         int output_type, uint32_t nsim, uint32_t seed, uint32_t n_threads,

@@ -67,3 +67,26 @@ def test_bsf_smoother_general_m_and_unusual_k(engine):
     assert np.array_equal(res["indices"], ref.indices) and res["logLik"] == ref.loglik
     sm = orc.filter_smoother(ref.alpha, ref.indices)
     assert np.array_equal(np.transpose(res["alpha"], (1, 0, 2)).view(np.uint64), sm.view(np.uint64))
+
+
+@pytest.mark.parametrize("period", [4, 12])
+def test_post_correction_with_a_seasonal_component(engine, period):
+    """is_correction_psi for bsm_ng with a seasonal component (m = 5 / 13): bsm_ng::update_model per draw
+    (src/model_bsm_ng.cpp:17-51), the run-time-m psi-APF per draw, trajectories and the weighted summary
+    merge (src/approx_mcmc.cpp:394-424) at run-time m"""
+    import data
+    model = seasonal_model(period, n=48)
+    mo = data.bsm_mcmc_output(model, 10, jitter=0.05)
+    ref = orc.post_correct(model, mo, 64, is_type=2, seed=3)
+    res = engine.post_correct(model, mo, 64, is_type="is2", seed=3, return_loglik=True)
+    assert np.array_equal(res["loglik"], ref.loglik)
+    assert np.array_equal(res["weights"], ref.weights)
+    mo1 = dict(mo, output_type=1)
+    ref1 = orc.post_correct(model, mo1, 32, is_type=3, seed=5)
+    res1 = engine.post_correct(model, mo1, 32, is_type="is3", seed=5)
+    assert np.array_equal(res1["alpha"].view(np.uint64), ref1.alpha.view(np.uint64))
+    mo2 = dict(mo, output_type=2)
+    ref2 = orc.post_correct(model, mo2, 32, is_type=1, seed=7)
+    res2 = engine.post_correct(model, mo2, 32, is_type="is1", seed=7)
+    np.testing.assert_allclose(res2["alphahat"], ref2.alphahat, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(res2["Vt"], ref2.Vt, rtol=1e-8, atol=1e-11)

@@ -91,8 +91,8 @@ def test_ung_parset_bsf(engine, m, tv):
     np.testing.assert_allclose(res2["Vt"], ref2.Vt, rtol=1e-8, atol=1e-12)
 
 
-def test_ung_parset_seasonal_weights_only(engine):
-    """m = 5 (run-time state dimension): weights (output_type 3) for any m <= 16"""
+def test_ung_parset_seasonal(engine):
+    """m = 5 (run-time state dimension): weights, trajectories and summaries"""
     import bssm_b200
     base = data.poisson_bsm_model(60)
     y = base.y
@@ -116,8 +116,15 @@ def test_ung_parset_seasonal_weights_only(engine):
     refb = orc.correction_parset(model, mo, 64, is_type=2, seed=3, bsf=True)
     resb = engine.post_correct(model, mo, 64, is_type="is2", seed=3, return_loglik=True, sampling_method="bsf")
     np.testing.assert_allclose(resb["loglik"], refb.loglik, rtol=1e-13)
-    with pytest.raises(Exception, match="m <= 3"):
-        engine.post_correct(model, dict(mo, output_type=1), 32, is_type="is2", seed=3)
+    mo1 = dict(mo, output_type=1)
+    ref1 = orc.correction_parset(model, mo1, 32, is_type=3, seed=5)
+    res1 = engine.post_correct(model, mo1, 32, is_type="is3", seed=5)
+    assert np.array_equal(res1["alpha"].view(np.uint64), ref1.alpha.view(np.uint64))
+    mo2 = dict(mo, output_type=2)
+    ref2 = orc.correction_parset(model, mo2, 32, is_type=1, seed=7, bsf=True)
+    res2 = engine.post_correct(model, mo2, 32, is_type="is1", seed=7, sampling_method="bsf")
+    np.testing.assert_allclose(res2["alphahat"], ref2.alphahat, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(res2["Vt"], ref2.Vt, rtol=1e-8, atol=1e-11)
 
 
 def mng_update_model():
