@@ -618,27 +618,27 @@ int launch_ung_filter(bssm_b200_job* J, uint32_t f0, uint32_t nf) {
                            "sde bsf (user model)");
     return launch_status(pfl::launch_sde_bsf(J->sde_model_id, fp, sp, J->geo, nf, J->stream), "sde bsf");
   }
-  if (J->kind == KIND_MNG && J->mng_draws) {
+  if (J->kind == KIND_MNG) {
     pf::MngParams gp = J->gp;
+    // per-filter strides are 0 unless the job carries one model per filter (parameter sets)
     gp.Z += (size_t)f0 * gp.fs_Z; gp.T += (size_t)f0 * gp.fs_T; gp.R += (size_t)f0 * gp.fs_R; gp.C += (size_t)f0 * gp.fs_C;
     gp.D += (size_t)f0 * gp.fs_D; gp.a1 += (size_t)f0 * gp.fs_a1; gp.LP1 += (size_t)f0 * gp.fs_LP1;
     gp.phi += (size_t)f0 * gp.fs_phi;
     if (gp.lconst_f) gp.lconst_f += f0;
-    if (J->method == BSSM_METHOD_PSI) {
+    const bool psi = J->method == BSSM_METHOD_PSI;
+    if (psi) {
       gp.approx_loglik += f0;
       gp.alphahat += (size_t)f0 * gp.fs_a; gp.Lt += (size_t)f0 * gp.fs_m; gp.Ct += (size_t)f0 * gp.fs_m;
       gp.ytilde += (size_t)f0 * gp.fs_np; gp.Htilde += (size_t)f0 * gp.fs_np; gp.scales += (size_t)f0 * gp.fs_n;
-      return launch_status(pfl::launch_mng_psi_draws(J->m, fp, gp, J->geo, nf, J->stream), "ssm_mng psi filter (draws)");
     }
-    return launch_status(pfl::launch_mng_bsf_draws(J->m, J->k, fp, gp, J->geo, nf, J->stream), "ssm_mng bsf (draws)");
-  }
-  if (J->kind == KIND_MNG) {
-    if (J->method == BSSM_METHOD_PSI) {
-      pf::MngParams gp = J->gp;
-      gp.approx_loglik += f0;
-      return launch_status(pfl::launch_mng_psi(J->m, fp, gp, J->geo, nf, J->stream), "ssm_mng psi filter (m)");
-    }
-    return launch_status(pfl::launch_mng_bsf(J->m, J->k, fp, J->gp, J->geo, nf, J->stream), "ssm_mng bsf (m,k)");
+    if (J->dyn)
+      return psi ? launch_status(pfl::launch_mng_psi_dyn(fp, gp, J->geo, nf, J->stream), "ssm_mng psi filter (run-time m)")
+                 : launch_status(pfl::launch_mng_bsf_dyn(fp, gp, J->geo, nf, J->stream), "ssm_mng bsf (run-time m)");
+    if (J->mng_draws)
+      return psi ? launch_status(pfl::launch_mng_psi_draws(J->m, fp, gp, J->geo, nf, J->stream), "ssm_mng psi filter (draws)")
+                 : launch_status(pfl::launch_mng_bsf_draws(J->m, J->k, fp, gp, J->geo, nf, J->stream), "ssm_mng bsf (draws)");
+    return psi ? launch_status(pfl::launch_mng_psi(J->m, fp, gp, J->geo, nf, J->stream), "ssm_mng psi filter (m)")
+               : launch_status(pfl::launch_mng_bsf(J->m, J->k, fp, gp, J->geo, nf, J->stream), "ssm_mng bsf (m,k)");
   }
   pf::UngParams up = J->up;
   up.Z += (size_t)f0 * up.fs_Z; up.D += (size_t)f0 * up.fs_D; // parameter sets: one model per filter
@@ -1125,6 +1125,7 @@ int bssm_b200_job_max_concurrent_filters(const bssm_b200_job* J) {
   else if (J->kind == KIND_SDE && J->sde_model_id >= BSSM_USER_MODEL_BASE)
     rc = pfl::occupancy_user_sde(J->sde_model_id, J->geo, J->sp.theta_u_stride != 0, &out);
   else if (J->kind == KIND_SDE) rc = pfl::occupancy_sde_bsf(J->geo, &out);
+  else if (J->kind == KIND_MNG && J->dyn) rc = pfl::occupancy_mng_dyn(J->geo, &out);
   else if (J->kind == KIND_MNG) rc = pfl::occupancy_mng_bsf(J->geo, &out);
   else if (J->dyn) rc = pfl::occupancy_ung_dyn(J->geo, &out);
   else if (J->method == BSSM_METHOD_PSI) rc = pfl::occupancy_ung_psi1(J->geo, &out);
@@ -1673,7 +1674,8 @@ static int create_mng_job(const bssm_mng_model* M, int method, uint32_t nsim, ui
       !M->phi || !M->distribution)
     return fail(BSSM_B200_ERR_ARG, "null argument");
   *job = nullptr;
-  if (M->p < 1 || M->p > 8 || M->m < 1 || M->k < 1 || M->k > M->m) return fail(BSSM_B200_ERR_ARG, "ssm_mng: 1 <= p <= 8, 1 <= k <= m");
+  if (M->p < 1 || M->p > 16 || M->m < 1 || M->m > 16 || M->k < 1 || M->k > M->m)
+    return fail(BSSM_B200_ERR_ARG, "ssm_mng: 1 <= p <= 16, 1 <= k <= m <= 16");
   for (int j = 0; j < M->p; ++j)
     if (M->distribution[j] < 1 || M->distribution[j] > 5) return fail(BSSM_B200_ERR_ARG, "ssm_mng: distribution codes 1..5");
   bssm_b200_job* J = new bssm_b200_job();
@@ -1683,6 +1685,13 @@ static int create_mng_job(const bssm_mng_model* M, int method, uint32_t nsim, ui
                       post > BSSM_POST_SMOOTHER ? BSSM_POST_NONE : post);
   if (rc) return rc;
   J->post = post; // PICK / SMOOTHER_MERGE: the IS-correction drivers
+  {
+    // (m, k) without a specialised instantiation (k_mng.cu): the run-time-m policies, two particles per thread
+    const int mk = m * 10 + k;
+    const bool inst = method == BSSM_METHOD_PSI ? m <= 3 : (mk == 11 || mk == 21 || mk == 22 || mk == 33);
+    J->dyn = !inst;
+    if (J->dyn && (rc = choose_geometry(nsim, n_filters, &J->geo, true))) return rc;
+  }
   std::vector<double> LP1;
   chol_posdiag(M->P1, m, LP1);
   std::vector<int> dist(M->distribution, M->distribution + p);
@@ -1695,7 +1704,7 @@ static int create_mng_job(const bssm_mng_model* M, int method, uint32_t nsim, ui
       (rc = J->dist_v.upload(dist.data(), p)))
     return rc;
   pf::MngParams& gp = J->gp;
-  gp.n = n; gp.p = p;
+  gp.n = n; gp.p = p; gp.m_dyn = m; gp.k_dyn = k;
   gp.Ztv = M->Ztv; gp.Ttv = M->Ttv; gp.Rtv = M->Rtv; gp.Dtv = M->Dtv; gp.Ctv = M->Ctv;
   gp.y = J->y.p; gp.u = J->u.p; gp.Z = J->Z.p; gp.T = J->T.p; gp.R = J->R.p; gp.a1 = J->a1.p; gp.LP1 = J->LP1.p;
   gp.D = J->D.p; gp.C = J->C.p; gp.phi = J->phi_v.p; gp.distribution = J->dist_v.p;
@@ -1741,7 +1750,6 @@ static int create_mng_job(const bssm_mng_model* M, int method, uint32_t nsim, ui
   }
   if (method == BSSM_METHOD_PSI && dm) {
     // approximate_for_is (src/model_ssm_mng.cpp:119-135) per draw on the host, OpenMP over draws
-    if (m > 3) return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_mng psi-APF: m <= 3 in this build");
     if (dm->modes.size() != (size_t)p * n * n_filters) return fail(BSSM_B200_ERR_ARG, "parameter set: p x n modes per filter");
     J->method = BSSM_METHOD_PSI;
     const size_t n1 = (size_t)n + 1, mm = (size_t)m * m, np = (size_t)n * p, nf = n_filters;
@@ -1774,7 +1782,6 @@ static int create_mng_job(const bssm_mng_model* M, int method, uint32_t nsim, ui
     gp.fs_a = (size_t)m * n1; gp.fs_m = mm * n1; gp.fs_np = np; gp.fs_n = (size_t)n;
   } else if (method == BSSM_METHOD_PSI) {
     // Gaussian approximation on the host (O(n (m^3 + p^3)), sequential in t), shared by all replicates
-    if (m > 3) return fail(BSSM_B200_ERR_UNSUPPORTED, "ssm_mng psi-APF: m <= 3 in this build");
     if (!M->initial_mode) return fail(BSSM_B200_ERR_ARG, "psi-APF needs initial_mode");
     if (M->max_iter < 1) return fail(BSSM_B200_ERR_ARG, "max_iter must be >= 1");
     J->method = BSSM_METHOD_PSI;

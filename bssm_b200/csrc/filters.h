@@ -21,6 +21,9 @@ int occupancy_ung_bsf(const Geometry&, int* out);
 int launch_ung_bsf_dyn(const pf::FilterParams&, const pf::UngParams&, const Geometry&, uint32_t nf, Stream);
 int launch_ung_psi_dyn(const pf::FilterParams&, const pf::UngParams&, const Geometry&, uint32_t nf, Stream);
 int occupancy_ung_dyn(const Geometry&, int* out);
+int launch_mng_bsf_dyn(const pf::FilterParams&, const pf::MngParams&, const Geometry&, uint32_t nf, Stream); // ssm_mng, m <= 16
+int launch_mng_psi_dyn(const pf::FilterParams&, const pf::MngParams&, const Geometry&, uint32_t nf, Stream);
+int occupancy_mng_dyn(const Geometry&, int* out);
 // k_mng.cu: multivariate-observation bootstrap filter and psi-APF (m <= 3)
 int launch_mng_bsf(int m, int k, const pf::FilterParams&, const pf::MngParams&, const Geometry&, uint32_t nf, Stream);
 int launch_mng_psi(int m, const pf::FilterParams&, const pf::MngParams&, const Geometry&, uint32_t nf, Stream);

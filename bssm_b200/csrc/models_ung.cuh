@@ -315,6 +315,7 @@ struct UngPsiM : GaussStep<UngPsiM<M_>, M_, M_, M_> {
 // FP64 pipe: there is no tile here that a tcgen05 MMA could usefully take (fp64, K = m <= 8).
 struct MngParams {
   int n, p;
+  int m_dyn, k_dyn; // state / noise dimensions for the run-time-m policies (models_ung_dyn.cuh)
   int Ztv, Ttv, Rtv, Dtv, Ctv;
   const double* y;     // n x p as R holds it (the reference transposes to p x n)
   const double* u;     // n x p

@@ -195,7 +195,7 @@ typedef struct {
 
 /* replaces: bsf(model_, nsim, seed, gaussian = FALSE, model_type = 0)
  *           src/R_bootstrap_filter.cpp:130-155 -> ssm_mng::bsf_filter
- *           src/model_ssm_mng.cpp:562-668 + filter_summary.  p <= 8. */
+ *           src/model_ssm_mng.cpp:562-668 + filter_summary.  p <= 16, m <= 16. */
 int bssm_b200_bsf_mng(const bssm_mng_model* model, uint32_t nsim, uint32_t seed, bssm_filter_out* out);
 /* replaces: bsf_smoother(..., model_type = 0) src/R_bootstrap_filter.cpp:360-385 */
 int bssm_b200_bsf_smoother_mng(const bssm_mng_model* model, uint32_t nsim, uint32_t seed,
@@ -205,7 +205,7 @@ int bssm_b200_job_create_mng(const bssm_mng_model* model, uint32_t nsim, uint32_
                              struct bssm_b200_job** job);
 /* replaces: psi_smoother(model_, nsim, seed, model_type = 0) src/R_psi.cpp:57-78 ->
  *           ssm_mng::psi_filter src/model_ssm_mng.cpp:461-559 + filter_smoother + summary.
- *           m <= 3, p <= 8; needs initial_mode / max_iter / conv_tol. */
+ *           m <= 16, p <= 16; needs initial_mode / max_iter / conv_tol. */
 int bssm_b200_psi_smoother_mng(const bssm_mng_model* model, uint32_t nsim, uint32_t seed,
                                bssm_filter_out* out);
 /* psi-APF filter only: ssm_mng::log_likelihood(method = 1) src/model_ssm_mng.cpp:138-172
@@ -444,7 +444,7 @@ int bssm_b200_is_correction_bsf_ung_parset(const bssm_ung_model* model, const bs
                                            bssm_postcorr_out* out);
 /* replaces: postcorrection_nongaussian(..., model_type = 0) -> approx_mcmc::is_correction_psi<ssm_mng>
  *           (src/approx_mcmc.cpp:1038-1157) and is_correction_bsf<ssm_mng> (:1159-1273).
- *           modes is p x n x n_stored (mode_storage, src/approx_mcmc.cpp:29).  m <= 3, p <= 8. */
+ *           modes is p x n x n_stored (mode_storage, src/approx_mcmc.cpp:29).  m <= 16, p <= 16. */
 int bssm_b200_postcorrection_mng_parset(const bssm_mng_model* model, const bssm_parset* parset,
                                         int output_type, uint32_t nsim, uint32_t seed, uint32_t n_threads,
                                         int is_type, const uint32_t* counts, const double* modes,

@@ -90,3 +90,67 @@ def test_post_correction_with_a_seasonal_component(engine, period):
     res2 = engine.post_correct(model, mo2, 32, is_type="is1", seed=7)
     np.testing.assert_allclose(res2["alphahat"], ref2.alphahat, rtol=1e-9, atol=1e-11)
     np.testing.assert_allclose(res2["Vt"], ref2.Vt, rtol=1e-8, atol=1e-11)
+
+
+def mng_structural_model(p, n=48, seed=5, season=True):
+    """p Poisson / negative binomial series, each with its own level, one common slope and (optionally) one
+    common quarterly seasonal: m = p + 1 (+ 3), the multivariate structural models of ssm_mng"""
+    rng = np.random.default_rng(seed)
+    m = p + 1 + (3 if season else 0)
+    T = np.eye(m)
+    T[:p, p] = 1.0  # every level moves with the common slope
+    if season:
+        T[p + 1:, p + 1:] = 0.0
+        T[p + 1, p + 1:] = -1.0
+        T[p + 2, p + 1] = 1.0
+        T[p + 3, p + 2] = 1.0
+    k = p + 1 + (1 if season else 0)
+    R = np.zeros((m, k))
+    for j in range(p):
+        R[j, j] = 0.08
+    R[p, p] = 0.01
+    if season:
+        R[p + 1, p + 1] = 0.03
+    Z = np.zeros((p, m))
+    Z[np.arange(p), np.arange(p)] = 1.0
+    if season:
+        Z[:, p + 1] = 1.0
+    a = np.zeros((n, m))
+    a[0, :p] = rng.normal(1.0, 0.3, size=p)
+    if season:
+        a[0, p + 1:] = [0.3, -0.1, -0.3]
+    for t in range(1, n):
+        a[t] = T @ a[t - 1] + R @ rng.normal(size=k)
+    sig = a @ Z.T
+    y = rng.poisson(np.exp(sig)).astype(float)
+    y[5, 0] = np.nan
+    y[9, :] = np.nan
+    dist = ["poisson" if j % 2 == 0 else "negative binomial" for j in range(p)]
+    P1 = np.diag(np.r_[np.full(p, 1.0), 0.01, np.full(m - p - 1, 0.25)])
+    a1 = np.r_[np.full(p, 1.0), np.zeros(m - p)]
+    return bssm_b200.ssm_mng(y, Z, T, R, a1=a1, P1=P1, distribution=dist, phi=np.full(p, 4.0))
+
+
+@pytest.mark.parametrize("p,season,N", [(2, True, 100), (2, True, 3000), (4, False, 500), (10, False, 300)])
+def test_mng_general_m(engine, p, season, N):
+    """ssm_mng with m > 3 and p up to 16 (m = 6 / 5 / 11): bootstrap filter and psi-APF at run-time m,
+    bit-exact against the oracle (src/model_ssm_mng.cpp:461-668)"""
+    model = mng_structural_model(p, season=season)
+    assert model.m > 3 and model.p == p
+    ref = orc.mng_bsf_filter(model, N, seed=1)
+    res = engine.bootstrap_filter(model, N, seed=1, return_indices=True)
+    assert np.array_equal(res["indices"], ref.indices)
+    assert np.array_equal(np.transpose(res["alpha"], (1, 0, 2)).view(np.uint64), ref.alpha.view(np.uint64))
+    assert res["logLik"] == pytest.approx(ref.loglik, rel=1e-13)  # constants summed once on the host
+    at, att, Pt, Ptt = orc.filter_summary(ref.alpha, ref.weights)
+    np.testing.assert_allclose(res["att"], att.T, rtol=1e-10, atol=1e-12)
+    refp = orc.mng_psi_filter(model, N, seed=3)
+    resp = engine.particle_smoother(model, N, method="psi", seed=3, return_indices=True)
+    assert resp["approx_logLik"] == refp.approx_loglik
+    assert np.array_equal(resp["indices"], refp.indices)
+    assert resp["logLik"] == refp.loglik
+    sm = orc.filter_smoother(refp.alpha, refp.indices)
+    assert np.array_equal(np.transpose(resp["alpha"], (1, 0, 2)).view(np.uint64), sm.view(np.uint64))
+    ah, Vt = orc.summary(sm)
+    np.testing.assert_allclose(resp["alphahat"], ah.T, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(resp["Vt"], Vt, rtol=1e-8, atol=1e-12)
