@@ -190,3 +190,34 @@ def test_user_nlg_equals_registry_model(engine, kind):
     assert np.array_equal(ra["loglik"], rb["loglik"]) and np.array_equal(ra["alpha"], rb["alpha"])
     with pytest.raises(Exception, match="bootstrap filter"):
         engine.particle_smoother(user, 100, method="psi", seed=1)
+
+
+def test_new_correction_paths_on_two_gpus(engine):
+    """parameter sets, the ssm_nlg bootstrap correction and a user SDE model through ONE C-ABI call with
+    n_threads = 2: shards on two devices (the run-time compiled kernels load on both), same results"""
+    if engine.lib().bssm_b200_device_count() < 2:
+        pytest.skip("needs two visible GPUs (gpurun --gpus 2)")
+    import test_gpu_parset as tp
+    model = tp.ung_update_model(m=2, tv=True)
+    mo = tp.draws(model, 40)
+    one = engine.post_correct(model, mo, 64, threads=1, is_type="is2", seed=3, return_loglik=True)
+    two = engine.post_correct(model, mo, 64, threads=2, is_type="is2", seed=3, return_loglik=True)
+    assert engine.lib().bssm_b200_last_gather().decode().startswith("nccl: 2 ranks")
+    assert np.array_equal(one["loglik"], two["loglik"]) and np.array_equal(one["weights"], two["weights"])
+    reg = data.gbm_model(40)
+    user = engine.ssm_sde(reg.y, engine.sde_register(GBM_SRC), reg.theta, reg.x0, reg.positive)
+    rng = np.random.default_rng(3)
+    ns = 30
+    theta = np.abs(np.asarray(reg.theta)[None, :] + 0.05 * rng.normal(size=(ns, 3)))
+    mos = {"theta": theta, "counts": (1 + rng.poisson(2, size=ns)).astype(np.uint32),
+           "approx_loglik": -30.0 + rng.normal(size=ns), "output_type": 1, "posterior": np.zeros(ns)}
+    ra = engine.post_correct(reg, mos, 64, threads=2, is_type="is2", seed=5, L=3, return_loglik=True)
+    rb = engine.post_correct(user, mos, 64, threads=2, is_type="is2", seed=5, L=3, return_loglik=True)
+    assert np.array_equal(ra["loglik"], rb["loglik"]) and np.array_equal(ra["alpha"], rb["alpha"])
+    g = data.growth_model(40)
+    thg = np.asarray(g.theta)[None, :] + 0.04 * rng.normal(size=(ns, 3))
+    mog = {"theta": thg, "counts": mos["counts"], "approx_loglik": -100.0 + rng.normal(size=ns), "output_type": 3,
+           "posterior": np.zeros(ns)}
+    g1 = engine.post_correct(g, mog, 64, threads=1, is_type="is2", seed=5, return_loglik=True, sampling_method="bsf")
+    g2 = engine.post_correct(g, mog, 64, threads=2, is_type="is2", seed=5, return_loglik=True, sampling_method="bsf")
+    assert np.array_equal(g1["loglik"], g2["loglik"])
