@@ -30,6 +30,9 @@ enum { SYNC_SMALL = 3 }; // Geometry::sync_mode value that selects this kernel (
 __device__ __forceinline__ void bar_named(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
+// the hand-over barrier between the two halves: they arrive from different places in the code, so it is a
+// named barrier with an explicit thread count (bar.sync 2, blockDim.x), not __syncthreads()
+__device__ __forceinline__ void bar_all() { bar_named(2, (int)blockDim.x); }
 __device__ __forceinline__ long long shfl_up_i64(long long v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 
 // Strata (pf_device.cuh) over thresholds in shared memory
@@ -67,8 +70,9 @@ __host__ __device__ inline size_t small_smem_bytes(uint32_t N) {
   return 2 * Model::M * Np * 8 + 2 * Np * 8 + 2 * CT * small_noise_bytes<Model>() + Np * 4;
 }
 
-template <class Model>
-__global__ void __launch_bounds__(1024, 1)
+// MAXT = 512 (N <= 512): the compiler may use up to 128 registers per thread -- occupancy is no concern here
+template <class Model, int MAXT = 1024>
+__global__ void __launch_bounds__(MAXT, 1)
 small_filter_kernel(const FilterParams fp, const typename Model::Params mp) {
   constexpr int M = Model::M;
   constexpr int P = 2;
@@ -109,57 +113,31 @@ small_filter_kernel(const FilterParams fp, const typename Model::Params mp) {
     ub[i0 + 1] = pf_u53_plus(rx.v[2], rx.v[3], pf_u32_to_f64(i0 + 1)) * invN;
   };
 
-  if (producer) {
-    // ---- one step ahead of the consumers: thresholds of step t and normals of column t + 1 in buffer t & 1
-    double loglik = model.loglik0();
-    // log-likelihood of step s from what consumer 0 posted (same operations, same order as pf_device.cuh)
-    auto account = [&](int s) {
-      const double* q = s_ll[s & 1];
-      if (q[0] != 0.0) {
-        if (s == 0) loglik = ((q[1] + loglik) + pf_log_normal(q[2] / Nd)) + q[3];
-        else loglik += (q[1] + pf_log_normal(q[2] / Nd)) + q[3];
-      }
-    };
-#if PF_PHASE_TIMING
-    unsigned long long busy = 0;
-#endif
-    for (int t = 0; t < n; ++t) {
-      const int b = t & 1;
-#if PF_PHASE_TIMING
-      const long long p0 = clock64();
-#endif
-      thresholds(t, ubs + (size_t)b * Np);
-      StepCtx ctx;
-      ctx.seed = fp.seed; ctx.filter = filter; ctx.t = (uint32_t)(t + 1); ctx.i0 = i0;
-      Noise nz;
-      model.template draw<P>(ctx, nz);
-      *reinterpret_cast<Noise*>(nzs + ((size_t)b * CT + j) * NZB) = nz;
-      if (j == 0 && t >= 2) account(t - 2); // step t - 2 was posted before the barrier that ended step t - 2
-#if PF_PHASE_TIMING
-      busy += (unsigned long long)(clock64() - p0);
-#endif
-      __syncthreads(); // hand-over: the consumers start step t (their barrier at the end of step t - 1)
-      if (s_stop) return;
+  auto produce = [&](int t) { // thresholds of step t and normals of column t + 1 into buffer t & 1
+    const int b = t & 1;
+    thresholds(t, ubs + (size_t)b * Np);
+    StepCtx ctx;
+    ctx.seed = fp.seed; ctx.filter = filter; ctx.t = (uint32_t)(t + 1); ctx.i0 = i0;
+    Noise nz;
+    model.template draw<P>(ctx, nz);
+    *reinterpret_cast<Noise*>(nzs + ((size_t)b * CT + j) * NZB) = nz;
+  };
+  // producer 0: log-likelihood of step s from what consumer 0 posted (same operations, same order as pf_device.cuh)
+  double loglik = model.loglik0();
+  auto account = [&](int s) {
+    const double* q = s_ll[s & 1];
+    if (q[0] != 0.0) {
+      if (s == 0) loglik = ((q[1] + loglik) + pf_log_normal(q[2] / Nd)) + q[3];
+      else loglik += (q[1] + pf_log_normal(q[2] / Nd)) + q[3];
     }
-    __syncthreads(); // the consumers have finished step n - 1
-    if (s_stop) return;
-    if (j == 0) {
-      if (n >= 2) account(n - 2);
-      account(n - 1);
-      fp.loglik[fidx] = loglik + model.loglik_end();
-      fp.stopped_at[fidx] = -1;
-    }
-#if PF_PHASE_TIMING
-#ifndef PF_PHASE_FINE
-    if (fp.phase_cycles && j == 0) fp.phase_cycles[(size_t)blockIdx.x * 6 + 5] = busy;
-#endif
-#endif
-    return;
-  }
+  };
 
-  // --------------------------------------------------------------- consumers
+  // ---- prologue: column 0 of the state (consumers), buffer 0 (producers)
   double x[P][M];
-  {
+  double carry[P] = {0.0, 0.0};
+  if (producer) {
+    if (n > 0) produce(0);
+  } else {
     StepCtx c0;
     c0.seed = fp.seed; c0.filter = filter; c0.t = 0u; c0.i0 = i0;
     model.template init_all<P>(c0, x);
@@ -171,203 +149,206 @@ small_filter_kernel(const FilterParams fp, const typename Model::Params mp) {
         if (i0 + p < N) alpha[(size_t)d * N + i0 + p] = x[p][d];
       }
   }
-  int stopped = -1;
-  double carry[P] = {0.0, 0.0};
-  __syncthreads(); // buffer 0 of the producers and column 0 of the state are in place
+  bar_all();
+
 #if PF_PHASE_TIMING
   // consumer thread 0: [0] weights + max, [1] exp + fixed-point scan, [2] ancestors, [3] gather + propagate,
-  // [4] waiting for the producers at the end of the step; [5] is the producers' busy time
-  unsigned long long ph[5] = {0, 0, 0, 0, 0};
-  const bool timing = fp.phase_cycles != nullptr && threadIdx.x == 0;
+  // [4] waiting at the hand-over; [5] is the producers' busy time (thread CT)
+  unsigned long long ph[6] = {0, 0, 0, 0, 0, 0};
+  const bool timing = fp.phase_cycles != nullptr && (threadIdx.x == 0 || threadIdx.x == CT);
   long long tc = timing ? clock64() : 0;
-#ifdef PF_PHASE_FINE // a second set of marks inside the first two phases (diagnostic builds only)
-  unsigned long long phf[6] = {0, 0, 0, 0, 0, 0};
-  long long tf = tc;
-#define PFS_FINE(i) if (timing) { long long now_ = clock64(); phf[i] += (unsigned long long)(now_ - tf); tf = now_; }
-#define PFS_PHASE(i) if (timing) { long long now_ = clock64(); ph[i] += (unsigned long long)(now_ - tc); tc = now_; tf = now_; }
-#else
-#define PFS_FINE(i)
 #define PFS_PHASE(i) if (timing) { long long now_ = clock64(); ph[i] += (unsigned long long)(now_ - tc); tc = now_; }
-#endif
 #else
 #define PFS_PHASE(i)
-#define PFS_FINE(i)
 #endif
 
-  for (int t = 0;; ++t) {
+  // ---- time loop: ONE hand-over barrier per step, reached by both halves at the same place
+  int stopped = -1;
+  bool halted = false;
+  for (int t = 0; t < n; ++t) {
     const int b = t & 1;
-    const bool obs = (t < n) && model.observed(t);
-    double w[P], lw[P], mx = 0.0, sc_t = 0.0;
-    PFS_FINE(0)
-    if (obs) {
-      model.begin_weight(t);
-      mx = -pf_inf();
-      bool bad = false;
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        lw[p] = (i0 + p < N) ? model.finish_logw(model.logw(x[p]), carry[p]) : -pf_inf();
-        bad = bad || (lw[p] != lw[p]);
-        mx = lw[p] > mx ? lw[p] : mx;
-      }
-      if (bad) mx = pf_inf();
-      sc_t = model.step_const();
-      PFS_FINE(1)
-      mx = warp_max_d(mx);
-      if (lane == 0) s_max[b][warp] = mx;
-      PFS_FINE(2)
-      bar_named(1, CT);
-      PFS_FINE(3)
-      if (nwarps <= 4) { // a few warps: every thread takes the maximum of the slots itself
-        double m2 = s_max[b][0];
-        for (uint32_t wv = 1; wv < nwarps; ++wv) { const double v = s_max[b][wv]; m2 = v > m2 ? v : m2; }
-        mx = m2;
-      } else {
-        mx = warp_max_d(lane < nwarps ? s_max[b][lane] : -pf_inf());
-      }
-      PFS_FINE(4)
-      if (!pf_isfinite(mx)) { // uniform over the filter
-        stopped = t;
-        if (threadIdx.x == 0) s_stop = 1;
-        __syncthreads(); // releases the producers (at the hand-over of step t + 1 or at the final one): they leave on s_stop
-        break;
-      }
-#pragma unroll
-      for (int p = 0; p < P; ++p) w[p] = pf_exp_nonpos(lw[p] - mx);
+    if (producer) {
+      if (t + 1 < n) produce(t + 1);
+      if (j == 0 && t >= 1) account(t - 1); // posted before the hand-over that ended step t - 1
+      PFS_PHASE(5)
     } else {
-#pragma unroll
-      for (int p = 0; p < P; ++p) w[p] = (i0 + p < N) ? 1.0 : 0.0;
-    }
-    if (wout) {
-#pragma unroll
-      for (int p = 0; p < P; ++p)
-        if (i0 + p < N) wout[(size_t)t * N + i0 + p] = w[p];
-    }
-    if (t == n) break;
-    PFS_FINE(5)
-    PFS_PHASE(0)
-
-    // ---- one scan of the fixed-point weights: sum and cumulative sums
-    long long qh[P], ql[P], th = 0, tl = 0;
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-      pf_fixsum tm = pf_fixsum_term(w[p]);
-      qh[p] = tm.hi; ql[p] = tm.lo;
-      th += tm.hi; tl += tm.lo;
-    }
-    long long ih = th, il = tl;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const long long vh = shfl_up_i64(ih, o), vl = shfl_up_i64(il, o);
-      if ((int)lane >= o) { ih += vh; il += vl; }
-    }
-    if (lane == 31) { s_h[b][warp] = ih; s_l[b][warp] = il; }
-    bar_named(1, CT);
-    long long rh = ih - th, rl = il - tl, Th = 0, Tl = 0;
-    for (uint32_t wv = 0; wv < nwarps; ++wv) {
-      const long long h = s_h[b][wv], l = s_l[b][wv];
-      Th += h; Tl += l;
-      if (wv < warp) { rh += h; rl += l; }
-    }
-    const double S = pf_fixsum_value(Th, Tl);
-    const double invS = 1.0 / S;
-    if (threadIdx.x == 0) { // the log-likelihood recursion is producer 0's
-      double* q = s_ll[b];
-      q[0] = obs ? 1.0 : 0.0; q[1] = mx; q[2] = S; q[3] = sc_t;
-    }
-
-    PFS_PHASE(1)
-    // ---- stratified resampling: offspring range of particle k is [count(p_{k-1}), count(p_k))
-    StrataS st;
-    st.u_ = ubs + (size_t)b * Np; st.N = N; st.Nd = Nd;
-    {
-      const double pk0 = (i0 == 0) ? 0.0 : ((i0 - 1 >= N - 1) ? 1.0 : pf_fixsum_value(rh, rl) * invS);
-      uint32_t lo = (i0 == 0) ? 0u : st.resolve(pk0, st.guess(pk0), st.u(st.guess(pk0)));
-      double pk[P];
-      uint32_t jj[P];
-      double uj[P];
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        rh += qh[p]; rl += ql[p];
-        pk[p] = (i0 + p >= N - 1) ? 1.0 : pf_fixsum_value(rh, rl) * invS;
-        jj[p] = st.guess(pk[p]);
-        uj[p] = st.u(jj[p]);
-      }
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        const uint32_t c = st.resolve(pk[p], jj[p], uj[p]);
-        const uint32_t val = i0 + p;
-        const uint32_t cnt = c > lo ? c - lo : 0u;
-        if (cnt) {
-          uint32_t* q = ancs + lo;
-          q[0] = val;
-          if (cnt > 1) {
-            q[1] = val;
-            if (cnt > 2) {
-              q[2] = val;
-              if (cnt > 3) q[3] = val;
-            }
-          }
-        }
-        const uint32_t ce = lo + PF_SCATTER_CAP;
-        const unsigned heavy = __ballot_sync(0xffffffffu, cnt > PF_SCATTER_CAP);
-        if (heavy) scatter_heavy(ancs, heavy, ce, c, val);
-        lo = c > lo ? c : lo;
-      }
-    }
-    bar_named(1, CT);
-    PFS_PHASE(2)
-
-    // ---- gather the ancestors from shared memory, propagate to column t + 1
-    {
-      StepCtx ctx;
-      ctx.seed = fp.seed; ctx.filter = filter; ctx.t = (uint32_t)(t + 1); ctx.i0 = i0;
-      model.begin_step(t);
-      const double* src = xs + (size_t)b * M * Np;
-      double* dsts = xs + (size_t)(b ^ 1) * M * Np;
-      double* dst = alpha + (size_t)(fp.keep_alpha ? t + 1 : ((t + 1) & 1)) * M * N;
-      uint32_t a[P];
-#pragma unroll
-      for (int p = 0; p < P; ++p) a[p] = (i0 + p < N) ? ancs[i0 + p] : 0u;
-      if (fp.keep_indices) {
-#pragma unroll
-        for (int p = 0; p < P; ++p)
-          if (i0 + p < N) iout[(size_t)t * N + i0 + p] = a[p];
-      }
-      double xa[P][M];
-#pragma unroll
-      for (int p = 0; p < P; ++p)
-#pragma unroll
-        for (int d = 0; d < M; ++d) xa[p][d] = src[(size_t)d * Np + a[p]];
-      const Noise nz = *reinterpret_cast<const Noise*>(nzs + ((size_t)b * CT + j) * NZB);
-      model.template propagate_all<P>(ctx, nz, xa, x, carry);
-#pragma unroll
-      for (int d = 0; d < M; ++d)
+      const bool obs = model.observed(t);
+      double w[P], lw[P], mx = 0.0, sc_t = 0.0;
+      bool stop_now = false;
+      if (obs) {
+        model.begin_weight(t);
+        mx = -pf_inf();
+        bool bad = false;
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-          dsts[(size_t)d * Np + i0 + p] = x[p][d];
-          if (i0 + p < N) dst[(size_t)d * N + i0 + p] = x[p][d];
+          lw[p] = (i0 + p < N) ? model.finish_logw(model.logw(x[p]), carry[p]) : -pf_inf();
+          bad = bad || (lw[p] != lw[p]);
+          mx = lw[p] > mx ? lw[p] : mx;
         }
+        if (bad) mx = pf_inf(); // a NaN log-weight must stop the filter
+        sc_t = model.step_const();
+        mx = warp_max_d(mx);
+        if (lane == 0) s_max[b][warp] = mx;
+        bar_named(1, CT);
+        if (nwarps <= 4) { // a few warps: every thread takes the maximum of the slots itself
+          double m2 = s_max[b][0];
+          for (uint32_t wv = 1; wv < nwarps; ++wv) { const double v = s_max[b][wv]; m2 = v > m2 ? v : m2; }
+          mx = m2;
+        } else {
+          mx = warp_max_d(lane < nwarps ? s_max[b][lane] : -pf_inf());
+        }
+        stop_now = !pf_isfinite(mx); // uniform over the filter
+#pragma unroll
+        for (int p = 0; p < P; ++p) w[p] = pf_exp_nonpos(lw[p] - mx);
+      } else {
+#pragma unroll
+        for (int p = 0; p < P; ++p) w[p] = (i0 + p < N) ? 1.0 : 0.0;
+      }
+      if (stop_now) {
+        stopped = t;
+        if (threadIdx.x == 0) s_stop = t + 1; // tagged with the step: a late reader of the previous hand-over cannot mistake it
+      } else {
+        if (wout) {
+#pragma unroll
+          for (int p = 0; p < P; ++p)
+            if (i0 + p < N) wout[(size_t)t * N + i0 + p] = w[p];
+        }
+        PFS_PHASE(0)
+
+        // ---- one scan of the fixed-point weights: sum and cumulative sums
+        long long qh[P], ql[P], th = 0, tl = 0;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          pf_fixsum tm = pf_fixsum_term(w[p]);
+          qh[p] = tm.hi; ql[p] = tm.lo;
+          th += tm.hi; tl += tm.lo;
+        }
+        long long ih = th, il = tl;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const long long vh = shfl_up_i64(ih, o), vl = shfl_up_i64(il, o);
+          if ((int)lane >= o) { ih += vh; il += vl; }
+        }
+        if (lane == 31) { s_h[b][warp] = ih; s_l[b][warp] = il; }
+        bar_named(1, CT);
+        long long rh = ih - th, rl = il - tl, Th = 0, Tl = 0;
+        for (uint32_t wv = 0; wv < nwarps; ++wv) {
+          const long long h = s_h[b][wv], l = s_l[b][wv];
+          Th += h; Tl += l;
+          if (wv < warp) { rh += h; rl += l; }
+        }
+        const double S = pf_fixsum_value(Th, Tl);
+        const double invS = 1.0 / S;
+        if (threadIdx.x == 0) { // the log-likelihood recursion is producer 0's
+          double* q = s_ll[b];
+          q[0] = obs ? 1.0 : 0.0; q[1] = mx; q[2] = S; q[3] = sc_t;
+        }
+        PFS_PHASE(1)
+
+        // ---- stratified resampling: offspring range of particle k is [count(p_{k-1}), count(p_k))
+        StrataS st;
+        st.u_ = ubs + (size_t)b * Np; st.N = N; st.Nd = Nd;
+        {
+          const double pk0 = (i0 == 0) ? 0.0 : ((i0 - 1 >= N - 1) ? 1.0 : pf_fixsum_value(rh, rl) * invS);
+          uint32_t lo = (i0 == 0) ? 0u : st.resolve(pk0, st.guess(pk0), st.u(st.guess(pk0)));
+          double pk[P];
+          uint32_t jj[P];
+          double uj[P];
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            rh += qh[p]; rl += ql[p];
+            pk[p] = (i0 + p >= N - 1) ? 1.0 : pf_fixsum_value(rh, rl) * invS;
+            jj[p] = st.guess(pk[p]);
+            uj[p] = st.u(jj[p]);
+          }
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            const uint32_t c = st.resolve(pk[p], jj[p], uj[p]);
+            const uint32_t val = i0 + p;
+            const uint32_t cnt = c > lo ? c - lo : 0u;
+            if (cnt) {
+              uint32_t* q = ancs + lo;
+              q[0] = val;
+              if (cnt > 1) {
+                q[1] = val;
+                if (cnt > 2) {
+                  q[2] = val;
+                  if (cnt > 3) q[3] = val;
+                }
+              }
+            }
+            const uint32_t ce = lo + PF_SCATTER_CAP;
+            const unsigned heavy = __ballot_sync(0xffffffffu, cnt > PF_SCATTER_CAP);
+            if (heavy) scatter_heavy(ancs, heavy, ce, c, val);
+            lo = c > lo ? c : lo;
+          }
+        }
+        bar_named(1, CT);
+        PFS_PHASE(2)
+
+        // ---- gather the ancestors from shared memory, propagate to column t + 1
+        {
+          StepCtx ctx;
+          ctx.seed = fp.seed; ctx.filter = filter; ctx.t = (uint32_t)(t + 1); ctx.i0 = i0;
+          model.begin_step(t);
+          const double* src = xs + (size_t)b * M * Np;
+          double* dsts = xs + (size_t)(b ^ 1) * M * Np;
+          double* dst = alpha + (size_t)(fp.keep_alpha ? t + 1 : ((t + 1) & 1)) * M * N;
+          uint32_t a[P];
+#pragma unroll
+          for (int p = 0; p < P; ++p) a[p] = (i0 + p < N) ? ancs[i0 + p] : 0u;
+          if (fp.keep_indices) {
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+              if (i0 + p < N) iout[(size_t)t * N + i0 + p] = a[p];
+          }
+          double xa[P][M];
+#pragma unroll
+          for (int p = 0; p < P; ++p)
+#pragma unroll
+            for (int d = 0; d < M; ++d) xa[p][d] = src[(size_t)d * Np + a[p]];
+          const Noise nz = *reinterpret_cast<const Noise*>(nzs + ((size_t)b * CT + j) * NZB);
+          model.template propagate_all<P>(ctx, nz, xa, x, carry);
+#pragma unroll
+          for (int d = 0; d < M; ++d)
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+              dsts[(size_t)d * Np + i0 + p] = x[p][d];
+              if (i0 + p < N) dst[(size_t)d * N + i0 + p] = x[p][d];
+            }
+        }
+        PFS_PHASE(3)
+      }
     }
-    // end of step t: the next state column is complete; the producers have filled buffer (t + 1) & 1
-    PFS_PHASE(3)
-    if (t + 1 < n) __syncthreads();
-    PFS_PHASE(4)
+    // hand-over: column t + 1 of the state is complete, the producers have filled buffer (t + 1) & 1,
+    // consumer 0 has posted step t
+    bar_all();
+    if (!producer) { PFS_PHASE(4) }
+    if (s_stop == t + 1) { halted = true; break; }
   }
 #undef PFS_PHASE
 #if PF_PHASE_TIMING
-  if (timing)
-#ifdef PF_PHASE_FINE
-    for (int i = 0; i < 6; ++i) fp.phase_cycles[(size_t)blockIdx.x * 6 + i] = phf[i];
-#else
-    for (int i = 0; i < 5; ++i) fp.phase_cycles[(size_t)blockIdx.x * 6 + i] = ph[i];
-#endif
+  if (timing) {
+    if (threadIdx.x == 0) for (int i = 0; i < 5; ++i) fp.phase_cycles[(size_t)blockIdx.x * 6 + i] = ph[i];
+    else fp.phase_cycles[(size_t)blockIdx.x * 6 + 5] = ph[5];
+  }
 #endif
 
-  if (stopped >= 0) {
+  if (halted) { // every thread saw it after the hand-over of the step that stopped
     if (threadIdx.x == 0) { fp.loglik[fidx] = -pf_inf(); fp.stopped_at[fidx] = stopped; }
     return;
   }
-  __syncthreads(); // step n - 1 is posted: producer 0 finishes the log-likelihood
+  if (producer) {
+    if (j == 0) {
+      if (n >= 1) account(n - 1);
+      fp.loglik[fidx] = loglik + model.loglik_end();
+      fp.stopped_at[fidx] = -1;
+    }
+  } else if (wout) { // column n is a pure prediction: unit weights
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+      if (i0 + p < N) wout[(size_t)n * N + i0 + p] = 1.0;
+  }
 }
 
 } // namespace pf

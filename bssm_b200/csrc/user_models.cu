@@ -170,7 +170,7 @@ std::string nlg_model_expr(int m, int k, bool per_filter) {
   return "pf::NlgFnBsf<pf::UserNlg, " + std::to_string(m) + ", " + std::to_string(k) + ", " + (per_filter ? "true" : "false") + ">";
 }
 std::string filter_kernel_expr(const std::string& model, const Geometry& g) {
-  if (g.sync_mode == pf::SYNC_SMALL) return "pf::small_filter_kernel<" + model + ">";
+  if (g.sync_mode == pf::SYNC_SMALL) return "pf::small_filter_kernel<" + model + ", " + (g.block <= 512 ? "512" : "1024") + ">";
   const bool small = g.block <= 512;
   return "pf::filter_kernel<" + model + ", " + std::to_string(g.P) + ", " +
          (small ? std::to_string(PF_SMALL_MAXT) + ", " + std::to_string(PF_SMALL_MINB) : std::string("1024, 1")) + ">";
