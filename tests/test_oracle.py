@@ -371,3 +371,76 @@ def test_parset_correction_reproduces_the_svm_update_model_path():
     res = orc.correction_parset(ung, mo, 48, is_type=2, seed=3)
     assert np.array_equal(res.loglik, ref.loglik)
     assert np.array_equal(res.weights, ref.weights)
+
+
+def _tv_smoother(y, Z, D, H2, T, C, RR, a1, P1):
+    """numpy Kalman filter + RTS smoother of a time-varying linear-Gaussian model with scalar observations:
+    y_t = D_t + Z_t' a_t + eps_t (var H2_t), a_{t+1} = C_t + T_t a_t + eta_t (cov RR_t).  Returns a_t | y_1..n, t = 0..n-1"""
+    n, m = len(y), len(a1)
+    ap, Pp = np.zeros((n + 1, m)), np.zeros((n + 1, m, m))
+    af, Pf = np.zeros((n, m)), np.zeros((n, m, m))
+    ap[0], Pp[0] = a1, P1
+    for t in range(n):
+        if np.isfinite(y[t]):
+            F = Z[t] @ Pp[t] @ Z[t] + H2[t]
+            K = Pp[t] @ Z[t] / F
+            af[t] = ap[t] + K * (y[t] - D[t] - Z[t] @ ap[t])
+            Pf[t] = Pp[t] - np.outer(K, K) * F
+        else:
+            af[t], Pf[t] = ap[t], Pp[t]
+        ap[t + 1] = C[t] + T[t] @ af[t]
+        Pp[t + 1] = T[t] @ Pf[t] @ T[t].T + RR[t]
+    asm = np.zeros((n, m))
+    nxt = None
+    for t in range(n - 1, -1, -1):
+        if nxt is None:
+            asm[t] = af[t]
+        else:
+            J = Pf[t] @ T[t].T @ np.linalg.pinv(Pp[t + 1])
+            asm[t] = af[t] + J @ (nxt - ap[t + 1])
+        nxt = asm[t]
+    return asm
+
+
+@pytest.mark.parametrize("kind", ["growth", "ar_exp", "sin_exp"])
+def test_nlg_approximation_is_a_fixed_point(kind):
+    """ssm_nlg::approximate (src/model_ssm_nlg.cpp:62-150) linearises Z_fn / T_fn at the mode and smooths the
+    linearised model until the mode reproduces itself.  Independent check of include/bssm_b200/nlg_gauss_approx.h:
+    the converged mode is a fixed point of a numpy smoother of the model linearised (numerical Jacobians) at it."""
+    if kind == "growth":
+        mdl = data.growth_model(60, missing=(7,))
+        H, R0, R1 = np.exp(mdl.theta)
+        dT, K, a11, a12, P11, P12 = mdl.known_params[:6]
+        Zf = lambda a: a[1]
+        def Tf(a):
+            r = np.exp(a[0]) / (1 + np.exp(a[0]))
+            e = np.exp(r * dT)
+            return np.array([a[0], K * a[1] * e / (K + a[1] * (e - 1))])
+        RR, a1, P1 = np.diag([R0 ** 2, R1 ** 2]), np.array([a11, a12]), np.diag([P11, P12])
+    elif kind == "ar_exp":
+        mdl = data.ar_exp_model(60, missing=(3,))
+        mu, rho, ls, lH = mdl.theta
+        H = np.exp(lH)
+        Zf = lambda a: np.exp(a[0])
+        Tf = lambda a: np.array([mu * (1 - rho) + rho * a[0]])
+        RR, a1, P1 = np.array([[np.exp(ls) ** 2]]), np.array([mu]), np.array([[np.exp(ls) ** 2 / (1 - rho ** 2)]])
+    else:
+        mdl = data.sin_exp_model(60)
+        H, R = np.exp(mdl.theta)
+        Zf = lambda a: np.exp(a[0])
+        Tf = lambda a: np.array([np.sin(a[0])])
+        RR, a1, P1 = np.array([[R ** 2]]), np.array([0.0]), np.array([[1.0]])
+    r = orc.nlg_psi_filter(mdl, 8, seed=1)
+    mode = r.mode.T.copy()  # n x m
+    n, m = mode.shape
+    h = 1e-6
+    Z, D, T, C = np.zeros((n, m)), np.zeros(n), np.zeros((n, m, m)), np.zeros((n, m))
+    for t in range(n):
+        for d in range(m):
+            e = np.zeros(m); e[d] = h
+            Z[t, d] = (Zf(mode[t] + e) - Zf(mode[t] - e)) / (2 * h)
+            T[t, :, d] = (Tf(mode[t] + e) - Tf(mode[t] - e)) / (2 * h)
+        D[t] = Zf(mode[t]) - Z[t] @ mode[t]
+        C[t] = Tf(mode[t]) - T[t] @ mode[t]
+    asm = _tv_smoother(mdl.y, Z, D, np.full(n, H ** 2), T, C, [RR] * n, a1, P1)
+    np.testing.assert_allclose(asm, mode, atol=2e-3, rtol=1e-3)
