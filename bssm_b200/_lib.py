@@ -156,6 +156,7 @@ def lib():
         c_double_p, C.c_uint32, c_double_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PostcorrOut)]
     L.bssm_b200_suggest_n_nongaussian.argtypes = pc_args + [c_double_p, C.c_uint32, c_uint32_p, C.c_uint32,
                                                             C.c_uint32, C.c_uint32, c_double_p]
+    L.bssm_b200_suggest_n_mng.argtypes = [C.POINTER(MngModel), c_uint32_p, C.c_uint32, C.c_uint32, C.c_uint32, c_double_p]
     L.bssm_b200_suggest_n_nonlinear.argtypes = [C.POINTER(NlgModel), c_double_p, C.c_uint32, c_uint32_p,
                                                 C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double,
                                                 c_double_p]

@@ -302,10 +302,31 @@ def suggest_N(model, theta, candidates=tuple(range(10, 101, 10)), replications=1
     if cand.size < 1 or np.any(cand < 1):
         raise ValueError("Argument 'candidates' should be vector of positive integers. ")
     theta = _lib.f64(np.ravel(theta))
-    if theta.size != np.size(model.theta):
-        raise ValueError("Length of 'theta' does not match length of 'model$theta'.")
     cand32 = np.ascontiguousarray(cand, dtype=np.uint32)
     sds = np.zeros(cand.size)
+    if getattr(model, "update_fn", None) is not None and model.cls in ("ssm_ung", "ssm_mng"):
+        # model.update_model(theta, update_fn), src/R_postcorrection.cpp:21-52: apply the closure here
+        import copy
+        mi = copy.copy(model)
+        for name, val in model.update_fn(theta).items():
+            if name == "phi" and model.cls == "ssm_ung":
+                mi.phi = float(val)
+            else:
+                own = getattr(model, name)
+                setattr(mi, name, _lib.f64(np.reshape(np.asarray(val, dtype=np.float64), np.shape(own), order="F")))
+        ms = mi.c_struct()
+        if model.cls == "ssm_mng":
+            check(lib().bssm_b200_suggest_n_mng(C.byref(ms), uptr(cand32), cand32.size, replications, int(seed), dptr(sds)))
+        else:
+            from ._lib import ThetaMap
+            tm = ThetaMap()
+            tm.model_type = 1
+            check(lib().bssm_b200_suggest_n_nongaussian(C.byref(ms), C.byref(tm), dptr(theta), theta.size, uptr(cand32),
+                                                        cand32.size, replications, int(seed), dptr(sds)))
+        below = np.nonzero(sds < 1)[0]
+        return {"N": int(cand[below[0]]) if below.size else None, "results": {"N": cand.copy(), "sd": sds}}
+    if theta.size != np.size(model.theta):
+        raise ValueError("Length of 'theta' does not match length of 'model$theta'.")
     ms = model.c_struct()
     if model.cls == "ssm_nlg":
         check(lib().bssm_b200_suggest_n_nonlinear(C.byref(ms), dptr(theta), theta.size, uptr(cand32), cand32.size,

@@ -2913,7 +2913,10 @@ int bssm_b200_suggest_n_nongaussian(const bssm_ung_model* M, const bssm_theta_ma
   bssm_ung_model Mi = *M;
   double par[6];
   std::vector<double> R, P1, xb;
-  if (M->m == 1 && !(map->model_type == 2 && map->n_xreg > 0)) {
+  if (map->model_type == 1) {
+    // ssm_ung: theta maps onto the model through an R closure (update_model(theta, update_fn),
+    // src/R_postcorrection.cpp:37-40); the caller has applied it, `M` IS the model at theta
+  } else if (M->m == 1 && !(map->model_type == 2 && map->n_xreg > 0)) {
     if (M->xbeta && map->n_xreg <= 0) return fail(BSSM_B200_ERR_ARG, "the model has regressors: theta_map needs n_xreg and xreg");
     int rc = theta_to_par(M, map, theta, n_par, par);
     if (rc) return rc;
@@ -2939,6 +2942,19 @@ int bssm_b200_suggest_n_nongaussian(const bssm_ung_model* M, const bssm_theta_ma
     bssm_b200_job* J = nullptr;
     int rc = create_ung_job(&Mi, BSSM_METHOD_PSI, candidates[c], seed, replications, c * replications, 0,
                             BSSM_POST_NONE, nullptr, nullptr, &J);
+    if (rc) return rc;
+    if ((rc = loglik_sd(J, replications, &sds[c]))) return rc;
+  }
+  return 0;
+}
+
+int bssm_b200_suggest_n_mng(const bssm_mng_model* M, const uint32_t* candidates, uint32_t n_candidates,
+                            uint32_t replications, uint32_t seed, double* sds) {
+  if (!M || !candidates || !sds || n_candidates == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
+  if (replications < 2) return fail(BSSM_B200_ERR_ARG, "replications must be >= 2");
+  for (uint32_t c = 0; c < n_candidates; ++c) {
+    bssm_b200_job* J = nullptr;
+    int rc = create_mng_job(M, BSSM_METHOD_PSI, candidates[c], seed, replications, c * replications, 0, BSSM_POST_NONE, &J);
     if (rc) return rc;
     if ((rc = loglik_sd(J, replications, &sds[c]))) return rc;
   }

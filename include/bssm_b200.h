@@ -502,6 +502,12 @@ int bssm_b200_suggest_n_nongaussian(const bssm_ung_model* model, const bssm_thet
                                     const double* theta, uint32_t n_par, const uint32_t* candidates,
                                     uint32_t n_candidates, uint32_t replications, uint32_t seed,
                                     double* sds);
+/* the same for model_type 0 (ssm_mng, src/R_postcorrection.cpp:21-36).  ssm_ung / ssm_mng map theta onto
+ * the model through an R closure (model.update_model(theta, update_fn)): the caller applies it and passes the
+ * model AT theta -- for ssm_ung through bssm_b200_suggest_n_nongaussian with map->model_type = 1 (theta is
+ * then not read), for ssm_mng here. */
+int bssm_b200_suggest_n_mng(const bssm_mng_model* model, const uint32_t* candidates, uint32_t n_candidates,
+                            uint32_t replications, uint32_t seed, double* sds);
 /* replaces: suggest_n_nonlinear(...) src/R_postcorrection.cpp:107-147 (registry models) */
 int bssm_b200_suggest_n_nonlinear(const bssm_nlg_model* model, const double* theta, uint32_t n_par,
                                   const uint32_t* candidates, uint32_t n_candidates,

@@ -298,17 +298,59 @@ SEXP _bssmb200_nongaussian_loglik(SEXP model_, SEXP nsim_, SEXP sampling_method_
 /* suggest_n_nongaussian(model_, theta, candidates, replications, seed, model_type): src/R_postcorrection.cpp:14-104 */
 SEXP _bssmb200_suggest_n_nongaussian(SEXP model_, SEXP theta_, SEXP candidates_, SEXP replications_, SEXP seed_,
                                      SEXP model_type_) {
-  bssm_ung_model M;
-  int n = (int)XLENGTH(list_get(model_, "y")), nc = (int)XLENGTH(candidates_);
-  double* xb = (double*)R_alloc(n, sizeof(double));
-  fill_ung(model_, &M, xb);
-  bssm_theta_map map;
-  fill_map(model_, asInteger(model_type_), &map);
+  const int model_type = asInteger(model_type_);
+  int nc = (int)XLENGTH(candidates_);
   uint32_t* cand = (uint32_t*)R_alloc(nc, sizeof(uint32_t));
   for (int i = 0; i < nc; i++) cand[i] = (uint32_t)REAL(candidates_)[i]; /* arma::vec candidates */
   SEXP sds = PROTECT(allocVector(REALSXP, nc));
+  const unsigned reps = (unsigned)asInteger(replications_), seed = (unsigned)asInteger(seed_);
+  bssm_parset ps;
+  if (model_type == 0) { /* ssm_mng: model.update_model(theta, update_fn), src/R_postcorrection.cpp:21-24 */
+    bssm_mng_model G;
+    fill_mng(model_, &G);
+    build_parset(model_, theta_, (int)XLENGTH(theta_), 1, G.p, &ps); /* one "draw": the slices are the arrays */
+    if (ps.phi) G.phi = ps.phi;
+    if (ps.Z) G.Z = ps.Z;
+    if (ps.T) G.T = ps.T;
+    if (ps.R) G.R = ps.R;
+    if (ps.a1) G.a1 = ps.a1;
+    if (ps.P1) G.P1 = ps.P1;
+    if (ps.D) G.D = ps.D;
+    if (ps.C) G.C = ps.C;
+    check_rc(bssm_b200_suggest_n_mng(&G, cand, (unsigned)nc, reps, seed, REAL(sds)));
+    UNPROTECT(1);
+    return sds;
+  }
+  bssm_ung_model M;
+  int n = (int)XLENGTH(list_get(model_, "y"));
+  double* xb = (double*)R_alloc(n, sizeof(double));
+  fill_ung(model_, &M, xb);
+  bssm_theta_map map;
+  if (model_type == 1) { /* ssm_ung with update_fn (:37-40): apply it here, the library gets the model at theta */
+    memset(&map, 0, sizeof(map));
+    map.model_type = 1;
+    build_parset(model_, theta_, (int)XLENGTH(theta_), 1, 1, &ps);
+    if (ps.phi) M.phi = ps.phi[0];
+    if (ps.Z) M.Z = ps.Z;
+    if (ps.T) M.T = ps.T;
+    if (ps.R) M.R = ps.R;
+    if (ps.a1) M.a1 = ps.a1;
+    if (ps.P1) M.P1 = ps.P1;
+    if (ps.D) M.D = ps.D;
+    if (ps.C) M.C = ps.C;
+    if (ps.beta) { /* compute_xbeta */
+      for (int t = 0; t < n; t++) {
+        double sum = 0;
+        for (int j = 0; j < ps.n_xreg; j++) sum += ps.xreg[t + (R_xlen_t)n * j] * ps.beta[j];
+        xb[t] = sum;
+      }
+      M.xbeta = xb;
+    }
+  } else {
+    fill_map(model_, model_type, &map);
+  }
   check_rc(bssm_b200_suggest_n_nongaussian(&M, &map, REAL(theta_), (unsigned)XLENGTH(theta_), cand, (unsigned)nc,
-                                           (unsigned)asInteger(replications_), (unsigned)asInteger(seed_), REAL(sds)));
+                                           reps, seed, REAL(sds)));
   UNPROTECT(1);
   return sds;
 }

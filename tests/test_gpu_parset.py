@@ -187,3 +187,28 @@ def test_parset_path_meets_the_svm_path(engine):
     ref = orc.correction_parset(ung, mo, 96, is_type=2, seed=3)
     assert np.array_equal(b["loglik"], ref.loglik)
     np.testing.assert_allclose(a["loglik"], b["loglik"], rtol=1e-12)
+
+
+def test_suggest_N_for_models_with_update_fn(engine):
+    """suggest_n_nongaussian(model_type = 1 | 0): model.update_model(theta, update_fn) then the sd of replicate
+    psi-APF log-likelihoods per candidate N (src/R_postcorrection.cpp:14-104)"""
+    import copy
+    reps, cands = 6, [16, 64]
+    model = ung_update_model(m=2)
+    theta = np.array([0.05, -0.1, 0.02])
+    res = engine.suggest_N(model, theta, candidates=cands, replications=reps, seed=5)
+    mi = copy.copy(model)
+    for name, val in model.update_fn(theta).items():
+        setattr(mi, name, np.asfortranarray(np.reshape(np.asarray(val, dtype=np.float64), np.shape(getattr(model, name)), order="F")))
+    for c, N in enumerate(cands):
+        ll = [orc.psi_filter_m(mi, N, seed=5, filt=c * reps + r).loglik for r in range(reps)]
+        assert res["results"]["sd"][c] == pytest.approx(np.std(ll, ddof=1), rel=1e-10)
+    g = mng_update_model()
+    thg = np.array([0.1, -0.05, 0.2])
+    resg = engine.suggest_N(g, thg, candidates=cands, replications=reps, seed=7)
+    gi = copy.copy(g)
+    for name, val in g.update_fn(thg).items():
+        setattr(gi, name, np.asfortranarray(np.reshape(np.asarray(val, dtype=np.float64), np.shape(getattr(g, name)), order="F")))
+    for c, N in enumerate(cands):
+        ll = [orc.mng_psi_filter(gi, N, seed=7, filt=c * reps + r).loglik for r in range(reps)]
+        assert resg["results"]["sd"][c] == pytest.approx(np.std(ll, ddof=1), rel=1e-10)
