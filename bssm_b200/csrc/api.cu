@@ -700,6 +700,7 @@ int bssm_b200_set_device(int device) {
 const char* bssm_b200_last_gather(void);
 void bssm_b200_shutdown(void) {
   bssm_b200_release_comm();
+  pfl::user_models_release();
   g_pool.release_all();
   {
     std::lock_guard<std::mutex> g(g_sctx.mu);

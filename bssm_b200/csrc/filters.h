@@ -46,6 +46,7 @@ int occupancy_sde_bsf(const Geometry&, int* out);
 int user_sde_register(const char* source, int* model_id);
 bool user_sde_exists(int model_id);
 const char* user_model_error();
+void user_models_release();
 int launch_user_sde(int model_id, const pf::FilterParams&, const pf::SdeParams&, const Geometry&, uint32_t nf, bool per_filter, Stream);
 int occupancy_user_sde(int model_id, const Geometry&, bool per_filter, int* out);
 // ssm_nlg bootstrap filter from user source (Z_fn, H_fn, T_fn, R_fn, a1_fn, P1_fn; p = 1, state dimension m, k etas)

@@ -185,6 +185,16 @@ UserModel* find(int model_id) {
 } // namespace
 
 const char* user_model_error() { return g_uerr.c_str(); }
+// bssm_b200_shutdown: unload the compiled kernels; the registered sources (and their ids) stay valid and
+// are compiled again on the next use
+void user_models_release() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& um : g_models) {
+    for (cudaLibrary_t lib : um->libs) cudaLibraryUnload(lib);
+    um->libs.clear();
+    um->kernels.clear();
+  }
+}
 bool user_sde_exists(int model_id) {
   std::lock_guard<std::mutex> lk(g_mu);
   UserModel* um = find(model_id);

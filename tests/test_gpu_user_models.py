@@ -221,3 +221,14 @@ def test_new_correction_paths_on_two_gpus(engine):
     g1 = engine.post_correct(g, mog, 64, threads=1, is_type="is2", seed=5, return_loglik=True, sampling_method="bsf")
     g2 = engine.post_correct(g, mog, 64, threads=2, is_type="is2", seed=5, return_loglik=True, sampling_method="bsf")
     assert np.array_equal(g1["loglik"], g2["loglik"])
+
+
+def test_user_models_survive_shutdown(engine):
+    """bssm_b200_shutdown unloads the run-time compiled kernels; registered ids stay valid (compiled again on use)"""
+    reg = data.gbm_model(30)
+    mid = engine.sde_register(GBM_SRC)
+    user = engine.ssm_sde(reg.y, mid, reg.theta, reg.x0, reg.positive)
+    a = engine.bootstrap_filter(user, 100, seed=2, L=2)["logLik"]
+    engine.lib().bssm_b200_shutdown()
+    b = engine.bootstrap_filter(user, 100, seed=2, L=2)["logLik"]
+    assert a == b == engine.bootstrap_filter(reg, 100, seed=2, L=2)["logLik"]
