@@ -298,6 +298,176 @@ void ung_approximate_m1(const bssm_ung_model* M, std::vector<double>& mode, std:
   }
 }
 
+// log g(y_t | signal) up to constants, src/model_ssm_ung.cpp:447-493 (host copy of pf::ung_log_obs)
+static double ung_log_obs_host(int dist, double s, double y, double u, double phi, double yphi2) {
+  switch (dist) {
+    case 0: return -0.5 * (s + yphi2 * pf_exp(-s));
+    case 1: return y * s - u * pf_exp(s);
+    case 2: return y * s - u * pf_log1p(pf_exp(s));
+    case 3: return y * s - (y + phi) * pf_log(phi + u * pf_exp(s));
+    default: return -phi * (s + (y * pf_exp(-s) / u));
+  }
+}
+
+// The psi-APF pre-pass for m = 1 on the HOST: what pf::ung_prepass_m1_kernel (prepass_ung.cuh) does for one
+// filter, expression by expression and in the same order, so that the two give the same bits
+// (tests/test_gpu_parity.py::test_host_prepass_equals_device_prepass).  It is a sequential O(n) chain of
+// dependent divisions: one GPU warp needs 0.9 ms for n = 1000, one host core 0.05 ms.  Jobs whose filters
+// share one model (replicates, the filter inside an MCMC loop) run it here, once; jobs with one model per
+// filter (post_correct: thousands of independent chains) run the kernel.
+struct PrepassHost {
+  std::vector<double> ah, Lt, Ct, yt, Ht, sc, rHt, yphi2; // n + 1 each (rows 0..n-1 used by the n-sized ones)
+  double approx_loglik = 0.0;
+};
+static void ung_prepass_m1_host(const bssm_ung_model* M, const double* mode, const double* mode_lin, double dist_const,
+                                PrepassHost& o) {
+  const int n = M->n, dist = M->distribution;
+  const double phi = M->phi, zero_tol = 1e-12, log2pi = std::log(2.0 * M_PI);
+  const double a1 = M->a1[0], P1 = M->P1[0];
+  auto Zt = [&](int t) { return M->Z[t * M->Ztv]; };
+  auto Tt = [&](int t) { return M->T[t * M->Ttv]; };
+  auto RRt = [&](int t) { double r = M->R[t * M->Rtv]; return r * r; };
+  auto Ct = [&](int t) { return M->C[t * M->Ctv]; };
+  auto Dt = [&](int t) { return M->D[t * M->Dtv]; };
+  const size_t n1 = (size_t)n + 1;
+  o.ah.assign(n1, 0.0); o.Lt.assign(n1, 0.0); o.Ct.assign(n1, 0.0); o.yt.assign(n1, 0.0); o.Ht.assign(n1, 0.0);
+  o.sc.assign(n1, 0.0); o.rHt.assign(n1, 0.0); o.yphi2.assign(n1, 0.0);
+  std::vector<double> vt(n), Ft(n), Kt(n);
+  double *ah = o.ah.data(), *Vt = o.Lt.data(), *cc = o.Ct.data(), *ay = o.yt.data(), *aH = o.Ht.data(), *sc = o.sc.data();
+  // ---- laplace_iter (:302-342) and update_scales (:241-292)
+  for (int t = 0; t < n; ++t) {
+    const double y = M->y[t], u = M->u[t];
+    double s = mode_lin[t];
+    double HH, yt;
+    switch (dist) {
+      case 0: {
+        double tmp = y;
+        if (std::fabs(tmp) < 1e-4) tmp = 1e-4;
+        double q = tmp / phi;
+        HH = 2.0 * pf_exp(s) / (q * q);
+        yt = s + 1.0 - 0.5 * HH;
+      } break;
+      case 1: {
+        HH = 1.0 / (pf_exp(s) * u);
+        yt = y * HH + s - 1.0;
+      } break;
+      case 2: {
+        double e = pf_exp(s);
+        HH = (1.0 + e) * (1.0 + e) / (u * e);
+        yt = y * HH + s - 1.0 - e;
+      } break;
+      case 3: {
+        double e = pf_exp(s) * u;
+        HH = (phi + e) * (phi + e) / (phi * e * (y + phi));
+        yt = s + (phi + e) * (y - e) / ((y + phi) * e);
+      } break;
+      default: {
+        double e = pf_exp(s) * u;
+        HH = e / (y * phi);
+        yt = s - e / y + 1;
+      } break;
+    }
+    const double H = std::sqrt(HH);
+    ay[t] = yt;
+    aH[t] = H;
+    o.rHt[t] = 1.0 / H;
+    { const double qy = y / phi; o.yphi2[t] = qy * qy; }
+    Ft[t] = HH;
+    double scale = 0.0;
+    s = mode[t];
+    if (std::isfinite(y)) {
+      double qy = y / phi;
+      double q = (yt - s) / H;
+      scale = ung_log_obs_host(dist, s, y, u, phi, qy * qy) + 0.5 * (q * q);
+    }
+    sc[t] = scale;
+  }
+  auto ytmp = [&](int t) { return M->xbeta ? ay[t] - M->xbeta[t] : ay[t]; };
+  // ---- approx_loglik (:519-528) and the forward pass of smoother_ccov (src/model_ssm_ulg.cpp:419-473)
+  {
+    double sumH = 0.0, sumR = 0.0;
+    for (int t = 0; t < n; ++t) sumH += aH[t];
+    { int nR = M->Rtv ? n : 1; for (int t = 0; t < nR; ++t) sumR += M->R[t]; }
+    const bool run_ll = !(sumH + sumR < zero_tol);
+    double gl = !run_ll ? -pf_inf() : 0.0;
+    double at = a1, Pl = P1, aht = a1, Pt = P1;
+    int nobs = 0;
+    double sumlog = 0.0, acc1 = 0.0, acc2 = 0.0;
+    ah[0] = a1; Vt[0] = P1;
+    for (int t = 0; t < n; ++t) {
+      const double z = Zt(t), Tk = Tt(t), RRk = RRt(t), Ck = Ct(t), Dk = Dt(t);
+      const double HH = Ft[t], yt = ytmp(t);
+      const bool yfin = std::isfinite(yt);
+      if (run_ll) {
+        double F = z * Pl * z + HH;
+        if (yfin && F > zero_tol) {
+          double v = yt - Dk - z * at;
+          double K = Pl * z / F;
+          at = Ck + Tk * (at + K * v);
+          Pl = Tk * (Pl - K * K * F) * Tk + RRk;
+          gl -= 0.5 * (log2pi + pf_log(F) + v * v / F);
+        } else {
+          at = Ck + Tk * at;
+          Pl = Tk * Pl * Tk + RRk;
+        }
+      }
+      if (std::isfinite(M->y[t])) { nobs++; sumlog += pf_log(aH[t]); }
+      if (t & 1) acc2 += sc[t]; else acc1 += sc[t];
+      const double F = z * Pt * z + HH;
+      double Kk = 0.0, vk = 0.0, ahn, Vn;
+      if (yfin && F > zero_tol) {
+        Kk = Pt * z / F;
+        vk = yt - Dk - z * aht;
+        ahn = Ck + Tk * (aht + Kk * vk);
+        const double tmp = 1.0 - Kk * z;
+        Vn = Tk * (tmp * Pt * tmp + Kk * HH * Kk) * Tk + RRk;
+      } else {
+        ahn = Ck + Tk * aht;
+        Vn = Tk * Pt * Tk + RRk;
+      }
+      Ft[t] = F; Kt[t] = Kk; vt[t] = vk; ah[t + 1] = ahn; Vt[t + 1] = Vn; cc[t] = Vn;
+      aht = ahn; Pt = Vn;
+    }
+    const double norm = -0.5 * nobs * log2pi - sumlog;
+    const double ct = dist_const - norm;
+    o.approx_loglik = gl + ct + (acc1 + acc2);
+  }
+  // ---- backward pass
+  {
+    double rt = 0.0, Nt = 0.0;
+    for (int t = n - 1; t >= 0; --t) {
+      const double z = Zt(t), Tk = Tt(t);
+      const double F = Ft[t], Kk = Kt[t], vk = vt[t];
+      const bool used = std::isfinite(ytmp(t)) && F > zero_tol;
+      const double L = used ? Tk * (1.0 - Kk * z) : Tk;
+      const double zFv = used ? z / F * vk : 0.0;
+      const double zzF = used ? z * z / F : 0.0;
+      const double V = Vt[t], ck = cc[t], ahk = ah[t];
+      const double ccn = V * L * (1.0 - Nt * ck);
+      if (used) {
+        rt = zFv + L * rt;
+        Nt = zzF + L * Nt * L;
+      } else {
+        rt = L * rt;
+        Nt = L * Nt * L;
+      }
+      const double ahn = ahk + V * rt;
+      const double Vn = V - V * Nt * V;
+      cc[t] = ccn; ah[t] = ahn; Vt[t] = Vn;
+    }
+    cc[n] = 0.0;
+  }
+  // ---- conditional_cov, scalar SVD branch (src/conditional_dist.cpp:8-32): t downwards, reads t - 1 unwritten
+  for (int t = n; t >= 1; --t) {
+    const double s = std::fabs(Vt[t - 1]);
+    const double tmp = (s > 2.220446049250313e-16 * s) ? cc[t - 1] * (1.0 / s) : 0.0;
+    double Vnew = Vt[t] - tmp * cc[t - 1];
+    Vnew = std::sqrt(std::fabs(Vnew));
+    Vt[t] = Vnew; cc[t] = tmp;
+  }
+  Vt[0] = std::sqrt(std::fabs(Vt[0]));
+}
+
 // Device memory is recycled between calls: a one-shot entry point allocates
 // gigabytes of outputs, and cudaMalloc / cudaFree of that size cost more than
 // the kernels.  Freed blocks are kept (up to BSSM_B200_POOL_GB, default 48) and
@@ -474,6 +644,7 @@ struct bssm_b200_job {
   bool xbeta_per_filter = false; // m = 1 psi-APF whose filters carry their own regression part (beta in theta)
   bool host_approx_per_filter = false; // psi-APF whose filters each carry a host-side approximation (any m)
   bool mng_draws = false; // ssm_mng with one model per filter (parameter sets)
+  bool host_prepass = false; // m = 1 psi-APF whose filters share one model: the pre-pass ran on the host
   // model on device
   DevBuf<double> y, Z, T, R, a1, P1, LP1, D, C, xbeta, u, mode, mode_lin;
   // psi pre-pass results
@@ -759,6 +930,32 @@ static int finish_job(bssm_b200_job* J, int out_flags, int post) {
   return 0;
 }
 
+// m = 1 psi-APF whose filters share one model: Newton sweeps (approximate()) and the pre-pass on the host,
+// one copy of the result for all filters of the job (pstride = 0)
+static int host_prepass_upload(bssm_b200_job* J, const bssm_ung_model* M) {
+  std::vector<double> mode, mode_lin;
+  ung_approximate_m1(M, mode, mode_lin);
+  PrepassHost ph;
+  ung_prepass_m1_host(M, mode.data(), mode_lin.data(), ung_dist_const(M), ph);
+  const size_t n1 = (size_t)J->n + 1, nf = J->n_filters;
+  // one staging buffer, one copy: [alphahat | Lt | Ct | ytilde | Htilde | scales | rHt | yphi2 | approx_loglik x nf | phi x nf]
+  std::vector<double> st(8 * n1 + 2 * nf);
+  const std::vector<double>* parts[8] = {&ph.ah, &ph.Lt, &ph.Ct, &ph.yt, &ph.Ht, &ph.sc, &ph.rHt, &ph.yphi2};
+  for (int a = 0; a < 8; ++a) std::copy(parts[a]->begin(), parts[a]->end(), st.begin() + a * n1);
+  for (size_t f = 0; f < nf; ++f) { st[8 * n1 + f] = ph.approx_loglik; st[8 * n1 + nf + f] = M->phi; }
+  int rc = J->alphahat.upload(st.data(), st.size());
+  if (rc) return rc;
+  double* b = J->alphahat.p;
+  pf::UngParams& up = J->up;
+  up.alphahat = b; up.Lt = b + n1; up.Ct = b + 2 * n1; up.ytilde = b + 3 * n1; up.Htilde = b + 4 * n1;
+  up.scales = b + 5 * n1; up.rHt = b + 6 * n1; up.yphi2 = b + 7 * n1;
+  up.approx_loglik = b + 8 * n1; up.phi_f = b + 8 * n1 + nf;
+  up.pstride = 0;
+  J->pstride = 0;
+  J->host_prepass = true;
+  return 0;
+}
+
 // draw_par (6 x n_filters: T, R, a1, P1, C, phi) and modes (n x n_filters) are
 // HOST arrays; when given, every filter has its own model and mode
 // (post_correct: update_model + approximate_for_is per draw)
@@ -975,6 +1172,14 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
     } else {
       if (!M->initial_mode) return fail(BSSM_B200_ERR_ARG, "psi-APF needs initial_mode");
       if (M->max_iter < 1) return fail(BSSM_B200_ERR_ARG, "max_iter must be >= 1");
+      if (!env_int("BSSM_B200_DEVICE_PREPASS", 0)) {
+        // the filters of the job share one model: the pre-pass is ONE sequential chain, the host's business
+        if ((rc = host_prepass_upload(J, M))) return rc;
+        if ((rc = finish_job(J, out_flags, post))) return rc;
+        guard.j = nullptr;
+        *job = J;
+        return 0;
+      }
       std::vector<double> mode, mode_lin;
       ung_approximate_m1(M, mode, mode_lin);
       if ((rc = J->mode.upload(mode.data(), n)) || (rc = J->mode_lin.upload(mode_lin.data(), n))) return rc;
@@ -1042,7 +1247,7 @@ static int job_launch_filters(bssm_b200_job* J) {
   int rc;
   J->launches = 0;
   CU(cudaEventRecord(J->ev[0], J->stream));
-  if (J->kind == KIND_UNG && J->method == BSSM_METHOD_PSI && J->m == 1 && !J->host_approx_per_filter) {
+  if (J->kind == KIND_UNG && J->method == BSSM_METHOD_PSI && J->m == 1 && !J->host_approx_per_filter && !J->host_prepass) {
     const uint32_t warps_per_block = 4;
     pf::ung_prepass_m1_kernel<<<cdiv(J->n_filters, warps_per_block), 32 * warps_per_block, 0, J->stream>>>(
         J->pp, J->n_filters);
@@ -1159,7 +1364,9 @@ int bssm_b200_job_fetch(bssm_b200_job* J, uint32_t f, bssm_filter_out* out) {
   CU(cudaMemcpy(&stopped, J->stopped.p + f, sizeof(int32_t), cudaMemcpyDeviceToHost));
   out->stopped_at = stopped;
   out->approx_loglik = 0.0;
-  if (J->method == BSSM_METHOD_PSI && J->approx_loglik.p)
+  if (J->method == BSSM_METHOD_PSI && J->host_prepass) // packed behind the pre-pass arrays (host_prepass_upload)
+    CU(cudaMemcpy(&out->approx_loglik, J->up.approx_loglik + f, sizeof(double), cudaMemcpyDeviceToHost));
+  else if (J->method == BSSM_METHOD_PSI && J->approx_loglik.p)
     CU(cudaMemcpy(&out->approx_loglik, J->approx_loglik.p + f, sizeof(double), cudaMemcpyDeviceToHost));
   out->device_ms = J->ms[0] + J->ms[1] + J->ms[2];
   // columns the filter never reached stay zero, as in the reference (arma::fill::zeros)
@@ -2252,6 +2459,7 @@ int bssm_b200_job_set_theta(bssm_b200_job* J, const bssm_ung_model* M, const bss
     if (J->pp.draw_par && J->pp.mode_stride != 0)
       return fail(BSSM_B200_ERR_ARG, "job_set_theta: post-correction jobs carry one theta per filter already");
     if (!M->initial_mode || M->max_iter < 1) return fail(BSSM_B200_ERR_ARG, "psi-APF needs initial_mode and max_iter >= 1");
+    if (J->host_prepass) return host_prepass_upload(J, &Mi); // update_model(theta), approximate(), pre-pass: all on the host
     std::vector<double> mode, mode_lin, dp((size_t)6 * nf);
     ung_approximate_m1(&Mi, mode, mode_lin);
     for (uint32_t f = 0; f < nf; ++f) memcpy(&dp[(size_t)6 * f], par, sizeof(par));

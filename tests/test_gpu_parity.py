@@ -229,7 +229,7 @@ def test_batch_of_group_filters_in_waves(engine, monkeypatch):
     monkeypatch.setenv("BSSM_B200_BLOCK", "256")
     job = engine.FilterJob(model, 30000, method="psi", seed=2, n_filters=12, out_flags=0)
     job.run()
-    assert job.launches() >= 2 + 1  # pre-pass + at least two waves
+    assert job.launches() >= 2  # at least two waves (the pre-pass of replicate filters runs on the host)
     ll = job.logliks()
     for f in (0, 7, 11):
         assert ll[f] == orc.psi_filter(model, 30000, seed=2, filt=f).loglik
@@ -482,3 +482,51 @@ def test_latency_kernel_equals_general_kernel(engine, kind, N, monkeypatch):
     if kind == "svm_psi":
         ref = orc.psi_filter(model, N, seed=3)
         assert np.array_equal(small["indices"], ref.indices) and small["logLik"] == ref.loglik
+
+
+def test_host_prepass_equals_device_prepass(engine, monkeypatch):
+    """m = 1 psi-APF jobs whose filters share one model run the pre-pass (laplace_iter, scales, approximate
+    log-likelihood, smoother_ccov, conditional_cov) on the host, jobs with one model per filter run
+    pf::ung_prepass_m1_kernel; BSSM_B200_DEVICE_PREPASS=1 forces the kernel.  Same expressions in the same
+    order: every output must have the same bits, for every distribution, with missing values, time-varying
+    coefficients, regressors, and through job_set_theta."""
+    import bssm_b200
+    rng = np.random.default_rng(6)
+    y = rng.poisson(3.0, size=70).astype(float)
+    n = y.size
+    models = [data.svm_model(90, missing=(0, 7, 8)), data.svm_model(33, rho=0.9, sd_ar=0.4, sigma=0.7, gen_seed=3)]
+    for dist, yy, phi, u in (("poisson", y, 1.0, 1.0), ("negative binomial", y, 2.5, 1.0),
+                             ("binomial", np.minimum(y, 10), 1.0, 10.0), ("gamma", y + 0.5, 2.0, 1.0)):
+        yy = yy.copy()
+        yy[11] = np.nan
+        models.append(engine.ar1_ng(yy, rho=0.8, sigma=0.2, mu=1.0, distribution=dist, phi=phi, u=u))
+    xreg = np.column_stack([np.sin(np.arange(n) / 5.0), np.linspace(-1, 1, n)])
+    models.append(engine.ar1_ng(y, rho=0.7, sigma=0.3, mu=0.5, distribution="poisson", xreg=xreg, beta=[0.3, -0.2]))
+    # time-varying Z, T, R, D, C (ssm_ung, m = 1)
+    tv = np.arange(n)
+    models.append(bssm_b200.ssm_ung(y, Z=(1.0 + 0.002 * tv)[None, :], T=(0.9 - 0.001 * tv)[None, None, :],
+                                    R=(0.2 + 0.001 * tv)[None, None, :], a1=[0.5], P1=[[0.4]], distribution="poisson",
+                                    D=0.01 * tv, C=(0.02 * np.cos(tv))[None, :]))
+    for k, model in enumerate(models):
+        host = engine.particle_smoother(model, 96, method="psi", seed=5, return_indices=True)
+        monkeypatch.setenv("BSSM_B200_DEVICE_PREPASS", "1")
+        dev = engine.particle_smoother(model, 96, method="psi", seed=5, return_indices=True)
+        monkeypatch.delenv("BSSM_B200_DEVICE_PREPASS")
+        assert host["approx_logLik"] == dev["approx_logLik"], k
+        assert host["logLik"] == dev["logLik"], k
+        for key in ("alpha", "weights", "indices", "alphahat", "Vt"):
+            assert np.array_equal(host[key], dev[key], equal_nan=True), (k, key)
+    # the filter inside an MCMC loop: new theta per iteration, replicates share it
+    model = data.svm_model(120)
+    theta = np.array([0.95, 0.25, 1.1])
+    ll = []
+    for forced in (False, True):
+        if forced:
+            monkeypatch.setenv("BSSM_B200_DEVICE_PREPASS", "1")
+        job = engine.FilterJob(model, 300, method="psi", seed=4, n_filters=3)
+        job.run()
+        job.set_theta(theta)
+        job.run()
+        ll.append(job.logliks().copy())
+        job.close()
+    assert np.array_equal(ll[0], ll[1])
