@@ -125,8 +125,8 @@ int choose_geometry(uint32_t N, uint32_t n_filters, Geometry* g, bool p2_only = 
   if (block > 1024) return fail(BSSM_B200_ERR_ARG, "geometry: too many particles per CTA");
   if (block < 32) block = 32;
   if (small_path && forced_ranks <= 0 && forced_P == 0 && forced_block == 0) {
-    P = 2; ranks = 1; mode = pf::SYNC_SMALL;
-    block = 2 * round32(cdiv(N, 2u)); // consumers + producers
+    P = 2; ranks = 1; mode = pf::SYNC_SMALL; // two particles per consumer thread: measured best (pf_small.cuh)
+    block = 2 * round32(cdiv(N, (uint32_t)P)); // consumers + producers
   }
   g->P = P; g->block = (int)block; g->ranks = ranks; g->sync_mode = mode;
   return 0;

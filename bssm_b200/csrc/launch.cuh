@@ -94,8 +94,9 @@ int launch_small(const pf::FilterParams& fp, const typename Model::Params& mp, c
   if constexpr (pf::ModelDyn<Model>::value) {
     return -1;
   } else {
-    auto kern = g.block <= 512 ? pf::small_filter_kernel<Model, 512> : pf::small_filter_kernel<Model, 1024>;
-    const size_t smem = pf::small_smem_bytes<Model>(fp.N);
+    if (g.P != 2) return -1;
+    auto kern = g.block <= 512 ? pf::small_filter_kernel<Model, 2, 512> : pf::small_filter_kernel<Model, 2, 1024>;
+    const size_t smem = pf::small_smem_bytes<Model, 2>(fp.N);
     if (smem > 48 * 1024) PFL_CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<n_filters, g.block, smem, stream>>>(fp, mp);
     PFL_CU(cudaGetLastError());

@@ -59,25 +59,32 @@ struct StrataS {
   }
 };
 
-// bytes of dynamic shared memory for N particles
-template <class Model>
+// bytes of dynamic shared memory for N particles, P per consumer thread
+template <class Model, int P>
 __host__ __device__ constexpr size_t small_noise_bytes() {
-  return (sizeof(typename Model::template Noise<2>) + 7) / 8 * 8;
+  return (sizeof(typename Model::template Noise<P>) + 7) / 8 * 8;
 }
-template <class Model>
+__host__ __device__ inline size_t small_consumers(uint32_t N, int P) { // consumer threads, a multiple of 32
+  return (size_t)((((N + P - 1) / P) + 31) / 32) * 32;
+}
+template <class Model, int P>
 __host__ __device__ inline size_t small_smem_bytes(uint32_t N) {
-  const size_t CT = (size_t)((((N + 1) / 2) + 31) / 32) * 32, Np = 2 * CT;
-  return 2 * Model::M * Np * 8 + 2 * Np * 8 + 2 * CT * small_noise_bytes<Model>() + Np * 4;
+  const size_t CT = small_consumers(N, P), Np = P * CT;
+  return 2 * Model::M * Np * 8 + 2 * Np * 8 + 2 * CT * small_noise_bytes<Model, P>() + Np * 4;
 }
 
-// MAXT = 512 (N <= 512): the compiler may use up to 128 registers per thread -- occupancy is no concern here
-template <class Model, int MAXT = 1024>
+// P particles per consumer thread.  Measured: P = 2 is the fastest -- fewer warps with four or eight particles
+// each (one consumer warp for N = 100, collectives by shuffles only) are SLOWER in proportion to P (2.45 ->
+// 3.3 us per step at N = 100, 4.96 -> 7.1 at N = 1000): the step is not a chain of latencies that more
+// independent work per thread could fill, it is bounded by fetching the straight-line code of one step
+// (~2 500 instructions per warp and step at P = 2, beyond the L0 instruction cache), and unrolling over
+// P multiplies it.  MAXT = 512 (N <= 512) lets the compiler use up to 128 registers.
+template <class Model, int P, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 small_filter_kernel(const FilterParams fp, const typename Model::Params mp) {
   constexpr int M = Model::M;
-  constexpr int P = 2;
   typedef typename Model::template Noise<P> Noise;
-  constexpr size_t NZB = small_noise_bytes<Model>();
+  constexpr size_t NZB = small_noise_bytes<Model, P>();
   extern __shared__ double smem_d[];
   __shared__ double s_max[2][32];
   __shared__ long long s_h[2][32], s_l[2][32];
@@ -87,10 +94,10 @@ small_filter_kernel(const FilterParams fp, const typename Model::Params mp) {
   const uint32_t N = fp.N;
   const int n = fp.n;
   const double Nd = (double)N, invN = 1.0 / Nd;
-  const uint32_t CT = blockDim.x >> 1, Np = 2 * CT;
+  const uint32_t CT = blockDim.x >> 1, Np = P * CT;
   const bool producer = threadIdx.x >= CT;
   const uint32_t j = producer ? threadIdx.x - CT : threadIdx.x;
-  const uint32_t i0 = 2 * j;
+  const uint32_t i0 = P * j;
   const uint32_t lane = threadIdx.x & 31, warp = j >> 5, nwarps = CT >> 5;
   const uint32_t fidx = blockIdx.x;
   const uint32_t filter = fp.first_filter + fidx;
@@ -108,9 +115,13 @@ small_filter_kernel(const FilterParams fp, const typename Model::Params mp) {
   if (threadIdx.x == 0) s_stop = 0;
 
   auto thresholds = [&](int t, double* ub) {
-    pf_u32x4 rx = pf_philox4x32_10(i0 >> 1, 0u, (uint32_t)t, filter, fp.seed, (uint32_t)PF_RNG_RESAMPLE);
-    ub[i0] = pf_u53_plus(rx.v[0], rx.v[1], pf_u32_to_f64(i0)) * invN;
-    ub[i0 + 1] = pf_u53_plus(rx.v[2], rx.v[3], pf_u32_to_f64(i0 + 1)) * invN;
+#pragma unroll
+    for (int h = 0; h < P / 2; ++h) {
+      const uint32_t jj = i0 + 2 * h;
+      pf_u32x4 rx = pf_philox4x32_10(jj >> 1, 0u, (uint32_t)t, filter, fp.seed, (uint32_t)PF_RNG_RESAMPLE);
+      ub[jj] = pf_u53_plus(rx.v[0], rx.v[1], pf_u32_to_f64(jj)) * invN;
+      ub[jj + 1] = pf_u53_plus(rx.v[2], rx.v[3], pf_u32_to_f64(jj + 1)) * invN;
+    }
   };
 
   auto produce = [&](int t) { // thresholds of step t and normals of column t + 1 into buffer t & 1
@@ -134,7 +145,9 @@ small_filter_kernel(const FilterParams fp, const typename Model::Params mp) {
 
   // ---- prologue: column 0 of the state (consumers), buffer 0 (producers)
   double x[P][M];
-  double carry[P] = {0.0, 0.0};
+  double carry[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) carry[p] = 0.0;
   if (producer) {
     if (n > 0) produce(0);
   } else {
@@ -188,9 +201,12 @@ small_filter_kernel(const FilterParams fp, const typename Model::Params mp) {
         if (bad) mx = pf_inf(); // a NaN log-weight must stop the filter
         sc_t = model.step_const();
         mx = warp_max_d(mx);
-        if (lane == 0) s_max[b][warp] = mx;
-        bar_named(1, CT);
-        if (nwarps <= 4) { // a few warps: every thread takes the maximum of the slots itself
+        if (nwarps == 1) {
+          // one consumer warp: the shuffles were the whole collective
+        } else if (lane == 0) s_max[b][warp] = mx;
+        if (nwarps > 1) bar_named(1, CT);
+        if (nwarps == 1) {
+        } else if (nwarps <= 4) { // a few warps: every thread takes the maximum of the slots itself
           double m2 = s_max[b][0];
           for (uint32_t wv = 1; wv < nwarps; ++wv) { const double v = s_max[b][wv]; m2 = v > m2 ? v : m2; }
           mx = m2;
@@ -229,13 +245,17 @@ small_filter_kernel(const FilterParams fp, const typename Model::Params mp) {
           const long long vh = shfl_up_i64(ih, o), vl = shfl_up_i64(il, o);
           if ((int)lane >= o) { ih += vh; il += vl; }
         }
-        if (lane == 31) { s_h[b][warp] = ih; s_l[b][warp] = il; }
-        bar_named(1, CT);
         long long rh = ih - th, rl = il - tl, Th = 0, Tl = 0;
-        for (uint32_t wv = 0; wv < nwarps; ++wv) {
-          const long long h = s_h[b][wv], l = s_l[b][wv];
-          Th += h; Tl += l;
-          if (wv < warp) { rh += h; rl += l; }
+        if (nwarps == 1) { // the warp's inclusive scan already holds the totals in lane 31
+          Th = __shfl_sync(0xffffffffu, ih, 31); Tl = __shfl_sync(0xffffffffu, il, 31);
+        } else {
+          if (lane == 31) { s_h[b][warp] = ih; s_l[b][warp] = il; }
+          bar_named(1, CT);
+          for (uint32_t wv = 0; wv < nwarps; ++wv) {
+            const long long h = s_h[b][wv], l = s_l[b][wv];
+            Th += h; Tl += l;
+            if (wv < warp) { rh += h; rl += l; }
+          }
         }
         const double S = pf_fixsum_value(Th, Tl);
         const double invS = 1.0 / S;
@@ -251,39 +271,44 @@ small_filter_kernel(const FilterParams fp, const typename Model::Params mp) {
         {
           const double pk0 = (i0 == 0) ? 0.0 : ((i0 - 1 >= N - 1) ? 1.0 : pf_fixsum_value(rh, rl) * invS);
           uint32_t lo = (i0 == 0) ? 0u : st.resolve(pk0, st.guess(pk0), st.u(st.guess(pk0)));
-          double pk[P];
-          uint32_t jj[P];
-          double uj[P];
+          constexpr int CH = P > 4 ? 4 : P; // chunks keep the live cumulative probabilities / thresholds few
 #pragma unroll
-          for (int p = 0; p < P; ++p) {
-            rh += qh[p]; rl += ql[p];
-            pk[p] = (i0 + p >= N - 1) ? 1.0 : pf_fixsum_value(rh, rl) * invS;
-            jj[p] = st.guess(pk[p]);
-            uj[p] = st.u(jj[p]);
-          }
+          for (int c0 = 0; c0 < P; c0 += CH) {
+            double pk[CH];
+            uint32_t jj[CH];
+            double uj[CH];
 #pragma unroll
-          for (int p = 0; p < P; ++p) {
-            const uint32_t c = st.resolve(pk[p], jj[p], uj[p]);
-            const uint32_t val = i0 + p;
-            const uint32_t cnt = c > lo ? c - lo : 0u;
-            if (cnt) {
-              uint32_t* q = ancs + lo;
-              q[0] = val;
-              if (cnt > 1) {
-                q[1] = val;
-                if (cnt > 2) {
-                  q[2] = val;
-                  if (cnt > 3) q[3] = val;
+            for (int q = 0; q < CH; ++q) {
+              const int p = c0 + q;
+              rh += qh[p]; rl += ql[p];
+              pk[q] = (i0 + p >= N - 1) ? 1.0 : pf_fixsum_value(rh, rl) * invS;
+              jj[q] = st.guess(pk[q]);
+              uj[q] = st.u(jj[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < CH; ++q) {
+              const uint32_t c = st.resolve(pk[q], jj[q], uj[q]);
+              const uint32_t val = i0 + c0 + q;
+              const uint32_t cnt = c > lo ? c - lo : 0u;
+              if (cnt) {
+                uint32_t* qa = ancs + lo;
+                qa[0] = val;
+                if (cnt > 1) {
+                  qa[1] = val;
+                  if (cnt > 2) {
+                    qa[2] = val;
+                    if (cnt > 3) qa[3] = val;
+                  }
                 }
               }
+              const uint32_t ce = lo + PF_SCATTER_CAP;
+              const unsigned heavy = __ballot_sync(0xffffffffu, cnt > PF_SCATTER_CAP);
+              if (heavy) scatter_heavy(ancs, heavy, ce, c, val);
+              lo = c > lo ? c : lo;
             }
-            const uint32_t ce = lo + PF_SCATTER_CAP;
-            const unsigned heavy = __ballot_sync(0xffffffffu, cnt > PF_SCATTER_CAP);
-            if (heavy) scatter_heavy(ancs, heavy, ce, c, val);
-            lo = c > lo ? c : lo;
           }
         }
-        bar_named(1, CT);
+        if (nwarps == 1) __syncwarp(); else bar_named(1, CT);
         PFS_PHASE(2)
 
         // ---- gather the ancestors from shared memory, propagate to column t + 1

@@ -170,7 +170,8 @@ std::string nlg_model_expr(int m, int k, bool per_filter) {
   return "pf::NlgFnBsf<pf::UserNlg, " + std::to_string(m) + ", " + std::to_string(k) + ", " + (per_filter ? "true" : "false") + ">";
 }
 std::string filter_kernel_expr(const std::string& model, const Geometry& g) {
-  if (g.sync_mode == pf::SYNC_SMALL) return "pf::small_filter_kernel<" + model + ", " + (g.block <= 512 ? "512" : "1024") + ">";
+  if (g.sync_mode == pf::SYNC_SMALL)
+    return "pf::small_filter_kernel<" + model + ", " + std::to_string(g.P) + ", " + (g.block <= 512 ? "512" : "1024") + ">";
   const bool small = g.block <= 512;
   return "pf::filter_kernel<" + model + ", " + std::to_string(g.P) + ", " +
          (small ? std::to_string(PF_SMALL_MAXT) + ", " + std::to_string(PF_SMALL_MINB) : std::string("1024, 1")) + ">";
@@ -231,13 +232,15 @@ int launch_user_sde(int model_id, const pf::FilterParams& fp, const pf::SdeParam
   int rc = get_kernel(*um, sde_kernel_expr(g, per_filter), &k);
   if (rc) return rc;
   void* args[2] = {const_cast<pf::FilterParams*>(&fp), const_cast<pf::SdeParams*>(&mp)};
-  return launch_kernel(k, args, g, nf, pf::small_smem_bytes<pf::SdeGbmBsf>(fp.N), stream); // same state dimension and noise record
+  // same state dimension and noise record as the registry policies
+  const size_t smem = pf::small_smem_bytes<pf::SdeGbmBsf, 2>(fp.N);
+  return launch_kernel(k, args, g, nf, smem, stream);
 }
 
 // shared-memory bytes of the latency kernel for an (m, k) Gaussian-step policy (pf_small.cuh)
-static size_t small_smem_mk(uint32_t N, int m, int k) {
-  const size_t CT = (size_t)((((N + 1) / 2) + 31) / 32) * 32, Np = 2 * CT;
-  return 2 * (size_t)m * Np * 8 + 2 * Np * 8 + 2 * CT * ((size_t)2 * k * 8) + Np * 4;
+static size_t small_smem_mk(uint32_t N, int m, int k, int P) {
+  const size_t CT = pf::small_consumers(N, P), Np = (size_t)P * CT;
+  return 2 * (size_t)m * Np * 8 + 2 * Np * 8 + 2 * CT * ((size_t)P * k * 8) + Np * 4;
 }
 
 int user_nlg_register(const char* source, int m, int k, int* model_id) {
@@ -273,7 +276,7 @@ int launch_user_nlg(int model_id, int m, int k, const pf::FilterParams& fp, cons
   int rc = get_kernel(*um, filter_kernel_expr(nlg_model_expr(m, k, per_filter), g), &kk);
   if (rc) return rc;
   void* args[2] = {const_cast<pf::FilterParams*>(&fp), const_cast<pf::NlgParams*>(&mp)};
-  return launch_kernel(kk, args, g, nf, small_smem_mk(fp.N, m, k), stream);
+  return launch_kernel(kk, args, g, nf, small_smem_mk(fp.N, m, k, g.P), stream);
 }
 
 // a1_fn / P1_fn on the device for nf parameter vectors: out (device) = nf x (m + m m)
