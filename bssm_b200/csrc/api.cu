@@ -2052,6 +2052,9 @@ static int run_fetch_streaming(bssm_b200_job* J, bssm_filter_out* out) {
   std::lock_guard<std::mutex> sguard(g_sctx.mu);
   CU(g_sctx.ensure());
   StreamCtx& R = g_sctx;
+  // whatever path leaves this function, copies that read the job's buffers on the second stream have finished
+  // before the caller may destroy the job (its buffers go back to the recycling pool)
+  struct S2Guard { cudaStream_t s; ~S2Guard() { cudaStreamSynchronize(s); } } s2guard{R.s2};
   *R.flag = 0;
   int* dflag = R.dflag;
   const int every = std::max(8, (n + 1) / std::max(1, env_int("BSSM_B200_STREAM_CHUNKS", 6)));
