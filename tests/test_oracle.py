@@ -444,3 +444,59 @@ def test_nlg_approximation_is_a_fixed_point(kind):
         C[t] = Tf(mode[t]) - T[t] @ mode[t]
     asm = _tv_smoother(mdl.y, Z, D, np.full(n, H ** 2), T, C, [RR] * n, a1, P1)
     np.testing.assert_allclose(asm, mode, atol=2e-3, rtol=1e-3)
+
+
+def test_bootstrap_correction_of_nlg_models_is_the_filter_per_draw():
+    """orc.is_correction_bsf_nlg (src/approx_mcmc.cpp:442-518) = update_model(theta_i) + bsf_filter with stream i:
+    weight_i = exp(loglik_i - approx_loglik_i), expanded draws for is3"""
+    model = data.growth_model(30)
+    rng = np.random.default_rng(2)
+    ns = 5
+    theta = np.asarray(model.theta)[None, :] + 0.05 * rng.normal(size=(ns, 3))
+    counts = np.array([1, 3, 2, 1, 2], dtype=np.uint32)
+    approx = -60.0 + rng.normal(size=ns)
+    mo = {"theta": theta, "counts": counts, "approx_loglik": approx, "output_type": 3, "posterior": np.zeros(ns)}
+    r = orc.is_correction_bsf_nlg(model, mo, 50, is_type=2, seed=4)
+    for i in range(ns):
+        mi = bssm_b200.ssm_nlg(model.y, "growth", theta=theta[i], known_params=model.known_params)
+        ll = orc.nlg_bsf_filter(mi, 50, seed=4, filt=i).loglik
+        assert r.loglik[i] == ll
+        assert r.weights[i] == pytest.approx(np.exp(ll - approx[i]), rel=1e-12)
+        assert r.posterior[i] == pytest.approx(ll - approx[i], abs=1e-10)
+    r3 = orc.is_correction_bsf_nlg(model, mo, 50, is_type=3, seed=4)
+    assert r3.weights.size == counts.sum()
+    src = np.repeat(np.arange(ns), counts)
+    mi = bssm_b200.ssm_nlg(model.y, "growth", theta=theta[src[4]], known_params=model.known_params)
+    assert r3.loglik[4] == orc.nlg_bsf_filter(mi, 50, seed=4, filt=4).loglik
+
+
+def test_oracle_runs_user_sde_functions_like_the_registry_model(tmp_path):
+    """the oracle takes an ssm_sde model as four function pointers (src/model_ssm_sde.h:8-11); the GBM example
+    compiled from source with g++ and passed that way gives the registry model's bits"""
+    import ctypes as C
+    import os
+    import subprocess
+    src = r'''
+    double drift(double x, const double* theta) { return theta[0] * x; }
+    double diffusion(double x, const double* theta) { const double tx = theta[1] * x; return tx > 0.0 ? tx : 0.0; }
+    double ddiffusion(double x, const double* theta) { return theta[1] * (x > 0.0 ? 1.0 : 0.0); }
+    double log_obs_density(double y, double x, const double* theta) {
+      const double q = (y - pf_log(x)) / theta[2];
+      return -(0.918938533204672741780329736406 + 0.5 * q * q + pf_log(theta[2]));
+    }'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cpp = tmp_path / "gbm.cpp"
+    cpp.write_text('#include "bssm_b200/pf_math.h"\nextern "C" {\n' + src + "\n}\n")
+    so = tmp_path / "gbm.so"
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-ffp-contract=off", "-I" + os.path.join(root, "include"), str(cpp),
+                    "-o", str(so)], check=True)
+    lib = C.CDLL(str(so))
+    f = orc.L().orc_sde_set_user
+    f.restype = None
+    f.argtypes = [C.c_void_p] * 4
+    f(*[C.cast(getattr(lib, nm), C.c_void_p) for nm in ("drift", "diffusion", "ddiffusion", "log_obs_density")])
+    reg = data.gbm_model(25)
+    user = bssm_b200.ssm_sde(reg.y, 1000, reg.theta, reg.x0, reg.positive)
+    a = orc.sde_bsf_filter(reg, 64, 3, seed=5)
+    b = orc.sde_bsf_filter(user, 64, 3, seed=5)
+    assert a.loglik == b.loglik and np.array_equal(a.indices, b.indices) and np.array_equal(a.alpha, b.alpha)
