@@ -28,6 +28,7 @@
 #include "models_ung.cuh"
 #include "prepass_ung.cuh"
 #include "smoother_kernels.cuh"
+#include "approx_device.cuh"
 #include "models_nlg_sde.cuh"
 #include "filters.h"
 #include "bssm_b200/ung_gauss_approx.h"
@@ -1115,6 +1116,69 @@ static int create_ung_job(const bssm_ung_model* M, int method, uint32_t nsim, ui
     if (dm->modes.size() != (size_t)n * n_filters) return fail(BSSM_B200_ERR_ARG, "per-draw models need per-draw modes");
     const size_t n1 = (size_t)n + 1, mm = (size_t)m * m, nf = n_filters;
     const bool has_xb = !dm->xbeta.empty();
+    if (!env_int("BSSM_B200_HOST_APPROX", 0)) {
+      // on the device, one thread per draw (approx_device.cuh): the draws are the parallelism.  The psi-APF reads
+      // only the approximation (and Z, D, phi, xbeta), so the job's T / R / a1 / P1 / C buffers can carry the
+      // per-draw arrays the approximation needs.
+      pf::ApproxParams ap;
+      memset(&ap, 0, sizeof(ap));
+      ap.n = n; ap.m = m; ap.k = k; ap.distribution = M->distribution;
+      ap.Ztv = M->Ztv; ap.Ttv = M->Ttv; ap.Rtv = M->Rtv; ap.Dtv = M->Dtv; ap.Ctv = M->Ctv;
+      ap.y = J->y.p; ap.u = J->u.p;
+      ap.Z = up.Z; ap.fs_Z = up.fs_Z; ap.D = up.D; ap.fs_D = up.fs_D; // shared, or per draw (parameter sets, above)
+      ap.T = J->T.p; ap.R = J->R.p; ap.a1 = J->a1.p; ap.P1 = J->P1.p; ap.C = J->C.p;
+      if ((rc = upload_slices(dm->T, J->T, (size_t)m * m * (M->Ttv ? n : 1), &ap.T, &ap.fs_T)) ||
+          (rc = upload_slices(dm->R, J->R, (size_t)m * k * (M->Rtv ? n : 1), &ap.R, &ap.fs_R)) ||
+          (rc = upload_slices(dm->C, J->C, (size_t)m * (M->Ctv ? n : 1), &ap.C, &ap.fs_C)) ||
+          (rc = upload_slices(dm->a1, J->a1, (size_t)m, &ap.a1, &ap.fs_a1)) ||
+          (rc = upload_slices(dm->P1, J->P1, mm, &ap.P1, &ap.fs_P1)))
+        return rc;
+      ap.has_xbeta = (has_xb || M->xbeta) ? 1 : 0;
+      if (has_xb) {
+        if ((rc = J->xbeta.upload(dm->xbeta.data(), dm->xbeta.size()))) return rc;
+        up.xbeta = J->xbeta.p;
+      }
+      ap.xbeta = J->xbeta.p; ap.fs_x = has_xb ? (size_t)n : 0;
+      ap.phi = M->phi;
+      if (!dm->phi.empty()) {
+        if ((rc = J->phi_f.upload(dm->phi.data(), nf))) return rc;
+        ap.phi_f = J->phi_f.p;
+      }
+      if ((rc = J->mode.upload(dm->modes.data(), dm->modes.size()))) return rc;
+      ap.modes = J->mode.p;
+      if ((rc = J->alphahat.alloc((size_t)m * n1 * nf)) || (rc = J->Lt.alloc(mm * n1 * nf)) || (rc = J->Ct.alloc(mm * n1 * nf)) ||
+          (rc = J->ytilde.alloc((size_t)n * nf)) || (rc = J->Htilde.alloc((size_t)n * nf)) || (rc = J->scales.alloc((size_t)n * nf)) ||
+          (rc = J->approx_loglik.alloc(nf)) || (rc = J->scratch.alloc((size_t)(m + 3) * n * nf)))
+        return rc;
+      CU(cudaMemsetAsync(J->approx_loglik.p, 0, sizeof(double) * nf, J->stream)); // approximate_for_is: approx_loglik = 0 (:159)
+      ap.alphahat = J->alphahat.p; ap.Lt = J->Lt.p; ap.Ct = J->Ct.p; ap.ytilde = J->ytilde.p; ap.Htilde = J->Htilde.p;
+      ap.scales = J->scales.p; ap.scratch = J->scratch.p;
+      ap.fs_a = (size_t)m * n1; ap.fs_m = mm * n1; ap.fs_n = (size_t)n;
+      CU(cudaEventRecord(J->ev[0], J->stream));
+      const uint32_t ab = cdiv((uint32_t)nf, 32);
+      if (m == 1) pf::ung_approx_for_is_kernel<1, true><<<ab, 32, 0, J->stream>>>(ap, (uint32_t)nf);
+      else if (m == 2) pf::ung_approx_for_is_kernel<2, true><<<ab, 32, 0, J->stream>>>(ap, (uint32_t)nf);
+      else if (m == 3) pf::ung_approx_for_is_kernel<3, true><<<ab, 32, 0, J->stream>>>(ap, (uint32_t)nf);
+      else pf::ung_approx_for_is_kernel<16, false><<<ab, 32, 0, J->stream>>>(ap, (uint32_t)nf);
+      CU(cudaGetLastError());
+      CU(cudaEventRecord(J->ev[1], J->stream));
+      CU(cudaStreamSynchronize(J->stream));
+      if (env_int("BSSM_B200_DEBUG_APPROX", 0)) {
+        float ams = 0;
+        cudaEventElapsedTime(&ams, J->ev[0], J->ev[1]);
+        fprintf(stderr, "[approx] %zu draws, m = %d, n = %d: %.3f ms on the device\n", nf, m, n, ams);
+      }
+      J->pstride = 0;
+      J->host_approx_per_filter = true; // = the filters carry ready-made approximations
+      up.phi_f = dm->phi.empty() ? nullptr : J->phi_f.p; up.alphahat = J->alphahat.p; up.Lt = J->Lt.p; up.Ct = J->Ct.p;
+      up.ytilde = J->ytilde.p; up.Htilde = J->Htilde.p; up.scales = J->scales.p;
+      up.approx_loglik = J->approx_loglik.p; up.pstride = 0;
+      up.fs_a = (size_t)m * n1; up.fs_m = mm * n1; up.fs_n = (size_t)n; up.fs_x = has_xb ? (size_t)n : 0;
+      if ((rc = finish_job(J, out_flags, post))) return rc;
+      guard.j = nullptr;
+      *job = J;
+      return 0;
+    }
     std::vector<double> ah((size_t)m * n1 * nf), Lt(mm * n1 * nf), Ct(mm * n1 * nf), yt((size_t)n * nf),
         Ht((size_t)n * nf), sc((size_t)n * nf), al(nf, 0.0);
 #pragma omp parallel for schedule(static)
@@ -2543,7 +2607,7 @@ static int postcorr_driver(int n, int m, int output_type, uint32_t nsim, int is_
   while (d0 < draw_end) {
     // a chunk = consecutive draws with the same particle count (is_type 1: nsim * count)
     const uint32_t N = is_type == 1 ? nsim * dl.count[d0] : nsim;
-    double per_filter = 64.0 * n1; // pre-pass arrays
+    double per_filter = 8.0 * n1 * (2.0 * m * m + 2.0 * m + 8.0); // approximation per draw: alphahat, L, C, pseudo-observations, scratch
     if (post != BSSM_POST_NONE) per_filter += (double)N * n1 * m * 8.0 * (output_type == 2 ? 2 : 1) + (double)N * n * 4.0;
     else per_filter += (double)N * (2 * m * 8.0 + 4.0 + 8.0);
     uint32_t maxc = (uint32_t)std::max(1.0, budget / per_filter);

@@ -1,4 +1,4 @@
-/* pf_smallmat.h -- deterministic small dense-matrix primitives (host only),
+/* pf_smallmat.h -- deterministic small dense-matrix primitives (host and device),
  * column-major like R / Armadillo.  Used by the host-side Gaussian-approximation
  * pre-pass of the psi-APF for m > 1 (product: bssm_b200/csrc/api.cu) and by the
  * CPU oracle, so that both evaluate products in the SAME summation order
@@ -18,8 +18,15 @@
 #include <math.h>
 #include <stddef.h>
 
+/* the same functions run inside the per-draw approximation kernel (bssm_b200/csrc/approx_device.cuh) */
+#if defined(__CUDACC__)
+#define PF_SM static __host__ __device__ inline
+#else
+#define PF_SM static inline
+#endif
+
 /* C (r x c) = A (r x k) * B (k x c) */
-static inline void pf_mm(const double* A, const double* B, double* C, int r, int k, int c) {
+PF_SM void pf_mm(const double* A, const double* B, double* C, int r, int k, int c) {
   for (int j = 0; j < c; ++j)
     for (int i = 0; i < r; ++i) {
       double s = 0.0;
@@ -28,7 +35,7 @@ static inline void pf_mm(const double* A, const double* B, double* C, int r, int
     }
 }
 /* C (r x c) = A (r x k) * B' where B is (c x k) */
-static inline void pf_mmt(const double* A, const double* B, double* C, int r, int k, int c) {
+PF_SM void pf_mmt(const double* A, const double* B, double* C, int r, int k, int c) {
   for (int j = 0; j < c; ++j)
     for (int i = 0; i < r; ++i) {
       double s = 0.0;
@@ -37,7 +44,7 @@ static inline void pf_mmt(const double* A, const double* B, double* C, int r, in
     }
 }
 /* C (r x c) = A' * B where A is (k x r), B is (k x c) */
-static inline void pf_mtm(const double* A, const double* B, double* C, int r, int k, int c) {
+PF_SM void pf_mtm(const double* A, const double* B, double* C, int r, int k, int c) {
   for (int j = 0; j < c; ++j)
     for (int i = 0; i < r; ++i) {
       double s = 0.0;
@@ -46,7 +53,7 @@ static inline void pf_mtm(const double* A, const double* B, double* C, int r, in
     }
 }
 /* arma::symmatu: copy the upper triangle onto the lower */
-static inline void pf_symmatu(double* A, int m) {
+PF_SM void pf_symmatu(double* A, int m) {
   for (int j = 0; j < m; ++j)
     for (int i = j + 1; i < m; ++i) A[i + (size_t)m * j] = A[j + (size_t)m * i];
 }
@@ -58,8 +65,10 @@ static inline void pf_symmatu(double* A, int m) {
  * normalised so that its largest-magnitude component is positive.  This stands
  * in for arma::svd_econ(U, s, V, X, "left") on symmetric X: s = |vals|, U = vecs
  * (src/conditional_dist.cpp:14, :21). */
-static inline void pf_jacobi_eig_sym(const double* X, int m, double* vals, double* vecs) {
-  double A[16 * 16];
+/* MAXMM: size of the work matrix (m * m <= MAXMM); the arithmetic does not depend on it */
+template <int MAXMM>
+PF_SM void pf_jacobi_eig_sym_t(const double* X, int m, double* vals, double* vecs) {
+  double A[MAXMM];
   for (int i = 0; i < m * m; ++i) A[i] = X[i];
   /* work on the symmetrised matrix */
   for (int j = 0; j < m; ++j)
@@ -120,6 +129,10 @@ static inline void pf_jacobi_eig_sym(const double* X, int m, double* vals, doubl
     if (vecs[big + m * j] < 0.0)
       for (int k = 0; k < m; ++k) vecs[k + m * j] = -vecs[k + m * j];
   }
+}
+
+PF_SM void pf_jacobi_eig_sym(const double* X, int m, double* vals, double* vecs) {
+  pf_jacobi_eig_sym_t<16 * 16>(X, m, vals, vecs);
 }
 
 #endif /* BSSM_B200_PF_SMALLMAT_H */

@@ -35,7 +35,7 @@
 namespace pfga {
 
 /* log g(y | signal) up to constants, src/model_ssm_ung.cpp:447-493 */
-inline double ung_log_obs(int dist, double s, double y, double u, double phi) {
+PF_HD double ung_log_obs(int dist, double s, double y, double u, double phi) {
   switch (dist) {
     case 0: return -0.5 * (s + (y / phi) * (y / phi) * pf_exp(-s));
     case 1: return y * s - u * pf_exp(s);

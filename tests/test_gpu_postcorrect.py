@@ -346,3 +346,18 @@ def test_bsf_is_correction_nlg(engine, kind):
     res2 = engine.post_correct(model, mo2, 32, is_type="is1", seed=7, sampling_method="bsf")
     np.testing.assert_allclose(res2["alphahat"], ref2.alphahat, rtol=1e-9, atol=1e-11)
     np.testing.assert_allclose(res2["Vt"], ref2.Vt, rtol=1e-8, atol=1e-12)
+
+
+def test_device_approximation_equals_host_approximation(engine, monkeypatch):
+    """per-draw Gaussian approximations for m > 1 (approximate_for_is: laplace_iter, scales, smoother_ccov,
+    conditional_cov by SVD) run on the device, one thread per draw (approx_device.cuh); BSSM_B200_HOST_APPROX=1
+    sends the same call through the host's OpenMP loop over include/bssm_b200/ung_gauss_approx.h.  Same bits."""
+    for kind in ("level_slope", "negbin_xreg", "noise"):
+        model = _bsm_case(kind)
+        mo = dict(data.bsm_mcmc_output(model, 24), output_type=2)
+        dev = engine.post_correct(model, mo, 64, is_type="is2", seed=3, return_loglik=True)
+        monkeypatch.setenv("BSSM_B200_HOST_APPROX", "1")
+        host = engine.post_correct(model, mo, 64, is_type="is2", seed=3, return_loglik=True)
+        monkeypatch.delenv("BSSM_B200_HOST_APPROX")
+        assert np.array_equal(dev["loglik"], host["loglik"]), kind
+        assert np.array_equal(dev["alphahat"], host["alphahat"]) and np.array_equal(dev["Vt"], host["Vt"]), kind
