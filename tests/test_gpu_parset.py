@@ -212,3 +212,24 @@ def test_suggest_N_for_models_with_update_fn(engine):
     for c, N in enumerate(cands):
         ll = [orc.mng_psi_filter(gi, N, seed=7, filt=c * reps + r).loglik for r in range(reps)]
         assert resg["results"]["sd"][c] == pytest.approx(np.std(ll, ddof=1), rel=1e-10)
+
+
+def test_parset_argument_errors(engine):
+    model = ung_update_model(m=2)
+    mo = draws(model, 4)
+    good = model.update_fn
+    model.update_fn = lambda th: {"T": np.zeros((3, 3))}  # wrong shape
+    with pytest.raises(ValueError, match="elements"):
+        engine.post_correct(model, mo, 32, is_type="is2", seed=1)
+    model.update_fn = lambda th: {"Q": 1.0}  # not a model component
+    with pytest.raises(ValueError, match="unknown components"):
+        engine.post_correct(model, mo, 32, is_type="is2", seed=1)
+    model.update_fn = good
+    bad = dict(mo, modes=mo["modes"][:, :3])
+    with pytest.raises(ValueError, match="disagree"):
+        engine.post_correct(model, bad, 32, is_type="is2", seed=1)
+    with pytest.raises(Exception, match="k <= m <= 4"):
+        engine.nlg_register("__device__ double Z_fn(int t, const double* a, const double* th, const double* kp) { return 0; }", 5, 1)
+    g = data.mng_model(30)
+    with pytest.raises(ValueError, match="update_fn"):
+        engine.post_correct(g, mo, 32, is_type="is2", seed=1)
