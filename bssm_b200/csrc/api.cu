@@ -2887,6 +2887,34 @@ static int make_nlg_draw_job(const bssm_nlg_model* M, const DrawList& dl, uint32
   J->method = BSSM_METHOD_PSI;
   J->post = post;
   J->nlg_model_id = M->model_id;
+  if (!env_int("BSSM_B200_HOST_APPROX", 0)) {
+    // one thread per draw on the device (approx_device.cuh): relinearise at the stored mode, smooth, pack
+    const int k = m;
+    std::vector<double> th((size_t)n_par * nf), md((size_t)m * n * nf);
+    for (uint32_t f = 0; f < nf; ++f) {
+      const uint32_t c = dl.src[d0 + f];
+      memcpy(&th[(size_t)n_par * f], theta + (size_t)c * n_par, sizeof(double) * n_par);
+      memcpy(&md[(size_t)m * n * f], modes + (size_t)m * n * c, sizeof(double) * m * n);
+    }
+    const double zero = 0.0;
+    const size_t per = (size_t)(2 * m + mm + (size_t)m * k + 3 + m + 2) * n;
+    if ((rc = J->y.upload(M->y, n)) || (rc = J->theta_u.upload(th.data(), th.size())) || (rc = J->mode.upload(md.data(), md.size())) ||
+        (rc = J->known_u.upload(M->n_known > 0 ? M->known_params : &zero, M->n_known > 0 ? (size_t)M->n_known : 1)) ||
+        (rc = J->stepc.alloc((size_t)32 * n * nf)) || (rc = J->alphahat.alloc((size_t)m * n1 * nf)) ||
+        (rc = J->Lt.alloc(mm * n1 * nf)) || (rc = J->Ct.alloc(mm * n1 * nf)) || (rc = J->approx_loglik.alloc(nf)) ||
+        (rc = J->scratch.alloc(per * nf)))
+      return rc;
+    CU(cudaMemsetAsync(J->approx_loglik.p, 0, sizeof(double) * nf, J->stream)); // the correction weight only (src/approx_mcmc.cpp:385)
+    pf::NlgApproxParams ap;
+    ap.n = n; ap.model_id = M->model_id; ap.n_par = (int)n_par;
+    ap.y = J->y.p; ap.theta = J->theta_u.p; ap.known = J->known_u.p; ap.modes = J->mode.p;
+    ap.stepc = J->stepc.p; ap.alphahat = J->alphahat.p; ap.Lt = J->Lt.p; ap.Ct = J->Ct.p; ap.scratch = J->scratch.p;
+    const uint32_t ab = cdiv(nf, 32);
+    if (m == 2) pf::nlg_approx_for_is_kernel<2, 2><<<ab, 32, 0, J->stream>>>(ap, nf);
+    else pf::nlg_approx_for_is_kernel<1, 1><<<ab, 32, 0, J->stream>>>(ap, nf);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(J->stream));
+  } else {
   std::vector<double> sc((size_t)32 * n * nf, 0.0), ah((size_t)m * n1 * nf), Lt(mm * n1 * nf), Ct(mm * n1 * nf),
       al(nf, 0.0);
   int bad = 0;
@@ -2911,6 +2939,7 @@ static int make_nlg_draw_job(const bssm_nlg_model* M, const DrawList& dl, uint32
       (rc = J->Lt.upload(Lt.data(), Lt.size())) || (rc = J->Ct.upload(Ct.data(), Ct.size())) ||
       (rc = J->approx_loglik.upload(al.data(), nf)))
     return rc;
+  }
   pf::NlgPsiParams& pp = J->npp;
   pp.n = n; pp.stepc = J->stepc.p; pp.alphahat = J->alphahat.p; pp.Lt = J->Lt.p; pp.Ct = J->Ct.p;
   pp.approx_loglik = J->approx_loglik.p;

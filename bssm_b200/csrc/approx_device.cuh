@@ -34,86 +34,30 @@ struct ApproxParams {
   double* scratch; // (m + 3) * n per draw: aHH, F, v, K
 };
 
-// FIXED: the state dimension IS MAXM (bsm_ng: 2 or 3) -- every loop over it unrolls and the small matrices live
-// in registers; otherwise m <= MAXM at run time (seasonal models) and they live in local memory.
+// smoother_ccov + conditional_cov of one approximating linear-Gaussian model with scalar observations
+// (pfga::UngApprox::smoother_and_conditional): pseudo-observations ay with variances aHH, model arrays as pointers
+// with time-variation flags.  Outputs ah (m x (n+1)), Pt -> L (m x m x (n+1)), ccov -> C (m x m x (n+1)).
+struct SmootherIO {
+  int n, m, k;
+  int Ztv, Ttv, Rtv, Dtv, Ctv;
+  const double *Zb, *Tb, *Rb, *Cb, *Db, *a1, *P1, *xb; // xb: regression part to subtract from ay, or null
+  const double *ay, *aHH;
+  double *ah, *Pt, *ccov, *sF, *sv, *sK;
+};
 template <int MAXM, bool FIXED>
-__global__ void __launch_bounds__(32) ung_approx_for_is_kernel(const ApproxParams p, uint32_t nf) {
-  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= nf) return;
+__device__ void smoother_ccov_conditional(const SmootherIO& io) {
   constexpr int MM = MAXM * MAXM;
-  const int n = p.n, m = FIXED ? MAXM : p.m, k = p.k, dist = p.distribution;
+  const int n = io.n, m = FIXED ? MAXM : io.m, k = io.k;
   const size_t mm = (size_t)m * m;
   const double zero_tol = 1e-12;
-  const double* Zb = p.Z + (size_t)f * p.fs_Z;
-  const double* Tb = p.T + (size_t)f * p.fs_T;
-  const double* Rb = p.R + (size_t)f * p.fs_R;
-  const double* Cb = p.C + (size_t)f * p.fs_C;
-  const double* Db = p.D + (size_t)f * p.fs_D;
-  const double* a1 = p.a1 + (size_t)f * p.fs_a1;
-  const double* P1 = p.P1 + (size_t)f * p.fs_P1;
-  const double* xb = p.has_xbeta ? p.xbeta + (size_t)f * p.fs_x : nullptr;
-  auto Z = [&](int t) { return Zb + (size_t)m * (t * p.Ztv); };
-  auto T = [&](int t) { return Tb + (size_t)m * m * (t * p.Ttv); };
-  auto R = [&](int t) { return Rb + (size_t)m * k * (t * p.Rtv); };
-  auto C = [&](int t) { return Cb + (size_t)m * (t * p.Ctv); };
-  auto D = [&](int t) { return Db[t * p.Dtv]; };
-  const double phi = p.phi_f ? p.phi_f[f] : p.phi;
-  const double* mode = p.modes + (size_t)f * n;
-  double* ah = p.alphahat + (size_t)f * p.fs_a;
-  double* Pt = p.Lt + (size_t)f * p.fs_m;
-  double* ccov = p.Ct + (size_t)f * p.fs_m;
-  double* ay = p.ytilde + (size_t)f * p.fs_n;
-  double* aH = p.Htilde + (size_t)f * p.fs_n;
-  double* sc = p.scales + (size_t)f * p.fs_n;
-  double* aHH = p.scratch + (size_t)f * (size_t)(m + 3) * n;
-  double* sF = aHH + n;
-  double* sv = sF + n;
-  double* sK = sv + n;
+  auto Z = [&](int t) { return io.Zb + (size_t)m * (t * io.Ztv); };
+  auto T = [&](int t) { return io.Tb + (size_t)m * m * (t * io.Ttv); };
+  auto R = [&](int t) { return io.Rb + (size_t)m * k * (t * io.Rtv); };
+  auto C = [&](int t) { return io.Cb + (size_t)m * (t * io.Ctv); };
+  auto D = [&](int t) { return io.Db[t * io.Dtv]; };
+  const double *a1 = io.a1, *P1 = io.P1, *xb = io.xb, *ay = io.ay, *aHH = io.aHH;
+  double *ah = io.ah, *Pt = io.Pt, *ccov = io.ccov, *sF = io.sF, *sv = io.sv, *sK = io.sK;
   auto ytmp = [&](int t) { return xb ? ay[t] - xb[t] : ay[t]; };
-
-  // ---- laplace_iter at the stored mode, update_scales
-  for (int t = 0; t < n; ++t) {
-    const double y = p.y[t], u = p.u[t], s = mode[t];
-    double HH, yt;
-    switch (dist) {
-      case 0: {
-        double tmp = y;
-        if (fabs(tmp) < 1e-4) tmp = 1e-4;
-        double q = tmp / phi;
-        HH = 2.0 * pf_exp(s) / (q * q);
-        yt = s + 1.0 - 0.5 * HH;
-      } break;
-      case 1: {
-        HH = 1.0 / (pf_exp(s) * u);
-        yt = y * HH + s - 1.0;
-      } break;
-      case 2: {
-        double e = pf_exp(s);
-        HH = (1.0 + e) * (1.0 + e) / (u * e);
-        yt = y * HH + s - 1.0 - e;
-      } break;
-      case 3: {
-        double e = pf_exp(s) * u;
-        HH = (phi + e) * (phi + e) / (phi * e * (y + phi));
-        yt = s + (phi + e) * (y - e) / ((y + phi) * e);
-      } break;
-      default: {
-        double e = pf_exp(s) * u;
-        HH = e / (y * phi);
-        yt = s - e / y + 1;
-      } break;
-    }
-    aHH[t] = HH;
-    ay[t] = yt;
-    const double H = sqrt(HH);
-    aH[t] = H;
-    double scale = 0.0;
-    if (pf_isfinite(y)) {
-      double q = (yt - s) / H;
-      scale = pfga::ung_log_obs(dist, s, y, u, phi) + 0.5 * (q * q);
-    }
-    sc[t] = scale;
-  }
 
   // ---- forward pass of smoother_ccov (Kalman filter, Joseph form)
   double A[MM], B[MM], X[MM], E[MM], rr[MM];
@@ -242,6 +186,228 @@ __global__ void __launch_bounds__(32) ung_approx_for_is_kernel(const ApproxParam
       factor(Pt + mm * t);
     }
     factor(Pt);
+  }
+}
+
+// FIXED: the state dimension IS MAXM (bsm_ng: 2 or 3) -- every loop over it unrolls and the small matrices live
+// in registers; otherwise m <= MAXM at run time (seasonal models) and they live in local memory.
+template <int MAXM, bool FIXED>
+__global__ void __launch_bounds__(32) ung_approx_for_is_kernel(const ApproxParams p, uint32_t nf) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  constexpr int MM = MAXM * MAXM;
+  const int n = p.n, m = FIXED ? MAXM : p.m, k = p.k, dist = p.distribution;
+  const size_t mm = (size_t)m * m;
+  const double zero_tol = 1e-12;
+  const double* Zb = p.Z + (size_t)f * p.fs_Z;
+  const double* Tb = p.T + (size_t)f * p.fs_T;
+  const double* Rb = p.R + (size_t)f * p.fs_R;
+  const double* Cb = p.C + (size_t)f * p.fs_C;
+  const double* Db = p.D + (size_t)f * p.fs_D;
+  const double* a1 = p.a1 + (size_t)f * p.fs_a1;
+  const double* P1 = p.P1 + (size_t)f * p.fs_P1;
+  const double* xb = p.has_xbeta ? p.xbeta + (size_t)f * p.fs_x : nullptr;
+  auto Z = [&](int t) { return Zb + (size_t)m * (t * p.Ztv); };
+  auto T = [&](int t) { return Tb + (size_t)m * m * (t * p.Ttv); };
+  auto R = [&](int t) { return Rb + (size_t)m * k * (t * p.Rtv); };
+  auto C = [&](int t) { return Cb + (size_t)m * (t * p.Ctv); };
+  auto D = [&](int t) { return Db[t * p.Dtv]; };
+  const double phi = p.phi_f ? p.phi_f[f] : p.phi;
+  const double* mode = p.modes + (size_t)f * n;
+  double* ah = p.alphahat + (size_t)f * p.fs_a;
+  double* Pt = p.Lt + (size_t)f * p.fs_m;
+  double* ccov = p.Ct + (size_t)f * p.fs_m;
+  double* ay = p.ytilde + (size_t)f * p.fs_n;
+  double* aH = p.Htilde + (size_t)f * p.fs_n;
+  double* sc = p.scales + (size_t)f * p.fs_n;
+  double* aHH = p.scratch + (size_t)f * (size_t)(m + 3) * n;
+  double* sF = aHH + n;
+  double* sv = sF + n;
+  double* sK = sv + n;
+  auto ytmp = [&](int t) { return xb ? ay[t] - xb[t] : ay[t]; };
+
+  // ---- laplace_iter at the stored mode, update_scales
+  for (int t = 0; t < n; ++t) {
+    const double y = p.y[t], u = p.u[t], s = mode[t];
+    double HH, yt;
+    switch (dist) {
+      case 0: {
+        double tmp = y;
+        if (fabs(tmp) < 1e-4) tmp = 1e-4;
+        double q = tmp / phi;
+        HH = 2.0 * pf_exp(s) / (q * q);
+        yt = s + 1.0 - 0.5 * HH;
+      } break;
+      case 1: {
+        HH = 1.0 / (pf_exp(s) * u);
+        yt = y * HH + s - 1.0;
+      } break;
+      case 2: {
+        double e = pf_exp(s);
+        HH = (1.0 + e) * (1.0 + e) / (u * e);
+        yt = y * HH + s - 1.0 - e;
+      } break;
+      case 3: {
+        double e = pf_exp(s) * u;
+        HH = (phi + e) * (phi + e) / (phi * e * (y + phi));
+        yt = s + (phi + e) * (y - e) / ((y + phi) * e);
+      } break;
+      default: {
+        double e = pf_exp(s) * u;
+        HH = e / (y * phi);
+        yt = s - e / y + 1;
+      } break;
+    }
+    aHH[t] = HH;
+    ay[t] = yt;
+    const double H = sqrt(HH);
+    aH[t] = H;
+    double scale = 0.0;
+    if (pf_isfinite(y)) {
+      double q = (yt - s) / H;
+      scale = pfga::ung_log_obs(dist, s, y, u, phi) + 0.5 * (q * q);
+    }
+    sc[t] = scale;
+  }
+
+  SmootherIO io;
+  io.n = n; io.m = m; io.k = k;
+  io.Ztv = p.Ztv; io.Ttv = p.Ttv; io.Rtv = p.Rtv; io.Dtv = p.Dtv; io.Ctv = p.Ctv;
+  io.Zb = Zb; io.Tb = Tb; io.Rb = Rb; io.Cb = Cb; io.Db = Db; io.a1 = a1; io.P1 = P1; io.xb = xb;
+  io.ay = ay; io.aHH = aHH;
+  io.ah = ah; io.Pt = Pt; io.ccov = ccov; io.sF = sF; io.sv = sv; io.sK = sK;
+  smoother_ccov_conditional<MAXM, FIXED>(io);
+}
+
+} // namespace pf
+
+// ------------------------------------------------------------------ ssm_nlg
+// approximate_for_is of an ssm_nlg registry model (src/model_ssm_nlg.cpp:153-186) per stored draw on the device:
+// relinearise Z_fn / T_fn at the stored mode (pfga::NlgApprox::linearise), smooth the linearised model (the
+// function above, everything time varying), factor the transition covariances of the true and the approximating
+// model (pfga::MvnFactor) and pack the 32 doubles per time point the psi-APF weights read (NlgPsiParams::stepc).
+#include "bssm_b200/nlg_gauss_approx.h"
+namespace pf {
+
+struct NlgApproxParams {
+  int n, model_id, n_par;
+  const double* y;      // n
+  const double* theta;  // n_par per draw
+  const double* known;  // known_params
+  const double* modes;  // m x n per draw
+  double *stepc, *alphahat, *Lt, *Ct; // per draw: 32 n, m (n+1), m m (n+1) twice
+  double* scratch;      // per draw: (2 m + m m + m k + 3 + m + 2) n
+};
+
+// log N factors of dmvnorm (pfga::MvnFactor::set) with fixed storage
+template <int M_>
+struct MvnFactorDev {
+  double rooti[M_ * M_], cst, var1;
+  __device__ void set(const double* S) {
+    constexpr int m = M_;
+    var1 = 0.0;
+    if (m == 1) { var1 = S[0]; rooti[0] = 0.0; cst = 1.8378770664093453 + pf_log(var1); return; }
+    double Lc[M_ * M_];
+    for (int e = 0; e < m * m; ++e) { Lc[e] = 0.0; rooti[e] = 0.0; }
+    for (int j = 0; j < m; ++j)
+      for (int i = j; i < m; ++i) {
+        double s = S[i + m * j];
+        for (int l = 0; l < j; ++l) s -= Lc[i + m * l] * Lc[j + m * l];
+        Lc[i + m * j] = (i == j) ? sqrt(s) : s / Lc[j + m * j];
+      }
+    for (int j = 0; j < m; ++j) {
+      rooti[j + m * j] = 1.0 / Lc[j + m * j];
+      for (int i = j + 1; i < m; ++i) {
+        double s = 0.0;
+        for (int l = j; l < i; ++l) s += Lc[i + m * l] * rooti[l + m * j];
+        rooti[i + m * j] = -s / Lc[i + m * i];
+      }
+    }
+    double sl = 0.0;
+    for (int i = 0; i < m; ++i) sl += pf_log(rooti[i + m * i]);
+    cst = sl - 0.5 * m * 1.8378770664093453;
+  }
+};
+
+template <int M_, int K_>
+__global__ void __launch_bounds__(32) nlg_approx_for_is_kernel(const NlgApproxParams p, uint32_t nf) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  constexpr int m = M_, k = K_, mm = M_ * M_, mk = M_ * K_;
+  const int n = p.n;
+  const size_t n1 = (size_t)n + 1;
+  pfga::NlgFns fn{p.model_id, p.theta + (size_t)f * p.n_par, p.known};
+  const double* mode = p.modes + (size_t)f * m * n;
+  double* sc = p.scratch + (size_t)f * (size_t)(2 * m + mm + mk + 3 + m + 2) * n;
+  double* Zv = sc;                 // m n
+  double* Tv = Zv + (size_t)m * n; // mm n
+  double* Rv = Tv + (size_t)mm * n; // mk n
+  double* Cv = Rv + (size_t)mk * n; // m n
+  double* Dv = Cv + (size_t)m * n;  // n
+  double* Hv = Dv + n;              // n
+  double* HHv = Hv + n;             // n
+  double* sF = HHv + n;             // n
+  double* sv = sF + n;              // n
+  double* sK = sv + n;              // m n
+  double a1[M_], P1[M_ * M_];
+  fn.a1_fn(a1);
+  fn.P1_fn(P1);
+  // ---- linearise at the stored mode (zs = ts = mode)
+  for (int t = 0; t < n; ++t) {
+    const double* az = mode + (size_t)m * t;
+    double tv[M_], tmpv[M_];
+    fn.Z_gn(t, az, Zv + (size_t)m * t);
+    Hv[t] = fn.H_fn(t, az);
+    fn.T_gn(t, az, Tv + (size_t)mm * t);
+    fn.R_fn(t, az, Rv + (size_t)mk * t);
+    double za = 0.0;
+    for (int d = 0; d < m; ++d) za += Zv[d + (size_t)m * t] * az[d];
+    Dv[t] = fn.Z_fn(t, az) - za;
+    fn.T_fn(t, az, tv);
+    pf_mm(Tv + (size_t)mm * t, az, tmpv, m, m, 1);
+    for (int d = 0; d < m; ++d) Cv[d + (size_t)m * t] = tv[d] - tmpv[d];
+    HHv[t] = Hv[t] * Hv[t];
+  }
+  // ---- smoother of the linearised model: ay = y, aHH = H^2 (NlgApprox::View)
+  SmootherIO io;
+  io.n = n; io.m = m; io.k = k;
+  io.Ztv = io.Ttv = io.Rtv = io.Dtv = io.Ctv = 1;
+  io.Zb = Zv; io.Tb = Tv; io.Rb = Rv; io.Cb = Cv; io.Db = Dv; io.a1 = a1; io.P1 = P1; io.xb = nullptr;
+  io.ay = p.y; io.aHH = HHv;
+  io.ah = p.alphahat + (size_t)f * m * n1; io.Pt = p.Lt + (size_t)f * mm * n1; io.ccov = p.Ct + (size_t)f * mm * n1;
+  io.sF = sF; io.sv = sv; io.sK = sK;
+  smoother_ccov_conditional<M_, true>(io);
+  // ---- the 32 doubles per time point (pack_nlg_step, api.cu; scales = 0 for approximate_for_is)
+  const double LOG2PI = 1.8378770664093453;
+  double* cb = p.stepc + (size_t)f * 32 * n;
+  for (int t = 0; t < n; ++t) {
+    double* c = cb + (size_t)32 * t;
+    for (int e = 0; e < 32; ++e) c[e] = 0.0;
+    const double Ht = Hv[t], HHt = Ht * Ht;
+    c[0] = p.y[t]; c[1] = LOG2PI + 2.0 * pf_log(Ht); c[2] = Ht; c[3] = LOG2PI + pf_log(HHt); c[4] = HHt;
+    c[5] = Dv[t]; c[8] = 0.0;
+    for (int d = 0; d < m; ++d) c[6 + d] = Zv[(size_t)m * t + d];
+    if (t >= 1) {
+      for (int d = 0; d < m; ++d) c[10 + d] = Cv[(size_t)m * (t - 1) + d];
+      for (int e = 0; e < mm; ++e) c[12 + e] = Tv[(size_t)mm * (t - 1) + e];
+      double rr[M_ * M_], Rt[M_ * K_], cov[M_ * M_];
+      MvnFactorDev<M_> fa, ft;
+      pf_mmt(Rv + (size_t)mk * (t - 1), Rv + (size_t)mk * (t - 1), rr, m, k, m);
+      fa.set(rr);
+      fn.R_fn(t - 1, mode + (size_t)m * (t - 1), Rt);
+      pf_mmt(Rt, Rt, cov, m, k, m);
+      ft.set(cov);
+      if (m == 1) {
+        c[16] = fa.var1;
+        c[21] = ft.var1;
+        c[26] = fn.theta[0]; c[27] = fn.theta[1];
+        if (p.model_id == BSSM_NLG_LINEAR_GAUSSIAN) { c[26] = 0.0; c[27] = 1.0; }
+      } else {
+        for (int e = 0; e < mm; ++e) { c[16 + e] = fa.rooti[e]; c[21 + e] = ft.rooti[e]; }
+      }
+      c[20] = fa.cst;
+      c[25] = ft.cst;
+    }
   }
 }
 

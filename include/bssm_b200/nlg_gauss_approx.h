@@ -34,6 +34,13 @@
 #include "bssm_b200/pf_smallmat.h"
 #include "bssm_b200/ung_gauss_approx.h"
 
+/* member functions that also run in device code */
+#if defined(__CUDACC__)
+#define PF_HDM __host__ __device__
+#else
+#define PF_HDM
+#endif
+
 namespace pfga {
 
 /* registry functors on the host; growth model: R/cpp_example_models.R:350-460 */
@@ -47,32 +54,32 @@ struct NlgFns {
   /* 2 = sine transition observed through exp(alpha) (m = k = 1), R/cpp_example_models.R:635-757,
    *     theta = (log H, log R);
    * 3 = linear-Gaussian random walk (m = k = 1), R/cpp_example_models.R:512-634, theta = (log H) */
-  int m() const { return model_id == 0 ? 2 : 1; }
-  int k() const { return model_id == 0 ? 2 : 1; }
-  void a1_fn(double* a1) const {
+  PF_HDM int m() const { return model_id == 0 ? 2 : 1; }
+  PF_HDM int k() const { return model_id == 0 ? 2 : 1; }
+  PF_HDM void a1_fn(double* a1) const {
     if (model_id == 2 || model_id == 3) { a1[0] = 0; return; }
     if (model_id == 1) { a1[0] = theta[0]; return; }
     a1[0] = known[2]; a1[1] = known[3];
   }
-  void P1_fn(double* P1) const {
+  PF_HDM void P1_fn(double* P1) const {
     if (model_id == 2 || model_id == 3) { P1[0] = 1; return; }
     if (model_id == 1) { const double e = pf_exp(theta[2]); P1[0] = e * e / (1 - theta[1] * theta[1]); return; }
     P1[0] = known[4]; P1[1] = 0; P1[2] = 0; P1[3] = known[5];
   }
-  double H_fn(int, const double*) const { return model_id == 1 ? pf_exp(theta[3]) : pf_exp(theta[0]); }
-  void R_fn(int, const double*, double* R) const {
+  PF_HDM double H_fn(int, const double*) const { return model_id == 1 ? pf_exp(theta[3]) : pf_exp(theta[0]); }
+  PF_HDM void R_fn(int, const double*, double* R) const {
     if (model_id == 3) { R[0] = 1; return; }
     if (model_id == 2) { R[0] = pf_exp(theta[1]); return; }
     if (model_id == 1) { R[0] = pf_exp(theta[2]); return; }
     R[0] = pf_exp(theta[1]); R[1] = 0; R[2] = 0; R[3] = pf_exp(theta[2]);
   }
-  double Z_fn(int, const double* alpha) const { return model_id == 3 ? alpha[0] : (model_id != 0 ? pf_exp(alpha[0]) : alpha[1]); }
-  void Z_gn(int, const double* alpha, double* Zg) const {
+  PF_HDM double Z_fn(int, const double* alpha) const { return model_id == 3 ? alpha[0] : (model_id != 0 ? pf_exp(alpha[0]) : alpha[1]); }
+  PF_HDM void Z_gn(int, const double* alpha, double* Zg) const {
     if (model_id == 3) { Zg[0] = 1.0; return; }
     if (model_id != 0) { Zg[0] = pf_exp(alpha[0]); return; }
     Zg[0] = 0.0; Zg[1] = 1.0;
   }
-  void T_fn(int, const double* alpha, double* an) const {
+  PF_HDM void T_fn(int, const double* alpha, double* an) const {
     if (model_id == 3) { an[0] = alpha[0]; return; }
     if (model_id == 2) { an[0] = pf_sin(alpha[0]); return; }
     if (model_id == 1) { an[0] = theta[0] * (1 - theta[1]) + theta[1] * alpha[0]; return; }
@@ -81,7 +88,7 @@ struct NlgFns {
     const double r = pf_exp(alpha[0]) / (1.0 + pf_exp(alpha[0]));
     an[1] = K * alpha[1] * pf_exp(r * dT) / (K + alpha[1] * (pf_exp(r * dT) - 1));
   }
-  void T_gn(int, const double* alpha, double* Tg) const { /* column-major m x m */
+  PF_HDM void T_gn(int, const double* alpha, double* Tg) const { /* column-major m x m */
     if (model_id == 3) { Tg[0] = 1.0; return; }
     if (model_id == 2) { Tg[0] = pf_cos(alpha[0]); return; }
     if (model_id == 1) { Tg[0] = theta[1]; return; }

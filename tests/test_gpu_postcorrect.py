@@ -361,3 +361,20 @@ def test_device_approximation_equals_host_approximation(engine, monkeypatch):
         monkeypatch.delenv("BSSM_B200_HOST_APPROX")
         assert np.array_equal(dev["loglik"], host["loglik"]), kind
         assert np.array_equal(dev["alphahat"], host["alphahat"]) and np.array_equal(dev["Vt"], host["Vt"]), kind
+
+
+@pytest.mark.parametrize("kind", ["growth", "ar_exp", "sin_exp"])
+def test_device_approximation_equals_host_approximation_nlg(engine, kind, monkeypatch):
+    """postcorrection_nonlinear: approximate_for_is per draw (relinearisation at the stored mode, smoother,
+    transition-density factors) on the device vs the host loop over include/bssm_b200/nlg_gauss_approx.h"""
+    model = {"growth": lambda: data.growth_model(50, missing=(4,)), "ar_exp": lambda: data.ar_exp_model(50, missing=(3,)),
+             "sin_exp": lambda: data.sin_exp_model(40)}[kind]()
+    mo = dict(data.growth_mcmc_output(model, 12, jitter=0.04), output_type=2)
+    dev = engine.post_correct(model, mo, 64, is_type="is2", seed=3, return_loglik=True)
+    monkeypatch.setenv("BSSM_B200_HOST_APPROX", "1")
+    host = engine.post_correct(model, mo, 64, is_type="is2", seed=3, return_loglik=True)
+    monkeypatch.delenv("BSSM_B200_HOST_APPROX")
+    assert np.array_equal(dev["loglik"], host["loglik"])
+    assert np.array_equal(dev["alphahat"], host["alphahat"]) and np.array_equal(dev["Vt"], host["Vt"])
+    ref = orc.post_correct(model, dict(mo, output_type=3), 64, is_type=2, seed=3)
+    assert np.array_equal(dev["loglik"], ref.loglik)
