@@ -58,6 +58,10 @@ __device__ void smoother_ccov_conditional(const SmootherIO& io) {
   const double *a1 = io.a1, *P1 = io.P1, *xb = io.xb, *ay = io.ay, *aHH = io.aHH;
   double *ah = io.ah, *Pt = io.Pt, *ccov = io.ccov, *sF = io.sF, *sv = io.sv, *sK = io.sK;
   auto ytmp = [&](int t) { return xb ? ay[t] - xb[t] : ay[t]; };
+#ifdef PF_APPROX_TIMING
+  const bool tim = blockIdx.x == 0 && threadIdx.x == 0;
+  long long tk0 = clock64();
+#endif
 
   // ---- forward pass of smoother_ccov (Kalman filter, Joseph form)
   double A[MM], B[MM], X[MM], E[MM], rr[MM];
@@ -112,6 +116,9 @@ __device__ void smoother_ccov_conditional(const SmootherIO& io) {
     for (int i = 0; i < m; ++i) at[i] = an[i];
   }
 
+#ifdef PF_APPROX_TIMING
+  long long tk1 = clock64();
+#endif
   // ---- backward pass
   {
     double rt[MAXM], Nt[MM], Lm[MM], lr[MAXM], tmpv[MAXM];
@@ -161,6 +168,9 @@ __device__ void smoother_ccov_conditional(const SmootherIO& io) {
     for (size_t e = 0; e < mm; ++e) ccov[mm * n + e] = 0.0;
   }
 
+#ifdef PF_APPROX_TIMING
+  long long tk2 = clock64();
+#endif
   // ---- conditional_cov, SVD branch (pfga::conditional_cov_svd)
   {
     const double eps = 2.220446049250313e-16;
@@ -187,6 +197,9 @@ __device__ void smoother_ccov_conditional(const SmootherIO& io) {
     }
     factor(Pt);
   }
+#ifdef PF_APPROX_TIMING
+  if (tim) printf("[approx cycles per t] forward %lld backward %lld conditional %lld\n", (tk1 - tk0) / n, (tk2 - tk1) / n, (clock64() - tk2) / n);
+#endif
 }
 
 // FIXED: the state dimension IS MAXM (bsm_ng: 2 or 3) -- every loop over it unrolls and the small matrices live

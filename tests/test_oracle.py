@@ -500,3 +500,17 @@ def test_oracle_runs_user_sde_functions_like_the_registry_model(tmp_path):
     a = orc.sde_bsf_filter(reg, 64, 3, seed=5)
     b = orc.sde_bsf_filter(user, 64, 3, seed=5)
     assert a.loglik == b.loglik and np.array_equal(a.indices, b.indices) and np.array_equal(a.alpha, b.alpha)
+
+
+def test_jacobi_stops_at_its_fixed_point_with_the_same_bits(tmp_path):
+    """pf_jacobi_eig_sym (include/bssm_b200/pf_smallmat.h, the stand-in for arma::svd_econ on symmetric matrices,
+    src/conditional_dist.cpp:14) leaves the sweep loop at the first sweep that changes nothing instead of always
+    running 60: same eigenvalues and eigenvectors, bit for bit, as the plain rule kept in tests/aux/"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "jac"
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "tests", "aux", "jacobi_fixed_point_check.cpp"), "-o", str(exe)], check=True)
+    tot, bad = map(int, subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split())
+    assert tot == 13 * 1500 and bad == 0
