@@ -2025,6 +2025,39 @@ static int create_mng_job(const bssm_mng_model* M, int method, uint32_t nsim, ui
     if (dm->modes.size() != (size_t)p * n * n_filters) return fail(BSSM_B200_ERR_ARG, "parameter set: p x n modes per filter");
     J->method = BSSM_METHOD_PSI;
     const size_t n1 = (size_t)n + 1, mm = (size_t)m * m, np = (size_t)n * p, nf = n_filters;
+    if (!env_int("BSSM_B200_HOST_APPROX", 0)) {
+      // one thread per draw on the device (approx_device.cuh); the per-draw model arrays are those uploaded above
+      pf::MngApproxParams ap;
+      memset(&ap, 0, sizeof(ap));
+      ap.n = n; ap.m = m; ap.k = k; ap.p = p;
+      ap.Ztv = M->Ztv; ap.Ttv = M->Ttv; ap.Rtv = M->Rtv; ap.Dtv = M->Dtv; ap.Ctv = M->Ctv;
+      ap.y = J->y.p; ap.u = J->u.p; ap.distribution = J->dist_v.p;
+      ap.Z = gp.Z; ap.fs_Z = gp.fs_Z; ap.T = gp.T; ap.fs_T = gp.fs_T; ap.R = gp.R; ap.fs_R = gp.fs_R;
+      ap.C = gp.C; ap.fs_C = gp.fs_C; ap.D = gp.D; ap.fs_D = gp.fs_D; ap.a1 = gp.a1; ap.fs_a1 = gp.fs_a1;
+      ap.phi = gp.phi; ap.fs_phi = gp.fs_phi;
+      if (!dm->P1.empty()) {
+        if ((rc = J->P1.upload(dm->P1.data(), dm->P1.size()))) return rc;
+        ap.fs_P1 = mm;
+      } else if ((rc = J->P1.upload(M->P1, mm))) {
+        return rc;
+      }
+      ap.P1 = J->P1.p;
+      const size_t per_t = (size_t)(3 * p + 1 + 2 * p) + 3 * (size_t)p * m;
+      if ((rc = J->mode.upload(dm->modes.data(), dm->modes.size())) || (rc = J->alphahat.alloc((size_t)m * n1 * nf)) ||
+          (rc = J->Lt.alloc(mm * n1 * nf)) || (rc = J->Ct.alloc(mm * n1 * nf)) || (rc = J->ytilde.alloc(np * nf)) ||
+          (rc = J->Htilde.alloc(np * nf)) || (rc = J->scales.alloc((size_t)n * nf)) || (rc = J->approx_loglik.alloc(nf)) ||
+          (rc = J->scratch.alloc(per_t * n * nf)))
+        return rc;
+      CU(cudaMemsetAsync(J->approx_loglik.p, 0, sizeof(double) * nf, J->stream));
+      ap.modes = J->mode.p;
+      ap.alphahat = J->alphahat.p; ap.Lt = J->Lt.p; ap.Ct = J->Ct.p; ap.ytilde = J->ytilde.p; ap.Htilde = J->Htilde.p;
+      ap.scales = J->scales.p; ap.scratch = J->scratch.p;
+      const uint32_t ab = cdiv((uint32_t)nf, 32);
+      if (m <= 3 && p <= 8) pf::mng_approx_for_is_kernel<3, 8><<<ab, 32, 0, J->stream>>>(ap, (uint32_t)nf);
+      else pf::mng_approx_for_is_kernel<16, 16><<<ab, 32, 0, J->stream>>>(ap, (uint32_t)nf);
+      CU(cudaGetLastError());
+      CU(cudaStreamSynchronize(J->stream));
+    } else {
     std::vector<double> ah((size_t)m * n1 * nf), Lt(mm * n1 * nf), Ct(mm * n1 * nf), yt(np * nf), Ht(np * nf),
         sc((size_t)n * nf), al(nf, 0.0);
 #pragma omp parallel for schedule(static)
@@ -2049,6 +2082,7 @@ static int create_mng_job(const bssm_mng_model* M, int method, uint32_t nsim, ui
         (rc = J->Htilde.upload(Ht.data(), Ht.size())) || (rc = J->scales.upload(sc.data(), sc.size())) ||
         (rc = J->approx_loglik.upload(al.data(), nf)))
       return rc;
+    }
     gp.alphahat = J->alphahat.p; gp.Lt = J->Lt.p; gp.Ct = J->Ct.p; gp.ytilde = J->ytilde.p;
     gp.Htilde = J->Htilde.p; gp.scales = J->scales.p; gp.approx_loglik = J->approx_loglik.p;
     gp.fs_a = (size_t)m * n1; gp.fs_m = mm * n1; gp.fs_np = np; gp.fs_n = (size_t)n;

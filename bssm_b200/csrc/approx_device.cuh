@@ -425,3 +425,287 @@ __global__ void __launch_bounds__(32) nlg_approx_for_is_kernel(const NlgApproxPa
 }
 
 } // namespace pf
+
+// ------------------------------------------------------------------ ssm_mng
+// approximate_for_is of an ssm_mng model per stored draw (pfga::MngApprox::run(mode), include/bssm_b200/
+// mng_gauss_approx.h; src/model_ssm_mng.cpp:119-135, 216-315, src/model_ssm_mlg.cpp:232-397): laplace_iter per
+// series, scales, the multivariate Kalman filter with masked missing series (Cholesky of F_t), the backward
+// recursion and conditional_cov.  One thread per draw, run-time (m, p); the same expressions and primitives as
+// the host header.
+#include "bssm_b200/mng_gauss_approx.h"
+namespace pf {
+
+struct MngApproxParams {
+  int n, m, k, p;
+  int Ztv, Ttv, Rtv, Dtv, Ctv;
+  const double *y, *u; // n x p
+  const int* distribution;
+  const double *Z, *T, *R, *a1, *P1, *D, *C, *phi; // per draw with stride fs_* (0 = shared)
+  size_t fs_Z, fs_T, fs_R, fs_a1, fs_P1, fs_D, fs_C, fs_phi;
+  const double* modes; // p x n per draw
+  double *alphahat, *Lt, *Ct, *ytilde, *Htilde, *scales; // per draw: m (n+1), m m (n+1) twice, n p twice (layout of y), n
+  double* scratch; // per draw: (3 p + 1 + 2 p + 3 p m) n
+};
+
+template <int MAXM, int MAXP>
+__global__ void __launch_bounds__(32) mng_approx_for_is_kernel(const MngApproxParams q, uint32_t nf) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  constexpr int MM = MAXM * MAXM, PP = MAXP * MAXP, PM = MAXP * MAXM;
+  const int n = q.n, m = q.m, k = q.k, p = q.p;
+  const size_t mm = (size_t)m * m, pm = (size_t)p * m, n1 = (size_t)n + 1;
+  const double* Zb = q.Z + (size_t)f * q.fs_Z;
+  const double* Tb = q.T + (size_t)f * q.fs_T;
+  const double* Rb = q.R + (size_t)f * q.fs_R;
+  const double* Cb = q.C + (size_t)f * q.fs_C;
+  const double* Db = q.D + (size_t)f * q.fs_D;
+  const double* a1 = q.a1 + (size_t)f * q.fs_a1;
+  const double* P1 = q.P1 + (size_t)f * q.fs_P1;
+  const double* phi = q.phi + (size_t)f * q.fs_phi;
+  auto Z = [&](int t) { return Zb + pm * (t * q.Ztv); };
+  auto T = [&](int t) { return Tb + mm * (t * q.Ttv); };
+  auto R = [&](int t) { return Rb + (size_t)m * k * (t * q.Rtv); };
+  auto C = [&](int t) { return Cb + (size_t)m * (t * q.Ctv); };
+  auto D = [&](int t) { return Db + (size_t)p * (t * q.Dtv); };
+  auto y = [&](int j, int t) { return q.y[t + (size_t)n * j]; };
+  auto u = [&](int j, int t) { return q.u[t + (size_t)n * j]; };
+  const double* mode = q.modes + (size_t)f * p * n;
+  double* ah = q.alphahat + (size_t)f * m * n1;
+  double* Pt = q.Lt + (size_t)f * mm * n1;
+  double* ccov = q.Ct + (size_t)f * mm * n1;
+  double* sc = q.scales + (size_t)f * n;
+  const size_t per_t = (size_t)(3 * p + 1 + 2 * p) + 3 * pm;
+  double* base = q.scratch + (size_t)f * per_t * n;
+  double* ay = base;                      // p n, element (j, t) at j + p t
+  double* aHH = ay + (size_t)p * n;
+  double* aH = aHH + (size_t)p * n;
+  double* s_nobs = aH + (size_t)p * n;    // n
+  double* s_hh = s_nobs + n;              // p n
+  double* s_v = s_hh + (size_t)p * n;     // p n
+  double* s_Zt = s_v + (size_t)p * n;     // p m n
+  double* s_ZF = s_Zt + pm * n;           // m p n
+  double* s_K = s_ZF + pm * n;            // m p n
+
+  // ---- laplace_iter (src/model_ssm_mng.cpp:268-315) and update_scales (:216-256)
+  for (int j = 0; j < p; ++j) {
+    const double ph = phi[j];
+    for (int t = 0; t < n; ++t) {
+      const size_t e = j + (size_t)p * t;
+      const double yy = y(j, t), uu = u(j, t), s = mode[e];
+      switch (q.distribution[j]) {
+        case 1: {
+          aHH[e] = 1.0 / (pf_exp(s) * uu);
+          ay[e] = yy * aHH[e] + s - 1.0;
+        } break;
+        case 2: {
+          const double ex = pf_exp(s);
+          aHH[e] = (1.0 + ex) * (1.0 + ex) / (uu * ex);
+          ay[e] = yy * aHH[e] + s - 1.0 - ex;
+        } break;
+        case 3: {
+          const double ex = pf_exp(s) * uu;
+          aHH[e] = (ph + ex) * (ph + ex) / (ph * ex * (yy + ph));
+          ay[e] = s + (ph + ex) * (yy - ex) / ((yy + ph) * ex);
+        } break;
+        case 4: {
+          const double ex = pf_exp(s) * uu;
+          aHH[e] = ex / (yy * ph);
+          ay[e] = s - ex / yy + 1;
+        } break;
+        default: {
+          aHH[e] = ph * ph;
+          ay[e] = yy;
+        } break;
+      }
+      aH[e] = sqrt(aHH[e]);
+    }
+  }
+  for (int t = 0; t < n; ++t) {
+    double sct = 0.0;
+    for (int j = 0; j < p; ++j) {
+      const size_t e = j + (size_t)p * t;
+      if (pf_isfinite(y(j, t))) {
+        const double yy = y(j, t), uu = u(j, t), s = mode[e], ph = phi[j];
+        double lo;
+        switch (q.distribution[j]) {
+          case 1: lo = yy * s - uu * pf_exp(s); break;
+          case 2: lo = yy * s - uu * pf_log1p(pf_exp(s)); break;
+          case 3: lo = yy * s - (yy + ph) * pf_log(ph + uu * pf_exp(s)); break;
+          case 4: lo = -ph * s - (yy * ph * pf_exp(-s) / uu); break;
+          default: { const double qq = (yy - s) / ph; lo = -0.5 * (qq * qq); } break;
+        }
+        sct += lo;
+        const double qd = (ay[e] - mode[e]) / aH[e];
+        sct += 0.5 * (qd * qd);
+      }
+    }
+    sc[t] = sct;
+  }
+  // pseudo-observations in the layout of y (n x p)
+  {
+    double* yo = q.ytilde + (size_t)f * n * p;
+    double* Ho = q.Htilde + (size_t)f * n * p;
+    for (int t = 0; t < n; ++t)
+      for (int j = 0; j < p; ++j) {
+        yo[t + (size_t)n * j] = ay[j + (size_t)p * t];
+        Ho[t + (size_t)n * j] = aH[j + (size_t)p * t];
+      }
+  }
+
+  // ---- forward pass: Kalman filter with the missing series masked (gain / predict_mean / predict_cov)
+  double A[MM], B[MM], X[MM], E[MM], rr[MM];
+  double at[MAXM], Pc[MM];
+  for (int i = 0; i < m; ++i) { at[i] = a1[i]; ah[i] = at[i]; }
+  for (size_t e = 0; e < mm; ++e) { Pc[e] = P1[e]; Pt[e] = Pc[e]; }
+  bool failed = false;
+  for (int t = 0; t < n && !failed; ++t) {
+    double* Zt = s_Zt + pm * t;
+    double* hh = s_hh + (size_t)p * t;
+    double* v = s_v + (size_t)p * t;
+    double* ZFinv = s_ZF + pm * t;
+    double* K = s_K + pm * t;
+    int nobs = 0;
+    for (size_t e = 0; e < pm; ++e) Zt[e] = Z(t)[e];
+    for (int j = 0; j < p; ++j) hh[j] = 1.0;
+    for (int j = 0; j < p; ++j) {
+      if (pf_isfinite(y(j, t))) { nobs++; hh[j] = aHH[j + (size_t)p * t]; }
+      else for (int d = 0; d < m; ++d) Zt[j + (size_t)p * d] = 0.0;
+    }
+    s_nobs[t] = (double)nobs;
+    if (nobs > 0) {
+      double Apm[PM], F[PP], cholF[PP], inv[PP], za[MAXP], W[PM];
+      pf_mm(Zt, Pc, Apm, p, m, m);
+      pf_mmt(Apm, Zt, F, p, m, p);
+      for (int j = 0; j < p; ++j) F[j + (size_t)p * j] += hh[j];
+      for (int e = 0; e < p * p; ++e) if (!pf_isfinite(F[e])) failed = true;
+      for (int j = 0; j < p; ++j) if (!(F[j + (size_t)p * j] > 0)) failed = true;
+      if (!failed && !pfga::chol_upper(F, p, cholF)) failed = true;
+      if (failed) break;
+      pfga::inv_upper(cholF, p, inv);
+      pf_mm(Zt, at, za, p, m, 1);
+      for (int j = 0; j < p; ++j) v[j] = pf_isfinite(y(j, t)) ? (ay[j + (size_t)p * t] - D(t)[j]) - za[j] : 0.0;
+      pf_mtm(Zt, inv, W, m, p, p);      /* Zt' inv */
+      pf_mmt(W, inv, ZFinv, m, p, p);   /* (Zt' inv) inv' */
+      pf_mm(Pc, ZFinv, K, m, m, p);
+    }
+    // predict_mean
+    double tmpv[MAXM], kv[MAXM], ta[MAXM], an[MAXM];
+    for (int i = 0; i < m; ++i) tmpv[i] = at[i];
+    if (nobs > 0) {
+      pf_mm(K, v, kv, m, p, 1);
+      for (int i = 0; i < m; ++i) tmpv[i] = at[i] + kv[i];
+    }
+    pf_mm(T(t), tmpv, ta, m, m, 1);
+    for (int i = 0; i < m; ++i) { an[i] = C(t)[i] + ta[i]; ah[(size_t)m * (t + 1) + i] = an[i]; }
+    // predict_cov
+    if (nobs > 0) {
+      double kz[MM], KH[PM], khk[MM];
+      pf_mm(K, Zt, kz, m, p, m);
+      for (int j = 0; j < m; ++j)
+        for (int i = 0; i < m; ++i) E[i + (size_t)m * j] = (i == j ? 1.0 : 0.0) - kz[i + (size_t)m * j];
+      pf_mm(E, Pc, A, m, m, m);
+      pf_mmt(A, E, B, m, m, m);
+      for (int j = 0; j < p; ++j)
+        for (int i = 0; i < m; ++i) KH[i + (size_t)m * j] = K[i + (size_t)m * j] * hh[j];
+      pf_mmt(KH, K, khk, m, p, m);
+      for (size_t e = 0; e < mm; ++e) X[e] = B[e] + khk[e];
+    } else {
+      for (size_t e = 0; e < mm; ++e) X[e] = Pc[e];
+    }
+    pf_mm(T(t), X, A, m, m, m);
+    pf_mmt(A, T(t), B, m, m, m);
+    pf_mmt(R(t), R(t), rr, m, k, m);
+    double Pn[MM];
+    for (size_t e = 0; e < mm; ++e) Pn[e] = B[e] + rr[e];
+    pf_symmatu(Pn, m);
+    for (size_t e = 0; e < mm; ++e) { Pt[mm * (t + 1) + e] = Pn[e]; ccov[mm * t + e] = Pn[e]; Pc[e] = Pn[e]; }
+    for (int i = 0; i < m; ++i) at[i] = an[i];
+  }
+  if (failed) { // a Cholesky of F_t failed: everything infinite, as on the host
+    const double inf = pf_inf();
+    for (size_t e = 0; e < (size_t)m * n1; ++e) ah[e] = inf;
+    for (size_t e = 0; e < mm * n1; ++e) { Pt[e] = inf; ccov[e] = inf; }
+    return;
+  }
+
+  // ---- backward pass
+  {
+    double rt[MAXM], Nt[MM], Lm[MM], lr[MAXM], tmpv[MAXM], zv[MAXM], zz[MM];
+    for (int i = 0; i < m; ++i) rt[i] = 0.0;
+    for (size_t e = 0; e < mm; ++e) Nt[e] = 0.0;
+    for (int t = n - 1; t >= 0; --t) {
+      const double* Zt = s_Zt + pm * t;
+      const double* v = s_v + (size_t)p * t;
+      const double* ZFinv = s_ZF + pm * t;
+      const double* K = s_K + pm * t;
+      const bool used = s_nobs[t] > 0.0;
+      const double* Tm;
+      if (used) {
+        double kz[MM];
+        pf_mm(K, Zt, kz, m, p, m);
+        for (int j = 0; j < m; ++j)
+          for (int i = 0; i < m; ++i) E[i + (size_t)m * j] = (i == j ? 1.0 : 0.0) - kz[i + (size_t)m * j];
+        pf_mm(T(t), E, Lm, m, m, m);
+        Tm = Lm;
+      } else {
+        Tm = T(t);
+      }
+      double* Pcur = Pt + mm * t;
+      double* cct = ccov + mm * t;
+      pf_mm(Nt, cct, A, m, m, m);
+      for (int j = 0; j < m; ++j)
+        for (int i = 0; i < m; ++i) X[i + (size_t)m * j] = (i == j ? 1.0 : 0.0) - A[i + (size_t)m * j];
+      pf_mmt(Pcur, Tm, B, m, m, m);
+      pf_mm(B, X, cct, m, m, m);
+      pf_mtm(Tm, rt, lr, m, m, 1);
+      pf_mtm(Tm, Nt, A, m, m, m);
+      pf_mm(A, Tm, B, m, m, m);
+      if (used) {
+        pf_mm(ZFinv, v, zv, m, p, 1);
+        pf_mm(ZFinv, Zt, zz, m, p, m);
+        for (int i = 0; i < m; ++i) rt[i] = zv[i] + lr[i];
+        for (size_t e = 0; e < mm; ++e) Nt[e] = zz[e] + B[e];
+      } else {
+        for (int i = 0; i < m; ++i) rt[i] = lr[i];
+        for (size_t e = 0; e < mm; ++e) Nt[e] = B[e];
+      }
+      pf_symmatu(Nt, m);
+      pf_mm(Pcur, rt, tmpv, m, m, 1);
+      for (int i = 0; i < m; ++i) ah[(size_t)m * t + i] += tmpv[i];
+      pf_mm(Pcur, Nt, A, m, m, m);
+      pf_mm(A, Pcur, B, m, m, m);
+      pf_symmatu(B, m);
+      for (size_t e = 0; e < mm; ++e) Pcur[e] -= B[e];
+    }
+    for (size_t e = 0; e < mm; ++e) ccov[mm * n + e] = 0.0;
+  }
+
+  // ---- conditional_cov, SVD branch (pfga::conditional_cov_svd)
+  {
+    const double eps = 2.220446049250313e-16;
+    double vals[MAXM], U[MM], W[MM];
+    auto factor = [&](double* V) {
+      pf_jacobi_eig_sym_t<MM>(V, m, vals, U);
+      for (int j = 0; j < m; ++j)
+        for (int i = 0; i < m; ++i) V[i + (size_t)m * j] = U[i + (size_t)m * j] * sqrt(fabs(vals[j]));
+    };
+    for (int t = n; t > 0; --t) {
+      pf_jacobi_eig_sym_t<MM>(Pt + mm * (t - 1), m, vals, U);
+      const double s0 = fabs(vals[0]);
+      pf_mtm(ccov + mm * (t - 1), U, W, m, m, m);
+      for (int j = 0; j < m; ++j) {
+        const double s = fabs(vals[j]);
+        const double inv = (s > eps * m * s0) ? 1.0 / s : 0.0;
+        for (int i = 0; i < m; ++i) W[i + (size_t)m * j] = W[i + (size_t)m * j] * inv;
+      }
+      pf_mmt(W, U, X, m, m, m);
+      pf_mm(X, ccov + mm * (t - 1), A, m, m, m);
+      for (size_t e = 0; e < mm; ++e) Pt[mm * t + e] -= A[e];
+      for (size_t e = 0; e < mm; ++e) ccov[mm * t + e] = X[e];
+      factor(Pt + mm * t);
+    }
+    factor(Pt);
+  }
+}
+
+} // namespace pf

@@ -39,7 +39,7 @@
 namespace pfga {
 
 /* upper Cholesky factor R (F = R'R) of a p x p matrix; false if not positive definite */
-inline bool chol_upper(const double* F, int p, double* R) {
+PF_SM bool chol_upper(const double* F, int p, double* R) {
   for (int e = 0; e < p * p; ++e) R[e] = 0.0;
   for (int j = 0; j < p; ++j)
     for (int i = 0; i <= j; ++i) {
@@ -47,7 +47,7 @@ inline bool chol_upper(const double* F, int p, double* R) {
       for (int l = 0; l < i; ++l) s -= R[l + (size_t)p * i] * R[l + (size_t)p * j];
       if (i == j) {
         if (!(s > 0.0)) return false;
-        R[j + (size_t)p * j] = std::sqrt(s);
+        R[j + (size_t)p * j] = sqrt(s);
       } else {
         R[i + (size_t)p * j] = s / R[i + (size_t)p * i];
       }
@@ -55,7 +55,7 @@ inline bool chol_upper(const double* F, int p, double* R) {
   return true;
 }
 /* X = R^{-1} for upper-triangular R */
-inline void inv_upper(const double* R, int p, double* X) {
+PF_SM void inv_upper(const double* R, int p, double* X) {
   for (int e = 0; e < p * p; ++e) X[e] = 0.0;
   for (int j = 0; j < p; ++j) {
     X[j + (size_t)p * j] = 1.0 / R[j + (size_t)p * j];

@@ -233,3 +233,19 @@ def test_parset_argument_errors(engine):
     g = data.mng_model(30)
     with pytest.raises(ValueError, match="update_fn"):
         engine.post_correct(g, mo, 32, is_type="is2", seed=1)
+
+
+def test_mng_device_approximation_equals_host_approximation(engine, monkeypatch):
+    """the per-draw approximation of ssm_mng parameter sets (multivariate Kalman filter with masked missing series,
+    Cholesky of F_t, backward recursion, conditional_cov) on the device vs the host loop over mng_gauss_approx.h"""
+    model = mng_update_model()
+    _, _, mode, _ = orc.mng_approx(model)
+    mo = draws(model, 10, rows=model.n * model.p)
+    mo["modes"] = np.asfortranarray(mode.ravel(order="F")[:, None] + 0.05 * (mo["modes"] - np.log(3.0)))
+    mo = dict(mo, output_type=2)
+    dev = engine.post_correct(model, mo, 64, is_type="is2", seed=3, return_loglik=True)
+    monkeypatch.setenv("BSSM_B200_HOST_APPROX", "1")
+    host = engine.post_correct(model, mo, 64, is_type="is2", seed=3, return_loglik=True)
+    monkeypatch.delenv("BSSM_B200_HOST_APPROX")
+    assert np.array_equal(dev["loglik"], host["loglik"])
+    assert np.array_equal(dev["alphahat"], host["alphahat"]) and np.array_equal(dev["Vt"], host["Vt"])
