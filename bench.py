@@ -233,6 +233,30 @@ def cpu_baseline_leg():
                       "a filter); oracle port, not the reference binary; cpu=%s" % (w["N"], n_sample, w["n"], cpu_model_name())}
 
 
+def bind_near_gpu(torch, local_rank):
+    """With several ranks on one host every rank copies ~1 GB per end-to-end call into pinned memory: keep the rank
+    (and with it the first touch of its pinned buffers) on the CPUs of the NUMA node its GPU hangs off
+    (/sys/bus/pci/devices/<bus id>/local_cpulist).  Returns a note for the JSON line; does nothing if unknown."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        txt = open("/sys/bus/pci/devices/%s/local_cpulist" % bus).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "not bound (no local cpus listed)"
+        os.sched_setaffinity(0, cpus)
+        return "bound to the %d cpus local to GPU %s" % (len(cpus), bus)
+    except Exception as e:  # no sysfs entry, no permission, old torch: run unbound
+        return "not bound (%s)" % type(e).__name__
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -267,6 +291,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     bssm_b200._lib.check(bssm_b200.lib().bssm_b200_set_device(local_rank))
+    affinity = bind_near_gpu(torch, local_rank) if world > 1 else "not bound (one rank)"
     dist = None
     if world > 1:
         # NCCL's INFO lines (communicator, ranks, NVLS / ring choice) go to STDERR so that stdout stays the
@@ -476,6 +501,7 @@ def main():
             "l2": "each step writes %.1f GB per GPU (>> 126 MB L2); no explicit flush" % (BYTES_PER_PS * B * N * n / 1e9),
             "single_filter_ms": s_ms, "single_filter_particle_steps_per_s": N * n / (s_ms * 1e-3),
             "wall_ms_per_step": wall_ms / args.steps,
+            "cpu_affinity": affinity,
             "kernels_ms_per_step": kernels_ms_max / args.steps,
             "pre_pass": "host, inside the timed step: update_model + approximate() + smoother pre-pass + upload "
                         "(one sequential chain shared by the replicate filters)",
