@@ -16,6 +16,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import FilterOut, check, dptr, lib, uptr
+from .models import Model
 
 METHOD_PSI, METHOD_BSF = 1, 2
 POST_NONE, POST_FILTER_SUMMARY, POST_SMOOTHER = 0, 1, 2
@@ -248,8 +249,49 @@ class FilterJob:
             pass
 
 
+def importance_sample(model, nsim, use_antithetic=True, max_iter=None, conv_tol=None, seed=1, return_loglik=False):
+    """importance_sample.nongaussian, R/importance_sample.R:41-70 -> importance_sample_ng
+    (src/R_importance_sample.cpp:9-75): `nsim` draws from the smoothing distribution of the approximating
+    Gaussian model (simulation smoother, one antithetic variable) and their importance weights.  Returns
+    alpha (n+1) x m x nsim and weights (nsim); ssm_ung family, nsim >= 2.  The reference never forwards
+    `use_antithetic` to simulate_states (its draws are always paired, :29); here FALSE draws nsim independent
+    trajectories."""
+    if not isinstance(model, Model) or model.distribution == "gaussian":
+        raise ValueError("importance_sample is implemented for non-Gaussian ssm_ung models (svm, bsm_ng, ar1_ng, ssm_ung)")
+    if not isinstance(use_antithetic, (bool, np.bool_)):
+        raise ValueError("Argument 'use_antithetic' should be TRUE or FALSE. ")
+    nsim, seed = _check_particles(model, nsim, seed)
+    keep = (model.max_iter, model.conv_tol)
+    try:
+        if max_iter is not None:
+            model.max_iter = int(max_iter)
+        if conv_tol is not None:
+            model.conv_tol = float(conv_tol)
+        ms = model.c_struct()
+        alpha = np.zeros((model.m, model.n + 1, nsim), order="F")
+        w = np.zeros(nsim)
+        ll = np.zeros(2)
+        check(lib().bssm_b200_importance_sample_ung(C.byref(ms), nsim, int(bool(use_antithetic)), seed, dptr(alpha),
+                                                    dptr(w), dptr(ll)))
+    finally:
+        model.max_iter, model.conv_tol = keep
+    out = {"alpha": np.transpose(alpha, (1, 0, 2)), "weights": w}
+    if return_loglik:
+        out["logLik"], out["approx_logLik"] = float(ll[0]), float(ll[1])
+    return out
+
+
 def logLik(model, particles, method="psi", seed=1, L=None):
-    """logLik (particle part), R/loglik.R:60-161: log-likelihood only."""
+    """logLik (particle part), R/loglik.R:60-161: log-likelihood only.  method "spdk" = non-sequential
+    importance sampling from the Gaussian approximation (src/model_ssm_ung.cpp:199-211)."""
+    if method == "spdk":
+        if not isinstance(model, Model) or model.distribution == "gaussian":
+            raise ValueError("method 'spdk': non-Gaussian ssm_ung models")
+        N, seed = _check_particles(model, particles, seed)
+        ms = model.c_struct()
+        ll = np.zeros(2)
+        check(lib().bssm_b200_importance_sample_ung(C.byref(ms), N, 1, seed, None, None, dptr(ll)))
+        return float(ll[0])
     job = FilterJob(model, particles, method=method, seed=seed, L=L)
     try:
         job.run()

@@ -29,6 +29,7 @@
 #include "prepass_ung.cuh"
 #include "smoother_kernels.cuh"
 #include "approx_device.cuh"
+#include "sim_smoother.cuh"
 #include "models_nlg_sde.cuh"
 #include "filters.h"
 #include "bssm_b200/ung_gauss_approx.h"
@@ -2298,6 +2299,93 @@ int bssm_b200_gaussian_psi_smoother(const bssm_ung_model* M, uint32_t nsim, uint
   pf::transpose_to_cube_kernel<<<dim3(cdiv(nsim, 32), cdiv(rows, 32)), dim3(32, 8)>>>(tm.p, cube.p, rows, nsim, 0u, rows);
   CU(cudaGetLastError());
   CU(cudaMemcpy(alpha, cube.p, sizeof(double) * (size_t)rows * nsim, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// importance_sample_ng for the ssm_ung family (src/R_importance_sample.cpp:9-75) and the SPDK branch of
+// ssm_ung::log_likelihood (src/model_ssm_ung.cpp:199-211): the Gaussian approximation and the gains of its
+// smoother on the host, once (O(n m^3)); the nsim simulated trajectories and their weights on the device.
+int bssm_b200_importance_sample_ung(const bssm_ung_model* M, uint32_t nsim, int use_antithetic, uint32_t seed,
+                                    double* alpha, double* weights, double* loglik) {
+  if (!M) return fail(BSSM_B200_ERR_ARG, "null argument");
+  if (M->n < 1 || M->m < 1 || M->k < 1 || M->k > M->m) return fail(BSSM_B200_ERR_ARG, "need n >= 1, 1 <= k <= m");
+  if (M->distribution < 0 || M->distribution > 4)
+    return fail(BSSM_B200_ERR_ARG, "importance_sample: non-Gaussian ssm_ung models (distribution 0..4)");
+  if (!M->u || !M->initial_mode) return fail(BSSM_B200_ERR_ARG, "importance_sample: u and initial_mode required");
+  if (M->m > 16) return fail(BSSM_B200_ERR_UNSUPPORTED, "state dimension m <= 16 in this build");
+  // nsim = 1 is the reference's separate single-draw shortcut (src/model_ssm_ulg.cpp:219-241): not a device job
+  if (nsim < 2) return fail(BSSM_B200_ERR_UNSUPPORTED, "importance_sample: nsim >= 2");
+  int rc = require_device();
+  if (rc) return rc;
+  const int n = M->n, m = M->m, k = M->k;
+  const size_t rows = (size_t)(n + 1) * m;
+  if (rows * nsim > ((size_t)1 << 32)) return fail(BSSM_B200_ERR_ARG, "importance_sample: (n + 1) m nsim <= 2^32");
+  pfga::UngApprox ga(M);
+  ga.run_head(nullptr);
+  pfga::UngApprox::SimGains sg;
+  std::vector<double> ahat;
+  ga.fast_smoother(ahat, &sg);
+  std::vector<double> LP1((size_t)m * m), rH(n), yp2(n);
+  psd_chol_host(M->P1, m, LP1.data()); // src/model_ssm_ulg.cpp:145
+  for (int t = 0; t < n; ++t) {
+    rH[t] = 1.0 / ga.aH[t];
+    const double q = M->y[t] / M->phi;
+    yp2[t] = q * q;
+  }
+  pf::SimParams sp{};
+  sp.n = n; sp.m = m; sp.k = k; sp.distribution = M->distribution;
+  sp.Ztv = M->Ztv; sp.Ttv = M->Ttv; sp.Rtv = M->Rtv; sp.Ctv = M->Ctv; sp.Dtv = M->Dtv;
+  sp.phi = M->phi; sp.seed = seed; sp.nsim = nsim; sp.antithetic = use_antithetic ? 1 : 0;
+  sp.nsim2 = use_antithetic ? nsim / 2 : nsim;
+  sp.threads = use_antithetic ? sp.nsim2 + (nsim & 1u) : nsim;
+  // one packed upload: every array below is a slice of it
+  std::vector<double> pack;
+  std::vector<std::pair<const double**, size_t>> slots;
+  auto put = [&](const double** dst, const double* src, size_t cnt) {
+    slots.emplace_back(dst, pack.size());
+    pack.insert(pack.end(), src, src + cnt);
+  };
+  const size_t mm = (size_t)m * m;
+  put(&sp.y, M->y, n); put(&sp.u, M->u, n);
+  if (M->xbeta) put(&sp.xbeta, M->xbeta, n);
+  put(&sp.Z, M->Z, (size_t)m * (M->Ztv ? n : 1)); put(&sp.T, M->T, mm * (M->Ttv ? n : 1));
+  put(&sp.R, M->R, (size_t)m * k * (M->Rtv ? n : 1)); put(&sp.C, M->C, (size_t)m * (M->Ctv ? n : 1));
+  put(&sp.D, M->D, M->Dtv ? n : 1); put(&sp.a1, M->a1, m); put(&sp.P1, M->P1, mm); put(&sp.LP1, LP1.data(), mm);
+  put(&sp.RR, sg.RR.data(), sg.RR.size());
+  put(&sp.ay, ga.ay.data(), n); put(&sp.aH, ga.aH.data(), n); put(&sp.rH, rH.data(), n); put(&sp.yphi2, yp2.data(), n);
+  put(&sp.F, sg.F.data(), n); put(&sp.K, sg.K.data(), (size_t)m * n); put(&sp.Lt, sg.Lt.data(), mm * n);
+  put(&sp.ahat, ahat.data(), rows);
+  DevBuf<double> dpack, tm, lw, v, r, cube;
+  if ((rc = dpack.upload(pack.data(), pack.size())) || (rc = tm.alloc(rows * nsim)) || (rc = lw.alloc(nsim)) ||
+      (rc = v.alloc((size_t)n * sp.threads)) || (rc = r.alloc((size_t)n * m * sp.threads)))
+    return rc;
+  for (auto& sl : slots) *sl.first = dpack.p + sl.second;
+  sp.alpha = tm.p; sp.logw = lw.p; sp.v = v.p; sp.r = r.p;
+  const dim3 grid(cdiv(sp.threads, 128));
+  const int mk = m > k ? m : k;
+  if (mk == 1) pf::sim_smoother_kernel<1><<<grid, 128>>>(sp);
+  else if (mk <= 4) pf::sim_smoother_kernel<4><<<grid, 128>>>(sp);
+  else pf::sim_smoother_kernel<16><<<grid, 128>>>(sp);
+  CU(cudaGetLastError());
+  std::vector<double> w(nsim);
+  CU(cudaMemcpy(w.data(), lw.p, sizeof(double) * nsim, cudaMemcpyDeviceToHost));
+  if (alpha) {
+    if ((rc = cube.alloc(rows * nsim))) return rc;
+    pf::transpose_to_cube_kernel<<<dim3(cdiv(nsim, 32), cdiv((uint32_t)rows, 32)), dim3(32, 8)>>>(
+        tm.p, cube.p, (uint32_t)rows, nsim, 0u, (uint32_t)rows);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(alpha, cube.p, sizeof(double) * rows * nsim, cudaMemcpyDeviceToHost));
+  }
+  // w - accu(scales), exp(w - max), mean (src/model_ssm_ung.cpp:206-210): nsim values, on the host
+  const double ssum = pfga::accu2(ga.scales.data(), (size_t)n);
+  double maxw = -std::numeric_limits<double>::infinity();
+  for (uint32_t i = 0; i < nsim; ++i) { w[i] -= ssum; if (w[i] > maxw) maxw = w[i]; }
+  for (uint32_t i = 0; i < nsim; ++i) w[i] = pf_exp(w[i] - maxw);
+  if (weights) std::copy(w.begin(), w.end(), weights);
+  if (loglik) {
+    loglik[0] = ga.approx_loglik + pf_log(pfga::accu2(w.data(), nsim) / nsim) + maxw;
+    loglik[1] = ga.approx_loglik;
+  }
   return 0;
 }
 

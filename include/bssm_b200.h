@@ -165,6 +165,18 @@ int bssm_b200_psi_smoother(const bssm_ung_model* model, uint32_t nsim, uint32_t 
  *           model->distribution must be BSSM_DIST_GAUSSIAN; alpha is m x (n+1) x nsim. */
 int bssm_b200_gaussian_psi_smoother(const bssm_ung_model* model, uint32_t nsim, uint32_t seed,
                                     double* alpha);
+/* importance_sample_ng(model_, nsim, use_antithetic, seed, model_type) for the ssm_ung family
+ * (src/R_importance_sample.cpp:9-75, RcppExports.cpp:1300) and the "spdk" method of
+ * nongaussian_loglik (src/R_loglik.cpp:41-87 -> ssm_ung::log_likelihood, src/model_ssm_ung.cpp:199-211):
+ * nsim >= 2 draws of the states from the smoothing distribution of the approximating Gaussian model
+ * (simulation smoother with one antithetic variable, src/model_ssm_ulg.cpp:141-217) and their
+ * importance weights.  alpha (m x (n+1) x nsim, or NULL), weights (nsim, exp(w - max w), or NULL),
+ * loglik (2 values or NULL: the SPDK estimate approx_loglik + log(mean(weights)) + max w, and
+ * approx_loglik).  Like the reference's simulate_states() declaration the smoother always pairs the
+ * draws when use_antithetic != 0 (draw i + nsim/2 mirrors draw i).  State dimension m <= 16. */
+int bssm_b200_importance_sample_ung(const bssm_ung_model* model, uint32_t nsim, int use_antithetic,
+                                    uint32_t seed, double* alpha, double* weights, double* loglik);
+
 /* psi-APF filter only (no backtrack/summary): the body of
  * ssm_ung::log_likelihood(method=1) src/model_ssm_ung.cpp:164-236 */
 int bssm_b200_psi_filter(const bssm_ung_model* model, uint32_t nsim, uint32_t seed,

@@ -402,12 +402,12 @@ PF_HD double pf_cos(double x) { double s, c; pf_sincos(x, &s, &c); return c; }
  *  filter = replicate / MCMC-draw index, so every filter of a batch has its
  *  own stream whatever GPU or CTA runs it.
  */
-enum { PF_RNG_NORMAL = 0, PF_RNG_RESAMPLE = 1, PF_RNG_PICK = 2 };
+enum { PF_RNG_NORMAL = 0, PF_RNG_RESAMPLE = 1, PF_RNG_PICK = 2, PF_RNG_SIM = 3 };
 
-/* Box-Muller pair for flat normal index pair `pair` */
-PF_HD void pf_normal_pair(uint32_t seed, uint32_t filter, uint32_t t, uint32_t sub,
-                          uint32_t pair, double* z0, double* z1) {
-  pf_u32x4 x = pf_philox4x32_10(pair, sub, t, filter, seed, (uint32_t)PF_RNG_NORMAL);
+/* Box-Muller pair for flat normal index pair `pair` of the stream with key (seed, purpose) */
+PF_HD void pf_normal_pair_of(uint32_t purpose, uint32_t seed, uint32_t filter, uint32_t t, uint32_t sub,
+                             uint32_t pair, double* z0, double* z1) {
+  pf_u32x4 x = pf_philox4x32_10(pair, sub, t, filter, seed, purpose);
   double u1 = pf_u53_open0(x.v[0], x.v[1]);
   double u2 = pf_u53(x.v[2], x.v[3]);
   double rad = sqrt(-2.0 * pf_log_normal(u1));
@@ -417,10 +417,25 @@ PF_HD void pf_normal_pair(uint32_t seed, uint32_t filter, uint32_t t, uint32_t s
   *z1 = rad * s;
 }
 
+PF_HD void pf_normal_pair(uint32_t seed, uint32_t filter, uint32_t t, uint32_t sub,
+                          uint32_t pair, double* z0, double* z1) {
+  pf_normal_pair_of((uint32_t)PF_RNG_NORMAL, seed, filter, t, sub, pair, z0, z1);
+}
+
 /* single normal with flat index f (convenience; evaluates the whole pair) */
 PF_HD double pf_normal(uint32_t seed, uint32_t filter, uint32_t t, uint32_t sub, uint32_t f) {
   double z0, z1;
   pf_normal_pair(seed, filter, t, sub, f >> 1, &z0, &z1);
+  return (f & 1u) ? z1 : z0;
+}
+
+/* PF_RNG_SIM: the normals of the simulation smoother (ssm_ulg::simulate_states, src/model_ssm_ulg.cpp:141-247),
+ * in the reference's consumption order per simulated trajectory i: column t = 0 takes m normals (the initial
+ * state, flat index i*m + d), column t >= 1 takes K = k + 1 (flat index i*K + d: d = 0 the observation noise of
+ * y_{t-1}, reserved also where y is missing, d = 1..k the state noise). */
+PF_HD double pf_sim_normal(uint32_t seed, uint32_t filter, uint32_t t, uint32_t f) {
+  double z0, z1;
+  pf_normal_pair_of((uint32_t)PF_RNG_SIM, seed, filter, t, 0u, f >> 1, &z0, &z1);
   return (f & 1u) ? z1 : z0;
 }
 

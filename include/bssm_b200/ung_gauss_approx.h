@@ -45,6 +45,16 @@ PF_HD double ung_log_obs(int dist, double s, double y, double u, double phi) {
   }
 }
 
+/* arma::accu of a vector: two accumulators over the even / odd elements [UNVENDORED], the
+ * convention every sum of this header that stands for accu() follows */
+inline double accu2(const double* x, size_t n) {
+  double a1 = 0.0, a2 = 0.0;
+  size_t j;
+  for (j = 1; j < n; j += 2) { a1 += x[j - 1]; a2 += x[j]; }
+  if ((j - 1) < n) a1 += x[j - 1];
+  return a1 + a2;
+}
+
 /* conditional_cov, SVD branch (src/conditional_dist.cpp:8-32), in place:
  * Pt (m x m x (n+1) smoothed covariances) becomes the factors L_t = U sqrt(s),
  * ccov (lag-one covariances) becomes C_t = Cov_{t-1}' V_{t-1}^+ */
@@ -224,8 +234,16 @@ struct UngApprox {
     return logLik;
   }
 
-  /* ssm_ulg::fast_smoother, src/model_ssm_ulg.cpp:252-305: at is m x (n+1) */
-  void fast_smoother(std::vector<double>& at) const {
+  /* what ssm_ulg::fast_precomputing_smoother keeps for the simulation smoother (src/model_ssm_ulg.cpp:359-413):
+   * F_t, K_t (m x n), L_t = T_t (I - K_t Z_t') (m x m x n; also for t = 0, which the reference rebuilds at :400),
+   * the time points that were updated and R_t R_t' */
+  struct SimGains {
+    std::vector<double> F, K, Lt, RR;
+    std::vector<char> used;
+  };
+  /* ssm_ulg::fast_smoother, src/model_ssm_ulg.cpp:252-305: at is m x (n+1); with `keep` it is
+   * fast_precomputing_smoother (:359-413, the same arithmetic) */
+  void fast_smoother(std::vector<double>& at, SimGains* keep = nullptr) const {
     at.assign((size_t)m * (n + 1), 0.0);
     std::vector<double> Pt(M->P1, M->P1 + (size_t)m * m), Pn((size_t)m * m);
     std::vector<Step> st(n);
@@ -274,6 +292,20 @@ struct UngApprox {
       RR(t, rr.data());
       pf_mm(rr.data(), &rt[(size_t)m * t], rrr.data(), m, m, 1);
       for (int i = 0; i < m; ++i) at[i + (size_t)m * (t + 1)] = C(t)[i] + ta[i] + rrr[i];
+    }
+    if (keep) {
+      const size_t mm = (size_t)m * m;
+      keep->F.assign(n, 0.0); keep->K.assign((size_t)m * n, 0.0); keep->Lt.assign(mm * n, 0.0);
+      keep->used.assign(used.begin(), used.end());
+      for (int t = 0; t < n; ++t) {
+        keep->F[t] = st[t].F;
+        if (!used[t]) continue;
+        for (int i = 0; i < m; ++i) keep->K[i + (size_t)m * t] = st[t].K[i];
+        Lmat(t, &keep->Lt[mm * t]);
+      }
+      const int nR = M->Rtv ? n : 1;
+      keep->RR.assign(mm * nR, 0.0);
+      for (int t = 0; t < nR; ++t) RR(t, &keep->RR[mm * t]);
     }
   }
 
@@ -372,6 +404,11 @@ struct UngApprox {
   /* the head of psi_filter: mode_in == nullptr -> approximate() + approx_loglik (:514-528);
    * mode_in != nullptr -> approximate_for_is (:143-161) */
   void run(const double* mode_in) {
+    run_head(mode_in);
+    smoother_and_conditional();
+  }
+  /* the same without the conditional covariances (all the simulation smoother needs) */
+  void run_head(const double* mode_in) {
     if (mode_in) {
       for (int t = 0; t < n; ++t) mode[t] = mode_in[t];
       laplace_iter(mode);
@@ -409,7 +446,6 @@ struct UngApprox {
       if ((j - 1) < n) a1 += scales[j - 1];
       approx_loglik = gl + (c - norm) + (a1 + a2);
     }
-    smoother_and_conditional();
   }
 };
 

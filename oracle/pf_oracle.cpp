@@ -887,6 +887,212 @@ double orc_ung_psi_filter_m(const bssm_ung_model* M, const double* mode_in, uint
   return loglik;
 }
 
+/* importance_sample_ng for the ssm_ung family (src/R_importance_sample.cpp:26-37) and the SPDK branch of
+ * ssm_ung::log_likelihood (src/model_ssm_ung.cpp:199-211): ssm_ulg::simulate_states with nsim > 1
+ * (src/model_ssm_ulg.cpp:141-217), fast_precomputing_smoother (:359-413) and fast_smoother with the stored
+ * gains (:311-357), restated here with the reference's loop structure (trajectory after trajectory, the
+ * smoother as three sweeps over vectors); only the Gaussian approximation itself (pseudo-observations,
+ * scales, approx_loglik) is the shared ung_gauss_approx.h.  Normals: pf_sim_normal (pf_math.h).
+ * alpha is m x (n+1) x nsim; weights = exp(w - max w); loglik[0] = SPDK estimate, loglik[1] = approx_loglik. */
+static void psd_chol(const double* x, int m, std::vector<double>& cholx);
+namespace {
+struct SimSmoother {
+  const bssm_ung_model* M;
+  const pfga::UngApprox& ga;
+  int n, m, k;
+  std::vector<double> Ft, Kt, Lt, xbeta;
+  static constexpr double zero_tol = 1e-12;
+  SimSmoother(const bssm_ung_model* M_, const pfga::UngApprox& ga_) : M(M_), ga(ga_), n(M_->n), m(M_->m), k(M_->k) {
+    Ft.assign(n, 0.0); Kt.assign((size_t)m * n, 0.0); Lt.assign((size_t)m * m * n, 0.0);
+    xbeta.assign(n, 0.0);
+    if (M->xbeta) for (int t = 0; t < n; ++t) xbeta[t] = M->xbeta[t];
+  }
+  const double* Z(int t) const { return M->Z + (size_t)m * (t * M->Ztv); }
+  const double* T(int t) const { return M->T + (size_t)m * m * (t * M->Ttv); }
+  const double* R(int t) const { return M->R + (size_t)m * k * (t * M->Rtv); }
+  const double* C(int t) const { return M->C + (size_t)m * (t * M->Ctv); }
+  double D(int t) const { return M->D[t * M->Dtv]; }
+  void matvec(const double* A, const double* x, double* out, bool transpose) const {
+    for (int i = 0; i < m; ++i) {
+      double s = 0.0;
+      for (int j = 0; j < m; ++j) s += (transpose ? A[j + m * i] : A[i + m * j]) * x[j];
+      out[i] = s;
+    }
+  }
+  /* the smoother of series y (n values): precompute = true fills Ft, Kt, Lt from the covariance recursion
+   * (:359-413), false uses them (:311-357).  at is m x (n+1). */
+  void smooth(const std::vector<double>& y, bool precompute, std::vector<double>& at) {
+    const size_t mm = (size_t)m * m;
+    at.assign((size_t)m * (n + 1), 0.0);
+    std::vector<double> Pt(M->P1, M->P1 + mm), vt(n, 0.0), ytmp(n), tmp(m), ta(m);
+    for (int i = 0; i < m; ++i) at[i] = M->a1[i];
+    for (int t = 0; t < n; ++t) ytmp[t] = M->xbeta ? y[t] - xbeta[t] : y[t];
+    for (int t = 0; t < n; ++t) {
+      double* a = &at[(size_t)m * t];
+      if (precompute) {
+        /* F = Z' P Z + HH */
+        std::vector<double> zp(m);
+        for (int j = 0; j < m; ++j) { double s = 0.0; for (int i = 0; i < m; ++i) s += Z(t)[i] * Pt[i + m * j]; zp[j] = s; }
+        double f = 0.0;
+        for (int i = 0; i < m; ++i) f += zp[i] * Z(t)[i];
+        Ft[t] = f + ga.aHH[t];
+      }
+      const bool used = std::isfinite(ytmp[t]) && Ft[t] > zero_tol;
+      if (used) {
+        if (precompute) {
+          std::vector<double> pz(m);
+          matvec(Pt.data(), Z(t), pz.data(), false);
+          for (int i = 0; i < m; ++i) Kt[i + (size_t)m * t] = pz[i] / Ft[t];
+        }
+        double za = 0.0;
+        for (int i = 0; i < m; ++i) za += Z(t)[i] * a[i];
+        vt[t] = ytmp[t] - D(t) - za;
+        for (int i = 0; i < m; ++i) tmp[i] = a[i] + Kt[i + (size_t)m * t] * vt[t];
+      } else {
+        for (int i = 0; i < m; ++i) tmp[i] = a[i];
+      }
+      matvec(T(t), tmp.data(), ta.data(), false);
+      for (int i = 0; i < m; ++i) at[i + (size_t)m * (t + 1)] = C(t)[i] + ta[i];
+      if (precompute) {
+        /* Joseph form, :372-376 */
+        std::vector<double> X(mm), A(mm), B(mm), J(mm), rr(mm);
+        if (used) {
+          for (int j = 0; j < m; ++j)
+            for (int i = 0; i < m; ++i) J[i + m * j] = (i == j ? 1.0 : 0.0) - Kt[i + (size_t)m * t] * Z(t)[j];
+          pf_mm(J.data(), Pt.data(), A.data(), m, m, m);
+          pf_mmt(A.data(), J.data(), B.data(), m, m, m);
+          for (int j = 0; j < m; ++j)
+            for (int i = 0; i < m; ++i)
+              X[i + m * j] = B[i + m * j] + Kt[i + (size_t)m * t] * ga.aHH[t] * Kt[j + (size_t)m * t];
+        } else {
+          X = Pt;
+        }
+        pf_mm(T(t), X.data(), A.data(), m, m, m);
+        pf_mmt(A.data(), T(t), B.data(), m, m, m);
+        pf_mmt(R(t), R(t), rr.data(), m, k, m);
+        for (size_t e = 0; e < mm; ++e) Pt[e] = B[e] + rr[e];
+        pf_symmatu(Pt.data(), m);
+      }
+    }
+    std::vector<double> rt((size_t)m * n, 0.0), lr(m), w(m), pw(m), J(mm);
+    auto Lmat = [&](int t, double* Lm) {
+      for (int j = 0; j < m; ++j)
+        for (int i = 0; i < m; ++i) J[i + m * j] = (i == j ? 1.0 : 0.0) - Kt[i + (size_t)m * t] * Z(t)[j];
+      pf_mm(T(t), J.data(), Lm, m, m, m);
+    };
+    for (int t = n - 1; t > 0; --t) {
+      if (std::isfinite(ytmp[t]) && Ft[t] > zero_tol) {
+        if (precompute) Lmat(t, &Lt[mm * t]);
+        matvec(&Lt[mm * t], &rt[(size_t)m * t], lr.data(), true);
+        for (int i = 0; i < m; ++i) rt[i + (size_t)m * (t - 1)] = Z(t)[i] / Ft[t] * vt[t] + lr[i];
+      } else {
+        matvec(T(t), &rt[(size_t)m * t], &rt[(size_t)m * (t - 1)], true);
+      }
+    }
+    if (std::isfinite(ytmp[0]) && Ft[0] > zero_tol) {
+      std::vector<double> L0(mm);
+      Lmat(0, L0.data());
+      matvec(L0.data(), &rt[0], lr.data(), true);
+      for (int i = 0; i < m; ++i) w[i] = Z(0)[i] / Ft[0] * vt[0] + lr[i];
+      matvec(M->P1, w.data(), pw.data(), false);
+    } else if (m == 1) {
+      pw[0] = M->P1[0] * T(0)[0] * rt[0]; /* 1 x 1 operands associate from the left */
+    } else {
+      matvec(T(0), &rt[0], w.data(), true);
+      matvec(M->P1, w.data(), pw.data(), false);
+    }
+    for (int i = 0; i < m; ++i) at[i] = M->a1[i] + pw[i];
+    std::vector<double> rr(mm), rrr(m);
+    for (int t = 0; t < n - 1; ++t) {
+      matvec(T(t), &at[(size_t)m * t], ta.data(), false);
+      pf_mmt(R(t), R(t), rr.data(), m, k, m);
+      matvec(rr.data(), &rt[(size_t)m * t], rrr.data(), false);
+      for (int i = 0; i < m; ++i) at[i + (size_t)m * (t + 1)] = C(t)[i] + ta[i] + rrr[i];
+    }
+  }
+};
+} // namespace
+
+extern "C" int orc_importance_sample_ung(const bssm_ung_model* M, uint32_t nsim, int use_antithetic, uint32_t seed,
+                                         double* alpha, double* weights, double* loglik, double* alphahat_out,
+                                         double* ytilde_out, double* Htilde_out) {
+  if (nsim < 2) return 1;
+  const int n = M->n, m = M->m, k = M->k;
+  pfga::UngApprox ga(M);
+  ga.run_head(nullptr);
+  Ung g(M);
+  g.ay = ga.ay; g.aH = ga.aH; g.scales = ga.scales;
+  SimSmoother S(M, ga);
+  std::vector<double> alphahat, L_P1;
+  S.smooth(ga.ay, true, alphahat);
+  if (alphahat_out) std::copy(alphahat.begin(), alphahat.end(), alphahat_out);
+  if (ytilde_out) std::copy(ga.ay.begin(), ga.ay.end(), ytilde_out);
+  if (Htilde_out) std::copy(ga.aH.begin(), ga.aH.end(), Htilde_out);
+  psd_chol(M->P1, m, L_P1);
+  const size_t sl = (size_t)m * (n + 1);
+  const uint32_t nsim2 = use_antithetic ? nsim / 2 : nsim;
+  std::vector<double> aplus(sl), yplus(n), sm, um(m), uk(k);
+  const uint32_t K1 = (uint32_t)k + 1;
+  auto simulate = [&](uint32_t i) { /* :165-182 */
+    for (int j = 0; j < m; ++j) um[j] = pf_sim_normal(seed, 0u, 0u, i * (uint32_t)m + j);
+    for (int d = 0; d < m; ++d) {
+      double s = 0.0;
+      for (int j = 0; j < m; ++j) s += L_P1[d + (size_t)m * j] * um[j];
+      aplus[d] = M->a1[d] + s;
+    }
+    for (int t = 0; t < n; ++t) {
+      const double* a = &aplus[(size_t)m * t];
+      yplus[t] = M->y[t];
+      if (std::isfinite(M->y[t])) {
+        double za = 0.0;
+        for (int d = 0; d < m; ++d) za += S.Z(t)[d] * a[d];
+        yplus[t] = S.xbeta[t] + S.D(t) + za + ga.aH[t] * pf_sim_normal(seed, 0u, (uint32_t)(t + 1), i * K1);
+      }
+      for (int j = 0; j < k; ++j) uk[j] = pf_sim_normal(seed, 0u, (uint32_t)(t + 1), i * K1 + 1 + j);
+      for (int d = 0; d < m; ++d) {
+        double ta = 0.0, ru = 0.0;
+        for (int j = 0; j < m; ++j) ta += S.T(t)[d + m * j] * a[j];
+        for (int j = 0; j < k; ++j) ru += S.R(t)[d + m * j] * uk[j];
+        aplus[d + (size_t)m * (t + 1)] = S.C(t)[d] + ta + ru;
+      }
+    }
+    S.smooth(yplus, false, sm);
+  };
+  for (uint32_t i = 0; i < nsim2; ++i) {
+    simulate(i);
+    double* ai = alpha + sl * i;
+    for (size_t e = 0; e < sl; ++e) ai[e] = -sm[e] + aplus[e]; /* :184 */
+    if (use_antithetic) {
+      double* aj = alpha + sl * (i + nsim2);
+      for (size_t e = 0; e < sl; ++e) aj[e] = alphahat[e] - ai[e]; /* :186 */
+    }
+    for (size_t e = 0; e < sl; ++e) ai[e] += alphahat[e]; /* :188 */
+  }
+  if (use_antithetic && 2 * nsim2 < nsim) { /* :190-217 */
+    simulate(nsim2);
+    double* ai = alpha + sl * (nsim - 1);
+    for (size_t e = 0; e < sl; ++e) ai[e] = alphahat[e] - sm[e] + aplus[e];
+  }
+  /* importance_weights (src/model_ssm_ung.cpp:372-378) */
+  std::vector<double> w(nsim, 0.0);
+  for (int t = 0; t < n; ++t) {
+    if (!std::isfinite(M->y[t])) continue;
+    for (uint32_t i = 0; i < nsim; ++i) w[i] += g.log_weight_pf(t, g.signal(t, alpha + sl * i + (size_t)m * t));
+  }
+  const double ssum = pfga::accu2(ga.scales.data(), (size_t)n);
+  double maxw = -ORC_INF;
+  for (uint32_t i = 0; i < nsim; ++i) { w[i] -= ssum; if (w[i] > maxw) maxw = w[i]; }
+  for (uint32_t i = 0; i < nsim; ++i) w[i] = pf_exp(w[i] - maxw);
+  if (weights) std::copy(w.begin(), w.end(), weights);
+  if (loglik) {
+    loglik[0] = ga.approx_loglik + pf_log(pfga::accu2(w.data(), nsim) / nsim) + maxw;
+    loglik[1] = ga.approx_loglik;
+  }
+  return 0;
+}
+/* the normals of the simulation smoother, for the numpy pin of tests/test_oracle.py */
+extern "C" double orc_sim_normal(uint32_t seed, uint32_t t, uint32_t f) { return pf_sim_normal(seed, 0u, t, f); }
+
 /* ------------------------------------------------------------------ a10 */
 /* filter_smoother, src/filter_smoother.cpp:5-18: alpha m x n1 x N in place */
 void orc_filter_smoother(double* alpha, const uint32_t* indices, int m, int n1, uint32_t N) {

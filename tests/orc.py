@@ -405,6 +405,32 @@ def psi_filter_m(model, N, seed, filt=0, arith=ARITH_REPRO, mode=None):
     return r
 
 
+def importance_sample(model, nsim, seed, use_antithetic=True, approx=False):
+    """simulation smoother + SPDK weights: alpha (m, n+1, nsim), weights, (logLik, approx_logLik), alphahat"""
+    lib = L()
+    lib.orc_importance_sample_ung.argtypes = [C.POINTER(UngModel), C.c_uint32, C.c_int, C.c_uint32] + [c_double_p] * 6
+    n, m = model.n, model.m
+    ms = model.c_struct()
+    alpha = np.zeros((m, n + 1, nsim), order="F")
+    w = np.zeros(nsim)
+    ll = np.zeros(2)
+    ah = np.zeros((m, n + 1), order="F")
+    yt, Ht = np.zeros(n), np.zeros(n)
+    rc = lib.orc_importance_sample_ung(C.byref(ms), nsim, int(use_antithetic), seed, dptr(alpha), dptr(w), dptr(ll),
+                                       dptr(ah), dptr(yt), dptr(Ht))
+    assert rc == 0
+    if approx:
+        return alpha, w, ll, ah, yt, Ht
+    return alpha, w, ll, ah
+
+
+def sim_normal(seed, t, f):
+    lib = L()
+    lib.orc_sim_normal.restype = C.c_double
+    lib.orc_sim_normal.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+    return lib.orc_sim_normal(seed, t, f)
+
+
 def mng_bsf_filter(model, N, seed, filt=0, arith=ARITH_REPRO):
     r = _alloc(model, N)
     ms = model.c_struct()

@@ -1,0 +1,88 @@
+"""SURVEY.md 8(f) rank 4, SPDK: importance_sample() and logLik(method = "spdk") -- the simulation smoother of
+the approximating Gaussian model (ssm_ulg::simulate_states, src/model_ssm_ulg.cpp:141-217, with the stored
+gains of fast_precomputing_smoother :359-413) and the importance weights of src/model_ssm_ung.cpp:199-211,
+372-378.  One thread per antithetic pair of trajectories (bssm_b200/csrc/sim_smoother.cuh) must give the
+oracle's bits: the oracle's restatement is pinned against dense numpy conditioning in tests/test_oracle.py."""
+import numpy as np
+import pytest
+
+import bssm_b200
+import data
+import orc
+from test_gpu_general_m import seasonal_model
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(res, ref):
+    alpha, w, ll, _ = ref
+    got = np.transpose(res["alpha"], (1, 0, 2))
+    assert np.array_equal(got.view(np.uint64), alpha.view(np.uint64))
+    assert np.array_equal(res["weights"].view(np.uint64), w.view(np.uint64))
+    assert res["logLik"] == ll[0] and res["approx_logLik"] == ll[1]
+
+
+@pytest.mark.parametrize("nsim", [2, 3, 64, 257, 1000])
+def test_importance_sample_svm(engine, nsim):
+    model = data.svm_model(n=300, missing=(0, 17, 299))
+    res = engine.importance_sample(model, nsim, seed=5, return_loglik=True)
+    _same(res, orc.importance_sample(model, nsim, 5))
+
+
+@pytest.mark.parametrize("nsim,antithetic", [(100, True), (101, True), (50, False), (51, False)])
+def test_importance_sample_poisson_bsm(engine, nsim, antithetic):
+    model = data.poisson_bsm_model(missing=(4, 50, 99))
+    res = engine.importance_sample(model, nsim, use_antithetic=antithetic, seed=2, return_loglik=True)
+    _same(res, orc.importance_sample(model, nsim, 2, use_antithetic=antithetic))
+    if antithetic:  # the mirrored halves average to the smoothed mean of the approximating model
+        h = nsim // 2
+        a = res["alpha"]
+        mid = 0.5 * (a[:, :, :h] + a[:, :, h:2 * h])
+        assert np.abs(mid - mid[:, :, :1]).max() < 1e-12
+
+
+@pytest.mark.parametrize("period,dist", [(4, "poisson"), (12, "negative binomial")])
+def test_importance_sample_seasonal(engine, period, dist):
+    """m = 5 and m = 13: the run-time-dimension instantiation"""
+    model = seasonal_model(period, dist=dist)
+    res = engine.importance_sample(model, 129, seed=8, return_loglik=True)
+    _same(res, orc.importance_sample(model, 129, 8))
+
+
+@pytest.mark.parametrize("dist", ["poisson", "binomial", "negative binomial", "gamma"])
+def test_importance_sample_ar1_ng_with_regressors(engine, dist):
+    rng = np.random.default_rng(4)
+    n = 60
+    x = rng.normal(size=n)
+    u = np.full(n, 10.0) if dist == "binomial" else np.ones(n)
+    lam = np.exp(0.4 + 0.3 * x)
+    if dist == "binomial":
+        y = rng.binomial(10, 1 / (1 + np.exp(-0.3 * x))).astype(float)
+    elif dist == "gamma":
+        y = rng.gamma(3.0, lam / 3.0)
+    else:
+        y = rng.poisson(lam).astype(float)
+    y[9] = np.nan
+    model = bssm_b200.ar1_ng(y, rho=0.8, sigma=0.3, mu=0.2, distribution=dist, phi=3.0, u=u, xreg=x[:, None],
+                             beta=np.array([0.3]))
+    res = engine.importance_sample(model, 200, seed=3, return_loglik=True)
+    _same(res, orc.importance_sample(model, 200, 3))
+
+
+def test_loglik_spdk(engine):
+    model = data.poisson_bsm_model()
+    ll = engine.logLik(model, 1000, method="spdk", seed=9)
+    ref = orc.importance_sample(model, 1000, 9)[2]
+    assert ll == ref[0]
+    psi = engine.logLik(model, 1000, method="psi", seed=9)
+    assert abs(ll - psi) < 0.05
+
+
+def test_importance_sample_argument_checks(engine):
+    model = data.poisson_bsm_model()
+    with pytest.raises(ValueError):
+        engine.importance_sample(model, 10, use_antithetic=1)
+    with pytest.raises(ValueError):
+        engine.importance_sample(model, 1)
+    with pytest.raises(ValueError):
+        engine.importance_sample(data.lg_model(), 10)

@@ -514,3 +514,89 @@ def test_jacobi_stops_at_its_fixed_point_with_the_same_bits(tmp_path):
                     os.path.join(root, "tests", "aux", "jacobi_fixed_point_check.cpp"), "-o", str(exe)], check=True)
     tot, bad = map(int, subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split())
     assert tot == 13 * 1500 and bad == 0
+
+
+def _dense_conditional_mean(model, ytilde, Htilde, ysim):
+    """E[alpha_0..alpha_n | y] of the linear-Gaussian model (ytilde's structure, sd Htilde) by conditioning the
+    joint normal of all states and the observed y with numpy: mean and covariance of the stacked states from
+    the recursion alpha_{t+1} = C + T alpha_t + R eta, then the textbook formula."""
+    n, m = model.n, model.m
+    Z = np.asarray(model.Z).reshape(m, -1)
+    T = np.asarray(model.T).reshape(m, m, -1)
+    R = np.asarray(model.R).reshape(m, model.k, -1)
+    Cm = np.asarray(model.C).reshape(m, -1)
+    D = np.ravel(model.D)
+    tv = lambda a, t: a[..., t if a.shape[-1] > 1 else 0]
+    mu = np.zeros((n + 1, m))
+    S = np.zeros((n + 1, m, n + 1, m))
+    mu[0] = np.ravel(model.a1)
+    S[0, :, 0, :] = np.asarray(model.P1).reshape(m, m)
+    for t in range(n):
+        Tt, Rt = tv(T, t), tv(R, t)
+        mu[t + 1] = tv(Cm, t) + Tt @ mu[t]
+        for s in range(t + 1):
+            S[t + 1, :, s, :] = Tt @ S[t, :, s, :]
+            S[s, :, t + 1, :] = S[t + 1, :, s, :].T
+        S[t + 1, :, t + 1, :] = Tt @ S[t, :, t, :] @ Tt.T + Rt @ Rt.T
+    Sf = S.reshape((n + 1) * m, (n + 1) * m)
+    obs = [t for t in range(n) if np.isfinite(ysim[t])]
+    A = np.zeros((len(obs), (n + 1) * m))
+    for r, t in enumerate(obs):
+        A[r, t * m:(t + 1) * m] = tv(Z, t)
+    d = np.array([tv(D, t) for t in obs])
+    Syy = A @ Sf @ A.T + np.diag(Htilde[obs] ** 2)
+    resid = ysim[obs] - (A @ mu.ravel() + d)
+    return (mu.ravel() + Sf @ A.T @ np.linalg.solve(Syy, resid)).reshape(n + 1, m).T
+
+
+def test_simulation_smoother_against_dense_gaussian_conditioning():
+    """The draws of the oracle's simulation smoother (ssm_ulg::simulate_states, src/model_ssm_ulg.cpp:141-217)
+    are alpha+ - E[alpha | y+] + E[alpha | ytilde]: rebuilt here with numpy from the same normals by conditioning
+    the dense joint normal -- pins the three-sweep smoother with stored gains, missing values included."""
+    rng = np.random.default_rng(11)
+    n = 12
+    y = rng.poisson(4, size=n).astype(float)
+    y[3] = np.nan
+    y[n - 1] = np.nan
+    model = bssm_b200.bsm_ng(y, sd_level=0.3, sd_slope=0.05, distribution="poisson", P1=np.diag([1.0, 0.5]))
+    m, k = model.m, model.k
+    seed, nsim = 5, 7
+    alpha, w, ll, ahat, yt, Ht = orc.importance_sample(model, nsim, seed, approx=True)
+    assert np.abs(ahat - _dense_conditional_mean(model, yt, Ht, yt)).max() < 1e-9
+    Z = np.asarray(model.Z).reshape(m, -1)[:, 0]
+    T = np.asarray(model.T).reshape(m, m, -1)[:, :, 0]
+    R = np.asarray(model.R).reshape(m, k, -1)[:, :, 0]
+    L1 = np.linalg.cholesky(np.asarray(model.P1).reshape(m, m))
+    nsim2 = nsim // 2
+    for i in list(range(nsim2)) + [nsim2]:
+        ap = np.zeros((m, n + 1))
+        yp = np.full(n, np.nan)
+        ap[:, 0] = np.ravel(model.a1) + L1 @ np.array([orc.sim_normal(seed, 0, i * m + d) for d in range(m)])
+        for t in range(n):
+            if np.isfinite(y[t]):
+                yp[t] = Z @ ap[:, t] + Ht[t] * orc.sim_normal(seed, t + 1, i * (k + 1))
+            uk = np.array([orc.sim_normal(seed, t + 1, i * (k + 1) + 1 + j) for j in range(k)])
+            ap[:, t + 1] = T @ ap[:, t] + R @ uk
+        draw = ap - _dense_conditional_mean(model, yt, Ht, yp) + ahat
+        if i < nsim2:
+            assert np.abs(alpha[:, :, i] - draw).max() < 1e-9
+            assert np.abs(alpha[:, :, i + nsim2] - (2 * ahat - draw)).max() < 1e-9
+        else:
+            assert np.abs(alpha[:, :, nsim - 1] - draw).max() < 1e-9  # the unpaired last draw of an odd nsim
+
+
+def test_spdk_loglik_agrees_with_the_psi_filter():
+    """SPDK and psi-APF estimate the same likelihood (src/model_ssm_ung.cpp:196-211): both correct approx_loglik
+    by importance weights of the same form"""
+    model = data.poisson_bsm_model()
+    _, w, ll, _ = orc.importance_sample(model, 4000, 3)
+    r = orc.psi_filter_m(model, 4000, 3)
+    assert ll[1] == r.approx_loglik
+    assert abs(ll[0] - r.loglik) < 0.05
+    assert w.max() == 1.0 and w.min() > 0.0
+    # svm (m = 1)
+    svm = data.svm_model(n=200)
+    _, _, ll, _ = orc.importance_sample(svm, 4000, 3)
+    r = orc.psi_filter(svm, 4000, 3)
+    assert ll[1] == r.approx_loglik
+    assert abs(ll[0] - r.loglik) < 0.3
