@@ -36,10 +36,18 @@ bsf_smoother <- function(model_, nsim, seed, gaussian, model_type) {
 }
 
 nongaussian_loglik <- function(model_, nsim, sampling_method, seed, model_type) {
-  if (sampling_method > 2 || nsim == 0)   # SPDK / pure approximation stay on the CPU path
+  # the pure approximation (nsim = 0), SPDK with a single draw and SPDK of ssm_mng stay on the CPU path
+  if (nsim == 0 || (sampling_method == 3 && (nsim < 2 || model_type == 0)))
     return(bssm:::nongaussian_loglik(model_, nsim, sampling_method, seed, model_type))
   model_$u <- rep_len(model_$u, length(model_$y))
   .Call("_bssmb200_nongaussian_loglik", model_, nsim, sampling_method, seed, model_type)
+}
+
+importance_sample_ng <- function(model_, nsim, use_antithetic, seed, model_type) {
+  if (model_type == 0 || nsim < 2)
+    return(bssm:::importance_sample_ng(model_, nsim, use_antithetic, seed, model_type))
+  model_$u <- rep_len(model_$u, length(model_$y))
+  .Call("_bssmb200_importance_sample_ng", model_, nsim, use_antithetic, seed, model_type)
 }
 
 suggest_n_nongaussian <- function(model_, theta, candidates, replications, seed, model_type) {
@@ -117,7 +125,7 @@ loglik_sde <- function(y, x0, positive, drift, diffusion, ddiffusion, log_prior_
 stratified_sample <- function(p, r, N) .Call("_bssmb200_stratified_sample", as.numeric(p), as.numeric(r), as.integer(N))
 
 # check_intmax caps particles at 1e5 (R/check_arguments.R:407-418); the GPU path lifts it
-for (f in c("bsf", "bsf_smoother", "psi_smoother", "nongaussian_loglik", "suggest_n_nongaussian",
+for (f in c("bsf", "bsf_smoother", "psi_smoother", "nongaussian_loglik", "importance_sample_ng", "suggest_n_nongaussian",
             "postcorrection_nongaussian", "bsf_nlg", "bsf_smoother_nlg", "psi_smoother_nlg",
             "postcorrection_nonlinear", "bsf_sde", "bsf_smoother_sde", "loglik_sde", "stratified_sample")) {
   fn <- get(f)

@@ -275,7 +275,7 @@ SEXP _bssmb200_bsf_smoother(SEXP model_, SEXP nsim_, SEXP seed_, SEXP gaussian_,
 }
 
 /* nongaussian_loglik(model_, nsim, sampling_method, seed, model_type): src/R_loglik.cpp:41-87.
- * sampling_method 1 = psi-APF, 2 = bootstrap filter; nothing but the scalar crosses PCIe. */
+ * sampling_method 1 = psi-APF, 2 = bootstrap filter, 3 = SPDK (ssm_ung family); nothing but the scalar crosses PCIe. */
 SEXP _bssmb200_nongaussian_loglik(SEXP model_, SEXP nsim_, SEXP sampling_method_, SEXP seed_, SEXP model_type_) {
   if (asInteger(model_type_) == 0) {
     int sm = asInteger(sampling_method_);
@@ -291,8 +291,32 @@ SEXP _bssmb200_nongaussian_loglik(SEXP model_, SEXP nsim_, SEXP sampling_method_
   int method = asInteger(sampling_method_);
   if (method == 1) check_rc(bssm_b200_psi_filter(&M, (unsigned)asInteger(nsim_), (unsigned)asInteger(seed_), &out));
   else if (method == 2) check_rc(bssm_b200_bsf(&M, (unsigned)asInteger(nsim_), (unsigned)asInteger(seed_), &out));
-  else error("bssm_b200: sampling_method must be 1 (psi) or 2 (bsf); SPDK stays on bssm's CPU path");
+  else if (method == 3) { /* SPDK, src/model_ssm_ung.cpp:199-211 */
+    double ll[2];
+    check_rc(bssm_b200_importance_sample_ung(&M, (unsigned)asInteger(nsim_), 1, (unsigned)asInteger(seed_), NULL, NULL, ll));
+    return ScalarReal(ll[0]);
+  } else error("bssm_b200: sampling_method must be 1 (psi), 2 (bsf) or 3 (spdk)");
   return ScalarReal(out.loglik);
+}
+
+/* importance_sample_ng(model_, nsim, use_antithetic, seed, model_type): src/R_importance_sample.cpp:9-75.
+ * list(alpha = m x (n+1) x nsim, weights = nsim); the R caller does the aperm (R/importance_sample.R:68). */
+SEXP _bssmb200_importance_sample_ng(SEXP model_, SEXP nsim_, SEXP use_antithetic_, SEXP seed_, SEXP model_type_) {
+  if (asInteger(model_type_) == 0) error("bssm_b200: importance_sample of ssm_mng models stays on bssm's CPU path");
+  bssm_ung_model M;
+  int n = (int)XLENGTH(list_get(model_, "y")), m = (int)XLENGTH(list_get(model_, "a1"));
+  double* xb = (double*)R_alloc(n, sizeof(double));
+  fill_ung(model_, &M, xb);
+  const unsigned N = (unsigned)asInteger(nsim_);
+  SEXP alpha = PROTECT(alloc3DArray(REALSXP, m, n + 1, N)), w = PROTECT(allocVector(REALSXP, N));
+  /* the reference's wrapper drops use_antithetic (simulate_states(nsim) pairs the draws, :29): so do we */
+  (void)use_antithetic_;
+  check_rc(bssm_b200_importance_sample_ung(&M, N, 1, (unsigned)asInteger(seed_), REAL(alpha), REAL(w), NULL));
+  const char* nm[] = {"alpha", "weights", ""};
+  SEXP res = PROTECT(mkNamed(VECSXP, nm));
+  SET_VECTOR_ELT(res, 0, alpha); SET_VECTOR_ELT(res, 1, w);
+  UNPROTECT(3);
+  return res;
 }
 
 /* suggest_n_nongaussian(model_, theta, candidates, replications, seed, model_type): src/R_postcorrection.cpp:14-104 */
@@ -640,6 +664,7 @@ static const R_CallMethodDef CallEntries[] = {
   {"_bssmb200_psi_smoother", (DL_FUNC)&_bssmb200_psi_smoother, 4},
   {"_bssmb200_bsf_smoother", (DL_FUNC)&_bssmb200_bsf_smoother, 5},
   {"_bssmb200_nongaussian_loglik", (DL_FUNC)&_bssmb200_nongaussian_loglik, 5},
+  {"_bssmb200_importance_sample_ng", (DL_FUNC)&_bssmb200_importance_sample_ng, 5},
   {"_bssmb200_suggest_n_nongaussian", (DL_FUNC)&_bssmb200_suggest_n_nongaussian, 6},
   {"_bssmb200_postcorrection_nongaussian", (DL_FUNC)&_bssmb200_postcorrection_nongaussian, 10},
   {"_bssmb200_bsf_nlg", (DL_FUNC)&_bssmb200_bsf_nlg, 18},
