@@ -111,6 +111,9 @@ def lib():
     L.bssm_b200_shutdown.restype = None
     L.bssm_b200_stratified_sample.argtypes = [c_double_p, C.c_uint32, c_double_p, C.c_uint32, c_uint32_p]
     L.bssm_b200_gaussian_psi_smoother.argtypes = [C.POINTER(UngModel), C.c_uint32, C.c_uint32, c_double_p]
+    L.bssm_b200_is_correction_spdk_ung_parset.argtypes = [C.POINTER(UngModel), C.POINTER(Parset), C.c_uint32, C.c_uint32,
+                                                          C.c_int, c_uint32_p, c_double_p, c_double_p, C.c_uint32,
+                                                          c_double_p, c_double_p]
     L.bssm_b200_importance_sample_ung.argtypes = [C.POINTER(UngModel), C.c_uint32, C.c_int, C.c_uint32, c_double_p,
                                                   c_double_p, c_double_p]
     L.bssm_b200_math_probe.argtypes = [C.c_int, c_double_p, c_double_p, C.c_uint32]

@@ -436,6 +436,33 @@ def n_draws(mcmc_output, is_type):
     return int(counts.sum()) if is_type == 3 else int(counts.size)
 
 
+def _is_correction_spdk(model, mcmc_output, N, it, seed, ot, draw_range):
+    """approx_mcmc::is_correction_spdk (src/approx_mcmc.cpp:606-678): the correction phase of
+    run_mcmc(..., sampling_method = "spdk") for ssm_ung models with an update_fn (parameter sets), theta output"""
+    if getattr(model, "update_fn", None) is None or model.cls != "ssm_ung":
+        raise ValueError("sampling_method 'spdk': ssm_ung models with an update_fn (theta -> dict of model components)")
+    if ot != 3 or draw_range is not None:
+        raise ValueError("sampling_method 'spdk': output_type 'theta' (3) and all draws in one call")
+    counts = np.ascontiguousarray(mcmc_output["counts"], dtype=np.uint32)
+    modes = np.asfortranarray(np.asarray(mcmc_output["modes"], dtype=np.float64).reshape(model.n, -1, order="F"))
+    if modes.shape[1] != counts.size or np.shape(mcmc_output["theta"])[0] != counts.size:
+        raise ValueError("theta, counts and modes disagree on the number of stored draws")
+    ps = build_parset(model, np.asarray(mcmc_output["theta"], dtype=np.float64))
+    al = mcmc_output.get("approx_loglik")
+    al = None if al is None else _lib.f64(np.ravel(al))
+    nd = n_draws(mcmc_output, it)
+    w, post = np.zeros(nd), np.zeros(nd)
+    ms = model.c_struct()
+    check(lib().bssm_b200_is_correction_spdk_ung_parset(C.byref(ms), C.byref(ps), N, seed, it, uptr(counts), dptr(modes),
+                                                        dptr(al), counts.size, dptr(w), dptr(post)))
+    res = dict(mcmc_output)
+    base = np.asarray(mcmc_output.get("posterior", np.zeros(counts.size)), dtype=np.float64)
+    if it == 3:
+        base = np.repeat(base, counts)
+    res["weights"], res["posterior"], res["mcmc_type"] = w, base + post, "is%d" % it
+    return res
+
+
 def post_correct(model, mcmc_output, particles, threads=1, is_type="is2", seed=1, draw_range=None,
                  return_loglik=False, L=None, sampling_method="psi"):
     """post_correct, R/post_correction.R:245-308 (nongaussian branch).
@@ -458,8 +485,10 @@ def post_correct(model, mcmc_output, particles, threads=1, is_type="is2", seed=1
     N, seed = _check_particles(model, particles, seed)
     it = {"is1": 1, "is2": 2, "is3": 3}[is_type.lower()]
     ot = int(mcmc_output.get("output_type", 3))
+    if sampling_method == "spdk":
+        return _is_correction_spdk(model, mcmc_output, N, it, seed, ot, draw_range)
     if sampling_method not in ("psi", "bsf"):
-        raise ValueError("sampling_method must be 'psi' or 'bsf'")
+        raise ValueError("sampling_method must be 'psi', 'bsf' or 'spdk'")
     bsf = sampling_method == "bsf" and model.cls != "ssm_sde"
     use_parset = getattr(model, "update_fn", None) is not None and model.cls in ("ssm_ung", "ssm_mng")
     if model.cls == "ssm_mng" and not use_parset:

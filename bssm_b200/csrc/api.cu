@@ -2302,90 +2302,229 @@ int bssm_b200_gaussian_psi_smoother(const bssm_ung_model* M, uint32_t nsim, uint
   return 0;
 }
 
-// importance_sample_ng for the ssm_ung family (src/R_importance_sample.cpp:9-75) and the SPDK branch of
-// ssm_ung::log_likelihood (src/model_ssm_ung.cpp:199-211): the Gaussian approximation and the gains of its
-// smoother on the host, once (O(n m^3)); the nsim simulated trajectories and their weights on the device.
-int bssm_b200_importance_sample_ung(const bssm_ung_model* M, uint32_t nsim, int use_antithetic, uint32_t seed,
-                                    double* alpha, double* weights, double* loglik) {
-  if (!M) return fail(BSSM_B200_ERR_ARG, "null argument");
-  if (M->n < 1 || M->m < 1 || M->k < 1 || M->k > M->m) return fail(BSSM_B200_ERR_ARG, "need n >= 1, 1 <= k <= m");
-  if (M->distribution < 0 || M->distribution > 4)
-    return fail(BSSM_B200_ERR_ARG, "importance_sample: non-Gaussian ssm_ung models (distribution 0..4)");
-  if (!M->u || !M->initial_mode) return fail(BSSM_B200_ERR_ARG, "importance_sample: u and initial_mode required");
-  if (M->m > 16) return fail(BSSM_B200_ERR_UNSUPPORTED, "state dimension m <= 16 in this build");
-  // nsim = 1 is the reference's separate single-draw shortcut (src/model_ssm_ulg.cpp:219-241): not a device job
-  if (nsim < 2) return fail(BSSM_B200_ERR_UNSUPPORTED, "importance_sample: nsim >= 2");
-  int rc = require_device();
-  if (rc) return rc;
+// ---------------------------------------------------------------- SPDK (simulation smoother + importance weights)
+namespace {
+// one model's inputs of pf::sim_smoother_kernel as offsets into its block of doubles
+struct SpdkLayout {
+  size_t y, u, xbeta, Z, T, R, C, D, a1, P1, LP1, RR, ay, aH, rH, yphi2, F, K, Lt, ahat, phi, total;
+  bool has_xbeta;
+  SpdkLayout(const bssm_ung_model* M, bool xb) : has_xbeta(xb) {
+    const size_t n = M->n, m = M->m, k = M->k, mm = m * m;
+    size_t o = 0;
+    auto take = [&](size_t cnt) { size_t at = o; o += cnt; return at; };
+    y = take(n); u = take(n); xbeta = take(xb ? n : 0);
+    Z = take(m * (M->Ztv ? n : 1)); T = take(mm * (M->Ttv ? n : 1)); R = take(m * k * (M->Rtv ? n : 1));
+    C = take(m * (M->Ctv ? n : 1)); D = take(M->Dtv ? n : 1); a1 = take(m); P1 = take(mm); LP1 = take(mm);
+    RR = take(mm * (M->Rtv ? n : 1));
+    ay = take(n); aH = take(n); rH = take(n); yphi2 = take(n); F = take(n); K = take(m * n); Lt = take(mm * n);
+    ahat = take(m * (n + 1)); phi = take(1);
+    total = o;
+  }
+};
+
+// The host part for one model: approximation (mode_in == nullptr: approximate(), src/model_ssm_ung.cpp:87-140;
+// else approximate_for_is at the stored mode, :143-161), scales, the smoothed mean of the pseudo-observations
+// and the gains of its smoother (fast_precomputing_smoother, src/model_ssm_ulg.cpp:359-413).
+void spdk_fill(const bssm_ung_model* M, const double* mode_in, const SpdkLayout& L, double* b, double* approx_ll,
+               double* ssum) {
   const int n = M->n, m = M->m, k = M->k;
-  const size_t rows = (size_t)(n + 1) * m;
-  if (rows * nsim > ((size_t)1 << 32)) return fail(BSSM_B200_ERR_ARG, "importance_sample: (n + 1) m nsim <= 2^32");
+  const size_t mm = (size_t)m * m;
   pfga::UngApprox ga(M);
-  ga.run_head(nullptr);
+  ga.run_head(mode_in);
   pfga::UngApprox::SimGains sg;
   std::vector<double> ahat;
   ga.fast_smoother(ahat, &sg);
-  std::vector<double> LP1((size_t)m * m), rH(n), yp2(n);
-  psd_chol_host(M->P1, m, LP1.data()); // src/model_ssm_ulg.cpp:145
+  auto put = [&](size_t at, const double* src, size_t cnt) { std::copy(src, src + cnt, b + at); };
+  put(L.y, M->y, n); put(L.u, M->u, n);
+  if (L.has_xbeta) put(L.xbeta, M->xbeta, n);
+  put(L.Z, M->Z, (size_t)m * (M->Ztv ? n : 1)); put(L.T, M->T, mm * (M->Ttv ? n : 1));
+  put(L.R, M->R, (size_t)m * k * (M->Rtv ? n : 1)); put(L.C, M->C, (size_t)m * (M->Ctv ? n : 1));
+  put(L.D, M->D, M->Dtv ? n : 1); put(L.a1, M->a1, m); put(L.P1, M->P1, mm);
+  psd_chol_host(M->P1, m, b + L.LP1); // src/model_ssm_ulg.cpp:145
+  put(L.RR, sg.RR.data(), sg.RR.size());
+  put(L.ay, ga.ay.data(), n); put(L.aH, ga.aH.data(), n);
   for (int t = 0; t < n; ++t) {
-    rH[t] = 1.0 / ga.aH[t];
+    b[L.rH + t] = 1.0 / ga.aH[t];
     const double q = M->y[t] / M->phi;
-    yp2[t] = q * q;
+    b[L.yphi2 + t] = q * q;
   }
+  put(L.F, sg.F.data(), n); put(L.K, sg.K.data(), (size_t)m * n); put(L.Lt, sg.Lt.data(), mm * n);
+  put(L.ahat, ahat.data(), (size_t)m * (n + 1));
+  b[L.phi] = M->phi;
+  *approx_ll = ga.approx_loglik;
+  *ssum = pfga::accu2(ga.scales.data(), (size_t)n);
+}
+
+// nf blocks (pack) -> the log-weights sum_t log_weights(t, alpha_i) of all trajectories, draw after draw
+// (nsim_f[f] each); alpha_out: nf == 1 only, m x (n+1) x nsim
+int spdk_launch(const bssm_ung_model* M, const SpdkLayout& L, const std::vector<double>& pack, uint32_t nf,
+                const uint32_t* nsim_f, int antithetic, uint32_t seed, uint32_t first_filter,
+                std::vector<double>& logw, double* alpha_out) {
+  const int n = M->n, m = M->m, k = M->k;
+  const size_t rows = (size_t)(n + 1) * m;
+  std::vector<uint32_t> toff(nf + 1, 0u), soff(nf + 1, 0u);
+  for (uint32_t f = 0; f < nf; ++f) {
+    const uint32_t ns = nsim_f[f];
+    soff[f + 1] = soff[f] + ns;
+    toff[f + 1] = toff[f] + (antithetic ? ns / 2 + (ns & 1u) : ns);
+  }
+  const size_t S = soff[nf], Tn = toff[nf];
   pf::SimParams sp{};
   sp.n = n; sp.m = m; sp.k = k; sp.distribution = M->distribution;
   sp.Ztv = M->Ztv; sp.Ttv = M->Ttv; sp.Rtv = M->Rtv; sp.Ctv = M->Ctv; sp.Dtv = M->Dtv;
-  sp.phi = M->phi; sp.seed = seed; sp.nsim = nsim; sp.antithetic = use_antithetic ? 1 : 0;
-  sp.nsim2 = use_antithetic ? nsim / 2 : nsim;
-  sp.threads = use_antithetic ? sp.nsim2 + (nsim & 1u) : nsim;
-  // one packed upload: every array below is a slice of it
-  std::vector<double> pack;
-  std::vector<std::pair<const double**, size_t>> slots;
-  auto put = [&](const double** dst, const double* src, size_t cnt) {
-    slots.emplace_back(dst, pack.size());
-    pack.insert(pack.end(), src, src + cnt);
-  };
-  const size_t mm = (size_t)m * m;
-  put(&sp.y, M->y, n); put(&sp.u, M->u, n);
-  if (M->xbeta) put(&sp.xbeta, M->xbeta, n);
-  put(&sp.Z, M->Z, (size_t)m * (M->Ztv ? n : 1)); put(&sp.T, M->T, mm * (M->Ttv ? n : 1));
-  put(&sp.R, M->R, (size_t)m * k * (M->Rtv ? n : 1)); put(&sp.C, M->C, (size_t)m * (M->Ctv ? n : 1));
-  put(&sp.D, M->D, M->Dtv ? n : 1); put(&sp.a1, M->a1, m); put(&sp.P1, M->P1, mm); put(&sp.LP1, LP1.data(), mm);
-  put(&sp.RR, sg.RR.data(), sg.RR.size());
-  put(&sp.ay, ga.ay.data(), n); put(&sp.aH, ga.aH.data(), n); put(&sp.rH, rH.data(), n); put(&sp.yphi2, yp2.data(), n);
-  put(&sp.F, sg.F.data(), n); put(&sp.K, sg.K.data(), (size_t)m * n); put(&sp.Lt, sg.Lt.data(), mm * n);
-  put(&sp.ahat, ahat.data(), rows);
+  sp.seed = seed; sp.antithetic = antithetic ? 1 : 0; sp.first_filter = first_filter;
   DevBuf<double> dpack, tm, lw, v, r, cube;
-  if ((rc = dpack.upload(pack.data(), pack.size())) || (rc = tm.alloc(rows * nsim)) || (rc = lw.alloc(nsim)) ||
-      (rc = v.alloc((size_t)n * sp.threads)) || (rc = r.alloc((size_t)n * m * sp.threads)))
+  DevBuf<uint32_t> doff;
+  int rc;
+  if ((rc = dpack.upload(pack.data(), pack.size())) || (rc = tm.alloc(rows * S)) || (rc = lw.alloc(S)) ||
+      (rc = v.alloc((size_t)n * Tn)) || (rc = r.alloc((size_t)n * m * Tn)))
     return rc;
-  for (auto& sl : slots) *sl.first = dpack.p + sl.second;
+  const double* b = dpack.p;
+  sp.y = b + L.y; sp.u = b + L.u; sp.xbeta = L.has_xbeta ? b + L.xbeta : nullptr;
+  sp.Z = b + L.Z; sp.T = b + L.T; sp.R = b + L.R; sp.C = b + L.C; sp.D = b + L.D; sp.a1 = b + L.a1;
+  sp.P1 = b + L.P1; sp.LP1 = b + L.LP1; sp.RR = b + L.RR; sp.ay = b + L.ay; sp.aH = b + L.aH; sp.rH = b + L.rH;
+  sp.yphi2 = b + L.yphi2; sp.F = b + L.F; sp.K = b + L.K; sp.Lt = b + L.Lt; sp.ahat = b + L.ahat;
+  sp.phi_f = b + L.phi; sp.phi = pack[L.phi];
   sp.alpha = tm.p; sp.logw = lw.p; sp.v = v.p; sp.r = r.p;
-  const dim3 grid(cdiv(sp.threads, 128));
+  if (nf == 1) { // one model: the scalar members, no search
+    sp.nf = 0; sp.nsim = nsim_f[0]; sp.nsim2 = antithetic ? sp.nsim / 2 : sp.nsim; sp.threads = toff[1];
+  } else {
+    std::vector<uint32_t> both(toff);
+    both.insert(both.end(), soff.begin(), soff.end());
+    if ((rc = doff.upload(both.data(), both.size()))) return rc;
+    sp.nf = nf; sp.fstride = L.total; sp.toff = doff.p; sp.soff = doff.p + (nf + 1);
+  }
+  sp.total_threads = (uint32_t)Tn;
+  const dim3 grid(cdiv((uint32_t)Tn, 128));
   const int mk = m > k ? m : k;
   if (mk == 1) pf::sim_smoother_kernel<1><<<grid, 128>>>(sp);
   else if (mk <= 4) pf::sim_smoother_kernel<4><<<grid, 128>>>(sp);
   else pf::sim_smoother_kernel<16><<<grid, 128>>>(sp);
   CU(cudaGetLastError());
-  std::vector<double> w(nsim);
-  CU(cudaMemcpy(w.data(), lw.p, sizeof(double) * nsim, cudaMemcpyDeviceToHost));
-  if (alpha) {
+  logw.resize(S);
+  CU(cudaMemcpy(logw.data(), lw.p, sizeof(double) * S, cudaMemcpyDeviceToHost));
+  if (alpha_out && nf == 1) {
+    const uint32_t nsim = nsim_f[0];
     if ((rc = cube.alloc(rows * nsim))) return rc;
     pf::transpose_to_cube_kernel<<<dim3(cdiv(nsim, 32), cdiv((uint32_t)rows, 32)), dim3(32, 8)>>>(
         tm.p, cube.p, (uint32_t)rows, nsim, 0u, (uint32_t)rows);
     CU(cudaGetLastError());
-    CU(cudaMemcpy(alpha, cube.p, sizeof(double) * rows * nsim, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(alpha_out, cube.p, sizeof(double) * rows * nsim, cudaMemcpyDeviceToHost));
   }
+  return 0;
+}
+
+int spdk_check_model(const bssm_ung_model* M, const char* who) {
+  if (!M) return fail(BSSM_B200_ERR_ARG, "null argument");
+  if (M->n < 1 || M->m < 1 || M->k < 1 || M->k > M->m) return fail(BSSM_B200_ERR_ARG, "need n >= 1, 1 <= k <= m");
+  if (M->distribution < 0 || M->distribution > 4)
+    return fail(BSSM_B200_ERR_ARG, std::string(who) + ": non-Gaussian ssm_ung models (distribution 0..4)");
+  if (!M->u || !M->initial_mode) return fail(BSSM_B200_ERR_ARG, std::string(who) + ": u and initial_mode required");
+  if (M->m > 16) return fail(BSSM_B200_ERR_UNSUPPORTED, "state dimension m <= 16 in this build");
+  return 0;
+}
+} // namespace
+
+// importance_sample_ng for the ssm_ung family (src/R_importance_sample.cpp:9-75) and the SPDK branch of
+// ssm_ung::log_likelihood (src/model_ssm_ung.cpp:199-211): the Gaussian approximation and the gains of its
+// smoother on the host, once (O(n m^3)); the nsim simulated trajectories and their weights on the device.
+int bssm_b200_importance_sample_ung(const bssm_ung_model* M, uint32_t nsim, int use_antithetic, uint32_t seed,
+                                    double* alpha, double* weights, double* loglik) {
+  int rc = spdk_check_model(M, "importance_sample");
+  if (rc) return rc;
+  // nsim = 1 is the reference's separate single-draw shortcut (src/model_ssm_ulg.cpp:219-241): not a device job
+  if (nsim < 2) return fail(BSSM_B200_ERR_UNSUPPORTED, "importance_sample: nsim >= 2");
+  if ((rc = require_device())) return rc;
+  if ((size_t)(M->n + 1) * M->m * nsim > ((size_t)1 << 32)) return fail(BSSM_B200_ERR_ARG, "importance_sample: (n + 1) m nsim <= 2^32");
+  const SpdkLayout L(M, M->xbeta != nullptr);
+  std::vector<double> pack(L.total), w;
+  double approx_ll, ssum;
+  spdk_fill(M, nullptr, L, pack.data(), &approx_ll, &ssum);
+  if ((rc = spdk_launch(M, L, pack, 1, &nsim, use_antithetic, seed, 0u, w, alpha))) return rc;
   // w - accu(scales), exp(w - max), mean (src/model_ssm_ung.cpp:206-210): nsim values, on the host
-  const double ssum = pfga::accu2(ga.scales.data(), (size_t)n);
   double maxw = -std::numeric_limits<double>::infinity();
   for (uint32_t i = 0; i < nsim; ++i) { w[i] -= ssum; if (w[i] > maxw) maxw = w[i]; }
   for (uint32_t i = 0; i < nsim; ++i) w[i] = pf_exp(w[i] - maxw);
   if (weights) std::copy(w.begin(), w.end(), weights);
   if (loglik) {
-    loglik[0] = ga.approx_loglik + pf_log(pfga::accu2(w.data(), nsim) / nsim) + maxw;
-    loglik[1] = ga.approx_loglik;
+    loglik[0] = approx_ll + pf_log(pfga::accu2(w.data(), nsim) / nsim) + maxw;
+    loglik[1] = approx_ll;
   }
+  return 0;
+}
+
+// approx_mcmc::is_correction_spdk (src/approx_mcmc.cpp:606-678) for ssm_ung models given as parameter sets
+// (parset_ung::update, src/parset_ng.cpp:84-124), output_type 3: per stored draw the model, its approximation at
+// the stored mode (approximate_for_is) and the gains on the host (one OpenMP loop over the draws), ALL simulated
+// trajectories of a chunk of draws in one launch.  weight_i = mean(exp(w - accu(scales))) (:637-639).
+int bssm_b200_is_correction_spdk_ung_parset(const bssm_ung_model* M, const bssm_parset* ps, uint32_t nsim,
+                                            uint32_t seed, int is_type, const uint32_t* counts, const double* modes,
+                                            const double* approx_loglik, uint32_t n_stored, double* weights,
+                                            double* posterior) {
+  int rc = spdk_check_model(M, "is_correction_spdk");
+  if (rc) return rc;
+  if (!ps || !counts || !modes || !weights || n_stored == 0) return fail(BSSM_B200_ERR_ARG, "null or empty argument");
+  if (ps->beta && (!ps->xreg || ps->n_xreg < 1)) return fail(BSSM_B200_ERR_ARG, "parset: beta needs xreg and n_xreg");
+  if (is_type < 1 || is_type > 3) return fail(BSSM_B200_ERR_ARG, "is_type must be 1, 2 or 3");
+  if (nsim < 2) return fail(BSSM_B200_ERR_UNSUPPORTED, "is_correction_spdk: nsim >= 2");
+  if ((rc = require_device())) return rc;
+  const size_t n = M->n, m = M->m, k = M->k;
+  // expand() for is_type 3 (src/approx_mcmc.cpp:49-88): one draw per repetition, each with its own stream
+  std::vector<uint32_t> src, ns;
+  for (uint32_t i = 0; i < n_stored; ++i) {
+    if (is_type == 3) for (uint32_t c = 0; c < counts[i]; ++c) { src.push_back(i); ns.push_back(nsim); }
+    else { src.push_back(i); ns.push_back(is_type == 1 ? nsim * counts[i] : nsim); }
+  }
+  const size_t nd = src.size();
+  const SpdkLayout L(M, M->xbeta != nullptr || ps->beta != nullptr);
+  // chunks of draws: at most 2^31 doubles of trajectories and 2^28 doubles of model blocks per launch
+  size_t d0 = 0;
+  while (d0 < nd) {
+    size_t d1 = d0, traj = 0;
+    while (d1 < nd) {
+      const bool fits = traj + ns[d1] <= ((size_t)1 << 31) / ((n + 1) * m) && (d1 - d0 + 1) * L.total <= ((size_t)1 << 28);
+      if (d1 > d0 && !fits) break;
+      traj += ns[d1];
+      ++d1;
+    }
+    const uint32_t nf = (uint32_t)(d1 - d0);
+    std::vector<double> pack(L.total * nf), al(nf), ss(nf), w; // al: 0 by definition of approximate_for_is
+#pragma omp parallel for schedule(static)
+    for (int64_t f = 0; f < (int64_t)nf; ++f) {
+      const uint32_t c = src[d0 + f];
+      bssm_ung_model Mi = *M; // parset_ung::update(model, c)
+      std::vector<double> xb;
+      if (ps->phi) Mi.phi = ps->phi[c];
+      if (ps->Z) Mi.Z = ps->Z + m * (M->Ztv ? n : 1) * c;
+      if (ps->T) Mi.T = ps->T + m * m * (M->Ttv ? n : 1) * c;
+      if (ps->R) Mi.R = ps->R + m * k * (M->Rtv ? n : 1) * c;
+      if (ps->a1) Mi.a1 = ps->a1 + m * c;
+      if (ps->P1) Mi.P1 = ps->P1 + m * m * c;
+      if (ps->D) Mi.D = ps->D + (M->Dtv ? n : 1) * c;
+      if (ps->C) Mi.C = ps->C + m * (M->Ctv ? n : 1) * c;
+      if (ps->beta) { // compute_xbeta, src/model_ssm_ung.h:83
+        xb.assign(n, 0.0);
+        for (size_t t = 0; t < n; ++t) {
+          double sum = 0.0;
+          for (int j = 0; j < ps->n_xreg; ++j) sum += ps->xreg[t + n * j] * ps->beta[(size_t)ps->n_xreg * c + j];
+          xb[t] = sum;
+        }
+        Mi.xbeta = xb.data();
+      }
+      spdk_fill(&Mi, modes + n * c, L, &pack[L.total * f], &al[f], &ss[f]);
+    }
+    if ((rc = spdk_launch(M, L, pack, nf, &ns[d0], 1, seed, (uint32_t)d0, w, nullptr))) return rc;
+    size_t o = 0;
+    for (uint32_t f = 0; f < nf; ++f) {
+      const uint32_t cnt = ns[d0 + f];
+      for (uint32_t i = 0; i < cnt; ++i) w[o + i] = pf_exp(w[o + i] - ss[f]);
+      weights[d0 + f] = pfga::accu2(&w[o], cnt) / cnt;
+      o += cnt;
+    }
+    d0 = d1;
+  }
+  if (posterior)
+    for (size_t i = 0; i < nd; ++i) posterior[i] = (approx_loglik ? approx_loglik[src[i]] : 0.0) + pf_log(weights[i]);
   return 0;
 }
 

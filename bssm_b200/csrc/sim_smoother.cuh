@@ -33,12 +33,58 @@ struct SimParams {
   double* alpha; // out: (n+1) x m x nsim
   double* logw;  // out: nsim, sum_t log_weights(t, alpha_i)
   double *v, *r; // scratch: n x threads, n x m x threads
+  // a batch of models (is_correction_spdk, src/approx_mcmc.cpp:606-678: one model and one approximation per
+  // stored draw): every input pointer above points into the block of draw 0 and draw f's block lies
+  // f * fstride doubles further on (phi: phi_f[f * fstride]); toff / soff (nf + 1 each) are the running sums of
+  // the draws' threads and trajectories, which also place their alpha / logw / v / r regions; draw f uses the
+  // random stream `first_filter + f`.  nf = 0: one model, the scalar members above.
+  uint32_t nf, first_filter, total_threads;
+  size_t fstride;
+  const uint32_t *toff, *soff;
+  const double* phi_f;
 };
+
+// the members of draw f of a batch, as a single-model parameter block
+__device__ __forceinline__ SimParams sim_params_of(const SimParams& p, uint32_t f) {
+  SimParams q = p;
+  const size_t o = (size_t)f * p.fstride;
+  q.y += o; q.u += o; if (q.xbeta) q.xbeta += o;
+  q.Z += o; q.T += o; q.R += o; q.C += o; q.D += o; q.a1 += o; q.P1 += o; q.LP1 += o; q.RR += o;
+  q.ay += o; q.aH += o; q.rH += o; q.yphi2 += o; q.F += o; q.K += o; q.Lt += o; q.ahat += o;
+  q.phi = p.phi_f[o];
+  const uint32_t t0 = p.toff[f], s0 = p.soff[f];
+  q.nsim = p.soff[f + 1] - s0;
+  q.threads = p.toff[f + 1] - t0;
+  q.nsim2 = p.antithetic ? q.nsim / 2 : q.nsim;
+  q.alpha += (size_t)s0 * (p.n + 1) * p.m;
+  q.logw += s0;
+  q.v += (size_t)t0 * p.n;
+  q.r += (size_t)t0 * p.n * p.m;
+  return q;
+}
+
+template <int MAXM>
+__device__ void sim_smoother_thread(const SimParams& p, uint32_t i, uint32_t filter);
 
 template <int MAXM>
 __global__ void __launch_bounds__(128) sim_smoother_kernel(const SimParams p) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.threads) return;
+  const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p.nf == 0) {
+    if (gi < p.threads) sim_smoother_thread<MAXM>(p, gi, p.first_filter);
+    return;
+  }
+  if (gi >= p.total_threads) return;
+  uint32_t lo = 0, hi = p.nf; // the draw whose thread range holds gi
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (p.toff[mid] <= gi) lo = mid; else hi = mid;
+  }
+  const SimParams q = sim_params_of(p, lo);
+  sim_smoother_thread<MAXM>(q, gi - p.toff[lo], p.first_filter + lo);
+}
+
+template <int MAXM>
+__device__ void sim_smoother_thread(const SimParams& p, const uint32_t i, const uint32_t filter) {
   const int n = p.n, m = p.m, k = p.k, K1 = p.k + 1;
   const size_t NS = p.nsim, NT = p.threads;
   // the trajectory without a partner: the last one of an odd nsim (:195-217)
@@ -49,7 +95,7 @@ __global__ void __launch_bounds__(128) sim_smoother_kernel(const SimParams p) {
   double a[MAXM], fa[MAXM], nx[MAXM], tmp[MAXM], z[MAXM + 1];
 
   // ---- sweep 1: alpha+, y+ and the filter of y+ (:165-182, :323-330)
-  for (int d = 0; d < m; ++d) z[d] = pf_sim_normal(p.seed, 0u, 0u, i * (uint32_t)m + d);
+  for (int d = 0; d < m; ++d) z[d] = pf_sim_normal(p.seed, filter, 0u, i * (uint32_t)m + d);
   for (int d = 0; d < m; ++d) {
     double s = 0.0;
     for (int j = 0; j < m; ++j) s += p.LP1[d + m * j] * z[j];
@@ -64,7 +110,7 @@ __global__ void __launch_bounds__(128) sim_smoother_kernel(const SimParams p) {
     const double* C = p.C + (size_t)m * (t * p.Ctv);
     const double Dt = p.D[t * p.Dtv];
     const double xb = p.xbeta ? p.xbeta[t] : 0.0;
-    for (int d = 0; d < K1; ++d) z[d] = pf_sim_normal(p.seed, 0u, (uint32_t)(t + 1), i * (uint32_t)K1 + d);
+    for (int d = 0; d < K1; ++d) z[d] = pf_sim_normal(p.seed, filter, (uint32_t)(t + 1), i * (uint32_t)K1 + d);
     double yp = p.y[t]; // stays missing where the data are missing
     if (pf_isfinite(yp)) {
       double za = 0.0;

@@ -454,6 +454,18 @@ int bssm_b200_is_correction_bsf_ung_parset(const bssm_ung_model* model, const bs
                                            int is_type, const uint32_t* counts, const double* approx_loglik,
                                            uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
                                            bssm_postcorr_out* out);
+/* approx_mcmc::is_correction_spdk (src/approx_mcmc.cpp:606-678; run_mcmc(mcmc_type = "is*",
+ * sampling_method = "spdk")) for ssm_ung models whose stored draws are given as the reference's own parameter
+ * sets (bssm_parset = parset_ung, src/parset_ng.h:11-40), output_type 3: for every stored draw the model,
+ * its approximation at the stored mode (modes: n x n_stored) and nsim (is_type 1: nsim * counts[i]) simulated
+ * trajectories; weights[i] = mean(exp(w - sum(scales))) (:637-639), posterior[i] = approx_loglik[i] (or 0 when
+ * NULL) + log(weights[i]) (:676-677).  is_type 3 expands the draws by their counts first (expand(), :49-88):
+ * weights / posterior then hold sum(counts) values, else n_stored.  Draw i uses the random stream i. */
+int bssm_b200_is_correction_spdk_ung_parset(const bssm_ung_model* model, const bssm_parset* parset,
+                                            uint32_t nsim, uint32_t seed, int is_type, const uint32_t* counts,
+                                            const double* modes, const double* approx_loglik, uint32_t n_stored,
+                                            double* weights, double* posterior);
+
 /* replaces: postcorrection_nongaussian(..., model_type = 0) -> approx_mcmc::is_correction_psi<ssm_mng>
  *           (src/approx_mcmc.cpp:1038-1157) and is_correction_bsf<ssm_mng> (:1159-1273).
  *           modes is p x n x n_stored (mode_storage, src/approx_mcmc.cpp:29).  m <= 16, p <= 16. */

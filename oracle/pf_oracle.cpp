@@ -1013,28 +1013,24 @@ struct SimSmoother {
 };
 } // namespace
 
-extern "C" int orc_importance_sample_ung(const bssm_ung_model* M, uint32_t nsim, int use_antithetic, uint32_t seed,
-                                         double* alpha, double* weights, double* loglik, double* alphahat_out,
-                                         double* ytilde_out, double* Htilde_out) {
-  if (nsim < 2) return 1;
+/* simulate_states (nsim > 1) + importance_weights for one approximated model: alpha m x (n+1) x nsim, w = the
+ * sums over t of log_weights(t, alpha_i); `filter` = the random stream */
+static void spdk_draws(const bssm_ung_model* M, const pfga::UngApprox& ga, uint32_t nsim, int use_antithetic,
+                       uint32_t seed, uint32_t filter, double* alpha, std::vector<double>& w,
+                       std::vector<double>& alphahat) {
   const int n = M->n, m = M->m, k = M->k;
-  pfga::UngApprox ga(M);
-  ga.run_head(nullptr);
   Ung g(M);
   g.ay = ga.ay; g.aH = ga.aH; g.scales = ga.scales;
   SimSmoother S(M, ga);
-  std::vector<double> alphahat, L_P1;
+  std::vector<double> L_P1;
   S.smooth(ga.ay, true, alphahat);
-  if (alphahat_out) std::copy(alphahat.begin(), alphahat.end(), alphahat_out);
-  if (ytilde_out) std::copy(ga.ay.begin(), ga.ay.end(), ytilde_out);
-  if (Htilde_out) std::copy(ga.aH.begin(), ga.aH.end(), Htilde_out);
   psd_chol(M->P1, m, L_P1);
   const size_t sl = (size_t)m * (n + 1);
   const uint32_t nsim2 = use_antithetic ? nsim / 2 : nsim;
   std::vector<double> aplus(sl), yplus(n), sm, um(m), uk(k);
   const uint32_t K1 = (uint32_t)k + 1;
   auto simulate = [&](uint32_t i) { /* :165-182 */
-    for (int j = 0; j < m; ++j) um[j] = pf_sim_normal(seed, 0u, 0u, i * (uint32_t)m + j);
+    for (int j = 0; j < m; ++j) um[j] = pf_sim_normal(seed, filter, 0u, i * (uint32_t)m + j);
     for (int d = 0; d < m; ++d) {
       double s = 0.0;
       for (int j = 0; j < m; ++j) s += L_P1[d + (size_t)m * j] * um[j];
@@ -1046,9 +1042,9 @@ extern "C" int orc_importance_sample_ung(const bssm_ung_model* M, uint32_t nsim,
       if (std::isfinite(M->y[t])) {
         double za = 0.0;
         for (int d = 0; d < m; ++d) za += S.Z(t)[d] * a[d];
-        yplus[t] = S.xbeta[t] + S.D(t) + za + ga.aH[t] * pf_sim_normal(seed, 0u, (uint32_t)(t + 1), i * K1);
+        yplus[t] = S.xbeta[t] + S.D(t) + za + ga.aH[t] * pf_sim_normal(seed, filter, (uint32_t)(t + 1), i * K1);
       }
-      for (int j = 0; j < k; ++j) uk[j] = pf_sim_normal(seed, 0u, (uint32_t)(t + 1), i * K1 + 1 + j);
+      for (int j = 0; j < k; ++j) uk[j] = pf_sim_normal(seed, filter, (uint32_t)(t + 1), i * K1 + 1 + j);
       for (int d = 0; d < m; ++d) {
         double ta = 0.0, ru = 0.0;
         for (int j = 0; j < m; ++j) ta += S.T(t)[d + m * j] * a[j];
@@ -1074,11 +1070,25 @@ extern "C" int orc_importance_sample_ung(const bssm_ung_model* M, uint32_t nsim,
     for (size_t e = 0; e < sl; ++e) ai[e] = alphahat[e] - sm[e] + aplus[e];
   }
   /* importance_weights (src/model_ssm_ung.cpp:372-378) */
-  std::vector<double> w(nsim, 0.0);
+  w.assign(nsim, 0.0);
   for (int t = 0; t < n; ++t) {
     if (!std::isfinite(M->y[t])) continue;
     for (uint32_t i = 0; i < nsim; ++i) w[i] += g.log_weight_pf(t, g.signal(t, alpha + sl * i + (size_t)m * t));
   }
+}
+
+extern "C" int orc_importance_sample_ung(const bssm_ung_model* M, uint32_t nsim, int use_antithetic, uint32_t seed,
+                                         double* alpha, double* weights, double* loglik, double* alphahat_out,
+                                         double* ytilde_out, double* Htilde_out) {
+  if (nsim < 2) return 1;
+  const int n = M->n;
+  pfga::UngApprox ga(M);
+  ga.run_head(nullptr);
+  std::vector<double> alphahat, w;
+  spdk_draws(M, ga, nsim, use_antithetic, seed, 0u, alpha, w, alphahat);
+  if (alphahat_out) std::copy(alphahat.begin(), alphahat.end(), alphahat_out);
+  if (ytilde_out) std::copy(ga.ay.begin(), ga.ay.end(), ytilde_out);
+  if (Htilde_out) std::copy(ga.aH.begin(), ga.aH.end(), Htilde_out);
   const double ssum = pfga::accu2(ga.scales.data(), (size_t)n);
   double maxw = -ORC_INF;
   for (uint32_t i = 0; i < nsim; ++i) { w[i] -= ssum; if (w[i] > maxw) maxw = w[i]; }
@@ -2502,6 +2512,43 @@ static void parset_update_mng(const bssm_mng_model* M, const bssm_parset* ps, ui
   if (ps->C) Mi.C = ps->C + m * (M->Ctv ? n : 1) * c;
 }
 extern "C" {
+
+/* approx_mcmc::is_correction_spdk (src/approx_mcmc.cpp:606-678), output_type 3, for parameter sets: per stored
+ * draw parset_ung::update, approximate_for_is at the stored mode, simulate_states(nsimc), weight =
+ * mean(exp(importance_weights - accu(scales))) (:636-639); posterior = approx_loglik + log(weight) (:676-677).
+ * Draw i uses the Philox stream `filter = i` instead of a per-thread engine (:621), as in is_correction_psi. */
+int orc_is_correction_spdk_ung_parset(const bssm_ung_model* M, const bssm_parset* ps, uint32_t nsim, uint32_t seed,
+                                      int threads, int is_type, const uint32_t* counts, const double* modes,
+                                      const double* approx_loglik, uint32_t n_stored, double* weights,
+                                      double* posterior) {
+  const size_t n = M->n, m = M->m;
+  std::vector<uint32_t> src, cnt;
+  for (uint32_t i = 0; i < n_stored; ++i) {
+    if (is_type == 3) for (uint32_t c = 0; c < counts[i]; ++c) { src.push_back(i); cnt.push_back(1u); }
+    else { src.push_back(i); cnt.push_back(counts[i]); }
+  }
+  const int64_t nd = (int64_t)src.size();
+#ifdef _OPENMP
+  if (threads < 1) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(threads)
+#endif
+  for (int64_t i = 0; i < nd; ++i) {
+    bssm_ung_model Mi;
+    std::vector<double> xb;
+    parset_update_ung(M, ps, src[i], Mi, xb);
+    pfga::UngApprox ga(&Mi);
+    ga.run_head(modes + n * src[i]);
+    unsigned int nsimc = nsim;
+    if (is_type == 1) nsimc *= cnt[i];
+    std::vector<double> alpha_i(m * (n + 1) * nsimc), w, ah;
+    spdk_draws(&Mi, ga, nsimc, 1, seed, (uint32_t)i, alpha_i.data(), w, ah);
+    const double ssum = pfga::accu2(ga.scales.data(), n);
+    for (uint32_t j = 0; j < nsimc; ++j) w[j] = pf_exp(w[j] - ssum);
+    weights[i] = pfga::accu2(w.data(), nsimc) / nsimc;
+  }
+  for (int64_t i = 0; i < nd; ++i) posterior[i] = (approx_loglik ? approx_loglik[src[i]] : 0.0) + pf_log(weights[i]);
+  return 0;
+}
 
 /* is_correction_psi<ssm_ung> (src/approx_mcmc.cpp:685-804; modes != null) and is_correction_bsf<ssm_ung>
  * (:806-921; approx_loglik != null) with the parameter sets of src/parset_ng.cpp */

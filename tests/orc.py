@@ -355,6 +355,27 @@ def correction_parset(model, mcmc_output, N, is_type=2, seed=1, threads=0, arith
     return r
 
 
+def correction_spdk_parset(model, mcmc_output, nsim, is_type=2, seed=1, threads=0):
+    """oracle of is_correction_spdk (src/approx_mcmc.cpp:606-678), output_type 3: (weights, posterior)"""
+    from bssm_b200.api import build_parset, n_draws
+    from bssm_b200._lib import Parset
+    counts = np.ascontiguousarray(mcmc_output["counts"], dtype=np.uint32)
+    ps = build_parset(model, np.asarray(mcmc_output["theta"], dtype=np.float64))
+    modes = np.asfortranarray(np.asarray(mcmc_output["modes"], dtype=np.float64).reshape(model.n, -1, order="F"))
+    al = mcmc_output.get("approx_loglik")
+    al = None if al is None else np.ascontiguousarray(al, dtype=np.float64)
+    nd = n_draws(mcmc_output, is_type)
+    w, post = np.zeros(nd), np.zeros(nd)
+    ms = model.c_struct()
+    f = L().orc_is_correction_spdk_ung_parset
+    f.argtypes = [C.POINTER(UngModel), C.POINTER(Parset), C.c_uint32, C.c_uint32, C.c_int, C.c_int, c_uint32_p,
+                  c_double_p, c_double_p, C.c_uint32, c_double_p, c_double_p]
+    rc = f(C.byref(ms), C.byref(ps), nsim, seed, threads, is_type, uptr(counts), dptr(modes), dptr(al), counts.size,
+           dptr(w), dptr(post))
+    assert rc == 0
+    return w, post
+
+
 def nlg_bsf_filter(model, N, seed, filt=0, arith=ARITH_REPRO):
     r = _alloc(model, N)
     ms = model.c_struct()

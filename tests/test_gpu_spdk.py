@@ -86,3 +86,45 @@ def test_importance_sample_argument_checks(engine):
         engine.importance_sample(model, 1)
     with pytest.raises(ValueError):
         engine.importance_sample(data.lg_model(), 10)
+
+
+@pytest.mark.parametrize("m,tv,is_type", [(1, False, 2), (2, False, 1), (2, True, 3)])
+def test_is_correction_spdk_parameter_sets(engine, m, tv, is_type):
+    """approx_mcmc::is_correction_spdk (src/approx_mcmc.cpp:606-678): one model, one approximation at the stored
+    mode and nsim (is1: nsim * count) simulated trajectories per stored draw, all draws in one launch"""
+    from test_gpu_parset import draws, ung_update_model
+    model = ung_update_model(m=m, tv=tv)
+    mo = draws(model, 13)
+    w, post = orc.correction_spdk_parset(model, mo, 30, is_type=is_type, seed=6)
+    res = engine.post_correct(model, mo, 30, is_type="is%d" % is_type, seed=6, sampling_method="spdk")
+    assert np.array_equal(res["weights"].view(np.uint64), w.view(np.uint64))
+    assert np.array_equal(res["posterior"], post)
+    assert len(set(res["weights"])) == len(w)  # every (expanded) draw has its own stream
+    # same target as the psi-APF correction of the same draws (E_g[prod_t w_t]); these stored "modes" are random, so
+    # the non-sequential sampler is heavy-tailed: only the typical draw is compared
+    psi = engine.post_correct(model, mo, 2000, is_type="is2", seed=6)
+    big = engine.post_correct(model, mo, 20000, is_type="is2", seed=6, sampling_method="spdk")
+    assert np.median(np.abs(np.log(big["weights"]) - np.log(psi["weights"]))) < 0.4
+
+
+def test_is_correction_spdk_with_regression_coefficients(engine):
+    """beta in the parameter set: every draw has its own x beta (compute_xbeta, src/model_ssm_ung.h:83)"""
+    rng = np.random.default_rng(8)
+    n = 40
+    x = rng.normal(size=(n, 2))
+    y = rng.poisson(np.exp(0.5 + 0.2 * x[:, 0])).astype(float)
+    y[11] = np.nan
+
+    def update_fn(theta):
+        return {"R": np.array([[0.1 * np.exp(theta[0])]]), "beta": np.array([0.2 + theta[1], theta[2]])}
+
+    model = bssm_b200.ssm_ung(y, [1.0], [[0.95]], [[0.1]], [0.3], [[0.4]], "poisson", xreg=x, beta=np.array([0.2, 0.0]),
+                              update_fn=update_fn)
+    theta = 0.1 * rng.normal(size=(9, 3))
+    mo = {"theta": theta, "counts": np.full(9, 2, dtype=np.uint32), "output_type": 3,
+          "modes": np.asfortranarray(0.5 + 0.1 * rng.normal(size=(n, 9))), "posterior": np.zeros(9),
+          "approx_loglik": -60.0 + rng.normal(size=9)}
+    w, post = orc.correction_spdk_parset(model, mo, 21, is_type=2, seed=2)
+    res = engine.post_correct(model, mo, 21, is_type="is2", seed=2, sampling_method="spdk")
+    assert np.array_equal(res["weights"].view(np.uint64), w.view(np.uint64))
+    assert np.array_equal(res["posterior"], post)
