@@ -454,12 +454,12 @@ int bssm_b200_is_correction_bsf_ung_parset(const bssm_ung_model* model, const bs
                                            int is_type, const uint32_t* counts, const double* approx_loglik,
                                            uint32_t n_stored, uint32_t draw_begin, uint32_t draw_end,
                                            bssm_postcorr_out* out);
-/* approx_mcmc::is_correction_spdk (src/approx_mcmc.cpp:606-678; run_mcmc(mcmc_type = "is*",
+/* approx_mcmc::is_correction_spdk (src/approx_mcmc.cpp:606-678, ssm_ung with parameter sets :923-1036; run_mcmc(mcmc_type = "is*",
  * sampling_method = "spdk")) for ssm_ung models whose stored draws are given as the reference's own parameter
  * sets (bssm_parset = parset_ung, src/parset_ng.h:11-40), output_type 3: for every stored draw the model,
  * its approximation at the stored mode (modes: n x n_stored) and nsim (is_type 1: nsim * counts[i]) simulated
- * trajectories; weights[i] = mean(exp(w - sum(scales))) (:637-639), posterior[i] = approx_loglik[i] (or 0 when
- * NULL) + log(weights[i]) (:676-677).  is_type 3 expands the draws by their counts first (expand(), :49-88):
+ * trajectories; weights[i] = mean(exp(w - sum(scales))) (:637-639, :959-961), posterior[i] = approx_loglik[i] (or 0 when
+ * NULL) + log(weights[i]) (:1034-1035).  is_type 3 expands the draws by their counts first (expand(), :49-88):
  * weights / posterior then hold sum(counts) values, else n_stored.  Draw i uses the random stream i. */
 int bssm_b200_is_correction_spdk_ung_parset(const bssm_ung_model* model, const bssm_parset* parset,
                                             uint32_t nsim, uint32_t seed, int is_type, const uint32_t* counts,
