@@ -2376,7 +2376,7 @@ int spdk_launch(const bssm_ung_model* M, const SpdkLayout& L, const std::vector<
   DevBuf<double> dpack, tm, lw, v, r, cube;
   DevBuf<uint32_t> doff;
   int rc;
-  if ((rc = dpack.upload(pack.data(), pack.size())) || (rc = tm.alloc(rows * S)) || (rc = lw.alloc(S)) ||
+  if ((rc = dpack.upload(pack.data(), L.total * nf)) || (rc = tm.alloc(rows * S)) || (rc = lw.alloc(S)) ||
       (rc = v.alloc((size_t)n * Tn)) || (rc = r.alloc((size_t)n * m * Tn)))
     return rc;
   const double* b = dpack.p;
@@ -2488,7 +2488,11 @@ int bssm_b200_is_correction_spdk_ung_parset(const bssm_ung_model* M, const bssm_
       ++d1;
     }
     const uint32_t nf = (uint32_t)(d1 - d0);
-    std::vector<double> pack(L.total * nf), al(nf), ss(nf), w; // al: 0 by definition of approximate_for_is
+    // the blocks of a chunk are tens of MB: the staging buffer is kept between calls (no first-touch faults again)
+    static thread_local std::vector<double> pack;
+    if (pack.size() < L.total * nf) pack.resize(L.total * nf);
+    double* const blocks = pack.data(); // (`pack` itself is thread-local: the OpenMP workers below must not name it)
+    std::vector<double> al(nf), ss(nf), w; // al: 0 by definition of approximate_for_is
 #pragma omp parallel for schedule(static)
     for (int64_t f = 0; f < (int64_t)nf; ++f) {
       const uint32_t c = src[d0 + f];
@@ -2511,7 +2515,7 @@ int bssm_b200_is_correction_spdk_ung_parset(const bssm_ung_model* M, const bssm_
         }
         Mi.xbeta = xb.data();
       }
-      spdk_fill(&Mi, modes + n * c, L, &pack[L.total * f], &al[f], &ss[f]);
+      spdk_fill(&Mi, modes + n * c, L, blocks + L.total * f, &al[f], &ss[f]);
     }
     if ((rc = spdk_launch(M, L, pack, nf, &ns[d0], 1, seed, (uint32_t)d0, w, nullptr))) return rc;
     size_t o = 0;

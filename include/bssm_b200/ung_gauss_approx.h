@@ -28,6 +28,7 @@
 #include <limits>
 #include <vector>
 
+#include <stdexcept>
 #include "bssm_b200.h"
 #include "bssm_b200/pf_math.h"
 #include "bssm_b200/pf_smallmat.h"
@@ -86,6 +87,11 @@ inline void conditional_cov_svd(int m, int n, std::vector<double>& Pt, std::vect
   factor(&Pt[0]);
 }
 
+/* the stack work arrays are sized for m = 16 and used up to the run-time m * m: gcc cannot see that */
+#if defined(__GNUC__) && !defined(__clang__)
+#pragma GCC diagnostic push
+#pragma GCC diagnostic ignored "-Wmaybe-uninitialized"
+#endif
 struct UngApprox {
   const bssm_ung_model* M;
   int n, m;
@@ -96,6 +102,7 @@ struct UngApprox {
   static constexpr double zero_tol = 1e-12; /* src/model_ssm_ulg.h:19 */
 
   explicit UngApprox(const bssm_ung_model* M_) : M(M_), n(M_->n), m(M_->m) {
+    if (m > MAXM) throw std::invalid_argument("UngApprox: state dimension m <= 16");
     xbeta.assign(n, 0.0);
     if (M->xbeta) for (int t = 0; t < n; ++t) xbeta[t] = M->xbeta[t];
     mode.assign(n, 0.0); ay.assign(n, 0.0); aH.assign(n, 0.0); aHH.assign(n, 0.0); scales.assign(n, 0.0);
@@ -155,20 +162,21 @@ struct UngApprox {
   }
 
   /* one Kalman step shared by the three recursions: returns whether y_t was used */
+  /* work arrays live on the stack (no allocation per time point): the engine and the oracle stop at m = 16 */
+  static constexpr int MAXM = 16;
   struct Step {
     double F, v;
-    std::vector<double> K;
+    double K[MAXM];
   };
   bool kalman_gain(int t, const double* at, const double* Pt, Step& st) const {
-    std::vector<double> zp(m);
-    pf_mtm(Z(t), Pt, zp.data(), 1, m, m);          /* Z' Pt */
+    double zp[MAXM];
+    pf_mtm(Z(t), Pt, zp, 1, m, m);          /* Z' Pt */
     double f = 0.0;
     for (int i = 0; i < m; ++i) f += zp[i] * Z(t)[i];
     st.F = f + aHH[t];
     const double yy = ytmp(t);
     if (!(std::isfinite(yy) && st.F > zero_tol)) return false;
-    st.K.resize(m);
-    pf_mm(Pt, Z(t), st.K.data(), m, m, 1);         /* Pt Z / F */
+    pf_mm(Pt, Z(t), st.K, m, m, 1);         /* Pt Z / F */
     for (int i = 0; i < m; ++i) st.K[i] = st.K[i] / st.F;
     double za = 0.0;
     for (int i = 0; i < m; ++i) za += Z(t)[i] * at[i];
@@ -176,28 +184,28 @@ struct UngApprox {
     return true;
   }
   void predict_mean(int t, const double* at, const Step* st, double* anext) const {
-    std::vector<double> tmp(m), ta(m);
+    double tmp[MAXM], ta[MAXM];
     for (int i = 0; i < m; ++i) tmp[i] = st ? at[i] + st->K[i] * st->v : at[i];
-    pf_mm(T(t), tmp.data(), ta.data(), m, m, 1);
+    pf_mm(T(t), tmp, ta, m, m, 1);
     for (int i = 0; i < m; ++i) anext[i] = C(t)[i] + ta[i];
   }
   /* Joseph form used by fast_smoother / smoother_ccov (:276-279, :441-443) */
   void predict_cov_joseph(int t, const double* Pt, const Step* st, double* Pnext) const {
-    std::vector<double> X((size_t)m * m), A((size_t)m * m), B((size_t)m * m), rr((size_t)m * m);
+    double X[MAXM * MAXM], A[MAXM * MAXM], B[MAXM * MAXM], rr[MAXM * MAXM];
     if (st) {
-      std::vector<double> tmp((size_t)m * m);
+      double tmp[MAXM * MAXM];
       for (int j = 0; j < m; ++j)
         for (int i = 0; i < m; ++i) tmp[i + (size_t)m * j] = (i == j ? 1.0 : 0.0) - st->K[i] * Z(t)[j];
-      pf_mm(tmp.data(), Pt, A.data(), m, m, m);
-      pf_mmt(A.data(), tmp.data(), B.data(), m, m, m);  /* tmp Pt tmp' */
+      pf_mm(tmp, Pt, A, m, m, m);
+      pf_mmt(A, tmp, B, m, m, m);  /* tmp Pt tmp' */
       for (int j = 0; j < m; ++j)
         for (int i = 0; i < m; ++i) X[i + (size_t)m * j] = B[i + (size_t)m * j] + st->K[i] * aHH[t] * st->K[j];
     } else {
       for (int e = 0; e < m * m; ++e) X[e] = Pt[e];
     }
-    pf_mm(T(t), X.data(), A.data(), m, m, m);
-    pf_mmt(A.data(), T(t), B.data(), m, m, m);
-    RR(t, rr.data());
+    pf_mm(T(t), X, A, m, m, m);
+    pf_mmt(A, T(t), B, m, m, m);
+    RR(t, rr);
     for (int e = 0; e < m * m; ++e) Pnext[e] = B[e] + rr[e];
     pf_symmatu(Pnext, m);
   }
@@ -216,12 +224,12 @@ struct UngApprox {
       Step st;
       if (kalman_gain(t, at.data(), Pt.data(), st)) {
         predict_mean(t, at.data(), &st, an.data());
-        std::vector<double> X((size_t)m * m), A((size_t)m * m), B((size_t)m * m), rr((size_t)m * m);
+        double X[MAXM * MAXM], A[MAXM * MAXM], B[MAXM * MAXM], rr[MAXM * MAXM];
         for (int j = 0; j < m; ++j)
           for (int i = 0; i < m; ++i) X[i + (size_t)m * j] = Pt[i + (size_t)m * j] - st.K[i] * st.K[j] * st.F;
-        pf_mm(T(t), X.data(), A.data(), m, m, m);
-        pf_mmt(A.data(), T(t), B.data(), m, m, m);
-        RR(t, rr.data());
+        pf_mm(T(t), X, A, m, m, m);
+        pf_mmt(A, T(t), B, m, m, m);
+        RR(t, rr);
         for (int e = 0; e < m * m; ++e) Pn[e] = B[e] + rr[e];
         pf_symmatu(Pn.data(), m);
         logLik -= 0.5 * (LOG2PI + pf_log(st.F) + st.v * st.v / st.F);
@@ -257,10 +265,10 @@ struct UngApprox {
     }
     std::vector<double> rt((size_t)m * n, 0.0);
     auto Lmat = [&](int t, double* Lm) { /* T (I - K Z') */
-      std::vector<double> tmp((size_t)m * m);
+      double tmp[MAXM * MAXM];
       for (int j = 0; j < m; ++j)
         for (int i = 0; i < m; ++i) tmp[i + (size_t)m * j] = (i == j ? 1.0 : 0.0) - st[t].K[i] * Z(t)[j];
-      pf_mm(T(t), tmp.data(), Lm, m, m, m);
+      pf_mm(T(t), tmp, Lm, m, m, m);
     };
     std::vector<double> Lm((size_t)m * m), lr(m);
     for (int t = n - 1; t > 0; --t) {
@@ -359,11 +367,11 @@ struct UngApprox {
     std::vector<double> rt(m, 0.0), Nt(mm, 0.0), Lm(mm), A(mm), B(mm), E(mm), lr(m), tmpv(m);
     for (int t = n - 1; t >= 0; --t) {
       const double* Tm;
-      std::vector<double> Ltmp(mm);
+      double Ltmp[MAXM * MAXM];
       if (used[t]) {
         for (int j = 0; j < m; ++j)
           for (int i = 0; i < m; ++i) Ltmp[i + (size_t)m * j] = (i == j ? 1.0 : 0.0) - st[t].K[i] * Z(t)[j];
-        pf_mm(T(t), Ltmp.data(), Lm.data(), m, m, m);
+        pf_mm(T(t), Ltmp, Lm.data(), m, m, m);
         Tm = Lm.data();
       } else {
         Tm = T(t);
@@ -448,6 +456,10 @@ struct UngApprox {
     }
   }
 };
+
+#if defined(__GNUC__) && !defined(__clang__)
+#pragma GCC diagnostic pop
+#endif
 
 } /* namespace pfga */
 #endif

@@ -44,3 +44,23 @@ print("%-30s %8s %14s %18s %14s %16s" % ("model", "nsim", "logLik ms", "with alp
 for r in rows:
     print("%-30s %8d %14.2f %18.2f %14.1f %16.6f%s" % (r[0], r[1], r[2], r[3], r[4], r[5],
                                                        "" if np.isnan(r[6]) else ("  (= oracle)" if r[5] == r[6] else "  (!= oracle %r)" % r[6])))
+
+# is_correction_spdk: one model + approximation per stored draw, all draws in one launch
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from test_gpu_parset import draws, ung_update_model  # noqa: E402
+
+print()
+print("is_correction_spdk (theta output), ssm_ung parameter sets, n = 200; oracle on all host cores (%d threads)"
+      % orc.L().orc_max_threads())
+print("(both arms evaluate update_fn for every draw in Python first: column 'update_fn ms', included in the two totals)")
+print("%-6s %8s %8s %14s %14s %14s %10s" % ("m", "draws", "nsim", "update_fn ms", "device call ms", "oracle ms", "same bits"))
+for m, ns, nsim in ((1, 2000, 10), (2, 2000, 10), (2, 2000, 100)):
+    model = ung_update_model(n=200, m=m)
+    mo = draws(model, ns)
+    bssm_b200.post_correct(model, mo, nsim, is_type="is2", seed=1, sampling_method="spdk")
+    ps_t = best(lambda: bssm_b200.api.build_parset(model, mo["theta"]), reps=3)
+    t_dev = best(lambda: bssm_b200.post_correct(model, mo, nsim, is_type="is2", seed=1, sampling_method="spdk"), reps=5)
+    t_cpu = best(lambda: orc.correction_spdk_parset(model, mo, nsim, is_type=2, seed=1), reps=3)
+    same = np.array_equal(bssm_b200.post_correct(model, mo, nsim, is_type="is2", seed=1, sampling_method="spdk")["weights"],
+                          orc.correction_spdk_parset(model, mo, nsim, is_type=2, seed=1)[0])
+    print("%-6d %8d %8d %14.1f %14.1f %14.1f %10s" % (m, ns, nsim, ps_t * 1e3, t_dev * 1e3, t_cpu * 1e3, same))
