@@ -2305,10 +2305,9 @@ int bssm_b200_gaussian_psi_smoother(const bssm_ung_model* M, uint32_t nsim, uint
 // ---------------------------------------------------------------- SPDK (simulation smoother + importance weights)
 namespace {
 // one model's inputs of pf::sim_smoother_kernel as offsets into its block of doubles
-struct SpdkLayout {
-  size_t y, u, xbeta, Z, T, R, C, D, a1, P1, LP1, RR, ay, aH, rH, yphi2, F, K, Lt, ahat, phi, total;
-  bool has_xbeta;
-  SpdkLayout(const bssm_ung_model* M, bool xb) : has_xbeta(xb) {
+struct SpdkLayout : pf::SimBlock {
+  SpdkLayout(const bssm_ung_model* M, bool xb) {
+    has_xbeta = xb ? 1 : 0;
     const size_t n = M->n, m = M->m, k = M->k, mm = m * m;
     size_t o = 0;
     auto take = [&](size_t cnt) { size_t at = o; o += cnt; return at; };
@@ -2322,18 +2321,10 @@ struct SpdkLayout {
   }
 };
 
-// The host part for one model: approximation (mode_in == nullptr: approximate(), src/model_ssm_ung.cpp:87-140;
-// else approximate_for_is at the stored mode, :143-161), scales, the smoothed mean of the pseudo-observations
-// and the gains of its smoother (fast_precomputing_smoother, src/model_ssm_ulg.cpp:359-413).
-void spdk_fill(const bssm_ung_model* M, const double* mode_in, const SpdkLayout& L, double* b, double* approx_ll,
-               double* ssum) {
+// the model part of a block: the arrays of the model itself and the factor of P1
+void spdk_fill_model(const bssm_ung_model* M, const SpdkLayout& L, double* b) {
   const int n = M->n, m = M->m, k = M->k;
   const size_t mm = (size_t)m * m;
-  pfga::UngApprox ga(M);
-  ga.run_head(mode_in);
-  pfga::UngApprox::SimGains sg;
-  std::vector<double> ahat;
-  ga.fast_smoother(ahat, &sg);
   auto put = [&](size_t at, const double* src, size_t cnt) { std::copy(src, src + cnt, b + at); };
   put(L.y, M->y, n); put(L.u, M->u, n);
   if (L.has_xbeta) put(L.xbeta, M->xbeta, n);
@@ -2341,6 +2332,23 @@ void spdk_fill(const bssm_ung_model* M, const double* mode_in, const SpdkLayout&
   put(L.R, M->R, (size_t)m * k * (M->Rtv ? n : 1)); put(L.C, M->C, (size_t)m * (M->Ctv ? n : 1));
   put(L.D, M->D, M->Dtv ? n : 1); put(L.a1, M->a1, m); put(L.P1, M->P1, mm);
   psd_chol_host(M->P1, m, b + L.LP1); // src/model_ssm_ulg.cpp:145
+  b[L.phi] = M->phi;
+}
+
+// The host part for one model: approximation (mode_in == nullptr: approximate(), src/model_ssm_ung.cpp:87-140;
+// else approximate_for_is at the stored mode, :143-161), scales, the smoothed mean of the pseudo-observations
+// and the gains of its smoother (fast_precomputing_smoother, src/model_ssm_ulg.cpp:359-413).
+void spdk_fill(const bssm_ung_model* M, const double* mode_in, const SpdkLayout& L, double* b, double* approx_ll,
+               double* ssum) {
+  const int n = M->n, m = M->m;
+  const size_t mm = (size_t)m * m;
+  pfga::UngApprox ga(M);
+  ga.run_head(mode_in);
+  pfga::UngApprox::SimGains sg;
+  std::vector<double> ahat;
+  ga.fast_smoother(ahat, &sg);
+  auto put = [&](size_t at, const double* src, size_t cnt) { std::copy(src, src + cnt, b + at); };
+  spdk_fill_model(M, L, b);
   put(L.RR, sg.RR.data(), sg.RR.size());
   put(L.ay, ga.ay.data(), n); put(L.aH, ga.aH.data(), n);
   for (int t = 0; t < n; ++t) {
@@ -2350,14 +2358,13 @@ void spdk_fill(const bssm_ung_model* M, const double* mode_in, const SpdkLayout&
   }
   put(L.F, sg.F.data(), n); put(L.K, sg.K.data(), (size_t)m * n); put(L.Lt, sg.Lt.data(), mm * n);
   put(L.ahat, ahat.data(), (size_t)m * (n + 1));
-  b[L.phi] = M->phi;
   *approx_ll = ga.approx_loglik;
   *ssum = pfga::accu2(ga.scales.data(), (size_t)n);
 }
 
 // nf blocks (pack) -> the log-weights sum_t log_weights(t, alpha_i) of all trajectories, draw after draw
 // (nsim_f[f] each); alpha_out: nf == 1 only, m x (n+1) x nsim
-int spdk_launch(const bssm_ung_model* M, const SpdkLayout& L, const std::vector<double>& pack, uint32_t nf,
+int spdk_launch(const bssm_ung_model* M, const SpdkLayout& L, const double* dblocks, double phi0, uint32_t nf,
                 const uint32_t* nsim_f, int antithetic, uint32_t seed, uint32_t first_filter,
                 std::vector<double>& logw, double* alpha_out) {
   const int n = M->n, m = M->m, k = M->k;
@@ -2373,18 +2380,18 @@ int spdk_launch(const bssm_ung_model* M, const SpdkLayout& L, const std::vector<
   sp.n = n; sp.m = m; sp.k = k; sp.distribution = M->distribution;
   sp.Ztv = M->Ztv; sp.Ttv = M->Ttv; sp.Rtv = M->Rtv; sp.Ctv = M->Ctv; sp.Dtv = M->Dtv;
   sp.seed = seed; sp.antithetic = antithetic ? 1 : 0; sp.first_filter = first_filter;
-  DevBuf<double> dpack, tm, lw, v, r, cube;
+  DevBuf<double> tm, lw, v, r, cube;
   DevBuf<uint32_t> doff;
   int rc;
-  if ((rc = dpack.upload(pack.data(), L.total * nf)) || (rc = tm.alloc(rows * S)) || (rc = lw.alloc(S)) ||
-      (rc = v.alloc((size_t)n * Tn)) || (rc = r.alloc((size_t)n * m * Tn)))
+  if ((rc = tm.alloc(rows * S)) || (rc = lw.alloc(S)) || (rc = v.alloc((size_t)n * Tn)) ||
+      (rc = r.alloc((size_t)n * m * Tn)))
     return rc;
-  const double* b = dpack.p;
+  const double* b = dblocks;
   sp.y = b + L.y; sp.u = b + L.u; sp.xbeta = L.has_xbeta ? b + L.xbeta : nullptr;
   sp.Z = b + L.Z; sp.T = b + L.T; sp.R = b + L.R; sp.C = b + L.C; sp.D = b + L.D; sp.a1 = b + L.a1;
   sp.P1 = b + L.P1; sp.LP1 = b + L.LP1; sp.RR = b + L.RR; sp.ay = b + L.ay; sp.aH = b + L.aH; sp.rH = b + L.rH;
   sp.yphi2 = b + L.yphi2; sp.F = b + L.F; sp.K = b + L.K; sp.Lt = b + L.Lt; sp.ahat = b + L.ahat;
-  sp.phi_f = b + L.phi; sp.phi = pack[L.phi];
+  sp.phi_f = b + L.phi; sp.phi = phi0;
   sp.alpha = tm.p; sp.logw = lw.p; sp.v = v.p; sp.r = r.p;
   if (nf == 1) { // one model: the scalar members, no search
     sp.nf = 0; sp.nsim = nsim_f[0]; sp.nsim2 = antithetic ? sp.nsim / 2 : sp.nsim; sp.threads = toff[1];
@@ -2440,7 +2447,9 @@ int bssm_b200_importance_sample_ung(const bssm_ung_model* M, uint32_t nsim, int 
   std::vector<double> pack(L.total), w;
   double approx_ll, ssum;
   spdk_fill(M, nullptr, L, pack.data(), &approx_ll, &ssum);
-  if ((rc = spdk_launch(M, L, pack, 1, &nsim, use_antithetic, seed, 0u, w, alpha))) return rc;
+  DevBuf<double> dpack;
+  if ((rc = dpack.upload(pack.data(), pack.size()))) return rc;
+  if ((rc = spdk_launch(M, L, dpack.p, M->phi, 1, &nsim, use_antithetic, seed, 0u, w, alpha))) return rc;
   // w - accu(scales), exp(w - max), mean (src/model_ssm_ung.cpp:206-210): nsim values, on the host
   double maxw = -std::numeric_limits<double>::infinity();
   for (uint32_t i = 0; i < nsim; ++i) { w[i] -= ssum; if (w[i] > maxw) maxw = w[i]; }
@@ -2454,9 +2463,10 @@ int bssm_b200_importance_sample_ung(const bssm_ung_model* M, uint32_t nsim, int 
 }
 
 // approx_mcmc::is_correction_spdk (src/approx_mcmc.cpp:606-678) for ssm_ung models given as parameter sets
-// (parset_ung::update, src/parset_ng.cpp:84-124), output_type 3: per stored draw the model, its approximation at
-// the stored mode (approximate_for_is) and the gains on the host (one OpenMP loop over the draws), ALL simulated
-// trajectories of a chunk of draws in one launch.  weight_i = mean(exp(w - accu(scales))) (:637-639).
+// (parset_ung::update, src/parset_ng.cpp:84-124), output_type 3: the host gathers every stored draw's model arrays
+// into its block; the approximation at the stored mode (approximate_for_is) and the smoother gains follow on the
+// device, one thread per draw (pf::spdk_gains_kernel), then ALL simulated trajectories of a chunk of draws in one
+// launch of the simulation smoother.  weight_i = mean(exp(w - accu(scales))) (:637-639).
 int bssm_b200_is_correction_spdk_ung_parset(const bssm_ung_model* M, const bssm_parset* ps, uint32_t nsim,
                                             uint32_t seed, int is_type, const uint32_t* counts, const double* modes,
                                             const double* approx_loglik, uint32_t n_stored, double* weights,
@@ -2477,6 +2487,8 @@ int bssm_b200_is_correction_spdk_ung_parset(const bssm_ung_model* M, const bssm_
   }
   const size_t nd = src.size();
   const SpdkLayout L(M, M->xbeta != nullptr || ps->beta != nullptr);
+  // BSSM_B200_HOST_APPROX=1: per-draw approximation and gains in an OpenMP loop on the host (A/B tests)
+  const bool host_approx = env_int("BSSM_B200_HOST_APPROX", 0) != 0;
   // chunks of draws: at most 2^31 doubles of trajectories and 2^28 doubles of model blocks per launch
   size_t d0 = 0;
   while (d0 < nd) {
@@ -2492,7 +2504,7 @@ int bssm_b200_is_correction_spdk_ung_parset(const bssm_ung_model* M, const bssm_
     static thread_local std::vector<double> pack;
     if (pack.size() < L.total * nf) pack.resize(L.total * nf);
     double* const blocks = pack.data(); // (`pack` itself is thread-local: the OpenMP workers below must not name it)
-    std::vector<double> al(nf), ss(nf), w; // al: 0 by definition of approximate_for_is
+    std::vector<double> al(nf), ss(nf), w, md(host_approx ? 0 : n * nf); // al: 0 by definition of approximate_for_is
 #pragma omp parallel for schedule(static)
     for (int64_t f = 0; f < (int64_t)nf; ++f) {
       const uint32_t c = src[d0 + f];
@@ -2515,9 +2527,32 @@ int bssm_b200_is_correction_spdk_ung_parset(const bssm_ung_model* M, const bssm_
         }
         Mi.xbeta = xb.data();
       }
-      spdk_fill(&Mi, modes + n * c, L, blocks + L.total * f, &al[f], &ss[f]);
+      if (host_approx) {
+        spdk_fill(&Mi, modes + n * c, L, blocks + L.total * f, &al[f], &ss[f]);
+      } else { // the model arrays only: approximation and gains follow on the device, one thread per draw
+        spdk_fill_model(&Mi, L, blocks + L.total * f);
+        std::copy(modes + n * c, modes + n * (c + 1), &md[n * f]);
+      }
     }
-    if ((rc = spdk_launch(M, L, pack, nf, &ns[d0], 1, seed, (uint32_t)d0, w, nullptr))) return rc;
+    DevBuf<double> dpack;
+    if ((rc = dpack.upload(blocks, L.total * nf))) return rc;
+    if (!host_approx) {
+      DevBuf<double> dmodes, dss, scratch;
+      if ((rc = dmodes.upload(md.data(), md.size())) || (rc = dss.alloc(nf)) || (rc = scratch.alloc((m + 2) * n * nf)))
+        return rc;
+      pf::SpdkGainParams gp{};
+      gp.n = M->n; gp.m = M->m; gp.k = M->k; gp.distribution = M->distribution;
+      gp.Ztv = M->Ztv; gp.Ttv = M->Ttv; gp.Rtv = M->Rtv; gp.Dtv = M->Dtv; gp.Ctv = M->Ctv;
+      gp.L = L; gp.blocks = dpack.p; gp.modes = dmodes.p; gp.ssum = dss.p; gp.scratch = scratch.p;
+      const dim3 grid(cdiv(nf, 32));
+      if (m == 1) pf::spdk_gains_kernel<1, true><<<grid, 32>>>(gp, nf);
+      else if (m == 2) pf::spdk_gains_kernel<2, true><<<grid, 32>>>(gp, nf);
+      else if (m == 3) pf::spdk_gains_kernel<3, true><<<grid, 32>>>(gp, nf);
+      else pf::spdk_gains_kernel<16, false><<<grid, 32>>>(gp, nf);
+      CU(cudaGetLastError());
+      CU(cudaMemcpy(ss.data(), dss.p, sizeof(double) * nf, cudaMemcpyDeviceToHost));
+    }
+    if ((rc = spdk_launch(M, L, dpack.p, blocks[L.phi], nf, &ns[d0], 1, seed, (uint32_t)d0, w, nullptr))) return rc;
     size_t o = 0;
     for (uint32_t f = 0; f < nf; ++f) {
       const uint32_t cnt = ns[d0 + f];

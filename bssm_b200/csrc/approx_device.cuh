@@ -14,6 +14,7 @@
 #include "pf_device.cuh"
 #include "bssm_b200/pf_smallmat.h"
 #include "bssm_b200/ung_gauss_approx.h"
+#include "sim_smoother.cuh"
 
 namespace pf {
 
@@ -290,6 +291,180 @@ __global__ void __launch_bounds__(32) ung_approx_for_is_kernel(const ApproxParam
   io.ay = ay; io.aHH = aHH;
   io.ah = ah; io.Pt = Pt; io.ccov = ccov; io.sF = sF; io.sv = sv; io.sK = sK;
   smoother_ccov_conditional<MAXM, FIXED>(io);
+}
+
+// ------------------------------------------------------------------ SPDK
+// approximate_for_is (laplace_iter at the stored mode + update_scales) and fast_precomputing_smoother
+// (src/model_ssm_ulg.cpp:359-413) of one stored draw per thread, for is_correction_spdk: what
+// pfga::UngApprox::run_head(mode) + fast_smoother(at, &gains) do on the host, written into the draw's block of
+// the simulation smoother (sim_smoother.cuh) -- pseudo-observations, 1 / sd, (y / phi)^2, F_t, K_t,
+// L_t = T_t (I - K_t Z_t'), R_t R_t', the smoothed mean -- plus accu(scales).  Same primitives, same order:
+// same bits as the host header (the oracle's independent restatement is the reference of the parity tests).
+struct SpdkGainParams {
+  int n, m, k, distribution;
+  int Ztv, Ttv, Rtv, Dtv, Ctv;
+  SimBlock L;
+  double* blocks;      // nf blocks of L.total doubles; the model part is filled in
+  const double* modes; // n per draw
+  double* ssum;        // nf: accu(scales)
+  double* scratch;     // (1 + 1 + m) * n per draw: v, scales, r
+};
+
+template <int MAXM, bool FIXED>
+__global__ void __launch_bounds__(32) spdk_gains_kernel(const SpdkGainParams p, uint32_t nf) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  constexpr int MM = MAXM * MAXM;
+  const int n = p.n, m = FIXED ? MAXM : p.m, k = p.k, dist = p.distribution;
+  const size_t mm = (size_t)m * m;
+  const double zero_tol = 1e-12;
+  double* b = p.blocks + (size_t)f * p.L.total;
+  const double *y = b + p.L.y, *u = b + p.L.u, *xb = p.L.has_xbeta ? b + p.L.xbeta : nullptr;
+  const double *Zb = b + p.L.Z, *Tb = b + p.L.T, *Rb = b + p.L.R, *Cb = b + p.L.C, *Db = b + p.L.D;
+  const double *a1 = b + p.L.a1, *P1 = b + p.L.P1;
+  const double phi = b[p.L.phi];
+  double *ay = b + p.L.ay, *aH = b + p.L.aH, *rH = b + p.L.rH, *yp2 = b + p.L.yphi2;
+  double *sF = b + p.L.F, *sK = b + p.L.K, *sL = b + p.L.Lt, *sRR = b + p.L.RR, *ah = b + p.L.ahat;
+  const double* mode = p.modes + (size_t)f * n;
+  double* sv = p.scratch + (size_t)f * (size_t)(m + 2) * n;
+  double* sc = sv + n;
+  double* rt = sc + n;
+  auto Z = [&](int t) { return Zb + (size_t)m * (t * p.Ztv); };
+  auto T = [&](int t) { return Tb + (size_t)m * m * (t * p.Ttv); };
+  auto R = [&](int t) { return Rb + (size_t)m * k * (t * p.Rtv); };
+  auto C = [&](int t) { return Cb + (size_t)m * (t * p.Ctv); };
+  auto D = [&](int t) { return Db[t * p.Dtv]; };
+  auto ytmp = [&](int t) { return xb ? ay[t] - xb[t] : ay[t]; };
+
+  // ---- laplace_iter at the stored mode, update_scales (as in ung_approx_for_is_kernel)
+  for (int t = 0; t < n; ++t) {
+    const double yt_ = y[t], ut = u[t], s = mode[t];
+    double HH, yt;
+    switch (dist) {
+      case 0: {
+        double tmp = yt_;
+        if (fabs(tmp) < 1e-4) tmp = 1e-4;
+        double q = tmp / phi;
+        HH = 2.0 * pf_exp(s) / (q * q);
+        yt = s + 1.0 - 0.5 * HH;
+      } break;
+      case 1: {
+        HH = 1.0 / (pf_exp(s) * ut);
+        yt = yt_ * HH + s - 1.0;
+      } break;
+      case 2: {
+        double e = pf_exp(s);
+        HH = (1.0 + e) * (1.0 + e) / (ut * e);
+        yt = yt_ * HH + s - 1.0 - e;
+      } break;
+      case 3: {
+        double e = pf_exp(s) * ut;
+        HH = (phi + e) * (phi + e) / (phi * e * (yt_ + phi));
+        yt = s + (phi + e) * (yt_ - e) / ((yt_ + phi) * e);
+      } break;
+      default: {
+        double e = pf_exp(s) * ut;
+        HH = e / (yt_ * phi);
+        yt = s - e / yt_ + 1;
+      } break;
+    }
+    const double H = sqrt(HH);
+    ay[t] = yt; aH[t] = H; rH[t] = 1.0 / H;
+    yp2[t] = HH; // the variance is parked here until the forward pass has used it
+    double scale = 0.0;
+    if (pf_isfinite(yt_)) {
+      double q = (yt - s) / H;
+      scale = pfga::ung_log_obs(dist, s, yt_, ut, phi) + 0.5 * (q * q);
+    }
+    sc[t] = scale;
+  }
+  { // arma::accu, two accumulators (pfga::accu2)
+    double s1 = 0.0, s2 = 0.0;
+    int j;
+    for (j = 1; j < n; j += 2) { s1 += sc[j - 1]; s2 += sc[j]; }
+    if ((j - 1) < n) s1 += sc[j - 1];
+    p.ssum[f] = s1 + s2;
+  }
+
+  // ---- forward pass: Kalman filter with the Joseph form (kalman_gain, predict_mean, predict_cov_joseph)
+  double A[MM], B[MM], X[MM], E[MM], rr[MM], Pc[MM], at[MAXM];
+  for (int i = 0; i < m; ++i) { at[i] = a1[i]; ah[i] = at[i]; }
+  for (size_t e = 0; e < mm; ++e) Pc[e] = P1[e];
+  for (int t = 0; t < n; ++t) {
+    double zp[MAXM], K[MAXM], tmpv[MAXM], ta[MAXM];
+    const double HH = yp2[t];
+    pf_mtm(Z(t), Pc, zp, 1, m, m);
+    double fs = 0.0;
+    for (int i = 0; i < m; ++i) fs += zp[i] * Z(t)[i];
+    const double F = fs + HH;
+    const double yy = ytmp(t);
+    const bool used = pf_isfinite(yy) && F > zero_tol;
+    double v = 0.0;
+    if (used) {
+      pf_mm(Pc, Z(t), K, m, m, 1);
+      for (int i = 0; i < m; ++i) K[i] = K[i] / F;
+      double za = 0.0;
+      for (int i = 0; i < m; ++i) za += Z(t)[i] * at[i];
+      v = yy - D(t) - za;
+    } else {
+      for (int i = 0; i < m; ++i) K[i] = 0.0;
+    }
+    sF[t] = F; sv[t] = v;
+    for (int i = 0; i < m; ++i) sK[(size_t)m * t + i] = K[i];
+    for (int i = 0; i < m; ++i) tmpv[i] = used ? at[i] + K[i] * v : at[i];
+    pf_mm(T(t), tmpv, ta, m, m, 1);
+    for (int i = 0; i < m; ++i) { at[i] = C(t)[i] + ta[i]; ah[(size_t)m * (t + 1) + i] = at[i]; }
+    if (used) {
+      for (int j = 0; j < m; ++j)
+        for (int i = 0; i < m; ++i) E[i + (size_t)m * j] = (i == j ? 1.0 : 0.0) - K[i] * Z(t)[j];
+      pf_mm(T(t), E, &sL[mm * t], m, m, m); // L_t = T_t (I - K_t Z_t'), kept for the simulated series
+      pf_mm(E, Pc, A, m, m, m);
+      pf_mmt(A, E, B, m, m, m);
+      for (int j = 0; j < m; ++j)
+        for (int i = 0; i < m; ++i) X[i + (size_t)m * j] = B[i + (size_t)m * j] + K[i] * HH * K[j];
+    } else {
+      for (size_t e = 0; e < mm; ++e) { X[e] = Pc[e]; sL[mm * t + e] = 0.0; }
+    }
+    pf_mm(T(t), X, A, m, m, m);
+    pf_mmt(A, T(t), B, m, m, m);
+    pf_mmt(R(t), R(t), rr, m, k, m);
+    if (p.Rtv || t == 0)
+      for (size_t e = 0; e < mm; ++e) sRR[mm * (p.Rtv ? t : 0) + e] = rr[e];
+    for (size_t e = 0; e < mm; ++e) Pc[e] = B[e] + rr[e];
+    pf_symmatu(Pc, m);
+    const double q = y[t] / phi; // (y_t / phi)^2 of the weights takes the parking place of the variance
+    yp2[t] = q * q;
+  }
+
+  // ---- backward pass for r_t and the smoothed mean (fast_smoother, src/model_ssm_ulg.cpp:335-354)
+  double lr[MAXM], w[MAXM], pw[MAXM];
+  for (int i = 0; i < m; ++i) rt[(size_t)m * (n - 1) + i] = 0.0;
+  for (int t = n - 1; t > 0; --t) {
+    const bool used = pf_isfinite(ytmp(t)) && sF[t] > zero_tol;
+    if (used) {
+      pf_mtm(&sL[mm * t], &rt[(size_t)m * t], lr, m, m, 1);
+      for (int i = 0; i < m; ++i) rt[(size_t)m * (t - 1) + i] = Z(t)[i] / sF[t] * sv[t] + lr[i];
+    } else {
+      pf_mtm(T(t), &rt[(size_t)m * t], &rt[(size_t)m * (t - 1)], m, m, 1);
+    }
+  }
+  if (pf_isfinite(ay[0]) && sF[0] > zero_tol) {
+    pf_mtm(sL, rt, lr, m, m, 1);
+    for (int i = 0; i < m; ++i) w[i] = Z(0)[i] / sF[0] * sv[0] + lr[i];
+    pf_mm(P1, w, pw, m, m, 1);
+  } else if (m == 1) {
+    pw[0] = P1[0] * T(0)[0] * rt[0];
+  } else {
+    pf_mtm(T(0), rt, w, m, m, 1);
+    pf_mm(P1, w, pw, m, m, 1);
+  }
+  for (int i = 0; i < m; ++i) { at[i] = a1[i] + pw[i]; ah[i] = at[i]; }
+  for (int t = 0; t < n - 1; ++t) {
+    double ta[MAXM], rrr[MAXM];
+    pf_mm(T(t), at, ta, m, m, 1);
+    pf_mm(&sRR[mm * (p.Rtv ? t : 0)], &rt[(size_t)m * t], rrr, m, m, 1);
+    for (int i = 0; i < m; ++i) { at[i] = C(t)[i] + ta[i] + rrr[i]; ah[(size_t)m * (t + 1) + i] = at[i]; }
+  }
 }
 
 } // namespace pf

@@ -20,6 +20,14 @@
 
 namespace pf {
 
+// one model's inputs of the simulation smoother as offsets into its block of doubles (the host packs the model
+// arrays; the approximation and the gains come from the host for one model and from spdk_gains_kernel for a
+// batch of stored draws)
+struct SimBlock {
+  size_t y, u, xbeta, Z, T, R, C, D, a1, P1, LP1, RR, ay, aH, rH, yphi2, F, K, Lt, ahat, phi, total;
+  int has_xbeta;
+};
+
 struct SimParams {
   int n, m, k, distribution;
   int Ztv, Ttv, Rtv, Ctv, Dtv;

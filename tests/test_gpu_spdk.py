@@ -128,3 +128,31 @@ def test_is_correction_spdk_with_regression_coefficients(engine):
     res = engine.post_correct(model, mo, 21, is_type="is2", seed=2, sampling_method="spdk")
     assert np.array_equal(res["weights"].view(np.uint64), w.view(np.uint64))
     assert np.array_equal(res["posterior"], post)
+
+
+def test_is_correction_spdk_device_gains_equal_host_gains(engine, monkeypatch):
+    """the per-draw approximation and smoother gains on the device (spdk_gains_kernel, one thread per draw) against
+    the host loop over the draws (BSSM_B200_HOST_APPROX=1): same bits, m = 1, 2 and 5"""
+    from test_gpu_parset import draws, ung_update_model
+    for model in (ung_update_model(m=1), ung_update_model(m=2, tv=True)):
+        mo = draws(model, 40)
+        dev = engine.post_correct(model, mo, 16, is_type="is1", seed=3, sampling_method="spdk")
+        monkeypatch.setenv("BSSM_B200_HOST_APPROX", "1")
+        host = engine.post_correct(model, mo, 16, is_type="is1", seed=3, sampling_method="spdk")
+        monkeypatch.delenv("BSSM_B200_HOST_APPROX")
+        assert np.array_equal(dev["weights"].view(np.uint64), host["weights"].view(np.uint64))
+    # m = 5 (run-time dimension): a seasonal model whose update_fn rescales the noise
+    base = seasonal_model(4)
+    R0 = np.array(base.R, dtype=float)
+
+    def update_fn(theta):
+        return {"R": R0 * np.exp(theta[0]), "P1": np.asarray(base.P1) * np.exp(theta[1])}
+
+    model = bssm_b200.ssm_ung(base.y, base.Z, base.T, base.R, base.a1, base.P1, "poisson", u=base.u, update_fn=update_fn)
+    rng = np.random.default_rng(2)
+    ns = 10
+    mo = {"theta": 0.1 * rng.normal(size=(ns, 2)), "counts": np.ones(ns, dtype=np.uint32), "output_type": 3,
+          "modes": np.asfortranarray(1.0 + 0.1 * rng.normal(size=(model.n, ns))), "posterior": np.zeros(ns)}
+    dev = engine.post_correct(model, mo, 20, is_type="is2", seed=4, sampling_method="spdk")
+    w, _ = orc.correction_spdk_parset(model, mo, 20, is_type=2, seed=4)
+    assert np.array_equal(dev["weights"].view(np.uint64), w.view(np.uint64))

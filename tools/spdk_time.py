@@ -52,15 +52,26 @@ from test_gpu_parset import draws, ung_update_model  # noqa: E402
 print()
 print("is_correction_spdk (theta output), ssm_ung parameter sets, n = 200; oracle on all host cores (%d threads)"
       % orc.L().orc_max_threads())
-print("(both arms evaluate update_fn for every draw in Python first: column 'update_fn ms', included in the two totals)")
-print("%-6s %8s %8s %14s %14s %14s %10s" % ("m", "draws", "nsim", "update_fn ms", "device call ms", "oracle ms", "same bits"))
-for m, ns, nsim in ((1, 2000, 10), (2, 2000, 10), (2, 2000, 100)):
+print("(update_fn is evaluated for every draw in Python before either arm runs: 'update_fn ms'; the two arms are timed")
+print(" with that parameter set already built; host approx = the same call with BSSM_B200_HOST_APPROX=1)")
+print("%-4s %7s %6s %13s %15s %15s %11s %10s" % ("m", "draws", "nsim", "update_fn ms", "device call ms", "host approx ms",
+                                                "oracle ms", "same bits"))
+_build = bssm_b200.api.build_parset
+for m, ns, nsim in ((1, 2000, 10), (2, 2000, 10), (2, 2000, 100), (2, 15000, 10)):
     model = ung_update_model(n=200, m=m)
     mo = draws(model, ns)
-    bssm_b200.post_correct(model, mo, nsim, is_type="is2", seed=1, sampling_method="spdk")
-    ps_t = best(lambda: bssm_b200.api.build_parset(model, mo["theta"]), reps=3)
-    t_dev = best(lambda: bssm_b200.post_correct(model, mo, nsim, is_type="is2", seed=1, sampling_method="spdk"), reps=5)
-    t_cpu = best(lambda: orc.correction_spdk_parset(model, mo, nsim, is_type=2, seed=1), reps=3)
-    same = np.array_equal(bssm_b200.post_correct(model, mo, nsim, is_type="is2", seed=1, sampling_method="spdk")["weights"],
-                          orc.correction_spdk_parset(model, mo, nsim, is_type=2, seed=1)[0])
-    print("%-6d %8d %8d %14.1f %14.1f %14.1f %10s" % (m, ns, nsim, ps_t * 1e3, t_dev * 1e3, t_cpu * 1e3, same))
+    ps_t = best(lambda: _build(model, mo["theta"]), reps=2)
+    ps = _build(model, mo["theta"])
+    bssm_b200.api.build_parset = lambda mdl, th: ps  # both arms reuse the parameter set
+    run = lambda: bssm_b200.post_correct(model, mo, nsim, is_type="is2", seed=1, sampling_method="spdk")
+    run()
+    t_dev = best(run, reps=5)
+    os.environ["BSSM_B200_HOST_APPROX"] = "1"
+    run()
+    t_host = best(run, reps=3)
+    del os.environ["BSSM_B200_HOST_APPROX"]
+    t_cpu = best(lambda: orc.correction_spdk_parset(model, mo, nsim, is_type=2, seed=1), reps=2)
+    same = np.array_equal(run()["weights"], orc.correction_spdk_parset(model, mo, nsim, is_type=2, seed=1)[0])
+    bssm_b200.api.build_parset = _build
+    print("%-4d %7d %6d %13.1f %15.1f %15.1f %11.1f %10s" % (m, ns, nsim, ps_t * 1e3, t_dev * 1e3, t_host * 1e3,
+                                                           t_cpu * 1e3, same))
