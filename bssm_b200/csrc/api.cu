@@ -2477,6 +2477,8 @@ int bssm_b200_is_correction_spdk_ung_parset(const bssm_ung_model* M, const bssm_
   if (ps->beta && (!ps->xreg || ps->n_xreg < 1)) return fail(BSSM_B200_ERR_ARG, "parset: beta needs xreg and n_xreg");
   if (is_type < 1 || is_type > 3) return fail(BSSM_B200_ERR_ARG, "is_type must be 1, 2 or 3");
   if (nsim < 2) return fail(BSSM_B200_ERR_UNSUPPORTED, "is_correction_spdk: nsim >= 2");
+  for (uint32_t i = 0; i < n_stored; ++i)
+    if (counts[i] < 1) return fail(BSSM_B200_ERR_ARG, "is_correction_spdk: counts must be >= 1");
   if ((rc = require_device())) return rc;
   const size_t n = M->n, m = M->m, k = M->k;
   // expand() for is_type 3 (src/approx_mcmc.cpp:49-88): one draw per repetition, each with its own stream

@@ -42,6 +42,11 @@ def test_no_cpu_fallback(engine):
         engine.bootstrap_filter(model, 16)
     with pytest.raises(engine.EngineError, match="no CUDA device"):
         engine.stratified_sample([0.5, 0.5], [0.1, 0.2])
+    # the SPDK entry points likewise: the simulation smoother has no host path in the product
+    with pytest.raises(engine.EngineError, match="no CUDA device"):
+        engine.importance_sample(model, 16)
+    with pytest.raises(engine.EngineError, match="no CUDA device"):
+        engine.logLik(model, 16, method="spdk")
 
 
 def test_argument_checks(engine):
@@ -55,6 +60,12 @@ def test_argument_checks(engine):
         engine.particle_smoother(model, 10, method="ekf")
     with pytest.raises(ValueError):
         engine.svm(np.zeros(5), 0.9, 0.1, sigma=1.0, mu=0.0)
+    with pytest.raises(ValueError):
+        engine.importance_sample(model, 1)
+    with pytest.raises(ValueError):
+        engine.importance_sample(data.lg_model(), 10)
+    with pytest.raises(ValueError):  # sampling_method "spdk" needs an ssm_ung model with an update_fn
+        engine.post_correct(model, data.svm_mcmc_output(model, 4), 10, sampling_method="spdk")
 
 
 def test_model_constructors_match_reference_layout(engine):
