@@ -102,8 +102,20 @@ __device__ void sim_smoother_thread(const SimParams& p, const uint32_t i, const 
   constexpr double zero_tol = 1e-12; // src/model_ssm_ulg.h:19
   double a[MAXM], fa[MAXM], nx[MAXM], tmp[MAXM], z[MAXM + 1];
 
+  // consecutive flat indices share a Box-Muller pair: one Philox call serves both (same values as pf_sim_normal)
+  uint32_t pair_t = 0xffffffffu, pair_id = 0xffffffffu;
+  double pz0 = 0.0, pz1 = 0.0;
+  auto sim_normal = [&](uint32_t t, uint32_t f) {
+    const uint32_t pr = f >> 1;
+    if (pr != pair_id || t != pair_t) {
+      pf_normal_pair_of((uint32_t)PF_RNG_SIM, p.seed, filter, t, 0u, pr, &pz0, &pz1);
+      pair_id = pr; pair_t = t;
+    }
+    return (f & 1u) ? pz1 : pz0;
+  };
+
   // ---- sweep 1: alpha+, y+ and the filter of y+ (:165-182, :323-330)
-  for (int d = 0; d < m; ++d) z[d] = pf_sim_normal(p.seed, filter, 0u, i * (uint32_t)m + d);
+  for (int d = 0; d < m; ++d) z[d] = sim_normal(0u, i * (uint32_t)m + d);
   for (int d = 0; d < m; ++d) {
     double s = 0.0;
     for (int j = 0; j < m; ++j) s += p.LP1[d + m * j] * z[j];
@@ -118,7 +130,7 @@ __device__ void sim_smoother_thread(const SimParams& p, const uint32_t i, const 
     const double* C = p.C + (size_t)m * (t * p.Ctv);
     const double Dt = p.D[t * p.Dtv];
     const double xb = p.xbeta ? p.xbeta[t] : 0.0;
-    for (int d = 0; d < K1; ++d) z[d] = pf_sim_normal(p.seed, filter, (uint32_t)(t + 1), i * (uint32_t)K1 + d);
+    for (int d = 0; d < K1; ++d) z[d] = sim_normal((uint32_t)(t + 1), i * (uint32_t)K1 + d);
     double yp = p.y[t]; // stays missing where the data are missing
     if (pf_isfinite(yp)) {
       double za = 0.0;
