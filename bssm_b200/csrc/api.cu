@@ -2502,8 +2502,10 @@ int bssm_b200_is_correction_spdk_ung_parset(const bssm_ung_model* M, const bssm_
       ++d1;
     }
     const uint32_t nf = (uint32_t)(d1 - d0);
-    // the blocks of a chunk are tens of MB: the staging buffer is kept between calls (no first-touch faults again)
+    // the blocks of a chunk are tens of MB: the staging buffer is kept between calls (no first-touch faults again),
+    // unless it grew beyond 256 MB -- such a buffer is handed back when the call ends
     static thread_local std::vector<double> pack;
+    struct Trim { std::vector<double>& v; ~Trim() { if (v.capacity() > ((size_t)1 << 25)) std::vector<double>().swap(v); } } trim{pack};
     if (pack.size() < L.total * nf) pack.resize(L.total * nf);
     double* const blocks = pack.data(); // (`pack` itself is thread-local: the OpenMP workers below must not name it)
     std::vector<double> al(nf), ss(nf), w, md(host_approx ? 0 : n * nf); // al: 0 by definition of approximate_for_is
