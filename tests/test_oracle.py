@@ -600,3 +600,36 @@ def test_spdk_loglik_agrees_with_the_psi_filter():
     r = orc.psi_filter(svm, 4000, 3)
     assert ll[1] == r.approx_loglik
     assert abs(ll[0] - r.loglik) < 0.3
+
+
+def test_spdk_correction_oracle_properties():
+    """is_correction_spdk restatement (src/approx_mcmc.cpp:606-678, :923-1036): results do not depend on the number
+    of threads (draw i owns stream i), is1 with unit counts is is2, is3 repeats a stored draw on fresh streams, and
+    a draw whose stored mode is the converged mode reproduces logLik(method = "spdk") - approx_loglik"""
+    from test_gpu_parset import draws, ung_update_model
+    model = ung_update_model(m=2, tv=True)
+    mo = draws(model, 9)
+    w1, p1 = orc.correction_spdk_parset(model, mo, 12, is_type=2, seed=5, threads=1)
+    w4, p4 = orc.correction_spdk_parset(model, mo, 12, is_type=2, seed=5, threads=4)
+    assert np.array_equal(w1, w4) and np.array_equal(p1, p4)
+    np.testing.assert_array_equal(p1, mo["approx_loglik"] + np.log(w1))
+    ones = dict(mo, counts=np.ones(9, dtype=np.uint32))
+    assert np.array_equal(orc.correction_spdk_parset(model, ones, 12, is_type=1, seed=5)[0],
+                          orc.correction_spdk_parset(model, ones, 12, is_type=2, seed=5)[0])
+    w3, _ = orc.correction_spdk_parset(model, mo, 12, is_type=3, seed=5)
+    assert w3.size == int(mo["counts"].sum()) and len(set(w3)) == w3.size
+    assert w3[0] == w1[0]  # expanded draw 0 is stored draw 0 on stream 0
+    # one stored draw = the model itself at its converged mode: weight = exp(logLik_spdk - approx_loglik)
+    base = data.poisson_bsm_model()
+    same = bssm_b200.ssm_ung(base.y, base.Z, base.T, base.R, base.a1, base.P1, "poisson", u=base.u,
+                             update_fn=lambda theta: {"R": np.array(base.R, dtype=float)})
+    mode = np.zeros(base.n)
+    orc.L().orc_ung_approx_mode_m.argtypes = [orc.C.POINTER(orc.UngModel), orc.c_double_p]
+    ms = same.c_struct()
+    orc.L().orc_ung_approx_mode_m(orc.C.byref(ms), orc.dptr(mode))
+    one = {"theta": np.zeros((1, 1)), "counts": np.ones(1, dtype=np.uint32), "modes": mode[:, None], "output_type": 3,
+           "posterior": np.zeros(1)}
+    w, _ = orc.correction_spdk_parset(same, one, 500, is_type=2, seed=7)
+    _, _, ll, _ = orc.importance_sample(base, 500, 7)
+    # (to the tolerance of approximate(): its pseudo-observations are linearised at the last-but-one iterate)
+    assert abs(np.log(w[0]) - (ll[0] - ll[1])) < 1e-4
